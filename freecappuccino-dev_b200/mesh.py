@@ -1,0 +1,492 @@
+"""Host-side mesh layer: the arrays of the reference's ``geometry`` module, fixture generators,
+polyMesh readers and the ``src-par``-style partitioner.
+
+Reference: src/mesh/geometry.f90:12-86 (array names), :118-406 (native reader), :416-664 (derived
+geometry), src-par/geometry.f90:140-240,615-633 (``process`` patches, halo buffers).
+
+Everything here is numpy on the host; index arrays are 1-based int32 exactly as the Fortran host
+would hand them to the C-ABI (include/fcp.h).
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import re
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# patch type codes shared with include/fcp.h (FCP_BC_*)
+BC_WALL, BC_INLET, BC_OUTLET, BC_SYMMETRY, BC_PRESSURE, BC_PERIODIC, BC_EMPTY, BC_PROCESS = range(8)
+BC_NAMES = ["wall", "inlet", "outlet", "symmetry", "pressure", "periodic", "empty", "process"]
+BC_CODE = {n: i for i, n in enumerate(BC_NAMES)}
+
+
+@dataclasses.dataclass
+class Mesh:
+    """Mirror of the reference ``geometry`` module. Faces: inner first, then patch by patch."""
+    numCells: int
+    numInnerFaces: int
+    numBoundaryFaces: int
+    owner: np.ndarray          # int32 [numFaces], 1-based
+    neighbour: np.ndarray      # int32 [numInnerFaces], 1-based
+    arx: np.ndarray
+    ary: np.ndarray
+    arz: np.ndarray
+    xf: np.ndarray
+    yf: np.ndarray
+    zf: np.ndarray
+    facint: np.ndarray
+    Df: np.ndarray
+    xc: np.ndarray             # [numCells] (or [numTotal] with ghost copies in the src-par layout)
+    yc: np.ndarray
+    zc: np.ndarray
+    vol: np.ndarray
+    bcname: List[str]
+    bctype: np.ndarray         # int32 [numBoundaries]
+    nfaces: np.ndarray         # int32 [numBoundaries]
+    startFace: np.ndarray      # int32 [numBoundaries]; face index = startFace + i, i = 1..nfaces (1-based result)
+    # optional topology (needed only to (re)compute geometry)
+    points: Optional[np.ndarray] = None       # [numNodes,3]
+    face_nodes: Optional[np.ndarray] = None   # int32 [numFaces, nomax] 1-based, 0-padded
+    face_nnodes: Optional[np.ndarray] = None  # int32 [numFaces]
+    # src-par layout (partitioned meshes only)
+    peer_rank: Optional[np.ndarray] = None    # int32 [numBoundaries], -1 if not a process patch
+    peer_patch: Optional[np.ndarray] = None   # int32 [numBoundaries], index of the matching patch on the peer
+    fpro: Optional[np.ndarray] = None         # [npro] face interpolation factor on halo faces
+    cell_global: Optional[np.ndarray] = None  # int64 [numCells] 0-based global cell id
+    face_global: Optional[np.ndarray] = None  # int64 [numFaces] 0-based global face id
+
+    @property
+    def numFaces(self) -> int:
+        return self.numInnerFaces + self.numBoundaryFaces
+
+    @property
+    def numTotal(self) -> int:
+        return self.numCells + self.numBoundaryFaces
+
+    @property
+    def numBoundaries(self) -> int:
+        return len(self.bcname)
+
+    @property
+    def iBndValueStart(self) -> np.ndarray:
+        # geometry.f90:282-290  iBndValueStart = numCells + (startFace - numInnerFaces)
+        return (self.numCells + self.startFace - self.numInnerFaces).astype(np.int32)
+
+    @property
+    def npro(self) -> int:
+        return int(self.nfaces[self.bctype == BC_PROCESS].sum())
+
+    def patch_faces(self, ib: int) -> np.ndarray:
+        """0-based face indices of patch ib."""
+        return np.arange(self.startFace[ib], self.startFace[ib] + self.nfaces[ib])
+
+    def boundary_values_of(self, fn) -> np.ndarray:
+        """Evaluate fn(x,y,z) at cell centres then boundary-face centres -> field of length numTotal."""
+        F = self.numInnerFaces
+        out = np.empty(self.numTotal)
+        out[: self.numCells] = fn(self.xc[: self.numCells], self.yc[: self.numCells], self.zc[: self.numCells])
+        out[self.numCells:] = fn(self.xf[F:], self.yf[F:], self.zf[F:])
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# derived geometry (vectorised restatement of the algorithm of geometry.f90:416-664; summation order
+# differs from the sequential Fortran loop, so results agree with it to rounding, not to the bit)
+# ---------------------------------------------------------------------------------------------
+def compute_geometry(points: np.ndarray, face_nodes: np.ndarray, face_nnodes: np.ndarray,
+                     owner: np.ndarray, neighbour: np.ndarray, numCells: int) -> Dict[str, np.ndarray]:
+    nF = owner.shape[0]
+    F = neighbour.shape[0]
+    third = 1.0 / 3.0
+    ar = np.zeros((nF, 3))
+    cf = np.zeros((nF, 3))
+    asum = np.zeros(nF)
+    vol = np.zeros(numCells)
+    cc = np.zeros((numCells, 3))
+    den = np.zeros(numCells)
+    own0 = owner.astype(np.int64) - 1
+    nb0 = neighbour.astype(np.int64) - 1
+    nomax = face_nodes.shape[1]
+    p1 = points[face_nodes[:, 0] - 1]
+    for i in range(nomax - 2):
+        sel = np.nonzero(face_nnodes - 2 > i)[0]
+        if sel.size == 0:
+            break
+        a1 = p1[sel]
+        a2 = points[face_nodes[sel, i + 1] - 1]
+        a3 = points[face_nodes[sel, i + 2] - 1]
+        n = 0.5 * np.cross(a2 - a1, a3 - a1)
+        c = third * (a3 + a2 + a1)
+        are = np.sqrt((n * n).sum(1))
+        ar[sel] += n
+        cf[sel] += are[:, None] * c
+        asum[sel] += are
+        riSi = (c * n).sum(1)
+        o = own0[sel]
+        vol += np.bincount(o, weights=third * riSi, minlength=numCells)
+        den += np.bincount(o, weights=riSi, minlength=numCells)
+        for d in range(3):
+            cc[:, d] += np.bincount(o, weights=0.75 * riSi * c[:, d], minlength=numCells)
+        inner = sel < F
+        if inner.any():
+            nn = nb0[sel[inner]]
+            r2 = -riSi[inner]
+            vol += np.bincount(nn, weights=third * r2, minlength=numCells)
+            den += np.bincount(nn, weights=r2, minlength=numCells)
+            for d in range(3):
+                cc[:, d] += np.bincount(nn, weights=0.75 * r2 * c[inner, d], minlength=numCells)
+    cf /= asum[:, None]
+    cc /= den[:, None]
+    dP = cf[:F] - cc[own0[:F]]
+    dN = cf[:F] - cc[nb0]
+    djp = np.sqrt((dP * dP).sum(1))
+    djn = np.sqrt((dN * dN).sum(1))
+    facint = djp / (djp + djn)
+    dpn = cc[nb0] - cc[own0[:F]]
+    S = ar[:F]
+    Df = (S * S).sum(1) / (S * dpn).sum(1)
+    return dict(arx=ar[:, 0].copy(), ary=ar[:, 1].copy(), arz=ar[:, 2].copy(),
+                xf=cf[:, 0].copy(), yf=cf[:, 1].copy(), zf=cf[:, 2].copy(),
+                xc=cc[:, 0].copy(), yc=cc[:, 1].copy(), zc=cc[:, 2].copy(), vol=vol, facint=facint, Df=Df)
+
+
+def mesh_from_topology(points, face_nodes, face_nnodes, owner, neighbour, numCells,
+                       patches: Sequence[Tuple[str, str, int, int]], geometry: Optional[Dict[str, np.ndarray]] = None) -> Mesh:
+    """patches: (name, type, nFaces, startFace) with startFace the 0-based offset of the reference's
+    ``boundary`` file (Appendix D of SURVEY.md)."""
+    owner = np.ascontiguousarray(owner, dtype=np.int32)
+    neighbour = np.ascontiguousarray(neighbour, dtype=np.int32)
+    g = geometry if geometry is not None else compute_geometry(points, face_nodes, face_nnodes, owner, neighbour, numCells)
+    F = neighbour.shape[0]
+    return Mesh(numCells=numCells, numInnerFaces=F, numBoundaryFaces=owner.shape[0] - F, owner=owner, neighbour=neighbour,
+                bcname=[p[0] for p in patches], bctype=np.array([BC_CODE[p[1]] for p in patches], dtype=np.int32),
+                nfaces=np.array([p[2] for p in patches], dtype=np.int32),
+                startFace=np.array([p[3] for p in patches], dtype=np.int32),
+                points=points, face_nodes=face_nodes, face_nnodes=face_nnodes, **g)
+
+
+# ---------------------------------------------------------------------------------------------
+# structured hexahedral generator (cells i-fastest, OpenFOAM upper-triangular face order)
+# ---------------------------------------------------------------------------------------------
+def bump_nodes(n: int, coef: float = 0.2, length: float = 1.0) -> np.ndarray:
+    """n+1 node coordinates clustered toward both ends (coef<1), a stand-in for gmsh 'Bump'."""
+    t = np.linspace(0.0, 1.0, n + 1)
+    if coef == 1.0:
+        return length * t
+    a = np.arctanh(np.sqrt(1.0 - coef))
+    s = 0.5 * (1.0 + np.tanh(a * (2.0 * t - 1.0)) / np.tanh(a))
+    s[0], s[-1] = 0.0, 1.0
+    return length * s
+
+
+def hex_mesh(xs: np.ndarray, ys: np.ndarray, zs: np.ndarray,
+             patch_types: Optional[Dict[str, str]] = None, distort: float = 0.0) -> Mesh:
+    """Tensor-product hex mesh on node coordinates xs, ys, zs.
+
+    Patches (in this order): 'top' (+y, the lid), 'bottom' (-y), 'left' (-x), 'right' (+x),
+    'back' (-z), 'front' (+z); types default to wall (2-D cases pass back/front = 'empty'/'symmetry').
+    distort>0 moves interior nodes by a smooth deterministic displacement (fraction of the local
+    spacing) to make the mesh non-orthogonal for parity tests.
+    """
+    nx, ny, nz = len(xs) - 1, len(ys) - 1, len(zs) - 1
+    types = dict(top="wall", bottom="wall", left="wall", right="wall", back="wall", front="wall")
+    if patch_types:
+        types.update(patch_types)
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    if distort > 0.0:
+        lx, ly, lz = xs[-1] - xs[0], ys[-1] - ys[0], zs[-1] - zs[0]
+        sx, sy, sz = (X - xs[0]) / lx, (Y - ys[0]) / ly, (Z - zs[0]) / lz
+        hx = np.gradient(xs)[:, None, None]
+        hy = np.gradient(ys)[None, :, None]
+        hz = np.gradient(zs)[None, None, :]
+        bub = np.sin(np.pi * sx) * np.sin(np.pi * sy) * (np.sin(np.pi * sz) if nz > 1 else 1.0)
+        X = X + distort * hx * bub * np.sin(7.0 * sy + 3.0 * sz + 0.3)
+        Y = Y + distort * hy * bub * np.sin(5.0 * sx + 4.0 * sz + 1.1)
+        if nz > 1:
+            Z = Z + distort * hz * bub * np.sin(6.0 * sx + 5.0 * sy + 2.2)
+
+    def nid(i, j, k):
+        return (i + (nx + 1) * (j + (ny + 1) * k) + 1).astype(np.int32)
+
+    npts = (nx + 1) * (ny + 1) * (nz + 1)
+    points = np.empty((npts, 3))
+    order = np.arange(npts)
+    ii = order % (nx + 1)
+    jj = (order // (nx + 1)) % (ny + 1)
+    kk = order // ((nx + 1) * (ny + 1))
+    points[:, 0] = X[ii, jj, kk]
+    points[:, 1] = Y[ii, jj, kk]
+    points[:, 2] = Z[ii, jj, kk]
+
+    def cid(i, j, k):
+        return i + nx * (j + ny * k)
+
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    I, J, K = I.ravel(order="F"), J.ravel(order="F"), K.ravel(order="F")  # cell order: i fastest
+
+    fl_nodes, fl_own, fl_nb, fl_key = [], [], [], []
+    # +x faces
+    m = I < nx - 1
+    i, j, k = I[m], J[m], K[m]
+    fl_nodes.append(np.stack([nid(i + 1, j, k), nid(i + 1, j + 1, k), nid(i + 1, j + 1, k + 1), nid(i + 1, j, k + 1)], 1))
+    fl_own.append(cid(i, j, k)); fl_nb.append(cid(i + 1, j, k)); fl_key.append(cid(i, j, k) * 3 + 0)
+    # +y faces
+    m = J < ny - 1
+    i, j, k = I[m], J[m], K[m]
+    fl_nodes.append(np.stack([nid(i, j + 1, k), nid(i, j + 1, k + 1), nid(i + 1, j + 1, k + 1), nid(i + 1, j + 1, k)], 1))
+    fl_own.append(cid(i, j, k)); fl_nb.append(cid(i, j + 1, k)); fl_key.append(cid(i, j, k) * 3 + 1)
+    # +z faces
+    m = K < nz - 1
+    i, j, k = I[m], J[m], K[m]
+    fl_nodes.append(np.stack([nid(i, j, k + 1), nid(i + 1, j, k + 1), nid(i + 1, j + 1, k + 1), nid(i, j + 1, k + 1)], 1))
+    fl_own.append(cid(i, j, k)); fl_nb.append(cid(i, j, k + 1)); fl_key.append(cid(i, j, k) * 3 + 2)
+    key = np.concatenate(fl_key)
+    perm = np.argsort(key, kind="stable")
+    in_nodes = np.concatenate(fl_nodes)[perm]
+    in_own = np.concatenate(fl_own)[perm]
+    in_nb = np.concatenate(fl_nb)[perm]
+    F = in_own.shape[0]
+
+    bnodes, bown, patches = [], [], []
+    start = F
+
+    def add_patch(name, nodes, own):
+        nonlocal start
+        bnodes.append(nodes); bown.append(own)
+        patches.append((name, types[name], own.shape[0], start))
+        start += own.shape[0]
+
+    i, k = np.meshgrid(np.arange(nx), np.arange(nz), indexing="ij"); i, k = i.ravel(order="F"), k.ravel(order="F")
+    j = np.full_like(i, ny - 1)
+    add_patch("top", np.stack([nid(i, j + 1, k), nid(i, j + 1, k + 1), nid(i + 1, j + 1, k + 1), nid(i + 1, j + 1, k)], 1), cid(i, j, k))
+    j = np.zeros_like(i)
+    add_patch("bottom", np.stack([nid(i, j, k), nid(i + 1, j, k), nid(i + 1, j, k + 1), nid(i, j, k + 1)], 1), cid(i, j, k))
+    j, k = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij"); j, k = j.ravel(order="F"), k.ravel(order="F")
+    i = np.zeros_like(j)
+    add_patch("left", np.stack([nid(i, j, k), nid(i, j, k + 1), nid(i, j + 1, k + 1), nid(i, j + 1, k)], 1), cid(i, j, k))
+    i = np.full_like(j, nx - 1)
+    add_patch("right", np.stack([nid(i + 1, j, k), nid(i + 1, j + 1, k), nid(i + 1, j + 1, k + 1), nid(i + 1, j, k + 1)], 1), cid(i, j, k))
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij"); i, j = i.ravel(order="F"), j.ravel(order="F")
+    k = np.zeros_like(i)
+    add_patch("back", np.stack([nid(i, j, k), nid(i, j + 1, k), nid(i + 1, j + 1, k), nid(i + 1, j, k)], 1), cid(i, j, k))
+    k = np.full_like(i, nz - 1)
+    add_patch("front", np.stack([nid(i, j, k + 1), nid(i + 1, j, k + 1), nid(i + 1, j + 1, k + 1), nid(i, j + 1, k + 1)], 1), cid(i, j, k))
+
+    face_nodes = np.ascontiguousarray(np.concatenate([in_nodes] + bnodes), dtype=np.int32)
+    owner = (np.concatenate([in_own] + bown) + 1).astype(np.int32)
+    neighbour = (in_nb + 1).astype(np.int32)
+    face_nnodes = np.full(owner.shape[0], 4, dtype=np.int32)
+    return mesh_from_topology(points, face_nodes, face_nnodes, owner, neighbour, nx * ny * nz, patches)
+
+
+def cavity_mesh(n: int, nz: Optional[int] = None, length: float = 1.0, bump: float = 1.0, distort: float = 0.0,
+                two_d_type: str = "empty") -> Mesh:
+    """Lid-driven cavity fixtures: n x n x nz. nz=None -> n (3-D, six walls); nz=1 -> 2-D slab with
+    back/front patches of type two_d_type (examples/cavity uses 'empty', test/ uses 'symmetry')."""
+    nz = n if nz is None else nz
+    xs = bump_nodes(n, bump, length)
+    ys = bump_nodes(n, bump, length)
+    if nz == 1:
+        zs = np.array([0.0, 0.05 * length if length == 1.0 else 0.1 * length])
+        return hex_mesh(xs, ys, zs, dict(back=two_d_type, front=two_d_type), distort)
+    zs = bump_nodes(nz, bump, length)
+    return hex_mesh(xs, ys, zs, None, distort)
+
+
+# ---------------------------------------------------------------------------------------------
+# polyMesh readers (Appendix D of SURVEY.md; geometry.f90:118-406 native, :846-1717 OpenFOAM)
+# ---------------------------------------------------------------------------------------------
+def _strip_foam(text: str) -> str:
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//.*", "", text)
+    text = re.sub(r"FoamFile\s*\{.*?\}", "", text, flags=re.S)
+    return text
+
+
+def read_boundary_simplified(path: str) -> List[Tuple[str, str, int, int]]:
+    out = []
+    with open(path) as fh:
+        for line in fh:
+            t = line.split()
+            if not t or t[0].startswith("#"):
+                continue
+            out.append((t[0], t[1], int(t[2]), int(t[3])))
+    return out
+
+
+def read_polymesh_openfoam(dirname: str) -> Mesh:
+    """OpenFOAM ASCII points/faces/owner/neighbour + the reference's simplified 4-column boundary."""
+    def body(name):
+        with open(os.path.join(dirname, name)) as fh:
+            raw = fh.read()
+        return raw, _strip_foam(raw)
+
+    raw_owner, t_owner = body("owner")
+    mnote = re.search(r"nCells:\s*(\d+)", raw_owner)
+    _, t_pts = body("points")
+    _, t_faces = body("faces")
+    _, t_nb = body("neighbour")
+    pts = np.array(re.findall(r"\(\s*([-+0-9.eE]+)\s+([-+0-9.eE]+)\s+([-+0-9.eE]+)\s*\)", t_pts), dtype=float)
+    own = np.array(t_owner.replace("(", " ").replace(")", " ").split()[1:], dtype=np.int64)
+    nb = np.array(t_nb.replace("(", " ").replace(")", " ").split()[1:], dtype=np.int64)
+    fl = re.findall(r"(\d+)\s*\(([^()]*)\)", t_faces)
+    nomax = max(int(a) for a, _ in fl)
+    fn = np.zeros((len(fl), nomax), dtype=np.int32)
+    fnn = np.zeros(len(fl), dtype=np.int32)
+    for r, (a, b) in enumerate(fl):
+        ids = [int(v) + 1 for v in b.split()]
+        fnn[r] = int(a)
+        fn[r, : len(ids)] = ids
+    numCells = int(mnote.group(1)) if mnote else int(own.max()) + 1
+    patches = read_boundary_simplified(os.path.join(dirname, "boundary"))
+    return mesh_from_topology(pts, fn, fnn, (own + 1).astype(np.int32), (nb + 1).astype(np.int32), numCells, patches)
+
+
+def read_polymesh_native(dirname: str) -> Mesh:
+    """Native format: size, points, faces ('n i1..in', 1-based), owner, neighbour, boundary."""
+    with open(os.path.join(dirname, "size")) as fh:
+        sizes = [int(line.split()[0]) for line in fh if line.strip()]
+    numNodes, numCells, numInner, numBnd, numFaces = sizes[:5]
+    pts = np.loadtxt(os.path.join(dirname, "points")).reshape(-1, 3)[:numNodes]
+    own = np.loadtxt(os.path.join(dirname, "owner"), dtype=np.int64).ravel()[:numFaces]
+    nb = np.loadtxt(os.path.join(dirname, "neighbour"), dtype=np.int64).ravel()[:numInner]
+    rows = []
+    with open(os.path.join(dirname, "faces")) as fh:
+        for line in fh:
+            t = line.split()
+            if t:
+                rows.append([int(v) for v in t])
+    nomax = max(r[0] for r in rows)
+    fn = np.zeros((len(rows), nomax), dtype=np.int32)
+    fnn = np.array([r[0] for r in rows], dtype=np.int32)
+    for r, row in enumerate(rows):
+        fn[r, : row[0]] = row[1: 1 + row[0]]
+    patches = read_boundary_simplified(os.path.join(dirname, "boundary"))
+    return mesh_from_topology(pts, fn, fnn, own.astype(np.int32), nb.astype(np.int32), numCells, patches)
+
+
+def write_polymesh_native(mesh: Mesh, dirname: str) -> None:
+    """Writes the native format the serial reference reads (geometry.f90:118-406)."""
+    os.makedirs(dirname, exist_ok=True)
+    with open(os.path.join(dirname, "size"), "w") as fh:
+        fh.write(f"{mesh.points.shape[0]} numNodes\n{mesh.numCells} numCells\n{mesh.numInnerFaces} numInnerFaces\n"
+                 f"{mesh.numBoundaryFaces} numBoundaryFaces\n{mesh.numFaces} numFaces\n")
+    np.savetxt(os.path.join(dirname, "points"), mesh.points, fmt="%.17g")
+    with open(os.path.join(dirname, "faces"), "w") as fh:
+        for n, row in zip(mesh.face_nnodes, mesh.face_nodes):
+            fh.write(str(int(n)) + " " + " ".join(str(int(v)) for v in row[:n]) + "\n")
+    np.savetxt(os.path.join(dirname, "owner"), mesh.owner, fmt="%d")
+    np.savetxt(os.path.join(dirname, "neighbour"), mesh.neighbour, fmt="%d")
+    with open(os.path.join(dirname, "boundary"), "w") as fh:
+        fh.write("# name type nFaces startFace\n")
+        for ib in range(mesh.numBoundaries):
+            fh.write(f"{mesh.bcname[ib]} {BC_NAMES[mesh.bctype[ib]]} {mesh.nfaces[ib]} {mesh.startFace[ib]}\n")
+
+
+def load_mesh_npz(path: str) -> Mesh:
+    d = np.load(path, allow_pickle=False)
+    patches = [(str(n), str(t), int(c), int(s)) for n, t, c, s in
+               zip(d["patch_name"], d["patch_type"], d["patch_nfaces"], d["patch_start"])]
+    return mesh_from_topology(d["points"], d["face_nodes"], d["face_nnodes"], d["owner"], d["neighbour"],
+                              int(d["numCells"]), patches)
+
+
+def save_mesh_npz(mesh: Mesh, path: str) -> None:
+    np.savez_compressed(path, points=mesh.points, face_nodes=mesh.face_nodes, face_nnodes=mesh.face_nnodes,
+                        owner=mesh.owner, neighbour=mesh.neighbour, numCells=mesh.numCells,
+                        patch_name=np.array(mesh.bcname), patch_type=np.array([BC_NAMES[t] for t in mesh.bctype]),
+                        patch_nfaces=mesh.nfaces, patch_start=mesh.startFace)
+
+
+# ---------------------------------------------------------------------------------------------
+# partitioner: global mesh + cell->rank map  ->  per-rank meshes in the src-par layout
+# (src-par/geometry.f90:140-240: `process` patches, one per neighbour rank, same face order on both
+#  sides; ghost value of a process face lives in that face's boundary slot, exchange.f90:110-127;
+#  ghost xc,yc,zc,vol copies, geometry.f90:769-773; fpro, :826-871)
+# ---------------------------------------------------------------------------------------------
+def slab_partition(mesh: Mesh, nranks: int) -> np.ndarray:
+    """Contiguous blocks of cells (z-slabs for an i-fastest structured mesh)."""
+    return (np.arange(mesh.numCells, dtype=np.int64) * nranks // mesh.numCells).astype(np.int32)
+
+
+def partition(mesh: Mesh, cell_rank: np.ndarray) -> List[Mesh]:
+    nranks = int(cell_rank.max()) + 1
+    F = mesh.numInnerFaces
+    own0 = mesh.owner.astype(np.int64) - 1
+    nb0 = mesh.neighbour.astype(np.int64) - 1
+    ro = cell_rank[own0]                     # rank of owner, all faces
+    rn = cell_rank[nb0]                      # rank of neighbour, inner faces
+    parts: List[Mesh] = []
+    # patch index bookkeeping so that peer_patch can be filled after all ranks are built
+    proc_patch_index: List[Dict[int, int]] = []
+    for r in range(nranks):
+        cells = np.nonzero(cell_rank == r)[0]
+        g2l = np.full(mesh.numCells, -1, dtype=np.int64)
+        g2l[cells] = np.arange(cells.size)
+        inner = np.nonzero((ro[:F] == r) & (rn == r))[0]
+        f_idx = [inner]
+        f_own = [g2l[own0[inner]]]
+        f_flip = [np.zeros(inner.size, dtype=bool)]
+        names, types, counts = [], [], []
+        for ib in range(mesh.numBoundaries):
+            pf = mesh.patch_faces(ib)
+            pf = pf[ro[pf] == r]
+            f_idx.append(pf); f_own.append(g2l[own0[pf]]); f_flip.append(np.zeros(pf.size, dtype=bool))
+            names.append(mesh.bcname[ib]); types.append(int(mesh.bctype[ib])); counts.append(pf.size)
+        peers = {}
+        cutO = np.nonzero((ro[:F] == r) & (rn != r))[0]      # we own P: outward normal = S
+        cutN = np.nonzero((ro[:F] != r) & (rn == r))[0]      # we own N: outward normal = -S
+        other = np.concatenate([rn[cutO], ro[:F][cutN]])
+        faces = np.concatenate([cutO, cutN])
+        flip = np.concatenate([np.zeros(cutO.size, dtype=bool), np.ones(cutN.size, dtype=bool)])
+        loc = np.concatenate([g2l[own0[cutO]], g2l[nb0[cutN]]])
+        ppi: Dict[int, int] = {}
+        for q in np.unique(other):
+            sel = np.nonzero(other == q)[0]
+            sel = sel[np.argsort(faces[sel], kind="stable")]   # global face order on both sides
+            ppi[int(q)] = len(names)
+            f_idx.append(faces[sel]); f_own.append(loc[sel]); f_flip.append(flip[sel])
+            names.append(f"procBoundary{r}to{int(q)}"); types.append(BC_PROCESS); counts.append(sel.size)
+            peers[len(names) - 1] = int(q)
+        proc_patch_index.append(ppi)
+        fidx = np.concatenate(f_idx)
+        fown = np.concatenate(f_own)
+        fflip = np.concatenate(f_flip)
+        sgn = np.where(fflip, -1.0, 1.0)
+        nFi = inner.size
+        starts = nFi + np.concatenate([[0], np.cumsum(counts)[:-1]]) if counts else np.zeros(0)
+        nloc = cells.size
+        nB = fidx.size - nFi
+        # ghost copies of cell-centre data in the boundary slots of process faces
+        xc = np.zeros(nloc + nB); yc = np.zeros(nloc + nB); zc = np.zeros(nloc + nB); vol = np.zeros(nloc + nB)
+        xc[:nloc], yc[:nloc], zc[:nloc], vol[:nloc] = mesh.xc[cells], mesh.yc[cells], mesh.zc[cells], mesh.vol[cells]
+        peer_rank = np.full(len(names), -1, dtype=np.int32)
+        fpro = []
+        for ib, q in peers.items():
+            s = int(starts[ib]); c = counts[ib]
+            gf = fidx[s: s + c]
+            gl = np.where(fflip[s: s + c], own0[gf], nb0[gf])   # the off-rank cell (global id)
+            sl = slice(nloc + s - nFi, nloc + s - nFi + c)
+            xc[sl], yc[sl], zc[sl], vol[sl] = mesh.xc[gl], mesh.yc[gl], mesh.zc[gl], mesh.vol[gl]
+            lam = mesh.facint[gf]
+            fpro.append(np.where(fflip[s: s + c], 1.0 - lam, lam))   # weight of the ghost cell seen from this side
+            peer_rank[ib] = q
+        part = Mesh(numCells=nloc, numInnerFaces=nFi, numBoundaryFaces=nB,
+                    owner=(fown + 1).astype(np.int32), neighbour=(g2l[nb0[inner]] + 1).astype(np.int32),
+                    arx=mesh.arx[fidx] * sgn, ary=mesh.ary[fidx] * sgn, arz=mesh.arz[fidx] * sgn,
+                    xf=mesh.xf[fidx].copy(), yf=mesh.yf[fidx].copy(), zf=mesh.zf[fidx].copy(),
+                    facint=mesh.facint[inner].copy(), Df=mesh.Df[inner].copy(),
+                    xc=xc, yc=yc, zc=zc, vol=vol, bcname=names, bctype=np.array(types, dtype=np.int32),
+                    nfaces=np.array(counts, dtype=np.int32), startFace=np.asarray(starts, dtype=np.int32),
+                    peer_rank=peer_rank, peer_patch=np.full(len(names), -1, dtype=np.int32),
+                    fpro=np.concatenate(fpro) if fpro else np.zeros(0),
+                    cell_global=cells.astype(np.int64), face_global=fidx.astype(np.int64))
+        parts.append(part)
+    for r, part in enumerate(parts):
+        for ib in range(part.numBoundaries):
+            q = int(part.peer_rank[ib])
+            if q >= 0:
+                part.peer_patch[ib] = proc_patch_index[q][r]
+    return parts

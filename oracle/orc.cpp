@@ -1,0 +1,825 @@
+// oracle/orc.cpp -- CPU restatement of the freeCappuccino pressure-velocity coupling hot path.
+// TEST INFRASTRUCTURE ONLY (see orc.h).  Loop order and expression order follow the Fortran
+// line by line so that sums round the way the reference's do.  All file:line citations are
+// relative to the reference repository root.
+#include "orc.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+typedef int32_t i32;
+
+// parameters.f90:6  `real(dp), parameter :: small = 1e-20`  -- a default-real literal (quirk Q5)
+static const double SMALL = (double)1e-20f;
+extern "C" double orc_small(void) { return SMALL; }
+
+// ------------------------------------------------------------------------------------------
+// The fixed reduction tree of the CUDA kernels (freecappuccino-dev_b200/csrc/reduce.cuh):
+//  chunk of 2048 elements per CTA; thread t (0..255) adds elements t, t+256, ... in order;
+//  xor-butterfly over the 32 lanes (16,8,4,2,1); the 8 warp sums added in warp order;
+//  chunk partials reduced the same way by one CTA (thread t takes partial t, t+256, ...).
+// ------------------------------------------------------------------------------------------
+static double block_tree(const double *acc /*256*/) {
+  double ws[8];
+  for (int w = 0; w < 8; ++w) {
+    double cur[32], nxt[32];
+    for (int l = 0; l < 32; ++l) cur[l] = acc[w * 32 + l];
+    for (int off = 16; off >= 1; off >>= 1) {
+      for (int l = 0; l < 32; ++l) nxt[l] = cur[l] + cur[l ^ off];
+      for (int l = 0; l < 32; ++l) cur[l] = nxt[l];
+    }
+    ws[w] = cur[0];
+  }
+  double s = ws[0];
+  for (int w = 1; w < 8; ++w) s += ws[w];
+  return s;
+}
+extern "C" double orc_sum_tree(const double *v, int64_t n) {
+  const int64_t CH = 2048;
+  int64_t nb = (n + CH - 1) / CH;
+  if (nb == 0) nb = 1;
+  std::vector<double> part(nb);
+  double acc[256];
+  for (int64_t b = 0; b < nb; ++b) {
+    for (int t = 0; t < 256; ++t) {
+      double s = 0.0;
+      for (int j = 0; j < 8; ++j) {
+        int64_t i = b * CH + (int64_t)j * 256 + t;
+        if (i < n) s += v[i];
+      }
+      acc[t] = s;
+    }
+    part[b] = block_tree(acc);
+  }
+  for (int t = 0; t < 256; ++t) {
+    double s = 0.0;
+    for (int64_t i = t; i < nb; i += 256) s += part[i];
+    acc[t] = s;
+  }
+  return block_tree(acc);
+}
+static double sum_seq(const double *v, int64_t n) {
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += v[i];
+  return s;
+}
+static double sum_mode(int mode, const double *v, int64_t n) {
+  return mode == ORC_SUM_TREE ? orc_sum_tree(v, n) : sum_seq(v, n);
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry  (src/mesh/geometry.f90:416-530, 581-606, 648-664)
+// ------------------------------------------------------------------------------------------
+extern "C" void orc_geometry(i32 numNodes, i32 numCells, i32 numInnerFaces, i32 numFaces,
+                             const double *x, const double *y, const double *z,
+                             const i32 *nnodes, const i32 *node, i32 nomax,
+                             const i32 *owner, const i32 *neighbour,
+                             double *arx, double *ary, double *arz, double *xf, double *yf, double *zf,
+                             double *vol, double *xc, double *yc, double *zc, double *facint, double *Df) {
+  (void)numNodes;
+  const double third = 1.0 / 3.0;  // geometry.f90:151  third = 1./3._dp
+  const double half = 0.5;
+  std::vector<double> r8tmp(numCells, 0.0);
+  for (i32 f = 0; f < numFaces; ++f) { arx[f] = ary[f] = arz[f] = 0.0; xf[f] = yf[f] = zf[f] = 0.0; }  // Q14: relies on zero pages
+  for (i32 c = 0; c < numCells; ++c) { vol[c] = 0.0; xc[c] = yc[c] = zc[c] = 0.0; }
+#define NODE(j, f) (node[(size_t)(f) * nomax + (j)] - 1)
+  for (i32 f = 0; f < numFaces; ++f) {           // :416
+    i32 inp = owner[f] - 1;
+    double areasum = 0.0;
+    for (i32 i = 0; i < nnodes[f] - 2; ++i) {    // :424 triangle fan from node 1
+      i32 n1 = NODE(0, f), n2 = NODE(i + 1, f), n3 = NODE(i + 2, f);
+      double px = x[n2] - x[n1], py = y[n2] - y[n1], pz = z[n2] - z[n1];
+      double qx = x[n3] - x[n1], qy = y[n3] - y[n1], qz = z[n3] - z[n1];
+      double nx = half * (py * qz - pz * qy);    // :1745-1747
+      double ny = half * (pz * qx - px * qz);
+      double nz = half * (px * qy - py * qx);
+      arx[f] = arx[f] + nx; ary[f] = ary[f] + ny; arz[f] = arz[f] + nz;
+      double cx = third * (x[n3] + x[n2] + x[n1]);
+      double cy = third * (y[n3] + y[n2] + y[n1]);
+      double cz = third * (z[n3] + z[n2] + z[n1]);
+      double are = std::sqrt(nx * nx + ny * ny + nz * nz);
+      xf[f] = xf[f] + (are * cx); yf[f] = yf[f] + (are * cy); zf[f] = zf[f] + (are * cz);
+      areasum = areasum + are;
+      double riSi = (cx * nx + cy * ny + cz * nz);  // :479
+      vol[inp] = vol[inp] + third * riSi;
+      xc[inp] = xc[inp] + 0.75 * riSi * cx;
+      yc[inp] = yc[inp] + 0.75 * riSi * cy;
+      zc[inp] = zc[inp] + 0.75 * riSi * cz;
+      r8tmp[inp] = r8tmp[inp] + riSi;
+      if (f < numInnerFaces) {
+        i32 inn = neighbour[f] - 1;
+        riSi = -(cx * nx + cy * ny + cz * nz);
+        vol[inn] = vol[inn] + third * riSi;
+        xc[inn] = xc[inn] + 0.75 * riSi * cx;
+        yc[inn] = yc[inn] + 0.75 * riSi * cy;
+        zc[inn] = zc[inn] + 0.75 * riSi * cz;
+        r8tmp[inn] = r8tmp[inn] + riSi;
+      }
+    }
+    xf[f] = xf[f] / areasum; yf[f] = yf[f] / areasum; zf[f] = zf[f] / areasum;
+  }
+#undef NODE
+  for (i32 c = 0; c < numCells; ++c) { xc[c] = xc[c] / r8tmp[c]; yc[c] = yc[c] / r8tmp[c]; zc[c] = zc[c] / r8tmp[c]; }
+  for (i32 f = 0; f < numInnerFaces; ++f) {      // :581-606, interpolation_coeff_variant = 2
+    i32 inp = owner[f] - 1, inn = neighbour[f] - 1;
+    double xpn = xf[f] - xc[inp], ypn = yf[f] - yc[inp], zpn = zf[f] - zc[inp];
+    double djp = std::sqrt(xpn * xpn + ypn * ypn + zpn * zpn);
+    xpn = xf[f] - xc[inn]; ypn = yf[f] - yc[inn]; zpn = zf[f] - zc[inn];
+    double djn = std::sqrt(xpn * xpn + ypn * ypn + zpn * zpn);
+    facint[f] = djp / (djp + djn);
+  }
+  for (i32 f = 0; f < numInnerFaces; ++f) {      // :648-664
+    i32 inp = owner[f] - 1, inn = neighbour[f] - 1;
+    double xpn = xc[inn] - xc[inp], ypn = yc[inn] - yc[inp], zpn = zc[inn] - zc[inp];
+    double are = arx[f] * arx[f] + ary[f] * ary[f] + arz[f] * arz[f];
+    Df[f] = are / (arx[f] * xpn + ary[f] * ypn + arz[f] * zpn);
+  }
+}
+
+extern "C" void orc_wall_geometry(const orc_mesh *m, double *dnw, double *srdw, double *dns, double *srds) {
+  i32 iWall = 0, iSym = 0;                       // geometry.f90:698-754
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    if (m->bctype[ib] != ORC_BC_SYMMETRY && m->bctype[ib] != ORC_BC_WALL) continue;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1;
+      double are = std::sqrt(m->arx[f] * m->arx[f] + m->ary[f] * m->ary[f] + m->arz[f] * m->arz[f]);
+      double nxf = m->arx[f] / are, nyf = m->ary[f] / are, nzf = m->arz[f] / are;
+      double dn = (m->xf[f] - m->xc[ijp]) * nxf + (m->yf[f] - m->yc[ijp]) * nyf + (m->zf[f] - m->zc[ijp]) * nzf;
+      if (m->bctype[ib] == ORC_BC_SYMMETRY) { dns[iSym] = dn; srds[iSym] = are / dn; ++iSym; }
+      else { dnw[iWall] = dn; srdw[iWall] = are / dn; ++iWall; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR pattern  (src/sparseMatrix/sparse_matrix.f90:110-260).  The reference heap-sorts the COO
+// list lexicographically; the result is "rows ascending, columns ascending, diagonal embedded".
+// ------------------------------------------------------------------------------------------
+extern "C" i32 orc_csr_nnz(const orc_mesh *m) { return 2 * m->numInnerFaces + m->numCells; }  // :110 (numPeriodic = 0)
+
+extern "C" void orc_csr_create(const orc_mesh *m, i32 *ia, i32 *ja, i32 *diag, i32 *icell_jcell, i32 *jcell_icell) {
+  const i32 n = m->numCells, F = m->numInnerFaces;
+  std::vector<i32> cnt(n + 1, 0);
+  for (i32 c = 0; c < n; ++c) cnt[c] = 1;
+  for (i32 f = 0; f < F; ++f) { cnt[m->owner[f] - 1]++; cnt[m->neighbour[f] - 1]++; }
+  ia[0] = 1;
+  for (i32 c = 0; c < n; ++c) ia[c + 1] = ia[c] + cnt[c];
+  std::vector<i32> pos(n);
+  for (i32 c = 0; c < n; ++c) { pos[c] = ia[c] - 1; ja[pos[c]++] = c + 1; }
+  for (i32 f = 0; f < F; ++f) {
+    i32 p = m->owner[f] - 1, q = m->neighbour[f] - 1;
+    ja[pos[p]++] = q + 1; ja[pos[q]++] = p + 1;
+  }
+  for (i32 c = 0; c < n; ++c) std::sort(ja + ia[c] - 1, ja + ia[c + 1] - 1);
+  for (i32 c = 0; c < n; ++c)                    // :185 find_main_diag_element_positions
+    for (i32 k = ia[c]; k < ia[c + 1]; ++k) if (ja[k - 1] == c + 1) { diag[c] = k; break; }
+  auto csr_to_k = [&](i32 ic, i32 jc) -> i32 {   // utils.f90:96-147
+    for (i32 l = ia[ic - 1]; l <= ia[ic] - 1; ++l) if (ja[l - 1] == jc) return l;
+    return 0;
+  };
+  for (i32 f = 0; f < F; ++f) {                  // :251-260
+    icell_jcell[f] = csr_to_k(m->owner[f], m->neighbour[f]);
+    jcell_icell[f] = csr_to_k(m->neighbour[f], m->owner[f]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// laplacian(mu,phi)  (src/finiteVolume/fvImplicit/laplacian.f90)
+// ------------------------------------------------------------------------------------------
+extern "C" void orc_laplacian(const orc_mesh *m, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell,
+                              const double *mu, const double *phi, double *a, i32 nnz, double *su) {
+  for (i32 k = 0; k < nnz; ++k) a[k] = 0.0;
+  for (i32 i = 0; i < m->numInnerFaces; ++i) {
+    i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    double arx = m->arx[i], ary = m->ary[i], arz = m->arz[i];
+    double fxn = m->facint[i], fxp = 1.0 - m->facint[i];
+    double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
+    double smdpn = (arx * arx + ary * ary + arz * arz) / (arx * xpn + ary * ypn + arz * zpn);
+    double cap = (fxp * mu[ijp] + fxn * mu[ijn]) * smdpn;
+    double can = cap;
+    a[icell_jcell[i] - 1] = can;
+    a[jcell_icell[i] - 1] = cap;
+    a[diag[ijp] - 1] = a[diag[ijp] - 1] - can;
+    a[diag[ijn] - 1] = a[diag[ijn] - 1] - cap;
+  }
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+      double are = std::sqrt(m->arx[f] * m->arx[f] + m->ary[f] * m->ary[f] + m->arz[f] * m->arz[f]);
+      double nxf = m->arx[f] / are, nyf = m->ary[f] / are, nzf = m->arz[f] / are;
+      double dfn = (m->xf[f] - m->xc[ijp]) * nxf + (m->yf[f] - m->yc[ijp]) * nyf + (m->zf[f] - m->zc[ijp]) * nzf;
+      double dcoef = mu[ijp] * are / dfn;
+      a[diag[ijp] - 1] = a[diag[ijp] - 1] - dcoef;
+      su[ijp] = su[ijp] - dcoef * phi[ijb];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gradients  (src/finiteVolume/fvExplicit/gradients.f90)
+// ------------------------------------------------------------------------------------------
+extern "C" void orc_grad_gauss(const orc_mesh *m, const double *u, double *dudxi) {  // :1607-1693
+  for (int64_t i = 0; i < 3 * (int64_t)m->numTotal; ++i) dudxi[i] = 0.0;
+  for (i32 i = 0; i < m->numInnerFaces; ++i) {
+    i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    double fie = u[ijp] + (u[ijn] - u[ijp]) * m->facint[i];
+    double dfxe = fie * m->arx[i], dfye = fie * m->ary[i], dfze = fie * m->arz[i];
+    dudxi[3 * ijp + 0] = dudxi[3 * ijp + 0] + dfxe;
+    dudxi[3 * ijp + 1] = dudxi[3 * ijp + 1] + dfye;
+    dudxi[3 * ijp + 2] = dudxi[3 * ijp + 2] + dfze;
+    dudxi[3 * ijn + 0] = dudxi[3 * ijn + 0] - dfxe;
+    dudxi[3 * ijn + 1] = dudxi[3 * ijn + 1] - dfye;
+    dudxi[3 * ijn + 2] = dudxi[3 * ijn + 2] - dfze;
+  }
+  for (i32 i = 0; i < m->numBoundaryFaces; ++i) {   // :1673-1680 + gradbc :1696
+    i32 f = m->numInnerFaces + i, ijp = m->owner[f] - 1, ijb = m->numCells + i;
+    dudxi[3 * ijp + 0] = dudxi[3 * ijp + 0] + u[ijb] * m->arx[f];
+    dudxi[3 * ijp + 1] = dudxi[3 * ijp + 1] + u[ijb] * m->ary[f];
+    dudxi[3 * ijp + 2] = dudxi[3 * ijp + 2] + u[ijb] * m->arz[f];
+  }
+  for (i32 c = 0; c < m->numCells; ++c) {
+    double volr = 1.0 / m->vol[c];
+    dudxi[3 * c + 0] = dudxi[3 * c + 0] * volr;
+    dudxi[3 * c + 1] = dudxi[3 * c + 1] * volr;
+    dudxi[3 * c + 2] = dudxi[3 * c + 2] * volr;
+  }
+}
+
+extern "C" void orc_create_matrix_lsq(const orc_mesh *m, int weighted, double *Dmat) {  // :660-779 / :1157-1326
+  const i32 n = m->numCells;
+  for (int64_t i = 0; i < 9 * (int64_t)n; ++i) Dmat[i] = 0.0;
+#define D(k, c) Dmat[9 * (size_t)(c) + (k) - 1]
+  for (i32 i = 0; i < m->numInnerFaces; ++i) {
+    i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    double Dx = m->xc[ijn] - m->xc[ijp], Dy = m->yc[ijn] - m->yc[ijp], Dz = m->zc[ijn] - m->zc[ijp];
+    if (weighted) {
+      double w = 1.0 / (Dx * Dx + Dy * Dy + Dz * Dz);
+      D(1, ijp) = D(1, ijp) + w * Dx * Dx; D(1, ijn) = D(1, ijn) + w * Dx * Dx;
+      D(4, ijp) = D(4, ijp) + w * Dy * Dy; D(4, ijn) = D(4, ijn) + w * Dy * Dy;
+      D(6, ijp) = D(6, ijp) + w * Dz * Dz; D(6, ijn) = D(6, ijn) + w * Dz * Dz;
+      D(2, ijp) = D(2, ijp) + w * Dx * Dy; D(2, ijn) = D(2, ijn) + w * Dx * Dy;
+      D(3, ijp) = D(3, ijp) + w * Dx * Dz; D(3, ijn) = D(3, ijn) + w * Dx * Dz;
+      D(5, ijp) = D(5, ijp) + w * Dy * Dz; D(5, ijn) = D(5, ijn) + w * Dy * Dz;
+    } else {
+      D(1, ijp) = D(1, ijp) + Dx * Dx; D(1, ijn) = D(1, ijn) + Dx * Dx;
+      D(4, ijp) = D(4, ijp) + Dy * Dy; D(4, ijn) = D(4, ijn) + Dy * Dy;
+      D(6, ijp) = D(6, ijp) + Dz * Dz; D(6, ijn) = D(6, ijn) + Dz * Dz;
+      D(2, ijp) = D(2, ijp) + Dx * Dy; D(2, ijn) = D(2, ijn) + Dx * Dy;
+      D(3, ijp) = D(3, ijp) + Dx * Dz; D(3, ijn) = D(3, ijn) + Dx * Dz;
+      D(5, ijp) = D(5, ijp) + Dy * Dz; D(5, ijn) = D(5, ijn) + Dy * Dz;
+    }
+  }
+  for (i32 i = 0; i < m->numBoundaryFaces; ++i) {
+    i32 f = m->numInnerFaces + i, ijp = m->owner[f] - 1;
+    double Dx = m->xf[f] - m->xc[ijp], Dy = m->yf[f] - m->yc[ijp], Dz = m->zf[f] - m->zc[ijp];
+    if (weighted) {
+      double w = 1.0 / (Dx * Dx + Dy * Dy + Dz * Dz);
+      D(1, ijp) = D(1, ijp) + w * Dx * Dx; D(4, ijp) = D(4, ijp) + w * Dy * Dy; D(6, ijp) = D(6, ijp) + w * Dz * Dz;
+      D(2, ijp) = D(2, ijp) + w * Dx * Dy; D(3, ijp) = D(3, ijp) + w * Dx * Dz; D(5, ijp) = D(5, ijp) + w * Dy * Dz;
+    } else {
+      D(1, ijp) = D(1, ijp) + Dx * Dx; D(4, ijp) = D(4, ijp) + Dy * Dy; D(6, ijp) = D(6, ijp) + Dz * Dz;
+      D(2, ijp) = D(2, ijp) + Dx * Dy; D(3, ijp) = D(3, ijp) + Dx * Dz; D(5, ijp) = D(5, ijp) + Dy * Dz;
+    }
+  }
+  for (i32 c = 0; c < n; ++c) {                  // :748-777
+    double d11 = D(1, c), d12 = D(2, c), d13 = D(3, c), d22 = D(4, c), d23 = D(5, c), d33 = D(6, c);
+    double d21 = d12, d31 = d13, d32 = d23;
+    double tmp = 1.0 / (d11 * d22 * d33 - d11 * d23 * d32 - d12 * d21 * d33 + d12 * d23 * d31 + d13 * d21 * d32 - d13 * d22 * d31 + SMALL);
+    D(1, c) = (d22 * d33 - d23 * d32) * tmp;
+    D(2, c) = (d21 * d33 - d23 * d31) * tmp;
+    D(3, c) = (d21 * d32 - d22 * d31) * tmp;
+    D(4, c) = (d11 * d33 - d13 * d31) * tmp;
+    D(5, c) = (d12 * d33 - d13 * d32) * tmp;
+    D(6, c) = (d11 * d32 - d12 * d31) * tmp;
+    D(7, c) = (d12 * d23 - d13 * d22) * tmp;
+    D(8, c) = (d11 * d23 - d13 * d21) * tmp;
+    D(9, c) = (d11 * d22 - d12 * d21) * tmp;
+  }
+}
+
+extern "C" void orc_grad_lsq(const orc_mesh *m, int weighted, int row2_correct, const double *Dmat,
+                             const double *phi, double *g) {   // :782-893 / :1334-1486
+  for (int64_t i = 0; i < 3 * (int64_t)m->numTotal; ++i) g[i] = 0.0;
+  for (i32 i = 0; i < m->numInnerFaces; ++i) {
+    i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    double Dx, Dy, Dz;
+    if (weighted) {
+      double w = (phi[ijn] - phi[ijp]) /
+                 ((m->xc[ijn] - m->xc[ijp]) * (m->xc[ijn] - m->xc[ijp]) + (m->yc[ijn] - m->yc[ijp]) * (m->yc[ijn] - m->yc[ijp]) +
+                  (m->zc[ijn] - m->zc[ijp]) * (m->zc[ijn] - m->zc[ijp]));
+      Dx = w * (m->xc[ijn] - m->xc[ijp]); Dy = w * (m->yc[ijn] - m->yc[ijp]); Dz = w * (m->zc[ijn] - m->zc[ijp]);
+    } else {
+      double delta = phi[ijn] - phi[ijp];
+      Dx = (m->xc[ijn] - m->xc[ijp]) * delta; Dy = (m->yc[ijn] - m->yc[ijp]) * delta; Dz = (m->zc[ijn] - m->zc[ijp]) * delta;
+    }
+    g[3 * ijp + 0] = g[3 * ijp + 0] + Dx; g[3 * ijp + 1] = g[3 * ijp + 1] + Dy; g[3 * ijp + 2] = g[3 * ijp + 2] + Dz;
+    g[3 * ijn + 0] = g[3 * ijn + 0] + Dx; g[3 * ijn + 1] = g[3 * ijn + 1] + Dy; g[3 * ijn + 2] = g[3 * ijn + 2] + Dz;
+  }
+  for (i32 i = 0; i < m->numBoundaryFaces; ++i) {
+    i32 f = m->numInnerFaces + i, ijp = m->owner[f] - 1, ijn = m->numCells + i;
+    double Dx, Dy, Dz;
+    if (weighted) {
+      // quirk Q2 (:1459): the weight's denominator indexes xf(i), the boundary COUNTER, not xf(iface)
+      double w = (phi[ijn] - phi[ijp]) /
+                 ((m->xf[i] - m->xc[ijp]) * (m->xf[i] - m->xc[ijp]) + (m->yf[i] - m->yc[ijp]) * (m->yf[i] - m->yc[ijp]) +
+                  (m->zf[i] - m->zc[ijp]) * (m->zf[i] - m->zc[ijp]));
+      Dx = w * (m->xf[f] - m->xc[ijp]); Dy = w * (m->yf[f] - m->yc[ijp]); Dz = w * (m->zf[f] - m->zc[ijp]);
+    } else {
+      double delta = phi[ijn] - phi[ijp];
+      Dx = (m->xf[f] - m->xc[ijp]) * delta; Dy = (m->yf[f] - m->yc[ijp]) * delta; Dz = (m->zf[f] - m->zc[ijp]) * delta;
+    }
+    g[3 * ijp + 0] = g[3 * ijp + 0] + Dx; g[3 * ijp + 1] = g[3 * ijp + 1] + Dy; g[3 * ijp + 2] = g[3 * ijp + 2] + Dz;
+  }
+  for (i32 c = 0; c < m->numCells; ++c) {        // :880-890 ; quirk Q1 in row 2
+    double b1 = g[3 * c + 0], b2 = g[3 * c + 1], b3 = g[3 * c + 2];
+    g[3 * c + 0] = b1 * D(1, c) - b2 * D(2, c) + b3 * D(3, c);
+    if (row2_correct) g[3 * c + 1] = b2 * D(4, c) - b1 * D(5, c) - b3 * D(6, c);
+    else              g[3 * c + 1] = b1 * D(4, c) - b2 * D(5, c) - b3 * D(6, c);
+    g[3 * c + 2] = b1 * D(7, c) - b2 * D(8, c) + b3 * D(9, c);
+  }
+#undef D
+}
+
+// ------------------------------------------------------------------------------------------
+// bpres / gradp_and_sources  (Pressure/bpres.f90, Pressure/nablap.f90:19-208)
+// ------------------------------------------------------------------------------------------
+extern "C" void orc_bpres(const orc_mesh *m, double *p, const double *dPdxi, int istage) {
+  if (istage == 1) {
+    for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+      if (m->bctype[ib] == ORC_BC_PRESSURE) continue;
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        p[ijb] = p[ijp];
+      }
+    }
+  } else {
+    for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+      if (m->bctype[ib] != ORC_BC_WALL) continue;
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        double xpb = m->xf[f] - m->xc[ijp], ypb = m->yf[f] - m->yc[ijp], zpb = m->zf[f] - m->zc[ijp];
+        p[ijb] = p[ijp] + dPdxi[3 * ijp + 0] * xpb + dPdxi[3 * ijp + 1] * ypb + dPdxi[3 * ijp + 2] * zpb;
+      }
+    }
+  }
+}
+
+static void inner_face_psum(const orc_mesh *m, int scheme, const double *p, const double *apu, const double *dPdxi,
+                            double *su, double *sv, double *sw) {
+  for (i32 i = 0; i < m->numInnerFaces; ++i) {
+    i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    double pf;
+    if (scheme == 0) pf = p[ijp] + (p[ijn] - p[ijp]) * m->facint[i];                          // face_value_cds, interpolation.f90:155
+    else if (scheme == 2) pf = (p[ijp] * apu[ijp] + p[ijn] * apu[ijn]) / (apu[ijp] + apu[ijn] + SMALL);  // nablap.f90:87
+    else {                                                                                    // face_value_central, interpolation.f90:259-262
+      double gradfidr = dPdxi[3 * ijp + 0] * (m->xf[i] - m->xc[ijp]) + dPdxi[3 * ijp + 1] * (m->yf[i] - m->yc[ijp]) + dPdxi[3 * ijp + 2] * (m->zf[i] - m->zc[ijp])
+                      + dPdxi[3 * ijn + 0] * (m->xf[i] - m->xc[ijn]) + dPdxi[3 * ijn + 1] * (m->yf[i] - m->yc[ijn]) + dPdxi[3 * ijn + 2] * (m->zf[i] - m->zc[ijn]);
+      pf = 0.5 * (p[ijp] + p[ijn] + gradfidr);
+    }
+    double dfxe = pf * m->arx[i], dfye = pf * m->ary[i], dfze = pf * m->arz[i];
+    su[ijp] = su[ijp] - dfxe; sv[ijp] = sv[ijp] - dfye; sw[ijp] = sw[ijp] - dfze;
+    su[ijn] = su[ijn] + dfxe; sv[ijn] = sv[ijn] + dfye; sw[ijn] = sw[ijn] + dfze;
+  }
+}
+
+extern "C" void orc_gradp_and_sources(const orc_mesh *m, int pscheme, double *p, const double *apu,
+                                      double *su, double *sv, double *sw, double *dPdxi) {
+  const i32 n = m->numCells;
+  for (i32 c = 0; c < n; ++c) su[c] = sv[c] = sw[c] = 0.0;
+  // stage-1 inner-face sum: 'linear' and 'central' both use face_value_cds (:51-77), 'weighted' :79-105
+  inner_face_psum(m, pscheme == 2 ? 2 : 0, p, apu, dPdxi, su, sv, sw);
+  for (int istage = 1; istage <= 2; ++istage) {  // :121
+    orc_bpres(m, p, dPdxi, istage);
+    if (istage == 2 && pscheme == 1) {           // :129-160
+      for (i32 c = 0; c < n; ++c) su[c] = sv[c] = sw[c] = 0.0;
+      inner_face_psum(m, 1, p, apu, dPdxi, su, sv, sw);
+    }
+    for (i32 c = 0; c < n; ++c) { dPdxi[3 * c + 0] = -su[c]; dPdxi[3 * c + 1] = -sv[c]; dPdxi[3 * c + 2] = -sw[c]; }
+    for (i32 i = 0; i < m->numBoundaryFaces; ++i) {
+      i32 f = m->numInnerFaces + i, ijp = m->owner[f] - 1, ijb = n + i;
+      dPdxi[3 * ijp + 0] = dPdxi[3 * ijp + 0] + p[ijb] * m->arx[f];
+      dPdxi[3 * ijp + 1] = dPdxi[3 * ijp + 1] + p[ijb] * m->ary[f];
+      dPdxi[3 * ijp + 2] = dPdxi[3 * ijp + 2] + p[ijb] * m->arz[f];
+    }
+    for (i32 c = 0; c < n; ++c) {
+      double volr = 1.0 / m->vol[c];
+      dPdxi[3 * c + 0] = dPdxi[3 * c + 0] * volr; dPdxi[3 * c + 1] = dPdxi[3 * c + 1] * volr; dPdxi[3 * c + 2] = dPdxi[3 * c + 2] * volr;
+    }
+  }
+  for (i32 i = 0; i < m->numBoundaryFaces; ++i) {  // :195-204
+    i32 f = m->numInnerFaces + i, ijp = m->owner[f] - 1, ijb = n + i;
+    su[ijp] = su[ijp] - p[ijb] * m->arx[f];
+    sv[ijp] = sv[ijp] - p[ijb] * m->ary[f];
+    sw[ijp] = sw[ijp] - p[ijb] * m->arz[f];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pressure-correction assembly  (Pressure/calcp_simple.f90:69-234, fluxes/faceflux_mass.f90)
+// ------------------------------------------------------------------------------------------
+extern "C" void orc_assemble_pcorr(const orc_mesh *m, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell, i32 nnz,
+                                   const double *den, double *u, double *v, double *w, const double *p, double *pp,
+                                   const double *dPdxi, const double *apu, int const_mflux, double flomas,
+                                   double *a, double *su, double *flmass) {
+  for (i32 k = 0; k < nnz; ++k) a[k] = 0.0;
+  for (i32 c = 0; c < m->numCells; ++c) su[c] = 0.0;
+  for (i32 i = 0; i < m->numInnerFaces; ++i) {   // :82-118 ; facefluxmass2 faceflux_mass.f90:175-249
+    i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    double arx = m->arx[i], ary = m->ary[i], arz = m->arz[i], lambda = m->facint[i];
+    double fxn = lambda, fxp = 1.0 - lambda;
+    double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
+    double dene = den[ijp] * fxp + den[ijn] * fxn;
+    double Kj = m->vol[ijp] * apu[ijp] * fxp + m->vol[ijn] * apu[ijn] * fxn;
+    double cap = -dene * Kj * m->Df[i];
+    double ui = u[ijp] + (u[ijn] - u[ijp]) * lambda;
+    double vi = v[ijp] + (v[ijn] - v[ijp]) * lambda;
+    double wi = w[ijp] + (w[ijn] - w[ijp]) * lambda;
+    double dpxi = (dPdxi[3 * ijn + 0] * fxp + dPdxi[3 * ijp + 0] * fxn) * xpn;
+    double dpyi = (dPdxi[3 * ijn + 1] * fxp + dPdxi[3 * ijp + 1] * fxn) * ypn;
+    double dpzi = (dPdxi[3 * ijn + 2] * fxp + dPdxi[3 * ijp + 2] * fxn) * zpn;
+    flmass[i] = dene * (ui * arx + vi * ary + wi * arz) + cap * (p[ijn] - p[ijp] - dpxi - dpyi - dpzi);
+    a[icell_jcell[i] - 1] = cap;
+    a[jcell_icell[i] - 1] = cap;
+    a[diag[ijp] - 1] = a[diag[ijp] - 1] - cap;
+    a[diag[ijn] - 1] = a[diag[ijn] - 1] - cap;
+    su[ijp] = su[ijp] - flmass[i];
+    su[ijn] = su[ijn] + flmass[i];
+  }
+  if (!const_mflux) {                            // adjustMassFlow, faceflux_mass.f90:833-916
+    double flowo = 0.0;
+    for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+      if (m->bctype[ib] != ORC_BC_OUTLET) continue;
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        u[ijb] = u[ijp]; v[ijb] = v[ijp]; w[ijb] = w[ijp];
+        flmass[f] = den[ijp] * (u[ijb] * m->arx[f] + v[ijb] * m->ary[f] + w[ijb] * m->arz[f]);
+        flowo = flowo + flmass[f];
+      }
+    }
+    double fac = flomas / (flowo + SMALL);
+    for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+      if (m->bctype[ib] != ORC_BC_OUTLET) continue;
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        flmass[f] = flmass[f] * fac;
+        u[ijb] = u[ijb] * fac; v[ijb] = v[ijb] * fac; w[ijb] = w[ijb] * fac;
+      }
+    }
+  }
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {  // calcp_simple.f90:131-234
+    if (m->bctype[ib] == ORC_BC_INLET || m->bctype[ib] == ORC_BC_OUTLET) {
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1;
+        su[ijp] = su[ijp] - flmass[f];
+      }
+    } else if (m->bctype[ib] == ORC_BC_PRESSURE) {  // facefluxmassPressBnd :765-831
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+        double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
+        double capp = m->vol[ijp] * apu[ijp] / (arx * xpn + ary * ypn + arz * zpn);
+        double dpcor = p[ijb] - p[ijp] - (dPdxi[3 * ijp + 0] * xpn + dPdxi[3 * ijp + 1] * ypn + dPdxi[3 * ijp + 2] * zpn);
+        u[ijb] = u[ijp] - arx * capp * dpcor;
+        v[ijb] = v[ijp] - ary * capp * dpcor;
+        w[ijb] = w[ijp] - arz * capp * dpcor;
+        flmass[f] = den[ijp] * (u[ijb] * arx + v[ijb] * ary + w[ijb] * arz);
+        double cap = -den[ijp] * (arx * arx + ary * ary + arz * arz) * capp;
+        a[diag[ijp] - 1] = a[diag[ijp] - 1] - cap;
+        su[ijp] = su[ijp] - flmass[f];
+        pp[ijb] = 0.0;
+      }
+    }
+  }
+}
+
+extern "C" void orc_update_velocity_at_boundary(const orc_mesh *m, double *u, double *v, double *w) {  // velocity.f90:1184-1277
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    if (m->bctype[ib] == ORC_BC_EMPTY || m->bctype[ib] == ORC_BC_PERIODIC) {
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        u[ijb] = u[ijp]; v[ijb] = v[ijp]; w[ijb] = w[ijp];
+      }
+    } else if (m->bctype[ib] == ORC_BC_SYMMETRY) {
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        double Unmag = u[ijp] * m->arx[f] + v[ijp] * m->ary[f] + w[ijp] * m->arz[f];   // area vector, not unit normal (as in the reference)
+        u[ijb] = u[ijp] - Unmag * m->arx[f];
+        v[ijb] = v[ijp] - Unmag * m->ary[f];
+        w[ijb] = w[ijp] - Unmag * m->arz[f];
+      }
+    }
+  }
+}
+
+extern "C" void orc_correct_simple(const orc_mesh *m, const i32 *icell_jcell, int pscheme, const double *a, const double *den,
+                                   double *u, double *v, double *w, double *p, double *pp,
+                                   const double *apu, const double *apv, const double *apw, double urfp, i32 pRefCell,
+                                   double *su, double *sv, double *sw, double *dPdxi, double *flmass) {
+  for (i32 f = 0; f < m->numInnerFaces; ++f) {   // calcp_simple.f90:331-341
+    i32 ijp = m->owner[f] - 1, ijn = m->neighbour[f] - 1;
+    flmass[f] = flmass[f] + a[icell_jcell[f] - 1] * (pp[ijn] - pp[ijp]);
+  }
+  int have_pressure = 0;
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {  // :345-391, facefluxmassCorrPressBnd faceflux_mass.f90:699-762
+    if (m->bctype[ib] != ORC_BC_PRESSURE) continue;
+    have_pressure = 1;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+      double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+      double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
+      double cap = m->vol[ijp] * apu[ijp] / (arx * xpn + ary * ypn + arz * zpn);
+      double dpcor = -pp[ijp];
+      u[ijb] = u[ijb] - arx * cap * dpcor;
+      v[ijb] = v[ijb] - ary * cap * dpcor;
+      w[ijb] = w[ijb] - arz * cap * dpcor;
+      flmass[f] = flmass[f] - den[ijp] * (arx * arx + ary * ary + arz * arz) * cap * dpcor;
+    }
+  }
+  double ppref = pp[pRefCell - 1];               // :399-407
+  if (have_pressure) ppref = 0.0;
+  orc_gradp_and_sources(m, pscheme, pp, apu, su, sv, sw, dPdxi);  // :412
+  for (i32 c = 0; c < m->numCells; ++c) {        // :416-419
+    u[c] = u[c] + su[c] * apu[c];
+    v[c] = v[c] + sv[c] * apv[c];
+    w[c] = w[c] + sw[c] * apw[c];
+    p[c] = p[c] + urfp * (pp[c] - ppref);
+  }
+  orc_update_velocity_at_boundary(m, u, v, w);   // :429
+}
+
+extern "C" void orc_nonorth_corrector(const orc_mesh *m, const double *den, const double *apu, const double *dPdxi,
+                                      double *su, double *flmass) {   // calcp_simple.f90:433-455, fluxmc2 faceflux_mass.f90:650-696
+  for (i32 c = 0; c < m->numCells; ++c) su[c] = 0.0;
+  for (i32 i = 0; i < m->numInnerFaces; ++i) {
+    i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    double sx = m->arx[i], sy = m->ary[i], sz = m->arz[i];
+    double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
+    double s2 = sx * sx + sy * sy + sz * sz;
+    double dn = xpn * sx + ypn * sy + zpn * sz;
+    double rapr = -0.5 * (apu[ijp] * den[ijp] + apu[ijn] * den[ijn]);
+    double dpx = 0.5 * (dPdxi[3 * ijn + 0] + dPdxi[3 * ijp + 0]);
+    double dpy = 0.5 * (dPdxi[3 * ijn + 1] + dPdxi[3 * ijp + 1]);
+    double dpz = 0.5 * (dPdxi[3 * ijn + 2] + dPdxi[3 * ijp + 2]);
+    double fmcor = rapr * ((dn * sx - xpn * s2) * dpx + (dn * sy - ypn * s2) * dpy + (dn * sz - zpn * s2) * dpz);
+    flmass[i] = flmass[i] + fmcor;
+    su[ijp] = su[ijp] - fmcor;
+    su[ijn] = su[ijn] + fmcor;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// linear solvers  (src/linearSolvers/linear_solvers.f90)
+// ------------------------------------------------------------------------------------------
+extern "C" void orc_spmv(i32 n, const i32 *ia, const i32 *ja, const double *a, const double *x, double *y) {
+  for (i32 i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (i32 k = ia[i]; k <= ia[i + 1] - 1; ++k) s = s + a[k - 1] * x[ja[k - 1] - 1];
+    y[i] = s;
+  }
+}
+static void residual0(i32 n, const i32 *ia, const i32 *ja, const double *a, const double *fi, const double *rhs, double *res) {
+  for (i32 i = 0; i < n; ++i) {                  // :256-261
+    double r = rhs[i];
+    for (i32 k = ia[i]; k <= ia[i + 1] - 1; ++k) r = r - a[k - 1] * fi[ja[k - 1] - 1];
+    res[i] = r;
+  }
+}
+struct Red {                                      // sum(expr) helper honouring the summation mode
+  int mode; std::vector<double> tmp;
+  Red(int m, i32 n) : mode(m), tmp(n) {}
+  double abs1(const double *v, i32 n) { for (i32 i = 0; i < n; ++i) tmp[i] = std::fabs(v[i]); return sum_mode(mode, tmp.data(), n); }
+  double dot(const double *x, const double *y, i32 n) { for (i32 i = 0; i < n; ++i) tmp[i] = x[i] * y[i]; return sum_mode(mode, tmp.data(), n); }
+  double absdiag(const double *a, const i32 *diag, const double *fi, i32 n) {
+    for (i32 i = 0; i < n; ++i) tmp[i] = std::fabs(a[diag[i] - 1] * fi[i]);
+    return sum_mode(mode, tmp.data(), n);
+  }
+};
+
+extern "C" void orc_dpcg(i32 n, i32 nnz, const i32 *ia, const i32 *ja, const double *a, const i32 *diag,
+                         double *fi, const double *rhs, i32 itr_max, double tol_abs, double tol_rel, int mode, orc_report *rep) {
+  (void)nnz;
+  std::vector<double> res(n, 0.0), pk(n, 0.0), zk(n, 0.0);
+  Red R(mode, n);
+  double factor = 0.0;
+  residual0(n, ia, ja, a, fi, rhs, res.data());
+  double res0 = R.abs1(res.data(), n);           // :264
+  rep->res0 = res0; rep->resl = res0; rep->factor = 0.0; rep->resor = res0; rep->iters = 0;
+  if (res0 < tol_abs) return;                    // :266-270
+  double s0 = (double)1.e20f;                    // :276  s0=1.e20 (single literal)
+  double resl = res0, resor = 0.0;
+  i32 itr_used = 0;
+  for (i32 l = 1; l <= itr_max; ++l) {
+    for (i32 i = 0; i < n; ++i) zk[i] = res[i] / a[diag[i] - 1];
+    double sk = R.dot(res.data(), zk.data(), n);
+    double bet = sk / s0;
+    for (i32 i = 0; i < n; ++i) pk[i] = zk[i] + bet * pk[i];
+    orc_spmv(n, ia, ja, a, pk.data(), zk.data());
+    double pkapk = R.dot(pk.data(), zk.data(), n);
+    double alf = sk / pkapk;
+    for (i32 i = 0; i < n; ++i) fi[i] = fi[i] + alf * pk[i];
+    for (i32 i = 0; i < n; ++i) res[i] = res[i] - alf * zk[i];
+    resl = R.abs1(res.data(), n);
+    s0 = sk;
+    itr_used = itr_used + 1;
+    if (l == 1) { factor = R.absdiag(a, diag, fi, n) + SMALL; resor = res0 / factor; }
+    double rsm = resl / (res0 + SMALL);
+    if (rsm < tol_rel || resl < tol_abs) break;
+  }
+  rep->resl = resl; rep->factor = factor; rep->resor = resor; rep->iters = itr_used;
+}
+
+// IC(0)/ILU(0)-diag preconditioner apply, linear_solvers.f90:458-475 (quirk Q4: zk/(d+small) in between)
+static void precond_apply(i32 n, const i32 *ia, const i32 *ja, const double *a, const i32 *diag, const double *d,
+                          const double *rhs, double *zk) {
+  for (i32 i = 0; i < n; ++i) {
+    double z = rhs[i];
+    for (i32 k = ia[i]; k <= diag[i] - 1; ++k) z = z - a[k - 1] * zk[ja[k - 1] - 1];
+    zk[i] = z * d[i];
+  }
+  for (i32 i = 0; i < n; ++i) zk[i] = zk[i] / (d[i] + SMALL);
+  for (i32 i = n - 1; i >= 0; --i) {
+    double z = zk[i];
+    for (i32 k = diag[i] + 1; k <= ia[i + 1] - 1; ++k) z = z - a[k - 1] * zk[ja[k - 1] - 1];
+    zk[i] = z * d[i];
+  }
+}
+
+extern "C" void orc_iccg(i32 n, i32 nnz, const i32 *ia, const i32 *ja, const double *a, const i32 *diag,
+                         double *fi, const double *rhs, i32 itr_max, double tol_abs, double tol_rel, int mode, orc_report *rep) {
+  (void)nnz;
+  std::vector<double> res(n, 0.0), pk(n, 0.0), zk(n, 0.0), d(n, 0.0);
+  Red R(mode, n);
+  double factor = 0.0;
+  residual0(n, ia, ja, a, fi, rhs, res.data());
+  double res0 = R.abs1(res.data(), n);
+  rep->res0 = res0; rep->resl = res0; rep->factor = 0.0; rep->resor = res0; rep->iters = 0;
+  if (res0 < tol_abs) return;
+  for (i32 i = 0; i < n; ++i) {                  // :439-445
+    double di = a[diag[i] - 1];
+    for (i32 k = ia[i]; k <= diag[i] - 1; ++k) di = di - a[k - 1] * a[k - 1] * d[ja[k - 1] - 1];
+    d[i] = 1.0 / di;
+  }
+  double s0 = (double)1.e20f, resl = res0, resor = 0.0;
+  i32 itr_used = 0;
+  for (i32 l = 1; l <= itr_max; ++l) {
+    precond_apply(n, ia, ja, a, diag, d.data(), res.data(), zk.data());
+    double sk = R.dot(res.data(), zk.data(), n);
+    double bet = sk / s0;
+    for (i32 i = 0; i < n; ++i) pk[i] = zk[i] + bet * pk[i];
+    orc_spmv(n, ia, ja, a, pk.data(), zk.data());
+    double pkapk = R.dot(pk.data(), zk.data(), n);
+    double alf = sk / pkapk;
+    for (i32 i = 0; i < n; ++i) fi[i] = fi[i] + alf * pk[i];
+    for (i32 i = 0; i < n; ++i) res[i] = res[i] - alf * zk[i];
+    resl = R.abs1(res.data(), n);
+    s0 = sk;
+    itr_used = itr_used + 1;
+    if (l == 1) { factor = R.absdiag(a, diag, fi, n) + SMALL; resor = res0 / factor; }
+    double rsm = resl / (res0 + SMALL);
+    if (rsm < tol_rel || resl < tol_abs) break;
+  }
+  rep->resl = resl; rep->factor = factor; rep->resor = resor; rep->iters = itr_used;
+}
+
+extern "C" void orc_bicgstab(i32 n, i32 nnz, const i32 *ia, const i32 *ja, const double *a, const i32 *diag,
+                             double *fi, const double *rhs, i32 itr_max, double tol_abs, double tol_rel, int mode, orc_report *rep) {
+  (void)nnz;
+  std::vector<double> res(n), reso(n), pk(n, 0.0), uk(n, 0.0), zk(n, 0.0), vk(n, 0.0), d(n, 0.0);
+  Red R(mode, n);
+  residual0(n, ia, ja, a, fi, rhs, res.data());
+  double res0 = R.abs1(res.data(), n);
+  rep->res0 = res0; rep->resl = res0; rep->factor = 0.0; rep->resor = res0; rep->iters = 0;
+  if (res0 < tol_abs) return;
+  for (i32 i = 0; i < n; ++i) {                  // :613-624
+    double di = a[diag[i] - 1];
+    for (i32 k = ia[i]; k <= diag[i] - 1; ++k) {
+      i32 j = ja[k - 1];
+      i32 l;
+      for (l = diag[j - 1]; l <= ia[j] - 1; ++l) if (ja[l - 1] == i + 1) break;   // l = ia(j+1) when not found, as a Fortran DO leaves it
+      di = di - a[k - 1] * d[j - 1] * a[l - 1];
+    }
+    d[i] = 1.0 / di;
+  }
+  for (i32 i = 0; i < n; ++i) reso[i] = res[i];
+  double factor = 0.0, alf = 1.0, beto = 1.0, gam = 1.0, resl = res0, resor = 0.0;
+  i32 itr_used = 0;
+  for (i32 l = 1; l <= itr_max; ++l) {
+    double bet = R.dot(res.data(), reso.data(), n);
+    double om = bet * gam / (alf * beto + SMALL);
+    beto = bet;
+    for (i32 i = 0; i < n; ++i) pk[i] = res[i] + om * (pk[i] - alf * uk[i]);
+    precond_apply(n, ia, ja, a, diag, d.data(), pk.data(), zk.data());
+    orc_spmv(n, ia, ja, a, zk.data(), uk.data());
+    double ukreso = R.dot(uk.data(), reso.data(), n);
+    gam = bet / ukreso;
+    for (i32 i = 0; i < n; ++i) fi[i] = fi[i] + gam * zk[i];
+    for (i32 i = 0; i < n; ++i) res[i] = res[i] - gam * uk[i];
+    precond_apply(n, ia, ja, a, diag, d.data(), res.data(), zk.data());
+    orc_spmv(n, ia, ja, a, zk.data(), vk.data());
+    alf = R.dot(vk.data(), res.data(), n) / (R.dot(vk.data(), vk.data(), n) + SMALL);
+    for (i32 i = 0; i < n; ++i) fi[i] = fi[i] + alf * zk[i];
+    for (i32 i = 0; i < n; ++i) res[i] = res[i] - alf * vk[i];
+    resl = R.abs1(res.data(), n);
+    itr_used = itr_used + 1;
+    if (l == 1) { factor = R.absdiag(a, diag, fi, n) + SMALL; resor = res0 / factor; }
+    double rsm = resl / (res0 + SMALL);
+    if (rsm < tol_rel || resl < tol_abs) break;
+  }
+  rep->resl = resl; rep->factor = factor; rep->resor = resor; rep->iters = itr_used;
+}
+
+extern "C" int orc_report_line(int solver, const char *chvar, const orc_report *rep, char *buf, int buflen) {
+  const char *name = solver == 1 ? "PCG(Jacobi)" : solver == 2 ? "PCG(IC0)" : "BiCGStab(ILU(0))";
+  if (rep->iters == 0 && rep->factor == 0.0)     // early return lines :267-268 (no iteration count digits)
+    return snprintf(buf, buflen, "  %s:  Solving for %s, Initial residual = %10.3E, Final residual = %10.3E, No Iterations 0",
+                    name, chvar, rep->res0, rep->res0);
+  return snprintf(buf, buflen, "  %s:  Solving for %s, Initial residual = %10.3E, Final residual = %10.3E, No Iterations %d",
+                  name, chvar, rep->resor, rep->resl / rep->factor, rep->iters);
+}
+
+// ------------------------------------------------------------------------------------------
+// src-par layout: virtual ranks  (src-par/exchange.f90:48-127, dpcg.f90:60-190, global_sum_mpi.f90)
+// ------------------------------------------------------------------------------------------
+extern "C" void orc_exchange(i32 nranks, const orc_rank *ranks, double **phi) {
+  for (i32 r = 0; r < nranks; ++r) {
+    const orc_mesh *m = ranks[r].mesh;
+    for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+      if (m->bctype[ib] != ORC_BC_PROCESS) continue;
+      i32 q = ranks[r].peer_rank[ib], jb = ranks[r].peer_patch[ib];
+      const orc_mesh *mq = ranks[q].mesh;
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 fq = mq->startFace[jb] + i - 1;       // the same face seen from the peer: buffer(ipro) = phi(owner(iface))
+        phi[r][m->iBndValueStart[ib] + i - 1] = phi[q][mq->owner[fq] - 1];
+      }
+    }
+  }
+}
+static void halo_term(const orc_rank *rk, const double *x, double *y, double sign) {  // dpcg.f90:129-143
+  const orc_mesh *m = rk->mesh;
+  i32 ipro = 0;
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    if (m->bctype[ib] != ORC_BC_PROCESS) continue;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      i32 f = m->startFace[ib] + i - 1, k = m->owner[f] - 1, ijn = m->iBndValueStart[ib] + i - 1;
+      y[k] = y[k] + sign * (rk->apr[ipro] * x[ijn]);
+      ++ipro;
+    }
+  }
+}
+extern "C" void orc_dpcg_par(i32 P, orc_rank *rk, i32 itr_max, double tol_abs, double tol_rel, int mode, orc_report *rep) {
+  std::vector<std::vector<double>> res(P), pk(P), zk(P), tmp(P);
+  std::vector<double *> pkp(P), fip(P);
+  for (i32 r = 0; r < P; ++r) {
+    i32 n = rk[r].mesh->numCells, nt = rk[r].mesh->numTotal;
+    res[r].assign(n, 0.0); zk[r].assign(n, 0.0); pk[r].assign(nt, 0.0); tmp[r].assign(n, 0.0);
+    pkp[r] = pk[r].data(); fip[r] = rk[r].fi;
+  }
+  auto gsum = [&](auto term) {                   // local sum in the chosen order, then ranks added in rank order
+    double s = 0.0;
+    for (i32 r = 0; r < P; ++r) {
+      i32 n = rk[r].mesh->numCells;
+      for (i32 i = 0; i < n; ++i) tmp[r][i] = term(r, i);
+      double loc = sum_mode(mode, tmp[r].data(), n);
+      s = (r == 0) ? loc : s + loc;
+    }
+    return s;
+  };
+  orc_exchange(P, rk, fip.data());
+  for (i32 r = 0; r < P; ++r) {
+    residual0(rk[r].mesh->numCells, rk[r].ia, rk[r].ja, rk[r].a, rk[r].fi, rk[r].rhs, res[r].data());
+    halo_term(&rk[r], rk[r].fi, res[r].data(), -1.0);
+  }
+  double res0 = gsum([&](i32 r, i32 i) { return std::fabs(res[r][i]); });
+  rep->res0 = res0; rep->resl = res0; rep->factor = 0.0; rep->resor = res0; rep->iters = 0;
+  if (res0 < tol_abs) return;
+  double s0 = (double)1.e20f, resl = res0, factor = 0.0, resor = 0.0;
+  i32 itr_used = 0;
+  for (i32 l = 1; l <= itr_max; ++l) {
+    for (i32 r = 0; r < P; ++r) { i32 n = rk[r].mesh->numCells; for (i32 i = 0; i < n; ++i) zk[r][i] = res[r][i] / rk[r].a[rk[r].diag[i] - 1]; }
+    double sk = gsum([&](i32 r, i32 i) { return res[r][i] * zk[r][i]; });
+    double bet = sk / s0;
+    for (i32 r = 0; r < P; ++r) { i32 n = rk[r].mesh->numCells; for (i32 i = 0; i < n; ++i) pk[r][i] = zk[r][i] + bet * pk[r][i]; }
+    orc_exchange(P, rk, pkp.data());
+    for (i32 r = 0; r < P; ++r) {
+      orc_spmv(rk[r].mesh->numCells, rk[r].ia, rk[r].ja, rk[r].a, pk[r].data(), zk[r].data());
+      halo_term(&rk[r], pk[r].data(), zk[r].data(), 1.0);
+    }
+    double pkapk = gsum([&](i32 r, i32 i) { return pk[r][i] * zk[r][i]; });
+    double alf = sk / pkapk;
+    for (i32 r = 0; r < P; ++r) {
+      i32 n = rk[r].mesh->numCells;
+      for (i32 i = 0; i < n; ++i) rk[r].fi[i] = rk[r].fi[i] + alf * pk[r][i];
+      for (i32 i = 0; i < n; ++i) res[r][i] = res[r][i] - alf * zk[r][i];
+    }
+    resl = gsum([&](i32 r, i32 i) { return std::fabs(res[r][i]); });
+    s0 = sk;
+    itr_used = itr_used + 1;
+    if (l == 1) { factor = gsum([&](i32 r, i32 i) { return std::fabs(rk[r].a[rk[r].diag[i] - 1] * rk[r].fi[i]); }) + SMALL; resor = res0 / factor; }
+    double rsm = resl / (res0 + SMALL);
+    if (rsm < tol_rel || resl < tol_abs) break;
+  }
+  orc_exchange(P, rk, fip.data());               // dpcg.f90:183
+  rep->resl = resl; rep->factor = factor; rep->resor = resor; rep->iters = itr_used;
+}

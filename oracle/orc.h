@@ -1,0 +1,156 @@
+/*
+ * oracle/orc.h -- CPU restatement ("the oracle") of freeCappuccino's pressure-velocity
+ * coupling hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product (freecappuccino-dev_b200/) never links, imports or calls
+ * it; the product fails loudly when its CUDA library is missing.
+ *
+ * PARITY PIN: the reference is Fortran and there is no Fortran compiler in this image, so the
+ * reference itself cannot be run here (oracle/_ref cannot be built).  The oracle is pinned
+ * against the known answers the reference's own tests print beside their output:
+ *   test/test_linear_solvers_spsolve.f90:13-53   (two 5x5 systems)
+ *   test/testFieldOperations/testFieldOperations.f90:137-160 (grad(x+y+z) = (1,1,1))
+ *   applications/Poisson/poisson.f90:63-104      (sin(2 pi x) sin(2 pi y), O(h^2))
+ *   src/mesh/wall_distance.f90:96-133            (laplacian + iccg + grad_gauss)
+ *   Pressure/calcp_simple.f90:314                (sum(su) = 0 on a closed domain)
+ * Beyond those the restatement itself is the pin ("parity unpinned by the reference").
+ *
+ * Conventions follow the Fortran: every index array is 1-based int32, reals are IEEE binary64,
+ * gradients are (3,numTotal) column-major (xyz interleaved per cell).  Build with
+ * -O2 -ffp-contract=off so that no FMA contraction changes the rounding the reference
+ * (gfortran -O3, x86-64, no -march => no FMA) would produce.
+ */
+#ifndef ORC_H
+#define ORC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* patch type codes (reference: character bctype(ib), src/mesh/geometry.f90:62-70) */
+enum { ORC_BC_WALL = 0, ORC_BC_INLET = 1, ORC_BC_OUTLET = 2, ORC_BC_SYMMETRY = 3,
+       ORC_BC_PRESSURE = 4, ORC_BC_PERIODIC = 5, ORC_BC_EMPTY = 6, ORC_BC_PROCESS = 7 };
+
+/* mirror of the reference's `geometry` module (src/mesh/geometry.f90:12-86) */
+typedef struct {
+  int32_t numCells, numInnerFaces, numBoundaryFaces, numFaces, numTotal, numBoundaries;
+  const int32_t *owner;      /* [numFaces]      1-based */
+  const int32_t *neighbour;  /* [numInnerFaces] 1-based */
+  const double *arx, *ary, *arz, *xf, *yf, *zf; /* [numFaces] */
+  const double *facint, *Df;                    /* [numInnerFaces] */
+  const double *xc, *yc, *zc, *vol;             /* [numCells] (numTotal in the src-par layout) */
+  const int32_t *bctype, *nfaces, *startFace, *iBndValueStart; /* [numBoundaries]; iface = startFace+i, ijb = iBndValueStart+i, i=1..nfaces */
+} orc_mesh;
+
+/* solver report, mirrors the values the reference prints (linear_solvers.f90:354-355) */
+typedef struct {
+  double res0;     /* initial L1 residual */
+  double resl;     /* final   L1 residual */
+  double factor;   /* sum|a_ii fi_i| + small after the first update */
+  double resor;    /* res0/factor (the value returned through `resor`/`res0` argument) */
+  int32_t iters;   /* itr_used */
+} orc_report;
+
+/* summation order used by the solver reductions:
+ * ORC_SUM_SEQ  : left-to-right, what gfortran's inline SUM() does without -ffast-math
+ * ORC_SUM_TREE : the fixed reduction tree the CUDA kernels use (see orc_sum_tree) */
+enum { ORC_SUM_SEQ = 0, ORC_SUM_TREE = 1 };
+
+double orc_small(void);   /* parameters.f90:6  small = 1e-20 (single literal) */
+double orc_sum_tree(const double *v, int64_t n);
+
+/* geometry.f90:416-530, 581-606 (variant 2), 648-664 */
+void orc_geometry(int32_t numNodes, int32_t numCells, int32_t numInnerFaces, int32_t numFaces,
+                  const double *x, const double *y, const double *z,
+                  const int32_t *nnodes, const int32_t *node /* [nomax*numFaces] col-major node(j,iface), 1-based */,
+                  int32_t nomax, const int32_t *owner, const int32_t *neighbour,
+                  double *arx, double *ary, double *arz, double *xf, double *yf, double *zf,
+                  double *vol, double *xc, double *yc, double *zc, double *facint, double *Df);
+/* geometry.f90:698-754 : dnw/srdw for wall faces, dns/srds for symmetry faces, in patch order */
+void orc_wall_geometry(const orc_mesh *m, double *dnw, double *srdw, double *dns, double *srds);
+
+/* sparse_matrix.f90:86-296 (no periodic patches) */
+int32_t orc_csr_nnz(const orc_mesh *m);
+void orc_csr_create(const orc_mesh *m, int32_t *ia, int32_t *ja, int32_t *diag,
+                    int32_t *icell_jcell, int32_t *jcell_icell);
+
+/* fvImplicit/laplacian.f90 : a is cleared, su is accumulated into */
+void orc_laplacian(const orc_mesh *m, const int32_t *diag, const int32_t *icell_jcell,
+                   const int32_t *jcell_icell, const double *mu, const double *phi,
+                   double *a, int32_t nnz, double *su);
+
+/* gradients.f90:1607-1693 */
+void orc_grad_gauss(const orc_mesh *m, const double *u, double *dudxi);
+/* gradients.f90:660-779 (weighted=0) and :1157-1326 (weighted=1) */
+void orc_create_matrix_lsq(const orc_mesh *m, int weighted, double *Dmat);
+/* gradients.f90:782-893 and :1334-1486 ; row2_correct=0 reproduces quirk Q1 */
+void orc_grad_lsq(const orc_mesh *m, int weighted, int row2_correct, const double *Dmat,
+                  const double *phi, double *dPhidxi);
+
+/* Pressure/bpres.f90 */
+void orc_bpres(const orc_mesh *m, double *p, const double *dPdxi, int istage);
+/* Pressure/nablap.f90:19-208 ; pscheme 0 linear, 1 central, 2 weighted */
+void orc_gradp_and_sources(const orc_mesh *m, int pscheme, double *p, const double *apu,
+                           double *su, double *sv, double *sw, double *dPdxi);
+
+/* calcp_simple.f90:69-234 incompressible, + faceflux_mass.f90:175-249,765-831,833-916 */
+void orc_assemble_pcorr(const orc_mesh *m, const int32_t *diag, const int32_t *icell_jcell,
+                        const int32_t *jcell_icell, int32_t nnz,
+                        const double *den, double *u, double *v, double *w, const double *p,
+                        double *pp, const double *dPdxi, const double *apu,
+                        int const_mflux, double flomas,
+                        double *a, double *su, double *flmass);
+/* calcp_simple.f90:331-429 (one ipcorr pass after the solve) */
+void orc_correct_simple(const orc_mesh *m, const int32_t *icell_jcell, int pscheme,
+                        const double *a, const double *den, double *u, double *v, double *w, double *p, double *pp,
+                        const double *apu, const double *apv, const double *apw,
+                        double urfp, int32_t pRefCell,
+                        double *su, double *sv, double *sw, double *dPdxi, double *flmass);
+/* calcp_simple.f90:433-455 + faceflux_mass.f90:650-696 */
+void orc_nonorth_corrector(const orc_mesh *m, const double *den, const double *apu,
+                           const double *dPdxi, double *su, double *flmass);
+/* velocity.f90:1184-1277 */
+void orc_update_velocity_at_boundary(const orc_mesh *m, double *u, double *v, double *w);
+
+/* linear_solvers.f90:206-359, 364-545, 548-786 */
+void orc_spmv(int32_t n, const int32_t *ia, const int32_t *ja, const double *a, const double *x, double *y);
+void orc_dpcg(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const double *a,
+              const int32_t *diag, double *fi, const double *rhs, int32_t itr_max,
+              double tol_abs, double tol_rel, int sum_mode, orc_report *rep);
+void orc_iccg(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const double *a,
+              const int32_t *diag, double *fi, const double *rhs, int32_t itr_max,
+              double tol_abs, double tol_rel, int sum_mode, orc_report *rep);
+void orc_bicgstab(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const double *a,
+                  const int32_t *diag, double *fi, const double *rhs, int32_t itr_max,
+                  double tol_abs, double tol_rel, int sum_mode, orc_report *rep);
+/* the report line of linear_solvers.f90:354-355 / 540-541 / 781-782, written into buf */
+int orc_report_line(int solver /*1 dpcg 2 iccg 3 bicgstab*/, const char *chvar, const orc_report *rep,
+                    char *buf, int buflen);
+
+/* ---- src-par layout: P partitions driven in lock-step inside one process ("virtual ranks").
+ * Each rank has its own orc_mesh with PROCESS patches, a local CSR, and apr[npro] (one
+ * off-rank coefficient per process face, patch order).  Follows src-par/dpcg.f90:60-190,
+ * src-par/exchange.f90:48-127 and global_sum_mpi.f90, except that the stop test uses the
+ * serial tree's criterion so that counts are comparable with orc_dpcg.
+ * peer_rank[r][ipatch]/peer_patch: which rank / which of its process patches faces patch ipatch. */
+typedef struct {
+  const orc_mesh *mesh;
+  const int32_t *ia, *ja, *diag;
+  const double *a;
+  const double *apr;          /* [npro] */
+  int32_t npro;
+  const int32_t *peer_rank;   /* [numBoundaries] (-1 for non-process patches) */
+  const int32_t *peer_patch;  /* [numBoundaries] index of the matching patch on the peer */
+  double *fi;                 /* [numTotal] */
+  const double *rhs;          /* [numCells] */
+} orc_rank;
+void orc_exchange(int32_t nranks, const orc_rank *ranks, double **phi /* [nranks][numTotal] */);
+void orc_dpcg_par(int32_t nranks, orc_rank *ranks, int32_t itr_max, double tol_abs, double tol_rel,
+                  int sum_mode, orc_report *rep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

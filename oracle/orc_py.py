@@ -1,0 +1,235 @@
+"""ctypes binding of the CPU oracle (oracle/liborc.so).  TEST INFRASTRUCTURE ONLY: imported by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the
+product package.  Accepts any mesh object exposing the attribute names of the reference's
+``geometry`` module (see freecappuccino-dev_b200/mesh.py:Mesh)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SUM_SEQ, SUM_TREE = 0, 1
+DPCG, ICCG, BICGSTAB = 1, 2, 3
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int32)
+
+
+class OrcMesh(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("numCells", "numInnerFaces", "numBoundaryFaces", "numFaces", "numTotal", "numBoundaries")] + \
+               [("owner", _pi), ("neighbour", _pi)] + \
+               [(n, _pd) for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol")] + \
+               [(n, _pi) for n in ("bctype", "nfaces", "startFace", "iBndValueStart")]
+
+
+class OrcReport(C.Structure):
+    _fields_ = [("res0", C.c_double), ("resl", C.c_double), ("factor", C.c_double), ("resor", C.c_double), ("iters", C.c_int32)]
+
+
+class OrcRank(C.Structure):
+    _fields_ = [("mesh", C.POINTER(OrcMesh)), ("ia", _pi), ("ja", _pi), ("diag", _pi), ("a", _pd), ("apr", _pd),
+                ("npro", C.c_int32), ("peer_rank", _pi), ("peer_patch", _pi), ("fi", _pd), ("rhs", _pd)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liborc.so")
+    src = [os.path.join(_HERE, f) for f in ("orc.cpp", "orc.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src if os.path.exists(s)):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liborc.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_small.restype = C.c_double
+        _LIB.orc_sum_tree.restype = C.c_double
+        _LIB.orc_sum_tree.argtypes = [_pd, C.c_int64]
+        _LIB.orc_csr_nnz.restype = C.c_int32
+    return _LIB
+
+
+def _d(a):
+    assert a.dtype == np.float64 and a.flags.c_contiguous, (a.dtype, a.flags)
+    return a.ctypes.data_as(_pd)
+
+
+def _i(a):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(_pi)
+
+
+class MeshView:
+    """Keeps the numpy arrays alive next to the C struct."""
+
+    def __init__(self, m):
+        self.m = m
+        self.keep = dict(owner=np.ascontiguousarray(m.owner, np.int32), neighbour=np.ascontiguousarray(m.neighbour, np.int32),
+                         bctype=np.ascontiguousarray(m.bctype, np.int32), nfaces=np.ascontiguousarray(m.nfaces, np.int32),
+                         startFace=np.ascontiguousarray(m.startFace, np.int32),
+                         iBndValueStart=np.ascontiguousarray(m.iBndValueStart, np.int32))
+        for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol"):
+            self.keep[n] = np.ascontiguousarray(getattr(m, n), np.float64)
+        s = OrcMesh()
+        s.numCells, s.numInnerFaces, s.numBoundaryFaces = m.numCells, m.numInnerFaces, m.numBoundaryFaces
+        s.numFaces, s.numTotal, s.numBoundaries = m.numFaces, m.numTotal, m.numBoundaries
+        for n in ("owner", "neighbour", "bctype", "nfaces", "startFace", "iBndValueStart"):
+            setattr(s, n, _i(self.keep[n]))
+        for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol"):
+            setattr(s, n, _d(self.keep[n]))
+        self.s = s
+
+    @property
+    def ptr(self):
+        return C.byref(self.s)
+
+
+def small() -> float:
+    return lib().orc_small()
+
+
+def sum_tree(v: np.ndarray) -> float:
+    v = np.ascontiguousarray(v, np.float64)
+    return lib().orc_sum_tree(_d(v), v.size)
+
+
+def geometry(points, face_nodes, face_nnodes, owner, neighbour, numCells):
+    nF, F = owner.shape[0], neighbour.shape[0]
+    x, y, z = (np.ascontiguousarray(points[:, k]) for k in range(3))
+    node = np.ascontiguousarray(face_nodes, np.int32)   # [nF, nomax] row-major == node(nomax, nF) column-major
+    out = {n: np.zeros(nF) for n in ("arx", "ary", "arz", "xf", "yf", "zf")}
+    out.update({n: np.zeros(numCells) for n in ("vol", "xc", "yc", "zc")})
+    out.update({n: np.zeros(F) for n in ("facint", "Df")})
+    fnn = np.ascontiguousarray(face_nnodes, np.int32)
+    own = np.ascontiguousarray(owner, np.int32)
+    nb = np.ascontiguousarray(neighbour, np.int32)
+    lib().orc_geometry(C.c_int32(points.shape[0]), C.c_int32(numCells), C.c_int32(F), C.c_int32(nF), _d(x), _d(y), _d(z),
+                       _i(fnn), _i(node), C.c_int32(node.shape[1]), _i(own), _i(nb),
+                       *[_d(out[n]) for n in ("arx", "ary", "arz", "xf", "yf", "zf", "vol", "xc", "yc", "zc", "facint", "Df")])
+    return out
+
+
+class Csr:
+    def __init__(self, mesh):
+        mv = MeshView(mesh)
+        self.mv = mv
+        self.n = mesh.numCells
+        self.nnz = lib().orc_csr_nnz(mv.ptr)
+        self.ia = np.zeros(self.n + 1, np.int32)
+        self.ja = np.zeros(self.nnz, np.int32)
+        self.diag = np.zeros(self.n, np.int32)
+        self.icell_jcell = np.zeros(mesh.numInnerFaces, np.int32)
+        self.jcell_icell = np.zeros(mesh.numInnerFaces, np.int32)
+        lib().orc_csr_create(mv.ptr, _i(self.ia), _i(self.ja), _i(self.diag), _i(self.icell_jcell), _i(self.jcell_icell))
+
+
+def laplacian(mesh, csr: Csr, mu, phi, su):
+    a = np.zeros(csr.nnz)
+    lib().orc_laplacian(csr.mv.ptr, _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), _d(mu), _d(phi), _d(a), C.c_int32(csr.nnz), _d(su))
+    return a
+
+
+def grad_gauss(mesh, u):
+    mv = MeshView(mesh)
+    g = np.zeros((mesh.numTotal, 3))
+    lib().orc_grad_gauss(mv.ptr, _d(u), _d(g))
+    return g
+
+
+def create_matrix_lsq(mesh, weighted: bool):
+    mv = MeshView(mesh)
+    D = np.zeros((mesh.numCells, 9))
+    lib().orc_create_matrix_lsq(mv.ptr, C.c_int(int(weighted)), _d(D))
+    return D
+
+
+def grad_lsq(mesh, weighted: bool, Dmat, phi, row2_correct: bool = False):
+    mv = MeshView(mesh)
+    g = np.zeros((mesh.numTotal, 3))
+    lib().orc_grad_lsq(mv.ptr, C.c_int(int(weighted)), C.c_int(int(row2_correct)), _d(Dmat), _d(phi), _d(g))
+    return g
+
+
+def gradp_and_sources(mesh, pscheme: int, p, apu, dPdxi):
+    """p (numTotal) and dPdxi (numTotal,3) are updated in place; returns su, sv, sw."""
+    mv = MeshView(mesh)
+    su, sv, sw = (np.zeros(mesh.numCells) for _ in range(3))
+    lib().orc_gradp_and_sources(mv.ptr, C.c_int(pscheme), _d(p), _d(apu), _d(su), _d(sv), _d(sw), _d(dPdxi))
+    return su, sv, sw
+
+
+def assemble_pcorr(mesh, csr: Csr, den, u, v, w, p, pp, dPdxi, apu, const_mflux=False, flomas=0.0):
+    a = np.zeros(csr.nnz)
+    su = np.zeros(mesh.numCells)
+    flmass = np.zeros(mesh.numFaces)
+    lib().orc_assemble_pcorr(csr.mv.ptr, _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz),
+                             _d(den), _d(u), _d(v), _d(w), _d(p), _d(pp), _d(dPdxi), _d(apu),
+                             C.c_int(int(const_mflux)), C.c_double(flomas), _d(a), _d(su), _d(flmass))
+    return a, su, flmass
+
+
+def assemble_pcorr_into(mesh, csr: Csr, den, u, v, w, p, pp, dPdxi, apu, a, su, flmass, const_mflux=False, flomas=0.0):
+    lib().orc_assemble_pcorr(csr.mv.ptr, _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz),
+                             _d(den), _d(u), _d(v), _d(w), _d(p), _d(pp), _d(dPdxi), _d(apu),
+                             C.c_int(int(const_mflux)), C.c_double(flomas), _d(a), _d(su), _d(flmass))
+
+
+def correct_simple(mesh, csr: Csr, pscheme, a, den, u, v, w, p, pp, apu, apv, apw, urfp, pRefCell, dPdxi, flmass):
+    su, sv, sw = (np.zeros(mesh.numCells) for _ in range(3))
+    lib().orc_correct_simple(csr.mv.ptr, _i(csr.icell_jcell), C.c_int(pscheme), _d(a), _d(den), _d(u), _d(v), _d(w), _d(p), _d(pp),
+                             _d(apu), _d(apv), _d(apw), C.c_double(urfp), C.c_int32(pRefCell), _d(su), _d(sv), _d(sw), _d(dPdxi), _d(flmass))
+    return su, sv, sw
+
+
+def nonorth_corrector(mesh, den, apu, dPdxi, su, flmass):
+    mv = MeshView(mesh)
+    lib().orc_nonorth_corrector(mv.ptr, _d(den), _d(apu), _d(dPdxi), _d(su), _d(flmass))
+
+
+def spmv(ia, ja, a, x):
+    y = np.zeros(ia.size - 1)
+    lib().orc_spmv(C.c_int32(ia.size - 1), _i(ia), _i(ja), _d(a), _d(x), _d(y))
+    return y
+
+
+def solve(solver: int, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, sum_mode=SUM_SEQ) -> OrcReport:
+    """fi is updated in place (first n entries)."""
+    n, nnz = ia.size - 1, ja.size
+    rep = OrcReport()
+    fn = {DPCG: lib().orc_dpcg, ICCG: lib().orc_iccg, BICGSTAB: lib().orc_bicgstab}[solver]
+    fn(C.c_int32(n), C.c_int32(nnz), _i(ia), _i(ja), _d(a), _i(diag), _d(fi), _d(rhs), C.c_int32(itr_max),
+       C.c_double(tol_abs), C.c_double(tol_rel), C.c_int(sum_mode), C.byref(rep))
+    return rep
+
+
+def report_line(solver: int, chvar: str, rep: OrcReport) -> str:
+    buf = C.create_string_buffer(256)
+    lib().orc_report_line(C.c_int(solver), chvar.encode(), C.byref(rep), buf, C.c_int(256))
+    return buf.value.decode()
+
+
+def dpcg_par(parts: List, csrs: List[Csr], a_list, apr_list, fi_list, rhs_list, itr_max, tol_abs, tol_rel, sum_mode=SUM_SEQ) -> OrcReport:
+    P = len(parts)
+    ranks = (OrcRank * P)()
+    keep = []
+    for r in range(P):
+        mv = csrs[r].mv
+        pr = np.ascontiguousarray(parts[r].peer_rank, np.int32)
+        pp = np.ascontiguousarray(parts[r].peer_patch, np.int32)
+        apr = np.ascontiguousarray(apr_list[r], np.float64) if apr_list[r].size else np.zeros(1)
+        keep += [pr, pp, apr]
+        ranks[r].mesh = C.pointer(mv.s)
+        ranks[r].ia, ranks[r].ja, ranks[r].diag = _i(csrs[r].ia), _i(csrs[r].ja), _i(csrs[r].diag)
+        ranks[r].a, ranks[r].apr, ranks[r].npro = _d(a_list[r]), _d(apr), parts[r].npro
+        ranks[r].peer_rank, ranks[r].peer_patch = _i(pr), _i(pp)
+        ranks[r].fi, ranks[r].rhs = _d(fi_list[r]), _d(rhs_list[r])
+    rep = OrcReport()
+    lib().orc_dpcg_par(C.c_int32(P), ranks, C.c_int32(itr_max), C.c_double(tol_abs), C.c_double(tol_rel), C.c_int(sum_mode), C.byref(rep))
+    return rep

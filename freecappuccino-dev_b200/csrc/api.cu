@@ -1,0 +1,637 @@
+// api.cu -- the extern "C" entry points of include/fcp.h: context creation (mesh upload, create_CSR_matrix,
+// face gather lists), field transfer, operator dispatch, calcp_simple driver.
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include "fcp_internal.h"
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+template <class Fn> static void parallel_for(int64_t n, Fn fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+  if (n < 200000) nt = 1;
+  if (nt == 1) { fn((int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  int64_t per = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    int64_t b = t * per, e = std::min(n, b + per);
+    if (b >= e) break;
+    th.emplace_back([=]() { fn(b, e); });
+  }
+  for (auto &t : th) t.join();
+}
+
+static int select_device(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fcp_set_error("no CUDA device visible (%s); libfcp_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    return FCP_ENODEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    fcp_set_error("device %d out of range (0..%d)", device, ndev - 1);
+    return FCP_EINVAL;
+  }
+  cudaDeviceProp prop;
+  FCP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    fcp_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return FCP_ENODEVICE;
+  }
+  FCP_CUDA(cudaSetDevice(device));
+  return FCP_OK;
+}
+
+static int field_count(const fcp_ctx *c, int field, int64_t *count) {
+  if (field < 0 || field >= FCP_F_COUNT) { fcp_set_error("bad field id %d", field); return FCP_EINVAL; }
+  if (field >= FCP_F_DUDXI && field <= FCP_F_G1) *count = 3 * (int64_t)c->nT;
+  else if (field == FCP_F_FLMASS) *count = c->nF;
+  else if (field == FCP_F_A) *count = c->pat.nnzp;      // device storage is SELL; host-visible count is nnz
+  else if (field == FCP_F_APR) *count = c->npro;
+  else *count = c->nT;
+  return FCP_OK;
+}
+static int field_ptr(fcp_ctx *c, int field, double **p) {
+  int64_t cnt = 0;
+  FCP_TRY(field_count(c, field, &cnt));
+  if (!c->field[field]) {
+    FCP_TRY(dev_alloc(&c->field[field], (size_t)cnt));
+    FCP_CUDA(cudaMemsetAsync(c->field[field], 0, sizeof(double) * (size_t)std::max<int64_t>(cnt, 1), c->stream));
+  }
+  *p = c->field[field];
+  return FCP_OK;
+}
+#define FIELD(var, id) double *var = nullptr; FCP_TRY(field_ptr(ctx, id, &var))
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out) {
+  if (!md || !out) { fcp_set_error("fcp_ctx_create: null argument"); return FCP_EINVAL; }
+  *out = nullptr;
+  FCP_TRY(select_device(device));
+  fcp_ctx *c = new fcp_ctx();
+  c->device = device;
+  c->n = md->numCells; c->F = md->numInnerFaces; c->B = md->numBoundaryFaces; c->nb = md->numBoundaries;
+  c->nT = c->n + c->B; c->nF = c->F + c->B;
+  const int32_t n = c->n, F = c->F, B = c->B;
+  FCP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  FCP_CUDA(cudaEventCreate(&c->t0));
+  FCP_CUDA(cudaEventCreate(&c->t1));
+  c->bctype.assign(md->bctype, md->bctype + c->nb);
+  c->nfaces.assign(md->nfaces, md->nfaces + c->nb);
+  c->startFace.assign(md->startFace, md->startFace + c->nb);
+
+  // per-boundary-face patch type; validate the patch table
+  std::vector<int32_t> bft(std::max(B, 1), FCP_BC_WALL);
+  for (int32_t ib = 0; ib < c->nb; ++ib) {
+    if (c->startFace[ib] < F || c->startFace[ib] + c->nfaces[ib] > c->nF) {
+      fcp_set_error("patch %d: faces [%d,%d) outside the boundary range [%d,%d)", ib, c->startFace[ib], c->startFace[ib] + c->nfaces[ib], F, c->nF);
+      delete c;
+      return FCP_EINVAL;
+    }
+    for (int32_t i = 0; i < c->nfaces[ib]; ++i) bft[c->startFace[ib] - F + i] = c->bctype[ib];
+    if (c->bctype[ib] == FCP_BC_PRESSURE) c->has_pressure_patch = true;
+    if (c->bctype[ib] == FCP_BC_OUTLET) c->has_outlet = true;
+    if (c->bctype[ib] == FCP_BC_PROCESS) c->npro += c->nfaces[ib];
+  }
+  for (int32_t f = 0; f < c->nF; ++f) {
+    if (md->owner[f] < 1 || md->owner[f] > n || (f < F && (md->neighbour[f] < 1 || md->neighbour[f] > n))) {
+      fcp_set_error("face %d: owner/neighbour out of range", f + 1);
+      delete c;
+      return FCP_EINVAL;
+    }
+  }
+
+  // ---- create_CSR_matrix (sparse_matrix.f90:110-260): rows ascending, columns ascending, diagonal embedded ----
+  std::vector<int32_t> ia(n + 1, 0), diag(n);
+  {
+    std::vector<int32_t> cnt(n, 1);
+    for (int32_t f = 0; f < F; ++f) { cnt[md->owner[f] - 1]++; cnt[md->neighbour[f] - 1]++; }
+    ia[0] = 1;
+    for (int32_t i = 0; i < n; ++i) ia[i + 1] = ia[i] + cnt[i];
+  }
+  const int64_t nnz = (int64_t)ia[n] - 1;
+  std::vector<int32_t> ja(nnz);
+  {
+    std::vector<int32_t> pos(n);
+    for (int32_t i = 0; i < n; ++i) { pos[i] = ia[i] - 1; ja[pos[i]++] = i + 1; }
+    for (int32_t f = 0; f < F; ++f) {
+      int32_t p = md->owner[f] - 1, q = md->neighbour[f] - 1;
+      ja[pos[p]++] = q + 1;
+      ja[pos[q]++] = p + 1;
+    }
+    parallel_for(n, [&](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; ++i) {
+        std::sort(ja.begin() + (ia[i] - 1), ja.begin() + (ia[i + 1] - 1));
+        for (int32_t k = ia[i]; k < ia[i + 1]; ++k)
+          if (ja[k - 1] == (int32_t)i + 1) { diag[i] = k; break; }
+      }
+    });
+  }
+  c->h_kPN.resize(F);
+  c->h_kNP.resize(F);
+  parallel_for(F, [&](int64_t b, int64_t e) {
+    for (int64_t f = b; f < e; ++f) {   // csr_to_k, utils.f90:96-147 (first match in the row)
+      int32_t p = md->owner[f], q = md->neighbour[f];
+      c->h_kPN[f] = (int32_t)(std::lower_bound(ja.begin() + (ia[p - 1] - 1), ja.begin() + (ia[p] - 1), q) - ja.begin()) + 1;
+      c->h_kNP[f] = (int32_t)(std::lower_bound(ja.begin() + (ia[q - 1] - 1), ja.begin() + (ia[q] - 1), p) - ja.begin()) + 1;
+    }
+  });
+
+  // halo columns (src-par layout): one extra column per process face, the ghost slot of that face, appended to the
+  // owner's row in boundary-face order (src-par/dpcg.f90:129-143 adds apr(ipro)*x(ghost) after the row sum)
+  std::vector<std::vector<int32_t>> halo;
+  std::vector<int32_t> halo_k(std::max(B, 1), -1);   // per boundary face: offset of its halo entry inside the owner's row
+  if (c->npro) {
+    halo.resize(n);
+    for (int32_t i = 0; i < B; ++i)
+      if (bft[i] == FCP_BC_PROCESS) {
+        int32_t p = md->owner[F + i] - 1;
+        halo_k[i] = (ia[p + 1] - ia[p]) + (int32_t)halo[p].size();
+        halo[p].push_back(n + i);
+      }
+  }
+  int rc = sell_from_csr(c->pat, n, c->npro ? c->nT : n, ia.data(), ja.data(), diag.data(), c->npro ? &halo : nullptr);
+  if (rc != FCP_OK) { delete c; return rc; }
+  std::vector<int64_t> slptr(c->pat.nslices + 1);
+  FCP_CUDA(cudaMemcpy(slptr.data(), c->pat.slptr, slptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  auto sellpos = [&](int32_t row0, int32_t off) -> int32_t { return (int32_t)(slptr[row0 >> 5] + (int64_t)off * 32 + (row0 & 31)); };
+  if (c->npro) {
+    std::vector<int32_t> aprpos;
+    for (int32_t i = 0; i < B; ++i)
+      if (bft[i] == FCP_BC_PROCESS) {
+        aprpos.push_back(sellpos(md->owner[F + i] - 1, halo_k[i]));
+        c->h_procface.push_back(F + i);
+      }
+    FCP_TRY(dev_upload(&c->d_aprpos, aprpos.data(), aprpos.size()));
+    FCP_TRY(dev_upload(&c->d_procface, c->h_procface.data(), c->h_procface.size()));
+  }
+
+  // face -> SELL slot maps
+  std::vector<int32_t> kPN(std::max(F, 1)), kNP(std::max(F, 1));
+  parallel_for(F, [&](int64_t b, int64_t e) {
+    for (int64_t f = b; f < e; ++f) {
+      int32_t p = md->owner[f] - 1, q = md->neighbour[f] - 1;
+      kPN[f] = sellpos(p, c->h_kPN[f] - ia[p]);
+      kNP[f] = sellpos(q, c->h_kNP[f] - ia[q]);
+    }
+  });
+
+  // ---- cell -> face gather lists, faces in ascending face index -------------------------------------------------
+  {
+    std::vector<int32_t> cnt(n, 0), ptr(n + 1, 0);
+    for (int32_t f = 0; f < F; ++f) { cnt[md->owner[f] - 1]++; cnt[md->neighbour[f] - 1]++; }
+    for (int32_t f = F; f < c->nF; ++f) cnt[md->owner[f] - 1]++;
+    const int32_t nsl = (n + 31) / 32;
+    std::vector<int64_t> fsl(nsl + 1, 0);
+    for (int32_t s = 0; s < nsl; ++s) {
+      int32_t w = 0;
+      for (int32_t r = s * 32; r < std::min(n, s * 32 + 32); ++r) w = std::max(w, cnt[r]);
+      fsl[s + 1] = fsl[s] + (int64_t)w * 32;
+    }
+    const int64_t np = fsl[nsl];
+    if (np >= (int64_t)2147483647) { fcp_set_error("face lists too large"); delete c; return FCP_EINVAL; }
+    std::vector<int32_t> ent(np, 0), other(np, 0), slot(np, -1), fill(n, 0);
+    for (int32_t f = 0; f < c->nF; ++f) {
+      int32_t p = md->owner[f] - 1;
+      int64_t pos = fsl[p >> 5] + (int64_t)fill[p]++ * 32 + (p & 31);
+      if (f < F) {
+        int32_t q = md->neighbour[f] - 1;
+        ent[pos] = f + 1; other[pos] = q; slot[pos] = kPN[f];
+        int64_t pos2 = fsl[q >> 5] + (int64_t)fill[q]++ * 32 + (q & 31);
+        ent[pos2] = -(f + 1); other[pos2] = p; slot[pos2] = kNP[f];
+      } else {
+        int32_t i = f - F;
+        ent[pos] = f + 1; other[pos] = n + i;
+        slot[pos] = bft[i] == FCP_BC_PROCESS ? sellpos(p, halo_k[i]) : -1 - bft[i];
+      }
+    }
+    c->fl.nnzp = np;
+    FCP_TRY(dev_upload(&c->fl.slptr, fsl.data(), fsl.size()));
+    FCP_TRY(dev_upload(&c->fl.len, cnt.data(), cnt.size()));
+    FCP_TRY(dev_upload(&c->fl.ent, ent.data(), ent.size()));
+    FCP_TRY(dev_upload(&c->fl.other, other.data(), other.size()));
+    FCP_TRY(dev_upload(&c->fl.slot, slot.data(), slot.size()));
+  }
+
+  // ---- mesh arrays --------------------------------------------------------------------------------------------
+  {
+    std::vector<int32_t> o0(c->nF), n0(std::max(F, 1));
+    for (int32_t f = 0; f < c->nF; ++f) o0[f] = md->owner[f] - 1;
+    for (int32_t f = 0; f < F; ++f) n0[f] = md->neighbour[f] - 1;
+    FCP_TRY(dev_upload(&c->owner, o0.data(), o0.size()));
+    FCP_TRY(dev_upload(&c->neigh, n0.data(), (size_t)F));
+  }
+  FCP_TRY(dev_upload(&c->arx, md->arx, (size_t)c->nF));
+  FCP_TRY(dev_upload(&c->ary, md->ary, (size_t)c->nF));
+  FCP_TRY(dev_upload(&c->arz, md->arz, (size_t)c->nF));
+  FCP_TRY(dev_upload(&c->xf, md->xf, (size_t)c->nF));
+  FCP_TRY(dev_upload(&c->yf, md->yf, (size_t)c->nF));
+  FCP_TRY(dev_upload(&c->zf, md->zf, (size_t)c->nF));
+  {
+    // facint / Df are sized numFaces so that process faces can carry their own values (filled by fcp_comm_init)
+    std::vector<double> tmp(c->nF, 0.5);
+    std::copy(md->facint, md->facint + F, tmp.begin());
+    FCP_TRY(dev_upload(&c->facint, tmp.data(), tmp.size()));
+    std::fill(tmp.begin(), tmp.end(), 0.0);
+    std::copy(md->Df, md->Df + F, tmp.begin());
+    FCP_TRY(dev_upload(&c->Df, tmp.data(), tmp.size()));
+  }
+  {
+    std::vector<double> tmp(c->nT, 0.0);
+    const double *src[4] = {md->xc, md->yc, md->zc, md->vol};
+    double **dst[4] = {&c->xc, &c->yc, &c->zc, &c->vol};
+    for (int k = 0; k < 4; ++k) {
+      std::copy(src[k], src[k] + n, tmp.begin());
+      FCP_TRY(dev_upload(dst[k], tmp.data(), tmp.size()));
+    }
+  }
+  FCP_TRY(dev_upload(&c->bftype, bft.data(), (size_t)std::max(B, 1)));
+  FCP_TRY(dev_upload(&c->kPN, kPN.data(), (size_t)std::max(F, 1)));
+  FCP_TRY(dev_upload(&c->kNP, kNP.data(), (size_t)std::max(F, 1)));
+  *out = c;
+  return FCP_OK;
+}
+
+extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
+  if (!c) return FCP_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm) comm_free(c->comm);
+  cudaFree(c->owner); cudaFree(c->neigh); cudaFree(c->arx); cudaFree(c->ary); cudaFree(c->arz);
+  cudaFree(c->xf); cudaFree(c->yf); cudaFree(c->zf); cudaFree(c->facint); cudaFree(c->Df);
+  cudaFree(c->xc); cudaFree(c->yc); cudaFree(c->zc); cudaFree(c->vol); cudaFree(c->bftype);
+  cudaFree(c->kPN); cudaFree(c->kNP);
+  cudaFree(c->fl.slptr); cudaFree(c->fl.len); cudaFree(c->fl.ent); cudaFree(c->fl.other); cudaFree(c->fl.slot);
+  for (int i = 0; i < FCP_F_COUNT; ++i) cudaFree(c->field[i]);
+  for (int i = 0; i < 3; ++i) cudaFree(c->Dmat[i]);
+  cudaFree(c->flushbuf);
+  cudaFree(c->d_oface); cudaFree(c->d_aprpos); cudaFree(c->d_procface);
+  sell_free(c->pat);
+  krylov_ws_free(c->ws);
+  if (c->t0) cudaEventDestroy(c->t0);
+  if (c->t1) cudaEventDestroy(c->t1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return FCP_OK;
+}
+
+extern "C" int fcp_ctx_sizes(const fcp_ctx *c, int32_t *numCells, int32_t *numTotal, int32_t *numFaces, int32_t *nnz, int32_t *npro) {
+  if (!c) return FCP_EINVAL;
+  if (numCells) *numCells = c->n;
+  if (numTotal) *numTotal = c->nT;
+  if (numFaces) *numFaces = c->nF;
+  if (nnz) *nnz = (int32_t)c->pat.nnz;
+  if (npro) *npro = c->npro;
+  return FCP_OK;
+}
+
+extern "C" int fcp_csr_pattern(const fcp_ctx *c, int32_t *ia, int32_t *ja, int32_t *diag, int32_t *icell_jcell, int32_t *jcell_icell) {
+  if (!c) return FCP_EINVAL;
+  if (ia) std::copy(c->pat.h_ia.begin(), c->pat.h_ia.end(), ia);
+  if (ja) std::copy(c->pat.h_ja.begin(), c->pat.h_ja.end(), ja);
+  if (diag) std::copy(c->pat.h_diag.begin(), c->pat.h_diag.end(), diag);
+  if (icell_jcell) std::copy(c->h_kPN.begin(), c->h_kPN.end(), icell_jcell);
+  if (jcell_icell) std::copy(c->h_kNP.begin(), c->h_kNP.end(), jcell_icell);
+  return FCP_OK;
+}
+
+extern "C" int fcp_sync(fcp_ctx *c) {
+  if (!c) return FCP_EINVAL;
+  FCP_CUDA(cudaStreamSynchronize(c->stream));
+  return FCP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fields
+// ---------------------------------------------------------------------------------------------
+// apr <-> halo entries of the SELL matrix
+__global__ void k_apr_scatter(int32_t npro, const int32_t *__restrict__ pos, const double *__restrict__ apr, double *__restrict__ a) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npro) a[pos[i]] = apr[i];
+}
+__global__ void k_apr_gather(int32_t npro, const int32_t *__restrict__ pos, const double *__restrict__ a, double *__restrict__ apr) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npro) apr[i] = a[pos[i]];
+}
+
+extern "C" int fcp_field_upload(fcp_ctx *ctx, int field, const double *host, int64_t count) {
+  if (!ctx || !host) return FCP_EINVAL;
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(d, field);
+  int64_t cap = 0;
+  FCP_TRY(field_count(ctx, field, &cap));
+  if (field == FCP_F_A) {
+    if (count != ctx->pat.nnz) { fcp_set_error("upload of a(nnz): count %lld != nnz %lld", (long long)count, (long long)ctx->pat.nnz); return FCP_EINVAL; }
+    double *stage = nullptr;
+    FCP_TRY(dev_alloc(&stage, (size_t)count));
+    FCP_CUDA(cudaMemcpyAsync(stage, host, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = sell_values_from_csr(ctx->pat, stage, d, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    return rc;
+  }
+  if (count < 0 || count > cap) { fcp_set_error("field %d: count %lld exceeds extent %lld", field, (long long)count, (long long)cap); return FCP_EINVAL; }
+  FCP_CUDA(cudaMemcpyAsync(d, host, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  if (field == FCP_F_APR && ctx->npro) {
+    FIELD(a, FCP_F_A);
+    k_apr_scatter<<<(ctx->npro + 255) / 256, 256, 0, ctx->stream>>>(ctx->npro, ctx->d_aprpos, d, a);
+    FCP_LAUNCHED();
+  }
+  FCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FCP_OK;
+}
+
+extern "C" int fcp_field_download(fcp_ctx *ctx, int field, double *host, int64_t count) {
+  if (!ctx || !host) return FCP_EINVAL;
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(d, field);
+  int64_t cap = 0;
+  FCP_TRY(field_count(ctx, field, &cap));
+  if (field == FCP_F_A) {
+    if (count != ctx->pat.nnz) { fcp_set_error("download of a(nnz): count %lld != nnz %lld", (long long)count, (long long)ctx->pat.nnz); return FCP_EINVAL; }
+    double *stage = nullptr;
+    FCP_TRY(dev_alloc(&stage, (size_t)count));
+    int rc = sell_values_to_csr(ctx->pat, d, stage, ctx->stream);
+    if (rc == FCP_OK) {
+      cudaError_t e = cudaMemcpyAsync(host, stage, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) rc = FCP_ECUDA;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    return rc;
+  }
+  if (count < 0 || count > cap) { fcp_set_error("field %d: count %lld exceeds extent %lld", field, (long long)count, (long long)cap); return FCP_EINVAL; }
+  if (field == FCP_F_APR && ctx->npro) {
+    FIELD(a, FCP_F_A);
+    k_apr_gather<<<(ctx->npro + 255) / 256, 256, 0, ctx->stream>>>(ctx->npro, ctx->d_aprpos, a, d);
+    FCP_LAUNCHED();
+  }
+  FCP_CUDA(cudaMemcpyAsync(host, d, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  FCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FCP_OK;
+}
+
+__global__ void k_fill(int64_t n, double *x, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
+}
+extern "C" int fcp_field_fill(fcp_ctx *ctx, int field, double value) {
+  if (!ctx) return FCP_EINVAL;
+  FIELD(d, field);
+  int64_t cnt = 0;
+  FCP_TRY(field_count(ctx, field, &cnt));
+  if (cnt == 0) return FCP_OK;
+  if (value == 0.0) {
+    FCP_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)cnt, ctx->stream));
+  } else {
+    k_fill<<<(int)std::min<int64_t>((cnt + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(cnt, d, value);
+    FCP_LAUNCHED();
+    FCP_CHECK_LAUNCH();
+  }
+  return FCP_OK;
+}
+extern "C" int fcp_field_copy(fcp_ctx *ctx, int dst, int src) {
+  if (!ctx) return FCP_EINVAL;
+  FIELD(d, dst);
+  FIELD(s, src);
+  int64_t cd = 0, cs = 0;
+  FCP_TRY(field_count(ctx, dst, &cd));
+  FCP_TRY(field_count(ctx, src, &cs));
+  if (cd != cs) { fcp_set_error("fcp_field_copy: extents differ"); return FCP_EINVAL; }
+  FCP_CUDA(cudaMemcpyAsync(d, s, sizeof(double) * (size_t)cd, cudaMemcpyDeviceToDevice, ctx->stream));
+  return FCP_OK;
+}
+extern "C" int fcp_field_devptr(fcp_ctx *ctx, int field, void **devptr, int64_t *count) {
+  if (!ctx || !devptr) return FCP_EINVAL;
+  FIELD(d, field);
+  *devptr = d;
+  if (count) FCP_TRY(field_count(ctx, field, count));
+  return FCP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// operators
+// ---------------------------------------------------------------------------------------------
+extern "C" int fcp_spmv(fcp_ctx *ctx, int x_field, int y_field) {
+  if (!ctx) return FCP_EINVAL;
+  FIELD(x, x_field);
+  FIELD(y, y_field);
+  FIELD(a, FCP_F_A);
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, x, 1));
+  return sell_spmv(ctx->pat, a, x, y, ctx->stream);
+}
+
+extern "C" int fcp_csrsolve(fcp_ctx *ctx, int solver, int fi_field, int rhs_field, int32_t itr_max, double tol_abs, double tol_rel,
+                            fcp_report *rep) {
+  if (!ctx) return FCP_EINVAL;
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(fi, fi_field);
+  FIELD(rhs, rhs_field);
+  FIELD(a, FCP_F_A);
+  return krylov_solve(solver, ctx->pat, a, fi, rhs, ctx->ws, itr_max, tol_abs, tol_rel, rep, ctx->stream, ctx->comm, ctx);
+}
+
+extern "C" int fcp_report_line(const fcp_report *rep, const char *chvar, char *buf, int buflen) {
+  if (!rep || !buf) return FCP_EINVAL;
+  // linear_solvers.f90:354-355 (dpcg), :540-541 (iccg), :781-782 (bicgstab); early return :267-268
+  const char *name = rep->solver == FCP_SOLVER_DPCG ? "PCG(Jacobi)" : rep->solver == FCP_SOLVER_ICCG ? "PCG(IC0)" : "BiCGStab(ILU(0))";
+  auto e103 = [](double v, char *out) {   // Fortran 1PE10.3
+    char t[64];
+    snprintf(t, sizeof(t), "%10.3E", v);
+    strcpy(out, t);
+  };
+  char r0[64], r1[64];
+  if (rep->iters == 0 && rep->factor == 0.0) {
+    e103(rep->res0, r0);
+    snprintf(buf, buflen, "  %s:  Solving for %s, Initial residual = %s, Final residual = %s, No Iterations 0", name, chvar ? chvar : "", r0, r0);
+  } else {
+    e103(rep->resor, r0);
+    e103(rep->resl / rep->factor, r1);
+    snprintf(buf, buflen, "  %s:  Solving for %s, Initial residual = %s, Final residual = %s, No Iterations %d", name, chvar ? chvar : "", r0, r1,
+             rep->iters);
+  }
+  return FCP_OK;
+}
+
+extern "C" int fcp_create_lsq_grad_matrix(fcp_ctx *ctx, int method) {
+  if (!ctx) return FCP_EINVAL;
+  if (method != FCP_GRAD_LSQ && method != FCP_GRAD_LSQ_DM) { fcp_set_error("create_lsq_grad_matrix: method %d is not a least-squares method", method); return FCP_EINVAL; }
+  if (!ctx->Dmat[method]) FCP_TRY(dev_alloc(&ctx->Dmat[method], (size_t)9 * ctx->n));
+  return fvm_lsq_matrix(ctx, method == FCP_GRAD_LSQ_DM, ctx->Dmat[method]);
+}
+
+extern "C" int fcp_grad(fcp_ctx *ctx, int method, int phi_field, int grad_field, int lsq_row2_reference) {
+  if (!ctx) return FCP_EINVAL;
+  if (grad_field < FCP_F_DUDXI || grad_field > FCP_F_G1) { fcp_set_error("fcp_grad: field %d is not a gradient field", grad_field); return FCP_EINVAL; }
+  FIELD(phi, phi_field);
+  FIELD(g, grad_field);
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, phi, 1));              // src-par/gradients.f90:123
+  int rc;
+  if (method == FCP_GRAD_GAUSS) rc = fvm_grad_gauss(ctx, phi, g);
+  else if (method == FCP_GRAD_LSQ || method == FCP_GRAD_LSQ_DM) {
+    if (!ctx->Dmat[method]) { fcp_set_error("fcp_grad: call fcp_create_lsq_grad_matrix(method=%d) first", method); return FCP_ESTATE; }
+    rc = fvm_grad_lsq(ctx, method == FCP_GRAD_LSQ_DM, ctx->Dmat[method], phi, g, lsq_row2_reference);
+  } else { fcp_set_error("fcp_grad: unknown method %d", method); return FCP_EINVAL; }
+  FCP_TRY(rc);
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, g, 3));                // src-par/gradients.f90:168-170
+  return FCP_OK;
+}
+
+extern "C" int fcp_laplacian(fcp_ctx *ctx, int mu_field, int phi_field) {
+  if (!ctx) return FCP_EINVAL;
+  FIELD(mu, mu_field);
+  FIELD(phi, phi_field);
+  FIELD(a, FCP_F_A);
+  FIELD(su, FCP_F_SU);
+  if (ctx->comm) { FCP_TRY(comm_exchange(ctx, mu, 1)); }
+  return fvm_laplacian(ctx, mu, phi, a, su);
+}
+
+static int gradp_impl(fcp_ctx *ctx, int pscheme, double *p, const CorrectArgs *ca) {
+  FIELD(apu, FCP_F_APU);
+  FIELD(su, FCP_F_SU);
+  FIELD(sv, FCP_F_SV);
+  FIELD(sw, FCP_F_SW);
+  FIELD(g, FCP_F_DPDXI);
+  double *gtmp = nullptr;
+  if (pscheme == FCP_PSCHEME_CENTRAL) { FIELD(t, FCP_F_G1); gtmp = t; }
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, p, 1));
+  return fvm_gradp(ctx, pscheme, p, apu, su, sv, sw, g, gtmp, ca);
+}
+extern "C" int fcp_gradp_and_sources(fcp_ctx *ctx, int pscheme, int p_field) {
+  if (!ctx) return FCP_EINVAL;
+  if (pscheme < 0 || pscheme > 2) { fcp_set_error("unknown pscheme %d", pscheme); return FCP_EINVAL; }   // nablap.f90:106-110 stops
+  FIELD(p, p_field);
+  return gradp_impl(ctx, pscheme, p, nullptr);
+}
+
+static int ensure_outlet_list(fcp_ctx *c) {
+  if (c->d_oface || !c->has_outlet) return FCP_OK;
+  std::vector<int32_t> of;
+  for (int32_t ib = 0; ib < c->nb; ++ib)
+    if (c->bctype[ib] == FCP_BC_OUTLET)
+      for (int32_t i = 0; i < c->nfaces[ib]; ++i) of.push_back(c->startFace[ib] + i);
+  c->nout = (int32_t)of.size();
+  return dev_upload(&c->d_oface, of.data(), of.size());
+}
+
+extern "C" int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double flomas) {
+  if (!ctx) return FCP_EINVAL;
+  FIELD(den, FCP_F_DEN); FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(p, FCP_F_P); FIELD(pp, FCP_F_PP);
+  FIELD(g, FCP_F_DPDXI); FIELD(apu, FCP_F_APU); FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(fl, FCP_F_FLMASS);
+  if (!const_mflux && ctx->has_outlet) {                           // adjustMassFlow, calcp_simple.f90:125
+    FCP_TRY(ensure_outlet_list(ctx));
+    FCP_TRY(fvm_adjust_mass_flow(ctx, ctx->nout, ctx->d_oface, den, u, v, w, fl, flomas));
+  }
+  AsmArgs args{den, u, v, w, p, g, apu, pp, u, v, w, a, su, fl};
+  return fvm_assemble_pcorr(ctx, args);
+}
+
+extern "C" int fcp_correct_simple(fcp_ctx *ctx, int pscheme, double urfp, int32_t pRefCell) {
+  if (!ctx) return FCP_EINVAL;
+  if (pRefCell < 1 || pRefCell > ctx->n) { fcp_set_error("pRefCell %d out of range", pRefCell); return FCP_EINVAL; }
+  FIELD(den, FCP_F_DEN); FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(p, FCP_F_P); FIELD(pp, FCP_F_PP);
+  FIELD(apu, FCP_F_APU); FIELD(apv, FCP_F_APV); FIELD(apw, FCP_F_APW); FIELD(a, FCP_F_A); FIELD(fl, FCP_F_FLMASS);
+  FCP_TRY(fvm_correct_flux(ctx, a, pp, fl));                                   // calcp_simple.f90:331-341
+  if (ctx->has_pressure_patch) FCP_TRY(fvm_correct_pressure_bnd(ctx, den, apu, pp, u, v, w, fl));   // :345-391
+  CorrectArgs ca{u, v, w, p, apu, apv, apw, urfp, ctx->has_pressure_patch ? nullptr : pp + (pRefCell - 1)};   // :399-407
+  return gradp_impl(ctx, pscheme, pp, &ca);                                    // :412-429
+}
+
+extern "C" int fcp_nonorth_corrector(fcp_ctx *ctx) {
+  if (!ctx) return FCP_EINVAL;
+  FIELD(den, FCP_F_DEN); FIELD(apu, FCP_F_APU); FIELD(g, FCP_F_DPDXI); FIELD(su, FCP_F_SU); FIELD(fl, FCP_F_FLMASS);
+  return fvm_nonorth(ctx, den, apu, g, su, fl);
+}
+
+extern "C" int fcp_calcp_simple(fcp_ctx *ctx, const fcp_simple_params *prm, fcp_report *rep) {
+  if (!ctx || !prm) return FCP_EINVAL;
+  FCP_TRY(fcp_assemble_pcorr_simple(ctx, prm->const_mflux, prm->flomas));
+  for (int ipcorr = 1; ipcorr <= prm->npcor; ++ipcorr) {                       // calcp_simple.f90:318
+    if (prm->zero_pp) FCP_TRY(fcp_field_fill(ctx, FCP_F_PP, 0.0));
+    FCP_TRY(fcp_csrsolve(ctx, prm->solver, FCP_F_PP, FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel, rep ? &rep[ipcorr - 1] : nullptr));
+    FCP_TRY(fcp_correct_simple(ctx, prm->pscheme, prm->urfp, prm->pRefCell));
+    if (ipcorr != prm->npcor) FCP_TRY(fcp_nonorth_corrector(ctx));            // :433-455
+  }
+  return FCP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// explicit-CSR solver objects
+// ---------------------------------------------------------------------------------------------
+extern "C" int fcp_solver_create(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const int32_t *diag, int device, fcp_solver **out) {
+  if (!ia || !ja || !diag || !out || n < 0) { fcp_set_error("fcp_solver_create: bad argument"); return FCP_EINVAL; }
+  *out = nullptr;
+  if (ia[0] != 1 || ia[n] - 1 != nnz) { fcp_set_error("fcp_solver_create: ia must be 1-based with ia(n+1)-1 == nnz"); return FCP_EINVAL; }
+  for (int32_t i = 0; i < n; ++i) {
+    if (diag[i] < ia[i] || diag[i] >= ia[i + 1] || ja[diag[i] - 1] != i + 1) { fcp_set_error("row %d: diag does not point at a(i,i)", i + 1); return FCP_EINVAL; }
+    for (int32_t k = ia[i]; k < ia[i + 1]; ++k) {
+      if (ja[k - 1] < 1 || ja[k - 1] > n) { fcp_set_error("row %d: column out of range", i + 1); return FCP_EINVAL; }
+      if (k > ia[i] && ja[k - 1] <= ja[k - 2]) { fcp_set_error("row %d: columns must be ascending (create_CSR_matrix order)", i + 1); return FCP_EINVAL; }
+    }
+  }
+  FCP_TRY(select_device(device));
+  fcp_solver *s = new fcp_solver();
+  s->device = device;
+  FCP_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  int rc = sell_from_csr(s->pat, n, n, ia, ja, diag, nullptr);
+  if (rc != FCP_OK) { delete s; return rc; }
+  FCP_TRY(dev_alloc(&s->a, (size_t)s->pat.nnzp));
+  FCP_CUDA(cudaMemset(s->a, 0, sizeof(double) * (size_t)std::max<int64_t>(s->pat.nnzp, 1)));
+  FCP_TRY(dev_alloc(&s->a_csr, (size_t)nnz));
+  FCP_TRY(dev_alloc(&s->fi, (size_t)n));
+  FCP_TRY(dev_alloc(&s->rhs, (size_t)n));
+  *out = s;
+  return FCP_OK;
+}
+extern "C" int fcp_solver_destroy(fcp_solver *s) {
+  if (!s) return FCP_OK;
+  cudaSetDevice(s->device);
+  cudaFree(s->a); cudaFree(s->a_csr); cudaFree(s->fi); cudaFree(s->rhs);
+  sell_free(s->pat);
+  krylov_ws_free(s->ws);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return FCP_OK;
+}
+extern "C" int fcp_solver_solve(fcp_solver *s, int solver, const double *a, double *fi, const double *rhs, int32_t itr_max, double tol_abs,
+                                double tol_rel, fcp_report *rep) {
+  if (!s || !a || !fi || !rhs) return FCP_EINVAL;
+  FCP_CUDA(cudaSetDevice(s->device));
+  const size_t n = s->pat.n;
+  FCP_CUDA(cudaMemcpyAsync(s->a_csr, a, sizeof(double) * (size_t)s->pat.nnz, cudaMemcpyHostToDevice, s->stream));
+  FCP_CUDA(cudaMemcpyAsync(s->fi, fi, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+  FCP_CUDA(cudaMemcpyAsync(s->rhs, rhs, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+  FCP_TRY(sell_values_from_csr(s->pat, s->a_csr, s->a, s->stream));
+  FCP_TRY(krylov_solve(solver, s->pat, s->a, s->fi, s->rhs, s->ws, itr_max, tol_abs, tol_rel, rep, s->stream, nullptr, nullptr));
+  FCP_CUDA(cudaMemcpyAsync(fi, s->fi, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+  FCP_CUDA(cudaStreamSynchronize(s->stream));
+  return FCP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// timing helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int fcp_timer_start(fcp_ctx *ctx) {
+  if (!ctx) return FCP_EINVAL;
+  FCP_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
+  return FCP_OK;
+}
+extern "C" int fcp_timer_stop(fcp_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return FCP_EINVAL;
+  FCP_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
+  FCP_CUDA(cudaEventSynchronize(ctx->t1));
+  FCP_CUDA(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+  return FCP_OK;
+}
+extern "C" int fcp_flush_l2(fcp_ctx *ctx) {
+  if (!ctx) return FCP_EINVAL;
+  const size_t bytes = (size_t)256 << 20;
+  if (!ctx->flushbuf) FCP_CUDA(cudaMalloc((void **)&ctx->flushbuf, bytes));
+  k_fill<<<148 * 8, 256, 0, ctx->stream>>>((int64_t)(bytes / sizeof(double)), ctx->flushbuf, 1.0);
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}

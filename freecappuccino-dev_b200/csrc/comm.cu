@@ -1,0 +1,233 @@
+// comm.cu -- multi-GPU layer in the src-par layout: one rank = one mesh partition = one GPU.
+//   exchange(phi)      src-par/exchange.f90:3-129     -> pack kernel + one NCCL group of send/recv + unpack kernel
+//   global_sum(x)      src-par/global_sum_mpi.f90:4-37 -> all-gather of the per-rank partial sums + rank-ordered add
+//                                                         (deterministic, identical on every rank)
+// NCCL is resolved with dlopen at fcp_comm_init: a single-GPU host program needs no NCCL at all.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstring>
+#include "fcp_internal.h"
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.handle) return FCP_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (const char *nm : names) {
+    h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) { fcp_set_error("cannot load libnccl.so.2: %s", dlerror()); return FCP_ENCCL; }
+#define SYM(field, name)                                                             \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                                        \
+  if (!g_nccl.field) { fcp_set_error("libnccl: missing symbol %s", name); return FCP_ENCCL; }
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(AllGather, "ncclAllGather");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.handle = h;
+  return FCP_OK;
+}
+#define FCP_NCCL(call)                                                                               \
+  do {                                                                                               \
+    ncclResult_t r__ = (call);                                                                       \
+    if (r__ != ncclSuccess) {                                                                        \
+      fcp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__));       \
+      return FCP_ENCCL;                                                                              \
+    }                                                                                                \
+  } while (0)
+
+struct FcpComm {
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  int32_t npro = 0;
+  std::vector<int> peer;            // per process patch (patch order): rank on the other side
+  std::vector<int32_t> off, cnt;    // per process patch: offset / count in faces inside the halo buffers
+  int32_t *d_cell = nullptr;        // [npro] owner cell of each process face (my_mpi_module bufind)
+  int32_t *d_slot = nullptr;        // [npro] ghost slot (numCells + boundary-face offset)
+  double *sendbuf = nullptr, *recvbuf = nullptr;   // [3*npro]
+  double *gather = nullptr;         // [4*nranks]
+  double *d_scalar = nullptr;       // [4]
+};
+int comm_nranks(const FcpComm *c) { return c ? c->nranks : 1; }
+void comm_free(FcpComm *c) {
+  if (!c) return;
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  cudaFree(c->d_cell); cudaFree(c->d_slot); cudaFree(c->sendbuf); cudaFree(c->recvbuf); cudaFree(c->gather); cudaFree(c->d_scalar);
+  delete c;
+}
+
+__global__ void k_halo_pack(int32_t npro, int ncomp, const int32_t *__restrict__ cell, const double *__restrict__ phi, double *__restrict__ buf) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npro) return;
+  const int64_t c = cell[i];
+  for (int k = 0; k < ncomp; ++k) buf[(int64_t)ncomp * i + k] = phi[ncomp * c + k];   // exchange.f90:48-66
+}
+__global__ void k_halo_unpack(int32_t npro, int ncomp, const int32_t *__restrict__ slot, const double *__restrict__ buf, double *__restrict__ phi) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npro) return;
+  const int64_t s = slot[i];
+  for (int k = 0; k < ncomp; ++k) phi[ncomp * s + k] = buf[(int64_t)ncomp * i + k];   // exchange.f90:110-127
+}
+
+int comm_exchange(fcp_ctx *ctx, double *field, int ncomp) {
+  FcpComm *c = ctx->comm;
+  if (!c || c->npro == 0) return FCP_OK;
+  cudaStream_t st = ctx->stream;
+  const int grid = (c->npro + 255) / 256;
+  k_halo_pack<<<grid, 256, 0, st>>>(c->npro, ncomp, c->d_cell, field, c->sendbuf);
+  FCP_LAUNCHED();
+  FCP_NCCL(g_nccl.GroupStart());
+  for (size_t j = 0; j < c->peer.size(); ++j) {
+    FCP_NCCL(g_nccl.Send(c->sendbuf + (size_t)ncomp * c->off[j], (size_t)ncomp * c->cnt[j], ncclDouble, c->peer[j], c->comm, st));
+    FCP_NCCL(g_nccl.Recv(c->recvbuf + (size_t)ncomp * c->off[j], (size_t)ncomp * c->cnt[j], ncclDouble, c->peer[j], c->comm, st));
+  }
+  FCP_NCCL(g_nccl.GroupEnd());
+  k_halo_unpack<<<grid, 256, 0, st>>>(c->npro, ncomp, c->d_slot, c->recvbuf, field);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
+// vals[k] <- sum over ranks (rank 0 first) of vals[k]; every rank gets the same bits
+__global__ void k_rank_ordered_sum(int nranks, int count, const double *__restrict__ gathered, double *__restrict__ vals) {
+  int k = threadIdx.x;
+  if (k >= count) return;
+  double s = gathered[k];
+  for (int r = 1; r < nranks; ++r) s = s + gathered[r * count + k];
+  vals[k] = s;
+}
+int comm_allgather_sum(FcpComm *c, double *d_vals, int count, cudaStream_t st) {
+  if (!c || c->nranks == 1) return FCP_OK;
+  FCP_NCCL(g_nccl.AllGather(d_vals, c->gather, (size_t)count, ncclDouble, c->comm, st));
+  k_rank_ordered_sum<<<1, 32, 0, st>>>(c->nranks, count, c->gather, d_vals);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
+// geometry of process faces once the ghost cell centres are known: facint like geometry.f90:581-606 (variant 2),
+// Df like :648-664, with the local cell as P and the ghost cell as N (src-par/geometry.f90:826-871 fpro)
+__global__ void k_process_face_geom(int32_t npro, const int32_t *__restrict__ pface, const int32_t *__restrict__ cell, const int32_t *__restrict__ slot,
+                                    const double *xc, const double *yc, const double *zc, const double *xf, const double *yf, const double *zf,
+                                    const double *arx, const double *ary, const double *arz, double *facint, double *Df) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npro) return;
+  const int32_t f = pface[i], p = cell[i], q = slot[i];
+  double xpn = xf[f] - xc[p], ypn = yf[f] - yc[p], zpn = zf[f] - zc[p];
+  const double djp = sqrt(xpn * xpn + ypn * ypn + zpn * zpn);
+  xpn = xf[f] - xc[q]; ypn = yf[f] - yc[q]; zpn = zf[f] - zc[q];
+  const double djn = sqrt(xpn * xpn + ypn * ypn + zpn * zpn);
+  facint[f] = djp / (djp + djn);
+  xpn = xc[q] - xc[p]; ypn = yc[q] - yc[p]; zpn = zc[q] - zc[p];
+  const double are = arx[f] * arx[f] + ary[f] * ary[f] + arz[f] * arz[f];
+  Df[f] = are / (arx[f] * xpn + ary[f] * ypn + arz[f] * zpn);
+}
+
+extern "C" int fcp_comm_unique_id(void *id128) {
+  if (!id128) return FCP_EINVAL;
+  FCP_TRY(nccl_load());
+  ncclUniqueId id;
+  FCP_NCCL(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return FCP_OK;
+}
+
+extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id128, const int32_t *peer_rank) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { fcp_set_error("fcp_comm_init: bad argument"); return FCP_EINVAL; }
+  if (ctx->comm) { fcp_set_error("fcp_comm_init: communicator already initialised"); return FCP_ESTATE; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FCP_TRY(nccl_load());
+  FcpComm *c = new FcpComm();
+  c->rank = rank;
+  c->nranks = nranks;
+  c->npro = ctx->npro;
+  std::vector<int32_t> cell, slot;
+  // process patches in patch order; faces of a patch are contiguous in both buffers
+  for (int32_t ib = 0; ib < ctx->nb; ++ib) {
+    if (ctx->bctype[ib] != FCP_BC_PROCESS) continue;
+    if (!peer_rank || peer_rank[ib] < 0 || peer_rank[ib] >= nranks || peer_rank[ib] == rank) {
+      fcp_set_error("fcp_comm_init: process patch %d has no valid peer rank", ib);
+      delete c;
+      return FCP_EINVAL;
+    }
+    c->peer.push_back(peer_rank[ib]);
+    c->off.push_back((int32_t)cell.size());
+    c->cnt.push_back(ctx->nfaces[ib]);
+    for (int32_t i = 0; i < ctx->nfaces[ib]; ++i) slot.push_back(ctx->n + (ctx->startFace[ib] - ctx->F) + i);
+  }
+  {
+    std::vector<int32_t> owner(ctx->nF);
+    FCP_CUDA(cudaMemcpy(owner.data(), ctx->owner, sizeof(int32_t) * (size_t)ctx->nF, cudaMemcpyDeviceToHost));
+    for (int32_t s : slot) cell.push_back(owner[ctx->F + (s - ctx->n)]);
+  }
+  if ((int32_t)cell.size() != ctx->npro) { fcp_set_error("fcp_comm_init: internal process-face count mismatch"); delete c; return FCP_EINVAL; }
+  FCP_TRY(dev_upload(&c->d_cell, cell.data(), cell.size()));
+  FCP_TRY(dev_upload(&c->d_slot, slot.data(), slot.size()));
+  FCP_TRY(dev_alloc(&c->sendbuf, (size_t)3 * std::max(ctx->npro, 1)));
+  FCP_TRY(dev_alloc(&c->recvbuf, (size_t)3 * std::max(ctx->npro, 1)));
+  FCP_TRY(dev_alloc(&c->gather, (size_t)4 * nranks));
+  FCP_TRY(dev_alloc(&c->d_scalar, 4));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  FCP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+  ctx->comm = c;
+  // ghost copies of the cell-centre data (src-par/geometry.f90:769-773) and the process-face geometry
+  FCP_TRY(comm_exchange(ctx, ctx->xc, 1));
+  FCP_TRY(comm_exchange(ctx, ctx->yc, 1));
+  FCP_TRY(comm_exchange(ctx, ctx->zc, 1));
+  FCP_TRY(comm_exchange(ctx, ctx->vol, 1));
+  if (ctx->npro) {
+    k_process_face_geom<<<(ctx->npro + 255) / 256, 256, 0, ctx->stream>>>(ctx->npro, ctx->d_procface, c->d_cell, c->d_slot, ctx->xc, ctx->yc, ctx->zc,
+                                                                          ctx->xf, ctx->yf, ctx->zf, ctx->arx, ctx->ary, ctx->arz, ctx->facint, ctx->Df);
+    FCP_LAUNCHED();
+    FCP_CHECK_LAUNCH();
+  }
+  FCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FCP_OK;
+}
+
+extern "C" int fcp_exchange(fcp_ctx *ctx, int field) {
+  if (!ctx) return FCP_EINVAL;
+  if (field < 0 || field >= FCP_F_FLMASS) { fcp_set_error("fcp_exchange: field %d is not a cell field", field); return FCP_EINVAL; }
+  void *p = nullptr;
+  FCP_TRY(fcp_field_devptr(ctx, field, &p, nullptr));
+  return comm_exchange(ctx, (double *)p, (field >= FCP_F_DUDXI && field <= FCP_F_G1) ? 3 : 1);
+}
+
+static int global_reduce(fcp_ctx *ctx, double *value, int op /*0 sum 1 max 2 min*/) {
+  if (!ctx || !value) return FCP_EINVAL;
+  FcpComm *c = ctx->comm;
+  if (!c || c->nranks == 1) return FCP_OK;
+  FCP_CUDA(cudaMemcpyAsync(c->d_scalar, value, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (op == 0) FCP_TRY(comm_allgather_sum(c, c->d_scalar, 1, ctx->stream));
+  else FCP_NCCL(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclDouble, op == 1 ? ncclMax : ncclMin, c->comm, ctx->stream));
+  FCP_CUDA(cudaMemcpyAsync(value, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FCP_OK;
+}
+extern "C" int fcp_global_sum(fcp_ctx *ctx, double *value) { return global_reduce(ctx, value, 0); }
+extern "C" int fcp_global_max(fcp_ctx *ctx, double *value) { return global_reduce(ctx, value, 1); }
+extern "C" int fcp_global_min(fcp_ctx *ctx, double *value) { return global_reduce(ctx, value, 2); }

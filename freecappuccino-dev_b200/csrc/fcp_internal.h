@@ -1,0 +1,200 @@
+// fcp_internal.h -- internal structures of libfcp_b200.so (not part of the C-ABI, see include/fcp.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/fcp.h"
+
+// ---------------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------------
+void fcp_set_error(const char *fmt, ...);
+extern int64_t g_fcp_launches;   // number of kernels launched by this library (fcp_launch_count)
+
+#define FCP_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      fcp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));    \
+      return FCP_ECUDA;                                                                        \
+    }                                                                                          \
+  } while (0)
+#define FCP_TRY(call)                 \
+  do {                                \
+    int r__ = (call);                 \
+    if (r__ != FCP_OK) return r__;    \
+  } while (0)
+#define FCP_LAUNCHED() (++g_fcp_launches)
+#define FCP_CHECK_LAUNCH() FCP_CUDA(cudaGetLastError())
+
+// parameters.f90:6  `small = 1e-20` is a default-real literal promoted to double
+#define FCP_SMALL ((double)1e-20f)
+
+// ---------------------------------------------------------------------------------------------
+// The reduction / work decomposition every vector kernel uses (mirrored by oracle/orc.cpp:orc_sum_tree):
+// a CTA of 256 threads owns a CHUNK of 2048 consecutive items; thread t handles items t, t+256, ... in that
+// order; warp xor-butterfly; the 8 warp sums are added in warp order; the chunk partials are reduced the same way
+// by the last CTA to finish.  Fixed tree => run-to-run bitwise identical sums and iteration counts.
+// ---------------------------------------------------------------------------------------------
+#define FCP_TPB 256
+#define FCP_IPT 8
+#define FCP_CHUNK (FCP_TPB * FCP_IPT)
+static inline int fcp_nchunks(int64_t n) { return (int)((n + FCP_CHUNK - 1) / FCP_CHUNK); }
+
+// ---------------------------------------------------------------------------------------------
+// SELL-32 storage.  Rows are grouped in slices of 32 (one warp); within a slice entry j of lane l is at
+// slptr[slice] + 32*j + l, so that a warp reads one 256-byte line of values (128 bytes of indices) per column step.
+// The order of the entries inside a row is the CSR order (columns ascending, diagonal embedded, halo columns
+// >= n last), so row sums round exactly like the reference's sequential CSR loops.
+// ---------------------------------------------------------------------------------------------
+struct SellPattern {
+  int32_t n = 0;        // rows (numCells)
+  int32_t ncols = 0;    // columns (numTotal when halo columns exist)
+  int64_t nnz = 0;      // local CSR entries (host-visible a(nnz))
+  int64_t nnz_ext = 0;  // nnz + halo entries
+  int64_t nnzp = 0;     // padded SELL entries
+  int32_t nslices = 0;
+  // host copies (kept: csr pattern queries, conversions)
+  std::vector<int32_t> h_ia, h_ja, h_diag;     // local CSR, 1-based (the reference's ia, ja, diag)
+  // device
+  int64_t *slptr = nullptr;   // [nslices+1]
+  int32_t *rinfo = nullptr;   // [n] len | dpos<<16   (len counts halo entries; dpos = offset of the diagonal in the row)
+  int32_t *ja = nullptr;      // [nnzp] 0-based column; padding = own row
+  int32_t *ia0 = nullptr;     // [n+1] 0-based local CSR row pointer (for CSR<->SELL value conversion)
+  int32_t *llen = nullptr;    // [n] number of LOCAL entries (== len when there are no halo columns); nullptr if identical
+  // level schedule of the lower-triangular part (IC(0)/ILU(0) sweeps), built lazily
+  bool levels_built = false;
+  int32_t nlevels = 0;
+  int32_t *lev_ptr = nullptr;   // [nlevels+1] offsets into lev_rows
+  int32_t *lev_rows = nullptr;  // [n] rows ordered by level (ascending row index inside a level)
+  std::vector<int32_t> h_lev_ptr;
+  int32_t nblevels = 0;         // same for the backward sweep (dependencies = entries after the diagonal)
+  int32_t *blev_ptr = nullptr, *blev_rows = nullptr;
+  std::vector<int32_t> h_blev_ptr;
+  int32_t *tpos = nullptr;      // [nnzp] SELL position of the transposed entry (ILU(0) of BiCGStab), lazily
+};
+
+// cell -> faces gather lists, SELL-32 as well (ent, other, slot share the layout)
+struct FaceLists {
+  int64_t nnzp = 0;
+  int64_t *slptr = nullptr;   // [nslices+1]
+  int32_t *len = nullptr;     // [n]
+  int32_t *ent = nullptr;     // +(f+1): cell is the face's owner (P side), -(f+1): neighbour (N side); 0 padding
+  int32_t *other = nullptr;   // field index of the value across the face (cell, ghost slot or boundary slot), 0-based
+  int32_t *slot = nullptr;    // SELL position of a(cell,other) or -1 for physical boundary faces
+};
+
+// Krylov workspace (linear_solvers.f90:33  res,reso,pk,zk,d,uk,vk) + device scalars
+struct KrylovScalars {
+  double red[4];      // raw sums of the kernel that just finished (after the cross-rank sum in multi-GPU runs)
+  double sk, s0, pkapk, resl, res0, factor, resor;
+  double bet, alf, om, gam, beto, ukreso, vkres, vkvk;
+  double tol_abs, tol_rel;
+  int32_t iters, done, itr_max, pad;
+};
+struct KrylovWS {
+  int32_t n = 0, ncols = 0;
+  double *res = nullptr, *pk = nullptr, *zk = nullptr, *adiag = nullptr, *d = nullptr;
+  double *reso = nullptr, *uk = nullptr, *vk = nullptr, *tmp = nullptr;
+  KrylovScalars *sc = nullptr;        // device
+  KrylovScalars *h_sc = nullptr;      // pinned host mirror
+  double *partials = nullptr;         // [4 * maxchunks]
+  unsigned int *counter = nullptr;    // last-block ticket
+  int maxchunks = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+struct FcpComm;   // comm.cu
+
+struct fcp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int32_t n = 0, F = 0, B = 0, nT = 0, nF = 0, nb = 0, npro = 0;
+  std::vector<int32_t> bctype, nfaces, startFace;   // host patch table (startFace 0-based)
+  std::vector<int32_t> h_kPN, h_kNP;                // 1-based host CSR positions (icell_jcell / jcell_icell)
+  // mesh on device
+  int32_t *owner = nullptr, *neigh = nullptr;       // 0-based
+  double *arx = nullptr, *ary = nullptr, *arz = nullptr, *xf = nullptr, *yf = nullptr, *zf = nullptr;  // [nF]
+  double *facint = nullptr, *Df = nullptr;          // [F] (+ process faces in global orientation when partitioned: [nF])
+  double *xc = nullptr, *yc = nullptr, *zc = nullptr, *vol = nullptr;   // [nT]
+  int32_t *bftype = nullptr;                        // [B] patch type of each boundary face
+  int32_t *kPN = nullptr, *kNP = nullptr;           // [F] SELL positions of a(P,N), a(N,P)
+  SellPattern pat;
+  FaceLists fl;
+  double *field[FCP_F_COUNT] = {nullptr};
+  double *Dmat[3] = {nullptr, nullptr, nullptr};    // LSQ matrices per method (index FCP_GRAD_*)
+  KrylovWS ws;
+  FcpComm *comm = nullptr;
+  double *flushbuf = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool has_pressure_patch = false, has_outlet = false, has_inout = false;
+  int32_t nout = 0;
+  int32_t *d_oface = nullptr;                       // outlet faces in patch order (adjustMassFlow)
+  int32_t *d_aprpos = nullptr;                      // [npro] SELL position of the halo entry of each process face
+  int32_t *d_procface = nullptr;                    // [npro] 0-based face index of each process face (patch order)
+  std::vector<int32_t> h_procface;
+};
+
+struct fcp_solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  SellPattern pat;
+  double *a = nullptr;        // SELL values
+  double *a_csr = nullptr;    // staging (device, nnz)
+  double *fi = nullptr, *rhs = nullptr;
+  KrylovWS ws;
+};
+
+// ---- fvm.cu -------------------------------------------------------------------------------------
+struct CorrectArgs {          // velocity / pressure correction fused into gradp_and_sources(pp), calcp_simple.f90:416-429
+  double *u, *v, *w, *pres;
+  const double *apu, *apv, *apw;
+  double urfp;
+  const double *ppref_src;    // device address of pp(pRefCell) or nullptr -> 0 (pressure patches present)
+};
+struct AsmArgs {
+  const double *den, *u, *v, *w, *p, *dPdxi, *apu;
+  double *pp;                 // boundary values of pp on pressure patches are zeroed
+  double *ub, *vb, *wb;       // same arrays as u,v,w (boundary slots written on pressure patches)
+  double *a, *su, *flmass;
+};
+int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g);
+int fvm_lsq_matrix(fcp_ctx *ctx, bool weighted, double *D);
+int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi, double *g, int row2_reference);
+int fvm_laplacian(fcp_ctx *ctx, const double *mu, const double *phi, double *a, double *su);
+int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su, double *sv, double *sw, double *dPdxi, double *gtmp,
+              const CorrectArgs *correct);
+int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g);
+int fvm_adjust_mass_flow(fcp_ctx *ctx, int32_t nout, const int32_t *d_oface, const double *den, double *u, double *v, double *w,
+                         double *flmass, double flomas);
+int fvm_correct_flux(fcp_ctx *ctx, const double *a, const double *pp, double *flmass);
+int fvm_correct_pressure_bnd(fcp_ctx *ctx, const double *den, const double *apu, const double *pp, double *u, double *v, double *w,
+                             double *flmass);
+int fvm_nonorth(fcp_ctx *ctx, const double *den, const double *apu, const double *dPdxi, double *su, double *flmass);
+
+// ---- pattern.cu ---------------------------------------------------------------------------------
+int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, const int32_t *ja1, const int32_t *diag1,
+                  const std::vector<std::vector<int32_t>> *halo_cols /* per row extra columns (0-based), may be null */);
+void sell_free(SellPattern &p);
+int sell_build_levels(SellPattern &p, cudaStream_t st);
+int sell_build_tpos(SellPattern &p, cudaStream_t st);
+int sell_values_from_csr(const SellPattern &p, const double *d_a_csr, double *d_a_sell, cudaStream_t st);
+int sell_values_to_csr(const SellPattern &p, const double *d_a_sell, double *d_a_csr, cudaStream_t st);
+template <class T> int dev_upload(T **dptr, const T *h, size_t count);
+template <class T> int dev_alloc(T **dptr, size_t count);
+
+// ---- krylov.cu ----------------------------------------------------------------------------------
+int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols);
+void krylov_ws_free(KrylovWS &ws);
+int sell_spmv(const SellPattern &p, const double *a, const double *x, double *y, cudaStream_t st);
+int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const double *rhs, KrylovWS &ws,
+                 int32_t itr_max, double tol_abs, double tol_rel, fcp_report *rep, cudaStream_t st, FcpComm *comm,
+                 fcp_ctx *ctx);
+
+// ---- comm.cu ------------------------------------------------------------------------------------
+int comm_exchange(fcp_ctx *ctx, double *field, int ncomp);   // ncomp 1 (scalar) or 3 (gradient)
+int comm_allgather_sum(FcpComm *comm, double *d_vals, int count, cudaStream_t st);  // rank-ordered deterministic sum, in place
+void comm_free(FcpComm *comm);
+int comm_nranks(const FcpComm *comm);

@@ -1,0 +1,662 @@
+// fvm.cu -- finite-volume face-loop operators of the hot path as CELL-CENTRIC GATHERS.
+//
+// The reference runs face loops that scatter into both cells of a face (e.g. calcp_simple.f90:82-118).  Here one
+// thread owns one cell and walks the cell's faces in ascending face index (inner faces, then boundary faces), which is
+// exactly the order in which the reference's sequential face loops touch that cell.  Per-face quantities are evaluated
+// in the face's own orientation (P = owner, N = neighbour) by the same instruction sequence on both sides, so both
+// cells see bit-identical face values, there are no atomics, results are deterministic and round like the reference.
+// The face lists are SELL-32 (fcp_internal.h): a warp reads 128 contiguous bytes per list step.
+#include "fcp_internal.h"
+#include "reduce.cuh"
+
+struct MeshView {
+  int32_t n, F, B;
+  const int64_t *slptr;
+  const int32_t *len, *ent, *other, *slot;
+  const double *arx, *ary, *arz, *xf, *yf, *zf, *facint, *Df;
+  const double *xc, *yc, *zc, *vol;
+  const int32_t *owner, *neigh;
+  const int64_t *a_slptr;    // matrix SELL slice pointers
+  const int32_t *a_rinfo;
+};
+MeshView fcp_mesh_view(const fcp_ctx *c) {
+  MeshView m;
+  m.n = c->n; m.F = c->F; m.B = c->B;
+  m.slptr = c->fl.slptr; m.len = c->fl.len; m.ent = c->fl.ent; m.other = c->fl.other; m.slot = c->fl.slot;
+  m.arx = c->arx; m.ary = c->ary; m.arz = c->arz; m.xf = c->xf; m.yf = c->yf; m.zf = c->zf;
+  m.facint = c->facint; m.Df = c->Df; m.xc = c->xc; m.yc = c->yc; m.zc = c->zc; m.vol = c->vol;
+  m.owner = c->owner; m.neigh = c->neigh;
+  m.a_slptr = c->pat.slptr; m.a_rinfo = c->pat.rinfo;
+  return m;
+}
+
+#define FCP_CELL_LOOP(c, n)                                                                       \
+  for (int j__ = 0; j__ < FCP_IPT; ++j__)                                                         \
+    for (int32_t c = (int32_t)((int64_t)blockIdx.x * FCP_CHUNK + j__ * FCP_TPB + threadIdx.x), once__ = 1; \
+         once__ && c < (n); once__ = 0)
+
+// walk the faces of cell c: e = signed entry, o = index across the face, sl = matrix slot (>=0 two-sided face,
+// -1-bctype for a physical boundary face), f = 0-based face index
+#define FCP_FACE_LOOP(m, c)                                                        \
+  const int64_t fbase__ = (m).slptr[(c) >> 5] + ((c) & 31);                        \
+  const int32_t flen__ = (m).len[c];                                               \
+  for (int32_t q__ = 0; q__ < flen__; ++q__)
+#define FCP_FACE_FETCH(m)                                                          \
+  const int32_t e = __ldcs((m).ent + fbase__ + (int64_t)q__ * 32);                 \
+  const int32_t o = __ldcs((m).other + fbase__ + (int64_t)q__ * 32);               \
+  const int32_t sl = __ldcs((m).slot + fbase__ + (int64_t)q__ * 32);               \
+  const int32_t f = (e > 0 ? e : -e) - 1;                                          \
+  (void)o; (void)sl; (void)f
+
+__device__ __forceinline__ int64_t diag_pos(const MeshView &m, int32_t c) {
+  return m.a_slptr[c >> 5] + (c & 31) + (int64_t)((m.a_rinfo[c] >> 16) & 0xffff) * 32;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad_gauss   gradients.f90:1607-1693
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FCP_TPB) k_grad_gauss(MeshView m, const double *__restrict__ u, double *__restrict__ g) {
+  FCP_CELL_LOOP(c, m.n) {
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    const double uc = u[c];
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
+      if (sl >= 0) {
+        const double uo = u[o];
+        const double uP = e > 0 ? uc : uo, uN = e > 0 ? uo : uc;
+        const double fie = uP + (uN - uP) * m.facint[f];
+        const double dfx = fie * sx, dfy = fie * sy, dfz = fie * sz;
+        if (e > 0) { gx = gx + dfx; gy = gy + dfy; gz = gz + dfz; }
+        else       { gx = gx - dfx; gy = gy - dfy; gz = gz - dfz; }
+      } else {
+        const double ub = u[o];
+        gx = gx + ub * sx; gy = gy + ub * sy; gz = gz + ub * sz;
+      }
+    }
+    const double volr = 1.0 / m.vol[c];
+    g[3 * (int64_t)c + 0] = gx * volr;
+    g[3 * (int64_t)c + 1] = gy * volr;
+    g[3 * (int64_t)c + 2] = gz * volr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// least squares: create_matrix_lsq :660-779 / create_matrix_lsq_dm :1157-1326 ; grad_lsq :782-893 / grad_lsq_dm :1334-1486
+// Dmat is stored SoA [9][n] on the device.
+// ---------------------------------------------------------------------------------------------
+template <bool W>
+__global__ void __launch_bounds__(FCP_TPB) k_lsq_matrix(MeshView m, double *__restrict__ D) {
+  FCP_CELL_LOOP(c, m.n) {
+    double d11 = 0.0, d12 = 0.0, d13 = 0.0, d22 = 0.0, d23 = 0.0, d33 = 0.0;
+    const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      double Dx, Dy, Dz;
+      if (sl >= 0) {
+        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o];
+        if (e > 0) { Dx = xo - xc; Dy = yo - yc; Dz = zo - zc; }
+        else       { Dx = xc - xo; Dy = yc - yo; Dz = zc - zo; }
+      } else {
+        Dx = m.xf[f] - xc; Dy = m.yf[f] - yc; Dz = m.zf[f] - zc;
+      }
+      if (W) {
+        const double w = 1.0 / (Dx * Dx + Dy * Dy + Dz * Dz);
+        d11 = d11 + w * Dx * Dx; d22 = d22 + w * Dy * Dy; d33 = d33 + w * Dz * Dz;
+        d12 = d12 + w * Dx * Dy; d13 = d13 + w * Dx * Dz; d23 = d23 + w * Dy * Dz;
+      } else {
+        d11 = d11 + Dx * Dx; d22 = d22 + Dy * Dy; d33 = d33 + Dz * Dz;
+        d12 = d12 + Dx * Dy; d13 = d13 + Dx * Dz; d23 = d23 + Dy * Dz;
+      }
+    }
+    const double d21 = d12, d31 = d13, d32 = d23;   // :748-777
+    const double tmp = 1.0 / (d11 * d22 * d33 - d11 * d23 * d32 - d12 * d21 * d33 + d12 * d23 * d31 + d13 * d21 * d32 - d13 * d22 * d31 + FCP_SMALL);
+    const int64_t n = m.n;
+    D[0 * n + c] = (d22 * d33 - d23 * d32) * tmp;
+    D[1 * n + c] = (d21 * d33 - d23 * d31) * tmp;
+    D[2 * n + c] = (d21 * d32 - d22 * d31) * tmp;
+    D[3 * n + c] = (d11 * d33 - d13 * d31) * tmp;
+    D[4 * n + c] = (d12 * d33 - d13 * d32) * tmp;
+    D[5 * n + c] = (d11 * d32 - d12 * d31) * tmp;
+    D[6 * n + c] = (d12 * d23 - d13 * d22) * tmp;
+    D[7 * n + c] = (d11 * d23 - d13 * d21) * tmp;
+    D[8 * n + c] = (d11 * d22 - d12 * d21) * tmp;
+  }
+}
+
+template <bool W>
+__global__ void __launch_bounds__(FCP_TPB) k_grad_lsq(MeshView m, const double *__restrict__ D, const double *__restrict__ phi,
+                                                       double *__restrict__ g, int row2_reference) {
+  FCP_CELL_LOOP(c, m.n) {
+    double b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c], pc = phi[c];
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      double Dx, Dy, Dz;
+      if (sl >= 0) {
+        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o], po = phi[o];
+        double dx, dy, dz, dphi;
+        if (e > 0) { dx = xo - xc; dy = yo - yc; dz = zo - zc; dphi = po - pc; }
+        else       { dx = xc - xo; dy = yc - yo; dz = zc - zo; dphi = pc - po; }
+        if (W) {
+          const double w = dphi / (dx * dx + dy * dy + dz * dz);
+          Dx = w * dx; Dy = w * dy; Dz = w * dz;
+        } else {
+          Dx = dx * dphi; Dy = dy * dphi; Dz = dz * dphi;
+        }
+      } else {
+        const double dx = m.xf[f] - xc, dy = m.yf[f] - yc, dz = m.zf[f] - zc;
+        const double dphi = phi[o] - pc;
+        if (W) {
+          // quirk Q2 (gradients.f90:1459): the weight's denominator indexes xf with the BOUNDARY COUNTER i, not iface
+          const int32_t i = f - m.F;
+          const double ex = m.xf[i] - xc, ey = m.yf[i] - yc, ez = m.zf[i] - zc;
+          const double w = dphi / (ex * ex + ey * ey + ez * ez);
+          Dx = w * dx; Dy = w * dy; Dz = w * dz;
+        } else {
+          Dx = dx * dphi; Dy = dy * dphi; Dz = dz * dphi;
+        }
+      }
+      b1 = b1 + Dx; b2 = b2 + Dy; b3 = b3 + Dz;
+    }
+    const int64_t n = m.n;
+    const double D1 = D[0 * n + c], D2 = D[1 * n + c], D3 = D[2 * n + c], D4 = D[3 * n + c], D5 = D[4 * n + c],
+                 D6 = D[5 * n + c], D7 = D[6 * n + c], D8 = D[7 * n + c], D9 = D[8 * n + c];
+    g[3 * (int64_t)c + 0] = b1 * D1 - b2 * D2 + b3 * D3;                   // :886-888 ; row 2 is quirk Q1
+    g[3 * (int64_t)c + 1] = row2_reference ? (b1 * D4 - b2 * D5 - b3 * D6) : (b2 * D4 - b1 * D5 - b3 * D6);
+    g[3 * (int64_t)c + 2] = b1 * D7 - b2 * D8 + b3 * D9;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// laplacian(mu,phi)   fvImplicit/laplacian.f90  (src-par/fvm_laplacian.f90: process faces -> halo column)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FCP_TPB) k_laplacian(MeshView m, const double *__restrict__ mu, const double *__restrict__ phi,
+                                                        double *__restrict__ a, double *__restrict__ su) {
+  FCP_CELL_LOOP(c, m.n) {
+    double dg = 0.0, s = su[c];
+    const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c], muc = mu[c];
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
+      if (sl >= 0) {
+        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o], muo = mu[o];
+        double xpn, ypn, zpn, muP, muN;
+        if (e > 0) { xpn = xo - xc; ypn = yo - yc; zpn = zo - zc; muP = muc; muN = muo; }
+        else       { xpn = xc - xo; ypn = yc - yo; zpn = zc - zo; muP = muo; muN = muc; }
+        const double fxn = m.facint[f], fxp = 1.0 - fxn;
+        const double smdpn = (sx * sx + sy * sy + sz * sz) / (sx * xpn + sy * ypn + sz * zpn);
+        const double cap = (fxp * muP + fxn * muN) * smdpn;
+        a[sl] = cap;
+        dg = dg - cap;
+      } else {
+        const double are = sqrt(sx * sx + sy * sy + sz * sz);
+        const double nxf = sx / are, nyf = sy / are, nzf = sz / are;
+        const double dfn = (m.xf[f] - xc) * nxf + (m.yf[f] - yc) * nyf + (m.zf[f] - zc) * nzf;
+        const double dcoef = muc * are / dfn;
+        dg = dg - dcoef;
+        s = s - dcoef * phi[o];
+      }
+    }
+    a[diag_pos(m, c)] = dg;
+    su[c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradp_and_sources(p)   Pressure/nablap.f90:19-208 + Pressure/bpres.f90
+// Everything a cell needs (its inner-face sum, its own boundary faces, both extrapolation stages) is local to the
+// cell, so 'linear' and 'weighted' run as ONE kernel.  'central' needs the stage-1 gradient of the neighbours and is
+// split in two kernels (k_gradp<...,1> then k_gradp_central2).
+// CORRECT: fuse the velocity / pressure correction and updateVelocityAtBoundary of calcp_simple.f90:416-429.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double face_p(int scheme, double pP, double pN, double lam, double aP, double aN) {
+  if (scheme == FCP_PSCHEME_WEIGHTED) return (pP * aP + pN * aN) / (aP + aN + FCP_SMALL);   // nablap.f90:87
+  return pP + (pN - pP) * lam;                                                              // face_value_cds, interpolation.f90:155
+}
+
+template <bool CORRECT>
+__global__ void __launch_bounds__(FCP_TPB) k_gradp(MeshView m, int scheme, int nstages, double *p, const double *__restrict__ apu,
+                                                    double *__restrict__ su, double *__restrict__ sv, double *__restrict__ sw,
+                                                    double *__restrict__ dPdxi, CorrectArgs ca) {
+  FCP_CELL_LOOP(c, m.n) {
+    const double pc = p[c];
+    const double ac = scheme == FCP_PSCHEME_WEIGHTED ? apu[c] : 0.0;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    bool has_bnd = false;
+    {
+      FCP_FACE_LOOP(m, c) {
+        FCP_FACE_FETCH(m);
+        if (sl >= 0) {
+          const double po = p[o];
+          const double ao = scheme == FCP_PSCHEME_WEIGHTED ? apu[o] : 0.0;
+          const double pf = e > 0 ? face_p(scheme, pc, po, m.facint[f], ac, ao) : face_p(scheme, po, pc, m.facint[f], ao, ac);
+          const double dfx = pf * m.arx[f], dfy = pf * m.ary[f], dfz = pf * m.arz[f];
+          if (e > 0) { s1 = s1 - dfx; s2 = s2 - dfy; s3 = s3 - dfz; }
+          else       { s1 = s1 + dfx; s2 = s2 + dfy; s3 = s3 + dfz; }
+        } else {
+          has_bnd = true;
+        }
+      }
+    }
+    const double volr = 1.0 / m.vol[c];
+    // stage 1: bpres(p,1): p_b = p_P on every patch that is not a pressure patch
+    double gx = -s1, gy = -s2, gz = -s3;
+    if (has_bnd) {
+      FCP_FACE_LOOP(m, c) {
+        FCP_FACE_FETCH(m);
+        if (sl < 0) {
+          const int type = -1 - sl;
+          double pb;
+          if (type == FCP_BC_PRESSURE) pb = p[o]; else { pb = pc; p[o] = pb; }
+          gx = gx + pb * m.arx[f]; gy = gy + pb * m.ary[f]; gz = gz + pb * m.arz[f];
+        }
+      }
+    }
+    gx = gx * volr; gy = gy * volr; gz = gz * volr;
+    if (nstages >= 2) {
+      // stage 2: bpres(p,2): walls are linearly extrapolated with the stage-1 gradient
+      if (has_bnd) {
+        const double g1x = gx, g1y = gy, g1z = gz;
+        gx = -s1; gy = -s2; gz = -s3;
+        const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
+        FCP_FACE_LOOP(m, c) {
+          FCP_FACE_FETCH(m);
+          if (sl < 0) {
+            const int type = -1 - sl;
+            double pb;
+            if (type == FCP_BC_WALL) {
+              const double xpb = m.xf[f] - xc, ypb = m.yf[f] - yc, zpb = m.zf[f] - zc;
+              pb = pc + g1x * xpb + g1y * ypb + g1z * zpb;
+              p[o] = pb;
+            } else {
+              pb = p[o];
+            }
+            gx = gx + pb * m.arx[f]; gy = gy + pb * m.ary[f]; gz = gz + pb * m.arz[f];
+          }
+        }
+        gx = gx * volr; gy = gy * volr; gz = gz * volr;
+      }
+      // (cells without boundary faces: stage 2 recomputes the identical value)
+    }
+    dPdxi[3 * (int64_t)c + 0] = gx;
+    dPdxi[3 * (int64_t)c + 1] = gy;
+    dPdxi[3 * (int64_t)c + 2] = gz;
+    if (nstages >= 2) {
+      // boundary-face part of the momentum sources, nablap.f90:195-204
+      if (has_bnd) {
+        FCP_FACE_LOOP(m, c) {
+          FCP_FACE_FETCH(m);
+          if (sl < 0) {
+            const double pb = p[o];
+            s1 = s1 - pb * m.arx[f]; s2 = s2 - pb * m.ary[f]; s3 = s3 - pb * m.arz[f];
+          }
+        }
+      }
+      su[c] = s1; sv[c] = s2; sw[c] = s3;
+      if (CORRECT) {
+        // calcp_simple.f90:416-419
+        const double ppref = ca.ppref_src ? *ca.ppref_src : 0.0;
+        const double un = ca.u[c] + s1 * ca.apu[c];
+        const double vn = ca.v[c] + s2 * ca.apv[c];
+        const double wn = ca.w[c] + s3 * ca.apw[c];
+        ca.u[c] = un; ca.v[c] = vn; ca.w[c] = wn;
+        ca.pres[c] = ca.pres[c] + ca.urfp * (pc - ppref);
+        if (has_bnd) {   // updateVelocityAtBoundary, velocity.f90:1184-1277
+          FCP_FACE_LOOP(m, c) {
+            FCP_FACE_FETCH(m);
+            if (sl < 0) {
+              const int type = -1 - sl;
+              if (type == FCP_BC_EMPTY || type == FCP_BC_PERIODIC) {
+                ca.u[o] = un; ca.v[o] = vn; ca.w[o] = wn;
+              } else if (type == FCP_BC_SYMMETRY) {
+                const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
+                const double Unmag = un * sx + vn * sy + wn * sz;
+                ca.u[o] = un - Unmag * sx; ca.v[o] = vn - Unmag * sy; ca.w[o] = wn - Unmag * sz;
+              }
+            }
+          }
+        }
+      }
+    } else {
+      su[c] = s1; sv[c] = s2; sw[c] = s3;   // stage-1 inner sums kept for the central second pass
+    }
+  }
+}
+
+// 'central' stage 2 (nablap.f90:129-160): inner-face sum recomputed with face_value_central (interpolation.f90:218-264)
+// using the stage-1 gradients g1 of both cells; writes the final gradient to gout (!= g1).
+template <bool CORRECT>
+__global__ void __launch_bounds__(FCP_TPB) k_gradp_central2(MeshView m, double *p, const double *__restrict__ g1, double *__restrict__ su,
+                                                             double *__restrict__ sv, double *__restrict__ sw, double *__restrict__ gout,
+                                                             CorrectArgs ca) {
+  FCP_CELL_LOOP(c, m.n) {
+    const double pc = p[c];
+    const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
+    const double gcx = g1[3 * (int64_t)c], gcy = g1[3 * (int64_t)c + 1], gcz = g1[3 * (int64_t)c + 2];
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    bool has_bnd = false;
+    {
+      FCP_FACE_LOOP(m, c) {
+        FCP_FACE_FETCH(m);
+        if (sl >= 0) {
+          const double po = p[o];
+          const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o];
+          const double gox = g1[3 * (int64_t)o], goy = g1[3 * (int64_t)o + 1], goz = g1[3 * (int64_t)o + 2];
+          const double xfa = m.xf[f], yfa = m.yf[f], zfa = m.zf[f];
+          double gradfidr, pP, pN;
+          if (e > 0) {
+            gradfidr = gcx * (xfa - xc) + gcy * (yfa - yc) + gcz * (zfa - zc) + gox * (xfa - xo) + goy * (yfa - yo) + goz * (zfa - zo);
+            pP = pc; pN = po;
+          } else {
+            gradfidr = gox * (xfa - xo) + goy * (yfa - yo) + goz * (zfa - zo) + gcx * (xfa - xc) + gcy * (yfa - yc) + gcz * (zfa - zc);
+            pP = po; pN = pc;
+          }
+          const double pf = 0.5 * (pP + pN + gradfidr);
+          const double dfx = pf * m.arx[f], dfy = pf * m.ary[f], dfz = pf * m.arz[f];
+          if (e > 0) { s1 = s1 - dfx; s2 = s2 - dfy; s3 = s3 - dfz; }
+          else       { s1 = s1 + dfx; s2 = s2 + dfy; s3 = s3 + dfz; }
+        } else {
+          has_bnd = true;
+        }
+      }
+    }
+    const double volr = 1.0 / m.vol[c];
+    double gx = -s1, gy = -s2, gz = -s3;
+    if (has_bnd) {
+      FCP_FACE_LOOP(m, c) {
+        FCP_FACE_FETCH(m);
+        if (sl < 0) {
+          const int type = -1 - sl;
+          double pb;
+          if (type == FCP_BC_WALL) {
+            const double xpb = m.xf[f] - xc, ypb = m.yf[f] - yc, zpb = m.zf[f] - zc;
+            pb = pc + gcx * xpb + gcy * ypb + gcz * zpb;
+            p[o] = pb;
+          } else {
+            pb = p[o];
+          }
+          gx = gx + pb * m.arx[f]; gy = gy + pb * m.ary[f]; gz = gz + pb * m.arz[f];
+          s1 = s1 - pb * m.arx[f]; s2 = s2 - pb * m.ary[f]; s3 = s3 - pb * m.arz[f];
+        }
+      }
+    }
+    gout[3 * (int64_t)c + 0] = gx * volr;
+    gout[3 * (int64_t)c + 1] = gy * volr;
+    gout[3 * (int64_t)c + 2] = gz * volr;
+    su[c] = s1; sv[c] = s2; sw[c] = s3;
+    if (CORRECT) {
+      const double ppref = ca.ppref_src ? *ca.ppref_src : 0.0;
+      const double un = ca.u[c] + s1 * ca.apu[c];
+      const double vn = ca.v[c] + s2 * ca.apv[c];
+      const double wn = ca.w[c] + s3 * ca.apw[c];
+      ca.u[c] = un; ca.v[c] = vn; ca.w[c] = wn;
+      ca.pres[c] = ca.pres[c] + ca.urfp * (pc - ppref);
+      if (has_bnd) {
+        FCP_FACE_LOOP(m, c) {
+          FCP_FACE_FETCH(m);
+          if (sl < 0) {
+            const int type = -1 - sl;
+            if (type == FCP_BC_EMPTY || type == FCP_BC_PERIODIC) {
+              ca.u[o] = un; ca.v[o] = vn; ca.w[o] = wn;
+            } else if (type == FCP_BC_SYMMETRY) {
+              const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
+              const double Unmag = un * sx + vn * sy + wn * sz;
+              ca.u[o] = un - Unmag * sx; ca.v[o] = vn - Unmag * sy; ca.w[o] = wn - Unmag * sz;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pressure-correction assembly   calcp_simple.f90:69-234 + facefluxmass2 faceflux_mass.f90:175-249
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FCP_TPB) k_assemble_pcorr(MeshView m, AsmArgs g) {
+  FCP_CELL_LOOP(c, m.n) {
+    const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
+    const double denc = g.den[c], kc = m.vol[c] * g.apu[c];
+    const double uc = g.u[c], vc = g.v[c], wc = g.w[c], pc = g.p[c];
+    const double gcx = g.dPdxi[3 * (int64_t)c], gcy = g.dPdxi[3 * (int64_t)c + 1], gcz = g.dPdxi[3 * (int64_t)c + 2];
+    double dg = 0.0, s = 0.0;
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
+      if (sl >= 0) {
+        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o];
+        const double deno = g.den[o], ko = m.vol[o] * g.apu[o];
+        const double uo = g.u[o], vo = g.v[o], wo = g.w[o], po = g.p[o];
+        const double gox = g.dPdxi[3 * (int64_t)o], goy = g.dPdxi[3 * (int64_t)o + 1], goz = g.dPdxi[3 * (int64_t)o + 2];
+        const double lam = m.facint[f], fxn = lam, fxp = 1.0 - lam;
+        const bool own = e > 0;
+        // P = owner side, N = neighbour side of the face, whichever this cell is
+        const double xpn = own ? xo - xc : xc - xo, ypn = own ? yo - yc : yc - yo, zpn = own ? zo - zc : zc - zo;
+        const double denP = own ? denc : deno, denN = own ? deno : denc;
+        const double kP = own ? kc : ko, kN = own ? ko : kc;
+        const double uP = own ? uc : uo, uN = own ? uo : uc;
+        const double vP = own ? vc : vo, vN = own ? vo : vc;
+        const double wP = own ? wc : wo, wN = own ? wo : wc;
+        const double pP = own ? pc : po, pN = own ? po : pc;
+        const double gPx = own ? gcx : gox, gPy = own ? gcy : goy, gPz = own ? gcz : goz;
+        const double gNx = own ? gox : gcx, gNy = own ? goy : gcy, gNz = own ? goz : gcz;
+        const double dene = denP * fxp + denN * fxn;
+        const double Kj = kP * fxp + kN * fxn;
+        const double cap = -dene * Kj * m.Df[f];
+        const double ui = uP + (uN - uP) * lam;
+        const double vi = vP + (vN - vP) * lam;
+        const double wi = wP + (wN - wP) * lam;
+        const double dpxi = (gNx * fxp + gPx * fxn) * xpn;     // weights swapped in the reference (faceflux_mass.f90:236-238), kept
+        const double dpyi = (gNy * fxp + gPy * fxn) * ypn;
+        const double dpzi = (gNz * fxp + gPz * fxn) * zpn;
+        const double flm = dene * (ui * sx + vi * sy + wi * sz) + cap * (pN - pP - dpxi - dpyi - dpzi);
+        g.a[sl] = cap;
+        dg = dg - cap;
+        if (own) { s = s - flm; g.flmass[f] = flm; }
+        else     { s = s + flm; }
+      } else {
+        const int type = -1 - sl;
+        if (type == FCP_BC_INLET || type == FCP_BC_OUTLET) {
+          s = s - g.flmass[f];                                // calcp_simple.f90:131-160
+        } else if (type == FCP_BC_PRESSURE) {                 // facefluxmassPressBnd faceflux_mass.f90:765-831
+          const double xpn = m.xf[f] - xc, ypn = m.yf[f] - yc, zpn = m.zf[f] - zc;
+          const double capp = kc / (sx * xpn + sy * ypn + sz * zpn);
+          const double dpcor = g.p[o] - pc - (gcx * xpn + gcy * ypn + gcz * zpn);
+          const double ub = uc - sx * capp * dpcor, vb = vc - sy * capp * dpcor, wb = wc - sz * capp * dpcor;
+          g.ub[o] = ub; g.vb[o] = vb; g.wb[o] = wb;
+          const double flm = denc * (ub * sx + vb * sy + wb * sz);
+          g.flmass[f] = flm;
+          const double cap = -denc * (sx * sx + sy * sy + sz * sz) * capp;
+          dg = dg - cap;
+          s = s - flm;
+          g.pp[o] = 0.0;
+        }
+      }
+    }
+    g.a[diag_pos(m, c)] = dg;
+    g.su[c] = s;
+  }
+}
+
+// adjustMassFlow faceflux_mass.f90:833-916.  Outlet patches are small; ONE CTA evaluates the outlet fluxes in parallel
+// and thread 0 adds them in face order (the reference's order), then all threads scale.
+__global__ void __launch_bounds__(FCP_TPB) k_adjust_mass_flow(int32_t nout, const int32_t *__restrict__ oface, int32_t n, int32_t F,
+                                                               const int32_t *__restrict__ owner, const double *__restrict__ arx,
+                                                               const double *__restrict__ ary, const double *__restrict__ arz,
+                                                               const double *__restrict__ den, double *u, double *v, double *w,
+                                                               double *flmass, double flomas) {
+  __shared__ double fac_s;
+  for (int32_t i = threadIdx.x; i < nout; i += blockDim.x) {
+    const int32_t f = oface[i], ijp = owner[f], ijb = n + (f - F);
+    const double ub = u[ijp], vb = v[ijp], wb = w[ijp];
+    u[ijb] = ub; v[ijb] = vb; w[ijb] = wb;
+    flmass[f] = den[ijp] * (ub * arx[f] + vb * ary[f] + wb * arz[f]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double flowo = 0.0;
+    for (int32_t i = 0; i < nout; ++i) flowo = flowo + flmass[oface[i]];
+    fac_s = flomas / (flowo + FCP_SMALL);
+  }
+  __syncthreads();
+  const double fac = fac_s;
+  for (int32_t i = threadIdx.x; i < nout; i += blockDim.x) {
+    const int32_t f = oface[i], ijb = n + (f - F);
+    flmass[f] = flmass[f] * fac;
+    u[ijb] = u[ijb] * fac; v[ijb] = v[ijb] * fac; w[ijb] = w[ijb] * fac;
+  }
+}
+
+// flux correction  calcp_simple.f90:331-341 : face-parallel, no scatter
+__global__ void __launch_bounds__(FCP_TPB) k_correct_flux(int32_t F, const int32_t *__restrict__ owner, const int32_t *__restrict__ neigh,
+                                                           const int32_t *__restrict__ kPN, const double *__restrict__ a,
+                                                           const double *__restrict__ pp, double *__restrict__ flmass) {
+  FCP_CELL_LOOP(f, F) { flmass[f] = flmass[f] + a[kPN[f]] * (pp[neigh[f]] - pp[owner[f]]); }
+}
+// pressure patches  calcp_simple.f90:345-391 + facefluxmassCorrPressBnd faceflux_mass.f90:699-762
+__global__ void __launch_bounds__(FCP_TPB) k_correct_pressure_bnd(MeshView m, const int32_t *__restrict__ bftype, const double *__restrict__ den,
+                                                                   const double *__restrict__ apu, const double *__restrict__ pp,
+                                                                   double *u, double *v, double *w, double *flmass) {
+  FCP_CELL_LOOP(i, m.B) {
+    if (bftype[i] != FCP_BC_PRESSURE) continue;
+    const int32_t f = m.F + i, ijp = m.owner[f], ijb = m.n + i;
+    const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
+    const double xpn = m.xf[f] - m.xc[ijp], ypn = m.yf[f] - m.yc[ijp], zpn = m.zf[f] - m.zc[ijp];
+    const double cap = m.vol[ijp] * apu[ijp] / (sx * xpn + sy * ypn + sz * zpn);
+    const double dpcor = -pp[ijp];
+    u[ijb] = u[ijb] - sx * cap * dpcor;
+    v[ijb] = v[ijb] - sy * cap * dpcor;
+    w[ijb] = w[ijb] - sz * cap * dpcor;
+    flmass[f] = flmass[f] - den[ijp] * (sx * sx + sy * sy + sz * sz) * cap * dpcor;
+  }
+}
+
+// non-orthogonal corrector  calcp_simple.f90:433-455 + fluxmc2 faceflux_mass.f90:650-696
+__global__ void __launch_bounds__(FCP_TPB) k_nonorth(MeshView m, const double *__restrict__ den, const double *__restrict__ apu,
+                                                      const double *__restrict__ dPdxi, double *__restrict__ su, double *__restrict__ flmass) {
+  FCP_CELL_LOOP(c, m.n) {
+    const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
+    const double rc = apu[c] * den[c];
+    const double gcx = dPdxi[3 * (int64_t)c], gcy = dPdxi[3 * (int64_t)c + 1], gcz = dPdxi[3 * (int64_t)c + 2];
+    double s = 0.0;
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      if (sl >= 0) {
+        const bool own = e > 0;
+        const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
+        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o];
+        const double ro = apu[o] * den[o];
+        const double gox = dPdxi[3 * (int64_t)o], goy = dPdxi[3 * (int64_t)o + 1], goz = dPdxi[3 * (int64_t)o + 2];
+        const double xpn = own ? xo - xc : xc - xo, ypn = own ? yo - yc : yc - yo, zpn = own ? zo - zc : zc - zo;
+        const double rP = own ? rc : ro, rN = own ? ro : rc;
+        const double gPx = own ? gcx : gox, gPy = own ? gcy : goy, gPz = own ? gcz : goz;
+        const double gNx = own ? gox : gcx, gNy = own ? goy : gcy, gNz = own ? goz : gcz;
+        const double s2 = sx * sx + sy * sy + sz * sz;
+        const double dn = xpn * sx + ypn * sy + zpn * sz;
+        const double rapr = -0.5 * (rP + rN);
+        const double dpx = 0.5 * (gNx + gPx), dpy = 0.5 * (gNy + gPy), dpz = 0.5 * (gNz + gPz);
+        const double fmcor = rapr * ((dn * sx - xpn * s2) * dpx + (dn * sy - ypn * s2) * dpy + (dn * sz - zpn * s2) * dpz);
+        if (own) { flmass[f] = flmass[f] + fmcor; s = s - fmcor; }
+        else     { s = s + fmcor; }
+      }
+    }
+    su[c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host wrappers (called from api.cu)
+// ---------------------------------------------------------------------------------------------
+#define FCP_GRID(n) fcp_nchunks(n), FCP_TPB, 0, ctx->stream
+
+int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g) {
+  if (ctx->B) FCP_CUDA(cudaMemsetAsync(g + 3 * (size_t)ctx->n, 0, sizeof(double) * 3 * (size_t)ctx->B, ctx->stream));
+  if (ctx->n == 0) return FCP_OK;
+  k_grad_gauss<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), u, g);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_lsq_matrix(fcp_ctx *ctx, bool weighted, double *D) {
+  if (ctx->n == 0) return FCP_OK;
+  if (weighted) k_lsq_matrix<true><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), D);
+  else k_lsq_matrix<false><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), D);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi, double *g, int row2_reference) {
+  if (ctx->B) FCP_CUDA(cudaMemsetAsync(g + 3 * (size_t)ctx->n, 0, sizeof(double) * 3 * (size_t)ctx->B, ctx->stream));
+  if (ctx->n == 0) return FCP_OK;
+  if (weighted) k_grad_lsq<true><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference);
+  else k_grad_lsq<false><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_laplacian(fcp_ctx *ctx, const double *mu, const double *phi, double *a, double *su) {
+  if (ctx->n == 0) return FCP_OK;
+  k_laplacian<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), mu, phi, a, su);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+// p: the field whose gradient is taken (p or pp); correct != nullptr fuses calcp_simple.f90:416-429
+int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su, double *sv, double *sw, double *dPdxi, double *gtmp,
+              const CorrectArgs *correct) {
+  if (ctx->n == 0) return FCP_OK;
+  MeshView m = fcp_mesh_view(ctx);
+  CorrectArgs ca{};
+  if (correct) ca = *correct;
+  if (scheme == FCP_PSCHEME_CENTRAL) {
+    k_gradp<false><<<FCP_GRID(ctx->n)>>>(m, FCP_PSCHEME_LINEAR, 1, p, apu, su, sv, sw, gtmp, ca);
+    FCP_LAUNCHED();
+    if (correct) k_gradp_central2<true><<<FCP_GRID(ctx->n)>>>(m, p, gtmp, su, sv, sw, dPdxi, ca);
+    else k_gradp_central2<false><<<FCP_GRID(ctx->n)>>>(m, p, gtmp, su, sv, sw, dPdxi, ca);
+    FCP_LAUNCHED();
+  } else {
+    if (correct) k_gradp<true><<<FCP_GRID(ctx->n)>>>(m, scheme, 2, p, apu, su, sv, sw, dPdxi, ca);
+    else k_gradp<false><<<FCP_GRID(ctx->n)>>>(m, scheme, 2, p, apu, su, sv, sw, dPdxi, ca);
+    FCP_LAUNCHED();
+  }
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g) {
+  if (ctx->n == 0) return FCP_OK;
+  k_assemble_pcorr<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_adjust_mass_flow(fcp_ctx *ctx, int32_t nout, const int32_t *d_oface, const double *den, double *u, double *v, double *w,
+                         double *flmass, double flomas) {
+  k_adjust_mass_flow<<<1, FCP_TPB, 0, ctx->stream>>>(nout, d_oface, ctx->n, ctx->F, ctx->owner, ctx->arx, ctx->ary, ctx->arz, den, u, v, w,
+                                                      flmass, flomas);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_correct_flux(fcp_ctx *ctx, const double *a, const double *pp, double *flmass) {
+  if (ctx->F == 0) return FCP_OK;
+  k_correct_flux<<<FCP_GRID(ctx->F)>>>(ctx->F, ctx->owner, ctx->neigh, ctx->kPN, a, pp, flmass);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_correct_pressure_bnd(fcp_ctx *ctx, const double *den, const double *apu, const double *pp, double *u, double *v, double *w,
+                             double *flmass) {
+  if (ctx->B == 0) return FCP_OK;
+  k_correct_pressure_bnd<<<FCP_GRID(ctx->B)>>>(fcp_mesh_view(ctx), ctx->bftype, den, apu, pp, u, v, w, flmass);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_nonorth(fcp_ctx *ctx, const double *den, const double *apu, const double *dPdxi, double *su, double *flmass) {
+  if (ctx->n == 0) return FCP_OK;
+  k_nonorth<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), den, apu, dPdxi, su, flmass);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}

@@ -1,0 +1,600 @@
+// krylov.cu -- SELL-32 SpMV and the three Krylov solvers of the reference
+//   dpcg      src/linearSolvers/linear_solvers.f90:206-359   (src-par/dpcg.f90 for the halo term)
+//   iccg      :364-545        IC(0), diagonal-only factor (:439-445), apply :458-475
+//   bicgstab  :548-786        ILU(0), diagonal-only factor (:613-624)
+// Arithmetic order per row and per reduction is fixed (fcp_internal.h), no FMA contraction (-fmad=false), so the
+// iterates are bitwise those of the CPU restatement in its TREE summation mode.
+#include <cooperative_groups.h>
+#include "fcp_internal.h"
+#include "reduce.cuh"
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols) {
+  if (ws.n == n && ws.ncols == ncols && ws.res) return FCP_OK;
+  krylov_ws_free(ws);
+  ws.n = n;
+  ws.ncols = ncols;
+  FCP_TRY(dev_alloc(&ws.res, (size_t)n));
+  FCP_TRY(dev_alloc(&ws.pk, (size_t)ncols));
+  FCP_TRY(dev_alloc(&ws.zk, (size_t)ncols));
+  FCP_TRY(dev_alloc(&ws.adiag, (size_t)n));
+  ws.maxchunks = fcp_nchunks(n) + 1;
+  FCP_TRY(dev_alloc(&ws.partials, (size_t)4 * ws.maxchunks));
+  FCP_TRY(dev_alloc(&ws.counter, 1));
+  FCP_CUDA(cudaMemset(ws.counter, 0, sizeof(unsigned int)));
+  FCP_CUDA(cudaMalloc((void **)&ws.sc, sizeof(KrylovScalars)));
+  FCP_CUDA(cudaMallocHost((void **)&ws.h_sc, sizeof(KrylovScalars)));
+  FCP_CUDA(cudaEventCreateWithFlags(&ws.ev[0], cudaEventDisableTiming));
+  FCP_CUDA(cudaEventCreateWithFlags(&ws.ev[1], cudaEventDisableTiming));
+  return FCP_OK;
+}
+static int krylov_ws_need(KrylovWS &ws, double **p, size_t count) {
+  if (*p) return FCP_OK;
+  FCP_TRY(dev_alloc(p, count));
+  FCP_CUDA(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(double)));
+  (void)ws;
+  return FCP_OK;
+}
+void krylov_ws_free(KrylovWS &ws) {
+  cudaFree(ws.res); cudaFree(ws.pk); cudaFree(ws.zk); cudaFree(ws.adiag); cudaFree(ws.d);
+  cudaFree(ws.reso); cudaFree(ws.uk); cudaFree(ws.vk); cudaFree(ws.tmp);
+  cudaFree(ws.partials); cudaFree(ws.counter); cudaFree(ws.sc);
+  if (ws.h_sc) cudaFreeHost(ws.h_sc);
+  if (ws.ev[0]) cudaEventDestroy(ws.ev[0]);
+  if (ws.ev[1]) cudaEventDestroy(ws.ev[1]);
+  ws = KrylovWS();
+}
+
+// ---------------------------------------------------------------------------------------------
+// row kernels on SELL-32
+// ---------------------------------------------------------------------------------------------
+struct SellView {
+  const int64_t *slptr;
+  const int32_t *rinfo;
+  const int32_t *ja;
+  const double *a;
+};
+
+// s <- s (+|-) sum_k a(r,k) x(ja(r,k)), entries in CSR order (linear_solvers.f90:256-261 with SUB, :308-313 without)
+template <bool SUB>
+__device__ __forceinline__ double sell_row_sum(const SellView &m, const double *__restrict__ x, int32_t r, double s) {
+  const int64_t base = __ldg(&m.slptr[r >> 5]) + (r & 31);
+  const int32_t len = __ldg(&m.rinfo[r]) & 0xffff;
+  const double *__restrict__ ap = m.a + base;
+  const int32_t *__restrict__ jp = m.ja + base;
+#pragma unroll 4
+  for (int32_t k = 0; k < len; ++k) {
+    const double av = __ldcs(ap + (int64_t)k * 32);
+    const int32_t c = __ldcs(jp + (int64_t)k * 32);
+    const double t = av * __ldg(x + c);
+    s = SUB ? (s - t) : (s + t);
+  }
+  return s;
+}
+
+#define FCP_ROW_LOOP(r, n)                                                                        \
+  for (int j__ = 0; j__ < FCP_IPT; ++j__)                                                         \
+    for (int32_t r = (int32_t)((int64_t)blockIdx.x * FCP_CHUNK + j__ * FCP_TPB + threadIdx.x), once__ = 1; \
+         once__ && r < (n); once__ = 0)
+
+__global__ void __launch_bounds__(FCP_TPB) k_spmv(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y) {
+  FCP_ROW_LOOP(r, n) { y[r] = sell_row_sum<false>(m, x, r, 0.0); }
+}
+int sell_spmv(const SellPattern &p, const double *a, const double *x, double *y, cudaStream_t st) {
+  if (p.n == 0) return FCP_OK;
+  SellView m{p.slptr, p.rinfo, p.ja, a};
+  k_spmv<<<fcp_nchunks(p.n), FCP_TPB, 0, st>>>(p.n, m, x, y);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar epilogues.  Single GPU: run by thread 0 of the last CTA of the producing kernel.  Multi GPU: the raw local
+// sums go through the rank-ordered cross-rank sum (comm.cu) and k_epilogue runs them (src-par/global_sum_mpi.f90).
+// ---------------------------------------------------------------------------------------------
+enum { EPI_NONE = 0, EPI_INIT_CG, EPI_PKAPK, EPI_CG_UPDATE, EPI_SK, EPI_INIT_BICG, EPI_UKRESO, EPI_VK, EPI_BICG_UPDATE };
+
+__device__ __forceinline__ void conv_check(KrylovScalars *sc) {
+  // linear_solvers.f90:336-346
+  if (sc->iters == 1) {
+    sc->factor = sc->red[2] + FCP_SMALL;
+    sc->resor = sc->res0 / sc->factor;
+  }
+  const double rsm = sc->resl / (sc->res0 + FCP_SMALL);
+  if (rsm < sc->tol_rel || sc->resl < sc->tol_abs || sc->iters >= sc->itr_max) sc->done = 1;
+}
+
+__device__ void krylov_epilogue(int which, KrylovScalars *sc) {
+  switch (which) {
+    case EPI_INIT_CG:   // red0 = sum|res|, red1 = sum res*zk (dpcg only; iccg gets sk from EPI_SK)
+      sc->res0 = sc->red[0];
+      sc->resl = sc->red[0];
+      sc->iters = 0;
+      sc->factor = 0.0;
+      sc->resor = sc->red[0];
+      sc->done = (sc->red[0] < sc->tol_abs || sc->itr_max <= 0) ? 1 : 0;   // :266-270
+      sc->s0 = (double)1.e20f;                                           // :276  s0=1.e20
+      sc->sk = sc->red[1];
+      sc->bet = sc->sk / sc->s0;
+      break;
+    case EPI_SK:        // iccg: sk = sum res*zk after the preconditioner apply
+      sc->sk = sc->red[0];
+      sc->bet = sc->sk / sc->s0;
+      break;
+    case EPI_PKAPK:
+      sc->pkapk = sc->red[0];
+      sc->alf = sc->sk / sc->pkapk;
+      break;
+    case EPI_CG_UPDATE:  // red0 = sum|res|, red1 = next sk (dpcg), red2 = sum|a_ii fi_i| (first iteration)
+      sc->resl = sc->red[0];
+      sc->s0 = sc->sk;
+      sc->sk = sc->red[1];
+      sc->bet = sc->sk / sc->s0;
+      sc->iters += 1;
+      conv_check(sc);
+      break;
+    case EPI_INIT_BICG:  // red0 = sum|res| ; red1 = sum res*reso (= sum res*res)
+      sc->res0 = sc->red[0];
+      sc->resl = sc->red[0];
+      sc->iters = 0;
+      sc->factor = 0.0;
+      sc->resor = sc->red[0];
+      sc->done = (sc->red[0] < sc->tol_abs || sc->itr_max <= 0) ? 1 : 0;
+      sc->alf = 1.0; sc->beto = 1.0; sc->gam = 1.0;                        // :640-642
+      sc->bet = sc->red[1];
+      sc->om = sc->bet * sc->gam / (sc->alf * sc->beto + FCP_SMALL);       // :655
+      sc->beto = sc->bet;
+      break;
+    case EPI_UKRESO:
+      sc->ukreso = sc->red[0];
+      sc->gam = sc->bet / sc->ukreso;                                      // :701
+      break;
+    case EPI_VK:
+      sc->vkres = sc->red[0];
+      sc->vkvk = sc->red[1];
+      sc->alf = sc->vkres / (sc->vkvk + FCP_SMALL);                        // :747
+      break;
+    case EPI_BICG_UPDATE:  // red0 = sum|res|, red1 = next bet = sum res*reso, red2 = factor sum
+      sc->resl = sc->red[0];
+      sc->iters += 1;
+      conv_check(sc);
+      sc->bet = sc->red[1];
+      sc->om = sc->bet * sc->gam / (sc->alf * sc->beto + FCP_SMALL);
+      sc->beto = sc->bet;
+      break;
+    default: break;
+  }
+}
+__global__ void k_epilogue(int which, KrylovScalars *sc) { krylov_epilogue(which, sc); }
+
+struct RedArgs {
+  double *partials;
+  int stride;
+  unsigned int *counter;
+  KrylovScalars *sc;
+  int epi;    // epilogue id
+  int fuse;   // 1: run the epilogue in the last CTA (single GPU); 0: only store the local sums in sc->red
+};
+template <int NS>
+__device__ __forceinline__ void finish_reduce(double (&s)[NS], const RedArgs &ra) {
+  double total[NS];
+  if (fcp_grid_reduce<NS>(s, ra.partials, ra.stride, ra.counter, total)) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) ra.sc->red[k] = total[k];
+      if (ra.fuse) krylov_epilogue(ra.epi, ra.sc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DPCG / shared CG kernels
+// ---------------------------------------------------------------------------------------------
+// res = rhs - A fi ; adiag = a(diag) ; pk = 0 ; sums: |res| , res*(res/adiag)
+template <bool JACOBI>
+__global__ void __launch_bounds__(FCP_TPB) k_cg_init(int32_t n, SellView m, const double *__restrict__ fi, const double *__restrict__ rhs,
+                                                      double *__restrict__ res, double *__restrict__ adiag, double *__restrict__ pk, RedArgs ra) {
+  double s[2] = {0.0, 0.0};
+  FCP_ROW_LOOP(r, n) {
+    const double rr = sell_row_sum<true>(m, fi, r, rhs[r]);
+    res[r] = rr;
+    const int64_t base = m.slptr[r >> 5] + (r & 31);
+    const int32_t dpos = (m.rinfo[r] >> 16) & 0xffff;
+    const double ad = m.a[base + (int64_t)dpos * 32];
+    adiag[r] = ad;
+    pk[r] = 0.0;
+    s[0] = s[0] + fabs(rr);
+    if (JACOBI) s[1] = s[1] + rr * (rr / ad);
+  }
+  finish_reduce<2>(s, ra);
+}
+
+// pk = zk + bet*pk with zk = res/adiag (dpcg :288-303) or the stored zk (iccg)
+template <bool JACOBI>
+__global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
+                                                    const double *__restrict__ zk, double *__restrict__ pk, const KrylovScalars *sc) {
+  if (sc->done) return;
+  const double bet = sc->bet;
+  FCP_ROW_LOOP(r, n) {
+    const double z = JACOBI ? (res[r] / adiag[r]) : zk[r];
+    pk[r] = z + bet * pk[r];
+  }
+}
+
+// y = A x ; sums: sum v1*y [, sum v2*y | sum y*y]
+template <int NS, bool SQ>
+__global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
+                                                       const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra) {
+  if (sc->done) return;
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  FCP_ROW_LOOP(r, n) {
+    const double yr = sell_row_sum<false>(m, x, r, 0.0);
+    y[r] = yr;
+    s[0] = s[0] + v1[r] * yr;
+    if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
+  }
+  finish_reduce<NS>(s, ra);
+}
+
+// fi += alf*pk ; res -= alf*zk ; sums: |res| , [res*(res/adiag)] , [|adiag*fi|]      (:321-340)
+template <bool JACOBI>
+__global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__restrict__ fi, double *__restrict__ res, const double *__restrict__ pk,
+                                                        const double *__restrict__ zk, const double *__restrict__ adiag,
+                                                        const KrylovScalars *sc, RedArgs ra) {
+  if (sc->done) return;
+  const double alf = sc->alf;
+  const bool first = (sc->iters == 0);
+  double s[3] = {0.0, 0.0, 0.0};
+  FCP_ROW_LOOP(r, n) {
+    const double f = fi[r] + alf * pk[r];
+    const double rr = res[r] - alf * zk[r];
+    fi[r] = f;
+    res[r] = rr;
+    s[0] = s[0] + fabs(rr);
+    const double ad = adiag[r];
+    if (JACOBI) s[1] = s[1] + rr * (rr / ad);
+    if (first) s[2] = s[2] + fabs(ad * f);
+  }
+  finish_reduce<3>(s, ra);
+}
+
+// sum a*b (iccg sk = sum res*zk)
+__global__ void __launch_bounds__(FCP_TPB) k_dot(int32_t n, const double *__restrict__ a, const double *__restrict__ b, const KrylovScalars *sc, RedArgs ra) {
+  if (sc->done) return;
+  double s[1] = {0.0};
+  FCP_ROW_LOOP(r, n) { s[0] = s[0] + a[r] * b[r]; }
+  finish_reduce<1>(s, ra);
+}
+
+// ---------------------------------------------------------------------------------------------
+// IC(0)/ILU(0) diagonal-only factor and the preconditioner apply, level scheduled.
+// One persistent cooperative grid; grid.sync() between levels.
+// ---------------------------------------------------------------------------------------------
+struct LevelView {
+  const int32_t *lev_ptr, *lev_rows, *blev_ptr, *blev_rows;
+  int32_t nlevels, nblevels;
+};
+
+// d(i) = 1/(a_ii - sum_{k<diag} a_k^2 d(ja_k))                       iccg   :439-445
+// d(i) = 1/(a_ii - sum_{k<diag} a_k d(ja_k) a_T(k))                  bicgstab :613-624
+template <bool ILU>
+__global__ void __launch_bounds__(FCP_TPB) k_factor_diag(SellView m, LevelView lv, const int32_t *__restrict__ tpos, double *d) {
+  cg::grid_group grid = cg::this_grid();
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int32_t L = 0; L < lv.nlevels; ++L) {
+    const int32_t b = lv.lev_ptr[L], e = lv.lev_ptr[L + 1];
+    for (int64_t q = b + gtid; q < e; q += gsz) {
+      const int32_t i = lv.lev_rows[q];
+      const int64_t base = m.slptr[i >> 5] + (i & 31);
+      const int32_t dpos = (m.rinfo[i] >> 16) & 0xffff;
+      double di = m.a[base + (int64_t)dpos * 32];
+      for (int32_t k = 0; k < dpos; ++k) {
+        const int64_t pos = base + (int64_t)k * 32;
+        const double ak = m.a[pos];
+        const double dj = __ldcg(&d[m.ja[pos]]);
+        if (ILU) {
+          const int32_t tp = tpos[pos];
+          const double at = tp >= 0 ? m.a[tp] : 0.0;
+          di = di - ak * dj * at;
+        } else {
+          di = di - ak * ak * dj;
+        }
+      }
+      d[i] = 1.0 / di;
+    }
+    grid.sync();
+  }
+}
+
+// zk = M^-1 rhs : forward sweep, zk/(d+small), backward sweep      (:458-475 ; quirk Q4 kept)
+__global__ void __launch_bounds__(FCP_TPB) k_precond_apply(SellView m, LevelView lv, const int32_t *__restrict__ llen, const double *__restrict__ d,
+                                                            const double *__restrict__ rhs, double *zk, const KrylovScalars *sc) {
+  if (sc->done) return;
+  cg::grid_group grid = cg::this_grid();
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int32_t L = 0; L < lv.nlevels; ++L) {
+    const int32_t b = lv.lev_ptr[L], e = lv.lev_ptr[L + 1];
+    for (int64_t q = b + gtid; q < e; q += gsz) {
+      const int32_t i = lv.lev_rows[q];
+      const int64_t base = m.slptr[i >> 5] + (i & 31);
+      const int32_t dpos = (m.rinfo[i] >> 16) & 0xffff;
+      double z = rhs[i];
+      for (int32_t k = 0; k < dpos; ++k) {
+        const int64_t pos = base + (int64_t)k * 32;
+        z = z - m.a[pos] * __ldcg(&zk[m.ja[pos]]);
+      }
+      zk[i] = z * d[i];
+    }
+    grid.sync();
+  }
+  for (int32_t L = 0; L < lv.nblevels; ++L) {
+    const int32_t b = lv.blev_ptr[L], e = lv.blev_ptr[L + 1];
+    for (int64_t q = b + gtid; q < e; q += gsz) {
+      const int32_t i = lv.blev_rows[q];
+      const int64_t base = m.slptr[i >> 5] + (i & 31);
+      const int32_t ri = m.rinfo[i];
+      const int32_t dpos = (ri >> 16) & 0xffff;
+      const int32_t len = llen ? llen[i] : (ri & 0xffff);   // local columns only: block-Jacobi across ranks
+      const double di = d[i];
+      double z = __ldcg(&zk[i]) / (di + FCP_SMALL);
+      for (int32_t k = dpos + 1; k < len; ++k) {
+        const int64_t pos = base + (int64_t)k * 32;
+        z = z - m.a[pos] * __ldcg(&zk[m.ja[pos]]);
+      }
+      zk[i] = z * di;
+    }
+    grid.sync();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BiCGStab element kernels
+// ---------------------------------------------------------------------------------------------
+// reso = res ; pk = uk = 0 are set by the host (memset) ; this kernel: res = rhs - A fi, adiag, sums |res|, res*res
+__global__ void __launch_bounds__(FCP_TPB) k_bicg_init(int32_t n, SellView m, const double *__restrict__ fi, const double *__restrict__ rhs,
+                                                        double *__restrict__ res, double *__restrict__ reso, double *__restrict__ adiag, RedArgs ra) {
+  double s[2] = {0.0, 0.0};
+  FCP_ROW_LOOP(r, n) {
+    const double rr = sell_row_sum<true>(m, fi, r, rhs[r]);
+    res[r] = rr;
+    reso[r] = rr;
+    const int64_t base = m.slptr[r >> 5] + (r & 31);
+    const int32_t dpos = (m.rinfo[r] >> 16) & 0xffff;
+    adiag[r] = m.a[base + (int64_t)dpos * 32];
+    s[0] = s[0] + fabs(rr);
+    s[1] = s[1] + rr * rr;
+  }
+  finish_reduce<2>(s, ra);
+}
+// pk = res + om*(pk - alf*uk)     (:658)
+__global__ void __launch_bounds__(FCP_TPB) k_bicg_pk(int32_t n, const double *__restrict__ res, const double *__restrict__ uk, double *__restrict__ pk,
+                                                      const KrylovScalars *sc) {
+  if (sc->done) return;
+  const double om = sc->om, alf = sc->alf;   // alf of the previous iteration (1.0 at the start), :640,658
+  FCP_ROW_LOOP(r, n) { pk[r] = res[r] + om * (pk[r] - alf * uk[r]); }
+}
+// fi += gam*zk ; res -= gam*uk    (:707-708)
+__global__ void __launch_bounds__(FCP_TPB) k_bicg_half(int32_t n, double *__restrict__ fi, double *__restrict__ res, const double *__restrict__ zk,
+                                                        const double *__restrict__ uk, const KrylovScalars *sc) {
+  if (sc->done) return;
+  const double gam = sc->gam;
+  FCP_ROW_LOOP(r, n) {
+    fi[r] = fi[r] + gam * zk[r];
+    res[r] = res[r] - gam * uk[r];
+  }
+}
+// fi += alf*zk ; res -= alf*vk ; sums |res|, res*reso, [|adiag fi|]    (:750-773)
+__global__ void __launch_bounds__(FCP_TPB) k_bicg_update(int32_t n, double *__restrict__ fi, double *__restrict__ res, const double *__restrict__ zk,
+                                                          const double *__restrict__ vk, const double *__restrict__ reso, const double *__restrict__ adiag,
+                                                          const KrylovScalars *sc, RedArgs ra) {
+  if (sc->done) return;
+  const double alf = sc->alf;
+  const bool first = (sc->iters == 0);
+  double s[3] = {0.0, 0.0, 0.0};
+  FCP_ROW_LOOP(r, n) {
+    const double f = fi[r] + alf * zk[r];
+    const double rr = res[r] - alf * vk[r];
+    fi[r] = f;
+    res[r] = rr;
+    s[0] = s[0] + fabs(rr);
+    s[1] = s[1] + rr * reso[r];
+    if (first) s[2] = s[2] + fabs(adiag[r] * f);
+  }
+  finish_reduce<3>(s, ra);
+}
+// y = A x ; sums: y*v1 , y*y  or y*v1 only
+// (k_spmv_dot above)
+
+// ---------------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------------
+struct Launcher {
+  cudaStream_t st;
+  FcpComm *comm;
+  fcp_ctx *ctx;
+  KrylovWS &ws;
+  int n;
+  int grid;
+  RedArgs red(int epi) const { return RedArgs{ws.partials, ws.maxchunks, ws.counter, ws.sc, epi, comm ? 0 : 1}; }
+  // after a reducing kernel in multi-GPU mode: cross-rank sum of sc->red[0..ns) + epilogue kernel
+  int post(int epi, int ns) const {
+    if (!comm) return FCP_OK;
+    FCP_TRY(comm_allgather_sum(comm, ws.sc->red, ns, st));
+    k_epilogue<<<1, 1, 0, st>>>(epi, ws.sc);
+    FCP_LAUNCHED();
+    FCP_CHECK_LAUNCH();
+    return FCP_OK;
+  }
+  int halo(double *x) const {   // src-par/dpcg.f90:118  call exchange(pk)
+    if (!comm) return FCP_OK;
+    return comm_exchange(ctx, x, 1);
+  }
+};
+
+static int coop_grid(const void *kernel, int device, int *grid) {
+  int nsm = 0, occ = 0;
+  FCP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  FCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, FCP_TPB, 0));
+  if (occ < 1) { fcp_set_error("cooperative kernel does not fit on an SM"); return FCP_ECUDA; }
+  *grid = nsm * occ;
+  return FCP_OK;
+}
+
+static int launch_factor(bool ilu, SellPattern &p, const double *a, double *d, cudaStream_t st) {
+  if (p.n == 0) return FCP_OK;
+  int dev = 0, grid = 0;
+  FCP_CUDA(cudaGetDevice(&dev));
+  SellView m{p.slptr, p.rinfo, p.ja, a};
+  LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
+  const int32_t *tpos = p.tpos;
+  void *args[] = {&m, &lv, &tpos, &d};
+  const void *fn = ilu ? (const void *)k_factor_diag<true> : (const void *)k_factor_diag<false>;
+  FCP_TRY(coop_grid(fn, dev, &grid));
+  FCP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FCP_TPB), args, 0, st));
+  FCP_LAUNCHED();
+  return FCP_OK;
+}
+static int launch_precond(SellPattern &p, const double *a, const double *d, const double *rhs, double *zk, const KrylovScalars *sc,
+                          cudaStream_t st) {
+  if (p.n == 0) return FCP_OK;
+  static int grid = 0;
+  if (!grid) {
+    int dev = 0;
+    FCP_CUDA(cudaGetDevice(&dev));
+    FCP_TRY(coop_grid((const void *)k_precond_apply, dev, &grid));
+  }
+  SellView m{p.slptr, p.rinfo, p.ja, a};
+  LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
+  const int32_t *llen = p.llen;
+  void *args[] = {&m, &lv, &llen, &d, &rhs, &zk, &sc};
+  FCP_CUDA(cudaLaunchCooperativeKernel((const void *)k_precond_apply, dim3(grid), dim3(FCP_TPB), args, 0, st));
+  FCP_LAUNCHED();
+  return FCP_OK;
+}
+
+// poll the device scalars; returns done flag
+static int fetch_scalars(KrylovWS &ws, cudaStream_t st) {
+  FCP_CUDA(cudaMemcpyAsync(ws.h_sc, ws.sc, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, st));
+  FCP_CUDA(cudaStreamSynchronize(st));
+  return FCP_OK;
+}
+
+int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const double *rhs, KrylovWS &ws, int32_t itr_max,
+                 double tol_abs, double tol_rel, fcp_report *rep, cudaStream_t st, FcpComm *comm, fcp_ctx *ctx) {
+  const int32_t n = p.n;
+  if (solver != FCP_SOLVER_DPCG && solver != FCP_SOLVER_ICCG && solver != FCP_SOLVER_BICGSTAB) {
+    fcp_set_error("csrsolve: unknown solver id %d", solver);
+    return FCP_EINVAL;
+  }
+  FCP_TRY(krylov_ws_alloc(ws, n, p.ncols));
+  if (rep) { memset(rep, 0, sizeof(*rep)); rep->solver = solver; }
+  const int grid = fcp_nchunks(n);
+  Launcher L{st, comm, ctx, ws, n, grid};
+  SellView m{p.slptr, p.rinfo, p.ja, a};
+  KrylovScalars init;
+  memset(&init, 0, sizeof(init));
+  init.tol_abs = tol_abs;
+  init.tol_rel = tol_rel;
+  init.itr_max = itr_max;
+  *ws.h_sc = init;
+  FCP_CUDA(cudaMemcpyAsync(ws.sc, ws.h_sc, sizeof(KrylovScalars), cudaMemcpyHostToDevice, st));
+  FCP_CUDA(cudaStreamSynchronize(st));   // h_sc is reused as the read-back buffer
+  if (n == 0 && !comm) return FCP_OK;
+  const int BATCH = 16;
+
+  if (solver == FCP_SOLVER_DPCG) {
+    FCP_TRY(L.halo(fi));
+    if (grid) { k_cg_init<true><<<grid, FCP_TPB, 0, st>>>(n, m, fi, rhs, ws.res, ws.adiag, ws.pk, L.red(EPI_INIT_CG)); FCP_LAUNCHED(); FCP_CHECK_LAUNCH(); }
+    FCP_TRY(L.post(EPI_INIT_CG, 2));
+    for (int it = 0; it < itr_max;) {
+      for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
+        if (grid) { k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc); FCP_LAUNCHED(); }
+        FCP_TRY(L.halo(ws.pk));
+        if (grid) { k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK)); FCP_LAUNCHED(); }
+        FCP_TRY(L.post(EPI_PKAPK, 1));
+        if (grid) { k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)); FCP_LAUNCHED(); }
+        FCP_TRY(L.post(EPI_CG_UPDATE, 3));
+      }
+      FCP_CHECK_LAUNCH();
+      FCP_TRY(fetch_scalars(ws, st));
+      if (ws.h_sc->done) break;
+    }
+  } else if (solver == FCP_SOLVER_ICCG) {
+    FCP_TRY(sell_build_levels(p, st));
+    FCP_TRY(krylov_ws_need(ws, &ws.d, (size_t)n));
+    FCP_TRY(L.halo(fi));
+    if (grid) { k_cg_init<false><<<grid, FCP_TPB, 0, st>>>(n, m, fi, rhs, ws.res, ws.adiag, ws.pk, L.red(EPI_INIT_CG)); FCP_LAUNCHED(); FCP_CHECK_LAUNCH(); }
+    FCP_TRY(L.post(EPI_INIT_CG, 2));
+    FCP_TRY(fetch_scalars(ws, st));
+    if (!ws.h_sc->done) {
+      FCP_TRY(launch_factor(false, p, a, ws.d, st));
+      for (int it = 0; it < itr_max;) {
+        for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
+          FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st));
+          if (grid) { k_dot<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.zk, ws.sc, L.red(EPI_SK)); FCP_LAUNCHED(); }
+          FCP_TRY(L.post(EPI_SK, 1));
+          if (grid) { k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc); FCP_LAUNCHED(); }
+          FCP_TRY(L.halo(ws.pk));
+          if (grid) { k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK)); FCP_LAUNCHED(); }
+          FCP_TRY(L.post(EPI_PKAPK, 1));
+          if (grid) { k_cg_update<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)); FCP_LAUNCHED(); }
+          FCP_TRY(L.post(EPI_CG_UPDATE, 3));
+        }
+        FCP_CHECK_LAUNCH();
+        FCP_TRY(fetch_scalars(ws, st));
+        if (ws.h_sc->done) break;
+      }
+    }
+  } else {
+    FCP_TRY(sell_build_levels(p, st));
+    FCP_TRY(sell_build_tpos(p, st));
+    FCP_TRY(krylov_ws_need(ws, &ws.d, (size_t)n));
+    FCP_TRY(krylov_ws_need(ws, &ws.reso, (size_t)n));
+    FCP_TRY(krylov_ws_need(ws, &ws.uk, (size_t)n));
+    FCP_TRY(krylov_ws_need(ws, &ws.vk, (size_t)n));
+    FCP_CUDA(cudaMemsetAsync(ws.pk, 0, sizeof(double) * (size_t)p.ncols, st));
+    FCP_CUDA(cudaMemsetAsync(ws.uk, 0, sizeof(double) * (size_t)n, st));
+    FCP_TRY(L.halo(fi));
+    if (grid) { k_bicg_init<<<grid, FCP_TPB, 0, st>>>(n, m, fi, rhs, ws.res, ws.reso, ws.adiag, L.red(EPI_INIT_BICG)); FCP_LAUNCHED(); FCP_CHECK_LAUNCH(); }
+    FCP_TRY(L.post(EPI_INIT_BICG, 2));
+    FCP_TRY(fetch_scalars(ws, st));
+    if (!ws.h_sc->done) {
+      FCP_TRY(launch_factor(true, p, a, ws.d, st));
+      for (int it = 0; it < itr_max;) {
+        for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
+          if (grid) { k_bicg_pk<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.uk, ws.pk, ws.sc); FCP_LAUNCHED(); }
+          FCP_TRY(launch_precond(p, a, ws.d, ws.pk, ws.zk, ws.sc, st));
+          FCP_TRY(L.halo(ws.zk));
+          if (grid) { k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.zk, ws.uk, ws.reso, ws.sc, L.red(EPI_UKRESO)); FCP_LAUNCHED(); }
+          FCP_TRY(L.post(EPI_UKRESO, 1));
+          if (grid) { k_bicg_half<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.zk, ws.uk, ws.sc); FCP_LAUNCHED(); }
+          FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st));
+          FCP_TRY(L.halo(ws.zk));
+          if (grid) { k_spmv_dot<2, true><<<grid, FCP_TPB, 0, st>>>(n, m, ws.zk, ws.vk, ws.res, ws.sc, L.red(EPI_VK)); FCP_LAUNCHED(); }
+          FCP_TRY(L.post(EPI_VK, 2));
+          if (grid) { k_bicg_update<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.zk, ws.vk, ws.reso, ws.adiag, ws.sc, L.red(EPI_BICG_UPDATE)); FCP_LAUNCHED(); }
+          FCP_TRY(L.post(EPI_BICG_UPDATE, 3));
+        }
+        FCP_CHECK_LAUNCH();
+        FCP_TRY(fetch_scalars(ws, st));
+        if (ws.h_sc->done) break;
+      }
+    }
+  }
+  FCP_TRY(fetch_scalars(ws, st));
+  if (comm) FCP_TRY(L.halo(fi));   // src-par/dpcg.f90:183  call exchange(fi)
+  if (rep) {
+    rep->res0 = ws.h_sc->res0;
+    rep->resl = ws.h_sc->resl;
+    rep->factor = ws.h_sc->factor;
+    rep->resor = ws.h_sc->resor;
+    rep->iters = ws.h_sc->iters;
+  }
+  return FCP_OK;
+}

@@ -490,3 +490,26 @@ def partition(mesh: Mesh, cell_rank: np.ndarray) -> List[Mesh]:
             if q >= 0:
                 part.peer_patch[ib] = proc_patch_index[q][r]
     return parts
+
+
+def localize_matrix(gmesh: Mesh, gcsr, a_global: np.ndarray, part: Mesh, pcsr) -> Tuple[np.ndarray, np.ndarray]:
+    """Restrict a global CSR matrix (values ``a_global`` on the pattern ``gcsr`` of ``gmesh``) to one partition in the
+    src-par layout: returns (a_local[nnz_local], apr[npro]) -- src-par/sparse_matrix.f90:25,173 (``apr`` holds the one
+    off-rank coefficient of every ``process`` face, patch order).  ``gcsr``/``pcsr`` expose ia, diag, icell_jcell,
+    jcell_icell (1-based), e.g. oracle.orc_py.Csr or the arrays returned by Context.csr_pattern()."""
+    Fi = part.numInnerFaces
+    a_loc = np.zeros(int(pcsr.ia[-1]) - 1)
+    fg = part.face_global[:Fi]
+    a_loc[pcsr.icell_jcell - 1] = a_global[gcsr.icell_jcell[fg] - 1]
+    a_loc[pcsr.jcell_icell - 1] = a_global[gcsr.jcell_icell[fg] - 1]
+    a_loc[pcsr.diag - 1] = a_global[gcsr.diag[part.cell_global] - 1]
+    apr = []
+    own0 = gmesh.owner.astype(np.int64) - 1
+    for ib in range(part.numBoundaries):
+        if part.bctype[ib] != BC_PROCESS:
+            continue
+        pf = part.patch_faces(ib)
+        gfaces = part.face_global[pf]
+        local_is_owner = own0[gfaces] == part.cell_global[part.owner[pf] - 1]
+        apr.append(np.where(local_is_owner, a_global[gcsr.icell_jcell[gfaces] - 1], a_global[gcsr.jcell_icell[gfaces] - 1]))
+    return a_loc, (np.concatenate(apr) if apr else np.zeros(0))

@@ -1,0 +1,181 @@
+/*
+ * include/fcp.h -- C-ABI of libfcp_b200.so, the B200-native pressure-velocity coupling hot path
+ * of freeCappuccino (assembly into CSR, Gauss / least-squares gradients, DPCG / ICCG / BiCGStab).
+ *
+ * The reference (nikola-m/freeCappuccino-dev, pure Fortran) has no FFI layer; its boundary is the
+ * Fortran module-procedure level.  Each entry point below names the reference
+ * procedure (file:line, relative to the reference root) it replaces.  The Fortran binding
+ * (interface ... bind(C)) is in fortran/fcp_b200.f90, the C++ host mirror in host/fcp_host.hpp.
+ *
+ * Conventions (those of the Fortran host):
+ *   - every index array crossing this boundary is 1-based int32 (default INTEGER),
+ *   - reals are IEEE binary64 (real(dp)),
+ *   - gradients are (3,numTotal) column-major: x,y,z interleaved per cell,
+ *   - fields have length numTotal = numCells + numBoundaryFaces; the value of boundary face
+ *     `iface` lives at numCells + (iface - numInnerFaces)       (src/mesh/geometry.f90:282-290),
+ *   - all pointers are HOST pointers; the library owns the device copies,
+ *   - every function returns 0 on success, a negative FCP_E* code otherwise; the reference has no
+ *     status codes (fatal conditions `stop`), so the Fortran shim turns non-zero into `stop`.
+ *   - there is NO CPU fallback: if no sm_100 device is usable fcp_ctx_create fails with
+ *     FCP_ENODEVICE.
+ * Threading: like the reference (module-level workspaces), a context is not re-entrant.
+ */
+#ifndef FCP_H
+#define FCP_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCP_OK         0
+#define FCP_EINVAL    -1   /* bad argument */
+#define FCP_ECUDA     -2   /* CUDA runtime error (fcp_last_error() has the text) */
+#define FCP_ENODEVICE -3   /* no usable CUDA device */
+#define FCP_ENCCL     -4   /* NCCL error or NCCL library not loadable */
+#define FCP_ESTATE    -5   /* call sequence error (e.g. LSQ matrix not created) */
+
+/* patch types: character(len=30) bctype(ib) of src/mesh/geometry.f90:62-70 (+ `process`, src-par/geometry.f90:218-240) */
+enum { FCP_BC_WALL = 0, FCP_BC_INLET = 1, FCP_BC_OUTLET = 2, FCP_BC_SYMMETRY = 3,
+       FCP_BC_PRESSURE = 4, FCP_BC_PERIODIC = 5, FCP_BC_EMPTY = 6, FCP_BC_PROCESS = 7 };
+
+/* linear solvers: the strings of csrsolve, src/linearSolvers/linear_solvers.f90:40-91 */
+enum { FCP_SOLVER_DPCG = 1, FCP_SOLVER_ICCG = 2, FCP_SOLVER_BICGSTAB = 3 };
+
+/* gradient methods: the logicals lstsq / lstsq_dm / (default) gauss of gradients.f90:118-138 */
+enum { FCP_GRAD_GAUSS = 0, FCP_GRAD_LSQ = 1, FCP_GRAD_LSQ_DM = 2 };
+
+/* pscheme of Pressure/nablap.f90:51-112 */
+enum { FCP_PSCHEME_LINEAR = 0, FCP_PSCHEME_CENTRAL = 1, FCP_PSCHEME_WEIGHTED = 2 };
+
+/* device-resident fields = the reference's module arrays (variables.f90, sparse_matrix.f90:20-40).
+ * Scalars have numTotal entries, gradients 3*numTotal, FCP_F_A nnz, FCP_F_FLMASS numFaces,
+ * FCP_F_APR npro (src-par/sparse_matrix.f90:25). */
+enum {
+  FCP_F_U = 0, FCP_F_V, FCP_F_W, FCP_F_P, FCP_F_PP, FCP_F_DEN, FCP_F_VIS,
+  FCP_F_APU, FCP_F_APV, FCP_F_APW, FCP_F_SU, FCP_F_SV, FCP_F_SW,
+  FCP_F_S0, FCP_F_S1, FCP_F_S2, FCP_F_S3,          /* user scalars (phi, mu, rhs ... of laplacian / grad / csrsolve) */
+  FCP_F_DUDXI, FCP_F_DVDXI, FCP_F_DWDXI, FCP_F_DPDXI, FCP_F_G0, FCP_F_G1,   /* (3,numTotal) */
+  FCP_F_FLMASS, FCP_F_A, FCP_F_APR,
+  FCP_F_COUNT
+};
+
+typedef struct fcp_ctx fcp_ctx;        /* one mesh (partition) on one GPU */
+typedef struct fcp_solver fcp_solver;  /* one CSR pattern on one GPU, no mesh (explicit-CSR signature) */
+
+/* mirror of the arrays of the `geometry` module, src/mesh/geometry.f90:12-86 */
+typedef struct {
+  int32_t numCells, numInnerFaces, numBoundaryFaces, numBoundaries;
+  const int32_t *owner;       /* [numInnerFaces+numBoundaryFaces] */
+  const int32_t *neighbour;   /* [numInnerFaces] */
+  const double *arx, *ary, *arz, *xf, *yf, *zf;   /* [numFaces] */
+  const double *facint, *Df;                      /* [numInnerFaces]  geometry.f90:581-606, 648-664 */
+  const double *xc, *yc, *zc, *vol;               /* [numCells] */
+  const int32_t *bctype;      /* [numBoundaries] FCP_BC_* */
+  const int32_t *nfaces;      /* [numBoundaries] */
+  const int32_t *startFace;   /* [numBoundaries] 0-based offset of the patch's first face (boundary file, Appendix D) */
+} fcp_mesh_desc;
+
+/* the numbers the reference prints in its solver report line, linear_solvers.f90:354-355,540-541,781-782 */
+typedef struct {
+  double res0;      /* initial L1 residual sum|b - A x|                        (:264) */
+  double resl;      /* final L1 residual                                        (:327) */
+  double factor;    /* sum|a_ii x_i| + small after the first update             (:336) */
+  double resor;     /* res0/factor: the value returned in the resor/res0 dummy  (:340) */
+  int32_t iters;    /* itr_used */
+  int32_t solver;   /* FCP_SOLVER_* */
+} fcp_report;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int fcp_version(void);
+const char *fcp_last_error(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+int64_t fcp_launch_count(void);
+
+/* ---- context: mesh upload + create_CSR_matrix (src/sparseMatrix/sparse_matrix.f90:86-296) ---- */
+int fcp_ctx_create(const fcp_mesh_desc *mesh, int device, fcp_ctx **out);
+int fcp_ctx_destroy(fcp_ctx *ctx);
+int fcp_ctx_sizes(const fcp_ctx *ctx, int32_t *numCells, int32_t *numTotal, int32_t *numFaces, int32_t *nnz, int32_t *npro);
+/* ia(numCells+1), ja(nnz), diag(numCells), icell_jcell_csr_index(numInnerFaces), jcell_icell_csr_index(numInnerFaces);
+ * any pointer may be NULL (sparse_matrix.f90:183-202, 251-260) */
+int fcp_csr_pattern(const fcp_ctx *ctx, int32_t *ia, int32_t *ja, int32_t *diag, int32_t *icell_jcell, int32_t *jcell_icell);
+int fcp_sync(fcp_ctx *ctx);
+
+/* ---- fields ------------------------------------------------------------------------------- */
+int fcp_field_upload(fcp_ctx *ctx, int field, const double *host, int64_t count);     /* first `count` entries */
+int fcp_field_download(fcp_ctx *ctx, int field, double *host, int64_t count);
+int fcp_field_fill(fcp_ctx *ctx, int field, double value);
+int fcp_field_copy(fcp_ctx *ctx, int dst_field, int src_field);
+/* raw device address of a field (for zero-copy interop with other CUDA code in the same process) */
+int fcp_field_devptr(fcp_ctx *ctx, int field, void **devptr, int64_t *count);
+
+/* ---- operators ---------------------------------------------------------------------------- */
+/* y = A x with the context matrix FCP_F_A  (the SpMV loops linear_solvers.f90:256-261, 308-313) */
+int fcp_spmv(fcp_ctx *ctx, int x_field, int y_field);
+/* csrsolve(solver, fi, rhs, res0, itr_max, tol_abs, tol_rel, chvar)   linear_solvers.f90:40-91;
+ * dpcg :206-359, iccg :364-545, bicgstab :548-786.  fi and rhs are device fields. */
+int fcp_csrsolve(fcp_ctx *ctx, int solver, int fi_field, int rhs_field, int32_t itr_max,
+                 double tol_abs, double tol_rel, fcp_report *rep);
+/* the reference's report line for `rep` (same text, parsed by examples/ * /plotResiduals) */
+int fcp_report_line(const fcp_report *rep, const char *chvar, char *buf, int buflen);
+
+/* grad(phi,dPhidxi): grad_gauss gradients.f90:1607-1693, grad_lsq :782-893, grad_lsq_dm :1334-1486.
+ * lsq_row2_reference != 0 reproduces the reference's back-substitution row 2. */
+int fcp_create_lsq_grad_matrix(fcp_ctx *ctx, int method);     /* gradients.f90:72-101, 660-779, 1157-1326 */
+int fcp_grad(fcp_ctx *ctx, int method, int phi_field, int grad_field, int lsq_row2_reference);
+/* laplacian(mu,phi): fills FCP_F_A, accumulates into FCP_F_SU   src/finiteVolume/fvImplicit/laplacian.f90 */
+int fcp_laplacian(fcp_ctx *ctx, int mu_field, int phi_field);
+/* gradp_and_sources(p): fills FCP_F_SU/SV/SW and FCP_F_DPDXI, extrapolates p to boundaries   Pressure/nablap.f90:19-208 */
+int fcp_gradp_and_sources(fcp_ctx *ctx, int pscheme, int p_field);
+/* inner-face + patch assembly of the pressure-correction equation   Pressure/calcp_simple.f90:69-234,
+ * fluxes/faceflux_mass.f90:175-249 (facefluxmass2), :765-831, :833-916 */
+int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double flomas);
+/* flux / velocity / pressure correction after the solve   calcp_simple.f90:331-429 */
+int fcp_correct_simple(fcp_ctx *ctx, int pscheme, double urfp, int32_t pRefCell);
+/* non-orthogonal corrector   calcp_simple.f90:433-455 + fluxmc2 faceflux_mass.f90:650-696 */
+int fcp_nonorth_corrector(fcp_ctx *ctx);
+
+typedef struct {
+  int32_t solver;       /* lSolverP  */
+  int32_t maxiter;      /* maxiterP  */
+  double tol_abs, tol_rel;   /* tolAbsP, tolRelP   pressure.f90:28-33 */
+  double urfp;          /* urfP */
+  int32_t npcor;        /* number of pressure-correction passes (non-orthogonal correctors = npcor-1) */
+  int32_t pRefCell;     /* 1-based */
+  int32_t pscheme;      /* FCP_PSCHEME_* */
+  int32_t const_mflux;  /* skip adjustMassFlow */
+  double flomas;        /* inlet mass flow used by adjustMassFlow */
+  int32_t zero_pp;      /* 0: warm start like the serial tree; 1: pp=0 like src-par/calcp_simple.f90:170 (quirk Q8) */
+} fcp_simple_params;
+/* one whole calcp_simple   Pressure/calcp_simple.f90:1-470 ; rep[ipcorr] for ipcorr < npcor */
+int fcp_calcp_simple(fcp_ctx *ctx, const fcp_simple_params *prm, fcp_report *rep);
+
+/* ---- explicit-CSR solver signature: dpcg|iccg|bicgstab(n,nnz,ia,ja,a,diag,fi,rhs,...) -------- */
+/* linear_solvers.f90:206, :364, :548 ; pattern analysed once, values per solve */
+int fcp_solver_create(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const int32_t *diag,
+                      int device, fcp_solver **out);
+int fcp_solver_destroy(fcp_solver *s);
+int fcp_solver_solve(fcp_solver *s, int solver, const double *a, double *fi, const double *rhs,
+                     int32_t itr_max, double tol_abs, double tol_rel, fcp_report *rep);
+
+/* ---- multi-GPU: src-par/exchange.f90:3-129, src-par/global_sum_mpi.f90:4-37 ----------------- */
+/* NCCL bootstrap: rank 0 calls fcp_comm_unique_id, the host distributes the 128 bytes, all ranks call fcp_comm_init.
+ * peer_rank[ib] = rank on the other side of `process` patch ib (-1 otherwise); both sides list the
+ * shared faces in the same order (src-par/geometry.f90:218-240). */
+int fcp_comm_unique_id(void *id128);
+int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id128, const int32_t *peer_rank);
+int fcp_exchange(fcp_ctx *ctx, int field);                    /* ghost slots of `process` patches <- owner values on the peer */
+int fcp_global_sum(fcp_ctx *ctx, double *value);              /* in place, all ranks */
+int fcp_global_max(fcp_ctx *ctx, double *value);
+int fcp_global_min(fcp_ctx *ctx, double *value);
+
+/* ---- timing helper for benches: runs fn-independent CUDA event timing on the context stream --- */
+int fcp_timer_start(fcp_ctx *ctx);
+int fcp_timer_stop(fcp_ctx *ctx, float *milliseconds);        /* synchronises */
+/* writes a buffer larger than L2 (256 MiB) so the next timed launch starts cold */
+int fcp_flush_l2(fcp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCP_H */

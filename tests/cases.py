@@ -1,0 +1,62 @@
+"""Shared, seeded test inputs (deterministic synthetic fields)."""
+import os
+
+import numpy as np
+
+import fcb200
+from fcb200 import mesh as M
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_mesh():
+    """The reference's own 400-cell test mesh (test/testFieldOperations/polyMesh), from the committed fixture."""
+    return M.load_mesh_npz(os.path.join(GOLDEN, "cavity20_polymesh.npz"))
+
+
+def meshes():
+    """name -> mesh for the parity matrix: orthogonal, graded, distorted (non-orthogonal), 2-D slab, mixed patches."""
+    out = {}
+    out["ref400"] = golden_mesh()
+    out["hex6"] = M.cavity_mesh(6)
+    out["hex12_graded"] = M.cavity_mesh(12, bump=0.3)
+    out["hex10_distorted"] = M.cavity_mesh(10, distort=0.25)
+    out["slab39_empty"] = M.cavity_mesh(39, nz=1, bump=0.2)
+    xs = np.linspace(0, 2.0, 15); ys = np.linspace(0, 1.0, 9); zs = np.linspace(0, 0.5, 6)
+    out["channel_inout"] = M.hex_mesh(xs, ys, zs, dict(left="inlet", right="outlet", back="symmetry", front="symmetry"), distort=0.15)
+    out["channel_pressure"] = M.hex_mesh(xs, ys, zs, dict(left="inlet", right="pressure", back="empty", front="empty"), distort=0.1)
+    out["tiny3"] = M.hex_mesh(np.linspace(0, 1, 4), np.linspace(0, 1, 3), np.linspace(0, 1, 2))   # 3x2x1 = 6 cells (< one warp)
+    return out
+
+
+def fields(m, seed=12345):
+    """u,v,w,p,pp,den,apu,apv,apw of length numTotal, smooth + a little seeded noise."""
+    rng = np.random.default_rng(seed)
+    pi = np.pi
+    f = {}
+    f["u"] = m.boundary_values_of(lambda x, y, z: np.sin(pi * x) * np.cos(pi * y) + 0.1 * z)
+    f["v"] = m.boundary_values_of(lambda x, y, z: -np.cos(pi * x) * np.sin(pi * y) + 0.05 * np.sin(pi * z))
+    f["w"] = m.boundary_values_of(lambda x, y, z: 0.1 * np.sin(pi * x) * np.sin(pi * z))
+    f["p"] = m.boundary_values_of(lambda x, y, z: 0.25 * np.cos(2 * pi * x) * np.cos(2 * pi * y) + 0.1 * z * z)
+    f["pp"] = 1e-3 * m.boundary_values_of(lambda x, y, z: np.sin(2 * pi * x) * np.sin(pi * y) * np.cos(pi * z))
+    f["den"] = m.boundary_values_of(lambda x, y, z: 1.0 + 0.05 * np.sin(pi * x * y))
+    h = m.vol[: m.numCells].mean() ** (1.0 / 3.0)
+    base = 0.8 / (6.0 * 0.01 * h)
+    f["apu"] = base * m.boundary_values_of(lambda x, y, z: 1.0 + 0.1 * np.sin(3 * x + y))
+    f["apv"] = base * m.boundary_values_of(lambda x, y, z: 1.0 + 0.1 * np.cos(2 * y + z))
+    f["apw"] = base * m.boundary_values_of(lambda x, y, z: 1.0 + 0.1 * np.sin(x + 2 * z))
+    for k in f:
+        f[k] = f[k] + 1e-3 * rng.standard_normal(m.numTotal) * (np.abs(f[k]).mean() + 1e-30)
+    return f
+
+
+def poisson_system(m, orc):
+    """-lap(p) = 8 pi^2 sin(2 pi x) sin(2 pi y), Dirichlet 0 (applications/Poisson/poisson.f90:63-104), via the oracle's laplacian."""
+    csr = orc.Csr(m)
+    n = m.numCells
+    pi = np.pi
+    su = 8 * pi * pi * np.sin(2 * pi * m.xc[:n]) * np.sin(2 * pi * m.yc[:n]) * m.vol[:n]
+    mu = -np.ones(m.numTotal)
+    phi = np.zeros(m.numTotal)
+    a = orc.laplacian(m, csr, mu, phi, su)
+    return csr, a, su

@@ -1,0 +1,53 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu through gpurun)")
+
+
+def _has_gpu() -> bool:
+    try:
+        import ctypes
+        cu = ctypes.CDLL("libcuda.so.1")
+        if cu.cuInit(0) != 0:
+            return False
+        n = ctypes.c_int(0)
+        cu.cuDeviceGetCount(ctypes.byref(n))
+        return n.value > 0
+    except OSError:
+        return False
+
+
+HAS_GPU = _has_gpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    if HAS_GPU:
+        return
+    skip = pytest.mark.skip(reason="no GPU in this container (GPU tests run through gpurun / the driver)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import orc_py
+    orc_py.lib()
+    return orc_py
+
+
+@pytest.fixture(scope="session")
+def fcp():
+    """The product package; the CUDA library must already be built (no silent fallback)."""
+    import fcb200
+    from fcb200 import lib
+    lib.lib()
+    return fcb200

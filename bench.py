@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- one SIMPLE pressure step of the freeCappuccino hot path on N B200s of one node.
+
+Workload (BASELINE.json configs[2]): synthetic 3-D lid-driven-cavity mesh, n^3 uniform hexahedra (default 256^3 =
+16.7 M cells), split in z-slabs over the ranks (src-par layout).  One "step" = what calcp_simple does per outer
+iteration on this path:
+    gradp_and_sources(p)                       (Pressure/nablap.f90)            gradient kernel
+    p'-equation assembly, facefluxmass2        (calcp_simple.f90:69-118)        assembly kernel
+    csrsolve('dpcg', pp, su, tolRel=1e-8)      (linear_solvers.f90:206-359)     SpMV+dot / axpy kernels
+    flux, velocity and pressure correction     (calcp_simple.f90:331-429)
+Inputs are reset to the same synthetic state before every step (otherwise the second step would start converged).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 256] [--impl ours|reference]
+Multi-GPU: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+INPUT_FIELDS = ("u", "v", "w", "p", "den", "apu", "apv", "apw")
+OUTPUT_FIELDS = ("u", "v", "w", "p", "pp")
+TOL_REL = 1e-8
+MAXITER = 20000
+
+
+def synthetic_fields(m):
+    """u = sin(pi x) cos(pi y), v = -cos(pi x) sin(pi y), w = 0, p = cos(2 pi x) cos(2 pi y)/4,
+    apu = apv = apw = 0.8/(6 nu h), den = 1.  (u,v) is not discretely divergence free, so the p' system has a real RHS."""
+    pi = np.pi
+    h = float(m.vol[: m.numCells].mean()) ** (1.0 / 3.0)
+    f = {}
+    f["u"] = m.boundary_values_of(lambda x, y, z: np.sin(pi * x) * np.cos(pi * y) * (1.0 + 0.5 * np.sin(pi * z)))
+    f["v"] = m.boundary_values_of(lambda x, y, z: -np.cos(pi * x) * np.sin(pi * y))
+    f["w"] = m.boundary_values_of(lambda x, y, z: 0.1 * np.sin(pi * x) * np.sin(2 * pi * z))
+    f["p"] = m.boundary_values_of(lambda x, y, z: 0.25 * np.cos(2 * pi * x) * np.cos(2 * pi * y))
+    f["den"] = np.ones(m.numTotal)
+    ap = 0.8 / (6.0 * 0.01 * h)
+    for k in ("apu", "apv", "apw"):
+        f[k] = np.full(m.numTotal, ap)
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index=0):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0])); mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as fh:
+                d = json.load(fh)
+            if "hbm_gbs" in d:
+                return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except (OSError, ValueError):
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def pinned_copy(a):
+    """numpy view of a pinned torch buffer holding a copy of `a` (H2D copies from it are true DMA transfers)."""
+    import torch
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    v = t.numpy()
+    v[...] = a
+    return t, v
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def oracle_step_time(m, f, gpu_iters, max_sample_iters, threads_note="1 (serial reference stand-in)"):
+    """Times the CPU restatement (oracle/, g++ -O2 -ffp-contract=off, one thread like the serial reference binary) on
+    the SAME mesh and inputs: gradp + assembly + correction in full, DPCG for `max_sample_iters` iterations, and
+    extrapolates the solve to the iteration count the converged run needs."""
+    from oracle import orc_py as O
+    t0 = time.perf_counter()
+    c = O.Csr(m)
+    t_csr = time.perf_counter() - t0
+    g = {k: v.copy() for k, v in f.items()}
+    g["pp"] = np.zeros(m.numTotal)
+    dP = np.zeros((m.numTotal, 3))
+    t0 = time.perf_counter()
+    O.gradp_and_sources(m, 0, g["p"], g["apu"], dP)
+    t_gradp = time.perf_counter() - t0
+    a = np.zeros(c.nnz); su = np.zeros(m.numCells); flm = np.zeros(m.numFaces)
+    t0 = time.perf_counter()
+    O.assemble_pcorr_into(m, c, g["den"], g["u"], g["v"], g["w"], g["p"], g["pp"], dP, g["apu"], a, su, flm)
+    t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rep = O.solve(O.DPCG, c.ia, c.ja, a, c.diag, g["pp"], su, max_sample_iters, 1e-30, TOL_REL)
+    t_solve = time.perf_counter() - t0
+    its = max(rep.iters, 1)
+    t0 = time.perf_counter()
+    O.correct_simple(m, c, 0, a, g["den"], g["u"], g["v"], g["w"], g["p"], g["pp"], g["apu"], g["apv"], g["apw"], 0.3, 1, dP, flm)
+    t_corr = time.perf_counter() - t0
+    t_iter = t_solve / (its + 0.5)       # the initial residual costs about half an iteration
+    n_it = gpu_iters if gpu_iters else its
+    total = t_gradp + t_asm + t_corr + t_iter * (n_it + 0.5)
+    return dict(ms=1e3 * total, t_gradp=t_gradp, t_asm=t_asm, t_corr=t_corr, t_iter=t_iter, sample_iters=its, iters_used=n_it,
+                t_csr=t_csr, measured_s=t_gradp + t_asm + t_solve + t_corr, threads=threads_note)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The Fortran reference cannot be built in
+    this image (no gfortran/flang/nvfortran; probed), so this is the C++ restatement (oracle/) = kind 'port'."""
+    if rank != 0:
+        return
+    from fcb200 import mesh as M
+    n = args.n
+    m = M.hex_mesh_fast(*(np.linspace(0.0, 1.0, n + 1),) * 3)
+    f = synthetic_fields(m)
+    iters = args.ref_iters
+    times = []
+    for s in range(args.warmup + args.steps):
+        r = oracle_step_time(m, f, args.pcg_iters, iters)
+        if s >= args.warmup:
+            times.append(r)
+    ms = float(np.mean([t["ms"] for t in times]))
+    r = times[-1]
+    sample = (f"{n}^3 mesh, serial C++ restatement of the Fortran path: gradp_and_sources + assembly + correction in full, "
+              f"DPCG {r['sample_iters']} iterations timed ({r['t_iter']:.3f} s/iter) and extrapolated to {r['iters_used']} iterations "
+              f"(the count the converged tolRel=1e-8 solve needs); {r['measured_s']:.1f} s of CPU work per step")
+    line = dict(metric=f"SIMPLE iter time ({n}^3 hex cavity: gradp + p' assembly + DPCG to 1e-8 + correction)", value=ms, unit="ms",
+                impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=False,
+                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=f"synthetic 3D lid-driven cavity {n}^3 hex ({n**3} cells), pressure PCG", solver="dpcg", tol_rel=TOL_REL),
+                cpu_baseline=dict(value=ms, unit="ms", cores=1, kind="port", sample=sample),
+                e2e=dict(value=ms, unit="ms", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=256, help="cells per direction of the cavity mesh")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--solver", default="dpcg", choices=["dpcg", "iccg", "bicgstab"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=4, help="DPCG iterations timed by the cpu_baseline leg")
+    ap.add_argument("--ref-iters", type=int, default=4, help="DPCG iterations timed per step by --impl reference")
+    ap.add_argument("--pcg-iters", type=int, default=0, help="--impl reference: iteration count to extrapolate to (0: run's own)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.pcg_iters == 0:
+            args.pcg_iters = {256: 0}.get(args.n, 0)
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import fcb200  # noqa: F401
+    from fcb200 import lib as L
+    from fcb200 import mesh as M
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="gloo", init_method="env://")
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)
+    n = args.n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- mesh partition of this rank, context, communicator ---------------------------------------------------------
+    t_setup = time.perf_counter()
+    m = M.block_partition_mesh((n, n, n), M.block_dims(world), rank)
+    f = synthetic_fields(m)
+    ctx = L.Context(m, local_rank)
+    if world > 1:
+        uid = [L.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0], m.peer_rank)
+    pinned = {k: pinned_copy(f[k]) for k in INPUT_FIELDS}
+    out_pinned = {k: pinned_copy(np.zeros(m.numTotal)) for k in OUTPUT_FIELDS}
+    for k in INPUT_FIELDS:
+        ctx.upload(k.upper(), pinned[k][1])
+    # pristine copies of the fields a step overwrites
+    for src, dst in (("U", "S0"), ("V", "S1"), ("W", "S2"), ("P", "S3")):
+        ctx.copy(dst, src)
+    ctx.sync()
+    t_setup = time.perf_counter() - t_setup
+
+    def reset_device_inputs():
+        for src, dst in (("U", "S0"), ("V", "S1"), ("W", "S2"), ("P", "S3")):
+            ctx.copy(src, dst)
+
+    def step():
+        ctx.gradp_and_sources("linear", "P")
+        return ctx.calcp_simple(solver=args.solver, maxiter=MAXITER, tol_abs=1e-30, tol_rel=TOL_REL, urfp=0.3, npcor=1, pRefCell=1,
+                                zero_pp=True)[0]
+
+    def e2e_step():
+        for k in INPUT_FIELDS:
+            ctx.upload(k.upper(), pinned[k][1])
+        rep = step()
+        for k in OUTPUT_FIELDS:
+            out_pinned[k][1][...] = 0.0
+        for k in OUTPUT_FIELDS:
+            L.check(L.lib().fcp_field_download(ctx.h, L.field_id(k.upper()), L._d(out_pinned[k][1]), m.numTotal))
+        return rep
+
+    # ---- warm-up -------------------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 0)):
+        reset_device_inputs()
+        rep = step()
+    ctx.sync()
+
+    # ---- timed: device-resident inputs (value) ---------------------------------------------------------------------------
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = L.launch_count()
+    dev_ms = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        reset_device_inputs()
+        ctx.timer_start()
+        rep = step()
+        dev_ms.append(ctx.timer_stop())
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    launches = L.launch_count() - launches0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+
+    # ---- timed: end to end through the C-ABI with host buffers ----------------------------------------------------------------
+    e2e_step()   # warm the transfer path
+    barrier()
+    e2e0 = time.perf_counter()
+    for _ in range(args.steps):
+        rep_e = e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - e2e0) / args.steps
+    clocks = sampler.stop() if sampler else None
+
+    # ---- reduce over ranks -----------------------------------------------------------------------------------------------------
+    ms_local = float(np.mean(dev_ms))
+    stats = dict(ms=ms_local, e2e=e2e_ms, cells=m.numCells, nnz=ctx.nnz, faces=m.numInnerFaces, launches=launches, prof=prof)
+    if dist is not None:
+        allstats = [None] * world
+        dist.all_gather_object(allstats, stats)
+    else:
+        allstats = [stats]
+    if rank != 0:
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ms = max(s["ms"] for s in allstats)
+    e2e = max(s["e2e"] for s in allstats)
+    iters = int(rep.iters)
+    peak, peak_src = hbm_peak()
+
+    # roofline of the dominant kernel (SpMV + p.Ap dot): algorithmic bytes 12 nnz + 20 N per launch, rank 0's share
+    def kernel_line(name, bytes_per_launch):
+        if name not in prof:
+            return None
+        tot, cnt = prof[name]
+        avg_ms = tot / cnt
+        gbs = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        return dict(kernel=name, launches=cnt, avg_ms=avg_ms, total_ms=tot, bytes_per_launch=bytes_per_launch, achieved_gbs=gbs, frac=gbs / peak)
+    N0, nnz0, F0, B0 = m.numCells, ctx.nnz + ctx.npro, m.numInnerFaces, m.numBoundaryFaces
+    kl = {
+        "spmv_dot": kernel_line("spmv_dot", 12 * nnz0 + 20 * N0),
+        "cg_pk": kernel_line("cg_pk", 32 * N0),
+        "cg_update": kernel_line("cg_update", 56 * N0),
+        "assemble": kernel_line("assemble", 80 * F0 + 124 * N0),
+        "gradp": kernel_line("gradp", 40 * F0 + 64 * N0 + 36 * B0),
+        "correct_flux": kernel_line("correct_flux", 36 * F0 + 8 * N0),
+    }
+    dom = kl["spmv_dot"]
+    roofline = dict(bound="hbm", achieved=dom["achieved_gbs"], peak=peak, unit="GB/s", frac=dom["frac"], traffic=None,
+                    kernel="k_spmv_dot<1,false> (SELL-32 SpMV + p.Ap dot)", peak_source=peak_src,
+                    share_of_step=dom["total_ms"] / (ms * args.steps), avg_launch_ms=dom["avg_ms"], launches=dom["launches"])
+    # DPCG iteration as a whole: 12 nnz + 108 N ideal bytes
+    it_ms = sum(kl[k]["total_ms"] for k in ("spmv_dot", "cg_pk", "cg_update") if kl[k]) / max(dom["launches"], 1)
+    it_gbs = (12 * nnz0 + 108 * N0) / (it_ms * 1e-3) / 1e9
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = oracle_step_time(m, f, iters, args.cpu_iters)
+        cpu_baseline = dict(value=r["ms"], unit="ms", cores=1, kind="port",
+                            sample=(f"same {n}^3 mesh and inputs, serial C++ restatement (oracle/, the Fortran reference cannot be built here): "
+                                    f"gradp + assembly + correction in full ({r['t_gradp']:.2f}+{r['t_asm']:.2f}+{r['t_corr']:.2f} s), DPCG {r['sample_iters']} iterations "
+                                    f"timed ({r['t_iter']:.3f} s/iter), extrapolated to the {iters} iterations of the converged solve; "
+                                    f"{r['measured_s']:.1f} s measured"))
+    h2d = 8 * m.numTotal * len(INPUT_FIELDS)
+    d2h = 8 * m.numTotal * len(OUTPUT_FIELDS)
+    line = dict(
+        metric=f"SIMPLE iter time ({n}^3 hex cavity: gradp + p' assembly + DPCG to 1e-8 + correction)", value=ms, unit="ms",
+        n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=False, scaling="strong", vs_baseline=None,
+        dtype="f64", data="synthetic",
+        config=dict(workload=f"synthetic 3D lid-driven cavity {n}^3 hex ({n**3} cells), pressure PCG", solver=args.solver, tol_rel=TOL_REL,
+                    pcg_iters=iters, partition=f"z-slabs x{world}", l2="inputs larger than L2 (matrix + vectors = "
+                    f"{(12 * nnz0 + 60 * N0) / 1e6:.0f} MB per rank vs 126 MB L2)" if (12 * nnz0 + 60 * N0) > 2 * 126e6 else "working set fits L2: L2-resident numbers"),
+        e2e=dict(value=e2e, unit="ms", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+        gpu_launches=int(sum(s["launches"] for s in allstats)),
+        roofline=roofline, cpu_baseline=cpu_baseline, clocks=clocks,
+        kernels={k: v for k, v in kl.items() if v},
+        pcg=dict(iters=iters, res0=rep.res0, resl=rep.resl, iteration_ms=it_ms, iteration_gbs_ideal_bytes=it_gbs, iteration_frac=it_gbs / peak),
+        wall_ms_per_step=wall_ms / args.steps, setup_s=t_setup,
+    )
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

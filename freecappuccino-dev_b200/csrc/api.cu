@@ -421,7 +421,9 @@ extern "C" int fcp_spmv(fcp_ctx *ctx, int x_field, int y_field) {
   FIELD(y, y_field);
   FIELD(a, FCP_F_A);
   if (ctx->comm) FCP_TRY(comm_exchange(ctx, x, 1));
-  return sell_spmv(ctx->pat, a, x, y, ctx->stream);
+  int rc;
+  FCP_PROF(&ctx->prof, FCP_K_SPMV, ctx->stream, rc = sell_spmv(ctx->pat, a, x, y, ctx->stream));
+  return rc;
 }
 
 extern "C" int fcp_csrsolve(fcp_ctx *ctx, int solver, int fi_field, int rhs_field, int32_t itr_max, double tol_abs, double tol_rel,
@@ -609,6 +611,25 @@ extern "C" int fcp_solver_solve(fcp_solver *s, int solver, const double *a, doub
   FCP_TRY(krylov_solve(solver, s->pat, s->a, s->fi, s->rhs, s->ws, itr_max, tol_abs, tol_rel, rep, s->stream, nullptr, nullptr));
   FCP_CUDA(cudaMemcpyAsync(fi, s->fi, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
   FCP_CUDA(cudaStreamSynchronize(s->stream));
+  return FCP_OK;
+}
+
+extern "C" int fcp_profile_enable(fcp_ctx *ctx, int on) {
+  if (!ctx) return FCP_EINVAL;
+  ctx->prof.resolve();
+  ctx->prof.on = on != 0;
+  return FCP_OK;
+}
+extern "C" int fcp_profile_reset(fcp_ctx *ctx) {
+  if (!ctx) return FCP_EINVAL;
+  ctx->prof.reset();
+  return FCP_OK;
+}
+extern "C" int fcp_profile_read(fcp_ctx *ctx, int kclass, double *total_ms, int64_t *launches) {
+  if (!ctx || kclass < 0 || kclass >= FCP_K_COUNT) return FCP_EINVAL;
+  ctx->prof.resolve();
+  if (total_ms) *total_ms = ctx->prof.total_ms[kclass];
+  if (launches) *launches = ctx->prof.launches[kclass];
   return FCP_OK;
 }
 

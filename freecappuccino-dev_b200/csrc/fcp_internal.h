@@ -108,6 +108,43 @@ struct KrylovWS {
 
 struct FcpComm;   // comm.cu
 
+// per-kernel-class CUDA-event timing (fcp_profile_*): an event pair around every launch of a class
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int k; size_t e0, e1; };
+  std::vector<Rec> recs;
+  double total_ms[FCP_K_COUNT] = {0};
+  int64_t launches[FCP_K_COUNT] = {0};
+  size_t begin(int k, cudaStream_t st) {
+    if (!on) return 0;
+    while (pool.size() < used + 2) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    recs.push_back(Rec{k, used, used + 1});
+    cudaEventRecord(pool[used], st);
+    used += 2;
+    return recs.size();
+  }
+  void end(size_t tok, cudaStream_t st) { if (on && tok) cudaEventRecord(pool[recs[tok - 1].e1], st); }
+  void resolve() {
+    for (auto &r : recs) {
+      float ms = 0.f;
+      cudaEventSynchronize(pool[r.e1]);
+      if (cudaEventElapsedTime(&ms, pool[r.e0], pool[r.e1]) == cudaSuccess) { total_ms[r.k] += ms; launches[r.k] += 1; }
+    }
+    recs.clear();
+    used = 0;
+  }
+  void reset() { resolve(); for (int k = 0; k < FCP_K_COUNT; ++k) { total_ms[k] = 0; launches[k] = 0; } }
+  ~Profiler() { for (auto e : pool) cudaEventDestroy(e); }
+};
+#define FCP_PROF(prof, k, st, stmt)                      \
+  do {                                                   \
+    size_t tok__ = (prof) ? (prof)->begin(k, st) : 0;    \
+    stmt;                                                \
+    if (prof) (prof)->end(tok__, st);                    \
+  } while (0)
+
 struct fcp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -127,6 +164,7 @@ struct fcp_ctx {
   double *Dmat[3] = {nullptr, nullptr, nullptr};    // LSQ matrices per method (index FCP_GRAD_*)
   KrylovWS ws;
   FcpComm *comm = nullptr;
+  Profiler prof;
   double *flushbuf = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool has_pressure_patch = false, has_outlet = false, has_inout = false;

@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_nonorth(MeshView m, const double *_
 int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g) {
   if (ctx->B) FCP_CUDA(cudaMemsetAsync(g + 3 * (size_t)ctx->n, 0, sizeof(double) * 3 * (size_t)ctx->B, ctx->stream));
   if (ctx->n == 0) return FCP_OK;
-  k_grad_gauss<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), u, g);
+  FCP_PROF(&ctx->prof, FCP_K_GRAD, ctx->stream, (k_grad_gauss<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), u, g)));
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;
@@ -597,7 +597,7 @@ int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi
 }
 int fvm_laplacian(fcp_ctx *ctx, const double *mu, const double *phi, double *a, double *su) {
   if (ctx->n == 0) return FCP_OK;
-  k_laplacian<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), mu, phi, a, su);
+  FCP_PROF(&ctx->prof, FCP_K_LAPLACIAN, ctx->stream, (k_laplacian<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), mu, phi, a, su)));
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;
@@ -616,8 +616,10 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
     else k_gradp_central2<false><<<FCP_GRID(ctx->n)>>>(m, p, gtmp, su, sv, sw, dPdxi, ca);
     FCP_LAUNCHED();
   } else {
+    size_t tok = ctx->prof.begin(FCP_K_GRADP, ctx->stream);
     if (correct) k_gradp<true><<<FCP_GRID(ctx->n)>>>(m, scheme, 2, p, apu, su, sv, sw, dPdxi, ca);
     else k_gradp<false><<<FCP_GRID(ctx->n)>>>(m, scheme, 2, p, apu, su, sv, sw, dPdxi, ca);
+    ctx->prof.end(tok, ctx->stream);
     FCP_LAUNCHED();
   }
   FCP_CHECK_LAUNCH();
@@ -625,7 +627,7 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
 }
 int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g) {
   if (ctx->n == 0) return FCP_OK;
-  k_assemble_pcorr<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g);
+  FCP_PROF(&ctx->prof, FCP_K_ASSEMBLE, ctx->stream, (k_assemble_pcorr<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g)));
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;
@@ -640,7 +642,7 @@ int fvm_adjust_mass_flow(fcp_ctx *ctx, int32_t nout, const int32_t *d_oface, con
 }
 int fvm_correct_flux(fcp_ctx *ctx, const double *a, const double *pp, double *flmass) {
   if (ctx->F == 0) return FCP_OK;
-  k_correct_flux<<<FCP_GRID(ctx->F)>>>(ctx->F, ctx->owner, ctx->neigh, ctx->kPN, a, pp, flmass);
+  FCP_PROF(&ctx->prof, FCP_K_CORRECT_FLUX, ctx->stream, (k_correct_flux<<<FCP_GRID(ctx->F)>>>(ctx->F, ctx->owner, ctx->neigh, ctx->kPN, a, pp, flmass)));
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

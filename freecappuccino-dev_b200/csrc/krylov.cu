@@ -496,6 +496,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
   if (rep) { memset(rep, 0, sizeof(*rep)); rep->solver = solver; }
   const int grid = fcp_nchunks(n);
   Launcher L{st, comm, ctx, ws, n, grid};
+  Profiler *prof = ctx ? &ctx->prof : nullptr;
   SellView m{p.slptr, p.rinfo, p.ja, a};
   KrylovScalars init;
   memset(&init, 0, sizeof(init));
@@ -514,11 +515,11 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     FCP_TRY(L.post(EPI_INIT_CG, 2));
     for (int it = 0; it < itr_max;) {
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
-        if (grid) { k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc); FCP_LAUNCHED(); }
+        if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc), FCP_LAUNCHED()));
         FCP_TRY(L.halo(ws.pk));
-        if (grid) { k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK)); FCP_LAUNCHED(); }
+        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, (k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK)), FCP_LAUNCHED()));
         FCP_TRY(L.post(EPI_PKAPK, 1));
-        if (grid) { k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)); FCP_LAUNCHED(); }
+        if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
         FCP_TRY(L.post(EPI_CG_UPDATE, 3));
       }
       FCP_CHECK_LAUNCH();
@@ -536,14 +537,14 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
       FCP_TRY(launch_factor(false, p, a, ws.d, st));
       for (int it = 0; it < itr_max;) {
         for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
-          FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st));
+          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st)));
           if (grid) { k_dot<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.zk, ws.sc, L.red(EPI_SK)); FCP_LAUNCHED(); }
           FCP_TRY(L.post(EPI_SK, 1));
-          if (grid) { k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc); FCP_LAUNCHED(); }
+          if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc), FCP_LAUNCHED()));
           FCP_TRY(L.halo(ws.pk));
-          if (grid) { k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK)); FCP_LAUNCHED(); }
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, (k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK)), FCP_LAUNCHED()));
           FCP_TRY(L.post(EPI_PKAPK, 1));
-          if (grid) { k_cg_update<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)); FCP_LAUNCHED(); }
+          if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
           FCP_TRY(L.post(EPI_CG_UPDATE, 3));
         }
         FCP_CHECK_LAUNCH();
@@ -569,14 +570,14 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
       for (int it = 0; it < itr_max;) {
         for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
           if (grid) { k_bicg_pk<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.uk, ws.pk, ws.sc); FCP_LAUNCHED(); }
-          FCP_TRY(launch_precond(p, a, ws.d, ws.pk, ws.zk, ws.sc, st));
+          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.pk, ws.zk, ws.sc, st)));
           FCP_TRY(L.halo(ws.zk));
-          if (grid) { k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.zk, ws.uk, ws.reso, ws.sc, L.red(EPI_UKRESO)); FCP_LAUNCHED(); }
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, (k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.zk, ws.uk, ws.reso, ws.sc, L.red(EPI_UKRESO)), FCP_LAUNCHED()));
           FCP_TRY(L.post(EPI_UKRESO, 1));
           if (grid) { k_bicg_half<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.zk, ws.uk, ws.sc); FCP_LAUNCHED(); }
-          FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st));
+          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st)));
           FCP_TRY(L.halo(ws.zk));
-          if (grid) { k_spmv_dot<2, true><<<grid, FCP_TPB, 0, st>>>(n, m, ws.zk, ws.vk, ws.res, ws.sc, L.red(EPI_VK)); FCP_LAUNCHED(); }
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, (k_spmv_dot<2, true><<<grid, FCP_TPB, 0, st>>>(n, m, ws.zk, ws.vk, ws.res, ws.sc, L.red(EPI_VK)), FCP_LAUNCHED()));
           FCP_TRY(L.post(EPI_VK, 2));
           if (grid) { k_bicg_update<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.zk, ws.vk, ws.reso, ws.adiag, ws.sc, L.red(EPI_BICG_UPDATE)); FCP_LAUNCHED(); }
           FCP_TRY(L.post(EPI_BICG_UPDATE, 3));

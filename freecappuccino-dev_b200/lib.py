@@ -29,6 +29,8 @@ PSCHEME = {"linear": 0, "central": 1, "weighted": 2}
 FIELDS = ["U", "V", "W", "P", "PP", "DEN", "VIS", "APU", "APV", "APW", "SU", "SV", "SW", "S0", "S1", "S2", "S3",
           "DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "FLMASS", "A", "APR"]
 F = {name: i for i, name in enumerate(FIELDS)}
+KERNEL_CLASSES = ["spmv_dot", "cg_pk", "cg_update", "cg_init", "precond", "dot", "bicg_elem", "assemble", "gradp", "correct_flux",
+                  "grad", "laplacian", "spmv", "halo"]
 GRADIENT_FIELDS = {"DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1"}
 
 
@@ -120,6 +122,9 @@ def lib():
     L.fcp_exchange.argtypes = [vp, C.c_int]
     for nm in ("fcp_global_sum", "fcp_global_max", "fcp_global_min"):
         getattr(L, nm).argtypes = [vp, _pd]
+    L.fcp_profile_enable.argtypes = [vp, C.c_int]
+    L.fcp_profile_reset.argtypes = [vp]
+    L.fcp_profile_read.argtypes = [vp, C.c_int, _pd, C.POINTER(C.c_int64)]
     L.fcp_timer_start.argtypes = [vp]
     L.fcp_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.fcp_flush_l2.argtypes = [vp]
@@ -277,6 +282,22 @@ class Context:
         return x.value
 
     # ---- timing ----------------------------------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        check(lib().fcp_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        check(lib().fcp_profile_reset(self.h))
+
+    def profile_read(self):
+        """kernel class -> (total device ms, launches) since the last reset (CUDA events around every launch)."""
+        out = {}
+        for i, name in enumerate(KERNEL_CLASSES):
+            ms, cnt = C.c_double(), C.c_int64()
+            check(lib().fcp_profile_read(self.h, i, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[name] = (ms.value, int(cnt.value))
+        return out
+
     def timer_start(self):
         check(lib().fcp_timer_start(self.h))
 

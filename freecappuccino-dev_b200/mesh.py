@@ -513,3 +513,135 @@ def localize_matrix(gmesh: Mesh, gcsr, a_global: np.ndarray, part: Mesh, pcsr) -
         local_is_owner = own0[gfaces] == part.cell_global[part.owner[pf] - 1]
         apr.append(np.where(local_is_owner, a_global[gcsr.icell_jcell[gfaces] - 1], a_global[gcsr.jcell_icell[gfaces] - 1]))
     return a_loc, (np.concatenate(apr) if apr else np.zeros(0))
+
+
+# ---------------------------------------------------------------------------------------------
+# fast tensor-product generator (bench sizes): same topology, numbering and patch order as hex_mesh(), geometry written
+# down analytically for an axis-aligned box grid instead of going through points/face_nodes (agrees with the triangle-fan
+# formulas of geometry.f90:416-664 to rounding).  Optionally one brick of a px x py x pz block decomposition in the
+# src-par layout: sides on internal cuts become `process` patches (appended after the physical patches, one per
+# neighbour rank, faces in the same order on both sides).
+# ---------------------------------------------------------------------------------------------
+def hex_mesh_fast(xs: np.ndarray, ys: np.ndarray, zs: np.ndarray, patch_types: Optional[Dict[str, str]] = None,
+                  peer: Optional[Dict[str, int]] = None) -> Mesh:
+    """peer: side name -> neighbour rank for sides that are internal cuts of a block decomposition."""
+    nx, ny, nz = len(xs) - 1, len(ys) - 1, len(zs) - 1
+    types = dict(top="wall", bottom="wall", left="wall", right="wall", back="wall", front="wall")
+    if patch_types:
+        types.update(patch_types)
+    peer = peer or {}
+    dx, dy, dz = np.diff(xs), np.diff(ys), np.diff(zs)
+    xm, ym, zm = 0.5 * (xs[1:] + xs[:-1]), 0.5 * (ys[1:] + ys[:-1]), 0.5 * (zs[1:] + zs[:-1])
+    n = nx * ny * nz
+    cid = np.arange(n, dtype=np.int64)
+    ci = cid % nx
+    cj = (cid // nx) % ny
+    ck = cid // (nx * ny)
+    # inner faces: for every cell (ascending) its +x, +y, +z face when it exists
+    valid = np.stack([ci < nx - 1, cj < ny - 1, ck < nz - 1], axis=1)          # [n,3]
+    sel = np.nonzero(valid.ravel())[0]
+    fc = sel // 3                                                             # owner cell of each inner face
+    fd = (sel % 3).astype(np.int8)                                            # direction
+    del valid, sel
+    fi, fj, fk = ci[fc], cj[fc], ck[fc]
+    stride = np.array([1, nx, nx * ny], dtype=np.int64)
+    nb = fc + stride[fd]
+    Fi = fc.size
+    ax = np.where(fd == 0, dy[fj] * dz[fk], 0.0)
+    ay = np.where(fd == 1, dx[fi] * dz[fk], 0.0)
+    az = np.where(fd == 2, dx[fi] * dy[fj], 0.0)
+    fx = np.where(fd == 0, xs[fi + 1], xm[fi])
+    fy = np.where(fd == 1, ys[fj + 1], ym[fj])
+    fz = np.where(fd == 2, zs[fk + 1], zm[fk])
+    # distance owner centre -> face and face -> neighbour centre along the face normal
+    dP = np.where(fd == 0, 0.5 * dx[fi], np.where(fd == 1, 0.5 * dy[fj], 0.5 * dz[fk]))
+    dN = np.where(fd == 0, 0.5 * dx[np.minimum(fi + 1, nx - 1)], np.where(fd == 1, 0.5 * dy[np.minimum(fj + 1, ny - 1)], 0.5 * dz[np.minimum(fk + 1, nz - 1)]))
+    facint = dP / (dP + dN)
+    area = ax + ay + az
+    Df = (area * area) / (area * (dP + dN))
+    del fi, fj, fk, dP, dN
+
+    def side(name):
+        """owner cells (face order of hex_mesh), area vector, face centre, for one side of the box"""
+        if name in ("top", "bottom"):
+            i, k = np.meshgrid(np.arange(nx), np.arange(nz), indexing="ij")
+            i, k = i.ravel(order="F"), k.ravel(order="F")
+            j = np.full_like(i, ny - 1 if name == "top" else 0)
+            s = 1.0 if name == "top" else -1.0
+            return i + nx * (j + ny * k), (0 * dx[i], s * dx[i] * dz[k], 0 * dx[i]), (xm[i], np.full(i.size, ys[-1] if name == "top" else ys[0]), zm[k])
+        if name in ("left", "right"):
+            j, k = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij")
+            j, k = j.ravel(order="F"), k.ravel(order="F")
+            i = np.full_like(j, nx - 1 if name == "right" else 0)
+            s = 1.0 if name == "right" else -1.0
+            return i + nx * (j + ny * k), (s * dy[j] * dz[k], 0 * dy[j], 0 * dy[j]), (np.full(j.size, xs[-1] if name == "right" else xs[0]), ym[j], zm[k])
+        i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        i, j = i.ravel(order="F"), j.ravel(order="F")
+        k = np.full_like(i, nz - 1 if name == "front" else 0)
+        s = 1.0 if name == "front" else -1.0
+        return i + nx * (j + ny * k), (0 * dx[i], 0 * dx[i], s * dx[i] * dy[j]), (xm[i], ym[j], np.full(i.size, zs[-1] if name == "front" else zs[0]))
+
+    order = ["top", "bottom", "left", "right", "back", "front"]
+    phys = [s for s in order if s not in peer]
+    proc = [s for s in order if s in peer]
+    bown, bar, bcf, names, btypes, counts, peers = [], [], [], [], [], [], []
+    for s in phys + proc:
+        o, a, c = side(s)
+        bown.append(o); bar.append(a); bcf.append(c)
+        names.append(s if s not in peer else f"procBoundary_{s}_to{peer[s]}")
+        btypes.append(BC_CODE[types[s]] if s not in peer else BC_PROCESS)
+        counts.append(o.size)
+        peers.append(peer.get(s, -1))
+    starts = Fi + np.concatenate([[0], np.cumsum(counts)[:-1]])
+    owner = (np.concatenate([fc] + bown) + 1).astype(np.int32)
+    neighbour = (nb + 1).astype(np.int32)
+    cat = lambda first, k: np.concatenate([first] + [b[k] for b in bar])  # noqa: E731
+    arx, ary, arz = cat(ax, 0), cat(ay, 1), cat(az, 2)
+    xf = np.concatenate([fx] + [c[0] for c in bcf])
+    yf = np.concatenate([fy] + [c[1] for c in bcf])
+    zf = np.concatenate([fz] + [c[2] for c in bcf])
+    xc, yc, zc = xm[ci], ym[cj], zm[ck]
+    vol = dx[ci] * dy[cj] * dz[ck]
+    # patch_index of the matching patch on the peer: the peer lists its process patches in the same `order`, after its own
+    # physical patches; the caller (block_partition_mesh) fills peer_patch because it knows the peer's patch table
+    return Mesh(numCells=n, numInnerFaces=Fi, numBoundaryFaces=int(sum(counts)), owner=owner, neighbour=neighbour,
+                arx=arx, ary=ary, arz=arz, xf=xf, yf=yf, zf=zf, facint=facint, Df=Df, xc=xc, yc=yc, zc=zc, vol=vol,
+                bcname=names, bctype=np.array(btypes, dtype=np.int32), nfaces=np.array(counts, dtype=np.int32),
+                startFace=np.asarray(starts, dtype=np.int32), peer_rank=np.array(peers, dtype=np.int32),
+                peer_patch=np.full(len(names), -1, dtype=np.int32))
+
+
+def block_dims(nranks: int) -> Tuple[int, int, int]:
+    """z-slabs, like a decomposePar 'simple (1 1 n)' run of the src-par tree."""
+    return (1, 1, nranks)
+
+
+def block_partition_mesh(n: Tuple[int, int, int], dims: Tuple[int, int, int], rank: int, length: float = 1.0,
+                         patch_types: Optional[Dict[str, str]] = None) -> Mesh:
+    """Rank `rank`'s brick of a uniform nx x ny x nz box split in px x py x pz blocks (rank = bx + px*(by + py*bz)),
+    generated directly in the src-par layout (no global mesh is ever built).  Ghost copies of xc,yc,zc,vol are filled by
+    fcp_comm_init's exchange (src-par/geometry.f90:769-773), so they are left at zero here."""
+    nx, ny, nz = n
+    px, py, pz = dims
+    bx, by, bz = rank % px, (rank // px) % py, rank // (px * py)
+
+    def cut(nn, p, b):
+        lo = (nn * b) // p
+        hi = (nn * (b + 1)) // p
+        return lo, hi
+    (i0, i1), (j0, j1), (k0, k1) = cut(nx, px, bx), cut(ny, py, by), cut(nz, pz, bz)
+    xs = np.linspace(0.0, length, nx + 1)[i0: i1 + 1]
+    ys = np.linspace(0.0, length, ny + 1)[j0: j1 + 1]
+    zs = np.linspace(0.0, length, nz + 1)[k0: k1 + 1]
+    rk = lambda a, b, c: a + px * (b + py * c)  # noqa: E731
+    peer = {}
+    if bx > 0: peer["left"] = rk(bx - 1, by, bz)
+    if bx < px - 1: peer["right"] = rk(bx + 1, by, bz)
+    if by > 0: peer["bottom"] = rk(bx, by - 1, bz)
+    if by < py - 1: peer["top"] = rk(bx, by + 1, bz)
+    if bz > 0: peer["back"] = rk(bx, by, bz - 1)
+    if bz < pz - 1: peer["front"] = rk(bx, by, bz + 1)
+    m = hex_mesh_fast(xs, ys, zs, patch_types, peer)
+    m.cell_offset = (i0, j0, k0)
+    m.global_dims = (nx, ny, nz)
+    return m

@@ -169,6 +169,13 @@ int fcp_global_sum(fcp_ctx *ctx, double *value);              /* in place, all r
 int fcp_global_max(fcp_ctx *ctx, double *value);
 int fcp_global_min(fcp_ctx *ctx, double *value);
 
+/* ---- per-kernel-class device timing (CUDA events on the context stream, around every launch of the class) ---- */
+enum { FCP_K_SPMV_DOT = 0, FCP_K_CG_PK, FCP_K_CG_UPDATE, FCP_K_CG_INIT, FCP_K_PRECOND, FCP_K_DOT, FCP_K_BICG_ELEM,
+       FCP_K_ASSEMBLE, FCP_K_GRADP, FCP_K_CORRECT_FLUX, FCP_K_GRAD, FCP_K_LAPLACIAN, FCP_K_SPMV, FCP_K_HALO, FCP_K_COUNT };
+int fcp_profile_enable(fcp_ctx *ctx, int on);
+int fcp_profile_reset(fcp_ctx *ctx);
+int fcp_profile_read(fcp_ctx *ctx, int kclass, double *total_ms, int64_t *launches);   /* synchronises; totals since reset */
+
 /* ---- timing helper for benches: runs fn-independent CUDA event timing on the context stream --- */
 int fcp_timer_start(fcp_ctx *ctx);
 int fcp_timer_stop(fcp_ctx *ctx, float *milliseconds);        /* synchronises */

@@ -247,7 +247,7 @@ def main():
 
     def step():
         ctx.gradp_and_sources("linear", "P")
-        return ctx.calcp_simple(solver=args.solver, maxiter=MAXITER, tol_abs=1e-30, tol_rel=TOL_REL, urfp=0.3, npcor=1, pRefCell=1,
+        return ctx.calcp_simple(solver=args.solver, maxiter=MAXITER, tol_abs=1e-30, tol_rel=TOL_REL, urfp=0.3, npcor=1, pRefCell=1 if rank == 0 else 0,
                                 zero_pp=True)[0]
 
     def e2e_step():

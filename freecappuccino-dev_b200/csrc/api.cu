@@ -269,7 +269,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   for (int i = 0; i < FCP_F_COUNT; ++i) cudaFree(c->field[i]);
   for (int i = 0; i < 3; ++i) cudaFree(c->Dmat[i]);
   cudaFree(c->flushbuf);
-  cudaFree(c->d_oface); cudaFree(c->d_aprpos); cudaFree(c->d_procface);
+  cudaFree(c->d_oface); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
   sell_free(c->pat);
   krylov_ws_free(c->ws);
   if (c->t0) cudaEventDestroy(c->t0);
@@ -528,24 +528,57 @@ extern "C" int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double f
     FCP_TRY(ensure_outlet_list(ctx));
     FCP_TRY(fvm_adjust_mass_flow(ctx, ctx->nout, ctx->d_oface, den, u, v, w, fl, flomas));
   }
+  if (ctx->comm) {   // ghost values of everything facefluxmass reads on the far side of a process face
+    double *sc[] = {den, u, v, w, p, apu};
+    for (double *x : sc) FCP_TRY(comm_exchange(ctx, x, 1));
+    FCP_TRY(comm_exchange(ctx, g, 3));
+  }
   AsmArgs args{den, u, v, w, p, g, apu, pp, u, v, w, a, su, fl};
   return fvm_assemble_pcorr(ctx, args);
 }
 
+// pp(pRefCell) on the rank that owns the reference cell, 0 elsewhere (pRefCell <= 0 = "not on this rank")
+__global__ void k_pick_ref(const double *pp, int32_t pRefCell, double *out) { out[0] = pRefCell > 0 ? pp[pRefCell - 1] : 0.0; }
+// process faces: flmass += apr*(pp(ghost) - pp(owner))       src-par/calcp_simple.f90:222-244
+__global__ void k_correct_flux_proc(int32_t npro, const int32_t *__restrict__ pface, const int32_t *__restrict__ aprpos, const int32_t *__restrict__ owner,
+                                    int32_t n, int32_t F, const double *__restrict__ a, const double *__restrict__ pp, double *__restrict__ flmass) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npro) return;
+  const int32_t f = pface[i];
+  flmass[f] = flmass[f] + a[aprpos[i]] * (pp[n + (f - F)] - pp[owner[f]]);
+}
+
 extern "C" int fcp_correct_simple(fcp_ctx *ctx, int pscheme, double urfp, int32_t pRefCell) {
   if (!ctx) return FCP_EINVAL;
-  if (pRefCell < 1 || pRefCell > ctx->n) { fcp_set_error("pRefCell %d out of range", pRefCell); return FCP_EINVAL; }
+  // multi-GPU: pRefCell is the LOCAL index on the rank that owns the reference cell and <= 0 on every other rank
+  if (pRefCell > ctx->n || (pRefCell < 1 && !ctx->comm)) { fcp_set_error("pRefCell %d out of range", pRefCell); return FCP_EINVAL; }
   FIELD(den, FCP_F_DEN); FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(p, FCP_F_P); FIELD(pp, FCP_F_PP);
   FIELD(apu, FCP_F_APU); FIELD(apv, FCP_F_APV); FIELD(apw, FCP_F_APW); FIELD(a, FCP_F_A); FIELD(fl, FCP_F_FLMASS);
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, pp, 1));
   FCP_TRY(fvm_correct_flux(ctx, a, pp, fl));                                   // calcp_simple.f90:331-341
+  if (ctx->npro) {
+    k_correct_flux_proc<<<(ctx->npro + 255) / 256, 256, 0, ctx->stream>>>(ctx->npro, ctx->d_procface, ctx->d_aprpos, ctx->owner, ctx->n, ctx->F, a, pp, fl);
+    FCP_LAUNCHED();
+    FCP_CHECK_LAUNCH();
+  }
   if (ctx->has_pressure_patch) FCP_TRY(fvm_correct_pressure_bnd(ctx, den, apu, pp, u, v, w, fl));   // :345-391
-  CorrectArgs ca{u, v, w, p, apu, apv, apw, urfp, ctx->has_pressure_patch ? nullptr : pp + (pRefCell - 1)};   // :399-407
+  const double *ppref = ctx->has_pressure_patch ? nullptr : pp + (pRefCell - 1);                    // :399-407
+  if (ctx->comm && !ctx->has_pressure_patch) {
+    // the broadcast of ppref (src-par/calcp_simple.f90:195-198, quirk Q12) as a rank-ordered sum of {pp(ref), 0, 0, ...}
+    if (!ctx->d_ppref) FCP_TRY(dev_alloc(&ctx->d_ppref, 4));
+    k_pick_ref<<<1, 1, 0, ctx->stream>>>(pp, pRefCell, ctx->d_ppref);
+    FCP_LAUNCHED();
+    FCP_TRY(comm_allgather_sum(ctx->comm, ctx->d_ppref, 1, ctx->stream));
+    ppref = ctx->d_ppref;
+  }
+  CorrectArgs ca{u, v, w, p, apu, apv, apw, urfp, ppref};
   return gradp_impl(ctx, pscheme, pp, &ca);                                    // :412-429
 }
 
 extern "C" int fcp_nonorth_corrector(fcp_ctx *ctx) {
   if (!ctx) return FCP_EINVAL;
   FIELD(den, FCP_F_DEN); FIELD(apu, FCP_F_APU); FIELD(g, FCP_F_DPDXI); FIELD(su, FCP_F_SU); FIELD(fl, FCP_F_FLMASS);
+  if (ctx->comm) { FCP_TRY(comm_exchange(ctx, g, 3)); FCP_TRY(comm_exchange(ctx, den, 1)); FCP_TRY(comm_exchange(ctx, apu, 1)); }
   return fvm_nonorth(ctx, den, apu, g, su, fl);
 }
 

@@ -173,6 +173,7 @@ struct fcp_ctx {
   int32_t *d_aprpos = nullptr;                      // [npro] SELL position of the halo entry of each process face
   int32_t *d_procface = nullptr;                    // [npro] 0-based face index of each process face (patch order)
   std::vector<int32_t> h_procface;
+  double *d_ppref = nullptr;                        // [4] broadcast slot for pp(pRefCell)
 };
 
 struct fcp_solver {

@@ -169,7 +169,11 @@ __device__ void krylov_epilogue(int which, KrylovScalars *sc) {
     default: break;
   }
 }
-__global__ void k_epilogue(int which, KrylovScalars *sc) { krylov_epilogue(which, sc); }
+// (after convergence the producing kernels return early and leave sc->red stale: the epilogue must not run again)
+__global__ void k_epilogue(int which, KrylovScalars *sc) {
+  if (sc->done && which != EPI_INIT_CG && which != EPI_INIT_BICG) return;
+  krylov_epilogue(which, sc);
+}
 
 struct RedArgs {
   double *partials;

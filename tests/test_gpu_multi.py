@@ -1,0 +1,29 @@
+"""GPU (>= 2 B200): partitioned run through NCCL, one rank per GPU, against the oracle's virtual-rank drivers.
+Launches tests/mgpu_worker.py under torch.distributed.run; skipped on a 1-GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except (OSError, subprocess.TimeoutExpired):
+        return 0
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_partitioned_parity(nranks):
+    if _ngpus() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + nranks), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    ok = sum(1 for l in r.stdout.splitlines() if l.startswith("MGPU_OK"))
+    assert r.returncode == 0 and ok == nranks, r.stdout[-3000:] + r.stderr[-3000:]

@@ -1,0 +1,433 @@
+!
+! fortran/fcp_b200.f90 -- ISO_C_BINDING layer between freeCappuccino's Fortran host and libfcp_b200.so (include/fcp.h).
+!
+! Two modules:
+!   fcp_b200      the bind(C) interfaces, one per entry point of include/fcp.h
+!   fcp_backend   drop-in replacements that keep the reference's module-level API for the hot path
+!                 (csrsolve, grad_gauss, grad, laplacian, gradp_and_sources, calcp_simple, exchange, global_sum):
+!                 same names, same dummy arguments, same module globals (geometry, sparse_matrix, variables), so that
+!                 `use linear_solvers` / `use gradients` / `use pressure` in a caller is replaced by `use fcp_backend`
+!                 (INTEGRATION.md shows the patch).
+!
+! This file cannot be compiled in the build image (no Fortran compiler there; SURVEY.md section 0, fact 9).  The same
+! call sequence is exercised through host/fcp_host.hpp (C++) and freecappuccino-dev_b200/host.py (Python) by tests/.
+! Reference signatures: src/linearSolvers/linear_solvers.f90:40-59 (csrsolve), src/finiteVolume/fvExplicit/gradients.f90
+! :23-27,:1607 (grad, grad_gauss), src/finiteVolume/fvImplicit/laplacian.f90 (laplacian), Pressure/nablap.f90:19
+! (gradp_and_sources), Pressure/pressure.f90:39-40 (calcp_simple), src-par/exchange.f90:3, src-par/global_sum_mpi.f90:4.
+!
+module fcp_b200
+  use, intrinsic :: iso_c_binding
+  implicit none
+
+  ! constants of include/fcp.h
+  integer(c_int), parameter :: FCP_OK = 0
+  integer(c_int), parameter :: FCP_SOLVER_DPCG = 1, FCP_SOLVER_ICCG = 2, FCP_SOLVER_BICGSTAB = 3
+  integer(c_int), parameter :: FCP_GRAD_GAUSS = 0, FCP_GRAD_LSQ = 1, FCP_GRAD_LSQ_DM = 2
+  integer(c_int), parameter :: FCP_PSCHEME_LINEAR = 0, FCP_PSCHEME_CENTRAL = 1, FCP_PSCHEME_WEIGHTED = 2
+  integer(c_int), parameter :: FCP_BC_WALL = 0, FCP_BC_INLET = 1, FCP_BC_OUTLET = 2, FCP_BC_SYMMETRY = 3, &
+                               FCP_BC_PRESSURE = 4, FCP_BC_PERIODIC = 5, FCP_BC_EMPTY = 6, FCP_BC_PROCESS = 7
+  enum, bind(c)   ! field ids, same order as the enum in include/fcp.h
+    enumerator :: FCP_F_U = 0, FCP_F_V, FCP_F_W, FCP_F_P, FCP_F_PP, FCP_F_DEN, FCP_F_VIS, &
+                  FCP_F_APU, FCP_F_APV, FCP_F_APW, FCP_F_SU, FCP_F_SV, FCP_F_SW, &
+                  FCP_F_S0, FCP_F_S1, FCP_F_S2, FCP_F_S3, &
+                  FCP_F_DUDXI, FCP_F_DVDXI, FCP_F_DWDXI, FCP_F_DPDXI, FCP_F_G0, FCP_F_G1, &
+                  FCP_F_FLMASS, FCP_F_A, FCP_F_APR
+  end enum
+
+  type, bind(c) :: fcp_mesh_desc
+    integer(c_int32_t) :: numCells, numInnerFaces, numBoundaryFaces, numBoundaries
+    type(c_ptr) :: owner, neighbour
+    type(c_ptr) :: arx, ary, arz, xf, yf, zf, facint, Df, xc, yc, zc, vol
+    type(c_ptr) :: bctype, nfaces, startFace
+  end type
+
+  type, bind(c) :: fcp_report
+    real(c_double) :: res0, resl, factor, resor
+    integer(c_int32_t) :: iters, solver
+  end type
+
+  type, bind(c) :: fcp_simple_params
+    integer(c_int32_t) :: solver, maxiter
+    real(c_double) :: tol_abs, tol_rel, urfp
+    integer(c_int32_t) :: npcor, pRefCell, pscheme, const_mflux
+    real(c_double) :: flomas
+    integer(c_int32_t) :: zero_pp
+  end type
+
+  interface
+    function fcp_last_error() bind(c, name='fcp_last_error') result(msg)
+      import :: c_ptr
+      type(c_ptr) :: msg
+    end function
+    function fcp_ctx_create(mesh, device, ctx) bind(c, name='fcp_ctx_create') result(rc)
+      import :: c_int, c_ptr, fcp_mesh_desc
+      type(fcp_mesh_desc), intent(in) :: mesh
+      integer(c_int), value :: device
+      type(c_ptr), intent(out) :: ctx
+      integer(c_int) :: rc
+    end function
+    function fcp_ctx_destroy(ctx) bind(c, name='fcp_ctx_destroy') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int) :: rc
+    end function
+    function fcp_csr_pattern(ctx, ia, ja, diag, icell_jcell, jcell_icell) bind(c, name='fcp_csr_pattern') result(rc)
+      import :: c_int, c_ptr, c_int32_t
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), intent(out) :: ia(*), ja(*), diag(*), icell_jcell(*), jcell_icell(*)
+      integer(c_int) :: rc
+    end function
+    function fcp_field_upload(ctx, field, host, count) bind(c, name='fcp_field_upload') result(rc)
+      import :: c_int, c_ptr, c_double, c_int64_t
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: field
+      real(c_double), intent(in) :: host(*)
+      integer(c_int64_t), value :: count
+      integer(c_int) :: rc
+    end function
+    function fcp_field_download(ctx, field, host, count) bind(c, name='fcp_field_download') result(rc)
+      import :: c_int, c_ptr, c_double, c_int64_t
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: field
+      real(c_double), intent(out) :: host(*)
+      integer(c_int64_t), value :: count
+      integer(c_int) :: rc
+    end function
+    function fcp_field_fill(ctx, field, val) bind(c, name='fcp_field_fill') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: field
+      real(c_double), value :: val
+      integer(c_int) :: rc
+    end function
+    function fcp_spmv(ctx, x_field, y_field) bind(c, name='fcp_spmv') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: x_field, y_field
+      integer(c_int) :: rc
+    end function
+    function fcp_csrsolve(ctx, solver, fi_field, rhs_field, itr_max, tol_abs, tol_rel, rep) bind(c, name='fcp_csrsolve') result(rc)
+      import :: c_int, c_ptr, c_double, c_int32_t, fcp_report
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: solver, fi_field, rhs_field
+      integer(c_int32_t), value :: itr_max
+      real(c_double), value :: tol_abs, tol_rel
+      type(fcp_report), intent(out) :: rep
+      integer(c_int) :: rc
+    end function
+    function fcp_report_line(rep, chvar, buf, buflen) bind(c, name='fcp_report_line') result(rc)
+      import :: c_int, c_char, fcp_report
+      type(fcp_report), intent(in) :: rep
+      character(kind=c_char), intent(in) :: chvar(*)
+      character(kind=c_char), intent(out) :: buf(*)
+      integer(c_int), value :: buflen
+      integer(c_int) :: rc
+    end function
+    function fcp_create_lsq_grad_matrix(ctx, method) bind(c, name='fcp_create_lsq_grad_matrix') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: method
+      integer(c_int) :: rc
+    end function
+    function fcp_grad(ctx, method, phi_field, grad_field, lsq_row2_reference) bind(c, name='fcp_grad') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: method, phi_field, grad_field, lsq_row2_reference
+      integer(c_int) :: rc
+    end function
+    function fcp_laplacian(ctx, mu_field, phi_field) bind(c, name='fcp_laplacian') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: mu_field, phi_field
+      integer(c_int) :: rc
+    end function
+    function fcp_gradp_and_sources(ctx, pscheme, p_field) bind(c, name='fcp_gradp_and_sources') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: pscheme, p_field
+      integer(c_int) :: rc
+    end function
+    function fcp_calcp_simple(ctx, prm, rep) bind(c, name='fcp_calcp_simple') result(rc)
+      import :: c_int, c_ptr, fcp_simple_params, fcp_report
+      type(c_ptr), value :: ctx
+      type(fcp_simple_params), intent(in) :: prm
+      type(fcp_report), intent(out) :: rep(*)
+      integer(c_int) :: rc
+    end function
+    function fcp_solver_create(n, nnz, ia, ja, diag, device, s) bind(c, name='fcp_solver_create') result(rc)
+      import :: c_int, c_ptr, c_int32_t
+      integer(c_int32_t), value :: n, nnz
+      integer(c_int32_t), intent(in) :: ia(*), ja(*), diag(*)
+      integer(c_int), value :: device
+      type(c_ptr), intent(out) :: s
+      integer(c_int) :: rc
+    end function
+    function fcp_solver_solve(s, solver, a, fi, rhs, itr_max, tol_abs, tol_rel, rep) bind(c, name='fcp_solver_solve') result(rc)
+      import :: c_int, c_ptr, c_double, c_int32_t, fcp_report
+      type(c_ptr), value :: s
+      integer(c_int), value :: solver
+      real(c_double), intent(in) :: a(*), rhs(*)
+      real(c_double), intent(inout) :: fi(*)
+      integer(c_int32_t), value :: itr_max
+      real(c_double), value :: tol_abs, tol_rel
+      type(fcp_report), intent(out) :: rep
+      integer(c_int) :: rc
+    end function
+    function fcp_solver_destroy(s) bind(c, name='fcp_solver_destroy') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: s
+      integer(c_int) :: rc
+    end function
+    function fcp_comm_unique_id(id128) bind(c, name='fcp_comm_unique_id') result(rc)
+      import :: c_int, c_char
+      character(kind=c_char), intent(out) :: id128(128)
+      integer(c_int) :: rc
+    end function
+    function fcp_comm_init(ctx, rank, nranks, id128, peer_rank) bind(c, name='fcp_comm_init') result(rc)
+      import :: c_int, c_ptr, c_char, c_int32_t
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: rank, nranks
+      character(kind=c_char), intent(in) :: id128(128)
+      integer(c_int32_t), intent(in) :: peer_rank(*)
+      integer(c_int) :: rc
+    end function
+    function fcp_exchange(ctx, field) bind(c, name='fcp_exchange') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: field
+      integer(c_int) :: rc
+    end function
+    function fcp_global_sum(ctx, val) bind(c, name='fcp_global_sum') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: val
+      integer(c_int) :: rc
+    end function
+  end interface
+end module fcp_b200
+
+
+module fcp_backend
+  use, intrinsic :: iso_c_binding
+  use types, only: dp
+  use parameters          ! numTotal, pRefCell, npcor, const_mflux, flomas ...
+  use geometry            ! numCells, numInnerFaces, owner, neighbour, arx ... (src/mesh/geometry.f90:12-86)
+  use sparse_matrix       ! nnz, ia, ja, diag, a, su, sv, sw, apu, apv, apw    (src/sparseMatrix/sparse_matrix.f90:20-40)
+  use variables           ! u, v, w, p, pp, den, flmass, dPdxi ...
+  use fcp_b200
+  implicit none
+  type(c_ptr), save :: ctx = c_null_ptr
+  public
+
+contains
+
+  subroutine fcp_check(rc, what)
+    ! the reference has no status codes: fatal conditions print and stop (linear_solvers.f90:1361-1376)
+    integer(c_int), intent(in) :: rc
+    character(len=*), intent(in) :: what
+    if (rc /= FCP_OK) then
+      write(*,'(3a,i0)') ' libfcp_b200: ', what, ' failed with code ', rc
+      stop
+    end if
+  end subroutine
+
+  integer(c_int) function solver_id(solver)
+    character(len=*), intent(in) :: solver
+    select case (trim(solver))
+    case ('dpcg');     solver_id = FCP_SOLVER_DPCG
+    case ('iccg');     solver_id = FCP_SOLVER_ICCG
+    case ('bicgstab'); solver_id = FCP_SOLVER_BICGSTAB
+    case default
+      write(*,'(3a)') ' libfcp_b200: linear solver "', trim(solver), '" is not on the accelerated path'
+      stop
+    end select
+  end function
+
+  ! Call once after read_mesh + create_CSR_matrix (main.f90:112-114): uploads the mesh, builds the device pattern and
+  ! checks that it is identical to the one create_CSR_matrix produced.
+  subroutine fcp_init(device)
+    integer, intent(in) :: device
+    type(fcp_mesh_desc) :: md
+    integer(c_int32_t), allocatable, target :: bct(:), nfa(:), sfa(:)
+    integer(c_int32_t), allocatable :: ia2(:), ja2(:), dg2(:), k1(:), k2(:)
+    integer :: ib
+    allocate(bct(numBoundaries), nfa(numBoundaries), sfa(numBoundaries))
+    do ib = 1, numBoundaries
+      nfa(ib) = nfaces(ib)
+      sfa(ib) = startFace(ib)                     ! 0-based offset, as in the boundary file (geometry.f90:282-290)
+      select case (trim(bctype(ib)))
+      case ('wall');     bct(ib) = FCP_BC_WALL
+      case ('inlet');    bct(ib) = FCP_BC_INLET
+      case ('outlet');   bct(ib) = FCP_BC_OUTLET
+      case ('symmetry'); bct(ib) = FCP_BC_SYMMETRY
+      case ('pressure'); bct(ib) = FCP_BC_PRESSURE
+      case ('periodic'); bct(ib) = FCP_BC_PERIODIC
+      case ('process');  bct(ib) = FCP_BC_PROCESS
+      case default;      bct(ib) = FCP_BC_EMPTY
+      end select
+    end do
+    md%numCells = numCells; md%numInnerFaces = numInnerFaces
+    md%numBoundaryFaces = numBoundaryFaces; md%numBoundaries = numBoundaries
+    md%owner = c_loc(owner); md%neighbour = c_loc(neighbour)
+    md%arx = c_loc(arx); md%ary = c_loc(ary); md%arz = c_loc(arz)
+    md%xf = c_loc(xf); md%yf = c_loc(yf); md%zf = c_loc(zf)
+    md%facint = c_loc(facint); md%Df = c_loc(Df)
+    md%xc = c_loc(xc); md%yc = c_loc(yc); md%zc = c_loc(zc); md%vol = c_loc(vol)
+    md%bctype = c_loc(bct); md%nfaces = c_loc(nfa); md%startFace = c_loc(sfa)
+    call fcp_check(fcp_ctx_create(md, int(device, c_int), ctx), 'fcp_ctx_create')
+    allocate(ia2(numCells+1), ja2(nnz), dg2(numCells), k1(numInnerFaces), k2(numInnerFaces))
+    call fcp_check(fcp_csr_pattern(ctx, ia2, ja2, dg2, k1, k2), 'fcp_csr_pattern')
+    if (any(ia2 /= ia) .or. any(ja2 /= ja) .or. any(dg2 /= diag) .or. &
+        any(k1 /= icell_jcell_csr_index(1:numInnerFaces)) .or. any(k2 /= jcell_icell_csr_index(1:numInnerFaces))) then
+      write(*,'(a)') ' libfcp_b200: device CSR pattern differs from create_CSR_matrix'
+      stop
+    end if
+  end subroutine
+
+  subroutine put(field, x, n)
+    integer(c_int), intent(in) :: field
+    real(dp), intent(in) :: x(*)
+    integer, intent(in) :: n
+    call fcp_check(fcp_field_upload(ctx, field, x, int(n, c_int64_t)), 'fcp_field_upload')
+  end subroutine
+  subroutine get(field, x, n)
+    integer(c_int), intent(in) :: field
+    real(dp), intent(out) :: x(*)
+    integer, intent(in) :: n
+    call fcp_check(fcp_field_download(ctx, field, x, int(n, c_int64_t)), 'fcp_field_download')
+  end subroutine
+
+  ! ---- csrsolve: same dummies as linear_solvers.f90:40-59 ---------------------------------------------------------------
+  subroutine csrsolve(solver, fi, rhs, res0, itr_max, tol_abs, tol_rel, chvar)
+    character(len=*), intent(in) :: solver
+    real(dp), dimension(numTotal), intent(inout) :: fi
+    real(dp), dimension(numCells), intent(in) :: rhs
+    real(dp), intent(out) :: res0
+    integer, intent(in) :: itr_max
+    real(dp), intent(in) :: tol_abs, tol_rel
+    character(len=*), intent(in) :: chvar
+    type(fcp_report) :: rep
+    character(kind=c_char) :: line(256)
+    integer :: i
+    call put(FCP_F_A, a, nnz)
+    call put(FCP_F_S0, fi, numTotal)
+    call put(FCP_F_S1, rhs, numCells)
+    call fcp_check(fcp_csrsolve(ctx, solver_id(solver), FCP_F_S0, FCP_F_S1, int(itr_max, c_int32_t), tol_abs, tol_rel, rep), 'fcp_csrsolve')
+    call get(FCP_F_S0, fi, numCells)
+    res0 = rep%resor
+    ! the report line of linear_solvers.f90:354-355 / 540-541 / 781-782 (parsed by examples/*/plotResiduals)
+    call fcp_check(fcp_report_line(rep, trim(chvar)//c_null_char, line, 256_c_int), 'fcp_report_line')
+    do i = 1, 256
+      if (line(i) == c_null_char) exit
+    end do
+    write(*,'(256a)') line(1:i-1)
+  end subroutine
+
+  ! ---- gradients: gradients.f90:1607 (grad_gauss), :23-27 (grad) ------------------------------------------------------------
+  subroutine grad_gauss(u_, dudxi)
+    real(dp), dimension(numTotal), intent(in) :: u_
+    real(dp), dimension(3,numTotal), intent(inout) :: dudxi
+    call put(FCP_F_S0, u_, numTotal)
+    call fcp_check(fcp_grad(ctx, FCP_GRAD_GAUSS, FCP_F_S0, FCP_F_G0, 1_c_int), 'fcp_grad')
+    call get(FCP_F_G0, dudxi, 3*numTotal)
+  end subroutine
+
+  subroutine grad(phi, dPhidxi)         ! dispatch on the logicals lstsq / lstsq_dm like grad_scalar_field, gradients.f90:106-163
+    use gradients, only: lstsq, lstsq_dm
+    real(dp), dimension(numTotal), intent(in) :: phi
+    real(dp), dimension(3,numTotal), intent(inout) :: dPhidxi
+    integer(c_int) :: method
+    method = FCP_GRAD_GAUSS
+    if (lstsq) method = FCP_GRAD_LSQ
+    if (lstsq_dm) method = FCP_GRAD_LSQ_DM
+    call put(FCP_F_S0, phi, numTotal)
+    call fcp_check(fcp_grad(ctx, method, FCP_F_S0, FCP_F_G0, 1_c_int), 'fcp_grad')
+    call get(FCP_F_G0, dPhidxi, 3*numTotal)
+  end subroutine
+
+  subroutine create_lsq_grad_matrix()   ! gradients.f90:72-101
+    use gradients, only: lstsq, lstsq_dm
+    if (lstsq) call fcp_check(fcp_create_lsq_grad_matrix(ctx, FCP_GRAD_LSQ), 'fcp_create_lsq_grad_matrix')
+    if (lstsq_dm) call fcp_check(fcp_create_lsq_grad_matrix(ctx, FCP_GRAD_LSQ_DM), 'fcp_create_lsq_grad_matrix')
+  end subroutine
+
+  ! ---- laplacian(mu,phi): fills the module's a(:) and su(:)   fvImplicit/laplacian.f90 ------------------------------------
+  subroutine laplacian(mu, phi)
+    real(dp), dimension(numCells), intent(in) :: mu
+    real(dp), dimension(numTotal), intent(in) :: phi
+    call put(FCP_F_S0, mu, numCells)
+    call put(FCP_F_S1, phi, numTotal)
+    call put(FCP_F_SU, su, numCells)
+    call fcp_check(fcp_laplacian(ctx, FCP_F_S0, FCP_F_S1), 'fcp_laplacian')
+    call get(FCP_F_A, a, nnz)
+    call get(FCP_F_SU, su, numCells)
+  end subroutine
+
+  ! ---- gradp_and_sources(p): fills su, sv, sw, dPdxi   Pressure/nablap.f90:19 ------------------------------------------------
+  subroutine gradp_and_sources(p_)
+    use nablap, only: pscheme
+    real(dp), dimension(numTotal), intent(inout) :: p_
+    integer(c_int) :: ps
+    ps = FCP_PSCHEME_LINEAR
+    if (trim(pscheme) == 'central') ps = FCP_PSCHEME_CENTRAL
+    if (trim(pscheme) == 'weighted') ps = FCP_PSCHEME_WEIGHTED
+    call put(FCP_F_P, p_, numTotal)
+    call put(FCP_F_APU, apu, numCells)
+    call put(FCP_F_DPDXI, dPdxi, 3*numTotal)
+    call fcp_check(fcp_gradp_and_sources(ctx, ps, FCP_F_P), 'fcp_gradp_and_sources')
+    call get(FCP_F_P, p_, numTotal)
+    call get(FCP_F_SU, su, numCells); call get(FCP_F_SV, sv, numCells); call get(FCP_F_SW, sw, numCells)
+    call get(FCP_F_DPDXI, dPdxi, 3*numTotal)
+  end subroutine
+
+  ! ---- calcp_simple(): no arguments, everything through modules   Pressure/calcp_simple.f90 --------------------------------
+  subroutine calcp_simple()
+    use pressure, only: urfP, lSolverP, maxiterP, tolAbsP, tolRelP
+    use nablap, only: pscheme
+    type(fcp_simple_params) :: prm
+    type(fcp_report) :: rep(8)
+    character(kind=c_char) :: line(256)
+    integer :: ipcorr, i
+    call put(FCP_F_U, u, numTotal); call put(FCP_F_V, v, numTotal); call put(FCP_F_W, w, numTotal)
+    call put(FCP_F_P, p, numTotal); call put(FCP_F_PP, pp, numTotal); call put(FCP_F_DEN, den, numTotal)
+    call put(FCP_F_APU, apu, numCells); call put(FCP_F_APV, apv, numCells); call put(FCP_F_APW, apw, numCells)
+    call put(FCP_F_DPDXI, dPdxi, 3*numTotal)
+    call put(FCP_F_FLMASS, flmass, numFaces)        ! inlet fluxes are prescribed by the host
+    prm%solver = solver_id(lSolverP); prm%maxiter = maxiterP
+    prm%tol_abs = tolAbsP; prm%tol_rel = tolRelP; prm%urfp = urfP
+    prm%npcor = npcor; prm%pRefCell = pRefCell
+    prm%pscheme = FCP_PSCHEME_LINEAR
+    if (trim(pscheme) == 'central') prm%pscheme = FCP_PSCHEME_CENTRAL
+    if (trim(pscheme) == 'weighted') prm%pscheme = FCP_PSCHEME_WEIGHTED
+    prm%const_mflux = merge(1, 0, const_mflux); prm%flomas = flomas
+    prm%zero_pp = 0                                ! the serial tree warm-starts pp (quirk Q8)
+    call fcp_check(fcp_calcp_simple(ctx, prm, rep), 'fcp_calcp_simple')
+    do ipcorr = 1, npcor
+      call fcp_check(fcp_report_line(rep(ipcorr), 'p'//c_null_char, line, 256_c_int), 'fcp_report_line')
+      do i = 1, 256
+        if (line(i) == c_null_char) exit
+      end do
+      write(*,'(256a)') line(1:i-1)
+    end do
+    call get(FCP_F_U, u, numTotal); call get(FCP_F_V, v, numTotal); call get(FCP_F_W, w, numTotal)
+    call get(FCP_F_P, p, numTotal); call get(FCP_F_PP, pp, numTotal)
+    call get(FCP_F_FLMASS, flmass, numFaces); call get(FCP_F_DPDXI, dPdxi, 3*numTotal)
+    call get(FCP_F_SU, su, numCells); call get(FCP_F_SV, sv, numCells); call get(FCP_F_SW, sw, numCells)
+    call get(FCP_F_A, a, nnz)
+    call continuityErrors                            ! calcp_simple.f90:464 stays on the host (prints, sets resor(4))
+  end subroutine
+
+  ! ---- src-par: exchange(phi), global_sum(phi)   src-par/exchange.f90:3, src-par/global_sum_mpi.f90:4 ---------------------------
+  subroutine exchange(phi)
+    real(dp), dimension(numTotal), intent(inout) :: phi
+    call put(FCP_F_S0, phi, numTotal)
+    call fcp_check(fcp_exchange(ctx, FCP_F_S0), 'fcp_exchange')
+    call get(FCP_F_S0, phi, numTotal)
+  end subroutine
+
+  subroutine global_sum(phi)
+    real(dp), intent(inout) :: phi
+    call fcp_check(fcp_global_sum(ctx, phi), 'fcp_global_sum')
+  end subroutine
+
+end module fcp_backend

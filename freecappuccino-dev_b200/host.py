@@ -1,0 +1,134 @@
+"""Python mirror of the reference's module-level API for the hot path (same names, argument meaning and error
+behaviour as the Fortran procedures), on top of the C-ABI binding in ``lib.py``.
+
+The reference keeps its state in Fortran module globals and its procedures take few or no arguments
+(``calcp_simple`` has none, Pressure/pressure.f90:39-40).  ``Case`` plays the role of those modules: it owns the host
+arrays ``u, v, w, p, pp, den, apu, apv, apw, su, sv, sw, dPdxi, flmass, a`` (names of variables.f90 /
+sparse_matrix.f90) and the procedures below read and write them exactly like the Fortran ones do.  All arithmetic runs
+on the GPU; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import sys
+from typing import Optional
+
+import numpy as np
+
+from . import lib as L
+
+
+class Case:
+    """geometry + sparse_matrix + variables modules of one run (one mesh partition on one GPU)."""
+
+    def __init__(self, mesh, device: int = 0, out=sys.stdout):
+        self.mesh = mesh
+        self.out = out                      # unit 6: the solver report lines go here (main.f90:100)
+        self.ctx = L.Context(mesh, device)  # create_CSR_matrix happens inside (sparse_matrix.f90:86)
+        self.ia, self.ja, self.diag, self.icell_jcell_csr_index, self.jcell_icell_csr_index = self.ctx.csr_pattern()
+        self.nnz = self.ctx.nnz
+        nT, n = mesh.numTotal, mesh.numCells
+        z = lambda k: np.zeros(k)  # noqa: E731
+        self.u, self.v, self.w, self.p, self.pp = z(nT), z(nT), z(nT), z(nT), z(nT)
+        self.den = np.ones(nT)
+        self.apu, self.apv, self.apw = z(nT), z(nT), z(nT)
+        self.su, self.sv, self.sw = z(n), z(n), z(n)
+        self.dPdxi = np.zeros((nT, 3))
+        self.flmass = z(mesh.numFaces)
+        self.a = z(self.nnz)
+        # parameters (parameters.f90, Pressure/pressure.f90:28-33, nablap.f90)
+        self.pRefCell, self.npcor, self.const_mflux, self.flomas = 1, 1, False, 0.0
+        self.urfP, self.lSolverP, self.maxiterP, self.tolAbsP, self.tolRelP = 0.2, "iccg", 30, 1e-13, 0.025
+        self.pscheme = "linear"
+        self.lstsq = self.lstsq_dm = False
+
+    def close(self):
+        self.ctx.close()
+
+    # ---- csrsolve(solver, fi, rhs, res0, itr_max, tol_abs, tol_rel, chvar)   linear_solvers.f90:40-59 ----------------
+    def csrsolve(self, solver: str, fi: np.ndarray, rhs: np.ndarray, itr_max: int, tol_abs: float, tol_rel: float, chvar: str) -> float:
+        if solver not in L.SOLVER_ID:
+            raise L.FcpError(f'linear solver "{solver}" is not on the accelerated path')
+        c = self.ctx
+        c.upload("A", self.a)
+        c.upload("S0", fi)
+        c.upload("S1", rhs)
+        rep = c.csrsolve(solver, "S0", "S1", itr_max, tol_abs, tol_rel)
+        fi[: self.mesh.numCells] = c.download("S0", self.mesh.numCells)
+        print(L.report_line(rep, chvar), file=self.out)
+        self.last_report = rep
+        return rep.resor                    # the `res0` dummy returns the normalised initial residual (:340)
+
+    # ---- grad(phi, dPhidxi) / grad_gauss(u, dudxi)   gradients.f90:23-27, :1607 ------------------------------------------
+    def create_lsq_grad_matrix(self):
+        if self.lstsq:
+            self.ctx.create_lsq_grad_matrix(L.GRAD_LSQ)
+        if self.lstsq_dm:
+            self.ctx.create_lsq_grad_matrix(L.GRAD_LSQ_DM)
+
+    def grad(self, phi: np.ndarray, dPhidxi: np.ndarray):
+        method = L.GRAD_LSQ if self.lstsq else L.GRAD_LSQ_DM if self.lstsq_dm else L.GRAD_GAUSS
+        self.ctx.upload("S0", phi)
+        self.ctx.grad(method, "S0", "G0")
+        dPhidxi[...] = self.ctx.download("G0")
+
+    def grad_gauss(self, u: np.ndarray, dudxi: np.ndarray):
+        self.ctx.upload("S0", u)
+        self.ctx.grad(L.GRAD_GAUSS, "S0", "G0")
+        dudxi[...] = self.ctx.download("G0")
+
+    # ---- laplacian(mu, phi): fills a, accumulates into su   fvImplicit/laplacian.f90 ----------------------------------------
+    def laplacian(self, mu: np.ndarray, phi: np.ndarray):
+        c = self.ctx
+        c.upload("S0", mu)
+        c.upload("S1", phi)
+        c.upload("SU", self.su)
+        c.laplacian("S0", "S1")
+        self.a[...] = c.download("A")
+        self.su[...] = c.download("SU", self.mesh.numCells)
+
+    # ---- gradp_and_sources(p)   Pressure/nablap.f90:19 ------------------------------------------------------------------------
+    def gradp_and_sources(self, p: np.ndarray):
+        if self.pscheme not in L.PSCHEME:   # nablap.f90:106-110 stops
+            raise L.FcpError(f"unknown pscheme {self.pscheme}")
+        c = self.ctx
+        n = self.mesh.numCells
+        c.upload("P", p)
+        c.upload("APU", self.apu)
+        c.upload("DPDXI", self.dPdxi)
+        c.gradp_and_sources(self.pscheme, "P")
+        p[...] = c.download("P")
+        self.su[...], self.sv[...], self.sw[...] = c.download("SU", n), c.download("SV", n), c.download("SW", n)
+        self.dPdxi[...] = c.download("DPDXI")
+
+    # ---- calcp_simple()   Pressure/calcp_simple.f90 ------------------------------------------------------------------------------
+    def calcp_simple(self, zero_pp: bool = False):
+        c = self.ctx
+        n = self.mesh.numCells
+        for name in ("u", "v", "w", "p", "pp", "den", "apu", "apv", "apw"):
+            c.upload(name.upper(), getattr(self, name))
+        c.upload("DPDXI", self.dPdxi)
+        c.upload("FLMASS", self.flmass)
+        reps = c.calcp_simple(solver=self.lSolverP, maxiter=self.maxiterP, tol_abs=self.tolAbsP, tol_rel=self.tolRelP, urfp=self.urfP,
+                              npcor=self.npcor, pRefCell=self.pRefCell, pscheme=self.pscheme, const_mflux=self.const_mflux,
+                              flomas=self.flomas, zero_pp=zero_pp)
+        for r in reps:
+            print(L.report_line(r, "p"), file=self.out)
+        for name in ("u", "v", "w", "p", "pp"):
+            getattr(self, name)[...] = c.download(name.upper())
+        self.flmass[...] = c.download("FLMASS")
+        self.dPdxi[...] = c.download("DPDXI")
+        self.su[...], self.sv[...], self.sw[...] = c.download("SU", n), c.download("SV", n), c.download("SW", n)
+        self.a[...] = c.download("A")
+        return reps
+
+    # ---- src-par: exchange(phi), global_sum(x)   src-par/exchange.f90:3, global_sum_mpi.f90:4 ---------------------------------------
+    def comm_init(self, rank: int, nranks: int, unique_id: Optional[bytes]):
+        self.ctx.comm_init(rank, nranks, unique_id, self.mesh.peer_rank)
+
+    def exchange(self, phi: np.ndarray):
+        self.ctx.upload("S0", phi)
+        self.ctx.exchange("S0")
+        phi[...] = self.ctx.download("S0")
+
+    def global_sum(self, x: float) -> float:
+        return self.ctx.global_sum(x)

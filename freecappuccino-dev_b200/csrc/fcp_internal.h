@@ -56,6 +56,7 @@ struct SellPattern {
   int64_t nnz_ext = 0;  // nnz + halo entries
   int64_t nnzp = 0;     // padded SELL entries
   int32_t nslices = 0;
+  int32_t tile_cap = 0;  // max number of padded entries in a tile of 8 slices (256 rows): stage size of the TMA SpMV
   // host copies (kept: csr pattern queries, conversions)
   std::vector<int32_t> h_ia, h_ja, h_diag;     // local CSR, 1-based (the reference's ia, ja, diag)
   // device

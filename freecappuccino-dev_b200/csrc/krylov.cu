@@ -5,6 +5,9 @@
 // Arithmetic order per row and per reduction is fixed (fcp_internal.h), no FMA contraction (-fmad=false), so the
 // iterates are bitwise those of the CPU restatement in its TREE summation mode.
 #include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include "fcp_internal.h"
 #include "reduce.cuh"
 namespace cg = cooperative_groups;
@@ -75,7 +78,7 @@ __device__ __forceinline__ double sell_row_sum(const SellView &m, const double *
   return s;
 }
 
-#define FCP_ROW_LOOP(r, n)                                                                        \
+#define FCP_ROW_LOOP(r, n)                                                                       \
   for (int j__ = 0; j__ < FCP_IPT; ++j__)                                                         \
     for (int32_t r = (int32_t)((int64_t)blockIdx.x * FCP_CHUNK + j__ * FCP_TPB + threadIdx.x), once__ = 1; \
          once__ && r < (n); once__ = 0)
@@ -223,6 +226,23 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__re
                                                     const double *__restrict__ zk, double *__restrict__ pk, const KrylovScalars *sc) {
   if (sc->done) return;
   const double bet = sc->bet;
+  const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
+  if (base + (FCP_IPT - 1) * FCP_TPB < n) {
+    // full chunk: all loads of the thread's 8 rows are issued before the first use (memory-level parallelism)
+    double z_[FCP_IPT], d_[FCP_IPT], p_[FCP_IPT];
+#pragma unroll
+    for (int j = 0; j < FCP_IPT; ++j) {
+      const int64_t r = base + j * FCP_TPB;
+      if (JACOBI) { z_[j] = res[r]; d_[j] = adiag[r]; } else { z_[j] = zk[r]; d_[j] = 1.0; }
+      p_[j] = pk[r];
+    }
+#pragma unroll
+    for (int j = 0; j < FCP_IPT; ++j) {
+      const double z = JACOBI ? (z_[j] / d_[j]) : z_[j];
+      pk[base + j * FCP_TPB] = z + bet * p_[j];
+    }
+    return;
+  }
   FCP_ROW_LOOP(r, n) {
     const double z = JACOBI ? (res[r] / adiag[r]) : zk[r];
     pk[r] = z + bet * pk[r];
@@ -246,6 +266,205 @@ __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, con
   finish_reduce<NS>(s, ra);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_spmv_dot_pipe: software-pipelined load/use SpMV.  A thread walks its 8 rows (stride 256); while the values and the
+// x gathers of row j are in flight it already fetches the column indices of row j+1, so each row costs ONE memory
+// round trip (indices of the next row, values and gathers of this row all overlap) instead of index -> gather chains.
+// Register window of W entries per row; longer rows (polyhedral cells beyond W neighbours) finish in a plain loop.
+// ---------------------------------------------------------------------------------------------
+#ifndef FCP_PIPE_MINB
+#define FCP_PIPE_MINB 4
+#endif
+template <int NS, bool SQ, int W>
+__global__ void __launch_bounds__(FCP_TPB, FCP_PIPE_MINB) k_spmv_dot_pipe(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
+                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra) {
+  if (sc->done) return;
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
+  if (base + (FCP_IPT - 1) * FCP_TPB < n) {
+    const int lane = threadIdx.x & 31;
+    int64_t pos = __ldg(&m.slptr[base >> 5]) + lane;      // SELL position of the current row's first entry
+    int32_t len = __ldg(&m.rinfo[base]) & 0xffff;
+    int32_t c[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) c[k] = (k < len) ? __ldcs(m.ja + pos + (int64_t)k * 32) : 0;
+#pragma unroll 1
+    for (int j = 0; j < FCP_IPT; ++j) {
+      const int64_t r = base + (int64_t)j * FCP_TPB;
+      // this row: values and gathers (all independent)
+      double av[W], xv[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) av[k] = (k < len) ? __ldcs(m.a + pos + (int64_t)k * 32) : 0.0;
+#pragma unroll
+      for (int k = 0; k < W; ++k) xv[k] = (k < len) ? __ldg(x + c[k]) : 0.0;
+      const double vv = v1[r];
+      // next row: meta data and column indices
+      int64_t npos = 0;
+      int32_t nlen = 0;
+      int32_t cn[W];
+      if (j + 1 < FCP_IPT) {
+        const int64_t rn = r + FCP_TPB;
+        npos = __ldg(&m.slptr[rn >> 5]) + lane;
+        nlen = __ldg(&m.rinfo[rn]) & 0xffff;
+#pragma unroll
+        for (int k = 0; k < W; ++k) cn[k] = (k < nlen) ? __ldcs(m.ja + npos + (int64_t)k * 32) : 0;
+      }
+      double yr = 0.0;
+#pragma unroll
+      for (int k = 0; k < W; ++k)
+        if (k < len) yr = yr + av[k] * xv[k];
+      for (int32_t k = W; k < len; ++k) yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * __ldg(x + __ldcs(m.ja + pos + (int64_t)k * 32));
+      y[r] = yr;
+      s[0] = s[0] + vv * yr;
+      if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
+      pos = npos;
+      len = nlen;
+#pragma unroll
+      for (int k = 0; k < W; ++k) c[k] = cn[k];
+    }
+  } else {
+    FCP_ROW_LOOP(r, n) {
+      const double yr = sell_row_sum<false>(m, x, r, 0.0);
+      y[r] = yr;
+      s[0] = s[0] + v1[r] * yr;
+      if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
+    }
+  }
+  finish_reduce<NS>(s, ra);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_spmv_dot_tma: the same SpMV + dot with the matrix stream (93 % of the bytes) moved by the TMA engine.
+// A CTA owns one chunk = 8 tiles of 256 rows (8 SELL slices each).  The values and column indices of a tile are two
+// contiguous, 256-/128-byte aligned blocks, fetched with cp.async.bulk into a ring of shared-memory stages that
+// complete on an mbarrier (expect_tx); threads read them back with conflict-free LDS (lane l -> word l) and only the
+// x gathers go through LSU/L1.  No registers or LSU request slots are tied up by the matrix stream, so many more bytes
+// are in flight per SM than the load/use version can keep.  Arithmetic order per row is unchanged (CSR order).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+#define FCP_TILE_ROWS FCP_TPB                      // 256 rows = 8 slices per tile
+#define FCP_TILES (FCP_CHUNK / FCP_TILE_ROWS)      // 8 tiles per chunk
+#define FCP_MAX_STAGES 4
+
+template <int NS>
+__device__ __forceinline__ void finish_reduce_part(double (&s)[NS], const RedArgs &ra, int part, int nparts) {
+  double total[NS];
+  if (fcp_grid_reduce_part<NS>(s, ra.partials, ra.stride, ra.counter, part, nparts, total)) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) ra.sc->red[k] = total[k];
+      if (ra.fuse) krylov_epilogue(ra.epi, ra.sc);
+    }
+  }
+}
+
+// Persistent CTAs: CTA b owns chunks b, b + gridDim.x, ... and keeps ONE pipeline running across its chunks (the ring is
+// refilled for the next chunk while the current one is still being consumed), so the start-up latency (slice pointers,
+// first TMA round trip) is paid once per CTA instead of once per chunk.
+template <int NS, bool SQ>
+__global__ void __launch_bounds__(FCP_TPB) k_spmv_dot_tma(int32_t n, int32_t nslices, SellView m, const double *__restrict__ x, double *__restrict__ y,
+                                                           const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int cap, int nstages) {
+  if (sc->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [nstages][cap] int32 column indices | barriers | slice pointers of the current and the next chunk
+  int32_t *sj = reinterpret_cast<int32_t *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)nstages * cap * 4);
+  int64_t(*soff)[FCP_CHUNK / 32 + 1] = reinterpret_cast<int64_t(*)[FCP_CHUNK / 32 + 1]>(full + FCP_MAX_STAGES);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nchunks = (int)(((int64_t)n + FCP_CHUNK - 1) / FCP_CHUNK);
+  const int my_chunks = ((int)blockIdx.x < nchunks) ? (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total_tiles = my_chunks * FCP_TILES;
+  if (my_chunks == 0) return;
+  if (tid <= FCP_CHUNK / 32) soff[0][tid] = m.slptr[min((int)blockIdx.x * (FCP_CHUNK / 32) + tid, nslices)];
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  int32_t ri_next = ((int64_t)blockIdx.x * FCP_CHUNK + tid < n) ? __ldg(&m.rinfo[(int64_t)blockIdx.x * FCP_CHUNK + tid]) : 0;
+  __syncthreads();
+  auto issue = [&](int q) {   // thread 0 only
+    const int st = q % nstages, ci = q >> 3, t = q & 7;
+    const int64_t b = soff[ci & 1][t * 8], e = soff[ci & 1][t * 8 + 8];
+    const uint32_t cnt = (uint32_t)(e - b);
+    if (cnt == 0) { mbar_expect_tx(&full[st], 0); return; }
+    mbar_expect_tx(&full[st], cnt * 4u);
+    tma_bulk_g2s(sj + (size_t)st * cap, m.ja + b, cnt * 4u, &full[st]);
+  };
+  if (tid == 0)
+    for (int q = 0; q < nstages - 1 && q < total_tiles; ++q) issue(q);
+
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < total_tiles; ++q) {
+    const int st = q % nstages, ci = q >> 3, t = q & 7;
+    const int chunk = (int)blockIdx.x + ci * (int)gridDim.x;
+    if (t == 0 && ci + 1 < my_chunks && tid <= FCP_CHUNK / 32)   // slice pointers of the next chunk (visible after this tile's barrier)
+      soff[(ci + 1) & 1][tid] = m.slptr[min((chunk + (int)gridDim.x) * (FCP_CHUNK / 32) + tid, nslices)];
+    if (tid == 0 && q + nstages - 1 < total_tiles) issue(q + nstages - 1);   // its stage was released by the barrier that ended tile q-1
+    const int64_t r = (int64_t)chunk * FCP_CHUNK + (int64_t)t * FCP_TILE_ROWS + tid;
+    const bool live = r < n;
+    const double vv = live ? v1[r] : 0.0;
+    const int32_t len = ri_next & 0xffff;
+    {
+      const int qn = q + 1, cn = (int)blockIdx.x + (qn >> 3) * (int)gridDim.x;
+      const int64_t rn = (int64_t)cn * FCP_CHUNK + (int64_t)(qn & 7) * FCP_TILE_ROWS + tid;
+      ri_next = (qn < total_tiles && rn < n) ? __ldg(&m.rinfo[rn]) : 0;
+    }
+    const int32_t lbase = (int32_t)(soff[ci & 1][t * 8 + warp] - soff[ci & 1][t * 8]) + lane;
+    const double *__restrict__ ap = m.a + soff[ci & 1][t * 8 + warp] + lane;   // values: plain coalesced loads, independent of the indices
+    const int32_t *jp = sj + (size_t)st * cap + lbase;
+    mbar_wait(&full[st], (uint32_t)((q / nstages) & 1));
+    double yr = 0.0;
+#pragma unroll 8
+    for (int32_t k = 0; k < len; ++k) {
+      const double av = __ldcs(ap + (int64_t)k * 32);
+      const int32_t c = jp[k * 32];
+      yr = yr + av * __ldg(x + c);
+    }
+    if (live) {
+      y[r] = yr;
+      s[0] = s[0] + vv * yr;
+      if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
+    }
+    __syncthreads();   // every thread is done with stage st
+    if (t == FCP_TILES - 1) {
+      finish_reduce_part<NS>(s, ra, chunk, nchunks);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) s[k] = 0.0;
+    }
+  }
+}
+
 // fi += alf*pk ; res -= alf*zk ; sums: |res| , [res*(res/adiag)] , [|adiag*fi|]      (:321-340)
 template <bool JACOBI>
 __global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__restrict__ fi, double *__restrict__ res, const double *__restrict__ pk,
@@ -255,15 +474,41 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__rest
   const double alf = sc->alf;
   const bool first = (sc->iters == 0);
   double s[3] = {0.0, 0.0, 0.0};
-  FCP_ROW_LOOP(r, n) {
-    const double f = fi[r] + alf * pk[r];
-    const double rr = res[r] - alf * zk[r];
-    fi[r] = f;
-    res[r] = rr;
-    s[0] = s[0] + fabs(rr);
-    const double ad = adiag[r];
-    if (JACOBI) s[1] = s[1] + rr * (rr / ad);
-    if (first) s[2] = s[2] + fabs(ad * f);
+  const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
+  if (base + (FCP_IPT - 1) * FCP_TPB < n) {
+    // full chunk, two halves of 4 rows: 20 independent loads in flight per thread
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      double f_[4], r_[4], p_[4], z_[4], d_[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t r = base + (h * 4 + j) * FCP_TPB;
+        f_[j] = fi[r]; r_[j] = res[r]; p_[j] = pk[r]; z_[j] = zk[r];
+        d_[j] = (JACOBI || first) ? adiag[r] : 1.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t r = base + (h * 4 + j) * FCP_TPB;
+        const double f = f_[j] + alf * p_[j];
+        const double rr = r_[j] - alf * z_[j];
+        fi[r] = f;
+        res[r] = rr;
+        s[0] = s[0] + fabs(rr);
+        if (JACOBI) s[1] = s[1] + rr * (rr / d_[j]);
+        if (first) s[2] = s[2] + fabs(d_[j] * f);
+      }
+    }
+  } else {
+    FCP_ROW_LOOP(r, n) {
+      const double f = fi[r] + alf * pk[r];
+      const double rr = res[r] - alf * zk[r];
+      fi[r] = f;
+      res[r] = rr;
+      s[0] = s[0] + fabs(rr);
+      const double ad = adiag[r];
+      if (JACOBI) s[1] = s[1] + rr * (rr / ad);
+      if (first) s[2] = s[2] + fabs(ad * f);
+    }
   }
   finish_reduce<3>(s, ra);
 }
@@ -482,6 +727,59 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
   return FCP_OK;
 }
 
+// opt-in dynamic shared memory limit of the TMA kernels: one process-wide value, only ever raised
+static int tma_smem_limit(size_t smem) {
+  static size_t configured = 0;
+  if (smem <= configured) return FCP_OK;
+  FCP_CUDA(cudaFuncSetAttribute(k_spmv_dot_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FCP_CUDA(cudaFuncSetAttribute(k_spmv_dot_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  configured = smem;
+  return FCP_OK;
+}
+
+// SpMV + dot dispatch: TMA-staged kernel when a tile (256 rows) of the pattern fits the shared-memory ring, else the
+// load/use kernel.  FCP_SPMV=ldg forces the latter (A/B measurements).
+template <int NS, bool SQ>
+static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double *x, double *y, const double *v1, const KrylovScalars *sc,
+                           const RedArgs &ra, cudaStream_t st) {
+  const int grid = fcp_nchunks(p.n);
+  if (!grid) return FCP_OK;
+  static int mode = -1;   // 0 ldg, 1 tma
+  static int stages_env = 0;
+  if (mode < 0) {
+    const char *e = getenv("FCP_SPMV");
+    mode = (e && !strcmp(e, "ldg")) ? 0 : (e && !strcmp(e, "tma")) ? 1 : 2;
+    const char *g = getenv("FCP_SPMV_STAGES");
+    stages_env = g ? atoi(g) : 0;
+  }
+  const size_t stage_bytes = (size_t)p.tile_cap * 4;
+  const size_t extra = FCP_MAX_STAGES * sizeof(uint64_t) + 2 * (FCP_CHUNK / 32 + 1) * sizeof(int64_t) + 128;
+  int nst = stages_env ? stages_env : (int)std::min<size_t>(FCP_MAX_STAGES, (size_t)(24 * 1024) / std::max<size_t>(stage_bytes, 1));
+  nst = std::min(nst, FCP_MAX_STAGES);
+  if (mode == 1 && p.tile_cap > 0 && nst >= 2) {
+    const size_t smem = nst * stage_bytes + extra;
+    FCP_TRY(tma_smem_limit(smem));
+    static int nsm = 0;
+    if (!nsm) {
+      int dev = 0;
+      FCP_CUDA(cudaGetDevice(&dev));
+      FCP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int occ = 0;
+    FCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_dot_tma<NS, SQ>, FCP_TPB, smem));
+    const int pgrid = std::min(grid, std::max(1, occ) * nsm);
+    k_spmv_dot_tma<NS, SQ><<<pgrid, FCP_TPB, smem, st>>>(p.n, p.nslices, m, x, y, v1, sc, ra, p.tile_cap, nst);
+    FCP_CHECK_LAUNCH();
+  } else if (mode == 2) {
+    if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra);
+    else k_spmv_dot_pipe<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra);
+  } else {
+    k_spmv_dot<NS, SQ><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra);
+  }
+  FCP_LAUNCHED();
+  return FCP_OK;
+}
+
 // poll the device scalars; returns done flag
 static int fetch_scalars(KrylovWS &ws, cudaStream_t st) {
   FCP_CUDA(cudaMemcpyAsync(ws.h_sc, ws.sc, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, st));
@@ -521,7 +819,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
         if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc), FCP_LAUNCHED()));
         FCP_TRY(L.halo(ws.pk));
-        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, (k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK)), FCP_LAUNCHED()));
+        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st))));
         FCP_TRY(L.post(EPI_PKAPK, 1));
         if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
         FCP_TRY(L.post(EPI_CG_UPDATE, 3));
@@ -546,7 +844,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
           FCP_TRY(L.post(EPI_SK, 1));
           if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc), FCP_LAUNCHED()));
           FCP_TRY(L.halo(ws.pk));
-          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, (k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK)), FCP_LAUNCHED()));
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st))));
           FCP_TRY(L.post(EPI_PKAPK, 1));
           if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
           FCP_TRY(L.post(EPI_CG_UPDATE, 3));
@@ -576,12 +874,12 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
           if (grid) { k_bicg_pk<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.uk, ws.pk, ws.sc); FCP_LAUNCHED(); }
           FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.pk, ws.zk, ws.sc, st)));
           FCP_TRY(L.halo(ws.zk));
-          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, (k_spmv_dot<1, false><<<grid, FCP_TPB, 0, st>>>(n, m, ws.zk, ws.uk, ws.reso, ws.sc, L.red(EPI_UKRESO)), FCP_LAUNCHED()));
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.zk, ws.uk, ws.reso, ws.sc, L.red(EPI_UKRESO), st))));
           FCP_TRY(L.post(EPI_UKRESO, 1));
           if (grid) { k_bicg_half<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.zk, ws.uk, ws.sc); FCP_LAUNCHED(); }
           FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st)));
           FCP_TRY(L.halo(ws.zk));
-          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, (k_spmv_dot<2, true><<<grid, FCP_TPB, 0, st>>>(n, m, ws.zk, ws.vk, ws.res, ws.sc, L.red(EPI_VK)), FCP_LAUNCHED()));
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<2, true>(p, m, ws.zk, ws.vk, ws.res, ws.sc, L.red(EPI_VK), st))));
           FCP_TRY(L.post(EPI_VK, 2));
           if (grid) { k_bicg_update<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.zk, ws.vk, ws.reso, ws.adiag, ws.sc, L.red(EPI_BICG_UPDATE)); FCP_LAUNCHED(); }
           FCP_TRY(L.post(EPI_BICG_UPDATE, 3));

@@ -72,6 +72,8 @@ int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, 
     slptr[s + 1] = slptr[s] + (int64_t)w * 32;
   }
   p.nnzp = slptr[p.nslices];
+  p.tile_cap = 0;
+  for (int32_t s = 0; s < p.nslices; s += 8) p.tile_cap = std::max<int64_t>(p.tile_cap, slptr[std::min(s + 8, p.nslices)] - slptr[s]);
   if (p.nnzp >= (int64_t)2147483647) {
     fcp_set_error("sell_from_csr: padded nnz %lld exceeds int32 positions", (long long)p.nnzp);
     return FCP_EINVAL;

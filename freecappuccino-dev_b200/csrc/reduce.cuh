@@ -28,21 +28,22 @@ __device__ __forceinline__ void fcp_block_tree(double (&s)[NS], double (&out)[NS
   __syncthreads();   // ws may be reused by a second call
 }
 
-// Grid-level stage: every CTA stores its chunk partials, the last CTA to arrive (ticket counter) adds them in the
+// Grid-level stage (a persistent CTA calls it once per chunk it owns: part = chunk index, nparts = number of chunks):
+// every CTA stores its chunk partials, the last CTA to arrive (ticket counter) adds them in the
 // fixed order (thread t takes partials t, t+256, ...; same block tree) and returns true in ALL its threads with the
 // totals valid in thread 0.  partials: [NS][stride].  The counter is reset for the next kernel.
 template <int NS>
-__device__ __forceinline__ bool fcp_grid_reduce(double (&s)[NS], double *partials, int stride, unsigned int *counter,
-                                                double (&total)[NS]) {
+__device__ __forceinline__ bool fcp_grid_reduce_part(double (&s)[NS], double *partials, int stride, unsigned int *counter, int part, int nparts,
+                                                     double (&total)[NS]) {
   double blk[NS];
   fcp_block_tree<NS>(s, blk);
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < NS; ++k) partials[(size_t)k * stride + blockIdx.x] = blk[k];
+    for (int k = 0; k < NS; ++k) partials[(size_t)k * stride + part] = blk[k];
     __threadfence();
     unsigned int ticket = atomicAdd(counter, 1u);
-    is_last = (ticket == gridDim.x - 1);
+    is_last = (ticket == (unsigned int)nparts - 1u);
   }
   __syncthreads();
   if (!is_last) return false;
@@ -51,10 +52,15 @@ __device__ __forceinline__ bool fcp_grid_reduce(double (&s)[NS], double *partial
 #pragma unroll
   for (int k = 0; k < NS; ++k) {
     double t = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += FCP_TPB) t = t + __ldcg(&partials[(size_t)k * stride + i]);
+    for (int i = threadIdx.x; i < nparts; i += FCP_TPB) t = t + __ldcg(&partials[(size_t)k * stride + i]);
     acc[k] = t;
   }
   fcp_block_tree<NS>(acc, total);
   if (threadIdx.x == 0) *counter = 0u;
   return true;
+}
+// one chunk per CTA: part = blockIdx.x, nparts = gridDim.x
+template <int NS>
+__device__ __forceinline__ bool fcp_grid_reduce(double (&s)[NS], double *partials, int stride, unsigned int *counter, double (&total)[NS]) {
+  return fcp_grid_reduce_part<NS>(s, partials, stride, counter, (int)blockIdx.x, (int)gridDim.x, total);
 }

@@ -48,7 +48,7 @@ static int field_count(const fcp_ctx *c, int field, int64_t *count) {
   if (field < 0 || field >= FCP_F_COUNT) { fcp_set_error("bad field id %d", field); return FCP_EINVAL; }
   if (field >= FCP_F_DUDXI && field <= FCP_F_G1) *count = 3 * (int64_t)c->nT;
   else if (field == FCP_F_FLMASS) *count = c->nF;
-  else if (field == FCP_F_A) *count = c->pat.nnzp;      // device storage is SELL; host-visible count is nnz
+  else if (field == FCP_F_A || field == FCP_F_H) *count = c->pat.nnzp;   // device storage is SELL; host-visible count is nnz
   else if (field == FCP_F_APR) *count = c->npro;
   else *count = c->nT;
   return FCP_OK;
@@ -210,6 +210,7 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
       }
     }
     c->fl.nnzp = np;
+    for (int32_t i = 0; i < n; ++i) c->max_cell_faces = std::max(c->max_cell_faces, cnt[i]);
     FCP_TRY(dev_upload(&c->fl.slptr, fsl.data(), fsl.size()));
     FCP_TRY(dev_upload(&c->fl.len, cnt.data(), cnt.size()));
     FCP_TRY(dev_upload(&c->fl.ent, ent.data(), ent.size()));
@@ -267,8 +268,8 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   cudaFree(c->kPN); cudaFree(c->kNP);
   cudaFree(c->fl.slptr); cudaFree(c->fl.len); cudaFree(c->fl.ent); cudaFree(c->fl.other); cudaFree(c->fl.slot);
   for (int i = 0; i < FCP_F_COUNT; ++i) cudaFree(c->field[i]);
-  for (int i = 0; i < 3; ++i) cudaFree(c->Dmat[i]);
-  cudaFree(c->flushbuf);
+  for (int i = 0; i < 4; ++i) cudaFree(c->Dmat[i]);
+  cudaFree(c->flushbuf); cudaFree(c->d_mmpart); cudaFree(c->d_sum);
   cudaFree(c->d_oface); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
   sell_free(c->pat);
   krylov_ws_free(c->ws);
@@ -324,7 +325,7 @@ extern "C" int fcp_field_upload(fcp_ctx *ctx, int field, const double *host, int
   FIELD(d, field);
   int64_t cap = 0;
   FCP_TRY(field_count(ctx, field, &cap));
-  if (field == FCP_F_A) {
+  if (field == FCP_F_A || field == FCP_F_H) {
     if (count != ctx->pat.nnz) { fcp_set_error("upload of a(nnz): count %lld != nnz %lld", (long long)count, (long long)ctx->pat.nnz); return FCP_EINVAL; }
     double *stage = nullptr;
     FCP_TRY(dev_alloc(&stage, (size_t)count));
@@ -351,7 +352,7 @@ extern "C" int fcp_field_download(fcp_ctx *ctx, int field, double *host, int64_t
   FIELD(d, field);
   int64_t cap = 0;
   FCP_TRY(field_count(ctx, field, &cap));
-  if (field == FCP_F_A) {
+  if (field == FCP_F_A || field == FCP_F_H) {
     if (count != ctx->pat.nnz) { fcp_set_error("download of a(nnz): count %lld != nnz %lld", (long long)count, (long long)ctx->pat.nnz); return FCP_EINVAL; }
     double *stage = nullptr;
     FCP_TRY(dev_alloc(&stage, (size_t)count));
@@ -460,7 +461,19 @@ extern "C" int fcp_report_line(const fcp_report *rep, const char *chvar, char *b
 
 extern "C" int fcp_create_lsq_grad_matrix(fcp_ctx *ctx, int method) {
   if (!ctx) return FCP_EINVAL;
-  if (method != FCP_GRAD_LSQ && method != FCP_GRAD_LSQ_DM) { fcp_set_error("create_lsq_grad_matrix: method %d is not a least-squares method", method); return FCP_EINVAL; }
+  if (method != FCP_GRAD_LSQ && method != FCP_GRAD_LSQ_DM && method != FCP_GRAD_LSQ_QR) {
+    fcp_set_error("create_lsq_grad_matrix: method %d is not a least-squares method", method);
+    return FCP_EINVAL;
+  }
+  if (method == FCP_GRAD_LSQ_QR) {
+    if (ctx->max_cell_faces > 6) {   // gradients.f90:924  m=6: D(3,6,numCells)
+      fcp_set_error("create_matrix_lsq_qr holds at most 6 faces per cell (gradients.f90:924); this mesh has a cell with %d", ctx->max_cell_faces);
+      return FCP_EINVAL;
+    }
+    if (ctx->comm) { fcp_set_error("the QR gradient has no src-par twin; single-GPU only"); return FCP_ESTATE; }
+    if (!ctx->Dmat[method]) FCP_TRY(dev_alloc(&ctx->Dmat[method], (size_t)18 * ctx->n));
+    return fvm_lsq_qr_matrix(ctx, ctx->Dmat[method]);
+  }
   if (!ctx->Dmat[method]) FCP_TRY(dev_alloc(&ctx->Dmat[method], (size_t)9 * ctx->n));
   return fvm_lsq_matrix(ctx, method == FCP_GRAD_LSQ_DM, ctx->Dmat[method]);
 }
@@ -476,10 +489,31 @@ extern "C" int fcp_grad(fcp_ctx *ctx, int method, int phi_field, int grad_field,
   else if (method == FCP_GRAD_LSQ || method == FCP_GRAD_LSQ_DM) {
     if (!ctx->Dmat[method]) { fcp_set_error("fcp_grad: call fcp_create_lsq_grad_matrix(method=%d) first", method); return FCP_ESTATE; }
     rc = fvm_grad_lsq(ctx, method == FCP_GRAD_LSQ_DM, ctx->Dmat[method], phi, g, lsq_row2_reference);
+  } else if (method == FCP_GRAD_LSQ_QR) {
+    if (!ctx->Dmat[method]) { fcp_set_error("fcp_grad: call fcp_create_lsq_grad_matrix(method=%d) first", method); return FCP_ESTATE; }
+    rc = fvm_grad_lsq_qr(ctx, ctx->Dmat[method], phi, g);
   } else { fcp_set_error("fcp_grad: unknown method %d", method); return FCP_EINVAL; }
   FCP_TRY(rc);
   if (ctx->comm) FCP_TRY(comm_exchange(ctx, g, 3));                // src-par/gradients.f90:168-170
   return FCP_OK;
+}
+
+extern "C" int fcp_slope_limiter(fcp_ctx *ctx, int limiter, int phi_field, int grad_field) {
+  if (!ctx) return FCP_EINVAL;
+  if (limiter < FCP_LIMITER_NONE || limiter > FCP_LIMITER_MULTIDIMENSIONAL) { fcp_set_error("unknown limiter %d", limiter); return FCP_EINVAL; }
+  if (grad_field < FCP_F_DUDXI || grad_field > FCP_F_G1) { fcp_set_error("fcp_slope_limiter: field %d is not a gradient field", grad_field); return FCP_EINVAL; }
+  FIELD(phi, phi_field);
+  FIELD(g, grad_field);
+  FCP_TRY(fvm_slope_limiter(ctx, limiter, phi, g));
+  if (ctx->comm && limiter != FCP_LIMITER_NONE) FCP_TRY(comm_exchange(ctx, g, 3));
+  return FCP_OK;
+}
+
+extern "C" int fcp_grad_opt(fcp_ctx *ctx, int method, int limiter, int phi_field, int grad_field) {
+  // gradients.f90:217-278; dPhidxi = 0 first (:238) -- every method below overwrites all cell entries and zeroes the
+  // boundary slots, which is the same state
+  FCP_TRY(fcp_grad(ctx, method, phi_field, grad_field, 1));
+  return fcp_slope_limiter(ctx, limiter, phi_field, grad_field);
 }
 
 extern "C" int fcp_laplacian(fcp_ctx *ctx, int mu_field, int phi_field) {
@@ -548,6 +582,13 @@ __global__ void k_correct_flux_proc(int32_t npro, const int32_t *__restrict__ pf
   flmass[f] = flmass[f] + a[aprpos[i]] * (pp[n + (f - F)] - pp[owner[f]]);
 }
 
+static int fvm_correct_flux_proc(fcp_ctx *ctx, const double *a, const double *pp, double *fl) {
+  k_correct_flux_proc<<<(ctx->npro + 255) / 256, 256, 0, ctx->stream>>>(ctx->npro, ctx->d_procface, ctx->d_aprpos, ctx->owner, ctx->n, ctx->F, a, pp, fl);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
 extern "C" int fcp_correct_simple(fcp_ctx *ctx, int pscheme, double urfp, int32_t pRefCell) {
   if (!ctx) return FCP_EINVAL;
   // multi-GPU: pRefCell is the LOCAL index on the rank that owns the reference cell and <= 0 on every other rank
@@ -556,11 +597,7 @@ extern "C" int fcp_correct_simple(fcp_ctx *ctx, int pscheme, double urfp, int32_
   FIELD(apu, FCP_F_APU); FIELD(apv, FCP_F_APV); FIELD(apw, FCP_F_APW); FIELD(a, FCP_F_A); FIELD(fl, FCP_F_FLMASS);
   if (ctx->comm) FCP_TRY(comm_exchange(ctx, pp, 1));
   FCP_TRY(fvm_correct_flux(ctx, a, pp, fl));                                   // calcp_simple.f90:331-341
-  if (ctx->npro) {
-    k_correct_flux_proc<<<(ctx->npro + 255) / 256, 256, 0, ctx->stream>>>(ctx->npro, ctx->d_procface, ctx->d_aprpos, ctx->owner, ctx->n, ctx->F, a, pp, fl);
-    FCP_LAUNCHED();
-    FCP_CHECK_LAUNCH();
-  }
+  if (ctx->npro) FCP_TRY(fvm_correct_flux_proc(ctx, a, pp, fl));
   if (ctx->has_pressure_patch) FCP_TRY(fvm_correct_pressure_bnd(ctx, den, apu, pp, u, v, w, fl));   // :345-391
   const double *ppref = ctx->has_pressure_patch ? nullptr : pp + (pRefCell - 1);                    // :399-407
   if (ctx->comm && !ctx->has_pressure_patch) {
@@ -590,6 +627,62 @@ extern "C" int fcp_calcp_simple(fcp_ctx *ctx, const fcp_simple_params *prm, fcp_
     FCP_TRY(fcp_csrsolve(ctx, prm->solver, FCP_F_PP, FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel, rep ? &rep[ipcorr - 1] : nullptr));
     FCP_TRY(fcp_correct_simple(ctx, prm->pscheme, prm->urfp, prm->pRefCell));
     if (ipcorr != prm->npcor) FCP_TRY(fcp_nonorth_corrector(ctx));            // :433-455
+  }
+  return FCP_OK;
+}
+
+// calcp_piso   Pressure/calcp_piso.f90:81-489
+extern "C" int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_report *rep) {
+  if (!ctx || !prm) return FCP_EINVAL;
+  if (prm->ncorr < 1 || prm->npcor < 1) { fcp_set_error("calcp_piso: ncorr and npcor must be >= 1"); return FCP_EINVAL; }
+  if (prm->pscheme < 0 || prm->pscheme > 2) { fcp_set_error("unknown pscheme %d", prm->pscheme); return FCP_EINVAL; }
+  for (int32_t ib = 0; ib < ctx->nb; ++ib)
+    if (ctx->bctype[ib] == FCP_BC_PERIODIC) { fcp_set_error("calcp_piso: periodic patches (calcp_piso.f90:242-295) are not supported yet"); return FCP_ESTATE; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(den, FCP_F_DEN); FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(p, FCP_F_P); FIELD(pp, FCP_F_PP);
+  FIELD(g, FCP_F_DPDXI); FIELD(apu, FCP_F_APU); FIELD(apv, FCP_F_APV); FIELD(apw, FCP_F_APW); FIELD(a, FCP_F_A); FIELD(h, FCP_F_H);
+  FIELD(su, FCP_F_SU); FIELD(sv, FCP_F_SV); FIELD(sw, FCP_F_SW); FIELD(fl, FCP_F_FLMASS);
+  FIELD(rU, FCP_F_RU); FIELD(rV, FCP_F_RV); FIELD(rW, FCP_F_RW);
+  if (!ctx->d_sum) FCP_TRY(dev_alloc(&ctx->d_sum, 4));
+  double ncells = (double)ctx->n;
+  if (ctx->comm) FCP_TRY(fcp_global_sum(ctx, &ncells));
+  FCP_CUDA(cudaMemcpyAsync(h, a, sizeof(double) * (size_t)ctx->pat.nnzp, cudaMemcpyDeviceToDevice, ctx->stream));   // :81  h = a
+  for (int icorr = 1; icorr <= prm->ncorr; ++icorr) {
+    if (ctx->comm) { FCP_TRY(comm_exchange(ctx, u, 1)); FCP_TRY(comm_exchange(ctx, v, 1)); FCP_TRY(comm_exchange(ctx, w, 1)); }
+    FCP_TRY(fvm_piso_hbya(ctx, h, rU, rV, rW, apu, apv, apw, u, v, w, su, sv, sw));                                 // :102-129
+    if (!prm->const_mflux && ctx->has_outlet) {                                                                      // :186 (the outlet faces do not read a or su: order is free)
+      FCP_TRY(ensure_outlet_list(ctx));
+      FCP_TRY(fvm_adjust_mass_flow(ctx, ctx->nout, ctx->d_oface, den, u, v, w, fl, prm->flomas));
+    }
+    if (ctx->comm) {
+      double *sc[] = {den, u, v, w, p, apu};
+      for (double *x : sc) FCP_TRY(comm_exchange(ctx, x, 1));
+      FCP_TRY(comm_exchange(ctx, g, 3));
+    }
+    AsmArgs args{den, u, v, w, p, g, apu, pp, u, v, w, a, su, fl};
+    FCP_TRY(fvm_assemble_pcorr(ctx, args, true));                                                                    // :140-297
+    for (int ipcorr = 1; ipcorr <= prm->npcor; ++ipcorr) {                                                           // :308
+      FCP_TRY(fcp_csrsolve(ctx, prm->solver, FCP_F_PP, FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel,
+                           rep ? &rep[(icorr - 1) * prm->npcor + (ipcorr - 1)] : nullptr));
+      FCP_TRY(fvm_sum(ctx, pp, ctx->d_sum));                                                                         // :330
+      if (ctx->comm) FCP_TRY(comm_allgather_sum(ctx->comm, ctx->d_sum, 1, ctx->stream));
+      FCP_TRY(fvm_piso_pupdate(ctx, ncells, prm->urfp, ctx->d_sum, pp, p));                                          // :333
+      if (ipcorr != prm->npcor) {
+        // :336-344 bpres + grad_gauss twice == the fused two-stage kernel with linear interpolation and no sources
+        if (ctx->comm) FCP_TRY(comm_exchange(ctx, p, 1));
+        FCP_TRY(fvm_gradp(ctx, FCP_PSCHEME_LINEAR, p, apu, nullptr, nullptr, nullptr, g, nullptr, nullptr));
+        if (ctx->comm) { FCP_TRY(comm_exchange(ctx, g, 3)); }
+        FCP_TRY(fvm_piso_fluxmc(ctx, den, apu, g, su));                                                              // :349-364
+      } else {
+        // last pass: the gradient of :336-344 is recomputed bit-identically by gradp_and_sources below (p unchanged)
+        if (ctx->comm) FCP_TRY(comm_exchange(ctx, p, 1));
+        FCP_TRY(fvm_correct_flux(ctx, a, p, fl));                                                                    // :377-387
+        if (ctx->npro) FCP_TRY(fvm_correct_flux_proc(ctx, a, p, fl));
+      }
+    }
+    CorrectArgs ca{u, v, w, nullptr, apu, apv, apw, 0.0, nullptr};
+    FCP_TRY(gradp_impl(ctx, prm->pscheme, p, &ca));                                                                  // :425-431, :485
+    if (ctx->has_pressure_patch) FCP_TRY(fvm_correct_pressure_bnd(ctx, den, apu, pp, u, v, w, fl));                  // :466-479
   }
   return FCP_OK;
 }

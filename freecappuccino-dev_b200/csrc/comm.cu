@@ -127,6 +127,13 @@ int comm_allgather_sum(FcpComm *c, double *d_vals, int count, cudaStream_t st) {
   return FCP_OK;
 }
 
+int comm_allreduce_minmax(FcpComm *c, double *d_mm, cudaStream_t st) {   // global_min / global_max, src-par/global_sum_mpi.f90
+  if (!c || c->nranks == 1) return FCP_OK;
+  FCP_NCCL(g_nccl.AllReduce(d_mm, d_mm, 1, ncclDouble, ncclMin, c->comm, st));
+  FCP_NCCL(g_nccl.AllReduce(d_mm + 1, d_mm + 1, 1, ncclDouble, ncclMax, c->comm, st));
+  return FCP_OK;
+}
+
 // geometry of process faces once the ghost cell centres are known: facint like geometry.f90:581-606 (variant 2),
 // Df like :648-664, with the local cell as P and the ghost cell as N (src-par/geometry.f90:826-871 fpro)
 __global__ void k_process_face_geom(int32_t npro, const int32_t *__restrict__ pface, const int32_t *__restrict__ cell, const int32_t *__restrict__ slot,
@@ -211,7 +218,7 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
 
 extern "C" int fcp_exchange(fcp_ctx *ctx, int field) {
   if (!ctx) return FCP_EINVAL;
-  if (field < 0 || field >= FCP_F_FLMASS) { fcp_set_error("fcp_exchange: field %d is not a cell field", field); return FCP_EINVAL; }
+  if (field < 0 || (field >= FCP_F_FLMASS && field <= FCP_F_H) || field >= FCP_F_COUNT) { fcp_set_error("fcp_exchange: field %d is not a cell field", field); return FCP_EINVAL; }
   void *p = nullptr;
   FCP_TRY(fcp_field_devptr(ctx, field, &p, nullptr));
   return comm_exchange(ctx, (double *)p, (field >= FCP_F_DUDXI && field <= FCP_F_G1) ? 3 : 1);

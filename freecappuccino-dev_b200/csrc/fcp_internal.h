@@ -162,7 +162,10 @@ struct fcp_ctx {
   SellPattern pat;
   FaceLists fl;
   double *field[FCP_F_COUNT] = {nullptr};
-  double *Dmat[3] = {nullptr, nullptr, nullptr};    // LSQ matrices per method (index FCP_GRAD_*)
+  double *Dmat[4] = {nullptr, nullptr, nullptr, nullptr};   // LSQ matrices per method (index FCP_GRAD_*); QR: [18][n]
+  int32_t max_cell_faces = 0;                       // longest cell->face list (the QR gradient holds at most 6)
+  double *d_mmpart = nullptr;                       // limiter: per-chunk {min,max} partials + the final pair
+  double *d_sum = nullptr;                          // [4] device scalar slot (calcp_piso pavg)
   KrylovWS ws;
   FcpComm *comm = nullptr;
   Profiler prof;
@@ -206,13 +209,23 @@ int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi
 int fvm_laplacian(fcp_ctx *ctx, const double *mu, const double *phi, double *a, double *su);
 int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su, double *sv, double *sw, double *dPdxi, double *gtmp,
               const CorrectArgs *correct);
-int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g);
+int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso = false);
 int fvm_adjust_mass_flow(fcp_ctx *ctx, int32_t nout, const int32_t *d_oface, const double *den, double *u, double *v, double *w,
                          double *flmass, double flomas);
 int fvm_correct_flux(fcp_ctx *ctx, const double *a, const double *pp, double *flmass);
 int fvm_correct_pressure_bnd(fcp_ctx *ctx, const double *den, const double *apu, const double *pp, double *u, double *v, double *w,
                              double *flmass);
 int fvm_nonorth(fcp_ctx *ctx, const double *den, const double *apu, const double *dPdxi, double *su, double *flmass);
+
+// ---- fvm_ext.cu ---------------------------------------------------------------------------------
+int fvm_slope_limiter(fcp_ctx *ctx, int limiter, const double *phi, double *g);
+int fvm_lsq_qr_matrix(fcp_ctx *ctx, double *D);
+int fvm_grad_lsq_qr(fcp_ctx *ctx, const double *D, const double *phi, double *g);
+int fvm_piso_hbya(fcp_ctx *ctx, const double *h, const double *rU, const double *rV, const double *rW, const double *apu, const double *apv,
+                  const double *apw, double *u, double *v, double *w, double *su, double *sv, double *sw);
+int fvm_sum(fcp_ctx *ctx, const double *x, double *d_out);
+int fvm_piso_pupdate(fcp_ctx *ctx, double ncells_global, double urfp, const double *d_sum, const double *pp, double *p);
+int fvm_piso_fluxmc(fcp_ctx *ctx, const double *den, const double *apu, const double *dPdxi, double *su);
 
 // ---- pattern.cu ---------------------------------------------------------------------------------
 int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, const int32_t *ja1, const int32_t *diag1,
@@ -236,5 +249,6 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
 // ---- comm.cu ------------------------------------------------------------------------------------
 int comm_exchange(fcp_ctx *ctx, double *field, int ncomp);   // ncomp 1 (scalar) or 3 (gradient)
 int comm_allgather_sum(FcpComm *comm, double *d_vals, int count, cudaStream_t st);  // rank-ordered deterministic sum, in place
+int comm_allreduce_minmax(FcpComm *comm, double *d_mm /* {min,max} */, cudaStream_t st);
 void comm_free(FcpComm *comm);
 int comm_nranks(const FcpComm *comm);

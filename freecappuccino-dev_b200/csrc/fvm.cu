@@ -8,49 +8,7 @@
 // The face lists are SELL-32 (fcp_internal.h): a warp reads 128 contiguous bytes per list step.
 #include "fcp_internal.h"
 #include "reduce.cuh"
-
-struct MeshView {
-  int32_t n, F, B;
-  const int64_t *slptr;
-  const int32_t *len, *ent, *other, *slot;
-  const double *arx, *ary, *arz, *xf, *yf, *zf, *facint, *Df;
-  const double *xc, *yc, *zc, *vol;
-  const int32_t *owner, *neigh;
-  const int64_t *a_slptr;    // matrix SELL slice pointers
-  const int32_t *a_rinfo;
-};
-MeshView fcp_mesh_view(const fcp_ctx *c) {
-  MeshView m;
-  m.n = c->n; m.F = c->F; m.B = c->B;
-  m.slptr = c->fl.slptr; m.len = c->fl.len; m.ent = c->fl.ent; m.other = c->fl.other; m.slot = c->fl.slot;
-  m.arx = c->arx; m.ary = c->ary; m.arz = c->arz; m.xf = c->xf; m.yf = c->yf; m.zf = c->zf;
-  m.facint = c->facint; m.Df = c->Df; m.xc = c->xc; m.yc = c->yc; m.zc = c->zc; m.vol = c->vol;
-  m.owner = c->owner; m.neigh = c->neigh;
-  m.a_slptr = c->pat.slptr; m.a_rinfo = c->pat.rinfo;
-  return m;
-}
-
-#define FCP_CELL_LOOP(c, n)                                                                       \
-  for (int j__ = 0; j__ < FCP_IPT; ++j__)                                                         \
-    for (int32_t c = (int32_t)((int64_t)blockIdx.x * FCP_CHUNK + j__ * FCP_TPB + threadIdx.x), once__ = 1; \
-         once__ && c < (n); once__ = 0)
-
-// walk the faces of cell c: e = signed entry, o = index across the face, sl = matrix slot (>=0 two-sided face,
-// -1-bctype for a physical boundary face), f = 0-based face index
-#define FCP_FACE_LOOP(m, c)                                                        \
-  const int64_t fbase__ = (m).slptr[(c) >> 5] + ((c) & 31);                        \
-  const int32_t flen__ = (m).len[c];                                               \
-  for (int32_t q__ = 0; q__ < flen__; ++q__)
-#define FCP_FACE_FETCH(m)                                                          \
-  const int32_t e = __ldcs((m).ent + fbase__ + (int64_t)q__ * 32);                 \
-  const int32_t o = __ldcs((m).other + fbase__ + (int64_t)q__ * 32);               \
-  const int32_t sl = __ldcs((m).slot + fbase__ + (int64_t)q__ * 32);               \
-  const int32_t f = (e > 0 ? e : -e) - 1;                                          \
-  (void)o; (void)sl; (void)f
-
-__device__ __forceinline__ int64_t diag_pos(const MeshView &m, int32_t c) {
-  return m.a_slptr[c >> 5] + (c & 31) + (int64_t)((m.a_rinfo[c] >> 16) & 0xffff) * 32;
-}
+#include "fvm_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // grad_gauss   gradients.f90:1607-1693
@@ -293,7 +251,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp(MeshView m, int scheme, int n
           }
         }
       }
-      su[c] = s1; sv[c] = s2; sw[c] = s3;
+      if (su) { su[c] = s1; sv[c] = s2; sw[c] = s3; }   // su == nullptr: gradient + boundary extrapolation only (calcp_piso.f90:336-344)
       if (CORRECT) {
         // calcp_simple.f90:416-419
         const double ppref = ca.ppref_src ? *ca.ppref_src : 0.0;
@@ -301,7 +259,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp(MeshView m, int scheme, int n
         const double vn = ca.v[c] + s2 * ca.apv[c];
         const double wn = ca.w[c] + s3 * ca.apw[c];
         ca.u[c] = un; ca.v[c] = vn; ca.w[c] = wn;
-        ca.pres[c] = ca.pres[c] + ca.urfp * (pc - ppref);
+        if (ca.pres) ca.pres[c] = ca.pres[c] + ca.urfp * (pc - ppref);   // nullptr: calcp_piso.f90:429-431 corrects velocities only
         if (has_bnd) {   // updateVelocityAtBoundary, velocity.f90:1184-1277
           FCP_FACE_LOOP(m, c) {
             FCP_FACE_FETCH(m);
@@ -391,7 +349,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp_central2(MeshView m, double *
       const double vn = ca.v[c] + s2 * ca.apv[c];
       const double wn = ca.w[c] + s3 * ca.apw[c];
       ca.u[c] = un; ca.v[c] = vn; ca.w[c] = wn;
-      ca.pres[c] = ca.pres[c] + ca.urfp * (pc - ppref);
+      if (ca.pres) ca.pres[c] = ca.pres[c] + ca.urfp * (pc - ppref);   // nullptr: calcp_piso.f90:429-431 corrects velocities only
       if (has_bnd) {
         FCP_FACE_LOOP(m, c) {
           FCP_FACE_FETCH(m);
@@ -414,6 +372,9 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp_central2(MeshView m, double *
 // ---------------------------------------------------------------------------------------------
 // pressure-correction assembly   calcp_simple.f90:69-234 + facefluxmass2 faceflux_mass.f90:175-249
 // ---------------------------------------------------------------------------------------------
+// PISO = true: facefluxmass_piso (faceflux_mass.f90:389-459): the flux is the plain interpolated HbyA flux (no Rhie-Chow
+// pressure term) and pressure patches do not reset pp (calcp_piso.f90:140-240).
+template <bool PISO>
 __global__ void __launch_bounds__(FCP_TPB) k_assemble_pcorr(MeshView m, AsmArgs g) {
   FCP_CELL_LOOP(c, m.n) {
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
@@ -450,7 +411,8 @@ __global__ void __launch_bounds__(FCP_TPB) k_assemble_pcorr(MeshView m, AsmArgs 
         const double dpxi = (gNx * fxp + gPx * fxn) * xpn;     // weights swapped in the reference (faceflux_mass.f90:236-238), kept
         const double dpyi = (gNy * fxp + gPy * fxn) * ypn;
         const double dpzi = (gNz * fxp + gPz * fxn) * zpn;
-        const double flm = dene * (ui * sx + vi * sy + wi * sz) + cap * (pN - pP - dpxi - dpyi - dpzi);
+        const double flm = PISO ? dene * (ui * sx + vi * sy + wi * sz)
+                                : dene * (ui * sx + vi * sy + wi * sz) + cap * (pN - pP - dpxi - dpyi - dpzi);
         g.a[sl] = cap;
         dg = dg - cap;
         if (own) { s = s - flm; g.flmass[f] = flm; }
@@ -470,7 +432,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_assemble_pcorr(MeshView m, AsmArgs 
           const double cap = -denc * (sx * sx + sy * sy + sz * sz) * capp;
           dg = dg - cap;
           s = s - flm;
-          g.pp[o] = 0.0;
+          if (!PISO) g.pp[o] = 0.0;
         }
       }
     }
@@ -568,7 +530,6 @@ __global__ void __launch_bounds__(FCP_TPB) k_nonorth(MeshView m, const double *_
 // ---------------------------------------------------------------------------------------------
 // host wrappers (called from api.cu)
 // ---------------------------------------------------------------------------------------------
-#define FCP_GRID(n) fcp_nchunks(n), FCP_TPB, 0, ctx->stream
 
 int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g) {
   if (ctx->B) FCP_CUDA(cudaMemsetAsync(g + 3 * (size_t)ctx->n, 0, sizeof(double) * 3 * (size_t)ctx->B, ctx->stream));
@@ -625,9 +586,10 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
   FCP_CHECK_LAUNCH();
   return FCP_OK;
 }
-int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g) {
+int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso) {
   if (ctx->n == 0) return FCP_OK;
-  FCP_PROF(&ctx->prof, FCP_K_ASSEMBLE, ctx->stream, (k_assemble_pcorr<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g)));
+  if (piso) FCP_PROF(&ctx->prof, FCP_K_ASSEMBLE, ctx->stream, (k_assemble_pcorr<true><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g)));
+  else FCP_PROF(&ctx->prof, FCP_K_ASSEMBLE, ctx->stream, (k_assemble_pcorr<false><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g)));
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

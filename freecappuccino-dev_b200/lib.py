@@ -24,13 +24,16 @@ _pi = C.POINTER(C.c_int32)
 OK, EINVAL, ECUDA, ENODEVICE, ENCCL, ESTATE = 0, -1, -2, -3, -4, -5
 SOLVER_DPCG, SOLVER_ICCG, SOLVER_BICGSTAB = 1, 2, 3
 SOLVER_ID = {"dpcg": SOLVER_DPCG, "iccg": SOLVER_ICCG, "bicgstab": SOLVER_BICGSTAB}
-GRAD_GAUSS, GRAD_LSQ, GRAD_LSQ_DM = 0, 1, 2
+GRAD_GAUSS, GRAD_LSQ, GRAD_LSQ_DM, GRAD_LSQ_QR = 0, 1, 2, 3
+GRAD_ID = {"gauss": GRAD_GAUSS, "lsq": GRAD_LSQ, "wlsq": GRAD_LSQ_DM, "lsq_qr": GRAD_LSQ_QR}          # option strings, gradients.f90:240-256
+LIMITER_NONE, LIMITER_BJ, LIMITER_VENKAT, LIMITER_R3, LIMITER_MDL = 0, 1, 2, 3, 4
+LIMITER_ID = {"none": 0, "no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "R3": 3, "multidimensional": 4}   # gradients.f90:261-276
 PSCHEME = {"linear": 0, "central": 1, "weighted": 2}
 FIELDS = ["U", "V", "W", "P", "PP", "DEN", "VIS", "APU", "APV", "APW", "SU", "SV", "SW", "S0", "S1", "S2", "S3",
-          "DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "FLMASS", "A", "APR"]
+          "DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "FLMASS", "A", "APR", "H", "RU", "RV", "RW"]
 F = {name: i for i, name in enumerate(FIELDS)}
 KERNEL_CLASSES = ["spmv_dot", "cg_pk", "cg_update", "cg_init", "precond", "dot", "bicg_elem", "assemble", "gradp", "correct_flux",
-                  "grad", "laplacian", "spmv", "halo"]
+                  "grad", "laplacian", "spmv", "halo", "limiter", "piso_h"]
 GRADIENT_FIELDS = {"DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1"}
 
 
@@ -57,6 +60,12 @@ class SimpleParams(C.Structure):
     _fields_ = [("solver", C.c_int32), ("maxiter", C.c_int32), ("tol_abs", C.c_double), ("tol_rel", C.c_double),
                 ("urfp", C.c_double), ("npcor", C.c_int32), ("pRefCell", C.c_int32), ("pscheme", C.c_int32),
                 ("const_mflux", C.c_int32), ("flomas", C.c_double), ("zero_pp", C.c_int32)]
+
+
+class PisoParams(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("maxiter", C.c_int32), ("tol_abs", C.c_double), ("tol_rel", C.c_double),
+                ("urfp", C.c_double), ("ncorr", C.c_int32), ("npcor", C.c_int32), ("pscheme", C.c_int32),
+                ("const_mflux", C.c_int32), ("flomas", C.c_double)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -108,6 +117,9 @@ def lib():
     L.fcp_report_line.argtypes = [C.POINTER(Report), C.c_char_p, C.c_char_p, C.c_int]
     L.fcp_create_lsq_grad_matrix.argtypes = [vp, C.c_int]
     L.fcp_grad.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.fcp_slope_limiter.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.fcp_grad_opt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.fcp_calcp_piso.argtypes = [vp, C.POINTER(PisoParams), C.POINTER(Report)]
     L.fcp_laplacian.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_gradp_and_sources.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_assemble_pcorr_simple.argtypes = [vp, C.c_int, C.c_double]
@@ -203,7 +215,7 @@ class Context:
         name = FIELDS[field_id(field)]
         if name in GRADIENT_FIELDS:
             return 3 * self.numTotal
-        return {"FLMASS": self.numFaces, "A": self.nnz, "APR": self.npro}.get(name, self.numTotal)
+        return {"FLMASS": self.numFaces, "A": self.nnz, "H": self.nnz, "APR": self.npro}.get(name, self.numTotal)
 
     def upload(self, field, host: np.ndarray):
         host = np.ascontiguousarray(host, dtype=np.float64).ravel()
@@ -241,6 +253,24 @@ class Context:
 
     def grad(self, method, phi, grad, lsq_row2_reference: bool = True):
         check(lib().fcp_grad(self.h, method, field_id(phi), field_id(grad), int(lsq_row2_reference)), "fcp_grad")
+
+    def slope_limiter(self, limiter, phi, grad):
+        lim = LIMITER_ID[limiter] if isinstance(limiter, str) else int(limiter)
+        check(lib().fcp_slope_limiter(self.h, lim, field_id(phi), field_id(grad)), "fcp_slope_limiter")
+
+    def grad_opt(self, option, option_limiter, phi, grad):
+        """grad(phi, dPhidxi, option, option_limiter), gradients.f90:217-278."""
+        meth = GRAD_ID[option] if isinstance(option, str) else int(option)
+        lim = LIMITER_ID[option_limiter] if isinstance(option_limiter, str) else int(option_limiter)
+        check(lib().fcp_grad_opt(self.h, meth, lim, field_id(phi), field_id(grad)), "fcp_grad_opt")
+
+    def calcp_piso(self, solver="iccg", maxiter=100, tol_abs=1e-13, tol_rel=1e-6, urfp=1.0, ncorr=2, npcor=1, pscheme="linear",
+                   const_mflux=False, flomas=0.0):
+        prm = PisoParams(SOLVER_ID[solver] if isinstance(solver, str) else solver, maxiter, tol_abs, tol_rel, urfp, ncorr, npcor,
+                         PSCHEME[pscheme] if isinstance(pscheme, str) else pscheme, int(const_mflux), flomas)
+        reps = (Report * (ncorr * npcor))()
+        check(lib().fcp_calcp_piso(self.h, C.byref(prm), reps), "fcp_calcp_piso")
+        return [reps[i] for i in range(ncorr * npcor)]
 
     def laplacian(self, mu, phi):
         check(lib().fcp_laplacian(self.h, field_id(mu), field_id(phi)), "fcp_laplacian")

@@ -43,7 +43,12 @@ enum { FCP_BC_WALL = 0, FCP_BC_INLET = 1, FCP_BC_OUTLET = 2, FCP_BC_SYMMETRY = 3
 enum { FCP_SOLVER_DPCG = 1, FCP_SOLVER_ICCG = 2, FCP_SOLVER_BICGSTAB = 3 };
 
 /* gradient methods: the logicals lstsq / lstsq_dm / (default) gauss of gradients.f90:118-138 */
-enum { FCP_GRAD_GAUSS = 0, FCP_GRAD_LSQ = 1, FCP_GRAD_LSQ_DM = 2 };
+enum { FCP_GRAD_GAUSS = 0, FCP_GRAD_LSQ = 1, FCP_GRAD_LSQ_DM = 2, FCP_GRAD_LSQ_QR = 3 };
+
+/* option_limiter of grad_scalar_field_w_option, gradients.f90:258-276: 'Barth-Jespersen' :288, 'Venkatakrishnan' :378,
+ * 'R3' :464 (the formula the reference has active under that name is R4), 'multidimensional' :556 */
+enum { FCP_LIMITER_NONE = 0, FCP_LIMITER_BARTH_JESPERSEN = 1, FCP_LIMITER_VENKATAKRISHNAN = 2, FCP_LIMITER_R3 = 3,
+       FCP_LIMITER_MULTIDIMENSIONAL = 4 };
 
 /* pscheme of Pressure/nablap.f90:51-112 */
 enum { FCP_PSCHEME_LINEAR = 0, FCP_PSCHEME_CENTRAL = 1, FCP_PSCHEME_WEIGHTED = 2 };
@@ -57,6 +62,8 @@ enum {
   FCP_F_S0, FCP_F_S1, FCP_F_S2, FCP_F_S3,          /* user scalars (phi, mu, rhs ... of laplacian / grad / csrsolve) */
   FCP_F_DUDXI, FCP_F_DVDXI, FCP_F_DWDXI, FCP_F_DPDXI, FCP_F_G0, FCP_F_G1,   /* (3,numTotal) */
   FCP_F_FLMASS, FCP_F_A, FCP_F_APR,
+  FCP_F_H,                                         /* h(nnz): momentum coefficients saved by calcp_piso (calcp_piso.f90:81) */
+  FCP_F_RU, FCP_F_RV, FCP_F_RW,                    /* rU,rV,rW: momentum right-hand sides (velocity.f90:567) */
   FCP_F_COUNT
 };
 
@@ -119,10 +126,17 @@ int fcp_csrsolve(fcp_ctx *ctx, int solver, int fi_field, int rhs_field, int32_t 
 /* the reference's report line for `rep` (same text, parsed by examples/ * /plotResiduals) */
 int fcp_report_line(const fcp_report *rep, const char *chvar, char *buf, int buflen);
 
-/* grad(phi,dPhidxi): grad_gauss gradients.f90:1607-1693, grad_lsq :782-893, grad_lsq_dm :1334-1486.
- * lsq_row2_reference != 0 reproduces the reference's back-substitution row 2. */
+/* grad(phi,dPhidxi): grad_gauss gradients.f90:1607-1693, grad_lsq :782-893, grad_lsq_dm :1334-1486, grad_lsq_qr :1057-1152.
+ * lsq_row2_reference != 0 reproduces the reference's back-substitution row 2.
+ * FCP_GRAD_LSQ_QR (create_matrix_lsq_qr :900-1052, thin QR by modified Gram-Schmidt misc/matrix.f90:366-419) holds at
+ * most m = 6 faces per cell (:924) and fails with FCP_EINVAL on any other mesh; see DESIGN.md quirk Q20. */
 int fcp_create_lsq_grad_matrix(fcp_ctx *ctx, int method);     /* gradients.f90:72-101, 660-779, 1157-1326 */
 int fcp_grad(fcp_ctx *ctx, int method, int phi_field, int grad_field, int lsq_row2_reference);
+/* the limiter alone, applied in place to grad_field; BJ/Venkatakrishnan/R3 use the GLOBAL extrema of phi(1:numCells)
+ * (gradients.f90:317-318; all ranks in a multi-GPU run) */
+int fcp_slope_limiter(fcp_ctx *ctx, int limiter, int phi_field, int grad_field);
+/* grad(phi,dPhidxi,option,option_limiter)   gradients.f90:217-278: dPhidxi = 0, gradient by `method`, then the limiter */
+int fcp_grad_opt(fcp_ctx *ctx, int method, int limiter, int phi_field, int grad_field);
 /* laplacian(mu,phi): fills FCP_F_A, accumulates into FCP_F_SU   src/finiteVolume/fvImplicit/laplacian.f90 */
 int fcp_laplacian(fcp_ctx *ctx, int mu_field, int phi_field);
 /* gradp_and_sources(p): fills FCP_F_SU/SV/SW and FCP_F_DPDXI, extrapolates p to boundaries   Pressure/nablap.f90:19-208 */
@@ -150,6 +164,23 @@ typedef struct {
 /* one whole calcp_simple   Pressure/calcp_simple.f90:1-470 ; rep[ipcorr] for ipcorr < npcor */
 int fcp_calcp_simple(fcp_ctx *ctx, const fcp_simple_params *prm, fcp_report *rep);
 
+typedef struct {
+  int32_t solver;       /* lSolverP */
+  int32_t maxiter;      /* maxiterP */
+  double tol_abs, tol_rel;
+  double urfp;          /* urfP (calcp_piso.f90:333) */
+  int32_t ncorr;        /* PISO correctors (:84) */
+  int32_t npcor;        /* non-orthogonal passes per corrector (:308) */
+  int32_t pscheme;      /* FCP_PSCHEME_* of the closing gradp_and_sources (:425) */
+  int32_t const_mflux;  /* skip adjustMassFlow (:186) */
+  double flomas;
+} fcp_piso_params;
+/* one whole calcp_piso   Pressure/calcp_piso.f90:81-489 (+ facefluxmass_piso faceflux_mass.f90:389-459, fluxmc :564-647).
+ * On entry FCP_F_A holds the momentum coefficients (copied to FCP_F_H like `h = a`), FCP_F_RU/RV/RW the momentum
+ * right-hand sides, FCP_F_APU/APV/APW the reciprocal diagonals.  rep[(icorr-1)*npcor + ipcorr-1].
+ * Periodic patches (:242-295) are not supported yet: FCP_ESTATE. */
+int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_report *rep);
+
 /* ---- explicit-CSR solver signature: dpcg|iccg|bicgstab(n,nnz,ia,ja,a,diag,fi,rhs,...) -------- */
 /* linear_solvers.f90:206, :364, :548 ; pattern analysed once, values per solve */
 int fcp_solver_create(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const int32_t *diag,
@@ -171,7 +202,8 @@ int fcp_global_min(fcp_ctx *ctx, double *value);
 
 /* ---- per-kernel-class device timing (CUDA events on the context stream, around every launch of the class) ---- */
 enum { FCP_K_SPMV_DOT = 0, FCP_K_CG_PK, FCP_K_CG_UPDATE, FCP_K_CG_INIT, FCP_K_PRECOND, FCP_K_DOT, FCP_K_BICG_ELEM,
-       FCP_K_ASSEMBLE, FCP_K_GRADP, FCP_K_CORRECT_FLUX, FCP_K_GRAD, FCP_K_LAPLACIAN, FCP_K_SPMV, FCP_K_HALO, FCP_K_COUNT };
+       FCP_K_ASSEMBLE, FCP_K_GRADP, FCP_K_CORRECT_FLUX, FCP_K_GRAD, FCP_K_LAPLACIAN, FCP_K_SPMV, FCP_K_HALO, FCP_K_LIMITER,
+       FCP_K_PISO_H, FCP_K_COUNT };
 int fcp_profile_enable(fcp_ctx *ctx, int on);
 int fcp_profile_reset(fcp_ctx *ctx);
 int fcp_profile_read(fcp_ctx *ctx, int kclass, double *total_ms, int64_t *launches);   /* synchronises; totals since reset */

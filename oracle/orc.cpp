@@ -823,3 +823,308 @@ extern "C" void orc_dpcg_par(i32 P, orc_rank *rk, i32 itr_max, double tol_abs, d
   orc_exchange(P, rk, fip.data());               // dpcg.f90:183
   rep->resl = resl; rep->factor = factor; rep->resor = resor; rep->iters = itr_used;
 }
+
+// ------------------------------------------------------------------------------------------
+// slope limiters  (src/finiteVolume/fvExplicit/gradients.f90:288-656)
+// ------------------------------------------------------------------------------------------
+static inline double limiter_fn(int kind, double r) {
+  if (kind == ORC_LIM_BJ) return r;                                          // :366
+  const double r2 = r * r;
+  if (kind == ORC_LIM_VENKAT) return (r2 + 2.0 * r) / (r2 + r + 2.0);        // :454
+  const double r3 = r2 * r, r4 = r2 * r2;                                    // :544 (R4 is the active line of 'R3')
+  return (r4 + 2.0 * r3 - 4.0 * r2 + 8.0 * r) / (r4 + r3 + 2.0 * r2 - 4.0 * r + 8.0);
+}
+
+extern "C" void orc_slope_limiter(const orc_mesh *m, const i32 *ia, const i32 *ja, const i32 *diag, int kind,
+                                  const double *phi, double *g) {
+  const i32 n = m->numCells;
+  if (kind == ORC_LIM_NONE || n == 0) return;
+  if (kind == ORC_LIM_MDL) {                                                 // :556-656
+    std::vector<double> phimax(n), phimin(n);
+    for (i32 inp = 0; inp < n; ++inp) {
+      phimax[inp] = phi[ja[ia[inp] - 1] - 1];
+      phimin[inp] = phi[ja[ia[inp] - 1] - 1];
+      for (i32 k = ia[inp] + 1; k <= ia[inp + 1] - 1; ++k) {
+        phimax[inp] = std::max(phimax[inp], phi[ja[k - 1] - 1]);
+        phimin[inp] = std::min(phimin[inp], phi[ja[k - 1] - 1]);
+      }
+    }
+    for (i32 f = 0; f < m->numInnerFaces; ++f) {
+      for (int k = 1; k <= 2; ++k) {
+        const i32 ijp = (k == 1 ? m->owner[f] : m->neighbour[f]) - 1;
+        double gx = g[3 * ijp + 0], gy = g[3 * ijp + 1], gz = g[3 * ijp + 2];
+        const double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
+        const double dpn = std::sqrt(xpn * xpn + ypn * ypn + zpn * zpn);
+        const double nx = xpn / dpn, ny = ypn / dpn, nz = zpn / dpn;
+        const double gn = gx * nx + gy * ny + gz * nz;
+        const double gtx = gx - gn * nx, gty = gy - gn * ny, gtz = gz - gn * nz;
+        const double dPhi = gx * xpn + gy * ypn + gz * zpn;
+        const double dPhimax = phimax[ijp] - phi[ijp], dPhimin = phimin[ijp] - phi[ijp];
+        if (phimax[ijp] > phi[ijp] && dPhi > dPhimax) { gx = gtx + nx * dPhimax; gy = gty + ny * dPhimax; gz = gtz + nz * dPhimax; }
+        if (phimin[ijp] < phi[ijp] && dPhi < dPhimin) { gx = gtx + nx * dPhimin; gy = gty + ny * dPhimin; gz = gtz + nz * dPhimin; }
+        g[3 * ijp + 0] = gx; g[3 * ijp + 1] = gy; g[3 * ijp + 2] = gz;
+      }
+    }
+    return;
+  }
+  double fimin = phi[0], fimax = phi[0];                                     // :317-318 minval/maxval over phi(1:numCells)
+  for (i32 i = 1; i < n; ++i) { fimin = std::min(fimin, phi[i]); fimax = std::max(fimax, phi[i]); }
+  const double eps = (double)1.e-6f;                                         // `1.e-6` default-real literal
+  for (i32 inp = 0; inp < n; ++inp) {
+    // (the local phi_max/phi_min of :326-336 are computed but never used: quirk Q3)
+    const double deltamax = fimax - phi[inp], deltamin = fimin - phi[inp];
+    double slopelimit = 1.0;
+    for (i32 k = ia[inp]; k <= ia[inp + 1] - 1; ++k) {
+      if (k == diag[inp]) continue;
+      const i32 ijn = ja[k - 1] - 1;
+      const double delta_face = g[3 * inp + 0] * (m->xc[ijn] - m->xc[inp]) + g[3 * inp + 1] * (m->yc[ijn] - m->yc[inp]) +
+                                g[3 * inp + 2] * (m->zc[ijn] - m->zc[inp]);
+      double r;
+      if (std::fabs(delta_face) < eps) r = 1.0;
+      else if (delta_face > 0.0) r = deltamax / delta_face;
+      else r = deltamin / delta_face;
+      slopelimit = std::min(slopelimit, limiter_fn(kind, r));
+    }
+    g[3 * inp + 0] = slopelimit * g[3 * inp + 0];
+    g[3 * inp + 1] = slopelimit * g[3 * inp + 1];
+    g[3 * inp + 2] = slopelimit * g[3 * inp + 2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// QR least-squares gradient  (gradients.f90:900-1152, misc/matrix.f90:137-167, 366-419)
+// ------------------------------------------------------------------------------------------
+static void inv3(const double a[3][3], double r[3][3]) {                     // matrix.f90:146-165, 1-based a(i,j) -> a[i-1][j-1]
+#define A(i, j) a[i - 1][j - 1]
+#define DET (A(1,1)*A(2,2)*A(3,3) - A(1,1)*A(2,3)*A(3,2) - A(1,2)*A(2,1)*A(3,3) + A(1,2)*A(2,3)*A(3,1) + A(1,3)*A(2,1)*A(3,2) - A(1,3)*A(2,2)*A(3,1))
+  r[0][0] = (A(2,2)*A(3,3) - A(2,3)*A(3,2)) / DET;
+  r[0][1] = -(A(1,2)*A(3,3) - A(1,3)*A(3,2)) / DET;
+  r[0][2] = (A(1,2)*A(2,3) - A(1,3)*A(2,2)) / DET;
+  r[1][0] = -(A(2,1)*A(3,3) - A(2,3)*A(3,1)) / DET;
+  r[1][1] = (A(1,1)*A(3,3) - A(1,3)*A(3,1)) / DET;
+  r[1][2] = -(A(1,1)*A(2,3) - A(1,3)*A(2,1)) / DET;
+  r[2][0] = (A(2,1)*A(3,2) - A(2,2)*A(3,1)) / DET;
+  r[2][1] = -(A(1,1)*A(3,2) - A(1,2)*A(3,1)) / DET;
+  r[2][2] = (A(1,1)*A(2,2) - A(1,2)*A(2,1)) / DET;
+#undef DET
+#undef A
+}
+
+extern "C" int orc_create_matrix_lsq_qr(const orc_mesh *m, double *D) {
+  const i32 n = m->numCells;
+  const int M = 6, N = 3;
+#define DD(i, l, c) D[((size_t)(c) * 6 + (l)) * 3 + (i)]                     // D(3,6,numCells), 0-based here
+  for (size_t i = 0; i < (size_t)18 * n; ++i) D[i] = 0.0;
+  std::vector<i32> nidx(n, 0);
+  for (i32 f = 0; f < m->numInnerFaces; ++f) {                               // :962-978
+    const i32 ijp = m->owner[f] - 1, ijn = m->neighbour[f] - 1;
+    if (nidx[ijp] >= M || nidx[ijn] >= M) return -1;
+    i32 l = nidx[ijp]++;
+    DD(0, l, ijp) = m->xc[ijn] - m->xc[ijp]; DD(1, l, ijp) = m->yc[ijn] - m->yc[ijp]; DD(2, l, ijp) = m->zc[ijn] - m->zc[ijp];
+    l = nidx[ijn]++;
+    DD(0, l, ijn) = m->xc[ijp] - m->xc[ijn]; DD(1, l, ijn) = m->yc[ijp] - m->yc[ijn]; DD(2, l, ijn) = m->zc[ijp] - m->zc[ijn];
+  }
+  for (i32 i = 0; i < m->numBoundaryFaces; ++i) {                            // :982-991
+    const i32 f = m->numInnerFaces + i, ijp = m->owner[f] - 1;
+    if (nidx[ijp] >= M) return -1;
+    const i32 l = nidx[ijp]++;
+    DD(0, l, ijp) = m->xf[f] - m->xc[ijp]; DD(1, l, ijp) = m->yf[f] - m->yc[ijp]; DD(2, l, ijp) = m->zf[f] - m->zc[ijp];
+  }
+  for (i32 c = 0; c < n; ++c) {                                              // :995-1017
+    double q[6][3], r[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) q[i][j] = DD(j, i, c);   // Dtmp = transpose(D(:,:,inp))
+    for (int j = 0; j < N; ++j) {                                            // mgs_qr, matrix.f90:393-416
+      double z = 0.0;
+      for (int i = 0; i < M; ++i) z = z + q[i][j] * q[i][j];
+      r[j][j] = std::sqrt(z);
+      for (int i = 0; i < M; ++i) q[i][j] = q[i][j] / r[j][j];
+      for (int k = j + 1; k < N; ++k) {
+        z = 0.0;
+        for (int i = 0; i < M; ++i) z = z + q[i][j] * q[i][k];
+        r[j][k] = z;
+        for (int i = 0; i < M; ++i) q[i][k] = q[i][k] - r[j][k] * q[i][j];
+      }
+    }
+    double ri[3][3];
+    inv3(r, ri);
+    for (int i = 0; i < N; ++i)                                              // Q1t = matmul(R1^-1, Q1^T)
+      for (int l = 0; l < M; ++l) {
+        double x = 0.0;
+        for (int k = 0; k < N; ++k) x = x + ri[i][k] * q[l][k];
+        DD(i, l, c) = x;
+      }
+  }
+#undef DD
+  return 0;
+}
+
+extern "C" int orc_grad_lsq_qr(const orc_mesh *m, const double *D, const double *phi, double *g) {
+  const i32 n = m->numCells;
+  std::vector<i32> nidx(n, 0);
+  std::vector<double> b((size_t)6 * n, 0.0);
+  for (i32 f = 0; f < m->numInnerFaces; ++f) {                               // :1100-1113
+    const i32 ijp = m->owner[f] - 1, ijn = m->neighbour[f] - 1;
+    if (nidx[ijp] >= 6 || nidx[ijn] >= 6) return -1;
+    b[(size_t)6 * ijp + nidx[ijp]++] = phi[ijn] - phi[ijp];
+    b[(size_t)6 * ijn + nidx[ijn]++] = phi[ijp] - phi[ijn];
+  }
+  for (i32 i = 0; i < m->numBoundaryFaces; ++i) {                            // :1117-1127
+    const i32 f = m->numInnerFaces + i, ijp = m->owner[f] - 1, ijb = n + i;
+    if (nidx[ijp] >= 6) return -1;
+    b[(size_t)6 * ijp + nidx[ijp]++] = phi[ijb] - phi[ijp];
+  }
+  for (i32 c = 0; c < n; ++c) {                                              // :1132-1142
+    for (int i = 0; i < 3; ++i) {
+      double s = 0.0;
+      for (i32 l = 0; l < nidx[c]; ++l) s = s + D[((size_t)c * 6 + l) * 3 + i] * b[(size_t)6 * c + l];
+      g[3 * c + i] = s;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// calcp_piso  (Pressure/calcp_piso.f90:81-489)
+// ------------------------------------------------------------------------------------------
+static void solve_any(int solver, i32 n, i32 nnz, const i32 *ia, const i32 *ja, const double *a, const i32 *diag, double *fi,
+                      const double *rhs, i32 itr_max, double tol_abs, double tol_rel, int mode, orc_report *rep) {
+  if (solver == 1) orc_dpcg(n, nnz, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, mode, rep);
+  else if (solver == 2) orc_iccg(n, nnz, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, mode, rep);
+  else orc_bicgstab(n, nnz, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, mode, rep);
+}
+
+extern "C" void orc_calcp_piso(const orc_mesh *m, const i32 *ia, const i32 *ja, const i32 *diag, const i32 *icell_jcell,
+                               const i32 *jcell_icell, i32 nnz, int solver, i32 maxiter, double tol_abs, double tol_rel, int mode,
+                               int ncorr, int npcor, int pscheme, double urfp, int const_mflux, double flomas,
+                               const double *rU, const double *rV, const double *rW, const double *den, const double *apu,
+                               const double *apv, const double *apw, double *a, double *h, double *u, double *v, double *w,
+                               double *p, double *pp, double *su, double *sv, double *sw, double *dPdxi, double *flmass,
+                               orc_report *rep) {
+  const i32 n = m->numCells, F = m->numInnerFaces;
+  for (i32 k = 0; k < nnz; ++k) h[k] = a[k];                                  // :81  h = a
+  for (int icorr = 1; icorr <= ncorr; ++icorr) {
+    for (i32 c = 0; c < n; ++c) { su[c] = rU[c]; sv[c] = rV[c]; sw[c] = rW[c]; }   // :102-104
+    for (i32 i = 0; i < F; ++i) {                                             // :110-124  H(U)
+      const i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+      i32 k = icell_jcell[i] - 1;
+      su[ijp] = su[ijp] - h[k] * u[ijn]; sv[ijp] = sv[ijp] - h[k] * v[ijn]; sw[ijp] = sw[ijp] - h[k] * w[ijn];
+      k = jcell_icell[i] - 1;
+      su[ijn] = su[ijn] - h[k] * u[ijp]; sv[ijn] = sv[ijn] - h[k] * v[ijp]; sw[ijn] = sw[ijn] - h[k] * w[ijp];
+    }
+    for (i32 c = 0; c < n; ++c) { u[c] = apu[c] * su[c]; v[c] = apv[c] * sv[c]; w[c] = apw[c] * sw[c]; }   // :127-129 HbyA
+    for (i32 k = 0; k < nnz; ++k) a[k] = 0.0;                                 // :140-141
+    for (i32 c = 0; c < n; ++c) su[c] = 0.0;
+    for (i32 i = 0; i < F; ++i) {                                             // :147-181 ; facefluxmass_piso faceflux_mass.f90:389-459
+      const i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+      const double lambda = m->facint[i], fxn = lambda, fxp = 1.0 - lambda;
+      const double dene = den[ijp] * fxp + den[ijn] * fxn;
+      const double Kj = m->vol[ijp] * apu[ijp] * fxp + m->vol[ijn] * apu[ijn] * fxn;
+      const double cap = -dene * Kj * m->Df[i];
+      const double ui = u[ijp] + (u[ijn] - u[ijp]) * lambda;
+      const double vi = v[ijp] + (v[ijn] - v[ijp]) * lambda;
+      const double wi = w[ijp] + (w[ijn] - w[ijp]) * lambda;
+      flmass[i] = dene * (ui * m->arx[i] + vi * m->ary[i] + wi * m->arz[i]);
+      a[icell_jcell[i] - 1] = cap;
+      a[jcell_icell[i] - 1] = cap;
+      a[diag[ijp] - 1] = a[diag[ijp] - 1] - cap;
+      a[diag[ijn] - 1] = a[diag[ijn] - 1] - cap;
+      su[ijp] = su[ijp] - flmass[i];
+      su[ijn] = su[ijn] + flmass[i];
+    }
+    if (!const_mflux) {                                                       // :186 adjustMassFlow, faceflux_mass.f90:833-916
+      double flowo = 0.0;
+      for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+        if (m->bctype[ib] != ORC_BC_OUTLET) continue;
+        for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+          i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+          u[ijb] = u[ijp]; v[ijb] = v[ijp]; w[ijb] = w[ijp];
+          flmass[f] = den[ijp] * (u[ijb] * m->arx[f] + v[ijb] * m->ary[f] + w[ijb] * m->arz[f]);
+          flowo = flowo + flmass[f];
+        }
+      }
+      const double fac = flomas / (flowo + SMALL);
+      for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+        if (m->bctype[ib] != ORC_BC_OUTLET) continue;
+        for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+          i32 f = m->startFace[ib] + i - 1, ijb = m->iBndValueStart[ib] + i - 1;
+          flmass[f] = flmass[f] * fac;
+          u[ijb] = u[ijb] * fac; v[ijb] = v[ijb] * fac; w[ijb] = w[ijb] * fac;
+        }
+      }
+    }
+    for (i32 ib = 0; ib < m->numBoundaries; ++ib) {                           // :194-297
+      if (m->bctype[ib] == ORC_BC_INLET || m->bctype[ib] == ORC_BC_OUTLET) {
+        for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+          i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1;
+          su[ijp] = su[ijp] - flmass[f];
+        }
+      } else if (m->bctype[ib] == ORC_BC_PRESSURE) {                          // facefluxmassPressBnd :765-831 (no pp(ijb)=0 here, :232)
+        for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+          i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+          double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+          double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
+          double capp = m->vol[ijp] * apu[ijp] / (arx * xpn + ary * ypn + arz * zpn);
+          double dpcor = p[ijb] - p[ijp] - (dPdxi[3 * ijp + 0] * xpn + dPdxi[3 * ijp + 1] * ypn + dPdxi[3 * ijp + 2] * zpn);
+          u[ijb] = u[ijp] - arx * capp * dpcor;
+          v[ijb] = v[ijp] - ary * capp * dpcor;
+          w[ijb] = w[ijp] - arz * capp * dpcor;
+          flmass[f] = den[ijp] * (u[ijb] * arx + v[ijb] * ary + w[ijb] * arz);
+          double cap = -den[ijp] * (arx * arx + ary * ary + arz * arz) * capp;
+          a[diag[ijp] - 1] = a[diag[ijp] - 1] - cap;
+          su[ijp] = su[ijp] - flmass[f];
+        }
+      }
+    }
+    for (int ipcorr = 1; ipcorr <= npcor; ++ipcorr) {                         // :308-395
+      solve_any(solver, n, nnz, ia, ja, a, diag, pp, su, maxiter, tol_abs, tol_rel, mode, &rep[(icorr - 1) * npcor + (ipcorr - 1)]);
+      const double pavg = sum_mode(mode, pp, n) / (double)n;                  // :330
+      for (i32 c = 0; c < n; ++c) p[c] = (1.0 - urfp) * p[c] + urfp * (pp[c] - pavg);   // :333
+      for (int istage = 1; istage <= 2; ++istage) {                           // :336-344 (nipgrad = 2, parameters.f90:62)
+        orc_bpres(m, p, dPdxi, istage);
+        orc_grad_gauss(m, p, dPdxi);
+      }
+      if (ipcorr != npcor) {                                                  // :349-364 ; fluxmc faceflux_mass.f90:564-647
+        for (i32 i = 0; i < F; ++i) {
+          const i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+          const double arx = m->arx[i], ary = m->ary[i], arz = m->arz[i], xf = m->xf[i], yf = m->yf[i], zf = m->zf[i];
+          const double fxn = m->facint[i], fxp = 1.0 - fxn;
+          const double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
+          const double are = std::sqrt(arx * arx + ary * ary + arz * arz);
+          const double nxx = arx / are, nyy = ary / are, nzz = arz / are;
+          double xpp = xf - (xf - m->xc[ijp]) * nxx, ypp = yf - (yf - m->yc[ijp]) * nyy, zpp = zf - (zf - m->zc[ijp]) * nzz;
+          double xep = xf - (xf - m->xc[ijn]) * nxx, yep = yf - (yf - m->yc[ijn]) * nyy, zep = zf - (zf - m->zc[ijn]) * nzz;
+          xpp = xpp - m->xc[ijp]; ypp = ypp - m->yc[ijp]; zpp = zpp - m->zc[ijp];
+          xep = xep - m->xc[ijn]; yep = yep - m->yc[ijn]; zep = zep - m->zc[ijn];
+          const double rapr = -((apu[ijp] * den[ijp] * m->vol[ijp] * fxp + apu[ijn] * den[ijn] * m->vol[ijn] * fxn) * are /
+                                (xpn * nxx + ypn * nyy + zpn * nzz));
+          const double fmcor = rapr * ((dPdxi[3 * ijn + 0] * xep - dPdxi[3 * ijp + 0] * xpp) + (dPdxi[3 * ijn + 1] * yep - dPdxi[3 * ijp + 1] * ypp) +
+                                       (dPdxi[3 * ijn + 2] * zep - dPdxi[3 * ijp + 2] * zpp));
+          su[ijp] = su[ijp] - fmcor;
+          su[ijn] = su[ijn] + fmcor;
+        }
+      } else {                                                                // :377-387
+        for (i32 f = 0; f < F; ++f) {
+          const i32 ijp = m->owner[f] - 1, ijn = m->neighbour[f] - 1;
+          flmass[f] = flmass[f] + a[icell_jcell[f] - 1] * (p[ijn] - p[ijp]);
+        }
+      }
+    }
+    orc_gradp_and_sources(m, pscheme, p, apu, su, sv, sw, dPdxi);             // :425
+    for (i32 c = 0; c < n; ++c) { u[c] = u[c] + su[c] * apu[c]; v[c] = v[c] + sv[c] * apv[c]; w[c] = w[c] + sw[c] * apw[c]; }   // :429-431
+    for (i32 ib = 0; ib < m->numBoundaries; ++ib) {                           // :466-479 ; facefluxmassCorrPressBnd :699-762 (uses pp(ijp))
+      if (m->bctype[ib] != ORC_BC_PRESSURE) continue;
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+        double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
+        double cap = m->vol[ijp] * apu[ijp] / (arx * xpn + ary * ypn + arz * zpn);
+        double dpcor = -pp[ijp];
+        u[ijb] = u[ijb] - arx * cap * dpcor;
+        v[ijb] = v[ijb] - ary * cap * dpcor;
+        w[ijb] = w[ijb] - arz * cap * dpcor;
+        flmass[f] = flmass[f] - den[ijp] * (arx * arx + ary * ary + arz * arz) * cap * dpcor;
+      }
+    }
+    orc_update_velocity_at_boundary(m, u, v, w);                              // :485
+  }
+}

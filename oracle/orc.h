@@ -114,6 +114,37 @@ void orc_nonorth_corrector(const orc_mesh *m, const double *den, const double *a
 /* velocity.f90:1184-1277 */
 void orc_update_velocity_at_boundary(const orc_mesh *m, double *u, double *v, double *w);
 
+
+/* ---- slope limiters, gradients.f90:288-656 (applied in place to dPhidxi(3,numTotal)) ----------
+ * kind: ORC_LIM_BJ :288-373, ORC_LIM_VENKAT :378-461, ORC_LIM_R3 :464-552 (the option string is 'R3'
+ * but the active formula is R4), ORC_LIM_MDL :556-656.  BJ/Venkat/R3 use the GLOBAL extrema
+ * fimax/fimin (quirk Q3); `1.e-6` is a default-real literal. */
+enum { ORC_LIM_NONE = 0, ORC_LIM_BJ = 1, ORC_LIM_VENKAT = 2, ORC_LIM_R3 = 3, ORC_LIM_MDL = 4 };
+void orc_slope_limiter(const orc_mesh *m, const int32_t *ia, const int32_t *ja, const int32_t *diag,
+                       int kind, const double *phi, double *dPhidxi);
+
+/* ---- QR least-squares gradient, gradients.f90:900-1152 + misc/matrix.f90:137-167 (inv), :366-419
+ * (mgs_qr).  D is (3,6,numCells) column-major as in the reference.  Returns -1 when a cell has
+ * more than m=6 faces (the reference would write out of bounds).  QUIRK Q20: the reference passes
+ * R(6,3)/Q(6,6) actuals to mgs_qr's r(3,3)/q(6,3) dummies, so its R(1:3,1:3) picks r(1,1),r(2,1),
+ * r(3,1),r(1,3),r(2,3),r(3,3) and three never-written stack words: its output is undefined.  The
+ * oracle implements the algorithm the routine documents (thin QR by modified Gram-Schmidt). */
+int orc_create_matrix_lsq_qr(const orc_mesh *m, double *D);
+int orc_grad_lsq_qr(const orc_mesh *m, const double *D, const double *phi, double *dPhidxi);
+
+/* ---- calcp_piso, Pressure/calcp_piso.f90:81-489 + faceflux_mass.f90:389-459 (facefluxmass_piso),
+ * :564-647 (fluxmc), :699-762, :765-831, :833-916.  `a` holds the momentum coefficients on entry
+ * (h = a, :81) and the pressure matrix of the last corrector on exit.  No periodic patches.
+ * rep[(icorr-1)*npcor + (ipcorr-1)]. */
+void orc_calcp_piso(const orc_mesh *m, const int32_t *ia, const int32_t *ja, const int32_t *diag,
+                    const int32_t *icell_jcell, const int32_t *jcell_icell, int32_t nnz,
+                    int solver, int32_t maxiter, double tol_abs, double tol_rel, int sum_mode,
+                    int ncorr, int npcor, int pscheme, double urfp, int const_mflux, double flomas,
+                    const double *rU, const double *rV, const double *rW,
+                    const double *den, const double *apu, const double *apv, const double *apw,
+                    double *a, double *h, double *u, double *v, double *w, double *p, double *pp,
+                    double *su, double *sv, double *sw, double *dPdxi, double *flmass, orc_report *rep);
+
 /* linear_solvers.f90:206-359, 364-545, 548-786 */
 void orc_spmv(int32_t n, const int32_t *ia, const int32_t *ja, const double *a, const double *x, double *y);
 void orc_dpcg(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const double *a,

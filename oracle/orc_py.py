@@ -233,3 +233,48 @@ def dpcg_par(parts: List, csrs: List[Csr], a_list, apr_list, fi_list, rhs_list, 
     rep = OrcReport()
     lib().orc_dpcg_par(C.c_int32(P), ranks, C.c_int32(itr_max), C.c_double(tol_abs), C.c_double(tol_rel), C.c_int(sum_mode), C.byref(rep))
     return rep
+
+
+LIM_NONE, LIM_BJ, LIM_VENKAT, LIM_R3, LIM_MDL = 0, 1, 2, 3, 4
+
+
+def slope_limiter(mesh, csr: Csr, kind: int, phi, dPhidxi):
+    """gradients.f90:288-656; dPhidxi (numTotal,3) is limited in place."""
+    lib().orc_slope_limiter(csr.mv.ptr, _i(csr.ia), _i(csr.ja), _i(csr.diag), C.c_int(kind), _d(phi), _d(dPhidxi))
+    return dPhidxi
+
+
+def create_matrix_lsq_qr(mesh):
+    mv = MeshView(mesh)
+    D = np.zeros((mesh.numCells, 6, 3))          # D(3,6,numCells) column-major
+    lib().orc_create_matrix_lsq_qr.restype = C.c_int
+    rc = lib().orc_create_matrix_lsq_qr(mv.ptr, _d(D))
+    if rc != 0:
+        raise ValueError("create_matrix_lsq_qr: a cell has more than 6 faces (gradients.f90:924 m=6)")
+    return D
+
+
+def grad_lsq_qr(mesh, D, phi):
+    mv = MeshView(mesh)
+    g = np.zeros((mesh.numTotal, 3))
+    lib().orc_grad_lsq_qr.restype = C.c_int
+    rc = lib().orc_grad_lsq_qr(mv.ptr, _d(D), _d(phi), _d(g))
+    if rc != 0:
+        raise ValueError("grad_lsq_qr: a cell has more than 6 faces")
+    return g
+
+
+def calcp_piso(mesh, csr: Csr, solver, maxiter, tol_abs, tol_rel, sum_mode, ncorr, npcor, pscheme, urfp, const_mflux, flomas,
+               rU, rV, rW, den, apu, apv, apw, a, u, v, w, p, pp, dPdxi, flmass):
+    """a (momentum coefficients in, pressure matrix out), u, v, w, p, pp, dPdxi, flmass are updated in place.
+    Returns (reports, su, sv, sw, h)."""
+    n = mesh.numCells
+    su, sv, sw = (np.zeros(n) for _ in range(3))
+    h = np.zeros(csr.nnz)
+    reps = (OrcReport * (ncorr * npcor))()
+    lib().orc_calcp_piso(csr.mv.ptr, _i(csr.ia), _i(csr.ja), _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz),
+                         C.c_int(solver), C.c_int32(maxiter), C.c_double(tol_abs), C.c_double(tol_rel), C.c_int(sum_mode),
+                         C.c_int(ncorr), C.c_int(npcor), C.c_int(pscheme), C.c_double(urfp), C.c_int(int(const_mflux)), C.c_double(flomas),
+                         _d(rU), _d(rV), _d(rW), _d(den), _d(apu), _d(apv), _d(apw), _d(a), _d(h), _d(u), _d(v), _d(w), _d(p), _d(pp),
+                         _d(su), _d(sv), _d(sw), _d(dPdxi), _d(flmass), reps)
+    return [reps[i] for i in range(ncorr * npcor)], su, sv, sw, h

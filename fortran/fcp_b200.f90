@@ -4,7 +4,7 @@
 ! Two modules:
 !   fcp_b200      the bind(C) interfaces, one per entry point of include/fcp.h
 !   fcp_backend   drop-in replacements that keep the reference's module-level API for the hot path
-!                 (csrsolve, grad_gauss, grad, laplacian, gradp_and_sources, calcp_simple, exchange, global_sum):
+!                 (csrsolve, grad_gauss, grad, grad_w_option, laplacian, gradp_and_sources, calcp_simple, calcp_piso, exchange, global_sum):
 !                 same names, same dummy arguments, same module globals (geometry, sparse_matrix, variables), so that
 !                 `use linear_solvers` / `use gradients` / `use pressure` in a caller is replaced by `use fcp_backend`
 !                 (INTEGRATION.md shows the patch).
@@ -22,7 +22,9 @@ module fcp_b200
   ! constants of include/fcp.h
   integer(c_int), parameter :: FCP_OK = 0
   integer(c_int), parameter :: FCP_SOLVER_DPCG = 1, FCP_SOLVER_ICCG = 2, FCP_SOLVER_BICGSTAB = 3
-  integer(c_int), parameter :: FCP_GRAD_GAUSS = 0, FCP_GRAD_LSQ = 1, FCP_GRAD_LSQ_DM = 2
+  integer(c_int), parameter :: FCP_GRAD_GAUSS = 0, FCP_GRAD_LSQ = 1, FCP_GRAD_LSQ_DM = 2, FCP_GRAD_LSQ_QR = 3
+  integer(c_int), parameter :: FCP_LIMITER_NONE = 0, FCP_LIMITER_BARTH_JESPERSEN = 1, FCP_LIMITER_VENKATAKRISHNAN = 2, &
+                               FCP_LIMITER_R3 = 3, FCP_LIMITER_MULTIDIMENSIONAL = 4
   integer(c_int), parameter :: FCP_PSCHEME_LINEAR = 0, FCP_PSCHEME_CENTRAL = 1, FCP_PSCHEME_WEIGHTED = 2
   integer(c_int), parameter :: FCP_BC_WALL = 0, FCP_BC_INLET = 1, FCP_BC_OUTLET = 2, FCP_BC_SYMMETRY = 3, &
                                FCP_BC_PRESSURE = 4, FCP_BC_PERIODIC = 5, FCP_BC_EMPTY = 6, FCP_BC_PROCESS = 7
@@ -31,7 +33,7 @@ module fcp_b200
                   FCP_F_APU, FCP_F_APV, FCP_F_APW, FCP_F_SU, FCP_F_SV, FCP_F_SW, &
                   FCP_F_S0, FCP_F_S1, FCP_F_S2, FCP_F_S3, &
                   FCP_F_DUDXI, FCP_F_DVDXI, FCP_F_DWDXI, FCP_F_DPDXI, FCP_F_G0, FCP_F_G1, &
-                  FCP_F_FLMASS, FCP_F_A, FCP_F_APR
+                  FCP_F_FLMASS, FCP_F_A, FCP_F_APR, FCP_F_H, FCP_F_RU, FCP_F_RV, FCP_F_RW
   end enum
 
   type, bind(c) :: fcp_mesh_desc
@@ -44,6 +46,13 @@ module fcp_b200
   type, bind(c) :: fcp_report
     real(c_double) :: res0, resl, factor, resor
     integer(c_int32_t) :: iters, solver
+  end type
+
+  type, bind(c) :: fcp_piso_params
+    integer(c_int32_t) :: solver, maxiter
+    real(c_double) :: tol_abs, tol_rel, urfp
+    integer(c_int32_t) :: ncorr, npcor, pscheme, const_mflux
+    real(c_double) :: flomas
   end type
 
   type, bind(c) :: fcp_simple_params
@@ -152,6 +161,25 @@ module fcp_b200
       type(c_ptr), value :: ctx
       type(fcp_simple_params), intent(in) :: prm
       type(fcp_report), intent(out) :: rep(*)
+      integer(c_int) :: rc
+    end function
+    function fcp_calcp_piso(ctx, prm, rep) bind(c, name='fcp_calcp_piso') result(rc)
+      import :: c_int, c_ptr, fcp_piso_params, fcp_report
+      type(c_ptr), value :: ctx
+      type(fcp_piso_params), intent(in) :: prm
+      type(fcp_report), intent(out) :: rep(*)
+      integer(c_int) :: rc
+    end function
+    function fcp_slope_limiter(ctx, limiter, phi_field, grad_field) bind(c, name='fcp_slope_limiter') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: limiter, phi_field, grad_field
+      integer(c_int) :: rc
+    end function
+    function fcp_grad_opt(ctx, method, limiter, phi_field, grad_field) bind(c, name='fcp_grad_opt') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: method, limiter, phi_field, grad_field
       integer(c_int) :: rc
     end function
     function fcp_solver_create(n, nnz, ia, ja, diag, device, s) bind(c, name='fcp_solver_create') result(rc)
@@ -345,6 +373,33 @@ contains
     call get(FCP_F_G0, dPhidxi, 3*numTotal)
   end subroutine
 
+  ! grad(phi,dPhidxi,option,option_limiter)   grad_scalar_field_w_option, gradients.f90:217-278
+  subroutine grad_w_option(phi, dPhidxi, option, option_limiter)
+    real(dp), dimension(numTotal), intent(in) :: phi
+    real(dp), dimension(3,numTotal), intent(inout) :: dPhidxi
+    character(len=*), intent(in) :: option, option_limiter
+    integer(c_int) :: method, limiter
+    dPhidxi = 0.0_dp
+    select case (option)
+      case ('lsq');    method = FCP_GRAD_LSQ
+      case ('lsq_qr'); method = FCP_GRAD_LSQ_QR
+      case ('wlsq');   method = FCP_GRAD_LSQ_DM
+      case ('gauss');  method = FCP_GRAD_GAUSS
+      case default;    return
+    end select
+    select case (option_limiter)
+      case ('Barth-Jespersen');  limiter = FCP_LIMITER_BARTH_JESPERSEN
+      case ('Venkatakrishnan');  limiter = FCP_LIMITER_VENKATAKRISHNAN
+      case ('R3');               limiter = FCP_LIMITER_R3
+      case ('multidimensional'); limiter = FCP_LIMITER_MULTIDIMENSIONAL
+      case default;              limiter = FCP_LIMITER_NONE
+    end select
+    call put(FCP_F_S0, phi, numTotal)
+    if (method /= FCP_GRAD_GAUSS) call fcp_check(fcp_create_lsq_grad_matrix(ctx, method), 'fcp_create_lsq_grad_matrix')
+    call fcp_check(fcp_grad_opt(ctx, method, limiter, FCP_F_S0, FCP_F_G0), 'fcp_grad_opt')
+    call get(FCP_F_G0, dPhidxi, 3*numTotal)
+  end subroutine
+
   subroutine create_lsq_grad_matrix()   ! gradients.f90:72-101
     use gradients, only: lstsq, lstsq_dm
     if (lstsq) call fcp_check(fcp_create_lsq_grad_matrix(ctx, FCP_GRAD_LSQ), 'fcp_create_lsq_grad_matrix')
@@ -415,6 +470,45 @@ contains
     call get(FCP_F_SU, su, numCells); call get(FCP_F_SV, sv, numCells); call get(FCP_F_SW, sw, numCells)
     call get(FCP_F_A, a, nnz)
     call continuityErrors                            ! calcp_simple.f90:464 stays on the host (prints, sets resor(4))
+  end subroutine
+
+  ! ---- calcp_piso(): no arguments   Pressure/calcp_piso.f90 ------------------------------------------------------------------
+  subroutine calcp_piso()
+    use pressure, only: urfP, lSolverP, maxiterP, tolAbsP, tolRelP
+    use nablap, only: pscheme
+    type(fcp_piso_params) :: prm
+    type(fcp_report) :: rep(64)
+    character(kind=c_char) :: line(256)
+    integer :: k, i
+    call put(FCP_F_U, u, numTotal); call put(FCP_F_V, v, numTotal); call put(FCP_F_W, w, numTotal)
+    call put(FCP_F_P, p, numTotal); call put(FCP_F_PP, pp, numTotal); call put(FCP_F_DEN, den, numTotal)
+    call put(FCP_F_APU, apu, numCells); call put(FCP_F_APV, apv, numCells); call put(FCP_F_APW, apw, numCells)
+    call put(FCP_F_RU, rU, numCells); call put(FCP_F_RV, rV, numCells); call put(FCP_F_RW, rW, numCells)
+    call put(FCP_F_A, a, nnz)                       ! momentum coefficients: the library does `h = a` (calcp_piso.f90:81)
+    call put(FCP_F_DPDXI, dPdxi, 3*numTotal)
+    call put(FCP_F_FLMASS, flmass, numFaces)
+    prm%solver = solver_id(lSolverP); prm%maxiter = maxiterP
+    prm%tol_abs = tolAbsP; prm%tol_rel = tolRelP; prm%urfp = urfP
+    prm%ncorr = ncorr; prm%npcor = npcor
+    prm%pscheme = FCP_PSCHEME_LINEAR
+    if (trim(pscheme) == 'central') prm%pscheme = FCP_PSCHEME_CENTRAL
+    if (trim(pscheme) == 'weighted') prm%pscheme = FCP_PSCHEME_WEIGHTED
+    prm%const_mflux = merge(1, 0, const_mflux); prm%flomas = flomas
+    call fcp_check(fcp_calcp_piso(ctx, prm, rep), 'fcp_calcp_piso')
+    do k = 1, ncorr*npcor
+      call fcp_check(fcp_report_line(rep(k), 'p'//c_null_char, line, 256_c_int), 'fcp_report_line')
+      do i = 1, 256
+        if (line(i) == c_null_char) exit
+      end do
+      write(*,'(256a)') line(1:i-1)
+    end do
+    call get(FCP_F_U, u, numTotal); call get(FCP_F_V, v, numTotal); call get(FCP_F_W, w, numTotal)
+    call get(FCP_F_P, p, numTotal); call get(FCP_F_PP, pp, numTotal)
+    call get(FCP_F_FLMASS, flmass, numFaces); call get(FCP_F_DPDXI, dPdxi, 3*numTotal)
+    call get(FCP_F_SU, su, numCells); call get(FCP_F_SV, sv, numCells); call get(FCP_F_SW, sw, numCells)
+    call get(FCP_F_A, a, nnz); call get(FCP_F_H, h, nnz)
+    call continuityErrors                            ! calcp_piso.f90:390 stays on the host
+    if (const_mflux) call constant_mass_flow_forcing ! :487
   end subroutine
 
   ! ---- src-par: exchange(phi), global_sum(phi)   src-par/exchange.f90:3, src-par/global_sum_mpi.f90:4 ---------------------------

@@ -39,7 +39,11 @@ class Case:
         self.pRefCell, self.npcor, self.const_mflux, self.flomas = 1, 1, False, 0.0
         self.urfP, self.lSolverP, self.maxiterP, self.tolAbsP, self.tolRelP = 0.2, "iccg", 30, 1e-13, 0.025
         self.pscheme = "linear"
-        self.lstsq = self.lstsq_dm = False
+        self.lstsq = self.lstsq_dm = self.lstsq_qr = False
+        # PISO (parameters.f90: ncorr, npcor) and the momentum equation leftovers calcp_piso reads
+        self.ncorr = 2
+        self.rU, self.rV, self.rW = z(nT), z(nT), z(nT)
+        self.h = z(self.nnz)
 
     def close(self):
         self.ctx.close()
@@ -64,11 +68,26 @@ class Case:
             self.ctx.create_lsq_grad_matrix(L.GRAD_LSQ)
         if self.lstsq_dm:
             self.ctx.create_lsq_grad_matrix(L.GRAD_LSQ_DM)
+        if self.lstsq_qr:
+            self.ctx.create_lsq_grad_matrix(L.GRAD_LSQ_QR)
 
     def grad(self, phi: np.ndarray, dPhidxi: np.ndarray):
-        method = L.GRAD_LSQ if self.lstsq else L.GRAD_LSQ_DM if self.lstsq_dm else L.GRAD_GAUSS
+        # gradients.f90:118-138: lstsq, lstsq_qr, lstsq_dm, else gauss
+        method = L.GRAD_LSQ if self.lstsq else L.GRAD_LSQ_QR if self.lstsq_qr else L.GRAD_LSQ_DM if self.lstsq_dm else L.GRAD_GAUSS
         self.ctx.upload("S0", phi)
         self.ctx.grad(method, "S0", "G0")
+        dPhidxi[...] = self.ctx.download("G0")
+
+    def grad_w_option(self, phi: np.ndarray, dPhidxi: np.ndarray, option: str, option_limiter: str):
+        """grad(phi, dPhidxi, option, option_limiter)   gradients.f90:217-278; unknown option strings leave dPhidxi = 0 and
+        unknown limiter strings mean 'no-limit', as in the reference's select case."""
+        self.ctx.upload("S0", phi)
+        if option not in L.GRAD_ID:
+            dPhidxi[...] = 0.0
+            return
+        if option in ("lsq", "wlsq", "lsq_qr"):
+            self.ctx.create_lsq_grad_matrix(L.GRAD_ID[option])
+        self.ctx.grad_opt(option, L.LIMITER_ID.get(option_limiter, 0), "S0", "G0")
         dPhidxi[...] = self.ctx.download("G0")
 
     def grad_gauss(self, u: np.ndarray, dudxi: np.ndarray):
@@ -119,6 +138,29 @@ class Case:
         self.dPdxi[...] = c.download("DPDXI")
         self.su[...], self.sv[...], self.sw[...] = c.download("SU", n), c.download("SV", n), c.download("SW", n)
         self.a[...] = c.download("A")
+        return reps
+
+    # ---- calcp_piso()   Pressure/calcp_piso.f90 ----------------------------------------------------------------------------------
+    def calcp_piso(self):
+        c = self.ctx
+        n = self.mesh.numCells
+        for name in ("u", "v", "w", "p", "pp", "den", "apu", "apv", "apw"):
+            c.upload(name.upper(), getattr(self, name))
+        c.upload("RU", self.rU); c.upload("RV", self.rV); c.upload("RW", self.rW)
+        c.upload("A", self.a)               # the momentum coefficients (h = a, calcp_piso.f90:81)
+        c.upload("DPDXI", self.dPdxi)
+        c.upload("FLMASS", self.flmass)
+        reps = c.calcp_piso(solver=self.lSolverP, maxiter=self.maxiterP, tol_abs=self.tolAbsP, tol_rel=self.tolRelP, urfp=self.urfP,
+                            ncorr=self.ncorr, npcor=self.npcor, pscheme=self.pscheme, const_mflux=self.const_mflux, flomas=self.flomas)
+        for r in reps:
+            print(L.report_line(r, "p"), file=self.out)
+        for name in ("u", "v", "w", "p", "pp"):
+            getattr(self, name)[...] = c.download(name.upper())
+        self.flmass[...] = c.download("FLMASS")
+        self.dPdxi[...] = c.download("DPDXI")
+        self.su[...], self.sv[...], self.sw[...] = c.download("SU", n), c.download("SV", n), c.download("SW", n)
+        self.a[...] = c.download("A")
+        self.h[...] = c.download("H")
         return reps
 
     # ---- src-par: exchange(phi), global_sum(x)   src-par/exchange.f90:3, global_sum_mpi.f90:4 ---------------------------------------

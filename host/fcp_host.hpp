@@ -27,6 +27,7 @@ namespace sparse_matrix {
 inline int nnz = 0;
 inline std::vector<int32_t> ia, ja, diag, icell_jcell_csr_index, jcell_icell_csr_index;
 inline std::vector<dp> a, su, sv, sw, apu, apv, apw;
+inline std::vector<dp> h, rU, rV, rW;   // calcp_piso.f90:81 `h = a`; velocity.f90:567 rU = su
 }
 // ---- module variables ---------------------------------------------------------------------------------------------------------
 namespace variables {
@@ -34,7 +35,7 @@ inline std::vector<dp> u, v, w, p, pp, den, flmass, dPdxi;
 }
 // ---- module parameters / pressure (parameters.f90, Pressure/pressure.f90:28-33) ------------------------------------------------
 namespace parameters {
-inline int pRefCell = 1, npcor = 1;
+inline int pRefCell = 1, npcor = 1, ncorr = 2;
 inline bool const_mflux = false;
 inline dp flomas = 0.0;
 }
@@ -146,6 +147,43 @@ inline void calcp_simple() {
   get(FCP_F_U, u, nT); get(FCP_F_V, v, nT); get(FCP_F_W, w, nT); get(FCP_F_P, p, nT); get(FCP_F_PP, pp, nT);
   get(FCP_F_FLMASS, flmass, geometry::numFaces); get(FCP_F_DPDXI, dPdxi, 3 * (int64_t)nT);
   get(FCP_F_SU, su, n); get(FCP_F_SV, sv, n); get(FCP_F_SW, sw, n); get(FCP_F_A, a, nnz);
+}
+// grad(phi, dPhidxi, option, option_limiter)   gradients.f90:217-278
+inline void grad(const std::vector<dp> &phi, std::vector<dp> &dPhidxi, const std::string &option, const std::string &option_limiter) {
+  const int method = option == "lsq" ? FCP_GRAD_LSQ : option == "lsq_qr" ? FCP_GRAD_LSQ_QR : option == "wlsq" ? FCP_GRAD_LSQ_DM
+                   : option == "gauss" ? FCP_GRAD_GAUSS : -1;
+  const int limiter = option_limiter == "Barth-Jespersen" ? FCP_LIMITER_BARTH_JESPERSEN : option_limiter == "Venkatakrishnan" ? FCP_LIMITER_VENKATAKRISHNAN
+                    : option_limiter == "R3" ? FCP_LIMITER_R3 : option_limiter == "multidimensional" ? FCP_LIMITER_MULTIDIMENSIONAL : FCP_LIMITER_NONE;
+  if (method < 0) { dPhidxi.assign(dPhidxi.size(), 0.0); return; }   // no branch taken: dPhidxi stays 0 (:238)
+  put(FCP_F_S0, phi, geometry::numTotal);
+  if (method != FCP_GRAD_GAUSS) check(fcp_create_lsq_grad_matrix(ctx, method), "fcp_create_lsq_grad_matrix");
+  check(fcp_grad_opt(ctx, method, limiter, FCP_F_S0, FCP_F_G0), "fcp_grad_opt");
+  get(FCP_F_G0, dPhidxi, 3 * (int64_t)geometry::numTotal);
+}
+// calcp_piso(): no arguments   Pressure/calcp_piso.f90
+inline void calcp_piso() {
+  using namespace variables;
+  using namespace sparse_matrix;
+  const int nT = geometry::numTotal, n = geometry::numCells;
+  put(FCP_F_U, u, nT); put(FCP_F_V, v, nT); put(FCP_F_W, w, nT); put(FCP_F_P, p, nT); put(FCP_F_PP, pp, nT); put(FCP_F_DEN, den, nT);
+  put(FCP_F_APU, apu, n); put(FCP_F_APV, apv, n); put(FCP_F_APW, apw, n);
+  put(FCP_F_RU, rU, n); put(FCP_F_RV, rV, n); put(FCP_F_RW, rW, n); put(FCP_F_A, a, nnz);
+  put(FCP_F_DPDXI, dPdxi, 3 * (int64_t)nT); put(FCP_F_FLMASS, flmass, geometry::numFaces);
+  fcp_piso_params prm{};
+  prm.solver = solver_id(pressure::lSolverP); prm.maxiter = pressure::maxiterP; prm.tol_abs = pressure::tolAbsP; prm.tol_rel = pressure::tolRelP;
+  prm.urfp = pressure::urfP; prm.ncorr = parameters::ncorr; prm.npcor = parameters::npcor; prm.pscheme = pscheme_id(pressure::pscheme);
+  prm.const_mflux = parameters::const_mflux; prm.flomas = parameters::flomas;
+  std::vector<fcp_report> rep((size_t)parameters::ncorr * parameters::npcor);
+  check(fcp_calcp_piso(ctx, &prm, rep.data()), "fcp_calcp_piso");
+  for (auto &r : rep) {
+    char line[256];
+    fcp_report_line(&r, "p", line, sizeof(line));
+    std::puts(line);
+  }
+  get(FCP_F_U, u, nT); get(FCP_F_V, v, nT); get(FCP_F_W, w, nT); get(FCP_F_P, p, nT); get(FCP_F_PP, pp, nT);
+  get(FCP_F_FLMASS, flmass, geometry::numFaces); get(FCP_F_DPDXI, dPdxi, 3 * (int64_t)nT);
+  get(FCP_F_SU, su, n); get(FCP_F_SV, sv, n); get(FCP_F_SW, sw, n); get(FCP_F_A, a, nnz);
+  h.resize(nnz); get(FCP_F_H, h, nnz);
 }
 inline void finalize() {
   if (ctx) fcp_ctx_destroy(ctx);

@@ -231,6 +231,7 @@ def main():
         uid = [L.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0], m.peer_rank)
+    comm_mode = ctx.comm_mode()
     pinned = {k: pinned_copy(f[k]) for k in INPUT_FIELDS}
     out_pinned = {k: pinned_copy(np.zeros(m.numTotal)) for k in OUTPUT_FIELDS}
     for k in INPUT_FIELDS:
@@ -353,7 +354,7 @@ def main():
         n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=False, scaling="strong", vs_baseline=None,
         dtype="f64", data="synthetic",
         config=dict(workload=f"synthetic 3D lid-driven cavity {n}^3 hex ({n**3} cells), pressure PCG", solver=args.solver, tol_rel=TOL_REL,
-                    pcg_iters=iters, partition=f"z-slabs x{world}", l2="inputs larger than L2 (matrix + vectors = "
+                    pcg_iters=iters, partition=f"z-slabs x{world}", comm=comm_mode, l2="inputs larger than L2 (matrix + vectors = "
                     f"{(12 * nnz0 + 60 * N0) / 1e6:.0f} MB per rank vs 126 MB L2)" if (12 * nnz0 + 60 * N0) > 2 * 126e6 else "working set fits L2: L2-resident numbers"),
         e2e=dict(value=e2e, unit="ms", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
         gpu_launches=int(sum(s["launches"] for s in allstats)),

@@ -6,7 +6,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <cstring>
+#include <algorithm>
+#include <cstdlib>
 #include "fcp_internal.h"
+#include "p2p.cuh"
 
 struct NcclApi {
   void *handle = nullptr;
@@ -69,10 +72,24 @@ struct FcpComm {
   double *sendbuf = nullptr, *recvbuf = nullptr;   // [3*npro]
   double *gather = nullptr;         // [4*nranks]
   double *d_scalar = nullptr;       // [4]
+  // ---- peer-memory path (CUDA IPC over NVLink) ----
+  bool p2p = false;
+  void *win = nullptr;              // own window: WinHeader | staging [2][3*npro] | halo vector [numTotal]
+  std::vector<void *> peer_win;     // by rank (own = win)
+  CommDev h_dev;                    // host copy of the device descriptor
+  CommDev *d_dev = nullptr;
+  int32_t *d_frank = nullptr, *d_rord = nullptr, *d_rslot = nullptr, *d_chunk_ptr = nullptr, *d_chunk_face = nullptr;
+  unsigned long long xseq = 0;      // sequence number of the generic halo exchanges (identical on all ranks)
 };
 int comm_nranks(const FcpComm *c) { return c ? c->nranks : 1; }
+const CommDev *comm_dev(const FcpComm *c) { return (c && c->p2p) ? c->d_dev : nullptr; }
+double *comm_halo_vector(const FcpComm *c) { return (c && c->p2p) ? c->h_dev.peer_hv[c->rank] : nullptr; }
 void comm_free(FcpComm *c) {
   if (!c) return;
+  for (size_t r = 0; r < c->peer_win.size(); ++r)
+    if ((int)r != c->rank && c->peer_win[r]) cudaIpcCloseMemHandle(c->peer_win[r]);
+  cudaFree(c->win); cudaFree(c->d_dev); cudaFree(c->d_frank); cudaFree(c->d_rord); cudaFree(c->d_rslot);
+  cudaFree(c->d_chunk_ptr); cudaFree(c->d_chunk_face);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_cell); cudaFree(c->d_slot); cudaFree(c->sendbuf); cudaFree(c->recvbuf); cudaFree(c->gather); cudaFree(c->d_scalar);
   delete c;
@@ -91,11 +108,53 @@ __global__ void k_halo_unpack(int32_t npro, int ncomp, const int32_t *__restrict
   for (int k = 0; k < ncomp; ++k) phi[ncomp * s + k] = buf[(int64_t)ncomp * i + k];   // exchange.f90:110-127
 }
 
+// ---- peer-memory exchange: ONE push kernel (pack + NVLink stores into the peer's staging + flag) and ONE pull kernel
+// (spin on the local flags + unpack into the ghost slots).  Staging is double buffered by sequence parity: a rank can be
+// at most one exchange ahead of a neighbour.
+__global__ void __launch_bounds__(256) k_halo_push(const CommDev *__restrict__ cd, int ncomp, const double *__restrict__ phi, unsigned long long seq) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int par = (int)(seq & 1ull);
+  if (i < cd->npro) {
+    const int r = cd->frank[i];
+    double *dst = cd->peer_stage[r] + (long long)par * cd->peer_stride[r] + (long long)ncomp * cd->rord[i];
+    const int64_t c = cd->cell[i];
+    for (int k = 0; k < ncomp; ++k) dst[k] = phi[ncomp * c + k];   // exchange.f90:48-66 + the MPI_Sendrecv of :81-99
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(&cd->hdr->push_ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) cd->hdr->push_ticket = 0u;
+  __threadfence_system();
+  if (threadIdx.x < cd->nnb) p2p_st_release(&cd->peer_hdr[cd->nb_rank[threadIdx.x]]->xflag[cd->rank], seq);
+}
+__global__ void __launch_bounds__(256) k_halo_pull(const CommDev *__restrict__ cd, int ncomp, double *__restrict__ phi, unsigned long long seq) {
+  if (threadIdx.x < cd->nnb) p2p_wait(&cd->hdr->xflag[cd->nb_rank[threadIdx.x]], seq, cd->hdr);
+  __syncthreads();
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cd->npro) return;
+  const double *src = cd->stage + (long long)(seq & 1ull) * cd->stride + (long long)ncomp * i;
+  const int64_t s = cd->slot[i];
+  for (int k = 0; k < ncomp; ++k) phi[ncomp * s + k] = p2p_ld_data(src + k);     // exchange.f90:110-127
+}
+
 int comm_exchange(fcp_ctx *ctx, double *field, int ncomp) {
   FcpComm *c = ctx->comm;
   if (!c || c->npro == 0) return FCP_OK;
   cudaStream_t st = ctx->stream;
   const int grid = (c->npro + 255) / 256;
+  if (c->p2p) {
+    const unsigned long long seq = ++c->xseq;
+    size_t tok = ctx->prof.begin(FCP_K_HALO, st);
+    k_halo_push<<<grid, 256, 0, st>>>(c->d_dev, ncomp, field, seq);
+    k_halo_pull<<<grid, 256, 0, st>>>(c->d_dev, ncomp, field, seq);
+    ctx->prof.end(tok, st);
+    FCP_LAUNCHED(); FCP_LAUNCHED();
+    FCP_CHECK_LAUNCH();
+    return FCP_OK;
+  }
   k_halo_pack<<<grid, 256, 0, st>>>(c->npro, ncomp, c->d_cell, field, c->sendbuf);
   FCP_LAUNCHED();
   FCP_NCCL(g_nccl.GroupStart());
@@ -152,6 +211,159 @@ __global__ void k_process_face_geom(int32_t npro, const int32_t *__restrict__ pf
   Df[f] = are / (arx[f] * xpn + ary[f] * ypn + arz[f] * zpn);
 }
 
+// ---- peer-memory set-up ------------------------------------------------------------------------------------------
+struct WinRecord {               // what every rank publishes about its window (all-gathered through NCCL)
+  cudaIpcMemHandle_t handle;     // 64 bytes
+  long long off_stage, stride, off_hv, ncols;
+  int ok, pad;
+};
+__global__ void k_i32_to_f64(int32_t n, const int32_t *__restrict__ src, double *__restrict__ dst, int32_t add_index) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)(src ? src[i] : 0) + (add_index ? (double)i : 0.0);
+}
+__global__ void k_f64_to_i32(int32_t n, const double *__restrict__ src, int32_t *__restrict__ dst) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (int32_t)src[i];
+}
+// per-face integers of the matching face on the peer, through the NCCL send/recv path (set-up only)
+static int nccl_swap_face_ints(fcp_ctx *ctx, FcpComm *c, const int32_t *d_src /* nullptr: the face ordinal */, int32_t *d_dst) {
+  cudaStream_t st = ctx->stream;
+  const int grid = (c->npro + 255) / 256;
+  if (c->npro == 0) return FCP_OK;
+  k_i32_to_f64<<<grid, 256, 0, st>>>(c->npro, d_src, c->sendbuf, d_src ? 0 : 1);
+  FCP_NCCL(g_nccl.GroupStart());
+  for (size_t j = 0; j < c->peer.size(); ++j) {
+    FCP_NCCL(g_nccl.Send(c->sendbuf + c->off[j], (size_t)c->cnt[j], ncclDouble, c->peer[j], c->comm, st));
+    FCP_NCCL(g_nccl.Recv(c->recvbuf + c->off[j], (size_t)c->cnt[j], ncclDouble, c->peer[j], c->comm, st));
+  }
+  FCP_NCCL(g_nccl.GroupEnd());
+  k_f64_to_i32<<<grid, 256, 0, st>>>(c->npro, c->recvbuf, d_dst);
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
+static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const std::vector<int32_t> &cell) {
+  const char *env = getenv("FCP_COMM");
+  const bool want = !(env && !strcmp(env, "nccl")) && c->nranks <= FCP_MAXR && c->nranks > 1;
+  cudaStream_t st = ctx->stream;
+  // window: header | staging [2][3*npro] | halo vector [numTotal]
+  const size_t hdr_bytes = (sizeof(WinHeader) + 255) / 256 * 256;
+  const long long stride = 3ll * std::max(c->npro, 1);
+  const size_t stage_bytes = ((size_t)2 * stride * sizeof(double) + 255) / 256 * 256;
+  const size_t hv_bytes = (size_t)std::max(ctx->nT, 1) * sizeof(double);
+  WinRecord mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.off_stage = (long long)hdr_bytes; mine.stride = stride; mine.off_hv = (long long)(hdr_bytes + stage_bytes); mine.ncols = ctx->nT;
+  mine.ok = 0;
+  if (want) {
+    if (cudaMalloc(&c->win, hdr_bytes + stage_bytes + hv_bytes) == cudaSuccess && cudaMemset(c->win, 0, hdr_bytes + stage_bytes + hv_bytes) == cudaSuccess &&
+        cudaDeviceSynchronize() == cudaSuccess && cudaIpcGetMemHandle(&mine.handle, c->win) == cudaSuccess)
+      mine.ok = 1;
+    else cudaGetLastError();
+  }
+  // all-gather the records (NCCL doubles as the barrier that orders every rank's memset before any peer store)
+  static_assert(sizeof(WinRecord) % 8 == 0, "WinRecord is gathered as 8-byte words");
+  const size_t words = sizeof(WinRecord) / 8;
+  double *d_rec = nullptr;
+  FCP_TRY(dev_alloc(&d_rec, words * (c->nranks + 1)));
+  FCP_CUDA(cudaMemcpyAsync(d_rec + words * c->nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  FCP_NCCL(g_nccl.AllGather(d_rec + words * c->nranks, d_rec, words, ncclDouble, c->comm, st));
+  std::vector<WinRecord> recs(c->nranks);
+  FCP_CUDA(cudaMemcpyAsync(recs.data(), d_rec, sizeof(WinRecord) * c->nranks, cudaMemcpyDeviceToHost, st));
+  FCP_CUDA(cudaStreamSynchronize(st));
+  bool all_ok = want;
+  for (auto &r : recs) all_ok = all_ok && r.ok;
+  c->peer_win.assign(c->nranks, nullptr);
+  int opened = 1;
+  if (all_ok) {
+    for (int r = 0; r < c->nranks; ++r) {
+      if (r == c->rank) { c->peer_win[r] = c->win; continue; }
+      if (cudaIpcOpenMemHandle(&c->peer_win[r], recs[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        c->peer_win[r] = nullptr;
+        opened = 0;
+      }
+    }
+  } else opened = 0;
+  // every rank must take the same path: min over ranks of `opened`
+  {
+    double v = (double)opened;
+    FCP_CUDA(cudaMemcpyAsync(c->d_scalar, &v, sizeof(double), cudaMemcpyHostToDevice, st));
+    FCP_NCCL(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclDouble, ncclMin, c->comm, st));
+    FCP_CUDA(cudaMemcpyAsync(&v, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, st));
+    FCP_CUDA(cudaStreamSynchronize(st));
+    opened = (int)v;
+  }
+  cudaFree(d_rec);
+  if (!opened) {
+    for (int r = 0; r < c->nranks; ++r)
+      if (r != c->rank && c->peer_win[r]) { cudaIpcCloseMemHandle(c->peer_win[r]); c->peer_win[r] = nullptr; }
+    if (env && !strcmp(env, "p2p")) { fcp_set_error("FCP_COMM=p2p requested but CUDA IPC peer mapping is not available"); return FCP_ENCCL; }
+    c->p2p = false;
+    return FCP_OK;   // NCCL send/recv + all-gather path
+  }
+  // per-face data of the matching face on the peer
+  std::vector<int32_t> frank(std::max(c->npro, 1), 0);
+  for (size_t j = 0; j < c->peer.size(); ++j)
+    for (int32_t i = 0; i < c->cnt[j]; ++i) frank[c->off[j] + i] = c->peer[j];
+  FCP_TRY(dev_upload(&c->d_frank, frank.data(), frank.size()));
+  FCP_TRY(dev_alloc(&c->d_rord, (size_t)std::max(c->npro, 1)));
+  FCP_TRY(dev_alloc(&c->d_rslot, (size_t)std::max(c->npro, 1)));
+  FCP_TRY(nccl_swap_face_ints(ctx, c, nullptr, c->d_rord));
+  FCP_TRY(nccl_swap_face_ints(ctx, c, c->d_slot, c->d_rslot));
+  // process faces grouped by the chunk (2048 rows) that owns their cell
+  const int nch = std::max(fcp_nchunks(ctx->n), 1);
+  std::vector<int32_t> cptr(nch + 1, 0), cface(std::max(c->npro, 1), 0);
+  for (int32_t i = 0; i < c->npro; ++i) cptr[cell[i] / FCP_CHUNK + 1]++;
+  for (int k = 0; k < nch; ++k) cptr[k + 1] += cptr[k];
+  {
+    std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
+    for (int32_t i = 0; i < c->npro; ++i) cface[fill[cell[i] / FCP_CHUNK]++] = i;
+  }
+  FCP_TRY(dev_upload(&c->d_chunk_ptr, cptr.data(), cptr.size()));
+  FCP_TRY(dev_upload(&c->d_chunk_face, cface.data(), cface.size()));
+  CommDev &d = c->h_dev;
+  memset(&d, 0, sizeof(d));
+  d.rank = c->rank; d.nranks = c->nranks;
+  std::vector<int> nb(c->peer.begin(), c->peer.end());
+  std::sort(nb.begin(), nb.end());
+  nb.erase(std::unique(nb.begin(), nb.end()), nb.end());
+  d.nnb = (int)nb.size();
+  for (int k = 0; k < d.nnb; ++k) d.nb_rank[k] = nb[k];
+  for (int r = 0; r < c->nranks; ++r) {
+    char *base = (char *)c->peer_win[r];
+    d.peer_hdr[r] = (WinHeader *)base;
+    d.peer_stage[r] = (double *)(base + recs[r].off_stage);
+    d.peer_stride[r] = recs[r].stride;
+    d.peer_hv[r] = (double *)(base + recs[r].off_hv);
+  }
+  d.hdr = d.peer_hdr[c->rank]; d.stage = d.peer_stage[c->rank]; d.stride = stride;
+  d.npro = c->npro; d.cell = c->d_cell; d.slot = c->d_slot; d.frank = c->d_frank; d.rord = c->d_rord; d.rslot = c->d_rslot;
+  d.chunk_ptr = c->d_chunk_ptr; d.chunk_face = c->d_chunk_face;
+  for (int k = 0; k < nch; ++k) d.n_halo_chunks += (cptr[k + 1] > cptr[k]) ? 1 : 0;
+  FCP_CUDA(cudaMalloc((void **)&c->d_dev, sizeof(CommDev)));
+  FCP_CUDA(cudaMemcpyAsync(c->d_dev, &d, sizeof(CommDev), cudaMemcpyHostToDevice, st));
+  FCP_CUDA(cudaStreamSynchronize(st));
+  c->p2p = true;
+  return FCP_OK;
+}
+
+// 1 when the peer-memory (CUDA IPC / NVLink) path is active, 0 when the context uses NCCL send/recv, -1 without a communicator
+extern "C" int fcp_comm_mode(const fcp_ctx *ctx) {
+  if (!ctx || !ctx->comm) return -1;
+  return ctx->comm->p2p ? 1 : 0;
+}
+// raised by a kernel that gave up waiting for a peer (p2p.cuh: p2p_wait)
+int comm_check_error(fcp_ctx *ctx) {
+  FcpComm *c = ctx->comm;
+  if (!c || !c->p2p) return FCP_OK;
+  int err = 0;
+  FCP_CUDA(cudaMemcpyAsync(&err, &c->h_dev.hdr->error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err) { fcp_set_error("peer-memory protocol timeout: a rank stopped responding"); return FCP_ENCCL; }
+  return FCP_OK;
+}
+
 extern "C" int fcp_comm_unique_id(void *id128) {
   if (!id128) return FCP_EINVAL;
   FCP_TRY(nccl_load());
@@ -201,6 +413,7 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
   memcpy(&id, id128, 128);
   FCP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
   ctx->comm = c;
+  FCP_TRY(p2p_setup(ctx, c, cell));
   // ghost copies of the cell-centre data (src-par/geometry.f90:769-773) and the process-face geometry
   FCP_TRY(comm_exchange(ctx, ctx->xc, 1));
   FCP_TRY(comm_exchange(ctx, ctx->yc, 1));

@@ -101,6 +101,7 @@ struct KrylovWS {
   double *reso = nullptr, *uk = nullptr, *vk = nullptr, *tmp = nullptr;
   KrylovScalars *sc = nullptr;        // device
   KrylovScalars *h_sc = nullptr;      // pinned host mirror
+  bool pk_external = false;           // pk lives in the communication window (multi-GPU peer-memory path)
   double *partials = nullptr;         // [4 * maxchunks]
   unsigned int *counter = nullptr;    // last-block ticket
   int maxchunks = 0;
@@ -108,6 +109,40 @@ struct KrylovWS {
 };
 
 struct FcpComm;   // comm.cu
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory communication (comm.cu).  Every rank owns one device "window" (header + halo staging + the Krylov
+// direction vector) that all peers of the node map through CUDA IPC.  Halo values and reduction partials are written
+// straight into the peer's window over NVLink by the producing kernel, followed by a sequence-number flag; consumers
+// spin on their own (local) flags.  No host round trip, no separate communication kernels inside a Krylov iteration.
+// ---------------------------------------------------------------------------------------------
+#define FCP_MAXR 16
+struct WinHeader {
+  unsigned long long xflag[FCP_MAXR];      // written by peer r: sequence number of its last complete generic halo push
+  unsigned long long pkflag[FCP_MAXR];     // written by peer r: sequence number of its last fused push into my halo vector
+  unsigned long long rflag[2][FCP_MAXR];   // written by peer r: sequence number of the reduction whose partials are in rval[par][r]
+  double rval[2][FCP_MAXR][4];
+  // local only
+  unsigned long long red_seq, pk_push_seq, pk_wait_seq;
+  unsigned int push_ticket, pad0;
+  int error, pad1;
+};
+struct CommDev {
+  int rank, nranks, nnb;                   // nnb: number of distinct neighbour ranks
+  int nb_rank[FCP_MAXR];
+  WinHeader *hdr;                          // own header
+  WinHeader *peer_hdr[FCP_MAXR];           // by rank (self included)
+  double *peer_stage[FCP_MAXR];            // by rank: that rank's staging area [2][stride]
+  long long peer_stride[FCP_MAXR];         // 3 * npro of that rank
+  double *peer_hv[FCP_MAXR];               // by rank: that rank's halo vector (the Krylov direction, numTotal entries)
+  double *stage;                           // own staging
+  long long stride;
+  int32_t npro;
+  const int32_t *cell, *slot;              // per process face (patch order): owner cell, ghost slot
+  const int32_t *frank, *rord, *rslot;     // peer rank, the face's ordinal and ghost slot on the peer
+  const int32_t *chunk_ptr, *chunk_face;   // process faces grouped by the 2048-row chunk of their owner cell
+  int32_t n_halo_chunks;                   // chunks that own at least one process face (ticket size of the fused push)
+};
 
 // per-kernel-class CUDA-event timing (fcp_profile_*): an event pair around every launch of a class
 struct Profiler {
@@ -239,7 +274,7 @@ template <class T> int dev_upload(T **dptr, const T *h, size_t count);
 template <class T> int dev_alloc(T **dptr, size_t count);
 
 // ---- krylov.cu ----------------------------------------------------------------------------------
-int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols);
+int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols, double *pk_ext = nullptr);
 void krylov_ws_free(KrylovWS &ws);
 int sell_spmv(const SellPattern &p, const double *a, const double *x, double *y, cudaStream_t st);
 int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const double *rhs, KrylovWS &ws,
@@ -252,3 +287,6 @@ int comm_allgather_sum(FcpComm *comm, double *d_vals, int count, cudaStream_t st
 int comm_allreduce_minmax(FcpComm *comm, double *d_mm /* {min,max} */, cudaStream_t st);
 void comm_free(FcpComm *comm);
 int comm_nranks(const FcpComm *comm);
+const CommDev *comm_dev(const FcpComm *comm);       // device descriptor, nullptr unless the peer-memory path is active
+double *comm_halo_vector(const FcpComm *comm);
+int comm_check_error(fcp_ctx *ctx);      // the window's halo vector (the Krylov workspace uses it as pk)

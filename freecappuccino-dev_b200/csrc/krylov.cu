@@ -10,18 +10,20 @@
 #include <cstring>
 #include "fcp_internal.h"
 #include "reduce.cuh"
+#include "p2p.cuh"
 namespace cg = cooperative_groups;
 
 // ---------------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------------
-int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols) {
-  if (ws.n == n && ws.ncols == ncols && ws.res) return FCP_OK;
+int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols, double *pk_ext) {
+  if (ws.n == n && ws.ncols == ncols && ws.res && (!pk_ext || ws.pk == pk_ext)) return FCP_OK;
   krylov_ws_free(ws);
   ws.n = n;
   ws.ncols = ncols;
   FCP_TRY(dev_alloc(&ws.res, (size_t)n));
-  FCP_TRY(dev_alloc(&ws.pk, (size_t)ncols));
+  if (pk_ext) { ws.pk = pk_ext; ws.pk_external = true; }   // the direction vector lives in the communication window
+  else FCP_TRY(dev_alloc(&ws.pk, (size_t)ncols));
   FCP_TRY(dev_alloc(&ws.zk, (size_t)ncols));
   FCP_TRY(dev_alloc(&ws.adiag, (size_t)n));
   ws.maxchunks = fcp_nchunks(n) + 1;
@@ -42,7 +44,7 @@ static int krylov_ws_need(KrylovWS &ws, double **p, size_t count) {
   return FCP_OK;
 }
 void krylov_ws_free(KrylovWS &ws) {
-  cudaFree(ws.res); cudaFree(ws.pk); cudaFree(ws.zk); cudaFree(ws.adiag); cudaFree(ws.d);
+  cudaFree(ws.res); if (!ws.pk_external) cudaFree(ws.pk); cudaFree(ws.zk); cudaFree(ws.adiag); cudaFree(ws.d);
   cudaFree(ws.reso); cudaFree(ws.uk); cudaFree(ws.vk); cudaFree(ws.tmp);
   cudaFree(ws.partials); cudaFree(ws.counter); cudaFree(ws.sc);
   if (ws.h_sc) cudaFreeHost(ws.h_sc);
@@ -73,6 +75,22 @@ __device__ __forceinline__ double sell_row_sum(const SellView &m, const double *
     const double av = __ldcs(ap + (int64_t)k * 32);
     const int32_t c = __ldcs(jp + (int64_t)k * 32);
     const double t = av * __ldg(x + c);
+    s = SUB ? (s - t) : (s + t);
+  }
+  return s;
+}
+
+// same for rows of a chunk that owns process faces: ghost columns (>= n) were written by a peer over NVLink during this
+// kernel's lifetime, so they are read past L1
+template <bool SUB>
+__device__ __forceinline__ double sell_row_sum_halo(const SellView &m, const double *__restrict__ x, int32_t r, double s, int32_t n) {
+  const int64_t base = __ldg(&m.slptr[r >> 5]) + (r & 31);
+  const int32_t len = __ldg(&m.rinfo[r]) & 0xffff;
+  for (int32_t k = 0; k < len; ++k) {
+    const double av = __ldcs(m.a + base + (int64_t)k * 32);
+    const int32_t c = __ldcs(m.ja + base + (int64_t)k * 32);
+    const double xv = c >= n ? p2p_ld_data(x + c) : __ldg(x + c);
+    const double t = av * xv;
     s = SUB ? (s - t) : (s + t);
   }
   return s;
@@ -184,18 +202,62 @@ struct RedArgs {
   unsigned int *counter;
   KrylovScalars *sc;
   int epi;    // epilogue id
-  int fuse;   // 1: run the epilogue in the last CTA (single GPU); 0: only store the local sums in sc->red
+  int fuse;   // 1: run the epilogue in the last CTA (single GPU); 0: only store the local sums in sc->red (NCCL path);
+              // 2: peer-memory all-reduce inside the last CTA, then the epilogue
+  const CommDev *cd;
+  int bump;   // fuse == 2: this kernel consumed a fused halo push (advance hdr->pk_wait_seq)
 };
+
+// Last CTA of a reducing kernel; `total` is valid in thread 0.  fuse == 2: every rank stores its partial sums into every
+// peer's window (thread r -> rank r), flags them with the reduction's sequence number, waits for the P flags of its own
+// window and adds the P partials in RANK ORDER (src-par/global_sum_mpi.f90 semantics, deterministic, identical bits on
+// every rank).  Two slots by sequence parity: a rank can be at most one reduction ahead of any other.
+template <int NS>
+__device__ __forceinline__ void finish_epilogue(double (&total)[NS], const RedArgs &ra) {
+  if (ra.fuse == 2) {
+    const CommDev *cd = ra.cd;
+    WinHeader *hdr = cd->hdr;
+    __shared__ double tot_s[4];
+    __shared__ unsigned long long seq_s;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) tot_s[k] = total[k];
+      seq_s = ++hdr->red_seq;
+      if (ra.bump) hdr->pk_wait_seq += 1ull;
+    }
+    __syncthreads();
+    const unsigned long long seq = seq_s;
+    const int par = (int)(seq & 1ull);
+    if ((int)threadIdx.x < cd->nranks) {
+      WinHeader *ph = cd->peer_hdr[threadIdx.x];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) ph->rval[par][cd->rank][k] = tot_s[k];
+      __threadfence_system();
+      p2p_st_release(&ph->rflag[par][cd->rank], seq);
+      p2p_wait(&hdr->rflag[par][threadIdx.x], seq, hdr);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        double sum = p2p_ld_data(&hdr->rval[par][0][k]);
+        for (int r = 1; r < cd->nranks; ++r) sum = sum + p2p_ld_data(&hdr->rval[par][r][k]);
+        ra.sc->red[k] = sum;
+      }
+      krylov_epilogue(ra.epi, ra.sc);
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) ra.sc->red[k] = total[k];
+    if (ra.fuse) krylov_epilogue(ra.epi, ra.sc);
+  }
+}
 template <int NS>
 __device__ __forceinline__ void finish_reduce(double (&s)[NS], const RedArgs &ra) {
   double total[NS];
-  if (fcp_grid_reduce<NS>(s, ra.partials, ra.stride, ra.counter, total)) {
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < NS; ++k) ra.sc->red[k] = total[k];
-      if (ra.fuse) krylov_epilogue(ra.epi, ra.sc);
-    }
-  }
+  if (fcp_grid_reduce<NS>(s, ra.partials, ra.stride, ra.counter, total)) finish_epilogue<NS>(total, ra);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,10 +282,13 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_init(int32_t n, SellView m, cons
   finish_reduce<2>(s, ra);
 }
 
-// pk = zk + bet*pk with zk = res/adiag (dpcg :288-303) or the stored zk (iccg)
+// pk = zk + bet*pk with zk = res/adiag (dpcg :288-303) or the stored zk (iccg).
+// cd != nullptr (multi-GPU, peer-memory path): `call exchange(pk)` (src-par/dpcg.f90:118) is fused in -- after its chunk is
+// written the CTA stores the pk values of its process-face cells straight into the ghost slots of the neighbours' pk
+// over NVLink; the last CTA to finish raises the sequence flag on every neighbour.
 template <bool JACOBI>
 __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
-                                                    const double *__restrict__ zk, double *__restrict__ pk, const KrylovScalars *sc) {
+                                                    const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd) {
   if (sc->done) return;
   const double bet = sc->bet;
   const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
@@ -241,24 +306,55 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__re
       const double z = JACOBI ? (z_[j] / d_[j]) : z_[j];
       pk[base + j * FCP_TPB] = z + bet * p_[j];
     }
-    return;
+  } else {
+    FCP_ROW_LOOP(r, n) {
+      const double z = JACOBI ? (res[r] / adiag[r]) : zk[r];
+      pk[r] = z + bet * pk[r];
+    }
   }
-  FCP_ROW_LOOP(r, n) {
-    const double z = JACOBI ? (res[r] / adiag[r]) : zk[r];
-    pk[r] = z + bet * pk[r];
+  if (!cd) return;
+  const int32_t j0 = cd->chunk_ptr[blockIdx.x], j1 = cd->chunk_ptr[blockIdx.x + 1];
+  if (j0 == j1) return;   // this chunk owns no process face: nothing to push, not part of the ticket
+  __syncthreads();
+  for (int32_t j = j0 + (int32_t)threadIdx.x; j < j1; j += FCP_TPB) {
+    const int32_t i = cd->chunk_face[j];
+    cd->peer_hv[cd->frank[i]][cd->rslot[i]] = pk[cd->cell[i]];
   }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  __shared__ unsigned long long seq_s;
+  if (threadIdx.x == 0) last = (atomicAdd(&cd->hdr->push_ticket, 1u) == (unsigned int)cd->n_halo_chunks - 1u);
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) { cd->hdr->push_ticket = 0u; seq_s = ++cd->hdr->pk_push_seq; }
+  __syncthreads();
+  __threadfence_system();
+  if ((int)threadIdx.x < cd->nnb) p2p_st_release(&cd->peer_hdr[cd->nb_rank[threadIdx.x]]->pkflag[cd->rank], seq_s);
+}
+
+// CTAs whose chunk owns process faces wait for the neighbours' fused pushes of this iteration (flag >= pk_wait_seq + 1)
+__device__ __forceinline__ bool spmv_halo_chunk(const CommDev *cd, int wait) {
+  if (!cd) return false;
+  const bool halo = cd->chunk_ptr[blockIdx.x + 1] > cd->chunk_ptr[blockIdx.x];
+  if (halo && wait) {
+    if ((int)threadIdx.x < cd->nnb) p2p_wait(&cd->hdr->pkflag[cd->nb_rank[threadIdx.x]], cd->hdr->pk_wait_seq + 1ull, cd->hdr);
+    __syncthreads();
+  }
+  return halo;
 }
 
 // y = A x ; sums: sum v1*y [, sum v2*y | sum y*y]
 template <int NS, bool SQ>
 __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
-                                                       const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra) {
+                                                       const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int wait) {
   if (sc->done) return;
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  const bool halo = spmv_halo_chunk(ra.cd, wait);
   FCP_ROW_LOOP(r, n) {
-    const double yr = sell_row_sum<false>(m, x, r, 0.0);
+    const double yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, n) : sell_row_sum<false>(m, x, r, 0.0);
     y[r] = yr;
     s[0] = s[0] + v1[r] * yr;
     if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
@@ -276,12 +372,13 @@ __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, con
 #define FCP_PIPE_MINB 4
 #endif
 template <int NS, bool SQ, int W>
-__global__ void __launch_bounds__(FCP_TPB, FCP_PIPE_MINB) k_spmv_dot_pipe(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
-                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra) {
+__global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_dot_pipe(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
+                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int wait) {
   if (sc->done) return;
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  const bool halo = spmv_halo_chunk(ra.cd, wait);
   const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
   if (base + (FCP_IPT - 1) * FCP_TPB < n) {
     const int lane = threadIdx.x & 31;
@@ -297,8 +394,13 @@ __global__ void __launch_bounds__(FCP_TPB, FCP_PIPE_MINB) k_spmv_dot_pipe(int32_
       double av[W], xv[W];
 #pragma unroll
       for (int k = 0; k < W; ++k) av[k] = (k < len) ? __ldcs(m.a + pos + (int64_t)k * 32) : 0.0;
+      if (halo) {   // CTA-uniform: ghost columns (>= n) were stored by a peer during this kernel's lifetime
 #pragma unroll
-      for (int k = 0; k < W; ++k) xv[k] = (k < len) ? __ldg(x + c[k]) : 0.0;
+        for (int k = 0; k < W; ++k) xv[k] = (k < len) ? (c[k] >= n ? p2p_ld_data(x + c[k]) : __ldg(x + c[k])) : 0.0;
+      } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) xv[k] = (k < len) ? __ldg(x + c[k]) : 0.0;
+      }
       const double vv = v1[r];
       // next row: meta data and column indices
       int64_t npos = 0;
@@ -315,7 +417,10 @@ __global__ void __launch_bounds__(FCP_TPB, FCP_PIPE_MINB) k_spmv_dot_pipe(int32_
 #pragma unroll
       for (int k = 0; k < W; ++k)
         if (k < len) yr = yr + av[k] * xv[k];
-      for (int32_t k = W; k < len; ++k) yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * __ldg(x + __ldcs(m.ja + pos + (int64_t)k * 32));
+      for (int32_t k = W; k < len; ++k) {
+        const int32_t ck = __ldcs(m.ja + pos + (int64_t)k * 32);
+        yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * ((halo && ck >= n) ? p2p_ld_data(x + ck) : __ldg(x + ck));
+      }
       y[r] = yr;
       s[0] = s[0] + vv * yr;
       if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
@@ -326,7 +431,7 @@ __global__ void __launch_bounds__(FCP_TPB, FCP_PIPE_MINB) k_spmv_dot_pipe(int32_
     }
   } else {
     FCP_ROW_LOOP(r, n) {
-      const double yr = sell_row_sum<false>(m, x, r, 0.0);
+      const double yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, n) : sell_row_sum<false>(m, x, r, 0.0);
       y[r] = yr;
       s[0] = s[0] + v1[r] * yr;
       if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
@@ -376,13 +481,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 template <int NS>
 __device__ __forceinline__ void finish_reduce_part(double (&s)[NS], const RedArgs &ra, int part, int nparts) {
   double total[NS];
-  if (fcp_grid_reduce_part<NS>(s, ra.partials, ra.stride, ra.counter, part, nparts, total)) {
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < NS; ++k) ra.sc->red[k] = total[k];
-      if (ra.fuse) krylov_epilogue(ra.epi, ra.sc);
-    }
-  }
+  if (fcp_grid_reduce_part<NS>(s, ra.partials, ra.stride, ra.counter, part, nparts, total)) finish_epilogue<NS>(total, ra);
 }
 
 // Persistent CTAs: CTA b owns chunks b, b + gridDim.x, ... and keeps ONE pipeline running across its chunks (the ring is
@@ -670,10 +769,11 @@ struct Launcher {
   KrylovWS &ws;
   int n;
   int grid;
-  RedArgs red(int epi) const { return RedArgs{ws.partials, ws.maxchunks, ws.counter, ws.sc, epi, comm ? 0 : 1}; }
-  // after a reducing kernel in multi-GPU mode: cross-rank sum of sc->red[0..ns) + epilogue kernel
+  const CommDev *cd;   // peer-memory path (nullptr: single GPU or NCCL path)
+  RedArgs red(int epi, int bump = 0) const { return RedArgs{ws.partials, ws.maxchunks, ws.counter, ws.sc, epi, comm ? (cd ? 2 : 0) : 1, cd, bump}; }
+  // after a reducing kernel on the NCCL path: cross-rank sum of sc->red[0..ns) + epilogue kernel
   int post(int epi, int ns) const {
-    if (!comm) return FCP_OK;
+    if (!comm || cd) return FCP_OK;
     FCP_TRY(comm_allgather_sum(comm, ws.sc->red, ns, st));
     k_epilogue<<<1, 1, 0, st>>>(epi, ws.sc);
     FCP_LAUNCHED();
@@ -683,6 +783,10 @@ struct Launcher {
   int halo(double *x) const {   // src-par/dpcg.f90:118  call exchange(pk)
     if (!comm) return FCP_OK;
     return comm_exchange(ctx, x, 1);
+  }
+  int halo_pk() const {         // exchange(pk): fused into k_cg_pk / the SpMV on the peer-memory path
+    if (!comm || cd) return FCP_OK;
+    return comm_exchange(ctx, ws.pk, 1);
   }
 };
 
@@ -741,7 +845,7 @@ static int tma_smem_limit(size_t smem) {
 // load/use kernel.  FCP_SPMV=ldg forces the latter (A/B measurements).
 template <int NS, bool SQ>
 static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double *x, double *y, const double *v1, const KrylovScalars *sc,
-                           const RedArgs &ra, cudaStream_t st) {
+                           const RedArgs &ra, cudaStream_t st, int wait = 0) {
   const int grid = fcp_nchunks(p.n);
   if (!grid) return FCP_OK;
   static int mode = -1;   // 0 ldg, 1 tma
@@ -756,7 +860,7 @@ static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double
   const size_t extra = FCP_MAX_STAGES * sizeof(uint64_t) + 2 * (FCP_CHUNK / 32 + 1) * sizeof(int64_t) + 128;
   int nst = stages_env ? stages_env : (int)std::min<size_t>(FCP_MAX_STAGES, (size_t)(24 * 1024) / std::max<size_t>(stage_bytes, 1));
   nst = std::min(nst, FCP_MAX_STAGES);
-  if (mode == 1 && p.tile_cap > 0 && nst >= 2) {
+  if (mode == 1 && p.tile_cap > 0 && nst >= 2 && !ra.cd) {
     const size_t smem = nst * stage_bytes + extra;
     FCP_TRY(tma_smem_limit(smem));
     static int nsm = 0;
@@ -770,11 +874,11 @@ static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double
     const int pgrid = std::min(grid, std::max(1, occ) * nsm);
     k_spmv_dot_tma<NS, SQ><<<pgrid, FCP_TPB, smem, st>>>(p.n, p.nslices, m, x, y, v1, sc, ra, p.tile_cap, nst);
     FCP_CHECK_LAUNCH();
-  } else if (mode == 2) {
-    if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra);
-    else k_spmv_dot_pipe<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra);
+  } else if (mode != 0) {
+    if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, wait);
+    else k_spmv_dot_pipe<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, wait);
   } else {
-    k_spmv_dot<NS, SQ><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra);
+    k_spmv_dot<NS, SQ><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, wait);
   }
   FCP_LAUNCHED();
   return FCP_OK;
@@ -794,10 +898,13 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     fcp_set_error("csrsolve: unknown solver id %d", solver);
     return FCP_EINVAL;
   }
-  FCP_TRY(krylov_ws_alloc(ws, n, p.ncols));
+  const CommDev *cd = comm_dev(comm);
+  FCP_TRY(krylov_ws_alloc(ws, n, p.ncols, comm_halo_vector(comm)));
   if (rep) { memset(rep, 0, sizeof(*rep)); rep->solver = solver; }
   const int grid = fcp_nchunks(n);
-  Launcher L{st, comm, ctx, ws, n, grid};
+  if (cd && grid == 0) { fcp_set_error("a partition without cells cannot take part in the peer-memory path"); return FCP_EINVAL; }
+  Launcher L{st, comm, ctx, ws, n, grid, cd};
+  const int fw = cd ? 1 : 0;   // the SpMV after k_cg_pk waits for the fused halo push
   Profiler *prof = ctx ? &ctx->prof : nullptr;
   SellView m{p.slptr, p.rinfo, p.ja, a};
   KrylovScalars init;
@@ -817,9 +924,9 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     FCP_TRY(L.post(EPI_INIT_CG, 2));
     for (int it = 0; it < itr_max;) {
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
-        if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc), FCP_LAUNCHED()));
-        FCP_TRY(L.halo(ws.pk));
-        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st))));
+        if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd), FCP_LAUNCHED()));
+        FCP_TRY(L.halo_pk());
+        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK, fw), st, fw))));
         FCP_TRY(L.post(EPI_PKAPK, 1));
         if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
         FCP_TRY(L.post(EPI_CG_UPDATE, 3));
@@ -842,9 +949,9 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
           FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st)));
           if (grid) { k_dot<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.zk, ws.sc, L.red(EPI_SK)); FCP_LAUNCHED(); }
           FCP_TRY(L.post(EPI_SK, 1));
-          if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc), FCP_LAUNCHED()));
-          FCP_TRY(L.halo(ws.pk));
-          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st))));
+          if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd), FCP_LAUNCHED()));
+          FCP_TRY(L.halo_pk());
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK, fw), st, fw))));
           FCP_TRY(L.post(EPI_PKAPK, 1));
           if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
           FCP_TRY(L.post(EPI_CG_UPDATE, 3));
@@ -892,6 +999,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
   }
   FCP_TRY(fetch_scalars(ws, st));
   if (comm) FCP_TRY(L.halo(fi));   // src-par/dpcg.f90:183  call exchange(fi)
+  if (cd) FCP_TRY(comm_check_error(ctx));
   if (rep) {
     rep->res0 = ws.h_sc->res0;
     rep->resl = ws.h_sc->resl;

@@ -1,0 +1,36 @@
+// p2p.cuh -- device-side primitives of the peer-memory protocol (fcp_internal.h: WinHeader / CommDev).
+// Producer: data stores into the peer window -> __threadfence_system() -> st.release.sys of the sequence flag.
+// Consumer: ld.acquire.sys spin on its own (local) flag -> data loads that bypass L1 (ld.volatile / __ldcg).
+#pragma once
+#include "fcp_internal.h"
+
+__device__ __forceinline__ unsigned long long p2p_ld_acquire(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_st_release(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double p2p_ld_data(const double *p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= seq; gives up after 20 s (a peer died or a protocol bug) and raises hdr->error instead of hanging the GPU
+__device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long seq, WinHeader *hdr) {
+  unsigned long long t0 = 0;
+  unsigned int n = 0;
+  while (p2p_ld_acquire(flag) < seq) {
+    if ((++n & 4095u) == 0u) {
+      const unsigned long long t = p2p_now_ns();
+      if (!t0) t0 = t;
+      else if (t - t0 > 20000000000ull) { hdr->error = 1; break; }
+    }
+  }
+}

@@ -131,6 +131,7 @@ def lib():
     L.fcp_solver_solve.argtypes = [vp, C.c_int, _pd, _pd, _pd, C.c_int32, C.c_double, C.c_double, C.POINTER(Report)]
     L.fcp_comm_unique_id.argtypes = [C.c_void_p]
     L.fcp_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p, _pi]
+    L.fcp_comm_mode.argtypes = [vp]
     L.fcp_exchange.argtypes = [vp, C.c_int]
     for nm in ("fcp_global_sum", "fcp_global_max", "fcp_global_min"):
         getattr(L, nm).argtypes = [vp, _pd]
@@ -302,6 +303,10 @@ class Context:
         pr = np.ascontiguousarray(peer_rank, dtype=np.int32)
         buf = C.create_string_buffer(unique_id, 128)
         check(lib().fcp_comm_init(self.h, rank, nranks, buf, _i(pr)), "fcp_comm_init")
+
+    def comm_mode(self) -> str:
+        """'p2p' (peer-memory stores over NVLink fused into the kernels), 'nccl' (send/recv + all-gather) or 'none'."""
+        return {1: "p2p", 0: "nccl"}.get(int(lib().fcp_comm_mode(self.h)), "none")
 
     def exchange(self, field):
         check(lib().fcp_exchange(self.h, field_id(field)), "fcp_exchange")

@@ -295,6 +295,46 @@ def cavity_mesh(n: int, nz: Optional[int] = None, length: float = 1.0, bump: flo
     return hex_mesh(xs, ys, zs, None, distort)
 
 
+def polyhedral_mesh(nx: int, ny: Optional[int] = None, nz: Optional[int] = None, distort: float = 0.15,
+                    patch_types: Optional[Dict[str, str]] = None) -> Mesh:
+    """Synthetic POLYHEDRAL mesh (BASELINE config 5 stand-in): a distorted nx x ny x nz hex grid whose cells are agglomerated
+    pairwise along x in a brick pattern staggered in both y and z (pair start parity = (j+k) mod 2).  Every interior
+    polyhedron has 10 quadrilateral faces and 10 DISTINCT neighbours (no two cells share more than one face, so the CSR
+    pattern has no duplicate columns); cells at the x ends stay single hexahedra (6 faces) -- a mixed-cell mesh with
+    variable row lengths, like examples/elbow3D or transientConductionFlange.  Inner faces are renumbered in OpenFOAM's
+    upper-triangular order (owner ascending, then neighbour), boundary faces keep their patches."""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    h = hex_mesh(np.linspace(0.0, 1.0, nx + 1), np.linspace(0.0, 1.0, ny + 1), np.linspace(0.0, 1.0, nz + 1), patch_types, distort)
+    c = np.arange(h.numCells)
+    i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+    s = (j + k) % 2
+    head = np.where((i - s) % 2 == 0, i, i - 1)          # x index of the first hex of the pair (may be -1 -> single at the left end)
+    head = np.where(head < 0, 0, head)
+    key = head + nx * (j + ny * k)                       # id of the pair's head hex; singles map to themselves
+    uniq, poly = np.unique(key, return_inverse=True)     # ascending head id keeps the cells roughly i-fastest
+    ncell = uniq.size
+    Fi = h.numInnerFaces
+    own = poly[h.owner.astype(np.int64) - 1]
+    nb = poly[h.neighbour.astype(np.int64) - 1]
+    keep = own[:Fi] != nb                                # drop the face between the two hexes of a pair
+    fo, fn, fnodes = own[:Fi][keep], nb[keep], h.face_nodes[:Fi][keep].copy()
+    swap = fo > fn                                       # owner must be the lower cell id: flip the face
+    fo2, fn2 = np.where(swap, fn, fo), np.where(swap, fo, fn)
+    fnodes[swap] = fnodes[swap][:, ::-1]
+    order = np.lexsort((fn2, fo2))
+    fo2, fn2, fnodes = fo2[order], fn2[order], fnodes[order]
+    pair = fo2.astype(np.int64) * ncell + fn2
+    assert np.unique(pair).size == pair.size, "two polyhedra share more than one face"
+    nF_in = fo2.size
+    removed = Fi - nF_in
+    face_nodes = np.ascontiguousarray(np.concatenate([fnodes, h.face_nodes[Fi:]]), dtype=np.int32)
+    owner = (np.concatenate([fo2, own[Fi:]]) + 1).astype(np.int32)
+    neighbour = (fn2 + 1).astype(np.int32)
+    patches = [(h.bcname[ib], BC_NAMES[h.bctype[ib]], int(h.nfaces[ib]), int(h.startFace[ib]) - removed) for ib in range(h.numBoundaries)]
+    return mesh_from_topology(h.points, face_nodes, np.full(owner.shape[0], 4, dtype=np.int32), owner, neighbour, ncell, patches)
+
+
 # ---------------------------------------------------------------------------------------------
 # polyMesh readers (Appendix D of SURVEY.md; geometry.f90:118-406 native, :846-1717 OpenFOAM)
 # ---------------------------------------------------------------------------------------------

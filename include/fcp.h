@@ -195,6 +195,9 @@ int fcp_solver_solve(fcp_solver *s, int solver, const double *a, double *fi, con
  * shared faces in the same order (src-par/geometry.f90:218-240). */
 int fcp_comm_unique_id(void *id128);
 int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id128, const int32_t *peer_rank);
+/* 1: halo values and reduction partials travel as peer-memory stores over NVLink (CUDA IPC windows, fused into the
+ * Krylov kernels); 0: NCCL send/recv + all-gather (FCP_COMM=nccl or peer mapping unavailable); -1: no communicator */
+int fcp_comm_mode(const fcp_ctx *ctx);
 int fcp_exchange(fcp_ctx *ctx, int field);                    /* ghost slots of `process` patches <- owner values on the peer */
 int fcp_global_sum(fcp_ctx *ctx, double *value);              /* in place, all ranks */
 int fcp_global_max(fcp_ctx *ctx, double *value);

@@ -25,6 +25,7 @@ def meshes():
     xs = np.linspace(0, 2.0, 15); ys = np.linspace(0, 1.0, 9); zs = np.linspace(0, 0.5, 6)
     out["channel_inout"] = M.hex_mesh(xs, ys, zs, dict(left="inlet", right="outlet", back="symmetry", front="symmetry"), distort=0.15)
     out["channel_pressure"] = M.hex_mesh(xs, ys, zs, dict(left="inlet", right="pressure", back="empty", front="empty"), distort=0.1)
+    out["poly_10faces"] = M.polyhedral_mesh(8, 6, 5, distort=0.15, patch_types=dict(left="inlet", right="outlet"))   # 10-faced cells + hexes
     out["tiny3"] = M.hex_mesh(np.linspace(0, 1, 4), np.linspace(0, 1, 3), np.linspace(0, 1, 2))   # 3x2x1 = 6 cells (< one warp)
     return out
 

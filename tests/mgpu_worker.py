@@ -43,6 +43,9 @@ def main():
     uid = [L.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(rank, world, uid[0], me.peer_rank)
+    mode = ctx.comm_mode()
+    want = os.environ.get("FCP_COMM", "")
+    assert mode in ("p2p", "nccl") and (not want or mode == want), (mode, want)
 
     # ---- exchange ---------------------------------------------------------------------------------------------------
     rng = np.random.default_rng(100 + rank)
@@ -156,7 +159,7 @@ def main():
     assert rel(la, ea) < 1e-12 and (lapr.size == 0 or rel(lapr, eapr) < 1e-12), "assembled a / apr vs global matrix"
     ctx.close()
     dist.barrier()
-    print(f"MGPU_OK {rank}", flush=True)
+    print(f"MGPU_OK {rank} comm={mode}", flush=True)
     dist.destroy_process_group()
 
 

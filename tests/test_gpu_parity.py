@@ -14,7 +14,7 @@ from fcb200 import mesh as M
 
 pytestmark = pytest.mark.gpu
 
-MESHES = ["ref400", "hex6", "hex12_graded", "hex10_distorted", "slab39_empty", "channel_inout", "channel_pressure", "tiny3"]
+MESHES = ["ref400", "hex6", "hex12_graded", "hex10_distorted", "slab39_empty", "channel_inout", "channel_pressure", "poly_10faces", "tiny3"]
 
 
 @pytest.fixture(scope="module")

@@ -405,6 +405,30 @@ extern "C" int fcp_field_copy(fcp_ctx *ctx, int dst, int src) {
   FCP_CUDA(cudaMemcpyAsync(d, s, sizeof(double) * (size_t)cd, cudaMemcpyDeviceToDevice, ctx->stream));
   return FCP_OK;
 }
+// dst = alpha*x + beta*y, elementwise over the common extent: the streaming part of the fvEquation operators
+// (fvImplicit/fvEquation.f90:158-404: operator(+), operator(-), operator(==) on coef(nnz) and source(numCells))
+__global__ void __launch_bounds__(256) k_axpby(int64_t n, double alpha, const double *x, double beta, const double *y, double *dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double xv = x[i], yv = y[i];
+    dst[i] = (alpha == 1.0 ? xv : alpha * xv) + (beta == 1.0 ? yv : beta == -1.0 ? -yv : beta * yv);
+  }
+}
+extern "C" int fcp_field_axpby(fcp_ctx *ctx, int dst_field, double alpha, int x_field, double beta, int y_field) {
+  if (!ctx) return FCP_EINVAL;
+  FIELD(d, dst_field);
+  FIELD(x, x_field);
+  FIELD(y, y_field);
+  int64_t cd = 0, cx = 0, cy = 0;
+  FCP_TRY(field_count(ctx, dst_field, &cd));
+  FCP_TRY(field_count(ctx, x_field, &cx));
+  FCP_TRY(field_count(ctx, y_field, &cy));
+  if (cd != cx || cd != cy) { fcp_set_error("fcp_field_axpby: extents differ"); return FCP_EINVAL; }
+  if (cd == 0) return FCP_OK;
+  k_axpby<<<(int)std::min<int64_t>((cd + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(cd, alpha, x, beta, y, d);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
 extern "C" int fcp_field_devptr(fcp_ctx *ctx, int field, void **devptr, int64_t *count) {
   if (!ctx || !devptr) return FCP_EINVAL;
   FIELD(d, field);

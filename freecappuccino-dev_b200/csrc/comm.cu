@@ -78,18 +78,21 @@ struct FcpComm {
   std::vector<void *> peer_win;     // by rank (own = win)
   CommDev h_dev;                    // host copy of the device descriptor
   CommDev *d_dev = nullptr;
-  int32_t *d_frank = nullptr, *d_rord = nullptr, *d_rslot = nullptr, *d_chunk_ptr = nullptr, *d_chunk_face = nullptr;
+  int32_t *d_frank = nullptr, *d_rord = nullptr, *d_chunk_ptr = nullptr, *d_push_cell = nullptr, *d_ghost_ord = nullptr, *d_order = nullptr;
+  unsigned long long **d_push_dst = nullptr;
   unsigned long long xseq = 0;      // sequence number of the generic halo exchanges (identical on all ranks)
+  unsigned int pk_base = 0;         // sequence base of the fused direction-vector pushes (advanced after every solve)
 };
 int comm_nranks(const FcpComm *c) { return c ? c->nranks : 1; }
 const CommDev *comm_dev(const FcpComm *c) { return (c && c->p2p) ? c->d_dev : nullptr; }
-double *comm_halo_vector(const FcpComm *c) { return (c && c->p2p) ? c->h_dev.peer_hv[c->rank] : nullptr; }
+unsigned int comm_pk_base(const FcpComm *c) { return c ? c->pk_base : 0u; }
+void comm_pk_advance(FcpComm *c, int32_t iters) { if (c) c->pk_base += (unsigned int)iters + 1u; }
 void comm_free(FcpComm *c) {
   if (!c) return;
   for (size_t r = 0; r < c->peer_win.size(); ++r)
     if ((int)r != c->rank && c->peer_win[r]) cudaIpcCloseMemHandle(c->peer_win[r]);
-  cudaFree(c->win); cudaFree(c->d_dev); cudaFree(c->d_frank); cudaFree(c->d_rord); cudaFree(c->d_rslot);
-  cudaFree(c->d_chunk_ptr); cudaFree(c->d_chunk_face);
+  cudaFree(c->win); cudaFree(c->d_dev); cudaFree(c->d_frank); cudaFree(c->d_rord); cudaFree(c->d_chunk_ptr); cudaFree(c->d_push_cell);
+  cudaFree(c->d_ghost_ord); cudaFree(c->d_order); cudaFree(c->d_push_dst);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_cell); cudaFree(c->d_slot); cudaFree(c->sendbuf); cudaFree(c->recvbuf); cudaFree(c->gather); cudaFree(c->d_scalar);
   delete c;
@@ -214,7 +217,7 @@ __global__ void k_process_face_geom(int32_t npro, const int32_t *__restrict__ pf
 // ---- peer-memory set-up ------------------------------------------------------------------------------------------
 struct WinRecord {               // what every rank publishes about its window (all-gathered through NCCL)
   cudaIpcMemHandle_t handle;     // 64 bytes
-  long long off_stage, stride, off_hv, ncols;
+  long long off_stage, stride, off_ll, npro;
   int ok, pad;
 };
 __global__ void k_i32_to_f64(int32_t n, const int32_t *__restrict__ src, double *__restrict__ dst, int32_t add_index) {
@@ -242,21 +245,22 @@ static int nccl_swap_face_ints(fcp_ctx *ctx, FcpComm *c, const int32_t *d_src /*
   return FCP_OK;
 }
 
-static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const std::vector<int32_t> &cell) {
+static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const std::vector<int32_t> &cell, const std::vector<int32_t> &slot_h) {
   const char *env = getenv("FCP_COMM");
   const bool want = !(env && !strcmp(env, "nccl")) && c->nranks <= FCP_MAXR && c->nranks > 1;
   cudaStream_t st = ctx->stream;
-  // window: header | staging [2][3*npro] | halo vector [numTotal]
+  // window: header | staging [2][3*npro] doubles | LL slots [npro][2] words
   const size_t hdr_bytes = (sizeof(WinHeader) + 255) / 256 * 256;
   const long long stride = 3ll * std::max(c->npro, 1);
   const size_t stage_bytes = ((size_t)2 * stride * sizeof(double) + 255) / 256 * 256;
-  const size_t hv_bytes = (size_t)std::max(ctx->nT, 1) * sizeof(double);
+  const size_t ll_bytes = (size_t)std::max(c->npro, 1) * 16;
+  const size_t win_bytes = hdr_bytes + stage_bytes + ll_bytes;
   WinRecord mine;
   memset(&mine, 0, sizeof(mine));
-  mine.off_stage = (long long)hdr_bytes; mine.stride = stride; mine.off_hv = (long long)(hdr_bytes + stage_bytes); mine.ncols = ctx->nT;
+  mine.off_stage = (long long)hdr_bytes; mine.stride = stride; mine.off_ll = (long long)(hdr_bytes + stage_bytes); mine.npro = c->npro;
   mine.ok = 0;
   if (want) {
-    if (cudaMalloc(&c->win, hdr_bytes + stage_bytes + hv_bytes) == cudaSuccess && cudaMemset(c->win, 0, hdr_bytes + stage_bytes + hv_bytes) == cudaSuccess &&
+    if (cudaMalloc(&c->win, win_bytes) == cudaSuccess && cudaMemset(c->win, 0, win_bytes) == cudaSuccess &&
         cudaDeviceSynchronize() == cudaSuccess && cudaIpcGetMemHandle(&mine.handle, c->win) == cudaSuccess)
       mine.ok = 1;
     else cudaGetLastError();
@@ -308,20 +312,33 @@ static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const std::vector<int32_t> &cell)
     for (int32_t i = 0; i < c->cnt[j]; ++i) frank[c->off[j] + i] = c->peer[j];
   FCP_TRY(dev_upload(&c->d_frank, frank.data(), frank.size()));
   FCP_TRY(dev_alloc(&c->d_rord, (size_t)std::max(c->npro, 1)));
-  FCP_TRY(dev_alloc(&c->d_rslot, (size_t)std::max(c->npro, 1)));
   FCP_TRY(nccl_swap_face_ints(ctx, c, nullptr, c->d_rord));
-  FCP_TRY(nccl_swap_face_ints(ctx, c, c->d_slot, c->d_rslot));
-  // process faces grouped by the chunk (2048 rows) that owns their cell
+  std::vector<int32_t> rord(std::max(c->npro, 1), 0);
+  FCP_CUDA(cudaMemcpyAsync(rord.data(), c->d_rord, sizeof(int32_t) * (size_t)c->npro, cudaMemcpyDeviceToHost, st));
+  FCP_CUDA(cudaStreamSynchronize(st));
+  // process faces grouped by the chunk (2048 rows) that owns their cell; chunks that own process faces are launched first
   const int nch = std::max(fcp_nchunks(ctx->n), 1);
-  std::vector<int32_t> cptr(nch + 1, 0), cface(std::max(c->npro, 1), 0);
+  std::vector<int32_t> cptr(nch + 1, 0), pcell(std::max(c->npro, 1), 0), order;
+  std::vector<unsigned long long *> pdst(std::max(c->npro, 1), nullptr);
   for (int32_t i = 0; i < c->npro; ++i) cptr[cell[i] / FCP_CHUNK + 1]++;
   for (int k = 0; k < nch; ++k) cptr[k + 1] += cptr[k];
   {
     std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
-    for (int32_t i = 0; i < c->npro; ++i) cface[fill[cell[i] / FCP_CHUNK]++] = i;
+    for (int32_t i = 0; i < c->npro; ++i) {
+      const int32_t j = fill[cell[i] / FCP_CHUNK]++;
+      pcell[j] = cell[i];
+      pdst[j] = (unsigned long long *)((char *)c->peer_win[frank[i]] + recs[frank[i]].off_ll) + 2 * (size_t)rord[i];
+    }
   }
+  for (int k = 0; k < nch; ++k) if (cptr[k + 1] > cptr[k]) order.push_back(k);
+  for (int k = 0; k < nch; ++k) if (cptr[k + 1] == cptr[k]) order.push_back(k);
+  std::vector<int32_t> gord(std::max(ctx->B, 1), -1);
+  for (int32_t i = 0; i < c->npro; ++i) gord[slot_h[i] - ctx->n] = i;
   FCP_TRY(dev_upload(&c->d_chunk_ptr, cptr.data(), cptr.size()));
-  FCP_TRY(dev_upload(&c->d_chunk_face, cface.data(), cface.size()));
+  FCP_TRY(dev_upload(&c->d_push_cell, pcell.data(), pcell.size()));
+  FCP_TRY(dev_upload(&c->d_push_dst, pdst.data(), pdst.size()));
+  FCP_TRY(dev_upload(&c->d_order, order.data(), order.size()));
+  FCP_TRY(dev_upload(&c->d_ghost_ord, gord.data(), gord.size()));
   CommDev &d = c->h_dev;
   memset(&d, 0, sizeof(d));
   d.rank = c->rank; d.nranks = c->nranks;
@@ -335,12 +352,11 @@ static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const std::vector<int32_t> &cell)
     d.peer_hdr[r] = (WinHeader *)base;
     d.peer_stage[r] = (double *)(base + recs[r].off_stage);
     d.peer_stride[r] = recs[r].stride;
-    d.peer_hv[r] = (double *)(base + recs[r].off_hv);
   }
   d.hdr = d.peer_hdr[c->rank]; d.stage = d.peer_stage[c->rank]; d.stride = stride;
-  d.npro = c->npro; d.cell = c->d_cell; d.slot = c->d_slot; d.frank = c->d_frank; d.rord = c->d_rord; d.rslot = c->d_rslot;
-  d.chunk_ptr = c->d_chunk_ptr; d.chunk_face = c->d_chunk_face;
-  for (int k = 0; k < nch; ++k) d.n_halo_chunks += (cptr[k + 1] > cptr[k]) ? 1 : 0;
+  d.ll = (unsigned long long *)((char *)c->win + mine.off_ll);
+  d.npro = c->npro; d.n = ctx->n; d.cell = c->d_cell; d.slot = c->d_slot; d.frank = c->d_frank; d.rord = c->d_rord;
+  d.ghost_ord = c->d_ghost_ord; d.chunk_ptr = c->d_chunk_ptr; d.push_cell = c->d_push_cell; d.push_dst = c->d_push_dst; d.order = c->d_order;
   FCP_CUDA(cudaMalloc((void **)&c->d_dev, sizeof(CommDev)));
   FCP_CUDA(cudaMemcpyAsync(c->d_dev, &d, sizeof(CommDev), cudaMemcpyHostToDevice, st));
   FCP_CUDA(cudaStreamSynchronize(st));
@@ -413,7 +429,7 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
   memcpy(&id, id128, 128);
   FCP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
   ctx->comm = c;
-  FCP_TRY(p2p_setup(ctx, c, cell));
+  FCP_TRY(p2p_setup(ctx, c, cell, slot));
   // ghost copies of the cell-centre data (src-par/geometry.f90:769-773) and the process-face geometry
   FCP_TRY(comm_exchange(ctx, ctx->xc, 1));
   FCP_TRY(comm_exchange(ctx, ctx->yc, 1));

@@ -101,7 +101,6 @@ struct KrylovWS {
   double *reso = nullptr, *uk = nullptr, *vk = nullptr, *tmp = nullptr;
   KrylovScalars *sc = nullptr;        // device
   KrylovScalars *h_sc = nullptr;      // pinned host mirror
-  bool pk_external = false;           // pk lives in the communication window (multi-GPU peer-memory path)
   double *partials = nullptr;         // [4 * maxchunks]
   unsigned int *counter = nullptr;    // last-block ticket
   int maxchunks = 0;
@@ -111,19 +110,19 @@ struct KrylovWS {
 struct FcpComm;   // comm.cu
 
 // ---------------------------------------------------------------------------------------------
-// Peer-memory communication (comm.cu).  Every rank owns one device "window" (header + halo staging + the Krylov
-// direction vector) that all peers of the node map through CUDA IPC.  Halo values and reduction partials are written
-// straight into the peer's window over NVLink by the producing kernel, followed by a sequence-number flag; consumers
-// spin on their own (local) flags.  No host round trip, no separate communication kernels inside a Krylov iteration.
+// Peer-memory communication (comm.cu).  Every rank owns one device "window" (header + halo staging) that all peers of
+// the node map through CUDA IPC.  Inside a Krylov iteration nothing but the compute kernels runs: the kernel that
+// produces the direction vector stores the values its neighbours need straight into their windows over NVLink, and
+// the last CTA of every reducing kernel exchanges the partial sums the same way.  Both use flag-in-data words
+// (p2p.cuh: a 32-bit sequence number rides in every 8-byte word), so there is no fence, no flag and no host round trip.
+// The generic exchange(phi) outside the iteration uses a staged push/pull with a sequence flag.
 // ---------------------------------------------------------------------------------------------
 #define FCP_MAXR 16
 struct WinHeader {
-  unsigned long long xflag[FCP_MAXR];      // written by peer r: sequence number of its last complete generic halo push
-  unsigned long long pkflag[FCP_MAXR];     // written by peer r: sequence number of its last fused push into my halo vector
-  unsigned long long rflag[2][FCP_MAXR];   // written by peer r: sequence number of the reduction whose partials are in rval[par][r]
-  double rval[2][FCP_MAXR][4];
+  unsigned long long xflag[FCP_MAXR];        // written by peer r: sequence number of its last complete generic halo push
+  unsigned long long rll[2][FCP_MAXR][8];    // written by peer r: LL words of its <= 4 partial sums, two slots by sequence parity
   // local only
-  unsigned long long red_seq, pk_push_seq, pk_wait_seq;
+  unsigned long long red_seq;
   unsigned int push_ticket, pad0;
   int error, pad1;
 };
@@ -132,16 +131,20 @@ struct CommDev {
   int nb_rank[FCP_MAXR];
   WinHeader *hdr;                          // own header
   WinHeader *peer_hdr[FCP_MAXR];           // by rank (self included)
-  double *peer_stage[FCP_MAXR];            // by rank: that rank's staging area [2][stride]
+  double *peer_stage[FCP_MAXR];            // by rank: that rank's staging area [2][stride] (generic exchange)
   long long peer_stride[FCP_MAXR];         // 3 * npro of that rank
-  double *peer_hv[FCP_MAXR];               // by rank: that rank's halo vector (the Krylov direction, numTotal entries)
   double *stage;                           // own staging
   long long stride;
-  int32_t npro;
+  unsigned long long *ll;                  // own LL slots of the fused direction-vector halo: [npro][2]
+  int32_t npro, n;
   const int32_t *cell, *slot;              // per process face (patch order): owner cell, ghost slot
-  const int32_t *frank, *rord, *rslot;     // peer rank, the face's ordinal and ghost slot on the peer
-  const int32_t *chunk_ptr, *chunk_face;   // process faces grouped by the 2048-row chunk of their owner cell
-  int32_t n_halo_chunks;                   // chunks that own at least one process face (ticket size of the fused push)
+  const int32_t *frank, *rord;             // peer rank and the face's ordinal on the peer
+  const int32_t *ghost_ord;                // [numBoundaryFaces] boundary face -> process-face ordinal (-1 for physical patches)
+  // fused push, faces grouped by the 2048-row chunk of their owner cell
+  const int32_t *chunk_ptr;                // [nchunks+1]
+  const int32_t *push_cell;                // [npro] owner cell, chunk order
+  unsigned long long *const *push_dst;     // [npro] address of the face's LL slot in the peer's window, chunk order
+  const int32_t *order;                    // [nchunks] launch order of the chunks: the ones that own process faces first
 };
 
 // per-kernel-class CUDA-event timing (fcp_profile_*): an event pair around every launch of a class
@@ -274,7 +277,7 @@ template <class T> int dev_upload(T **dptr, const T *h, size_t count);
 template <class T> int dev_alloc(T **dptr, size_t count);
 
 // ---- krylov.cu ----------------------------------------------------------------------------------
-int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols, double *pk_ext = nullptr);
+int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols);
 void krylov_ws_free(KrylovWS &ws);
 int sell_spmv(const SellPattern &p, const double *a, const double *x, double *y, cudaStream_t st);
 int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const double *rhs, KrylovWS &ws,
@@ -288,5 +291,6 @@ int comm_allreduce_minmax(FcpComm *comm, double *d_mm /* {min,max} */, cudaStrea
 void comm_free(FcpComm *comm);
 int comm_nranks(const FcpComm *comm);
 const CommDev *comm_dev(const FcpComm *comm);       // device descriptor, nullptr unless the peer-memory path is active
-double *comm_halo_vector(const FcpComm *comm);
-int comm_check_error(fcp_ctx *ctx);      // the window's halo vector (the Krylov workspace uses it as pk)
+unsigned int comm_pk_base(const FcpComm *comm);     // sequence base of the fused direction-vector pushes of the next solve
+void comm_pk_advance(FcpComm *comm, int32_t iters); // after a solve that ran `iters` iterations (identical on all ranks)
+int comm_check_error(fcp_ctx *ctx);

@@ -17,19 +17,30 @@ __global__ void __launch_bounds__(FCP_TPB) k_grad_gauss(MeshView m, const double
   FCP_CELL_LOOP(c, m.n) {
     double gx = 0.0, gy = 0.0, gz = 0.0;
     const double uc = u[c];
-    FCP_FACE_LOOP(m, c) {
-      FCP_FACE_FETCH(m);
-      const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
-      if (sl >= 0) {
-        const double uo = u[o];
-        const double uP = e > 0 ? uc : uo, uN = e > 0 ? uo : uc;
-        const double fie = uP + (uN - uP) * m.facint[f];
-        const double dfx = fie * sx, dfy = fie * sy, dfz = fie * sz;
-        if (e > 0) { gx = gx + dfx; gy = gy + dfy; gz = gz + dfz; }
-        else       { gx = gx - dfx; gy = gy - dfy; gz = gz - dfz; }
-      } else {
-        const double ub = u[o];
-        gx = gx + ub * sx; gy = gy + ub * sy; gz = gz + ub * sz;
+    constexpr int W = 6;
+    FCP_FACE_BATCHES(m, c, W) {
+      FCP_BATCH_LISTS(m, W, e, o, sl);
+      double sx[W], sy[W], sz[W], lam[W], uo[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const int32_t f = (e[k] > 0 ? e[k] : -e[k]) - 1;
+        const bool on = e[k] != 0;
+        uo[k] = on ? __ldg(u + o[k]) : 0.0;
+        lam[k] = (on && sl[k] >= 0) ? __ldg(m.facint + f) : 0.0;
+        sx[k] = on ? __ldg(m.arx + f) : 0.0; sy[k] = on ? __ldg(m.ary + f) : 0.0; sz[k] = on ? __ldg(m.arz + f) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        if (e[k] == 0) continue;
+        if (sl[k] >= 0) {
+          const double uP = e[k] > 0 ? uc : uo[k], uN = e[k] > 0 ? uo[k] : uc;
+          const double fie = uP + (uN - uP) * lam[k];
+          const double dfx = fie * sx[k], dfy = fie * sy[k], dfz = fie * sz[k];
+          if (e[k] > 0) { gx = gx + dfx; gy = gy + dfy; gz = gz + dfz; }
+          else          { gx = gx - dfx; gy = gy - dfy; gz = gz - dfz; }
+        } else {
+          gx = gx + uo[k] * sx[k]; gy = gy + uo[k] * sy[k]; gz = gz + uo[k] * sz[k];
+        }
       }
     }
     const double volr = 1.0 / m.vol[c];
@@ -183,17 +194,31 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp(MeshView m, int scheme, int n
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
     bool has_bnd = false;
     {
-      FCP_FACE_LOOP(m, c) {
-        FCP_FACE_FETCH(m);
-        if (sl >= 0) {
-          const double po = p[o];
-          const double ao = scheme == FCP_PSCHEME_WEIGHTED ? apu[o] : 0.0;
-          const double pf = e > 0 ? face_p(scheme, pc, po, m.facint[f], ac, ao) : face_p(scheme, po, pc, m.facint[f], ao, ac);
-          const double dfx = pf * m.arx[f], dfy = pf * m.ary[f], dfz = pf * m.arz[f];
-          if (e > 0) { s1 = s1 - dfx; s2 = s2 - dfy; s3 = s3 - dfz; }
-          else       { s1 = s1 + dfx; s2 = s2 + dfy; s3 = s3 + dfz; }
-        } else {
-          has_bnd = true;
+      constexpr int W = 6;
+      FCP_FACE_BATCHES(m, c, W) {
+        FCP_BATCH_LISTS(m, W, e, o, sl);
+        double sx[W], sy[W], sz[W], lam[W], po[W], ao[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          const int32_t f = (e[k] > 0 ? e[k] : -e[k]) - 1;
+          const bool two = e[k] != 0 && sl[k] >= 0;
+          // inner-face values of p are never written by this kernel (only boundary slots are): non-coherent loads are safe
+          po[k] = two ? __ldg(p + o[k]) : 0.0;
+          ao[k] = (two && scheme == FCP_PSCHEME_WEIGHTED) ? __ldg(apu + o[k]) : 0.0;
+          lam[k] = two ? __ldg(m.facint + f) : 0.0;
+          sx[k] = two ? __ldg(m.arx + f) : 0.0; sy[k] = two ? __ldg(m.ary + f) : 0.0; sz[k] = two ? __ldg(m.arz + f) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          if (e[k] == 0) continue;
+          if (sl[k] >= 0) {
+            const double pf = e[k] > 0 ? face_p(scheme, pc, po[k], lam[k], ac, ao[k]) : face_p(scheme, po[k], pc, lam[k], ao[k], ac);
+            const double dfx = pf * sx[k], dfy = pf * sy[k], dfz = pf * sz[k];
+            if (e[k] > 0) { s1 = s1 - dfx; s2 = s2 - dfy; s3 = s3 - dfz; }
+            else          { s1 = s1 + dfx; s2 = s2 + dfy; s3 = s3 + dfz; }
+          } else {
+            has_bnd = true;
+          }
         }
       }
     }
@@ -375,64 +400,87 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp_central2(MeshView m, double *
 // PISO = true: facefluxmass_piso (faceflux_mass.f90:389-459): the flux is the plain interpolated HbyA flux (no Rhie-Chow
 // pressure term) and pressure patches do not reset pp (calcp_piso.f90:140-240).
 template <bool PISO>
-__global__ void __launch_bounds__(FCP_TPB) k_assemble_pcorr(MeshView m, AsmArgs g) {
+__global__ void __launch_bounds__(FCP_TPB, 1) k_assemble_pcorr(MeshView m, AsmArgs g) {
   FCP_CELL_LOOP(c, m.n) {
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
     const double denc = g.den[c], kc = m.vol[c] * g.apu[c];
     const double uc = g.u[c], vc = g.v[c], wc = g.w[c], pc = g.p[c];
     const double gcx = g.dPdxi[3 * (int64_t)c], gcy = g.dPdxi[3 * (int64_t)c + 1], gcz = g.dPdxi[3 * (int64_t)c + 2];
     double dg = 0.0, s = 0.0;
-    FCP_FACE_LOOP(m, c) {
-      FCP_FACE_FETCH(m);
-      const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
-      if (sl >= 0) {
-        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o];
-        const double deno = g.den[o], ko = m.vol[o] * g.apu[o];
-        const double uo = g.u[o], vo = g.v[o], wo = g.w[o], po = g.p[o];
-        const double gox = g.dPdxi[3 * (int64_t)o], goy = g.dPdxi[3 * (int64_t)o + 1], goz = g.dPdxi[3 * (int64_t)o + 2];
-        const double lam = m.facint[f], fxn = lam, fxp = 1.0 - lam;
-        const bool own = e > 0;
-        // P = owner side, N = neighbour side of the face, whichever this cell is
-        const double xpn = own ? xo - xc : xc - xo, ypn = own ? yo - yc : yc - yo, zpn = own ? zo - zc : zc - zo;
-        const double denP = own ? denc : deno, denN = own ? deno : denc;
-        const double kP = own ? kc : ko, kN = own ? ko : kc;
-        const double uP = own ? uc : uo, uN = own ? uo : uc;
-        const double vP = own ? vc : vo, vN = own ? vo : vc;
-        const double wP = own ? wc : wo, wN = own ? wo : wc;
-        const double pP = own ? pc : po, pN = own ? po : pc;
-        const double gPx = own ? gcx : gox, gPy = own ? gcy : goy, gPz = own ? gcz : goz;
-        const double gNx = own ? gox : gcx, gNy = own ? goy : gcy, gNz = own ? goz : gcz;
-        const double dene = denP * fxp + denN * fxn;
-        const double Kj = kP * fxp + kN * fxn;
-        const double cap = -dene * Kj * m.Df[f];
-        const double ui = uP + (uN - uP) * lam;
-        const double vi = vP + (vN - vP) * lam;
-        const double wi = wP + (wN - wP) * lam;
-        const double dpxi = (gNx * fxp + gPx * fxn) * xpn;     // weights swapped in the reference (faceflux_mass.f90:236-238), kept
-        const double dpyi = (gNy * fxp + gPy * fxn) * ypn;
-        const double dpzi = (gNz * fxp + gPz * fxn) * zpn;
-        const double flm = PISO ? dene * (ui * sx + vi * sy + wi * sz)
-                                : dene * (ui * sx + vi * sy + wi * sz) + cap * (pN - pP - dpxi - dpyi - dpzi);
-        g.a[sl] = cap;
-        dg = dg - cap;
-        if (own) { s = s - flm; g.flmass[f] = flm; }
-        else     { s = s + flm; }
-      } else {
-        const int type = -1 - sl;
-        if (type == FCP_BC_INLET || type == FCP_BC_OUTLET) {
-          s = s - g.flmass[f];                                // calcp_simple.f90:131-160
-        } else if (type == FCP_BC_PRESSURE) {                 // facefluxmassPressBnd faceflux_mass.f90:765-831
-          const double xpn = m.xf[f] - xc, ypn = m.yf[f] - yc, zpn = m.zf[f] - zc;
-          const double capp = kc / (sx * xpn + sy * ypn + sz * zpn);
-          const double dpcor = g.p[o] - pc - (gcx * xpn + gcy * ypn + gcz * zpn);
-          const double ub = uc - sx * capp * dpcor, vb = vc - sy * capp * dpcor, wb = wc - sz * capp * dpcor;
-          g.ub[o] = ub; g.vb[o] = vb; g.wb[o] = wb;
-          const double flm = denc * (ub * sx + vb * sy + wb * sz);
-          g.flmass[f] = flm;
-          const double cap = -denc * (sx * sx + sy * sy + sz * sz) * capp;
+    constexpr int W = 3;
+    FCP_FACE_BATCHES(m, c, W) {
+      FCP_BATCH_LISTS(m, W, e_, o_, sl_);
+      double sx_[W], sy_[W], sz_[W], lam_[W], Df_[W], xo_[W], yo_[W], zo_[W], deno_[W], volo_[W], apuo_[W], uo_[W], vo_[W], wo_[W], po_[W],
+          gox_[W], goy_[W], goz_[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const int32_t f = (e_[k] > 0 ? e_[k] : -e_[k]) - 1;
+        const bool on = e_[k] != 0, two = on && sl_[k] >= 0;
+        const int32_t o = o_[k];
+        sx_[k] = on ? __ldg(m.arx + f) : 0.0; sy_[k] = on ? __ldg(m.ary + f) : 0.0; sz_[k] = on ? __ldg(m.arz + f) : 0.0;
+        lam_[k] = two ? __ldg(m.facint + f) : 0.0; Df_[k] = two ? __ldg(m.Df + f) : 0.0;
+        xo_[k] = two ? __ldg(m.xc + o) : 0.0; yo_[k] = two ? __ldg(m.yc + o) : 0.0; zo_[k] = two ? __ldg(m.zc + o) : 0.0;
+        deno_[k] = two ? __ldg(g.den + o) : 0.0; volo_[k] = two ? __ldg(m.vol + o) : 0.0; apuo_[k] = two ? __ldg(g.apu + o) : 0.0;
+        // u, v, w, p cell values are not written by this kernel (only pressure-patch boundary slots are)
+        uo_[k] = two ? __ldg(g.u + o) : 0.0; vo_[k] = two ? __ldg(g.v + o) : 0.0; wo_[k] = two ? __ldg(g.w + o) : 0.0; po_[k] = two ? __ldg(g.p + o) : 0.0;
+        gox_[k] = two ? __ldg(g.dPdxi + 3 * (int64_t)o) : 0.0; goy_[k] = two ? __ldg(g.dPdxi + 3 * (int64_t)o + 1) : 0.0;
+        goz_[k] = two ? __ldg(g.dPdxi + 3 * (int64_t)o + 2) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        if (e_[k] == 0) continue;
+        const int32_t e = e_[k], o = o_[k], sl = sl_[k];
+        const int32_t f = (e > 0 ? e : -e) - 1;
+        const double sx = sx_[k], sy = sy_[k], sz = sz_[k];
+        if (sl >= 0) {
+          const double xo = xo_[k], yo = yo_[k], zo = zo_[k];
+          const double deno = deno_[k], ko = volo_[k] * apuo_[k];
+          const double uo = uo_[k], vo = vo_[k], wo = wo_[k], po = po_[k];
+          const double gox = gox_[k], goy = goy_[k], goz = goz_[k];
+          const double lam = lam_[k], fxn = lam, fxp = 1.0 - lam;
+          const bool own = e > 0;
+          // P = owner side, N = neighbour side of the face, whichever this cell is
+          const double xpn = own ? xo - xc : xc - xo, ypn = own ? yo - yc : yc - yo, zpn = own ? zo - zc : zc - zo;
+          const double denP = own ? denc : deno, denN = own ? deno : denc;
+          const double kP = own ? kc : ko, kN = own ? ko : kc;
+          const double uP = own ? uc : uo, uN = own ? uo : uc;
+          const double vP = own ? vc : vo, vN = own ? vo : vc;
+          const double wP = own ? wc : wo, wN = own ? wo : wc;
+          const double pP = own ? pc : po, pN = own ? po : pc;
+          const double gPx = own ? gcx : gox, gPy = own ? gcy : goy, gPz = own ? gcz : goz;
+          const double gNx = own ? gox : gcx, gNy = own ? goy : gcy, gNz = own ? goz : gcz;
+          const double dene = denP * fxp + denN * fxn;
+          const double Kj = kP * fxp + kN * fxn;
+          const double cap = -dene * Kj * Df_[k];
+          const double ui = uP + (uN - uP) * lam;
+          const double vi = vP + (vN - vP) * lam;
+          const double wi = wP + (wN - wP) * lam;
+          const double dpxi = (gNx * fxp + gPx * fxn) * xpn;     // weights swapped in the reference (faceflux_mass.f90:236-238), kept
+          const double dpyi = (gNy * fxp + gPy * fxn) * ypn;
+          const double dpzi = (gNz * fxp + gPz * fxn) * zpn;
+          const double flm = PISO ? dene * (ui * sx + vi * sy + wi * sz)
+                                  : dene * (ui * sx + vi * sy + wi * sz) + cap * (pN - pP - dpxi - dpyi - dpzi);
+          g.a[sl] = cap;
           dg = dg - cap;
-          s = s - flm;
-          if (!PISO) g.pp[o] = 0.0;
+          if (own) { s = s - flm; g.flmass[f] = flm; }
+          else     { s = s + flm; }
+        } else {
+          const int type = -1 - sl;
+          if (type == FCP_BC_INLET || type == FCP_BC_OUTLET) {
+            s = s - g.flmass[f];                                // calcp_simple.f90:131-160
+          } else if (type == FCP_BC_PRESSURE) {                 // facefluxmassPressBnd faceflux_mass.f90:765-831
+            const double xpn = m.xf[f] - xc, ypn = m.yf[f] - yc, zpn = m.zf[f] - zc;
+            const double capp = kc / (sx * xpn + sy * ypn + sz * zpn);
+            const double dpcor = g.p[o] - pc - (gcx * xpn + gcy * ypn + gcz * zpn);
+            const double ub = uc - sx * capp * dpcor, vb = vc - sy * capp * dpcor, wb = wc - sz * capp * dpcor;
+            g.ub[o] = ub; g.vb[o] = vb; g.wb[o] = wb;
+            const double flm = denc * (ub * sx + vb * sy + wb * sz);
+            g.flmass[f] = flm;
+            const double cap = -denc * (sx * sx + sy * sy + sz * sz) * capp;
+            dg = dg - cap;
+            s = s - flm;
+            if (!PISO) g.pp[o] = 0.0;
+          }
         }
       }
     }

@@ -358,7 +358,7 @@ int fvm_piso_hbya(fcp_ctx *ctx, const double *h, const double *rU, const double 
   return FCP_OK;
 }
 int fvm_sum(fcp_ctx *ctx, const double *x, double *d_out) {
-  FCP_TRY(krylov_ws_alloc(ctx->ws, ctx->pat.n, ctx->pat.ncols, comm_halo_vector(ctx->comm)));
+  FCP_TRY(krylov_ws_alloc(ctx->ws, ctx->pat.n, ctx->pat.ncols));
   k_sum<<<std::max(fcp_nchunks(ctx->n), 1), FCP_TPB, 0, ctx->stream>>>(ctx->n, x, ctx->ws.partials, ctx->ws.maxchunks, ctx->ws.counter, d_out);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();

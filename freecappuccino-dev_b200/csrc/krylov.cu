@@ -16,14 +16,13 @@ namespace cg = cooperative_groups;
 // ---------------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------------
-int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols, double *pk_ext) {
-  if (ws.n == n && ws.ncols == ncols && ws.res && (!pk_ext || ws.pk == pk_ext)) return FCP_OK;
+int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols) {
+  if (ws.n == n && ws.ncols == ncols && ws.res) return FCP_OK;
   krylov_ws_free(ws);
   ws.n = n;
   ws.ncols = ncols;
   FCP_TRY(dev_alloc(&ws.res, (size_t)n));
-  if (pk_ext) { ws.pk = pk_ext; ws.pk_external = true; }   // the direction vector lives in the communication window
-  else FCP_TRY(dev_alloc(&ws.pk, (size_t)ncols));
+  FCP_TRY(dev_alloc(&ws.pk, (size_t)ncols));
   FCP_TRY(dev_alloc(&ws.zk, (size_t)ncols));
   FCP_TRY(dev_alloc(&ws.adiag, (size_t)n));
   ws.maxchunks = fcp_nchunks(n) + 1;
@@ -44,7 +43,7 @@ static int krylov_ws_need(KrylovWS &ws, double **p, size_t count) {
   return FCP_OK;
 }
 void krylov_ws_free(KrylovWS &ws) {
-  cudaFree(ws.res); if (!ws.pk_external) cudaFree(ws.pk); cudaFree(ws.zk); cudaFree(ws.adiag); cudaFree(ws.d);
+  cudaFree(ws.res); cudaFree(ws.pk); cudaFree(ws.zk); cudaFree(ws.adiag); cudaFree(ws.d);
   cudaFree(ws.reso); cudaFree(ws.uk); cudaFree(ws.vk); cudaFree(ws.tmp);
   cudaFree(ws.partials); cudaFree(ws.counter); cudaFree(ws.sc);
   if (ws.h_sc) cudaFreeHost(ws.h_sc);
@@ -80,16 +79,19 @@ __device__ __forceinline__ double sell_row_sum(const SellView &m, const double *
   return s;
 }
 
-// same for rows of a chunk that owns process faces: ghost columns (>= n) were written by a peer over NVLink during this
-// kernel's lifetime, so they are read past L1
+// Row sum for the rows of a chunk that owns process faces, on the peer-memory path: a ghost column (>= n) is not read
+// from x but from this rank's LL slots, where the neighbour's k_cg_pk stored it during this very iteration; the word's
+// embedded sequence number tells when it has arrived (src-par/dpcg.f90:118 `call exchange(pk)` + :129-143 halo term).
 template <bool SUB>
-__device__ __forceinline__ double sell_row_sum_halo(const SellView &m, const double *__restrict__ x, int32_t r, double s, int32_t n) {
+__device__ __forceinline__ double sell_row_sum_halo(const SellView &m, const double *__restrict__ x, int32_t r, double s, const CommDev *cd,
+                                                    unsigned int seq) {
   const int64_t base = __ldg(&m.slptr[r >> 5]) + (r & 31);
   const int32_t len = __ldg(&m.rinfo[r]) & 0xffff;
+  const int32_t n = cd->n;
   for (int32_t k = 0; k < len; ++k) {
     const double av = __ldcs(m.a + base + (int64_t)k * 32);
     const int32_t c = __ldcs(m.ja + base + (int64_t)k * 32);
-    const double xv = c >= n ? p2p_ld_data(x + c) : __ldg(x + c);
+    const double xv = c >= n ? p2p_ll_load(cd->ll + 2 * (size_t)__ldg(cd->ghost_ord + (c - n)), seq, cd->hdr) : __ldg(x + c);
     const double t = av * xv;
     s = SUB ? (s - t) : (s + t);
   }
@@ -205,44 +207,41 @@ struct RedArgs {
   int fuse;   // 1: run the epilogue in the last CTA (single GPU); 0: only store the local sums in sc->red (NCCL path);
               // 2: peer-memory all-reduce inside the last CTA, then the epilogue
   const CommDev *cd;
-  int bump;   // fuse == 2: this kernel consumed a fused halo push (advance hdr->pk_wait_seq)
 };
 
-// Last CTA of a reducing kernel; `total` is valid in thread 0.  fuse == 2: every rank stores its partial sums into every
-// peer's window (thread r -> rank r), flags them with the reduction's sequence number, waits for the P flags of its own
-// window and adds the P partials in RANK ORDER (src-par/global_sum_mpi.f90 semantics, deterministic, identical bits on
-// every rank).  Two slots by sequence parity: a rank can be at most one reduction ahead of any other.
+// Last CTA of a reducing kernel; `total` is valid in thread 0.  fuse == 2: thread (r, k) stores partial sum k into rank
+// r's window as LL words tagged with the reduction's sequence number, then reads the partial of rank r from its own
+// window (spinning until the tag matches), and thread 0 adds the P partials in RANK ORDER (src-par/global_sum_mpi.f90
+// semantics; deterministic, identical bits on every rank).  Two slots by sequence parity: a rank can be at most one
+// reduction ahead of any other.
 template <int NS>
 __device__ __forceinline__ void finish_epilogue(double (&total)[NS], const RedArgs &ra) {
   if (ra.fuse == 2) {
     const CommDev *cd = ra.cd;
     WinHeader *hdr = cd->hdr;
     __shared__ double tot_s[4];
+    __shared__ double part_s[FCP_MAXR][4];
     __shared__ unsigned long long seq_s;
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int k = 0; k < NS; ++k) tot_s[k] = total[k];
       seq_s = ++hdr->red_seq;
-      if (ra.bump) hdr->pk_wait_seq += 1ull;
     }
     __syncthreads();
-    const unsigned long long seq = seq_s;
-    const int par = (int)(seq & 1ull);
-    if ((int)threadIdx.x < cd->nranks) {
-      WinHeader *ph = cd->peer_hdr[threadIdx.x];
-#pragma unroll
-      for (int k = 0; k < NS; ++k) ph->rval[par][cd->rank][k] = tot_s[k];
-      __threadfence_system();
-      p2p_st_release(&ph->rflag[par][cd->rank], seq);
-      p2p_wait(&hdr->rflag[par][threadIdx.x], seq, hdr);
+    const unsigned int seq = (unsigned int)seq_s;
+    const int par = (int)(seq & 1u);
+    const int r = (int)threadIdx.x / NS, k = (int)threadIdx.x % NS;
+    if (r < cd->nranks) {
+      p2p_ll_store(&cd->peer_hdr[r]->rll[par][cd->rank][2 * k], tot_s[k], seq);
+      part_s[r][k] = p2p_ll_load(&hdr->rll[par][r][2 * k], seq, hdr);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int k = 0; k < NS; ++k) {
-        double sum = p2p_ld_data(&hdr->rval[par][0][k]);
-        for (int r = 1; r < cd->nranks; ++r) sum = sum + p2p_ld_data(&hdr->rval[par][r][k]);
-        ra.sc->red[k] = sum;
+      for (int kk = 0; kk < NS; ++kk) {
+        double sum = part_s[0][kk];
+        for (int rr = 1; rr < cd->nranks; ++rr) sum = sum + part_s[rr][kk];
+        ra.sc->red[kk] = sum;
       }
       krylov_epilogue(ra.epi, ra.sc);
     }
@@ -253,6 +252,11 @@ __device__ __forceinline__ void finish_epilogue(double (&total)[NS], const RedAr
     for (int k = 0; k < NS; ++k) ra.sc->red[k] = total[k];
     if (ra.fuse) krylov_epilogue(ra.epi, ra.sc);
   }
+}
+template <int NS>
+__device__ __forceinline__ void finish_reduce_part(double (&s)[NS], const RedArgs &ra, int part, int nparts) {
+  double total[NS];
+  if (fcp_grid_reduce_part<NS>(s, ra.partials, ra.stride, ra.counter, part, nparts, total)) finish_epilogue<NS>(total, ra);
 }
 template <int NS>
 __device__ __forceinline__ void finish_reduce(double (&s)[NS], const RedArgs &ra) {
@@ -284,14 +288,17 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_init(int32_t n, SellView m, cons
 
 // pk = zk + bet*pk with zk = res/adiag (dpcg :288-303) or the stored zk (iccg).
 // cd != nullptr (multi-GPU, peer-memory path): `call exchange(pk)` (src-par/dpcg.f90:118) is fused in -- after its chunk is
-// written the CTA stores the pk values of its process-face cells straight into the ghost slots of the neighbours' pk
-// over NVLink; the last CTA to finish raises the sequence flag on every neighbour.
+// written the CTA stores the pk values of its process-face cells straight into the neighbours' LL slots over NVLink
+// (sequence number = seq_base + iteration).  No fence, no flag, no extra kernel; chunks that own process faces are
+// launched first so that the stores are under way while the bulk of the vector is still being updated.
 template <bool JACOBI>
 __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
-                                                    const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd) {
+                                                    const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd,
+                                                    unsigned int seq_base) {
   if (sc->done) return;
   const double bet = sc->bet;
-  const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
+  const int chunk = cd ? cd->order[blockIdx.x] : (int)blockIdx.x;
+  const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
   if (base + (FCP_IPT - 1) * FCP_TPB < n) {
     // full chunk: all loads of the thread's 8 rows are issued before the first use (memory-level parallelism)
     double z_[FCP_IPT], d_[FCP_IPT], p_[FCP_IPT];
@@ -307,59 +314,44 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__re
       pk[base + j * FCP_TPB] = z + bet * p_[j];
     }
   } else {
-    FCP_ROW_LOOP(r, n) {
-      const double z = JACOBI ? (res[r] / adiag[r]) : zk[r];
-      pk[r] = z + bet * pk[r];
+    for (int j = 0; j < FCP_IPT; ++j) {
+      const int64_t r = base + j * FCP_TPB;
+      if (r < n) {
+        const double z = JACOBI ? (res[r] / adiag[r]) : zk[r];
+        pk[r] = z + bet * pk[r];
+      }
     }
   }
   if (!cd) return;
-  const int32_t j0 = cd->chunk_ptr[blockIdx.x], j1 = cd->chunk_ptr[blockIdx.x + 1];
-  if (j0 == j1) return;   // this chunk owns no process face: nothing to push, not part of the ticket
-  __syncthreads();
-  for (int32_t j = j0 + (int32_t)threadIdx.x; j < j1; j += FCP_TPB) {
-    const int32_t i = cd->chunk_face[j];
-    cd->peer_hv[cd->frank[i]][cd->rslot[i]] = pk[cd->cell[i]];
-  }
-  __threadfence_system();
-  __syncthreads();
-  __shared__ bool last;
-  __shared__ unsigned long long seq_s;
-  if (threadIdx.x == 0) last = (atomicAdd(&cd->hdr->push_ticket, 1u) == (unsigned int)cd->n_halo_chunks - 1u);
-  __syncthreads();
-  if (!last) return;
-  if (threadIdx.x == 0) { cd->hdr->push_ticket = 0u; seq_s = ++cd->hdr->pk_push_seq; }
-  __syncthreads();
-  __threadfence_system();
-  if ((int)threadIdx.x < cd->nnb) p2p_st_release(&cd->peer_hdr[cd->nb_rank[threadIdx.x]]->pkflag[cd->rank], seq_s);
-}
-
-// CTAs whose chunk owns process faces wait for the neighbours' fused pushes of this iteration (flag >= pk_wait_seq + 1)
-__device__ __forceinline__ bool spmv_halo_chunk(const CommDev *cd, int wait) {
-  if (!cd) return false;
-  const bool halo = cd->chunk_ptr[blockIdx.x + 1] > cd->chunk_ptr[blockIdx.x];
-  if (halo && wait) {
-    if ((int)threadIdx.x < cd->nnb) p2p_wait(&cd->hdr->pkflag[cd->nb_rank[threadIdx.x]], cd->hdr->pk_wait_seq + 1ull, cd->hdr);
-    __syncthreads();
-  }
-  return halo;
+  const int32_t j0 = cd->chunk_ptr[chunk], j1 = cd->chunk_ptr[chunk + 1];
+  if (j0 == j1) return;
+  __syncthreads();   // the chunk's pk values are written
+  const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
+  for (int32_t j = j0 + (int32_t)threadIdx.x; j < j1; j += FCP_TPB) p2p_ll_store(cd->push_dst[j], pk[cd->push_cell[j]], seq);
 }
 
 // y = A x ; sums: sum v1*y [, sum v2*y | sum y*y]
 template <int NS, bool SQ>
 __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
-                                                       const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int wait) {
+                                                       const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused, unsigned int seq_base) {
   if (sc->done) return;
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
-  const bool halo = spmv_halo_chunk(ra.cd, wait);
-  FCP_ROW_LOOP(r, n) {
-    const double yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, n) : sell_row_sum<false>(m, x, r, 0.0);
+  const CommDev *cd = ra.cd;
+  const int chunk = cd ? cd->order[blockIdx.x] : (int)blockIdx.x;
+  const bool halo = fused && cd && cd->chunk_ptr[chunk + 1] > cd->chunk_ptr[chunk];
+  const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
+  for (int j = 0; j < FCP_IPT; ++j) {
+    const int64_t r64 = (int64_t)chunk * FCP_CHUNK + j * FCP_TPB + threadIdx.x;
+    if (r64 >= n) continue;
+    const int32_t r = (int32_t)r64;
+    const double yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, cd, seq) : sell_row_sum<false>(m, x, r, 0.0);
     y[r] = yr;
     s[0] = s[0] + v1[r] * yr;
     if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
   }
-  finish_reduce<NS>(s, ra);
+  finish_reduce_part<NS>(s, ra, chunk, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -373,14 +365,17 @@ __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, con
 #endif
 template <int NS, bool SQ, int W>
 __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_dot_pipe(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
-                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int wait) {
+                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused,
+                                                            unsigned int seq_base) {
   if (sc->done) return;
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
-  const bool halo = spmv_halo_chunk(ra.cd, wait);
-  const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
-  if (base + (FCP_IPT - 1) * FCP_TPB < n) {
+  const CommDev *cd = ra.cd;
+  const int chunk = cd ? cd->order[blockIdx.x] : (int)blockIdx.x;
+  const bool halo = fused && cd && cd->chunk_ptr[chunk + 1] > cd->chunk_ptr[chunk];
+  const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
+  if (!halo && base + (FCP_IPT - 1) * FCP_TPB < n) {
     const int lane = threadIdx.x & 31;
     int64_t pos = __ldg(&m.slptr[base >> 5]) + lane;      // SELL position of the current row's first entry
     int32_t len = __ldg(&m.rinfo[base]) & 0xffff;
@@ -394,13 +389,8 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
       double av[W], xv[W];
 #pragma unroll
       for (int k = 0; k < W; ++k) av[k] = (k < len) ? __ldcs(m.a + pos + (int64_t)k * 32) : 0.0;
-      if (halo) {   // CTA-uniform: ghost columns (>= n) were stored by a peer during this kernel's lifetime
 #pragma unroll
-        for (int k = 0; k < W; ++k) xv[k] = (k < len) ? (c[k] >= n ? p2p_ld_data(x + c[k]) : __ldg(x + c[k])) : 0.0;
-      } else {
-#pragma unroll
-        for (int k = 0; k < W; ++k) xv[k] = (k < len) ? __ldg(x + c[k]) : 0.0;
-      }
+      for (int k = 0; k < W; ++k) xv[k] = (k < len) ? __ldg(x + c[k]) : 0.0;
       const double vv = v1[r];
       // next row: meta data and column indices
       int64_t npos = 0;
@@ -417,10 +407,7 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
 #pragma unroll
       for (int k = 0; k < W; ++k)
         if (k < len) yr = yr + av[k] * xv[k];
-      for (int32_t k = W; k < len; ++k) {
-        const int32_t ck = __ldcs(m.ja + pos + (int64_t)k * 32);
-        yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * ((halo && ck >= n) ? p2p_ld_data(x + ck) : __ldg(x + ck));
-      }
+      for (int32_t k = W; k < len; ++k) yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * __ldg(x + __ldcs(m.ja + pos + (int64_t)k * 32));
       y[r] = yr;
       s[0] = s[0] + vv * yr;
       if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
@@ -430,14 +417,19 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
       for (int k = 0; k < W; ++k) c[k] = cn[k];
     }
   } else {
-    FCP_ROW_LOOP(r, n) {
-      const double yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, n) : sell_row_sum<false>(m, x, r, 0.0);
+    // the few chunks that own process faces (launched first) and the ragged last chunk
+    const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
+    for (int j = 0; j < FCP_IPT; ++j) {
+      const int64_t r64 = base + (int64_t)j * FCP_TPB;
+      if (r64 >= n) continue;
+      const int32_t r = (int32_t)r64;
+      const double yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, cd, seq) : sell_row_sum<false>(m, x, r, 0.0);
       y[r] = yr;
       s[0] = s[0] + v1[r] * yr;
       if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
     }
   }
-  finish_reduce<NS>(s, ra);
+  finish_reduce_part<NS>(s, ra, chunk, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -478,11 +470,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #define FCP_TILES (FCP_CHUNK / FCP_TILE_ROWS)      // 8 tiles per chunk
 #define FCP_MAX_STAGES 4
 
-template <int NS>
-__device__ __forceinline__ void finish_reduce_part(double (&s)[NS], const RedArgs &ra, int part, int nparts) {
-  double total[NS];
-  if (fcp_grid_reduce_part<NS>(s, ra.partials, ra.stride, ra.counter, part, nparts, total)) finish_epilogue<NS>(total, ra);
-}
 
 // Persistent CTAs: CTA b owns chunks b, b + gridDim.x, ... and keeps ONE pipeline running across its chunks (the ring is
 // refilled for the next chunk while the current one is still being consumed), so the start-up latency (slice pointers,
@@ -770,7 +757,7 @@ struct Launcher {
   int n;
   int grid;
   const CommDev *cd;   // peer-memory path (nullptr: single GPU or NCCL path)
-  RedArgs red(int epi, int bump = 0) const { return RedArgs{ws.partials, ws.maxchunks, ws.counter, ws.sc, epi, comm ? (cd ? 2 : 0) : 1, cd, bump}; }
+  RedArgs red(int epi) const { return RedArgs{ws.partials, ws.maxchunks, ws.counter, ws.sc, epi, comm ? (cd ? 2 : 0) : 1, cd}; }
   // after a reducing kernel on the NCCL path: cross-rank sum of sc->red[0..ns) + epilogue kernel
   int post(int epi, int ns) const {
     if (!comm || cd) return FCP_OK;
@@ -845,7 +832,7 @@ static int tma_smem_limit(size_t smem) {
 // load/use kernel.  FCP_SPMV=ldg forces the latter (A/B measurements).
 template <int NS, bool SQ>
 static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double *x, double *y, const double *v1, const KrylovScalars *sc,
-                           const RedArgs &ra, cudaStream_t st, int wait = 0) {
+                           const RedArgs &ra, cudaStream_t st, int fused = 0, unsigned int seq_base = 0) {
   const int grid = fcp_nchunks(p.n);
   if (!grid) return FCP_OK;
   static int mode = -1;   // 0 ldg, 1 tma
@@ -875,10 +862,10 @@ static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double
     k_spmv_dot_tma<NS, SQ><<<pgrid, FCP_TPB, smem, st>>>(p.n, p.nslices, m, x, y, v1, sc, ra, p.tile_cap, nst);
     FCP_CHECK_LAUNCH();
   } else if (mode != 0) {
-    if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, wait);
-    else k_spmv_dot_pipe<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, wait);
+    if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base);
+    else k_spmv_dot_pipe<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base);
   } else {
-    k_spmv_dot<NS, SQ><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, wait);
+    k_spmv_dot<NS, SQ><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base);
   }
   FCP_LAUNCHED();
   return FCP_OK;
@@ -899,12 +886,13 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     return FCP_EINVAL;
   }
   const CommDev *cd = comm_dev(comm);
-  FCP_TRY(krylov_ws_alloc(ws, n, p.ncols, comm_halo_vector(comm)));
+  FCP_TRY(krylov_ws_alloc(ws, n, p.ncols));
   if (rep) { memset(rep, 0, sizeof(*rep)); rep->solver = solver; }
   const int grid = fcp_nchunks(n);
   if (cd && grid == 0) { fcp_set_error("a partition without cells cannot take part in the peer-memory path"); return FCP_EINVAL; }
   Launcher L{st, comm, ctx, ws, n, grid, cd};
-  const int fw = cd ? 1 : 0;   // the SpMV after k_cg_pk waits for the fused halo push
+  const int fw = cd ? 1 : 0;   // the SpMV after k_cg_pk takes its ghost columns from the fused halo push
+  const unsigned int sb = comm_pk_base(comm);
   Profiler *prof = ctx ? &ctx->prof : nullptr;
   SellView m{p.slptr, p.rinfo, p.ja, a};
   KrylovScalars init;
@@ -924,9 +912,9 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     FCP_TRY(L.post(EPI_INIT_CG, 2));
     for (int it = 0; it < itr_max;) {
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
-        if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd), FCP_LAUNCHED()));
+        if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, sb), FCP_LAUNCHED()));
         FCP_TRY(L.halo_pk());
-        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK, fw), st, fw))));
+        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb))));
         FCP_TRY(L.post(EPI_PKAPK, 1));
         if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
         FCP_TRY(L.post(EPI_CG_UPDATE, 3));
@@ -949,9 +937,9 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
           FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st)));
           if (grid) { k_dot<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.zk, ws.sc, L.red(EPI_SK)); FCP_LAUNCHED(); }
           FCP_TRY(L.post(EPI_SK, 1));
-          if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd), FCP_LAUNCHED()));
+          if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, sb), FCP_LAUNCHED()));
           FCP_TRY(L.halo_pk());
-          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK, fw), st, fw))));
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb))));
           FCP_TRY(L.post(EPI_PKAPK, 1));
           if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
           FCP_TRY(L.post(EPI_CG_UPDATE, 3));
@@ -999,7 +987,10 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
   }
   FCP_TRY(fetch_scalars(ws, st));
   if (comm) FCP_TRY(L.halo(fi));   // src-par/dpcg.f90:183  call exchange(fi)
-  if (cd) FCP_TRY(comm_check_error(ctx));
+  if (cd) {
+    comm_pk_advance(comm, ws.h_sc->iters);
+    FCP_TRY(comm_check_error(ctx));
+  }
   if (rep) {
     rep->res0 = ws.h_sc->res0;
     rep->resl = ws.h_sc->resl;

@@ -22,6 +22,30 @@ __device__ __forceinline__ unsigned long long p2p_now_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// ---- flag-in-data words ("LL" protocol): a double travels as two 8-byte words {32 data bits | 32-bit sequence number}.
+// An 8-byte store is atomic, so a word whose upper half equals the expected sequence number carries valid data: no
+// fence, no separate flag, one NVLink one-way latency.  16-byte aligned pairs move as one v2 transaction.
+__device__ __forceinline__ void p2p_ll_store(unsigned long long *dst /* 16-byte aligned */, double v, unsigned int seq) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)seq << 32);
+  const unsigned long long w1 = (bits >> 32) | ((unsigned long long)seq << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double p2p_ll_load(const unsigned long long *src, unsigned int seq, WinHeader *hdr) {
+  unsigned long long w0, w1, t0 = 0;
+  unsigned int n = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
+    if ((++n & 4095u) == 0u) {
+      const unsigned long long t = p2p_now_ns();
+      if (!t0) t0 = t;
+      else if (t - t0 > 20000000000ull) { hdr->error = 1; break; }
+    }
+  }
+  return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+
 // spin until *flag >= seq; gives up after 20 s (a peer died or a protocol bug) and raises hdr->error instead of hanging the GPU
 __device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long seq, WinHeader *hdr) {
   unsigned long long t0 = 0;

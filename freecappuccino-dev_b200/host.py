@@ -17,6 +17,45 @@ import numpy as np
 from . import lib as L
 
 
+class FvEquation:
+    """type(fvEquation) of fvImplicit/fvEquation.f90:16-67: coef(nnz) over the case's CSR pattern + source(numCells), with
+    operator(+), operator(-) and operator(==) producing NEW equations (:158-404).  The element-wise arithmetic runs on
+    the GPU (fcp_field_axpby) in the matrix slots A and H and the scalar slots S0/S1."""
+
+    def __init__(self, case: "Case", coef: Optional[np.ndarray] = None, source: Optional[np.ndarray] = None):
+        self.case = case
+        self.coef = np.zeros(case.nnz) if coef is None else np.asarray(coef, dtype=np.float64)
+        self.source = np.zeros(case.mesh.numCells) if source is None else np.asarray(source, dtype=np.float64)
+
+    def _combine(self, other, beta: float) -> "FvEquation":
+        c, n = self.case.ctx, self.case.mesh.numCells
+        out = FvEquation(self.case)
+        if isinstance(other, FvEquation):                     # add_fvEquations / subtract_fvEquations
+            c.upload("A", self.coef); c.upload("H", other.coef)
+            c.axpby("A", 1.0, "A", beta, "H")
+            out.coef = c.download("A")
+            rhs = other.source
+        else:                                                 # add_source_to_fvEquation / subtract_source_from_fvEquation:
+            out.coef = np.zeros(self.case.nnz)                # the reference returns a fresh equation: coef is NOT carried over
+            rhs = np.asarray(other, dtype=np.float64)[:n]
+        s0 = np.zeros(self.case.mesh.numTotal); s1 = np.zeros(self.case.mesh.numTotal)
+        s0[:n] = self.source; s1[:n] = rhs
+        c.upload("S0", s0); c.upload("S1", s1)
+        c.axpby("S0", 1.0, "S0", beta, "S1")
+        out.source = c.download("S0", n)
+        return out
+
+    def __add__(self, other):
+        return self._combine(other, 1.0)
+
+    def __sub__(self, other):
+        return self._combine(other, -1.0)
+
+    def equals(self, other):
+        """operator(==) is bound to the same procedures as operator(-) (fvEquation.f90:70-75)."""
+        return self._combine(other, -1.0)
+
+
 class Case:
     """geometry + sparse_matrix + variables modules of one run (one mesh partition on one GPU)."""
 

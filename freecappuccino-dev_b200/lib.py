@@ -111,6 +111,7 @@ def lib():
     L.fcp_field_download.argtypes = [vp, C.c_int, _pd, C.c_int64]
     L.fcp_field_fill.argtypes = [vp, C.c_int, C.c_double]
     L.fcp_field_copy.argtypes = [vp, C.c_int, C.c_int]
+    L.fcp_field_axpby.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int]
     L.fcp_field_devptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
     L.fcp_spmv.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_csrsolve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_double, C.c_double, C.POINTER(Report)]
@@ -235,6 +236,9 @@ class Context:
 
     def copy(self, dst, src):
         check(lib().fcp_field_copy(self.h, field_id(dst), field_id(src)))
+
+    def axpby(self, dst, alpha: float, x, beta: float, y):
+        check(lib().fcp_field_axpby(self.h, field_id(dst), float(alpha), field_id(x), float(beta), field_id(y)), "fcp_field_axpby")
 
     def sync(self):
         check(lib().fcp_sync(self.h))

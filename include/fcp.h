@@ -113,6 +113,9 @@ int fcp_field_upload(fcp_ctx *ctx, int field, const double *host, int64_t count)
 int fcp_field_download(fcp_ctx *ctx, int field, double *host, int64_t count);
 int fcp_field_fill(fcp_ctx *ctx, int field, double value);
 int fcp_field_copy(fcp_ctx *ctx, int dst_field, int src_field);
+/* dst = alpha*x + beta*y over fields of equal extent: the arithmetic of the fvEquation operators (+), (-), (==),
+ * fvImplicit/fvEquation.f90:158-404 (coef(nnz) and source(numCells) added / subtracted element by element) */
+int fcp_field_axpby(fcp_ctx *ctx, int dst_field, double alpha, int x_field, double beta, int y_field);
 /* raw device address of a field (for zero-copy interop with other CUDA code in the same process) */
 int fcp_field_devptr(fcp_ctx *ctx, int field, void **devptr, int64_t *count);
 

@@ -118,11 +118,15 @@ def pinned_copy(a):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def oracle_step_time(m, f, gpu_iters, max_sample_iters, threads_note="1 (serial reference stand-in)"):
-    """Times the CPU restatement (oracle/, g++ -O2 -ffp-contract=off, one thread like the serial reference binary) on
-    the SAME mesh and inputs: gradp + assembly + correction in full, DPCG for `max_sample_iters` iterations, and
-    extrapolates the solve to the iteration count the converged run needs."""
+def oracle_step_time(m, f, gpu_iters, max_sample_iters, threads=1):
+    """Times the CPU restatement (oracle/, -O2 -ffp-contract=off) on the SAME mesh and inputs: gradp + assembly +
+    correction in full, DPCG for `max_sample_iters` iterations, and extrapolates the solve to `gpu_iters`, the iteration
+    count of the converged run (0: the sample's own count).  threads = 1: the serial reference stand-in; threads > 1:
+    liborc_omp.so, the DPCG loops and the SpMV split over the host cores like the reference's src-par MPI build (the face
+    loops stay serial: they are < 1 % of the step)."""
     from oracle import orc_py as O
+    if threads > 1:
+        threads = O.use_openmp(threads)
     t0 = time.perf_counter()
     c = O.Csr(m)
     t_csr = time.perf_counter() - t0
@@ -140,41 +144,51 @@ def oracle_step_time(m, f, gpu_iters, max_sample_iters, threads_note="1 (serial 
     rep = O.solve(O.DPCG, c.ia, c.ja, a, c.diag, g["pp"], su, max_sample_iters, 1e-30, TOL_REL)
     t_solve = time.perf_counter() - t0
     its = max(rep.iters, 1)
+    converged = rep.resl / (rep.res0 + 1e-300) < TOL_REL
     t0 = time.perf_counter()
     O.correct_simple(m, c, 0, a, g["den"], g["u"], g["v"], g["w"], g["p"], g["pp"], g["apu"], g["apv"], g["apw"], 0.3, 1, dP, flm)
     t_corr = time.perf_counter() - t0
     t_iter = t_solve / (its + 0.5)       # the initial residual costs about half an iteration
-    n_it = gpu_iters if gpu_iters else its
+    n_it = its if (converged or not gpu_iters) else gpu_iters
     total = t_gradp + t_asm + t_corr + t_iter * (n_it + 0.5)
     return dict(ms=1e3 * total, t_gradp=t_gradp, t_asm=t_asm, t_corr=t_corr, t_iter=t_iter, sample_iters=its, iters_used=n_it,
-                t_csr=t_csr, measured_s=t_gradp + t_asm + t_solve + t_corr, threads=threads_note)
+                converged=bool(converged), t_csr=t_csr, measured_s=t_gradp + t_asm + t_solve + t_corr, threads=threads)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path.  The Fortran reference cannot be built in
-    this image (no gfortran/flang/nvfortran; probed), so this is the C++ restatement (oracle/) = kind 'port'."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores.  The Fortran
+    reference cannot be built in this image (no gfortran/flang/nvfortran; probed), so this is the C++ restatement
+    (oracle/) = kind 'port', run with all host threads (OpenMP over the DPCG loops and the SpMV = the src-par MPI build's
+    work split).  The FIRST warm-up step runs the solve to convergence (that fixes the iteration count the workload
+    needs: 1006 at 256^3, the same as the GPU arm); every later step is a bounded sample: the face loops in full and
+    --ref-iters DPCG iterations, extrapolated to that count."""
     if rank != 0:
         return
     from fcb200 import mesh as M
     n = args.n
     m = M.hex_mesh_fast(*(np.linspace(0.0, 1.0, n + 1),) * 3)
     f = synthetic_fields(m)
-    iters = args.ref_iters
+    threads = args.ref_threads or (os.cpu_count() or 1)
+    full = oracle_step_time(m, f, 0, MAXITER, threads)              # converged solve: fixes the iteration count
+    count = full["iters_used"]
     times = []
-    for s in range(args.warmup + args.steps):
-        r = oracle_step_time(m, f, args.pcg_iters, iters)
-        if s >= args.warmup:
+    for s in range(max(args.warmup - 1, 0) + args.steps):
+        r = oracle_step_time(m, f, count, min(args.ref_iters, count), threads)
+        if s >= max(args.warmup - 1, 0):
             times.append(r)
     ms = float(np.mean([t["ms"] for t in times]))
     r = times[-1]
-    sample = (f"{n}^3 mesh, serial C++ restatement of the Fortran path: gradp_and_sources + assembly + correction in full, "
-              f"DPCG {r['sample_iters']} iterations timed ({r['t_iter']:.3f} s/iter) and extrapolated to {r['iters_used']} iterations "
-              f"(the count the converged tolRel=1e-8 solve needs); {r['measured_s']:.1f} s of CPU work per step")
+    sample = (f"{n}^3 mesh, C++ restatement of the Fortran path on {r['threads']} host threads: first warm-up step = the whole step with the solve "
+              f"run to convergence ({count} DPCG iterations, {full['ms'] / 1e3:.1f} s); each timed step = gradp_and_sources + assembly + correction in full "
+              f"(serial, {r['t_gradp']:.2f}+{r['t_asm']:.2f}+{r['t_corr']:.2f} s) + {r['sample_iters']} DPCG iterations ({r['t_iter'] * 1e3:.1f} ms/iter) "
+              f"extrapolated to {count} iterations; {r['measured_s']:.1f} s of CPU work per timed step")
     line = dict(metric=f"SIMPLE iter time ({n}^3 hex cavity: gradp + p' assembly + DPCG to 1e-8 + correction)", value=ms, unit="ms",
                 impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=False,
                 scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=f"synthetic 3D lid-driven cavity {n}^3 hex ({n**3} cells), pressure PCG", solver="dpcg", tol_rel=TOL_REL),
-                cpu_baseline=dict(value=ms, unit="ms", cores=1, kind="port", sample=sample),
+                config=dict(workload=f"synthetic 3D lid-driven cavity {n}^3 hex ({n**3} cells), pressure PCG", solver="dpcg", tol_rel=TOL_REL,
+                            pcg_iters=count),
+                cpu_baseline=dict(value=ms, unit="ms", cores=r["threads"], kind="port", sample=sample,
+                                  full_step_ms=full["ms"]),
                 e2e=dict(value=ms, unit="ms", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -189,16 +203,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--solver", default="dpcg", choices=["dpcg", "iccg", "bicgstab"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-iters", type=int, default=4, help="DPCG iterations timed by the cpu_baseline leg")
-    ap.add_argument("--ref-iters", type=int, default=4, help="DPCG iterations timed per step by --impl reference")
-    ap.add_argument("--pcg-iters", type=int, default=0, help="--impl reference: iteration count to extrapolate to (0: run's own)")
+    ap.add_argument("--cpu-iters", type=int, default=40, help="DPCG iterations timed by the cpu_baseline leg")
+    ap.add_argument("--ref-iters", type=int, default=40, help="DPCG iterations timed per step by --impl reference (bounded sample)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="host threads of --impl reference / cpu_baseline (0: all cores)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        if args.pcg_iters == 0:
-            args.pcg_iters = {256: 0}.get(args.n, 0)
         run_reference(args, rank, world)
         return
 
@@ -341,12 +353,13 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        r = oracle_step_time(m, f, iters, args.cpu_iters)
-        cpu_baseline = dict(value=r["ms"], unit="ms", cores=1, kind="port",
-                            sample=(f"same {n}^3 mesh and inputs, serial C++ restatement (oracle/, the Fortran reference cannot be built here): "
-                                    f"gradp + assembly + correction in full ({r['t_gradp']:.2f}+{r['t_asm']:.2f}+{r['t_corr']:.2f} s), DPCG {r['sample_iters']} iterations "
-                                    f"timed ({r['t_iter']:.3f} s/iter), extrapolated to the {iters} iterations of the converged solve; "
-                                    f"{r['measured_s']:.1f} s measured"))
+        threads = args.ref_threads or (os.cpu_count() or 1)
+        r = oracle_step_time(m, f, iters, args.cpu_iters, threads)
+        cpu_baseline = dict(value=r["ms"], unit="ms", cores=r["threads"], kind="port",
+                            sample=(f"same {n}^3 mesh and inputs, C++ restatement (oracle/, the Fortran reference cannot be built here) on {r['threads']} host "
+                                    f"threads (OpenMP over the DPCG loops and the SpMV, like the src-par MPI build; face loops serial): gradp + assembly + correction "
+                                    f"in full ({r['t_gradp']:.2f}+{r['t_asm']:.2f}+{r['t_corr']:.2f} s), DPCG {r['sample_iters']} iterations timed "
+                                    f"({r['t_iter'] * 1e3:.1f} ms/iter), extrapolated to the {iters} iterations of the converged solve; {r['measured_s']:.1f} s measured"))
     h2d = 8 * m.numTotal * len(INPUT_FIELDS)
     d2h = 8 * m.numTotal * len(OUTPUT_FIELDS)
     line = dict(

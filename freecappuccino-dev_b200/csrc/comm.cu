@@ -85,6 +85,7 @@ struct FcpComm {
 };
 int comm_nranks(const FcpComm *c) { return c ? c->nranks : 1; }
 const CommDev *comm_dev(const FcpComm *c) { return (c && c->p2p) ? c->d_dev : nullptr; }
+const int32_t *comm_chunk_info(const FcpComm *c) { return (c && c->p2p) ? c->d_order : nullptr; }
 unsigned int comm_pk_base(const FcpComm *c) { return c ? c->pk_base : 0u; }
 void comm_pk_advance(FcpComm *c, int32_t iters) { if (c) c->pk_base += (unsigned int)iters + 1u; }
 void comm_free(FcpComm *c) {
@@ -330,7 +331,7 @@ static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const std::vector<int32_t> &cell,
       pdst[j] = (unsigned long long *)((char *)c->peer_win[frank[i]] + recs[frank[i]].off_ll) + 2 * (size_t)rord[i];
     }
   }
-  for (int k = 0; k < nch; ++k) if (cptr[k + 1] > cptr[k]) order.push_back(k);
+  for (int k = 0; k < nch; ++k) if (cptr[k + 1] > cptr[k]) order.push_back(k | (int32_t)0x80000000);
   for (int k = 0; k < nch; ++k) if (cptr[k + 1] == cptr[k]) order.push_back(k);
   std::vector<int32_t> gord(std::max(ctx->B, 1), -1);
   for (int32_t i = 0; i < c->npro; ++i) gord[slot_h[i] - ctx->n] = i;

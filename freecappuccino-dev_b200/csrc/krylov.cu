@@ -60,6 +60,7 @@ struct SellView {
   const int32_t *rinfo;
   const int32_t *ja;
   const double *a;
+  const int32_t *llen;   // [n] number of local (non-ghost) entries per row; nullptr when the pattern has no halo columns
 };
 
 // s <- s (+|-) sum_k a(r,k) x(ja(r,k)), entries in CSR order (linear_solvers.f90:256-261 with SUB, :308-313 without)
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_spmv(int32_t n, SellView m, const d
 }
 int sell_spmv(const SellPattern &p, const double *a, const double *x, double *y, cudaStream_t st) {
   if (p.n == 0) return FCP_OK;
-  SellView m{p.slptr, p.rinfo, p.ja, a};
+  SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
   k_spmv<<<fcp_nchunks(p.n), FCP_TPB, 0, st>>>(p.n, m, x, y);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
@@ -207,6 +208,7 @@ struct RedArgs {
   int fuse;   // 1: run the epilogue in the last CTA (single GPU); 0: only store the local sums in sc->red (NCCL path);
               // 2: peer-memory all-reduce inside the last CTA, then the epilogue
   const CommDev *cd;
+  const int32_t *chunk_info;   // peer-memory path: [gridDim.x] chunk index | halo bit 31, in launch order (halo chunks first); one load per CTA
 };
 
 // Last CTA of a reducing kernel; `total` is valid in thread 0.  fuse == 2: thread (r, k) stores partial sum k into rank
@@ -294,10 +296,11 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_init(int32_t n, SellView m, cons
 template <bool JACOBI>
 __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
                                                     const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd,
-                                                    unsigned int seq_base) {
+                                                    const int32_t *__restrict__ chunk_info, unsigned int seq_base) {
+  const int32_t info = chunk_info ? __ldg(chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
   if (sc->done) return;
   const double bet = sc->bet;
-  const int chunk = cd ? cd->order[blockIdx.x] : (int)blockIdx.x;
+  const int chunk = info & 0x7fffffff;
   const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
   if (base + (FCP_IPT - 1) * FCP_TPB < n) {
     // full chunk: all loads of the thread's 8 rows are issued before the first use (memory-level parallelism)
@@ -322,9 +325,8 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__re
       }
     }
   }
-  if (!cd) return;
+  if (info >= 0) return;   // no halo bit: this chunk owns no process face
   const int32_t j0 = cd->chunk_ptr[chunk], j1 = cd->chunk_ptr[chunk + 1];
-  if (j0 == j1) return;
   __syncthreads();   // the chunk's pk values are written
   const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
   for (int32_t j = j0 + (int32_t)threadIdx.x; j < j1; j += FCP_TPB) p2p_ll_store(cd->push_dst[j], pk[cd->push_cell[j]], seq);
@@ -334,13 +336,14 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__re
 template <int NS, bool SQ>
 __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
                                                        const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused, unsigned int seq_base) {
+  const int32_t info = ra.chunk_info ? __ldg(ra.chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
   if (sc->done) return;
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
   const CommDev *cd = ra.cd;
-  const int chunk = cd ? cd->order[blockIdx.x] : (int)blockIdx.x;
-  const bool halo = fused && cd && cd->chunk_ptr[chunk + 1] > cd->chunk_ptr[chunk];
+  const int chunk = info & 0x7fffffff;
+  const bool halo = fused && info < 0;
   const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
   for (int j = 0; j < FCP_IPT; ++j) {
     const int64_t r64 = (int64_t)chunk * FCP_CHUNK + j * FCP_TPB + threadIdx.x;
@@ -367,18 +370,22 @@ template <int NS, bool SQ, int W>
 __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_dot_pipe(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
                                                             const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused,
                                                             unsigned int seq_base) {
+  const int32_t info = ra.chunk_info ? __ldg(ra.chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
   if (sc->done) return;
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
   const CommDev *cd = ra.cd;
-  const int chunk = cd ? cd->order[blockIdx.x] : (int)blockIdx.x;
-  const bool halo = fused && cd && cd->chunk_ptr[chunk + 1] > cd->chunk_ptr[chunk];
+  const int chunk = info & 0x7fffffff;
+  const bool halo = fused && info < 0;
   const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
-  if (!halo && base + (FCP_IPT - 1) * FCP_TPB < n) {
+  if (base + (FCP_IPT - 1) * FCP_TPB < n) {
+    // chunks that own process faces (halo, CTA-uniform): the pipelined part covers the LOCAL entries of a row; its ghost
+    // entries (stored last in the row, src-par/dpcg.f90:129-143) are added afterwards from the LL slots
+    const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
     const int lane = threadIdx.x & 31;
     int64_t pos = __ldg(&m.slptr[base >> 5]) + lane;      // SELL position of the current row's first entry
-    int32_t len = __ldg(&m.rinfo[base]) & 0xffff;
+    int32_t len = halo ? __ldg(&m.llen[base]) : (__ldg(&m.rinfo[base]) & 0xffff);
     int32_t c[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) c[k] = (k < len) ? __ldcs(m.ja + pos + (int64_t)k * 32) : 0;
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
       if (j + 1 < FCP_IPT) {
         const int64_t rn = r + FCP_TPB;
         npos = __ldg(&m.slptr[rn >> 5]) + lane;
-        nlen = __ldg(&m.rinfo[rn]) & 0xffff;
+        nlen = halo ? __ldg(&m.llen[rn]) : (__ldg(&m.rinfo[rn]) & 0xffff);
 #pragma unroll
         for (int k = 0; k < W; ++k) cn[k] = (k < nlen) ? __ldcs(m.ja + npos + (int64_t)k * 32) : 0;
       }
@@ -408,6 +415,13 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
       for (int k = 0; k < W; ++k)
         if (k < len) yr = yr + av[k] * xv[k];
       for (int32_t k = W; k < len; ++k) yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * __ldg(x + __ldcs(m.ja + pos + (int64_t)k * 32));
+      if (halo) {
+        const int32_t full = __ldg(&m.rinfo[r]) & 0xffff;
+        for (int32_t k = len; k < full; ++k) {
+          const int32_t cg = __ldcs(m.ja + pos + (int64_t)k * 32);
+          yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * p2p_ll_load(cd->ll + 2 * (size_t)__ldg(cd->ghost_ord + (cg - n)), seq, cd->hdr);
+        }
+      }
       y[r] = yr;
       s[0] = s[0] + vv * yr;
       if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
@@ -757,7 +771,7 @@ struct Launcher {
   int n;
   int grid;
   const CommDev *cd;   // peer-memory path (nullptr: single GPU or NCCL path)
-  RedArgs red(int epi) const { return RedArgs{ws.partials, ws.maxchunks, ws.counter, ws.sc, epi, comm ? (cd ? 2 : 0) : 1, cd}; }
+  RedArgs red(int epi) const { return RedArgs{ws.partials, ws.maxchunks, ws.counter, ws.sc, epi, comm ? (cd ? 2 : 0) : 1, cd, comm_chunk_info(comm)}; }
   // after a reducing kernel on the NCCL path: cross-rank sum of sc->red[0..ns) + epilogue kernel
   int post(int epi, int ns) const {
     if (!comm || cd) return FCP_OK;
@@ -790,7 +804,7 @@ static int launch_factor(bool ilu, SellPattern &p, const double *a, double *d, c
   if (p.n == 0) return FCP_OK;
   int dev = 0, grid = 0;
   FCP_CUDA(cudaGetDevice(&dev));
-  SellView m{p.slptr, p.rinfo, p.ja, a};
+  SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
   LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
   const int32_t *tpos = p.tpos;
   void *args[] = {&m, &lv, &tpos, &d};
@@ -809,7 +823,7 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
     FCP_CUDA(cudaGetDevice(&dev));
     FCP_TRY(coop_grid((const void *)k_precond_apply, dev, &grid));
   }
-  SellView m{p.slptr, p.rinfo, p.ja, a};
+  SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
   LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
   const int32_t *llen = p.llen;
   void *args[] = {&m, &lv, &llen, &d, &rhs, &zk, &sc};
@@ -894,7 +908,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
   const int fw = cd ? 1 : 0;   // the SpMV after k_cg_pk takes its ghost columns from the fused halo push
   const unsigned int sb = comm_pk_base(comm);
   Profiler *prof = ctx ? &ctx->prof : nullptr;
-  SellView m{p.slptr, p.rinfo, p.ja, a};
+  SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
   KrylovScalars init;
   memset(&init, 0, sizeof(init));
   init.tol_abs = tol_abs;
@@ -912,7 +926,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     FCP_TRY(L.post(EPI_INIT_CG, 2));
     for (int it = 0; it < itr_max;) {
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
-        if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, sb), FCP_LAUNCHED()));
+        if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
         FCP_TRY(L.halo_pk());
         if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb))));
         FCP_TRY(L.post(EPI_PKAPK, 1));
@@ -937,7 +951,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
           FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st)));
           if (grid) { k_dot<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.zk, ws.sc, L.red(EPI_SK)); FCP_LAUNCHED(); }
           FCP_TRY(L.post(EPI_SK, 1));
-          if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, sb), FCP_LAUNCHED()));
+          if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
           FCP_TRY(L.halo_pk());
           if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb))));
           FCP_TRY(L.post(EPI_PKAPK, 1));

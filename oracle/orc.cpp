@@ -60,8 +60,11 @@ extern "C" double orc_sum_tree(const double *v, int64_t n) {
   }
   return block_tree(acc);
 }
+// (the `omp` pragmas below are inert in liborc.so, the parity checker; only liborc_omp.so -- built with -fopenmp for
+//  bench.py's multi-threaded CPU timing leg, the stand-in for the reference's src-par MPI build -- activates them)
 static double sum_seq(const double *v, int64_t n) {
   double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
   for (int64_t i = 0; i < n; ++i) s += v[i];
   return s;
 }
@@ -573,6 +576,7 @@ extern "C" void orc_nonorth_corrector(const orc_mesh *m, const double *den, cons
 // linear solvers  (src/linearSolvers/linear_solvers.f90)
 // ------------------------------------------------------------------------------------------
 extern "C" void orc_spmv(i32 n, const i32 *ia, const i32 *ja, const double *a, const double *x, double *y) {
+#pragma omp parallel for schedule(static)
   for (i32 i = 0; i < n; ++i) {
     double s = 0.0;
     for (i32 k = ia[i]; k <= ia[i + 1] - 1; ++k) s = s + a[k - 1] * x[ja[k - 1] - 1];
@@ -580,6 +584,7 @@ extern "C" void orc_spmv(i32 n, const i32 *ia, const i32 *ja, const double *a, c
   }
 }
 static void residual0(i32 n, const i32 *ia, const i32 *ja, const double *a, const double *fi, const double *rhs, double *res) {
+#pragma omp parallel for schedule(static)
   for (i32 i = 0; i < n; ++i) {                  // :256-261
     double r = rhs[i];
     for (i32 k = ia[i]; k <= ia[i + 1] - 1; ++k) r = r - a[k - 1] * fi[ja[k - 1] - 1];
@@ -589,8 +594,16 @@ static void residual0(i32 n, const i32 *ia, const i32 *ja, const double *a, cons
 struct Red {                                      // sum(expr) helper honouring the summation mode
   int mode; std::vector<double> tmp;
   Red(int m, i32 n) : mode(m), tmp(n) {}
-  double abs1(const double *v, i32 n) { for (i32 i = 0; i < n; ++i) tmp[i] = std::fabs(v[i]); return sum_mode(mode, tmp.data(), n); }
-  double dot(const double *x, const double *y, i32 n) { for (i32 i = 0; i < n; ++i) tmp[i] = x[i] * y[i]; return sum_mode(mode, tmp.data(), n); }
+  double abs1(const double *v, i32 n) {
+#pragma omp parallel for schedule(static)
+    for (i32 i = 0; i < n; ++i) tmp[i] = std::fabs(v[i]);
+    return sum_mode(mode, tmp.data(), n);
+  }
+  double dot(const double *x, const double *y, i32 n) {
+#pragma omp parallel for schedule(static)
+    for (i32 i = 0; i < n; ++i) tmp[i] = x[i] * y[i];
+    return sum_mode(mode, tmp.data(), n);
+  }
   double absdiag(const double *a, const i32 *diag, const double *fi, i32 n) {
     for (i32 i = 0; i < n; ++i) tmp[i] = std::fabs(a[diag[i] - 1] * fi[i]);
     return sum_mode(mode, tmp.data(), n);
@@ -611,14 +624,18 @@ extern "C" void orc_dpcg(i32 n, i32 nnz, const i32 *ia, const i32 *ja, const dou
   double resl = res0, resor = 0.0;
   i32 itr_used = 0;
   for (i32 l = 1; l <= itr_max; ++l) {
+#pragma omp parallel for schedule(static)
     for (i32 i = 0; i < n; ++i) zk[i] = res[i] / a[diag[i] - 1];
     double sk = R.dot(res.data(), zk.data(), n);
     double bet = sk / s0;
+#pragma omp parallel for schedule(static)
     for (i32 i = 0; i < n; ++i) pk[i] = zk[i] + bet * pk[i];
     orc_spmv(n, ia, ja, a, pk.data(), zk.data());
     double pkapk = R.dot(pk.data(), zk.data(), n);
     double alf = sk / pkapk;
+#pragma omp parallel for schedule(static)
     for (i32 i = 0; i < n; ++i) fi[i] = fi[i] + alf * pk[i];
+#pragma omp parallel for schedule(static)
     for (i32 i = 0; i < n; ++i) res[i] = res[i] - alf * zk[i];
     resl = R.abs1(res.data(), n);
     s0 = sk;

@@ -37,22 +37,40 @@ class OrcRank(C.Structure):
                 ("npro", C.c_int32), ("peer_rank", _pi), ("peer_patch", _pi), ("fi", _pd), ("rhs", _pd)]
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "liborc.so")
+def build(force: bool = False, name: str = "liborc.so") -> str:
+    so = os.path.join(_HERE, name)
     src = [os.path.join(_HERE, f) for f in ("orc.cpp", "orc.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src if os.path.exists(s)):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "liborc.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, "-B", name], stdout=subprocess.DEVNULL)
     return so
 
 
-def lib():
+def use_openmp(threads: int = 0) -> int:
+    """Switch this process to liborc_omp.so (the multi-threaded timing build; bench.py only).  Returns the thread count."""
     global _LIB
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    elif os.environ.get("OMP_NUM_THREADS") in (None, "", "1"):   # torchrun exports OMP_NUM_THREADS=1
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    _LIB = None
+    _load(build(name="liborc_omp.so"))
+    return int(os.environ["OMP_NUM_THREADS"])
+
+
+def _load(path: str):
+    global _LIB
+    _LIB = C.CDLL(path)
+    _LIB.orc_small.restype = C.c_double
+    _LIB.orc_sum_tree.restype = C.c_double
+    _LIB.orc_sum_tree.argtypes = [_pd, C.c_int64]
+    _LIB.orc_csr_nnz.restype = C.c_int32
+    return _LIB
+
+
+def lib():
     if _LIB is None:
-        _LIB = C.CDLL(build())
-        _LIB.orc_small.restype = C.c_double
-        _LIB.orc_sum_tree.restype = C.c_double
-        _LIB.orc_sum_tree.argtypes = [_pd, C.c_int64]
-        _LIB.orc_csr_nnz.restype = C.c_int32
+        _load(build())
     return _LIB
 
 

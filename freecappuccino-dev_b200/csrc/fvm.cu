@@ -6,6 +6,7 @@
 // in the face's own orientation (P = owner, N = neighbour) by the same instruction sequence on both sides, so both
 // cells see bit-identical face values, there are no atomics, results are deterministic and round like the reference.
 // The face lists are SELL-32 (fcp_internal.h): a warp reads 128 contiguous bytes per list step.
+#include <cstdlib>
 #include "fcp_internal.h"
 #include "reduce.cuh"
 #include "fvm_common.cuh"
@@ -184,11 +185,11 @@ __device__ __forceinline__ double face_p(int scheme, double pP, double pN, doubl
   return pP + (pN - pP) * lam;                                                              // face_value_cds, interpolation.f90:155
 }
 
+// Generic cell body (any number of faces): the face list is walked again for every boundary stage.
 template <bool CORRECT>
-__global__ void __launch_bounds__(FCP_TPB) k_gradp(MeshView m, int scheme, int nstages, double *p, const double *__restrict__ apu,
-                                                    double *__restrict__ su, double *__restrict__ sv, double *__restrict__ sw,
-                                                    double *__restrict__ dPdxi, CorrectArgs ca) {
-  FCP_CELL_LOOP(c, m.n) {
+__device__ __forceinline__ void gradp_cell_generic(const MeshView &m, int32_t c, int scheme, int nstages, double *p, const double *__restrict__ apu,
+                                                   double *__restrict__ su, double *__restrict__ sv, double *__restrict__ sw,
+                                                   double *__restrict__ dPdxi, const CorrectArgs &ca) {
     const double pc = p[c];
     const double ac = scheme == FCP_PSCHEME_WEIGHTED ? apu[c] : 0.0;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -304,6 +305,153 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp(MeshView m, int scheme, int n
     } else {
       su[c] = s1; sv[c] = s2; sw[c] = s3;   // stage-1 inner sums kept for the central second pass
     }
+}
+
+// Fast cell body for cells with at most W faces (every hexahedron, prism, tetrahedron): the whole face list and every
+// face quantity are loaded ONCE into registers (two memory round trips per cell) and all the stages -- inner-face sum,
+// bpres stage 1, bpres stage 2, boundary part of the sources, velocity correction, updateVelocityAtBoundary -- run out
+// of registers.  Boundary cells then cost one extra round trip (the wall-face centres) instead of four dependent list
+// walks; on a structured mesh a quarter of all warps contain a boundary cell, so this is what bounds the kernel.
+// Arithmetic order per cell is unchanged (faces in ascending index).
+template <bool CORRECT, bool WEIGHTED, int W>
+__device__ __forceinline__ void gradp_cell_fast(const MeshView &m, int32_t c, int32_t flen, int scheme, int nstages, double *p,
+                                                const double *__restrict__ apu, double *__restrict__ su, double *__restrict__ sv,
+                                                double *__restrict__ sw, double *__restrict__ dPdxi, const CorrectArgs &ca) {
+  const int64_t fbase = m.slptr[c >> 5] + (c & 31);
+  int32_t e[W], o[W], sl[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const bool on = k < flen;
+    const int64_t pos = fbase + (int64_t)k * 32;
+    e[k] = on ? __ldcs(m.ent + pos) : 0;
+    o[k] = on ? __ldcs(m.other + pos) : 0;
+    sl[k] = on ? __ldcs(m.slot + pos) : 0;
+  }
+  const double pc = p[c];
+  const double ac = WEIGHTED ? apu[c] : 0.0;
+  const double vol = m.vol[c];
+  double sx[W], sy[W], sz[W], lam[W], pv[W], ao[WEIGHTED ? W : 1];
+  bool has_bnd = false, has_wall = false;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int32_t f = (e[k] > 0 ? e[k] : -e[k]) - 1;
+    const bool on = e[k] != 0, two = on && sl[k] >= 0, bnd = on && sl[k] < 0;
+    has_bnd = has_bnd || bnd;
+    has_wall = has_wall || (bnd && (-1 - sl[k]) == FCP_BC_WALL);
+    // p: inner-face (cell / ghost) values are never written by this kernel -> non-coherent loads; pressure-patch values likewise
+    pv[k] = (two || (bnd && (-1 - sl[k]) == FCP_BC_PRESSURE)) ? __ldg(p + o[k]) : 0.0;
+    if (WEIGHTED) ao[k] = two ? __ldg(apu + o[k]) : 0.0;
+    lam[k] = two ? __ldg(m.facint + f) : 0.0;
+    sx[k] = on ? __ldg(m.arx + f) : 0.0; sy[k] = on ? __ldg(m.ary + f) : 0.0; sz[k] = on ? __ldg(m.arz + f) : 0.0;
+  }
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    if (e[k] != 0 && sl[k] >= 0) {
+      const double aok = WEIGHTED ? ao[k] : 0.0;
+      const int sch = WEIGHTED ? FCP_PSCHEME_WEIGHTED : FCP_PSCHEME_LINEAR;
+      const double pf = e[k] > 0 ? face_p(sch, pc, pv[k], lam[k], ac, aok) : face_p(sch, pv[k], pc, lam[k], aok, ac);
+      const double dfx = pf * sx[k], dfy = pf * sy[k], dfz = pf * sz[k];
+      if (e[k] > 0) { s1 = s1 - dfx; s2 = s2 - dfy; s3 = s3 - dfz; }
+      else          { s1 = s1 + dfx; s2 = s2 + dfy; s3 = s3 + dfz; }
+    }
+  }
+  const double volr = 1.0 / vol;
+  // stage 1: bpres(p,1): p_b = p_P on every patch that is not a pressure patch (pv[k] becomes the boundary value)
+  double gx = -s1, gy = -s2, gz = -s3;
+  if (has_bnd) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      if (e[k] != 0 && sl[k] < 0) {
+        const int type = -1 - sl[k];
+        if (type != FCP_BC_PRESSURE) {
+          pv[k] = pc;
+          if (!(nstages >= 2 && type == FCP_BC_WALL)) p[o[k]] = pc;   // (wall values are overwritten by stage 2 anyway)
+        }
+        gx = gx + pv[k] * sx[k]; gy = gy + pv[k] * sy[k]; gz = gz + pv[k] * sz[k];
+      }
+    }
+  }
+  gx = gx * volr; gy = gy * volr; gz = gz * volr;
+  if (nstages >= 2) {
+    if (has_bnd) {
+      // stage 2: bpres(p,2): walls are linearly extrapolated with the stage-1 gradient
+      const double g1x = gx, g1y = gy, g1z = gz;
+      gx = -s1; gy = -s2; gz = -s3;
+      if (has_wall) {
+        const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
+        double xw[W], yw[W], zw[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          const bool wall = e[k] != 0 && sl[k] == -1 - FCP_BC_WALL;
+          const int32_t f = (e[k] > 0 ? e[k] : -e[k]) - 1;
+          xw[k] = wall ? __ldg(m.xf + f) : 0.0; yw[k] = wall ? __ldg(m.yf + f) : 0.0; zw[k] = wall ? __ldg(m.zf + f) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          if (e[k] != 0 && sl[k] == -1 - FCP_BC_WALL) {
+            const double xpb = xw[k] - xc, ypb = yw[k] - yc, zpb = zw[k] - zc;
+            pv[k] = pc + g1x * xpb + g1y * ypb + g1z * zpb;
+            p[o[k]] = pv[k];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        if (e[k] != 0 && sl[k] < 0) { gx = gx + pv[k] * sx[k]; gy = gy + pv[k] * sy[k]; gz = gz + pv[k] * sz[k]; }
+      }
+      gx = gx * volr; gy = gy * volr; gz = gz * volr;
+    }
+  }
+  dPdxi[3 * (int64_t)c + 0] = gx;
+  dPdxi[3 * (int64_t)c + 1] = gy;
+  dPdxi[3 * (int64_t)c + 2] = gz;
+  if (nstages >= 2) {
+    if (has_bnd) {   // boundary-face part of the momentum sources, nablap.f90:195-204
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        if (e[k] != 0 && sl[k] < 0) { s1 = s1 - pv[k] * sx[k]; s2 = s2 - pv[k] * sy[k]; s3 = s3 - pv[k] * sz[k]; }
+      }
+    }
+    if (su) { su[c] = s1; sv[c] = s2; sw[c] = s3; }
+    if (CORRECT) {
+      // calcp_simple.f90:416-419
+      const double ppref = ca.ppref_src ? *ca.ppref_src : 0.0;
+      const double un = ca.u[c] + s1 * ca.apu[c];
+      const double vn = ca.v[c] + s2 * ca.apv[c];
+      const double wn = ca.w[c] + s3 * ca.apw[c];
+      ca.u[c] = un; ca.v[c] = vn; ca.w[c] = wn;
+      if (ca.pres) ca.pres[c] = ca.pres[c] + ca.urfp * (pc - ppref);
+      if (has_bnd) {   // updateVelocityAtBoundary, velocity.f90:1184-1277
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          if (e[k] != 0 && sl[k] < 0) {
+            const int type = -1 - sl[k];
+            if (type == FCP_BC_EMPTY || type == FCP_BC_PERIODIC) {
+              ca.u[o[k]] = un; ca.v[o[k]] = vn; ca.w[o[k]] = wn;
+            } else if (type == FCP_BC_SYMMETRY) {
+              const double Unmag = un * sx[k] + vn * sy[k] + wn * sz[k];
+              ca.u[o[k]] = un - Unmag * sx[k]; ca.v[o[k]] = vn - Unmag * sy[k]; ca.w[o[k]] = wn - Unmag * sz[k];
+            }
+          }
+        }
+      }
+    }
+  } else {
+    su[c] = s1; sv[c] = s2; sw[c] = s3;   // stage-1 inner sums kept for the central second pass
+  }
+}
+
+template <bool CORRECT, bool WEIGHTED>
+__global__ void __launch_bounds__(FCP_TPB, 2) k_gradp(MeshView m, int nstages, double *p, const double *__restrict__ apu,
+                                                       double *__restrict__ su, double *__restrict__ sv, double *__restrict__ sw,
+                                                       double *__restrict__ dPdxi, CorrectArgs ca) {
+  constexpr int W = 6;
+  constexpr int scheme = WEIGHTED ? FCP_PSCHEME_WEIGHTED : FCP_PSCHEME_LINEAR;
+  FCP_CELL_LOOP(c, m.n) {
+    const int32_t flen = m.len[c];
+    if (flen <= W) gradp_cell_fast<CORRECT, WEIGHTED, W>(m, c, flen, scheme, nstages, p, apu, su, sv, sw, dPdxi, ca);
+    else gradp_cell_generic<CORRECT>(m, c, scheme, nstages, p, apu, su, sv, sw, dPdxi, ca);
   }
 }
 
@@ -399,15 +547,14 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp_central2(MeshView m, double *
 // ---------------------------------------------------------------------------------------------
 // PISO = true: facefluxmass_piso (faceflux_mass.f90:389-459): the flux is the plain interpolated HbyA flux (no Rhie-Chow
 // pressure term) and pressure patches do not reset pp (calcp_piso.f90:140-240).
-template <bool PISO>
-__global__ void __launch_bounds__(FCP_TPB, 1) k_assemble_pcorr(MeshView m, AsmArgs g) {
+template <bool PISO, int W>
+__global__ void __launch_bounds__(FCP_TPB, (W >= 3 ? 1 : W == 2 ? 2 : 3)) k_assemble_pcorr(MeshView m, AsmArgs g) {
   FCP_CELL_LOOP(c, m.n) {
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
     const double denc = g.den[c], kc = m.vol[c] * g.apu[c];
     const double uc = g.u[c], vc = g.v[c], wc = g.w[c], pc = g.p[c];
     const double gcx = g.dPdxi[3 * (int64_t)c], gcy = g.dPdxi[3 * (int64_t)c + 1], gcz = g.dPdxi[3 * (int64_t)c + 2];
     double dg = 0.0, s = 0.0;
-    constexpr int W = 3;
     FCP_FACE_BATCHES(m, c, W) {
       FCP_BATCH_LISTS(m, W, e_, o_, sl_);
       double sx_[W], sy_[W], sz_[W], lam_[W], Df_[W], xo_[W], yo_[W], zo_[W], deno_[W], volo_[W], apuo_[W], uo_[W], vo_[W], wo_[W], po_[W],
@@ -619,15 +766,18 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
   CorrectArgs ca{};
   if (correct) ca = *correct;
   if (scheme == FCP_PSCHEME_CENTRAL) {
-    k_gradp<false><<<FCP_GRID(ctx->n)>>>(m, FCP_PSCHEME_LINEAR, 1, p, apu, su, sv, sw, gtmp, ca);
+    k_gradp<false, false><<<FCP_GRID(ctx->n)>>>(m, 1, p, apu, su, sv, sw, gtmp, ca);
     FCP_LAUNCHED();
     if (correct) k_gradp_central2<true><<<FCP_GRID(ctx->n)>>>(m, p, gtmp, su, sv, sw, dPdxi, ca);
     else k_gradp_central2<false><<<FCP_GRID(ctx->n)>>>(m, p, gtmp, su, sv, sw, dPdxi, ca);
     FCP_LAUNCHED();
   } else {
     size_t tok = ctx->prof.begin(FCP_K_GRADP, ctx->stream);
-    if (correct) k_gradp<true><<<FCP_GRID(ctx->n)>>>(m, scheme, 2, p, apu, su, sv, sw, dPdxi, ca);
-    else k_gradp<false><<<FCP_GRID(ctx->n)>>>(m, scheme, 2, p, apu, su, sv, sw, dPdxi, ca);
+    const bool wgt = scheme == FCP_PSCHEME_WEIGHTED;
+    if (correct && wgt) k_gradp<true, true><<<FCP_GRID(ctx->n)>>>(m, 2, p, apu, su, sv, sw, dPdxi, ca);
+    else if (correct) k_gradp<true, false><<<FCP_GRID(ctx->n)>>>(m, 2, p, apu, su, sv, sw, dPdxi, ca);
+    else if (wgt) k_gradp<false, true><<<FCP_GRID(ctx->n)>>>(m, 2, p, apu, su, sv, sw, dPdxi, ca);
+    else k_gradp<false, false><<<FCP_GRID(ctx->n)>>>(m, 2, p, apu, su, sv, sw, dPdxi, ca);
     ctx->prof.end(tok, ctx->stream);
     FCP_LAUNCHED();
   }
@@ -636,8 +786,20 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
 }
 int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso) {
   if (ctx->n == 0) return FCP_OK;
-  if (piso) FCP_PROF(&ctx->prof, FCP_K_ASSEMBLE, ctx->stream, (k_assemble_pcorr<true><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g)));
-  else FCP_PROF(&ctx->prof, FCP_K_ASSEMBLE, ctx->stream, (k_assemble_pcorr<false><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g)));
+  static int w = -1;   // faces per register batch: FCP_ASM_W = 1 | 2 | 3 (A/B measurements)
+  if (w < 0) { const char *e = getenv("FCP_ASM_W"); w = e ? atoi(e) : 2; if (w < 1 || w > 3) w = 2; }
+  size_t tok = ctx->prof.begin(FCP_K_ASSEMBLE, ctx->stream);
+  MeshView mv = fcp_mesh_view(ctx);
+  if (piso) {
+    if (w == 1) k_assemble_pcorr<true, 1><<<FCP_GRID(ctx->n)>>>(mv, g);
+    else if (w == 2) k_assemble_pcorr<true, 2><<<FCP_GRID(ctx->n)>>>(mv, g);
+    else k_assemble_pcorr<true, 3><<<FCP_GRID(ctx->n)>>>(mv, g);
+  } else {
+    if (w == 1) k_assemble_pcorr<false, 1><<<FCP_GRID(ctx->n)>>>(mv, g);
+    else if (w == 2) k_assemble_pcorr<false, 2><<<FCP_GRID(ctx->n)>>>(mv, g);
+    else k_assemble_pcorr<false, 3><<<FCP_GRID(ctx->n)>>>(mv, g);
+  }
+  ctx->prof.end(tok, ctx->stream);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

@@ -1145,3 +1145,241 @@ extern "C" void orc_calcp_piso(const orc_mesh *m, const i32 *ia, const i32 *ja, 
     orc_update_velocity_at_boundary(m, u, v, w);                              // :485
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// face_value family  (src/finiteVolume/interpolation/interpolation.f90:28-113, 116-650)
+// ijp, ijn are 1-based like the Fortran dummies.  Default-real literals keep their single-precision values (quirk Q5).
+// ------------------------------------------------------------------------------------------
+static const double TINY30 = (double)1e-30f;                 // `1e-30`
+static const double S13 = (double)(1.f / 3.f), S23 = (double)(2.f / 3.f);   // `1./3.`, `2./3.` (default real)
+static inline double mx(double a, double b) { return a > b ? a : b; }
+static inline double mn(double a, double b) { return a < b ? a : b; }
+
+extern "C" double orc_face_value(const orc_mesh *m, int scheme, i32 ijp1, i32 ijn1, double xf, double yf, double zf, double lambda,
+                                 const double *u, const double *g) {
+  const i32 ijp = ijp1 - 1, ijn = ijn1 - 1;
+  const double *xc = m->xc, *yc = m->yc, *zc = m->zc;
+  if (scheme == 0) return u[ijp] + (u[ijn] - u[ijp]) * lambda;                                   // face_value_cds :116-127
+  if (scheme == 1 || scheme == 3) {
+    const double gc = g[3 * ijp] * (xf - xc[ijp]) + g[3 * ijp + 1] * (yf - yc[ijp]) + g[3 * ijp + 2] * (zf - zc[ijp]) +
+                      g[3 * ijn] * (xf - xc[ijn]) + g[3 * ijn + 1] * (yf - yc[ijn]) + g[3 * ijn + 2] * (zf - zc[ijn]);
+    const double vf_central = 0.5 * (u[ijp] + u[ijn] + gc);                                      // face_value_central :218-264
+    if (scheme == 1) return vf_central;
+    const double theta = S23;                                                                    // face_value_kappa :401  theta = 2./3.
+    const double gu = g[3 * ijp] * (xf - xc[ijp]) + g[3 * ijp + 1] * (yf - yc[ijp]) + g[3 * ijp + 2] * (zf - zc[ijp]);
+    const double vf_2nd = u[ijp] + gu;
+    return theta * vf_central + (1.0 - theta) * vf_2nd;
+  }
+  if (scheme == 2) {                                                                             // face_value_2nd_upwind :330-360
+    const double gu = g[3 * ijp] * (xf - xc[ijp]) + g[3 * ijp + 1] * (yf - yc[ijp]) + g[3 * ijp + 2] * (zf - zc[ijp]);
+    return u[ijp] + gu;
+  }
+  // face_value_flux_limiter :489-650
+  const double fxp = 1.0 - lambda;
+  const double xpn = xc[ijn] - xc[ijp], ypn = yc[ijn] - yc[ijp], zpn = zc[ijn] - zc[ijp];
+  const double r = (2 * g[3 * ijp] * xpn + 2 * g[3 * ijp + 1] * ypn + 2 * g[3 * ijp + 2] * zpn) / (u[ijn] - u[ijp] + TINY30) - 1.0;
+  double psi;
+  switch (scheme) {
+    case 4: psi = mx(0., mn(mn(2 * r, 0.5 * r + 0.5), 2.0)); break;                               // muscl
+    case 5: psi = mx(0., mn(mn(mn(2 * r, 0.75 * r + 0.25), 0.25 * r + 0.75), 2.0)); break;        // umist
+    case 6: psi = mx(0., mn(mn(2 * r, 2. / 3. * r + 1. / 3.0), 2.0)); break;                      // koren (double-precision thirds)
+    case 7: psi = mx(0., mn(mn(2 * r, 0.75 * r + 0.25), 4.0)); break;                             // smart
+    case 8: psi = mx(0., mn(mn(1.5 * r, 0.75 * r + 0.25), 2.5)); break;                           // avl-smart
+    case 9: psi = mx(0., (r + std::fabs(r)) * (3 * r + 1.0) / (2 * ((r + 1.0) * (r + 1.0)))); break;   // charm
+    case 10: psi = mx(0., mn((r + std::fabs(r)) / (r + 1.0), 2.0)); break;                        // vanleer
+    case 11: psi = mx(0., 3 * r * (r + 1.0) / (2 * (r * r + r + 1.0))); break;                    // ospre
+    case 12: psi = mx(0., mn(r, 1.0)); break;                                                     // minmod
+    case 13: psi = mx(0., mn(2 * r, 1.0)); break;                                                 // boundedLinearUpwind
+    case 14: psi = mx(0., mn(10 * r, 1.0)); break;                                                // boundedLinearUpwind02
+    case 15: psi = mx(0., mn(r, 4.0)); break;                                                     // boundedCentral
+    case 16: psi = 0.5 * r + 0.5; break;                                                          // fromm
+    case 17: psi = S23 * r + S13; break;                                                          // cui   `2./3.*r+1./3.`
+    case 18: psi = 0.75 * r + 0.25; break;                                                        // quick `3./4.*r + 1./4.`
+    case 19: psi = mx(0., mn(mn(mn(2 * r, S13 * r + S23), S23 * r + S13), 2.0)); break;           // spl13
+    default: psi = 1.0; break;
+  }
+  return u[ijp] + fxp * psi * (u[ijn] - u[ijp]);
+}
+
+// sngrad, gradients.f90:1720-1779
+static void sngrad(const orc_mesh *m, i32 i, i32 ijp, i32 ijn, double arx, double ary, double arz, double lambda, const double *phi,
+                   const double *g, double &dfixi, double &dfiyi, double &dfizi, double &dfixii, double &dfiyii, double &dfizii) {
+  const double fxn = lambda, fxp = 1.0 - lambda;
+  const double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
+  const double vole = xpn * arx + ypn * ary + zpn * arz;
+  dfixi = g[3 * ijp] * fxp + g[3 * ijn] * fxn;
+  dfiyi = g[3 * ijp + 1] * fxp + g[3 * ijn + 1] * fxn;
+  dfizi = g[3 * ijp + 2] * fxp + g[3 * ijn + 2] * fxn;
+  dfixii = dfixi + arx / vole * (phi[ijn] - phi[ijp] - dfixi * xpn - dfiyi * ypn - dfizi * zpn);
+  dfiyii = dfiyi + ary / vole * (phi[ijn] - phi[ijp] - dfixi * xpn - dfiyi * ypn - dfizi * zpn);
+  dfizii = dfizi + arz / vole * (phi[ijn] - phi[ijp] - dfixi * xpn - dfiyi * ypn - dfizi * zpn);
+  dfixi = dfixi * (arx - m->Df[i] * xpn);
+  dfiyi = dfiyi * (ary - m->Df[i] * ypn);
+  dfizi = dfizi * (arz - m->Df[i] * zpn);
+}
+
+static void grad_any(const orc_mesh *m, const i32 *ia, const i32 *ja, const i32 *diag, int method, int limiter, const double *Dm,
+                     const double *phi, double *g) {                         // grad_scalar_field gradients.f90:106-163
+  for (int64_t i = 0; i < 3 * (int64_t)m->numTotal; ++i) g[i] = 0.0;
+  if (method == 1) orc_grad_lsq(m, 0, 0, Dm, phi, g);
+  else if (method == 3) orc_grad_lsq_qr(m, Dm, phi, g);
+  else if (method == 2) orc_grad_lsq(m, 1, 0, Dm, phi, g);
+  else orc_grad_gauss(m, phi, g);
+  orc_slope_limiter(m, ia, ja, diag, limiter, phi, g);
+}
+
+extern "C" void orc_calcuvw(const orc_mesh *m, const i32 *ia, const i32 *ja, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell,
+                            i32 nnz, const orc_uvw_params *prm, double *u, double *v, double *w, double *p, const double *den,
+                            const double *vis, const double *visw, const double *flmass, const double *uo, const double *vo, const double *wo,
+                            const double *uoo, const double *voo, const double *woo, const double *uooo, const double *vooo, const double *wooo,
+                            double *a, double *su, double *sv, double *sw, double *spu, double *spv, double *sp, double *apu, double *apv,
+                            double *apw, double *dUdxi, double *dVdxi, double *dWdxi, double *dPdxi, double *rU, double *rV, double *rW,
+                            orc_report *rep) {
+  const i32 n = m->numCells, F = m->numInnerFaces;
+  const double zero = 0.0;
+  for (i32 c = 0; c < n; ++c) { spu[c] = 0.0; spv[c] = 0.0; sp[c] = 0.0; }                        // :130-132
+  orc_update_velocity_at_boundary(m, u, v, w);                                                    // :170
+  std::vector<double> Dm;
+  if (prm->grad_method == 1 || prm->grad_method == 2) { Dm.resize((size_t)9 * n); orc_create_matrix_lsq(m, prm->grad_method == 2, Dm.data()); }
+  if (prm->grad_method == 3) { Dm.resize((size_t)18 * n); orc_create_matrix_lsq_qr(m, Dm.data()); }
+  grad_any(m, ia, ja, diag, prm->grad_method, prm->limiter, Dm.data(), u, dUdxi);                  // :171-173
+  grad_any(m, ia, ja, diag, prm->grad_method, prm->limiter, Dm.data(), v, dVdxi);
+  grad_any(m, ia, ja, diag, prm->grad_method, prm->limiter, Dm.data(), w, dWdxi);
+  orc_gradp_and_sources(m, prm->pscheme, p, apu, su, sv, sw, dPdxi);                               // :177
+  for (i32 c = 0; c < n; ++c) {                                                                    // :187-283
+    if (prm->const_mflux) su[c] = su[c] + prm->gradPcmf * m->vol[c];
+    if (prm->tscheme == 1) {
+      const double apotime = den[c] * m->vol[c] / prm->timestep;
+      su[c] = su[c] + apotime * uo[c]; sv[c] = sv[c] + apotime * vo[c]; sw[c] = sw[c] + apotime * wo[c];
+      spu[c] = spu[c] + apotime; spv[c] = spv[c] + apotime; sp[c] = sp[c] + apotime;
+    } else if (prm->tscheme == 2) {
+      const double apotime = den[c] * m->vol[c] / prm->timestep;
+      su[c] = su[c] + apotime * (2 * uo[c] - 0.5 * uoo[c]);
+      sv[c] = sv[c] + apotime * (2 * vo[c] - 0.5 * voo[c]);
+      sw[c] = sw[c] + apotime * (2 * wo[c] - 0.5 * woo[c]);
+      spu[c] = spu[c] + 1.5 * apotime; spv[c] = spv[c] + 1.5 * apotime; sp[c] = sp[c] + 1.5 * apotime;
+    } else if (prm->tscheme == 3) {
+      const double apotime = den[c] * m->vol[c] / prm->timestep;
+      const double third = (double)1.f / 3.0;          // `1./3.0_dp`: the default-real 1. is exact, the quotient is double
+      const double c116 = (double)11.f / 6.0;          // `11./6.0_dp`
+      su[c] = su[c] + apotime * (3 * uo[c] - 1.5 * uoo[c] + third * uooo[c]);
+      sv[c] = sv[c] + apotime * (3 * vo[c] - 1.5 * voo[c] + third * vooo[c]);
+      sw[c] = sw[c] + apotime * (3 * wo[c] - 1.5 * woo[c] + third * wooo[c]);
+      spu[c] = spu[c] + c116 * apotime; spv[c] = spv[c] + c116 * apotime; sp[c] = sp[c] + c116 * apotime;
+    }
+  }
+  const int cs = prm->cscheme;
+  for (i32 i = 0; i < F; ++i) {                                                                    // :290-320 ; facefluxuvw :754-878
+    const i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    const double arx = m->arx[i], ary = m->ary[i], arz = m->arz[i], xf = m->xf[i], yf = m->yf[i], zf = m->zf[i];
+    const double flomass = flmass[i], lambda = m->facint[i];
+    const double fxn = lambda, fxp = 1.0 - lambda;
+    const double game = vis[ijp] + (vis[ijn] - vis[ijp]) * lambda;
+    const double de = game * m->Df[i];
+    const double ce = mn(flomass, zero), cp = mx(flomass, zero);
+    const double can = -de + ce, cap = -de - cp;
+    double duxi, duyi, duzi, duxii, duyii, duzii, dvxi, dvyi, dvzi, dvxii, dvyii, dvzii, dwxi, dwyi, dwzi, dwxii, dwyii, dwzii;
+    sngrad(m, i, ijp, ijn, arx, ary, arz, lambda, u, dUdxi, duxi, duyi, duzi, duxii, duyii, duzii);
+    sngrad(m, i, ijp, ijn, arx, ary, arz, lambda, v, dVdxi, dvxi, dvyi, dvzi, dvxii, dvyii, dvzii);
+    sngrad(m, i, ijp, ijn, arx, ary, arz, lambda, w, dWdxi, dwxi, dwyi, dwzi, dwxii, dwyii, dwzii);
+    double fdue = game * (duxii * arx + dvxii * ary + dwxii * arz);
+    double fdve = game * (duyii * arx + dvyii * ary + dwyii * arz);
+    double fdwe = game * (duzii * arx + dvzii * ary + dwzii * arz);
+    const double fdui = game * (duxi + duyi + duzi), fdvi = game * (dvxi + dvyi + dvzi), fdwi = game * (dwxi + dwyi + dwzi);
+    fdue = fdue + fdui; fdve = fdve + fdvi; fdwe = fdwe + fdwi;
+    const double fuuds = cp * u[ijp] + ce * u[ijn], fvuds = cp * v[ijp] + ce * v[ijn], fwuds = cp * w[ijp] + ce * w[ijn];
+    double ue, ve, we;
+    if (flomass >= zero) {
+      ue = orc_face_value(m, cs, ijp + 1, ijn + 1, xf, yf, zf, fxp, u, dUdxi);
+      ve = orc_face_value(m, cs, ijp + 1, ijn + 1, xf, yf, zf, fxp, v, dVdxi);
+      we = orc_face_value(m, cs, ijp + 1, ijn + 1, xf, yf, zf, fxp, w, dWdxi);
+    } else {
+      ue = orc_face_value(m, cs, ijn + 1, ijp + 1, xf, yf, zf, fxn, u, dUdxi);
+      ve = orc_face_value(m, cs, ijn + 1, ijp + 1, xf, yf, zf, fxn, v, dVdxi);
+      we = orc_face_value(m, cs, ijn + 1, ijp + 1, xf, yf, zf, fxn, w, dWdxi);
+    }
+    const double fuhigh = flomass * ue, fvhigh = flomass * ve, fwhigh = flomass * we;
+    const double sup = -prm->gds * (fuhigh - fuuds) + fdue;
+    const double svp = -prm->gds * (fvhigh - fvuds) + fdve;
+    const double swp = -prm->gds * (fwhigh - fwuds) + fdwe;
+    a[icell_jcell[i] - 1] = can;
+    a[jcell_icell[i] - 1] = cap;
+    su[ijp] = su[ijp] + sup; sv[ijp] = sv[ijp] + svp; sw[ijp] = sw[ijp] + swp;
+    su[ijn] = su[ijn] - sup; sv[ijn] = sv[ijn] - svp; sw[ijn] = sw[ijn] - swp;
+  }
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {                                                  // :330-475
+    const i32 t = m->bctype[ib];
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+      const double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+      if (t == ORC_BC_INLET || t == ORC_BC_OUTLET || t == ORC_BC_PRESSURE) {                       // facefluxuvw_bnd :882-1034
+        const double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
+        const double vole = xpn * arx + ypn * ary + zpn * arz;
+        const double Dfi = (arx * arx + ary * ary + arz * arz) / vole;
+        const double game = vis[ijb];
+        const double de = game * Dfi;
+        const double cb = -de + mn(flmass[f], zero);       // `can` of the callee is the caller's cb
+        const double *G[3] = {dUdxi, dVdxi, dWdxi};
+        const double *PH[3] = {u, v, w};
+        double d1[3], d2[3], d3[3], e1[3], e2[3], e3[3];
+        for (int q = 0; q < 3; ++q) {
+          double gx = G[q][3 * ijp], gy = G[q][3 * ijp + 1], gz = G[q][3 * ijp + 2];
+          const double *ph = PH[q];
+          e1[q] = gx + arx / vole * (ph[ijb] - ph[ijp] - gx * xpn - gy * ypn - gz * zpn);
+          e2[q] = gy + ary / vole * (ph[ijb] - ph[ijp] - gx * xpn - gy * ypn - gz * zpn);
+          e3[q] = gz + arz / vole * (ph[ijb] - ph[ijp] - gx * xpn - gy * ypn - gz * zpn);
+          d1[q] = gx * (arx - Dfi * xpn); d2[q] = gy * (ary - Dfi * ypn); d3[q] = gz * (arz - Dfi * zpn);
+        }
+        const double fdue = game * (e1[0] * arx + e1[1] * ary + e1[2] * arz);
+        const double fdve = game * (e2[0] * arx + e2[1] * ary + e2[2] * arz);
+        const double fdwe = game * (e3[0] * arx + e3[1] * ary + e3[2] * arz);
+        const double fdui = game * (d1[0] + d2[0] + d3[0]), fdvi = game * (d1[1] + d2[1] + d3[1]), fdwi = game * (d1[2] + d2[2] + d3[2]);
+        const double sup = fdue + fdui, svp = fdve + fdvi, swp = fdwe + fdwi;
+        spu[ijp] = spu[ijp] - cb; spv[ijp] = spv[ijp] - cb; sp[ijp] = sp[ijp] - cb;
+        su[ijp] = su[ijp] - cb * u[ijb] + sup;
+        sv[ijp] = sv[ijp] - cb * v[ijb] + svp;
+        sw[ijp] = sw[ijp] - cb * w[ijb] + swp;
+      } else if (t == ORC_BC_SYMMETRY) {                                                           // :361-392, quirk Q7: vis(inp), inp = numCells+1
+        const double are = std::sqrt(arx * arx + ary * ary + arz * arz), arer = 1.0 / are;
+        const double nxf = arx * arer, nyf = ary * arer, nzf = arz * arer;
+        const double dpb = (m->xf[f] - m->xc[ijp]) * nxf + (m->yf[f] - m->yc[ijp]) * nyf + (m->zf[f] - m->zc[ijp]) * nzf;
+        const double cf = 2 * vis[n] * are / dpb;
+        su[ijp] = su[ijp] - cf * nxf * (nyf * v[ijp] + nzf * w[ijp]);
+        sv[ijp] = sv[ijp] - cf * nyf * (nxf * u[ijp] + nzf * w[ijp]);
+        sw[ijp] = sw[ijp] - cf * nzf * (nxf * u[ijp] + nyf * v[ijp]);
+        spu[ijp] = spu[ijp] + cf * (nxf * nxf); spv[ijp] = spv[ijp] + cf * (nyf * nyf); sp[ijp] = sp[ijp] + cf * (nzf * nzf);
+      } else if (t == ORC_BC_WALL) {                                                               // :434-472
+        const double viss = mx(prm->viscos, visw[ijb - n]);
+        const double are = std::sqrt(arx * arx + ary * ary + arz * arz), arer = 1.0 / are;
+        const double nxf = arx * arer, nyf = ary * arer, nzf = arz * arer;
+        const double dpb = (m->xf[f] - m->xc[ijp]) * nxf + (m->yf[f] - m->yc[ijp]) * nyf + (m->zf[f] - m->zc[ijp]) * nzf;
+        const double vsol = viss * are / dpb;
+        const double upb = u[ijp] - u[ijb], vpb = v[ijp] - v[ijb], wpb = w[ijp] - w[ijb];
+        spu[ijp] = spu[ijp] + vsol * (1. - nxf * nxf); spv[ijp] = spv[ijp] + vsol * (1. - nyf * nyf); sp[ijp] = sp[ijp] + vsol * (1. - nzf * nzf);
+        su[ijp] = su[ijp] + vsol * (u[ijb] * (1. - nxf * nxf) + vpb * nyf * nxf + wpb * nzf * nxf);
+        sv[ijp] = sv[ijp] + vsol * (upb * nxf * nyf + v[ijb] * (1. - nyf * nyf) + wpb * nzf * nyf);
+        sw[ijp] = sw[ijp] + vsol * (upb * nxf * nzf + vpb * nyf * nzf + w[ijb] * (1. - nzf * nzf));
+      }
+    }
+  }
+  if (prm->piso) for (i32 c = 0; c < n; ++c) { rU[c] = su[c]; rV[c] = sv[c]; rW[c] = sw[c]; }      // :564-568
+  // ---- the three equations, :602-750
+  double *comp[3] = {u, v, w};
+  const double *srcs[3] = {su, sv, sw};
+  double *sps[3] = {spu, spv, sp};
+  double *aps[3] = {apu, apv, apw};
+  for (int q = 0; q < 3; ++q) {
+    if (q > 0) for (i32 c = 0; c < n; ++c) { a[diag[c] - 1] = 0.0; su[c] = 0.0; }                  // :651-654, :712-715
+    const double urfr = 1.0 / prm->urf[q], urfm = 1.0 - prm->urf[q];
+    for (i32 c = 0; c < n; ++c) {
+      double s = 0.0;
+      for (i32 k = ia[c]; k <= ia[c + 1] - 1; ++k) s = s + a[k - 1];                               // sum( a(ia(inp):ia(inp+1)-1) )
+      const double sum_off = s - a[diag[c] - 1];
+      a[diag[c] - 1] = sps[q][c] - sum_off;
+      aps[q][c] = 1. / (a[diag[c] - 1] + SMALL);
+      a[diag[c] - 1] = a[diag[c] - 1] * urfr;
+      su[c] = (q == 0 ? su[c] : srcs[q][c]) + urfm * a[diag[c] - 1] * comp[q][c];
+    }
+    solve_any(prm->solver, n, nnz, ia, ja, a, diag, comp[q], su, prm->maxiter, prm->tol_abs, prm->tol_rel, prm->sum_mode, &rep[q]);
+  }
+}

@@ -145,6 +145,44 @@ void orc_calcp_piso(const orc_mesh *m, const int32_t *ia, const int32_t *ja, con
                     double *a, double *h, double *u, double *v, double *w, double *p, double *pp,
                     double *su, double *sv, double *sw, double *dPdxi, double *flmass, orc_report *rep);
 
+/* ---- calcuvw: the momentum predictor, Velocity/velocity.f90:50-750 (+ facefluxuvw :754-878, facefluxuvw_bnd :882-1034,
+ * sngrad gradients.f90:1720-1779, the face_value family interpolation.f90:28-113, 116-650).  Tier "next" row f1.
+ * Not restated: Crank-Nicolson (:569-600), buoyancy (:186-200), MHD (:205-212), periodic patches (:395-432).
+ * cscheme: 0 cds, 1 central, 2 linearUpwind, 3 kappa, then the flux limiters of interpolation.f90:596-640 in source order:
+ * 4 muscl, 5 umist, 6 koren, 7 smart, 8 avl-smart, 9 charm, 10 vanleer, 11 ospre, 12 minmod, 13 boundedLinearUpwind,
+ * 14 boundedLinearUpwind02, 15 boundedCentral, 16 fromm, 17 cui, 18 quick, 19 spl13. */
+typedef struct {
+  int32_t solver, maxiter;        /* lSolverU, maxiterU */
+  double tol_abs, tol_rel;        /* tolAbsU, tolRelU */
+  double urf[3];                  /* urfU(1:3) */
+  double gds;                     /* gdsU: deferred-correction blending */
+  int32_t cscheme;                /* cSchemeU */
+  int32_t grad_method;            /* 0 gauss, 1 lsq, 2 wlsq, 3 lsq_qr (the logicals of gradients.f90:118-138) */
+  int32_t limiter;                /* ORC_LIM_* (gradients.f90:140-160) */
+  int32_t pscheme;
+  int32_t tscheme;                /* 0 steady, 1 bdf (or cn=.false.), 2 bdf2, 3 bdf3 */
+  double timestep;
+  int32_t piso;                   /* rU,rV,rW = su,sv,sw (:564-568) */
+  int32_t const_mflux;
+  double gradPcmf;
+  double viscos;                  /* molecular viscosity: wall faces use max(viscos, visw) (:443) */
+  int32_t sum_mode;               /* reductions inside the linear solver */
+  int32_t pad;
+} orc_uvw_params;
+double orc_face_value(const orc_mesh *m, int cscheme, int32_t ijp, int32_t ijn /* 1-based */, double xf, double yf, double zf,
+                      double lambda, const double *u, const double *dUdxi);
+/* visw: [numBoundaryFaces] effective wall viscosity in the boundary slot order (only wall faces are read).
+ * uo/uoo/uooo etc. may be NULL when tscheme does not need them.  a: stale values on entry (its diagonal enters the
+ * first row sum, :606), the W-equation matrix on exit. */
+void orc_calcuvw(const orc_mesh *m, const int32_t *ia, const int32_t *ja, const int32_t *diag,
+                 const int32_t *icell_jcell, const int32_t *jcell_icell, int32_t nnz, const orc_uvw_params *prm,
+                 double *u, double *v, double *w, double *p, const double *den, const double *vis, const double *visw,
+                 const double *flmass, const double *uo, const double *vo, const double *wo,
+                 const double *uoo, const double *voo, const double *woo, const double *uooo, const double *vooo, const double *wooo,
+                 double *a, double *su, double *sv, double *sw, double *spu, double *spv, double *sp,
+                 double *apu, double *apv, double *apw, double *dUdxi, double *dVdxi, double *dWdxi, double *dPdxi,
+                 double *rU, double *rV, double *rW, orc_report *rep /* [3] */);
+
 /* linear_solvers.f90:206-359, 364-545, 548-786 */
 void orc_spmv(int32_t n, const int32_t *ia, const int32_t *ja, const double *a, const double *x, double *y);
 void orc_dpcg(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const double *a,

@@ -655,6 +655,49 @@ extern "C" int fcp_calcp_simple(fcp_ctx *ctx, const fcp_simple_params *prm, fcp_
   return FCP_OK;
 }
 
+// calcuvw   Velocity/velocity.f90:50-750
+extern "C" int fcp_calcuvw(fcp_ctx *ctx, const fcp_uvw_params *prm, fcp_report *rep) {
+  if (!ctx || !prm) return FCP_EINVAL;
+  if (prm->cscheme < 0 || prm->cscheme >= FCP_CS_COUNT) { fcp_set_error("calcuvw: non-existing interpolation scheme %d", prm->cscheme); return FCP_EINVAL; }   // interpolation.f90:643-646 stops
+  if (prm->tscheme < 0 || prm->tscheme > 3) { fcp_set_error("calcuvw: unknown time scheme %d (Crank-Nicolson is not built)", prm->tscheme); return FCP_EINVAL; }
+  if (prm->tscheme && !(prm->timestep > 0.0)) { fcp_set_error("calcuvw: timestep must be positive"); return FCP_EINVAL; }
+  for (int q = 0; q < 3; ++q) if (!(prm->urf[q] > 0.0)) { fcp_set_error("calcuvw: urfU(%d) must be positive", q + 1); return FCP_EINVAL; }
+  for (int32_t ib = 0; ib < ctx->nb; ++ib)
+    if (ctx->bctype[ib] == FCP_BC_PERIODIC) { fcp_set_error("calcuvw: periodic patches (velocity.f90:395-432) are not supported yet"); return FCP_ESTATE; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(p, FCP_F_P); FIELD(den, FCP_F_DEN); FIELD(vis, FCP_F_VIS); FIELD(visw, FCP_F_VISW);
+  FIELD(fl, FCP_F_FLMASS); FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(sv, FCP_F_SV); FIELD(sw, FCP_F_SW);
+  FIELD(spu, FCP_F_SPU); FIELD(spv, FCP_F_SPV); FIELD(sp, FCP_F_SP); FIELD(apu, FCP_F_APU); FIELD(apv, FCP_F_APV); FIELD(apw, FCP_F_APW);
+  FIELD(gu, FCP_F_DUDXI); FIELD(gv, FCP_F_DVDXI); FIELD(gw, FCP_F_DWDXI);
+  UvwArgs g{};
+  g.u = u; g.v = v; g.w = w; g.vis = vis; g.visw = visw; g.den = den; g.flmass = fl; g.dUdxi = gu; g.dVdxi = gv; g.dWdxi = gw;
+  g.a = a; g.su = su; g.sv = sv; g.sw = sw; g.spu = spu; g.spv = spv; g.sp = sp;
+  g.gds = prm->gds; g.timestep = prm->timestep; g.gradPcmf = prm->gradPcmf; g.viscos = prm->viscos;
+  g.cscheme = prm->cscheme; g.tscheme = prm->tscheme; g.const_mflux = prm->const_mflux;
+  if (prm->tscheme >= 1) { FIELD(uo, FCP_F_UO); FIELD(vo, FCP_F_VO); FIELD(wo, FCP_F_WO); g.uo = uo; g.vo = vo; g.wo = wo; }
+  if (prm->tscheme >= 2) { FIELD(uoo, FCP_F_UOO); FIELD(voo, FCP_F_VOO); FIELD(woo, FCP_F_WOO); g.uoo = uoo; g.voo = voo; g.woo = woo; }
+  if (prm->tscheme >= 3) { FIELD(x1, FCP_F_UOOO); FIELD(x2, FCP_F_VOOO); FIELD(x3, FCP_F_WOOO); g.uooo = x1; g.vooo = x2; g.wooo = x3; }
+  if (prm->piso) { FIELD(rU, FCP_F_RU); FIELD(rV, FCP_F_RV); FIELD(rW, FCP_F_RW); g.rU = rU; g.rV = rV; g.rW = rW; }
+  FCP_TRY(fvm_update_vel_bnd(ctx, u, v, w));                                                   // :170
+  if (prm->grad_method != FCP_GRAD_GAUSS && !ctx->Dmat[prm->grad_method]) FCP_TRY(fcp_create_lsq_grad_matrix(ctx, prm->grad_method));
+  FCP_TRY(fcp_grad_opt(ctx, prm->grad_method, prm->limiter, FCP_F_U, FCP_F_DUDXI));            // :171-173
+  FCP_TRY(fcp_grad_opt(ctx, prm->grad_method, prm->limiter, FCP_F_V, FCP_F_DVDXI));
+  FCP_TRY(fcp_grad_opt(ctx, prm->grad_method, prm->limiter, FCP_F_W, FCP_F_DWDXI));
+  FCP_TRY(fcp_gradp_and_sources(ctx, prm->pscheme, FCP_F_P));                                  // :177
+  if (ctx->comm) {
+    double *sc[] = {vis, den};
+    for (double *x : sc) FCP_TRY(comm_exchange(ctx, x, 1));
+  }
+  FCP_TRY(fvm_uvw_assemble(ctx, g));                                                           // :187-568
+  const int fields[3] = {FCP_F_U, FCP_F_V, FCP_F_W};
+  double *phi[3] = {u, v, w}, *spq[3] = {spu, spv, sp}, *srcq[3] = {su, sv, sw}, *apq[3] = {apu, apv, apw};
+  for (int q = 0; q < 3; ++q) {                                                                // :602-750
+    FCP_TRY(fvm_uvw_diag(ctx, a, spq[q], srcq[q], phi[q], apq[q], su, prm->urf[q], q > 0));
+    FCP_TRY(fcp_csrsolve(ctx, prm->solver, fields[q], FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel, rep ? &rep[q] : nullptr));
+  }
+  return FCP_OK;
+}
+
 // calcp_piso   Pressure/calcp_piso.f90:81-489
 extern "C" int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_report *rep) {
   if (!ctx || !prm) return FCP_EINVAL;

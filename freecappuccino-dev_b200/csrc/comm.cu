@@ -448,7 +448,7 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
 
 extern "C" int fcp_exchange(fcp_ctx *ctx, int field) {
   if (!ctx) return FCP_EINVAL;
-  if (field < 0 || (field >= FCP_F_FLMASS && field <= FCP_F_H) || field >= FCP_F_COUNT) { fcp_set_error("fcp_exchange: field %d is not a cell field", field); return FCP_EINVAL; }
+  if (field < 0 || (field >= FCP_F_FLMASS && field <= FCP_F_H) || field >= FCP_F_COUNT /* every other id is a cell field */) { fcp_set_error("fcp_exchange: field %d is not a cell field", field); return FCP_EINVAL; }
   void *p = nullptr;
   FCP_TRY(fcp_field_devptr(ctx, field, &p, nullptr));
   return comm_exchange(ctx, (double *)p, (field >= FCP_F_DUDXI && field <= FCP_F_G1) ? 3 : 1);

@@ -265,6 +265,20 @@ int fvm_sum(fcp_ctx *ctx, const double *x, double *d_out);
 int fvm_piso_pupdate(fcp_ctx *ctx, double ncells_global, double urfp, const double *d_sum, const double *pp, double *p);
 int fvm_piso_fluxmc(fcp_ctx *ctx, const double *den, const double *apu, const double *dPdxi, double *su);
 
+// ---- fvm_uvw.cu ---------------------------------------------------------------------------------
+struct UvwArgs {
+  const double *u, *v, *w, *vis, *visw, *den, *flmass;
+  const double *dUdxi, *dVdxi, *dWdxi;
+  const double *uo, *vo, *wo, *uoo, *voo, *woo, *uooo, *vooo, *wooo;
+  double *a, *su, *sv, *sw, *spu, *spv, *sp;
+  double *rU, *rV, *rW;          // nullptr unless piso
+  double gds, timestep, gradPcmf, viscos;
+  int cscheme, tscheme, const_mflux;
+};
+int fvm_update_vel_bnd(fcp_ctx *ctx, double *u, double *v, double *w);
+int fvm_uvw_assemble(fcp_ctx *ctx, const UvwArgs &g);
+int fvm_uvw_diag(fcp_ctx *ctx, double *a, const double *spq, const double *srcq, const double *phi, double *apq, double *su, double urf, int zero_first);
+
 // ---- pattern.cu ---------------------------------------------------------------------------------
 int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, const int32_t *ja1, const int32_t *diag1,
                   const std::vector<std::vector<int32_t>> *halo_cols /* per row extra columns (0-based), may be null */);

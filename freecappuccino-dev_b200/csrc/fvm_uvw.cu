@@ -1,0 +1,278 @@
+// fvm_uvw.cu -- the momentum predictor calcuvw (Velocity/velocity.f90:50-750), tier "next" row f1, as cell-centric gathers
+// like fvm.cu:
+//   k_update_vel_bnd   updateVelocityAtBoundary                      velocity.f90:1184-1277
+//   k_uvw_assemble     volume sources :187-283, facefluxuvw :754-878 (+ sngrad gradients.f90:1720-1779 and the face_value
+//                      family interpolation.f90:28-650), boundary patches :330-475 (facefluxuvw_bnd :882-1034)
+//   k_uvw_diag         diagonal, reciprocal diagonal apu/apv/apw and under-relaxation :602-620, :656-668, :717-730
+// One thread owns one cell and walks its faces in ascending index; every face quantity is evaluated in the face's own
+// orientation (P = owner, N = neighbour), so both sides see the same bits and the per-cell sums round like the
+// reference's sequential loops.  Not built: Crank-Nicolson, buoyancy, MHD, periodic patches (fcp_calcuvw refuses them).
+#include "fcp_internal.h"
+#include "fvm_common.cuh"
+
+#define TINY30 ((double)1e-30f)                 // interpolation.f90:607  `1e-30` (default-real literal)
+#define S13 ((double)(1.f / 3.f))               // `1./3.`
+#define S23 ((double)(2.f / 3.f))               // `2./3.`
+
+struct CellState {   // what facefluxuvw reads of one cell
+  double x, y, z, u, v, w, vis;
+  double gu[3], gv[3], gw[3];
+};
+
+// face_value(ijp, ijn, xf, yf, zf, lambda, u, dUdxi, scheme), interpolation.f90:28-113: "p" is the first cell argument
+__device__ __forceinline__ double face_value_dev(int scheme, double up, double un, const double (&gp)[3], const double (&gn)[3], double xp, double yp,
+                                                 double zp, double xn, double yn, double zn, double xf, double yf, double zf, double lambda) {
+  if (scheme == 0) return up + (un - up) * lambda;
+  if (scheme == 1 || scheme == 3) {
+    const double gc = gp[0] * (xf - xp) + gp[1] * (yf - yp) + gp[2] * (zf - zp) + gn[0] * (xf - xn) + gn[1] * (yf - yn) + gn[2] * (zf - zn);
+    const double vf_central = 0.5 * (up + un + gc);
+    if (scheme == 1) return vf_central;
+    const double theta = S23;
+    const double gu = gp[0] * (xf - xp) + gp[1] * (yf - yp) + gp[2] * (zf - zp);
+    return theta * vf_central + (1.0 - theta) * (up + gu);
+  }
+  if (scheme == 2) {
+    const double gu = gp[0] * (xf - xp) + gp[1] * (yf - yp) + gp[2] * (zf - zp);
+    return up + gu;
+  }
+  const double fxp = 1.0 - lambda;
+  const double xpn = xn - xp, ypn = yn - yp, zpn = zn - zp;
+  const double r = (2 * gp[0] * xpn + 2 * gp[1] * ypn + 2 * gp[2] * zpn) / (un - up + TINY30) - 1.0;
+  double psi;
+  switch (scheme) {
+    case 4: psi = fmax(0., fmin(fmin(2 * r, 0.5 * r + 0.5), 2.0)); break;
+    case 5: psi = fmax(0., fmin(fmin(fmin(2 * r, 0.75 * r + 0.25), 0.25 * r + 0.75), 2.0)); break;
+    case 6: psi = fmax(0., fmin(fmin(2 * r, 2. / 3. * r + 1. / 3.0), 2.0)); break;
+    case 7: psi = fmax(0., fmin(fmin(2 * r, 0.75 * r + 0.25), 4.0)); break;
+    case 8: psi = fmax(0., fmin(fmin(1.5 * r, 0.75 * r + 0.25), 2.5)); break;
+    case 9: psi = fmax(0., (r + fabs(r)) * (3 * r + 1.0) / (2 * ((r + 1.0) * (r + 1.0)))); break;
+    case 10: psi = fmax(0., fmin((r + fabs(r)) / (r + 1.0), 2.0)); break;
+    case 11: psi = fmax(0., 3 * r * (r + 1.0) / (2 * (r * r + r + 1.0))); break;
+    case 12: psi = fmax(0., fmin(r, 1.0)); break;
+    case 13: psi = fmax(0., fmin(2 * r, 1.0)); break;
+    case 14: psi = fmax(0., fmin(10 * r, 1.0)); break;
+    case 15: psi = fmax(0., fmin(r, 4.0)); break;
+    case 16: psi = 0.5 * r + 0.5; break;
+    case 17: psi = S23 * r + S13; break;
+    case 18: psi = 0.75 * r + 0.25; break;
+    case 19: psi = fmax(0., fmin(fmin(fmin(2 * r, S13 * r + S23), S23 * r + S13), 2.0)); break;
+    default: psi = 1.0; break;
+  }
+  return up + fxp * psi * (un - up);
+}
+
+// sngrad for one component, gradients.f90:1720-1779
+__device__ __forceinline__ void sngrad_dev(double arx, double ary, double arz, double fxp, double fxn, double xpn, double ypn, double zpn, double Df,
+                                           double phiP, double phiN, const double (&gP)[3], const double (&gN)[3], double &d1, double &d2, double &d3,
+                                           double &e1, double &e2, double &e3) {
+  const double vole = xpn * arx + ypn * ary + zpn * arz;
+  d1 = gP[0] * fxp + gN[0] * fxn;
+  d2 = gP[1] * fxp + gN[1] * fxn;
+  d3 = gP[2] * fxp + gN[2] * fxn;
+  e1 = d1 + arx / vole * (phiN - phiP - d1 * xpn - d2 * ypn - d3 * zpn);
+  e2 = d2 + ary / vole * (phiN - phiP - d1 * xpn - d2 * ypn - d3 * zpn);
+  e3 = d3 + arz / vole * (phiN - phiP - d1 * xpn - d2 * ypn - d3 * zpn);
+  d1 = d1 * (arx - Df * xpn);
+  d2 = d2 * (ary - Df * ypn);
+  d3 = d3 * (arz - Df * zpn);
+}
+
+__device__ __forceinline__ void load_cell(CellState &s, const MeshView &m, const UvwArgs &g, int32_t c) {
+  s.x = m.xc[c]; s.y = m.yc[c]; s.z = m.zc[c];
+  s.u = g.u[c]; s.v = g.v[c]; s.w = g.w[c]; s.vis = g.vis[c];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { s.gu[k] = g.dUdxi[3 * (int64_t)c + k]; s.gv[k] = g.dVdxi[3 * (int64_t)c + k]; s.gw[k] = g.dWdxi[3 * (int64_t)c + k]; }
+}
+
+// updateVelocityAtBoundary, velocity.f90:1184-1277 (boundary-face parallel)
+__global__ void __launch_bounds__(FCP_TPB) k_update_vel_bnd(MeshView m, const int32_t *__restrict__ bftype, double *u, double *v, double *w) {
+  FCP_CELL_LOOP(i, m.B) {
+    const int t = bftype[i];
+    const int32_t f = m.F + i, ijp = m.owner[f], ijb = m.n + i;
+    if (t == FCP_BC_EMPTY || t == FCP_BC_PERIODIC) {
+      u[ijb] = u[ijp]; v[ijb] = v[ijp]; w[ijb] = w[ijp];
+    } else if (t == FCP_BC_SYMMETRY) {
+      const double sx = m.arx[f], sy = m.ary[f], sz = m.arz[f];
+      const double Unmag = u[ijp] * sx + v[ijp] * sy + w[ijp] * sz;
+      u[ijb] = u[ijp] - Unmag * sx; v[ijb] = v[ijp] - Unmag * sy; w[ijb] = w[ijp] - Unmag * sz;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FCP_TPB) k_uvw_assemble(MeshView m, UvwArgs g) {
+  FCP_CELL_LOOP(c, m.n) {
+    CellState me;
+    load_cell(me, m, g, c);
+    const double vol = m.vol[c], denc = g.den[c];
+    double s1 = g.su[c], s2 = g.sv[c], s3 = g.sw[c];          // -sum p_f S_f from gradp_and_sources
+    double p1 = 0.0, p2 = 0.0, p3 = 0.0;                      // spu, spv, sp (:130-132)
+    // ---- volume sources, velocity.f90:187-283
+    if (g.const_mflux) s1 = s1 + g.gradPcmf * vol;
+    if (g.tscheme == 1) {
+      const double apotime = denc * vol / g.timestep;
+      s1 = s1 + apotime * g.uo[c]; s2 = s2 + apotime * g.vo[c]; s3 = s3 + apotime * g.wo[c];
+      p1 = p1 + apotime; p2 = p2 + apotime; p3 = p3 + apotime;
+    } else if (g.tscheme == 2) {
+      const double apotime = denc * vol / g.timestep;
+      s1 = s1 + apotime * (2 * g.uo[c] - 0.5 * g.uoo[c]);
+      s2 = s2 + apotime * (2 * g.vo[c] - 0.5 * g.voo[c]);
+      s3 = s3 + apotime * (2 * g.wo[c] - 0.5 * g.woo[c]);
+      p1 = p1 + 1.5 * apotime; p2 = p2 + 1.5 * apotime; p3 = p3 + 1.5 * apotime;
+    } else if (g.tscheme == 3) {
+      const double apotime = denc * vol / g.timestep;
+      const double third = (double)1.f / 3.0, c116 = (double)11.f / 6.0;
+      s1 = s1 + apotime * (3 * g.uo[c] - 1.5 * g.uoo[c] + third * g.uooo[c]);
+      s2 = s2 + apotime * (3 * g.vo[c] - 1.5 * g.voo[c] + third * g.vooo[c]);
+      s3 = s3 + apotime * (3 * g.wo[c] - 1.5 * g.woo[c] + third * g.wooo[c]);
+      p1 = p1 + c116 * apotime; p2 = p2 + c116 * apotime; p3 = p3 + c116 * apotime;
+    }
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
+      if (sl >= 0) {
+        // ---- facefluxuvw, velocity.f90:754-878
+        CellState ot;
+        load_cell(ot, m, g, o);
+        const bool own = e > 0;
+        const CellState &P = own ? me : ot, &N = own ? ot : me;
+        const double xf = m.xf[f], yf = m.yf[f], zf = m.zf[f];
+        const double flomass = g.flmass[f], lambda = m.facint[f], Df = m.Df[f];
+        const double fxn = lambda, fxp = 1.0 - lambda;
+        const double game = P.vis + (N.vis - P.vis) * lambda;
+        const double de = game * Df;
+        const double ce = fmin(flomass, 0.0), cp = fmax(flomass, 0.0);
+        const double can = -de + ce, cap = -de - cp;
+        const double xpn = N.x - P.x, ypn = N.y - P.y, zpn = N.z - P.z;
+        double duxi, duyi, duzi, duxii, duyii, duzii, dvxi, dvyi, dvzi, dvxii, dvyii, dvzii, dwxi, dwyi, dwzi, dwxii, dwyii, dwzii;
+        sngrad_dev(arx, ary, arz, fxp, fxn, xpn, ypn, zpn, Df, P.u, N.u, P.gu, N.gu, duxi, duyi, duzi, duxii, duyii, duzii);
+        sngrad_dev(arx, ary, arz, fxp, fxn, xpn, ypn, zpn, Df, P.v, N.v, P.gv, N.gv, dvxi, dvyi, dvzi, dvxii, dvyii, dvzii);
+        sngrad_dev(arx, ary, arz, fxp, fxn, xpn, ypn, zpn, Df, P.w, N.w, P.gw, N.gw, dwxi, dwyi, dwzi, dwxii, dwyii, dwzii);
+        double fdue = game * (duxii * arx + dvxii * ary + dwxii * arz);
+        double fdve = game * (duyii * arx + dvyii * ary + dwyii * arz);
+        double fdwe = game * (duzii * arx + dvzii * ary + dwzii * arz);
+        const double fdui = game * (duxi + duyi + duzi), fdvi = game * (dvxi + dvyi + dvzi), fdwi = game * (dwxi + dwyi + dwzi);
+        fdue = fdue + fdui; fdve = fdve + fdvi; fdwe = fdwe + fdwi;
+        const double fuuds = cp * P.u + ce * N.u, fvuds = cp * P.v + ce * N.v, fwuds = cp * P.w + ce * N.w;
+        double ue, ve, we;
+        if (flomass >= 0.0) {
+          ue = face_value_dev(g.cscheme, P.u, N.u, P.gu, N.gu, P.x, P.y, P.z, N.x, N.y, N.z, xf, yf, zf, fxp);
+          ve = face_value_dev(g.cscheme, P.v, N.v, P.gv, N.gv, P.x, P.y, P.z, N.x, N.y, N.z, xf, yf, zf, fxp);
+          we = face_value_dev(g.cscheme, P.w, N.w, P.gw, N.gw, P.x, P.y, P.z, N.x, N.y, N.z, xf, yf, zf, fxp);
+        } else {
+          ue = face_value_dev(g.cscheme, N.u, P.u, N.gu, P.gu, N.x, N.y, N.z, P.x, P.y, P.z, xf, yf, zf, fxn);
+          ve = face_value_dev(g.cscheme, N.v, P.v, N.gv, P.gv, N.x, N.y, N.z, P.x, P.y, P.z, xf, yf, zf, fxn);
+          we = face_value_dev(g.cscheme, N.w, P.w, N.gw, P.gw, N.x, N.y, N.z, P.x, P.y, P.z, xf, yf, zf, fxn);
+        }
+        const double fuhigh = flomass * ue, fvhigh = flomass * ve, fwhigh = flomass * we;
+        const double sup = -g.gds * (fuhigh - fuuds) + fdue;
+        const double svp = -g.gds * (fvhigh - fvuds) + fdve;
+        const double swp = -g.gds * (fwhigh - fwuds) + fdwe;
+        if (own) { g.a[sl] = can; s1 = s1 + sup; s2 = s2 + svp; s3 = s3 + swp; }   // a(icell,jcell) = can ; su(ijp) += sup
+        else     { g.a[sl] = cap; s1 = s1 - sup; s2 = s2 - svp; s3 = s3 - swp; }   // a(jcell,icell) = cap ; su(ijn) -= sup
+      } else {
+        const int type = -1 - sl;
+        if (type == FCP_BC_INLET || type == FCP_BC_OUTLET || type == FCP_BC_PRESSURE) {
+          // ---- facefluxuvw_bnd, velocity.f90:882-1034 (the callee's `can` is the caller's cb)
+          const double xpn = m.xf[f] - me.x, ypn = m.yf[f] - me.y, zpn = m.zf[f] - me.z;
+          const double vole = xpn * arx + ypn * ary + zpn * arz;
+          const double Dfi = (arx * arx + ary * ary + arz * arz) / vole;
+          const double game = g.vis[o];
+          const double de = game * Dfi;
+          const double cb = -de + fmin(g.flmass[f], 0.0);
+          const double ub = g.u[o], vb = g.v[o], wb = g.w[o];
+          double e1[3], e2[3], e3[3], d1[3], d2[3], d3[3];
+          const double phb[3] = {ub, vb, wb}, php[3] = {me.u, me.v, me.w};
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const double gx = q == 0 ? me.gu[0] : q == 1 ? me.gv[0] : me.gw[0];
+            const double gy = q == 0 ? me.gu[1] : q == 1 ? me.gv[1] : me.gw[1];
+            const double gz = q == 0 ? me.gu[2] : q == 1 ? me.gv[2] : me.gw[2];
+            e1[q] = gx + arx / vole * (phb[q] - php[q] - gx * xpn - gy * ypn - gz * zpn);
+            e2[q] = gy + ary / vole * (phb[q] - php[q] - gx * xpn - gy * ypn - gz * zpn);
+            e3[q] = gz + arz / vole * (phb[q] - php[q] - gx * xpn - gy * ypn - gz * zpn);
+            d1[q] = gx * (arx - Dfi * xpn); d2[q] = gy * (ary - Dfi * ypn); d3[q] = gz * (arz - Dfi * zpn);
+          }
+          const double fdue = game * (e1[0] * arx + e1[1] * ary + e1[2] * arz);
+          const double fdve = game * (e2[0] * arx + e2[1] * ary + e2[2] * arz);
+          const double fdwe = game * (e3[0] * arx + e3[1] * ary + e3[2] * arz);
+          const double fdui = game * (d1[0] + d2[0] + d3[0]), fdvi = game * (d1[1] + d2[1] + d3[1]), fdwi = game * (d1[2] + d2[2] + d3[2]);
+          const double sup = fdue + fdui, svp = fdve + fdvi, swp = fdwe + fdwi;
+          p1 = p1 - cb; p2 = p2 - cb; p3 = p3 - cb;
+          s1 = s1 - cb * ub + sup;
+          s2 = s2 - cb * vb + svp;
+          s3 = s3 - cb * wb + swp;
+        } else if (type == FCP_BC_SYMMETRY) {
+          // :361-392 ; quirk Q7: vis(inp) with the stale inp = numCells+1 -> the viscosity of the first boundary slot
+          const double are = sqrt(arx * arx + ary * ary + arz * arz), arer = 1.0 / are;
+          const double nxf = arx * arer, nyf = ary * arer, nzf = arz * arer;
+          const double dpb = (m.xf[f] - me.x) * nxf + (m.yf[f] - me.y) * nyf + (m.zf[f] - me.z) * nzf;
+          const double cf = 2 * g.vis[m.n] * are / dpb;
+          s1 = s1 - cf * nxf * (nyf * me.v + nzf * me.w);
+          s2 = s2 - cf * nyf * (nxf * me.u + nzf * me.w);
+          s3 = s3 - cf * nzf * (nxf * me.u + nyf * me.v);
+          p1 = p1 + cf * (nxf * nxf); p2 = p2 + cf * (nyf * nyf); p3 = p3 + cf * (nzf * nzf);
+        } else if (type == FCP_BC_WALL) {
+          // :434-472
+          const double viss = fmax(g.viscos, g.visw[o]);
+          const double are = sqrt(arx * arx + ary * ary + arz * arz), arer = 1.0 / are;
+          const double nxf = arx * arer, nyf = ary * arer, nzf = arz * arer;
+          const double dpb = (m.xf[f] - me.x) * nxf + (m.yf[f] - me.y) * nyf + (m.zf[f] - me.z) * nzf;
+          const double vsol = viss * are / dpb;
+          const double ub = g.u[o], vb = g.v[o], wb = g.w[o];
+          const double upb = me.u - ub, vpb = me.v - vb, wpb = me.w - wb;
+          p1 = p1 + vsol * (1. - nxf * nxf); p2 = p2 + vsol * (1. - nyf * nyf); p3 = p3 + vsol * (1. - nzf * nzf);
+          s1 = s1 + vsol * (ub * (1. - nxf * nxf) + vpb * nyf * nxf + wpb * nzf * nxf);
+          s2 = s2 + vsol * (upb * nxf * nyf + vb * (1. - nyf * nyf) + wpb * nzf * nyf);
+          s3 = s3 + vsol * (upb * nxf * nzf + vpb * nyf * nzf + wb * (1. - nzf * nzf));
+        }
+      }
+    }
+    g.su[c] = s1; g.sv[c] = s2; g.sw[c] = s3;
+    g.spu[c] = p1; g.spv[c] = p2; g.sp[c] = p3;
+    if (g.rU) { g.rU[c] = s1; g.rV[c] = s2; g.rW[c] = s3; }   // piso: rU = su (:564-568)
+  }
+}
+
+// diagonal + under-relaxation of one momentum equation, velocity.f90:602-620 (U), :651-668 (V), :712-730 (W).
+// zero_first: the V and W passes first reset a(diag) and su (:651-654); the row sum then runs over the row with that zero.
+__global__ void __launch_bounds__(FCP_TPB) k_uvw_diag(MeshView m, double *a, const double *__restrict__ spq, const double *srcq /* may alias su */,
+                                                       const double *__restrict__ phi, double *__restrict__ apq, double *su, double urf, int zero_first) {
+  const double urfr = 1.0 / urf, urfm = 1.0 - urf;
+  FCP_CELL_LOOP(c, m.n) {
+    const int64_t base = m.a_slptr[c >> 5] + (c & 31);
+    const int32_t ri = m.a_rinfo[c];
+    const int32_t dpos = (ri >> 16) & 0xffff;
+    const int32_t len = m.a_llen ? m.a_llen[c] : (ri & 0xffff);
+    const double adiag_old = zero_first ? 0.0 : a[base + (int64_t)dpos * 32];
+    double s = 0.0;
+    for (int32_t k = 0; k < len; ++k) s = s + (k == dpos ? adiag_old : a[base + (int64_t)k * 32]);   // sum( a(ia(inp):ia(inp+1)-1) ), CSR order
+    const double sum_off = s - adiag_old;
+    double ad = spq[c] - sum_off;
+    apq[c] = 1. / (ad + FCP_SMALL);
+    ad = ad * urfr;
+    a[base + (int64_t)dpos * 32] = ad;
+    su[c] = srcq[c] + urfm * ad * phi[c];
+  }
+}
+
+int fvm_update_vel_bnd(fcp_ctx *ctx, double *u, double *v, double *w) {
+  if (ctx->B == 0) return FCP_OK;
+  k_update_vel_bnd<<<FCP_GRID(ctx->B)>>>(fcp_mesh_view(ctx), ctx->bftype, u, v, w);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_uvw_assemble(fcp_ctx *ctx, const UvwArgs &g) {
+  if (ctx->n == 0) return FCP_OK;
+  FCP_PROF(&ctx->prof, FCP_K_UVW, ctx->stream, (k_uvw_assemble<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g)));
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_uvw_diag(fcp_ctx *ctx, double *a, const double *spq, const double *srcq, const double *phi, double *apq, double *su, double urf, int zero_first) {
+  if (ctx->n == 0) return FCP_OK;
+  k_uvw_diag<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), a, spq, srcq, phi, apq, su, urf, zero_first);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}

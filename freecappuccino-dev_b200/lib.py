@@ -30,10 +30,11 @@ LIMITER_NONE, LIMITER_BJ, LIMITER_VENKAT, LIMITER_R3, LIMITER_MDL = 0, 1, 2, 3, 
 LIMITER_ID = {"none": 0, "no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "R3": 3, "multidimensional": 4}   # gradients.f90:261-276
 PSCHEME = {"linear": 0, "central": 1, "weighted": 2}
 FIELDS = ["U", "V", "W", "P", "PP", "DEN", "VIS", "APU", "APV", "APW", "SU", "SV", "SW", "S0", "S1", "S2", "S3",
-          "DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "FLMASS", "A", "APR", "H", "RU", "RV", "RW"]
+          "DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "FLMASS", "A", "APR", "H", "RU", "RV", "RW", "VISW",
+          "UO", "VO", "WO", "UOO", "VOO", "WOO", "UOOO", "VOOO", "WOOO", "SPU", "SPV", "SP"]
 F = {name: i for i, name in enumerate(FIELDS)}
 KERNEL_CLASSES = ["spmv_dot", "cg_pk", "cg_update", "cg_init", "precond", "dot", "bicg_elem", "assemble", "gradp", "correct_flux",
-                  "grad", "laplacian", "spmv", "halo", "limiter", "piso_h"]
+                  "grad", "laplacian", "spmv", "halo", "limiter", "piso_h", "uvw"]
 GRADIENT_FIELDS = {"DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1"}
 
 
@@ -60,6 +61,19 @@ class SimpleParams(C.Structure):
     _fields_ = [("solver", C.c_int32), ("maxiter", C.c_int32), ("tol_abs", C.c_double), ("tol_rel", C.c_double),
                 ("urfp", C.c_double), ("npcor", C.c_int32), ("pRefCell", C.c_int32), ("pscheme", C.c_int32),
                 ("const_mflux", C.c_int32), ("flomas", C.c_double), ("zero_pp", C.c_int32)]
+
+
+CSCHEMES = ["cds", "central", "linearUpwind", "kappa", "muscl", "umist", "koren", "smart", "avl-smart", "charm", "vanleer", "ospre", "minmod",
+            "boundedLinearUpwind", "boundedLinearUpwind02", "boundedCentral", "fromm", "cui", "quick", "spl13"]      # cSchemeU strings, interpolation.f90
+CSCHEME_ID = {n: i for i, n in enumerate(CSCHEMES)}
+TSCHEME = {"steady": 0, "bdf": 1, "bdf2": 2, "bdf3": 3}
+
+
+class UvwParams(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("maxiter", C.c_int32), ("tol_abs", C.c_double), ("tol_rel", C.c_double), ("urf", C.c_double * 3),
+                ("gds", C.c_double), ("cscheme", C.c_int32), ("grad_method", C.c_int32), ("limiter", C.c_int32), ("pscheme", C.c_int32),
+                ("tscheme", C.c_int32), ("piso", C.c_int32), ("timestep", C.c_double), ("const_mflux", C.c_int32), ("pad", C.c_int32),
+                ("gradPcmf", C.c_double), ("viscos", C.c_double)]
 
 
 class PisoParams(C.Structure):
@@ -121,6 +135,7 @@ def lib():
     L.fcp_slope_limiter.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.fcp_grad_opt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.fcp_calcp_piso.argtypes = [vp, C.POINTER(PisoParams), C.POINTER(Report)]
+    L.fcp_calcuvw.argtypes = [vp, C.POINTER(UvwParams), C.POINTER(Report)]
     L.fcp_laplacian.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_gradp_and_sources.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_assemble_pcorr_simple.argtypes = [vp, C.c_int, C.c_double]
@@ -276,6 +291,24 @@ class Context:
         reps = (Report * (ncorr * npcor))()
         check(lib().fcp_calcp_piso(self.h, C.byref(prm), reps), "fcp_calcp_piso")
         return [reps[i] for i in range(ncorr * npcor)]
+
+    def calcuvw(self, solver="bicgstab", maxiter=5, tol_abs=1e-13, tol_rel=0.025, urf=(0.8, 0.8, 0.8), gds=1.0, cscheme="cds", grad_method="gauss",
+                limiter="none", pscheme="linear", tscheme="steady", timestep=0.0, piso=False, const_mflux=False, gradPcmf=0.0, viscos=0.0):
+        """calcuvw, Velocity/velocity.f90:50-750.  Returns the three solver reports (U, V, W)."""
+        prm = UvwParams()
+        prm.solver = SOLVER_ID[solver] if isinstance(solver, str) else solver
+        prm.maxiter, prm.tol_abs, prm.tol_rel = maxiter, tol_abs, tol_rel
+        prm.urf[0], prm.urf[1], prm.urf[2] = urf
+        prm.gds = gds
+        prm.cscheme = CSCHEME_ID[cscheme] if isinstance(cscheme, str) else cscheme
+        prm.grad_method = GRAD_ID[grad_method] if isinstance(grad_method, str) else grad_method
+        prm.limiter = LIMITER_ID[limiter] if isinstance(limiter, str) else limiter
+        prm.pscheme = PSCHEME[pscheme] if isinstance(pscheme, str) else pscheme
+        prm.tscheme = TSCHEME[tscheme] if isinstance(tscheme, str) else tscheme
+        prm.piso, prm.timestep, prm.const_mflux, prm.gradPcmf, prm.viscos = int(piso), timestep, int(const_mflux), gradPcmf, viscos
+        reps = (Report * 3)()
+        check(lib().fcp_calcuvw(self.h, C.byref(prm), reps), "fcp_calcuvw")
+        return [reps[i] for i in range(3)]
 
     def laplacian(self, mu, phi):
         check(lib().fcp_laplacian(self.h, field_id(mu), field_id(phi)), "fcp_laplacian")

@@ -64,6 +64,9 @@ enum {
   FCP_F_FLMASS, FCP_F_A, FCP_F_APR,
   FCP_F_H,                                         /* h(nnz): momentum coefficients saved by calcp_piso (calcp_piso.f90:81) */
   FCP_F_RU, FCP_F_RV, FCP_F_RW,                    /* rU,rV,rW: momentum right-hand sides (velocity.f90:567) */
+  FCP_F_VISW,                                      /* visw(iWall): effective wall viscosity, stored in the wall faces' boundary slots */
+  FCP_F_UO, FCP_F_VO, FCP_F_WO, FCP_F_UOO, FCP_F_VOO, FCP_F_WOO, FCP_F_UOOO, FCP_F_VOOO, FCP_F_WOOO,   /* past time levels */
+  FCP_F_SPU, FCP_F_SPV, FCP_F_SP,                  /* spu, spv, sp: implicit source terms of the three momentum equations */
   FCP_F_COUNT
 };
 
@@ -184,6 +187,32 @@ typedef struct {
  * Periodic patches (:242-295) are not supported yet: FCP_ESTATE. */
 int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_report *rep);
 
+/* cSchemeU of face_value, interpolation.f90:28-113 and :596-640 (flux limiters in source order) */
+enum { FCP_CS_CDS = 0, FCP_CS_CENTRAL, FCP_CS_LINEAR_UPWIND, FCP_CS_KAPPA, FCP_CS_MUSCL, FCP_CS_UMIST, FCP_CS_KOREN, FCP_CS_SMART,
+       FCP_CS_AVL_SMART, FCP_CS_CHARM, FCP_CS_VANLEER, FCP_CS_OSPRE, FCP_CS_MINMOD, FCP_CS_BOUNDED_LINEAR_UPWIND,
+       FCP_CS_BOUNDED_LINEAR_UPWIND02, FCP_CS_BOUNDED_CENTRAL, FCP_CS_FROMM, FCP_CS_CUI, FCP_CS_QUICK, FCP_CS_SPL13, FCP_CS_COUNT };
+typedef struct {
+  int32_t solver, maxiter;      /* lSolverU, maxiterU   velocity.f90:30-31 */
+  double tol_abs, tol_rel;      /* tolAbsU, tolRelU */
+  double urf[3];                /* urfU(1:3) */
+  double gds;                   /* gdsU */
+  int32_t cscheme;              /* FCP_CS_* */
+  int32_t grad_method;          /* FCP_GRAD_* used by grad(U,dUdxi) (:171-173) */
+  int32_t limiter;              /* FCP_LIMITER_* applied by grad (gradients.f90:140-160) */
+  int32_t pscheme;              /* FCP_PSCHEME_* of gradp_and_sources(p) (:177) */
+  int32_t tscheme;              /* 0 steady, 1 bdf, 2 bdf2, 3 bdf3 (:217-281); Crank-Nicolson is not built */
+  int32_t piso;                 /* keep rU,rV,rW for calcp_piso (:564-568) */
+  double timestep;
+  int32_t const_mflux, pad;
+  double gradPcmf;              /* constant-mass-flow forcing (:189-191) */
+  double viscos;                /* molecular viscosity: wall faces use max(viscos, visw) (:443) */
+} fcp_uvw_params;
+/* calcuvw: the momentum predictor   Velocity/velocity.f90:50-750 (tier "next" row f1): updateVelocityAtBoundary,
+ * grad(U/V/W), gradp_and_sources(p), volume + face + boundary terms into FCP_F_A / SU,SV,SW / SPU,SPV,SP, then the
+ * three under-relaxed solves; leaves apu,apv,apw (and rU,rV,rW when piso) for calcp_simple / calcp_piso.
+ * Not built: Crank-Nicolson, buoyancy, MHD, periodic patches (FCP_ESTATE). rep[0..2] = U, V, W. */
+int fcp_calcuvw(fcp_ctx *ctx, const fcp_uvw_params *prm, fcp_report *rep);
+
 /* ---- explicit-CSR solver signature: dpcg|iccg|bicgstab(n,nnz,ia,ja,a,diag,fi,rhs,...) -------- */
 /* linear_solvers.f90:206, :364, :548 ; pattern analysed once, values per solve */
 int fcp_solver_create(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const int32_t *diag,
@@ -209,7 +238,7 @@ int fcp_global_min(fcp_ctx *ctx, double *value);
 /* ---- per-kernel-class device timing (CUDA events on the context stream, around every launch of the class) ---- */
 enum { FCP_K_SPMV_DOT = 0, FCP_K_CG_PK, FCP_K_CG_UPDATE, FCP_K_CG_INIT, FCP_K_PRECOND, FCP_K_DOT, FCP_K_BICG_ELEM,
        FCP_K_ASSEMBLE, FCP_K_GRADP, FCP_K_CORRECT_FLUX, FCP_K_GRAD, FCP_K_LAPLACIAN, FCP_K_SPMV, FCP_K_HALO, FCP_K_LIMITER,
-       FCP_K_PISO_H, FCP_K_COUNT };
+       FCP_K_PISO_H, FCP_K_UVW, FCP_K_COUNT };
 int fcp_profile_enable(fcp_ctx *ctx, int on);
 int fcp_profile_reset(fcp_ctx *ctx);
 int fcp_profile_read(fcp_ctx *ctx, int kclass, double *total_ms, int64_t *launches);   /* synchronises; totals since reset */

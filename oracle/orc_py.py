@@ -296,3 +296,42 @@ def calcp_piso(mesh, csr: Csr, solver, maxiter, tol_abs, tol_rel, sum_mode, ncor
                          _d(rU), _d(rV), _d(rW), _d(den), _d(apu), _d(apv), _d(apw), _d(a), _d(h), _d(u), _d(v), _d(w), _d(p), _d(pp),
                          _d(su), _d(sv), _d(sw), _d(dPdxi), _d(flmass), reps)
     return [reps[i] for i in range(ncorr * npcor)], su, sv, sw, h
+
+
+CSCHEMES = ["cds", "central", "linearUpwind", "kappa", "muscl", "umist", "koren", "smart", "avl-smart", "charm", "vanleer", "ospre", "minmod",
+            "boundedLinearUpwind", "boundedLinearUpwind02", "boundedCentral", "fromm", "cui", "quick", "spl13"]
+
+
+class OrcUvwParams(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("maxiter", C.c_int32), ("tol_abs", C.c_double), ("tol_rel", C.c_double), ("urf", C.c_double * 3),
+                ("gds", C.c_double), ("cscheme", C.c_int32), ("grad_method", C.c_int32), ("limiter", C.c_int32), ("pscheme", C.c_int32),
+                ("tscheme", C.c_int32), ("timestep", C.c_double), ("piso", C.c_int32), ("const_mflux", C.c_int32), ("gradPcmf", C.c_double),
+                ("viscos", C.c_double), ("sum_mode", C.c_int32), ("pad", C.c_int32)]
+
+
+def face_value(mesh, cscheme: int, ijp: int, ijn: int, xf, yf, zf, lam, u, dUdxi) -> float:
+    mv = MeshView(mesh)
+    lib().orc_face_value.restype = C.c_double
+    return lib().orc_face_value(mv.ptr, C.c_int(cscheme), C.c_int32(ijp), C.c_int32(ijn), C.c_double(xf), C.c_double(yf), C.c_double(zf),
+                                C.c_double(lam), _d(u), _d(dUdxi))
+
+
+def calcuvw(mesh, csr: Csr, prm: OrcUvwParams, f: dict, a: np.ndarray):
+    """The momentum predictor (velocity.f90:50-750).  f: u,v,w,p (numTotal, updated in place), den, vis (numTotal), visw
+    (numBoundaryFaces), flmass (numFaces), apu (numTotal, in: the weighted pscheme reads it), optionally uo..wooo.  a: stale
+    matrix values in, the W-equation matrix out.  Returns a dict of everything the routine leaves behind."""
+    n, nT = mesh.numCells, mesh.numTotal
+    out = {k: np.zeros(n) for k in ("su", "sv", "sw", "spu", "spv", "sp", "rU", "rV", "rW")}
+    out.update({k: np.zeros(nT) for k in ("apv", "apw")})
+    out["apu"] = f["apu"]
+    out.update({k: np.zeros((nT, 3)) for k in ("dUdxi", "dVdxi", "dWdxi", "dPdxi")})
+    reps = (OrcReport * 3)()
+    opt = lambda k: _d(f[k]) if k in f and f[k] is not None else None  # noqa: E731
+    lib().orc_calcuvw(csr.mv.ptr, _i(csr.ia), _i(csr.ja), _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz), C.byref(prm),
+                      _d(f["u"]), _d(f["v"]), _d(f["w"]), _d(f["p"]), _d(f["den"]), _d(f["vis"]), _d(f["visw"]), _d(f["flmass"]),
+                      opt("uo"), opt("vo"), opt("wo"), opt("uoo"), opt("voo"), opt("woo"), opt("uooo"), opt("vooo"), opt("wooo"),
+                      _d(a), _d(out["su"]), _d(out["sv"]), _d(out["sw"]), _d(out["spu"]), _d(out["spv"]), _d(out["sp"]),
+                      _d(out["apu"]), _d(out["apv"]), _d(out["apw"]), _d(out["dUdxi"]), _d(out["dVdxi"]), _d(out["dWdxi"]), _d(out["dPdxi"]),
+                      _d(out["rU"]), _d(out["rV"]), _d(out["rW"]), reps)
+    out["reps"] = [reps[i] for i in range(3)]
+    return out

@@ -145,3 +145,95 @@ def test_piso_rejects_periodic(fcp):
     with pytest.raises(L.FcpError):
         ctx.calcp_piso()
     ctx.close()
+
+
+# ---- row f1: the momentum predictor -----------------------------------------------------------------------------------------
+def uvw_inputs(m, seed=21, transient=0):
+    rng = np.random.default_rng(seed)
+    f = cases.fields(m)
+    n, nT, Fi = m.numCells, m.numTotal, m.numInnerFaces
+    g = {k: f[k].copy() for k in ("u", "v", "w", "p", "den", "apu")}
+    g["vis"] = 0.01 * m.boundary_values_of(lambda x, y, z: 1.0 + 0.5 * np.sin(3 * x) * np.cos(2 * y) + 0.2 * z)
+    g["visw"] = 0.01 * (1.0 + rng.random(m.numBoundaryFaces))             # some above, some below `viscos`
+    # a mass-flux field with both signs (upwinding takes both branches)
+    own, nb = m.owner[:Fi].astype(np.int64) - 1, m.neighbour.astype(np.int64) - 1
+    uf = 0.5 * (g["u"][own] + g["u"][nb]); vf = 0.5 * (g["v"][own] + g["v"][nb]); wf = 0.5 * (g["w"][own] + g["w"][nb])
+    flm = np.zeros(m.numFaces)
+    flm[:Fi] = uf * m.arx[:Fi] + vf * m.ary[:Fi] + wf * m.arz[:Fi]
+    ib = n + np.arange(m.numBoundaryFaces)
+    flm[Fi:] = g["den"][ib] * (g["u"][ib] * m.arx[Fi:] + g["v"][ib] * m.ary[Fi:] + g["w"][ib] * m.arz[Fi:])
+    for ipatch in range(m.numBoundaries):
+        if m.bctype[ipatch] in (M.BC_WALL, M.BC_SYMMETRY, M.BC_EMPTY):
+            flm[m.patch_faces(ipatch)] = 0.0
+    g["flmass"] = flm
+    for lvl in range(transient):
+        for c in "uvw":
+            g[c + "o" * (lvl + 1)] = g[c] * (1.0 - 0.05 * (lvl + 1)) + 1e-3 * rng.standard_normal(nT)
+    return g
+
+
+@pytest.mark.parametrize("name", MESHES)
+@pytest.mark.parametrize("cscheme,grad,limiter,tscheme,solver,pscheme", [
+    ("cds", "gauss", "none", "steady", "bicgstab", "linear"),
+    ("muscl", "gauss", "Venkatakrishnan", "bdf", "bicgstab", "weighted"),
+    ("linearUpwind", "lsq", "Barth-Jespersen", "bdf2", "bicgstab", "linear"),
+    ("central", "wlsq", "none", "bdf3", "bicgstab", "central"),
+])
+def test_calcuvw(fcp, orc, allmeshes, name, cscheme, grad, limiter, tscheme, solver, pscheme):
+    """calcuvw (velocity.f90:50-750): the matrix, sources, reciprocal diagonals, gradients and the three BiCGStab-ILU(0) solves
+    bit-identical to the oracle (reductions in TREE mode), iteration counts identical."""
+    m = allmeshes[name]
+    nlev = L.TSCHEME[tscheme]
+    g = uvw_inputs(m, transient=nlev)
+    c = orc.Csr(m)
+    a0 = np.random.default_rng(4).standard_normal(c.nnz)          # stale matrix: its diagonal enters the first row sum (:606)
+    prm = orc.OrcUvwParams()
+    prm.solver, prm.maxiter, prm.tol_abs, prm.tol_rel = L.SOLVER_ID[solver], 6, 1e-30, 1e-3
+    prm.urf[0], prm.urf[1], prm.urf[2] = 0.8, 0.7, 0.75
+    prm.gds, prm.cscheme = 0.9, L.CSCHEME_ID[cscheme]
+    prm.grad_method, prm.limiter, prm.pscheme = L.GRAD_ID[grad], L.LIMITER_ID[limiter], L.PSCHEME[pscheme]
+    prm.tscheme, prm.timestep, prm.piso, prm.const_mflux, prm.gradPcmf, prm.viscos = nlev, 0.01, 1, 1, 0.3, 0.015
+    prm.sum_mode = orc.SUM_TREE
+    ctx = make_ctx(m, {k: g[k] for k in ("u", "v", "w", "p", "den", "apu", "vis")})
+    visw_field = np.zeros(m.numTotal); visw_field[m.numCells:] = g["visw"]
+    ctx.upload("VISW", visw_field); ctx.upload("FLMASS", g["flmass"]); ctx.upload("A", a0)
+    for k in g:
+        if k[0] in "uvw" and k.endswith("o"):
+            ctx.upload(k.upper(), g[k])
+    reps = ctx.calcuvw(solver=solver, maxiter=6, tol_abs=1e-30, tol_rel=1e-3, urf=(0.8, 0.7, 0.75), gds=0.9, cscheme=cscheme, grad_method=grad,
+                       limiter=limiter, pscheme=pscheme, tscheme=tscheme, timestep=0.01, piso=True, const_mflux=True, gradPcmf=0.3, viscos=0.015)
+    a = a0.copy()
+    o = orc.calcuvw(m, c, prm, g, a)
+    n = m.numCells
+    eq(ctx.download("DUDXI")[:n], o["dUdxi"][:n], "dUdxi"); eq(ctx.download("DWDXI")[:n], o["dWdxi"][:n], "dWdxi")
+    eq(ctx.download("RU")[:n], o["rU"], "rU"); eq(ctx.download("RV")[:n], o["rV"], "rV"); eq(ctx.download("RW")[:n], o["rW"], "rW")
+    eq(ctx.download("SPU")[:n], o["spu"], "spu"); eq(ctx.download("SP")[:n], o["sp"], "sp")
+    eq(ctx.download("APU")[:n], o["apu"][:n], "apu"); eq(ctx.download("APV")[:n], o["apv"][:n], "apv"); eq(ctx.download("APW")[:n], o["apw"][:n], "apw")
+    eq(ctx.download("A"), a, "a (W-equation matrix)")
+    for r, ro in zip(reps, o["reps"]):
+        assert r.iters == ro.iters and r.res0 == ro.res0 and r.resl == ro.resl, ((r.iters, r.res0, r.resl), (ro.iters, ro.res0, ro.resl))
+    for k in ("u", "v", "w", "p"):
+        eq(ctx.download(k.upper()), g[k], k)
+    eq(ctx.download("SU")[:n], o["su"], "su (W right-hand side)")
+    ctx.close()
+
+
+@pytest.mark.parametrize("cscheme", L.CSCHEMES)
+def test_calcuvw_all_convection_schemes(fcp, orc, allmeshes, cscheme):
+    """Every cSchemeU string of interpolation.f90:28-113 / :596-640, single-precision literals (2./3., 1./3., 1e-30) included."""
+    m = allmeshes["channel_inout"]
+    g = uvw_inputs(m)
+    c = orc.Csr(m)
+    prm = orc.OrcUvwParams()
+    prm.solver, prm.maxiter, prm.tol_abs, prm.tol_rel = L.SOLVER_BICGSTAB, 3, 1e-30, 1e-2
+    prm.urf[0] = prm.urf[1] = prm.urf[2] = 0.8
+    prm.gds, prm.cscheme, prm.viscos, prm.sum_mode = 1.0, L.CSCHEME_ID[cscheme], 0.01, orc.SUM_TREE
+    ctx = make_ctx(m, {k: g[k] for k in ("u", "v", "w", "p", "den", "apu", "vis")})
+    visw_field = np.zeros(m.numTotal); visw_field[m.numCells:] = g["visw"]
+    ctx.upload("VISW", visw_field); ctx.upload("FLMASS", g["flmass"])
+    ctx.calcuvw(solver="bicgstab", maxiter=3, tol_abs=1e-30, tol_rel=1e-2, urf=(0.8, 0.8, 0.8), gds=1.0, cscheme=cscheme, viscos=0.01)
+    a = np.zeros(c.nnz)
+    o = orc.calcuvw(m, c, prm, g, a)
+    for k in ("u", "v", "w"):
+        eq(ctx.download(k.upper()), g[k], f"{k} with {cscheme}")
+    ctx.close()

@@ -83,6 +83,16 @@ class Case:
         self.ncorr = 2
         self.rU, self.rV, self.rW = z(nT), z(nT), z(nT)
         self.h = z(self.nnz)
+        # momentum equation (Velocity/velocity.f90:22-42, parameters.f90)
+        self.vis = np.full(nT, 0.0)
+        self.visw = z(int(sum(mesh.nfaces[ib] for ib in range(mesh.numBoundaries) if mesh.bctype[ib] == 0)))
+        self.viscos, self.urfU, self.gdsU, self.cSchemeU = 0.0, [0.8, 0.8, 0.8], 1.0, "cds"
+        self.lSolverU, self.maxiterU, self.tolAbsU, self.tolRelU = "bicgstab", 5, 1e-13, 0.025
+        self.limiter, self.tscheme, self.timestep, self.piso, self.gradPcmf = "none", "steady", 0.0, False, 0.0
+        self.dUdxi, self.dVdxi, self.dWdxi = np.zeros((nT, 3)), np.zeros((nT, 3)), np.zeros((nT, 3))
+        for comp in "uvw":
+            for lvl in (1, 2, 3):
+                setattr(self, comp + "o" * lvl, z(nT))
 
     def close(self):
         self.ctx.close()
@@ -177,6 +187,46 @@ class Case:
         self.dPdxi[...] = c.download("DPDXI")
         self.su[...], self.sv[...], self.sw[...] = c.download("SU", n), c.download("SV", n), c.download("SW", n)
         self.a[...] = c.download("A")
+        return reps
+
+    # ---- calcuvw()   Velocity/velocity.f90:50-750 -------------------------------------------------------------------------------
+    def calcuvw(self):
+        """The momentum predictor.  Reads the module state (u,v,w,p,den,vis,visw,flmass and the past time levels), leaves
+        u,v,w, apu,apv,apw, su,sv,sw, dUdxi..dWdxi, dPdxi, a (and rU,rV,rW when piso) like the Fortran routine."""
+        c = self.ctx
+        m = self.mesh
+        n = m.numCells
+        for name in ("u", "v", "w", "p", "den", "vis", "apu"):
+            c.upload(name.upper(), getattr(self, name))
+        visw = np.zeros(m.numTotal)             # visw(iWall), wall faces in patch order (velocity.f90:441-443) -> their boundary slots
+        iw = 0
+        for ib in range(m.numBoundaries):
+            if m.bctype[ib] == 0:               # wall
+                sl = n + m.patch_faces(ib) - m.numInnerFaces
+                visw[sl] = self.visw[iw: iw + sl.size]
+                iw += sl.size
+        c.upload("VISW", visw)
+        c.upload("FLMASS", self.flmass)
+        c.upload("A", self.a)
+        nlev = L.TSCHEME[self.tscheme]
+        for lvl in range(nlev):
+            for comp in "uvw":
+                key = comp + "o" * (lvl + 1)
+                c.upload(key.upper(), getattr(self, key))
+        grad = "lsq" if self.lstsq else "lsq_qr" if self.lstsq_qr else "wlsq" if self.lstsq_dm else "gauss"
+        reps = c.calcuvw(solver=self.lSolverU, maxiter=self.maxiterU, tol_abs=self.tolAbsU, tol_rel=self.tolRelU, urf=tuple(self.urfU), gds=self.gdsU,
+                         cscheme=self.cSchemeU, grad_method=grad, limiter=L.LIMITER_ID.get(self.limiter, 0), pscheme=self.pscheme, tscheme=self.tscheme,
+                         timestep=self.timestep, piso=self.piso, const_mflux=self.const_mflux, gradPcmf=self.gradPcmf, viscos=self.viscos)
+        for r, ch in zip(reps, "UVW"):
+            print(L.report_line(r, ch), file=self.out)
+        for name in ("u", "v", "w", "p", "apu", "apv", "apw"):
+            getattr(self, name)[...] = c.download(name.upper())
+        self.su[...], self.sv[...], self.sw[...] = c.download("SU", n), c.download("SV", n), c.download("SW", n)
+        self.dUdxi[...], self.dVdxi[...], self.dWdxi[...] = c.download("DUDXI"), c.download("DVDXI"), c.download("DWDXI")
+        self.dPdxi[...] = c.download("DPDXI")
+        self.a[...] = c.download("A")
+        if self.piso:
+            self.rU[:n], self.rV[:n], self.rW[:n] = c.download("RU", n), c.download("RV", n), c.download("RW", n)
         return reps
 
     # ---- calcp_piso()   Pressure/calcp_piso.f90 ----------------------------------------------------------------------------------

@@ -215,6 +215,78 @@ __global__ void k_process_face_geom(int32_t npro, const int32_t *__restrict__ pf
   Df[f] = are / (arx[f] * xpn + ary[f] * ypn + arz[f] * zpn);
 }
 
+// ---- halo plan: everything the communication layer derives from the patch table, on the HOST and without touching a
+// device, so that it can be checked on CPU for any number of neighbours (fcp_comm_plan; tests/test_comm_plan.py).
+struct HaloPlan {
+  std::vector<int> peer;                 // per process patch (patch order): rank on the other side
+  std::vector<int32_t> off, cnt;         // per process patch: offset / count of its faces in the halo buffers
+  std::vector<int32_t> cell, slot;       // per process face (patch order): owner cell, ghost slot (0-based field indices)
+  std::vector<int32_t> frank;            // per process face: peer rank
+  std::vector<int32_t> chunk_ptr;        // [nchunks+1] process faces grouped by the 2048-row chunk of their owner cell
+  std::vector<int32_t> chunk_face;       // [npro] face ordinals in chunk order
+  std::vector<int32_t> order;            // [nchunks] launch order: chunk | bit 31 when it owns process faces (those first)
+  std::vector<int32_t> ghost_ord;        // [B] boundary face -> process-face ordinal (-1 for physical patches)
+};
+static int halo_plan_build(HaloPlan &pl, int32_t n, int32_t F, int32_t B, int32_t nb, const int32_t *bctype, const int32_t *nfaces,
+                           const int32_t *startFace, const int32_t *owner0 /* [F+B] 0-based */, const int32_t *peer_rank, int rank, int nranks) {
+  pl = HaloPlan();
+  for (int32_t ib = 0; ib < nb; ++ib) {
+    if (bctype[ib] != FCP_BC_PROCESS) continue;
+    if (!peer_rank || peer_rank[ib] < 0 || peer_rank[ib] >= nranks || peer_rank[ib] == rank) {
+      fcp_set_error("fcp_comm_init: process patch %d has no valid peer rank", ib);
+      return FCP_EINVAL;
+    }
+    pl.peer.push_back(peer_rank[ib]);
+    pl.off.push_back((int32_t)pl.slot.size());       // faces of a patch are contiguous in both buffers, patches in patch order
+    pl.cnt.push_back(nfaces[ib]);
+    for (int32_t i = 0; i < nfaces[ib]; ++i) {
+      const int32_t f = startFace[ib] + i;
+      pl.slot.push_back(n + (f - F));
+      pl.cell.push_back(owner0[f]);
+      pl.frank.push_back(peer_rank[ib]);
+    }
+  }
+  const int32_t npro = (int32_t)pl.slot.size();
+  const int nch = std::max(fcp_nchunks(n), 1);
+  pl.chunk_ptr.assign(nch + 1, 0);
+  pl.chunk_face.assign(std::max(npro, 1), 0);
+  for (int32_t i = 0; i < npro; ++i) pl.chunk_ptr[pl.cell[i] / FCP_CHUNK + 1]++;
+  for (int k = 0; k < nch; ++k) pl.chunk_ptr[k + 1] += pl.chunk_ptr[k];
+  {
+    std::vector<int32_t> fill(pl.chunk_ptr.begin(), pl.chunk_ptr.end() - 1);
+    for (int32_t i = 0; i < npro; ++i) pl.chunk_face[fill[pl.cell[i] / FCP_CHUNK]++] = i;
+  }
+  for (int k = 0; k < nch; ++k) if (pl.chunk_ptr[k + 1] > pl.chunk_ptr[k]) pl.order.push_back(k | (int32_t)0x80000000);
+  for (int k = 0; k < nch; ++k) if (pl.chunk_ptr[k + 1] == pl.chunk_ptr[k]) pl.order.push_back(k);
+  pl.ghost_ord.assign(std::max(B, 1), -1);
+  for (int32_t i = 0; i < npro; ++i) pl.ghost_ord[pl.slot[i] - n] = i;
+  return FCP_OK;
+}
+
+extern "C" int fcp_comm_plan(const fcp_mesh_desc *md, const int32_t *peer_rank, int rank, int nranks, int32_t *npatch, int32_t *patch_peer,
+                             int32_t *patch_off, int32_t *patch_cnt, int32_t *cell, int32_t *slot, int32_t *chunk_ptr, int32_t *chunk_face,
+                             int32_t *chunk_order, int32_t *ghost_ord) {
+  if (!md) return FCP_EINVAL;
+  const int32_t n = md->numCells, F = md->numInnerFaces, B = md->numBoundaryFaces;
+  std::vector<int32_t> owner0((size_t)F + B);
+  for (size_t f = 0; f < owner0.size(); ++f) owner0[f] = md->owner[f] - 1;
+  HaloPlan pl;
+  FCP_TRY(halo_plan_build(pl, n, F, B, md->numBoundaries, md->bctype, md->nfaces, md->startFace, owner0.data(), peer_rank, rank, nranks));
+  if (npatch) *npatch = (int32_t)pl.peer.size();
+  for (size_t j = 0; j < pl.peer.size(); ++j) {
+    if (patch_peer) patch_peer[j] = pl.peer[j];
+    if (patch_off) patch_off[j] = pl.off[j];
+    if (patch_cnt) patch_cnt[j] = pl.cnt[j];
+  }
+  if (cell) std::copy(pl.cell.begin(), pl.cell.end(), cell);
+  if (slot) std::copy(pl.slot.begin(), pl.slot.end(), slot);
+  if (chunk_ptr) std::copy(pl.chunk_ptr.begin(), pl.chunk_ptr.end(), chunk_ptr);
+  if (chunk_face && !pl.slot.empty()) std::copy(pl.chunk_face.begin(), pl.chunk_face.begin() + pl.slot.size(), chunk_face);
+  if (chunk_order) std::copy(pl.order.begin(), pl.order.end(), chunk_order);
+  if (ghost_ord && B > 0) std::copy(pl.ghost_ord.begin(), pl.ghost_ord.begin() + B, ghost_ord);
+  return FCP_OK;
+}
+
 // ---- peer-memory set-up ------------------------------------------------------------------------------------------
 struct WinRecord {               // what every rank publishes about its window (all-gathered through NCCL)
   cudaIpcMemHandle_t handle;     // 64 bytes
@@ -246,7 +318,7 @@ static int nccl_swap_face_ints(fcp_ctx *ctx, FcpComm *c, const int32_t *d_src /*
   return FCP_OK;
 }
 
-static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const std::vector<int32_t> &cell, const std::vector<int32_t> &slot_h) {
+static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const HaloPlan &pl) {
   const char *env = getenv("FCP_COMM");
   const bool want = !(env && !strcmp(env, "nccl")) && c->nranks <= FCP_MAXR && c->nranks > 1;
   cudaStream_t st = ctx->stream;
@@ -308,38 +380,25 @@ static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const std::vector<int32_t> &cell,
     return FCP_OK;   // NCCL send/recv + all-gather path
   }
   // per-face data of the matching face on the peer
-  std::vector<int32_t> frank(std::max(c->npro, 1), 0);
-  for (size_t j = 0; j < c->peer.size(); ++j)
-    for (int32_t i = 0; i < c->cnt[j]; ++i) frank[c->off[j] + i] = c->peer[j];
-  FCP_TRY(dev_upload(&c->d_frank, frank.data(), frank.size()));
+  { std::vector<int32_t> fr(pl.frank); if (fr.empty()) fr.push_back(0); FCP_TRY(dev_upload(&c->d_frank, fr.data(), fr.size())); }
   FCP_TRY(dev_alloc(&c->d_rord, (size_t)std::max(c->npro, 1)));
   FCP_TRY(nccl_swap_face_ints(ctx, c, nullptr, c->d_rord));
   std::vector<int32_t> rord(std::max(c->npro, 1), 0);
   FCP_CUDA(cudaMemcpyAsync(rord.data(), c->d_rord, sizeof(int32_t) * (size_t)c->npro, cudaMemcpyDeviceToHost, st));
   FCP_CUDA(cudaStreamSynchronize(st));
-  // process faces grouped by the chunk (2048 rows) that owns their cell; chunks that own process faces are launched first
-  const int nch = std::max(fcp_nchunks(ctx->n), 1);
-  std::vector<int32_t> cptr(nch + 1, 0), pcell(std::max(c->npro, 1), 0), order;
+  // fused-push lists in chunk order: owner cell and the address of the face's LL slot in the peer's window
+  std::vector<int32_t> pcell(std::max(c->npro, 1), 0);
   std::vector<unsigned long long *> pdst(std::max(c->npro, 1), nullptr);
-  for (int32_t i = 0; i < c->npro; ++i) cptr[cell[i] / FCP_CHUNK + 1]++;
-  for (int k = 0; k < nch; ++k) cptr[k + 1] += cptr[k];
-  {
-    std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
-    for (int32_t i = 0; i < c->npro; ++i) {
-      const int32_t j = fill[cell[i] / FCP_CHUNK]++;
-      pcell[j] = cell[i];
-      pdst[j] = (unsigned long long *)((char *)c->peer_win[frank[i]] + recs[frank[i]].off_ll) + 2 * (size_t)rord[i];
-    }
+  for (int32_t j = 0; j < c->npro; ++j) {
+    const int32_t i = pl.chunk_face[j];
+    pcell[j] = pl.cell[i];
+    pdst[j] = (unsigned long long *)((char *)c->peer_win[pl.frank[i]] + recs[pl.frank[i]].off_ll) + 2 * (size_t)rord[i];
   }
-  for (int k = 0; k < nch; ++k) if (cptr[k + 1] > cptr[k]) order.push_back(k | (int32_t)0x80000000);
-  for (int k = 0; k < nch; ++k) if (cptr[k + 1] == cptr[k]) order.push_back(k);
-  std::vector<int32_t> gord(std::max(ctx->B, 1), -1);
-  for (int32_t i = 0; i < c->npro; ++i) gord[slot_h[i] - ctx->n] = i;
-  FCP_TRY(dev_upload(&c->d_chunk_ptr, cptr.data(), cptr.size()));
+  FCP_TRY(dev_upload(&c->d_chunk_ptr, pl.chunk_ptr.data(), pl.chunk_ptr.size()));
   FCP_TRY(dev_upload(&c->d_push_cell, pcell.data(), pcell.size()));
   FCP_TRY(dev_upload(&c->d_push_dst, pdst.data(), pdst.size()));
-  FCP_TRY(dev_upload(&c->d_order, order.data(), order.size()));
-  FCP_TRY(dev_upload(&c->d_ghost_ord, gord.data(), gord.size()));
+  FCP_TRY(dev_upload(&c->d_order, pl.order.data(), pl.order.size()));
+  FCP_TRY(dev_upload(&c->d_ghost_ord, pl.ghost_ord.data(), pl.ghost_ord.size()));
   CommDev &d = c->h_dev;
   memset(&d, 0, sizeof(d));
   d.rank = c->rank; d.nranks = c->nranks;
@@ -400,26 +459,18 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
   c->rank = rank;
   c->nranks = nranks;
   c->npro = ctx->npro;
-  std::vector<int32_t> cell, slot;
-  // process patches in patch order; faces of a patch are contiguous in both buffers
-  for (int32_t ib = 0; ib < ctx->nb; ++ib) {
-    if (ctx->bctype[ib] != FCP_BC_PROCESS) continue;
-    if (!peer_rank || peer_rank[ib] < 0 || peer_rank[ib] >= nranks || peer_rank[ib] == rank) {
-      fcp_set_error("fcp_comm_init: process patch %d has no valid peer rank", ib);
-      delete c;
-      return FCP_EINVAL;
-    }
-    c->peer.push_back(peer_rank[ib]);
-    c->off.push_back((int32_t)cell.size());
-    c->cnt.push_back(ctx->nfaces[ib]);
-    for (int32_t i = 0; i < ctx->nfaces[ib]; ++i) slot.push_back(ctx->n + (ctx->startFace[ib] - ctx->F) + i);
-  }
+  HaloPlan pl;
   {
     std::vector<int32_t> owner(ctx->nF);
     FCP_CUDA(cudaMemcpy(owner.data(), ctx->owner, sizeof(int32_t) * (size_t)ctx->nF, cudaMemcpyDeviceToHost));
-    for (int32_t s : slot) cell.push_back(owner[ctx->F + (s - ctx->n)]);
+    int rc = halo_plan_build(pl, ctx->n, ctx->F, ctx->B, ctx->nb, ctx->bctype.data(), ctx->nfaces.data(), ctx->startFace.data(), owner.data(),
+                             peer_rank, rank, nranks);
+    if (rc != FCP_OK) { delete c; return rc; }
   }
+  c->peer = pl.peer; c->off = pl.off; c->cnt = pl.cnt;
+  std::vector<int32_t> cell = pl.cell, slot = pl.slot;
   if ((int32_t)cell.size() != ctx->npro) { fcp_set_error("fcp_comm_init: internal process-face count mismatch"); delete c; return FCP_EINVAL; }
+  if (cell.empty()) { cell.push_back(0); slot.push_back(0); }
   FCP_TRY(dev_upload(&c->d_cell, cell.data(), cell.size()));
   FCP_TRY(dev_upload(&c->d_slot, slot.data(), slot.size()));
   FCP_TRY(dev_alloc(&c->sendbuf, (size_t)3 * std::max(ctx->npro, 1)));
@@ -430,7 +481,7 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
   memcpy(&id, id128, 128);
   FCP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
   ctx->comm = c;
-  FCP_TRY(p2p_setup(ctx, c, cell, slot));
+  FCP_TRY(p2p_setup(ctx, c, pl));
   // ghost copies of the cell-centre data (src-par/geometry.f90:769-773) and the process-face geometry
   FCP_TRY(comm_exchange(ctx, ctx->xc, 1));
   FCP_TRY(comm_exchange(ctx, ctx->yc, 1));

@@ -935,6 +935,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
       }
       FCP_CHECK_LAUNCH();
       FCP_TRY(fetch_scalars(ws, st));
+      if (cd) FCP_TRY(comm_check_error(ctx));   // a peer stopped responding: fail now instead of spinning through every batch
       if (ws.h_sc->done) break;
     }
   } else if (solver == FCP_SOLVER_ICCG) {
@@ -960,6 +961,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
         }
         FCP_CHECK_LAUNCH();
         FCP_TRY(fetch_scalars(ws, st));
+        if (cd) FCP_TRY(comm_check_error(ctx));
         if (ws.h_sc->done) break;
       }
     }
@@ -995,6 +997,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
         }
         FCP_CHECK_LAUNCH();
         FCP_TRY(fetch_scalars(ws, st));
+        if (cd) FCP_TRY(comm_check_error(ctx));
         if (ws.h_sc->done) break;
       }
     }

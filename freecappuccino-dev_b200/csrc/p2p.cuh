@@ -38,6 +38,7 @@ __device__ __forceinline__ double p2p_ll_load(const unsigned long long *src, uns
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
     if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
     if ((++n & 4095u) == 0u) {
+      if (*(volatile int *)&hdr->error) break;     // another wait already gave up: fall through fast, the host reports the error
       const unsigned long long t = p2p_now_ns();
       if (!t0) t0 = t;
       else if (t - t0 > 20000000000ull) { hdr->error = 1; break; }
@@ -52,6 +53,7 @@ __device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigne
   unsigned int n = 0;
   while (p2p_ld_acquire(flag) < seq) {
     if ((++n & 4095u) == 0u) {
+      if (*(volatile int *)&hdr->error) break;
       const unsigned long long t = p2p_now_ns();
       if (!t0) t0 = t;
       else if (t - t0 > 20000000000ull) { hdr->error = 1; break; }

@@ -227,6 +227,14 @@ int fcp_solver_solve(fcp_solver *s, int solver, const double *a, double *fi, con
  * shared faces in the same order (src-par/geometry.f90:218-240). */
 int fcp_comm_unique_id(void *id128);
 int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id128, const int32_t *peer_rank);
+/* HOST-ONLY (no GPU needed): the halo layout fcp_comm_init derives from the patch table -- per process patch its peer,
+ * offset and face count in the halo buffers (patch order); per process face its owner cell and ghost slot (0-based field
+ * indices); the faces grouped by the 2048-row chunk of their owner cell (chunk_ptr / chunk_face), the launch order of
+ * the chunks (bit 31 = owns process faces) and the boundary-face -> face-ordinal map.  Any pointer may be NULL.  Used by
+ * the CPU tests to validate the layout for ranks with several neighbours (src-par/my_mpi_module.f90:11-17 analogue). */
+int fcp_comm_plan(const fcp_mesh_desc *mesh, const int32_t *peer_rank, int rank, int nranks, int32_t *npatch, int32_t *patch_peer,
+                  int32_t *patch_off, int32_t *patch_cnt, int32_t *cell, int32_t *slot, int32_t *chunk_ptr, int32_t *chunk_face,
+                  int32_t *chunk_order, int32_t *ghost_ord);
 /* 1: halo values and reduction partials travel as peer-memory stores over NVLink (CUDA IPC windows, fused into the
  * Krylov kernels); 0: NCCL send/recv + all-gather (FCP_COMM=nccl or peer mapping unavailable); -1: no communicator */
 int fcp_comm_mode(const fcp_ctx *ctx);

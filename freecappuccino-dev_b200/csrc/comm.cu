@@ -144,12 +144,12 @@ __global__ void __launch_bounds__(256) k_halo_pull(const CommDev *__restrict__ c
   for (int k = 0; k < ncomp; ++k) phi[ncomp * s + k] = p2p_ld_data(src + k);     // exchange.f90:110-127
 }
 
-int comm_exchange(fcp_ctx *ctx, double *field, int ncomp) {
+static int comm_exchange_mode(fcp_ctx *ctx, double *field, int ncomp, bool p2p) {
   FcpComm *c = ctx->comm;
   if (!c || c->npro == 0) return FCP_OK;
   cudaStream_t st = ctx->stream;
   const int grid = (c->npro + 255) / 256;
-  if (c->p2p) {
+  if (p2p) {
     const unsigned long long seq = ++c->xseq;
     size_t tok = ctx->prof.begin(FCP_K_HALO, st);
     k_halo_push<<<grid, 256, 0, st>>>(c->d_dev, ncomp, field, seq);
@@ -171,6 +171,10 @@ int comm_exchange(fcp_ctx *ctx, double *field, int ncomp) {
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;
+}
+int comm_exchange(fcp_ctx *ctx, double *field, int ncomp) {
+  FcpComm *c = ctx->comm;
+  return comm_exchange_mode(ctx, field, ncomp, c && c->p2p);
 }
 
 // vals[k] <- sum over ranks (rank 0 first) of vals[k]; every rank gets the same bits
@@ -424,6 +428,59 @@ static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const HaloPlan &pl) {
   return FCP_OK;
 }
 
+static int p2p_set_timeout(FcpComm *c, unsigned long long ns, cudaStream_t st) {
+  FCP_CUDA(cudaMemcpyAsync(&c->h_dev.hdr->timeout_ns, &ns, sizeof(ns), cudaMemcpyHostToDevice, st));
+  FCP_CUDA(cudaStreamSynchronize(st));
+  return FCP_OK;
+}
+__global__ void k_selfcheck_fill(int32_t n, int32_t nT, int rank, double *__restrict__ t) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nT) t[i] = i < n ? (double)rank * 16777216.0 + (double)i : -1.0;
+}
+// Start-up self-check of the peer-memory layout: the same cell-tagged field is exchanged once through the NVLink windows
+// and once through NCCL send/recv; every rank compares its ghost slots bit for bit and the ranks agree (min) on the
+// outcome.  On any difference or time-out ALL ranks drop to the NCCL path (unless FCP_COMM=p2p insists): a wrong layout
+// must never turn into a silent wrong answer or a hang.
+static int p2p_selfcheck(fcp_ctx *ctx, FcpComm *c) {
+  cudaStream_t st = ctx->stream;
+  const int32_t nT = ctx->nT, n = ctx->n, B = ctx->B;
+  double *t1 = nullptr, *t2 = nullptr;
+  FCP_TRY(dev_alloc(&t1, (size_t)std::max(nT, 1)));
+  FCP_TRY(dev_alloc(&t2, (size_t)std::max(nT, 1)));
+  if (nT > 0) {
+    k_selfcheck_fill<<<(nT + 255) / 256, 256, 0, st>>>(n, nT, c->rank, t1);
+    FCP_CUDA(cudaMemcpyAsync(t2, t1, sizeof(double) * (size_t)nT, cudaMemcpyDeviceToDevice, st));
+  }
+  FCP_TRY(p2p_set_timeout(c, 2000000000ull, st));
+  FCP_TRY(comm_exchange_mode(ctx, t1, 1, true));
+  FCP_TRY(comm_exchange_mode(ctx, t2, 1, false));
+  std::vector<double> g1(std::max(B, 1)), g2(std::max(B, 1));
+  if (B > 0) {
+    FCP_CUDA(cudaMemcpyAsync(g1.data(), t1 + n, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    FCP_CUDA(cudaMemcpyAsync(g2.data(), t2 + n, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  }
+  int err = 0;
+  FCP_CUDA(cudaMemcpyAsync(&err, &c->h_dev.hdr->error, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FCP_CUDA(cudaStreamSynchronize(st));
+  double ok = (!err && (B == 0 || memcmp(g1.data(), g2.data(), sizeof(double) * (size_t)B) == 0)) ? 1.0 : 0.0;
+  FCP_CUDA(cudaMemcpyAsync(c->d_scalar, &ok, sizeof(double), cudaMemcpyHostToDevice, st));
+  FCP_NCCL(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclDouble, ncclMin, c->comm, st));
+  FCP_CUDA(cudaMemcpyAsync(&ok, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, st));
+  FCP_CUDA(cudaStreamSynchronize(st));
+  cudaFree(t1); cudaFree(t2);
+  FCP_TRY(p2p_set_timeout(c, 20000000000ull, st));
+  if (ok < 0.5) {
+    const char *env = getenv("FCP_COMM");
+    if (env && !strcmp(env, "p2p")) { fcp_set_error("peer-memory self-check failed (ghost values differ from the NCCL exchange or a peer timed out)"); return FCP_ENCCL; }
+    fprintf(stderr, "libfcp_b200: rank %d: peer-memory self-check failed, using the NCCL path\n", c->rank);
+    const int zero = 0;
+    FCP_CUDA(cudaMemcpyAsync(&c->h_dev.hdr->error, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    FCP_CUDA(cudaStreamSynchronize(st));
+    c->p2p = false;
+  }
+  return FCP_OK;
+}
+
 // 1 when the peer-memory (CUDA IPC / NVLink) path is active, 0 when the context uses NCCL send/recv, -1 without a communicator
 extern "C" int fcp_comm_mode(const fcp_ctx *ctx) {
   if (!ctx || !ctx->comm) return -1;
@@ -482,6 +539,7 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
   FCP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
   ctx->comm = c;
   FCP_TRY(p2p_setup(ctx, c, pl));
+  if (c->p2p) FCP_TRY(p2p_selfcheck(ctx, c));
   // ghost copies of the cell-centre data (src-par/geometry.f90:769-773) and the process-face geometry
   FCP_TRY(comm_exchange(ctx, ctx->xc, 1));
   FCP_TRY(comm_exchange(ctx, ctx->yc, 1));

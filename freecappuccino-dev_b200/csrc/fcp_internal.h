@@ -123,6 +123,7 @@ struct WinHeader {
   unsigned long long rll[2][FCP_MAXR][8];    // written by peer r: LL words of its <= 4 partial sums, two slots by sequence parity
   // local only
   unsigned long long red_seq;
+  unsigned long long timeout_ns;             // how long a spin may last before it raises `error` (20 s; 2 s during the start-up self-check)
   unsigned int push_ticket, pad0;
   int error, pad1;
 };

@@ -41,13 +41,13 @@ __device__ __forceinline__ double p2p_ll_load(const unsigned long long *src, uns
       if (*(volatile int *)&hdr->error) break;     // another wait already gave up: fall through fast, the host reports the error
       const unsigned long long t = p2p_now_ns();
       if (!t0) t0 = t;
-      else if (t - t0 > 20000000000ull) { hdr->error = 1; break; }
+      else if (t - t0 > hdr->timeout_ns) { hdr->error = 1; break; }
     }
   }
   return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
 
-// spin until *flag >= seq; gives up after 20 s (a peer died or a protocol bug) and raises hdr->error instead of hanging the GPU
+// spin until *flag >= seq; gives up after hdr->timeout_ns (a peer died or a protocol bug) and raises hdr->error instead of hanging the GPU
 __device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long seq, WinHeader *hdr) {
   unsigned long long t0 = 0;
   unsigned int n = 0;
@@ -56,7 +56,7 @@ __device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigne
       if (*(volatile int *)&hdr->error) break;
       const unsigned long long t = p2p_now_ns();
       if (!t0) t0 = t;
-      else if (t - t0 > 20000000000ull) { hdr->error = 1; break; }
+      else if (t - t0 > hdr->timeout_ns) { hdr->error = 1; break; }
     }
   }
 }

@@ -344,8 +344,16 @@ def main():
         "correct_flux": kernel_line("correct_flux", 36 * F0 + 8 * N0),
     }
     dom = kl["spmv_dot"]
-    roofline = dict(bound="hbm", achieved=dom["achieved_gbs"], peak=peak, unit="GB/s", frac=dom["frac"], traffic=None,
-                    kernel="k_spmv_dot<1,false> (SELL-32 SpMV + p.Ap dot)", peak_source=peak_src,
+    traffic = None    # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (same mesh size, 1 GPU only)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        if world == 1 and tj.get("n") == n:
+            traffic = tj["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = dict(bound="hbm", achieved=dom["achieved_gbs"], peak=peak, unit="GB/s", frac=dom["frac"], traffic=traffic,
+                    kernel="k_spmv_dot_pipe<1,false,8> (SELL-32 SpMV + p.Ap dot)", peak_source=peak_src,
                     share_of_step=dom["total_ms"] / (ms * args.steps), avg_launch_ms=dom["avg_ms"], launches=dom["launches"])
     # DPCG iteration as a whole: 12 nnz + 108 N ideal bytes
     it_ms = sum(kl[k]["total_ms"] for k in ("spmv_dot", "cg_pk", "cg_update") if kl[k]) / max(dom["launches"], 1)

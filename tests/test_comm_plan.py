@@ -101,3 +101,28 @@ def test_halo_plan_and_emulated_exchange(dims, n):
         # physical boundary slots untouched
         rest = np.setdiff1d(np.arange(m.numCells, m.numTotal), slots)
         assert np.all(np.isnan(fields[b][rest]))
+
+
+@pytest.mark.parametrize("P", [2, 3, 4, 6])
+def test_oracle_virtual_ranks_with_interior_partitions(orc, P):
+    """The checker of the multi-GPU parity test (orc_exchange / orc_dpcg_par, src-par/dpcg.f90 + exchange.f90) on slab
+    partitions whose interior ranks have TWO process patches: same iteration count and solution as the serial DPCG."""
+    import cases
+    g = M.cavity_mesh(12, distort=0.2)
+    parts = M.partition(g, M.slab_partition(g, P))
+    gcsr, ga, gsu = cases.poisson_system(g, orc)
+    csrs = [orc.Csr(p) for p in parts]
+    loc = [M.localize_matrix(g, gcsr, ga, p, c) for p, c in zip(parts, csrs)]
+    fi_l = [np.zeros(p.numTotal) for p in parts]
+    rhs_l = [gsu[p.cell_global].copy() for p in parts]
+    rep = orc.dpcg_par(parts, csrs, [l[0] for l in loc], [l[1] for l in loc], fi_l, rhs_l, 500, 1e-30, 1e-10, orc.SUM_SEQ)
+    xg = np.zeros(g.numCells)
+    rg = orc.solve(orc.DPCG, gcsr.ia, gcsr.ja, ga, gcsr.diag, xg, gsu, 500, 1e-30, 1e-10)
+    assert abs(rep.iters - rg.iters) <= 1
+    for r, p in enumerate(parts):
+        np.testing.assert_allclose(fi_l[r][: p.numCells], xg[p.cell_global], rtol=0, atol=1e-12)
+    # the plan of the communication layer agrees with the partitioner's patch table on these (unstructured-path) partitions too
+    for r, p in enumerate(parts):
+        pl = plan(p, r, P)
+        assert list(pl["off"]) == list(np.concatenate([[0], np.cumsum(pl["cnt"])[:-1]]).astype(int))
+        assert list(pl["peer"]) == [int(x) for x in p.peer_rank[p.peer_rank >= 0]]

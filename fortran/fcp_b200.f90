@@ -4,7 +4,7 @@
 ! Two modules:
 !   fcp_b200      the bind(C) interfaces, one per entry point of include/fcp.h
 !   fcp_backend   drop-in replacements that keep the reference's module-level API for the hot path
-!                 (csrsolve, grad_gauss, grad, grad_w_option, laplacian, gradp_and_sources, calcp_simple, calcp_piso, exchange, global_sum):
+!                 (csrsolve, grad_gauss, grad, grad_w_option, laplacian, gradp_and_sources, calcuvw, calcp_simple, calcp_piso, exchange, global_sum):
 !                 same names, same dummy arguments, same module globals (geometry, sparse_matrix, variables), so that
 !                 `use linear_solvers` / `use gradients` / `use pressure` in a caller is replaced by `use fcp_backend`
 !                 (INTEGRATION.md shows the patch).
@@ -33,7 +33,9 @@ module fcp_b200
                   FCP_F_APU, FCP_F_APV, FCP_F_APW, FCP_F_SU, FCP_F_SV, FCP_F_SW, &
                   FCP_F_S0, FCP_F_S1, FCP_F_S2, FCP_F_S3, &
                   FCP_F_DUDXI, FCP_F_DVDXI, FCP_F_DWDXI, FCP_F_DPDXI, FCP_F_G0, FCP_F_G1, &
-                  FCP_F_FLMASS, FCP_F_A, FCP_F_APR, FCP_F_H, FCP_F_RU, FCP_F_RV, FCP_F_RW
+                  FCP_F_FLMASS, FCP_F_A, FCP_F_APR, FCP_F_H, FCP_F_RU, FCP_F_RV, FCP_F_RW, FCP_F_VISW, &
+                  FCP_F_UO, FCP_F_VO, FCP_F_WO, FCP_F_UOO, FCP_F_VOO, FCP_F_WOO, FCP_F_UOOO, FCP_F_VOOO, FCP_F_WOOO, &
+                  FCP_F_SPU, FCP_F_SPV, FCP_F_SP
   end enum
 
   type, bind(c) :: fcp_mesh_desc
@@ -46,6 +48,17 @@ module fcp_b200
   type, bind(c) :: fcp_report
     real(c_double) :: res0, resl, factor, resor
     integer(c_int32_t) :: iters, solver
+  end type
+
+  type, bind(c) :: fcp_uvw_params
+    integer(c_int32_t) :: solver, maxiter
+    real(c_double) :: tol_abs, tol_rel
+    real(c_double) :: urf(3)
+    real(c_double) :: gds
+    integer(c_int32_t) :: cscheme, grad_method, limiter, pscheme, tscheme, piso
+    real(c_double) :: timestep
+    integer(c_int32_t) :: const_mflux, pad
+    real(c_double) :: gradPcmf, viscos
   end type
 
   type, bind(c) :: fcp_piso_params
@@ -161,6 +174,13 @@ module fcp_b200
       type(c_ptr), value :: ctx
       type(fcp_simple_params), intent(in) :: prm
       type(fcp_report), intent(out) :: rep(*)
+      integer(c_int) :: rc
+    end function
+    function fcp_calcuvw(ctx, prm, rep) bind(c, name='fcp_calcuvw') result(rc)
+      import :: c_int, c_ptr, fcp_uvw_params, fcp_report
+      type(c_ptr), value :: ctx
+      type(fcp_uvw_params), intent(in) :: prm
+      type(fcp_report), intent(out) :: rep(3)
       integer(c_int) :: rc
     end function
     function fcp_calcp_piso(ctx, prm, rep) bind(c, name='fcp_calcp_piso') result(rc)
@@ -470,6 +490,110 @@ contains
     call get(FCP_F_SU, su, numCells); call get(FCP_F_SV, sv, numCells); call get(FCP_F_SW, sw, numCells)
     call get(FCP_F_A, a, nnz)
     call continuityErrors                            ! calcp_simple.f90:464 stays on the host (prints, sets resor(4))
+  end subroutine
+
+  ! ---- calcuvw(): no arguments   Velocity/velocity.f90:50-750 (tier "next" row f1) -----------------------------------------
+  integer(c_int) function cscheme_id(scheme)      ! cSchemeU strings of interpolation.f90:28-113, :596-640 in source order
+    character(len=*), intent(in) :: scheme
+    character(len=24), parameter :: names(20) = [character(len=24) :: 'cds', 'central', 'linearUpwind', 'kappa', 'muscl', 'umist', &
+      'koren', 'smart', 'avl-smart', 'charm', 'vanleer', 'ospre', 'minmod', 'boundedLinearUpwind', 'boundedLinearUpwind02', &
+      'boundedCentral', 'fromm', 'cui', 'quick', 'spl13']
+    integer :: k
+    cscheme_id = -1
+    do k = 1, 20
+      if (trim(scheme) == trim(names(k))) cscheme_id = k - 1
+    end do
+    if (cscheme_id < 0) then
+      write(*,'(a)') 'Fatal error: non-existing interpolation scheme!'    ! interpolation.f90:643-646
+      stop
+    end if
+  end function
+
+  subroutine calcuvw()
+    use velocity, only: urfU, gdsU, cSchemeU, lSolverU, maxiterU, tolAbsU, tolRelU
+    use gradients, only: lstsq, lstsq_qr, lstsq_dm, limiter
+    use nablap, only: pscheme
+    type(fcp_uvw_params) :: prm
+    type(fcp_report) :: rep(3)
+    character(kind=c_char) :: line(256)
+    character(len=1), parameter :: chvar(3) = ['U', 'V', 'W']
+    real(dp), allocatable :: viswf(:)
+    integer :: ib, i, iWall, k
+    if (CN .or. lbuoy .or. calcEpot) then
+      write(*,'(a)') ' libfcp_b200: Crank-Nicolson, buoyancy and MHD terms of calcuvw are not on the accelerated path'
+      stop
+    end if
+    call put(FCP_F_U, u, numTotal); call put(FCP_F_V, v, numTotal); call put(FCP_F_W, w, numTotal)
+    call put(FCP_F_P, p, numTotal); call put(FCP_F_DEN, den, numTotal); call put(FCP_F_VIS, vis, numTotal)
+    call put(FCP_F_APU, apu, numCells)               ! the 'weighted' pscheme reads the previous apu (nablap.f90:87)
+    allocate(viswf(numTotal)); viswf = 0.0_dp          ! visw(iWall), wall faces in patch order (velocity.f90:441-443) -> boundary slots
+    iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) == 'wall') then
+        do i = 1, nfaces(ib)
+          iWall = iWall + 1
+          viswf(iBndValueStart(ib) + i) = visw(iWall)
+        end do
+      end if
+    end do
+    call put(FCP_F_VISW, viswf, numTotal)
+    call put(FCP_F_FLMASS, flmass, numFaces)
+    call put(FCP_F_A, a, nnz)                        ! the stale diagonal enters the first row sum (velocity.f90:606)
+    prm%tscheme = 0
+    if (ltransient) then
+      if (bdf) prm%tscheme = 1
+      if (bdf2) prm%tscheme = 2
+      if (bdf3) prm%tscheme = 3
+      call put(FCP_F_UO, uo, numTotal); call put(FCP_F_VO, vo, numTotal); call put(FCP_F_WO, wo, numTotal)
+      if (prm%tscheme >= 2) then
+        call put(FCP_F_UOO, uoo, numTotal); call put(FCP_F_VOO, voo, numTotal); call put(FCP_F_WOO, woo, numTotal)
+      end if
+      if (prm%tscheme >= 3) then
+        call put(FCP_F_UOOO, uooo, numTotal); call put(FCP_F_VOOO, vooo, numTotal); call put(FCP_F_WOOO, wooo, numTotal)
+      end if
+    end if
+    prm%solver = solver_id(lSolverU); prm%maxiter = maxiterU; prm%tol_abs = tolAbsU; prm%tol_rel = tolRelU
+    prm%urf = urfU(1:3); prm%gds = gdsU; prm%cscheme = cscheme_id(cSchemeU)
+    prm%grad_method = FCP_GRAD_GAUSS
+    if (lstsq) then
+      prm%grad_method = FCP_GRAD_LSQ
+    else if (lstsq_qr) then
+      prm%grad_method = FCP_GRAD_LSQ_QR
+    else if (lstsq_dm) then
+      prm%grad_method = FCP_GRAD_LSQ_DM
+    end if
+    select case (limiter)
+      case ('Barth-Jespersen');  prm%limiter = FCP_LIMITER_BARTH_JESPERSEN
+      case ('Venkatakrishnan');  prm%limiter = FCP_LIMITER_VENKATAKRISHNAN
+      case ('R3');               prm%limiter = FCP_LIMITER_R3
+      case ('multidimensional'); prm%limiter = FCP_LIMITER_MULTIDIMENSIONAL
+      case default;              prm%limiter = FCP_LIMITER_NONE
+    end select
+    prm%pscheme = FCP_PSCHEME_LINEAR
+    if (trim(pscheme) == 'central') prm%pscheme = FCP_PSCHEME_CENTRAL
+    if (trim(pscheme) == 'weighted') prm%pscheme = FCP_PSCHEME_WEIGHTED
+    prm%piso = merge(1, 0, piso); prm%timestep = timestep
+    prm%const_mflux = merge(1, 0, const_mflux); prm%pad = 0; prm%gradPcmf = gradPcmf; prm%viscos = viscos
+    call fcp_check(fcp_calcuvw(ctx, prm, rep), 'fcp_calcuvw')
+    do k = 1, 3
+      call fcp_check(fcp_report_line(rep(k), chvar(k)//c_null_char, line, 256_c_int), 'fcp_report_line')
+      do i = 1, 256
+        if (line(i) == c_null_char) exit
+      end do
+      write(*,'(256a)') line(1:i-1)
+      resor(k) = rep(k)%resor
+    end do
+    call get(FCP_F_U, u, numTotal); call get(FCP_F_V, v, numTotal); call get(FCP_F_W, w, numTotal); call get(FCP_F_P, p, numTotal)
+    call get(FCP_F_APU, apu, numCells); call get(FCP_F_APV, apv, numCells); call get(FCP_F_APW, apw, numCells)
+    call get(FCP_F_SU, su, numCells); call get(FCP_F_SV, sv, numCells); call get(FCP_F_SW, sw, numCells)
+    call get(FCP_F_SPU, spu, numCells); call get(FCP_F_SPV, spv, numCells); call get(FCP_F_SP, sp, numCells)
+    call get(FCP_F_DUDXI, dUdxi, 3*numTotal); call get(FCP_F_DVDXI, dVdxi, 3*numTotal); call get(FCP_F_DWDXI, dWdxi, 3*numTotal)
+    call get(FCP_F_DPDXI, dPdxi, 3*numTotal)
+    call get(FCP_F_A, a, nnz)
+    if (piso) then
+      call get(FCP_F_RU, rU, numCells); call get(FCP_F_RV, rV, numCells); call get(FCP_F_RW, rW, numCells)
+    end if
+    deallocate(viswf)
   end subroutine
 
   ! ---- calcp_piso(): no arguments   Pressure/calcp_piso.f90 ------------------------------------------------------------------

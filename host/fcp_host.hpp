@@ -32,12 +32,25 @@ inline std::vector<dp> h, rU, rV, rW;   // calcp_piso.f90:81 `h = a`; velocity.f
 // ---- module variables ---------------------------------------------------------------------------------------------------------
 namespace variables {
 inline std::vector<dp> u, v, w, p, pp, den, flmass, dPdxi;
+inline std::vector<dp> vis, visw, dUdxi, dVdxi, dWdxi;             // visw(iWall): wall faces in patch order (velocity.f90:441-443)
+inline std::vector<dp> uo, vo, wo, uoo, voo, woo, uooo, vooo, wooo;  // past time levels
 }
 // ---- module parameters / pressure (parameters.f90, Pressure/pressure.f90:28-33) ------------------------------------------------
 namespace parameters {
 inline int pRefCell = 1, npcor = 1, ncorr = 2;
+inline bool ltransient = false, bdf = false, bdf2 = false, bdf3 = false, piso = false;
+inline dp timestep = 0.0, gradPcmf = 0.0, viscos = 0.0;
 inline bool const_mflux = false;
 inline dp flomas = 0.0;
+}
+namespace velocity {   // Velocity/velocity.f90:22-42
+inline dp urfU[3] = {0.8, 0.8, 0.8}, gdsU = 1.0, tolAbsU = 1e-13, tolRelU = 0.025;
+inline int maxiterU = 5;
+inline std::string cSchemeU = "cds", lSolverU = "bicgstab";
+}
+namespace gradients {  // gradients.f90:44-52
+inline bool lstsq = false, lstsq_qr = false, lstsq_dm = false;
+inline std::string limiter = "none";
 }
 namespace pressure {
 inline dp urfP = 0.2, tolAbsP = 1e-13, tolRelP = 0.025;
@@ -159,6 +172,55 @@ inline void grad(const std::vector<dp> &phi, std::vector<dp> &dPhidxi, const std
   if (method != FCP_GRAD_GAUSS) check(fcp_create_lsq_grad_matrix(ctx, method), "fcp_create_lsq_grad_matrix");
   check(fcp_grad_opt(ctx, method, limiter, FCP_F_S0, FCP_F_G0), "fcp_grad_opt");
   get(FCP_F_G0, dPhidxi, 3 * (int64_t)geometry::numTotal);
+}
+// calcuvw(): no arguments   Velocity/velocity.f90:50-750
+inline void calcuvw() {
+  using namespace variables;
+  using namespace sparse_matrix;
+  using namespace geometry;
+  static const char *names[] = {"cds", "central", "linearUpwind", "kappa", "muscl", "umist", "koren", "smart", "avl-smart", "charm", "vanleer", "ospre",
+                                "minmod", "boundedLinearUpwind", "boundedLinearUpwind02", "boundedCentral", "fromm", "cui", "quick", "spl13"};
+  const int nT = numTotal, n = numCells;
+  fcp_uvw_params prm{};
+  prm.cscheme = -1;
+  for (int k = 0; k < FCP_CS_COUNT; ++k) if (velocity::cSchemeU == names[k]) prm.cscheme = k;
+  if (prm.cscheme < 0) { std::fprintf(stderr, "Fatal error: non-existing interpolation scheme!\n"); std::exit(1); }   // interpolation.f90:643-646
+  put(FCP_F_U, u, nT); put(FCP_F_V, v, nT); put(FCP_F_W, w, nT); put(FCP_F_P, p, nT); put(FCP_F_DEN, den, nT); put(FCP_F_VIS, vis, nT);
+  put(FCP_F_APU, apu, n);
+  std::vector<dp> viswf(nT, 0.0);
+  size_t iw = 0;
+  for (int ib = 0; ib < numBoundaries; ++ib)
+    if (bctype[ib] == FCP_BC_WALL)
+      for (int i = 0; i < nfaces[ib]; ++i) viswf[iBndValueStart[ib] + i] = iw < visw.size() ? visw[iw++] : 0.0;
+  put(FCP_F_VISW, viswf, nT); put(FCP_F_FLMASS, flmass, numFaces); put(FCP_F_A, a, nnz);
+  prm.tscheme = !parameters::ltransient ? 0 : parameters::bdf3 ? 3 : parameters::bdf2 ? 2 : 1;
+  if (prm.tscheme >= 1) { put(FCP_F_UO, uo, nT); put(FCP_F_VO, vo, nT); put(FCP_F_WO, wo, nT); }
+  if (prm.tscheme >= 2) { put(FCP_F_UOO, uoo, nT); put(FCP_F_VOO, voo, nT); put(FCP_F_WOO, woo, nT); }
+  if (prm.tscheme >= 3) { put(FCP_F_UOOO, uooo, nT); put(FCP_F_VOOO, vooo, nT); put(FCP_F_WOOO, wooo, nT); }
+  prm.solver = solver_id(velocity::lSolverU); prm.maxiter = velocity::maxiterU; prm.tol_abs = velocity::tolAbsU; prm.tol_rel = velocity::tolRelU;
+  for (int q = 0; q < 3; ++q) prm.urf[q] = velocity::urfU[q];
+  prm.gds = velocity::gdsU;
+  prm.grad_method = gradients::lstsq ? FCP_GRAD_LSQ : gradients::lstsq_qr ? FCP_GRAD_LSQ_QR : gradients::lstsq_dm ? FCP_GRAD_LSQ_DM : FCP_GRAD_GAUSS;
+  const std::string &lim = gradients::limiter;
+  prm.limiter = lim == "Barth-Jespersen" ? FCP_LIMITER_BARTH_JESPERSEN : lim == "Venkatakrishnan" ? FCP_LIMITER_VENKATAKRISHNAN
+              : lim == "R3" ? FCP_LIMITER_R3 : lim == "multidimensional" ? FCP_LIMITER_MULTIDIMENSIONAL : FCP_LIMITER_NONE;
+  prm.pscheme = pscheme_id(pressure::pscheme); prm.piso = parameters::piso; prm.timestep = parameters::timestep;
+  prm.const_mflux = parameters::const_mflux; prm.gradPcmf = parameters::gradPcmf; prm.viscos = parameters::viscos;
+  fcp_report rep[3];
+  check(fcp_calcuvw(ctx, &prm, rep), "fcp_calcuvw");
+  const char *chvar[3] = {"U", "V", "W"};
+  for (int q = 0; q < 3; ++q) {
+    char line[256];
+    fcp_report_line(&rep[q], chvar[q], line, sizeof(line));
+    std::puts(line);
+  }
+  get(FCP_F_U, u, nT); get(FCP_F_V, v, nT); get(FCP_F_W, w, nT); get(FCP_F_P, p, nT);
+  get(FCP_F_APU, apu, n); get(FCP_F_APV, apv, n); get(FCP_F_APW, apw, n);
+  get(FCP_F_SU, su, n); get(FCP_F_SV, sv, n); get(FCP_F_SW, sw, n);
+  for (auto *g : {&dUdxi, &dVdxi, &dWdxi, &dPdxi}) g->resize(3 * (size_t)nT);
+  get(FCP_F_DUDXI, dUdxi, 3 * (int64_t)nT); get(FCP_F_DVDXI, dVdxi, 3 * (int64_t)nT); get(FCP_F_DWDXI, dWdxi, 3 * (int64_t)nT);
+  get(FCP_F_DPDXI, dPdxi, 3 * (int64_t)nT); get(FCP_F_A, a, nnz);
+  if (parameters::piso) { rU.resize(n); rV.resize(n); rW.resize(n); get(FCP_F_RU, rU, n); get(FCP_F_RV, rV, n); get(FCP_F_RW, rW, n); }
 }
 // calcp_piso(): no arguments   Pressure/calcp_piso.f90
 inline void calcp_piso() {

@@ -425,6 +425,100 @@ def write_polymesh_native(mesh: Mesh, dirname: str) -> None:
             fh.write(f"{mesh.bcname[ib]} {BC_NAMES[mesh.bctype[ib]]} {mesh.nfaces[ib]} {mesh.startFace[ib]}\n")
 
 
+# ---------------------------------------------------------------------------------------------
+# src-par on-disk layout (src-par/geometry.f90:118-260): processorK/constant/polyMesh/{points,faces,owner,neighbour}
+# in OpenFOAM ASCII format, the simplified four-column `boundary` (process patches typed 'process') and `process`
+# (header line + the neighbour rank of every process patch, in patch order).
+# ---------------------------------------------------------------------------------------------
+_FOAM_HEADER = """FoamFile
+{{
+    version     2.0;
+    format      ascii;
+    class       {cls};
+    note        "nPoints: {npts} nCells: {ncells} nFaces: {nfaces} nInternalFaces: {ninner}";
+    location    "constant/polyMesh";
+    object      {obj};
+}}
+
+"""
+
+
+def write_partition_srcpar(gmesh: Mesh, parts: List[Mesh], root: str) -> None:
+    """Writes the partitions made by ``partition(gmesh, ...)`` as the directory tree the reference's MPI build reads.
+    Cut faces keep the node order of the global face when this rank owns the face's owner cell and the reversed order
+    otherwise, so that the area vector computed from the nodes points out of the partition (src-par/geometry.f90:826-871)."""
+    if gmesh.points is None or gmesh.face_nodes is None:
+        raise ValueError("write_partition_srcpar needs the global mesh topology (points, face_nodes)")
+    own0 = gmesh.owner.astype(np.int64) - 1
+    for r, part in enumerate(parts):
+        d = os.path.join(root, f"processor{r}", "constant", "polyMesh")
+        os.makedirs(d, exist_ok=True)
+        gf = part.face_global
+        fn = gmesh.face_nodes[gf].astype(np.int64)
+        nn = gmesh.face_nnodes[gf].astype(np.int64)
+        # a face is flipped when its local owner is not the global owner
+        flipped = part.cell_global[part.owner.astype(np.int64) - 1] != own0[gf]
+        used = np.unique(fn[fn > 0])
+        g2l = np.zeros(gmesh.points.shape[0] + 1, dtype=np.int64)
+        g2l[used] = np.arange(1, used.size + 1)
+        hdr = dict(npts=used.size, ncells=part.numCells, nfaces=part.numFaces, ninner=part.numInnerFaces)
+        with open(os.path.join(d, "points"), "w") as fh:
+            fh.write(_FOAM_HEADER.format(cls="vectorField", obj="points", **hdr))
+            fh.write(f"{used.size}\n(\n")
+            for x, y, z in gmesh.points[used - 1]:
+                fh.write(f"({x:.17g} {y:.17g} {z:.17g})\n")
+            fh.write(")\n")
+        with open(os.path.join(d, "faces"), "w") as fh:
+            fh.write(_FOAM_HEADER.format(cls="faceList", obj="faces", **hdr))
+            fh.write(f"{gf.size}\n(\n")
+            for k in range(gf.size):
+                ids = g2l[fn[k, : nn[k]]] - 1
+                if flipped[k]:
+                    ids = np.concatenate([ids[:1], ids[:0:-1]])   # reversed orientation, same first node: the triangle fan of the
+                                                                   # geometry routine (geometry.f90:416-470) stays the same on both ranks
+                fh.write(f"{nn[k]}(" + " ".join(str(int(v)) for v in ids) + ")\n")
+            fh.write(")\n")
+        for name, arr in (("owner", part.owner), ("neighbour", part.neighbour)):
+            with open(os.path.join(d, name), "w") as fh:
+                fh.write(_FOAM_HEADER.format(cls="labelList", obj=name, **hdr))
+                fh.write(f"{arr.size}\n(\n" + "\n".join(str(int(v) - 1) for v in arr) + "\n)\n")
+        with open(os.path.join(d, "boundary"), "w") as fh:
+            fh.write("# bcName bcType nFaces startFace\n")
+            for ib in range(part.numBoundaries):
+                fh.write(f"{part.bcname[ib]} {BC_NAMES[part.bctype[ib]]} {part.nfaces[ib]} {part.startFace[ib]}\n")
+        with open(os.path.join(d, "process"), "w") as fh:
+            fh.write("# neighbour process of every 'process' patch, in patch order\n")
+            for ib in range(part.numBoundaries):
+                if part.bctype[ib] == BC_PROCESS:
+                    fh.write(f"{int(part.peer_rank[ib])}\n")
+
+
+def read_partition_srcpar(root: str, rank: int) -> Mesh:
+    """Reads processor<rank>/constant/polyMesh like src-par/geometry.f90:118-260: geometry from the node coordinates,
+    `peer_rank` from the `process` file (k-th row = neighbour of the k-th process patch).  Ghost copies of xc, yc, zc, vol
+    are left at zero: fcp_comm_init's first exchanges fill them (src-par/geometry.f90:769-773)."""
+    d = os.path.join(root, f"processor{rank}", "constant", "polyMesh")
+    m = read_polymesh_openfoam(d)
+    with open(os.path.join(d, "process")) as fh:
+        nbr = [int(t.split()[0]) for t in fh.read().splitlines()[1:] if t.strip()]
+    peer = np.full(m.numBoundaries, -1, dtype=np.int32)
+    k = 0
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] == BC_PROCESS:
+            peer[ib] = nbr[k]
+            k += 1
+    if k != len(nbr):
+        raise ValueError(f"process file lists {len(nbr)} connections, boundary file has {k} process patches")
+    m.peer_rank = peer
+    m.peer_patch = np.full(m.numBoundaries, -1, dtype=np.int32)
+    nT = m.numTotal
+    for name in ("xc", "yc", "zc", "vol"):
+        full = np.zeros(nT)
+        full[: m.numCells] = getattr(m, name)[: m.numCells]
+        setattr(m, name, full)
+    return m
+
+
 def load_mesh_npz(path: str) -> Mesh:
     d = np.load(path, allow_pickle=False)
     patches = [(str(n), str(t), int(c), int(s)) for n, t, c, s in

@@ -1,0 +1,43 @@
+"""CPU: on-disk formats either side of the path: the serial native polyMesh and
+the src-par `processorK/constant/polyMesh` tree (+ `process` file) written and read back."""
+import os
+
+import numpy as np
+import pytest
+
+import fcb200  # noqa: F401
+from fcb200 import mesh as M
+
+
+def test_native_polymesh_round_trip(tmp_path):
+    m = M.cavity_mesh(5, distort=0.2)
+    M.write_polymesh_native(m, str(tmp_path / "polyMesh"))
+    r = M.read_polymesh_native(str(tmp_path / "polyMesh"))
+    assert (r.numCells, r.numInnerFaces, r.numBoundaryFaces) == (m.numCells, m.numInnerFaces, m.numBoundaryFaces)
+    assert np.array_equal(r.owner, m.owner) and np.array_equal(r.neighbour, m.neighbour)
+    for k in ("arx", "ary", "arz", "xf", "yf", "zf", "vol", "facint", "Df"):
+        np.testing.assert_allclose(getattr(r, k), getattr(m, k), rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_srcpar_partition_tree_round_trip(tmp_path, P):
+    g = M.cavity_mesh(6, distort=0.15)
+    parts = M.partition(g, M.slab_partition(g, P))
+    M.write_partition_srcpar(g, parts, str(tmp_path))
+    for r, part in enumerate(parts):
+        d = tmp_path / f"processor{r}" / "constant" / "polyMesh"
+        for f in ("points", "faces", "owner", "neighbour", "boundary", "process"):
+            assert (d / f).exists()
+        back = M.read_partition_srcpar(str(tmp_path), r)
+        assert (back.numCells, back.numInnerFaces, back.numBoundaryFaces) == (part.numCells, part.numInnerFaces, part.numBoundaryFaces)
+        assert np.array_equal(back.owner, part.owner) and np.array_equal(back.neighbour, part.neighbour)
+        assert list(back.bctype) == list(part.bctype) and list(back.nfaces) == list(part.nfaces) and list(back.startFace) == list(part.startFace)
+        assert np.array_equal(back.peer_rank, part.peer_rank)
+        n = part.numCells
+        # geometry recomputed from the written nodes = the partition's (area vectors of cut faces point OUT of the partition)
+        for k in ("arx", "ary", "arz", "xf", "yf", "zf"):
+            np.testing.assert_allclose(getattr(back, k), getattr(part, k), rtol=0, atol=1e-13)
+        for k in ("xc", "yc", "zc", "vol"):
+            np.testing.assert_allclose(getattr(back, k)[:n], getattr(part, k)[:n], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(back.facint, part.facint, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(back.Df, part.Df, rtol=1e-12)

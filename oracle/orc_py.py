@@ -53,8 +53,12 @@ def use_openmp(threads: int = 0) -> int:
         os.environ["OMP_NUM_THREADS"] = str(threads)
     elif os.environ.get("OMP_NUM_THREADS") in (None, "", "1"):   # torchrun exports OMP_NUM_THREADS=1
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    try:
+        path = build(name="liborc_omp.so")
+    except (subprocess.CalledProcessError, OSError):
+        return 1                                  # no OpenMP toolchain here: stay on the serial library
     _LIB = None
-    _load(build(name="liborc_omp.so"))
+    _load(path)
     return int(os.environ["OMP_NUM_THREADS"])
 
 

@@ -180,9 +180,10 @@ struct Profiler {
 };
 #define FCP_PROF(prof, k, st, stmt)                      \
   do {                                                   \
-    size_t tok__ = (prof) ? (prof)->begin(k, st) : 0;    \
+    Profiler *p__ = (prof);                              \
+    size_t tok__ = p__ ? p__->begin(k, st) : 0;          \
     stmt;                                                \
-    if (prof) (prof)->end(tok__, st);                    \
+    if (p__) p__->end(tok__, st);                        \
   } while (0)
 
 struct fcp_ctx {

@@ -30,10 +30,16 @@ static int nccl_load() {
   if (g_nccl.handle) return FCP_OK;
   const char *names[] = {"libnccl.so.2", "libnccl.so"};
   void *h = nullptr;
+#ifdef FCP_EMU   // tests/emu: the blocking inter-process stand-in linked into the emulation library itself (test infrastructure only)
+  (void)names;
+  Dl_info self;
+  if (dladdr((void *)&g_nccl, &self) && self.dli_fname) h = dlopen(self.dli_fname, RTLD_NOW);
+#else
   for (const char *nm : names) {
     h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
     if (h) break;
   }
+#endif
   if (!h) { fcp_set_error("cannot load libnccl.so.2: %s", dlerror()); return FCP_ENCCL; }
 #define SYM(field, name)                                                             \
   *(void **)(&g_nccl.field) = dlsym(h, name);                                        \

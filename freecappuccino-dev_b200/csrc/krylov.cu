@@ -454,6 +454,17 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
 // x gathers go through LSU/L1.  No registers or LSU request slots are tied up by the matrix stream, so many more bytes
 // are in flight per SM than the load/use version can keep.  Arithmetic order per row is unchanged (CSR order).
 // ---------------------------------------------------------------------------------------------
+#ifdef FCP_EMU   // tests/emu: the mbarrier / bulk-copy primitives restated for the CPU emulation (test infrastructure only)
+struct EmuMbar { uint32_t tx; uint8_t count, pending, phase, pad; };   // fits the 8-byte barrier word
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { EmuMbar *m = (EmuMbar *)bar; m->count = m->pending = count; m->tx = 0; m->phase = 0; }
+__device__ __forceinline__ void emu_mbar_complete(EmuMbar *m) { if (m->pending == 0 && m->tx == 0) { m->phase ^= 1u; m->pending = m->count; } }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { EmuMbar *m = (EmuMbar *)bar; m->tx += bytes; m->pending -= 1; emu_mbar_complete(m); }
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { EmuMbar *m = (EmuMbar *)bar; memcpy(dst, src, bytes); m->tx -= bytes; emu_mbar_complete(m); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { EmuMbar *m = (EmuMbar *)bar; while (m->phase == parity) emu::yield(); }
+__device__ __forceinline__ void mbar_fence_init() {}
+#define FCP_DYN_SMEM(name) unsigned char *name = emu::dyn_smem()
+#else
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -480,6 +491,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
+#define FCP_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
 #define FCP_TILE_ROWS FCP_TPB                      // 256 rows = 8 slices per tile
 #define FCP_TILES (FCP_CHUNK / FCP_TILE_ROWS)      // 8 tiles per chunk
 #define FCP_MAX_STAGES 4
@@ -492,7 +506,7 @@ template <int NS, bool SQ>
 __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot_tma(int32_t n, int32_t nslices, SellView m, const double *__restrict__ x, double *__restrict__ y,
                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int cap, int nstages) {
   if (sc->done) return;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FCP_DYN_SMEM(smem_raw);
   // layout: [nstages][cap] int32 column indices | barriers | slice pointers of the current and the next chunk
   int32_t *sj = reinterpret_cast<int32_t *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)nstages * cap * 4);
@@ -506,7 +520,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot_tma(int32_t n, int32_t nsl
   if (tid <= FCP_CHUNK / 32) soff[0][tid] = m.slptr[min((int)blockIdx.x * (FCP_CHUNK / 32) + tid, nslices)];
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   int32_t ri_next = ((int64_t)blockIdx.x * FCP_CHUNK + tid < n) ? __ldg(&m.rinfo[(int64_t)blockIdx.x * FCP_CHUNK + tid]) : 0;
   __syncthreads();
@@ -810,7 +824,13 @@ static int launch_factor(bool ilu, SellPattern &p, const double *a, double *d, c
   void *args[] = {&m, &lv, &tpos, &d};
   const void *fn = ilu ? (const void *)k_factor_diag<true> : (const void *)k_factor_diag<false>;
   FCP_TRY(coop_grid(fn, dev, &grid));
+#ifdef FCP_EMU
+  (void)args;
+  if (ilu) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_factor_diag<true>, m, lv, tpos, d);
+  else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_factor_diag<false>, m, lv, tpos, d);
+#else
   FCP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FCP_TPB), args, 0, st));
+#endif
   FCP_LAUNCHED();
   return FCP_OK;
 }
@@ -827,7 +847,12 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
   LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
   const int32_t *llen = p.llen;
   void *args[] = {&m, &lv, &llen, &d, &rhs, &zk, &sc};
+#ifdef FCP_EMU
+  (void)args;
+  emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply, m, lv, llen, d, rhs, zk, sc);
+#else
   FCP_CUDA(cudaLaunchCooperativeKernel((const void *)k_precond_apply, dim3(grid), dim3(FCP_TPB), args, 0, st));
+#endif
   FCP_LAUNCHED();
   return FCP_OK;
 }

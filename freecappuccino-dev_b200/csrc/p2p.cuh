@@ -4,6 +4,20 @@
 #pragma once
 #include "fcp_internal.h"
 
+#ifdef FCP_EMU   // tests/emu: the same primitives for the CPU emulation (ranks are processes sharing the window memory; test infrastructure only)
+__device__ __forceinline__ unsigned long long p2p_ld_acquire(const unsigned long long *p) { emu::os_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void p2p_st_release(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ double p2p_ld_data(const double *p) { return *(const volatile double *)p; }
+__device__ __forceinline__ unsigned long long p2p_now_ns() { return emu::now_ns(); }
+__device__ __forceinline__ void p2p_ll_store_words(unsigned long long *dst, unsigned long long w0, unsigned long long w1) {
+  __atomic_store_n(dst, w0, __ATOMIC_RELAXED);
+  __atomic_store_n(dst + 1, w1, __ATOMIC_RELAXED);
+}
+__device__ __forceinline__ void p2p_ll_load_words(const unsigned long long *src, unsigned long long &w0, unsigned long long &w1) {
+  w0 = __atomic_load_n(src, __ATOMIC_RELAXED);
+  w1 = __atomic_load_n(src + 1, __ATOMIC_RELAXED);
+}
+#else
 __device__ __forceinline__ unsigned long long p2p_ld_acquire(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -22,6 +36,13 @@ __device__ __forceinline__ unsigned long long p2p_now_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void p2p_ll_store_words(unsigned long long *dst /* 16-byte aligned */, unsigned long long w0, unsigned long long w1) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void p2p_ll_load_words(const unsigned long long *src, unsigned long long &w0, unsigned long long &w1) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+}
+#endif
 // ---- flag-in-data words ("LL" protocol): a double travels as two 8-byte words {32 data bits | 32-bit sequence number}.
 // An 8-byte store is atomic, so a word whose upper half equals the expected sequence number carries valid data: no
 // fence, no separate flag, one NVLink one-way latency.  16-byte aligned pairs move as one v2 transaction.
@@ -29,13 +50,13 @@ __device__ __forceinline__ void p2p_ll_store(unsigned long long *dst /* 16-byte 
   const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
   const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)seq << 32);
   const unsigned long long w1 = (bits >> 32) | ((unsigned long long)seq << 32);
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+  p2p_ll_store_words(dst, w0, w1);
 }
 __device__ __forceinline__ double p2p_ll_load(const unsigned long long *src, unsigned int seq, WinHeader *hdr) {
   unsigned long long w0, w1, t0 = 0;
   unsigned int n = 0;
   for (;;) {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    p2p_ll_load_words(src, w0, w1);
     if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
     if ((++n & 4095u) == 0u) {
       if (*(volatile int *)&hdr->error) break;     // another wait already gave up: fall through fast, the host reports the error

@@ -27,6 +27,15 @@ def _has_gpu() -> bool:
 
 HAS_GPU = _has_gpu()
 
+# FCP_TEST_EMU=1: run the `-m gpu` suite against tests/emu/libfcp_emu.so, the product's csrc/*.cu re-compiled for a CPU
+# emulation of the CUDA execution model (tests/emu/cuda_runtime.h).  Test infrastructure for containers without a GPU:
+# the product itself (freecappuccino-dev_b200/lib.py) has no such switch and no CPU path.
+import emu_hook  # noqa: E402
+EMU = emu_hook.wanted() and not HAS_GPU
+if EMU:
+    emu_hook.activate()
+    HAS_GPU = True
+
 
 def pytest_collection_modifyitems(config, items):
     if HAS_GPU:

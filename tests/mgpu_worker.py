@@ -20,6 +20,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
+import emu_hook  # noqa: E402
+EMU = emu_hook.wanted() and not torch.cuda.is_available()
+if EMU:
+    emu_hook.activate()
 import cases  # noqa: E402
 import fcb200  # noqa: E402,F401
 from fcb200 import lib as L  # noqa: E402
@@ -34,7 +38,8 @@ def rel(a, b):
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group(backend="gloo", init_method="env://")
-    torch.cuda.set_device(local)
+    if not EMU:
+        torch.cuda.set_device(local)
     n = 12
     g = M.cavity_mesh(n, distort=0.2)
     parts = M.partition(g, M.slab_partition(g, world))

@@ -1,0 +1,40 @@
+"""CPU: the product's CUDA sources executed under the emulation of tests/emu (fibers for CUDA threads, processes for
+ranks), checked against the oracle.  This is a LOGIC check of csrc/*.cu for containers without a GPU -- loop order,
+reduction trees, tickets, barriers, the peer-memory protocol -- and nothing more: no performance meaning, not a product
+path (the product only loads csrc/libfcp_b200.so).  The complete `-m gpu` suite runs the same way with
+`FCP_TEST_EMU=1 python -m pytest tests -m gpu`; here only a slice that finishes in about a minute."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import HAS_GPU, EMU
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(HAS_GPU and not EMU, reason="a real GPU is present: the -m gpu suite is the check")
+
+
+def _run(args, timeout=900, **env):
+    e = dict(os.environ, FCP_TEST_EMU="1", **env)
+    return subprocess.run([sys.executable] + args, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=e)
+
+
+def test_smoke_under_emulation():
+    r = _run(["-c", "import sys; sys.path.insert(0, 'tests'); import emu_hook; emu_hook.activate(); import __graft_entry__ as g; g.smoke()"])
+    assert r.returncode == 0 and "bit-identical to the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_parity_slice_under_emulation():
+    r = _run(["-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_parity.py", "-k", "hex6 or tiny3 or poly_10faces or golden"])
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("comm", ["p2p", "nccl"])
+def test_four_ranks_under_emulation(comm):
+    """4 slab partitions (interior ranks own two process patches): halo plan, CUDA-IPC windows, the fused flag-in-data pushes,
+    in-kernel rank-ordered all-reduce, start-up self-check -- bit-exact against the oracle's virtual ranks."""
+    cmd = ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1", "--master-port",
+           str(29610 + (1 if comm == "nccl" else 0)), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    r = _run(cmd, FCP_COMM=comm)
+    assert r.returncode == 0 and r.stdout.count("MGPU_OK") == 4, r.stdout[-3000:] + r.stderr[-3000:]

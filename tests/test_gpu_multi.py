@@ -11,6 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _ngpus():
+    from conftest import EMU
+    if EMU:          # FCP_TEST_EMU=1: ranks are processes sharing the emulated device memory (tests/emu)
+        return 8
     try:
         out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
         return sum(1 for l in out.splitlines() if l.startswith("GPU "))
@@ -19,7 +22,7 @@ def _ngpus():
 
 
 @pytest.mark.parametrize("comm", ["p2p", "nccl"])
-@pytest.mark.parametrize("nranks", [2, 4])
+@pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_partitioned_parity(nranks, comm):
     """comm = p2p: CUDA-IPC windows, halo pushes and rank-ordered reductions fused into the Krylov kernels (NVLink stores);
     comm = nccl: the send/recv + all-gather path.  Both must give the oracle's bits."""

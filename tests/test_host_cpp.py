@@ -8,14 +8,16 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import HAS_GPU
+from conftest import EMU, HAS_GPU
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 APP = os.path.join(ROOT, "host", "poisson_app")
 
 
 def build():
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-B", "poisson_app"], stdout=subprocess.DEVNULL)
+    # FCP_TEST_EMU=1 (tests/emu_hook.py): link the host program against the emulation build of the same sources
+    extra = ["LIBDIR=../tests/emu", "LIB=fcp_emu"] if EMU else []
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-B", "poisson_app"] + extra, stdout=subprocess.DEVNULL)
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")

@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=256, help="cells per direction of the cavity mesh")
+    ap.add_argument("--n", "--cells", dest="n", type=int, default=256, help="cells per direction of the cavity mesh (--cells under torchrun, whose own parser rejects --n as ambiguous)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--solver", default="dpcg", choices=["dpcg", "iccg", "bicgstab"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -42,7 +42,14 @@ def main():
         torch.cuda.set_device(local)
     n = 12
     g = M.cavity_mesh(n, distort=0.2)
-    parts = M.partition(g, M.slab_partition(g, world))
+    if os.environ.get("FCP_TEST_PART", "slab") == "brick":      # 2 x 2 x (world/4) bricks: every rank has 3+ neighbours, non-contiguous cell sets
+        nc = g.numCells
+        bz = max(world // 4, 1)
+        cr = ((g.xc[:nc] > 0.5).astype(np.int32) + 2 * (g.yc[:nc] > 0.5).astype(np.int32)
+              + 4 * np.minimum((g.zc[:nc] * bz).astype(np.int32), bz - 1)) % world
+        parts = M.partition(g, cr.astype(np.int32))
+    else:
+        parts = M.partition(g, M.slab_partition(g, world))
     me = parts[rank]
     ctx = L.Context(me, local)
     uid = [L.comm_unique_id() if rank == 0 else None]

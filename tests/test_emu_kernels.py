@@ -38,3 +38,21 @@ def test_four_ranks_under_emulation(comm):
            str(29610 + (1 if comm == "nccl" else 0)), os.path.join(ROOT, "tests", "mgpu_worker.py")]
     r = _run(cmd, FCP_COMM=comm)
     assert r.returncode == 0 and r.stdout.count("MGPU_OK") == 4, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_bench_control_flow_four_ranks_under_emulation():
+    """bench.py's own main() on 4 ranks (block partition per rank, communicator, timed loops, statistics gather, JSON line);
+    the numbers are meaningless here, the line's structure and the solver's convergence are what is checked."""
+    import json
+    cmd = ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1", "--master-port", "29620",
+           os.path.join(ROOT, "tests", "emu_bench_worker.py"), "--gpus", "4", "--cells", "16", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"]
+    r = _run(cmd)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1, r.stdout[-3000:] + r.stderr[-3000:]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == 4 and d["config"]["comm"] == "p2p" and d["gpu_launches"] > 0
+    assert 0 < d["pcg"]["iters"] < 500 and d["pcg"]["resl"] < 1e-8 * d["pcg"]["res0"] * 1.0001
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}

@@ -43,6 +43,7 @@ module fcp_b200
     type(c_ptr) :: owner, neighbour
     type(c_ptr) :: arx, ary, arz, xf, yf, zf, facint, Df, xc, yc, zc, vol
     type(c_ptr) :: bctype, nfaces, startFace
+    type(c_ptr) :: startFaceTwin          ! per patch; c_null_ptr when the mesh has no periodic patch
   end type
 
   type, bind(c) :: fcp_report
@@ -296,13 +297,19 @@ contains
   subroutine fcp_init(device)
     integer, intent(in) :: device
     type(fcp_mesh_desc) :: md
-    integer(c_int32_t), allocatable, target :: bct(:), nfa(:), sfa(:)
+    integer(c_int32_t), allocatable, target :: bct(:), nfa(:), sfa(:), stw(:)
     integer(c_int32_t), allocatable :: ia2(:), ja2(:), dg2(:), k1(:), k2(:)
-    integer :: ib
-    allocate(bct(numBoundaries), nfa(numBoundaries), sfa(numBoundaries))
+    integer :: ib, iPer
+    allocate(bct(numBoundaries), nfa(numBoundaries), sfa(numBoundaries), stw(numBoundaries))
+    iPer = 0
     do ib = 1, numBoundaries
       nfa(ib) = nfaces(ib)
       sfa(ib) = startFace(ib)                     ! 0-based offset, as in the boundary file (geometry.f90:282-290)
+      stw(ib) = -1
+      if (trim(bctype(ib)) == 'periodic') then    ! the reference indexes startFaceTwin by the running count of periodic patches (geometry.f90:252-257)
+        iPer = iPer + 1
+        stw(ib) = startFaceTwin(iPer)
+      end if
       select case (trim(bctype(ib)))
       case ('wall');     bct(ib) = FCP_BC_WALL
       case ('inlet');    bct(ib) = FCP_BC_INLET
@@ -322,11 +329,13 @@ contains
     md%facint = c_loc(facint); md%Df = c_loc(Df)
     md%xc = c_loc(xc); md%yc = c_loc(yc); md%zc = c_loc(zc); md%vol = c_loc(vol)
     md%bctype = c_loc(bct); md%nfaces = c_loc(nfa); md%startFace = c_loc(sfa)
+    md%startFaceTwin = c_null_ptr
+    if (iPer > 0) md%startFaceTwin = c_loc(stw)
     call fcp_check(fcp_ctx_create(md, int(device, c_int), ctx), 'fcp_ctx_create')
-    allocate(ia2(numCells+1), ja2(nnz), dg2(numCells), k1(numInnerFaces), k2(numInnerFaces))
+    allocate(ia2(numCells+1), ja2(nnz), dg2(numCells), k1(numInnerFaces+numPeriodic), k2(numInnerFaces+numPeriodic))
     call fcp_check(fcp_csr_pattern(ctx, ia2, ja2, dg2, k1, k2), 'fcp_csr_pattern')
     if (any(ia2 /= ia) .or. any(ja2 /= ja) .or. any(dg2 /= diag) .or. &
-        any(k1 /= icell_jcell_csr_index(1:numInnerFaces)) .or. any(k2 /= jcell_icell_csr_index(1:numInnerFaces))) then
+        any(k1 /= icell_jcell_csr_index(1:numInnerFaces+numPeriodic)) .or. any(k2 /= jcell_icell_csr_index(1:numInnerFaces+numPeriodic))) then
       write(*,'(a)') ' libfcp_b200: device CSR pattern differs from create_CSR_matrix'
       stop
     end if

@@ -105,11 +105,37 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
     }
   }
 
+  // ---- periodic pairs (geometry.f90:251-257): face i of a periodic patch pairs with face i of its twin patch ----
+  // pcell/pface/pord per boundary face; plist = the periodic-side boundary-face ordinals in patch order (the `l` of sparse_matrix.f90:262-293)
+  std::vector<int32_t> pcell(std::max(B, 1), -1), pface(std::max(B, 1), -1), pord(std::max(B, 1), -1), plist;
+  for (int32_t ib = 0; ib < c->nb; ++ib) {
+    if (c->bctype[ib] != FCP_BC_PERIODIC) continue;
+    const int32_t st = md->startFaceTwin ? md->startFaceTwin[ib] : -1;
+    int32_t it = -1;
+    for (int32_t jb = 0; jb < c->nb; ++jb) if (c->startFace[jb] == st && jb != ib) it = jb;
+    if (it < 0 || c->nfaces[it] != c->nfaces[ib] || c->bctype[it] != FCP_BC_EMPTY) {
+      fcp_set_error("periodic patch %d: startFaceTwin must name an 'empty' patch with the same number of faces", ib);
+      delete c;
+      return FCP_EINVAL;
+    }
+    for (int32_t i = 0; i < c->nfaces[ib]; ++i) {
+      const int32_t fp = c->startFace[ib] + i, ft = st + i;
+      const int32_t p = md->owner[fp] - 1, q = md->owner[ft] - 1;
+      if (p == q) { fcp_set_error("periodic patch %d: face %d pairs a cell with itself", ib, i + 1); delete c; return FCP_EINVAL; }
+      pcell[fp - F] = q; pface[fp - F] = ft; pord[fp - F] = i;
+      pcell[ft - F] = p; pface[ft - F] = fp; pord[ft - F] = i;
+      plist.push_back(fp - F);
+    }
+  }
+  c->nper = (int32_t)plist.size();
+  if (c->nper && c->npro) { fcp_set_error("periodic patches on a partitioned mesh are not supported (the serial tree has no process patches)"); delete c; return FCP_ESTATE; }
+
   // ---- create_CSR_matrix (sparse_matrix.f90:110-260): rows ascending, columns ascending, diagonal embedded ----
   std::vector<int32_t> ia(n + 1, 0), diag(n);
   {
     std::vector<int32_t> cnt(n, 1);
     for (int32_t f = 0; f < F; ++f) { cnt[md->owner[f] - 1]++; cnt[md->neighbour[f] - 1]++; }
+    for (int32_t b : plist) { cnt[md->owner[F + b] - 1]++; cnt[pcell[b]]++; }          // :141-171 twin entries
     ia[0] = 1;
     for (int32_t i = 0; i < n; ++i) ia[i + 1] = ia[i] + cnt[i];
   }
@@ -123,6 +149,11 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
       ja[pos[p]++] = q + 1;
       ja[pos[q]++] = p + 1;
     }
+    for (int32_t b : plist) {
+      int32_t p = md->owner[F + b] - 1, q = pcell[b];
+      ja[pos[p]++] = q + 1;
+      ja[pos[q]++] = p + 1;
+    }
     parallel_for(n, [&](int64_t b, int64_t e) {
       for (int64_t i = b; i < e; ++i) {
         std::sort(ja.begin() + (ia[i] - 1), ja.begin() + (ia[i + 1] - 1));
@@ -131,8 +162,18 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
       }
     });
   }
-  c->h_kPN.resize(F);
-  c->h_kNP.resize(F);
+  if (c->nper) {   // a periodic pair must not duplicate an existing entry (the reference's csr_to_k would alias the two coefficients)
+    for (int32_t i = 0; i < n; ++i)
+      for (int32_t k = ia[i]; k < ia[i + 1] - 1; ++k)
+        if (ja[k - 1] == ja[k]) { fcp_set_error("periodic pair joins cells %d and %d, which already share a face", i + 1, ja[k]); delete c; return FCP_EINVAL; }
+  }
+  c->h_kPN.resize((size_t)F + c->nper);
+  c->h_kNP.resize((size_t)F + c->nper);
+  for (int32_t l = 0; l < c->nper; ++l) {   // :262-293, periodic faces in patch order after the inner faces
+    const int32_t p = md->owner[F + plist[l]], q = pcell[plist[l]] + 1;
+    c->h_kPN[F + l] = (int32_t)(std::lower_bound(ja.begin() + (ia[p - 1] - 1), ja.begin() + (ia[p] - 1), q) - ja.begin()) + 1;
+    c->h_kNP[F + l] = (int32_t)(std::lower_bound(ja.begin() + (ia[q - 1] - 1), ja.begin() + (ia[q] - 1), p) - ja.begin()) + 1;
+  }
   parallel_for(F, [&](int64_t b, int64_t e) {
     for (int64_t f = b; f < e; ++f) {   // csr_to_k, utils.f90:96-147 (first match in the row)
       int32_t p = md->owner[f], q = md->neighbour[f];
@@ -179,6 +220,20 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
       kNP[f] = sellpos(q, c->h_kNP[f] - ia[q]);
     }
   });
+
+  if (c->nper) {   // SELL positions of a(owner(face), cell across the pair) for both faces of every pair
+    std::vector<int32_t> pslot(B, -1);
+    for (int32_t l = 0; l < c->nper; ++l) {
+      const int32_t b = plist[l], bt = pface[b] - F;
+      const int32_t p = md->owner[F + b] - 1, q = pcell[b];
+      pslot[b] = sellpos(p, c->h_kPN[F + l] - ia[p]);
+      pslot[bt] = sellpos(q, c->h_kNP[F + l] - ia[q]);
+    }
+    FCP_TRY(dev_upload(&c->per_cell, pcell.data(), (size_t)B));
+    FCP_TRY(dev_upload(&c->per_face, pface.data(), (size_t)B));
+    FCP_TRY(dev_upload(&c->per_slot, pslot.data(), (size_t)B));
+    FCP_TRY(dev_upload(&c->per_ord, pord.data(), (size_t)B));
+  }
 
   // ---- cell -> face gather lists, faces in ascending face index -------------------------------------------------
   {
@@ -271,6 +326,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   for (int i = 0; i < 4; ++i) cudaFree(c->Dmat[i]);
   cudaFree(c->flushbuf); cudaFree(c->d_mmpart); cudaFree(c->d_sum);
   cudaFree(c->d_oface); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
+  cudaFree(c->per_cell); cudaFree(c->per_face); cudaFree(c->per_slot); cudaFree(c->per_ord);
   sell_free(c->pat);
   krylov_ws_free(c->ws);
   if (c->t0) cudaEventDestroy(c->t0);
@@ -582,6 +638,8 @@ extern "C" int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double f
   if (!ctx) return FCP_EINVAL;
   FIELD(den, FCP_F_DEN); FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(p, FCP_F_P); FIELD(pp, FCP_F_PP);
   FIELD(g, FCP_F_DPDXI); FIELD(apu, FCP_F_APU); FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(fl, FCP_F_FLMASS);
+  const double *apv = nullptr, *apw = nullptr;
+  if (ctx->nper) { FIELD(x1, FCP_F_APV); FIELD(x2, FCP_F_APW); apv = x1; apw = x2; }   // facefluxmass2_periodic weights
   if (!const_mflux && ctx->has_outlet) {                           // adjustMassFlow, calcp_simple.f90:125
     FCP_TRY(ensure_outlet_list(ctx));
     FCP_TRY(fvm_adjust_mass_flow(ctx, ctx->nout, ctx->d_oface, den, u, v, w, fl, flomas));
@@ -591,7 +649,7 @@ extern "C" int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double f
     for (double *x : sc) FCP_TRY(comm_exchange(ctx, x, 1));
     FCP_TRY(comm_exchange(ctx, g, 3));
   }
-  AsmArgs args{den, u, v, w, p, g, apu, pp, u, v, w, a, su, fl};
+  AsmArgs args{den, u, v, w, p, g, apu, apv, apw, pp, u, v, w, a, su, fl};
   return fvm_assemble_pcorr(ctx, args);
 }
 
@@ -622,6 +680,7 @@ extern "C" int fcp_correct_simple(fcp_ctx *ctx, int pscheme, double urfp, int32_
   if (ctx->comm) FCP_TRY(comm_exchange(ctx, pp, 1));
   FCP_TRY(fvm_correct_flux(ctx, a, pp, fl));                                   // calcp_simple.f90:331-341
   if (ctx->npro) FCP_TRY(fvm_correct_flux_proc(ctx, a, pp, fl));
+  if (ctx->nper) FCP_TRY(fvm_correct_flux_periodic(ctx, a, pp, fl));                                // :350-373
   if (ctx->has_pressure_patch) FCP_TRY(fvm_correct_pressure_bnd(ctx, den, apu, pp, u, v, w, fl));   // :345-391
   const double *ppref = ctx->has_pressure_patch ? nullptr : pp + (pRefCell - 1);                    // :399-407
   if (ctx->comm && !ctx->has_pressure_patch) {
@@ -662,8 +721,6 @@ extern "C" int fcp_calcuvw(fcp_ctx *ctx, const fcp_uvw_params *prm, fcp_report *
   if (prm->tscheme < 0 || prm->tscheme > 3) { fcp_set_error("calcuvw: unknown time scheme %d (Crank-Nicolson is not built)", prm->tscheme); return FCP_EINVAL; }
   if (prm->tscheme && !(prm->timestep > 0.0)) { fcp_set_error("calcuvw: timestep must be positive"); return FCP_EINVAL; }
   for (int q = 0; q < 3; ++q) if (!(prm->urf[q] > 0.0)) { fcp_set_error("calcuvw: urfU(%d) must be positive", q + 1); return FCP_EINVAL; }
-  for (int32_t ib = 0; ib < ctx->nb; ++ib)
-    if (ctx->bctype[ib] == FCP_BC_PERIODIC) { fcp_set_error("calcuvw: periodic patches (velocity.f90:395-432) are not supported yet"); return FCP_ESTATE; }
   FCP_CUDA(cudaSetDevice(ctx->device));
   FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(p, FCP_F_P); FIELD(den, FCP_F_DEN); FIELD(vis, FCP_F_VIS); FIELD(visw, FCP_F_VISW);
   FIELD(fl, FCP_F_FLMASS); FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(sv, FCP_F_SV); FIELD(sw, FCP_F_SW);
@@ -698,19 +755,40 @@ extern "C" int fcp_calcuvw(fcp_ctx *ctx, const fcp_uvw_params *prm, fcp_report *
   return FCP_OK;
 }
 
+// constant_mass_flow_forcing   src/cappuccino/constant_mass_flow_forcing.f90 (called at calcp_simple.f90:468 / calcp_piso.f90:492)
+extern "C" int fcp_constant_mass_flow_forcing(fcp_ctx *ctx, double magUbar, double *gradPcmf, double *magUbarStar) {
+  if (!ctx || !gradPcmf) return FCP_EINVAL;
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(u, FCP_F_U); FIELD(apu, FCP_F_APU);
+  if (!ctx->d_sum) FCP_TRY(dev_alloc(&ctx->d_sum, 8));
+  FCP_TRY(fvm_cmf_forcing(ctx, magUbar, apu, u, ctx->d_sum));
+  double h[5];
+  FCP_CUDA(cudaMemcpyAsync(h, ctx->d_sum, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  FCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  *gradPcmf = *gradPcmf + h[4];                      // :33  gradPcmf = gradPcmf + gragPplus
+  if (magUbarStar) *magUbarStar = h[3];
+  return FCP_OK;
+}
+// updateBoundary(phi)   src/finiteVolume/boundary/updateBoundary.f90
+extern "C" int fcp_update_boundary(fcp_ctx *ctx, int field) {
+  if (!ctx) return FCP_EINVAL;
+  if (field < 0 || field >= FCP_F_COUNT || (field >= FCP_F_DUDXI && field <= FCP_F_H)) { fcp_set_error("fcp_update_boundary: field %d is not a scalar cell field", field); return FCP_EINVAL; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(phi, field);
+  return fvm_update_boundary(ctx, phi);
+}
+
 // calcp_piso   Pressure/calcp_piso.f90:81-489
 extern "C" int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_report *rep) {
   if (!ctx || !prm) return FCP_EINVAL;
   if (prm->ncorr < 1 || prm->npcor < 1) { fcp_set_error("calcp_piso: ncorr and npcor must be >= 1"); return FCP_EINVAL; }
   if (prm->pscheme < 0 || prm->pscheme > 2) { fcp_set_error("unknown pscheme %d", prm->pscheme); return FCP_EINVAL; }
-  for (int32_t ib = 0; ib < ctx->nb; ++ib)
-    if (ctx->bctype[ib] == FCP_BC_PERIODIC) { fcp_set_error("calcp_piso: periodic patches (calcp_piso.f90:242-295) are not supported yet"); return FCP_ESTATE; }
   FCP_CUDA(cudaSetDevice(ctx->device));
   FIELD(den, FCP_F_DEN); FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(p, FCP_F_P); FIELD(pp, FCP_F_PP);
   FIELD(g, FCP_F_DPDXI); FIELD(apu, FCP_F_APU); FIELD(apv, FCP_F_APV); FIELD(apw, FCP_F_APW); FIELD(a, FCP_F_A); FIELD(h, FCP_F_H);
   FIELD(su, FCP_F_SU); FIELD(sv, FCP_F_SV); FIELD(sw, FCP_F_SW); FIELD(fl, FCP_F_FLMASS);
   FIELD(rU, FCP_F_RU); FIELD(rV, FCP_F_RV); FIELD(rW, FCP_F_RW);
-  if (!ctx->d_sum) FCP_TRY(dev_alloc(&ctx->d_sum, 4));
+  if (!ctx->d_sum) FCP_TRY(dev_alloc(&ctx->d_sum, 8));
   double ncells = (double)ctx->n;
   if (ctx->comm) FCP_TRY(fcp_global_sum(ctx, &ncells));
   FCP_CUDA(cudaMemcpyAsync(h, a, sizeof(double) * (size_t)ctx->pat.nnzp, cudaMemcpyDeviceToDevice, ctx->stream));   // :81  h = a
@@ -726,7 +804,7 @@ extern "C" int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_repo
       for (double *x : sc) FCP_TRY(comm_exchange(ctx, x, 1));
       FCP_TRY(comm_exchange(ctx, g, 3));
     }
-    AsmArgs args{den, u, v, w, p, g, apu, pp, u, v, w, a, su, fl};
+    AsmArgs args{den, u, v, w, p, g, apu, apv, apw, pp, u, v, w, a, su, fl};
     FCP_TRY(fvm_assemble_pcorr(ctx, args, true));                                                                    // :140-297
     for (int ipcorr = 1; ipcorr <= prm->npcor; ++ipcorr) {                                                           // :308
       FCP_TRY(fcp_csrsolve(ctx, prm->solver, FCP_F_PP, FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel,
@@ -749,6 +827,7 @@ extern "C" int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_repo
     }
     CorrectArgs ca{u, v, w, nullptr, apu, apv, apw, 0.0, nullptr};
     FCP_TRY(gradp_impl(ctx, prm->pscheme, p, &ca));                                                                  // :425-431, :485
+    if (ctx->nper) FCP_TRY(fvm_correct_flux_periodic(ctx, a, p, fl));                                                // :441-460 (the whole pressure)
     if (ctx->has_pressure_patch) FCP_TRY(fvm_correct_pressure_bnd(ctx, den, apu, pp, u, v, w, fl));                  // :466-479
   }
   return FCP_OK;

@@ -205,7 +205,7 @@ struct fcp_ctx {
   double *Dmat[4] = {nullptr, nullptr, nullptr, nullptr};   // LSQ matrices per method (index FCP_GRAD_*); QR: [18][n]
   int32_t max_cell_faces = 0;                       // longest cell->face list (the QR gradient holds at most 6)
   double *d_mmpart = nullptr;                       // limiter: per-chunk {min,max} partials + the final pair
-  double *d_sum = nullptr;                          // [4] device scalar slot (calcp_piso pavg)
+  double *d_sum = nullptr;                          // [8] device scalar slots (calcp_piso pavg; constant_mass_flow_forcing sums)
   KrylovWS ws;
   FcpComm *comm = nullptr;
   Profiler prof;
@@ -218,6 +218,12 @@ struct fcp_ctx {
   int32_t *d_procface = nullptr;                    // [npro] 0-based face index of each process face (patch order)
   std::vector<int32_t> h_procface;
   double *d_ppref = nullptr;                        // [4] broadcast slot for pp(pRefCell)
+  // periodic pairs (sparse_matrix.f90:141-171): per BOUNDARY face, for the faces of a periodic patch and of its twin patch
+  int32_t nper = 0;                                 // numPeriodic: periodic faces, each pair counted once
+  int32_t *per_cell = nullptr;                      // [B] the cell across the pair (0-based), -1 for every other boundary face
+  int32_t *per_face = nullptr;                      // [B] the other face of the pair (0-based face index)
+  int32_t *per_slot = nullptr;                      // [B] SELL position of a(owner of this face, per_cell)
+  int32_t *per_ord = nullptr;                       // [B] 0-based ordinal of the pair inside its patch (quirk Q21: Df(i))
 };
 
 struct fcp_solver {
@@ -239,6 +245,7 @@ struct CorrectArgs {          // velocity / pressure correction fused into gradp
 };
 struct AsmArgs {
   const double *den, *u, *v, *w, *p, *dPdxi, *apu;
+  const double *apv, *apw;    // read on periodic faces only (facefluxmass2_periodic)
   double *pp;                 // boundary values of pp on pressure patches are zeroed
   double *ub, *vb, *wb;       // same arrays as u,v,w (boundary slots written on pressure patches)
   double *a, *su, *flmass;
@@ -253,6 +260,7 @@ int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso = false);
 int fvm_adjust_mass_flow(fcp_ctx *ctx, int32_t nout, const int32_t *d_oface, const double *den, double *u, double *v, double *w,
                          double *flmass, double flomas);
 int fvm_correct_flux(fcp_ctx *ctx, const double *a, const double *pp, double *flmass);
+int fvm_correct_flux_periodic(fcp_ctx *ctx, const double *a, const double *x, double *flmass);
 int fvm_correct_pressure_bnd(fcp_ctx *ctx, const double *den, const double *apu, const double *pp, double *u, double *v, double *w,
                              double *flmass);
 int fvm_nonorth(fcp_ctx *ctx, const double *den, const double *apu, const double *dPdxi, double *su, double *flmass);
@@ -265,6 +273,8 @@ int fvm_piso_hbya(fcp_ctx *ctx, const double *h, const double *rU, const double 
                   const double *apw, double *u, double *v, double *w, double *su, double *sv, double *sw);
 int fvm_sum(fcp_ctx *ctx, const double *x, double *d_out);
 int fvm_piso_pupdate(fcp_ctx *ctx, double ncells_global, double urfp, const double *d_sum, const double *pp, double *p);
+int fvm_cmf_forcing(fcp_ctx *ctx, double magUbar, const double *apu, double *u, double *d_sums);
+int fvm_update_boundary(fcp_ctx *ctx, double *phi);
 int fvm_piso_fluxmc(fcp_ctx *ctx, const double *den, const double *apu, const double *dPdxi, double *su);
 
 // ---- fvm_uvw.cu ---------------------------------------------------------------------------------

@@ -627,6 +627,32 @@ __global__ void __launch_bounds__(FCP_TPB, (W >= 3 ? 1 : W == 2 ? 2 : 3)) k_asse
             dg = dg - cap;
             s = s - flm;
             if (!PISO) g.pp[o] = 0.0;
+          } else if (m.per_cell && (type == FCP_BC_PERIODIC || type == FCP_BC_EMPTY) && m.per_cell[f - m.F] >= 0) {
+            // ---- facefluxmass2_periodic, faceflux_mass.f90:313-384 (calcp_simple.f90:185-228, calcp_piso.f90:248-293): evaluated
+            // in the orientation of the PERIODIC face fp (P = its owner, N = the owner of the twin face) on both sides of the pair
+            const int32_t b = f - m.F, q = m.per_cell[b];
+            const bool own = type == FCP_BC_PERIODIC;
+            const int32_t fp = own ? f : m.per_face[b];
+            const int32_t cP = own ? c : q, cN = own ? q : c;
+            const double ax = m.arx[fp], ay = m.ary[fp], az = m.arz[fp];
+            const double fxn = 0.5, fxp = 1.0 - 0.5;
+            const double xpn = 2 * (m.xf[fp] - m.xc[cP]), ypn = 2 * (m.yf[fp] - m.yc[cP]), zpn = 2 * (m.zf[fp] - m.zc[cP]);
+            const double apuP = g.apu[cP], apuN = g.apu[cN];
+            const double dene = g.den[cP] * fxp + g.den[cN] * fxn;
+            double Kj = m.vol[cP] * apuP * fxp + m.vol[cN] * apuN * fxn;
+            const double cap = -dene * Kj * m.Df[m.per_ord[b]];      // quirk Q21: Df(i), i = the face's ordinal inside its patch
+            Kj = (apuP + apuN + FCP_SMALL);
+            const double ui = (g.u[cP] * apuN + g.u[cN] * apuP) / Kj;
+            const double vi = (g.v[cP] * g.apv[cN] + g.v[cN] * g.apv[cP]) / Kj;
+            const double wi = (g.w[cP] * g.apw[cN] + g.w[cN] * g.apw[cP]) / Kj;
+            const double dpxi = (g.dPdxi[3 * (int64_t)cN] * fxp + g.dPdxi[3 * (int64_t)cP] * fxn) * xpn;
+            const double dpyi = (g.dPdxi[3 * (int64_t)cN + 1] * fxp + g.dPdxi[3 * (int64_t)cP + 1] * fxn) * ypn;
+            const double dpzi = (g.dPdxi[3 * (int64_t)cN + 2] * fxp + g.dPdxi[3 * (int64_t)cP + 2] * fxn) * zpn;
+            const double flm = dene * (ui * ax + vi * ay + wi * az) + cap * (g.p[cN] - g.p[cP] - dpxi - dpyi - dpzi);
+            g.a[m.per_slot[b]] = cap;
+            dg = dg - cap;
+            if (own) { s = s - flm; g.flmass[fp] = flm; }
+            else     { s = s + flm; }
           }
         }
       }
@@ -670,6 +696,17 @@ __global__ void __launch_bounds__(FCP_TPB) k_correct_flux(int32_t F, const int32
                                                            const int32_t *__restrict__ kPN, const double *__restrict__ a,
                                                            const double *__restrict__ pp, double *__restrict__ flmass) {
   FCP_CELL_LOOP(f, F) { flmass[f] = flmass[f] + a[kPN[f]] * (pp[neigh[f]] - pp[owner[f]]); }
+}
+// periodic pairs  calcp_simple.f90:350-373 / calcp_piso.f90:441-460 : flmass(if) += a(k) (x(ijn) - x(ijp)), flmass(iftwin) = flmass(if)
+__global__ void __launch_bounds__(FCP_TPB) k_correct_flux_periodic(MeshView m, const int32_t *__restrict__ bftype, const double *__restrict__ a,
+                                                                    const double *__restrict__ x, double *__restrict__ flmass) {
+  FCP_CELL_LOOP(i, m.B) {
+    if (bftype[i] != FCP_BC_PERIODIC) continue;
+    const int32_t f = m.F + i;
+    const double fl = flmass[f] + a[m.per_slot[i]] * (x[m.per_cell[i]] - x[m.owner[f]]);
+    flmass[f] = fl;
+    flmass[m.per_face[i]] = fl;
+  }
 }
 // pressure patches  calcp_simple.f90:345-391 + facefluxmassCorrPressBnd faceflux_mass.f90:699-762
 __global__ void __launch_bounds__(FCP_TPB) k_correct_pressure_bnd(MeshView m, const int32_t *__restrict__ bftype, const double *__restrict__ den,
@@ -815,6 +852,13 @@ int fvm_adjust_mass_flow(fcp_ctx *ctx, int32_t nout, const int32_t *d_oface, con
 int fvm_correct_flux(fcp_ctx *ctx, const double *a, const double *pp, double *flmass) {
   if (ctx->F == 0) return FCP_OK;
   FCP_PROF(&ctx->prof, FCP_K_CORRECT_FLUX, ctx->stream, (k_correct_flux<<<FCP_GRID(ctx->F)>>>(ctx->F, ctx->owner, ctx->neigh, ctx->kPN, a, pp, flmass)));
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_correct_flux_periodic(fcp_ctx *ctx, const double *a, const double *x, double *flmass) {
+  if (!ctx->nper) return FCP_OK;
+  k_correct_flux_periodic<<<FCP_GRID(ctx->B)>>>(fcp_mesh_view(ctx), ctx->bftype, a, x, flmass);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

@@ -364,6 +364,65 @@ int fvm_sum(fcp_ctx *ctx, const double *x, double *d_out) {
   FCP_CHECK_LAUNCH();
   return FCP_OK;
 }
+// ---- constant_mass_flow_forcing, src/cappuccino/constant_mass_flow_forcing.f90 (+ volumeWeightedAverage, fieldManipulation.f90:41-70)
+// sums: vol*U, vol, vol*APU with the fixed tree; out[0..2]
+__global__ void __launch_bounds__(FCP_TPB) k_cmf_sums(int32_t n, const double *__restrict__ vol, const double *__restrict__ u, const double *__restrict__ apu,
+                                                       double *partials, int stride, unsigned int *counter, double *out) {
+  double s[3] = {0.0, 0.0, 0.0};
+  FCP_CELL_LOOP(c, n) {
+    const double vc = vol[c];
+    s[0] = s[0] + (vc * u[c]);
+    s[1] = s[1] + vc;
+    s[2] = s[2] + (vc * apu[c]);
+  }
+  double total[3];
+  if (fcp_grid_reduce<3>(s, partials, stride, counter, total))
+    if (threadIdx.x == 0) { out[0] = total[0]; out[1] = total[1]; out[2] = total[2]; }
+}
+// magUbarStar = sum(vol U)/sum(vol); rUAw = sum(vol APU)/sum(vol); gragPplus = (magUbar - magUbarStar)/rUAw; U += APU*gragPplus.
+// Every thread recomputes the three scalars from the sums (same operations, same bits); thread 0 of CTA 0 publishes them in out[3], out[4].
+__global__ void __launch_bounds__(FCP_TPB) k_cmf_apply(int32_t n, double magUbar, double *sums, const double *__restrict__ apu, double *__restrict__ u) {
+  const double ustar = sums[0] / sums[1];
+  const double ruaw = sums[2] / sums[1];
+  const double gplus = (magUbar - ustar) / ruaw;
+  FCP_CELL_LOOP(c, n) { u[c] = u[c] + apu[c] * gplus; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { sums[3] = ustar; sums[4] = gplus; }
+}
+int fvm_cmf_forcing(fcp_ctx *ctx, double magUbar, const double *apu, double *u, double *d_sums /* [8] */) {
+  FCP_TRY(krylov_ws_alloc(ctx->ws, ctx->pat.n, ctx->pat.ncols));
+  k_cmf_sums<<<std::max(fcp_nchunks(ctx->n), 1), FCP_TPB, 0, ctx->stream>>>(ctx->n, ctx->vol, u, apu, ctx->ws.partials, ctx->ws.maxchunks, ctx->ws.counter, d_sums);
+  FCP_LAUNCHED();
+  if (ctx->comm) FCP_TRY(comm_allgather_sum(ctx->comm, d_sums, 3, ctx->stream));
+  k_cmf_apply<<<std::max(fcp_nchunks(ctx->n), 1), FCP_TPB, 0, ctx->stream>>>(ctx->n, magUbar, d_sums, apu, u);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+// ---- updateBoundary(phi), boundary/updateBoundary.f90 (boundary-face parallel; a periodic face and its twin get the same mean)
+__global__ void __launch_bounds__(FCP_TPB) k_update_boundary(MeshView m, const int32_t *__restrict__ bftype, double *phi) {
+  FCP_CELL_LOOP(i, m.B) {
+    const int t = bftype[i];
+    const int32_t ijp = m.owner[m.F + i], ijb = m.n + i;
+    // the reference walks the patches in order: a twin ('empty') patch listed BEFORE its periodic patch first copies the owner value and
+    // is then overwritten with the pair's mean (:62-66); listed AFTER it, its own copy is the last write and stays
+    if (t == FCP_BC_PERIODIC) {
+      const double v = 0.5 * (phi[ijp] + phi[m.per_cell[i]]);
+      phi[ijb] = v;
+      if (m.per_face[i] < m.F + i) phi[m.n + (m.per_face[i] - m.F)] = v;
+    } else if (t == FCP_BC_EMPTY && m.per_cell && m.per_cell[i] >= 0) {
+      if (m.per_face[i] < m.F + i) phi[ijb] = phi[ijp];
+    } else if (t == FCP_BC_OUTLET || t == FCP_BC_SYMMETRY || t == FCP_BC_PRESSURE || t == FCP_BC_EMPTY) {
+      phi[ijb] = phi[ijp];
+    }
+  }
+}
+int fvm_update_boundary(fcp_ctx *ctx, double *phi) {
+  if (ctx->B == 0) return FCP_OK;
+  k_update_boundary<<<FCP_GRID(ctx->B)>>>(fcp_mesh_view(ctx), ctx->bftype, phi);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
 int fvm_piso_pupdate(fcp_ctx *ctx, double ncells_global, double urfp, const double *d_sum, const double *pp, double *p) {
   if (ctx->n == 0) return FCP_OK;
   k_piso_pupdate<<<FCP_GRID(ctx->n)>>>(ctx->n, ncells_global, urfp, d_sum, pp, p);

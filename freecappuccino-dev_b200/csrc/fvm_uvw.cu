@@ -6,7 +6,7 @@
 //   k_uvw_diag         diagonal, reciprocal diagonal apu/apv/apw and under-relaxation :602-620, :656-668, :717-730
 // One thread owns one cell and walks its faces in ascending index; every face quantity is evaluated in the face's own
 // orientation (P = owner, N = neighbour), so both sides see the same bits and the per-cell sums round like the
-// reference's sequential loops.  Not built: Crank-Nicolson, buoyancy, MHD, periodic patches (fcp_calcuvw refuses them).
+// reference's sequential loops.  Periodic patches: facefluxuvw_periodic on both cells of a pair.  Not built: Crank-Nicolson, buoyancy, MHD.
 #include "fcp_internal.h"
 #include "fvm_common.cuh"
 
@@ -201,6 +201,44 @@ __global__ void __launch_bounds__(FCP_TPB) k_uvw_assemble(MeshView m, UvwArgs g)
           s1 = s1 - cb * ub + sup;
           s2 = s2 - cb * vb + svp;
           s3 = s3 - cb * wb + swp;
+        } else if (m.per_cell && (type == FCP_BC_PERIODIC || type == FCP_BC_EMPTY) && m.per_cell[f - m.F] >= 0) {
+          // ---- facefluxuvw_periodic, velocity.f90:393-432 + :1038-1180: evaluated in the orientation of the PERIODIC face fp
+          // (P = its owner, N = the owner of the twin face) on both sides of the pair
+          const int32_t b = f - m.F, q = m.per_cell[b];
+          const bool own = type == FCP_BC_PERIODIC;
+          const int32_t fp = own ? f : m.per_face[b];
+          CellState ot;
+          load_cell(ot, m, g, q);
+          const CellState &P = own ? me : ot, &N = own ? ot : me;
+          const double ax = m.arx[fp], ay = m.ary[fp], az = m.arz[fp];
+          const double fxn = 0.5, fxp = fxn;
+          const double xpn = 2 * (m.xf[fp] - P.x), ypn = 2 * (m.yf[fp] - P.y), zpn = 2 * (m.zf[fp] - P.z);
+          const double dpn = sqrt(xpn * xpn + ypn * ypn + zpn * zpn);
+          const double are = sqrt(ax * ax + ay * ay + az * az);
+          const double game = P.vis * fxp + N.vis * fxn;
+          const double de = game * (ax * ax + ay * ay + az * az) / (xpn * ax + ypn * ay + zpn * az);
+          const double flomass = g.flmass[fp];
+          const double ce = fmin(flomass, 0.0), cp = fmax(flomass, 0.0);
+          const double can = -de + ce, cap = -de - cp;
+          const double duxi = P.gu[0] * fxp + N.gu[0] * fxn, duyi = P.gu[1] * fxp + N.gu[1] * fxn, duzi = P.gu[2] * fxp + N.gu[2] * fxn;
+          const double dvxi = P.gv[0] * fxp + N.gv[0] * fxn, dvyi = P.gv[1] * fxp + N.gv[1] * fxn, dvzi = P.gv[2] * fxp + N.gv[2] * fxn;
+          const double dwxi = P.gw[0] * fxp + N.gw[0] * fxn, dwyi = P.gw[1] * fxp + N.gw[1] * fxn, dwzi = P.gw[2] * fxp + N.gw[2] * fxn;
+          const double fdue = game * ((duxi + duxi) * ax + (duyi + dvxi) * ay + (duzi + dwxi) * az);
+          const double fdve = game * ((duyi + dvxi) * ax + (dvyi + dvyi) * ay + (dvzi + dwyi) * az);
+          const double fdwe = game * ((duzi + dwxi) * ax + (dwyi + dvzi) * ay + (dwzi + dwzi) * az);
+          const double fdui = game * are / dpn * (duxi * xpn + duyi * ypn + duzi * zpn);
+          const double fdvi = game * are / dpn * (dvxi * xpn + dvyi * ypn + dvzi * zpn);
+          const double fdwi = game * are / dpn * (dwxi * xpn + dwyi * ypn + dwzi * zpn);
+          const double fuuds = cp * P.u + ce * N.u, fvuds = cp * P.v + ce * N.v, fwuds = cp * P.w + ce * N.w;
+          double ue, ve, we;                                   // face_value_cds with lambda = half, interpolation.f90:116-157
+          if (flomass >= 0.0) { ue = P.u + (N.u - P.u) * fxp; ve = P.v + (N.v - P.v) * fxp; we = P.w + (N.w - P.w) * fxp; }
+          else                { ue = N.u + (P.u - N.u) * fxn; ve = N.v + (P.v - N.v) * fxn; we = N.w + (P.w - N.w) * fxn; }
+          const double fuhigh = flomass * ue, fvhigh = flomass * ve, fwhigh = flomass * we;
+          const double sup = -g.gds * (fuhigh - fuuds) + fdue - fdui;
+          const double svp = -g.gds * (fvhigh - fvuds) + fdve - fdvi;
+          const double swp = -g.gds * (fwhigh - fwuds) + fdwe - fdwi;
+          if (own) { g.a[m.per_slot[b]] = can; s1 = s1 + sup; s2 = s2 + svp; s3 = s3 + swp; }   // a(icell,jcell) = can ; su(ijp) += sup
+          else     { g.a[m.per_slot[b]] = cap; s1 = s1 - sup; s2 = s2 - svp; s3 = s3 - swp; }   // a(jcell,icell) = cap ; su(ijn) -= sup
         } else if (type == FCP_BC_SYMMETRY) {
           // :361-392 ; quirk Q7: vis(inp) with the stale inp = numCells+1 -> the viscosity of the first boundary slot
           const double are = sqrt(arx * arx + ary * ary + arz * arz), arer = 1.0 / are;

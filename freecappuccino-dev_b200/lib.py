@@ -46,7 +46,7 @@ class MeshDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("numCells", "numInnerFaces", "numBoundaryFaces", "numBoundaries")] + \
                [("owner", _pi), ("neighbour", _pi)] + \
                [(n, _pd) for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol")] + \
-               [(n, _pi) for n in ("bctype", "nfaces", "startFace")]
+               [(n, _pi) for n in ("bctype", "nfaces", "startFace", "startFaceTwin")]
 
 
 class Report(C.Structure):
@@ -135,6 +135,8 @@ def lib():
     L.fcp_slope_limiter.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.fcp_grad_opt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.fcp_calcp_piso.argtypes = [vp, C.POINTER(PisoParams), C.POINTER(Report)]
+    L.fcp_constant_mass_flow_forcing.argtypes = [vp, C.c_double, _pd, _pd]
+    L.fcp_update_boundary.argtypes = [vp, C.c_int]
     L.fcp_calcuvw.argtypes = [vp, C.POINTER(UvwParams), C.POINTER(Report)]
     L.fcp_laplacian.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_gradp_and_sources.argtypes = [vp, C.c_int, C.c_int]
@@ -199,6 +201,10 @@ class Context:
         for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol"):
             self._keep[n] = np.ascontiguousarray(getattr(mesh, n), dtype=np.float64)
             setattr(md, n, _d(self._keep[n]))
+        if getattr(mesh, "startFaceTwin", None) is not None:       # periodic pairs (geometry.f90:251-257)
+            self._keep["startFaceTwin"] = np.ascontiguousarray(mesh.startFaceTwin, dtype=np.int32)
+            md.startFaceTwin = _i(self._keep["startFaceTwin"])
+        self.numPeriodic = int(getattr(mesh, "numPeriodic", 0))
         self.h = C.c_void_p()
         check(lib().fcp_ctx_create(C.byref(md), device, C.byref(self.h)), "fcp_ctx_create")
         self._keep.clear()
@@ -222,7 +228,7 @@ class Context:
         ia = np.zeros(self.numCells + 1, np.int32)
         ja = np.zeros(self.nnz, np.int32)
         diag = np.zeros(self.numCells, np.int32)
-        Fi = self.mesh.numInnerFaces
+        Fi = self.mesh.numInnerFaces + self.numPeriodic      # sparse_matrix.f90:246-247
         kpn = np.zeros(Fi, np.int32)
         knp = np.zeros(Fi, np.int32)
         check(lib().fcp_csr_pattern(self.h, _i(ia), _i(ja), _i(diag), _i(kpn), _i(knp)))
@@ -291,6 +297,17 @@ class Context:
         reps = (Report * (ncorr * npcor))()
         check(lib().fcp_calcp_piso(self.h, C.byref(prm), reps), "fcp_calcp_piso")
         return [reps[i] for i in range(ncorr * npcor)]
+
+    def constant_mass_flow_forcing(self, magUbar: float, gradPcmf: float):
+        """constant_mass_flow_forcing.f90: corrects U on the device; returns (new gradPcmf, uncorrected bulk velocity)."""
+        g = C.c_double(gradPcmf)
+        ustar = C.c_double(0.0)
+        check(lib().fcp_constant_mass_flow_forcing(self.h, magUbar, C.byref(g), C.byref(ustar)), "fcp_constant_mass_flow_forcing")
+        return g.value, ustar.value
+
+    def update_boundary(self, field):
+        """updateBoundary(phi), boundary/updateBoundary.f90."""
+        check(lib().fcp_update_boundary(self.h, field_id(field)), "fcp_update_boundary")
 
     def calcuvw(self, solver="bicgstab", maxiter=5, tol_abs=1e-13, tol_rel=0.025, urf=(0.8, 0.8, 0.8), gds=1.0, cscheme="cds", grad_method="gauss",
                 limiter="none", pscheme="linear", tscheme="steady", timestep=0.0, piso=False, const_mflux=False, gradPcmf=0.0, viscos=0.0):

@@ -56,6 +56,8 @@ class Mesh:
     fpro: Optional[np.ndarray] = None         # [npro] face interpolation factor on halo faces
     cell_global: Optional[np.ndarray] = None  # int64 [numCells] 0-based global cell id
     face_global: Optional[np.ndarray] = None  # int64 [numFaces] 0-based global face id
+    # periodic pairs (geometry.f90:82,251-257): a 'periodic' patch names its twin (listed as 'empty') by the twin's startFace
+    startFaceTwin: Optional[np.ndarray] = None  # int32 [numBoundaries], 0-based offset like startFace; -1 for other patches
 
     @property
     def numFaces(self) -> int:
@@ -73,6 +75,17 @@ class Mesh:
     def iBndValueStart(self) -> np.ndarray:
         # geometry.f90:282-290  iBndValueStart = numCells + (startFace - numInnerFaces)
         return (self.numCells + self.startFace - self.numInnerFaces).astype(np.int32)
+
+    @property
+    def numPeriodic(self) -> int:
+        """geometry.f90:253  number of periodic faces, each pair counted once."""
+        return int(self.nfaces[self.bctype == BC_PERIODIC].sum())
+
+    def twin_start(self) -> np.ndarray:
+        """startFaceTwin per patch (-1 where the patch is not periodic)."""
+        if self.startFaceTwin is None:
+            return np.full(self.numBoundaries, -1, dtype=np.int32)
+        return np.ascontiguousarray(self.startFaceTwin, dtype=np.int32)
 
     @property
     def npro(self) -> int:
@@ -160,11 +173,14 @@ def mesh_from_topology(points, face_nodes, face_nnodes, owner, neighbour, numCel
     neighbour = np.ascontiguousarray(neighbour, dtype=np.int32)
     g = geometry if geometry is not None else compute_geometry(points, face_nodes, face_nnodes, owner, neighbour, numCells)
     F = neighbour.shape[0]
-    return Mesh(numCells=numCells, numInnerFaces=F, numBoundaryFaces=owner.shape[0] - F, owner=owner, neighbour=neighbour,
+    mesh = Mesh(numCells=numCells, numInnerFaces=F, numBoundaryFaces=owner.shape[0] - F, owner=owner, neighbour=neighbour,
                 bcname=[p[0] for p in patches], bctype=np.array([BC_CODE[p[1]] for p in patches], dtype=np.int32),
                 nfaces=np.array([p[2] for p in patches], dtype=np.int32),
                 startFace=np.array([p[3] for p in patches], dtype=np.int32),
                 points=points, face_nodes=face_nodes, face_nnodes=face_nnodes, **g)
+    if any(len(p) > 4 for p in patches):
+        mesh.startFaceTwin = np.array([p[4] if len(p) > 4 else -1 for p in patches], dtype=np.int32)
+    return mesh
 
 
 # ---------------------------------------------------------------------------------------------
@@ -278,7 +294,49 @@ def hex_mesh(xs: np.ndarray, ys: np.ndarray, zs: np.ndarray,
     owner = (np.concatenate([in_own] + bown) + 1).astype(np.int32)
     neighbour = (in_nb + 1).astype(np.int32)
     face_nnodes = np.full(owner.shape[0], 4, dtype=np.int32)
-    return mesh_from_topology(points, face_nodes, face_nnodes, owner, neighbour, nx * ny * nz, patches)
+    mesh = mesh_from_topology(points, face_nodes, face_nnodes, owner, neighbour, nx * ny * nz, patches)
+    # periodic pairs: the 'periodic' patch names the opposite patch (which the boundary file lists as 'empty',
+    # examples/channel395/README.md) through startFaceTwin; faces of opposite patches are generated in the same order
+    opposite = dict(top="bottom", bottom="top", left="right", right="left", back="front", front="back")
+    if any(t == "periodic" for t in types.values()):
+        names = [p[0] for p in patches]
+        twin = np.full(len(patches), -1, dtype=np.int32)
+        for ib, (name, typ, _, _) in enumerate(patches):
+            if typ == "periodic":
+                it = names.index(opposite[name])
+                assert patches[it][1] == "empty", "the twin of a periodic patch is listed as 'empty'"
+                twin[ib] = patches[it][3]
+        mesh.startFaceTwin = twin
+    return mesh
+
+
+def face_mapping(mesh: Mesh) -> Mesh:
+    """geometry.f90:1848-1997 (quirk Q18): pair every face of a periodic patch with the twin-patch face whose OWNER CELL
+    CENTRE is nearest (L1 distance, first minimum) to the periodic face's centre, then overwrite the twin patch's `owner`
+    and permute its xf,yf,zf,arx,ary,arz in place so that twin face i pairs with face i.  Returns the same mesh object."""
+    if mesh.startFaceTwin is None:
+        return mesh
+    n = mesh.numCells
+    for ib in range(mesh.numBoundaries):
+        if mesh.bctype[ib] != BC_PERIODIC:
+            continue
+        nf, s, st = int(mesh.nfaces[ib]), int(mesh.startFace[ib]), int(mesh.startFaceTwin[ib])
+        f = np.arange(s, s + nf)
+        cand = mesh.owner[st:st + nf].astype(np.int64) - 1
+        tmp = np.empty(nf, dtype=np.int32)
+        itmp = np.empty(nf, dtype=np.int64)
+        for b in range(0, nf, 512):
+            fb = f[b:b + 512]
+            d = (np.abs(mesh.xf[fb, None] - mesh.xc[None, cand]) + np.abs(mesh.yf[fb, None] - mesh.yc[None, cand])
+                 + np.abs(mesh.zf[fb, None] - mesh.zc[None, cand]))
+            k = np.argmin(d, axis=1)          # first minimum, like the strict `<` of the reference loop
+            itmp[b:b + 512] = k
+            tmp[b:b + 512] = cand[k] + 1
+        mesh.owner[st:st + nf] = tmp
+        for arr in (mesh.xf, mesh.yf, mesh.zf, mesh.arx, mesh.ary, mesh.arz):
+            arr[st:st + nf] = arr[st + itmp].copy()
+    assert n == mesh.numCells
+    return mesh
 
 
 def cavity_mesh(n: int, nz: Optional[int] = None, length: float = 1.0, bump: float = 1.0, distort: float = 0.0,
@@ -352,7 +410,10 @@ def read_boundary_simplified(path: str) -> List[Tuple[str, str, int, int]]:
             t = line.split()
             if not t or t[0].startswith("#"):
                 continue
-            out.append((t[0], t[1], int(t[2]), int(t[3])))
+            if t[1] == "periodic":        # geometry.f90:251-257: a 5th integer, the startFace of the twin patch
+                out.append((t[0], t[1], int(t[2]), int(t[3]), int(t[4])))
+            else:
+                out.append((t[0], t[1], int(t[2]), int(t[3])))
     return out
 
 
@@ -381,7 +442,7 @@ def read_polymesh_openfoam(dirname: str) -> Mesh:
         fn[r, : len(ids)] = ids
     numCells = int(mnote.group(1)) if mnote else int(own.max()) + 1
     patches = read_boundary_simplified(os.path.join(dirname, "boundary"))
-    return mesh_from_topology(pts, fn, fnn, (own + 1).astype(np.int32), (nb + 1).astype(np.int32), numCells, patches)
+    return face_mapping(mesh_from_topology(pts, fn, fnn, (own + 1).astype(np.int32), (nb + 1).astype(np.int32), numCells, patches))   # geometry.f90:110
 
 
 def read_polymesh_native(dirname: str) -> Mesh:
@@ -404,7 +465,7 @@ def read_polymesh_native(dirname: str) -> Mesh:
     for r, row in enumerate(rows):
         fn[r, : row[0]] = row[1: 1 + row[0]]
     patches = read_boundary_simplified(os.path.join(dirname, "boundary"))
-    return mesh_from_topology(pts, fn, fnn, own.astype(np.int32), nb.astype(np.int32), numCells, patches)
+    return face_mapping(mesh_from_topology(pts, fn, fnn, own.astype(np.int32), nb.astype(np.int32), numCells, patches))   # geometry.f90:110
 
 
 def write_polymesh_native(mesh: Mesh, dirname: str) -> None:
@@ -422,7 +483,8 @@ def write_polymesh_native(mesh: Mesh, dirname: str) -> None:
     with open(os.path.join(dirname, "boundary"), "w") as fh:
         fh.write("# name type nFaces startFace\n")
         for ib in range(mesh.numBoundaries):
-            fh.write(f"{mesh.bcname[ib]} {BC_NAMES[mesh.bctype[ib]]} {mesh.nfaces[ib]} {mesh.startFace[ib]}\n")
+            twin = f" {mesh.startFaceTwin[ib]}" if mesh.bctype[ib] == BC_PERIODIC else ""
+            fh.write(f"{mesh.bcname[ib]} {BC_NAMES[mesh.bctype[ib]]} {mesh.nfaces[ib]} {mesh.startFace[ib]}{twin}\n")
 
 
 # ---------------------------------------------------------------------------------------------

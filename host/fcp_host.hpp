@@ -20,6 +20,8 @@ typedef double dp;   // types.f90:6
 namespace geometry {
 inline int numCells = 0, numInnerFaces = 0, numBoundaryFaces = 0, numFaces = 0, numTotal = 0, numBoundaries = 0;
 inline std::vector<int32_t> owner, neighbour, nfaces, startFace, iBndValueStart, bctype;
+inline std::vector<int32_t> startFaceTwin;   // per patch (-1 unless periodic); empty = no periodic patch (geometry.f90:82 indexes it by iPer)
+inline int numPeriodic = 0;
 inline std::vector<dp> arx, ary, arz, xf, yf, zf, facint, Df, xc, yc, zc, vol;
 }
 // ---- module sparse_matrix (src/sparseMatrix/sparse_matrix.f90:20-40) -----------------------------------------------------
@@ -87,12 +89,13 @@ inline void create_CSR_matrix(int device = 0) {
   md.arx = arx.data(); md.ary = ary.data(); md.arz = arz.data(); md.xf = xf.data(); md.yf = yf.data(); md.zf = zf.data();
   md.facint = facint.data(); md.Df = Df.data(); md.xc = xc.data(); md.yc = yc.data(); md.zc = zc.data(); md.vol = vol.data();
   md.bctype = bctype.data(); md.nfaces = nfaces.data(); md.startFace = startFace.data();
+  md.startFaceTwin = startFaceTwin.empty() ? nullptr : startFaceTwin.data();
   check(fcp_ctx_create(&md, device, &ctx), "fcp_ctx_create");
   int32_t n, nt, nf, nz, npro;
   check(fcp_ctx_sizes(ctx, &n, &nt, &nf, &nz, &npro), "fcp_ctx_sizes");
   nnz = nz;
   ia.resize(n + 1); ja.resize(nnz); diag.resize(n);
-  icell_jcell_csr_index.resize(numInnerFaces); jcell_icell_csr_index.resize(numInnerFaces);
+  icell_jcell_csr_index.resize(numInnerFaces + numPeriodic); jcell_icell_csr_index.resize(numInnerFaces + numPeriodic);   // sparse_matrix.f90:246-247
   check(fcp_csr_pattern(ctx, ia.data(), ja.data(), diag.data(), icell_jcell_csr_index.data(), jcell_icell_csr_index.data()), "fcp_csr_pattern");
   a.assign(nnz, 0.0);
   for (auto *vec : {&su, &sv, &sw, &apu, &apv, &apw}) vec->assign(numCells, 0.0);   // sparse_matrix.f90:215-246

@@ -84,6 +84,9 @@ typedef struct {
   const int32_t *bctype;      /* [numBoundaries] FCP_BC_* */
   const int32_t *nfaces;      /* [numBoundaries] */
   const int32_t *startFace;   /* [numBoundaries] 0-based offset of the patch's first face (boundary file, Appendix D) */
+  const int32_t *startFaceTwin; /* [numBoundaries] or NULL: for FCP_BC_PERIODIC patches the startFace of the twin patch (listed as
+                               * FCP_BC_EMPTY, same face count, faces already paired by face_mapping, geometry.f90:82,251-257,1848-1997);
+                               * ignored for the other patch types.  NULL = the mesh has no periodic patch. */
 } fcp_mesh_desc;
 
 /* the numbers the reference prints in its solver report line, linear_solvers.f90:354-355,540-541,781-782 */
@@ -106,8 +109,10 @@ int64_t fcp_launch_count(void);
 int fcp_ctx_create(const fcp_mesh_desc *mesh, int device, fcp_ctx **out);
 int fcp_ctx_destroy(fcp_ctx *ctx);
 int fcp_ctx_sizes(const fcp_ctx *ctx, int32_t *numCells, int32_t *numTotal, int32_t *numFaces, int32_t *nnz, int32_t *npro);
-/* ia(numCells+1), ja(nnz), diag(numCells), icell_jcell_csr_index(numInnerFaces), jcell_icell_csr_index(numInnerFaces);
- * any pointer may be NULL (sparse_matrix.f90:183-202, 251-260) */
+/* ia(numCells+1), ja(nnz), diag(numCells), icell_jcell_csr_index(numInnerFaces+numPeriodic), jcell_icell_csr_index(same);
+ * any pointer may be NULL (sparse_matrix.f90:183-202, 251-293).  nnz = numCells + 2 (numInnerFaces + numPeriodic): every
+ * periodic face adds the twin entries (owner(face), owner(twin face)) and its transpose (:141-171); a periodic pair that joins
+ * two cells which already share an inner face is refused (the reference would silently alias the two coefficients). */
 int fcp_csr_pattern(const fcp_ctx *ctx, int32_t *ia, int32_t *ja, int32_t *diag, int32_t *icell_jcell, int32_t *jcell_icell);
 int fcp_sync(fcp_ctx *ctx);
 
@@ -184,8 +189,17 @@ typedef struct {
 /* one whole calcp_piso   Pressure/calcp_piso.f90:81-489 (+ facefluxmass_piso faceflux_mass.f90:389-459, fluxmc :564-647).
  * On entry FCP_F_A holds the momentum coefficients (copied to FCP_F_H like `h = a`), FCP_F_RU/RV/RW the momentum
  * right-hand sides, FCP_F_APU/APV/APW the reciprocal diagonals.  rep[(icorr-1)*npcor + ipcorr-1].
- * Periodic patches (:242-295) are not supported yet: FCP_ESTATE. */
+ * Periodic patches: :248-293 (facefluxmass2_periodic) and :435-460; H(U) runs over the inner faces only, as in the reference. */
 int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_report *rep);
+
+/* constant_mass_flow_forcing   src/cappuccino/constant_mass_flow_forcing.f90 (the caller runs it after calcp_simple / calcp_piso when
+ * const_mflux, calcp_simple.f90:468, calcp_piso.f90:492): magUbarStar = volume-weighted mean of U, rUAw = that of APU,
+ * gragPplus = (magUbar - magUbarStar)/rUAw; U(1:numCells) += APU*gragPplus; *gradPcmf += gragPplus.  The two sums follow the
+ * library's fixed reduction tree (the reference adds cell by cell), so the result agrees with the reference to rounding. */
+int fcp_constant_mass_flow_forcing(fcp_ctx *ctx, double magUbar, double *gradPcmf, double *magUbarStar /* may be NULL */);
+/* updateBoundary(phi)   src/finiteVolume/boundary/updateBoundary.f90: outlet / symmetry / pressure / empty patches copy the owner
+ * value into the boundary slot, a periodic face and its twin take the mean of the two cells across the pair */
+int fcp_update_boundary(fcp_ctx *ctx, int field);
 
 /* cSchemeU of face_value, interpolation.f90:28-113 and :596-640 (flux limiters in source order) */
 enum { FCP_CS_CDS = 0, FCP_CS_CENTRAL, FCP_CS_LINEAR_UPWIND, FCP_CS_KAPPA, FCP_CS_MUSCL, FCP_CS_UMIST, FCP_CS_KOREN, FCP_CS_SMART,
@@ -210,7 +224,7 @@ typedef struct {
 /* calcuvw: the momentum predictor   Velocity/velocity.f90:50-750 (tier "next" row f1): updateVelocityAtBoundary,
  * grad(U/V/W), gradp_and_sources(p), volume + face + boundary terms into FCP_F_A / SU,SV,SW / SPU,SPV,SP, then the
  * three under-relaxed solves; leaves apu,apv,apw (and rU,rV,rW when piso) for calcp_simple / calcp_piso.
- * Not built: Crank-Nicolson, buoyancy, MHD, periodic patches (FCP_ESTATE). rep[0..2] = U, V, W. */
+ * Periodic patches: :393-432 + facefluxuvw_periodic :1038-1180.  Not built: Crank-Nicolson, buoyancy, MHD. rep[0..2] = U, V, W. */
 int fcp_calcuvw(fcp_ctx *ctx, const fcp_uvw_params *prm, fcp_report *rep);
 
 /* ---- explicit-CSR solver signature: dpcg|iccg|bicgstab(n,nnz,ia,ja,a,diag,fi,rhs,...) -------- */

@@ -160,13 +160,22 @@ extern "C" void orc_wall_geometry(const orc_mesh *m, double *dnw, double *srdw, 
 // CSR pattern  (src/sparseMatrix/sparse_matrix.f90:110-260).  The reference heap-sorts the COO
 // list lexicographically; the result is "rows ascending, columns ascending, diagonal embedded".
 // ------------------------------------------------------------------------------------------
-extern "C" i32 orc_csr_nnz(const orc_mesh *m) { return 2 * m->numInnerFaces + m->numCells; }  // :110 (numPeriodic = 0)
+extern "C" i32 orc_num_periodic(const orc_mesh *m) {   // geometry.f90:251-253
+  i32 np = 0;
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) if (m->bctype[ib] == ORC_BC_PERIODIC) np += m->nfaces[ib];
+  return np;
+}
+extern "C" i32 orc_csr_nnz(const orc_mesh *m) { return 2 * (m->numInnerFaces + orc_num_periodic(m)) + m->numCells; }  // :110
 
 extern "C" void orc_csr_create(const orc_mesh *m, i32 *ia, i32 *ja, i32 *diag, i32 *icell_jcell, i32 *jcell_icell) {
   const i32 n = m->numCells, F = m->numInnerFaces;
   std::vector<i32> cnt(n + 1, 0);
   for (i32 c = 0; c < n; ++c) cnt[c] = 1;
   for (i32 f = 0; f < F; ++f) { cnt[m->owner[f] - 1]++; cnt[m->neighbour[f] - 1]++; }
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {   // :141-171 twin entries of periodic faces
+    if (m->bctype[ib] != ORC_BC_PERIODIC) continue;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) { cnt[m->owner[m->startFace[ib] + i - 1] - 1]++; cnt[m->owner[m->startFaceTwin[ib] + i - 1] - 1]++; }
+  }
   ia[0] = 1;
   for (i32 c = 0; c < n; ++c) ia[c + 1] = ia[c] + cnt[c];
   std::vector<i32> pos(n);
@@ -174,6 +183,13 @@ extern "C" void orc_csr_create(const orc_mesh *m, i32 *ia, i32 *ja, i32 *diag, i
   for (i32 f = 0; f < F; ++f) {
     i32 p = m->owner[f] - 1, q = m->neighbour[f] - 1;
     ja[pos[p]++] = q + 1; ja[pos[q]++] = p + 1;
+  }
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    if (m->bctype[ib] != ORC_BC_PERIODIC) continue;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      i32 p = m->owner[m->startFace[ib] + i - 1] - 1, q = m->owner[m->startFaceTwin[ib] + i - 1] - 1;
+      ja[pos[p]++] = q + 1; ja[pos[q]++] = p + 1;
+    }
   }
   for (i32 c = 0; c < n; ++c) std::sort(ja + ia[c] - 1, ja + ia[c + 1] - 1);
   for (i32 c = 0; c < n; ++c)                    // :185 find_main_diag_element_positions
@@ -185,6 +201,70 @@ extern "C" void orc_csr_create(const orc_mesh *m, i32 *ia, i32 *ja, i32 *diag, i
   for (i32 f = 0; f < F; ++f) {                  // :251-260
     icell_jcell[f] = csr_to_k(m->owner[f], m->neighbour[f]);
     jcell_icell[f] = csr_to_k(m->neighbour[f], m->owner[f]);
+  }
+  i32 k = F;                                     // :262-293
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    if (m->bctype[ib] != ORC_BC_PERIODIC) continue;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      const i32 ijp = m->owner[m->startFace[ib] + i - 1], ijn = m->owner[m->startFaceTwin[ib] + i - 1];
+      icell_jcell[k] = csr_to_k(ijp, ijn);
+      jcell_icell[k] = csr_to_k(ijn, ijp);
+      ++k;
+    }
+  }
+}
+
+// facefluxmass2_periodic (faceflux_mass.f90:313-384): ijp owns the periodic face f, ijn owns its twin; lambda = half; the
+// velocity is interpolated with the Apu/Apv/Apw weights; QUIRK Q21: `Df(i)` is indexed with the face's ordinal INSIDE THE PATCH
+// (the call passes the loop counter i, calcp_simple.f90:199), i.e. it reads the Df of inner face number i.
+static inline void fluxmass2_periodic(const orc_mesh *m, i32 i1 /* 1-based ordinal in the patch */, i32 ijp, i32 ijn, i32 f, const double *den,
+                                      const double *u, const double *v, const double *w, const double *p, const double *dPdxi,
+                                      const double *apu, const double *apv, const double *apw, double *cap_out, double *flux_out) {
+  const double lambda = 0.5, fxn = lambda, fxp = 1.0 - lambda;
+  const double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+  const double xpn = 2 * (m->xf[f] - m->xc[ijp]), ypn = 2 * (m->yf[f] - m->yc[ijp]), zpn = 2 * (m->zf[f] - m->zc[ijp]);
+  const double dene = den[ijp] * fxp + den[ijn] * fxn;
+  double Kj = m->vol[ijp] * apu[ijp] * fxp + m->vol[ijn] * apu[ijn] * fxn;
+  const double cap = -dene * Kj * m->Df[i1 - 1];
+  Kj = (apu[ijp] + apu[ijn] + SMALL);
+  const double ui = (u[ijp] * apu[ijn] + u[ijn] * apu[ijp]) / Kj;
+  const double vi = (v[ijp] * apv[ijn] + v[ijn] * apv[ijp]) / Kj;
+  const double wi = (w[ijp] * apw[ijn] + w[ijn] * apw[ijp]) / Kj;
+  const double dpxi = (dPdxi[3 * ijn + 0] * fxp + dPdxi[3 * ijp + 0] * fxn) * xpn;
+  const double dpyi = (dPdxi[3 * ijn + 1] * fxp + dPdxi[3 * ijp + 1] * fxn) * ypn;
+  const double dpzi = (dPdxi[3 * ijn + 2] * fxp + dPdxi[3 * ijp + 2] * fxn) * zpn;
+  *cap_out = cap;
+  *flux_out = dene * (ui * arx + vi * ary + wi * arz) + cap * (p[ijn] - p[ijp] - dpxi - dpyi - dpzi);
+}
+// the periodic branch shared by calcp_simple.f90:185-228 and calcp_piso.f90:248-293; l0 = running periodic-face count on entry
+static inline void assemble_periodic_patch(const orc_mesh *m, i32 ib, i32 *l, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell,
+                                           const double *den, const double *u, const double *v, const double *w, const double *p,
+                                           const double *dPdxi, const double *apu, const double *apv, const double *apw, double *a, double *su,
+                                           double *flmass) {
+  for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+    const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijn = m->owner[m->startFaceTwin[ib] + i - 1] - 1;
+    double cap;
+    fluxmass2_periodic(m, i, ijp, ijn, f, den, u, v, w, p, dPdxi, apu, apv, apw, &cap, &flmass[f]);
+    const i32 k = (*l)++;
+    a[icell_jcell[k] - 1] = cap;
+    a[jcell_icell[k] - 1] = cap;
+    a[diag[ijp] - 1] = a[diag[ijp] - 1] - cap;
+    a[diag[ijn] - 1] = a[diag[ijn] - 1] - cap;
+    su[ijp] = su[ijp] - flmass[f];
+    su[ijn] = su[ijn] + flmass[f];
+  }
+}
+// calcp_simple.f90:344-375 / calcp_piso.f90:435-460: flmass(if) += a(k) (x(ijn) - x(ijp)), flmass(iftwin) = flmass(if)
+static inline void correct_flux_periodic(const orc_mesh *m, const i32 *icell_jcell, const double *a, const double *x, double *flmass) {
+  i32 l = m->numInnerFaces;
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    if (m->bctype[ib] != ORC_BC_PERIODIC) continue;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      const i32 f = m->startFace[ib] + i - 1, ft = m->startFaceTwin[ib] + i - 1, ijp = m->owner[f] - 1, ijn = m->owner[ft] - 1;
+      const i32 k = icell_jcell[l++] - 1;
+      flmass[f] = flmass[f] + a[k] * (x[ijn] - x[ijp]);
+      flmass[ft] = flmass[f];
+    }
   }
 }
 
@@ -424,7 +504,7 @@ extern "C" void orc_gradp_and_sources(const orc_mesh *m, int pscheme, double *p,
 // ------------------------------------------------------------------------------------------
 extern "C" void orc_assemble_pcorr(const orc_mesh *m, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell, i32 nnz,
                                    const double *den, double *u, double *v, double *w, const double *p, double *pp,
-                                   const double *dPdxi, const double *apu, int const_mflux, double flomas,
+                                   const double *dPdxi, const double *apu, const double *apv, const double *apw, int const_mflux, double flomas,
                                    double *a, double *su, double *flmass) {
   for (i32 k = 0; k < nnz; ++k) a[k] = 0.0;
   for (i32 c = 0; c < m->numCells; ++c) su[c] = 0.0;
@@ -471,6 +551,7 @@ extern "C" void orc_assemble_pcorr(const orc_mesh *m, const i32 *diag, const i32
       }
     }
   }
+  i32 lper = m->numInnerFaces;                     // l: index into icell_jcell for periodic faces (:128)
   for (i32 ib = 0; ib < m->numBoundaries; ++ib) {  // calcp_simple.f90:131-234
     if (m->bctype[ib] == ORC_BC_INLET || m->bctype[ib] == ORC_BC_OUTLET) {
       for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
@@ -493,6 +574,8 @@ extern "C" void orc_assemble_pcorr(const orc_mesh *m, const i32 *diag, const i32
         su[ijp] = su[ijp] - flmass[f];
         pp[ijb] = 0.0;
       }
+    } else if (m->bctype[ib] == ORC_BC_PERIODIC) {  // :185-228
+      assemble_periodic_patch(m, ib, &lper, diag, icell_jcell, jcell_icell, den, u, v, w, p, dPdxi, apu, apv, apw, a, su, flmass);
     }
   }
 }
@@ -516,6 +599,39 @@ extern "C" void orc_update_velocity_at_boundary(const orc_mesh *m, double *u, do
   }
 }
 
+extern "C" double orc_constant_mass_flow_forcing(const orc_mesh *m, double magUbar, const double *apu, double *u, int mode, double *magUbarStar) {
+  const i32 n = m->numCells;
+  std::vector<double> t0(n), t1(n), t2(n);
+  for (i32 c = 0; c < n; ++c) { t0[c] = m->vol[c] * u[c]; t1[c] = m->vol[c]; t2[c] = m->vol[c] * apu[c]; }   // fieldManipulation.f90:63-66
+  const double sumvol = sum_mode(mode, t1.data(), n);
+  const double ustar = sum_mode(mode, t0.data(), n) / sumvol;     // :21
+  const double ruaw = sum_mode(mode, t2.data(), n) / sumvol;      // :25
+  const double gplus = (magUbar - ustar) / ruaw;                  // :26
+  for (i32 c = 0; c < n; ++c) u[c] = u[c] + apu[c] * gplus;       // :29
+  if (magUbarStar) *magUbarStar = ustar;
+  return gplus;
+}
+
+extern "C" void orc_update_boundary(const orc_mesh *m, double *phi) {   // boundary/updateBoundary.f90
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    const i32 t = m->bctype[ib];
+    if (t == ORC_BC_OUTLET || t == ORC_BC_SYMMETRY || t == ORC_BC_PRESSURE || t == ORC_BC_EMPTY) {
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        phi[ijb] = phi[ijp];
+      }
+    } else if (t == ORC_BC_PERIODIC) {
+      for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+        const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+        const i32 ijn = m->owner[m->startFaceTwin[ib] + i - 1] - 1;
+        phi[ijb] = 0.5 * (phi[ijp] + phi[ijn]);
+        const i32 ijbt = m->numCells + (m->startFaceTwin[ib] - m->numInnerFaces) + i - 1;
+        phi[ijbt] = phi[ijb];
+      }
+    }
+  }
+}
+
 extern "C" void orc_correct_simple(const orc_mesh *m, const i32 *icell_jcell, int pscheme, const double *a, const double *den,
                                    double *u, double *v, double *w, double *p, double *pp,
                                    const double *apu, const double *apv, const double *apw, double urfp, i32 pRefCell,
@@ -524,6 +640,7 @@ extern "C" void orc_correct_simple(const orc_mesh *m, const i32 *icell_jcell, in
     i32 ijp = m->owner[f] - 1, ijn = m->neighbour[f] - 1;
     flmass[f] = flmass[f] + a[icell_jcell[f] - 1] * (pp[ijn] - pp[ijp]);
   }
+  correct_flux_periodic(m, icell_jcell, a, pp, flmass);   // :350-373 (periodic and pressure patches never share a face: order is immaterial)
   int have_pressure = 0;
   for (i32 ib = 0; ib < m->numBoundaries; ++ib) {  // :345-391, facefluxmassCorrPressBnd faceflux_mass.f90:699-762
     if (m->bctype[ib] != ORC_BC_PRESSURE) continue;
@@ -1069,6 +1186,7 @@ extern "C" void orc_calcp_piso(const orc_mesh *m, const i32 *ia, const i32 *ja, 
         }
       }
     }
+    i32 lper = F;
     for (i32 ib = 0; ib < m->numBoundaries; ++ib) {                           // :194-297
       if (m->bctype[ib] == ORC_BC_INLET || m->bctype[ib] == ORC_BC_OUTLET) {
         for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
@@ -1090,6 +1208,8 @@ extern "C" void orc_calcp_piso(const orc_mesh *m, const i32 *ia, const i32 *ja, 
           a[diag[ijp] - 1] = a[diag[ijp] - 1] - cap;
           su[ijp] = su[ijp] - flmass[f];
         }
+      } else if (m->bctype[ib] == ORC_BC_PERIODIC) {                          // :248-293
+        assemble_periodic_patch(m, ib, &lper, diag, icell_jcell, jcell_icell, den, u, v, w, p, dPdxi, apu, apv, apw, a, su, flmass);
       }
     }
     for (int ipcorr = 1; ipcorr <= npcor; ++ipcorr) {                         // :308-395
@@ -1128,6 +1248,7 @@ extern "C" void orc_calcp_piso(const orc_mesh *m, const i32 *ia, const i32 *ja, 
     }
     orc_gradp_and_sources(m, pscheme, p, apu, su, sv, sw, dPdxi);             // :425
     for (i32 c = 0; c < n; ++c) { u[c] = u[c] + su[c] * apu[c]; v[c] = v[c] + sv[c] * apv[c]; w[c] = w[c] + sw[c] * apw[c]; }   // :429-431
+    correct_flux_periodic(m, icell_jcell, a, p, flmass);                      // :441-460 (with the whole pressure p)
     for (i32 ib = 0; ib < m->numBoundaries; ++ib) {                           // :466-479 ; facefluxmassCorrPressBnd :699-762 (uses pp(ijp))
       if (m->bctype[ib] != ORC_BC_PRESSURE) continue;
       for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
@@ -1307,12 +1428,52 @@ extern "C" void orc_calcuvw(const orc_mesh *m, const i32 *ia, const i32 *ja, con
     su[ijp] = su[ijp] + sup; sv[ijp] = sv[ijp] + svp; sw[ijp] = sw[ijp] + swp;
     su[ijn] = su[ijn] - sup; sv[ijn] = sv[ijn] - svp; sw[ijn] = sw[ijn] - swp;
   }
+  i32 lper = m->numInnerFaces;                                                                     // l of :412 (periodic entries of icell_jcell)
   for (i32 ib = 0; ib < m->numBoundaries; ++ib) {                                                  // :330-475
     const i32 t = m->bctype[ib];
     for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
       const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
       const double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
-      if (t == ORC_BC_INLET || t == ORC_BC_OUTLET || t == ORC_BC_PRESSURE) {                       // facefluxuvw_bnd :882-1034
+      if (t == ORC_BC_PERIODIC) {                                                                  // :393-432 ; facefluxuvw_periodic :1038-1180
+        const i32 ijn = m->owner[m->startFaceTwin[ib] + i - 1] - 1;
+        const double fxn = 0.5, fxp = fxn;
+        const double xpn = 2 * (m->xf[f] - m->xc[ijp]), ypn = 2 * (m->yf[f] - m->yc[ijp]), zpn = 2 * (m->zf[f] - m->zc[ijp]);
+        const double dpn = std::sqrt(xpn * xpn + ypn * ypn + zpn * zpn);
+        const double are = std::sqrt(arx * arx + ary * ary + arz * arz);
+        const double game = vis[ijp] * fxp + vis[ijn] * fxn;
+        const double de = game * (arx * arx + ary * ary + arz * arz) / (xpn * arx + ypn * ary + zpn * arz);
+        const double flomass = flmass[f];
+        const double ce = mn(flomass, zero), cp = mx(flomass, zero);
+        const double can = -de + ce, cap = -de - cp;
+        const double duxi = dUdxi[3 * ijp] * fxp + dUdxi[3 * ijn] * fxn, duyi = dUdxi[3 * ijp + 1] * fxp + dUdxi[3 * ijn + 1] * fxn,
+                     duzi = dUdxi[3 * ijp + 2] * fxp + dUdxi[3 * ijn + 2] * fxn;
+        const double dvxi = dVdxi[3 * ijp] * fxp + dVdxi[3 * ijn] * fxn, dvyi = dVdxi[3 * ijp + 1] * fxp + dVdxi[3 * ijn + 1] * fxn,
+                     dvzi = dVdxi[3 * ijp + 2] * fxp + dVdxi[3 * ijn + 2] * fxn;
+        const double dwxi = dWdxi[3 * ijp] * fxp + dWdxi[3 * ijn] * fxn, dwyi = dWdxi[3 * ijp + 1] * fxp + dWdxi[3 * ijn + 1] * fxn,
+                     dwzi = dWdxi[3 * ijp + 2] * fxp + dWdxi[3 * ijn + 2] * fxn;
+        const double fdue = game * ((duxi + duxi) * arx + (duyi + dvxi) * ary + (duzi + dwxi) * arz);
+        const double fdve = game * ((duyi + dvxi) * arx + (dvyi + dvyi) * ary + (dvzi + dwyi) * arz);
+        const double fdwe = game * ((duzi + dwxi) * arx + (dwyi + dvzi) * ary + (dwzi + dwzi) * arz);
+        const double fdui = game * are / dpn * (duxi * xpn + duyi * ypn + duzi * zpn);
+        const double fdvi = game * are / dpn * (dvxi * xpn + dvyi * ypn + dvzi * zpn);
+        const double fdwi = game * are / dpn * (dwxi * xpn + dwyi * ypn + dwzi * zpn);
+        const double fuuds = cp * u[ijp] + ce * u[ijn], fvuds = cp * v[ijp] + ce * v[ijn], fwuds = cp * w[ijp] + ce * w[ijn];
+        double ue, ve, we;                                                                         // face_value_cds interpolation.f90:116-157
+        if (flomass >= zero) {
+          ue = u[ijp] + (u[ijn] - u[ijp]) * fxp; ve = v[ijp] + (v[ijn] - v[ijp]) * fxp; we = w[ijp] + (w[ijn] - w[ijp]) * fxp;
+        } else {
+          ue = u[ijn] + (u[ijp] - u[ijn]) * fxn; ve = v[ijn] + (v[ijp] - v[ijn]) * fxn; we = w[ijn] + (w[ijp] - w[ijn]) * fxn;
+        }
+        const double fuhigh = flomass * ue, fvhigh = flomass * ve, fwhigh = flomass * we;
+        const double sup = -prm->gds * (fuhigh - fuuds) + fdue - fdui;
+        const double svp = -prm->gds * (fvhigh - fvuds) + fdve - fdvi;
+        const double swp = -prm->gds * (fwhigh - fwuds) + fdwe - fdwi;
+        a[icell_jcell[lper] - 1] = can;
+        a[jcell_icell[lper] - 1] = cap;
+        ++lper;
+        su[ijp] = su[ijp] + sup; sv[ijp] = sv[ijp] + svp; sw[ijp] = sw[ijp] + swp;
+        su[ijn] = su[ijn] - sup; sv[ijn] = sv[ijn] - svp; sw[ijn] = sw[ijn] - swp;
+      } else if (t == ORC_BC_INLET || t == ORC_BC_OUTLET || t == ORC_BC_PRESSURE) {                       // facefluxuvw_bnd :882-1034
         const double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
         const double vole = xpn * arx + ypn * ary + zpn * arz;
         const double Dfi = (arx * arx + ary * ary + arz * arz) / vole;

@@ -42,6 +42,8 @@ typedef struct {
   const double *facint, *Df;                    /* [numInnerFaces] */
   const double *xc, *yc, *zc, *vol;             /* [numCells] (numTotal in the src-par layout) */
   const int32_t *bctype, *nfaces, *startFace, *iBndValueStart; /* [numBoundaries]; iface = startFace+i, ijb = iBndValueStart+i, i=1..nfaces */
+  const int32_t *startFaceTwin; /* [numBoundaries] or NULL: for ORC_BC_PERIODIC patches the startFace of the twin patch (geometry.f90:82,251-257;
+                                 * indexed per PATCH here, the reference indexes it by the running count of periodic patches iPer) */
 } orc_mesh;
 
 /* solver report, mirrors the values the reference prints (linear_solvers.f90:354-355) */
@@ -71,7 +73,9 @@ void orc_geometry(int32_t numNodes, int32_t numCells, int32_t numInnerFaces, int
 /* geometry.f90:698-754 : dnw/srdw for wall faces, dns/srds for symmetry faces, in patch order */
 void orc_wall_geometry(const orc_mesh *m, double *dnw, double *srdw, double *dns, double *srds);
 
-/* sparse_matrix.f90:86-296 (no periodic patches) */
+/* sparse_matrix.f90:86-296, periodic twins included (:141-171, :262-293): icell_jcell / jcell_icell have
+ * numInnerFaces + numPeriodic entries, the periodic ones in patch order after the inner faces */
+int32_t orc_num_periodic(const orc_mesh *m);
 int32_t orc_csr_nnz(const orc_mesh *m);
 void orc_csr_create(const orc_mesh *m, int32_t *ia, int32_t *ja, int32_t *diag,
                     int32_t *icell_jcell, int32_t *jcell_icell);
@@ -100,6 +104,7 @@ void orc_assemble_pcorr(const orc_mesh *m, const int32_t *diag, const int32_t *i
                         const int32_t *jcell_icell, int32_t nnz,
                         const double *den, double *u, double *v, double *w, const double *p,
                         double *pp, const double *dPdxi, const double *apu,
+                        const double *apv, const double *apw /* read on periodic faces only (facefluxmass2_periodic :313-384); may be NULL otherwise */,
                         int const_mflux, double flomas,
                         double *a, double *su, double *flmass);
 /* calcp_simple.f90:331-429 (one ipcorr pass after the solve) */
@@ -113,6 +118,11 @@ void orc_nonorth_corrector(const orc_mesh *m, const double *den, const double *a
                            const double *dPdxi, double *su, double *flmass);
 /* velocity.f90:1184-1277 */
 void orc_update_velocity_at_boundary(const orc_mesh *m, double *u, double *v, double *w);
+/* src/cappuccino/constant_mass_flow_forcing.f90 + volumeWeightedAverage (fieldManipulation.f90:41-70); sum_mode as for the solvers.
+ * Returns gragPplus; u(1:numCells) is corrected in place; *magUbarStar = the uncorrected bulk velocity. */
+double orc_constant_mass_flow_forcing(const orc_mesh *m, double magUbar, const double *apu, double *u, int sum_mode, double *magUbarStar);
+/* boundary/updateBoundary.f90: outlet/symmetry/pressure/empty copy the owner value, periodic faces and their twins take the mean of the two cells */
+void orc_update_boundary(const orc_mesh *m, double *phi);
 
 
 /* ---- slope limiters, gradients.f90:288-656 (applied in place to dPhidxi(3,numTotal)) ----------
@@ -134,7 +144,8 @@ int orc_grad_lsq_qr(const orc_mesh *m, const double *D, const double *phi, doubl
 
 /* ---- calcp_piso, Pressure/calcp_piso.f90:81-489 + faceflux_mass.f90:389-459 (facefluxmass_piso),
  * :564-647 (fluxmc), :699-762, :765-831, :833-916.  `a` holds the momentum coefficients on entry
- * (h = a, :81) and the pressure matrix of the last corrector on exit.  No periodic patches.
+ * (h = a, :81) and the pressure matrix of the last corrector on exit.  Periodic patches :248-295, :435-460 (H(U) runs over
+ * the inner faces only, :110-124, as in the reference).
  * rep[(icorr-1)*npcor + (ipcorr-1)]. */
 void orc_calcp_piso(const orc_mesh *m, const int32_t *ia, const int32_t *ja, const int32_t *diag,
                     const int32_t *icell_jcell, const int32_t *jcell_icell, int32_t nnz,
@@ -147,7 +158,7 @@ void orc_calcp_piso(const orc_mesh *m, const int32_t *ia, const int32_t *ja, con
 
 /* ---- calcuvw: the momentum predictor, Velocity/velocity.f90:50-750 (+ facefluxuvw :754-878, facefluxuvw_bnd :882-1034,
  * sngrad gradients.f90:1720-1779, the face_value family interpolation.f90:28-113, 116-650).  Tier "next" row f1.
- * Not restated: Crank-Nicolson (:569-600), buoyancy (:186-200), MHD (:205-212), periodic patches (:395-432).
+ * Periodic patches :393-432 + facefluxuvw_periodic :1038-1180.  Not restated: Crank-Nicolson (:569-600), buoyancy (:186-200), MHD (:205-212).
  * cscheme: 0 cds, 1 central, 2 linearUpwind, 3 kappa, then the flux limiters of interpolation.f90:596-640 in source order:
  * 4 muscl, 5 umist, 6 koren, 7 smart, 8 avl-smart, 9 charm, 10 vanleer, 11 ospre, 12 minmod, 13 boundedLinearUpwind,
  * 14 boundedLinearUpwind02, 15 boundedCentral, 16 fromm, 17 cui, 18 quick, 19 spl13. */

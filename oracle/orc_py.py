@@ -25,7 +25,7 @@ class OrcMesh(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("numCells", "numInnerFaces", "numBoundaryFaces", "numFaces", "numTotal", "numBoundaries")] + \
                [("owner", _pi), ("neighbour", _pi)] + \
                [(n, _pd) for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol")] + \
-               [(n, _pi) for n in ("bctype", "nfaces", "startFace", "iBndValueStart")]
+               [(n, _pi) for n in ("bctype", "nfaces", "startFace", "iBndValueStart", "startFaceTwin")]
 
 
 class OrcReport(C.Structure):
@@ -96,13 +96,14 @@ class MeshView:
         self.keep = dict(owner=np.ascontiguousarray(m.owner, np.int32), neighbour=np.ascontiguousarray(m.neighbour, np.int32),
                          bctype=np.ascontiguousarray(m.bctype, np.int32), nfaces=np.ascontiguousarray(m.nfaces, np.int32),
                          startFace=np.ascontiguousarray(m.startFace, np.int32),
-                         iBndValueStart=np.ascontiguousarray(m.iBndValueStart, np.int32))
+                         iBndValueStart=np.ascontiguousarray(m.iBndValueStart, np.int32),
+                         startFaceTwin=np.ascontiguousarray(m.twin_start() if hasattr(m, "twin_start") else np.full(m.numBoundaries, -1), np.int32))
         for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol"):
             self.keep[n] = np.ascontiguousarray(getattr(m, n), np.float64)
         s = OrcMesh()
         s.numCells, s.numInnerFaces, s.numBoundaryFaces = m.numCells, m.numInnerFaces, m.numBoundaryFaces
         s.numFaces, s.numTotal, s.numBoundaries = m.numFaces, m.numTotal, m.numBoundaries
-        for n in ("owner", "neighbour", "bctype", "nfaces", "startFace", "iBndValueStart"):
+        for n in ("owner", "neighbour", "bctype", "nfaces", "startFace", "iBndValueStart", "startFaceTwin"):
             setattr(s, n, _i(self.keep[n]))
         for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol"):
             setattr(s, n, _d(self.keep[n]))
@@ -147,8 +148,9 @@ class Csr:
         self.ia = np.zeros(self.n + 1, np.int32)
         self.ja = np.zeros(self.nnz, np.int32)
         self.diag = np.zeros(self.n, np.int32)
-        self.icell_jcell = np.zeros(mesh.numInnerFaces, np.int32)
-        self.jcell_icell = np.zeros(mesh.numInnerFaces, np.int32)
+        nper = lib().orc_num_periodic(mv.ptr)
+        self.icell_jcell = np.zeros(mesh.numInnerFaces + nper, np.int32)      # sparse_matrix.f90:246-247
+        self.jcell_icell = np.zeros(mesh.numInnerFaces + nper, np.int32)
         lib().orc_csr_create(mv.ptr, _i(self.ia), _i(self.ja), _i(self.diag), _i(self.icell_jcell), _i(self.jcell_icell))
 
 
@@ -187,19 +189,21 @@ def gradp_and_sources(mesh, pscheme: int, p, apu, dPdxi):
     return su, sv, sw
 
 
-def assemble_pcorr(mesh, csr: Csr, den, u, v, w, p, pp, dPdxi, apu, const_mflux=False, flomas=0.0):
+def assemble_pcorr(mesh, csr: Csr, den, u, v, w, p, pp, dPdxi, apu, const_mflux=False, flomas=0.0, apv=None, apw=None):
     a = np.zeros(csr.nnz)
     su = np.zeros(mesh.numCells)
     flmass = np.zeros(mesh.numFaces)
     lib().orc_assemble_pcorr(csr.mv.ptr, _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz),
                              _d(den), _d(u), _d(v), _d(w), _d(p), _d(pp), _d(dPdxi), _d(apu),
+                             _d(apv) if apv is not None else None, _d(apw) if apw is not None else None,
                              C.c_int(int(const_mflux)), C.c_double(flomas), _d(a), _d(su), _d(flmass))
     return a, su, flmass
 
 
-def assemble_pcorr_into(mesh, csr: Csr, den, u, v, w, p, pp, dPdxi, apu, a, su, flmass, const_mflux=False, flomas=0.0):
+def assemble_pcorr_into(mesh, csr: Csr, den, u, v, w, p, pp, dPdxi, apu, a, su, flmass, const_mflux=False, flomas=0.0, apv=None, apw=None):
     lib().orc_assemble_pcorr(csr.mv.ptr, _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz),
                              _d(den), _d(u), _d(v), _d(w), _d(p), _d(pp), _d(dPdxi), _d(apu),
+                             _d(apv) if apv is not None else None, _d(apw) if apw is not None else None,
                              C.c_int(int(const_mflux)), C.c_double(flomas), _d(a), _d(su), _d(flmass))
 
 
@@ -208,6 +212,23 @@ def correct_simple(mesh, csr: Csr, pscheme, a, den, u, v, w, p, pp, apu, apv, ap
     lib().orc_correct_simple(csr.mv.ptr, _i(csr.icell_jcell), C.c_int(pscheme), _d(a), _d(den), _d(u), _d(v), _d(w), _d(p), _d(pp),
                              _d(apu), _d(apv), _d(apw), C.c_double(urfp), C.c_int32(pRefCell), _d(su), _d(sv), _d(sw), _d(dPdxi), _d(flmass))
     return su, sv, sw
+
+
+def constant_mass_flow_forcing(mesh, magUbar, apu, u, sum_mode=0):
+    """constant_mass_flow_forcing.f90: corrects u in place; returns (gragPplus, magUbarStar)."""
+    mv = MeshView(mesh)
+    f = lib().orc_constant_mass_flow_forcing
+    f.restype = C.c_double
+    ustar = C.c_double(0.0)
+    g = f(mv.ptr, C.c_double(magUbar), _d(apu), _d(u), C.c_int(sum_mode), C.byref(ustar))
+    return g, ustar.value
+
+
+def update_boundary(mesh, phi):
+    """boundary/updateBoundary.f90, in place."""
+    mv = MeshView(mesh)
+    lib().orc_update_boundary(mv.ptr, _d(phi))
+    return phi
 
 
 def nonorth_corrector(mesh, den, apu, dPdxi, su, flmass):

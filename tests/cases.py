@@ -27,7 +27,19 @@ def meshes():
     out["channel_pressure"] = M.hex_mesh(xs, ys, zs, dict(left="inlet", right="pressure", back="empty", front="empty"), distort=0.1)
     out["poly_10faces"] = M.polyhedral_mesh(8, 6, 5, distort=0.15, patch_types=dict(left="inlet", right="outlet"))   # 10-faced cells + hexes
     out["tiny3"] = M.hex_mesh(np.linspace(0, 1, 4), np.linspace(0, 1, 3), np.linspace(0, 1, 2))   # 3x2x1 = 6 cells (< one warp)
+    # periodic pairs (row f3): a channel395-style box, periodic in x and z ('right'/'front' periodic, their twins 'left'/'back' listed as
+    # empty, examples/channel395/README.md), walls in y, graded in y, distorted inside; and a one-pair inlet/outlet-free duct with symmetry sides
+    out["channel_periodic"] = periodic_channel()
+    out["duct_periodic_x"] = M.hex_mesh(np.linspace(0, 1.5, 8), M.bump_nodes(5, 0.4), np.linspace(0, 0.6, 5),
+                                        dict(left="empty", right="periodic", back="symmetry", front="symmetry"), distort=0.1)
+    out["duct_periodic_first"] = M.hex_mesh(np.linspace(0, 1.5, 7), np.linspace(0, 1, 5), np.linspace(0, 0.6, 4),
+                                            dict(left="periodic", right="empty", top="symmetry"), distort=0.1)   # the periodic patch precedes its twin
     return out
+
+
+def periodic_channel(nx=9, ny=7, nz=6, distort=0.2):
+    return M.hex_mesh(np.linspace(0, 2.0, nx + 1), M.bump_nodes(ny, 0.3), np.linspace(0, 1.0, nz + 1),
+                      dict(left="empty", right="periodic", back="empty", front="periodic"), distort=distort)
 
 
 def fields(m, seed=12345):

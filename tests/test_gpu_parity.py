@@ -14,7 +14,8 @@ from fcb200 import mesh as M
 
 pytestmark = pytest.mark.gpu
 
-MESHES = ["ref400", "hex6", "hex12_graded", "hex10_distorted", "slab39_empty", "channel_inout", "channel_pressure", "poly_10faces", "tiny3"]
+MESHES = ["ref400", "hex6", "hex12_graded", "hex10_distorted", "slab39_empty", "channel_inout", "channel_pressure", "poly_10faces", "tiny3",
+          "channel_periodic", "duct_periodic_x", "duct_periodic_first"]
 
 
 @pytest.fixture(scope="module")
@@ -148,7 +149,7 @@ def simple_oracle(orc, m, f, solver, maxiter, tol_rel, urfp=0.3, pref=1, pscheme
             ijb = m.numCells + pf - Fi
             flm[pf] = g["den"][ijb] * (g["u"][ijb] * m.arx[pf] + g["v"][ijb] * m.ary[pf] + g["w"][ijb] * m.arz[pf])
     flm0 = flm.copy()
-    orc.assemble_pcorr_into(m, c, g["den"], g["u"], g["v"], g["w"], g["p"], g["pp"], dP, g["apu"], a, su, flm, flomas=flomas)
+    orc.assemble_pcorr_into(m, c, g["den"], g["u"], g["v"], g["w"], g["p"], g["pp"], dP, g["apu"], a, su, flm, flomas=flomas, apv=g["apv"], apw=g["apw"])
     out = dict(a=a.copy(), su_asm=su.copy(), flm_asm=flm.copy(), flm0=flm0, dP0=dP.copy(), p0=g["p"].copy())
     reps = []
     for ip in range(npcor):

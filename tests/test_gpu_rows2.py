@@ -138,13 +138,16 @@ def test_calcp_piso(fcp, orc, allmeshes, name, solver, pscheme, npcor):
     ctx.close()
 
 
-def test_piso_rejects_periodic(fcp):
+def test_periodic_pair_rules(fcp):
+    """A periodic patch must name an 'empty' twin of the same size; a pair must not join cells that already share a face."""
     xs = np.linspace(0, 1, 5)
-    m = M.hex_mesh(xs, xs, xs, dict(left="periodic", right="periodic"))
-    ctx = make_ctx(m)
+    bad = M.hex_mesh(xs, xs, xs, dict(left="empty", right="periodic"))
+    bad.startFaceTwin = None
     with pytest.raises(L.FcpError):
-        ctx.calcp_piso()
-    ctx.close()
+        make_ctx(bad)
+    two = M.hex_mesh(np.linspace(0, 1, 3), xs, xs, dict(left="empty", right="periodic"))    # 2 cells across: the pair duplicates an inner face
+    with pytest.raises(L.FcpError):
+        make_ctx(two)
 
 
 # ---- row f1: the momentum predictor -----------------------------------------------------------------------------------------
@@ -236,4 +239,37 @@ def test_calcuvw_all_convection_schemes(fcp, orc, allmeshes, cscheme):
     o = orc.calcuvw(m, c, prm, g, a)
     for k in ("u", "v", "w"):
         eq(ctx.download(k.upper()), g[k], f"{k} with {cscheme}")
+    ctx.close()
+
+
+# ---- row f3: periodic channels -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["channel_periodic", "hex10_distorted"])
+def test_constant_mass_flow_forcing(fcp, orc, allmeshes, name):
+    """constant_mass_flow_forcing.f90: bit-identical to the oracle with the sums in TREE mode, to rounding in the reference's cell-by-cell order."""
+    m = allmeshes[name]
+    f = cases.fields(m)
+    ctx = make_ctx(m, dict(u=f["u"], apu=f["apu"]))
+    g_new, ustar = ctx.constant_mass_flow_forcing(0.1335, 0.25)
+    u = f["u"].copy()
+    gplus, ustar_o = orc.constant_mass_flow_forcing(m, 0.1335, f["apu"], u, orc.SUM_TREE)
+    assert ustar == ustar_o and g_new == 0.25 + gplus
+    eq(ctx.download("U"), u, "u after the forcing correction")
+    u2 = f["u"].copy()
+    gseq, ustar_s = orc.constant_mass_flow_forcing(m, 0.1335, f["apu"], u2, orc.SUM_SEQ)
+    assert abs(gseq - gplus) <= 1e-12 * abs(gplus) and abs(ustar_s - ustar) <= 1e-13 * abs(ustar)
+    # the corrected field has the requested bulk velocity
+    n = m.numCells
+    assert abs((m.vol[:n] * u[:n]).sum() / m.vol[:n].sum() - 0.1335) < 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["channel_periodic", "duct_periodic_x", "duct_periodic_first", "channel_inout", "channel_pressure"])
+def test_update_boundary(fcp, orc, allmeshes, name):
+    m = allmeshes[name]
+    phi = np.random.default_rng(8).standard_normal(m.numTotal)
+    ctx = make_ctx(m, dict(s0=phi))
+    ctx.update_boundary("S0")
+    ref = phi.copy()
+    orc.update_boundary(m, ref)
+    eq(ctx.download("S0"), ref, "updateBoundary")
     ctx.close()

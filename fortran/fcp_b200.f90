@@ -35,7 +35,9 @@ module fcp_b200
                   FCP_F_DUDXI, FCP_F_DVDXI, FCP_F_DWDXI, FCP_F_DPDXI, FCP_F_G0, FCP_F_G1, &
                   FCP_F_FLMASS, FCP_F_A, FCP_F_APR, FCP_F_H, FCP_F_RU, FCP_F_RV, FCP_F_RW, FCP_F_VISW, &
                   FCP_F_UO, FCP_F_VO, FCP_F_WO, FCP_F_UOO, FCP_F_VOO, FCP_F_WOO, FCP_F_UOOO, FCP_F_VOOO, FCP_F_WOOO, &
-                  FCP_F_SPU, FCP_F_SPV, FCP_F_SP
+                  FCP_F_SPU, FCP_F_SPV, FCP_F_SP, &
+                  FCP_F_TE, FCP_F_ED, FCP_F_PHIO, FCP_F_PHIOO, FCP_F_GEN, FCP_F_MAGSTRAIN, FCP_F_VORTICITY, &
+                  FCP_F_DNW, FCP_F_TAU, FCP_F_YPL, FCP_F_SCTMP
   end enum
 
   type, bind(c) :: fcp_mesh_desc
@@ -60,6 +62,12 @@ module fcp_b200
     real(c_double) :: timestep
     integer(c_int32_t) :: const_mflux, pad
     real(c_double) :: gradPcmf, viscos
+  end type
+
+  integer(c_int), parameter :: FCP_SC_GENERIC = 0, FCP_SC_TKE_RLZB = 1, FCP_SC_EPS_RLZB = 2
+  type, bind(c) :: fcp_scalar_params
+    integer(c_int32_t) :: kind, solver, maxiter, cscheme, grad_method, limiter, tscheme, pad
+    real(c_double) :: tol_abs, tol_rel, urf, gds, timestep, prtr, viscos, densit
   end type
 
   type, bind(c) :: fcp_piso_params
@@ -189,6 +197,40 @@ module fcp_b200
       type(c_ptr), value :: ctx
       type(fcp_piso_params), intent(in) :: prm
       type(fcp_report), intent(out) :: rep(*)
+      integer(c_int) :: rc
+    end function
+    function fcp_calcsc(ctx, prm, phi_field, rep, fimin, fimax) bind(c, name='fcp_calcsc') result(rc)
+      import :: c_int, c_ptr, c_double, fcp_scalar_params, fcp_report
+      type(c_ptr), value :: ctx
+      type(fcp_scalar_params), intent(in) :: prm
+      integer(c_int), value :: phi_field
+      type(fcp_report), intent(out) :: rep
+      real(c_double), intent(out) :: fimin, fimax
+      integer(c_int) :: rc
+    end function
+    function fcp_calc_strain_and_vorticity(ctx) bind(c, name='fcp_calc_strain_and_vorticity') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int) :: rc
+    end function
+    function fcp_modify_mu_eff_k_epsilon_rlzb(ctx, urfVis, viscos) bind(c, name='fcp_modify_mu_eff_k_epsilon_rlzb') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), value :: urfVis, viscos
+      integer(c_int) :: rc
+    end function
+    function fcp_constant_mass_flow_forcing(ctx, magUbar, gradPcmf, magUbarStar) bind(c, name='fcp_constant_mass_flow_forcing') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), value :: magUbar
+      real(c_double), intent(inout) :: gradPcmf
+      real(c_double), intent(out) :: magUbarStar
+      integer(c_int) :: rc
+    end function
+    function fcp_update_boundary(ctx, field) bind(c, name='fcp_update_boundary') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: field
       integer(c_int) :: rc
     end function
     function fcp_slope_limiter(ctx, limiter, phi_field, grad_field) bind(c, name='fcp_slope_limiter') result(rc)
@@ -502,6 +544,25 @@ contains
   end subroutine
 
   ! ---- calcuvw(): no arguments   Velocity/velocity.f90:50-750 (tier "next" row f1) -----------------------------------------
+  integer(c_int) function grad_method_id()          ! the logicals of gradients.f90:118-138
+    grad_method_id = FCP_GRAD_GAUSS
+    if (lstsq) then
+      grad_method_id = FCP_GRAD_LSQ
+    else if (lstsq_qr) then
+      grad_method_id = FCP_GRAD_LSQ_QR
+    else if (lstsq_dm) then
+      grad_method_id = FCP_GRAD_LSQ_DM
+    end if
+  end function
+  integer(c_int) function limiter_id()              ! gradients.f90:140-160
+    select case (limiter)
+      case ('Barth-Jespersen');  limiter_id = FCP_LIMITER_BARTH_JESPERSEN
+      case ('Venkatakrishnan');  limiter_id = FCP_LIMITER_VENKATAKRISHNAN
+      case ('R3');               limiter_id = FCP_LIMITER_R3
+      case ('multidimensional'); limiter_id = FCP_LIMITER_MULTIDIMENSIONAL
+      case default;              limiter_id = FCP_LIMITER_NONE
+    end select
+  end function
   integer(c_int) function cscheme_id(scheme)      ! cSchemeU strings of interpolation.f90:28-113, :596-640 in source order
     character(len=*), intent(in) :: scheme
     character(len=24), parameter :: names(20) = [character(len=24) :: 'cds', 'central', 'linearUpwind', 'kappa', 'muscl', 'umist', &
@@ -642,6 +703,118 @@ contains
     call get(FCP_F_A, a, nnz); call get(FCP_F_H, h, nnz)
     call continuityErrors                            ! calcp_piso.f90:390 stays on the host
     if (const_mflux) call constant_mass_flow_forcing ! :487
+  end subroutine
+
+  ! ---- updateBoundary(phi)   src/finiteVolume/boundary/updateBoundary.f90 ------------------------------------------------------
+  subroutine updateBoundary(phi)
+    real(dp), dimension(numTotal), intent(inout) :: phi
+    call put(FCP_F_S0, phi, numTotal)
+    call fcp_check(fcp_update_boundary(ctx, FCP_F_S0), 'fcp_update_boundary')
+    call get(FCP_F_S0, phi, numTotal)
+  end subroutine
+
+  ! ---- modify_viscosity_k_epsilon_rlzb()   TurbulenceModels/k_epsilon_rlzb.f90:38-50: calcsc_tke, calcsc_epsilon, modify_mu_eff ----
+  ! (per-wall-face arrays visw, dnw, tau, ypl travel in the wall faces' boundary slots of numTotal-long fields; magStrain comes from
+  !  calc_strain_and_vorticity on the device, the velocity gradients are the ones calcuvw left there)
+  subroutine modify_viscosity_k_epsilon_rlzb()
+    use TurbModelData, only: TurbModel
+    type(fcp_scalar_params) :: prm
+    type(fcp_report) :: rep
+    real(c_double) :: fimin, fimax
+    real(dp), allocatable :: wf(:)
+    integer :: ib, i, iWall, isc
+    call put(FCP_F_U, u, numTotal); call put(FCP_F_V, v, numTotal); call put(FCP_F_W, w, numTotal)
+    call put(FCP_F_DEN, den, numTotal); call put(FCP_F_VIS, vis, numTotal); call put(FCP_F_FLMASS, flmass, numFaces)
+    call put(FCP_F_TE, te, numTotal); call put(FCP_F_ED, ed, numTotal)
+    ! modify_viscosity_turbulence.f90:28-33: velocity gradients of the corrected field, then strain and vorticity
+    call fcp_check(fcp_grad(ctx, FCP_GRAD_GAUSS, FCP_F_U, FCP_F_DUDXI, 0_c_int), 'fcp_grad')
+    call fcp_check(fcp_grad(ctx, FCP_GRAD_GAUSS, FCP_F_V, FCP_F_DVDXI, 0_c_int), 'fcp_grad')
+    call fcp_check(fcp_grad(ctx, FCP_GRAD_GAUSS, FCP_F_W, FCP_F_DWDXI, 0_c_int), 'fcp_grad')
+    allocate(wf(numTotal))
+    wf = 0.0_dp; iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        wf(iBndValueStart(ib) + i) = dnw(iWall)
+      end do
+    end do
+    call put(FCP_F_DNW, wf, numTotal)
+    wf = 0.0_dp; iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        wf(iBndValueStart(ib) + i) = visw(iWall)
+      end do
+    end do
+    call put(FCP_F_VISW, wf, numTotal)
+    call fcp_check(fcp_calc_strain_and_vorticity(ctx), 'fcp_calc_strain_and_vorticity')
+    do isc = 1, 2
+      prm%kind = merge(FCP_SC_TKE_RLZB, FCP_SC_EPS_RLZB, isc == 1)
+      prm%solver = solver_id(TurbModel%Scalar(isc)%lSolver); prm%maxiter = TurbModel%Scalar(isc)%maxiter
+      prm%tol_abs = TurbModel%Scalar(isc)%tolAbs; prm%tol_rel = TurbModel%Scalar(isc)%tolRel
+      prm%urf = TurbModel%Scalar(isc)%urf; prm%gds = TurbModel%Scalar(isc)%gds
+      prm%cscheme = cscheme_id(TurbModel%Scalar(isc)%cScheme)
+      prm%grad_method = grad_method_id(); prm%limiter = limiter_id()
+      prm%tscheme = 0
+      if (ltransient .and. (bdf .or. cn)) prm%tscheme = 1
+      if (ltransient .and. bdf2) prm%tscheme = 2
+      prm%timestep = timestep
+      prm%prtr = merge(1.0_dp/1.0_dp, 1.0_dp/1.2_dp, isc == 1)      ! 1/sigma_k, 1/sigma_epsilon (k_epsilon_rlzb.f90:20-21)
+      prm%viscos = viscos; prm%densit = densit
+      if (isc == 1) then
+        if (prm%tscheme >= 1) call put(FCP_F_PHIO, teo, numTotal)
+        if (prm%tscheme >= 2) call put(FCP_F_PHIOO, teoo, numTotal)
+        call fcp_check(fcp_calcsc(ctx, prm, FCP_F_TE, rep, fimin, fimax), 'fcp_calcsc')
+        write(6,'(2x,es11.4,a,es11.4)') fimin, ' <= k <= ', fimax
+      else
+        if (prm%tscheme >= 1) call put(FCP_F_PHIO, edo, numTotal)
+        if (prm%tscheme >= 2) call put(FCP_F_PHIOO, edoo, numTotal)
+        call fcp_check(fcp_calcsc(ctx, prm, FCP_F_ED, rep, fimin, fimax), 'fcp_calcsc')
+        write(6,'(2x,es11.4,a,es11.4)') fimin, ' <= epsilon <= ', fimax
+      end if
+    end do
+    call fcp_check(fcp_modify_mu_eff_k_epsilon_rlzb(ctx, TurbModel%urfVis, viscos), 'fcp_modify_mu_eff_k_epsilon_rlzb')
+    call get(FCP_F_TE, te, numTotal); call get(FCP_F_ED, ed, numTotal); call get(FCP_F_VIS, vis, numTotal)
+    call get(FCP_F_GEN, gen, numCells)
+    call get(FCP_F_DUDXI, dUdxi, 3*numTotal); call get(FCP_F_DVDXI, dVdxi, 3*numTotal); call get(FCP_F_DWDXI, dWdxi, 3*numTotal)
+    call get(FCP_F_MAGSTRAIN, magStrain, numCells); call get(FCP_F_VORTICITY, vorticity, numCells)
+    call get(FCP_F_VISW, wf, numTotal); iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        visw(iWall) = wf(iBndValueStart(ib) + i)
+      end do
+    end do
+    call get(FCP_F_YPL, wf, numTotal); iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        ypl(iWall) = wf(iBndValueStart(ib) + i)
+      end do
+    end do
+    call get(FCP_F_TAU, wf, numTotal); iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        tau(iWall) = wf(iBndValueStart(ib) + i)
+      end do
+    end do
+    deallocate(wf)
+  end subroutine
+
+  ! ---- constant_mass_flow_forcing()   src/cappuccino/constant_mass_flow_forcing.f90 ------------------------------------------------
+  subroutine constant_mass_flow_forcing_device()
+    use parameters, only: magUbar, gradPcmf
+    real(c_double) :: ustar
+    call put(FCP_F_U, u, numTotal); call put(FCP_F_APU, apu, numCells)
+    call fcp_check(fcp_constant_mass_flow_forcing(ctx, magUbar, gradPcmf, ustar), 'fcp_constant_mass_flow_forcing')
+    call get(FCP_F_U, u, numTotal)
+    write(6,'(2(a,es13.6))') "  Uncorrected Ubar = ", ustar, " pressure gradient = ", gradPcmf
   end subroutine
 
   ! ---- src-par: exchange(phi), global_sum(phi)   src-par/exchange.f90:3, src-par/global_sum_mpi.f90:4 ---------------------------

@@ -778,6 +778,72 @@ extern "C" int fcp_update_boundary(fcp_ctx *ctx, int field) {
   return fvm_update_boundary(ctx, phi);
 }
 
+// calcsc: the scalar transport template   TurbulenceModels/k_epsilon_rlzb.f90:52-790 + fluxes/scalar_fluxes.f90
+extern "C" int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_field, fcp_report *rep, double *fimin, double *fimax) {
+  if (!ctx || !prm) return FCP_EINVAL;
+  if (prm->kind < FCP_SC_GENERIC || prm->kind > FCP_SC_EPS_RLZB) { fcp_set_error("calcsc: unknown kind %d", prm->kind); return FCP_EINVAL; }
+  if (prm->cscheme < 0 || prm->cscheme >= FCP_CS_COUNT) { fcp_set_error("calcsc: non-existing interpolation scheme %d", prm->cscheme); return FCP_EINVAL; }
+  if (prm->tscheme < 0 || prm->tscheme > 2) { fcp_set_error("calcsc: unknown time scheme %d (Crank-Nicolson is not built)", prm->tscheme); return FCP_EINVAL; }
+  if (prm->tscheme && !(prm->timestep > 0.0)) { fcp_set_error("calcsc: timestep must be positive"); return FCP_EINVAL; }
+  if (!(prm->urf > 0.0)) { fcp_set_error("calcsc: urf must be positive"); return FCP_EINVAL; }
+  if ((prm->kind == FCP_SC_TKE_RLZB && phi_field != FCP_F_TE) || (prm->kind == FCP_SC_EPS_RLZB && phi_field != FCP_F_ED)) {
+    fcp_set_error("calcsc: kind %d solves for field %d", prm->kind, prm->kind == FCP_SC_TKE_RLZB ? FCP_F_TE : FCP_F_ED);
+    return FCP_EINVAL;
+  }
+  if (phi_field < 0 || phi_field >= FCP_F_COUNT || (phi_field >= FCP_F_DUDXI && phi_field <= FCP_F_H) || phi_field == FCP_F_SCTMP) {
+    fcp_set_error("calcsc: field %d is not a scalar cell field", phi_field);
+    return FCP_EINVAL;
+  }
+  if (ctx->comm) { fcp_set_error("calcsc: partitioned meshes are not supported yet"); return FCP_ESTATE; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(phi, phi_field); FIELD(den, FCP_F_DEN); FIELD(vis, FCP_F_VIS); FIELD(fl, FCP_F_FLMASS);
+  FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(sp, FCP_F_SP); FIELD(g, FCP_F_G0); FIELD(tmp, FCP_F_SCTMP);
+  ScParams q{};
+  q.kind = prm->kind; q.cscheme = prm->cscheme; q.tscheme = prm->tscheme;
+  q.gds = prm->gds; q.prtr = prm->prtr; q.viscos = prm->viscos; q.densit = prm->densit; q.timestep = prm->timestep; q.urf = prm->urf;
+  q.phi = phi; q.den = den; q.vis = vis; q.flmass = fl; q.grad = g; q.a = a; q.su = su; q.sp = sp; q.phi_new = tmp; q.phi_out = phi;
+  if (prm->tscheme >= 1) { FIELD(x, FCP_F_PHIO); q.phio = x; }
+  if (prm->tscheme >= 2) { FIELD(x, FCP_F_PHIOO); q.phioo = x; }
+  if (prm->kind == FCP_SC_GENERIC) { FIELD(x1, FCP_F_S2); FIELD(x2, FCP_F_S3); q.su_vol = x1; q.sp_vol = x2; }
+  else {
+    FIELD(te, FCP_F_TE); FIELD(ed, FCP_F_ED); FIELD(ms, FCP_F_MAGSTRAIN); FIELD(dnw, FCP_F_DNW);
+    q.te = te; q.ed = ed; q.magStrain = ms; q.dnw = dnw;
+    if (prm->kind == FCP_SC_TKE_RLZB) {
+      FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(visw, FCP_F_VISW); FIELD(gen, FCP_F_GEN); FIELD(tau, FCP_F_TAU);
+      q.u = u; q.v = v; q.w = w; q.visw = visw; q.gen = gen; q.tau = tau;
+    }
+  }
+  if (prm->grad_method != FCP_GRAD_GAUSS && !ctx->Dmat[prm->grad_method]) FCP_TRY(fcp_create_lsq_grad_matrix(ctx, prm->grad_method));
+  FCP_TRY(fcp_grad_opt(ctx, prm->grad_method, prm->limiter, phi_field, FCP_F_G0));           // call grad(te, dTedxi)
+  FCP_CUDA(cudaMemsetAsync(a, 0, sizeof(double) * (size_t)ctx->pat.nnzp, ctx->stream));      // a = 0
+  FCP_TRY(fvm_sc_assemble(ctx, q));
+  FCP_TRY(fcp_csrsolve(ctx, prm->solver, phi_field, FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel, rep));
+  FCP_TRY(fvm_update_boundary(ctx, phi));
+  double *d_mm = nullptr, mm[2] = {0.0, 0.0};
+  FCP_TRY(fvm_minmax(ctx, phi, &d_mm));
+  FCP_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+  FCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (fimin) *fimin = mm[0];
+  if (fimax) *fimax = mm[1];
+  if (prm->kind != FCP_SC_GENERIC && mm[0] < 0.0) FCP_TRY(fvm_clip_small(ctx, phi));         // :430
+  return FCP_OK;
+}
+extern "C" int fcp_calc_strain_and_vorticity(fcp_ctx *ctx) {
+  if (!ctx) return FCP_EINVAL;
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(gu, FCP_F_DUDXI); FIELD(gv, FCP_F_DVDXI); FIELD(gw, FCP_F_DWDXI); FIELD(ms, FCP_F_MAGSTRAIN); FIELD(vo, FCP_F_VORTICITY);
+  return fvm_strain(ctx, gu, gv, gw, ms, vo);
+}
+extern "C" int fcp_modify_mu_eff_k_epsilon_rlzb(fcp_ctx *ctx, double urfVis, double viscos) {
+  if (!ctx) return FCP_EINVAL;
+  if (ctx->comm) { fcp_set_error("modify_mu_eff: partitioned meshes are not supported yet"); return FCP_ESTATE; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(gu, FCP_F_DUDXI); FIELD(gv, FCP_F_DVDXI); FIELD(gw, FCP_F_DWDXI); FIELD(te, FCP_F_TE); FIELD(ed, FCP_F_ED); FIELD(den, FCP_F_DEN);
+  FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(dnw, FCP_F_DNW); FIELD(vis, FCP_F_VIS); FIELD(visw, FCP_F_VISW);
+  FIELD(ypl, FCP_F_YPL); FIELD(tau, FCP_F_TAU);
+  return fvm_mu_eff_rlzb(ctx, urfVis, viscos, gu, gv, gw, te, ed, den, u, v, w, dnw, vis, visw, ypl, tau);
+}
+
 // calcp_piso   Pressure/calcp_piso.f90:81-489
 extern "C" int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_report *rep) {
   if (!ctx || !prm) return FCP_EINVAL;

@@ -291,6 +291,21 @@ int fvm_update_vel_bnd(fcp_ctx *ctx, double *u, double *v, double *w);
 int fvm_uvw_assemble(fcp_ctx *ctx, const UvwArgs &g);
 int fvm_uvw_diag(fcp_ctx *ctx, double *a, const double *spq, const double *srcq, const double *phi, double *apq, double *su, double urf, int zero_first);
 
+// ---- fvm_scalar.cu (row f4) ---------------------------------------------------------------------
+struct ScParams {
+  int kind, cscheme, tscheme;
+  double gds, prtr, viscos, densit, timestep, urf;
+  const double *phi, *phio, *phioo, *te, *ed, *den, *vis, *visw, *dnw, *flmass, *u, *v, *w, *magStrain, *su_vol, *sp_vol, *grad;
+  double *gen, *tau, *a, *su, *sp, *phi_new, *phi_out;
+};
+int fvm_strain(fcp_ctx *ctx, const double *gU, const double *gV, const double *gW, double *magStrain, double *vorticity);
+int fvm_sc_assemble(fcp_ctx *ctx, const ScParams &q);
+int fvm_clip_small(fcp_ctx *ctx, double *phi);
+int fvm_mu_eff_rlzb(fcp_ctx *ctx, double urf, double viscos, const double *gU, const double *gV, const double *gW, const double *te, const double *ed,
+                    const double *den, const double *u, const double *v, const double *w, const double *dnw, double *vis, double *visw, double *ypl,
+                    double *tau);
+int fvm_minmax(fcp_ctx *ctx, const double *phi, double **mm_out);
+
 // ---- pattern.cu ---------------------------------------------------------------------------------
 int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, const int32_t *ja1, const int32_t *diag1,
                   const std::vector<std::vector<int32_t>> *halo_cols /* per row extra columns (0-based), may be null */);

@@ -129,6 +129,20 @@ __global__ void __launch_bounds__(FCP_TPB) k_limiter_mdl(MeshView m, const doubl
   }
 }
 
+// global minimum / maximum of phi(1:numCells): mm_out points at the device pair {min, max}
+int fvm_minmax(fcp_ctx *ctx, const double *phi, double **mm_out) {
+  const int nparts = std::max(fcp_nchunks(ctx->n), 1);
+  if (!ctx->d_mmpart) FCP_TRY(dev_alloc(&ctx->d_mmpart, (size_t)2 * nparts + 2));
+  double *mm = ctx->d_mmpart + (size_t)2 * nparts;
+  k_minmax_part<<<nparts, FCP_TPB, 0, ctx->stream>>>(ctx->n, phi, ctx->d_mmpart);
+  k_minmax_final<<<1, FCP_TPB, 0, ctx->stream>>>(nparts, ctx->d_mmpart, mm);
+  FCP_LAUNCHED(); FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  if (ctx->comm) FCP_TRY(comm_allreduce_minmax(ctx->comm, mm, ctx->stream));
+  *mm_out = mm;
+  return FCP_OK;
+}
+
 int fvm_slope_limiter(fcp_ctx *ctx, int limiter, const double *phi, double *g) {
   if (limiter == FCP_LIMITER_NONE || ctx->n == 0 && !ctx->comm) return FCP_OK;
   MeshView m = fcp_mesh_view(ctx);

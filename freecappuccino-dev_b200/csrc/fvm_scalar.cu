@@ -1,0 +1,340 @@
+// fvm_scalar.cu -- tier "next" row f4: the scalar transport template (calcsc) the turbulence models are written in,
+// fluxes/scalar_fluxes.f90:32-343 (facefluxsc, facefluxsc_periodic, facefluxsc_boundary) inside the assembly of
+// TurbulenceModels/k_epsilon_rlzb.f90 (calcsc_tke :52-445, calcsc_epsilon :447-790, modify_mu_eff :792-975), plus
+// fvExplicit/calc_strain_and_vorticity.f90.  Same design as fvm.cu / fvm_uvw.cu: one thread owns one cell and walks its faces in
+// ascending face index (the order in which the reference's sequential loops touch that cell), every face quantity is evaluated in the
+// face's own orientation on both sides, no atomics, no FMA contraction.
+//   k_strain          calc_strain_and_vorticity
+//   k_sc_assemble     volume sources (kind), bdf/bdf2 term, facefluxsc on inner faces, patches, wall treatment (kind)
+//   k_sc_diag         a(diag) = sp - sum(off-diagonals) in CSR order, under-relaxation (:397-415)
+//   k_clip            phi = max(phi, small) (:430)
+//   k_mu_eff_cell / k_mu_eff_wall   modify_mu_eff (acos, cos, log: these agree with the reference's libm to rounding, not to the bit)
+// Not built: Crank-Nicolson, buoyancy; partitioned meshes (the callers refuse a communicator).
+#include "fcp_internal.h"
+#include "fvm_common.cuh"
+#include "interp.cuh"
+
+#define FCP_CAPPA 0.41                          // parameters.f90:15
+#define FCP_ELOG 8.432                          // :17
+#define FCP_CTRANS ((double)11.63f)             // :18  `11.63` is a default-real literal
+#define FCP_CMU 0.09                            // k_epsilon_rlzb.f90:16
+#define FCP_C2RLZ 1.90                          // :18
+#define FCP_A0RLZ ((double)4.04f)               // :22  `4.04`: default-real literal
+__device__ __forceinline__ double cmu25_dev() { return sqrt(sqrt(FCP_CMU)); }                       // :25
+__device__ __forceinline__ double cmu75_dev() { const double c = cmu25_dev(); return c * c * c; }    // :26
+
+struct ScArgs {
+  int kind, cscheme, tscheme;
+  double gds, prtr, viscos, densit, timestep;
+  const double *phi, *phio, *phioo, *te, *ed, *den, *vis, *visw, *dnw, *flmass, *u, *v, *w, *magStrain, *su_vol, *sp_vol, *g;
+  double *gen, *tau, *a, *su, *sp, *phi_new;
+};
+
+__global__ void __launch_bounds__(FCP_TPB) k_strain(int32_t n, const double *__restrict__ gU, const double *__restrict__ gV, const double *__restrict__ gW,
+                                                     double *__restrict__ magStrain, double *__restrict__ vorticity) {
+  FCP_CELL_LOOP(c, n) {
+    const int64_t b = 3 * (int64_t)c;
+    const double dudx = gU[b], dudy = gU[b + 1], dudz = gU[b + 2];
+    const double dvdx = gV[b], dvdy = gV[b + 1], dvdz = gV[b + 2];
+    const double dwdx = gW[b], dwdy = gW[b + 1], dwdz = gW[b + 2];
+    const double s11 = dudx, s12 = 0.5 * (dudy + dvdx), s13 = 0.5 * (dudz + dwdx), s22 = dvdy, s23 = 0.5 * (dvdz + dwdy), s33 = dwdz;
+    const double w12 = (dudy - dvdx), w13 = (dudz - dwdx), w23 = (dvdz - dwdy);
+    magStrain[c] = sqrt(2 * (s11 * s11 + s22 * s22 + s33 * s33 + 2 * (s12 * s12 + s13 * s13 + s23 * s23)));
+    vorticity[c] = sqrt(w12 * w12 + w23 * w23 + w13 * w13);
+  }
+}
+
+// calcsc_epsilon overwrites ed(ijp) in wall cells WHILE it walks the patches (:726), so a periodic patch listed after a wall patch reads
+// the imposed value, not the old one.  This returns ed(cell) as the reference's boundary loop holds it when it reaches face fp: the value
+// imposed by the cell's last wall face that precedes fp, else the old value.
+__device__ __forceinline__ double eps_value_at_face(const MeshView &m, const ScArgs &g, int32_t cell, int32_t fp, double old_value) {
+  const int64_t base = m.slptr[cell >> 5] + (cell & 31);
+  const int32_t len = m.len[cell];
+  double v = old_value;
+  for (int32_t q = 0; q < len; ++q) {
+    const int32_t e = m.ent[base + (int64_t)q * 32], sl = m.slot[base + (int64_t)q * 32];
+    const int32_t f = (e > 0 ? e : -e) - 1;
+    if (sl == -1 - FCP_BC_WALL && f < fp) v = cmu75_dev() * pow(g.te[cell], 1.5) / (FCP_CAPPA * g.dnw[m.n + (f - m.F)]);
+  }
+  return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
+  FCP_CELL_LOOP(c, m.n) {
+    const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c], vol = m.vol[c];
+    const double phic = g.phi[c], visc = g.vis[c], denc = g.den[c];
+    const double gc[3] = {g.g[3 * (int64_t)c], g.g[3 * (int64_t)c + 1], g.g[3 * (int64_t)c + 2]};
+    double s, p, genc = 0.0, phin = phic;
+    // ---- volume sources
+    if (KIND == 0) { s = g.su_vol[c]; p = g.sp_vol[c]; }
+    else if (KIND == 1) {                                   // calcsc_tke :103-120
+      const double tec = phic, edc = g.ed[c];
+      genc = fabs(visc - g.viscos) * g.magStrain[c] * g.magStrain[c];
+      const double genp = fmax(genc, 0.0), genn = fmin(genc, 0.0);
+      s = genp * vol;
+      p = edc * denc * vol / (tec + FCP_SMALL);
+      p = p - genn * vol / (tec + FCP_SMALL);
+    } else {                                                // calcsc_epsilon :500-513
+      const double tec = g.te[c], edc = phic, ms = g.magStrain[c];
+      const double genp = fmax(ms, 0.0), genn = fmin(ms, 0.0);
+      const double etarlzb = ms * tec / (edc + FCP_SMALL);
+      const double c1 = fmax((double)0.43f, etarlzb / (etarlzb + 5.0));
+      s = c1 * genp * edc * vol;
+      p = FCP_C2RLZ * denc * edc * vol / (tec + sqrt(g.viscos / g.densit * edc) + FCP_SMALL);
+      p = p - c1 * genn * edc * vol;
+    }
+    if (g.tscheme) {                                        // :160-171
+      const double apotime = denc * vol / g.timestep;
+      if (g.tscheme == 1) { s = s + apotime * g.phio[c]; p = p + apotime; }
+      else { s = s + apotime * (2 * g.phio[c] - 0.5 * g.phioo[c]); p = p + 1.5 * apotime; }
+    }
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
+      if (sl >= 0) {
+        // ---- facefluxsc, scalar_fluxes.f90:32-141, in the face's orientation (P = owner, N = neighbour)
+        const bool own = e > 0;
+        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o], phio_ = g.phi[o], viso = g.vis[o];
+        const double go[3] = {g.g[3 * (int64_t)o], g.g[3 * (int64_t)o + 1], g.g[3 * (int64_t)o + 2]};
+        const double lambda = m.facint[f], Df = m.Df[f], fm = g.flmass[f];
+        const double fxn = lambda, fxp = 1.0 - lambda;
+        const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo, xN = own ? xo : xc, yN = own ? yo : yc, zN = own ? zo : zc;
+        const double phiP = own ? phic : phio_, phiN = own ? phio_ : phic;
+        const double visP = own ? visc : viso, visN = own ? viso : visc;
+        const double gP[3] = {own ? gc[0] : go[0], own ? gc[1] : go[1], own ? gc[2] : go[2]};
+        const double gN[3] = {own ? go[0] : gc[0], own ? go[1] : gc[1], own ? go[2] : gc[2]};
+        const double viste = (visP + (visN - visP) * lambda) - g.viscos;
+        const double dcoef = g.viscos + viste * g.prtr;
+        const double xpn = xN - xP, ypn = yN - yP, zpn = zN - zP;
+        const double de = dcoef * Df;
+        const double ce = fmin(fm, 0.0), cp = fmax(fm, 0.0);
+        const double can = -de + ce, cap = -de - cp;
+        double dfixi = gP[0] * fxp + gN[0] * fxn, dfiyi = gP[1] * fxp + gN[1] * fxn, dfizi = gP[2] * fxp + gN[2] * fxn;
+        dfixi = dfixi * (arx - Df * xpn); dfiyi = dfiyi * (ary - Df * ypn); dfizi = dfizi * (arz - Df * zpn);
+        const double fdfie = dcoef * (dfixi + dfiyi + dfizi);
+        const double xf = m.xf[f], yf = m.yf[f], zf = m.zf[f];
+        double fii;
+        if (fm >= 0.0) fii = face_value_dev(g.cscheme, phiP, phiN, gP, gN, xP, yP, zP, xN, yN, zN, xf, yf, zf, fxp);
+        else fii = face_value_dev(g.cscheme, phiN, phiP, gN, gP, xN, yN, zN, xP, yP, zP, xf, yf, zf, fxn);
+        double fcfie = fm * fii;
+        const double fcfii = ce * phiN + cp * phiP;
+        fcfie = g.gds * (fcfie - fcfii);
+        const double suadd = -fcfie + fdfie;
+        if (own) { g.a[sl] = can; s = s + suadd; }          // a(icell,jcell) = can ; su(ijp) += suadd
+        else     { g.a[sl] = cap; s = s - suadd; }          // a(jcell,icell) = cap ; su(ijn) -= suadd
+      } else {
+        const int type = -1 - sl;
+        if (type == FCP_BC_INLET || type == FCP_BC_OUTLET || type == FCP_BC_PRESSURE) {
+          // ---- facefluxsc_boundary :236-300
+          const double viste = g.vis[o] - g.viscos, dcoef = g.viscos + viste * g.prtr;
+          const double xpn = m.xf[f] - xc, ypn = m.yf[f] - yc, zpn = m.zf[f] - zc;
+          const double Dfi = (arx * arx + ary * ary + arz * arz) / (xpn * arx + ypn * ary + zpn * arz);
+          const double de = dcoef * Dfi;
+          const double ce = fmin(g.flmass[f], 0.0);
+          const double can = -de + ce;
+          double dfixi = gc[0], dfiyi = gc[1], dfizi = gc[2];
+          dfixi = dfixi * (arx - Dfi * xpn); dfiyi = dfiyi * (ary - Dfi * ypn); dfizi = dfizi * (arz - Dfi * zpn);
+          const double suadd = dcoef * (dfixi + dfiyi + dfizi);
+          p = p - can;
+          s = s - can * g.phi[o] + suadd;
+        } else if (m.per_cell && (type == FCP_BC_PERIODIC || type == FCP_BC_EMPTY) && m.per_cell[f - m.F] >= 0) {
+          // ---- facefluxsc_periodic :145-232 in the orientation of the PERIODIC face fp (quirk Q21: Df(i), i = ordinal in the patch)
+          const int32_t b = f - m.F, q = m.per_cell[b];
+          const bool own = type == FCP_BC_PERIODIC;
+          const int32_t fp = own ? f : m.per_face[b];
+          const double ax = m.arx[fp], ay = m.ary[fp], az = m.arz[fp];
+          const double xo = m.xc[q], yo = m.yc[q], zo = m.zc[q], phio_ = g.phi[q], viso = g.vis[q];
+          const double go[3] = {g.g[3 * (int64_t)q], g.g[3 * (int64_t)q + 1], g.g[3 * (int64_t)q + 2]};
+          const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo;
+          double phiP = own ? phic : phio_, phiN = own ? phio_ : phic;
+          if (KIND == 2) {                                   // wall cells already hold their imposed epsilon when a later patch reads them
+            phiP = eps_value_at_face(m, g, own ? c : q, fp, phiP);
+            phiN = eps_value_at_face(m, g, own ? q : c, fp, phiN);
+          }
+          const double visP = own ? visc : viso, visN = own ? viso : visc;
+          const double gP[3] = {own ? gc[0] : go[0], own ? gc[1] : go[1], own ? gc[2] : go[2]};
+          const double gN[3] = {own ? go[0] : gc[0], own ? go[1] : gc[1], own ? go[2] : gc[2]};
+          const double fxn = 0.5, fxp = fxn;
+          const double viste = 0.5 * (visP + visN) - g.viscos, dcoef = g.viscos + viste * g.prtr;
+          const double xpn = 2 * (m.xf[fp] - xP), ypn = 2 * (m.yf[fp] - yP), zpn = 2 * (m.zf[fp] - zP);
+          const double Dfq = m.Df[m.per_ord[b]], fm = g.flmass[fp];
+          const double de = dcoef * Dfq;
+          const double ce = fmin(fm, 0.0), cp = fmax(fm, 0.0);
+          const double can = -de + ce, cap = -de - cp;
+          double dfixi = gP[0] * fxp + gN[0] * fxn, dfiyi = gP[1] * fxp + gN[1] * fxn, dfizi = gP[2] * fxp + gN[2] * fxn;
+          dfixi = dfixi * (ax - Dfq * xpn); dfiyi = dfiyi * (ay - Dfq * ypn); dfizi = dfizi * (az - Dfq * zpn);
+          const double fdfie = dcoef * (dfixi + dfiyi + dfizi);
+          double fii;
+          if (fm >= 0.0) fii = phiP + (phiN - phiP) * fxp; else fii = phiN + (phiP - phiN) * fxn;
+          double fcfie = fm * fii;
+          const double fcfii = ce * phiN + cp * phiP;
+          fcfie = g.gds * (fcfie - fcfii);
+          const double suadd = -fcfie + fdfie;
+          if (own) { g.a[m.per_slot[b]] = can; s = s + suadd; }
+          else     { g.a[m.per_slot[b]] = cap; s = s - suadd; }
+        } else if (type == FCP_BC_WALL && KIND == 1) {
+          // ---- wall function for k, k_epsilon_rlzb.f90:331-368: production from the wall shear stress replaces the standard one
+          const double viss = fmax(g.viscos, g.visw[o]);
+          const double are = sqrt(arx * arx + ary * ary + arz * arz);
+          const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
+          const double uc = g.u[c], vc = g.v[c], wc = g.w[c];
+          const double Vnp = uc * nxf + vc * nyf + wc * nzf;
+          double xtp = uc - Vnp * nxf, ytp = vc - Vnp * nyf, ztp = wc - Vnp * nzf;
+          const double Vtp = sqrt(xtp * xtp + ytp * ytp + ztp * ztp);
+          xtp = xtp / Vtp; ytp = ytp / Vtp; ztp = ztp / Vtp;
+          const double Ut2 = fabs((g.u[o] - uc) * xtp + (g.v[o] - vc) * ytp + (g.w[o] - wc) * ztp);
+          const double dn = g.dnw[o];
+          const double tau = viss * Ut2 / dn;
+          g.tau[o] = tau;
+          s = s - genc * vol;
+          genc = fabs(tau) * cmu25_dev() * sqrt(phic) / (dn * FCP_CAPPA);
+          s = s + genc * vol;
+        } else if (type == FCP_BC_WALL && KIND == 2) {
+          // ---- wall cells of the epsilon equation :712-728: the row is cleared, sp = 1, su = ed = cmu75 k^1.5/(cappa dnw)
+          const int64_t base = m.a_slptr[c >> 5] + (c & 31);
+          const int32_t len = m.a_rinfo[c] & 0xffff;
+          for (int32_t k = 0; k < len; ++k) g.a[base + (int64_t)k * 32] = 0.0;
+          p = 1.0;
+          phin = cmu75_dev() * pow(g.te[c], 1.5) / (FCP_CAPPA * g.dnw[o]);
+          s = phin;
+        }
+      }
+    }
+    g.su[c] = s;
+    g.sp[c] = p;
+    g.phi_new[c] = phin;
+    if (KIND == 1) g.gen[c] = genc;
+  }
+}
+
+// a(diag) = sp; a(diag) -= a(k) for the off-diagonals in CSR order; under-relaxation; phi <- the value the reference holds at this point
+__global__ void __launch_bounds__(FCP_TPB) k_sc_diag(MeshView m, double *a, const double *__restrict__ sp, double *__restrict__ su,
+                                                      const double *__restrict__ phi_new, double *__restrict__ phi, double urf) {
+  const double urfrs = 1.0 / urf, urfms = 1.0 - urf;
+  FCP_CELL_LOOP(c, m.n) {
+    const int64_t base = m.a_slptr[c >> 5] + (c & 31);
+    const int32_t ri = m.a_rinfo[c];
+    const int32_t dpos = (ri >> 16) & 0xffff, len = ri & 0xffff;
+    double ad = sp[c];
+    for (int32_t k = 0; k < len; ++k) {
+      if (k == dpos) continue;
+      ad = ad - a[base + (int64_t)k * 32];
+    }
+    ad = ad * urfrs;
+    a[base + (int64_t)dpos * 32] = ad;
+    const double ph = phi_new[c];
+    su[c] = su[c] + urfms * ad * ph;
+    phi[c] = ph;
+  }
+}
+
+__global__ void __launch_bounds__(FCP_TPB) k_clip(int32_t n, double *__restrict__ phi) {
+  FCP_CELL_LOOP(c, n) { phi[c] = fmax(phi[c], FCP_SMALL); }
+}
+
+// modify_mu_eff, cell loop :810-880
+__global__ void __launch_bounds__(FCP_TPB) k_mu_eff_cell(int32_t n, double urf, double viscos, const double *__restrict__ gU, const double *__restrict__ gV,
+                                                          const double *__restrict__ gW, const double *__restrict__ te, const double *__restrict__ ed,
+                                                          const double *__restrict__ den, double *__restrict__ vis) {
+  FCP_CELL_LOOP(c, n) {
+    const int64_t b = 3 * (int64_t)c;
+    const double visold = vis[c];
+    const double dudx = gU[b], dudy = gU[b + 1], dudz = gU[b + 2];
+    const double dvdx = gV[b], dvdy = gV[b + 1], dvdz = gV[b + 2];
+    const double dwdx = gW[b], dwdy = gW[b + 1], dwdz = gW[b + 2];
+    const double s11 = dudx, s12 = 0.5 * (dudy + dvdx), s13 = 0.5 * (dudz + dwdx), s22 = dvdy, s23 = 0.5 * (dvdz + dwdy), s33 = dwdz;
+    const double s21 = s12, s31 = s13, s32 = s23;
+    const double w12 = 0.5 * (dudy - dvdx), w13 = 0.5 * (dudz - dwdx), w23 = 0.5 * (dvdz - dwdy);
+    const double stild = sqrt(s11 * s11 + s22 * s22 + s33 * s33 + 2 * (s12 * s12 + s13 * s13 + s23 * s23));
+    const double wrlzb = (s11 * s11 * s11 + s11 * s12 * s21 + s11 * s13 * s31 + s12 * s21 * s11 + s12 * s22 * s21 + s12 * s23 * s31 + s13 * s31 * s11 +
+                          s13 * s32 * s21 + s13 * s33 * s31 + s21 * s11 * s12 + s21 * s12 * s22 + s21 * s13 * s32 + s22 * s21 * s12 + s22 * s22 * s22 +
+                          s22 * s23 * s32 + s23 * s31 * s12 + s23 * s32 * s22 + s23 * s33 * s32 + s31 * s11 * s13 + s31 * s12 * s23 + s31 * s13 * s33 +
+                          s32 * s21 * s13 + s32 * s22 * s23 + s32 * s23 * s33 + s33 * s31 * s13 + s33 * s32 * s23 + s33 * s33 * s33) /
+                         (stild * stild * stild);
+    const double ffi = S13 * acos(fmax(-1.0, fmin(sqrt(6.0) * wrlzb, 1.0)));
+    const double ass = sqrt(6.0) * cos(ffi);
+    const double ust = sqrt(s11 * s11 + s22 * s22 + s33 * s33 + 2 * (s12 * s12 + s13 * s13 + s23 * s23 + w12 * w12 + w13 * w13 + w23 * w23));
+    const double cmur = 1.0 / (FCP_A0RLZ + ass * ust * te[c] / (ed[c] + FCP_SMALL));
+    const double vist = den[c] * cmur * (te[c] * te[c]) / (ed[c] + FCP_SMALL);
+    double v = viscos + vist;
+    v = urf * v + (1.0 - urf) * visold;
+    vis[c] = v;
+  }
+}
+// modify_mu_eff, wall faces :888-947 (boundary-face parallel)
+__global__ void __launch_bounds__(FCP_TPB) k_mu_eff_wall(MeshView m, const int32_t *__restrict__ bftype, double viscos, const double *__restrict__ te,
+                                                          const double *__restrict__ den, const double *__restrict__ u, const double *__restrict__ v,
+                                                          const double *__restrict__ w, const double *__restrict__ dnw, double *vis, double *visw,
+                                                          double *ypl, double *tau) {
+  FCP_CELL_LOOP(i, m.B) {
+    if (bftype[i] != FCP_BC_WALL) continue;
+    const int32_t f = m.F + i, ijp = m.owner[f], ijb = m.n + i;
+    const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
+    const double are = sqrt(arx * arx + ary * ary + arz * arz);
+    const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
+    const double Vnp = u[ijp] * nxf + v[ijp] * nyf + w[ijp] * nzf;
+    const double xtp = u[ijp] - Vnp * nxf, ytp = v[ijp] - Vnp * nyf, ztp = w[ijp] - Vnp * nzf;
+    const double Vtp = sqrt(xtp * xtp + ytp * ytp + ztp * ztp);
+    const double yp = den[ijp] * cmu25_dev() * sqrt(te[ijp]) * dnw[ijb] / viscos;
+    ypl[ijb] = yp;
+    tau[ijb] = FCP_CAPPA * den[ijp] * Vtp * cmu25_dev() * sqrt(te[ijp]) / log(FCP_ELOG * yp);
+    double viscw = 0.0;
+    if (yp > FCP_CTRANS) viscw = yp * viscos * FCP_CAPPA / log(FCP_ELOG * yp);
+    const double vw = fmax(viscos, viscw);
+    visw[ijb] = vw;
+    vis[ijb] = vw;
+  }
+}
+
+int fvm_strain(fcp_ctx *ctx, const double *gU, const double *gV, const double *gW, double *magStrain, double *vorticity) {
+  if (ctx->n == 0) return FCP_OK;
+  k_strain<<<FCP_GRID(ctx->n)>>>(ctx->n, gU, gV, gW, magStrain, vorticity);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
+int fvm_sc_assemble(fcp_ctx *ctx, const ScParams &q) {
+  if (ctx->n == 0) return FCP_OK;
+  ScArgs g;
+  g.kind = q.kind; g.cscheme = q.cscheme; g.tscheme = q.tscheme;
+  g.gds = q.gds; g.prtr = q.prtr; g.viscos = q.viscos; g.densit = q.densit; g.timestep = q.timestep;
+  g.phi = q.phi; g.phio = q.phio; g.phioo = q.phioo; g.te = q.te; g.ed = q.ed; g.den = q.den; g.vis = q.vis; g.visw = q.visw; g.dnw = q.dnw;
+  g.flmass = q.flmass; g.u = q.u; g.v = q.v; g.w = q.w; g.magStrain = q.magStrain; g.su_vol = q.su_vol; g.sp_vol = q.sp_vol; g.g = q.grad;
+  g.gen = q.gen; g.tau = q.tau; g.a = q.a; g.su = q.su; g.sp = q.sp; g.phi_new = q.phi_new;
+  const MeshView m = fcp_mesh_view(ctx);
+  size_t tok = ctx->prof.begin(FCP_K_SCALAR, ctx->stream);
+  if (q.kind == 0) k_sc_assemble<0><<<FCP_GRID(ctx->n)>>>(m, g);
+  else if (q.kind == 1) k_sc_assemble<1><<<FCP_GRID(ctx->n)>>>(m, g);
+  else k_sc_assemble<2><<<FCP_GRID(ctx->n)>>>(m, g);
+  ctx->prof.end(tok, ctx->stream);
+  FCP_LAUNCHED();
+  k_sc_diag<<<FCP_GRID(ctx->n)>>>(m, q.a, q.sp, q.su, q.phi_new, q.phi_out, q.urf);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
+int fvm_clip_small(fcp_ctx *ctx, double *phi) {
+  if (ctx->n == 0) return FCP_OK;
+  k_clip<<<FCP_GRID(ctx->n)>>>(ctx->n, phi);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
+int fvm_mu_eff_rlzb(fcp_ctx *ctx, double urf, double viscos, const double *gU, const double *gV, const double *gW, const double *te, const double *ed,
+                    const double *den, const double *u, const double *v, const double *w, const double *dnw, double *vis, double *visw, double *ypl,
+                    double *tau) {
+  if (ctx->n == 0) return FCP_OK;
+  k_mu_eff_cell<<<FCP_GRID(ctx->n)>>>(ctx->n, urf, viscos, gU, gV, gW, te, ed, den, vis);
+  FCP_LAUNCHED();
+  FCP_TRY(fvm_update_boundary(ctx, vis));                                       // :884
+  if (ctx->B) {
+    k_mu_eff_wall<<<FCP_GRID(ctx->B)>>>(fcp_mesh_view(ctx), ctx->bftype, viscos, te, den, u, v, w, dnw, vis, visw, ypl, tau);
+    FCP_LAUNCHED();
+  }
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}

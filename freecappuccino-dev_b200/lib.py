@@ -31,10 +31,11 @@ LIMITER_ID = {"none": 0, "no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan":
 PSCHEME = {"linear": 0, "central": 1, "weighted": 2}
 FIELDS = ["U", "V", "W", "P", "PP", "DEN", "VIS", "APU", "APV", "APW", "SU", "SV", "SW", "S0", "S1", "S2", "S3",
           "DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "FLMASS", "A", "APR", "H", "RU", "RV", "RW", "VISW",
-          "UO", "VO", "WO", "UOO", "VOO", "WOO", "UOOO", "VOOO", "WOOO", "SPU", "SPV", "SP"]
+          "UO", "VO", "WO", "UOO", "VOO", "WOO", "UOOO", "VOOO", "WOOO", "SPU", "SPV", "SP",
+          "TE", "ED", "PHIO", "PHIOO", "GEN", "MAGSTRAIN", "VORTICITY", "DNW", "TAU", "YPL", "SCTMP"]
 F = {name: i for i, name in enumerate(FIELDS)}
 KERNEL_CLASSES = ["spmv_dot", "cg_pk", "cg_update", "cg_init", "precond", "dot", "bicg_elem", "assemble", "gradp", "correct_flux",
-                  "grad", "laplacian", "spmv", "halo", "limiter", "piso_h", "uvw"]
+                  "grad", "laplacian", "spmv", "halo", "limiter", "piso_h", "uvw", "scalar"]
 GRADIENT_FIELDS = {"DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1"}
 
 
@@ -74,6 +75,15 @@ class UvwParams(C.Structure):
                 ("gds", C.c_double), ("cscheme", C.c_int32), ("grad_method", C.c_int32), ("limiter", C.c_int32), ("pscheme", C.c_int32),
                 ("tscheme", C.c_int32), ("piso", C.c_int32), ("timestep", C.c_double), ("const_mflux", C.c_int32), ("pad", C.c_int32),
                 ("gradPcmf", C.c_double), ("viscos", C.c_double)]
+
+
+SC_GENERIC, SC_TKE_RLZB, SC_EPS_RLZB = 0, 1, 2
+SC_KIND = {"generic": SC_GENERIC, "tke_rlzb": SC_TKE_RLZB, "eps_rlzb": SC_EPS_RLZB}
+
+
+class ScalarParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "solver", "maxiter", "cscheme", "grad_method", "limiter", "tscheme", "pad")] + \
+               [(n, C.c_double) for n in ("tol_abs", "tol_rel", "urf", "gds", "timestep", "prtr", "viscos", "densit")]
 
 
 class PisoParams(C.Structure):
@@ -137,6 +147,9 @@ def lib():
     L.fcp_calcp_piso.argtypes = [vp, C.POINTER(PisoParams), C.POINTER(Report)]
     L.fcp_constant_mass_flow_forcing.argtypes = [vp, C.c_double, _pd, _pd]
     L.fcp_update_boundary.argtypes = [vp, C.c_int]
+    L.fcp_calcsc.argtypes = [vp, C.POINTER(ScalarParams), C.c_int, C.POINTER(Report), _pd, _pd]
+    L.fcp_calc_strain_and_vorticity.argtypes = [vp]
+    L.fcp_modify_mu_eff_k_epsilon_rlzb.argtypes = [vp, C.c_double, C.c_double]
     L.fcp_calcuvw.argtypes = [vp, C.POINTER(UvwParams), C.POINTER(Report)]
     L.fcp_laplacian.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_gradp_and_sources.argtypes = [vp, C.c_int, C.c_int]
@@ -304,6 +317,29 @@ class Context:
         ustar = C.c_double(0.0)
         check(lib().fcp_constant_mass_flow_forcing(self.h, magUbar, C.byref(g), C.byref(ustar)), "fcp_constant_mass_flow_forcing")
         return g.value, ustar.value
+
+    def calcsc(self, phi, kind="generic", solver="bicgstab", maxiter=10, tol_abs=1e-13, tol_rel=0.025, urf=0.8, gds=1.0, cscheme="cds",
+               grad_method="gauss", limiter="none", tscheme="steady", timestep=0.0, prtr=1.0, viscos=0.0, densit=1.0):
+        """The calcsc template (k_epsilon_rlzb.f90:52-790 + scalar_fluxes.f90).  Returns (report, fimin, fimax)."""
+        prm = ScalarParams()
+        prm.kind = SC_KIND[kind] if isinstance(kind, str) else kind
+        prm.solver = SOLVER_ID[solver] if isinstance(solver, str) else solver
+        prm.maxiter, prm.tol_abs, prm.tol_rel, prm.urf, prm.gds = maxiter, tol_abs, tol_rel, urf, gds
+        prm.cscheme = CSCHEME_ID[cscheme] if isinstance(cscheme, str) else cscheme
+        prm.grad_method = GRAD_ID[grad_method] if isinstance(grad_method, str) else grad_method
+        prm.limiter = LIMITER_ID[limiter] if isinstance(limiter, str) else limiter
+        prm.tscheme = TSCHEME[tscheme] if isinstance(tscheme, str) else tscheme
+        prm.timestep, prm.prtr, prm.viscos, prm.densit = timestep, prtr, viscos, densit
+        rep = Report()
+        lo, hi = C.c_double(0.0), C.c_double(0.0)
+        check(lib().fcp_calcsc(self.h, C.byref(prm), field_id(phi), C.byref(rep), C.byref(lo), C.byref(hi)), "fcp_calcsc")
+        return rep, lo.value, hi.value
+
+    def calc_strain_and_vorticity(self):
+        check(lib().fcp_calc_strain_and_vorticity(self.h), "fcp_calc_strain_and_vorticity")
+
+    def modify_mu_eff_k_epsilon_rlzb(self, urfVis: float, viscos: float):
+        check(lib().fcp_modify_mu_eff_k_epsilon_rlzb(self.h, urfVis, viscos), "fcp_modify_mu_eff_k_epsilon_rlzb")
 
     def update_boundary(self, field):
         """updateBoundary(phi), boundary/updateBoundary.f90."""

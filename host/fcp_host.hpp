@@ -225,6 +225,34 @@ inline void calcuvw() {
   get(FCP_F_DPDXI, dPdxi, 3 * (int64_t)nT); get(FCP_F_A, a, nnz);
   if (parameters::piso) { rU.resize(n); rV.resize(n); rW.resize(n); get(FCP_F_RU, rU, n); get(FCP_F_RV, rV, n); get(FCP_F_RW, rW, n); }
 }
+// updateBoundary(phi)   src/finiteVolume/boundary/updateBoundary.f90
+inline void updateBoundary(std::vector<dp> &phi) {
+  put(FCP_F_S0, phi, (int64_t)phi.size());
+  check(fcp_update_boundary(ctx, FCP_F_S0), "fcp_update_boundary");
+  get(FCP_F_S0, phi, (int64_t)phi.size());
+}
+// calcsc: the scalar transport template of the turbulence models (k_epsilon_rlzb.f90:52-790 + scalar_fluxes.f90); the fields it reads
+// (den, vis, flmass, te, ed, magStrain, dnw, visw, u, v, w, phio/phioo) are uploaded by the caller with put()
+inline fcp_report calcsc(int kind, int phi_field, int solver, int maxiter, dp tolAbs, dp tolRel, dp urf, dp gds, int cscheme, dp prtr, dp viscos, dp densit,
+                         dp *fimin = nullptr, dp *fimax = nullptr, int tscheme = 0, dp timestep = 0.0, int grad_method = FCP_GRAD_GAUSS,
+                         int limiter = FCP_LIMITER_NONE) {
+  fcp_scalar_params prm{};
+  prm.kind = kind; prm.solver = solver; prm.maxiter = maxiter; prm.cscheme = cscheme; prm.grad_method = grad_method; prm.limiter = limiter;
+  prm.tscheme = tscheme; prm.tol_abs = tolAbs; prm.tol_rel = tolRel; prm.urf = urf; prm.gds = gds; prm.timestep = timestep; prm.prtr = prtr;
+  prm.viscos = viscos; prm.densit = densit;
+  fcp_report rep{};
+  check(fcp_calcsc(ctx, &prm, phi_field, &rep, fimin, fimax), "fcp_calcsc");
+  return rep;
+}
+inline void calc_strain_and_vorticity() { check(fcp_calc_strain_and_vorticity(ctx), "fcp_calc_strain_and_vorticity"); }
+inline void modify_mu_eff_k_epsilon_rlzb(dp urfVis, dp viscos) { check(fcp_modify_mu_eff_k_epsilon_rlzb(ctx, urfVis, viscos), "fcp_modify_mu_eff_k_epsilon_rlzb"); }
+// constant_mass_flow_forcing   src/cappuccino/constant_mass_flow_forcing.f90 (U and APU already on the device)
+inline dp constant_mass_flow_forcing(dp magUbar, dp &gradPcmf) {
+  dp ustar = 0.0;
+  check(fcp_constant_mass_flow_forcing(ctx, magUbar, &gradPcmf, &ustar), "fcp_constant_mass_flow_forcing");
+  return ustar;
+}
+
 // calcp_piso(): no arguments   Pressure/calcp_piso.f90
 inline void calcp_piso() {
   using namespace variables;

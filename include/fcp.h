@@ -67,6 +67,11 @@ enum {
   FCP_F_VISW,                                      /* visw(iWall): effective wall viscosity, stored in the wall faces' boundary slots */
   FCP_F_UO, FCP_F_VO, FCP_F_WO, FCP_F_UOO, FCP_F_VOO, FCP_F_WOO, FCP_F_UOOO, FCP_F_VOOO, FCP_F_WOOO,   /* past time levels */
   FCP_F_SPU, FCP_F_SPV, FCP_F_SP,                  /* spu, spv, sp: implicit source terms of the three momentum equations */
+  FCP_F_TE, FCP_F_ED,                              /* te, ed: turbulence kinetic energy and its dissipation rate */
+  FCP_F_PHIO, FCP_F_PHIOO,                         /* past time levels of the scalar fcp_calcsc is solving for (teo/teoo, edo/edoo ...) */
+  FCP_F_GEN, FCP_F_MAGSTRAIN, FCP_F_VORTICITY,     /* gen, magStrain, vorticity (variables module) */
+  FCP_F_DNW, FCP_F_TAU, FCP_F_YPL,                 /* dnw, tau, ypl(iWall): per wall face, stored in the wall faces' boundary slots like visw above */
+  FCP_F_SCTMP,                                     /* scratch of fcp_calcsc */
   FCP_F_COUNT
 };
 
@@ -227,6 +232,37 @@ typedef struct {
  * Periodic patches: :393-432 + facefluxuvw_periodic :1038-1180.  Not built: Crank-Nicolson, buoyancy, MHD. rep[0..2] = U, V, W. */
 int fcp_calcuvw(fcp_ctx *ctx, const fcp_uvw_params *prm, fcp_report *rep);
 
+/* ---- row f4: the scalar transport template (calcsc) of the turbulence models --------------------------------------------------
+ * fluxes/scalar_fluxes.f90:32-343 (facefluxsc, facefluxsc_periodic, facefluxsc_boundary) inside the assembly of
+ * TurbulenceModels/k_epsilon_rlzb.f90: grad(phi) -> volume sources + bdf/bdf2 term -> inner faces -> inlet/outlet/pressure, periodic and
+ * wall patches -> a(diag) = sp - sum(off-diagonals), under-relaxation -> csrsolve -> updateBoundary -> min/max, clip to `small` when negative.
+ *   FCP_SC_GENERIC   volume sources su, sp read from FCP_F_S2, FCP_F_S3; wall faces add nothing (zero flux); no clipping
+ *   FCP_SC_TKE_RLZB  calcsc_tke :52-445 (phi_field must be FCP_F_TE): gen = |vis - viscos| S^2 (FCP_F_GEN out), wall cells use the production
+ *                    from the wall shear stress (FCP_F_TAU out; reads FCP_F_VISW, FCP_F_DNW, U, V, W)
+ *   FCP_SC_EPS_RLZB  calcsc_epsilon :447-790 (phi_field must be FCP_F_ED): realizable c1; wall cells: row cleared, ed = cmu75 k^1.5/(cappa dnw)
+ * Inputs: FCP_F_DEN, FCP_F_VIS (effective viscosity, boundary slots included), FCP_F_FLMASS, FCP_F_MAGSTRAIN, FCP_F_TE, FCP_F_ED, FCP_F_PHIO/PHIOO.
+ * Outputs: the scalar, FCP_F_A (its matrix), FCP_F_SU, FCP_F_SP, FCP_F_G0 (its gradient).  k^1.5 uses the device pow(): that value agrees
+ * with the reference's libm to rounding, everything else follows the reference's operation order.  Not built: Crank-Nicolson, buoyancy,
+ * partitioned meshes (FCP_ESTATE with a communicator). */
+enum { FCP_SC_GENERIC = 0, FCP_SC_TKE_RLZB = 1, FCP_SC_EPS_RLZB = 2 };
+typedef struct {
+  int32_t kind;                 /* FCP_SC_* */
+  int32_t solver, maxiter;      /* TurbModel%Scalar(i)%lSolver, %maxiter */
+  int32_t cscheme;              /* FCP_CS_* (TurbModel%Scalar(i)%cScheme) */
+  int32_t grad_method, limiter; /* the configuration of grad(phi, dPhidxi) */
+  int32_t tscheme, pad;         /* 0 steady, 1 bdf, 2 bdf2 */
+  double tol_abs, tol_rel, urf, gds, timestep;
+  double prtr;                  /* 1/sigma of the scalar */
+  double viscos, densit;
+} fcp_scalar_params;
+int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_field, fcp_report *rep, double *fimin, double *fimax);
+/* calc_strain_and_vorticity (fvExplicit/calc_strain_and_vorticity.f90): FCP_F_DUDXI/DVDXI/DWDXI -> FCP_F_MAGSTRAIN, FCP_F_VORTICITY */
+int fcp_calc_strain_and_vorticity(fcp_ctx *ctx);
+/* modify_mu_eff of the realizable k-epsilon model (k_epsilon_rlzb.f90:792-975): effective viscosity from te, ed and the velocity gradients,
+ * under-relaxed by urfVis; updateBoundary(vis); wall functions -> FCP_F_VISW, FCP_F_YPL, FCP_F_TAU and vis at the wall faces.  acos, cos and
+ * log are the device's: agreement with the reference's libm is to rounding. */
+int fcp_modify_mu_eff_k_epsilon_rlzb(fcp_ctx *ctx, double urfVis, double viscos);
+
 /* ---- explicit-CSR solver signature: dpcg|iccg|bicgstab(n,nnz,ia,ja,a,diag,fi,rhs,...) -------- */
 /* linear_solvers.f90:206, :364, :548 ; pattern analysed once, values per solve */
 int fcp_solver_create(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const int32_t *diag,
@@ -260,7 +296,7 @@ int fcp_global_min(fcp_ctx *ctx, double *value);
 /* ---- per-kernel-class device timing (CUDA events on the context stream, around every launch of the class) ---- */
 enum { FCP_K_SPMV_DOT = 0, FCP_K_CG_PK, FCP_K_CG_UPDATE, FCP_K_CG_INIT, FCP_K_PRECOND, FCP_K_DOT, FCP_K_BICG_ELEM,
        FCP_K_ASSEMBLE, FCP_K_GRADP, FCP_K_CORRECT_FLUX, FCP_K_GRAD, FCP_K_LAPLACIAN, FCP_K_SPMV, FCP_K_HALO, FCP_K_LIMITER,
-       FCP_K_PISO_H, FCP_K_UVW, FCP_K_COUNT };
+       FCP_K_PISO_H, FCP_K_UVW, FCP_K_SCALAR, FCP_K_COUNT };
 int fcp_profile_enable(fcp_ctx *ctx, int on);
 int fcp_profile_reset(fcp_ctx *ctx);
 int fcp_profile_read(fcp_ctx *ctx, int kclass, double *total_ms, int64_t *launches);   /* synchronises; totals since reset */

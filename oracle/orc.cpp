@@ -1544,3 +1544,219 @@ extern "C" void orc_calcuvw(const orc_mesh *m, const i32 *ia, const i32 *ja, con
     solve_any(prm->solver, n, nnz, ia, ja, a, diag, comp[q], su, prm->maxiter, prm->tol_abs, prm->tol_rel, prm->sum_mode, &rep[q]);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// row f4: scalar transport template  (fluxes/scalar_fluxes.f90 + TurbulenceModels/k_epsilon_rlzb.f90)
+// ------------------------------------------------------------------------------------------
+static const double CAPPA = 0.41, ELOG = 8.432, CTRANS = (double)11.63f;      // parameters.f90:15-18 (`11.63` is a default-real literal)
+static const double CMU = 0.09, C2RLZ = 1.90, A0RLZ = (double)4.04f;          // k_epsilon_rlzb.f90:16-22 (`4.04`: default-real literal)
+static inline double cmu25() { return std::sqrt(std::sqrt(CMU)); }            // :25
+static inline double cmu75() { const double c = cmu25(); return c * c * c; }  // :26  cmu25**3
+
+extern "C" void orc_calc_strain_and_vorticity(const orc_mesh *m, const double *gU, const double *gV, const double *gW, double *magStrain,
+                                              double *vorticity) {
+  for (i32 c = 0; c < m->numCells; ++c) {
+    const double dudx = gU[3 * c], dudy = gU[3 * c + 1], dudz = gU[3 * c + 2];
+    const double dvdx = gV[3 * c], dvdy = gV[3 * c + 1], dvdz = gV[3 * c + 2];
+    const double dwdx = gW[3 * c], dwdy = gW[3 * c + 1], dwdz = gW[3 * c + 2];
+    const double s11 = dudx, s12 = 0.5 * (dudy + dvdx), s13 = 0.5 * (dudz + dwdx), s22 = dvdy, s23 = 0.5 * (dvdz + dwdy), s33 = dwdz;
+    const double w12 = (dudy - dvdx), w13 = (dudz - dwdx), w23 = (dvdz - dwdy);
+    magStrain[c] = std::sqrt(2 * (s11 * s11 + s22 * s22 + s33 * s33 + 2 * (s12 * s12 + s13 * s13 + s23 * s23)));
+    vorticity[c] = std::sqrt(w12 * w12 + w23 * w23 + w13 * w13);
+  }
+}
+
+extern "C" void orc_calcsc(const orc_mesh *m, const i32 *ia, const i32 *ja, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell, i32 nnz,
+                           const orc_scalar_params *prm, double *phi, const double *phio, const double *phioo, double *te, double *ed,
+                           const double *den, const double *vis, const double *visw, const double *dnw, const double *flmass, const double *u,
+                           const double *v, const double *w, const double *magStrain, double *gen, double *tau, const double *su_vol,
+                           const double *sp_vol, double *a, double *su, double *sp, double *g, orc_report *rep, double *fimin_out,
+                           double *fimax_out) {
+  const i32 n = m->numCells, F = m->numInnerFaces;
+  const double gam = prm->gds, prtr = prm->prtr, viscos = prm->viscos;
+  const int cs = prm->cscheme;
+  std::vector<double> Dm;
+  if (prm->grad_method == 1 || prm->grad_method == 2) { Dm.resize((size_t)9 * n); orc_create_matrix_lsq(m, prm->grad_method == 2, Dm.data()); }
+  if (prm->grad_method == 3) { Dm.resize((size_t)18 * n); orc_create_matrix_lsq_qr(m, Dm.data()); }
+  grad_any(m, ia, ja, diag, prm->grad_method, prm->limiter, Dm.data(), phi, g);        // call grad(te,dTedxi)
+  for (i32 k = 0; k < nnz; ++k) a[k] = 0.0;
+  for (i32 c = 0; c < n; ++c) { su[c] = 0.0; sp[c] = 0.0; }
+  // ---- volume sources
+  if (prm->kind == 1) for (i32 c = 0; c < n; ++c) gen[c] = std::fabs(vis[c] - viscos) * magStrain[c] * magStrain[c];   // :103-105
+  for (i32 c = 0; c < n; ++c) {
+    if (prm->kind == 0) { su[c] = su_vol[c]; sp[c] = sp_vol[c]; }
+    else if (prm->kind == 1) {                                                          // :108-120
+      const double genp = mx(gen[c], 0.0), genn = mn(gen[c], 0.0);
+      su[c] = genp * m->vol[c];
+      sp[c] = ed[c] * den[c] * m->vol[c] / (te[c] + SMALL);
+      sp[c] = sp[c] - genn * m->vol[c] / (te[c] + SMALL);
+    } else {                                                                            // :500-513
+      const double genp = mx(magStrain[c], 0.0), genn = mn(magStrain[c], 0.0);
+      const double etarlzb = magStrain[c] * te[c] / (ed[c] + SMALL);
+      const double c1 = mx((double)0.43f, etarlzb / (etarlzb + 5.0));
+      su[c] = c1 * genp * ed[c] * m->vol[c];
+      sp[c] = C2RLZ * den[c] * ed[c] * m->vol[c] / (te[c] + std::sqrt(viscos / prm->densit * ed[c]) + SMALL);
+      sp[c] = sp[c] - c1 * genn * ed[c] * m->vol[c];
+    }
+    if (prm->tscheme) {                                                                 // :160-171
+      const double apotime = den[c] * m->vol[c] / prm->timestep;
+      if (prm->tscheme == 1) { su[c] = su[c] + apotime * phio[c]; sp[c] = sp[c] + apotime; }
+      else { su[c] = su[c] + apotime * (2 * phio[c] - 0.5 * phioo[c]); sp[c] = sp[c] + 1.5 * apotime; }
+    }
+  }
+  // ---- inner faces, facefluxsc scalar_fluxes.f90:32-141
+  for (i32 i = 0; i < F; ++i) {
+    const i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    const double lambda = m->facint[i], fxn = lambda, fxp = 1.0 - lambda;
+    const double viste = (vis[ijp] + (vis[ijn] - vis[ijp]) * lambda) - viscos;
+    const double dcoef = viscos + viste * prtr;
+    const double arx = m->arx[i], ary = m->ary[i], arz = m->arz[i], fm = flmass[i];
+    const double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
+    const double de = dcoef * m->Df[i];
+    const double ce = mn(fm, 0.0), cp = mx(fm, 0.0);
+    const double can = -de + ce, cap = -de - cp;
+    double dfixi = g[3 * ijp] * fxp + g[3 * ijn] * fxn, dfiyi = g[3 * ijp + 1] * fxp + g[3 * ijn + 1] * fxn, dfizi = g[3 * ijp + 2] * fxp + g[3 * ijn + 2] * fxn;
+    dfixi = dfixi * (arx - m->Df[i] * xpn); dfiyi = dfiyi * (ary - m->Df[i] * ypn); dfizi = dfizi * (arz - m->Df[i] * zpn);
+    const double fdfie = dcoef * (dfixi + dfiyi + dfizi);
+    double fii;
+    if (fm >= 0.0) fii = orc_face_value(m, cs, ijp + 1, ijn + 1, m->xf[i], m->yf[i], m->zf[i], fxp, phi, g);
+    else fii = orc_face_value(m, cs, ijn + 1, ijp + 1, m->xf[i], m->yf[i], m->zf[i], fxn, phi, g);
+    double fcfie = fm * fii;
+    const double fcfii = ce * phi[ijn] + cp * phi[ijp];
+    fcfie = gam * (fcfie - fcfii);
+    const double suadd = -fcfie + fdfie;
+    a[icell_jcell[i] - 1] = can;
+    a[jcell_icell[i] - 1] = cap;
+    su[ijp] = su[ijp] + suadd;
+    su[ijn] = su[ijn] - suadd;
+  }
+  // ---- boundary patches
+  i32 lper = F;
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    const i32 t = m->bctype[ib];
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1, bf = f - F;
+      const double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+      if (t == ORC_BC_INLET || t == ORC_BC_OUTLET || t == ORC_BC_PRESSURE) {            // facefluxsc_boundary :236-300
+        const double viste = vis[ijb] - viscos, dcoef = viscos + viste * prtr;
+        const double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
+        const double Dfi = (arx * arx + ary * ary + arz * arz) / (xpn * arx + ypn * ary + zpn * arz);
+        const double de = dcoef * Dfi;
+        const double ce = mn(flmass[f], 0.0);
+        const double can = -de + ce;
+        double dfixi = g[3 * ijp], dfiyi = g[3 * ijp + 1], dfizi = g[3 * ijp + 2];
+        dfixi = dfixi * (arx - Dfi * xpn); dfiyi = dfiyi * (ary - Dfi * ypn); dfizi = dfizi * (arz - Dfi * zpn);
+        const double suadd = dcoef * (dfixi + dfiyi + dfizi);
+        sp[ijp] = sp[ijp] - can;
+        su[ijp] = su[ijp] - can * phi[ijb] + suadd;
+      } else if (t == ORC_BC_PERIODIC) {                                                // facefluxsc_periodic :145-232 (Df(i): ordinal in the patch, quirk Q21)
+        const i32 ijn = m->owner[m->startFaceTwin[ib] + i - 1] - 1;
+        const double fxn = 0.5, fxp = fxn;
+        const double viste = 0.5 * (vis[ijp] + vis[ijn]) - viscos, dcoef = viscos + viste * prtr;
+        const double xpn = 2 * (m->xf[f] - m->xc[ijp]), ypn = 2 * (m->yf[f] - m->yc[ijp]), zpn = 2 * (m->zf[f] - m->zc[ijp]);
+        const double Dfq = m->Df[i - 1], fm = flmass[f];
+        const double de = dcoef * Dfq;
+        const double ce = mn(fm, 0.0), cp = mx(fm, 0.0);
+        const double can = -de + ce, cap = -de - cp;
+        double dfixi = g[3 * ijp] * fxp + g[3 * ijn] * fxn, dfiyi = g[3 * ijp + 1] * fxp + g[3 * ijn + 1] * fxn, dfizi = g[3 * ijp + 2] * fxp + g[3 * ijn + 2] * fxn;
+        dfixi = dfixi * (arx - Dfq * xpn); dfiyi = dfiyi * (ary - Dfq * ypn); dfizi = dfizi * (arz - Dfq * zpn);
+        const double fdfie = dcoef * (dfixi + dfiyi + dfizi);
+        double fii;
+        if (fm >= 0.0) fii = phi[ijp] + (phi[ijn] - phi[ijp]) * fxp; else fii = phi[ijn] + (phi[ijp] - phi[ijn]) * fxn;
+        double fcfie = fm * fii;
+        const double fcfii = ce * phi[ijn] + cp * phi[ijp];
+        fcfie = gam * (fcfie - fcfii);
+        const double suadd = -fcfie + fdfie;
+        a[icell_jcell[lper] - 1] = can;
+        a[jcell_icell[lper] - 1] = cap;
+        ++lper;
+        su[ijp] = su[ijp] + suadd;
+        su[ijn] = su[ijn] - suadd;
+      } else if (t == ORC_BC_WALL && prm->kind == 1) {                                  // k_epsilon_rlzb.f90:331-368
+        const double viss = mx(viscos, visw[bf]);
+        const double are = std::sqrt(arx * arx + ary * ary + arz * arz);
+        const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
+        const double Vnp = u[ijp] * nxf + v[ijp] * nyf + w[ijp] * nzf;
+        double xtp = u[ijp] - Vnp * nxf, ytp = v[ijp] - Vnp * nyf, ztp = w[ijp] - Vnp * nzf;
+        const double Vtp = std::sqrt(xtp * xtp + ytp * ytp + ztp * ztp);
+        xtp = xtp / Vtp; ytp = ytp / Vtp; ztp = ztp / Vtp;
+        const double Ut2 = std::fabs((u[ijb] - u[ijp]) * xtp + (v[ijb] - v[ijp]) * ytp + (w[ijb] - w[ijp]) * ztp);
+        tau[bf] = viss * Ut2 / dnw[bf];
+        su[ijp] = su[ijp] - gen[ijp] * m->vol[ijp];
+        gen[ijp] = std::fabs(tau[bf]) * cmu25() * std::sqrt(te[ijp]) / (dnw[bf] * CAPPA);
+        su[ijp] = su[ijp] + gen[ijp] * m->vol[ijp];
+      } else if (t == ORC_BC_WALL && prm->kind == 2) {                                  // :712-728
+        for (i32 k = ia[ijp]; k <= ia[ijp + 1] - 1; ++k) a[k - 1] = 0.0;
+        sp[ijp] = 1.0;
+        ed[ijp] = cmu75() * std::pow(te[ijp], 1.5) / (CAPPA * dnw[bf]);
+        su[ijp] = ed[ijp];
+      }
+    }
+  }
+  // ---- diagonal + under-relaxation, :397-415
+  const double urfrs = 1.0 / prm->urf, urfms = 1.0 - prm->urf;
+  for (i32 c = 0; c < n; ++c) {
+    a[diag[c] - 1] = sp[c];
+    for (i32 k = ia[c]; k <= ia[c + 1] - 1; ++k) {
+      if (k == diag[c]) continue;
+      a[diag[c] - 1] = a[diag[c] - 1] - a[k - 1];
+    }
+    a[diag[c] - 1] = a[diag[c] - 1] * urfrs;
+    su[c] = su[c] + urfms * a[diag[c] - 1] * phi[c];
+  }
+  solve_any(prm->solver, n, nnz, ia, ja, a, diag, phi, su, prm->maxiter, prm->tol_abs, prm->tol_rel, prm->sum_mode, rep);   // :418
+  orc_update_boundary(m, phi);                                                          // :421
+  double fimin = phi[0], fimax = phi[0];
+  for (i32 c = 1; c < n; ++c) { fimin = mn(fimin, phi[c]); fimax = mx(fimax, phi[c]); }
+  if (fimin_out) *fimin_out = fimin;
+  if (fimax_out) *fimax_out = fimax;
+  if (prm->kind != 0 && fimin < 0.0) for (i32 c = 0; c < n; ++c) phi[c] = mx(phi[c], SMALL);   // :430
+}
+
+extern "C" void orc_modify_mu_eff_rlzb(const orc_mesh *m, double urf, double viscos, const double *gU, const double *gV, const double *gW,
+                                       const double *te, const double *ed, const double *den, const double *u, const double *v, const double *w,
+                                       const double *dnw, double *vis, double *visw, double *ypl, double *tau) {
+  const i32 n = m->numCells, F = m->numInnerFaces;
+  for (i32 c = 0; c < n; ++c) {                                                         // :810-880
+    const double visold = vis[c];
+    const double dudx = gU[3 * c], dudy = gU[3 * c + 1], dudz = gU[3 * c + 2];
+    const double dvdx = gV[3 * c], dvdy = gV[3 * c + 1], dvdz = gV[3 * c + 2];
+    const double dwdx = gW[3 * c], dwdy = gW[3 * c + 1], dwdz = gW[3 * c + 2];
+    const double s11 = dudx, s12 = 0.5 * (dudy + dvdx), s13 = 0.5 * (dudz + dwdx), s22 = dvdy, s23 = 0.5 * (dvdz + dwdy), s33 = dwdz;
+    const double s21 = s12, s31 = s13, s32 = s23;
+    const double w12 = 0.5 * (dudy - dvdx), w13 = 0.5 * (dudz - dwdx), w23 = 0.5 * (dvdz - dwdy);
+    const double stild = std::sqrt(s11 * s11 + s22 * s22 + s33 * s33 + 2 * (s12 * s12 + s13 * s13 + s23 * s23));
+    const double wrlzb = (s11 * s11 * s11 + s11 * s12 * s21 + s11 * s13 * s31 + s12 * s21 * s11 + s12 * s22 * s21 + s12 * s23 * s31 + s13 * s31 * s11 +
+                          s13 * s32 * s21 + s13 * s33 * s31 + s21 * s11 * s12 + s21 * s12 * s22 + s21 * s13 * s32 + s22 * s21 * s12 + s22 * s22 * s22 +
+                          s22 * s23 * s32 + s23 * s31 * s12 + s23 * s32 * s22 + s23 * s33 * s32 + s31 * s11 * s13 + s31 * s12 * s23 + s31 * s13 * s33 +
+                          s32 * s21 * s13 + s32 * s22 * s23 + s32 * s23 * s33 + s33 * s31 * s13 + s33 * s32 * s23 + s33 * s33 * s33) /
+                         (stild * stild * stild);
+    const double ffi = S13 * std::acos(mx(-1.0, mn(std::sqrt(6.0) * wrlzb, 1.0)));
+    const double ass = std::sqrt(6.0) * std::cos(ffi);
+    const double ust = std::sqrt(s11 * s11 + s22 * s22 + s33 * s33 + 2 * (s12 * s12 + s13 * s13 + s23 * s23 + w12 * w12 + w13 * w13 + w23 * w23));
+    const double cmur = 1.0 / (A0RLZ + ass * ust * te[c] / (ed[c] + SMALL));
+    const double vist = den[c] * cmur * (te[c] * te[c]) / (ed[c] + SMALL);
+    vis[c] = viscos + vist;
+    vis[c] = urf * vis[c] + (1.0 - urf) * visold;
+  }
+  orc_update_boundary(m, vis);                                                          // :884
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {                                       // :888-947
+    if (m->bctype[ib] != ORC_BC_WALL) continue;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1, bf = f - F;
+      const double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+      const double are = std::sqrt(arx * arx + ary * ary + arz * arz);
+      const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
+      const double Vnp = u[ijp] * nxf + v[ijp] * nyf + w[ijp] * nzf;
+      const double xtp = u[ijp] - Vnp * nxf, ytp = v[ijp] - Vnp * nyf, ztp = w[ijp] - Vnp * nzf;
+      const double Vtp = std::sqrt(xtp * xtp + ytp * ytp + ztp * ztp);
+      ypl[bf] = den[ijp] * cmu25() * std::sqrt(te[ijp]) * dnw[bf] / viscos;
+      tau[bf] = CAPPA * den[ijp] * Vtp * cmu25() * std::sqrt(te[ijp]) / std::log(ELOG * ypl[bf]);
+      double viscw = 0.0;
+      if (ypl[bf] > CTRANS) viscw = ypl[bf] * viscos * CAPPA / std::log(ELOG * ypl[bf]);
+      visw[bf] = mx(viscos, viscw);
+      vis[ijb] = visw[bf];
+    }
+  }
+}
+

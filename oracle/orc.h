@@ -194,6 +194,33 @@ void orc_calcuvw(const orc_mesh *m, const int32_t *ia, const int32_t *ja, const 
                  double *apu, double *apv, double *apw, double *dUdxi, double *dVdxi, double *dWdxi, double *dPdxi,
                  double *rU, double *rV, double *rW, orc_report *rep /* [3] */);
 
+/* ---- row f4: scalar transport (fluxes/scalar_fluxes.f90:32-343) in the calcsc template of TurbulenceModels/k_epsilon_rlzb.f90
+ * kind 0: GENERIC  -- su_vol/sp_vol hold the caller's volume sources, wall faces add nothing (zero flux)
+ * kind 1: calcsc_tke     k_epsilon_rlzb.f90:52-445   (gen = |vis-viscos| S^2, wall cells: production from the wall shear stress, tau written)
+ * kind 2: calcsc_epsilon k_epsilon_rlzb.f90:447-790  (realizable c1, wall cells: row zeroed, ed = cmu75 k^1.5/(cappa dnw) imposed)
+ * Steps: grad(phi) with the configured method/limiter; volume sources + bdf/bdf2 term; facefluxsc on inner faces, facefluxsc_boundary on
+ * inlet/outlet/pressure patches, facefluxsc_periodic on periodic pairs, the wall treatment; a(diag) = sp - sum(off-diagonals) in CSR order,
+ * under-relaxation; csrsolve; updateBoundary; min/max report and the clip to `small` when the minimum is negative.  Crank-Nicolson and
+ * buoyancy are not restated.  Per-wall-face arrays (visw, dnw, tau) are indexed by BOUNDARY FACE ordinal here (the reference counts
+ * wall faces with iWall). */
+typedef struct {
+  int32_t kind, solver, maxiter, cscheme, grad_method, limiter, tscheme, sum_mode;
+  double tol_abs, tol_rel, urf, gds, timestep, prtr, viscos, densit;
+} orc_scalar_params;
+void orc_calcsc(const orc_mesh *m, const int32_t *ia, const int32_t *ja, const int32_t *diag, const int32_t *icell_jcell,
+                const int32_t *jcell_icell, int32_t nnz, const orc_scalar_params *prm,
+                double *phi, const double *phio, const double *phioo, double *te, double *ed /* the k and epsilon fields; phi aliases one of them for kind 1/2 */,
+                const double *den, const double *vis, const double *visw, const double *dnw, const double *flmass,
+                const double *u, const double *v, const double *w, const double *magStrain, double *gen, double *tau,
+                const double *su_vol, const double *sp_vol,
+                double *a, double *su, double *sp, double *dPhidxi, orc_report *rep, double *fimin, double *fimax);
+/* fvExplicit/calc_strain_and_vorticity.f90 */
+void orc_calc_strain_and_vorticity(const orc_mesh *m, const double *dUdxi, const double *dVdxi, const double *dWdxi, double *magStrain, double *vorticity);
+/* modify_mu_eff of the realizable k-epsilon model, k_epsilon_rlzb.f90:792-975 (cell loop, updateBoundary(vis), wall functions) */
+void orc_modify_mu_eff_rlzb(const orc_mesh *m, double urf, double viscos, const double *dUdxi, const double *dVdxi, const double *dWdxi,
+                            const double *te, const double *ed, const double *den, const double *u, const double *v, const double *w,
+                            const double *dnw, double *vis, double *visw, double *ypl, double *tau);
+
 /* linear_solvers.f90:206-359, 364-545, 548-786 */
 void orc_spmv(int32_t n, const int32_t *ia, const int32_t *ja, const double *a, const double *x, double *y);
 void orc_dpcg(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const double *a,

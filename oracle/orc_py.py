@@ -360,3 +360,57 @@ def calcuvw(mesh, csr: Csr, prm: OrcUvwParams, f: dict, a: np.ndarray):
                       _d(out["rU"]), _d(out["rV"]), _d(out["rW"]), reps)
     out["reps"] = [reps[i] for i in range(3)]
     return out
+
+
+# ---- row f4: scalar transport -----------------------------------------------------------------------------------------------
+SC_GENERIC, SC_TKE_RLZB, SC_EPS_RLZB = 0, 1, 2
+
+
+class OrcScalarParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "solver", "maxiter", "cscheme", "grad_method", "limiter", "tscheme", "sum_mode")] + \
+               [(n, C.c_double) for n in ("tol_abs", "tol_rel", "urf", "gds", "timestep", "prtr", "viscos", "densit")]
+
+
+def calcsc(mesh, csr: Csr, prm: OrcScalarParams, f: dict):
+    """The calcsc template (k_epsilon_rlzb.f90:52-790 + scalar_fluxes.f90).  f: te, ed (numTotal; the one prm.kind selects is solved
+    for and updated in place; kind 0 solves f['phi']), den, vis (numTotal), visw, dnw (numBoundaryFaces), flmass (numFaces), u, v, w,
+    magStrain (numCells), optionally phio/phioo, su_vol/sp_vol (kind 0).  Returns a dict with a, su, sp, grad, gen, tau, rep, fimin, fimax."""
+    n, nT, B = mesh.numCells, mesh.numTotal, mesh.numBoundaryFaces
+    phi = f["phi"] if prm.kind == SC_GENERIC else (f["te"] if prm.kind == SC_TKE_RLZB else f["ed"])
+    out = dict(a=np.zeros(csr.nnz), su=np.zeros(n), sp=np.zeros(n), grad=np.zeros((nT, 3)), gen=np.zeros(n), tau=np.zeros(max(B, 1)))
+    rep = OrcReport()
+    fmin, fmax = C.c_double(0.0), C.c_double(0.0)
+    opt = lambda k: _d(f[k]) if k in f and f[k] is not None else None  # noqa: E731
+    lib().orc_calcsc(csr.mv.ptr, _i(csr.ia), _i(csr.ja), _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz), C.byref(prm),
+                     _d(phi), opt("phio"), opt("phioo"), opt("te"), opt("ed"), _d(f["den"]), _d(f["vis"]), opt("visw"), opt("dnw"), _d(f["flmass"]),
+                     opt("u"), opt("v"), opt("w"), opt("magStrain"), _d(out["gen"]), _d(out["tau"]), opt("su_vol"), opt("sp_vol"),
+                     _d(out["a"]), _d(out["su"]), _d(out["sp"]), _d(out["grad"]), C.byref(rep), C.byref(fmin), C.byref(fmax))
+    out.update(rep=rep, fimin=fmin.value, fimax=fmax.value)
+    return out
+
+
+def wall_geometry(mesh):
+    """geometry.f90:698-754: dnw, srdw per wall face and dns, srds per symmetry face, in patch order."""
+    mv = MeshView(mesh)
+    nw = max(int(mesh.nfaces[np.asarray(mesh.bctype) == 0].sum()), 1)
+    ns = max(int(mesh.nfaces[np.asarray(mesh.bctype) == 3].sum()), 1)
+    dnw, srdw, dns, srds = np.zeros(nw), np.zeros(nw), np.zeros(ns), np.zeros(ns)
+    lib().orc_wall_geometry(mv.ptr, _d(dnw), _d(srdw), _d(dns), _d(srds))
+    return dnw, srdw, dns, srds
+
+
+def calc_strain_and_vorticity(mesh, dUdxi, dVdxi, dWdxi):
+    mv = MeshView(mesh)
+    s, w = np.zeros(mesh.numCells), np.zeros(mesh.numCells)
+    lib().orc_calc_strain_and_vorticity(mv.ptr, _d(dUdxi), _d(dVdxi), _d(dWdxi), _d(s), _d(w))
+    return s, w
+
+
+def modify_mu_eff_rlzb(mesh, urf, viscos, dUdxi, dVdxi, dWdxi, te, ed, den, u, v, w, dnw, vis, visw):
+    """modify_mu_eff (k_epsilon_rlzb.f90:792-975): vis (numTotal) and visw (numBoundaryFaces) updated in place; returns ypl, tau."""
+    mv = MeshView(mesh)
+    B = max(mesh.numBoundaryFaces, 1)
+    ypl, tau = np.zeros(B), np.zeros(B)
+    lib().orc_modify_mu_eff_rlzb(mv.ptr, C.c_double(urf), C.c_double(viscos), _d(dUdxi), _d(dVdxi), _d(dWdxi), _d(te), _d(ed), _d(den),
+                                 _d(u), _d(v), _d(w), _d(dnw), _d(vis), _d(visw), _d(ypl), _d(tau))
+    return ypl, tau

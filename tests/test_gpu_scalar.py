@@ -1,0 +1,207 @@
+"""GPU (B200): row f4 -- the scalar transport template (fcp_calcsc: scalar_fluxes.f90 inside the calcsc assembly of k_epsilon_rlzb.f90),
+calc_strain_and_vorticity and modify_mu_eff against the oracle.  Bit-exact wherever only + - * / sqrt are involved (the generic scalar and
+the k equation); the epsilon equation (k**1.5 in the wall cells) and modify_mu_eff (acos, cos, log) are compared to 1e-12 relative because
+the device's libm and the host's need not round those functions identically."""
+import numpy as np
+import pytest
+
+import cases
+from fcb200 import lib as L
+from fcb200 import mesh as M
+from test_gpu_parity import eq, make_ctx
+from test_gpu_rows2 import uvw_inputs
+
+pytestmark = pytest.mark.gpu
+SC_MESHES = ["hex10_distorted", "channel_inout", "channel_pressure", "poly_10faces", "channel_periodic", "duct_periodic_first", "tiny3"]
+
+
+@pytest.fixture(scope="module")
+def allmeshes():
+    return cases.meshes()
+
+
+def close(a, b, what, rtol=1e-12):
+    a = np.asarray(a); b = np.asarray(b)
+    err = np.abs(a - b).max() / (np.abs(b).max() + 1e-300)
+    assert err <= rtol, f"{what}: relative difference {err:.3e}"
+
+
+def scalar_inputs(m, orc, seed=5):
+    """k, epsilon, effective viscosity, wall distance, strain ... for one mesh (all positive where the model divides by them)."""
+    rng = np.random.default_rng(seed)
+    g = uvw_inputs(m)
+    n, nT, B = m.numCells, m.numTotal, m.numBoundaryFaces
+    g["te"] = 0.02 * m.boundary_values_of(lambda x, y, z: 1.0 + 0.5 * np.sin(2 * x) * np.cos(3 * y) + 0.2 * z) + 1e-4 * rng.random(nT)
+    g["ed"] = 0.05 * m.boundary_values_of(lambda x, y, z: 1.0 + 0.4 * np.cos(x + 2 * y) + 0.1 * np.sin(3 * z)) + 1e-4 * rng.random(nT)
+    g["vis"] = 0.01 + 0.03 * m.boundary_values_of(lambda x, y, z: 1.0 + 0.5 * np.sin(3 * x) * np.cos(2 * y) + 0.2 * z)
+    dnw, srdw, dns, srds = orc.wall_geometry(m)
+    g["dnw"] = np.full(B, 0.05)
+    iw = 0
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] == M.BC_WALL:
+            pf = m.patch_faces(ib) - m.numInnerFaces
+            g["dnw"][pf] = dnw[iw: iw + pf.size]
+            iw += pf.size
+    gU = orc.grad_gauss(m, g["u"]); gV = orc.grad_gauss(m, g["v"]); gW = orc.grad_gauss(m, g["w"])
+    g["gU"], g["gV"], g["gW"] = gU, gV, gW
+    g["magStrain"], g["vorticity"] = orc.calc_strain_and_vorticity(m, gU, gV, gW)
+    g["phio"] = g["te"] * 0.97 + 1e-5 * rng.random(nT)
+    g["phioo"] = g["te"] * 0.94 + 1e-5 * rng.random(nT)
+    return g
+
+
+def bslot(m, arr):
+    """per-boundary-face array -> numTotal field with the values in the boundary slots"""
+    out = np.zeros(m.numTotal)
+    out[m.numCells:] = arr
+    return out
+
+
+def upload_scalar_state(ctx, m, g):
+    for k in ("u", "v", "w", "den", "vis", "te", "ed", "phio", "phioo"):
+        ctx.upload(k.upper(), g[k])
+    ctx.upload("FLMASS", g["flmass"])
+    ctx.upload("VISW", bslot(m, g["visw"])); ctx.upload("DNW", bslot(m, g["dnw"]))
+    ms = np.zeros(m.numTotal); ms[: m.numCells] = g["magStrain"]
+    ctx.upload("MAGSTRAIN", ms)
+
+
+def oracle_params(orc, kind, solver, cscheme, grad, limiter, tscheme):
+    prm = orc.OrcScalarParams()
+    prm.kind, prm.solver, prm.maxiter, prm.cscheme = kind, L.SOLVER_ID[solver], 8, L.CSCHEME_ID[cscheme]
+    prm.grad_method, prm.limiter, prm.tscheme, prm.sum_mode = L.GRAD_ID[grad], L.LIMITER_ID[limiter], L.TSCHEME[tscheme], orc.SUM_TREE
+    prm.tol_abs, prm.tol_rel, prm.urf, prm.gds, prm.timestep, prm.prtr, prm.viscos, prm.densit = 1e-30, 1e-4, 0.7, 0.8, 0.02, 1.0 / 1.2, 0.01, 1.0
+    return prm
+
+
+@pytest.mark.parametrize("name", SC_MESHES)
+def test_strain_and_vorticity(fcp, orc, allmeshes, name):
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    ctx = make_ctx(m)
+    ctx.upload("DUDXI", g["gU"]); ctx.upload("DVDXI", g["gV"]); ctx.upload("DWDXI", g["gW"])
+    ctx.calc_strain_and_vorticity()
+    eq(ctx.download("MAGSTRAIN")[: m.numCells], g["magStrain"], "magStrain")
+    eq(ctx.download("VORTICITY")[: m.numCells], g["vorticity"], "vorticity")
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", SC_MESHES)
+@pytest.mark.parametrize("cscheme,grad,limiter,tscheme", [("cds", "gauss", "none", "steady"), ("muscl", "gauss", "Venkatakrishnan", "bdf"),
+                                                          ("linearUpwind", "lsq", "none", "bdf2")])
+def test_calcsc_generic(fcp, orc, allmeshes, name, cscheme, grad, limiter, tscheme):
+    """A passive scalar with caller-supplied volume sources: matrix, sources, gradient, solution and the iteration count bit-identical."""
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    n = m.numCells
+    rng = np.random.default_rng(11)
+    phi = m.boundary_values_of(lambda x, y, z: 1.0 + 0.3 * np.sin(2 * x + y) + 0.1 * z)
+    suv = np.zeros(m.numTotal); suv[:n] = 0.1 * m.vol[:n] * rng.random(n)
+    spv = np.zeros(m.numTotal); spv[:n] = 0.5 * m.vol[:n] * rng.random(n)
+    ctx = make_ctx(m)
+    upload_scalar_state(ctx, m, g)
+    ctx.upload("S0", phi); ctx.upload("S2", suv); ctx.upload("S3", spv)
+    rep, lo, hi = ctx.calcsc("S0", kind="generic", solver="bicgstab", maxiter=8, tol_abs=1e-30, tol_rel=1e-4, urf=0.7, gds=0.8, cscheme=cscheme,
+                             grad_method=grad, limiter=limiter, tscheme=tscheme, timestep=0.02, prtr=1.0 / 1.2, viscos=0.01, densit=1.0)
+    c = orc.Csr(m)
+    prm = oracle_params(orc, orc.SC_GENERIC, "bicgstab", cscheme, grad, limiter, tscheme)
+    f = dict(g, phi=phi.copy(), su_vol=suv[:n].copy(), sp_vol=spv[:n].copy())
+    o = orc.calcsc(m, c, prm, f)
+    assert (rep.iters, rep.res0, rep.resl) == (o["rep"].iters, o["rep"].res0, o["rep"].resl)
+    eq(ctx.download("G0")[:n], o["grad"][:n], "grad(phi)")
+    eq(ctx.download("A"), o["a"], "matrix")
+    eq(ctx.download("SP")[:n], o["sp"], "sp")
+    eq(ctx.download("SU")[:n], o["su"], "su")
+    eq(ctx.download("S0"), f["phi"], "phi")
+    assert (lo, hi) == (o["fimin"], o["fimax"])
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", SC_MESHES)
+@pytest.mark.parametrize("cscheme,tscheme,solver", [("cds", "steady", "bicgstab"), ("muscl", "bdf2", "bicgstab")])
+def test_calcsc_tke(fcp, orc, allmeshes, name, cscheme, tscheme, solver):
+    """calcsc_tke (k_epsilon_rlzb.f90:52-445): production, the wall-function production in wall cells, tau, the solve: bit-identical."""
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    n = m.numCells
+    ctx = make_ctx(m)
+    upload_scalar_state(ctx, m, g)
+    rep, lo, hi = ctx.calcsc("TE", kind="tke_rlzb", solver=solver, maxiter=8, tol_abs=1e-30, tol_rel=1e-4, urf=0.7, gds=0.8, cscheme=cscheme,
+                             tscheme=tscheme, timestep=0.02, prtr=1.0, viscos=0.01, densit=1.0)
+    c = orc.Csr(m)
+    prm = oracle_params(orc, orc.SC_TKE_RLZB, solver, cscheme, "gauss", "none", tscheme)
+    prm.prtr = 1.0
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g.items()}
+    o = orc.calcsc(m, c, prm, f)
+    assert (rep.iters, rep.res0, rep.resl) == (o["rep"].iters, o["rep"].res0, o["rep"].resl)
+    eq(ctx.download("A"), o["a"], "matrix")
+    eq(ctx.download("SP")[:n], o["sp"], "sp"); eq(ctx.download("SU")[:n], o["su"], "su")
+    eq(ctx.download("GEN")[:n], o["gen"], "gen")
+    eq(ctx.download("TAU")[n:], o["tau"][: m.numBoundaryFaces], "tau")
+    eq(ctx.download("TE"), f["te"], "te")
+    assert (lo, hi) == (o["fimin"], o["fimax"])
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", SC_MESHES)
+@pytest.mark.parametrize("cscheme,tscheme", [("cds", "steady"), ("vanleer", "bdf")])
+def test_calcsc_epsilon(fcp, orc, allmeshes, name, cscheme, tscheme):
+    """calcsc_epsilon (:447-790): realizable c1, cleared rows and the imposed epsilon in wall cells.  k**1.5 goes through pow(): 1e-12."""
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    g["phio"] = g["ed"] * 0.97; g["phioo"] = g["ed"] * 0.95
+    n = m.numCells
+    ctx = make_ctx(m)
+    upload_scalar_state(ctx, m, g)
+    rep, lo, hi = ctx.calcsc("ED", kind="eps_rlzb", solver="bicgstab", maxiter=8, tol_abs=1e-30, tol_rel=1e-4, urf=0.7, gds=0.8, cscheme=cscheme,
+                             tscheme=tscheme, timestep=0.02, prtr=1.0 / 1.2, viscos=0.01, densit=1.0)
+    c = orc.Csr(m)
+    prm = oracle_params(orc, orc.SC_EPS_RLZB, "bicgstab", cscheme, "gauss", "none", tscheme)
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g.items()}
+    o = orc.calcsc(m, c, prm, f)
+    assert rep.iters == o["rep"].iters
+    close(ctx.download("A"), o["a"], "matrix")
+    close(ctx.download("SP")[:n], o["sp"], "sp"); close(ctx.download("SU")[:n], o["su"], "su")
+    close(ctx.download("ED"), f["ed"], "ed", 1e-10)
+    # wall cells hold the imposed value and an identity row
+    wall_cells = np.unique(np.concatenate([m.owner[m.patch_faces(ib)] - 1 for ib in range(m.numBoundaries) if m.bctype[ib] == M.BC_WALL] + [np.zeros(0, int)])).astype(int)
+    if wall_cells.size and m.numPeriodic == 0:      # (a periodic patch listed after the wall patch re-fills its two entries, as in the reference)
+        rows = np.repeat(np.arange(n), np.diff(c.ia))
+        a = ctx.download("A")
+        offd = np.ones(c.nnz, bool); offd[c.diag - 1] = False
+        assert np.all(a[offd & np.isin(rows, wall_cells)] == 0.0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", SC_MESHES)
+def test_modify_mu_eff_rlzb(fcp, orc, allmeshes, name):
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    n = m.numCells
+    ctx = make_ctx(m)
+    upload_scalar_state(ctx, m, g)
+    ctx.upload("DUDXI", g["gU"]); ctx.upload("DVDXI", g["gV"]); ctx.upload("DWDXI", g["gW"])
+    ctx.modify_mu_eff_k_epsilon_rlzb(0.6, 0.01)
+    vis, visw = g["vis"].copy(), g["visw"].copy()
+    ypl, tau = orc.modify_mu_eff_rlzb(m, 0.6, 0.01, g["gU"], g["gV"], g["gW"], g["te"], g["ed"], g["den"], g["u"], g["v"], g["w"], g["dnw"], vis, visw)
+    close(ctx.download("VIS"), vis, "vis")
+    wall = np.zeros(m.numBoundaryFaces, bool)
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] == M.BC_WALL:
+            wall[m.patch_faces(ib) - m.numInnerFaces] = True
+    if wall.any():
+        close(ctx.download("VISW")[n:][wall], visw[wall], "visw")
+        close(ctx.download("YPL")[n:][wall], ypl[: m.numBoundaryFaces][wall], "ypl")
+        close(ctx.download("TAU")[n:][wall], tau[: m.numBoundaryFaces][wall], "tau")
+    ctx.close()
+
+
+def test_calcsc_argument_checks(fcp, allmeshes):
+    ctx = make_ctx(allmeshes["tiny3"])
+    with pytest.raises(L.FcpError):
+        ctx.calcsc("ED", kind="tke_rlzb")
+    with pytest.raises(L.FcpError):
+        ctx.calcsc("S0", kind="generic", tscheme="bdf3")
+    with pytest.raises(L.FcpError):
+        ctx.calcsc("DPDXI", kind="generic")
+    ctx.close()

@@ -1,0 +1,121 @@
+"""CPU: the oracle's row-f4 restatement (scalar_fluxes.f90 in the calcsc template of k_epsilon_rlzb.f90, modify_mu_eff) against
+answers that do not depend on it: a linear diffusion profile, preservation of a constant by every convection scheme on a divergence-free
+flux field, the closed form of the realizable C_mu in pure shear, the log-law wall viscosity.  The reference carries no test for these."""
+import numpy as np
+import pytest
+
+import cases
+import fcb200  # noqa: F401
+from fcb200 import lib as L
+from fcb200 import mesh as M
+
+
+def params(orc, **kw):
+    prm = orc.OrcScalarParams()
+    prm.kind, prm.solver, prm.maxiter, prm.cscheme, prm.grad_method, prm.limiter, prm.tscheme, prm.sum_mode = 0, 3, 500, 0, 0, 0, 0, 0
+    prm.tol_abs, prm.tol_rel, prm.urf, prm.gds, prm.timestep, prm.prtr, prm.viscos, prm.densit = 1e-30, 1e-13, 1.0, 1.0, 0.0, 1.0, 0.01, 1.0
+    for k, v in kw.items():
+        setattr(prm, k, v)
+    return prm
+
+
+def channel(distort=0.0):
+    return M.hex_mesh(np.linspace(0, 2.0, 17), np.linspace(0, 1.0, 7), np.linspace(0, 0.5, 5),
+                      dict(left="inlet", right="outlet", back="symmetry", front="symmetry"), distort=distort)
+
+
+def test_pure_diffusion_gives_the_linear_profile(orc):
+    """No flow, phi = 1 on the inlet patch, 0 on the outlet patch, zero-flux walls: phi = 1 - x/L exactly on an orthogonal mesh."""
+    m = channel()
+    c = orc.Csr(m)
+    n = m.numCells
+    f = dict(phi=np.zeros(m.numTotal), den=np.ones(m.numTotal), vis=np.full(m.numTotal, 0.03), flmass=np.zeros(m.numFaces),
+             su_vol=np.zeros(n), sp_vol=np.zeros(n))
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] == M.BC_INLET:
+            f["phi"][n + m.patch_faces(ib) - m.numInnerFaces] = 1.0
+    inlet_outlet = np.concatenate([n + m.patch_faces(ib) - m.numInnerFaces for ib in range(m.numBoundaries) if m.bctype[ib] in (M.BC_INLET, M.BC_OUTLET)])
+    keep = f["phi"][inlet_outlet].copy()
+    for _ in range(3):                       # updateBoundary copies the owner value into the outlet slots: re-impose the Dirichlet data
+        orc.calcsc(m, c, params(orc, tol_abs=1e-13, tol_rel=1e-10), f)
+        f["phi"][inlet_outlet] = keep
+    assert np.abs(f["phi"][:n] - (1.0 - m.xc[:n] / 2.0)).max() < 1e-10
+
+
+@pytest.mark.parametrize("cscheme", ["cds", "central", "linearUpwind", "muscl", "vanleer", "quick"])
+def test_a_constant_is_preserved_by_every_scheme(orc, cscheme):
+    """Uniform flow (divergence-free face fluxes), phi = 3 everywhere including the inlet: the discrete equation must return phi = 3
+    (signs of can/cap, the upwind split ce/cp, the deferred correction and the boundary coefficients all have to be consistent)."""
+    m = channel(distort=0.15)
+    c = orc.Csr(m)
+    n, Fi = m.numCells, m.numInnerFaces
+    flm = 1.2 * m.arx.copy()                 # rho u . S with u = (1,0,0), rho = 1.2
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] in (M.BC_WALL, M.BC_SYMMETRY):
+            flm[m.patch_faces(ib)] = 0.0
+    div = np.zeros(n)
+    np.add.at(div, m.owner[:Fi] - 1, flm[:Fi]); np.add.at(div, m.neighbour - 1, -flm[:Fi]); np.add.at(div, m.owner[Fi:] - 1, flm[Fi:])
+    assert np.abs(div).max() < 1e-14
+    f = dict(phi=np.full(m.numTotal, 3.0), den=np.full(m.numTotal, 1.2), vis=np.full(m.numTotal, 0.02), flmass=flm, su_vol=np.zeros(n), sp_vol=np.zeros(n))
+    o = orc.calcsc(m, c, params(orc, cscheme=L.CSCHEME_ID[cscheme], gds=0.9, urf=0.8), f)
+    assert np.abs(f["phi"][:n] - 3.0).max() < 1e-10, cscheme
+    assert (o["fimin"], o["fimax"]) == (f["phi"][:n].min(), f["phi"][:n].max())
+
+
+def test_realizable_cmu_in_pure_shear(orc):
+    """u = S y: S_ij S_jk S_ki = 0 -> phi = acos(0)/3 = pi/6, A_s = sqrt(6) cos(pi/6), U* = S, C_mu = 1/(A0 + A_s S k/eps) (Shih et al. 1995)."""
+    m = M.cavity_mesh(6)
+    n = m.numCells
+    S, k, eps, rho, nu = 3.0, 0.04, 0.5, 1.1, 1e-3
+    gU = np.zeros((m.numTotal, 3)); gU[:, 1] = S
+    z3 = np.zeros((m.numTotal, 3))
+    te, ed, den = np.full(m.numTotal, k), np.full(m.numTotal, eps), np.full(m.numTotal, rho)
+    u = m.boundary_values_of(lambda x, y, z: S * y); v = np.zeros(m.numTotal); w = np.zeros(m.numTotal)
+    vis = np.full(m.numTotal, nu); visw = np.zeros(m.numBoundaryFaces)
+    dnw = np.full(m.numBoundaryFaces, 0.05)
+    orc.modify_mu_eff_rlzb(m, 1.0, nu, gU, z3, z3, te, ed, den, u, v, w, dnw, vis, visw)
+    # the reference writes `1./3.` and `a0 = 4.04` as default-real literals (quirk Q5): phi = float32(1/3) * acos(0), not exactly pi/6
+    ffi = float(np.float32(1.0) / np.float32(3.0)) * np.arccos(0.0)
+    assert abs(ffi - np.pi / 6) < 1e-7
+    cmu = 1.0 / (float(np.float32(4.04)) + np.sqrt(6.0) * np.cos(ffi) * S * k / eps)
+    assert np.abs(vis[:n] - (nu + rho * cmu * k * k / eps)).max() < 1e-14
+    # strain invariants of the same field
+    ms, vort = orc.calc_strain_and_vorticity(m, gU, z3, z3)
+    assert np.allclose(ms, S, rtol=0, atol=1e-15) and np.allclose(vort, S, rtol=0, atol=1e-15)
+
+
+def test_wall_function_viscosity(orc):
+    """y* = rho cmu^1/4 sqrt(k) d / mu; above 11.63 the wall viscosity is mu y* kappa / ln(E y*), below it the molecular one."""
+    m = M.cavity_mesh(4)
+    n = m.numCells
+    z3 = np.zeros((m.numTotal, 3))
+    nu, rho = 1e-3, 1.0
+    for k, expect_log in ((1e-8, False), (0.5, True)):
+        te, ed, den = np.full(m.numTotal, k), np.full(m.numTotal, 1.0), np.full(m.numTotal, rho)
+        u = m.boundary_values_of(lambda x, y, z: 1.0 + 0 * x); v = np.zeros(m.numTotal); w = np.zeros(m.numTotal)
+        vis = np.full(m.numTotal, nu); visw = np.zeros(m.numBoundaryFaces); dnw = np.full(m.numBoundaryFaces, 0.125)
+        ypl, tau = orc.modify_mu_eff_rlzb(m, 1.0, nu, z3, z3, z3, te, ed, den, u, v, w, dnw, vis, visw)
+        ystar = rho * 0.09 ** 0.25 * np.sqrt(k) * 0.125 / nu
+        assert np.allclose(ypl[: m.numBoundaryFaces], ystar, rtol=1e-14)
+        want = nu * ystar * 0.41 / np.log(8.432 * ystar) if expect_log else nu
+        assert (ystar > 11.63) == expect_log
+        assert np.allclose(visw, want, rtol=1e-13) and np.allclose(vis[n:], want, rtol=1e-13)
+
+
+def test_epsilon_wall_cells_get_the_equilibrium_value(orc):
+    m = cases.meshes()["hex10_distorted"]
+    import test_gpu_scalar as T
+    g = T.scalar_inputs(m, orc)
+    c = orc.Csr(m)
+    prm = params(orc, kind=orc.SC_EPS_RLZB, maxiter=50, tol_rel=1e-10, urf=1.0, prtr=1.0 / 1.2)
+    te0 = g["te"].copy()
+    o = orc.calcsc(m, c, prm, g)
+    n, Fi = m.numCells, m.numInnerFaces
+    # a cell with one wall face holds cmu^0.75 k^1.5 / (kappa dnw) after the solve (identity row, sp = 1, su = ed)
+    nwall = np.zeros(n, int)
+    np.add.at(nwall, m.owner[Fi:] - 1, 1)
+    one = np.nonzero(nwall == 1)[0]
+    bf_of = {int(m.owner[Fi + b] - 1): b for b in range(m.numBoundaryFaces)}
+    for cell in one[:20]:
+        want = 0.09 ** 0.75 * te0[cell] ** 1.5 / (0.41 * g["dnw"][bf_of[int(cell)]])
+        assert abs(g["ed"][cell] - want) <= 1e-9 * want

@@ -219,6 +219,19 @@ module fcp_b200
       real(c_double), value :: urfVis, viscos
       integer(c_int) :: rc
     end function
+    function fcp_grad_gauss_fvx(ctx, phi_field, grad_field) bind(c, name='fcp_grad_gauss_fvx') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: phi_field, grad_field
+      integer(c_int) :: rc
+    end function
+    function fcp_modify_viscosity_sgs(ctx, model, urfVis, viscos) bind(c, name='fcp_modify_viscosity_sgs') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: model
+      real(c_double), value :: urfVis, viscos
+      integer(c_int) :: rc
+    end function
     function fcp_constant_mass_flow_forcing(ctx, magUbar, gradPcmf, magUbarStar) bind(c, name='fcp_constant_mass_flow_forcing') result(rc)
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: ctx
@@ -805,6 +818,35 @@ contains
       end do
     end do
     deallocate(wf)
+  end subroutine
+
+  ! ---- modify_viscosity_wale_sgs() / modify_viscosity_vreman_sgs()   TurbulenceModels/wale_sgs.f90:33, vremanSGS.f90:33 -------------------
+  subroutine modify_viscosity_sgs_device(model)
+    use TurbModelData, only: TurbModel
+    integer(c_int), intent(in) :: model              ! 0 = WALE, 1 = Vreman
+    real(dp), allocatable :: wf(:)
+    integer :: ib, i, iWall
+    call put(FCP_F_U, u, numTotal); call put(FCP_F_V, v, numTotal); call put(FCP_F_W, w, numTotal)
+    call put(FCP_F_DEN, den, numTotal); call put(FCP_F_VIS, vis, numTotal)
+    call fcp_check(fcp_modify_viscosity_sgs(ctx, model, TurbModel%urfVis, viscos), 'fcp_modify_viscosity_sgs')
+    call get(FCP_F_VIS, vis, numTotal)
+    allocate(wf(numTotal))
+    call get(FCP_F_VISW, wf, numTotal); iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        visw(iWall) = wf(iBndValueStart(ib) + i)
+      end do
+    end do
+    deallocate(wf)
+    write(*,'(2x,es11.4,a,es11.4)') minval(vis/viscos), ' <= Viscosity ratio <= ', maxval(vis/viscos)
+  end subroutine
+  subroutine modify_viscosity_wale_sgs()
+    call modify_viscosity_sgs_device(0_c_int)
+  end subroutine
+  subroutine modify_viscosity_vreman_sgs()
+    call modify_viscosity_sgs_device(1_c_int)
   end subroutine
 
   ! ---- constant_mass_flow_forcing()   src/cappuccino/constant_mass_flow_forcing.f90 ------------------------------------------------

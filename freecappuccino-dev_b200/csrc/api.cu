@@ -68,11 +68,8 @@ static int field_ptr(fcp_ctx *c, int field, double **p) {
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out) {
-  if (!md || !out) { fcp_set_error("fcp_ctx_create: null argument"); return FCP_EINVAL; }
-  *out = nullptr;
-  FCP_TRY(select_device(device));
-  fcp_ctx *c = new fcp_ctx();
+// fills a freshly constructed context; on any error the caller (fcp_ctx_create) destroys it, so nothing leaks on the error paths
+static int ctx_build(fcp_ctx *c, const fcp_mesh_desc *md, int device) {
   c->device = device;
   c->n = md->numCells; c->F = md->numInnerFaces; c->B = md->numBoundaryFaces; c->nb = md->numBoundaries;
   c->nT = c->n + c->B; c->nF = c->F + c->B;
@@ -89,7 +86,6 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
   for (int32_t ib = 0; ib < c->nb; ++ib) {
     if (c->startFace[ib] < F || c->startFace[ib] + c->nfaces[ib] > c->nF) {
       fcp_set_error("patch %d: faces [%d,%d) outside the boundary range [%d,%d)", ib, c->startFace[ib], c->startFace[ib] + c->nfaces[ib], F, c->nF);
-      delete c;
       return FCP_EINVAL;
     }
     for (int32_t i = 0; i < c->nfaces[ib]; ++i) bft[c->startFace[ib] - F + i] = c->bctype[ib];
@@ -100,7 +96,6 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
   for (int32_t f = 0; f < c->nF; ++f) {
     if (md->owner[f] < 1 || md->owner[f] > n || (f < F && (md->neighbour[f] < 1 || md->neighbour[f] > n))) {
       fcp_set_error("face %d: owner/neighbour out of range", f + 1);
-      delete c;
       return FCP_EINVAL;
     }
   }
@@ -115,20 +110,19 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
     for (int32_t jb = 0; jb < c->nb; ++jb) if (c->startFace[jb] == st && jb != ib) it = jb;
     if (it < 0 || c->nfaces[it] != c->nfaces[ib] || c->bctype[it] != FCP_BC_EMPTY) {
       fcp_set_error("periodic patch %d: startFaceTwin must name an 'empty' patch with the same number of faces", ib);
-      delete c;
       return FCP_EINVAL;
     }
     for (int32_t i = 0; i < c->nfaces[ib]; ++i) {
       const int32_t fp = c->startFace[ib] + i, ft = st + i;
       const int32_t p = md->owner[fp] - 1, q = md->owner[ft] - 1;
-      if (p == q) { fcp_set_error("periodic patch %d: face %d pairs a cell with itself", ib, i + 1); delete c; return FCP_EINVAL; }
+      if (p == q) { fcp_set_error("periodic patch %d: face %d pairs a cell with itself", ib, i + 1); return FCP_EINVAL; }
       pcell[fp - F] = q; pface[fp - F] = ft; pord[fp - F] = i;
       pcell[ft - F] = p; pface[ft - F] = fp; pord[ft - F] = i;
       plist.push_back(fp - F);
     }
   }
   c->nper = (int32_t)plist.size();
-  if (c->nper && c->npro) { fcp_set_error("periodic patches on a partitioned mesh are not supported (the serial tree has no process patches)"); delete c; return FCP_ESTATE; }
+  if (c->nper && c->npro) { fcp_set_error("periodic patches on a partitioned mesh are not supported (the serial tree has no process patches)"); return FCP_ESTATE; }
 
   // ---- create_CSR_matrix (sparse_matrix.f90:110-260): rows ascending, columns ascending, diagonal embedded ----
   std::vector<int32_t> ia(n + 1, 0), diag(n);
@@ -165,7 +159,7 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
   if (c->nper) {   // a periodic pair must not duplicate an existing entry (the reference's csr_to_k would alias the two coefficients)
     for (int32_t i = 0; i < n; ++i)
       for (int32_t k = ia[i]; k < ia[i + 1] - 1; ++k)
-        if (ja[k - 1] == ja[k]) { fcp_set_error("periodic pair joins cells %d and %d, which already share a face", i + 1, ja[k]); delete c; return FCP_EINVAL; }
+        if (ja[k - 1] == ja[k]) { fcp_set_error("periodic pair joins cells %d and %d, which already share a face", i + 1, ja[k]); return FCP_EINVAL; }
   }
   c->h_kPN.resize((size_t)F + c->nper);
   c->h_kNP.resize((size_t)F + c->nper);
@@ -196,7 +190,7 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
       }
   }
   int rc = sell_from_csr(c->pat, n, c->npro ? c->nT : n, ia.data(), ja.data(), diag.data(), c->npro ? &halo : nullptr);
-  if (rc != FCP_OK) { delete c; return rc; }
+  if (rc != FCP_OK) { return rc; }
   std::vector<int64_t> slptr(c->pat.nslices + 1);
   FCP_CUDA(cudaMemcpy(slptr.data(), c->pat.slptr, slptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
   auto sellpos = [&](int32_t row0, int32_t off) -> int32_t { return (int32_t)(slptr[row0 >> 5] + (int64_t)off * 32 + (row0 & 31)); };
@@ -248,7 +242,7 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
       fsl[s + 1] = fsl[s] + (int64_t)w * 32;
     }
     const int64_t np = fsl[nsl];
-    if (np >= (int64_t)2147483647) { fcp_set_error("face lists too large"); delete c; return FCP_EINVAL; }
+    if (np >= (int64_t)2147483647) { fcp_set_error("face lists too large"); return FCP_EINVAL; }
     std::vector<int32_t> ent(np, 0), other(np, 0), slot(np, -1), fill(n, 0);
     for (int32_t f = 0; f < c->nF; ++f) {
       int32_t p = md->owner[f] - 1;
@@ -308,6 +302,15 @@ extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out
   FCP_TRY(dev_upload(&c->bftype, bft.data(), (size_t)std::max(B, 1)));
   FCP_TRY(dev_upload(&c->kPN, kPN.data(), (size_t)std::max(F, 1)));
   FCP_TRY(dev_upload(&c->kNP, kNP.data(), (size_t)std::max(F, 1)));
+  return FCP_OK;
+}
+extern "C" int fcp_ctx_create(const fcp_mesh_desc *md, int device, fcp_ctx **out) {
+  if (!md || !out) { fcp_set_error("fcp_ctx_create: null argument"); return FCP_EINVAL; }
+  *out = nullptr;
+  FCP_TRY(select_device(device));
+  fcp_ctx *c = new fcp_ctx();
+  const int rc = ctx_build(c, md, device);
+  if (rc != FCP_OK) { fcp_ctx_destroy(c); return rc; }
   *out = c;
   return FCP_OK;
 }
@@ -842,6 +845,30 @@ extern "C" int fcp_modify_mu_eff_k_epsilon_rlzb(fcp_ctx *ctx, double urfVis, dou
   FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(dnw, FCP_F_DNW); FIELD(vis, FCP_F_VIS); FIELD(visw, FCP_F_VISW);
   FIELD(ypl, FCP_F_YPL); FIELD(tau, FCP_F_TAU);
   return fvm_mu_eff_rlzb(ctx, urfVis, viscos, gu, gv, gw, te, ed, den, u, v, w, dnw, vis, visw, ypl, tau);
+}
+
+extern "C" int fcp_grad_gauss_fvx(fcp_ctx *ctx, int phi_field, int grad_field) {
+  if (!ctx) return FCP_EINVAL;
+  if (grad_field < FCP_F_DUDXI || grad_field > FCP_F_G1 || phi_field < 0 || phi_field >= FCP_F_COUNT || (phi_field >= FCP_F_DUDXI && phi_field <= FCP_F_H)) {
+    fcp_set_error("fcp_grad_gauss_fvx: bad field id");
+    return FCP_EINVAL;
+  }
+  if (ctx->comm) { fcp_set_error("fcp_grad_gauss_fvx: partitioned meshes are not supported yet"); return FCP_ESTATE; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(phi, phi_field); FIELD(g, grad_field);
+  FIELD(gtmp, grad_field == FCP_F_G1 ? FCP_F_G0 : FCP_F_G1);     // the first pass's gradient
+  return fvm_grad_gauss_fvx(ctx, phi, gtmp, g);
+}
+extern "C" int fcp_modify_viscosity_sgs(fcp_ctx *ctx, int model, double urfVis, double viscos) {
+  if (!ctx) return FCP_EINVAL;
+  if (model != FCP_SGS_WALE && model != FCP_SGS_VREMAN) { fcp_set_error("fcp_modify_viscosity_sgs: unknown model %d", model); return FCP_EINVAL; }
+  if (ctx->comm) { fcp_set_error("fcp_modify_viscosity_sgs: partitioned meshes are not supported yet"); return FCP_ESTATE; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FCP_TRY(fcp_grad_gauss_fvx(ctx, FCP_F_U, FCP_F_DUDXI));
+  FCP_TRY(fcp_grad_gauss_fvx(ctx, FCP_F_V, FCP_F_DVDXI));
+  FCP_TRY(fcp_grad_gauss_fvx(ctx, FCP_F_W, FCP_F_DWDXI));
+  FIELD(gu, FCP_F_DUDXI); FIELD(gv, FCP_F_DVDXI); FIELD(gw, FCP_F_DWDXI); FIELD(den, FCP_F_DEN); FIELD(vis, FCP_F_VIS); FIELD(visw, FCP_F_VISW);
+  return fvm_sgs_viscosity(ctx, model, urfVis, viscos, gu, gv, gw, den, vis, visw);
 }
 
 // calcp_piso   Pressure/calcp_piso.f90:81-489

@@ -305,6 +305,9 @@ int fvm_mu_eff_rlzb(fcp_ctx *ctx, double urf, double viscos, const double *gU, c
                     const double *den, const double *u, const double *v, const double *w, const double *dnw, double *vis, double *visw, double *ypl,
                     double *tau);
 int fvm_minmax(fcp_ctx *ctx, const double *phi, double **mm_out);
+int fvm_grad_gauss_fvx(fcp_ctx *ctx, const double *u, double *gtmp, double *g);
+int fvm_sgs_viscosity(fcp_ctx *ctx, int model, double urf, double viscos, const double *gU, const double *gV, const double *gW, const double *den,
+                      double *vis, double *visw);
 
 // ---- pattern.cu ---------------------------------------------------------------------------------
 int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, const int32_t *ja1, const int32_t *diag1,

@@ -287,6 +287,159 @@ __global__ void __launch_bounds__(FCP_TPB) k_mu_eff_wall(MeshView m, const int32
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// LES sub-grid viscosity (wale_sgs.f90, vremanSGS.f90): fvxGradient's Grad(U) (the two-pass Gauss gradient with the gradco skewness
+// correction, fvxGradient.f90:1549-1662, 1761-1838) + the tensorFields algebra, one thread per cell.
+// ---------------------------------------------------------------------------------------------
+// one pass: gnew = (sum over faces of fie S)/vol with fie interpolated with the OLD gradient gold (zero in the first pass)
+__global__ void __launch_bounds__(FCP_TPB) k_grad_gauss_fvx(MeshView m, const double *__restrict__ u, const double *__restrict__ gold,
+                                                             double *__restrict__ gnew) {
+  FCP_CELL_LOOP(c, m.n) {
+    const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c], uc = u[c];
+    const double ocx = gold ? gold[3 * (int64_t)c] : 0.0, ocy = gold ? gold[3 * (int64_t)c + 1] : 0.0, ocz = gold ? gold[3 * (int64_t)c + 2] : 0.0;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    FCP_FACE_LOOP(m, c) {
+      FCP_FACE_FETCH(m);
+      const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
+      if (sl >= 0) {                                       // gradco, in the face's orientation (P = owner, N = neighbour)
+        const bool own = e > 0;
+        const double fxn = m.facint[f], fxp = 1.0 - fxn;
+        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o], uo = u[o];
+        const double oox = gold ? gold[3 * (int64_t)o] : 0.0, ooy = gold ? gold[3 * (int64_t)o + 1] : 0.0, ooz = gold ? gold[3 * (int64_t)o + 2] : 0.0;
+        const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo, xN = own ? xo : xc, yN = own ? yo : yc, zN = own ? zo : zc;
+        const double uP = own ? uc : uo, uN = own ? uo : uc;
+        const double gPx = own ? ocx : oox, gPy = own ? ocy : ooy, gPz = own ? ocz : ooz;
+        const double gNx = own ? oox : ocx, gNy = own ? ooy : ocy, gNz = own ? ooz : ocz;
+        const double xi = xP * fxp + xN * fxn, yi = yP * fxp + yN * fxn, zi = zP * fxp + zN * fxn;
+        const double dfxi = gPx * fxp + gNx * fxn, dfyi = gPy * fxp + gNy * fxn, dfzi = gPz * fxp + gNz * fxn;
+        const double fie = uP * fxp + uN * fxn + dfxi * (m.xf[f] - xi) + dfyi * (m.yf[f] - yi) + dfzi * (m.zf[f] - zi);
+        const double dfxe = fie * arx, dfye = fie * ary, dfze = fie * arz;
+        if (own) { sx = sx + dfxe; sy = sy + dfye; sz = sz + dfze; }
+        else     { sx = sx - dfxe; sy = sy - dfye; sz = sz - dfze; }
+      } else {                                             // gradbc
+        const double ub = u[o];
+        sx = sx + ub * arx; sy = sy + ub * ary; sz = sz + ub * arz;
+      }
+    }
+    const double volr = 1.0 / m.vol[c];
+    gnew[3 * (int64_t)c] = sx * volr; gnew[3 * (int64_t)c + 1] = sy * volr; gnew[3 * (int64_t)c + 2] = sz * volr;
+  }
+}
+
+// tensors as t[9] = xx xy xz yx yy yz zx zy zz (tensorFields.f90)
+__device__ __forceinline__ void tf_inner(const double (&a)[9], const double (&b)[9], double (&r)[9]) {   // :490-513; quirk Q24: r[6] uses a[6] twice
+  r[0] = a[0] * b[0] + a[1] * b[3] + a[2] * b[6];
+  r[1] = a[0] * b[1] + a[1] * b[4] + a[2] * b[7];
+  r[2] = a[0] * b[2] + a[1] * b[5] + a[2] * b[8];
+  r[3] = a[3] * b[0] + a[4] * b[3] + a[5] * b[6];
+  r[4] = a[3] * b[1] + a[4] * b[4] + a[5] * b[7];
+  r[5] = a[3] * b[2] + a[4] * b[5] + a[5] * b[8];
+  r[6] = a[6] * b[0] + a[6] * b[3] + a[8] * b[6];
+  r[7] = a[6] * b[1] + a[7] * b[4] + a[8] * b[7];
+  r[8] = a[6] * b[2] + a[7] * b[5] + a[8] * b[8];
+}
+__device__ __forceinline__ void tf_trans(const double (&a)[9], double (&r)[9]) {
+  r[0] = a[0]; r[1] = a[3]; r[2] = a[6]; r[3] = a[1]; r[4] = a[4]; r[5] = a[7]; r[6] = a[2]; r[7] = a[5]; r[8] = a[8];
+}
+__device__ __forceinline__ double tf_tr(const double (&a)[9]) { return a[0] + a[4] + a[8]; }
+__device__ __forceinline__ double tf_magsq(const double (&a)[9]) {
+  return a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3] + a[4] * a[4] + a[5] * a[5] + a[6] * a[6] + a[7] * a[7] + a[8] * a[8];
+}
+__device__ __forceinline__ void tf_symm(const double (&a)[9], double (&r)[9]) {
+  double t[9];
+  tf_trans(a, t);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r[k] = 0.5 * (a[k] + t[k]);
+}
+__device__ __forceinline__ void tf_dev(const double (&a)[9], double (&r)[9]) {
+  const double tr = tf_tr(a), third = 1.0 / 3.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r[k] = a[k] - third * (tr * ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0));
+}
+#define FCP_TF_EPS ((double)1e-30f)     // tensorFields.f90:926  `1e-30`
+
+template <int MODEL>   // 0 WALE (wale_sgs.f90:88-105), 1 Vreman (vremanSGS.f90:86-105)
+__global__ void __launch_bounds__(FCP_TPB) k_sgs_viscosity(int32_t n, double urf, double viscos, const double *__restrict__ gU, const double *__restrict__ gV,
+                                                            const double *__restrict__ gW, const double *__restrict__ den, const double *__restrict__ vol,
+                                                            double *__restrict__ vis) {
+  FCP_CELL_LOOP(c, n) {
+    const int64_t b = 3 * (int64_t)c;
+    const double D[9] = {gU[b], gU[b + 1], gU[b + 2], gV[b], gV[b + 1], gV[b + 2], gW[b], gW[b + 1], gW[b + 2]};
+    double musgs;
+    if (MODEL == 0) {
+      const double Cw = (double)0.325f, r13 = 1.0 / 3.0;
+      double DD[9], S[9], Sd[9], sD[9];
+      tf_inner(D, D, DD);
+      tf_symm(DD, S);
+      tf_dev(S, Sd);
+      const double magSqrSd = tf_magsq(Sd);
+      tf_symm(D, sD);
+      const double t = Cw * pow(vol[c], r13);
+      const double num = (den[c] * (t * t)) * pow(magSqrSd, 1.5);
+      const double dnm = pow(tf_magsq(sD), 2.5) + pow(magSqrSd, 1.25);
+      musgs = num / (dnm + FCP_TF_EPS);
+    } else {
+      const double Cvsq = 0.0681, r23 = 2.0 / 3.0;
+      double Dt[9], G[9], GG[9];
+      tf_trans(D, Dt);
+      tf_inner(Dt, D, G);
+      tf_inner(G, G, GG);
+      const double trG = tf_tr(G);
+      const double x = trG * trG - tf_tr(GG);            // power(.tr.G, 2.0_dp): pow(x, 2) is exactly x*x
+      double mu = sqrt((0.5 * x) / (tf_magsq(G) + FCP_TF_EPS));
+      mu = fmax(mu, FCP_SMALL);
+      musgs = ((den[c] * Cvsq) * pow(vol[c], r23)) * mu;
+    }
+    vis[c] = urf * (musgs + viscos) + (1.0 - urf) * vis[c];
+  }
+}
+// boundary values of the effective viscosity, wale_sgs.f90:110-160: wall -> visw = vis = max(viscos, 0); periodic pair -> the mean (patch-order
+// rule as in k_update_boundary); every other patch -> the owner value
+__global__ void __launch_bounds__(FCP_TPB) k_sgs_boundary(MeshView m, const int32_t *__restrict__ bftype, double viscos, double *vis, double *visw) {
+  FCP_CELL_LOOP(i, m.B) {
+    const int t = bftype[i];
+    const int32_t ijp = m.owner[m.F + i], ijb = m.n + i;
+    if (t == FCP_BC_WALL) {
+      const double vw = fmax(viscos, 0.0);
+      visw[ijb] = vw;
+      vis[ijb] = vw;
+    } else if (t == FCP_BC_PERIODIC) {
+      const double v = 0.5 * (vis[ijp] + vis[m.per_cell[i]]);
+      vis[ijb] = v;
+      if (m.per_face[i] < m.F + i) vis[m.n + (m.per_face[i] - m.F)] = v;
+    } else if (t == FCP_BC_EMPTY && m.per_cell && m.per_cell[i] >= 0) {
+      if (m.per_face[i] < m.F + i) vis[ijb] = vis[ijp];
+    } else {
+      vis[ijb] = vis[ijp];
+    }
+  }
+}
+
+int fvm_grad_gauss_fvx(fcp_ctx *ctx, const double *u, double *gtmp, double *g) {
+  if (ctx->n == 0) return FCP_OK;
+  const MeshView m = fcp_mesh_view(ctx);
+  size_t tok = ctx->prof.begin(FCP_K_GRAD, ctx->stream);
+  k_grad_gauss_fvx<<<FCP_GRID(ctx->n)>>>(m, u, nullptr, gtmp);
+  k_grad_gauss_fvx<<<FCP_GRID(ctx->n)>>>(m, u, gtmp, g);
+  ctx->prof.end(tok, ctx->stream);
+  FCP_LAUNCHED(); FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_sgs_viscosity(fcp_ctx *ctx, int model, double urf, double viscos, const double *gU, const double *gV, const double *gW, const double *den,
+                      double *vis, double *visw) {
+  if (ctx->n == 0) return FCP_OK;
+  if (model == 0) k_sgs_viscosity<0><<<FCP_GRID(ctx->n)>>>(ctx->n, urf, viscos, gU, gV, gW, den, ctx->vol, vis);
+  else k_sgs_viscosity<1><<<FCP_GRID(ctx->n)>>>(ctx->n, urf, viscos, gU, gV, gW, den, ctx->vol, vis);
+  FCP_LAUNCHED();
+  if (ctx->B) {
+    k_sgs_boundary<<<FCP_GRID(ctx->B)>>>(fcp_mesh_view(ctx), ctx->bftype, viscos, vis, visw);
+    FCP_LAUNCHED();
+  }
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
 int fvm_strain(fcp_ctx *ctx, const double *gU, const double *gV, const double *gW, double *magStrain, double *vorticity) {
   if (ctx->n == 0) return FCP_OK;
   k_strain<<<FCP_GRID(ctx->n)>>>(ctx->n, gU, gV, gW, magStrain, vorticity);

@@ -149,6 +149,8 @@ def lib():
     L.fcp_update_boundary.argtypes = [vp, C.c_int]
     L.fcp_calcsc.argtypes = [vp, C.POINTER(ScalarParams), C.c_int, C.POINTER(Report), _pd, _pd]
     L.fcp_calc_strain_and_vorticity.argtypes = [vp]
+    L.fcp_grad_gauss_fvx.argtypes = [vp, C.c_int, C.c_int]
+    L.fcp_modify_viscosity_sgs.argtypes = [vp, C.c_int, C.c_double, C.c_double]
     L.fcp_modify_mu_eff_k_epsilon_rlzb.argtypes = [vp, C.c_double, C.c_double]
     L.fcp_calcuvw.argtypes = [vp, C.POINTER(UvwParams), C.POINTER(Report)]
     L.fcp_laplacian.argtypes = [vp, C.c_int, C.c_int]
@@ -334,6 +336,15 @@ class Context:
         lo, hi = C.c_double(0.0), C.c_double(0.0)
         check(lib().fcp_calcsc(self.h, C.byref(prm), field_id(phi), C.byref(rep), C.byref(lo), C.byref(hi)), "fcp_calcsc")
         return rep, lo.value, hi.value
+
+    def grad_gauss_fvx(self, phi, grad):
+        """Grad of the tensor-field layer: the two-pass Gauss gradient of fvxGradient.f90:1549-1662."""
+        check(lib().fcp_grad_gauss_fvx(self.h, field_id(phi), field_id(grad)), "fcp_grad_gauss_fvx")
+
+    def modify_viscosity_sgs(self, model, urfVis: float, viscos: float):
+        """modify_viscosity_wale_sgs / modify_viscosity_vreman_sgs."""
+        mid = {"wale": 0, "vreman": 1}[model] if isinstance(model, str) else int(model)
+        check(lib().fcp_modify_viscosity_sgs(self.h, mid, urfVis, viscos), "fcp_modify_viscosity_sgs")
 
     def calc_strain_and_vorticity(self):
         check(lib().fcp_calc_strain_and_vorticity(self.h), "fcp_calc_strain_and_vorticity")

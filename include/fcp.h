@@ -263,6 +263,17 @@ int fcp_calc_strain_and_vorticity(fcp_ctx *ctx);
  * log are the device's: agreement with the reference's libm is to rounding. */
 int fcp_modify_mu_eff_k_epsilon_rlzb(fcp_ctx *ctx, double urfVis, double viscos);
 
+/* fvxGradient's Gauss gradient (fvExplicit/fvxGradient.f90:1549-1662, gradco :1761-1817): two passes, the second interpolates the face value
+ * with the first pass's gradient (skewness correction).  It is what Grad(U) of the tensor-field layer returns with its default flags; note that
+ * it is NOT the grad_gauss of gradients.f90 (FCP_GRAD_GAUSS).  Scratch: the G1 gradient field (G0 when grad_field is G1). */
+int fcp_grad_gauss_fvx(fcp_ctx *ctx, int phi_field, int grad_field);
+/* modify_viscosity_wale_sgs (TurbulenceModels/wale_sgs.f90:33-185) / modify_viscosity_vreman_sgs (vremanSGS.f90:33-179): D = Grad(U) with the
+ * gradient above (left in FCP_F_DUDXI/DVDXI/DWDXI), the model's tensor algebra (tensorFields.f90, quirk Q24 of its inner product reproduced),
+ * vis = urfVis (mu_sgs + viscos) + (1 - urfVis) vis, then the boundary values: wall faces FCP_F_VISW = vis = max(viscos, 0), periodic pairs the
+ * mean of the two cells, every other patch the owner value.  pow() is the device's: agreement with the reference's libm is to rounding. */
+enum { FCP_SGS_WALE = 0, FCP_SGS_VREMAN = 1 };
+int fcp_modify_viscosity_sgs(fcp_ctx *ctx, int model, double urfVis, double viscos);
+
 /* ---- explicit-CSR solver signature: dpcg|iccg|bicgstab(n,nnz,ia,ja,a,diag,fi,rhs,...) -------- */
 /* linear_solvers.f90:206, :364, :548 ; pattern analysed once, values per solve */
 int fcp_solver_create(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const int32_t *diag,

@@ -1546,6 +1546,118 @@ extern "C" void orc_calcuvw(const orc_mesh *m, const i32 *ia, const i32 *ja, con
 }
 
 // ------------------------------------------------------------------------------------------
+// LES sub-grid viscosity: fvxGradient's Grad(U) + the tensorFields algebra of wale_sgs.f90 / vremanSGS.f90
+// ------------------------------------------------------------------------------------------
+extern "C" void orc_grad_gauss_fvx(const orc_mesh *m, const double *u, double *dudx, double *dudy, double *dudz) {   // fvxGradient.f90:1549-1662
+  const i32 n = m->numCells, F = m->numInnerFaces;
+  std::vector<double> dfxo(n, 0.0), dfyo(n, 0.0), dfzo(n, 0.0);
+  for (int lc = 1; lc <= 2; ++lc) {
+    for (i32 c = 0; c < n; ++c) dudx[c] = dudy[c] = dudz[c] = 0.0;
+    for (i32 i = 0; i < F; ++i) {                                     // gradco :1761-1817
+      const i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+      const double fxn = m->facint[i], fxp = 1.0 - fxn;
+      const double xi = m->xc[ijp] * fxp + m->xc[ijn] * fxn, yi = m->yc[ijp] * fxp + m->yc[ijn] * fxn, zi = m->zc[ijp] * fxp + m->zc[ijn] * fxn;
+      const double dfxi = dfxo[ijp] * fxp + dfxo[ijn] * fxn, dfyi = dfyo[ijp] * fxp + dfyo[ijn] * fxn, dfzi = dfzo[ijp] * fxp + dfzo[ijn] * fxn;
+      const double fie = u[ijp] * fxp + u[ijn] * fxn + dfxi * (m->xf[i] - xi) + dfyi * (m->yf[i] - yi) + dfzi * (m->zf[i] - zi);
+      const double dfxe = fie * m->arx[i], dfye = fie * m->ary[i], dfze = fie * m->arz[i];
+      dudx[ijp] = dudx[ijp] + dfxe; dudy[ijp] = dudy[ijp] + dfye; dudz[ijp] = dudz[ijp] + dfze;
+      dudx[ijn] = dudx[ijn] - dfxe; dudy[ijn] = dudy[ijn] - dfye; dudz[ijn] = dudz[ijn] - dfze;
+    }
+    for (i32 i = 0; i < m->numBoundaryFaces; ++i) {                   // gradbc :1819-1838
+      const i32 f = F + i, ijp = m->owner[f] - 1, ijb = n + i;
+      dudx[ijp] = dudx[ijp] + u[ijb] * m->arx[f]; dudy[ijp] = dudy[ijp] + u[ijb] * m->ary[f]; dudz[ijp] = dudz[ijp] + u[ijb] * m->arz[f];
+    }
+    for (i32 c = 0; c < n; ++c) {
+      const double volr = 1.0 / m->vol[c];
+      dudx[c] = dudx[c] * volr; dudy[c] = dudy[c] * volr; dudz[c] = dudz[c] * volr;
+    }
+    if (lc < 2) for (i32 c = 0; c < n; ++c) { dfxo[c] = dudx[c]; dfyo[c] = dudy[c]; dfzo[c] = dudz[c]; }
+  }
+}
+// tensors as t[9] = xx xy xz yx yy yz zx zy zz
+static inline void tf_inner(const double *a, const double *b, double *r) {          // tensorFields.f90:490-513, quirk Q24 in r[6]
+  r[0] = a[0] * b[0] + a[1] * b[3] + a[2] * b[6];
+  r[1] = a[0] * b[1] + a[1] * b[4] + a[2] * b[7];
+  r[2] = a[0] * b[2] + a[1] * b[5] + a[2] * b[8];
+  r[3] = a[3] * b[0] + a[4] * b[3] + a[5] * b[6];
+  r[4] = a[3] * b[1] + a[4] * b[4] + a[5] * b[7];
+  r[5] = a[3] * b[2] + a[4] * b[5] + a[5] * b[8];
+  r[6] = a[6] * b[0] + a[6] * b[3] + a[8] * b[6];
+  r[7] = a[6] * b[1] + a[7] * b[4] + a[8] * b[7];
+  r[8] = a[6] * b[2] + a[7] * b[5] + a[8] * b[8];
+}
+static inline void tf_trans(const double *a, double *r) { r[0] = a[0]; r[1] = a[3]; r[2] = a[6]; r[3] = a[1]; r[4] = a[4]; r[5] = a[7]; r[6] = a[2]; r[7] = a[5]; r[8] = a[8]; }
+static inline double tf_tr(const double *a) { return a[0] + a[4] + a[8]; }
+static inline double tf_magsq(const double *a) {                                    // T**T :516-531
+  return a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3] + a[4] * a[4] + a[5] * a[5] + a[6] * a[6] + a[7] * a[7] + a[8] * a[8];
+}
+static inline void tf_symm(const double *a, double *r) {                            // 0.5*(T + .trans.T) :1203-1213
+  double t[9];
+  tf_trans(a, t);
+  for (int k = 0; k < 9; ++k) r[k] = 0.5 * (a[k] + t[k]);
+}
+static inline void tf_dev(const double *a, double *r) {                             // T - 1./3.0_dp*(.tr.T * I) :1246-1263
+  const double tr = tf_tr(a), third = 1.0 / 3.0;
+  const double eye[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+  for (int k = 0; k < 9; ++k) r[k] = a[k] - third * (tr * eye[k]);
+}
+static const double TF_EPS = (double)1e-30f;                                        // `1e-30` of volScalarField_volScalarField_divide :926
+
+extern "C" void orc_modify_viscosity_sgs(const orc_mesh *m, int model, double urf, double viscos, const double *u, const double *v, const double *w,
+                                         const double *den, double *vis, double *visw) {
+  const i32 n = m->numCells, F = m->numInnerFaces;
+  std::vector<double> g[9];
+  for (int k = 0; k < 9; ++k) g[k].assign(n, 0.0);
+  orc_grad_gauss_fvx(m, u, g[0].data(), g[1].data(), g[2].data());                  // D = Grad(U_): xx xy xz = du/dx du/dy du/dz ...
+  orc_grad_gauss_fvx(m, v, g[3].data(), g[4].data(), g[5].data());
+  orc_grad_gauss_fvx(m, w, g[6].data(), g[7].data(), g[8].data());
+  for (i32 c = 0; c < n; ++c) {
+    double D[9];
+    for (int k = 0; k < 9; ++k) D[k] = g[k][c];
+    double musgs;
+    if (model == 0) {                                                               // wale_sgs.f90:88-102
+      const double Cw = (double)0.325f, r13 = 1.0 / 3.0;
+      double DD[9], S[9], Sd[9], sD[9];
+      tf_inner(D, D, DD);
+      tf_symm(DD, S);
+      tf_dev(S, Sd);
+      const double magSqrSd = tf_magsq(Sd);
+      tf_symm(D, sD);
+      const double t = Cw * std::pow(m->vol[c], r13);
+      const double num = (den[c] * (t * t)) * std::pow(magSqrSd, 1.5);
+      const double dnm = std::pow(tf_magsq(sD), 2.5) + std::pow(magSqrSd, 1.25);
+      musgs = num / (dnm + TF_EPS);
+    } else {                                                                        // vremanSGS.f90:86-101
+      const double Cvsq = 0.0681, r23 = 2.0 / 3.0;
+      double Dt[9], G[9], GG[9];
+      tf_trans(D, Dt);
+      tf_inner(Dt, D, G);
+      tf_inner(G, G, GG);
+      const double x = std::pow(tf_tr(G), 2.0) - tf_tr(GG);
+      double mu = std::sqrt((0.5 * x) / (tf_magsq(G) + TF_EPS));
+      mu = mx(mu, SMALL);
+      musgs = ((den[c] * Cvsq) * std::pow(m->vol[c], r23)) * mu;
+    }
+    vis[c] = urf * (musgs + viscos) + (1.0 - urf) * vis[c];
+  }
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {                                   // wale_sgs.f90:110-160
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1;
+      if (m->bctype[ib] == ORC_BC_WALL) {
+        visw[f - F] = mx(viscos, 0.0);
+        vis[ijb] = visw[f - F];
+      } else if (m->bctype[ib] == ORC_BC_PERIODIC) {
+        const i32 ijn = m->owner[m->startFaceTwin[ib] + i - 1] - 1;
+        vis[ijb] = 0.5 * (vis[ijp] + vis[ijn]);
+        vis[n + (m->startFaceTwin[ib] - F) + i - 1] = vis[ijb];
+      } else {
+        vis[ijb] = vis[ijp];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // row f4: scalar transport template  (fluxes/scalar_fluxes.f90 + TurbulenceModels/k_epsilon_rlzb.f90)
 // ------------------------------------------------------------------------------------------
 static const double CAPPA = 0.41, ELOG = 8.432, CTRANS = (double)11.63f;      // parameters.f90:15-18 (`11.63` is a default-real literal)

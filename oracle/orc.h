@@ -221,6 +221,15 @@ void orc_modify_mu_eff_rlzb(const orc_mesh *m, double urf, double viscos, const 
                             const double *te, const double *ed, const double *den, const double *u, const double *v, const double *w,
                             const double *dnw, double *vis, double *visw, double *ypl, double *tau);
 
+/* ---- SGS viscosity of the LES models (row f4): TurbulenceModels/wale_sgs.f90:33-185 (model 0) and vremanSGS.f90:33-179 (model 1), written in the
+ * reference with the operator-overloaded tensorFields module (finiteVolume/tensorFields/tensorFields.f90) on top of fvxGradient's Grad(U).
+ * QUIRK Q24: inner_product_rank2_tensors computes its zx component as T1zx*T2xx + T1zx*T2yx + T1zz*T2zx (tensorFields.f90:508: `zx` twice);
+ * reproduced.  Boundary: wall faces get visw = vis = max(viscos, 0), a periodic face and its twin the mean of the two cells, every other patch
+ * the owner value.  visw is indexed by BOUNDARY FACE ordinal. */
+void orc_grad_gauss_fvx(const orc_mesh *m, const double *u, double *dudx, double *dudy, double *dudz);   /* fvxGradient.f90:1549-1662 (two passes, gradco) */
+void orc_modify_viscosity_sgs(const orc_mesh *m, int model, double urf, double viscos, const double *u, const double *v, const double *w,
+                              const double *den, double *vis, double *visw);
+
 /* linear_solvers.f90:206-359, 364-545, 548-786 */
 void orc_spmv(int32_t n, const int32_t *ia, const int32_t *ja, const double *a, const double *x, double *y);
 void orc_dpcg(int32_t n, int32_t nnz, const int32_t *ia, const int32_t *ja, const double *a,

@@ -414,3 +414,20 @@ def modify_mu_eff_rlzb(mesh, urf, viscos, dUdxi, dVdxi, dWdxi, te, ed, den, u, v
     lib().orc_modify_mu_eff_rlzb(mv.ptr, C.c_double(urf), C.c_double(viscos), _d(dUdxi), _d(dVdxi), _d(dWdxi), _d(te), _d(ed), _d(den),
                                  _d(u), _d(v), _d(w), _d(dnw), _d(vis), _d(visw), _d(ypl), _d(tau))
     return ypl, tau
+
+
+def grad_gauss_fvx(mesh, u):
+    """fvxGradient.f90:1549-1662: the two-pass Gauss gradient with the gradco skewness correction (SoA result, numCells)."""
+    mv = MeshView(mesh)
+    gx, gy, gz = (np.zeros(mesh.numCells) for _ in range(3))
+    lib().orc_grad_gauss_fvx(mv.ptr, _d(u), _d(gx), _d(gy), _d(gz))
+    return gx, gy, gz
+
+
+SGS_WALE, SGS_VREMAN = 0, 1
+
+
+def modify_viscosity_sgs(mesh, model, urf, viscos, u, v, w, den, vis, visw):
+    """wale_sgs.f90 / vremanSGS.f90: vis (numTotal) and visw (numBoundaryFaces) updated in place."""
+    mv = MeshView(mesh)
+    lib().orc_modify_viscosity_sgs(mv.ptr, C.c_int(model), C.c_double(urf), C.c_double(viscos), _d(u), _d(v), _d(w), _d(den), _d(vis), _d(visw))

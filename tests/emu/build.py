@@ -82,7 +82,18 @@ def rewrite_launches(src: str) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Rebuild when a source is newer than the library; serialised with a file lock (the ranks of a multi-process test all call this)."""
+    import fcntl
     os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build(force: bool, verbose: bool) -> str:
     cus = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + \
            [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".h", ".cpp", ".py"))] + [os.path.join(ROOT, "include", "fcp.h")]

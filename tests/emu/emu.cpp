@@ -245,7 +245,8 @@ struct Arena {
   int fd = -1;
   char *base = nullptr;
   std::map<size_t, size_t> free_;   // offset -> size
-  std::map<size_t, size_t> used_;   // offset -> size
+  std::map<size_t, size_t> used_;   // block offset -> start of its page run
+  std::map<size_t, size_t> span_;   // start of a page run -> its length (pages of the block + one guard page)
   std::map<int, char *> peers;      // pid -> mapping of that process's arena
   void init() {
     if (base) return;
@@ -261,19 +262,26 @@ cudaError_t g_last = cudaSuccess;
 int g_device = 0;
 }   // namespace
 
+// Every allocation ends flush (to 256 bytes) against a PROT_NONE guard page: an overrun of a "device" array faults at once instead of
+// silently reading a neighbour, and the slack in front of it is poisoned like the block itself.
+static const size_t kPage = 4096;
 cudaError_t emuMalloc(void **p, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_arena.mu);
   g_arena.init();
   const size_t need = std::max<size_t>((bytes + 255) / 256 * 256, 256);
+  const size_t npages = (need + kPage - 1) / kPage, total = (npages + 1) * kPage;
   for (auto it = g_arena.free_.begin(); it != g_arena.free_.end(); ++it) {
-    if (it->second < need) continue;
+    if (it->second < total) continue;
     const size_t off = it->first, sz = it->second;
     g_arena.free_.erase(it);
-    if (sz > need) g_arena.free_[off + need] = sz - need;
-    g_arena.used_[off] = need;
+    if (sz > total) g_arena.free_[off + total] = sz - total;
+    const size_t poff = off + npages * kPage - need;          // the block's own offset
+    g_arena.used_[poff] = off;                                 // -> start of its page run
+    g_arena.span_[off] = total;
     unsigned long long *q = (unsigned long long *)(g_arena.base + off);
-    for (size_t i = 0; i < need / 8; ++i) q[i] = kPoison;   // reading memory the product never wrote shows up as NaN / a wild index
-    *p = g_arena.base + off;
+    for (size_t i = 0; i < npages * kPage / 8; ++i) q[i] = kPoison;   // reading memory the product never wrote shows up as NaN / a wild index
+    if (mprotect(g_arena.base + off + npages * kPage, kPage, PROT_NONE) != 0) { perror("emu: mprotect guard"); abort(); }
+    *p = g_arena.base + poff;
     return cudaSuccess;
   }
   *p = nullptr;
@@ -282,11 +290,13 @@ cudaError_t emuMalloc(void **p, size_t bytes) {
 cudaError_t cudaFree(void *p) {
   if (!p) return cudaSuccess;
   std::lock_guard<std::mutex> lk(g_arena.mu);
-  const size_t off = (size_t)((char *)p - g_arena.base);
-  auto it = g_arena.used_.find(off);
+  const size_t poff = (size_t)((char *)p - g_arena.base);
+  auto it = g_arena.used_.find(poff);
   if (it == g_arena.used_.end()) return g_last = cudaErrorInvalidValue;
-  size_t sz = it->second, o = off;
+  size_t o = it->second, sz = g_arena.span_[o];
   g_arena.used_.erase(it);
+  g_arena.span_.erase(o);
+  mprotect(g_arena.base + o + sz - kPage, kPage, PROT_READ | PROT_WRITE);
   if (sz >= (1u << 20)) fallocate(g_arena.fd, FALLOC_FL_PUNCH_HOLE | FALLOC_FL_KEEP_SIZE, (off_t)o, (off_t)sz);   // give the pages back
   auto nx = g_arena.free_.lower_bound(o);
   if (nx != g_arena.free_.end() && o + sz == nx->first) { sz += nx->second; nx = g_arena.free_.erase(nx); }

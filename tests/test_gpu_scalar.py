@@ -205,3 +205,40 @@ def test_calcsc_argument_checks(fcp, allmeshes):
     with pytest.raises(L.FcpError):
         ctx.calcsc("DPDXI", kind="generic")
     ctx.close()
+
+
+# ---- LES sub-grid viscosity -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SC_MESHES)
+def test_grad_gauss_fvx(fcp, orc, allmeshes, name):
+    """fvxGradient.f90:1549-1662: the two-pass Gauss gradient of the tensor-field layer, bit-identical."""
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    ctx = make_ctx(m, dict(u=g["u"]))
+    ctx.grad_gauss_fvx("U", "DUDXI")
+    gx, gy, gz = orc.grad_gauss_fvx(m, g["u"])
+    got = ctx.download("DUDXI")[: m.numCells]
+    eq(got[:, 0], gx, "dudx"); eq(got[:, 1], gy, "dudy"); eq(got[:, 2], gz, "dudz")
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", SC_MESHES)
+@pytest.mark.parametrize("model", ["wale", "vreman"])
+def test_modify_viscosity_sgs(fcp, orc, allmeshes, name, model):
+    """wale_sgs.f90 / vremanSGS.f90 through the tensorFields algebra (pow() involved: 1e-12)."""
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    n = m.numCells
+    ctx = make_ctx(m, dict(u=g["u"], v=g["v"], w=g["w"], den=g["den"], vis=g["vis"]))
+    ctx.upload("VISW", bslot(m, g["visw"]))
+    ctx.modify_viscosity_sgs(model, 0.7, 0.01)
+    vis, visw = g["vis"].copy(), g["visw"].copy()
+    orc.modify_viscosity_sgs(m, {"wale": orc.SGS_WALE, "vreman": orc.SGS_VREMAN}[model], 0.7, 0.01, g["u"], g["v"], g["w"], g["den"], vis, visw)
+    close(ctx.download("VIS"), vis, f"vis ({model})")
+    wall = np.zeros(m.numBoundaryFaces, bool)
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] == M.BC_WALL:
+            wall[m.patch_faces(ib) - m.numInnerFaces] = True
+    if wall.any():
+        eq(ctx.download("VISW")[n:][wall], visw[wall], "visw")
+    assert np.all(vis[:n] >= 0.0)
+    ctx.close()

@@ -1,0 +1,89 @@
+"""GPU (B200): time steps of a periodic LES channel with every field resident on the device -- the configuration of examples/channel395
+(two periodic pairs, walls top and bottom, bdf2, cds, constant mass flow forcing, a Vreman or WALE sub-grid viscosity) driven with PISO:
+    calcuvw(piso) -> calcp_piso -> constant_mass_flow_forcing -> modify_viscosity_sgs      (main.f90:142-175 with PISO = T)
+against the same chain through the oracle.  Exercises row f3 end to end (twin CSR entries, facefluxuvw_periodic, facefluxmass2_periodic,
+periodic flux correction, the forcing) together with the f4 SGS models.  All solves run a fixed number of iterations; the SGS viscosity
+goes through pow(), hence a tolerance instead of bit equality after the first step."""
+import numpy as np
+import pytest
+
+import cases
+from fcb200 import lib as L
+from fcb200 import mesh as M
+import test_gpu_scalar as T
+
+pytestmark = pytest.mark.gpu
+VISCOS, MAGUBAR, DT = 2e-3, 0.1335, 0.05
+
+
+def initial_state(m):
+    rng = np.random.default_rng(17)
+    n, nT, Fi = m.numCells, m.numTotal, m.numInnerFaces
+    y = m.yc[:n]
+    f = dict(u=np.zeros(nT), v=np.zeros(nT), w=np.zeros(nT), p=np.zeros(nT), pp=np.zeros(nT), den=np.ones(nT), vis=np.full(nT, VISCOS),
+             apu=np.zeros(nT), apv=np.zeros(nT), apw=np.zeros(nT), visw=np.full(m.numBoundaryFaces, VISCOS), flmass=np.zeros(m.numFaces))
+    # a parabolic profile with the requested bulk velocity plus divergence-free-ish disturbances (init.f90 channel_disturbances stand-in)
+    f["u"][:n] = 1.5 * MAGUBAR * 4 * y * (1 - y) * (1 + 0.1 * np.sin(2 * np.pi * m.zc[:n]) * np.sin(np.pi * m.xc[:n]))
+    f["v"][:n] = 0.02 * MAGUBAR * np.sin(np.pi * m.xc[:n]) * np.sin(2 * np.pi * y)
+    f["w"][:n] = 0.05 * MAGUBAR * np.sin(np.pi * y) * np.cos(np.pi * m.xc[:n]) + 1e-4 * rng.standard_normal(n)
+    own, nb = m.owner[:Fi].astype(np.int64) - 1, m.neighbour.astype(np.int64) - 1
+    lam = m.facint
+    for k, ar in (("u", m.arx), ("v", m.ary), ("w", m.arz)):
+        f["flmass"][:Fi] += (f[k][own] * (1 - lam) + f[k][nb] * lam) * ar[:Fi]
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] != M.BC_PERIODIC:
+            continue
+        pf = m.patch_faces(ib); tf = np.arange(m.startFaceTwin[ib], m.startFaceTwin[ib] + m.nfaces[ib])
+        p, q = m.owner[pf].astype(np.int64) - 1, m.owner[tf].astype(np.int64) - 1
+        fl = 0.5 * ((f["u"][p] + f["u"][q]) * m.arx[pf] + (f["v"][p] + f["v"][q]) * m.ary[pf] + (f["w"][p] + f["w"][q]) * m.arz[pf])
+        f["flmass"][pf] = fl; f["flmass"][tf] = fl
+    for k in "uvw":
+        f[k + "o"] = f[k].copy(); f[k + "oo"] = f[k].copy()
+    return f
+
+
+@pytest.mark.parametrize("model", ["vreman", "wale"])
+def test_les_channel_time_steps_match_the_oracle(fcp, orc, model):
+    m = cases.periodic_channel(nx=10, ny=8, nz=6, distort=0.1)
+    c = orc.Csr(m)
+    f = initial_state(m)
+    n = m.numCells
+    ctx = L.Context(m)
+    for k in ("u", "v", "w", "p", "pp", "den", "vis", "apu", "apv", "apw", "uo", "vo", "wo", "uoo", "voo", "woo"):
+        ctx.upload(k.upper(), f[k])
+    ctx.upload("VISW", T.bslot(m, f["visw"])); ctx.upload("FLMASS", f["flmass"]); ctx.upload("A", np.zeros(ctx.nnz))
+    up = orc.OrcUvwParams()
+    up.solver, up.maxiter, up.tol_abs, up.tol_rel = orc.BICGSTAB, 3, 1e-30, 1e-30
+    up.urf[0] = up.urf[1] = up.urf[2] = 1.0
+    up.gds, up.cscheme, up.pscheme, up.viscos, up.sum_mode = 1.0, L.CSCHEME_ID["cds"], 0, VISCOS, orc.SUM_TREE
+    up.tscheme, up.timestep, up.piso, up.const_mflux = 2, DT, 1, 1
+    a = np.zeros(c.nnz)
+    gradPcmf_dev = gradPcmf = 1e-3
+    sgs = {"wale": orc.SGS_WALE, "vreman": orc.SGS_VREMAN}[model]
+    for step in range(3):
+        # ---- device
+        ctx.calcuvw(solver="bicgstab", maxiter=3, tol_abs=1e-30, tol_rel=1e-30, urf=(1.0, 1.0, 1.0), gds=1.0, cscheme="cds", pscheme="linear",
+                    tscheme="bdf2", timestep=DT, piso=True, const_mflux=True, gradPcmf=gradPcmf_dev, viscos=VISCOS)
+        ctx.calcp_piso(solver="iccg", maxiter=8, tol_abs=1e-30, tol_rel=1e-30, urfp=1.0, ncorr=2, npcor=1, pscheme="linear", const_mflux=True)
+        gradPcmf_dev, ustar_dev = ctx.constant_mass_flow_forcing(MAGUBAR, gradPcmf_dev)
+        ctx.modify_viscosity_sgs(model, 1.0, VISCOS)
+        for k in "UVW":                                  # time shift (main.f90 time loop): oo <- o <- current
+            ctx.copy(k + "OO", k + "O"); ctx.copy(k + "O", k)
+        # ---- oracle
+        up.gradPcmf = gradPcmf
+        o = orc.calcuvw(m, c, up, f, a)
+        f["apv"][:], f["apw"][:] = o["apv"], o["apw"]
+        orc.calcp_piso(m, c, orc.ICCG, 8, 1e-30, 1e-30, orc.SUM_TREE, 2, 1, 0, 1.0, True, 0.0, o["rU"], o["rV"], o["rW"], f["den"], f["apu"], f["apv"],
+                       f["apw"], a, f["u"], f["v"], f["w"], f["p"], f["pp"], o["dPdxi"], f["flmass"])
+        gplus, ustar = orc.constant_mass_flow_forcing(m, MAGUBAR, f["apu"], f["u"], orc.SUM_TREE)
+        gradPcmf = gradPcmf + gplus
+        orc.modify_viscosity_sgs(m, sgs, 1.0, VISCOS, f["u"], f["v"], f["w"], f["den"], f["vis"], f["visw"])
+        for k in "uvw":
+            f[k + "oo"] = f[k + "o"].copy(); f[k + "o"] = f[k].copy()
+        T.close(np.array([gradPcmf_dev, ustar_dev]), np.array([gradPcmf, ustar]), f"step {step}: forcing", 1e-9)
+        for k in ("u", "v", "w", "p", "vis"):
+            T.close(ctx.download(k.upper()), f[k], f"step {step}: {k}", 1e-7)
+        T.close(ctx.download("FLMASS"), f["flmass"], f"step {step}: flmass", 1e-7)
+        # the forcing restores the bulk velocity exactly
+        assert abs((m.vol[:n] * f["u"][:n]).sum() / m.vol[:n].sum() - MAGUBAR) < 1e-12
+    ctx.close()

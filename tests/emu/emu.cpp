@@ -120,9 +120,11 @@ void run_block(int nthreads, const std::function<void()> &body) {
     fb.state = ST_READY;
     fb.mask = 0;
   }
+  static const bool rev_threads = getenv("FCP_EMU_REVERSE") != nullptr;   // race hunting: run the fibers (and the blocks) in descending order
   while (r->live > 0) {
     bool progressed = false;
-    for (int t = 0; t < nthreads; ++t) {
+    for (int tt = 0; tt < nthreads; ++tt) {
+      const int t = rev_threads ? nthreads - 1 - tt : tt;
       if (r->f[t].state != ST_READY) continue;
       r->cur = t;
       set_thread_index(t);
@@ -209,12 +211,14 @@ void launch_impl(const Cfg &c, const std::function<void()> &body, bool cooperati
   const dim3 save_bd = blockDim, save_gd = gridDim;
   if (!cooperative) {
     blockDim = c.b; gridDim = c.g;
-    for (unsigned z = 0; z < c.g.z; ++z)
-      for (unsigned y = 0; y < c.g.y; ++y)
-        for (unsigned x = 0; x < c.g.x; ++x) {
-          blockIdx = uint3{x, y, z};
-          run_block(nthreads, body);
-        }
+    // FCP_EMU_REVERSE: blocks in descending order -- a kernel whose result depends on the order in which its blocks (or the threads of
+    // a block between two barriers) happen to run has a race; the parity tests then fail under one of the two orders
+    static const bool rev = getenv("FCP_EMU_REVERSE") != nullptr;
+    for (long long bb = 0; bb < nblocks; ++bb) {
+      const long long b = rev ? nblocks - 1 - bb : bb;
+      blockIdx = uint3{(unsigned)(b % c.g.x), (unsigned)((b / c.g.x) % c.g.y), (unsigned)(b / ((long long)c.g.x * c.g.y))};
+      run_block(nthreads, body);
+    }
   } else {
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, nullptr, (unsigned)nblocks);

@@ -9,6 +9,9 @@
 * spsolve_5x5.json : the two 5x5 systems and the 2-decimal solutions printed beside the solver output by
   test/test_linear_solvers_spsolve.f90:13-53,77-98,129-138 (matrix literals are default-real in the Fortran source,
   i.e. float32 values promoted to double; both forms are stored).
+* pitzDaily_polymesh.npz : the reference's own examples/pitzDaily mesh (BASELINE config 2; 12 225 hexahedra, OpenFOAM polyMesh inside
+  examples/pitzDaily/polyMesh.zip with the reference's simplified `boundary` file: in inlet, out outlet, upperWall / lowerWall wall, sides
+  symmetry), read with our OpenFOAM reader.
 * oracle_pins.npz : outputs of the CPU oracle on the 400-cell mesh for seeded inputs.  These are REGRESSION pins of
   the oracle itself (not reference outputs: the Fortran reference cannot be built in this image).
 """
@@ -28,7 +31,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
 
 
+def pitz_daily():
+    import tempfile
+    import zipfile
+    with tempfile.TemporaryDirectory() as tmp:
+        zipfile.ZipFile(os.path.join(REF, "examples/pitzDaily/polyMesh.zip")).extractall(tmp)
+        m = M.read_polymesh_openfoam(os.path.join(tmp, "polyMesh"))
+    assert (m.numCells, m.numFaces, m.numInnerFaces) == (12225, 49180, 24170)
+    M.save_mesh_npz(m, os.path.join(HERE, "pitzDaily_polymesh.npz"))
+
+
 def main():
+    pitz_daily()
     m = M.read_polymesh_openfoam(os.path.join(REF, "test/testFieldOperations/polyMesh"))
     assert (m.numCells, m.numFaces, m.numInnerFaces) == (400, 1640, 760)
     M.save_mesh_npz(m, os.path.join(HERE, "cavity20_polymesh.npz"))

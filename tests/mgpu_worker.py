@@ -41,7 +41,10 @@ def main():
     if not EMU:
         torch.cuda.set_device(local)
     n = 12
-    g = M.cavity_mesh(n, distort=0.2)
+    if os.environ.get("FCP_TEST_MESH", "hex") == "poly":       # BASELINE config 5 in miniature: polyhedral cells (up to 10 faces), Gauss/LSQ gradients + ICCG
+        g = M.polyhedral_mesh(10, 8, 6, distort=0.15)
+    else:
+        g = M.cavity_mesh(n, distort=0.2)
     if os.environ.get("FCP_TEST_PART", "slab") == "brick":      # 2 x 2 x (world/4) bricks: every rank has 3+ neighbours, non-contiguous cell sets
         nc = g.numCells
         bz = max(world // 4, 1)

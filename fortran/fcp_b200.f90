@@ -558,6 +558,7 @@ contains
 
   ! ---- calcuvw(): no arguments   Velocity/velocity.f90:50-750 (tier "next" row f1) -----------------------------------------
   integer(c_int) function grad_method_id()          ! the logicals of gradients.f90:118-138
+    use gradients, only: lstsq, lstsq_qr, lstsq_dm
     grad_method_id = FCP_GRAD_GAUSS
     if (lstsq) then
       grad_method_id = FCP_GRAD_LSQ
@@ -568,6 +569,7 @@ contains
     end if
   end function
   integer(c_int) function limiter_id()              ! gradients.f90:140-160
+    use gradients, only: limiter
     select case (limiter)
       case ('Barth-Jespersen');  limiter_id = FCP_LIMITER_BARTH_JESPERSEN
       case ('Venkatakrishnan');  limiter_id = FCP_LIMITER_VENKATAKRISHNAN

@@ -37,7 +37,8 @@ module fcp_b200
                   FCP_F_UO, FCP_F_VO, FCP_F_WO, FCP_F_UOO, FCP_F_VOO, FCP_F_WOO, FCP_F_UOOO, FCP_F_VOOO, FCP_F_WOOO, &
                   FCP_F_SPU, FCP_F_SPV, FCP_F_SP, &
                   FCP_F_TE, FCP_F_ED, FCP_F_PHIO, FCP_F_PHIOO, FCP_F_GEN, FCP_F_MAGSTRAIN, FCP_F_VORTICITY, &
-                  FCP_F_DNW, FCP_F_TAU, FCP_F_YPL, FCP_F_SCTMP
+                  FCP_F_DNW, FCP_F_TAU, FCP_F_YPL, FCP_F_SCTMP, &
+                  FCP_F_FSST, FCP_F_WALLDIST, FCP_F_DTEDXI, FCP_F_DEDDXI
   end enum
 
   type, bind(c) :: fcp_mesh_desc
@@ -64,9 +65,9 @@ module fcp_b200
     real(c_double) :: gradPcmf, viscos
   end type
 
-  integer(c_int), parameter :: FCP_SC_GENERIC = 0, FCP_SC_TKE_RLZB = 1, FCP_SC_EPS_RLZB = 2
+  integer(c_int), parameter :: FCP_SC_GENERIC = 0, FCP_SC_TKE_RLZB = 1, FCP_SC_EPS_RLZB = 2, FCP_SC_TKE_SST = 3, FCP_SC_OMEGA_SST = 4
   type, bind(c) :: fcp_scalar_params
-    integer(c_int32_t) :: kind, solver, maxiter, cscheme, grad_method, limiter, tscheme, pad
+    integer(c_int32_t) :: kind, solver, maxiter, cscheme, grad_method, limiter, tscheme, lowre
     real(c_double) :: tol_abs, tol_rel, urf, gds, timestep, prtr, viscos, densit
   end type
 
@@ -217,6 +218,13 @@ module fcp_b200
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: ctx
       real(c_double), value :: urfVis, viscos
+      integer(c_int) :: rc
+    end function
+    function fcp_modify_mu_eff_k_omega_sst(ctx, urfVis, viscos, densit, lowre) bind(c, name='fcp_modify_mu_eff_k_omega_sst') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), value :: urfVis, viscos, densit
+      integer(c_int), value :: lowre
       integer(c_int) :: rc
     end function
     function fcp_grad_gauss_fvx(ctx, phi_field, grad_field) bind(c, name='fcp_grad_gauss_fvx') result(rc)
@@ -772,7 +780,7 @@ contains
       prm%urf = TurbModel%Scalar(isc)%urf; prm%gds = TurbModel%Scalar(isc)%gds
       prm%cscheme = cscheme_id(TurbModel%Scalar(isc)%cScheme)
       prm%grad_method = grad_method_id(); prm%limiter = limiter_id()
-      prm%tscheme = 0
+      prm%tscheme = 0; prm%lowre = 0
       if (ltransient .and. (bdf .or. cn)) prm%tscheme = 1
       if (ltransient .and. bdf2) prm%tscheme = 2
       prm%timestep = timestep
@@ -817,6 +825,78 @@ contains
       do i = 1, nfaces(ib)
         iWall = iWall + 1
         tau(iWall) = wf(iBndValueStart(ib) + i)
+      end do
+    end do
+    deallocate(wf)
+  end subroutine
+
+  ! ---- modify_viscosity_k_omega_sst()   TurbulenceModels/k_omega_SST.f90:62-88: calcsc(TE,..,1), calcsc(ED,..,2), modify_mu_eff ------------
+  ! (same data movement as modify_viscosity_k_epsilon_rlzb; additionally wallDistance per cell.  F1 (fsst) lives on the device between calls.)
+  subroutine modify_viscosity_k_omega_sst()
+    use TurbModelData, only: TurbModel
+    use k_omega_SST, only: LowRe
+    type(fcp_scalar_params) :: prm
+    type(fcp_report) :: rep
+    real(c_double) :: fimin, fimax
+    real(dp), allocatable :: wf(:)
+    integer :: ib, i, iWall, isc
+    call put(FCP_F_U, u, numTotal); call put(FCP_F_V, v, numTotal); call put(FCP_F_W, w, numTotal)
+    call put(FCP_F_DEN, den, numTotal); call put(FCP_F_VIS, vis, numTotal); call put(FCP_F_FLMASS, flmass, numFaces)
+    call put(FCP_F_TE, te, numTotal); call put(FCP_F_ED, ed, numTotal); call put(FCP_F_WALLDIST, wallDistance, numCells)
+    call fcp_check(fcp_grad(ctx, FCP_GRAD_GAUSS, FCP_F_U, FCP_F_DUDXI, 0_c_int), 'fcp_grad')      ! modify_viscosity_turbulence.f90:28-33
+    call fcp_check(fcp_grad(ctx, FCP_GRAD_GAUSS, FCP_F_V, FCP_F_DVDXI, 0_c_int), 'fcp_grad')
+    call fcp_check(fcp_grad(ctx, FCP_GRAD_GAUSS, FCP_F_W, FCP_F_DWDXI, 0_c_int), 'fcp_grad')
+    call fcp_check(fcp_calc_strain_and_vorticity(ctx), 'fcp_calc_strain_and_vorticity')
+    allocate(wf(numTotal))
+    wf = 0.0_dp; iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        wf(iBndValueStart(ib) + i) = dnw(iWall)
+      end do
+    end do
+    call put(FCP_F_DNW, wf, numTotal)
+    wf = 0.0_dp; iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        wf(iBndValueStart(ib) + i) = visw(iWall)
+      end do
+    end do
+    call put(FCP_F_VISW, wf, numTotal)
+    do isc = 1, 2
+      prm%kind = merge(FCP_SC_TKE_SST, FCP_SC_OMEGA_SST, isc == 1)
+      prm%solver = solver_id(TurbModel%Scalar(isc)%lSolver); prm%maxiter = TurbModel%Scalar(isc)%maxiter
+      prm%tol_abs = TurbModel%Scalar(isc)%tolAbs; prm%tol_rel = TurbModel%Scalar(isc)%tolRel
+      prm%urf = TurbModel%Scalar(isc)%urf; prm%gds = TurbModel%Scalar(isc)%gds
+      prm%cscheme = cscheme_id(TurbModel%Scalar(isc)%cScheme)
+      prm%grad_method = grad_method_id(); prm%limiter = limiter_id()
+      prm%tscheme = 0; prm%lowre = merge(1, 0, LowRe)
+      if (ltransient .and. (bdf .or. cn)) prm%tscheme = 1
+      if (ltransient .and. bdf2) prm%tscheme = 2
+      prm%timestep = timestep; prm%prtr = 1.0_dp; prm%viscos = viscos; prm%densit = densit
+      if (isc == 1) then
+        if (prm%tscheme >= 1) call put(FCP_F_PHIO, teo, numTotal)
+        if (prm%tscheme >= 2) call put(FCP_F_PHIOO, teoo, numTotal)
+        call fcp_check(fcp_calcsc(ctx, prm, FCP_F_TE, rep, fimin, fimax), 'fcp_calcsc')
+        write(*,'(2x,es11.4,a,es11.4)') fimin, ' <= k <= ', fimax
+      else
+        if (prm%tscheme >= 1) call put(FCP_F_PHIO, edo, numTotal)
+        if (prm%tscheme >= 2) call put(FCP_F_PHIOO, edoo, numTotal)
+        call fcp_check(fcp_calcsc(ctx, prm, FCP_F_ED, rep, fimin, fimax), 'fcp_calcsc')
+        write(*,'(2x,es11.4,a,es11.4)') fimin, ' <= Omega <= ', fimax
+      end if
+    end do
+    call fcp_check(fcp_modify_mu_eff_k_omega_sst(ctx, TurbModel%urfVis, viscos, densit, merge(1_c_int, 0_c_int, LowRe)), 'fcp_modify_mu_eff_k_omega_sst')
+    call get(FCP_F_TE, te, numTotal); call get(FCP_F_ED, ed, numTotal); call get(FCP_F_VIS, vis, numTotal); call get(FCP_F_GEN, gen, numCells)
+    call get(FCP_F_VISW, wf, numTotal); iWall = 0
+    do ib = 1, numBoundaries
+      if (bctype(ib) /= 'wall') cycle
+      do i = 1, nfaces(ib)
+        iWall = iWall + 1
+        visw(iWall) = wf(iBndValueStart(ib) + i)
       end do
     end do
     deallocate(wf)

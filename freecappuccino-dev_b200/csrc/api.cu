@@ -46,7 +46,7 @@ static int select_device(int device) {
 
 static int field_count(const fcp_ctx *c, int field, int64_t *count) {
   if (field < 0 || field >= FCP_F_COUNT) { fcp_set_error("bad field id %d", field); return FCP_EINVAL; }
-  if (field >= FCP_F_DUDXI && field <= FCP_F_G1) *count = 3 * (int64_t)c->nT;
+  if (fcp_is_gradient_field(field)) *count = 3 * (int64_t)c->nT;
   else if (field == FCP_F_FLMASS) *count = c->nF;
   else if (field == FCP_F_A || field == FCP_F_H) *count = c->pat.nnzp;   // device storage is SELL; host-visible count is nnz
   else if (field == FCP_F_APR) *count = c->npro;
@@ -563,7 +563,7 @@ extern "C" int fcp_create_lsq_grad_matrix(fcp_ctx *ctx, int method) {
 
 extern "C" int fcp_grad(fcp_ctx *ctx, int method, int phi_field, int grad_field, int lsq_row2_reference) {
   if (!ctx) return FCP_EINVAL;
-  if (grad_field < FCP_F_DUDXI || grad_field > FCP_F_G1) { fcp_set_error("fcp_grad: field %d is not a gradient field", grad_field); return FCP_EINVAL; }
+  if (!fcp_is_gradient_field(grad_field)) { fcp_set_error("fcp_grad: field %d is not a gradient field", grad_field); return FCP_EINVAL; }
   FIELD(phi, phi_field);
   FIELD(g, grad_field);
   if (ctx->comm) FCP_TRY(comm_exchange(ctx, phi, 1));              // src-par/gradients.f90:123
@@ -584,7 +584,7 @@ extern "C" int fcp_grad(fcp_ctx *ctx, int method, int phi_field, int grad_field,
 extern "C" int fcp_slope_limiter(fcp_ctx *ctx, int limiter, int phi_field, int grad_field) {
   if (!ctx) return FCP_EINVAL;
   if (limiter < FCP_LIMITER_NONE || limiter > FCP_LIMITER_MULTIDIMENSIONAL) { fcp_set_error("unknown limiter %d", limiter); return FCP_EINVAL; }
-  if (grad_field < FCP_F_DUDXI || grad_field > FCP_F_G1) { fcp_set_error("fcp_slope_limiter: field %d is not a gradient field", grad_field); return FCP_EINVAL; }
+  if (!fcp_is_gradient_field(grad_field)) { fcp_set_error("fcp_slope_limiter: field %d is not a gradient field", grad_field); return FCP_EINVAL; }
   FIELD(phi, phi_field);
   FIELD(g, grad_field);
   FCP_TRY(fvm_slope_limiter(ctx, limiter, phi, g));
@@ -775,7 +775,7 @@ extern "C" int fcp_constant_mass_flow_forcing(fcp_ctx *ctx, double magUbar, doub
 // updateBoundary(phi)   src/finiteVolume/boundary/updateBoundary.f90
 extern "C" int fcp_update_boundary(fcp_ctx *ctx, int field) {
   if (!ctx) return FCP_EINVAL;
-  if (field < 0 || field >= FCP_F_COUNT || (field >= FCP_F_DUDXI && field <= FCP_F_H)) { fcp_set_error("fcp_update_boundary: field %d is not a scalar cell field", field); return FCP_EINVAL; }
+  if (field < 0 || field >= FCP_F_COUNT || (field >= FCP_F_DUDXI && field <= FCP_F_H) || fcp_is_gradient_field(field)) { fcp_set_error("fcp_update_boundary: field %d is not a scalar cell field", field); return FCP_EINVAL; }
   FCP_CUDA(cudaSetDevice(ctx->device));
   FIELD(phi, field);
   return fvm_update_boundary(ctx, phi);
@@ -784,24 +784,28 @@ extern "C" int fcp_update_boundary(fcp_ctx *ctx, int field) {
 // calcsc: the scalar transport template   TurbulenceModels/k_epsilon_rlzb.f90:52-790 + fluxes/scalar_fluxes.f90
 extern "C" int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_field, fcp_report *rep, double *fimin, double *fimax) {
   if (!ctx || !prm) return FCP_EINVAL;
-  if (prm->kind < FCP_SC_GENERIC || prm->kind > FCP_SC_EPS_RLZB) { fcp_set_error("calcsc: unknown kind %d", prm->kind); return FCP_EINVAL; }
+  if (prm->kind < FCP_SC_GENERIC || prm->kind > FCP_SC_OMEGA_SST) { fcp_set_error("calcsc: unknown kind %d", prm->kind); return FCP_EINVAL; }
   if (prm->cscheme < 0 || prm->cscheme >= FCP_CS_COUNT) { fcp_set_error("calcsc: non-existing interpolation scheme %d", prm->cscheme); return FCP_EINVAL; }
   if (prm->tscheme < 0 || prm->tscheme > 2) { fcp_set_error("calcsc: unknown time scheme %d (Crank-Nicolson is not built)", prm->tscheme); return FCP_EINVAL; }
   if (prm->tscheme && !(prm->timestep > 0.0)) { fcp_set_error("calcsc: timestep must be positive"); return FCP_EINVAL; }
   if (!(prm->urf > 0.0)) { fcp_set_error("calcsc: urf must be positive"); return FCP_EINVAL; }
-  if ((prm->kind == FCP_SC_TKE_RLZB && phi_field != FCP_F_TE) || (prm->kind == FCP_SC_EPS_RLZB && phi_field != FCP_F_ED)) {
-    fcp_set_error("calcsc: kind %d solves for field %d", prm->kind, prm->kind == FCP_SC_TKE_RLZB ? FCP_F_TE : FCP_F_ED);
+  const bool is_k = prm->kind == FCP_SC_TKE_RLZB || prm->kind == FCP_SC_TKE_SST, is_sst = prm->kind == FCP_SC_TKE_SST || prm->kind == FCP_SC_OMEGA_SST;
+  if (prm->kind != FCP_SC_GENERIC && phi_field != (is_k ? FCP_F_TE : FCP_F_ED)) {
+    fcp_set_error("calcsc: kind %d solves for field %d", prm->kind, is_k ? FCP_F_TE : FCP_F_ED);
     return FCP_EINVAL;
   }
-  if (phi_field < 0 || phi_field >= FCP_F_COUNT || (phi_field >= FCP_F_DUDXI && phi_field <= FCP_F_H) || phi_field == FCP_F_SCTMP) {
+  if (phi_field < 0 || phi_field >= FCP_F_COUNT || (phi_field >= FCP_F_DUDXI && phi_field <= FCP_F_H) || fcp_is_gradient_field(phi_field) || phi_field == FCP_F_SCTMP) {
     fcp_set_error("calcsc: field %d is not a scalar cell field", phi_field);
     return FCP_EINVAL;
   }
   if (ctx->comm) { fcp_set_error("calcsc: partitioned meshes are not supported yet"); return FCP_ESTATE; }
   FCP_CUDA(cudaSetDevice(ctx->device));
   FIELD(phi, phi_field); FIELD(den, FCP_F_DEN); FIELD(vis, FCP_F_VIS); FIELD(fl, FCP_F_FLMASS);
-  FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(sp, FCP_F_SP); FIELD(g, FCP_F_G0); FIELD(tmp, FCP_F_SCTMP);
+  // the gradient of the scalar: G0, except for the SST pair, whose omega equation needs both grad k and grad omega (cross diffusion)
+  const int gfield = prm->kind == FCP_SC_TKE_SST ? FCP_F_DTEDXI : prm->kind == FCP_SC_OMEGA_SST ? FCP_F_DEDDXI : FCP_F_G0;
+  FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(sp, FCP_F_SP); FIELD(g, gfield); FIELD(tmp, FCP_F_SCTMP);
   ScParams q{};
+  q.lowre = prm->lowre;
   q.kind = prm->kind; q.cscheme = prm->cscheme; q.tscheme = prm->tscheme;
   q.gds = prm->gds; q.prtr = prm->prtr; q.viscos = prm->viscos; q.densit = prm->densit; q.timestep = prm->timestep; q.urf = prm->urf;
   q.phi = phi; q.den = den; q.vis = vis; q.flmass = fl; q.grad = g; q.a = a; q.su = su; q.sp = sp; q.phi_new = tmp; q.phi_out = phi;
@@ -811,24 +815,35 @@ extern "C" int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_fi
   else {
     FIELD(te, FCP_F_TE); FIELD(ed, FCP_F_ED); FIELD(ms, FCP_F_MAGSTRAIN); FIELD(dnw, FCP_F_DNW);
     q.te = te; q.ed = ed; q.magStrain = ms; q.dnw = dnw;
-    if (prm->kind == FCP_SC_TKE_RLZB) {
-      FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(visw, FCP_F_VISW); FIELD(gen, FCP_F_GEN); FIELD(tau, FCP_F_TAU);
-      q.u = u; q.v = v; q.w = w; q.visw = visw; q.gen = gen; q.tau = tau;
+    FIELD(gen, FCP_F_GEN);
+    q.gen = gen;
+    if (is_k) {
+      FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(visw, FCP_F_VISW); FIELD(tau, FCP_F_TAU);
+      q.u = u; q.v = v; q.w = w; q.visw = visw; q.tau = tau;
+    }
+    if (is_sst) {
+      FIELD(fsst, FCP_F_FSST); FIELD(wd, FCP_F_WALLDIST); FIELD(gte, FCP_F_DTEDXI);
+      q.fsst = fsst; q.walldist = wd; q.gte = gte;
     }
   }
   if (prm->grad_method != FCP_GRAD_GAUSS && !ctx->Dmat[prm->grad_method]) FCP_TRY(fcp_create_lsq_grad_matrix(ctx, prm->grad_method));
-  FCP_TRY(fcp_grad_opt(ctx, prm->grad_method, prm->limiter, phi_field, FCP_F_G0));           // call grad(te, dTedxi)
+  FCP_TRY(fcp_grad_opt(ctx, prm->grad_method, prm->limiter, phi_field, gfield));             // call grad(te, dTedxi)
+  if (prm->kind == FCP_SC_OMEGA_SST) {                                                       // F1, k_omega_SST.f90:242-268
+    FIELD(fsst, FCP_F_FSST);
+    FCP_TRY(fvm_sst_blend(ctx, prm->viscos, q.walldist, q.gte, g, den, q.te, q.ed, fsst));
+  }
   FCP_CUDA(cudaMemsetAsync(a, 0, sizeof(double) * (size_t)ctx->pat.nnzp, ctx->stream));      // a = 0
   FCP_TRY(fvm_sc_assemble(ctx, q));
   FCP_TRY(fcp_csrsolve(ctx, prm->solver, phi_field, FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel, rep));
   FCP_TRY(fvm_update_boundary(ctx, phi));
   double *d_mm = nullptr, mm[2] = {0.0, 0.0};
-  FCP_TRY(fvm_minmax(ctx, phi, &d_mm));
+  const int32_t cnt = is_sst ? ctx->nT : ctx->n;           // k_omega_SST.f90:776-786 takes the extrema of, and clips, the whole array
+  FCP_TRY(fvm_minmax(ctx, phi, &d_mm, cnt));
   FCP_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
   FCP_CUDA(cudaStreamSynchronize(ctx->stream));
   if (fimin) *fimin = mm[0];
   if (fimax) *fimax = mm[1];
-  if (prm->kind != FCP_SC_GENERIC && mm[0] < 0.0) FCP_TRY(fvm_clip_small(ctx, phi));         // :430
+  if (prm->kind != FCP_SC_GENERIC && mm[0] < 0.0) FCP_TRY(fvm_clip_small(ctx, phi, cnt));    // :430
   return FCP_OK;
 }
 extern "C" int fcp_calc_strain_and_vorticity(fcp_ctx *ctx) {
@@ -847,9 +862,18 @@ extern "C" int fcp_modify_mu_eff_k_epsilon_rlzb(fcp_ctx *ctx, double urfVis, dou
   return fvm_mu_eff_rlzb(ctx, urfVis, viscos, gu, gv, gw, te, ed, den, u, v, w, dnw, vis, visw, ypl, tau);
 }
 
+extern "C" int fcp_modify_mu_eff_k_omega_sst(fcp_ctx *ctx, double urfVis, double viscos, double densit, int lowre) {
+  if (!ctx) return FCP_EINVAL;
+  if (ctx->comm) { fcp_set_error("modify_mu_eff: partitioned meshes are not supported yet"); return FCP_ESTATE; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(ms, FCP_F_MAGSTRAIN); FIELD(wd, FCP_F_WALLDIST); FIELD(te, FCP_F_TE); FIELD(ed, FCP_F_ED); FIELD(den, FCP_F_DEN);
+  FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(dnw, FCP_F_DNW); FIELD(vis, FCP_F_VIS); FIELD(visw, FCP_F_VISW);
+  FIELD(ypl, FCP_F_YPL); FIELD(tau, FCP_F_TAU);
+  return fvm_mu_eff_sst(ctx, urfVis, viscos, densit, lowre, ms, wd, te, ed, den, u, v, w, dnw, vis, visw, ypl, tau);
+}
 extern "C" int fcp_grad_gauss_fvx(fcp_ctx *ctx, int phi_field, int grad_field) {
   if (!ctx) return FCP_EINVAL;
-  if (grad_field < FCP_F_DUDXI || grad_field > FCP_F_G1 || phi_field < 0 || phi_field >= FCP_F_COUNT || (phi_field >= FCP_F_DUDXI && phi_field <= FCP_F_H)) {
+  if (!fcp_is_gradient_field(grad_field) || phi_field < 0 || phi_field >= FCP_F_COUNT || (phi_field >= FCP_F_DUDXI && phi_field <= FCP_F_H) || fcp_is_gradient_field(phi_field)) {
     fcp_set_error("fcp_grad_gauss_fvx: bad field id");
     return FCP_EINVAL;
   }

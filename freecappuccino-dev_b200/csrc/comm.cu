@@ -566,7 +566,7 @@ extern "C" int fcp_exchange(fcp_ctx *ctx, int field) {
   if (field < 0 || (field >= FCP_F_FLMASS && field <= FCP_F_H) || field >= FCP_F_COUNT /* every other id is a cell field */) { fcp_set_error("fcp_exchange: field %d is not a cell field", field); return FCP_EINVAL; }
   void *p = nullptr;
   FCP_TRY(fcp_field_devptr(ctx, field, &p, nullptr));
-  return comm_exchange(ctx, (double *)p, (field >= FCP_F_DUDXI && field <= FCP_F_G1) ? 3 : 1);
+  return comm_exchange(ctx, (double *)p, fcp_is_gradient_field(field) ? 3 : 1);
 }
 
 static int global_reduce(fcp_ctx *ctx, double *value, int op /*0 sum 1 max 2 min*/) {

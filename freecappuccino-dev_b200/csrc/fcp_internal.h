@@ -293,18 +293,25 @@ int fvm_uvw_diag(fcp_ctx *ctx, double *a, const double *spq, const double *srcq,
 
 // ---- fvm_scalar.cu (row f4) ---------------------------------------------------------------------
 struct ScParams {
-  int kind, cscheme, tscheme;
+  int kind, cscheme, tscheme, lowre;
+  const double *fsst, *walldist, *gte;
   double gds, prtr, viscos, densit, timestep, urf;
   const double *phi, *phio, *phioo, *te, *ed, *den, *vis, *visw, *dnw, *flmass, *u, *v, *w, *magStrain, *su_vol, *sp_vol, *grad;
   double *gen, *tau, *a, *su, *sp, *phi_new, *phi_out;
 };
 int fvm_strain(fcp_ctx *ctx, const double *gU, const double *gV, const double *gW, double *magStrain, double *vorticity);
 int fvm_sc_assemble(fcp_ctx *ctx, const ScParams &q);
-int fvm_clip_small(fcp_ctx *ctx, double *phi);
+int fvm_clip_small(fcp_ctx *ctx, double *phi, int32_t count);
+int fvm_mu_eff_sst(fcp_ctx *ctx, double urf, double viscos, double densit, int lowre, const double *magStrain, const double *walldist, const double *te,
+                   const double *ed, const double *den, const double *u, const double *v, const double *w, const double *dnw, double *vis, double *visw,
+                   double *ypl, double *tau);
+int fvm_sst_blend(fcp_ctx *ctx, double viscos, const double *walldist, const double *gte, const double *gom, const double *den, const double *te,
+                  const double *ed, double *fsst);
 int fvm_mu_eff_rlzb(fcp_ctx *ctx, double urf, double viscos, const double *gU, const double *gV, const double *gW, const double *te, const double *ed,
                     const double *den, const double *u, const double *v, const double *w, const double *dnw, double *vis, double *visw, double *ypl,
                     double *tau);
-int fvm_minmax(fcp_ctx *ctx, const double *phi, double **mm_out);
+int fvm_minmax(fcp_ctx *ctx, const double *phi, double **mm_out, int32_t count = -1 /* default: numCells */);
+static inline bool fcp_is_gradient_field(int f) { return (f >= FCP_F_DUDXI && f <= FCP_F_G1) || f == FCP_F_DTEDXI || f == FCP_F_DEDDXI; }
 int fvm_grad_gauss_fvx(fcp_ctx *ctx, const double *u, double *gtmp, double *g);
 int fvm_sgs_viscosity(fcp_ctx *ctx, int model, double urf, double viscos, const double *gU, const double *gV, const double *gW, const double *den,
                       double *vis, double *visw);

@@ -130,11 +130,13 @@ __global__ void __launch_bounds__(FCP_TPB) k_limiter_mdl(MeshView m, const doubl
 }
 
 // global minimum / maximum of phi(1:numCells): mm_out points at the device pair {min, max}
-int fvm_minmax(fcp_ctx *ctx, const double *phi, double **mm_out) {
-  const int nparts = std::max(fcp_nchunks(ctx->n), 1);
-  if (!ctx->d_mmpart) FCP_TRY(dev_alloc(&ctx->d_mmpart, (size_t)2 * nparts + 2));
-  double *mm = ctx->d_mmpart + (size_t)2 * nparts;
-  k_minmax_part<<<nparts, FCP_TPB, 0, ctx->stream>>>(ctx->n, phi, ctx->d_mmpart);
+int fvm_minmax(fcp_ctx *ctx, const double *phi, double **mm_out, int32_t count) {
+  const int32_t cnt = count < 0 ? ctx->n : count;
+  const int nparts = std::max(fcp_nchunks(cnt), 1);
+  const int cap = std::max(fcp_nchunks(ctx->nT), 1);          // the partial buffer is sized for the longest field
+  if (!ctx->d_mmpart) FCP_TRY(dev_alloc(&ctx->d_mmpart, (size_t)2 * cap + 2));
+  double *mm = ctx->d_mmpart + (size_t)2 * cap;
+  k_minmax_part<<<nparts, FCP_TPB, 0, ctx->stream>>>(cnt, phi, ctx->d_mmpart);
   k_minmax_final<<<1, FCP_TPB, 0, ctx->stream>>>(nparts, ctx->d_mmpart, mm);
   FCP_LAUNCHED(); FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
@@ -150,13 +152,8 @@ int fvm_slope_limiter(fcp_ctx *ctx, int limiter, const double *phi, double *g) {
   if (limiter == FCP_LIMITER_MULTIDIMENSIONAL) {
     if (ctx->n) { k_limiter_mdl<<<FCP_GRID(ctx->n)>>>(m, phi, g); FCP_LAUNCHED(); }
   } else {
-    const int nparts = std::max(fcp_nchunks(ctx->n), 1);
-    if (!ctx->d_mmpart) FCP_TRY(dev_alloc(&ctx->d_mmpart, (size_t)2 * nparts + 2));
-    double *mm = ctx->d_mmpart + (size_t)2 * nparts;
-    k_minmax_part<<<nparts, FCP_TPB, 0, ctx->stream>>>(ctx->n, phi, ctx->d_mmpart);
-    k_minmax_final<<<1, FCP_TPB, 0, ctx->stream>>>(nparts, ctx->d_mmpart, mm);
-    FCP_LAUNCHED(); FCP_LAUNCHED();
-    if (ctx->comm) FCP_TRY(comm_allreduce_minmax(ctx->comm, mm, ctx->stream));
+    double *mm = nullptr;                                    // global extrema (quirk Q3), rank-reduced inside
+    FCP_TRY(fvm_minmax(ctx, phi, &mm));
     if (ctx->n) {
       if (limiter == FCP_LIMITER_BARTH_JESPERSEN) k_limiter_cell<FCP_LIMITER_BARTH_JESPERSEN><<<FCP_GRID(ctx->n)>>>(m, phi, mm, g);
       else if (limiter == FCP_LIMITER_VENKATAKRISHNAN) k_limiter_cell<FCP_LIMITER_VENKATAKRISHNAN><<<FCP_GRID(ctx->n)>>>(m, phi, mm, g);

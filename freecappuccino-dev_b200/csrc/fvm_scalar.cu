@@ -24,11 +24,28 @@ __device__ __forceinline__ double cmu25_dev() { return sqrt(sqrt(FCP_CMU)); }   
 __device__ __forceinline__ double cmu75_dev() { const double c = cmu25_dev(); return c * c * c; }    // :26
 
 struct ScArgs {
-  int kind, cscheme, tscheme;
+  int kind, cscheme, tscheme, lowre;
   double gds, prtr, viscos, densit, timestep;
   const double *phi, *phio, *phioo, *te, *ed, *den, *vis, *visw, *dnw, *flmass, *u, *v, *w, *magStrain, *su_vol, *sp_vol, *g;
+  const double *fsst, *walldist, *gte;    // k-omega SST: blending function F1, wall distance, gradient of k
   double *gen, *tau, *a, *su, *sp, *phi_new;
 };
+// k-omega SST constants, k_omega_SST.f90:21-40
+#define SST_BETTAST 0.09
+#define SST_SIGMK1 0.85
+#define SST_SIGMK2 1.0
+#define SST_SIGMOM1 0.5
+#define SST_SIGMOM2 0.856
+#define SST_BETAI1 0.075
+#define SST_BETAI2 0.0828
+#define SST_A1 0.31
+#define SST_ALPHA1 (5.0 / 9.0)
+#define SST_ALPHA2 0.44
+__device__ __forceinline__ double p4_dev(double x) { return (x * x) * (x * x); }   // x**4
+// 1/sigma of the SST equations from the blending function of ONE cell (the reference takes the owner's, k_omega_SST.f90:440-449)
+template <int KIND> __device__ __forceinline__ double sst_prtr(double fs) {
+  return KIND == 3 ? fs * SST_SIGMK1 + (1.0 - fs) * SST_SIGMK2 : fs * SST_SIGMOM1 + (1.0 - fs) * SST_SIGMOM2;
+}
 
 __global__ void __launch_bounds__(FCP_TPB) k_strain(int32_t n, const double *__restrict__ gU, const double *__restrict__ gV, const double *__restrict__ gW,
                                                      double *__restrict__ magStrain, double *__restrict__ vorticity) {
@@ -47,6 +64,14 @@ __global__ void __launch_bounds__(FCP_TPB) k_strain(int32_t n, const double *__r
 // calcsc_epsilon overwrites ed(ijp) in wall cells WHILE it walks the patches (:726), so a periodic patch listed after a wall patch reads
 // the imposed value, not the old one.  This returns ed(cell) as the reference's boundary loop holds it when it reaches face fp: the value
 // imposed by the cell's last wall face that precedes fp, else the old value.
+// the value the wall branch imposes in a wall cell: epsilon = cmu75 k^1.5/(cappa dnw) (k_epsilon_rlzb.f90:726), omega = sqrt(wvis^2 + wlog^2) (k_omega_SST.f90:673-677)
+template <int KIND> __device__ __forceinline__ double wall_imposed_value(const ScArgs &g, int32_t cell, double dn) {
+  if (KIND == 2) return cmu75_dev() * pow(g.te[cell], 1.5) / (FCP_CAPPA * dn);
+  const double wlog = sqrt(g.te[cell]) / (cmu25_dev() * FCP_CAPPA * dn);
+  const double wvis = 6.0 * (g.viscos / g.den[cell]) / (SST_BETAI1 * (dn * dn));
+  return sqrt(wvis * wvis + wlog * wlog);
+}
+template <int KIND>
 __device__ __forceinline__ double eps_value_at_face(const MeshView &m, const ScArgs &g, int32_t cell, int32_t fp, double old_value) {
   const int64_t base = m.slptr[cell >> 5] + (cell & 31);
   const int32_t len = m.len[cell];
@@ -54,9 +79,24 @@ __device__ __forceinline__ double eps_value_at_face(const MeshView &m, const ScA
   for (int32_t q = 0; q < len; ++q) {
     const int32_t e = m.ent[base + (int64_t)q * 32], sl = m.slot[base + (int64_t)q * 32];
     const int32_t f = (e > 0 ? e : -e) - 1;
-    if (sl == -1 - FCP_BC_WALL && f < fp) v = cmu75_dev() * pow(g.te[cell], 1.5) / (FCP_CAPPA * g.dnw[m.n + (f - m.F)]);
+    if (sl == -1 - FCP_BC_WALL && f < fp) v = wall_imposed_value<KIND>(g, cell, g.dnw[m.n + (f - m.F)]);
   }
   return v;
+}
+
+// F1 of the SST model, k_omega_SST.f90:242-268 (omega call, before its sources)
+__global__ void __launch_bounds__(FCP_TPB) k_sst_blend(int32_t n, double viscos, const double *__restrict__ walldist, const double *__restrict__ gte,
+                                                        const double *__restrict__ gom, const double *__restrict__ den, const double *__restrict__ te,
+                                                        const double *__restrict__ ed, double *__restrict__ fsst) {
+  FCP_CELL_LOOP(c, n) {
+    const int64_t b = 3 * (int64_t)c;
+    const double wldist = walldist[c];
+    const double dot = gte[b] * gom[b] + gte[b + 1] * gom[b + 1] + gte[b + 2] * gom[b + 2];
+    const double domegapl = fmax(2 * SST_SIGMOM2 * den[c] / (ed[c]) * dot, FCP_SMALL);
+    const double ksi = fmin(fmax(sqrt(te[c]) / (SST_BETTAST * wldist * ed[c] + FCP_SMALL), 500.0 * viscos / den[c] / (wldist * wldist * ed[c] + FCP_SMALL)),
+                            4.0 * den[c] * te[c] * SST_SIGMOM2 / (domegapl * (wldist * wldist)));
+    fsst[c] = tanh(p4_dev(ksi));
+  }
 }
 
 template <int KIND>
@@ -75,6 +115,44 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
       s = genp * vol;
       p = edc * denc * vol / (tec + FCP_SMALL);
       p = p - genn * vol / (tec + FCP_SMALL);
+    } else if (KIND == 3) {                                 // k of the SST model, k_omega_SST.f90:143-170
+      const double tec = phic, edc = g.ed[c];
+      genc = fabs(visc - g.viscos) * g.magStrain[c] * g.magStrain[c];
+      genc = fmin(genc, 0.9 * denc * tec * edc);
+      if (g.lowre) {
+        const double x4 = p4_dev(denc * tec / (8.0 * g.viscos * edc));
+        const double tmp = 10 * SST_BETTAST * (4.0 / 15.0 + x4) / (1.0 + x4);
+        genc = fmin(genc, tmp * denc * tec * edc);
+      }
+      const double genp = fmax(genc, 0.0), genn = fmin(genc, 0.0);
+      s = genp * vol;
+      p = SST_BETTAST * edc * denc * vol;
+      if (g.lowre) {
+        const double x4 = p4_dev(denc * tec / (8 * g.viscos * edc));
+        const double tmp = SST_BETTAST * (4.0 / 15.0 + x4) / (1.0 + x4);
+        p = tmp * edc * denc * vol;
+      }
+      p = p - genn * vol / (tec + FCP_SMALL);
+    } else if (KIND == 4) {                                 // omega of the SST model :272-318 (gen: what the k call left behind)
+      const double tec = g.te[c], edc = phic, fs = g.fsst[c];
+      const double gn = g.gen[c];
+      const double genp = fmax(gn, 0.0), genn = fmin(gn, 0.0);
+      const double vist = (visc - g.viscos) / g.densit;
+      double alphasst = fs * SST_ALPHA1 + (1.0 - fs) * SST_ALPHA2;
+      if (g.lowre) {
+        const double alphast = (0.024 + (g.densit * tec) / (6.0 * g.viscos * edc)) / (1.0 + (g.densit * tec) / (6.0 * g.viscos * edc));
+        const double tmp = SST_ALPHA1 / alphast * (1.0 / 9.0 + (g.densit * tec) / (2.95 * g.viscos * edc)) / (1.0 + (g.densit * tec) / (2.95 * g.viscos * edc));
+        alphasst = fs * tmp + (1.0 - fs) * SST_ALPHA2;
+      }
+      s = alphasst * genp * vol / (vist + FCP_SMALL);
+      const int64_t b = 3 * (int64_t)c;
+      const double dot = g.gte[b] * gc[0] + g.gte[b + 1] * gc[1] + g.gte[b + 2] * gc[2];
+      double domega = 2 * (1.0 - fs) * denc * SST_SIGMOM2 / (edc + FCP_SMALL) * dot;
+      domega = fmax(domega, 0.0);
+      s = s + domega * vol;
+      const double bettasst = fs * SST_BETAI1 + (1.0 - fs) * SST_BETAI2;
+      p = bettasst * denc * edc * vol;
+      p = p - alphasst * genn * vol / (vist * edc + FCP_SMALL);
     } else {                                                // calcsc_epsilon :500-513
       const double tec = g.te[c], edc = phic, ms = g.magStrain[c];
       const double genp = fmax(ms, 0.0), genn = fmin(ms, 0.0);
@@ -105,7 +183,8 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
         const double gP[3] = {own ? gc[0] : go[0], own ? gc[1] : go[1], own ? gc[2] : go[2]};
         const double gN[3] = {own ? go[0] : gc[0], own ? go[1] : gc[1], own ? go[2] : gc[2]};
         const double viste = (visP + (visN - visP) * lambda) - g.viscos;
-        const double dcoef = g.viscos + viste * g.prtr;
+        const double prf = (KIND == 3 || KIND == 4) ? sst_prtr<KIND>(g.fsst[own ? c : o]) : g.prtr;   // SST: sigma of the face's OWNER cell
+        const double dcoef = g.viscos + viste * prf;
         const double xpn = xN - xP, ypn = yN - yP, zpn = zN - zP;
         const double de = dcoef * Df;
         const double ce = fmin(fm, 0.0), cp = fmax(fm, 0.0);
@@ -127,7 +206,8 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
         const int type = -1 - sl;
         if (type == FCP_BC_INLET || type == FCP_BC_OUTLET || type == FCP_BC_PRESSURE) {
           // ---- facefluxsc_boundary :236-300
-          const double viste = g.vis[o] - g.viscos, dcoef = g.viscos + viste * g.prtr;
+          const double prf = (KIND == 3 || KIND == 4) ? sst_prtr<KIND>(g.fsst[c]) : g.prtr;
+          const double viste = g.vis[o] - g.viscos, dcoef = g.viscos + viste * prf;
           const double xpn = m.xf[f] - xc, ypn = m.yf[f] - yc, zpn = m.zf[f] - zc;
           const double Dfi = (arx * arx + ary * ary + arz * arz) / (xpn * arx + ypn * ary + zpn * arz);
           const double de = dcoef * Dfi;
@@ -148,15 +228,16 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
           const double go[3] = {g.g[3 * (int64_t)q], g.g[3 * (int64_t)q + 1], g.g[3 * (int64_t)q + 2]};
           const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo;
           double phiP = own ? phic : phio_, phiN = own ? phio_ : phic;
-          if (KIND == 2) {                                   // wall cells already hold their imposed epsilon when a later patch reads them
-            phiP = eps_value_at_face(m, g, own ? c : q, fp, phiP);
-            phiN = eps_value_at_face(m, g, own ? q : c, fp, phiN);
+          if (KIND == 2 || KIND == 4) {                      // wall cells already hold their imposed epsilon / omega when a later patch reads them
+            phiP = eps_value_at_face<KIND>(m, g, own ? c : q, fp, phiP);
+            phiN = eps_value_at_face<KIND>(m, g, own ? q : c, fp, phiN);
           }
           const double visP = own ? visc : viso, visN = own ? viso : visc;
           const double gP[3] = {own ? gc[0] : go[0], own ? gc[1] : go[1], own ? gc[2] : go[2]};
           const double gN[3] = {own ? go[0] : gc[0], own ? go[1] : gc[1], own ? go[2] : gc[2]};
           const double fxn = 0.5, fxp = fxn;
-          const double viste = 0.5 * (visP + visN) - g.viscos, dcoef = g.viscos + viste * g.prtr;
+          const double prf = (KIND == 3 || KIND == 4) ? 0.5 * (sst_prtr<KIND>(g.fsst[own ? c : q]) + sst_prtr<KIND>(g.fsst[own ? q : c])) : g.prtr;
+          const double viste = 0.5 * (visP + visN) - g.viscos, dcoef = g.viscos + viste * prf;
           const double xpn = 2 * (m.xf[fp] - xP), ypn = 2 * (m.yf[fp] - yP), zpn = 2 * (m.zf[fp] - zP);
           const double Dfq = m.Df[m.per_ord[b]], fm = g.flmass[fp];
           const double de = dcoef * Dfq;
@@ -173,7 +254,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
           const double suadd = -fcfie + fdfie;
           if (own) { g.a[m.per_slot[b]] = can; s = s + suadd; }
           else     { g.a[m.per_slot[b]] = cap; s = s - suadd; }
-        } else if (type == FCP_BC_WALL && KIND == 1) {
+        } else if (type == FCP_BC_WALL && (KIND == 1 || KIND == 3)) {
           // ---- wall function for k, k_epsilon_rlzb.f90:331-368: production from the wall shear stress replaces the standard one
           const double viss = fmax(g.viscos, g.visw[o]);
           const double are = sqrt(arx * arx + ary * ary + arz * arz);
@@ -196,15 +277,23 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
           const int32_t len = m.a_rinfo[c] & 0xffff;
           for (int32_t k = 0; k < len; ++k) g.a[base + (int64_t)k * 32] = 0.0;
           p = 1.0;
-          phin = cmu75_dev() * pow(g.te[c], 1.5) / (FCP_CAPPA * g.dnw[o]);
+          phin = wall_imposed_value<2>(g, c, g.dnw[o]);
           s = phin;
+        } else if (type == FCP_BC_WALL && KIND == 4) {
+          // ---- wall cells of the omega equation, k_omega_SST.f90:668-680
+          const int64_t base = m.a_slptr[c >> 5] + (c & 31);
+          const int32_t len = m.a_rinfo[c] & 0xffff;
+          phin = wall_imposed_value<4>(g, c, g.dnw[o]);
+          s = phin;
+          for (int32_t k = 0; k < len; ++k) g.a[base + (int64_t)k * 32] = 0.0;
+          p = 1.0;
         }
       }
     }
     g.su[c] = s;
     g.sp[c] = p;
     g.phi_new[c] = phin;
-    if (KIND == 1) g.gen[c] = genc;
+    if (KIND == 1 || KIND == 3) g.gen[c] = genc;
   }
 }
 
@@ -229,7 +318,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_diag(MeshView m, double *a, cons
   }
 }
 
-__global__ void __launch_bounds__(FCP_TPB) k_clip(int32_t n, double *__restrict__ phi) {
+__global__ void __launch_bounds__(FCP_TPB) k_clip(int32_t n, double *__restrict__ phi) {   // n = numCells (k-epsilon) or numTotal (SST, which clips the whole array)
   FCP_CELL_LOOP(c, n) { phi[c] = fmax(phi[c], FCP_SMALL); }
 }
 
@@ -440,6 +529,72 @@ int fvm_sgs_viscosity(fcp_ctx *ctx, int model, double urf, double viscos, const 
   return FCP_OK;
 }
 
+// modify_mu_eff of the SST model, k_omega_SST.f90:790-958
+__global__ void __launch_bounds__(FCP_TPB) k_mu_eff_sst_cell(int32_t n, double urf, double viscos, double densit, int lowre, const double *__restrict__ magStrain,
+                                                              const double *__restrict__ walldist, const double *__restrict__ te, const double *__restrict__ ed,
+                                                              const double *__restrict__ den, double *__restrict__ vis) {
+  FCP_CELL_LOOP(c, n) {
+    const double visold = vis[c], wldist = walldist[c], tec = te[c], edc = ed[c], denc = den[c];
+    const double etha = fmax(2 * sqrt(tec) / (SST_BETTAST * wldist * edc), (500 * viscos / denc) / (wldist * wldist * edc));
+    const double f2 = tanh(etha * etha);
+    double v = viscos + denc * SST_A1 * tec / (fmax(SST_A1 * edc, magStrain[c] * f2));
+    if (lowre) {
+      const double alphast = (0.024 + (densit * tec) / (6 * viscos * edc)) / (1.0 + (densit * tec) / (6 * viscos * edc));
+      v = viscos + denc * tec / (edc + FCP_SMALL) * 1.0 / fmax(1.0 / alphast, magStrain[c] * f2 / (SST_A1 * edc));
+    }
+    vis[c] = urf * v + (1.0 - urf) * visold;
+  }
+}
+__global__ void __launch_bounds__(FCP_TPB) k_mu_eff_sst_wall(MeshView m, const int32_t *__restrict__ bftype, double viscos, double densit,
+                                                              const double *__restrict__ te, const double *__restrict__ den, const double *__restrict__ u,
+                                                              const double *__restrict__ v, const double *__restrict__ w, const double *__restrict__ dnw,
+                                                              double *vis, double *visw, double *ypl, double *tau) {
+  FCP_CELL_LOOP(i, m.B) {
+    if (bftype[i] != FCP_BC_WALL) continue;
+    const int32_t f = m.F + i, ijp = m.owner[f], ijb = m.n + i;
+    const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
+    const double are = sqrt(arx * arx + ary * ary + arz * arz);
+    const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
+    const double Vnp = u[ijp] * nxf + v[ijp] * nyf + w[ijp] * nzf;
+    const double xtp = u[ijp] - Vnp * nxf, ytp = v[ijp] - Vnp * nyf, ztp = w[ijp] - Vnp * nzf;
+    const double Vtp = sqrt(xtp * xtp + ytp * ytp + ztp * ztp);
+    const double dn = dnw[ijb];
+    const double Utau = sqrt(viscos * Vtp / (densit * dn) + cmu25_dev() * te[ijp]);
+    const double yp = den[ijp] * Utau * dn / viscos;
+    ypl[ijb] = yp;
+    const double Utaulog = 1.0 / FCP_CAPPA * log(FCP_ELOG * yp);
+    const double uv2 = yp * yp, ul2 = Utaulog * Utaulog;
+    const double Upl = sqrt(sqrt(uv2 * uv2 + ul2 * ul2));
+    const double viscw = den[ijp] * Utau * dn / Upl;
+    tau[ijb] = den[ijp] * ((Vtp / Upl) * (Vtp / Upl));
+    const double vw = fmax(viscos, viscw);
+    visw[ijb] = vw;
+    vis[ijb] = vw;
+  }
+}
+int fvm_mu_eff_sst(fcp_ctx *ctx, double urf, double viscos, double densit, int lowre, const double *magStrain, const double *walldist, const double *te,
+                   const double *ed, const double *den, const double *u, const double *v, const double *w, const double *dnw, double *vis, double *visw,
+                   double *ypl, double *tau) {
+  if (ctx->n == 0) return FCP_OK;
+  k_mu_eff_sst_cell<<<FCP_GRID(ctx->n)>>>(ctx->n, urf, viscos, densit, lowre, magStrain, walldist, te, ed, den, vis);
+  FCP_LAUNCHED();
+  FCP_TRY(fvm_update_boundary(ctx, vis));
+  if (ctx->B) {
+    k_mu_eff_sst_wall<<<FCP_GRID(ctx->B)>>>(fcp_mesh_view(ctx), ctx->bftype, viscos, densit, te, den, u, v, w, dnw, vis, visw, ypl, tau);
+    FCP_LAUNCHED();
+  }
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_sst_blend(fcp_ctx *ctx, double viscos, const double *walldist, const double *gte, const double *gom, const double *den, const double *te,
+                  const double *ed, double *fsst) {
+  if (ctx->n == 0) return FCP_OK;
+  k_sst_blend<<<FCP_GRID(ctx->n)>>>(ctx->n, viscos, walldist, gte, gom, den, te, ed, fsst);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+
 int fvm_strain(fcp_ctx *ctx, const double *gU, const double *gV, const double *gW, double *magStrain, double *vorticity) {
   if (ctx->n == 0) return FCP_OK;
   k_strain<<<FCP_GRID(ctx->n)>>>(ctx->n, gU, gV, gW, magStrain, vorticity);
@@ -456,11 +611,14 @@ int fvm_sc_assemble(fcp_ctx *ctx, const ScParams &q) {
   g.phi = q.phi; g.phio = q.phio; g.phioo = q.phioo; g.te = q.te; g.ed = q.ed; g.den = q.den; g.vis = q.vis; g.visw = q.visw; g.dnw = q.dnw;
   g.flmass = q.flmass; g.u = q.u; g.v = q.v; g.w = q.w; g.magStrain = q.magStrain; g.su_vol = q.su_vol; g.sp_vol = q.sp_vol; g.g = q.grad;
   g.gen = q.gen; g.tau = q.tau; g.a = q.a; g.su = q.su; g.sp = q.sp; g.phi_new = q.phi_new;
+  g.fsst = q.fsst; g.walldist = q.walldist; g.gte = q.gte; g.lowre = q.lowre;
   const MeshView m = fcp_mesh_view(ctx);
   size_t tok = ctx->prof.begin(FCP_K_SCALAR, ctx->stream);
   if (q.kind == 0) k_sc_assemble<0><<<FCP_GRID(ctx->n)>>>(m, g);
   else if (q.kind == 1) k_sc_assemble<1><<<FCP_GRID(ctx->n)>>>(m, g);
-  else k_sc_assemble<2><<<FCP_GRID(ctx->n)>>>(m, g);
+  else if (q.kind == 2) k_sc_assemble<2><<<FCP_GRID(ctx->n)>>>(m, g);
+  else if (q.kind == 3) k_sc_assemble<3><<<FCP_GRID(ctx->n)>>>(m, g);
+  else k_sc_assemble<4><<<FCP_GRID(ctx->n)>>>(m, g);
   ctx->prof.end(tok, ctx->stream);
   FCP_LAUNCHED();
   k_sc_diag<<<FCP_GRID(ctx->n)>>>(m, q.a, q.sp, q.su, q.phi_new, q.phi_out, q.urf);
@@ -469,9 +627,9 @@ int fvm_sc_assemble(fcp_ctx *ctx, const ScParams &q) {
   return FCP_OK;
 }
 
-int fvm_clip_small(fcp_ctx *ctx, double *phi) {
-  if (ctx->n == 0) return FCP_OK;
-  k_clip<<<FCP_GRID(ctx->n)>>>(ctx->n, phi);
+int fvm_clip_small(fcp_ctx *ctx, double *phi, int32_t count) {
+  if (count == 0) return FCP_OK;
+  k_clip<<<FCP_GRID(count)>>>(count, phi);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

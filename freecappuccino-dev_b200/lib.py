@@ -32,11 +32,12 @@ PSCHEME = {"linear": 0, "central": 1, "weighted": 2}
 FIELDS = ["U", "V", "W", "P", "PP", "DEN", "VIS", "APU", "APV", "APW", "SU", "SV", "SW", "S0", "S1", "S2", "S3",
           "DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "FLMASS", "A", "APR", "H", "RU", "RV", "RW", "VISW",
           "UO", "VO", "WO", "UOO", "VOO", "WOO", "UOOO", "VOOO", "WOOO", "SPU", "SPV", "SP",
-          "TE", "ED", "PHIO", "PHIOO", "GEN", "MAGSTRAIN", "VORTICITY", "DNW", "TAU", "YPL", "SCTMP"]
+          "TE", "ED", "PHIO", "PHIOO", "GEN", "MAGSTRAIN", "VORTICITY", "DNW", "TAU", "YPL", "SCTMP",
+          "FSST", "WALLDIST", "DTEDXI", "DEDDXI"]
 F = {name: i for i, name in enumerate(FIELDS)}
 KERNEL_CLASSES = ["spmv_dot", "cg_pk", "cg_update", "cg_init", "precond", "dot", "bicg_elem", "assemble", "gradp", "correct_flux",
                   "grad", "laplacian", "spmv", "halo", "limiter", "piso_h", "uvw", "scalar"]
-GRADIENT_FIELDS = {"DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1"}
+GRADIENT_FIELDS = {"DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "DTEDXI", "DEDDXI"}
 
 
 class FcpError(RuntimeError):
@@ -77,12 +78,12 @@ class UvwParams(C.Structure):
                 ("gradPcmf", C.c_double), ("viscos", C.c_double)]
 
 
-SC_GENERIC, SC_TKE_RLZB, SC_EPS_RLZB = 0, 1, 2
-SC_KIND = {"generic": SC_GENERIC, "tke_rlzb": SC_TKE_RLZB, "eps_rlzb": SC_EPS_RLZB}
+SC_GENERIC, SC_TKE_RLZB, SC_EPS_RLZB, SC_TKE_SST, SC_OMEGA_SST = 0, 1, 2, 3, 4
+SC_KIND = {"generic": SC_GENERIC, "tke_rlzb": SC_TKE_RLZB, "eps_rlzb": SC_EPS_RLZB, "tke_sst": SC_TKE_SST, "omega_sst": SC_OMEGA_SST}
 
 
 class ScalarParams(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("kind", "solver", "maxiter", "cscheme", "grad_method", "limiter", "tscheme", "pad")] + \
+    _fields_ = [(n, C.c_int32) for n in ("kind", "solver", "maxiter", "cscheme", "grad_method", "limiter", "tscheme", "lowre")] + \
                [(n, C.c_double) for n in ("tol_abs", "tol_rel", "urf", "gds", "timestep", "prtr", "viscos", "densit")]
 
 
@@ -152,6 +153,7 @@ def lib():
     L.fcp_grad_gauss_fvx.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_modify_viscosity_sgs.argtypes = [vp, C.c_int, C.c_double, C.c_double]
     L.fcp_modify_mu_eff_k_epsilon_rlzb.argtypes = [vp, C.c_double, C.c_double]
+    L.fcp_modify_mu_eff_k_omega_sst.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int]
     L.fcp_calcuvw.argtypes = [vp, C.POINTER(UvwParams), C.POINTER(Report)]
     L.fcp_laplacian.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_gradp_and_sources.argtypes = [vp, C.c_int, C.c_int]
@@ -321,7 +323,7 @@ class Context:
         return g.value, ustar.value
 
     def calcsc(self, phi, kind="generic", solver="bicgstab", maxiter=10, tol_abs=1e-13, tol_rel=0.025, urf=0.8, gds=1.0, cscheme="cds",
-               grad_method="gauss", limiter="none", tscheme="steady", timestep=0.0, prtr=1.0, viscos=0.0, densit=1.0):
+               grad_method="gauss", limiter="none", tscheme="steady", timestep=0.0, prtr=1.0, viscos=0.0, densit=1.0, lowre=False):
         """The calcsc template (k_epsilon_rlzb.f90:52-790 + scalar_fluxes.f90).  Returns (report, fimin, fimax)."""
         prm = ScalarParams()
         prm.kind = SC_KIND[kind] if isinstance(kind, str) else kind
@@ -331,7 +333,7 @@ class Context:
         prm.grad_method = GRAD_ID[grad_method] if isinstance(grad_method, str) else grad_method
         prm.limiter = LIMITER_ID[limiter] if isinstance(limiter, str) else limiter
         prm.tscheme = TSCHEME[tscheme] if isinstance(tscheme, str) else tscheme
-        prm.timestep, prm.prtr, prm.viscos, prm.densit = timestep, prtr, viscos, densit
+        prm.timestep, prm.prtr, prm.viscos, prm.densit, prm.lowre = timestep, prtr, viscos, densit, int(lowre)
         rep = Report()
         lo, hi = C.c_double(0.0), C.c_double(0.0)
         check(lib().fcp_calcsc(self.h, C.byref(prm), field_id(phi), C.byref(rep), C.byref(lo), C.byref(hi)), "fcp_calcsc")
@@ -351,6 +353,9 @@ class Context:
 
     def modify_mu_eff_k_epsilon_rlzb(self, urfVis: float, viscos: float):
         check(lib().fcp_modify_mu_eff_k_epsilon_rlzb(self.h, urfVis, viscos), "fcp_modify_mu_eff_k_epsilon_rlzb")
+
+    def modify_mu_eff_k_omega_sst(self, urfVis: float, viscos: float, densit: float, lowre: bool = False):
+        check(lib().fcp_modify_mu_eff_k_omega_sst(self.h, urfVis, viscos, densit, int(lowre)), "fcp_modify_mu_eff_k_omega_sst")
 
     def update_boundary(self, field):
         """updateBoundary(phi), boundary/updateBoundary.f90."""

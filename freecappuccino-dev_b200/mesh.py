@@ -800,11 +800,21 @@ def hex_mesh_fast(xs: np.ndarray, ys: np.ndarray, zs: np.ndarray, patch_types: O
     vol = dx[ci] * dy[cj] * dz[ck]
     # patch_index of the matching patch on the peer: the peer lists its process patches in the same `order`, after its own
     # physical patches; the caller (block_partition_mesh) fills peer_patch because it knows the peer's patch table
-    return Mesh(numCells=n, numInnerFaces=Fi, numBoundaryFaces=int(sum(counts)), owner=owner, neighbour=neighbour,
+    mesh = Mesh(numCells=n, numInnerFaces=Fi, numBoundaryFaces=int(sum(counts)), owner=owner, neighbour=neighbour,
                 arx=arx, ary=ary, arz=arz, xf=xf, yf=yf, zf=zf, facint=facint, Df=Df, xc=xc, yc=yc, zc=zc, vol=vol,
                 bcname=names, bctype=np.array(btypes, dtype=np.int32), nfaces=np.array(counts, dtype=np.int32),
                 startFace=np.asarray(starts, dtype=np.int32), peer_rank=np.array(peers, dtype=np.int32),
                 peer_patch=np.full(len(names), -1, dtype=np.int32))
+    if BC_PERIODIC in btypes:          # periodic pairs: the twin is the opposite side, listed as 'empty' (faces of opposite sides share their order)
+        opposite = dict(top="bottom", bottom="top", left="right", right="left", back="front", front="back")
+        twin = np.full(len(names), -1, dtype=np.int32)
+        for ib, nm in enumerate(names):
+            if btypes[ib] == BC_PERIODIC:
+                it = names.index(opposite[nm])
+                assert btypes[it] == BC_EMPTY, "the twin of a periodic patch is listed as 'empty'"
+                twin[ib] = starts[it]
+        mesh.startFaceTwin = twin
+    return mesh
 
 
 def block_dims(nranks: int) -> Tuple[int, int, int]:

@@ -246,6 +246,9 @@ inline fcp_report calcsc(int kind, int phi_field, int solver, int maxiter, dp to
 }
 // modify_viscosity_wale_sgs / modify_viscosity_vreman_sgs (u, v, w, den, vis already on the device)
 inline void modify_viscosity_sgs(int model, dp urfVis, dp viscos) { check(fcp_modify_viscosity_sgs(ctx, model, urfVis, viscos), "fcp_modify_viscosity_sgs"); }
+inline void modify_mu_eff_k_omega_sst(dp urfVis, dp viscos, dp densit, bool lowRe = false) {
+  check(fcp_modify_mu_eff_k_omega_sst(ctx, urfVis, viscos, densit, lowRe ? 1 : 0), "fcp_modify_mu_eff_k_omega_sst");
+}
 inline void calc_strain_and_vorticity() { check(fcp_calc_strain_and_vorticity(ctx), "fcp_calc_strain_and_vorticity"); }
 inline void modify_mu_eff_k_epsilon_rlzb(dp urfVis, dp viscos) { check(fcp_modify_mu_eff_k_epsilon_rlzb(ctx, urfVis, viscos), "fcp_modify_mu_eff_k_epsilon_rlzb"); }
 // constant_mass_flow_forcing   src/cappuccino/constant_mass_flow_forcing.f90 (U and APU already on the device)

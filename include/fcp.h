@@ -72,6 +72,8 @@ enum {
   FCP_F_GEN, FCP_F_MAGSTRAIN, FCP_F_VORTICITY,     /* gen, magStrain, vorticity (variables module) */
   FCP_F_DNW, FCP_F_TAU, FCP_F_YPL,                 /* dnw, tau, ypl(iWall): per wall face, stored in the wall faces' boundary slots like visw above */
   FCP_F_SCTMP,                                     /* scratch of fcp_calcsc */
+  FCP_F_FSST, FCP_F_WALLDIST,                      /* k-omega SST: blending function F1 (fsst), wallDistance per cell */
+  FCP_F_DTEDXI, FCP_F_DEDDXI,                      /* (3,numTotal): gradients of k and omega kept by the SST pair (cross diffusion) */
   FCP_F_COUNT
 };
 
@@ -244,13 +246,18 @@ int fcp_calcuvw(fcp_ctx *ctx, const fcp_uvw_params *prm, fcp_report *rep);
  * Outputs: the scalar, FCP_F_A (its matrix), FCP_F_SU, FCP_F_SP, FCP_F_G0 (its gradient).  k^1.5 uses the device pow(): that value agrees
  * with the reference's libm to rounding, everything else follows the reference's operation order.  Not built: Crank-Nicolson, buoyancy,
  * partitioned meshes (FCP_ESTATE with a communicator). */
-enum { FCP_SC_GENERIC = 0, FCP_SC_TKE_RLZB = 1, FCP_SC_EPS_RLZB = 2 };
+/*   FCP_SC_TKE_SST / FCP_SC_OMEGA_SST   the k and omega equations of TurbulenceModels/k_omega_SST.f90:91-788 (omega lives in FCP_F_ED as in the
+ *                    reference): production limiter, F1 = tanh(ksi^4) (FCP_F_FSST, written by the omega call, read by both -- the k call uses the
+ *                    previous one, zero on the first call), cross diffusion from FCP_F_DTEDXI . FCP_F_DEDDXI, sigma from the OWNER cell of a face,
+ *                    omega imposed in wall cells, extrema and clip over the whole array; needs FCP_F_WALLDIST; `lowre` = the module's LowRe switch */
+enum { FCP_SC_GENERIC = 0, FCP_SC_TKE_RLZB = 1, FCP_SC_EPS_RLZB = 2, FCP_SC_TKE_SST = 3, FCP_SC_OMEGA_SST = 4 };
 typedef struct {
   int32_t kind;                 /* FCP_SC_* */
   int32_t solver, maxiter;      /* TurbModel%Scalar(i)%lSolver, %maxiter */
   int32_t cscheme;              /* FCP_CS_* (TurbModel%Scalar(i)%cScheme) */
   int32_t grad_method, limiter; /* the configuration of grad(phi, dPhidxi) */
-  int32_t tscheme, pad;         /* 0 steady, 1 bdf, 2 bdf2 */
+  int32_t tscheme;              /* 0 steady, 1 bdf, 2 bdf2 */
+  int32_t lowre;                /* k-omega SST only: LowRe (k_omega_SST.f90:19) */
   double tol_abs, tol_rel, urf, gds, timestep;
   double prtr;                  /* 1/sigma of the scalar */
   double viscos, densit;
@@ -262,6 +269,10 @@ int fcp_calc_strain_and_vorticity(fcp_ctx *ctx);
  * under-relaxed by urfVis; updateBoundary(vis); wall functions -> FCP_F_VISW, FCP_F_YPL, FCP_F_TAU and vis at the wall faces.  acos, cos and
  * log are the device's: agreement with the reference's libm is to rounding. */
 int fcp_modify_mu_eff_k_epsilon_rlzb(fcp_ctx *ctx, double urfVis, double viscos);
+/* modify_mu_eff of the k-omega SST model (k_omega_SST.f90:790-958): F2 = tanh(etha^2), vis = viscos + den a1 k / max(a1 omega, S F2) (LowRe variant),
+ * updateBoundary(vis), automatic wall treatment (u+ blended from the viscous and the log law) -> FCP_F_VISW, FCP_F_YPL, FCP_F_TAU.  tanh and log are
+ * the device's. */
+int fcp_modify_mu_eff_k_omega_sst(fcp_ctx *ctx, double urfVis, double viscos, double densit, int lowre);
 
 /* fvxGradient's Gauss gradient (fvExplicit/fvxGradient.f90:1549-1662, gradco :1761-1817): two passes, the second interpolates the face value
  * with the first pass's gradient (skewness correction).  It is what Grad(U) of the tensor-field layer returns with its default flags; note that

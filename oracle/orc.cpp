@@ -1683,7 +1683,7 @@ extern "C" void orc_calcsc(const orc_mesh *m, const i32 *ia, const i32 *ja, cons
                            const double *den, const double *vis, const double *visw, const double *dnw, const double *flmass, const double *u,
                            const double *v, const double *w, const double *magStrain, double *gen, double *tau, const double *su_vol,
                            const double *sp_vol, double *a, double *su, double *sp, double *g, orc_report *rep, double *fimin_out,
-                           double *fimax_out) {
+                           double *fimax_out, double *fsst, const double *walldist, const double *dTEdxi, int lowre) {
   const i32 n = m->numCells, F = m->numInnerFaces;
   const double gam = prm->gds, prtr = prm->prtr, viscos = prm->viscos;
   const int cs = prm->cscheme;
@@ -1695,14 +1695,63 @@ extern "C" void orc_calcsc(const orc_mesh *m, const i32 *ia, const i32 *ja, cons
   for (i32 c = 0; c < n; ++c) { su[c] = 0.0; sp[c] = 0.0; }
   // ---- volume sources
   if (prm->kind == 1) for (i32 c = 0; c < n; ++c) gen[c] = std::fabs(vis[c] - viscos) * magStrain[c] * magStrain[c];   // :103-105
+  // ---- k-omega SST (k_omega_SST.f90:91-788): kind 3 = k (ifi = 1), kind 4 = omega (ifi = 2, stored in `ed` like in the reference)
+  const double BETTAST = 0.09, SIGMK1 = 0.85, SIGMK2 = 1.0, SIGMOM1 = 0.5, SIGMOM2 = 0.856, BETAI1 = 0.075, BETAI2 = 0.0828, ALPHA1 = 5.0 / 9.0, ALPHA2 = 0.44;
+  const double densit = prm->densit;
+  auto p4 = [](double x) { return (x * x) * (x * x); };                                  // x**4
+  if (prm->kind == 3) for (i32 c = 0; c < n; ++c) {                                      // :143-153
+    gen[c] = std::fabs(vis[c] - viscos) * magStrain[c] * magStrain[c];
+    gen[c] = mn(gen[c], 0.9 * den[c] * te[c] * ed[c]);
+    if (lowre) {
+      const double x4 = p4(den[c] * te[c] / (8.0 * viscos * ed[c]));
+      const double tmp = 10 * BETTAST * (4.0 / 15.0 + x4) / (1.0 + x4);
+      gen[c] = mn(gen[c], tmp * den[c] * te[c] * ed[c]);
+    }
+  }
+  if (prm->kind == 4) for (i32 c = 0; c < n; ++c) {                                      // :242-268  the blending function F1
+    const double wldist = walldist[c];
+    const double dot = dTEdxi[3 * c] * g[3 * c] + dTEdxi[3 * c + 1] * g[3 * c + 1] + dTEdxi[3 * c + 2] * g[3 * c + 2];
+    const double domegapl = mx(2 * SIGMOM2 * den[c] / (ed[c]) * dot, SMALL);             // `1e-20`: default-real literal
+    const double ksi = mn(mx(std::sqrt(te[c]) / (BETTAST * wldist * ed[c] + SMALL), 500.0 * viscos / den[c] / (wldist * wldist * ed[c] + SMALL)),
+                          4.0 * den[c] * te[c] * SIGMOM2 / (domegapl * (wldist * wldist)));
+    fsst[c] = std::tanh(p4(ksi));
+  }
   for (i32 c = 0; c < n; ++c) {
+    if (prm->kind == 3) {                                                                // :155-170
+      const double genp = mx(gen[c], 0.0), genn = mn(gen[c], 0.0);
+      su[c] = genp * m->vol[c];
+      sp[c] = BETTAST * ed[c] * den[c] * m->vol[c];
+      if (lowre) {
+        const double x4 = p4(den[c] * te[c] / (8 * viscos * ed[c]));
+        const double tmp = BETTAST * (4.0 / 15.0 + x4) / (1.0 + x4);
+        sp[c] = tmp * ed[c] * den[c] * m->vol[c];
+      }
+      sp[c] = sp[c] - genn * m->vol[c] / (te[c] + SMALL);
+    } else if (prm->kind == 4) {                                                         // :272-318
+      const double genp = mx(gen[c], 0.0), genn = mn(gen[c], 0.0);
+      const double vist = (vis[c] - viscos) / densit;
+      double alphasst = fsst[c] * ALPHA1 + (1.0 - fsst[c]) * ALPHA2;
+      if (lowre) {
+        const double alphast = (0.024 + (densit * te[c]) / (6.0 * viscos * ed[c])) / (1.0 + (densit * te[c]) / (6.0 * viscos * ed[c]));
+        const double tmp = ALPHA1 / alphast * (1.0 / 9.0 + (densit * te[c]) / (2.95 * viscos * ed[c])) / (1.0 + (densit * te[c]) / (2.95 * viscos * ed[c]));
+        alphasst = fsst[c] * tmp + (1.0 - fsst[c]) * ALPHA2;
+      }
+      su[c] = alphasst * genp * m->vol[c] / (vist + SMALL);
+      const double dot = dTEdxi[3 * c] * g[3 * c] + dTEdxi[3 * c + 1] * g[3 * c + 1] + dTEdxi[3 * c + 2] * g[3 * c + 2];
+      double domega = 2 * (1.0 - fsst[c]) * den[c] * SIGMOM2 / (ed[c] + SMALL) * dot;
+      domega = mx(domega, 0.0);
+      su[c] = su[c] + domega * m->vol[c];
+      const double bettasst = fsst[c] * BETAI1 + (1.0 - fsst[c]) * BETAI2;
+      sp[c] = bettasst * den[c] * ed[c] * m->vol[c];
+      sp[c] = sp[c] - alphasst * genn * m->vol[c] / (vist * ed[c] + SMALL);
+    }
     if (prm->kind == 0) { su[c] = su_vol[c]; sp[c] = sp_vol[c]; }
     else if (prm->kind == 1) {                                                          // :108-120
       const double genp = mx(gen[c], 0.0), genn = mn(gen[c], 0.0);
       su[c] = genp * m->vol[c];
       sp[c] = ed[c] * den[c] * m->vol[c] / (te[c] + SMALL);
       sp[c] = sp[c] - genn * m->vol[c] / (te[c] + SMALL);
-    } else {                                                                            // :500-513
+    } else if (prm->kind == 2) {                                                        // :500-513
       const double genp = mx(magStrain[c], 0.0), genn = mn(magStrain[c], 0.0);
       const double etarlzb = magStrain[c] * te[c] / (ed[c] + SMALL);
       const double c1 = mx((double)0.43f, etarlzb / (etarlzb + 5.0));
@@ -1721,7 +1770,10 @@ extern "C" void orc_calcsc(const orc_mesh *m, const i32 *ia, const i32 *ja, cons
     const i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
     const double lambda = m->facint[i], fxn = lambda, fxp = 1.0 - lambda;
     const double viste = (vis[ijp] + (vis[ijn] - vis[ijp]) * lambda) - viscos;
-    const double dcoef = viscos + viste * prtr;
+    double prf = prtr;
+    if (prm->kind == 3) prf = fsst[ijp] * SIGMK1 + (1.0 - fsst[ijp]) * SIGMK2;            // k_omega_SST.f90:440-449: the OWNER's value only
+    if (prm->kind == 4) prf = fsst[ijp] * SIGMOM1 + (1.0 - fsst[ijp]) * SIGMOM2;
+    const double dcoef = viscos + viste * prf;
     const double arx = m->arx[i], ary = m->ary[i], arz = m->arz[i], fm = flmass[i];
     const double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
     const double de = dcoef * m->Df[i];
@@ -1750,7 +1802,10 @@ extern "C" void orc_calcsc(const orc_mesh *m, const i32 *ia, const i32 *ja, cons
       const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1, bf = f - F;
       const double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
       if (t == ORC_BC_INLET || t == ORC_BC_OUTLET || t == ORC_BC_PRESSURE) {            // facefluxsc_boundary :236-300
-        const double viste = vis[ijb] - viscos, dcoef = viscos + viste * prtr;
+        double prf = prtr;
+        if (prm->kind == 3) prf = fsst[ijp] * SIGMK1 + (1.0 - fsst[ijp]) * SIGMK2;
+        if (prm->kind == 4) prf = fsst[ijp] * SIGMOM1 + (1.0 - fsst[ijp]) * SIGMOM2;
+        const double viste = vis[ijb] - viscos, dcoef = viscos + viste * prf;
         const double xpn = m->xf[f] - m->xc[ijp], ypn = m->yf[f] - m->yc[ijp], zpn = m->zf[f] - m->zc[ijp];
         const double Dfi = (arx * arx + ary * ary + arz * arz) / (xpn * arx + ypn * ary + zpn * arz);
         const double de = dcoef * Dfi;
@@ -1764,7 +1819,10 @@ extern "C" void orc_calcsc(const orc_mesh *m, const i32 *ia, const i32 *ja, cons
       } else if (t == ORC_BC_PERIODIC) {                                                // facefluxsc_periodic :145-232 (Df(i): ordinal in the patch, quirk Q21)
         const i32 ijn = m->owner[m->startFaceTwin[ib] + i - 1] - 1;
         const double fxn = 0.5, fxp = fxn;
-        const double viste = 0.5 * (vis[ijp] + vis[ijn]) - viscos, dcoef = viscos + viste * prtr;
+        double prf = prtr;
+        if (prm->kind == 3) prf = 0.5 * ((fsst[ijp] * SIGMK1 + (1.0 - fsst[ijp]) * SIGMK2) + (fsst[ijn] * SIGMK1 + (1.0 - fsst[ijn]) * SIGMK2));
+        if (prm->kind == 4) prf = 0.5 * ((fsst[ijp] * SIGMOM1 + (1.0 - fsst[ijp]) * SIGMOM2) + (fsst[ijn] * SIGMOM1 + (1.0 - fsst[ijn]) * SIGMOM2));
+        const double viste = 0.5 * (vis[ijp] + vis[ijn]) - viscos, dcoef = viscos + viste * prf;
         const double xpn = 2 * (m->xf[f] - m->xc[ijp]), ypn = 2 * (m->yf[f] - m->yc[ijp]), zpn = 2 * (m->zf[f] - m->zc[ijp]);
         const double Dfq = m->Df[i - 1], fm = flmass[f];
         const double de = dcoef * Dfq;
@@ -1784,7 +1842,14 @@ extern "C" void orc_calcsc(const orc_mesh *m, const i32 *ia, const i32 *ja, cons
         ++lper;
         su[ijp] = su[ijp] + suadd;
         su[ijn] = su[ijn] - suadd;
-      } else if (t == ORC_BC_WALL && prm->kind == 1) {                                  // k_epsilon_rlzb.f90:331-368
+      } else if (t == ORC_BC_WALL && prm->kind == 4) {                                  // k_omega_SST.f90:668-680
+        const double wlog = std::sqrt(te[ijp]) / (cmu25() * CAPPA * dnw[bf]);
+        const double wvis = 6.0 * (viscos / den[ijp]) / (BETAI1 * (dnw[bf] * dnw[bf]));
+        ed[ijp] = std::sqrt(wvis * wvis + wlog * wlog);
+        su[ijp] = ed[ijp];
+        for (i32 k = ia[ijp]; k <= ia[ijp + 1] - 1; ++k) a[k - 1] = 0.0;
+        sp[ijp] = 1.0;
+      } else if (t == ORC_BC_WALL && (prm->kind == 1 || prm->kind == 3)) {              // k_epsilon_rlzb.f90:331-368 == k_omega_SST.f90:636-666
         const double viss = mx(viscos, visw[bf]);
         const double are = std::sqrt(arx * arx + ary * ary + arz * arz);
         const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
@@ -1818,11 +1883,53 @@ extern "C" void orc_calcsc(const orc_mesh *m, const i32 *ia, const i32 *ja, cons
   }
   solve_any(prm->solver, n, nnz, ia, ja, a, diag, phi, su, prm->maxiter, prm->tol_abs, prm->tol_rel, prm->sum_mode, rep);   // :418
   orc_update_boundary(m, phi);                                                          // :421
+  const i32 nmm = (prm->kind == 3 || prm->kind == 4) ? m->numTotal : n;      // k_omega_SST.f90:776-786 takes minval(fi), fi = max(fi, small) over the WHOLE array
   double fimin = phi[0], fimax = phi[0];
-  for (i32 c = 1; c < n; ++c) { fimin = mn(fimin, phi[c]); fimax = mx(fimax, phi[c]); }
+  for (i32 c = 1; c < nmm; ++c) { fimin = mn(fimin, phi[c]); fimax = mx(fimax, phi[c]); }
   if (fimin_out) *fimin_out = fimin;
   if (fimax_out) *fimax_out = fimax;
-  if (prm->kind != 0 && fimin < 0.0) for (i32 c = 0; c < n; ++c) phi[c] = mx(phi[c], SMALL);   // :430
+  if (prm->kind != 0 && fimin < 0.0) for (i32 c = 0; c < nmm; ++c) phi[c] = mx(phi[c], SMALL);   // :430
+}
+
+extern "C" void orc_modify_mu_eff_sst(const orc_mesh *m, double urf, double viscos, double densit, int lowre, const double *magStrain,
+                                      const double *walldist, const double *te, const double *ed, const double *den, const double *u, const double *v,
+                                      const double *w, const double *dnw, double *vis, double *visw, double *ypl, double *tau) {   // k_omega_SST.f90:790-958
+  const i32 n = m->numCells, F = m->numInnerFaces;
+  const double BETTAST = 0.09, A1 = 0.31;
+  for (i32 c = 0; c < n; ++c) {
+    const double visold = vis[c], wldist = walldist[c];
+    const double etha = mx(2 * std::sqrt(te[c]) / (BETTAST * wldist * ed[c]), (500 * viscos / den[c]) / (wldist * wldist * ed[c]));
+    const double f2 = std::tanh(etha * etha);
+    vis[c] = viscos + den[c] * A1 * te[c] / (mx(A1 * ed[c], magStrain[c] * f2));
+    if (lowre) {
+      const double alphast = (0.024 + (densit * te[c]) / (6 * viscos * ed[c])) / (1.0 + (densit * te[c]) / (6 * viscos * ed[c]));
+      vis[c] = viscos + den[c] * te[c] / (ed[c] + SMALL) * 1.0 / mx(1.0 / alphast, magStrain[c] * f2 / (A1 * ed[c]));
+    }
+    vis[c] = urf * vis[c] + (1.0 - urf) * visold;
+  }
+  orc_update_boundary(m, vis);
+  for (i32 ib = 0; ib < m->numBoundaries; ++ib) {
+    if (m->bctype[ib] != ORC_BC_WALL) continue;
+    for (i32 i = 1; i <= m->nfaces[ib]; ++i) {
+      const i32 f = m->startFace[ib] + i - 1, ijp = m->owner[f] - 1, ijb = m->iBndValueStart[ib] + i - 1, bf = f - F;
+      const double arx = m->arx[f], ary = m->ary[f], arz = m->arz[f];
+      const double are = std::sqrt(arx * arx + ary * ary + arz * arz);
+      const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
+      const double Vnp = u[ijp] * nxf + v[ijp] * nyf + w[ijp] * nzf;
+      const double xtp = u[ijp] - Vnp * nxf, ytp = v[ijp] - Vnp * nyf, ztp = w[ijp] - Vnp * nzf;
+      const double Vtp = std::sqrt(xtp * xtp + ytp * ytp + ztp * ztp);
+      const double Utau = std::sqrt(viscos * Vtp / (densit * dnw[bf]) + cmu25() * te[ijp]);
+      ypl[bf] = den[ijp] * Utau * dnw[bf] / viscos;
+      const double Utauvis = ypl[bf];
+      const double Utaulog = (double)1.0f / CAPPA * std::log(ELOG * ypl[bf]);
+      const double uv2 = Utauvis * Utauvis, ul2 = Utaulog * Utaulog;
+      const double Upl = std::sqrt(std::sqrt(uv2 * uv2 + ul2 * ul2));
+      const double viscw = den[ijp] * Utau * dnw[bf] / Upl;
+      tau[bf] = den[ijp] * ((Vtp / Upl) * (Vtp / Upl));
+      visw[bf] = mx(viscos, viscw);
+      vis[ijb] = visw[bf];
+    }
+  }
 }
 
 extern "C" void orc_modify_mu_eff_rlzb(const orc_mesh *m, double urf, double viscos, const double *gU, const double *gV, const double *gW,

@@ -213,7 +213,15 @@ void orc_calcsc(const orc_mesh *m, const int32_t *ia, const int32_t *ja, const i
                 const double *den, const double *vis, const double *visw, const double *dnw, const double *flmass,
                 const double *u, const double *v, const double *w, const double *magStrain, double *gen, double *tau,
                 const double *su_vol, const double *sp_vol,
-                double *a, double *su, double *sp, double *dPhidxi, orc_report *rep, double *fimin, double *fimax);
+                double *a, double *su, double *sp, double *dPhidxi, orc_report *rep, double *fimin, double *fimax,
+                double *fsst /* kinds 3, 4: the SST blending function F1 (written by kind 4, read by both) */, const double *walldist,
+                const double *dTEdxi /* kind 4: the gradient of k the k call left behind */, int lowre);
+/* kinds 3 and 4 of orc_calcsc: the k and omega equations of TurbulenceModels/k_omega_SST.f90:91-788 (same template; production limiter,
+ * F1 = tanh(ksi^4), cross diffusion, blended constants, sigma taken from the OWNER cell of a face, omega imposed in wall cells, min/max and
+ * the clip taken over the whole array).  modify_mu_eff :790-958. */
+void orc_modify_mu_eff_sst(const orc_mesh *m, double urf, double viscos, double densit, int lowre, const double *magStrain, const double *walldist,
+                           const double *te, const double *ed, const double *den, const double *u, const double *v, const double *w,
+                           const double *dnw, double *vis, double *visw, double *ypl, double *tau);
 /* fvExplicit/calc_strain_and_vorticity.f90 */
 void orc_calc_strain_and_vorticity(const orc_mesh *m, const double *dUdxi, const double *dVdxi, const double *dWdxi, double *magStrain, double *vorticity);
 /* modify_mu_eff of the realizable k-epsilon model, k_epsilon_rlzb.f90:792-975 (cell loop, updateBoundary(vis), wall functions) */

@@ -363,7 +363,7 @@ def calcuvw(mesh, csr: Csr, prm: OrcUvwParams, f: dict, a: np.ndarray):
 
 
 # ---- row f4: scalar transport -----------------------------------------------------------------------------------------------
-SC_GENERIC, SC_TKE_RLZB, SC_EPS_RLZB = 0, 1, 2
+SC_GENERIC, SC_TKE_RLZB, SC_EPS_RLZB, SC_TKE_SST, SC_OMEGA_SST = 0, 1, 2, 3, 4
 
 
 class OrcScalarParams(C.Structure):
@@ -376,15 +376,17 @@ def calcsc(mesh, csr: Csr, prm: OrcScalarParams, f: dict):
     for and updated in place; kind 0 solves f['phi']), den, vis (numTotal), visw, dnw (numBoundaryFaces), flmass (numFaces), u, v, w,
     magStrain (numCells), optionally phio/phioo, su_vol/sp_vol (kind 0).  Returns a dict with a, su, sp, grad, gen, tau, rep, fimin, fimax."""
     n, nT, B = mesh.numCells, mesh.numTotal, mesh.numBoundaryFaces
-    phi = f["phi"] if prm.kind == SC_GENERIC else (f["te"] if prm.kind == SC_TKE_RLZB else f["ed"])
-    out = dict(a=np.zeros(csr.nnz), su=np.zeros(n), sp=np.zeros(n), grad=np.zeros((nT, 3)), gen=np.zeros(n), tau=np.zeros(max(B, 1)))
+    phi = f["phi"] if prm.kind == SC_GENERIC else (f["te"] if prm.kind in (SC_TKE_RLZB, SC_TKE_SST) else f["ed"])
+    out = dict(a=np.zeros(csr.nnz), su=np.zeros(n), sp=np.zeros(n), grad=np.zeros((nT, 3)), tau=np.zeros(max(B, 1)))
+    out["gen"] = f["gen"] if prm.kind == SC_OMEGA_SST else np.zeros(n)        # the omega equation reads the production the k call left behind
     rep = OrcReport()
     fmin, fmax = C.c_double(0.0), C.c_double(0.0)
     opt = lambda k: _d(f[k]) if k in f and f[k] is not None else None  # noqa: E731
     lib().orc_calcsc(csr.mv.ptr, _i(csr.ia), _i(csr.ja), _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz), C.byref(prm),
                      _d(phi), opt("phio"), opt("phioo"), opt("te"), opt("ed"), _d(f["den"]), _d(f["vis"]), opt("visw"), opt("dnw"), _d(f["flmass"]),
                      opt("u"), opt("v"), opt("w"), opt("magStrain"), _d(out["gen"]), _d(out["tau"]), opt("su_vol"), opt("sp_vol"),
-                     _d(out["a"]), _d(out["su"]), _d(out["sp"]), _d(out["grad"]), C.byref(rep), C.byref(fmin), C.byref(fmax))
+                     _d(out["a"]), _d(out["su"]), _d(out["sp"]), _d(out["grad"]), C.byref(rep), C.byref(fmin), C.byref(fmax),
+                     opt("fsst"), opt("walldist"), opt("dTEdxi"), C.c_int(int(f.get("lowre", 0))))
     out.update(rep=rep, fimin=fmin.value, fimax=fmax.value)
     return out
 
@@ -397,6 +399,16 @@ def wall_geometry(mesh):
     dnw, srdw, dns, srds = np.zeros(nw), np.zeros(nw), np.zeros(ns), np.zeros(ns)
     lib().orc_wall_geometry(mv.ptr, _d(dnw), _d(srdw), _d(dns), _d(srds))
     return dnw, srdw, dns, srds
+
+
+def modify_mu_eff_sst(mesh, urf, viscos, densit, lowre, magStrain, walldist, te, ed, den, u, v, w, dnw, vis, visw):
+    """modify_mu_eff of k_omega_SST.f90:790-958: vis and visw updated in place; returns ypl, tau."""
+    mv = MeshView(mesh)
+    B = max(mesh.numBoundaryFaces, 1)
+    ypl, tau = np.zeros(B), np.zeros(B)
+    lib().orc_modify_mu_eff_sst(mv.ptr, C.c_double(urf), C.c_double(viscos), C.c_double(densit), C.c_int(int(lowre)), _d(magStrain), _d(walldist),
+                                _d(te), _d(ed), _d(den), _d(u), _d(v), _d(w), _d(dnw), _d(vis), _d(visw), _d(ypl), _d(tau))
+    return ypl, tau
 
 
 def calc_strain_and_vorticity(mesh, dUdxi, dVdxi, dWdxi):

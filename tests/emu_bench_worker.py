@@ -30,4 +30,10 @@ def _unpinned_copy(a):
 
 
 bench.pinned_copy = _unpinned_copy
-bench.main()
+if len(sys.argv) > 1 and sys.argv[1] == "rows":          # tools/bench_rows.py (per-kernel timings of the rows beyond the headline step)
+    sys.argv.pop(1)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_rows
+    bench_rows.main()
+else:
+    bench.main()

@@ -242,3 +242,65 @@ def test_modify_viscosity_sgs(fcp, orc, allmeshes, name, model):
         eq(ctx.download("VISW")[n:][wall], visw[wall], "visw")
     assert np.all(vis[:n] >= 0.0)
     ctx.close()
+
+
+# ---- k-omega SST -------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SC_MESHES)
+@pytest.mark.parametrize("lowre,tscheme,cscheme", [(False, "steady", "cds"), (True, "bdf", "muscl")])
+def test_k_omega_sst_pair(fcp, orc, allmeshes, name, lowre, tscheme, cscheme):
+    """modify_viscosity_k_omega_sst (k_omega_SST.f90:62-88): calcsc(k), calcsc(omega), modify_mu_eff in sequence, twice (the second k call
+    reads the F1 of the first omega call).  The k equation is libm-free and bit-identical on the first pass; F1 and F2 go through tanh, the
+    wall functions through log, so everything downstream is compared at 1e-10."""
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    n, nT = m.numCells, m.numTotal
+    g["ed"] = 40.0 * g["ed"]                                   # omega-like magnitudes
+    g["walldist"] = np.zeros(nT); g["walldist"][:n] = 0.02 + np.minimum(np.abs(m.yc[:n] - m.yc[:n].min()), np.abs(m.yc[:n].max() - m.yc[:n]))
+    g["fsst"] = np.zeros(nT)
+    g["lowre"] = int(lowre)
+    ctx = make_ctx(m)
+    upload_scalar_state(ctx, m, g)
+    ctx.upload("WALLDIST", g["walldist"])
+    c = orc.Csr(m)
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g.items()}
+    f["gen"] = np.zeros(n)
+    for rep_no in range(2):
+        common = dict(solver="bicgstab", maxiter=6, tol_abs=1e-30, tol_rel=1e-30, urf=0.7, gds=0.8, cscheme=cscheme, tscheme=tscheme, timestep=0.02,
+                      viscos=0.01, densit=1.0, lowre=lowre)
+        ctx.upload("PHIO", f["te"] * 0.97); ctx.upload("PHIOO", f["te"] * 0.95)
+        rk, lok, hik = ctx.calcsc("TE", kind="tke_sst", **common)
+        gen_dev = ctx.download("GEN")[:n]
+        a_k = ctx.download("A")
+        ctx.upload("PHIO", f["ed"] * 0.97); ctx.upload("PHIOO", f["ed"] * 0.95)
+        ro, loo, hio = ctx.calcsc("ED", kind="omega_sst", **common)
+        ctx.modify_mu_eff_k_omega_sst(0.8, 0.01, 1.0, lowre)
+        # ---- oracle
+        prm = oracle_params(orc, orc.SC_TKE_SST, "bicgstab", cscheme, "gauss", "none", tscheme)
+        prm.maxiter, prm.tol_rel = 6, 1e-30
+        f["phio"], f["phioo"] = f["te"] * 0.97, f["te"] * 0.95
+        ok = orc.calcsc(m, c, prm, f)
+        f["gen"] = ok["gen"]; f["dTEdxi"] = ok["grad"]
+        prm.kind = orc.SC_OMEGA_SST
+        f["phio"], f["phioo"] = f["ed"] * 0.97, f["ed"] * 0.95
+        oo = orc.calcsc(m, c, prm, f)
+        ypl, tau = orc.modify_mu_eff_sst(m, 0.8, 0.01, 1.0, lowre, f["magStrain"], f["walldist"], f["te"], f["ed"], f["den"], f["u"], f["v"], f["w"],
+                                         f["dnw"], f["vis"], f["visw"])
+        if rep_no == 0:
+            eq(a_k, ok["a"], "k matrix (first pass)")
+            eq(gen_dev, ok["gen"], "gen (first pass)")
+            assert (rk.iters, rk.res0, rk.resl) == (ok["rep"].iters, ok["rep"].res0, ok["rep"].resl)
+        assert rk.iters == ok["rep"].iters and ro.iters == oo["rep"].iters
+        close(ctx.download("FSST")[:n], f["fsst"][:n], f"pass {rep_no}: F1", 1e-10)
+        close(ctx.download("TE"), f["te"], f"pass {rep_no}: k", 1e-10)
+        close(ctx.download("ED"), f["ed"], f"pass {rep_no}: omega", 1e-9)
+        close(ctx.download("VIS"), f["vis"], f"pass {rep_no}: vis", 1e-9)
+        close(np.array([lok, hik, loo, hio]), np.array([ok["fimin"], ok["fimax"], oo["fimin"], oo["fimax"]]), "extrema", 1e-9)
+    wall = np.zeros(m.numBoundaryFaces, bool)
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] == M.BC_WALL:
+            wall[m.patch_faces(ib) - m.numInnerFaces] = True
+    if wall.any():
+        close(ctx.download("VISW")[n:][wall], f["visw"][wall], "visw", 1e-9)
+        close(ctx.download("YPL")[n:][wall], ypl[: m.numBoundaryFaces][wall], "ypl", 1e-9)
+        close(ctx.download("TAU")[n:][wall], tau[: m.numBoundaryFaces][wall], "tau", 1e-9)
+    ctx.close()

@@ -151,3 +151,32 @@ def test_sgs_models_in_pure_shear(orc):
         orc.modify_viscosity_sgs(m, model, 1.0, nu, u, v, w, np.ones(m.numTotal), vis, visw)
         assert np.abs(vis[:n] - nu).max() < 1e-12, model
         assert np.all(visw == nu)
+
+
+def test_sst_closed_forms(orc):
+    """k-omega SST (Menter 1994 / 2003) on uniform fields: with S = 0 the eddy viscosity is rho k / omega; with zero gradients the third argument
+    of F1 drops out and F1 = tanh(max(sqrt(k)/(beta* d omega), 500 nu/(d^2 omega))^4), near 1 at the wall and near 0 far from it; the omega
+    imposed in wall cells is sqrt((6 nu/(beta1 d^2))^2 + (sqrt(k)/(cmu^1/4 kappa d))^2)."""
+    m = M.cavity_mesh(6)
+    n, nT, B = m.numCells, m.numTotal, m.numBoundaryFaces
+    c = orc.Csr(m)
+    k, om, rho, nu = 0.02, 30.0, 1.0, 1e-4
+    d = np.zeros(nT); d[:n] = np.minimum.reduce([m.xc[:n], 1 - m.xc[:n], m.yc[:n], 1 - m.yc[:n], m.zc[:n], 1 - m.zc[:n]])
+    te, ed, den = np.full(nT, k), np.full(nT, om), np.full(nT, rho)
+    vis = np.full(nT, nu); visw = np.zeros(B)
+    u = np.full(nT, 0.3); v = np.zeros(nT); w = np.zeros(nT)
+    orc.modify_mu_eff_sst(m, 1.0, nu, rho, False, np.zeros(n), d, te, ed, den, u, v, w, np.full(B, 0.08), vis, visw)
+    assert np.abs(vis[:n] - (nu + rho * k / om)).max() < 1e-15
+    prm = params(orc, kind=orc.SC_OMEGA_SST, maxiter=1, viscos=nu, densit=rho)
+    f = dict(te=te, ed=ed.copy(), den=den, vis=np.full(nT, nu + rho * k / om), visw=np.full(B, nu), dnw=np.full(B, 0.08), flmass=np.zeros(m.numFaces),
+             u=u, v=v, w=w, magStrain=np.zeros(n), gen=np.zeros(n), fsst=np.zeros(nT), walldist=d, dTEdxi=np.zeros((nT, 3)))
+    orc.calcsc(m, c, prm, f)
+    ksi = np.maximum(np.sqrt(k) / (0.09 * d[:n] * om + 1e-20), 500 * nu / rho / (d[:n] ** 2 * om + 1e-20))
+    assert np.allclose(f["fsst"][:n], np.tanh(ksi ** 4), rtol=1e-13, atol=0)
+    near, far = d[:n] < 0.1, d[:n] > 0.4
+    assert f["fsst"][:n][near].min() > 0.1 > f["fsst"][:n][far].max()
+    # wall cells hold the imposed omega after the (identity-row) solve
+    Fi = m.numInnerFaces
+    nwall = np.zeros(n, int); np.add.at(nwall, m.owner[Fi:] - 1, 1)
+    want = np.sqrt((6 * nu / rho / (0.075 * 0.08 ** 2)) ** 2 + (np.sqrt(k) / (0.09 ** 0.25 * 0.41 * 0.08)) ** 2)
+    assert np.allclose(f["ed"][:n][nwall >= 1], want, rtol=1e-12)

@@ -227,6 +227,12 @@ module fcp_b200
       integer(c_int), value :: lowre
       integer(c_int) :: rc
     end function
+    function fcp_wall_distance(ctx, rep) bind(c, name='fcp_wall_distance') result(rc)
+      import :: c_int, c_ptr, fcp_report
+      type(c_ptr), value :: ctx
+      type(fcp_report), intent(out) :: rep
+      integer(c_int) :: rc
+    end function
     function fcp_grad_gauss_fvx(ctx, phi_field, grad_field) bind(c, name='fcp_grad_gauss_fvx') result(rc)
       import :: c_int, c_ptr
       type(c_ptr), value :: ctx
@@ -726,6 +732,20 @@ contains
     call get(FCP_F_A, a, nnz); call get(FCP_F_H, h, nnz)
     call continuityErrors                            ! calcp_piso.f90:390 stays on the host
     if (const_mflux) call constant_mass_flow_forcing ! :487
+  end subroutine
+
+  ! ---- wall_distance()   src/mesh/wall_distance.f90:55-133 (module geometry owns wallDistance(numCells)) ------------------------------------
+  subroutine wall_distance()
+    type(fcp_report) :: rep
+    character(kind=c_char) :: line(256)
+    integer :: i
+    call fcp_check(fcp_wall_distance(ctx, rep), 'fcp_wall_distance')
+    call fcp_check(fcp_report_line(rep, 'Wdis'//c_null_char, line, 256_c_int), 'fcp_report_line')
+    do i = 1, 256
+      if (line(i) == c_null_char) exit
+    end do
+    write(*,'(256a)') line(1:i-1)
+    call get(FCP_F_WALLDIST, wallDistance, numCells)
   end subroutine
 
   ! ---- updateBoundary(phi)   src/finiteVolume/boundary/updateBoundary.f90 ------------------------------------------------------

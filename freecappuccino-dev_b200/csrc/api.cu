@@ -846,6 +846,21 @@ extern "C" int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_fi
   if (prm->kind != FCP_SC_GENERIC && mm[0] < 0.0) FCP_TRY(fvm_clip_small(ctx, phi, cnt));    // :430
   return FCP_OK;
 }
+// wall_distance   src/mesh/wall_distance.f90:75-133: laplacian(1, phi) with every patch Dirichlet 0, q = -vol, iccg(500, 1e-12, 1e-10), owner values into
+// the non-wall boundary slots, grad_gauss, d = -|grad phi| + sqrt(|grad phi|^2 + 2 phi).  Uses S0 (phi), S1 (mu), SU (q), G0, A.
+extern "C" int fcp_wall_distance(fcp_ctx *ctx, fcp_report *rep) {
+  if (!ctx) return FCP_EINVAL;
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FCP_TRY(fcp_field_fill(ctx, FCP_F_S1, 1.0));                                            // :89  mu = 1
+  FCP_TRY(fcp_field_fill(ctx, FCP_F_S0, 0.0));                                            // :86  phi = 0
+  FCP_TRY(fcp_laplacian(ctx, FCP_F_S1, FCP_F_S0));                                        // :92
+  FIELD(q, FCP_F_SU); FIELD(phi, FCP_F_S0); FIELD(g, FCP_F_G0); FIELD(wd, FCP_F_WALLDIST);
+  FCP_TRY(fvm_neg_vol(ctx, q));                                                           // :83
+  FCP_TRY(fcp_csrsolve(ctx, FCP_SOLVER_ICCG, FCP_F_S0, FCP_F_SU, 500, 1e-12, 1e-10, rep)); // :95-101
+  FCP_TRY(fvm_wall_distance_finish(ctx, 0, phi, g, wd));                                  // :105-118
+  FCP_TRY(fcp_grad(ctx, FCP_GRAD_GAUSS, FCP_F_S0, FCP_F_G0, 1));                          // :121
+  return fvm_wall_distance_finish(ctx, 1, phi, g, wd);                                    // :124-125
+}
 extern "C" int fcp_calc_strain_and_vorticity(fcp_ctx *ctx) {
   if (!ctx) return FCP_EINVAL;
   FCP_CUDA(cudaSetDevice(ctx->device));

@@ -275,6 +275,8 @@ int fvm_sum(fcp_ctx *ctx, const double *x, double *d_out);
 int fvm_piso_pupdate(fcp_ctx *ctx, double ncells_global, double urfp, const double *d_sum, const double *pp, double *p);
 int fvm_cmf_forcing(fcp_ctx *ctx, double magUbar, const double *apu, double *u, double *d_sums);
 int fvm_update_boundary(fcp_ctx *ctx, double *phi);
+int fvm_neg_vol(fcp_ctx *ctx, double *q);
+int fvm_wall_distance_finish(fcp_ctx *ctx, int stage, double *phi, const double *g, double *wd);
 int fvm_piso_fluxmc(fcp_ctx *ctx, const double *den, const double *apu, const double *dPdxi, double *su);
 
 // ---- fvm_uvw.cu ---------------------------------------------------------------------------------

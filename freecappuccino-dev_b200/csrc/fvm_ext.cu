@@ -434,6 +434,40 @@ int fvm_update_boundary(fcp_ctx *ctx, double *phi) {
   FCP_CHECK_LAUNCH();
   return FCP_OK;
 }
+// ---- wall distance, src/mesh/wall_distance.f90:75-133 (the pieces that are not laplacian / csrsolve / grad_gauss)
+__global__ void __launch_bounds__(FCP_TPB) k_neg_vol(int32_t n, const double *__restrict__ vol, double *__restrict__ q) {
+  FCP_CELL_LOOP(c, n) { q[c] = -vol[c]; }                                  // :83  q = -Vol(1:numCells)
+}
+__global__ void __launch_bounds__(FCP_TPB) k_copy_owner_nonwall(MeshView m, const int32_t *__restrict__ bftype, double *phi) {
+  FCP_CELL_LOOP(i, m.B) {                                                   // :107-118  every patch but 'wall' takes the owner value
+    if (bftype[i] != FCP_BC_WALL) phi[m.n + i] = phi[m.owner[m.F + i]];
+  }
+}
+__global__ void __launch_bounds__(FCP_TPB) k_wall_distance(int32_t n, const double *__restrict__ g, const double *__restrict__ phi, double *__restrict__ wd) {
+  FCP_CELL_LOOP(c, n) {                                                     // :124-125
+    const double gx = g[3 * (int64_t)c], gy = g[3 * (int64_t)c + 1], gz = g[3 * (int64_t)c + 2];
+    wd[c] = -sqrt(gx * gx + gy * gy + gz * gz) + sqrt(gx * gx + gy * gy + gz * gz + 2 * phi[c]);
+  }
+}
+int fvm_neg_vol(fcp_ctx *ctx, double *q) {
+  if (ctx->n == 0) return FCP_OK;
+  k_neg_vol<<<FCP_GRID(ctx->n)>>>(ctx->n, ctx->vol, q);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
+int fvm_wall_distance_finish(fcp_ctx *ctx, int stage, double *phi, const double *g, double *wd) {
+  if (stage == 0) {
+    if (ctx->B == 0) return FCP_OK;
+    k_copy_owner_nonwall<<<FCP_GRID(ctx->B)>>>(fcp_mesh_view(ctx), ctx->bftype, phi);
+  } else {
+    if (ctx->n == 0) return FCP_OK;
+    k_wall_distance<<<FCP_GRID(ctx->n)>>>(ctx->n, g, phi, wd);
+  }
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  return FCP_OK;
+}
 int fvm_piso_pupdate(fcp_ctx *ctx, double ncells_global, double urfp, const double *d_sum, const double *pp, double *p) {
   if (ctx->n == 0) return FCP_OK;
   k_piso_pupdate<<<FCP_GRID(ctx->n)>>>(ctx->n, ncells_global, urfp, d_sum, pp, p);

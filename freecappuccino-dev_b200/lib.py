@@ -150,6 +150,7 @@ def lib():
     L.fcp_update_boundary.argtypes = [vp, C.c_int]
     L.fcp_calcsc.argtypes = [vp, C.POINTER(ScalarParams), C.c_int, C.POINTER(Report), _pd, _pd]
     L.fcp_calc_strain_and_vorticity.argtypes = [vp]
+    L.fcp_wall_distance.argtypes = [vp, C.POINTER(Report)]
     L.fcp_grad_gauss_fvx.argtypes = [vp, C.c_int, C.c_int]
     L.fcp_modify_viscosity_sgs.argtypes = [vp, C.c_int, C.c_double, C.c_double]
     L.fcp_modify_mu_eff_k_epsilon_rlzb.argtypes = [vp, C.c_double, C.c_double]
@@ -347,6 +348,12 @@ class Context:
         """modify_viscosity_wale_sgs / modify_viscosity_vreman_sgs."""
         mid = {"wale": 0, "vreman": 1}[model] if isinstance(model, str) else int(model)
         check(lib().fcp_modify_viscosity_sgs(self.h, mid, urfVis, viscos), "fcp_modify_viscosity_sgs")
+
+    def wall_distance(self):
+        """wall_distance.f90:75-133 -> field WALLDIST; returns the ICCG report."""
+        rep = Report()
+        check(lib().fcp_wall_distance(self.h, C.byref(rep)), "fcp_wall_distance")
+        return rep
 
     def calc_strain_and_vorticity(self):
         check(lib().fcp_calc_strain_and_vorticity(self.h), "fcp_calc_strain_and_vorticity")

@@ -249,6 +249,8 @@ inline void modify_viscosity_sgs(int model, dp urfVis, dp viscos) { check(fcp_mo
 inline void modify_mu_eff_k_omega_sst(dp urfVis, dp viscos, dp densit, bool lowRe = false) {
   check(fcp_modify_mu_eff_k_omega_sst(ctx, urfVis, viscos, densit, lowRe ? 1 : 0), "fcp_modify_mu_eff_k_omega_sst");
 }
+// wall_distance (src/mesh/wall_distance.f90): result in field FCP_F_WALLDIST
+inline fcp_report wall_distance() { fcp_report rep{}; check(fcp_wall_distance(ctx, &rep), "fcp_wall_distance"); return rep; }
 inline void calc_strain_and_vorticity() { check(fcp_calc_strain_and_vorticity(ctx), "fcp_calc_strain_and_vorticity"); }
 inline void modify_mu_eff_k_epsilon_rlzb(dp urfVis, dp viscos) { check(fcp_modify_mu_eff_k_epsilon_rlzb(ctx, urfVis, viscos), "fcp_modify_mu_eff_k_epsilon_rlzb"); }
 // constant_mass_flow_forcing   src/cappuccino/constant_mass_flow_forcing.f90 (U and APU already on the device)

@@ -263,6 +263,10 @@ typedef struct {
   double viscos, densit;
 } fcp_scalar_params;
 int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_field, fcp_report *rep, double *fimin, double *fimax);
+/* wall_distance (src/mesh/wall_distance.f90:75-133): the Poisson-equation wall distance -- laplacian(1, phi) (every patch Dirichlet, as the reference's
+ * laplacian does), q = -vol, csrsolve('iccg', 500, 1e-12, 1e-10), owner values into the boundary slots of every patch but 'wall', grad_gauss,
+ * d = -|grad phi| + sqrt(|grad phi|^2 + 2 phi) -> FCP_F_WALLDIST.  Scratch: FCP_F_S0 (phi), FCP_F_S1, FCP_F_SU, FCP_F_G0, FCP_F_A.  rep may be NULL. */
+int fcp_wall_distance(fcp_ctx *ctx, fcp_report *rep);
 /* calc_strain_and_vorticity (fvExplicit/calc_strain_and_vorticity.f90): FCP_F_DUDXI/DVDXI/DWDXI -> FCP_F_MAGSTRAIN, FCP_F_VORTICITY */
 int fcp_calc_strain_and_vorticity(fcp_ctx *ctx);
 /* modify_mu_eff of the realizable k-epsilon model (k_epsilon_rlzb.f90:792-975): effective viscosity from te, ed and the velocity gradients,

@@ -304,3 +304,30 @@ def test_k_omega_sst_pair(fcp, orc, allmeshes, name, lowre, tscheme, cscheme):
         close(ctx.download("YPL")[n:][wall], ypl[: m.numBoundaryFaces][wall], "ypl", 1e-9)
         close(ctx.download("TAU")[n:][wall], tau[: m.numBoundaryFaces][wall], "tau", 1e-9)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["hex10_distorted", "channel_inout", "poly_10faces", "channel_periodic"])
+def test_wall_distance(fcp, orc, allmeshes, name):
+    """src/mesh/wall_distance.f90:75-133 on the device against the same pipeline through the oracle (laplacian + IC(0)-CG + owner values into the
+    non-wall boundary slots + grad_gauss + the distance formula): bit-identical, same iteration count."""
+    m = allmeshes[name]
+    n = m.numCells
+    ctx = make_ctx(m)
+    rep = ctx.wall_distance()
+    c = orc.Csr(m)
+    su = np.zeros(n)
+    phi = np.zeros(m.numTotal)
+    a = orc.laplacian(m, c, np.ones(m.numTotal), phi, su)
+    q = -m.vol[:n].copy()
+    orep = orc.solve(orc.ICCG, c.ia, c.ja, a, c.diag, phi, q, 500, 1e-12, 1e-10, orc.SUM_TREE)
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] != M.BC_WALL:
+            pf = m.patch_faces(ib)
+            phi[n + pf - m.numInnerFaces] = phi[m.owner[pf] - 1]
+    g = orc.grad_gauss(m, phi)[:n]
+    gg = g[:, 0] * g[:, 0] + g[:, 1] * g[:, 1] + g[:, 2] * g[:, 2]
+    wd = -np.sqrt(gg) + np.sqrt(gg + 2 * phi[:n])
+    assert (rep.iters, rep.res0, rep.resl) == (orep.iters, orep.res0, orep.resl)
+    eq(ctx.download("WALLDIST")[:n], wd, "wall distance")
+    assert wd.min() > 0
+    ctx.close()

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_limiter_cell(MeshView m, const doub
     const int64_t base = m.a_slptr[c >> 5] + (c & 31);
     const int32_t ri = m.a_rinfo[c];
     const int32_t dpos = (ri >> 16) & 0xffff;
-    const int32_t len = m.a_llen ? m.a_llen[c] : (ri & 0xffff);
+    const int32_t len = ri & 0xffff;     // the whole row: on a partition the cells across process faces are neighbours like any other (ghost copies)
     double slopelimit = 1.0;
     for (int32_t k = 0; k < len; ++k) {
       if (k == dpos) continue;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_limiter_mdl(MeshView m, const doubl
   FCP_CELL_LOOP(c, m.n) {
     const int64_t base = m.a_slptr[c >> 5] + (c & 31);
     const int32_t ri = m.a_rinfo[c];
-    const int32_t len = m.a_llen ? m.a_llen[c] : (ri & 0xffff);
+    const int32_t len = ri & 0xffff;     // whole row, halo columns included
     const double pc = phi[c];
     double phimax = phi[m.a_ja[base]], phimin = phimax;
     for (int32_t k = 1; k < len; ++k) {
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_limiter_mdl(MeshView m, const doubl
     double gx = g[3 * (int64_t)c], gy = g[3 * (int64_t)c + 1], gz = g[3 * (int64_t)c + 2];
     FCP_FACE_LOOP(m, c) {
       FCP_FACE_FETCH(m);
-      if (f >= m.F) continue;   // inner faces only (:588)
+      if (f >= m.F && sl < 0) continue;   // inner faces only (:588); a process face is an inner face of the unpartitioned mesh
       const double xpn = m.xf[f] - xc, ypn = m.yf[f] - yc, zpn = m.zf[f] - zc;
       const double dpn = sqrt(xpn * xpn + ypn * ypn + zpn * zpn);
       const double nx = xpn / dpn, ny = ypn / dpn, nz = zpn / dpn;

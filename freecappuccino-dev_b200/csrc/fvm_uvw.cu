@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_uvw_diag(MeshView m, double *a, con
     const int64_t base = m.a_slptr[c >> 5] + (c & 31);
     const int32_t ri = m.a_rinfo[c];
     const int32_t dpos = (ri >> 16) & 0xffff;
-    const int32_t len = m.a_llen ? m.a_llen[c] : (ri & 0xffff);
+    const int32_t len = ri & 0xffff;     // the whole row: on a partition the halo coefficients apr(ipro) belong to the diagonal too (src-par/calcuvw.f90:259-265 adds them through spu)
     const double adiag_old = zero_first ? 0.0 : a[base + (int64_t)dpos * 32];
     double s = 0.0;
     for (int32_t k = 0; k < len; ++k) s = s + (k == dpos ? adiag_old : a[base + (int64_t)k * 32]);   // sum( a(ia(inp):ia(inp+1)-1) ), CSR order

@@ -798,7 +798,10 @@ extern "C" int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_fi
     fcp_set_error("calcsc: field %d is not a scalar cell field", phi_field);
     return FCP_EINVAL;
   }
-  if (ctx->comm) { fcp_set_error("calcsc: partitioned meshes are not supported yet"); return FCP_ESTATE; }
+  if (ctx->comm && is_sst) {   // sigma is taken from the OWNER of a face; a process face sees its local cell as owner on both ranks
+    fcp_set_error("calcsc: the SST pair is not available on partitioned meshes yet");
+    return FCP_ESTATE;
+  }
   FCP_CUDA(cudaSetDevice(ctx->device));
   FIELD(phi, phi_field); FIELD(den, FCP_F_DEN); FIELD(vis, FCP_F_VIS); FIELD(fl, FCP_F_FLMASS);
   // the gradient of the scalar: G0, except for the SST pair, whose omega equation needs both grad k and grad omega (cross diffusion)
@@ -833,6 +836,7 @@ extern "C" int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_fi
     FCP_TRY(fvm_sst_blend(ctx, prm->viscos, q.walldist, q.gte, g, den, q.te, q.ed, fsst));
   }
   FCP_CUDA(cudaMemsetAsync(a, 0, sizeof(double) * (size_t)ctx->pat.nnzp, ctx->stream));      // a = 0
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, vis, 1));       // ghost values of what facefluxsc reads across a process face (phi and its gradient: done by grad)
   FCP_TRY(fvm_sc_assemble(ctx, q));
   FCP_TRY(fcp_csrsolve(ctx, prm->solver, phi_field, FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel, rep));
   FCP_TRY(fvm_update_boundary(ctx, phi));
@@ -869,8 +873,7 @@ extern "C" int fcp_calc_strain_and_vorticity(fcp_ctx *ctx) {
 }
 extern "C" int fcp_modify_mu_eff_k_epsilon_rlzb(fcp_ctx *ctx, double urfVis, double viscos) {
   if (!ctx) return FCP_EINVAL;
-  if (ctx->comm) { fcp_set_error("modify_mu_eff: partitioned meshes are not supported yet"); return FCP_ESTATE; }
-  FCP_CUDA(cudaSetDevice(ctx->device));
+  FCP_CUDA(cudaSetDevice(ctx->device));      // cell- and boundary-face-local: nothing to exchange (the next consumer of vis exchanges its ghost values)
   FIELD(gu, FCP_F_DUDXI); FIELD(gv, FCP_F_DVDXI); FIELD(gw, FCP_F_DWDXI); FIELD(te, FCP_F_TE); FIELD(ed, FCP_F_ED); FIELD(den, FCP_F_DEN);
   FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(dnw, FCP_F_DNW); FIELD(vis, FCP_F_VIS); FIELD(visw, FCP_F_VISW);
   FIELD(ypl, FCP_F_YPL); FIELD(tau, FCP_F_TAU);
@@ -879,7 +882,6 @@ extern "C" int fcp_modify_mu_eff_k_epsilon_rlzb(fcp_ctx *ctx, double urfVis, dou
 
 extern "C" int fcp_modify_mu_eff_k_omega_sst(fcp_ctx *ctx, double urfVis, double viscos, double densit, int lowre) {
   if (!ctx) return FCP_EINVAL;
-  if (ctx->comm) { fcp_set_error("modify_mu_eff: partitioned meshes are not supported yet"); return FCP_ESTATE; }
   FCP_CUDA(cudaSetDevice(ctx->device));
   FIELD(ms, FCP_F_MAGSTRAIN); FIELD(wd, FCP_F_WALLDIST); FIELD(te, FCP_F_TE); FIELD(ed, FCP_F_ED); FIELD(den, FCP_F_DEN);
   FIELD(u, FCP_F_U); FIELD(v, FCP_F_V); FIELD(w, FCP_F_W); FIELD(dnw, FCP_F_DNW); FIELD(vis, FCP_F_VIS); FIELD(visw, FCP_F_VISW);
@@ -892,16 +894,15 @@ extern "C" int fcp_grad_gauss_fvx(fcp_ctx *ctx, int phi_field, int grad_field) {
     fcp_set_error("fcp_grad_gauss_fvx: bad field id");
     return FCP_EINVAL;
   }
-  if (ctx->comm) { fcp_set_error("fcp_grad_gauss_fvx: partitioned meshes are not supported yet"); return FCP_ESTATE; }
   FCP_CUDA(cudaSetDevice(ctx->device));
   FIELD(phi, phi_field); FIELD(g, grad_field);
   FIELD(gtmp, grad_field == FCP_F_G1 ? FCP_F_G0 : FCP_F_G1);     // the first pass's gradient
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, phi, 1));
   return fvm_grad_gauss_fvx(ctx, phi, gtmp, g);
 }
 extern "C" int fcp_modify_viscosity_sgs(fcp_ctx *ctx, int model, double urfVis, double viscos) {
   if (!ctx) return FCP_EINVAL;
   if (model != FCP_SGS_WALE && model != FCP_SGS_VREMAN) { fcp_set_error("fcp_modify_viscosity_sgs: unknown model %d", model); return FCP_EINVAL; }
-  if (ctx->comm) { fcp_set_error("fcp_modify_viscosity_sgs: partitioned meshes are not supported yet"); return FCP_ESTATE; }
   FCP_CUDA(cudaSetDevice(ctx->device));
   FCP_TRY(fcp_grad_gauss_fvx(ctx, FCP_F_U, FCP_F_DUDXI));
   FCP_TRY(fcp_grad_gauss_fvx(ctx, FCP_F_V, FCP_F_DVDXI));

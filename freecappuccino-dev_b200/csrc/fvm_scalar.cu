@@ -9,7 +9,8 @@
 //   k_sc_diag         a(diag) = sp - sum(off-diagonals) in CSR order, under-relaxation (:397-415)
 //   k_clip            phi = max(phi, small) (:430)
 //   k_mu_eff_cell / k_mu_eff_wall   modify_mu_eff (acos, cos, log: these agree with the reference's libm to rounding, not to the bit)
-// Not built: Crank-Nicolson, buoyancy; partitioned meshes (the callers refuse a communicator).
+// Not built: Crank-Nicolson, buoyancy.  Partitioned meshes: a process face is a two-sided face with its ghost cell (phi, its gradient and vis are
+// exchanged by the callers); the SST pair is single-GPU only (sigma comes from the face's owner, and both ranks see themselves as the owner).
 #include "fcp_internal.h"
 #include "fvm_common.cuh"
 #include "interp.cuh"
@@ -167,8 +168,16 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
       if (g.tscheme == 1) { s = s + apotime * g.phio[c]; p = p + apotime; }
       else { s = s + apotime * (2 * g.phio[c] - 0.5 * g.phioo[c]); p = p + 1.5 * apotime; }
     }
-    FCP_FACE_LOOP(m, c) {
+    // On a partition the process faces sit BEHIND the physical patches in the cell's list, but they are inner faces of the unpartitioned mesh:
+    // the reference's order is "inner faces, then the patches", and the wall branches of the epsilon / omega equations overwrite what the inner
+    // faces wrote (row, su, sp).  Two passes restore that order: two-sided faces first, boundary faces second.
+    const int npass = m.a_llen ? 2 : 1;
+    const int64_t fbase__ = m.slptr[c >> 5] + (c & 31);
+    const int32_t flen__ = m.len[c];
+    for (int pass = 0; pass < npass; ++pass)
+    for (int32_t q__ = 0; q__ < flen__; ++q__) {
       FCP_FACE_FETCH(m);
+      if (npass == 2 && ((sl >= 0) != (pass == 0))) continue;
       const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
       if (sl >= 0) {
         // ---- facefluxsc, scalar_fluxes.f90:32-141, in the face's orientation (P = owner, N = neighbour)
@@ -509,9 +518,11 @@ int fvm_grad_gauss_fvx(fcp_ctx *ctx, const double *u, double *gtmp, double *g) {
   const MeshView m = fcp_mesh_view(ctx);
   size_t tok = ctx->prof.begin(FCP_K_GRAD, ctx->stream);
   k_grad_gauss_fvx<<<FCP_GRID(ctx->n)>>>(m, u, nullptr, gtmp);
+  FCP_LAUNCHED();
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, gtmp, 3));      // the second pass interpolates the first pass's gradient across process faces
   k_grad_gauss_fvx<<<FCP_GRID(ctx->n)>>>(m, u, gtmp, g);
   ctx->prof.end(tok, ctx->stream);
-  FCP_LAUNCHED(); FCP_LAUNCHED();
+  FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;
 }

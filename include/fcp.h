@@ -244,8 +244,8 @@ int fcp_calcuvw(fcp_ctx *ctx, const fcp_uvw_params *prm, fcp_report *rep);
  *   FCP_SC_EPS_RLZB  calcsc_epsilon :447-790 (phi_field must be FCP_F_ED): realizable c1; wall cells: row cleared, ed = cmu75 k^1.5/(cappa dnw)
  * Inputs: FCP_F_DEN, FCP_F_VIS (effective viscosity, boundary slots included), FCP_F_FLMASS, FCP_F_MAGSTRAIN, FCP_F_TE, FCP_F_ED, FCP_F_PHIO/PHIOO.
  * Outputs: the scalar, FCP_F_A (its matrix), FCP_F_SU, FCP_F_SP, FCP_F_G0 (its gradient).  k^1.5 uses the device pow(): that value agrees
- * with the reference's libm to rounding, everything else follows the reference's operation order.  Not built: Crank-Nicolson, buoyancy,
- * partitioned meshes (FCP_ESTATE with a communicator). */
+ * with the reference's libm to rounding, everything else follows the reference's operation order.  Not built: Crank-Nicolson, buoyancy.
+ * Partitioned meshes: supported except for the SST pair (FCP_ESTATE with a communicator). */
 /*   FCP_SC_TKE_SST / FCP_SC_OMEGA_SST   the k and omega equations of TurbulenceModels/k_omega_SST.f90:91-788 (omega lives in FCP_F_ED as in the
  *                    reference): production limiter, F1 = tanh(ksi^4) (FCP_F_FSST, written by the omega call, read by both -- the k call uses the
  *                    previous one, zero on the first call), cross diffusion from FCP_F_DTEDXI . FCP_F_DEDDXI, sigma from the OWNER cell of a face,

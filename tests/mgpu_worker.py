@@ -246,6 +246,51 @@ def main():
     pl, pg = ctx2.download("P")[:nl], gp["p"][me.cell_global]
     assert rel(pl - pl.mean(), pg - pg.mean()) < 1e-6 or True      # (the pressure level is fixed by the mean over ALL cells: compared through the fluxes below)
     assert rel(ctx2.download("FLMASS") * sign, gu["flmass"][me.face_global]) < 1e-7, "calcp_piso fluxes"
+    # ---- row f4 on the partitions: calcsc (generic, k, epsilon), modify_mu_eff, the fvx gradient and the SGS models vs the unpartitioned oracle ----
+    import test_gpu_scalar as TS
+    gs = TS.scalar_inputs(g, O)
+    nb_l = me.numBoundaryFaces
+    for k in ("u", "v", "w", "den", "vis", "te", "ed"):
+        ctx2.upload(k.upper(), local_field(gs[k]))
+    ctx2.upload("FLMASS", sign * gs["flmass"][me.face_global])
+    ctx2.upload("VISW", local_bslot(gs["visw"])); ctx2.upload("DNW", local_bslot(gs["dnw"]))
+    msl = np.zeros(me.numTotal); msl[:nl] = gs["magStrain"][me.cell_global]
+    ctx2.upload("MAGSTRAIN", msl)
+    sc = dict(solver="bicgstab", maxiter=400, tol_abs=1e-30, tol_rel=1e-13, urf=0.7, gds=0.8, cscheme="muscl", limiter="Venkatakrishnan", viscos=0.01, densit=1.0)
+    sprm = TS.oracle_params(O, O.SC_TKE_RLZB, "bicgstab", "muscl", "gauss", "Venkatakrishnan", "steady")
+    sprm.maxiter, sprm.tol_rel, sprm.sum_mode = 400, 1e-13, O.SUM_SEQ
+    fo = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in gs.items()}
+    ctx2.calcsc("TE", kind="tke_rlzb", prtr=1.0, **sc)
+    sprm.prtr = 1.0
+    O.calcsc(g, c0, sprm, fo)
+    assert rel(ctx2.download("TE")[:nl], fo["te"][me.cell_global]) < 1e-8, "partitioned k equation"
+    rep_e, _, _ = ctx2.calcsc("ED", kind="eps_rlzb", prtr=1 / 1.2, **sc)
+    sprm.kind, sprm.prtr = O.SC_EPS_RLZB, 1 / 1.2
+    oe_ = O.calcsc(g, c0, sprm, fo)
+    if os.environ.get("FCP_TEST_DEBUG"):
+        ea_, eapr_ = M.localize_matrix(g, c0, oe_["a"], me, csrs[rank])
+        da = np.abs(ctx2.download("A") - ea_); 
+        print(rank, "DEBUG eps a", rel(ctx2.download("A"), ea_), "nbad", int((da > 1e-10 * np.abs(ea_).max()).sum()), "apr", (rel(ctx2.download("APR"), eapr_) if eapr_.size else 0),
+              "su", rel(ctx2.download("SU")[:nl], oe_["su"][me.cell_global]), "sp", rel(ctx2.download("SP")[:nl], oe_["sp"][me.cell_global]), flush=True)
+        print(rank, "DEBUG eps solve", rep_e.iters, rep_e.res0, rep_e.resl, "| oracle", oe_["rep"].iters, oe_["rep"].res0, oe_["rep"].resl, flush=True)
+    if os.environ.get("FCP_TEST_DEBUG"):
+        d = np.abs(ctx2.download("ED")[:nl] - fo["ed"][me.cell_global])
+        print(rank, "DEBUG eps rel", rel(ctx2.download("ED")[:nl], fo["ed"][me.cell_global]), "bad", int((d > 1e-8 * np.abs(fo["ed"]).max()).sum()), "of", nl, flush=True)
+    assert rel(ctx2.download("ED")[:nl], fo["ed"][me.cell_global]) < 1e-8, "partitioned epsilon equation"
+    for comp, gfield in (("U", "DUDXI"), ("V", "DVDXI"), ("W", "DWDXI")):
+        ctx2.grad(L.GRAD_GAUSS, comp, gfield)
+    ctx2.modify_mu_eff_k_epsilon_rlzb(0.6, 0.01)
+    O.modify_mu_eff_rlzb(g, 0.6, 0.01, gs["gU"], gs["gV"], gs["gW"], fo["te"], fo["ed"], fo["den"], fo["u"], fo["v"], fo["w"], fo["dnw"], fo["vis"], fo["visw"])
+    assert rel(ctx2.download("VIS")[:nl], fo["vis"][me.cell_global]) < 1e-9, "partitioned modify_mu_eff"
+    ctx2.grad_gauss_fvx("U", "G0")
+    gx, gy, gz = O.grad_gauss_fvx(g, gs["u"])
+    gl = ctx2.download("G0")[:nl]
+    assert max(rel(gl[:, 0], gx[me.cell_global]), rel(gl[:, 1], gy[me.cell_global]), rel(gl[:, 2], gz[me.cell_global])) < 1e-12, "partitioned fvx gradient"
+    ctx2.upload("VIS", local_field(gs["vis"]))
+    ctx2.modify_viscosity_sgs("vreman", 0.7, 0.01)
+    vis_o, visw_o = gs["vis"].copy(), gs["visw"].copy()
+    O.modify_viscosity_sgs(g, O.SGS_VREMAN, 0.7, 0.01, gs["u"], gs["v"], gs["w"], gs["den"], vis_o, visw_o)
+    assert rel(ctx2.download("VIS")[:nl], vis_o[me.cell_global]) < 1e-11, "partitioned Vreman viscosity"
     ctx2.close()
     ctx.close()
     dist.barrier()

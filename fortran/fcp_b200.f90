@@ -47,6 +47,7 @@ module fcp_b200
     type(c_ptr) :: arx, ary, arz, xf, yf, zf, facint, Df, xc, yc, zc, vol
     type(c_ptr) :: bctype, nfaces, startFace
     type(c_ptr) :: startFaceTwin          ! per patch; c_null_ptr when the mesh has no periodic patch
+    type(c_ptr) :: DfPeriodic             ! c_null_ptr in the serial tree (the library then reads Df(i) like calcp_simple.f90:199 does)
   end type
 
   type, bind(c) :: fcp_report
@@ -399,6 +400,7 @@ contains
     md%xc = c_loc(xc); md%yc = c_loc(yc); md%zc = c_loc(zc); md%vol = c_loc(vol)
     md%bctype = c_loc(bct); md%nfaces = c_loc(nfa); md%startFace = c_loc(sfa)
     md%startFaceTwin = c_null_ptr
+    md%DfPeriodic = c_null_ptr
     if (iPer > 0) md%startFaceTwin = c_loc(stw)
     call fcp_check(fcp_ctx_create(md, int(device, c_int), ctx), 'fcp_ctx_create')
     allocate(ia2(numCells+1), ja2(nnz), dg2(numCells), k1(numInnerFaces+numPeriodic), k2(numInnerFaces+numPeriodic))

@@ -105,10 +105,12 @@ static int ctx_build(fcp_ctx *c, const fcp_mesh_desc *md, int device) {
   std::vector<int32_t> pcell(std::max(B, 1), -1), pface(std::max(B, 1), -1), pord(std::max(B, 1), -1), plist;
   for (int32_t ib = 0; ib < c->nb; ++ib) {
     if (c->bctype[ib] != FCP_BC_PERIODIC) continue;
+    if (c->nfaces[ib] == 0) continue;             // a partition that does not touch this periodic boundary
     const int32_t st = md->startFaceTwin ? md->startFaceTwin[ib] : -1;
-    int32_t it = -1;
-    for (int32_t jb = 0; jb < c->nb; ++jb) if (c->startFace[jb] == st && jb != ib) it = jb;
-    if (it < 0 || c->nfaces[it] != c->nfaces[ib] || c->bctype[it] != FCP_BC_EMPTY) {
+    int32_t it = -1;                              // (empty patches share their startFace with the next one: match the size and the type too)
+    for (int32_t jb = 0; jb < c->nb && it < 0; ++jb)
+      if (jb != ib && c->startFace[jb] == st && c->nfaces[jb] == c->nfaces[ib] && c->bctype[jb] == FCP_BC_EMPTY) it = jb;
+    if (it < 0) {
       fcp_set_error("periodic patch %d: startFaceTwin must name an 'empty' patch with the same number of faces", ib);
       return FCP_EINVAL;
     }
@@ -122,7 +124,6 @@ static int ctx_build(fcp_ctx *c, const fcp_mesh_desc *md, int device) {
     }
   }
   c->nper = (int32_t)plist.size();
-  if (c->nper && c->npro) { fcp_set_error("periodic patches on a partitioned mesh are not supported (the serial tree has no process patches)"); return FCP_ESTATE; }
 
   // ---- create_CSR_matrix (sparse_matrix.f90:110-260): rows ascending, columns ascending, diagonal embedded ----
   std::vector<int32_t> ia(n + 1, 0), diag(n);
@@ -226,7 +227,14 @@ static int ctx_build(fcp_ctx *c, const fcp_mesh_desc *md, int device) {
     FCP_TRY(dev_upload(&c->per_cell, pcell.data(), (size_t)B));
     FCP_TRY(dev_upload(&c->per_face, pface.data(), (size_t)B));
     FCP_TRY(dev_upload(&c->per_slot, pslot.data(), (size_t)B));
-    FCP_TRY(dev_upload(&c->per_ord, pord.data(), (size_t)B));
+    std::vector<double> pdf(B, 0.0);              // quirk Q21: "Df(i)" = the Df of inner face number i, unless the host supplies the global mesh's value
+    for (int32_t b = 0; b < B; ++b)
+      if (pord[b] >= 0) {
+        if (md->DfPeriodic) pdf[b] = md->DfPeriodic[b];
+        else if (pord[b] < F) pdf[b] = md->Df[pord[b]];
+        else { fcp_set_error("periodic patch with more faces (%d) than the mesh has inner faces: Df(i) of calcp_simple.f90:199 is out of range", pord[b] + 1); return FCP_EINVAL; }
+      }
+    FCP_TRY(dev_upload(&c->per_df, pdf.data(), (size_t)B));
   }
 
   // ---- cell -> face gather lists, faces in ascending face index -------------------------------------------------
@@ -329,7 +337,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   for (int i = 0; i < 4; ++i) cudaFree(c->Dmat[i]);
   cudaFree(c->flushbuf); cudaFree(c->d_mmpart); cudaFree(c->d_sum);
   cudaFree(c->d_oface); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
-  cudaFree(c->per_cell); cudaFree(c->per_face); cudaFree(c->per_slot); cudaFree(c->per_ord);
+  cudaFree(c->per_cell); cudaFree(c->per_face); cudaFree(c->per_slot); cudaFree(c->per_df);
   sell_free(c->pat);
   krylov_ws_free(c->ws);
   if (c->t0) cudaEventDestroy(c->t0);

@@ -223,7 +223,7 @@ struct fcp_ctx {
   int32_t *per_cell = nullptr;                      // [B] the cell across the pair (0-based), -1 for every other boundary face
   int32_t *per_face = nullptr;                      // [B] the other face of the pair (0-based face index)
   int32_t *per_slot = nullptr;                      // [B] SELL position of a(owner of this face, per_cell)
-  int32_t *per_ord = nullptr;                       // [B] 0-based ordinal of the pair inside its patch (quirk Q21: Df(i))
+  double *per_df = nullptr;                         // [B] the "Df(i)" of the pair (quirk Q21: the Df of inner face number i = the pair's ordinal in its patch)
 };
 
 struct fcp_solver {

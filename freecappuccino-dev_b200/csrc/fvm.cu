@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(FCP_TPB, (W >= 3 ? 1 : W == 2 ? 2 : 3)) k_asse
             const double apuP = g.apu[cP], apuN = g.apu[cN];
             const double dene = g.den[cP] * fxp + g.den[cN] * fxn;
             double Kj = m.vol[cP] * apuP * fxp + m.vol[cN] * apuN * fxn;
-            const double cap = -dene * Kj * m.Df[m.per_ord[b]];      // quirk Q21: Df(i), i = the face's ordinal inside its patch
+            const double cap = -dene * Kj * m.per_df[b];      // quirk Q21: Df(i), i = the face's ordinal inside its patch
             Kj = (apuP + apuN + FCP_SMALL);
             const double ui = (g.u[cP] * apuN + g.u[cN] * apuP) / Kj;
             const double vi = (g.v[cP] * g.apv[cN] + g.v[cN] * g.apv[cP]) / Kj;

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
           const double prf = (KIND == 3 || KIND == 4) ? 0.5 * (sst_prtr<KIND>(g.fsst[own ? c : q]) + sst_prtr<KIND>(g.fsst[own ? q : c])) : g.prtr;
           const double viste = 0.5 * (visP + visN) - g.viscos, dcoef = g.viscos + viste * prf;
           const double xpn = 2 * (m.xf[fp] - xP), ypn = 2 * (m.yf[fp] - yP), zpn = 2 * (m.zf[fp] - zP);
-          const double Dfq = m.Df[m.per_ord[b]], fm = g.flmass[fp];
+          const double Dfq = m.per_df[b], fm = g.flmass[fp];
           const double de = dcoef * Dfq;
           const double ce = fmin(fm, 0.0), cp = fmax(fm, 0.0);
           const double can = -de + ce, cap = -de - cp;

@@ -48,7 +48,7 @@ class MeshDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("numCells", "numInnerFaces", "numBoundaryFaces", "numBoundaries")] + \
                [("owner", _pi), ("neighbour", _pi)] + \
                [(n, _pd) for n in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "xc", "yc", "zc", "vol")] + \
-               [(n, _pi) for n in ("bctype", "nfaces", "startFace", "startFaceTwin")]
+               [(n, _pi) for n in ("bctype", "nfaces", "startFace", "startFaceTwin")] + [("DfPeriodic", _pd)]
 
 
 class Report(C.Structure):
@@ -222,6 +222,9 @@ class Context:
         if getattr(mesh, "startFaceTwin", None) is not None:       # periodic pairs (geometry.f90:251-257)
             self._keep["startFaceTwin"] = np.ascontiguousarray(mesh.startFaceTwin, dtype=np.int32)
             md.startFaceTwin = _i(self._keep["startFaceTwin"])
+        if getattr(mesh, "DfPeriodic", None) is not None:          # partitions: the global mesh's "Df(i)" per periodic face (quirk Q21)
+            self._keep["DfPeriodic"] = np.ascontiguousarray(mesh.DfPeriodic, dtype=np.float64)
+            md.DfPeriodic = _d(self._keep["DfPeriodic"])
         self.numPeriodic = int(getattr(mesh, "numPeriodic", 0))
         self.h = C.c_void_p()
         check(lib().fcp_ctx_create(C.byref(md), device, C.byref(self.h)), "fcp_ctx_create")

@@ -58,6 +58,7 @@ class Mesh:
     face_global: Optional[np.ndarray] = None  # int64 [numFaces] 0-based global face id
     # periodic pairs (geometry.f90:82,251-257): a 'periodic' patch names its twin (listed as 'empty') by the twin's startFace
     startFaceTwin: Optional[np.ndarray] = None  # int32 [numBoundaries], 0-based offset like startFace; -1 for other patches
+    DfPeriodic: Optional[np.ndarray] = None   # [numBoundaryFaces] partitions only: the "Df(i)" the GLOBAL mesh uses for each periodic face (quirk Q21)
 
     @property
     def numFaces(self) -> int:
@@ -631,6 +632,18 @@ def partition(mesh: Mesh, cell_rank: np.ndarray) -> List[Mesh]:
             pf = pf[ro[pf] == r]
             f_idx.append(pf); f_own.append(g2l[own0[pf]]); f_flip.append(np.zeros(pf.size, dtype=bool))
             names.append(mesh.bcname[ib]); types.append(int(mesh.bctype[ib])); counts.append(pf.size)
+        # periodic pairs: a rank keeps face i of a periodic patch together with face i of its twin (the partition must not separate a pair)
+        twin_local = np.full(mesh.numBoundaries, -1, dtype=np.int64)
+        if mesh.startFaceTwin is not None:
+            for ib in range(mesh.numBoundaries):
+                if mesh.bctype[ib] != BC_PERIODIC:
+                    continue
+                it = [jb for jb in range(mesh.numBoundaries) if jb != ib and mesh.startFace[jb] == mesh.startFaceTwin[ib] and mesh.nfaces[jb] == mesh.nfaces[ib]][0]
+                keep_p = ro[mesh.patch_faces(ib)] == r
+                keep_t = ro[mesh.patch_faces(it)] == r
+                if not np.array_equal(keep_p, keep_t):
+                    raise ValueError(f"partition separates periodic pairs of patch {mesh.bcname[ib]}: keep both cells of a pair on one rank")
+                twin_local[ib] = it
         peers = {}
         cutO = np.nonzero((ro[:F] == r) & (rn != r))[0]      # we own P: outward normal = S
         cutN = np.nonzero((ro[:F] != r) & (rn == r))[0]      # we own N: outward normal = -S
@@ -679,6 +692,26 @@ def partition(mesh: Mesh, cell_rank: np.ndarray) -> List[Mesh]:
                     peer_rank=peer_rank, peer_patch=np.full(len(names), -1, dtype=np.int32),
                     fpro=np.concatenate(fpro) if fpro else np.zeros(0),
                     cell_global=cells.astype(np.int64), face_global=fidx.astype(np.int64))
+        if (twin_local >= 0).any():
+            tw = np.full(len(names), -1, dtype=np.int32)
+            for ib in range(mesh.numBoundaries):
+                if twin_local[ib] >= 0:
+                    tw[ib] = int(starts[twin_local[ib]])
+            part.startFaceTwin = tw
+            # quirk Q21: the reference reads Df(i), i = the face's ordinal in its (global) patch = the Df of GLOBAL inner face i
+            dfp = np.zeros(nB)
+            for ib in range(mesh.numBoundaries):
+                if twin_local[ib] < 0:
+                    continue
+                gpf = mesh.patch_faces(ib)
+                ordinal = {int(fg): i for i, fg in enumerate(gpf)}
+                for jb in (ib, int(twin_local[ib])):
+                    s0 = int(starts[jb]); cn = counts[jb]
+                    gfaces = fidx[s0: s0 + cn]
+                    base = gpf if jb == ib else mesh.patch_faces(jb)
+                    pos = {int(fg): i for i, fg in enumerate(base)}
+                    dfp[s0 - nFi: s0 - nFi + cn] = [mesh.Df[pos[int(fg)]] for fg in gfaces]
+            part.DfPeriodic = dfp
         parts.append(part)
     for r, part in enumerate(parts):
         for ib in range(part.numBoundaries):
@@ -696,8 +729,24 @@ def localize_matrix(gmesh: Mesh, gcsr, a_global: np.ndarray, part: Mesh, pcsr) -
     Fi = part.numInnerFaces
     a_loc = np.zeros(int(pcsr.ia[-1]) - 1)
     fg = part.face_global[:Fi]
-    a_loc[pcsr.icell_jcell - 1] = a_global[gcsr.icell_jcell[fg] - 1]
-    a_loc[pcsr.jcell_icell - 1] = a_global[gcsr.jcell_icell[fg] - 1]
+    a_loc[pcsr.icell_jcell[:Fi] - 1] = a_global[gcsr.icell_jcell[fg] - 1]
+    a_loc[pcsr.jcell_icell[:Fi] - 1] = a_global[gcsr.jcell_icell[fg] - 1]
+    if part.numPeriodic:                      # the twin entries of periodic pairs: positions F + l, l counting periodic faces in patch order
+        gl = {}
+        l = 0
+        for ib in range(gmesh.numBoundaries):
+            if gmesh.bctype[ib] == BC_PERIODIC:
+                for fgl in gmesh.patch_faces(ib):
+                    gl[int(fgl)] = gmesh.numInnerFaces + l
+                    l += 1
+        l = 0
+        for ib in range(part.numBoundaries):
+            if part.bctype[ib] == BC_PERIODIC:
+                for fl in part.patch_faces(ib):
+                    k = gl[int(part.face_global[fl])]
+                    a_loc[pcsr.icell_jcell[Fi + l] - 1] = a_global[gcsr.icell_jcell[k] - 1]
+                    a_loc[pcsr.jcell_icell[Fi + l] - 1] = a_global[gcsr.jcell_icell[k] - 1]
+                    l += 1
     a_loc[pcsr.diag - 1] = a_global[gcsr.diag[part.cell_global] - 1]
     apr = []
     own0 = gmesh.owner.astype(np.int64) - 1

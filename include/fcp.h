@@ -94,6 +94,10 @@ typedef struct {
   const int32_t *startFaceTwin; /* [numBoundaries] or NULL: for FCP_BC_PERIODIC patches the startFace of the twin patch (listed as
                                * FCP_BC_EMPTY, same face count, faces already paired by face_mapping, geometry.f90:82,251-257,1848-1997);
                                * ignored for the other patch types.  NULL = the mesh has no periodic patch. */
+  const double *DfPeriodic;   /* [numBoundaryFaces] or NULL.  The reference reads `Df(i)` for periodic face i of a patch, i.e. the Df of INNER face
+                               * number i (quirk Q21, calcp_simple.f90:199).  NULL: the library does the same with this mesh's own inner faces.  A
+                               * partitioned run that must reproduce the unpartitioned reference passes here, per boundary face, the value the
+                               * GLOBAL mesh would have used (the partitioner knows it); entries of non-periodic faces are ignored. */
 } fcp_mesh_desc;
 
 /* the numbers the reference prints in its solver report line, linear_solvers.f90:354-355,540-541,781-782 */

@@ -41,11 +41,90 @@ def _bcast_uid(dist, rank):
     return uid[0]
 
 
+def periodic_main(rank, world, local):
+    """BASELINE config 4 in miniature on partitions: a channel periodic in x and z, cut into y-slabs (no pair is separated), one PISO time step with
+    constant-mass-flow forcing and the Vreman viscosity against the unpartitioned oracle (every solve run to convergence)."""
+    import test_gpu_zz_les_channel_loop as LES
+    g = cases.periodic_channel(nx=8, ny=8, nz=6, distort=0.1)
+    n_g = g.numCells
+    yn = (g.yc[:n_g] - g.yc[:n_g].min()) / (g.yc[:n_g].max() - g.yc[:n_g].min() + 1e-12)
+    parts = M.partition(g, np.minimum((yn * world).astype(np.int32), world - 1))
+    me = parts[rank]
+    nl = me.numCells
+    assert me.numPeriodic > 0 and me.npro > 0
+    ctx = L.Context(me, local)
+    ctx.comm_init(rank, world, _bcast_uid(dist, rank), me.peer_rank)
+    cl = O.Csr(me)
+    ia, ja, diag, kpn, knp = ctx.csr_pattern()
+    assert np.array_equal(ia, cl.ia) and np.array_equal(ja, cl.ja) and np.array_equal(kpn, cl.icell_jcell) and np.array_equal(knp, cl.jcell_icell)
+    f = LES.initial_state(g)
+    own_g = g.owner.astype(np.int64) - 1
+    sign = np.where(own_g[me.face_global] == me.cell_global[me.owner.astype(np.int64) - 1], 1.0, -1.0)
+
+    def lf(v):                                    # global field (numTotal) -> local field, boundary slots of physical patches included
+        out = np.zeros(me.numTotal)
+        out[:nl] = v[me.cell_global]
+        for ib in range(me.numBoundaries):
+            if me.bctype[ib] != M.BC_PROCESS:
+                pf = me.patch_faces(ib)
+                out[nl + pf - me.numInnerFaces] = v[n_g + me.face_global[pf] - g.numInnerFaces]
+        return out
+    for k in ("u", "v", "w", "p", "pp", "den", "vis", "apu", "apv", "apw", "uo", "vo", "wo", "uoo", "voo", "woo"):
+        ctx.upload(k.upper(), lf(f[k]))
+    visw = np.zeros(me.numTotal); visw[nl:] = LES.VISCOS
+    ctx.upload("VISW", visw); ctx.upload("FLMASS", sign * f["flmass"][me.face_global]); ctx.upload("A", np.zeros(ctx.nnz))
+    ctx.calcuvw(solver="bicgstab", maxiter=400, tol_abs=1e-30, tol_rel=1e-13, urf=(1.0, 1.0, 1.0), gds=1.0, cscheme="cds", pscheme="linear",
+                tscheme="bdf2", timestep=LES.DT, piso=True, const_mflux=True, gradPcmf=1e-3, viscos=LES.VISCOS)
+    dbg = {}
+    if os.environ.get("FCP_TEST_DEBUG"):
+        dbg = {k: ctx.download(k) for k in ("U", "V", "W", "A", "APU", "RU", "RV", "RW", "SPU")}
+        dbg["APR"] = ctx.download("APR")
+    ctx.calcp_piso(solver="iccg", maxiter=800, tol_abs=1e-30, tol_rel=1e-13, urfp=1.0, ncorr=2, npcor=1, pscheme="linear", const_mflux=True)
+    if dbg:
+        dbg["U2"] = ctx.download("U"); dbg["FL2"] = ctx.download("FLMASS")
+    gP, ustar = ctx.constant_mass_flow_forcing(LES.MAGUBAR, 1e-3)
+    ctx.modify_viscosity_sgs("vreman", 1.0, LES.VISCOS)
+    # ---- the unpartitioned oracle
+    c0 = O.Csr(g)
+    up = O.OrcUvwParams()
+    up.solver, up.maxiter, up.tol_abs, up.tol_rel = O.BICGSTAB, 400, 1e-30, 1e-13
+    up.urf[0] = up.urf[1] = up.urf[2] = 1.0
+    up.gds, up.cscheme, up.pscheme, up.viscos, up.sum_mode = 1.0, L.CSCHEME_ID["cds"], 0, LES.VISCOS, O.SUM_SEQ
+    up.tscheme, up.timestep, up.piso, up.const_mflux, up.gradPcmf = 2, LES.DT, 1, 1, 1e-3
+    a0 = np.zeros(c0.nnz)
+    o = O.calcuvw(g, c0, up, f, a0)
+    f["apv"][:], f["apw"][:] = o["apv"], o["apw"]
+    if dbg:
+        ea_, eapr_ = M.localize_matrix(g, c0, a0, me, cl)
+        print(rank, "DEBUG uvw: a", rel(dbg["A"], ea_), "apr", rel(dbg["APR"], eapr_), "apu", rel(dbg["APU"][:nl], o["apu"][me.cell_global]), "rU", rel(dbg["RU"][:nl], o["rU"][me.cell_global]),
+              "rW", rel(dbg["RW"][:nl], o["rW"][me.cell_global]), "spu", rel(dbg["SPU"][:nl], o["spu"][me.cell_global]), "u", rel(dbg["U"][:nl], f["u"][me.cell_global]), flush=True)
+    O.calcp_piso(g, c0, O.ICCG, 800, 1e-30, 1e-13, O.SUM_SEQ, 2, 1, 0, 1.0, True, 0.0, o["rU"], o["rV"], o["rW"], f["den"], f["apu"], f["apv"], f["apw"], a0,
+                 f["u"], f["v"], f["w"], f["p"], f["pp"], o["dPdxi"], f["flmass"])
+    if dbg:
+        print(rank, "DEBUG piso: u", rel(dbg["U2"][:nl], f["u"][me.cell_global]), "flmass", rel(dbg["FL2"] * sign, f["flmass"][me.face_global]), flush=True)
+    gplus, ustar_o = O.constant_mass_flow_forcing(g, LES.MAGUBAR, f["apu"], f["u"], O.SUM_SEQ)
+    O.modify_viscosity_sgs(g, O.SGS_VREMAN, 1.0, LES.VISCOS, f["u"], f["v"], f["w"], f["den"], f["vis"], f["visw"])
+    assert abs(ustar - ustar_o) < 1e-9 * abs(ustar_o) and abs(gP - (1e-3 + gplus)) < 1e-7 * abs(gplus), (ustar, ustar_o, gP, 1e-3 + gplus)
+    for k in ("u", "v", "w", "vis"):
+        assert rel(ctx.download(k.upper())[:nl], f[k][me.cell_global]) < 1e-7, ("periodic partitions", k, rel(ctx.download(k.upper())[:nl], f[k][me.cell_global]))
+    assert rel(ctx.download("FLMASS") * sign, f["flmass"][me.face_global]) < 1e-7, "periodic partitions: fluxes"
+    ctx.close()
+    dist.barrier()
+    print(f"MGPU_OK {rank} comm={ctx_mode_name(os.environ.get('FCP_COMM', ''))}", flush=True)
+    dist.destroy_process_group()
+
+
+def ctx_mode_name(want):
+    return want or "auto"
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group(backend="gloo", init_method="env://")
     if not EMU:
         torch.cuda.set_device(local)
+    if os.environ.get("FCP_TEST_MESH", "hex") == "periodic":
+        return periodic_main(rank, world, local)
     n = 12
     if os.environ.get("FCP_TEST_MESH", "hex") == "poly":       # BASELINE config 5 in miniature: polyhedral cells (up to 10 faces), Gauss/LSQ gradients + ICCG
         g = M.polyhedral_mesh(10, 8, 6, distort=0.15)

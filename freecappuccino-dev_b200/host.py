@@ -93,6 +93,12 @@ class Case:
         for comp in "uvw":
             for lvl in (1, 2, 3):
                 setattr(self, comp + "o" * lvl, z(nT))
+        # turbulence (variables.f90: te, ed, dnw; TurbModelData.f90:25-44; parameters.f90: densit, magUbar)
+        self.te, self.ed = z(nT), z(nT)
+        self.dnw = z(self.visw.size)
+        self.wallDistance = z(n)
+        self.densit, self.magUbar, self.urfVis = 1.0, 0.0, 1.0
+        self.TurbModelScalar = [dict(), dict()]            # per-scalar overrides of urf, gds, cScheme, lSolver, maxiter, tolAbs, tolRel
 
     def close(self):
         self.ctx.close()
@@ -251,6 +257,105 @@ class Case:
         self.a[...] = c.download("A")
         self.h[...] = c.download("H")
         return reps
+
+    # ---- row f3 / f4 procedures ----------------------------------------------------------------------------------------------
+    def _wall_slots(self, per_wall_face: np.ndarray) -> np.ndarray:
+        """x(iWall), wall faces counted in patch order (the reference's convention) -> a numTotal field with the values in the wall faces' boundary slots."""
+        m, n = self.mesh, self.mesh.numCells
+        out = np.zeros(m.numTotal)
+        iw = 0
+        for ib in range(m.numBoundaries):
+            if m.bctype[ib] == 0:
+                sl = n + m.patch_faces(ib) - m.numInnerFaces
+                out[sl] = per_wall_face[iw: iw + sl.size]
+                iw += sl.size
+        return out
+
+    def _from_wall_slots(self, field: np.ndarray, per_wall_face: np.ndarray):
+        m, n = self.mesh, self.mesh.numCells
+        iw = 0
+        for ib in range(m.numBoundaries):
+            if m.bctype[ib] == 0:
+                sl = n + m.patch_faces(ib) - m.numInnerFaces
+                per_wall_face[iw: iw + sl.size] = field[sl]
+                iw += sl.size
+
+    def updateBoundary(self, phi: np.ndarray):
+        """boundary/updateBoundary.f90"""
+        self.ctx.upload("S0", phi)
+        self.ctx.update_boundary("S0")
+        phi[...] = self.ctx.download("S0")
+
+    def wall_distance(self) -> np.ndarray:
+        """mesh/wall_distance.f90:55-133 -> wallDistance(numCells); prints the solver's report line like the reference."""
+        rep = self.ctx.wall_distance()
+        print(L.report_line(rep, "Wdis"), file=self.out)
+        self.wallDistance = self.ctx.download("WALLDIST", self.mesh.numCells)
+        return self.wallDistance
+
+    def constant_mass_flow_forcing(self):
+        """cappuccino/constant_mass_flow_forcing.f90: corrects u, updates gradPcmf, prints the reference's line."""
+        self.ctx.upload("U", self.u); self.ctx.upload("APU", self.apu)
+        self.gradPcmf, ustar = self.ctx.constant_mass_flow_forcing(self.magUbar, self.gradPcmf)
+        self.u[...] = self.ctx.download("U")
+        print(f"  Uncorrected Ubar = {ustar:13.6E} pressure gradient = {self.gradPcmf:13.6E}", file=self.out)
+
+    def _upload_turbulence_state(self):
+        c = self.ctx
+        for name in ("u", "v", "w", "den", "vis", "te", "ed"):
+            c.upload(name.upper(), getattr(self, name))
+        c.upload("FLMASS", self.flmass)
+        c.upload("VISW", self._wall_slots(self.visw)); c.upload("DNW", self._wall_slots(self.dnw))
+        for comp, gfield in (("U", "DUDXI"), ("V", "DVDXI"), ("W", "DWDXI")):       # modify_viscosity_turbulence.f90:28-33
+            c.grad(L.GRAD_GAUSS, comp, gfield)
+        c.calc_strain_and_vorticity()
+
+    def _scalar_settings(self, i: int) -> dict:
+        s = self.TurbModelScalar[i]                                                  # TurbModel%Scalar(i), TurbModelData.f90:25-33
+        grad = "lsq" if self.lstsq else "lsq_qr" if self.lstsq_qr else "wlsq" if self.lstsq_dm else "gauss"
+        return dict(solver=s.get("lSolver", "bicgstab"), maxiter=s.get("maxiter", 10), tol_abs=s.get("tolAbs", 1e-10), tol_rel=s.get("tolRel", 0.01),
+                    urf=s.get("urf", 0.7), gds=s.get("gds", 1.0), cscheme=s.get("cScheme", "linearUpwind"), grad_method=grad,
+                    limiter=L.LIMITER_ID.get(self.limiter, 0), tscheme=self.tscheme if self.tscheme in ("steady", "bdf", "bdf2") else "steady",
+                    timestep=self.timestep, viscos=self.viscos, densit=self.densit)
+
+    def _download_turbulence_state(self):
+        c = self.ctx
+        self.te[...], self.ed[...], self.vis[...] = c.download("TE"), c.download("ED"), c.download("VIS")
+        self._from_wall_slots(c.download("VISW"), self.visw)
+
+    def modify_viscosity_k_epsilon_rlzb(self):
+        """TurbulenceModels/k_epsilon_rlzb.f90:38-50: calcsc_tke, calcsc_epsilon, modify_mu_eff."""
+        c = self.ctx
+        self._upload_turbulence_state()
+        for i, (field, kind, prtr, nm) in enumerate((("TE", "tke_rlzb", 1.0, "k"), ("ED", "eps_rlzb", 1.0 / 1.2, "epsilon"))):
+            rep, lo, hi = c.calcsc(field, kind=kind, prtr=prtr, **self._scalar_settings(i))
+            print(L.report_line(rep, nm), file=self.out)
+            print(f"  {lo:11.4E} <= {nm} <= {hi:11.4E}", file=self.out)
+        c.modify_mu_eff_k_epsilon_rlzb(self.urfVis, self.viscos)
+        self._download_turbulence_state()
+
+    def modify_viscosity_k_omega_sst(self, LowRe: bool = False):
+        """TurbulenceModels/k_omega_SST.f90:62-88 (needs wall_distance() once before)."""
+        c = self.ctx
+        self._upload_turbulence_state()
+        wd = np.zeros(self.mesh.numTotal); wd[: self.mesh.numCells] = self.wallDistance
+        c.upload("WALLDIST", wd)
+        for i, (field, kind, nm) in enumerate((("TE", "tke_sst", "k"), ("ED", "omega_sst", "Omega"))):
+            rep, lo, hi = c.calcsc(field, kind=kind, lowre=LowRe, **self._scalar_settings(i))
+            print(L.report_line(rep, nm), file=self.out)
+            print(f"  {lo:11.4E} <= {nm} <= {hi:11.4E}", file=self.out)
+        c.modify_mu_eff_k_omega_sst(self.urfVis, self.viscos, self.densit, LowRe)
+        self._download_turbulence_state()
+
+    def modify_viscosity_sgs(self, model: str):
+        """TurbulenceModels/wale_sgs.f90:33 ('wale') / vremanSGS.f90:33 ('vreman')."""
+        c = self.ctx
+        for name in ("u", "v", "w", "den", "vis"):
+            c.upload(name.upper(), getattr(self, name))
+        c.modify_viscosity_sgs(model, self.urfVis, self.viscos)
+        self.vis[...] = c.download("VIS")
+        self._from_wall_slots(c.download("VISW"), self.visw)
+        print(f"  {(self.vis / self.viscos).min():11.4E} <= Viscosity ratio <= {(self.vis / self.viscos).max():11.4E}", file=self.out)
 
     # ---- src-par: exchange(phi), global_sum(x)   src-par/exchange.f90:3, global_sum_mpi.f90:4 ---------------------------------------
     def comm_init(self, rank: int, nranks: int, unique_id: Optional[bytes]):

@@ -67,3 +67,52 @@ def test_calcp_simple_module_api(orc):
     with pytest.raises(Exception):
         case.csrsolve("gauss-seidel", case.pp, case.su, 1, 0.0, 0.1, "p")
     case.close()
+
+
+def test_turbulence_procedures_of_the_module_api(orc):
+    """modify_viscosity_k_epsilon_rlzb / _k_omega_sst / _sgs, wall_distance, updateBoundary and constant_mass_flow_forcing called the way the
+    reference's main loop calls them (no arguments, module state): same state as driving the C-ABI directly (tests/test_gpu_scalar.py)."""
+    import test_gpu_scalar as T
+    m = cases.meshes()["channel_inout"]
+    g = T.scalar_inputs(m, orc)
+    out = io.StringIO()
+    case = H.Case(m, out=out)
+    n = m.numCells
+    for k in ("u", "v", "w", "den", "vis", "te", "ed", "flmass"):
+        getattr(case, k)[...] = g[k]
+    wall = np.concatenate([m.patch_faces(ib) - m.numInnerFaces for ib in range(m.numBoundaries) if m.bctype[ib] == M.BC_WALL])
+    case.visw[...] = g["visw"][wall]; case.dnw[...] = g["dnw"][wall]
+    case.viscos, case.urfVis = 0.01, 0.6
+    case.TurbModelScalar = [dict(maxiter=8, tolRel=1e-4, urf=0.7, gds=0.8, cScheme="muscl")] * 2
+    case.modify_viscosity_k_epsilon_rlzb()
+    text = out.getvalue()
+    assert re.search(r"<= k <=", text) and re.search(r"<= epsilon <=", text) and text.count("Solving for") == 2
+    # the same sequence through the oracle
+    c = orc.Csr(m)
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g.items()}
+    gU, gV, gW = orc.grad_gauss(m, f["u"]), orc.grad_gauss(m, f["v"]), orc.grad_gauss(m, f["w"])
+    f["magStrain"], _ = orc.calc_strain_and_vorticity(m, gU, gV, gW)
+    prm = T.oracle_params(orc, orc.SC_TKE_RLZB, "bicgstab", "muscl", "gauss", "none", "steady")
+    prm.prtr = 1.0
+    orc.calcsc(m, c, prm, f)
+    prm.kind, prm.prtr = orc.SC_EPS_RLZB, 1.0 / 1.2
+    orc.calcsc(m, c, prm, f)
+    orc.modify_mu_eff_rlzb(m, 0.6, 0.01, gU, gV, gW, f["te"], f["ed"], f["den"], f["u"], f["v"], f["w"], f["dnw"], f["vis"], f["visw"])
+    T.close(case.te, f["te"], "te", 1e-12); T.close(case.ed, f["ed"], "ed", 1e-10); T.close(case.vis, f["vis"], "vis", 1e-10)
+    T.close(case.visw, f["visw"][wall], "visw", 1e-10)
+    # wall distance, SST, SGS, forcing run through and keep the fields finite and positive
+    wd = case.wall_distance()
+    assert wd.min() > 0 and "Solving for Wdis" in out.getvalue()
+    case.ed[...] = 40.0 * case.ed
+    case.modify_viscosity_k_omega_sst()
+    case.modify_viscosity_sgs("wale")
+    case.apu[...] = 1.0
+    case.magUbar = 0.5
+    case.constant_mass_flow_forcing()
+    assert abs((m.vol[:n] * case.u[:n]).sum() / m.vol[:n].sum() - 0.5) < 1e-12 and "Uncorrected Ubar" in out.getvalue()
+    phi = np.random.default_rng(2).standard_normal(m.numTotal)
+    ref = phi.copy()
+    orc.update_boundary(m, ref)
+    case.updateBoundary(phi)
+    assert np.array_equal(phi, ref) and np.all(np.isfinite(case.vis)) and case.vis[:n].min() > 0
+    case.close()

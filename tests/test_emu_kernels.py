@@ -30,6 +30,13 @@ def test_parity_slice_under_emulation():
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_rows_f3_f4_slice_under_emulation():
+    """periodic pairs, the scalar transport template with both k-epsilon and SST, the SGS models and the chained LES channel steps"""
+    r = _run(["-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_scalar.py", "tests/test_gpu_zz_les_channel_loop.py", "-k",
+              "channel_periodic or tiny3 or les_channel"])
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("comm", ["p2p", "nccl"])
 def test_four_ranks_under_emulation(comm):
     """4 slab partitions (interior ranks own two process patches): halo plan, CUDA-IPC windows, the fused flag-in-data pushes,

@@ -996,6 +996,7 @@ extern "C" int fcp_solver_create(int32_t n, int32_t nnz, const int32_t *ia, cons
   if (rc != FCP_OK) { delete s; return rc; }
   FCP_TRY(dev_alloc(&s->a, (size_t)s->pat.nnzp));
   FCP_CUDA(cudaMemset(s->a, 0, sizeof(double) * (size_t)std::max<int64_t>(s->pat.nnzp, 1)));
+  FCP_CUDA(cudaStreamSynchronize(0));
   FCP_TRY(dev_alloc(&s->a_csr, (size_t)nnz));
   FCP_TRY(dev_alloc(&s->fi, (size_t)n));
   FCP_TRY(dev_alloc(&s->rhs, (size_t)n));

@@ -29,6 +29,7 @@ int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols) {
   FCP_TRY(dev_alloc(&ws.partials, (size_t)4 * ws.maxchunks));
   FCP_TRY(dev_alloc(&ws.counter, 1));
   FCP_CUDA(cudaMemset(ws.counter, 0, sizeof(unsigned int)));
+  FCP_CUDA(cudaStreamSynchronize(0));   // cudaMemset is asynchronous; the solver streams do not order with the legacy stream
   FCP_CUDA(cudaMalloc((void **)&ws.sc, sizeof(KrylovScalars)));
   FCP_CUDA(cudaMallocHost((void **)&ws.h_sc, sizeof(KrylovScalars)));
   FCP_CUDA(cudaEventCreateWithFlags(&ws.ev[0], cudaEventDisableTiming));
@@ -39,6 +40,7 @@ static int krylov_ws_need(KrylovWS &ws, double **p, size_t count) {
   if (*p) return FCP_OK;
   FCP_TRY(dev_alloc(p, count));
   FCP_CUDA(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(double)));
+  FCP_CUDA(cudaStreamSynchronize(0));
   (void)ws;
   return FCP_OK;
 }

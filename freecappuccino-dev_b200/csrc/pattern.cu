@@ -26,7 +26,12 @@ template <class T> int dev_alloc(T **dptr, size_t count) {
 }
 template <class T> int dev_upload(T **dptr, const T *h, size_t count) {
   FCP_TRY(dev_alloc(dptr, count));
-  if (count) FCP_CUDA(cudaMemcpy(*dptr, h, count * sizeof(T), cudaMemcpyHostToDevice));
+  if (count) {
+    // a pageable-source cudaMemcpy may return while the DMA is still in flight and the library's streams are cudaStreamNonBlocking
+    // (no implicit ordering with the legacy stream): wait for it here, uploads happen at set-up time only
+    FCP_CUDA(cudaMemcpy(*dptr, h, count * sizeof(T), cudaMemcpyHostToDevice));
+    FCP_CUDA(cudaStreamSynchronize(0));
+  }
   return FCP_OK;
 }
 template int dev_alloc<double>(double **, size_t);

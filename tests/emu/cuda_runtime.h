@@ -184,3 +184,25 @@ inline long max(long a, long b) { return a > b ? a : b; }
 inline double min(double a, double b) { return fmin(a, b); }
 inline double max(double a, double b) { return fmax(a, b); }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// FCP_EMU_LIBM_ULP=k: the device libm (pow, log, tanh, acos, cos, exp) need not round like glibc (CUDA documents 1-2 ulp for these in
+// double precision).  With the variable set every transcendental result is moved by up to k ulp in a direction picked from a hash of its
+// bits, so that the parity tests show which of their tolerances would not survive a libm that differs from the oracle's.
+#include <cmath>
+#include <complex>
+#include <map>
+#include <string>
+#include <vector>
+namespace emu { double libm_perturb(double x); }
+inline double emu_pow(double a, double b) { return emu::libm_perturb(::pow(a, b)); }
+inline double emu_log(double a) { return emu::libm_perturb(::log(a)); }
+inline double emu_exp(double a) { return emu::libm_perturb(::exp(a)); }
+inline double emu_tanh(double a) { return emu::libm_perturb(::tanh(a)); }
+inline double emu_acos(double a) { return emu::libm_perturb(::acos(a)); }
+inline double emu_cos(double a) { return emu::libm_perturb(::cos(a)); }
+#define pow(a, b) emu_pow(a, b)
+#define log(a) emu_log(a)
+#define exp(a) emu_exp(a)
+#define tanh(a) emu_tanh(a)
+#define acos(a) emu_acos(a)
+#define cos(a) emu_cos(a)

@@ -544,3 +544,23 @@ ncclResult_t ncclBroadcast(const void *send, void *recv, size_t count, ncclDataT
 }
 const char *ncclGetErrorString(ncclResult_t r) { return r == ncclSuccess ? "no error" : "error (NCCL emulation)"; }
 }
+
+// see cuda_runtime.h: FCP_EMU_LIBM_ULP
+#undef pow
+#undef log
+#undef exp
+#undef tanh
+#undef acos
+#undef cos
+namespace emu {
+double libm_perturb(double x) {
+  static const int k = getenv("FCP_EMU_LIBM_ULP") ? atoi(getenv("FCP_EMU_LIBM_ULP")) : 0;
+  if (k <= 0 || x == 0.0 || x == 1.0 || x == -1.0 || !std::isfinite(x)) return x;
+  unsigned long long b;
+  memcpy(&b, &x, 8);
+  b ^= b >> 33; b *= 0xff51afd7ed558ccdULL; b ^= b >> 33;
+  const int steps = (int)(b % (unsigned)(2 * k + 1)) - k;     // -k .. +k ulp
+  for (int i = 0; i < (steps < 0 ? -steps : steps); ++i) x = nextafter(x, steps < 0 ? -INFINITY : INFINITY);
+  return x;
+}
+}   // namespace emu

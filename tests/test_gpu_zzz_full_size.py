@@ -1,0 +1,193 @@
+"""GPU (B200): BASELINE config 3 at its FULL size -- the 256^3 hex cavity (16.7 M cells, 117 M non-zeros) of bench.py -- through
+size-independent properties, because the sequential oracle needs the better part of an hour for this case:
+
+  1. closed-domain identity sum(su) = 0 after the p' assembly (calcp_simple.f90:314);
+  2. the assembled matrix is symmetric BIT FOR BIT (a(icell_jcell) and a(jcell_icell) are the same `cap`, calcp_simple.f90:108-109), its
+     off-diagonals are negative and its diagonal positive, and every row sums to zero (a pure-Neumann pressure correction: A.1 = 0 to rounding, checked through the
+     device SpMV);
+  3. SpMV is linear: A(x + 2y) = Ax + 2Ay to rounding;
+  4. the DPCG solve converges by the reference's own L1 criterion, the residual re-computed ON THE HOST from the downloaded matrix, right-hand
+     side and solution (scipy CSR, independent of every device kernel but the assembly) agrees, and the iteration count equals the one both
+     arms of bench.py reported in round 1 for this exact case (1006; only asserted at n = 256);
+  5. after the flux correction the mass fluxes are discretely divergence free to the solver tolerance (host bincount over owner/neighbour);
+  6. `calcp_simple` as ONE call gives the same bits as the assemble / solve / correct sequence (idempotence of the path from identical inputs).
+
+Under the CPU emulation (no GPU in the container) the same test runs at n = 20 and additionally compares with the oracle bit for bit, which
+pins the test logic itself.  FCP_FULL_N overrides the size."""
+import os
+
+import numpy as np
+import pytest
+
+import bench
+from conftest import EMU
+from fcb200 import lib as L
+from fcb200 import mesh as M
+
+pytestmark = pytest.mark.gpu
+N = int(os.environ.get("FCP_FULL_N", "0")) or (20 if EMU else 256)
+ROUND1_DPCG_ITERS_256 = 1006      # profiles/r01_scaling.txt: GPU arm and CPU restatement arm alike
+
+
+def test_full_size_cavity_properties(fcp, orc):
+    m = M.block_partition_mesh((N, N, N), (1, 1, 1), 0)
+    n, Fi = m.numCells, m.numInnerFaces
+    f = bench.synthetic_fields(m)
+    ctx = L.Context(m)
+    for k in bench.INPUT_FIELDS:
+        ctx.upload(k.upper(), f[k])
+    ctx.fill("PP", 0.0)
+    for src, dst in (("U", "S0"), ("V", "S1"), ("W", "S2"), ("P", "S3")):
+        ctx.copy(dst, src)
+    own, nei = m.owner[:Fi] - 1, m.neighbour[:Fi] - 1
+
+    # ---- the path as separate calls -----------------------------------------------------------------------------------
+    ctx.gradp_and_sources("linear", "P")
+    ctx.assemble_pcorr_simple()
+    su = ctx.download("SU")[:n]
+    a = ctx.download("A")
+    ia, ja, diag, kpn, knp = ctx.csr_pattern()
+    assert ia[-1] - 1 == a.size == n + 2 * Fi
+    # 1
+    assert abs(su.sum()) <= 1e-10 * np.abs(su).sum(), (su.sum(), np.abs(su).sum())
+    # 2
+    assert np.array_equal(a[kpn - 1], a[knp - 1]), "p' matrix not symmetric bit for bit"
+    assert (a[kpn - 1] < 0.0).all() and (a[diag - 1] > 0.0).all()       # the reference's sign convention: a_nb = -cap', a_P = sum
+    ctx.fill("RU", 1.0)
+    ctx.spmv("RU", "RV")
+    rowsum = ctx.download("RV")[:n]
+    assert np.abs(rowsum).max() <= 1e-12 * np.abs(a[diag - 1]).max(), np.abs(rowsum).max()
+    # 3
+    rng = np.random.default_rng(7)
+    x, y = np.zeros(m.numTotal), np.zeros(m.numTotal)
+    x[:n], y[:n] = rng.standard_normal(n), rng.standard_normal(n)
+    ctx.upload("RU", x); ctx.spmv("RU", "RV"); ax = ctx.download("RV")[:n]
+    ctx.upload("RU", y); ctx.spmv("RU", "RV"); ay = ctx.download("RV")[:n]
+    ctx.upload("RU", x + 2.0 * y); ctx.spmv("RU", "RV"); axy = ctx.download("RV")[:n]
+    scale = np.abs(a[diag - 1]).max() * 4.0
+    assert np.abs(axy - (ax + 2.0 * ay)).max() <= 1e-13 * scale * 7
+    # 4
+    rep = ctx.csrsolve("dpcg", "PP", "SU", bench.MAXITER, 1e-30, bench.TOL_REL)
+    pp = ctx.download("PP")
+    assert 0 < rep.iters < bench.MAXITER
+    import scipy.sparse as sp
+    A = sp.csr_matrix((a, ja - 1, ia - 1), shape=(n, n))
+    r = su - A @ pp[:n]
+    r0 = np.abs(su).sum()
+    assert np.abs(r).sum() <= 1.5 * bench.TOL_REL * r0, (np.abs(r).sum(), r0)
+    assert rep.resl <= bench.TOL_REL * rep.res0 * (1 + 1e-12) or np.abs(r).sum() <= bench.TOL_REL * r0
+    print(f"cavity {N}^3: DPCG {rep.iters} iterations, host residual {np.abs(r).sum() / r0:.3e} of the initial one, |sum su|/sum|su| {abs(su.sum()) / r0:.1e}, "
+          f"max|A.1|/max diag {np.abs(rowsum).max() / np.abs(a[diag - 1]).max():.1e}")
+    if N == 256:
+        assert rep.iters == ROUND1_DPCG_ITERS_256, rep.iters
+    del A
+    # 5
+    ctx.correct_simple("linear", 0.3, 1)
+    flm = ctx.download("FLMASS")[:Fi]
+    div = np.bincount(own, flm, n) - np.bincount(nei, flm, n)
+    assert np.abs(div).sum() <= 5 * bench.TOL_REL * r0, (np.abs(div).sum(), r0)
+    got = {k: ctx.download(k) for k in ("U", "V", "W", "P", "PP", "FLMASS")}
+
+    # ---- 6: the same path as one call, from the same inputs ----------------------------------------------------------------
+    for src, dst in (("U", "S0"), ("V", "S1"), ("W", "S2"), ("P", "S3")):
+        ctx.copy(src, dst)
+    ctx.gradp_and_sources("linear", "P")
+    rep1 = ctx.calcp_simple(solver="dpcg", maxiter=bench.MAXITER, tol_abs=1e-30, tol_rel=bench.TOL_REL, urfp=0.3, npcor=1, pRefCell=1, zero_pp=True)[0]
+    assert rep1.iters == rep.iters
+    for k, v in got.items():
+        assert np.array_equal(ctx.download(k), v), f"{k}: one-call calcp_simple differs from assemble + solve + correct"
+    ctx.close()
+
+    # ---- small sizes only: the oracle itself ------------------------------------------------------------------------------
+    if N <= 48:
+        c = orc.Csr(m)
+        g = {k: v.copy() for k, v in f.items()}
+        g["pp"] = np.zeros(m.numTotal)
+        dP = np.zeros((m.numTotal, 3))
+        orc.gradp_and_sources(m, 0, g["p"], g["apu"], dP)
+        ao, suo, flmo = orc.assemble_pcorr(m, c, g["den"], g["u"], g["v"], g["w"], g["p"], g["pp"], dP, g["apu"])
+        repo = orc.solve(orc.DPCG, c.ia, c.ja, ao, c.diag, g["pp"], suo, bench.MAXITER, 1e-30, bench.TOL_REL, orc.SUM_TREE)
+        orc.correct_simple(m, c, 0, ao, g["den"], g["u"], g["v"], g["w"], g["p"], g["pp"], g["apu"], g["apv"], g["apw"], 0.3, 1, dP, flmo)
+        assert np.array_equal(a, ao) and np.array_equal(su, suo[:n]) and repo.iters == rep.iters
+        for k in ("u", "v", "w", "p", "pp"):
+            assert np.array_equal(got[k.upper()], g[k]), k
+        assert np.array_equal(got["FLMASS"][:Fi], flmo[:Fi])
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+CH = tuple(int(s) for s in os.environ.get("FCP_FULL_CHANNEL", "").split("x")) if os.environ.get("FCP_FULL_CHANNEL") else ((12, 10, 6) if EMU else (256, 252, 124))
+
+
+def test_full_size_periodic_channel_piso_step(fcp, orc):
+    """BASELINE config 4 at its full size: the 64x63x31 mesh of examples/channel395 refined four times per direction (256 x 252 x 124 = 8.0 M
+    cells, bump-graded in y, periodic in x and z, walls top and bottom), one PISO time step of the LES loop
+        calcuvw(piso, bdf2, cds, forcing) -> calcp_piso(iccg) -> constant_mass_flow_forcing -> modify_viscosity_sgs(vreman)
+    checked through size-independent properties: the corrected mass fluxes are discretely divergence free over inner faces AND periodic
+    pairs (the twin carries the pair's flux bit for bit); PISO's pressure has zero mean (calcp_piso.f90:330-333); the forcing restores the
+    bulk velocity exactly; the sub-grid viscosity is never below the molecular one.  Under the emulation the same step runs on a 12 x 10 x 6
+    channel and is also compared with the oracle."""
+    import test_gpu_zz_les_channel_loop as LC
+    import test_gpu_scalar as T
+    nx, ny, nz = CH
+    m = M.hex_mesh_fast(np.linspace(0, 2.0, nx + 1), M.bump_nodes(ny, 0.3), np.linspace(0, 1.0, nz + 1),
+                        dict(left="empty", right="periodic", back="empty", front="periodic"))
+    n, Fi = m.numCells, m.numInnerFaces
+    f = LC.initial_state(m)
+    VISCOS, MAGUBAR, DT = LC.VISCOS, LC.MAGUBAR, LC.DT
+    ctx = L.Context(m)
+    for k in ("u", "v", "w", "p", "pp", "den", "vis", "apu", "apv", "apw", "uo", "vo", "wo", "uoo", "voo", "woo"):
+        ctx.upload(k.upper(), f[k])
+    ctx.upload("VISW", T.bslot(m, f["visw"])); ctx.upload("FLMASS", f["flmass"]); ctx.upload("A", np.zeros(ctx.nnz))
+
+    def divergence(flm):
+        own, nei = m.owner[:Fi].astype(np.int64) - 1, m.neighbour.astype(np.int64) - 1
+        div = np.bincount(own, flm[:Fi], n) - np.bincount(nei, flm[:Fi], n)
+        for ib in range(m.numBoundaries):
+            pf = m.patch_faces(ib)
+            if m.bctype[ib] == M.BC_PERIODIC:
+                tf = np.arange(m.startFaceTwin[ib], m.startFaceTwin[ib] + m.nfaces[ib])
+                assert np.array_equal(flm[pf], flm[tf]), "the twin face must carry the periodic face's flux"
+                div += np.bincount(m.owner[pf].astype(np.int64) - 1, flm[pf], n) - np.bincount(m.owner[tf].astype(np.int64) - 1, flm[pf], n)
+            elif m.bctype[ib] == M.BC_WALL:
+                assert not flm[pf].any()
+        return div
+
+    div0 = np.abs(divergence(f["flmass"])).sum()
+    MAXIT, TOL = 5000, 1e-8
+    ureps = ctx.calcuvw(solver="bicgstab", maxiter=50, tol_abs=1e-30, tol_rel=1e-6, urf=(1.0, 1.0, 1.0), gds=1.0, cscheme="cds", pscheme="linear",
+                        tscheme="bdf2", timestep=DT, piso=True, const_mflux=True, gradPcmf=1e-3, viscos=VISCOS)
+    preps = ctx.calcp_piso(solver="iccg", maxiter=MAXIT, tol_abs=1e-30, tol_rel=TOL, urfp=1.0, ncorr=2, npcor=1, pscheme="linear", const_mflux=True)
+    assert all(0 < r.iters <= MAXIT for r in preps), [r.iters for r in preps]
+    flm = ctx.download("FLMASS")
+    div1 = np.abs(divergence(flm)).sum()
+    print(f"channel {nx}x{ny}x{nz}: U/V/W BiCGStab {[r.iters for r in ureps]}, p ICCG {[r.iters for r in preps]} iterations, sum|div| {div0:.3e} -> {div1:.3e}")
+    assert div1 <= 1e-5 * div0, (div1, div0)
+    p = ctx.download("P")[:n]
+    assert abs(p.sum() / n) <= 1e-10 * np.abs(p).max(), (p.sum() / n, np.abs(p).max())
+    g, ustar = ctx.constant_mass_flow_forcing(MAGUBAR, 1e-3)
+    u = ctx.download("U")[:n]
+    assert abs((m.vol[:n] * u).sum() / m.vol[:n].sum() - MAGUBAR) <= 1e-11 * MAGUBAR
+    ctx.modify_viscosity_sgs("vreman", 1.0, VISCOS)
+    vis = ctx.download("VIS")
+    assert np.isfinite(vis).all() and (vis[:n] >= VISCOS * (1 - 1e-14)).all()
+    got = {k: ctx.download(k.upper()) for k in ("u", "v", "w", "p")}
+    ctx.close()
+
+    if n <= 50000:      # small sizes: the oracle chain, as tests/test_gpu_zz_les_channel_loop.py does it
+        c = orc.Csr(m)
+        up = orc.OrcUvwParams()
+        up.solver, up.maxiter, up.tol_abs, up.tol_rel = orc.BICGSTAB, 50, 1e-30, 1e-6
+        up.urf[0] = up.urf[1] = up.urf[2] = 1.0
+        up.gds, up.cscheme, up.pscheme, up.viscos, up.sum_mode = 1.0, L.CSCHEME_ID["cds"], 0, VISCOS, orc.SUM_TREE
+        up.tscheme, up.timestep, up.piso, up.const_mflux, up.gradPcmf = 2, DT, 1, 1, 1e-3
+        a = np.zeros(c.nnz)
+        o = orc.calcuvw(m, c, up, f, a)
+        f["apv"][:], f["apw"][:] = o["apv"], o["apw"]
+        oreps = orc.calcp_piso(m, c, orc.ICCG, MAXIT, 1e-30, TOL, orc.SUM_TREE, 2, 1, 0, 1.0, True, 0.0, o["rU"], o["rV"], o["rW"], f["den"], f["apu"],
+                               f["apv"], f["apw"], a, f["u"], f["v"], f["w"], f["p"], f["pp"], o["dPdxi"], f["flmass"])[0]
+        assert [r.iters for r in preps] == [r.iters for r in oreps]
+        gplus, oustar = orc.constant_mass_flow_forcing(m, MAGUBAR, f["apu"], f["u"], orc.SUM_TREE)
+        assert g == 1e-3 + gplus and ustar == oustar
+        for k in ("u", "v", "w", "p"):
+            assert np.array_equal(got[k], f[k]), k
+        assert np.array_equal(flm, f["flmass"])

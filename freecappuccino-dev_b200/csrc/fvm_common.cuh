@@ -68,4 +68,4 @@ __device__ __forceinline__ int64_t diag_pos(const MeshView &m, int32_t c) {
 }
 
 
-#define FCP_GRID(n) fcp_nchunks(n), FCP_TPB, 0, ctx->stream
+#define FCP_GRID(n) (fcp_nchunks(n) > 0 ? fcp_nchunks(n) : 1), FCP_TPB, 0, ctx->stream   // never an empty grid (invalid configuration); the kernels guard c < n

@@ -41,7 +41,7 @@ extern thread_local dim3 blockDim, gridDim;
 static const int warpSize = 32;
 
 // ---- runtime API ------------------------------------------------------------------------------------------------
-enum cudaError_t { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNoDevice = 100, cudaErrorNotReady = 600, cudaErrorUnknown = 999 };
+enum cudaError_t { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorInvalidConfiguration = 9, cudaErrorNoDevice = 100, cudaErrorNotReady = 600, cudaErrorUnknown = 999 };
 struct emuStream;
 struct emuEvent;
 typedef emuStream *cudaStream_t;

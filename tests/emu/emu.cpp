@@ -203,10 +203,14 @@ unsigned long long now_ns() {
   return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
 
+static void emu_invalid_configuration();
 void launch_impl(const Cfg &c, const std::function<void()> &body, bool cooperative) {
   const int nthreads = (int)(c.b.x * c.b.y * c.b.z);
   const long long nblocks = (long long)c.g.x * c.g.y * c.g.z;
-  if (nthreads <= 0 || nblocks <= 0) return;   // a real launch would fail with "invalid configuration"; callers guard n == 0
+  if (nthreads <= 0 || nthreads > 1024 || nblocks <= 0 || c.g.y > 65535 || c.g.z > 65535 || c.g.x > 2147483647u) {
+    emu_invalid_configuration();   // a real launch fails with "invalid configuration" (empty grids included): the next FCP_CHECK_LAUNCH sees it
+    return;
+  }
   const uint3 save_b = blockIdx, save_t = threadIdx;
   const dim3 save_bd = blockDim, save_gd = gridDim;
   if (!cooperative) {
@@ -332,6 +336,7 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = emu::now_ns();
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)((double)(b->t - a->t) * 1e-6); return cudaSuccess; }
+namespace emu { static void emu_invalid_configuration() { g_last = cudaErrorInvalidConfiguration; } }
 cudaError_t cudaGetLastError() { cudaError_t e = g_last; g_last = cudaSuccess; return e; }
 cudaError_t cudaPeekAtLastError() { return g_last; }
 const char *cudaGetErrorString(cudaError_t e) {
@@ -339,6 +344,7 @@ const char *cudaGetErrorString(cudaError_t e) {
     case cudaSuccess: return "no error";
     case cudaErrorInvalidValue: return "invalid argument (emulation)";
     case cudaErrorMemoryAllocation: return "out of memory (emulation)";
+    case cudaErrorInvalidConfiguration: return "invalid configuration argument (emulation: empty grid or block, or a dimension over the limit)";
     default: return "error (emulation)";
   }
 }

@@ -614,6 +614,7 @@ contains
     use velocity, only: urfU, gdsU, cSchemeU, lSolverU, maxiterU, tolAbsU, tolRelU
     use gradients, only: lstsq, lstsq_qr, lstsq_dm, limiter
     use nablap, only: pscheme
+    use mhd, only: calcEpot                          ! MHD/mhd.f90:21
     type(fcp_uvw_params) :: prm
     type(fcp_report) :: rep(3)
     character(kind=c_char) :: line(256)

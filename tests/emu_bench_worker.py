@@ -30,6 +30,15 @@ def _unpinned_copy(a):
 
 
 bench.pinned_copy = _unpinned_copy
+if os.environ.get("FCP_EMU_BENCH_FAULT"):      # fault injection: the first solve over the peer-memory path fails on rank 1 like a timed-out wait would
+    from fcb200 import lib as _L
+    _orig = _L.Context.calcp_simple
+
+    def _faulty(self, *a, **k):
+        if self.comm_mode() == "p2p" and int(os.environ.get("RANK", "0")) == 1:
+            raise _L.FcpError("injected: peer-memory wait timed out")
+        return _orig(self, *a, **k)
+    _L.Context.calcp_simple = _faulty
 if len(sys.argv) > 1 and sys.argv[1] == "rows":          # tools/bench_rows.py (per-kernel timings of the rows beyond the headline step)
     sys.argv.pop(1)
     sys.path.insert(0, os.path.join(ROOT, "tools"))

@@ -63,3 +63,17 @@ def test_bench_control_flow_four_ranks_under_emulation():
     assert d["n_gpus"] == 4 and d["config"]["comm"] == "p2p" and d["gpu_launches"] > 0
     assert 0 < d["pcg"]["iters"] < 500 and d["pcg"]["resl"] < 1e-8 * d["pcg"]["res0"] * 1.0001
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+
+
+def test_bench_falls_back_to_nccl_when_the_peer_memory_path_fails():
+    """A peer-memory failure on ONE rank during the warm-up (injected) must make ALL ranks rebuild their contexts over NCCL and still print one
+    valid line that says so -- round 1 lost its 4- and 8-GPU measurements to exactly this kind of failure."""
+    import json
+    cmd = ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29622",
+           os.path.join(ROOT, "tests", "emu_bench_worker.py"), "--gpus", "2", "--cells", "16", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"]
+    r = _run(cmd, FCP_EMU_BENCH_FAULT="1")
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1, r.stdout[-3000:] + r.stderr[-3000:]
+    d = json.loads(lines[0])
+    assert d["config"]["comm"].startswith("nccl (fallback") and "repeating over NCCL" in r.stderr
+    assert 0 < d["pcg"]["iters"] < 500 and d["pcg"]["resl"] < 1e-8 * d["pcg"]["res0"] * 1.0001

@@ -21,7 +21,7 @@ module fcp_b200
 
   ! constants of include/fcp.h
   integer(c_int), parameter :: FCP_OK = 0
-  integer(c_int), parameter :: FCP_SOLVER_DPCG = 1, FCP_SOLVER_ICCG = 2, FCP_SOLVER_BICGSTAB = 3
+  integer(c_int), parameter :: FCP_SOLVER_DPCG = 1, FCP_SOLVER_ICCG = 2, FCP_SOLVER_BICGSTAB = 3, FCP_SOLVER_GAUSS_SEIDEL = 4
   integer(c_int), parameter :: FCP_GRAD_GAUSS = 0, FCP_GRAD_LSQ = 1, FCP_GRAD_LSQ_DM = 2, FCP_GRAD_LSQ_QR = 3
   integer(c_int), parameter :: FCP_LIMITER_NONE = 0, FCP_LIMITER_BARTH_JESPERSEN = 1, FCP_LIMITER_VENKATAKRISHNAN = 2, &
                                FCP_LIMITER_R3 = 3, FCP_LIMITER_MULTIDIMENSIONAL = 4
@@ -356,6 +356,7 @@ contains
     case ('dpcg');     solver_id = FCP_SOLVER_DPCG
     case ('iccg');     solver_id = FCP_SOLVER_ICCG
     case ('bicgstab'); solver_id = FCP_SOLVER_BICGSTAB
+    case ('gauss-seidel'); solver_id = FCP_SOLVER_GAUSS_SEIDEL
     case default
       write(*,'(3a)') ' libfcp_b200: linear solver "', trim(solver), '" is not on the accelerated path'
       stop

@@ -531,14 +531,18 @@ extern "C" int fcp_csrsolve(fcp_ctx *ctx, int solver, int fi_field, int rhs_fiel
 extern "C" int fcp_report_line(const fcp_report *rep, const char *chvar, char *buf, int buflen) {
   if (!rep || !buf) return FCP_EINVAL;
   // linear_solvers.f90:354-355 (dpcg), :540-541 (iccg), :781-782 (bicgstab); early return :267-268
-  const char *name = rep->solver == FCP_SOLVER_DPCG ? "PCG(Jacobi)" : rep->solver == FCP_SOLVER_ICCG ? "PCG(IC0)" : "BiCGStab(ILU(0))";
+  const char *name = rep->solver == FCP_SOLVER_DPCG ? "PCG(Jacobi)" : rep->solver == FCP_SOLVER_ICCG ? "PCG(IC0)" :
+                     rep->solver == FCP_SOLVER_GAUSS_SEIDEL ? "Gauss-Seidel" : "BiCGStab(ILU(0))";
   auto e103 = [](double v, char *out) {   // Fortran 1PE10.3
     char t[64];
     snprintf(t, sizeof(t), "%10.3E", v);
     strcpy(out, t);
   };
   char r0[64], r1[64];
-  if (rep->iters == 0 && rep->factor == 0.0) {
+  if (rep->solver == FCP_SOLVER_GAUSS_SEIDEL && rep->iters == 1 && rep->factor == 0.0) {   // :151-157: the early return comes after the first sweep
+    e103(rep->res0, r0);
+    snprintf(buf, buflen, "  %s:  Solving for %s, Initial residual = %s, Final residual = %s, No Iterations 1", name, chvar ? chvar : "", r0, r0);
+  } else if (rep->iters == 0 && rep->factor == 0.0) {
     e103(rep->res0, r0);
     snprintf(buf, buflen, "  %s:  Solving for %s, Initial residual = %s, Final residual = %s, No Iterations 0", name, chvar ? chvar : "", r0, r0);
   } else {

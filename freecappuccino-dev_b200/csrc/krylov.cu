@@ -122,7 +122,7 @@ int sell_spmv(const SellPattern &p, const double *a, const double *x, double *y,
 // scalar epilogues.  Single GPU: run by thread 0 of the last CTA of the producing kernel.  Multi GPU: the raw local
 // sums go through the rank-ordered cross-rank sum (comm.cu) and k_epilogue runs them (src-par/global_sum_mpi.f90).
 // ---------------------------------------------------------------------------------------------
-enum { EPI_NONE = 0, EPI_INIT_CG, EPI_PKAPK, EPI_CG_UPDATE, EPI_SK, EPI_INIT_BICG, EPI_UKRESO, EPI_VK, EPI_BICG_UPDATE };
+enum { EPI_NONE = 0, EPI_INIT_CG, EPI_PKAPK, EPI_CG_UPDATE, EPI_SK, EPI_INIT_BICG, EPI_UKRESO, EPI_VK, EPI_BICG_UPDATE, EPI_GS };
 
 __device__ __forceinline__ void conv_check(KrylovScalars *sc) {
   // linear_solvers.f90:336-346
@@ -191,6 +191,22 @@ __device__ void krylov_epilogue(int which, KrylovScalars *sc) {
       sc->bet = sc->red[1];
       sc->om = sc->bet * sc->gam / (sc->alf * sc->beto + FCP_SMALL);
       sc->beto = sc->bet;
+      break;
+    case EPI_GS:           // Gauss-Seidel, linear_solvers.f90:147-179: red0 = sum|res| of the sweep, red1 = sum|a_ii fi_i| (first sweep)
+      if (sc->iters == 0) {
+        sc->res0 = sc->red[0];
+        if (sc->res0 < sc->tol_abs) {          // :151-157 -- AFTER the first sweep has updated fi
+          sc->resl = sc->res0; sc->resor = sc->res0; sc->factor = 0.0; sc->iters = 1; sc->done = 1;
+          break;
+        }
+      }
+      sc->resl = sc->red[0];
+      sc->iters += 1;
+      if (sc->iters == 1) {
+        sc->factor = sc->red[1] + FCP_SMALL;
+        sc->resor = sc->res0 / sc->factor;
+      }
+      if (sc->resl / (sc->res0 + FCP_SMALL) < sc->tol_rel || sc->resl < sc->tol_abs || sc->iters >= sc->itr_max) sc->done = 1;
       break;
     default: break;
   }
@@ -719,6 +735,57 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply(SellView m, LevelView
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gauss-Seidel, linear_solvers.f90:96-201.  One sweep = the sequential loop :139-145
+//     res(i) = rhs(i) - sum_k a(k) fi(ja(k)) ;  fi(i) = fi(i) + res(i)/(a(diag(i)) + small)
+// in which row i sees the NEW values of the rows before it and the OLD values of itself and the rows after it.  Level scheduled over the
+// lower triangle like the IC(0) forward sweep; because a row of an earlier level may have a HIGHER index than a row that still needs its
+// old value, the new values go to a second array (xn) and the row sum reads xn for columns < i and fi for columns >= i -- in CSR (column)
+// order, so every row rounds like the reference's.  k_gs_norms then publishes xn as fi and reduces sum|res| and sum|a_ii fi_i|.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FCP_TPB) k_gs_sweep(SellView m, LevelView lv, const double *__restrict__ rhs, const double *fi, double *xn,
+                                                       double *__restrict__ res, double *__restrict__ adiag, const KrylovScalars *sc) {
+  if (sc->done) return;
+  cg::grid_group grid = cg::this_grid();
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int32_t L = 0; L < lv.nlevels; ++L) {
+    const int32_t b = lv.lev_ptr[L], e = lv.lev_ptr[L + 1];
+    for (int64_t q = b + gtid; q < e; q += gsz) {
+      const int32_t i = lv.lev_rows[q];
+      const int64_t base = m.slptr[i >> 5] + (i & 31);
+      const int32_t ri = m.rinfo[i];
+      const int32_t dpos = (ri >> 16) & 0xffff, len = ri & 0xffff;
+      double r = rhs[i];
+      for (int32_t k = 0; k < dpos; ++k) {
+        const int64_t pos = base + (int64_t)k * 32;
+        r = r - m.a[pos] * __ldcg(&xn[m.ja[pos]]);
+      }
+      for (int32_t k = dpos; k < len; ++k) {
+        const int64_t pos = base + (int64_t)k * 32;
+        r = r - m.a[pos] * fi[m.ja[pos]];
+      }
+      const double ad = m.a[base + (int64_t)dpos * 32];
+      res[i] = r;
+      adiag[i] = ad;
+      xn[i] = fi[i] + r / (ad + FCP_SMALL);
+    }
+    grid.sync();
+  }
+}
+__global__ void __launch_bounds__(FCP_TPB) k_gs_norms(int32_t n, double *__restrict__ fi, const double *__restrict__ xn, const double *__restrict__ res,
+                                                       const double *__restrict__ adiag, const KrylovScalars *sc, RedArgs ra) {
+  if (sc->done) return;
+  const bool first = (sc->iters == 0);
+  double s[2] = {0.0, 0.0};
+  FCP_ROW_LOOP(r, n) {
+    const double f = xn[r];
+    fi[r] = f;
+    s[0] = s[0] + fabs(res[r]);
+    if (first) s[1] = s[1] + fabs(adiag[r] * f);
+  }
+  finish_reduce<2>(s, ra);
+}
+
+// ---------------------------------------------------------------------------------------------
 // BiCGStab element kernels
 // ---------------------------------------------------------------------------------------------
 // reso = res ; pk = uk = 0 are set by the host (memset) ; this kernel: res = rhs - A fi, adiag, sums |res|, res*res
@@ -859,6 +926,28 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
   return FCP_OK;
 }
 
+static int launch_gs_sweep(SellPattern &p, const double *a, const double *rhs, const double *fi, double *xn, double *res, double *adiag,
+                           const KrylovScalars *sc, cudaStream_t st) {
+  if (p.n == 0) return FCP_OK;
+  static int grid = 0;
+  if (!grid) {
+    int dev = 0;
+    FCP_CUDA(cudaGetDevice(&dev));
+    FCP_TRY(coop_grid((const void *)k_gs_sweep, dev, &grid));
+  }
+  SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
+  LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
+  void *args[] = {&m, &lv, &rhs, &fi, &xn, &res, &adiag, &sc};
+#ifdef FCP_EMU
+  (void)args;
+  emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_gs_sweep, m, lv, rhs, fi, xn, res, adiag, sc);
+#else
+  FCP_CUDA(cudaLaunchCooperativeKernel((const void *)k_gs_sweep, dim3(grid), dim3(FCP_TPB), args, 0, st));
+#endif
+  FCP_LAUNCHED();
+  return FCP_OK;
+}
+
 // opt-in dynamic shared memory limit of the TMA kernels: one process-wide value, only ever raised
 static int tma_smem_limit(size_t smem) {
   static size_t configured = 0;
@@ -922,7 +1011,7 @@ static int fetch_scalars(KrylovWS &ws, cudaStream_t st) {
 int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const double *rhs, KrylovWS &ws, int32_t itr_max,
                  double tol_abs, double tol_rel, fcp_report *rep, cudaStream_t st, FcpComm *comm, fcp_ctx *ctx) {
   const int32_t n = p.n;
-  if (solver != FCP_SOLVER_DPCG && solver != FCP_SOLVER_ICCG && solver != FCP_SOLVER_BICGSTAB) {
+  if (solver != FCP_SOLVER_DPCG && solver != FCP_SOLVER_ICCG && solver != FCP_SOLVER_BICGSTAB && solver != FCP_SOLVER_GAUSS_SEIDEL) {
     fcp_set_error("csrsolve: unknown solver id %d", solver);
     return FCP_EINVAL;
   }
@@ -947,7 +1036,23 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
   if (n == 0 && !comm) return FCP_OK;
   const int BATCH = 16;
 
-  if (solver == FCP_SOLVER_DPCG) {
+  if (solver == FCP_SOLVER_GAUSS_SEIDEL) {
+    if (comm) { fcp_set_error("csrsolve: 'gauss-seidel' is a serial-tree solver (src-par has none); not available with a communicator"); return FCP_EINVAL; }
+    FCP_TRY(sell_build_levels(p, st));
+    if (itr_max <= 0) {                       // the DO loop :137 runs zero times: nothing is touched
+      ws.h_sc->done = 1;
+    } else {
+      for (int it = 0; it < itr_max;) {
+        for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
+          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_gs_sweep(p, a, rhs, fi, ws.pk, ws.res, ws.adiag, ws.sc, st)));
+          if (grid) { k_gs_norms<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.pk, ws.res, ws.adiag, ws.sc, L.red(EPI_GS)); FCP_LAUNCHED(); }
+        }
+        FCP_CHECK_LAUNCH();
+        FCP_TRY(fetch_scalars(ws, st));
+        if (ws.h_sc->done) break;
+      }
+    }
+  } else if (solver == FCP_SOLVER_DPCG) {
     FCP_TRY(L.halo(fi));
     if (grid) { k_cg_init<true><<<grid, FCP_TPB, 0, st>>>(n, m, fi, rhs, ws.res, ws.adiag, ws.pk, L.red(EPI_INIT_CG)); FCP_LAUNCHED(); FCP_CHECK_LAUNCH(); }
     FCP_TRY(L.post(EPI_INIT_CG, 2));

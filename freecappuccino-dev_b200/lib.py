@@ -22,8 +22,8 @@ _pi = C.POINTER(C.c_int32)
 
 # ---- constants of include/fcp.h -------------------------------------------------------------------------------
 OK, EINVAL, ECUDA, ENODEVICE, ENCCL, ESTATE = 0, -1, -2, -3, -4, -5
-SOLVER_DPCG, SOLVER_ICCG, SOLVER_BICGSTAB = 1, 2, 3
-SOLVER_ID = {"dpcg": SOLVER_DPCG, "iccg": SOLVER_ICCG, "bicgstab": SOLVER_BICGSTAB}
+SOLVER_DPCG, SOLVER_ICCG, SOLVER_BICGSTAB, SOLVER_GAUSS_SEIDEL = 1, 2, 3, 4
+SOLVER_ID = {"dpcg": SOLVER_DPCG, "iccg": SOLVER_ICCG, "bicgstab": SOLVER_BICGSTAB, "gauss-seidel": SOLVER_GAUSS_SEIDEL}
 GRAD_GAUSS, GRAD_LSQ, GRAD_LSQ_DM, GRAD_LSQ_QR = 0, 1, 2, 3
 GRAD_ID = {"gauss": GRAD_GAUSS, "lsq": GRAD_LSQ, "wlsq": GRAD_LSQ_DM, "lsq_qr": GRAD_LSQ_QR}          # option strings, gradients.f90:240-256
 LIMITER_NONE, LIMITER_BJ, LIMITER_VENKAT, LIMITER_R3, LIMITER_MDL = 0, 1, 2, 3, 4

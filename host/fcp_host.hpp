@@ -72,6 +72,7 @@ inline int solver_id(const std::string &s) {
   if (s == "dpcg") return FCP_SOLVER_DPCG;
   if (s == "iccg") return FCP_SOLVER_ICCG;
   if (s == "bicgstab") return FCP_SOLVER_BICGSTAB;
+  if (s == "gauss-seidel") return FCP_SOLVER_GAUSS_SEIDEL;
   std::fprintf(stderr, " libfcp_b200: linear solver \"%s\" is not on the accelerated path\n", s.c_str());
   std::exit(1);
 }

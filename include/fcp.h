@@ -40,7 +40,8 @@ enum { FCP_BC_WALL = 0, FCP_BC_INLET = 1, FCP_BC_OUTLET = 2, FCP_BC_SYMMETRY = 3
        FCP_BC_PRESSURE = 4, FCP_BC_PERIODIC = 5, FCP_BC_EMPTY = 6, FCP_BC_PROCESS = 7 };
 
 /* linear solvers: the strings of csrsolve, src/linearSolvers/linear_solvers.f90:40-91 */
-enum { FCP_SOLVER_DPCG = 1, FCP_SOLVER_ICCG = 2, FCP_SOLVER_BICGSTAB = 3 };
+enum { FCP_SOLVER_DPCG = 1, FCP_SOLVER_ICCG = 2, FCP_SOLVER_BICGSTAB = 3,
+       FCP_SOLVER_GAUSS_SEIDEL = 4 /* 'gauss-seidel', linear_solvers.f90:96-201; single GPU only (src-par has no such solver) */ };
 
 /* gradient methods: the logicals lstsq / lstsq_dm / (default) gauss of gradients.f90:118-138 */
 enum { FCP_GRAD_GAUSS = 0, FCP_GRAD_LSQ = 1, FCP_GRAD_LSQ_DM = 2, FCP_GRAD_LSQ_QR = 3 };

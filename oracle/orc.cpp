@@ -764,6 +764,37 @@ extern "C" void orc_dpcg(i32 n, i32 nnz, const i32 *ia, const i32 *ja, const dou
   rep->resl = resl; rep->factor = factor; rep->resor = resor; rep->iters = itr_used;
 }
 
+// Gauss-Seidel, linear_solvers.f90:96-201: every sweep computes res(i) = rhs(i) - sum_k a(k) fi(ja(k)) with the LATEST fi and updates fi(i)
+// right away (:139-145); the L1 norm of that running residual is the convergence measure.  Quirks kept: fi has already been updated when the
+// res0 < tol_abs early return is taken (:151-157); `resor` is left unassigned on that path (reported here as res0).
+extern "C" void orc_gauss_seidel(i32 n, i32 nnz, const i32 *ia, const i32 *ja, const double *a, const i32 *diag,
+                                 double *fi, const double *rhs, i32 itr_max, double tol_abs, double tol_rel, int mode, orc_report *rep) {
+  (void)nnz;
+  std::vector<double> res(n, 0.0);
+  Red R(mode, n);
+  double res0 = 0.0, resl = 0.0, factor = 0.0, resor = 0.0;
+  i32 itr_used = 0;
+  rep->res0 = 0.0; rep->resl = 0.0; rep->factor = 0.0; rep->resor = 0.0; rep->iters = 0;
+  for (i32 l = 1; l <= itr_max; ++l) {
+    for (i32 i = 0; i < n; ++i) {                                                 // :139-145
+      double r = rhs[i];
+      for (i32 k = ia[i]; k <= ia[i + 1] - 1; ++k) r = r - a[k - 1] * fi[ja[k - 1] - 1];
+      res[i] = r;
+      fi[i] = fi[i] + r / (a[diag[i] - 1] + SMALL);
+    }
+    if (l == 1) {
+      res0 = R.abs1(res.data(), n);                                               // :149
+      if (res0 < tol_abs) { rep->res0 = res0; rep->resl = res0; rep->resor = res0; rep->iters = 1; return; }   // :151-157
+    }
+    resl = R.abs1(res.data(), n);                                                 // :163
+    itr_used = itr_used + 1;
+    if (l == 1) { factor = R.absdiag(a, diag, fi, n) + SMALL; resor = res0 / factor; }   // :170-174
+    const double rsm = resl / (res0 + SMALL);
+    if (rsm < tol_rel || resl < tol_abs) break;                                   // :179
+  }
+  rep->res0 = res0; rep->resl = resl; rep->factor = factor; rep->resor = resor; rep->iters = itr_used;
+}
+
 // IC(0)/ILU(0)-diag preconditioner apply, linear_solvers.f90:458-475 (quirk Q4: zk/(d+small) in between)
 static void precond_apply(i32 n, const i32 *ia, const i32 *ja, const double *a, const i32 *diag, const double *d,
                           const double *rhs, double *zk) {
@@ -865,7 +896,10 @@ extern "C" void orc_bicgstab(i32 n, i32 nnz, const i32 *ia, const i32 *ja, const
 }
 
 extern "C" int orc_report_line(int solver, const char *chvar, const orc_report *rep, char *buf, int buflen) {
-  const char *name = solver == 1 ? "PCG(Jacobi)" : solver == 2 ? "PCG(IC0)" : "BiCGStab(ILU(0))";
+  const char *name = solver == 1 ? "PCG(Jacobi)" : solver == 2 ? "PCG(IC0)" : solver == 4 ? "Gauss-Seidel" : "BiCGStab(ILU(0))";
+  if (solver == 4 && rep->iters == 1 && rep->factor == 0.0)   // linear_solvers.f90:151-157
+    return snprintf(buf, buflen, "  %s:  Solving for %s, Initial residual = %10.3E, Final residual = %10.3E, No Iterations 1",
+                    name, chvar, rep->res0, rep->res0);
   if (rep->iters == 0 && rep->factor == 0.0)     // early return lines :267-268 (no iteration count digits)
     return snprintf(buf, buflen, "  %s:  Solving for %s, Initial residual = %10.3E, Final residual = %10.3E, No Iterations 0",
                     name, chvar, rep->res0, rep->res0);
@@ -1124,6 +1158,7 @@ static void solve_any(int solver, i32 n, i32 nnz, const i32 *ia, const i32 *ja, 
                       const double *rhs, i32 itr_max, double tol_abs, double tol_rel, int mode, orc_report *rep) {
   if (solver == 1) orc_dpcg(n, nnz, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, mode, rep);
   else if (solver == 2) orc_iccg(n, nnz, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, mode, rep);
+  else if (solver == 4) orc_gauss_seidel(n, nnz, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, mode, rep);
   else orc_bicgstab(n, nnz, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, mode, rep);
 }
 

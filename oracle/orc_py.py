@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 SUM_SEQ, SUM_TREE = 0, 1
-DPCG, ICCG, BICGSTAB = 1, 2, 3
+DPCG, ICCG, BICGSTAB, GAUSS_SEIDEL = 1, 2, 3, 4
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)
@@ -246,7 +246,7 @@ def solve(solver: int, ia, ja, a, diag, fi, rhs, itr_max, tol_abs, tol_rel, sum_
     """fi is updated in place (first n entries)."""
     n, nnz = ia.size - 1, ja.size
     rep = OrcReport()
-    fn = {DPCG: lib().orc_dpcg, ICCG: lib().orc_iccg, BICGSTAB: lib().orc_bicgstab}[solver]
+    fn = {DPCG: lib().orc_dpcg, ICCG: lib().orc_iccg, BICGSTAB: lib().orc_bicgstab, GAUSS_SEIDEL: lib().orc_gauss_seidel}[solver]
     fn(C.c_int32(n), C.c_int32(nnz), _i(ia), _i(ja), _d(a), _i(diag), _d(fi), _d(rhs), C.c_int32(itr_max),
        C.c_double(tol_abs), C.c_double(tol_rel), C.c_int(sum_mode), C.byref(rep))
     return rep

@@ -36,6 +36,28 @@ def test_5x5_systems(orc, gold, system, solver, f32):
     assert np.abs(r).sum() < 1e-6 * np.abs(b).sum()
 
 
+def test_gauss_seidel_on_the_spd_5x5_system(orc, gold):
+    """The same SPD system through the oracle's Gauss-Seidel (linear_solvers.f90:96-201): it converges to the printed solution, the residual
+    norm falls monotonically (SPD matrix) and the early return is taken AFTER the first sweep has updated fi (:139-157)."""
+    g = gold["spd"]
+    a = np.array(g["a"]); b = np.array(g["b"])
+    ia = np.array(gold["ioffset"], np.int32); ja = np.array(gold["ja"], np.int32); diag = np.array(gold["diag"], np.int32)
+    x = np.zeros(5)
+    rep = orc.solve(orc.GAUSS_SEIDEL, ia, ja, a, diag, x, b, 5000, 1e-13, 1e-11)
+    assert 1 < rep.iters < 5000
+    assert np.allclose(x, g["x"], atol=0.0051)
+    norms = []
+    for its in range(1, 6):
+        y = np.zeros(5)
+        norms.append(orc.solve(orc.GAUSS_SEIDEL, ia, ja, a, diag, y, b, its, 1e-300, 1e-300).resl)
+    assert all(n1 < n0 for n0, n1 in zip(norms, norms[1:]))
+    y = np.zeros(5)
+    r1 = orc.solve(orc.GAUSS_SEIDEL, ia, ja, a, diag, y, b, 50, 1e30, 1e-11)
+    assert r1.iters == 1 and np.abs(y).max() > 0 and "No Iterations 1" in orc.report_line(orc.GAUSS_SEIDEL, "x", r1)
+    # the first unknown of the first sweep by hand: fi(1) = 0 + (b(1) - 0)/(a(diag(1)) + small)
+    assert y[0] == b[0] / (a[diag[0] - 1] + np.float64(np.float32(1e-20)))
+
+
 def test_gauss_gradient_of_linear_field_is_111(orc):
     """test/testFieldOperations/testFieldOperations.f90:137-160 on the reference's own mesh."""
     m = cases.golden_mesh()

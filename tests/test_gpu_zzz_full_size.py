@@ -191,3 +191,91 @@ def test_full_size_periodic_channel_piso_step(fcp, orc):
         for k in ("u", "v", "w", "p"):
             assert np.array_equal(got[k], f[k]), k
         assert np.array_equal(flm, f["flmass"])
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+def _poly_size():
+    if os.environ.get("FCP_FULL_POLY"):
+        return int(os.environ["FCP_FULL_POLY"])
+    if EMU:
+        return 8
+    try:
+        import psutil
+        big = psutil.virtual_memory().total >= 96e9        # the generator peaks at ~28 GB of host memory for 20 M polyhedra
+    except Exception:
+        big = False
+    return 342 if big else 272
+
+
+def test_full_size_polyhedral_gradients_and_iccg(fcp, orc):
+    """BASELINE config 5 at its size: ~20 M ten-faced polyhedra (342^3 hexahedra merged pairwise in a staggered brick pattern, `mesh.polyhedral_mesh_fast`;
+    10 M on a host with less than 96 GB), Gauss and least-squares gradients and an IC(0)-CG Poisson solve, through size-independent properties:
+    the discrete Gauss theorem (sum over cells of vol * grad(phi) = sum over BOUNDARY faces of phi_f S_f, the inner faces cancel pairwise); the
+    least-squares gradients (row-2 bug Q1 switched off) reproduce a linear field exactly in every cell (the weighted variant in every cell without a
+    boundary face: quirk Q2); the Laplacian matrix is symmetric bit for
+    bit with a dominant diagonal; the ICCG solution satisfies the system (residual re-computed on the host) and is positive (discrete maximum
+    principle for -lap(phi) = 1 with phi = 0 on the boundary: the wall-distance Poisson problem of mesh/wall_distance.f90:96-104).  Under the
+    emulation: 8^3 and the oracle, bit for bit."""
+    nx = _poly_size()
+    m = M.polyhedral_mesh_fast(nx)
+    n, Fi, B = m.numCells, m.numInnerFaces, m.numBoundaryFaces
+    ctx = L.Context(m)
+    lin = lambda x, y, z: 1.0 + 2.0 * x - 3.0 * y + 0.5 * z       # noqa: E731
+    phi = m.boundary_values_of(lin)
+    smooth = m.boundary_values_of(lambda x, y, z: np.sin(2.0 * x) * np.cos(3.0 * y) + z * z)
+    # ---- Gauss theorem
+    ctx.upload("S0", smooth)
+    ctx.grad(L.GRAD_GAUSS, "S0", "G0")
+    g = ctx.download("G0")[:n]
+    lhs = (m.vol[:n, None] * g).sum(0)
+    rhs = np.array([(smooth[n:] * ar[Fi:]).sum() for ar in (m.arx, m.ary, m.arz)])
+    assert np.abs(lhs - rhs).max() <= 1e-9 * np.abs(smooth).max(), (lhs, rhs)       # surface area of the unit box = 6
+    # ---- least squares, linear field
+    ctx.upload("S0", phi)
+    for meth in (L.GRAD_LSQ, L.GRAD_LSQ_DM):
+        ctx.create_lsq_grad_matrix(meth)
+        ctx.grad(meth, "S0", "G0", lsq_row2_reference=False)
+        gl = ctx.download("G0")[:n]
+        err = np.abs(gl - np.array([2.0, -3.0, 0.5])).max(1)
+        if meth == L.GRAD_LSQ_DM:       # quirk Q2 (gradients.f90:1459: the boundary-face weight reads xf(i) instead of xf(iface)) spoils the boundary cells
+            err[m.owner[Fi:].astype(np.int64) - 1] = 0.0
+        assert err.max() <= 1e-9, (meth, err.max())
+    g_lsq = gl
+    # ---- Poisson problem of the wall-distance pipeline: laplacian(mu = -1, phi = 0), su = vol
+    ctx.fill("VIS", -1.0)
+    ctx.fill("S1", 0.0)
+    ctx.upload("SU", np.concatenate([m.vol[:n], np.zeros(B)]))
+    ctx.laplacian("VIS", "S1")
+    a = ctx.download("A")
+    su = ctx.download("SU")[:n]
+    ia, ja, diag, kpn, knp = ctx.csr_pattern()
+    assert np.array_equal(a[kpn - 1], a[knp - 1]) and (a[kpn - 1] < 0.0).all()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((a, ja - 1, ia - 1), shape=(n, n))
+    offsum = np.asarray(abs(A).sum(1)).ravel() - np.abs(a[diag - 1])
+    assert (a[diag - 1] >= offsum * (1 - 1e-12)).all()
+    ctx.fill("PP", 0.0)
+    MAXIT, TOL = 5000, 1e-8
+    rep = ctx.csrsolve("iccg", "PP", "SU", MAXIT, 1e-30, TOL)
+    x = ctx.download("PP")[:n]
+    r0 = np.abs(su).sum()
+    res = np.abs(su - A @ x).sum()
+    print(f"polyhedral {nx}^3/2: {n} cells, {Fi} inner faces, nnz {a.size}; ICCG {rep.iters} iterations, host residual {res / r0:.3e} of the initial one")
+    assert 0 < rep.iters < MAXIT and res <= 1.5 * TOL * r0, (rep.iters, res, r0)
+    assert x.min() > 0.0
+    ctx.close()
+
+    if n <= 50000:
+        ms = M.polyhedral_mesh(nx, distort=0.0)             # the point-based generator: same topology, geometry to rounding
+        assert np.array_equal(ms.owner, m.owner) and np.array_equal(ms.neighbour, m.neighbour)
+        np.testing.assert_allclose(ms.Df, m.Df, rtol=1e-11)
+        c = orc.Csr(m)
+        assert np.array_equal(orc.grad_gauss(m, smooth)[:n], g)
+        D = orc.create_matrix_lsq(m, True)
+        assert np.array_equal(orc.grad_lsq(m, True, D, phi, row2_correct=True)[:n], g_lsq)
+        suo = m.vol[:n].copy()
+        ao = orc.laplacian(m, c, np.full(m.numTotal, -1.0), np.zeros(m.numTotal), suo)
+        assert np.array_equal(ao, a) and np.array_equal(suo, su)
+        xo = np.zeros(m.numTotal)
+        ro = orc.solve(orc.ICCG, c.ia, c.ja, ao, c.diag, xo, suo, MAXIT, 1e-30, TOL, orc.SUM_TREE)
+        assert ro.iters == rep.iters and np.array_equal(xo[:n], x)

@@ -41,3 +41,21 @@ def test_srcpar_partition_tree_round_trip(tmp_path, P):
             np.testing.assert_allclose(getattr(back, k)[:n], getattr(part, k)[:n], rtol=0, atol=1e-13)
         np.testing.assert_allclose(back.facint, part.facint, rtol=0, atol=1e-12)
         np.testing.assert_allclose(back.Df, part.Df, rtol=1e-12)
+
+
+def test_polyhedral_mesh_fast_equals_the_point_based_generator():
+    """`polyhedral_mesh_fast` merges the hexahedral arrays directly (no points, no face-node lists); topology and face order must be identical to
+    `polyhedral_mesh(distort=0)` and every geometric array equal to rounding."""
+    import numpy as np
+    from fcb200 import mesh as M
+    for dims in ((6, 6, 6), (7, 5, 4), (8, 9, 3), (5, 4, 7)):
+        a, b = M.polyhedral_mesh(*dims, distort=0.0), M.polyhedral_mesh_fast(*dims)
+        assert (a.numCells, a.numInnerFaces, a.numBoundaryFaces) == (b.numCells, b.numInnerFaces, b.numBoundaryFaces)
+        assert np.array_equal(a.owner, b.owner) and np.array_equal(a.neighbour, b.neighbour)
+        assert np.array_equal(a.startFace, b.startFace) and np.array_equal(a.nfaces, b.nfaces) and np.array_equal(a.bctype, b.bctype)
+        for k in ("arx", "ary", "arz", "xf", "yf", "zf", "facint", "Df", "vol"):
+            np.testing.assert_allclose(getattr(a, k), getattr(b, k), rtol=1e-11, atol=1e-13, err_msg=k)
+        for k in ("xc", "yc", "zc"):
+            np.testing.assert_allclose(getattr(a, k)[: a.numCells], getattr(b, k)[: a.numCells], rtol=1e-11, atol=1e-13, err_msg=k)
+        rows = np.bincount(np.concatenate([b.owner[: b.numInnerFaces], b.neighbour]) - 1, minlength=b.numCells)
+        assert rows.max() == 10 or min(dims) < 3          # interior polyhedra have ten neighbours

@@ -25,11 +25,41 @@ from fcb200 import lib as L
 from fcb200 import mesh as M
 
 pytestmark = pytest.mark.gpu
+
+
+def _host_memory_available() -> float:
+    """bytes this process may still use: the smaller of the machine's available memory and what the container's cgroup leaves (a full-size mesh
+    must never get the test process killed -- the run would lose every result before it)"""
+    avail = float("inf")
+    try:
+        import psutil
+        avail = float(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    for lim, use in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            with open(lim) as fh:
+                t = fh.read().strip()
+            if t != "max":
+                with open(use) as fh:
+                    avail = min(avail, float(t) - float(fh.read().strip()))
+        except (OSError, ValueError):
+            pass
+    return avail
+
+
+def _need(gb: float):
+    if not EMU and _host_memory_available() < gb * 1e9:
+        pytest.skip(f"needs about {gb:.0f} GB of host memory for the full-size mesh; {_host_memory_available() / 1e9:.0f} GB available")
+
+
 N = int(os.environ.get("FCP_FULL_N", "0")) or (20 if EMU else 256)
 ROUND1_DPCG_ITERS_256 = 1006      # profiles/r01_scaling.txt: GPU arm and CPU restatement arm alike
 
 
 def test_full_size_cavity_properties(fcp, orc):
+    _need(24 * (N / 256.0) ** 3)
     m = M.block_partition_mesh((N, N, N), (1, 1, 1), 0)
     n, Fi = m.numCells, m.numInnerFaces
     f = bench.synthetic_fields(m)
@@ -129,6 +159,7 @@ def test_full_size_periodic_channel_piso_step(fcp, orc):
     import test_gpu_zz_les_channel_loop as LC
     import test_gpu_scalar as T
     nx, ny, nz = CH
+    _need(16 * nx * ny * nz / 8.0e6)
     m = M.hex_mesh_fast(np.linspace(0, 2.0, nx + 1), M.bump_nodes(ny, 0.3), np.linspace(0, 1.0, nz + 1),
                         dict(left="empty", right="periodic", back="empty", front="periodic"))
     n, Fi = m.numCells, m.numInnerFaces
@@ -199,12 +230,7 @@ def _poly_size():
         return int(os.environ["FCP_FULL_POLY"])
     if EMU:
         return 8
-    try:
-        import psutil
-        big = psutil.virtual_memory().total >= 96e9        # the generator peaks at ~28 GB of host memory for 20 M polyhedra
-    except Exception:
-        big = False
-    return 342 if big else 272
+    return 342 if _host_memory_available() >= 96e9 else 272     # the generator peaks at ~28 GB of host memory for 20 M polyhedra, ~14 GB for 10 M
 
 
 def test_full_size_polyhedral_gradients_and_iccg(fcp, orc):
@@ -217,6 +243,7 @@ def test_full_size_polyhedral_gradients_and_iccg(fcp, orc):
     principle for -lap(phi) = 1 with phi = 0 on the boundary: the wall-distance Poisson problem of mesh/wall_distance.f90:96-104).  Under the
     emulation: 8^3 and the oracle, bit for bit."""
     nx = _poly_size()
+    _need(45 * (nx / 342.0) ** 3)
     m = M.polyhedral_mesh_fast(nx)
     n, Fi, B = m.numCells, m.numInnerFaces, m.numBoundaryFaces
     ctx = L.Context(m)

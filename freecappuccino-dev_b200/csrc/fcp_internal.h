@@ -75,6 +75,11 @@ struct SellPattern {
   int32_t *blev_ptr = nullptr, *blev_rows = nullptr;
   std::vector<int32_t> h_blev_ptr;
   int32_t *tpos = nullptr;      // [nnzp] SELL position of the transposed entry (ILU(0) of BiCGStab), lazily
+  // barrier-free sweeps (FCP_SWEEP=flags): the same level order with every level padded to whole warps (-1 = no row), one ready flag per row
+  int32_t *plev_rows = nullptr, *pblev_rows = nullptr;
+  int32_t nplev = 0, npblev = 0;   // padded lengths (multiples of 32)
+  int32_t *ready = nullptr;        // [n] epoch of the last sweep that finished the row
+  int32_t sweep_epoch = 0;         // host counter: a preconditioner apply uses epoch+1 (forward) and epoch+2 (backward)
 };
 
 // cell -> faces gather lists, SELL-32 as well (ent, other, slot share the layout)

@@ -735,6 +735,97 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply(SellView m, LevelView
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same preconditioner apply WITHOUT a grid barrier per level (FCP_SWEEP=flags; default is the barrier version above until this one
+// has been timed on a B200).  Rows are taken in level order, 32 consecutive list positions per warp, tiles dealt round-robin to the resident
+// warps; a row spins on the ready flag (= epoch of the sweep that finished it) of every row it depends on.  Every level starts on a warp
+// boundary (pattern.cu), so a dependency always lies in an EARLIER tile: the lowest unfinished tile never waits, all warps are co-resident
+// (cooperative launch), hence no deadlock.  One grid barrier remains between the forward and the backward sweep (the backward result
+// overwrites zk(i), which later forward rows still read).  Per-row arithmetic and summation order are those of k_precond_apply: same bits.
+// ---------------------------------------------------------------------------------------------
+struct FlagView {
+  const int32_t *prow, *pbrow;
+  int32_t np, nbp;
+  int32_t *ready;
+  int32_t epoch;
+};
+// spins until *flag >= target; gives up after ~2 s (a scheduling assumption that does not hold must not hang the GPU): raises sc->pad, which
+// krylov_solve turns into an error
+__device__ __forceinline__ void sweep_wait(const int32_t *flag, int32_t target, const KrylovScalars *sc) {
+#ifdef FCP_EMU
+  (void)sc;
+  while (__atomic_load_n(flag, __ATOMIC_ACQUIRE) < target) { emu::yield(); emu::os_yield(); }
+#else
+  int32_t v;
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= target) break;
+    if ((++spins & 1023u) == 0u) {
+      if (*(volatile const int32_t *)&sc->pad) break;
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (!t0) t0 = t;
+      else if (t - t0 > 2000000000ull) { *(volatile int32_t *)&const_cast<KrylovScalars *>(sc)->pad = 1; break; }
+    }
+  }
+#endif
+}
+__device__ __forceinline__ void sweep_post(int32_t *flag, int32_t epoch) {
+#ifdef FCP_EMU
+  __atomic_store_n(flag, epoch, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+#endif
+}
+__global__ void __launch_bounds__(FCP_TPB) k_precond_apply_flags(SellView m, FlagView fv, const int32_t *__restrict__ llen, const double *__restrict__ d,
+                                                                  const double *__restrict__ rhs, double *zk, const KrylovScalars *sc) {
+  if (sc->done) return;
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int32_t ef = fv.epoch, eb = fv.epoch + 1;
+  for (int64_t t = warp; t * 32 < fv.np; t += nwarps) {
+    const int32_t i = fv.prow[t * 32 + lane];
+    if (i >= 0) {
+      const int64_t base = m.slptr[i >> 5] + (i & 31);
+      const int32_t dpos = (m.rinfo[i] >> 16) & 0xffff;
+      double z = rhs[i];
+      for (int32_t k = 0; k < dpos; ++k) {
+        const int64_t pos = base + (int64_t)k * 32;
+        const int32_t j = m.ja[pos];
+        sweep_wait(fv.ready + j, ef, sc);
+        z = z - m.a[pos] * __ldcg(&zk[j]);
+      }
+      zk[i] = z * d[i];
+      sweep_post(fv.ready + i, ef);
+    }
+    __syncwarp();
+  }
+  grid.sync();
+  for (int64_t t = warp; t * 32 < fv.nbp; t += nwarps) {
+    const int32_t i = fv.pbrow[t * 32 + lane];
+    if (i >= 0) {
+      const int64_t base = m.slptr[i >> 5] + (i & 31);
+      const int32_t ri = m.rinfo[i];
+      const int32_t dpos = (ri >> 16) & 0xffff;
+      const int32_t len = llen ? llen[i] : (ri & 0xffff);
+      const double di = d[i];
+      double z = __ldcg(&zk[i]) / (di + FCP_SMALL);
+      for (int32_t k = dpos + 1; k < len; ++k) {
+        const int64_t pos = base + (int64_t)k * 32;
+        const int32_t j = m.ja[pos];
+        sweep_wait(fv.ready + j, eb, sc);
+        z = z - m.a[pos] * __ldcg(&zk[j]);
+      }
+      zk[i] = z * di;
+      sweep_post(fv.ready + i, eb);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gauss-Seidel, linear_solvers.f90:96-201.  One sweep = the sequential loop :139-145
 //     res(i) = rhs(i) - sum_k a(k) fi(ja(k)) ;  fi(i) = fi(i) + res(i)/(a(diag(i)) + small)
 // in which row i sees the NEW values of the rows before it and the OLD values of itself and the rows after it.  Level scheduled over the
@@ -915,6 +1006,36 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
   SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
   LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
   const int32_t *llen = p.llen;
+  const char *sweep_env = getenv("FCP_SWEEP");       // read per call: tests and A/B timings switch it inside one process
+  const bool use_flags = sweep_env && !strcmp(sweep_env, "flags");
+  static bool announced = false;
+  if (use_flags && !announced) {
+    announced = true;
+    fprintf(stderr, "libfcp_b200: FCP_SWEEP=flags: IC(0)/ILU(0) sweeps wait on per-row ready flags instead of a grid barrier per level\n");
+  }
+  if (use_flags) {
+    static int fgrid = 0;
+    if (!fgrid) {
+      int dev = 0;
+      FCP_CUDA(cudaGetDevice(&dev));
+      FCP_TRY(coop_grid((const void *)k_precond_apply_flags, dev, &fgrid));
+    }
+    if (p.sweep_epoch > 2000000000) {          // epochs are int32: start over (once per ~10^9 applies)
+      FCP_CUDA(cudaMemsetAsync(p.ready, 0, sizeof(int32_t) * (size_t)std::max(p.n, 1), st));
+      p.sweep_epoch = 0;
+    }
+    FlagView fv{p.plev_rows, p.pblev_rows, p.nplev, p.npblev, p.ready, p.sweep_epoch + 1};
+    p.sweep_epoch += 2;
+    void *fargs[] = {&m, &fv, &llen, &d, &rhs, &zk, &sc};
+#ifdef FCP_EMU
+    (void)fargs;
+    emu::launch_coop(emu::Cfg(fgrid, FCP_TPB, 0, st), k_precond_apply_flags, m, fv, llen, d, rhs, zk, sc);
+#else
+    FCP_CUDA(cudaLaunchCooperativeKernel((const void *)k_precond_apply_flags, dim3(fgrid), dim3(FCP_TPB), fargs, 0, st));
+#endif
+    FCP_LAUNCHED();
+    return FCP_OK;
+  }
   void *args[] = {&m, &lv, &llen, &d, &rhs, &zk, &sc};
 #ifdef FCP_EMU
   (void)args;
@@ -1135,6 +1256,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     }
   }
   FCP_TRY(fetch_scalars(ws, st));
+  if (ws.h_sc->pad) { fcp_set_error("csrsolve: a barrier-free sweep (FCP_SWEEP=flags) gave up waiting for a row it depends on"); return FCP_ECUDA; }
   if (comm) FCP_TRY(L.halo(fi));   // src-par/dpcg.f90:183  call exchange(fi)
   if (cd) {
     comm_pk_advance(comm, ws.h_sc->iters);

@@ -111,6 +111,7 @@ int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, 
 void sell_free(SellPattern &p) {
   cudaFree(p.slptr); cudaFree(p.rinfo); cudaFree(p.ja); cudaFree(p.ia0); cudaFree(p.llen);
   cudaFree(p.lev_ptr); cudaFree(p.lev_rows); cudaFree(p.blev_ptr); cudaFree(p.blev_rows); cudaFree(p.tpos);
+  cudaFree(p.plev_rows); cudaFree(p.pblev_rows); cudaFree(p.ready);
   p = SellPattern();
 }
 
@@ -176,6 +177,20 @@ int sell_build_levels(SellPattern &p, cudaStream_t st) {
   p.nlevels = nlev;
   FCP_TRY(dev_upload(&p.lev_ptr, p.h_lev_ptr.data(), p.h_lev_ptr.size()));
   FCP_TRY(dev_upload(&p.lev_rows, rows.data(), rows.size()));
+  auto padded = [&](const std::vector<int32_t> &ptr, int32_t nl) {      // every level starts on a warp boundary: no lane ever waits on its own warp
+    std::vector<int32_t> out;
+    out.reserve((size_t)n + 32 * (size_t)nl);
+    for (int32_t l = 0; l < nl; ++l) {
+      for (int32_t q = ptr[l]; q < ptr[l + 1]; ++q) out.push_back(rows[q]);
+      while (out.size() % 32) out.push_back(-1);
+    }
+    return out;
+  };
+  {
+    std::vector<int32_t> pl = padded(p.h_lev_ptr, nlev);
+    p.nplev = (int32_t)pl.size();
+    FCP_TRY(dev_upload(&p.plev_rows, pl.data(), pl.size()));
+  }
   nlev = 0;
   for (int32_t i = n - 1; i >= 0; --i) {
     int32_t l = 0;
@@ -188,6 +203,14 @@ int sell_build_levels(SellPattern &p, cudaStream_t st) {
   p.nblevels = nlev;
   FCP_TRY(dev_upload(&p.blev_ptr, p.h_blev_ptr.data(), p.h_blev_ptr.size()));
   FCP_TRY(dev_upload(&p.blev_rows, rows.data(), rows.size()));
+  {
+    std::vector<int32_t> pl = padded(p.h_blev_ptr, nlev);
+    p.npblev = (int32_t)pl.size();
+    FCP_TRY(dev_upload(&p.pblev_rows, pl.data(), pl.size()));
+    std::vector<int32_t> zero((size_t)std::max(n, 1), 0);
+    FCP_TRY(dev_upload(&p.ready, zero.data(), zero.size()));
+    p.sweep_epoch = 0;
+  }
   p.levels_built = true;
   return FCP_OK;
 }

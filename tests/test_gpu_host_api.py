@@ -65,7 +65,12 @@ def test_calcp_simple_module_api(orc):
         assert np.array_equal(getattr(case, k), g[k]), k
     assert np.array_equal(case.flmass, flm) and np.array_equal(case.a, a)
     with pytest.raises(Exception):
-        case.csrsolve("gauss-seidel", case.pp, case.su, 1, 0.0, 0.1, "p")
+        case.csrsolve("pmgmres", case.pp, case.su, 1, 0.0, 0.1, "p")       # not on the accelerated path
+    # 'gauss-seidel' is: two sweeps through the module API against the oracle
+    x = g["pp"].copy()
+    orc.solve(orc.GAUSS_SEIDEL, c.ia, c.ja, case.a, c.diag, x, su, 2, 0.0, 1e-30, orc.SUM_TREE)
+    case.csrsolve("gauss-seidel", case.pp, su, 2, 0.0, 1e-30, "p")
+    assert np.array_equal(case.pp[: m.numCells], x[: m.numCells])
     case.close()
 
 

@@ -159,7 +159,10 @@ def test_calcsc_epsilon(fcp, orc, allmeshes, name, cscheme, tscheme):
     prm = oracle_params(orc, orc.SC_EPS_RLZB, "bicgstab", cscheme, "gauss", "none", tscheme)
     f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g.items()}
     o = orc.calcsc(m, c, prm, f)
-    assert rep.iters == o["rep"].iters
+    # on a mesh whose every cell is a wall cell (tiny3) the system is the identity with the imposed value on both sides: the initial residual is
+    # zero or one rounding error of pow() -- then the count is 0 or 1 depending on the libm's last bit (found with FCP_EMU_LIBM_ULP=3)
+    degenerate = max(rep.res0, o["rep"].res0) <= 1e-13 * np.abs(f["ed"][:n]).sum()
+    assert rep.iters == o["rep"].iters or (degenerate and abs(rep.iters - o["rep"].iters) <= 1)
     close(ctx.download("A"), o["a"], "matrix")
     close(ctx.download("SP")[:n], o["sp"], "sp"); close(ctx.download("SU")[:n], o["su"], "su")
     close(ctx.download("ED"), f["ed"], "ed", 1e-10)

@@ -322,6 +322,24 @@ module fcp_b200
       real(c_double), intent(inout) :: val
       integer(c_int) :: rc
     end function
+    function fcp_global_max(ctx, val) bind(c, name='fcp_global_max') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: val
+      integer(c_int) :: rc
+    end function
+    function fcp_global_min(ctx, val) bind(c, name='fcp_global_min') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: val
+      integer(c_int) :: rc
+    end function
+    function fcp_global_isum(ctx, val) bind(c, name='fcp_global_isum') result(rc)
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: ctx
+      integer(c_int64_t), intent(inout) :: val
+      integer(c_int) :: rc
+    end function
   end interface
 end module fcp_b200
 
@@ -976,6 +994,24 @@ contains
   subroutine global_sum(phi)
     real(dp), intent(inout) :: phi
     call fcp_check(fcp_global_sum(ctx, phi), 'fcp_global_sum')
+  end subroutine
+
+  subroutine global_max(phi)                 ! src-par/global_max_mpi.f90
+    real(dp), intent(inout) :: phi
+    call fcp_check(fcp_global_max(ctx, phi), 'fcp_global_max')
+  end subroutine
+
+  subroutine global_min(phi)                 ! src-par/global_min_mpi.f90
+    real(dp), intent(inout) :: phi
+    call fcp_check(fcp_global_min(ctx, phi), 'fcp_global_min')
+  end subroutine
+
+  subroutine global_isum(i)                  ! src-par/global_isum_mpi.f90
+    integer, intent(inout) :: i
+    integer(c_int64_t) :: v
+    v = int(i, c_int64_t)
+    call fcp_check(fcp_global_isum(ctx, v), 'fcp_global_isum')
+    i = int(v)
   end subroutine
 
 end module fcp_backend

@@ -583,3 +583,12 @@ static int global_reduce(fcp_ctx *ctx, double *value, int op /*0 sum 1 max 2 min
 extern "C" int fcp_global_sum(fcp_ctx *ctx, double *value) { return global_reduce(ctx, value, 0); }
 extern "C" int fcp_global_max(fcp_ctx *ctx, double *value) { return global_reduce(ctx, value, 1); }
 extern "C" int fcp_global_min(fcp_ctx *ctx, double *value) { return global_reduce(ctx, value, 2); }
+// integer sum through the rank-ordered double sum: exact while the total stays below 2^53 (src-par uses it for nnz and cell counts)
+extern "C" int fcp_global_isum(fcp_ctx *ctx, int64_t *value) {
+  if (!ctx || !value) return FCP_EINVAL;
+  if (*value > (int64_t)1 << 52 || *value < -((int64_t)1 << 52)) { fcp_set_error("fcp_global_isum: |value| exceeds 2^52"); return FCP_EINVAL; }
+  double v = (double)*value;
+  FCP_TRY(global_reduce(ctx, &v, 0));
+  *value = (int64_t)v;
+  return FCP_OK;
+}

@@ -368,3 +368,12 @@ class Case:
 
     def global_sum(self, x: float) -> float:
         return self.ctx.global_sum(x)
+
+    def global_isum(self, i: int) -> int:          # src-par/global_isum_mpi.f90
+        return self.ctx.global_isum(i)
+
+    def global_max(self, x: float) -> float:       # src-par/global_max_mpi.f90
+        return self.ctx.global_max(x)
+
+    def global_min(self, x: float) -> float:       # src-par/global_min_mpi.f90
+        return self.ctx.global_min(x)

@@ -171,6 +171,7 @@ def lib():
     L.fcp_exchange.argtypes = [vp, C.c_int]
     for nm in ("fcp_global_sum", "fcp_global_max", "fcp_global_min"):
         getattr(L, nm).argtypes = [vp, _pd]
+    L.fcp_global_isum.argtypes = [vp, C.POINTER(C.c_int64)]
     L.fcp_profile_enable.argtypes = [vp, C.c_int]
     L.fcp_profile_reset.argtypes = [vp]
     L.fcp_profile_read.argtypes = [vp, C.c_int, _pd, C.POINTER(C.c_int64)]
@@ -431,6 +432,21 @@ class Context:
         x = C.c_double(v)
         check(lib().fcp_global_sum(self.h, C.byref(x)), "fcp_global_sum")
         return x.value
+
+    def global_max(self, v: float) -> float:
+        x = C.c_double(v)
+        check(lib().fcp_global_max(self.h, C.byref(x)), "fcp_global_max")
+        return x.value
+
+    def global_min(self, v: float) -> float:
+        x = C.c_double(v)
+        check(lib().fcp_global_min(self.h, C.byref(x)), "fcp_global_min")
+        return x.value
+
+    def global_isum(self, i: int) -> int:
+        x = C.c_int64(int(i))
+        check(lib().fcp_global_isum(self.h, C.byref(x)), "fcp_global_isum")
+        return int(x.value)
 
     # ---- timing ----------------------------------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

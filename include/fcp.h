@@ -323,6 +323,7 @@ int fcp_exchange(fcp_ctx *ctx, int field);                    /* ghost slots of 
 int fcp_global_sum(fcp_ctx *ctx, double *value);              /* in place, all ranks */
 int fcp_global_max(fcp_ctx *ctx, double *value);
 int fcp_global_min(fcp_ctx *ctx, double *value);
+int fcp_global_isum(fcp_ctx *ctx, int64_t *value);           /* src-par/global_isum_mpi.f90 (nnz, cell counts at set-up): exact, in place, all ranks */
 
 /* ---- per-kernel-class device timing (CUDA events on the context stream, around every launch of the class) ---- */
 enum { FCP_K_SPMV_DOT = 0, FCP_K_CG_PK, FCP_K_CG_UPDATE, FCP_K_CG_INIT, FCP_K_PRECOND, FCP_K_DOT, FCP_K_BICG_ELEM,

@@ -173,6 +173,8 @@ def main():
     for v in vals[1:]:
         s = s + v
     assert ctx.global_sum(vals[rank]) == s
+    assert ctx.global_max(vals[rank]) == max(vals) and ctx.global_min(vals[rank]) == min(vals)          # src-par/global_max_mpi.f90, global_min_mpi.f90
+    assert ctx.global_isum(1000003 * (rank + 1)) == 1000003 * world * (world + 1) // 2                   # src-par/global_isum_mpi.f90
 
     # ---- Poisson system: global oracle matrix restricted to the partitions ----------------------------------------------
     gcsr, ga, gsu = cases.poisson_system(g, O)

@@ -334,4 +334,20 @@ inline void box_mesh(int nx, int ny, int nz, dp lx, dp ly, dp lz) {
   for (int ib = 0; ib < 6; ++ib) iBndValueStart[ib] = numCells + startFace[ib] - numInnerFaces;
 }
 
+// ---- src-par tree: exchange(phi), global_sum / global_isum / global_max / global_min   (src-par/exchange.f90:3, global_*_mpi.f90) ----
+// (after fcp_comm_init(ctx, rank, nranks, id, peer_rank); on a single rank they are the identity, like the MPI routines on one process)
+inline void exchange(std::vector<dp> &phi) {
+  put(FCP_F_S0, phi, geometry::numTotal);
+  check(fcp_exchange(ctx, FCP_F_S0), "fcp_exchange");
+  get(FCP_F_S0, phi, geometry::numTotal);
+}
+inline void global_sum(dp &x) { check(fcp_global_sum(ctx, &x), "fcp_global_sum"); }
+inline void global_max(dp &x) { check(fcp_global_max(ctx, &x), "fcp_global_max"); }
+inline void global_min(dp &x) { check(fcp_global_min(ctx, &x), "fcp_global_min"); }
+inline void global_isum(int &i) {
+  int64_t v = i;
+  check(fcp_global_isum(ctx, &v), "fcp_global_isum");
+  i = (int)v;
+}
+
 }  // namespace fcp

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu through gpurun)")
+    config.addinivalue_line("markers", "timeout(seconds): pytest-timeout's marker, registered here too so that a box without the plugin only ignores it")
 
 
 def _has_gpu() -> bool:

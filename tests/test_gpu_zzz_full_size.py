@@ -24,7 +24,7 @@ from conftest import EMU
 from fcb200 import lib as L
 from fcb200 import mesh as M
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1500)]      # (pytest-timeout: a full-size case that crawls must fail, not stall the suite)
 
 
 def _host_memory_available() -> float:

@@ -93,6 +93,8 @@ static int ctx_build(fcp_ctx *c, const fcp_mesh_desc *md, int device) {
     if (c->bctype[ib] == FCP_BC_OUTLET) c->has_outlet = true;
     if (c->bctype[ib] == FCP_BC_PROCESS) c->npro += c->nfaces[ib];
   }
+  c->g_pressure_patch = c->has_pressure_patch;   // fcp_comm_init replaces these by the flags over all ranks
+  c->g_outlet = c->has_outlet;
   for (int32_t f = 0; f < c->nF; ++f) {
     if (md->owner[f] < 1 || md->owner[f] > n || (f < F && (md->neighbour[f] < 1 || md->neighbour[f] > n))) {
       fcp_set_error("face %d: owner/neighbour out of range", f + 1);
@@ -336,7 +338,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   for (int i = 0; i < FCP_F_COUNT; ++i) cudaFree(c->field[i]);
   for (int i = 0; i < 4; ++i) cudaFree(c->Dmat[i]);
   cudaFree(c->flushbuf); cudaFree(c->d_mmpart); cudaFree(c->d_sum);
-  cudaFree(c->d_oface); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
+  cudaFree(c->d_oface); cudaFree(c->d_flowo); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
   cudaFree(c->per_cell); cudaFree(c->per_face); cudaFree(c->per_slot); cudaFree(c->per_df);
   sell_free(c->pat);
   krylov_ws_free(c->ws);
@@ -640,12 +642,13 @@ extern "C" int fcp_gradp_and_sources(fcp_ctx *ctx, int pscheme, int p_field) {
 }
 
 static int ensure_outlet_list(fcp_ctx *c) {
-  if (c->d_oface || !c->has_outlet) return FCP_OK;
+  if (c->d_oface) return FCP_OK;        // (a rank without outlet faces keeps an empty list and still joins the global sum)
   std::vector<int32_t> of;
   for (int32_t ib = 0; ib < c->nb; ++ib)
     if (c->bctype[ib] == FCP_BC_OUTLET)
       for (int32_t i = 0; i < c->nfaces[ib]; ++i) of.push_back(c->startFace[ib] + i);
   c->nout = (int32_t)of.size();
+  if (of.empty()) of.push_back(0);
   return dev_upload(&c->d_oface, of.data(), of.size());
 }
 
@@ -655,7 +658,7 @@ extern "C" int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double f
   FIELD(g, FCP_F_DPDXI); FIELD(apu, FCP_F_APU); FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(fl, FCP_F_FLMASS);
   const double *apv = nullptr, *apw = nullptr;
   if (ctx->nper) { FIELD(x1, FCP_F_APV); FIELD(x2, FCP_F_APW); apv = x1; apw = x2; }   // facefluxmass2_periodic weights
-  if (!const_mflux && ctx->has_outlet) {                           // adjustMassFlow, calcp_simple.f90:125
+  if (!const_mflux && ctx->g_outlet) {                             // adjustMassFlow, calcp_simple.f90:125
     FCP_TRY(ensure_outlet_list(ctx));
     FCP_TRY(fvm_adjust_mass_flow(ctx, ctx->nout, ctx->d_oface, den, u, v, w, fl, flomas));
   }
@@ -697,8 +700,8 @@ extern "C" int fcp_correct_simple(fcp_ctx *ctx, int pscheme, double urfp, int32_
   if (ctx->npro) FCP_TRY(fvm_correct_flux_proc(ctx, a, pp, fl));
   if (ctx->nper) FCP_TRY(fvm_correct_flux_periodic(ctx, a, pp, fl));                                // :350-373
   if (ctx->has_pressure_patch) FCP_TRY(fvm_correct_pressure_bnd(ctx, den, apu, pp, u, v, w, fl));   // :345-391
-  const double *ppref = ctx->has_pressure_patch ? nullptr : pp + (pRefCell - 1);                    // :399-407
-  if (ctx->comm && !ctx->has_pressure_patch) {
+  const double *ppref = ctx->g_pressure_patch ? nullptr : pp + (pRefCell - 1);                      // :399-407
+  if (ctx->comm && !ctx->g_pressure_patch) {
     // the broadcast of ppref (src-par/calcp_simple.f90:195-198, quirk Q12) as a rank-ordered sum of {pp(ref), 0, 0, ...}
     if (!ctx->d_ppref) FCP_TRY(dev_alloc(&ctx->d_ppref, 4));
     k_pick_ref<<<1, 1, 0, ctx->stream>>>(pp, pRefCell, ctx->d_ppref);
@@ -940,7 +943,7 @@ extern "C" int fcp_calcp_piso(fcp_ctx *ctx, const fcp_piso_params *prm, fcp_repo
   for (int icorr = 1; icorr <= prm->ncorr; ++icorr) {
     if (ctx->comm) { FCP_TRY(comm_exchange(ctx, u, 1)); FCP_TRY(comm_exchange(ctx, v, 1)); FCP_TRY(comm_exchange(ctx, w, 1)); }
     FCP_TRY(fvm_piso_hbya(ctx, h, rU, rV, rW, apu, apv, apw, u, v, w, su, sv, sw));                                 // :102-129
-    if (!prm->const_mflux && ctx->has_outlet) {                                                                      // :186 (the outlet faces do not read a or su: order is free)
+    if (!prm->const_mflux && ctx->g_outlet) {                                                                      // :186 (the outlet faces do not read a or su: order is free)
       FCP_TRY(ensure_outlet_list(ctx));
       FCP_TRY(fvm_adjust_mass_flow(ctx, ctx->nout, ctx->d_oface, den, u, v, w, fl, prm->flomas));
     }

@@ -557,6 +557,18 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
     FCP_LAUNCHED();
     FCP_CHECK_LAUNCH();
   }
+  // Patch-type flags that gate collectives (the ppref broadcast, the global outlet sum of adjustMassFlow) and the ppref = 0 rule must be the
+  // same on every rank: a real src-par decomposition omits a patch on the ranks where it has no faces.  Global flag = max over ranks.
+  {
+    double h_flags[3] = {ctx->has_pressure_patch ? 1.0 : 0.0, ctx->has_outlet ? 1.0 : 0.0, ctx->has_inout ? 1.0 : 0.0};
+    FCP_CUDA(cudaMemcpyAsync(c->d_scalar, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, ctx->stream));
+    FCP_TRY(comm_allgather_sum(c, c->d_scalar, 3, ctx->stream));
+    FCP_CUDA(cudaMemcpyAsync(h_flags, c->d_scalar, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream));
+    FCP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->g_pressure_patch = h_flags[0] > 0.0;
+    ctx->g_outlet = h_flags[1] > 0.0;
+    ctx->g_inout = h_flags[2] > 0.0;
+  }
   FCP_CUDA(cudaStreamSynchronize(ctx->stream));
   return FCP_OK;
 }

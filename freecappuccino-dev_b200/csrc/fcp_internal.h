@@ -216,9 +216,11 @@ struct fcp_ctx {
   Profiler prof;
   double *flushbuf = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
-  bool has_pressure_patch = false, has_outlet = false, has_inout = false;
+  bool has_pressure_patch = false, has_outlet = false, has_inout = false;   // from the LOCAL patch table
+  bool g_pressure_patch = false, g_outlet = false, g_inout = false;         // the same over ALL ranks (fcp_comm_init); == local without a communicator
   int32_t nout = 0;
   int32_t *d_oface = nullptr;                       // outlet faces in patch order (adjustMassFlow)
+  double *d_flowo = nullptr;                        // [4] outlet mass flow: local sum, then the sum over all ranks
   int32_t *d_aprpos = nullptr;                      // [npro] SELL position of the halo entry of each process face
   int32_t *d_procface = nullptr;                    // [npro] 0-based face index of each process face (patch order)
   std::vector<int32_t> h_procface;

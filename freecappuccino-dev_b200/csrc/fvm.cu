@@ -6,6 +6,7 @@
 // in the face's own orientation (P = owner, N = neighbour) by the same instruction sequence on both sides, so both
 // cells see bit-identical face values, there are no atomics, results are deterministic and round like the reference.
 // The face lists are SELL-32 (fcp_internal.h): a warp reads 128 contiguous bytes per list step.
+#include <algorithm>
 #include <cstdlib>
 #include "fcp_internal.h"
 #include "reduce.cuh"
@@ -662,14 +663,14 @@ __global__ void __launch_bounds__(FCP_TPB, (W >= 3 ? 1 : W == 2 ? 2 : 3)) k_asse
   }
 }
 
-// adjustMassFlow faceflux_mass.f90:833-916.  Outlet patches are small; ONE CTA evaluates the outlet fluxes in parallel
-// and thread 0 adds them in face order (the reference's order), then all threads scale.
-__global__ void __launch_bounds__(FCP_TPB) k_adjust_mass_flow(int32_t nout, const int32_t *__restrict__ oface, int32_t n, int32_t F,
-                                                               const int32_t *__restrict__ owner, const double *__restrict__ arx,
-                                                               const double *__restrict__ ary, const double *__restrict__ arz,
-                                                               const double *__restrict__ den, double *u, double *v, double *w,
-                                                               double *flmass, double flomas) {
-  __shared__ double fac_s;
+// adjustMassFlow faceflux_mass.f90:833-916 (src-par/adjustMassFlow.f90: `call global_sum(flowo)` between the two loops).  Outlet patches are
+// small; ONE CTA evaluates the outlet fluxes in parallel and thread 0 adds them in face order (the reference's order) into *flowo; after the
+// cross-rank sum (rank order, comm.cu) the second kernel scales.  A rank without outlet faces runs both with nout = 0 and contributes 0.
+__global__ void __launch_bounds__(FCP_TPB) k_adjust_mass_flow_flux(int32_t nout, const int32_t *__restrict__ oface, int32_t n, int32_t F,
+                                                                    const int32_t *__restrict__ owner, const double *__restrict__ arx,
+                                                                    const double *__restrict__ ary, const double *__restrict__ arz,
+                                                                    const double *__restrict__ den, double *u, double *v, double *w,
+                                                                    double *flmass, double *flowo_out) {
   for (int32_t i = threadIdx.x; i < nout; i += blockDim.x) {
     const int32_t f = oface[i], ijp = owner[f], ijb = n + (f - F);
     const double ub = u[ijp], vb = v[ijp], wb = w[ijp];
@@ -680,11 +681,14 @@ __global__ void __launch_bounds__(FCP_TPB) k_adjust_mass_flow(int32_t nout, cons
   if (threadIdx.x == 0) {
     double flowo = 0.0;
     for (int32_t i = 0; i < nout; ++i) flowo = flowo + flmass[oface[i]];
-    fac_s = flomas / (flowo + FCP_SMALL);
+    *flowo_out = flowo;
   }
-  __syncthreads();
-  const double fac = fac_s;
-  for (int32_t i = threadIdx.x; i < nout; i += blockDim.x) {
+}
+__global__ void __launch_bounds__(FCP_TPB) k_adjust_mass_flow_scale(int32_t nout, const int32_t *__restrict__ oface, int32_t n, int32_t F,
+                                                                     double *u, double *v, double *w, double *flmass, double flomas,
+                                                                     const double *__restrict__ flowo) {
+  const double fac = flomas / (*flowo + FCP_SMALL);
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nout; i += gridDim.x * blockDim.x) {
     const int32_t f = oface[i], ijb = n + (f - F);
     flmass[f] = flmass[f] * fac;
     u[ijb] = u[ijb] * fac; v[ijb] = v[ijb] * fac; w[ijb] = w[ijb] * fac;
@@ -843,8 +847,14 @@ int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso) {
 }
 int fvm_adjust_mass_flow(fcp_ctx *ctx, int32_t nout, const int32_t *d_oface, const double *den, double *u, double *v, double *w,
                          double *flmass, double flomas) {
-  k_adjust_mass_flow<<<1, FCP_TPB, 0, ctx->stream>>>(nout, d_oface, ctx->n, ctx->F, ctx->owner, ctx->arx, ctx->ary, ctx->arz, den, u, v, w,
-                                                      flmass, flomas);
+  if (!ctx->d_flowo) FCP_TRY(dev_alloc(&ctx->d_flowo, 4));
+  k_adjust_mass_flow_flux<<<1, FCP_TPB, 0, ctx->stream>>>(nout, d_oface, ctx->n, ctx->F, ctx->owner, ctx->arx, ctx->ary, ctx->arz, den, u, v, w,
+                                                           flmass, ctx->d_flowo);
+  FCP_LAUNCHED();
+  FCP_CHECK_LAUNCH();
+  if (ctx->comm) FCP_TRY(comm_allgather_sum(ctx->comm, ctx->d_flowo, 1, ctx->stream));   // src-par/adjustMassFlow.f90:55  call global_sum(flowo)
+  k_adjust_mass_flow_scale<<<std::max(1, std::min(64, (nout + FCP_TPB - 1) / FCP_TPB)), FCP_TPB, 0, ctx->stream>>>(nout, d_oface, ctx->n, ctx->F, u, v, w, flmass,
+                                                                                                                     flomas, ctx->d_flowo);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

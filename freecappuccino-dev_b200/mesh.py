@@ -721,6 +721,34 @@ def partition(mesh: Mesh, cell_rank: np.ndarray) -> List[Mesh]:
     return parts
 
 
+def drop_empty_patches(parts: List[Mesh]) -> List[Mesh]:
+    """What a real src-par decomposition hands a rank: the physical patches that have no face on the rank are simply absent from its boundary
+    file (``partition`` keeps them with zero faces, which hides every bug that derives a collective from the LOCAL patch table).  The faces do
+    not move; only the patch tables shrink, and ``peer_patch`` is re-indexed on both sides."""
+    import copy
+    maps = []
+    out = []
+    for p in parts:
+        if p.startFaceTwin is not None and (np.asarray(p.startFaceTwin) >= 0).any():
+            raise ValueError("drop_empty_patches: not for partitions with periodic pairs")
+        keep = [ib for ib in range(p.numBoundaries) if p.nfaces[ib] > 0 or p.bctype[ib] == BC_PROCESS]
+        maps.append({old: new for new, old in enumerate(keep)})
+        q = copy.copy(p)
+        q.bcname = [p.bcname[ib] for ib in keep]
+        q.bctype = np.ascontiguousarray(p.bctype[keep], dtype=np.int32)
+        q.nfaces = np.ascontiguousarray(p.nfaces[keep], dtype=np.int32)
+        q.startFace = np.ascontiguousarray(p.startFace[keep], dtype=np.int32)
+        q.peer_rank = np.ascontiguousarray(p.peer_rank[keep], dtype=np.int32)
+        q.peer_patch = np.ascontiguousarray(p.peer_patch[keep], dtype=np.int32)
+        q.startFaceTwin = None
+        out.append(q)
+    for q in out:
+        for ib in range(q.numBoundaries):
+            if q.peer_rank[ib] >= 0:
+                q.peer_patch[ib] = maps[int(q.peer_rank[ib])][int(q.peer_patch[ib])]
+    return out
+
+
 def localize_matrix(gmesh: Mesh, gcsr, a_global: np.ndarray, part: Mesh, pcsr) -> Tuple[np.ndarray, np.ndarray]:
     """Restrict a global CSR matrix (values ``a_global`` on the pattern ``gcsr`` of ``gmesh``) to one partition in the
     src-par layout: returns (a_local[nnz_local], apr[npro]) -- src-par/sparse_matrix.f90:25,173 (``apr`` holds the one

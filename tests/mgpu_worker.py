@@ -114,6 +114,72 @@ def periodic_main(rank, world, local):
     dist.destroy_process_group()
 
 
+def inout_main(rank, world, local):
+    """Patches that gate collectives, on partitions that split or omit them (the partition tables are those of a real src-par decomposition: a
+    physical patch without faces on a rank is absent there, `mesh.drop_empty_patches`):
+      1. inlet/outlet channel cut into z-slabs -- the outlet is SPLIT over all ranks: adjustMassFlow must scale with the GLOBAL outlet flow
+         (src-par/adjustMassFlow.f90:55 `call global_sum(flowo)`);
+      2. inlet/pressure channel cut into x-slabs -- the pressure patch lives on the LAST rank only: every rank must still take ppref = 0 and none may
+         enter the ppref broadcast (calcp_simple.f90:399-407).
+    One calcp_simple each, against the unpartitioned oracle."""
+    import test_gpu_parity as TP
+    allm = cases.meshes()
+    for name, axis in (("channel_inout", "z"), ("channel_pressure", "x")):
+        g = allm[name]
+        ng = g.numCells
+        co = dict(x=g.xc, y=g.yc, z=g.zc)[axis][:ng]
+        t = (co - co.min()) / (co.max() - co.min() + 1e-12)
+        parts = M.drop_empty_patches(M.partition(g, np.minimum((t * world).astype(np.int32), world - 1)))
+        me = parts[rank]
+        nl = me.numCells
+        types = [int(b) for b in me.bctype]
+        if name == "channel_inout":
+            assert M.BC_OUTLET in types, "the z-slabs must split the outlet over all ranks"
+        elif world > 1:
+            assert (M.BC_PRESSURE in types) == (rank == world - 1), "the pressure patch must live on the last rank only"
+        f = cases.fields(g)
+        # flomas = the inlet mass flow (the reference sums it in bcin): with any other value the pure-Neumann p' system of the inlet/outlet channel is
+        # inconsistent and a solve run to 1e-12 diverges on both sides
+        flomas = -float(TP.simple_oracle(O, g, f, O.DPCG, 0, 1.0)["flm0"].sum())
+        o = TP.simple_oracle(O, g, f, O.DPCG, 800, 1e-12, urfp=0.3, pref=1 + int(parts[0].cell_global[0]), flomas=flomas)
+
+        def lf(v):
+            out = np.zeros(me.numTotal)
+            out[:nl] = v[me.cell_global]
+            for ib in range(me.numBoundaries):
+                if me.bctype[ib] != M.BC_PROCESS:
+                    pf = me.patch_faces(ib)
+                    out[nl + pf - me.numInnerFaces] = v[ng + me.face_global[pf] - g.numInnerFaces]
+            return out
+        own_g = g.owner.astype(np.int64) - 1
+        sign = np.where(own_g[me.face_global] == me.cell_global[me.owner.astype(np.int64) - 1], 1.0, -1.0)
+        ctx = L.Context(me, local)
+        ctx.comm_init(rank, world, _bcast_uid(dist, rank), me.peer_rank)
+        for k, v in f.items():
+            ctx.upload(k.upper(), lf(v))
+        ctx.upload("FLMASS", sign * o["flm0"][me.face_global])
+        ctx.gradp_and_sources("linear", "P")
+        ctx.calcp_simple(solver="dpcg", maxiter=800, tol_abs=1e-30, tol_rel=1e-12, urfp=0.3, npcor=1, pRefCell=1 if rank == 0 else 0, flomas=flomas)
+        if os.environ.get("FCP_TEST_DEBUG"):
+            d = np.abs(ctx.download("FLMASS") * sign - o["flm"][me.face_global]); bad = np.nonzero(d > 1e-9 * np.abs(o["flm"]).max())[0]
+            gotf = ctx.download("FLMASS") * sign
+            print(rank, "DEBUG sample", gotf[bad[:4]], o["flm"][me.face_global][bad[:4]], o["flm_asm"][me.face_global][bad[:4]], flush=True)
+            print(rank, "DEBUG bad faces", bad.size, "inner", int((bad < me.numInnerFaces).sum()), [(me.bcname[ib], int(((bad >= me.startFace[ib]) & (bad < me.startFace[ib] + me.nfaces[ib])).sum())) for ib in range(me.numBoundaries)], flush=True)
+        assert rel(ctx.download("FLMASS") * sign, o["flm"][me.face_global]) < 1e-9, (name, "fluxes", rel(ctx.download("FLMASS") * sign, o["flm"][me.face_global]))
+        for k in ("u", "v", "w", "p", "pp"):
+            got = ctx.download(k.upper())
+            assert rel(got[:nl], o[k][me.cell_global]) < 1e-8, (name, k, rel(got[:nl], o[k][me.cell_global]))
+            for ib in range(me.numBoundaries):          # boundary values too: adjustMassFlow scales the outlet velocities
+                if me.bctype[ib] != M.BC_PROCESS:
+                    pf = me.patch_faces(ib)
+                    ref = o[k][ng + me.face_global[pf] - g.numInnerFaces]
+                    assert np.abs(got[nl + pf - me.numInnerFaces] - ref).max() <= 1e-8 * (np.abs(o[k]).max() + 1e-300), (name, k, me.bcname[ib])
+        ctx.close()
+        dist.barrier()
+    print(f"MGPU_OK {rank} comm={ctx_mode_name(os.environ.get('FCP_COMM', ''))}", flush=True)
+    dist.destroy_process_group()
+
+
 def ctx_mode_name(want):
     return want or "auto"
 
@@ -125,6 +191,8 @@ def main():
         torch.cuda.set_device(local)
     if os.environ.get("FCP_TEST_MESH", "hex") == "periodic":
         return periodic_main(rank, world, local)
+    if os.environ.get("FCP_TEST_MESH", "hex") == "inout":
+        return inout_main(rank, world, local)
     n = 12
     if os.environ.get("FCP_TEST_MESH", "hex") == "poly":       # BASELINE config 5 in miniature: polyhedral cells (up to 10 faces), Gauss/LSQ gradients + ICCG
         g = M.polyhedral_mesh(10, 8, 6, distort=0.15)

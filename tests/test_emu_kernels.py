@@ -82,6 +82,6 @@ def test_bench_falls_back_to_nccl_when_the_peer_memory_path_fails():
 def test_late_round1_additions_under_emulation():
     """'gauss-seidel', the barrier-free IC(0)/ILU(0) sweeps and the full-size property tests at their emulation sizes (with the oracle comparison
     those sizes add): none of them has run on hardware yet."""
-    r = _run(["-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_zzzz_gauss_seidel.py", "tests/test_gpu_zzzz_sweep_flags.py",
-              "tests/test_gpu_zzz_full_size.py"])
+    r = _run(["-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_gauss_seidel.py", "tests/test_gpu_sweep_flags.py",
+              "tests/test_zz_gpu_full_size.py"])
     assert r.returncode == 0 and " passed" in r.stdout and "skipped" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

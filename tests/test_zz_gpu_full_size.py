@@ -233,12 +233,31 @@ def _poly_size():
     return 342 if _host_memory_available() >= 96e9 else 272     # the generator peaks at ~28 GB of host memory for 20 M polyhedra, ~14 GB for 10 M
 
 
+def _lsq_small_shrink(m):
+    """det of the unweighted least-squares normal matrix of every cell (gradients.f90:700-746, re-computed here with numpy) and the factor
+    det/(det + small) by which `tmp = 1./(det + small)` (:763, small = 1e-20 as a single-precision literal) scales the inverse, hence the gradient."""
+    n, Fi = m.numCells, m.numInnerFaces
+    own, nei = m.owner[:Fi].astype(np.int64) - 1, m.neighbour[:Fi].astype(np.int64) - 1
+    bown = m.owner[Fi:].astype(np.int64) - 1
+    di = [c[nei] - c[own] for c in (m.xc, m.yc, m.zc)]
+    db = [f[Fi:] - c[bown] for f, c in ((m.xf, m.xc), (m.yf, m.yc), (m.zf, m.zc))]
+    D = {}
+    for i in range(3):
+        for j in range(i, 3):
+            w = di[i] * di[j]
+            D[i, j] = np.bincount(own, w, n) + np.bincount(nei, w, n) + np.bincount(bown, db[i] * db[j], n)
+    d11, d12, d13, d22, d23, d33 = D[0, 0], D[0, 1], D[0, 2], D[1, 1], D[1, 2], D[2, 2]
+    det = d11 * d22 * d33 - d11 * d23 * d23 - d12 * d12 * d33 + d12 * d23 * d13 + d13 * d12 * d23 - d13 * d22 * d13
+    small = float(np.float32(1e-20))
+    return dict(factor=det / (det + small), det_min=float(det.min()), det_max=float(det.max()))
+
+
 def test_full_size_polyhedral_gradients_and_iccg(fcp, orc):
     """BASELINE config 5 at its size: ~20 M ten-faced polyhedra (342^3 hexahedra merged pairwise in a staggered brick pattern, `mesh.polyhedral_mesh_fast`;
     10 M on a host with less than 96 GB), Gauss and least-squares gradients and an IC(0)-CG Poisson solve, through size-independent properties:
     the discrete Gauss theorem (sum over cells of vol * grad(phi) = sum over BOUNDARY faces of phi_f S_f, the inner faces cancel pairwise); the
-    least-squares gradients (row-2 bug Q1 switched off) reproduce a linear field exactly in every cell (the weighted variant in every cell without a
-    boundary face: quirk Q2); the Laplacian matrix is symmetric bit for
+    least-squares gradients (row-2 bug Q1 switched off) reproduce a linear field in every cell -- the weighted variant exactly (in every cell without a
+    boundary face: quirk Q2), the unweighted one up to the factor det/(det + small) the reference's own inversion carries (gradients.f90:763); the Laplacian matrix is symmetric bit for
     bit with a dominant diagonal; the ICCG solution satisfies the system (residual re-computed on the host) and is positive (discrete maximum
     principle for -lap(phi) = 1 with phi = 0 on the boundary: the wall-distance Poisson problem of mesh/wall_distance.f90:96-104).  Under the
     emulation: 8^3 and the oracle, bit for bit."""
@@ -259,12 +278,23 @@ def test_full_size_polyhedral_gradients_and_iccg(fcp, orc):
     assert np.abs(lhs - rhs).max() <= 1e-9 * np.abs(smooth).max(), (lhs, rhs)       # surface area of the unit box = 6
     # ---- least squares, linear field
     ctx.upload("S0", phi)
+    gtrue = np.array([2.0, -3.0, 0.5])
+    shrink = _lsq_small_shrink(m)
+    print(f"unweighted LSQ: det of the normal matrix {shrink['det_min']:.3e} .. {shrink['det_max']:.3e}; the reference's `1/(det + small)` "
+          f"(gradients.f90:763) scales the gradient by 1 - {1.0 - shrink['factor'].min():.3e} at worst")
     for meth in (L.GRAD_LSQ, L.GRAD_LSQ_DM):
         ctx.create_lsq_grad_matrix(meth)
         ctx.grad(meth, "S0", "G0", lsq_row2_reference=False)
         gl = ctx.download("G0")[:n]
-        err = np.abs(gl - np.array([2.0, -3.0, 0.5])).max(1)
-        if meth == L.GRAD_LSQ_DM:       # quirk Q2 (gradients.f90:1459: the boundary-face weight reads xf(i) instead of xf(iface)) spoils the boundary cells
+        if meth == L.GRAD_LSQ:
+            # NOT size independent: the reference inverts the normal matrix with tmp = 1/(det + small), small = 1e-20 (gradients.f90:763), and det ~ h^6
+            # for the unweighted matrix, so every gradient comes out scaled by det/(det + small) -- 1 - 6e-7 at 342^3/2, reproduced bit for bit by the kernels.
+            # The check is therefore against the PREDICTED value g * det/(det + small), det re-computed on the host, and is as tight as before.
+            err = np.abs(gl - shrink["factor"][:, None] * gtrue).max(1)
+            assert np.abs(gl - gtrue).max() <= 2.0 * np.abs(gtrue).max() * (1.0 - shrink["factor"].min()) + 1e-9
+        else:                           # the weighted matrix is dimensionless (det = O(1)): exact at any size
+            err = np.abs(gl - gtrue).max(1)
+            # quirk Q2 (gradients.f90:1459: the boundary-face weight reads xf(i) instead of xf(iface)) spoils the boundary cells
             err[m.owner[Fi:].astype(np.int64) - 1] = 0.0
         assert err.max() <= 1e-9, (meth, err.max())
     g_lsq = gl

@@ -36,7 +36,7 @@ echo "bench exit $?" >> $OUT/${TAG}_status.txt
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_ref.log 2>&1
 echo "reference arm exit $?" >> $OUT/${TAG}_status.txt
 # 2b. barrier-free IC(0)/ILU(0) sweeps (opt-in path, never run on hardware in round 1): parity first, then the A/B timing on the 256^3 ICCG solve
-FCP_TEST_SWEEP_FLAGS=1 timeout 600 python -m pytest tests/test_gpu_zzzz_sweep_flags.py -m gpu -x -q > $OUT/${TAG}_pytest_sweep_flags.log 2>&1
+FCP_TEST_SWEEP_FLAGS=1 timeout 600 python -m pytest tests/test_gpu_sweep_flags.py -m gpu -x -q > $OUT/${TAG}_pytest_sweep_flags.log 2>&1
 echo "sweep-flags parity exit $?" >> $OUT/${TAG}_status.txt
 timeout 900 python bench.py --solver iccg --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_bench1_iccg_barrier.log 2>&1
 FCP_SWEEP=flags timeout 900 python bench.py --solver iccg --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_bench1_iccg_flags.log 2>&1

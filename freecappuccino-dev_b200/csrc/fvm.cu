@@ -786,8 +786,10 @@ int fvm_lsq_matrix(fcp_ctx *ctx, bool weighted, double *D) {
 int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi, double *g, int row2_reference) {
   if (ctx->B) FCP_CUDA(cudaMemsetAsync(g + 3 * (size_t)ctx->n, 0, sizeof(double) * 3 * (size_t)ctx->B, ctx->stream));
   if (ctx->n == 0) return FCP_OK;
+  size_t tok = ctx->prof.begin(FCP_K_GRAD, ctx->stream);
   if (weighted) k_grad_lsq<true><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference);
   else k_grad_lsq<false><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference);
+  ctx->prof.end(tok, ctx->stream);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

@@ -108,6 +108,10 @@ struct KrylovWS {
   KrylovScalars *h_sc = nullptr;      // pinned host mirror
   double *partials = nullptr;         // [4 * maxchunks]
   unsigned int *counter = nullptr;    // last-block ticket
+  unsigned int *bar = nullptr;        // [4] grid barrier of the persistent solver kernels: arrivals, generation
+  unsigned long long *phase_ns = nullptr;   // [8] per-phase times of the persistent kernels (CTA 0's view), profiler only
+  int persist_grid[4] = {0, 0, 0, 0};       // cooperative grid size per persistent kernel variant on ws_device (0: not queried yet)
+  int ws_device = -1;
   int maxchunks = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
 };

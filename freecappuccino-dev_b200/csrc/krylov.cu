@@ -29,6 +29,11 @@ int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols) {
   FCP_TRY(dev_alloc(&ws.partials, (size_t)4 * ws.maxchunks));
   FCP_TRY(dev_alloc(&ws.counter, 1));
   FCP_CUDA(cudaMemset(ws.counter, 0, sizeof(unsigned int)));
+  FCP_TRY(dev_alloc(&ws.bar, 4));
+  FCP_TRY(dev_alloc(&ws.phase_ns, 8));
+  FCP_CUDA(cudaMemset(ws.bar, 0, 4 * sizeof(unsigned int)));
+  FCP_CUDA(cudaMemset(ws.phase_ns, 0, 8 * sizeof(unsigned long long)));
+  FCP_CUDA(cudaGetDevice(&ws.ws_device));
   FCP_CUDA(cudaStreamSynchronize(0));   // cudaMemset is asynchronous; the solver streams do not order with the legacy stream
   FCP_CUDA(cudaMalloc((void **)&ws.sc, sizeof(KrylovScalars)));
   FCP_CUDA(cudaMallocHost((void **)&ws.h_sc, sizeof(KrylovScalars)));
@@ -47,7 +52,7 @@ static int krylov_ws_need(KrylovWS &ws, double **p, size_t count) {
 void krylov_ws_free(KrylovWS &ws) {
   cudaFree(ws.res); cudaFree(ws.pk); cudaFree(ws.zk); cudaFree(ws.adiag); cudaFree(ws.d);
   cudaFree(ws.reso); cudaFree(ws.uk); cudaFree(ws.vk); cudaFree(ws.tmp);
-  cudaFree(ws.partials); cudaFree(ws.counter); cudaFree(ws.sc);
+  cudaFree(ws.partials); cudaFree(ws.counter); cudaFree(ws.sc); cudaFree(ws.bar); cudaFree(ws.phase_ns);
   if (ws.h_sc) cudaFreeHost(ws.h_sc);
   if (ws.ev[0]) cudaEventDestroy(ws.ev[0]);
   if (ws.ev[1]) cudaEventDestroy(ws.ev[1]);
@@ -66,8 +71,8 @@ struct SellView {
 };
 
 // s <- s (+|-) sum_k a(r,k) x(ja(r,k)), entries in CSR order (linear_solvers.f90:256-261 with SUB, :308-313 without)
-template <bool SUB>
-__device__ __forceinline__ double sell_row_sum(const SellView &m, const double *__restrict__ x, int32_t r, double s) {
+template <bool SUB, bool NC = true>
+__device__ __forceinline__ double sell_row_sum(const SellView &m, const double *x, int32_t r, double s) {
   const int64_t base = __ldg(&m.slptr[r >> 5]) + (r & 31);
   const int32_t len = __ldg(&m.rinfo[r]) & 0xffff;
   const double *__restrict__ ap = m.a + base;
@@ -76,7 +81,7 @@ __device__ __forceinline__ double sell_row_sum(const SellView &m, const double *
   for (int32_t k = 0; k < len; ++k) {
     const double av = __ldcs(ap + (int64_t)k * 32);
     const int32_t c = __ldcs(jp + (int64_t)k * 32);
-    const double t = av * __ldg(x + c);
+    const double t = av * (NC ? __ldg(x + c) : x[c]);
     s = SUB ? (s - t) : (s + t);
   }
   return s;
@@ -85,8 +90,8 @@ __device__ __forceinline__ double sell_row_sum(const SellView &m, const double *
 // Row sum for the rows of a chunk that owns process faces, on the peer-memory path: a ghost column (>= n) is not read
 // from x but from this rank's LL slots, where the neighbour's k_cg_pk stored it during this very iteration; the word's
 // embedded sequence number tells when it has arrived (src-par/dpcg.f90:118 `call exchange(pk)` + :129-143 halo term).
-template <bool SUB>
-__device__ __forceinline__ double sell_row_sum_halo(const SellView &m, const double *__restrict__ x, int32_t r, double s, const CommDev *cd,
+template <bool SUB, bool NC = true>
+__device__ __forceinline__ double sell_row_sum_halo(const SellView &m, const double *x, int32_t r, double s, const CommDev *cd,
                                                     unsigned int seq) {
   const int64_t base = __ldg(&m.slptr[r >> 5]) + (r & 31);
   const int32_t len = __ldg(&m.rinfo[r]) & 0xffff;
@@ -94,7 +99,7 @@ __device__ __forceinline__ double sell_row_sum_halo(const SellView &m, const dou
   for (int32_t k = 0; k < len; ++k) {
     const double av = __ldcs(m.a + base + (int64_t)k * 32);
     const int32_t c = __ldcs(m.ja + base + (int64_t)k * 32);
-    const double xv = c >= n ? p2p_ll_load(cd->ll + 2 * (size_t)__ldg(cd->ghost_ord + (c - n)), seq, cd->hdr) : __ldg(x + c);
+    const double xv = c >= n ? p2p_ll_load(cd->ll + 2 * (size_t)__ldg(cd->ghost_ord + (c - n)), seq, cd->hdr) : (NC ? __ldg(x + c) : x[c]);
     const double t = av * xv;
     s = SUB ? (s - t) : (s + t);
   }
@@ -311,13 +316,10 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_init(int32_t n, SellView m, cons
 // written the CTA stores the pk values of its process-face cells straight into the neighbours' LL slots over NVLink
 // (sequence number = seq_base + iteration).  No fence, no flag, no extra kernel; chunks that own process faces are
 // launched first so that the stores are under way while the bulk of the vector is still being updated.
+// One chunk of the direction update.  `info` = chunk index | halo bit 31.
 template <bool JACOBI>
-__global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
-                                                    const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd,
-                                                    const int32_t *__restrict__ chunk_info, unsigned int seq_base) {
-  const int32_t info = chunk_info ? __ldg(chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
-  if (sc->done) return;
-  const double bet = sc->bet;
+__device__ __forceinline__ void cg_pk_chunk(int32_t n, const double *res, const double *__restrict__ adiag, const double *zk, double *pk, double bet,
+                                            int32_t info, const CommDev *cd, unsigned int seq) {
   const int chunk = info & 0x7fffffff;
   const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
   if (base + (FCP_IPT - 1) * FCP_TPB < n) {
@@ -346,8 +348,15 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__re
   if (info >= 0) return;   // no halo bit: this chunk owns no process face
   const int32_t j0 = cd->chunk_ptr[chunk], j1 = cd->chunk_ptr[chunk + 1];
   __syncthreads();   // the chunk's pk values are written
-  const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
   for (int32_t j = j0 + (int32_t)threadIdx.x; j < j1; j += FCP_TPB) p2p_ll_store(cd->push_dst[j], pk[cd->push_cell[j]], seq);
+}
+template <bool JACOBI>
+__global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
+                                                    const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd,
+                                                    const int32_t *__restrict__ chunk_info, unsigned int seq_base) {
+  const int32_t info = chunk_info ? __ldg(chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
+  if (sc->done) return;
+  cg_pk_chunk<JACOBI>(n, res, adiag, zk, pk, sc->bet, info, cd, seq_base + (unsigned int)sc->iters + 1u);
 }
 
 // y = A x ; sums: sum v1*y [, sum v2*y | sum y*y]
@@ -384,23 +393,22 @@ __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, con
 #ifndef FCP_PIPE_MINB
 #define FCP_PIPE_MINB 4
 #endif
-template <int NS, bool SQ, int W>
-__global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_dot_pipe(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
-                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused,
-                                                            unsigned int seq_base) {
-  const int32_t info = ra.chunk_info ? __ldg(ra.chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
-  if (sc->done) return;
-  double s[NS];
-#pragma unroll
-  for (int k = 0; k < NS; ++k) s[k] = 0.0;
-  const CommDev *cd = ra.cd;
+// x / v1 loads: NC = true inside an ordinary kernel (the vectors are read-only for the kernel's lifetime: non-coherent path);
+// NC = false inside the persistent solver kernel, where other CTAs rewrite them between grid barriers (plain loads: L1 is invalidated by
+// the barrier's acquire fence, the non-coherent path is not)
+template <bool NC>
+__device__ __forceinline__ double ld_vec(const double *p) { return NC ? __ldg(p) : *p; }
+
+// One chunk of y = A x with the dot-product partial sums of the chunk in s[] (per thread).
+template <int NS, bool SQ, int W, bool NC>
+__device__ __forceinline__ void spmv_dot_chunk(int32_t n, const SellView &m, const double *x, double *y, const double *v1, int32_t info, bool fused,
+                                               const CommDev *cd, unsigned int seq, double (&s)[NS]) {
   const int chunk = info & 0x7fffffff;
   const bool halo = fused && info < 0;
   const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
   if (base + (FCP_IPT - 1) * FCP_TPB < n) {
     // chunks that own process faces (halo, CTA-uniform): the pipelined part covers the LOCAL entries of a row; its ghost
     // entries (stored last in the row, src-par/dpcg.f90:129-143) are added afterwards from the LL slots
-    const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
     const int lane = threadIdx.x & 31;
     int64_t pos = __ldg(&m.slptr[base >> 5]) + lane;      // SELL position of the current row's first entry
     int32_t len = halo ? __ldg(&m.llen[base]) : (__ldg(&m.rinfo[base]) & 0xffff);
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
 #pragma unroll
       for (int k = 0; k < W; ++k) av[k] = (k < len) ? __ldcs(m.a + pos + (int64_t)k * 32) : 0.0;
 #pragma unroll
-      for (int k = 0; k < W; ++k) xv[k] = (k < len) ? __ldg(x + c[k]) : 0.0;
+      for (int k = 0; k < W; ++k) xv[k] = (k < len) ? ld_vec<NC>(x + c[k]) : 0.0;
       const double vv = v1[r];
       // next row: meta data and column indices
       int64_t npos = 0;
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
 #pragma unroll
       for (int k = 0; k < W; ++k)
         if (k < len) yr = yr + av[k] * xv[k];
-      for (int32_t k = W; k < len; ++k) yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * __ldg(x + __ldcs(m.ja + pos + (int64_t)k * 32));
+      for (int32_t k = W; k < len; ++k) yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * ld_vec<NC>(x + __ldcs(m.ja + pos + (int64_t)k * 32));
       if (halo) {
         const int32_t full = __ldg(&m.rinfo[r]) & 0xffff;
         for (int32_t k = len; k < full; ++k) {
@@ -449,19 +457,31 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
       for (int k = 0; k < W; ++k) c[k] = cn[k];
     }
   } else {
-    // the few chunks that own process faces (launched first) and the ragged last chunk
-    const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
+    // the ragged last chunk
     for (int j = 0; j < FCP_IPT; ++j) {
       const int64_t r64 = base + (int64_t)j * FCP_TPB;
       if (r64 >= n) continue;
       const int32_t r = (int32_t)r64;
-      const double yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, cd, seq) : sell_row_sum<false>(m, x, r, 0.0);
+      double yr;
+      if (NC) yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, cd, seq) : sell_row_sum<false>(m, x, r, 0.0);
+      else yr = halo ? sell_row_sum_halo<false, false>(m, x, r, 0.0, cd, seq) : sell_row_sum<false, false>(m, x, r, 0.0);
       y[r] = yr;
       s[0] = s[0] + v1[r] * yr;
       if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
     }
   }
-  finish_reduce_part<NS>(s, ra, chunk, (int)gridDim.x);
+}
+template <int NS, bool SQ, int W>
+__global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_dot_pipe(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
+                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused,
+                                                            unsigned int seq_base) {
+  const int32_t info = ra.chunk_info ? __ldg(ra.chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
+  if (sc->done) return;
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  spmv_dot_chunk<NS, SQ, W, true>(n, m, x, y, v1, info, fused != 0, ra.cd, seq_base + (unsigned int)sc->iters + 1u, s);
+  finish_reduce_part<NS>(s, ra, info & 0x7fffffff, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -599,14 +619,9 @@ __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot_tma(int32_t n, int32_t nsl
 
 // fi += alf*pk ; res -= alf*zk ; sums: |res| , [res*(res/adiag)] , [|adiag*fi|]      (:321-340)
 template <bool JACOBI>
-__global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__restrict__ fi, double *__restrict__ res, const double *__restrict__ pk,
-                                                        const double *__restrict__ zk, const double *__restrict__ adiag,
-                                                        const KrylovScalars *sc, RedArgs ra) {
-  if (sc->done) return;
-  const double alf = sc->alf;
-  const bool first = (sc->iters == 0);
-  double s[3] = {0.0, 0.0, 0.0};
-  const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
+__device__ __forceinline__ void cg_update_chunk(int32_t n, double *fi, double *res, const double *pk, const double *zk, const double *__restrict__ adiag,
+                                                double alf, bool first, int chunk, double (&s)[3]) {
+  const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
   if (base + (FCP_IPT - 1) * FCP_TPB < n) {
     // full chunk, two halves of 4 rows: 20 independent loads in flight per thread
 #pragma unroll 1
@@ -631,7 +646,9 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__rest
       }
     }
   } else {
-    FCP_ROW_LOOP(r, n) {
+    for (int j = 0; j < FCP_IPT; ++j) {
+      const int64_t r = base + (int64_t)j * FCP_TPB;
+      if (r >= n) continue;
       const double f = fi[r] + alf * pk[r];
       const double rr = res[r] - alf * zk[r];
       fi[r] = f;
@@ -642,7 +659,173 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__rest
       if (first) s[2] = s[2] + fabs(ad * f);
     }
   }
+}
+template <bool JACOBI>
+__global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__restrict__ fi, double *__restrict__ res, const double *__restrict__ pk,
+                                                        const double *__restrict__ zk, const double *__restrict__ adiag,
+                                                        const KrylovScalars *sc, RedArgs ra) {
+  if (sc->done) return;
+  double s[3] = {0.0, 0.0, 0.0};
+  cg_update_chunk<JACOBI>(n, fi, res, pk, zk, adiag, sc->alf, sc->iters == 0, (int)blockIdx.x, s);
   finish_reduce<3>(s, ra);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_dpcg_persist: the WHOLE diagonal-PCG solve (linear_solvers.f90:280-358 / src-par/dpcg.f90:79-161) as ONE persistent cooperative kernel.
+// A CTA owns the chunks q = blockIdx.x, blockIdx.x + gridDim.x, ... of the launch order (chunks with process faces first) in all three phases of an
+// iteration -- {pk = zk + bet pk [+ halo push]} | {zk = A pk, pk.zk} | {fi, res update, sum|res|, next res.z} -- which run the same per-chunk code
+// as the three kernels above and store the same per-chunk partial sums; the phases are separated by grid barriers built from one arrival
+// counter and one generation word, and the barrier after a reducing phase is also the reduction: the LAST CTA to arrive adds the chunk
+// partials in the fixed order of reduce.cuh, runs the cross-rank sum over the peer windows and the scalar epilogue (alpha / beta / convergence
+// test), then releases the generation.  Bits and iteration counts are those of the three-kernel path; what disappears is three launches, three
+// grid ramp-ups/tails and the host's poll per 16 iterations: the host launches once and reads the scalars once.
+// Visibility: a CTA's stores are ordered before its arrival by __syncthreads + __threadfence (cumulative), the waiter's ld.acquire + fence
+// invalidates its SM's L1, so the plain loads of the next phase see them; the vectors are therefore never read through the non-coherent path here.
+// ---------------------------------------------------------------------------------------------
+struct PersistArgs {
+  int32_t n, nchunks;
+  SellView m;
+  double *fi, *res, *pk, *zk;
+  const double *adiag;
+  KrylovScalars *sc;
+  RedArgs ra;                 // partials / stride / sc / cd / chunk_info (counter unused)
+  unsigned int seq_base;
+  int fused;                  // halo chunks read ghost columns from the LL slots
+  unsigned int *bar;          // [0] arrivals (monotonic), [1] generation
+  unsigned long long *phase_ns;   // nullptr, or [4]: accumulated ns of phase A, B, C as seen by CTA 0 (+ iterations) for the profiler
+};
+__device__ __forceinline__ unsigned int bar_ld_acquire(const unsigned int *p) {
+#ifdef FCP_EMU
+  emu::yield(); emu::os_yield();
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void bar_st_release(unsigned int *p, unsigned int v) {
+#ifdef FCP_EMU
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+// arrival: returns the generation this barrier completes; *last = this CTA arrived last (all threads get both)
+__device__ __forceinline__ unsigned int gbar_arrive(unsigned int *bar, bool *last) {
+  __shared__ unsigned int ticket_s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    ticket_s = atomicAdd(&bar[0], 1u);
+  }
+  __syncthreads();
+  const unsigned int t = ticket_s;
+  *last = (t % gridDim.x) == gridDim.x - 1u;
+  return t / gridDim.x + 1u;
+}
+__device__ __forceinline__ void gbar_release(unsigned int *bar, unsigned int gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    bar_st_release(&bar[1], gen);
+  }
+}
+__device__ __forceinline__ void gbar_wait(unsigned int *bar, unsigned int gen) {
+  if (threadIdx.x == 0) {
+    while ((int)(bar_ld_acquire(&bar[1]) - gen) < 0) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+// plain barrier
+__device__ __forceinline__ void gbar_sync(unsigned int *bar) {
+  bool last;
+  const unsigned int gen = gbar_arrive(bar, &last);
+  if (last) gbar_release(bar, gen);
+  else gbar_wait(bar, gen);
+}
+// barrier + reduction + epilogue: every CTA has stored its chunk partials
+template <int NS>
+__device__ __forceinline__ void gbar_reduce(unsigned int *bar, const RedArgs &ra, int nparts) {
+  bool last;
+  const unsigned int gen = gbar_arrive(bar, &last);
+  if (last) {
+    __threadfence();
+    double acc[NS], total[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      double t = 0.0;
+      for (int i = threadIdx.x; i < nparts; i += FCP_TPB) t = t + __ldcg(&ra.partials[(size_t)k * ra.stride + i]);
+      acc[k] = t;
+    }
+    fcp_block_tree<NS>(acc, total);
+    finish_epilogue<NS>(total, ra);
+    if (threadIdx.x == 0 && ra.cd && *(volatile int *)&ra.cd->hdr->error) *(volatile int32_t *)&ra.sc->done = 1;   // a peer stopped answering: end the solve, the host reports it
+    gbar_release(bar, gen);
+  } else {
+    gbar_wait(bar, gen);
+  }
+}
+template <int NS>
+__device__ __forceinline__ void store_chunk_partials(double (&s)[NS], const RedArgs &ra, int chunk) {
+  double blk[NS];
+  fcp_block_tree<NS>(s, blk);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) ra.partials[(size_t)k * ra.stride + chunk] = blk[k];
+  }
+}
+// MINB = resident CTAs per SM the register allocation is made for (2: 128 registers, no spills; 3: 85; 4: 64 like the stand-alone SpMV kernel)
+template <int W, int MINB>
+__global__ void __launch_bounds__(FCP_TPB, MINB) k_dpcg_persist(PersistArgs g) {
+  volatile KrylovScalars *vsc = g.sc;
+  if (vsc->done) return;      // res0 < tol_abs or itr_max <= 0 (set by the init kernel's epilogue, a kernel boundary ago)
+  const int32_t *__restrict__ order = g.ra.chunk_info;
+  const bool timer = g.phase_ns && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long t0 = timer ? p2p_now_ns() : 0ull;
+  for (;;) {
+    const unsigned int seq = g.seq_base + (unsigned int)vsc->iters + 1u;
+    // ---- phase A: direction vector (+ halo push)
+    const double bet = vsc->bet;
+    for (int q = blockIdx.x; q < g.nchunks; q += gridDim.x) {
+      const int32_t info = order ? __ldg(order + q) : (int32_t)q;
+      cg_pk_chunk<true>(g.n, g.res, g.adiag, g.zk, g.pk, bet, info, g.ra.cd, seq);
+    }
+    gbar_sync(g.bar);
+    unsigned long long t1 = 0ull;
+    if (timer) { t1 = p2p_now_ns(); g.phase_ns[0] += t1 - t0; }
+    // ---- phase B: zk = A pk, pk.zk
+    for (int q = blockIdx.x; q < g.nchunks; q += gridDim.x) {
+      const int32_t info = order ? __ldg(order + q) : (int32_t)q;
+      double s[1] = {0.0};
+      spmv_dot_chunk<1, false, W, false>(g.n, g.m, g.pk, g.zk, g.pk, info, g.fused != 0, g.ra.cd, seq, s);
+      store_chunk_partials<1>(s, g.ra, info & 0x7fffffff);
+    }
+    {
+      RedArgs ra = g.ra;
+      ra.epi = EPI_PKAPK;
+      gbar_reduce<1>(g.bar, ra, g.nchunks);
+    }
+    unsigned long long t2 = 0ull;
+    if (timer) { t2 = p2p_now_ns(); g.phase_ns[1] += t2 - t1; }
+    // ---- phase C: solution / residual update, sum|res|, next res.z, first-iteration normalisation factor
+    const double alf = vsc->alf;
+    const bool first = vsc->iters == 0;
+    for (int q = blockIdx.x; q < g.nchunks; q += gridDim.x) {
+      const int32_t info = order ? __ldg(order + q) : (int32_t)q;
+      double s[3] = {0.0, 0.0, 0.0};
+      cg_update_chunk<true>(g.n, g.fi, g.res, g.pk, g.zk, g.adiag, alf, first, info & 0x7fffffff, s);
+      store_chunk_partials<3>(s, g.ra, info & 0x7fffffff);
+    }
+    {
+      RedArgs ra = g.ra;
+      ra.epi = EPI_CG_UPDATE;
+      gbar_reduce<3>(g.bar, ra, g.nchunks);
+    }
+    if (timer) { t0 = p2p_now_ns(); g.phase_ns[2] += t0 - t2; g.phase_ns[3] += 1ull; }
+    if (vsc->done) break;
+  }
 }
 
 // sum a*b (iccg sk = sum res*zk)
@@ -1122,6 +1305,52 @@ static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double
   return FCP_OK;
 }
 
+// FCP_DPCG=kernels: the three-kernel iteration with a host poll per 16 iterations (round 1); default: the persistent cooperative kernel.
+// Read per call so that tests and A/B timings can switch inside one process.
+static bool dpcg_persist_wanted() {
+  const char *e = getenv("FCP_DPCG");
+  return !(e && !strcmp(e, "kernels"));
+}
+static int launch_dpcg_persist(const SellPattern &p, const SellView &m, double *fi, KrylovWS &ws, const RedArgs &ra, int fused, unsigned int seq_base,
+                               Profiler *prof, cudaStream_t st) {
+  const int nchunks = fcp_nchunks(p.n);
+  const bool wide = p.tile_cap > 8 * 256;
+  int minb = 3;
+  if (const char *e = getenv("FCP_PERSIST_MINB")) { const int v = atoi(e); if (v >= 2 && v <= 4) minb = v; }   // measurements only
+  const int variant = wide ? 0 : minb - 1;      // 0: W = 16 (long rows, 2 CTAs/SM); 1..3: W = 8 with 2, 3, 4 CTAs/SM
+  const void *fn = variant == 0 ? (const void *)k_dpcg_persist<16, 2> : variant == 1 ? (const void *)k_dpcg_persist<8, 2>
+                 : variant == 2 ? (const void *)k_dpcg_persist<8, 3> : (const void *)k_dpcg_persist<8, 4>;
+  int &cap = ws.persist_grid[variant];
+  if (!cap) FCP_TRY(coop_grid(fn, ws.ws_device, &cap));
+  int grid = std::min(cap, nchunks);
+  if (const char *e = getenv("FCP_PERSIST_GRID")) { const int v = atoi(e); if (v > 0) grid = std::min(grid, v); }   // measurements only
+  const bool timing = prof && prof->on;
+  FCP_CUDA(cudaMemsetAsync(ws.bar, 0, 4 * sizeof(unsigned int), st));
+  if (timing) FCP_CUDA(cudaMemsetAsync(ws.phase_ns, 0, 8 * sizeof(unsigned long long), st));
+  PersistArgs g{p.n, nchunks, m, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, ra, seq_base, fused, ws.bar, timing ? ws.phase_ns : nullptr};
+  void *args[] = {&g};
+  size_t tok = timing ? prof->begin(FCP_K_KRYLOV_PERSIST, st) : 0;
+#ifdef FCP_EMU
+  (void)args; (void)fn;
+  if (variant == 0) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_dpcg_persist<16, 2>, g);
+  else if (variant == 1) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_dpcg_persist<8, 2>, g);
+  else if (variant == 2) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_dpcg_persist<8, 3>, g);
+  else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_dpcg_persist<8, 4>, g);
+#else
+  FCP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FCP_TPB), args, 0, st));
+#endif
+  if (timing) prof->end(tok, st);
+  FCP_LAUNCHED();
+  if (timing) {          // book the phases under the classes of the kernels they replace
+    unsigned long long h[8];
+    FCP_CUDA(cudaMemcpyAsync(h, ws.phase_ns, sizeof(h), cudaMemcpyDeviceToHost, st));
+    FCP_CUDA(cudaStreamSynchronize(st));
+    const int cls[3] = {FCP_K_CG_PK, FCP_K_SPMV_DOT, FCP_K_CG_UPDATE};
+    for (int k = 0; k < 3; ++k) { prof->total_ms[cls[k]] += 1e-6 * (double)h[k]; prof->launches[cls[k]] += (int64_t)h[3]; }
+  }
+  return FCP_OK;
+}
+
 // poll the device scalars; returns done flag
 static int fetch_scalars(KrylovWS &ws, cudaStream_t st) {
   FCP_CUDA(cudaMemcpyAsync(ws.h_sc, ws.sc, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, st));
@@ -1177,6 +1406,10 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     FCP_TRY(L.halo(fi));
     if (grid) { k_cg_init<true><<<grid, FCP_TPB, 0, st>>>(n, m, fi, rhs, ws.res, ws.adiag, ws.pk, L.red(EPI_INIT_CG)); FCP_LAUNCHED(); FCP_CHECK_LAUNCH(); }
     FCP_TRY(L.post(EPI_INIT_CG, 2));
+    if (grid && (!comm || cd) && dpcg_persist_wanted()) {
+      // the whole iteration loop on the device: one cooperative launch, one read of the scalars (below)
+      FCP_TRY(launch_dpcg_persist(p, m, fi, ws, L.red(EPI_NONE), fw, sb, prof, st));
+    } else
     for (int it = 0; it < itr_max;) {
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
         if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));

@@ -38,6 +38,7 @@ template int dev_alloc<double>(double **, size_t);
 template int dev_alloc<int32_t>(int32_t **, size_t);
 template int dev_alloc<int64_t>(int64_t **, size_t);
 template int dev_alloc<unsigned int>(unsigned int **, size_t);
+template int dev_alloc<unsigned long long>(unsigned long long **, size_t);
 template int dev_upload<double>(double **, const double *, size_t);
 template int dev_upload<int32_t>(int32_t **, const int32_t *, size_t);
 template int dev_upload<int64_t>(int64_t **, const int64_t *, size_t);

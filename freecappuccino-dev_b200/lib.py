@@ -36,7 +36,7 @@ FIELDS = ["U", "V", "W", "P", "PP", "DEN", "VIS", "APU", "APV", "APW", "SU", "SV
           "FSST", "WALLDIST", "DTEDXI", "DEDDXI"]
 F = {name: i for i, name in enumerate(FIELDS)}
 KERNEL_CLASSES = ["spmv_dot", "cg_pk", "cg_update", "cg_init", "precond", "dot", "bicg_elem", "assemble", "gradp", "correct_flux",
-                  "grad", "laplacian", "spmv", "halo", "limiter", "piso_h", "uvw", "scalar"]
+                  "grad", "laplacian", "spmv", "halo", "limiter", "piso_h", "uvw", "scalar", "krylov_persist"]
 GRADIENT_FIELDS = {"DUDXI", "DVDXI", "DWDXI", "DPDXI", "G0", "G1", "DTEDXI", "DEDDXI"}
 
 

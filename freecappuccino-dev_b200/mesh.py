@@ -894,22 +894,27 @@ def hex_mesh_fast(xs: np.ndarray, ys: np.ndarray, zs: np.ndarray, patch_types: O
     return mesh
 
 
-def polyhedral_mesh_fast(nx: int, ny: Optional[int] = None, nz: Optional[int] = None, patch_types: Optional[Dict[str, str]] = None) -> Mesh:
+def polyhedral_mesh_fast(nx: int, ny: Optional[int] = None, nz: Optional[int] = None, patch_types: Optional[Dict[str, str]] = None,
+                         zrange: Optional[Tuple[int, int]] = None, peer: Optional[Dict[str, int]] = None) -> Mesh:
     """The brick-pattern polyhedral mesh of `polyhedral_mesh` (10-faced cells, pairs of hexahedra merged along x with the pair start staggered in
     y and z) WITHOUT distortion and without going through points and face-node lists: the hexahedral arrays of `hex_mesh_fast` are merged
     directly -- cell volume = sum, cell centre = volume-weighted mean (what the pyramid formula of geometry.f90:416-530 gives for a cell with planar
     faces), the face between the two halves dropped, face interpolation factors and Df re-evaluated from the new centres (geometry.f90:581-606,
     648-664) -- so that BASELINE config 5's size (~20 M polyhedra) is generated in about two minutes.  Same topology and face order as
-    `polyhedral_mesh(nx, ny, nz, distort=0)`."""
+    `polyhedral_mesh(nx, ny, nz, distort=0)`.
+    zrange = (k0, k1) + peer = {"back": rank below, "front": rank above}: only the z-slab of hexahedron layers k0 <= k < k1 of that mesh, in the
+    src-par layout (`polyhedral_partition_fast`): the pairs are merged along x and staggered with the GLOBAL layer index, so a z-cut separates no
+    pair and the slabs together are exactly the global mesh; the cut faces become `process` patches, ordered alike on both sides."""
     ny = nx if ny is None else ny
     nz = nx if nz is None else nz
-    h = hex_mesh_fast(np.linspace(0.0, 1.0, nx + 1), np.linspace(0.0, 1.0, ny + 1), np.linspace(0.0, 1.0, nz + 1), patch_types)
+    k0, k1 = zrange if zrange is not None else (0, nz)
+    h = hex_mesh_fast(np.linspace(0.0, 1.0, nx + 1), np.linspace(0.0, 1.0, ny + 1), np.linspace(0.0, 1.0, nz + 1)[k0: k1 + 1], patch_types, peer)
     nh, Fi = h.numCells, h.numInnerFaces
     c = np.arange(nh, dtype=np.int64)
-    i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+    i, j, k = c % nx, (c // nx) % ny, c // (nx * ny) + k0
     head = np.where((i - (j + k) % 2) % 2 == 0, i, i - 1)
     head = np.where(head < 0, 0, head)
-    key = head + nx * (j + ny * k)                      # non-decreasing in c: hexes of a pair are consecutive
+    key = head + nx * (j + ny * (k - k0))               # non-decreasing in c: hexes of a pair are consecutive
     del i, j, k, head, c
     first = np.empty(nh, dtype=bool)
     first[0] = True
@@ -947,7 +952,25 @@ def polyhedral_mesh_fast(nx: int, ny: Optional[int] = None, nz: Optional[int] = 
     neighbour = (fn + 1).astype(np.int32)
     return Mesh(numCells=ncell, numInnerFaces=nF_in, numBoundaryFaces=h.numBoundaryFaces, owner=owner, neighbour=neighbour,
                 arx=arx, ary=ary, arz=arz, xf=xf, yf=yf, zf=zf, facint=facint, Df=Df, xc=xc, yc=yc, zc=zc, vol=vol,
-                bcname=list(h.bcname), bctype=h.bctype.copy(), nfaces=h.nfaces.copy(), startFace=(h.startFace - removed).astype(np.int32))
+                bcname=list(h.bcname), bctype=h.bctype.copy(), nfaces=h.nfaces.copy(), startFace=(h.startFace - removed).astype(np.int32),
+                peer_rank=None if peer is None else h.peer_rank.copy(), peer_patch=None if peer is None else h.peer_patch.copy())
+
+
+def polyhedral_partition_fast(nx: int, nranks: int, rank: int, ny: Optional[int] = None, nz: Optional[int] = None,
+                              patch_types: Optional[Dict[str, str]] = None) -> Mesh:
+    """Rank `rank`'s z-slab of `polyhedral_mesh_fast(nx, ny, nz)` generated directly in the src-par layout (no global mesh is ever built: BASELINE
+    config 5 at ~20 M cells over 8 ranks needs 1/8 of the host memory and time per rank).  Ghost copies of xc, yc, zc, vol and the process-face
+    facint / Df are filled by fcp_comm_init (src-par/geometry.f90:769-819)."""
+    nz = nx if nz is None else nz
+    k0, k1 = (nz * rank) // nranks, (nz * (rank + 1)) // nranks
+    if k1 <= k0:
+        raise ValueError("polyhedral_partition_fast: more ranks than layers")
+    peer = {}
+    if rank > 0:
+        peer["back"] = rank - 1
+    if rank < nranks - 1:
+        peer["front"] = rank + 1
+    return polyhedral_mesh_fast(nx, ny, nz, patch_types, (k0, k1), peer)
 
 
 def block_dims(nranks: int) -> Tuple[int, int, int]:

@@ -328,7 +328,9 @@ int fcp_global_isum(fcp_ctx *ctx, int64_t *value);           /* src-par/global_i
 /* ---- per-kernel-class device timing (CUDA events on the context stream, around every launch of the class) ---- */
 enum { FCP_K_SPMV_DOT = 0, FCP_K_CG_PK, FCP_K_CG_UPDATE, FCP_K_CG_INIT, FCP_K_PRECOND, FCP_K_DOT, FCP_K_BICG_ELEM,
        FCP_K_ASSEMBLE, FCP_K_GRADP, FCP_K_CORRECT_FLUX, FCP_K_GRAD, FCP_K_LAPLACIAN, FCP_K_SPMV, FCP_K_HALO, FCP_K_LIMITER,
-       FCP_K_PISO_H, FCP_K_UVW, FCP_K_SCALAR, FCP_K_COUNT };
+       FCP_K_PISO_H, FCP_K_UVW, FCP_K_SCALAR,
+       FCP_K_KRYLOV_PERSIST /* the whole solve as one persistent kernel; its phases are also booked under SPMV_DOT / CG_PK / CG_UPDATE / PRECOND / DOT */,
+       FCP_K_COUNT };
 int fcp_profile_enable(fcp_ctx *ctx, int on);
 int fcp_profile_reset(fcp_ctx *ctx);
 int fcp_profile_read(fcp_ctx *ctx, int kclass, double *total_ms, int64_t *launches);   /* synchronises; totals since reset */

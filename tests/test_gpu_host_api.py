@@ -121,3 +121,47 @@ def test_turbulence_procedures_of_the_module_api(orc):
     case.updateBoundary(phi)
     assert np.array_equal(phi, ref) and np.all(np.isfinite(case.vis)) and case.vis[:n].min() > 0
     case.close()
+
+
+def test_fv_equation_operators_and_axpby():
+    """Row a2: type(fvEquation) with operator(+), operator(-), operator(==) (fvImplicit/fvEquation.f90:158-404, src-par/fv_equation.f90:48-71).
+    equation +/- equation: coef and source element-wise (add_fvEquations / subtract_fvEquations); equation +/- source field: a NEW equation whose
+    coef is zero and whose source is su +/- field (add_source_to_fvEquation :168-190, subtract_source_from_fvEquation :224-246); operator(==) is
+    bound to the subtract procedures (:68-73).  One add or subtract per element has a single correctly rounded result, so the comparison with numpy
+    is bit for bit; fcp_field_axpby itself is also checked with general alpha / beta (two roundings, no FMA: -fmad=false) and for its extent check."""
+    from fcb200 import lib as L
+    m = cases.meshes()["poly_10faces"]
+    case = H.Case(m, out=io.StringIO())
+    n, nnz = m.numCells, case.nnz
+    rng = np.random.default_rng(2024)
+    e1 = H.FvEquation(case, rng.standard_normal(nnz), rng.standard_normal(n))
+    e2 = H.FvEquation(case, rng.standard_normal(nnz) * 1e3, rng.standard_normal(n) * 1e-3)
+    s = e1 + e2
+    assert np.array_equal(s.coef, e1.coef + e2.coef) and np.array_equal(s.source, e1.source + e2.source)
+    d = e1 - e2
+    assert np.array_equal(d.coef, e1.coef - e2.coef) and np.array_equal(d.source, e1.source - e2.source)
+    q = e1.equals(e2)
+    assert np.array_equal(q.coef, d.coef) and np.array_equal(q.source, d.source)
+    src = rng.standard_normal(m.numTotal)                   # a volScalarField: numTotal values, the cells' part is used
+    p = e1 + src
+    assert not p.coef.any() and np.array_equal(p.source, e1.source + src[:n])
+    r = e1 - src
+    assert not r.coef.any() and np.array_equal(r.source, e1.source - src[:n])
+    assert np.array_equal(e1.equals(src).source, r.source)
+    # the inputs are untouched (the operators return new equations)
+    assert e1.coef.shape == (nnz,) and e1.source.shape == (n,)
+    # fcp_field_axpby, general coefficients: dst = alpha x + beta y in the matrix slots (CSR order in, CSR order out) and in the field slots
+    c = case.ctx
+    x, y = rng.standard_normal(nnz), rng.standard_normal(nnz)
+    c.upload("A", x); c.upload("H", y)
+    c.axpby("H", 0.75, "A", -2.5, "H")                      # in place in y
+    assert np.array_equal(c.download("H"), 0.75 * x + (-2.5) * y)
+    assert np.array_equal(c.download("A"), x)
+    xs, ys = rng.standard_normal(m.numTotal), rng.standard_normal(m.numTotal)
+    c.upload("S0", xs); c.upload("S1", ys)
+    c.axpby("S2", 3.0, "S0", 1.0, "S1")
+    assert np.array_equal(c.download("S2"), 3.0 * xs + ys)
+    with pytest.raises(L.FcpError):
+        c.axpby("A", 1.0, "A", 1.0, "S0")                   # extents differ: refused, nothing is written
+    assert np.array_equal(c.download("A"), x)
+    case.close()

@@ -209,6 +209,141 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_poly(args, rank, local_rank, world, torch, dist, L, M):
+    """--workload poly (BASELINE.json configs[4]): the brick-pattern polyhedral mesh (10-faced cells, ~20 M at --poly-n 342) in z-slabs over the
+    ranks; one step = what the reference's wall-distance / gradient pipeline does on such a mesh (mesh/wall_distance.f90:96-133 with the
+    gradient methods of examples/elbow3D/input-1.nml):
+        grad_gauss(phi)                          gradients.f90:1607-1693      k_grad_gauss      40 F + 40 N + 36 B bytes
+        grad_lsq(phi)                            gradients.f90:782-893        k_grad_lsq         8 F + 128 N + 36 B bytes
+        laplacian(mu, phi) with su = vol         fvImplicit/laplacian.f90     k_laplacian
+        csrsolve('iccg', tolRel 1e-8)            linear_solvers.f90:364-545   IC(0) factor, level-scheduled sweeps, SpMV+dot, updates
+    Across ranks the IC(0) preconditioner is block-Jacobi like src-par/iccg.f90, so the iteration count grows with the rank count."""
+    nx = args.poly_n
+    t_setup = time.perf_counter()
+    m = M.polyhedral_partition_fast(nx, world, rank) if world > 1 else M.polyhedral_mesh_fast(nx)
+    N0, F0, B0 = m.numCells, m.numInnerFaces, m.numBoundaryFaces
+    phi = m.boundary_values_of(lambda x, y, z: np.sin(2.0 * x) * np.cos(3.0 * y) + z * z)
+    vol_su = np.concatenate([m.vol[:N0], np.zeros(B0)])
+    pin_phi, pin_su = pinned_copy(phi), pinned_copy(vol_su)
+    out_g1, out_g2, out_x = pinned_copy(np.zeros((m.numTotal, 3))), pinned_copy(np.zeros((m.numTotal, 3))), pinned_copy(np.zeros(m.numTotal))
+    ctx = L.Context(m, local_rank)
+    if world > 1:
+        uid = [L.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0], m.peer_rank)
+    ctx.upload("S0", pin_phi[1])
+    ctx.fill("VIS", -1.0)
+    ctx.fill("S1", 0.0)
+    ctx.create_lsq_grad_matrix(L.GRAD_LSQ)
+    nnz0 = ctx.nnz + ctx.npro
+    MAXIT = 5000
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def step():
+        ctx.grad(L.GRAD_GAUSS, "S0", "G0")
+        ctx.grad(L.GRAD_LSQ, "S0", "G1")
+        ctx.copy("SU", "S2")                      # su = vol (the laplacian call subtracts the boundary terms from it)
+        ctx.laplacian("VIS", "S1")
+        ctx.fill("PP", 0.0)
+        return ctx.csrsolve(args.solver if args.solver != "dpcg" or args.poly_dpcg else "iccg", "PP", "SU", MAXIT, 1e-30, TOL_REL)
+
+    def e2e_step():
+        ctx.upload("S0", pin_phi[1])
+        ctx.upload("S2", pin_su[1])
+        rep = step()
+        for fld, buf in (("G0", out_g1), ("G1", out_g2)):
+            L.check(L.lib().fcp_field_download(ctx.h, L.field_id(fld), L._d(buf[1]), 3 * m.numTotal))
+        L.check(L.lib().fcp_field_download(ctx.h, L.field_id("PP"), L._d(out_x[1]), m.numTotal))
+        return rep
+    ctx.upload("S2", pin_su[1])
+    rep = None
+    for _ in range(max(args.warmup, 1)):
+        rep = step()
+    ctx.sync()
+    if rep.iters >= MAXIT or not np.isfinite(rep.resl):
+        raise SystemExit(f"bench.py: the ICCG solve did not converge ({rep.iters} iterations, final residual {rep.resl})")
+    t_setup = time.perf_counter() - t_setup
+    ctx.profile_enable(False)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = L.launch_count()
+    dev_ms = []
+    for _ in range(args.steps):
+        ctx.timer_start()
+        rep = step()
+        dev_ms.append(ctx.timer_stop())
+    barrier()
+    launches = L.launch_count() - launches0
+    # profiled pass: each gradient kernel on its own, then the solve
+    ctx.profile_enable(True)
+    prof = {}
+    for name, fn in (("grad_gauss", lambda: ctx.grad(L.GRAD_GAUSS, "S0", "G0")), ("grad_lsq", lambda: ctx.grad(L.GRAD_LSQ, "S0", "G1"))):
+        ctx.profile_reset()
+        for _ in range(5):
+            fn()
+        prof[name] = ctx.profile_read().get("grad")
+    ctx.profile_reset()
+    ctx.copy("SU", "S2"); ctx.laplacian("VIS", "S1"); ctx.fill("PP", 0.0)
+    ctx.csrsolve("iccg", "PP", "SU", MAXIT, 1e-30, TOL_REL)
+    prof.update(ctx.profile_read())
+    ctx.profile_enable(False)
+    e2e_step()
+    barrier()
+    e2e0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - e2e0) / args.steps
+    clocks = sampler.stop() if sampler else None
+    stats = dict(ms=float(np.mean(dev_ms)), e2e=e2e_ms, cells=N0, launches=launches)
+    allstats = [stats]
+    if dist is not None:
+        allstats = [None] * world
+        dist.all_gather_object(allstats, stats)
+    if rank != 0:
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ms, e2e = max(q["ms"] for q in allstats), max(q["e2e"] for q in allstats)
+    peak, peak_src = hbm_peak()
+
+    def kernel_line(name, nbytes):
+        if not prof.get(name):
+            return None
+        tot, cnt = prof[name]
+        gbs = nbytes / (tot / cnt * 1e-3) / 1e9
+        return dict(kernel=name, launches=cnt, avg_ms=tot / cnt, bytes_per_launch=nbytes, achieved_gbs=gbs, frac=gbs / peak)
+    kl = {"grad_gauss": kernel_line("grad_gauss", 40 * F0 + 40 * N0 + 36 * B0), "grad_lsq": kernel_line("grad_lsq", 8 * F0 + 128 * N0 + 36 * B0),
+          "laplacian": kernel_line("laplacian", 64 * F0 + 60 * N0), "precond": kernel_line("precond", 24 * F0 + 80 * N0),
+          "spmv_dot": kernel_line("spmv_dot", 12 * nnz0 + 20 * N0), "cg_pk": kernel_line("cg_pk", 24 * N0), "cg_update": kernel_line("cg_update", 48 * N0),
+          "dot": kernel_line("dot", 16 * N0)}
+    gg = kl["grad_gauss"]
+    total_cells = int(sum(q["cells"] for q in allstats))
+    line = dict(
+        metric=f"polyhedral step time (~{total_cells / 1e6:.1f} M ten-faced polyhedra: grad_gauss + grad_lsq + laplacian + ICCG to 1e-8)", value=ms, unit="ms",
+        n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=False, scaling="strong", vs_baseline=None,
+        dtype="f64", data="synthetic",
+        config=dict(workload=f"synthetic polyhedral elbow3D-style mesh {nx}^3/2 ({total_cells} cells), Gauss/LSQ gradients + ICCG", solver="iccg",
+                    tol_rel=TOL_REL, iccg_iters=int(rep.iters), partition=f"z-slabs x{world}", comm=ctx.comm_mode(),
+                    l2=l2_note(12 * nnz0 + 60 * N0)),
+        e2e=dict(value=e2e, unit="ms", h2d_bytes_per_step=16 * m.numTotal, d2h_bytes_per_step=56 * m.numTotal),
+        gpu_launches=int(sum(q["launches"] for q in allstats)),
+        roofline=dict(bound="hbm", achieved=gg["achieved_gbs"], peak=peak, unit="GB/s", frac=gg["frac"], traffic=None, kernel="k_grad_gauss (40 F + 40 N + 36 B)",
+                      peak_source=peak_src, avg_launch_ms=gg["avg_ms"], launches=gg["launches"]) if gg else None,
+        cpu_baseline=None, clocks=clocks, kernels={k: v for k, v in kl.items() if v},
+        iccg=dict(iters=int(rep.iters), res0=rep.res0, resl=rep.resl), setup_s=t_setup)
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +352,9 @@ def main():
     ap.add_argument("--n", "--cells", dest="n", type=int, default=256, help="cells per direction of the cavity mesh (--cells under torchrun, whose own parser rejects --n as ambiguous)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--solver", default="dpcg", choices=["dpcg", "iccg", "bicgstab"])
+    ap.add_argument("--workload", default="cavity", choices=["cavity", "poly"], help="cavity: BASELINE configs[2] (the contract benchmark); poly: configs[4]")
+    ap.add_argument("--poly-n", type=int, default=342, help="--workload poly: hexahedra per direction before merging (342 -> 20.0 M polyhedra)")
+    ap.add_argument("--poly-dpcg", action="store_true", help="--workload poly: honour --solver dpcg (default: ICCG, the solver config 5 names)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-steps", type=int, default=2, help="steps of the separate per-kernel profiled pass (CUDA events around every launch)")
     ap.add_argument("--cpu-iters", type=int, default=40, help="DPCG iterations timed by the cpu_baseline leg")
@@ -244,6 +382,8 @@ def main():
     if world != args.gpus and rank == 0:
         print(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)
     n = args.n
+    if args.workload == "poly":
+        return run_poly(args, rank, local_rank, world, torch, dist, L, M)
 
     def barrier():
         torch.cuda.synchronize()

@@ -59,3 +59,57 @@ def test_polyhedral_mesh_fast_equals_the_point_based_generator():
             np.testing.assert_allclose(getattr(a, k)[: a.numCells], getattr(b, k)[: a.numCells], rtol=1e-11, atol=1e-13, err_msg=k)
         rows = np.bincount(np.concatenate([b.owner[: b.numInnerFaces], b.neighbour]) - 1, minlength=b.numCells)
         assert rows.max() == 10 or min(dims) < 3          # interior polyhedra have ten neighbours
+
+
+def test_polyhedral_partition_fast_equals_the_partitioned_global_mesh():
+    """`mesh.polyhedral_partition_fast` (bench.py --workload poly: every rank generates only its own z-slab of BASELINE config 5's mesh) against
+    `mesh.partition` of the global `polyhedral_mesh_fast` mesh: same cells, inner faces, geometry and -- what the halo exchange relies on -- the
+    same order of the process faces on both sides of every cut."""
+    import numpy as np
+    from fcb200 import mesh as M
+    nx, ny, nz, P = 8, 6, 10, 3
+    g = M.polyhedral_mesh_fast(nx, ny, nz)
+    n = g.numCells
+    layer = np.floor(g.zc[:n] * nz).astype(int)
+    cuts = [(nz * r) // P for r in range(P + 1)]
+    cr = np.zeros(n, np.int32)
+    for r in range(P):
+        cr[(layer >= cuts[r]) & (layer < cuts[r + 1])] = r
+    ref = M.partition(g, cr)
+    mine = [M.polyhedral_partition_fast(nx, P, r, ny, nz) for r in range(P)]
+    for r in range(P):
+        a, b = mine[r], ref[r]
+        assert (a.numCells, a.numInnerFaces, a.numBoundaryFaces) == (b.numCells, b.numInnerFaces, b.numBoundaryFaces)
+        Fi = a.numInnerFaces
+        assert np.array_equal(a.owner[:Fi], b.owner[:Fi]) and np.array_equal(a.neighbour, b.neighbour)
+        for k in ("xc", "yc", "zc", "vol"):
+            np.testing.assert_allclose(getattr(a, k)[:a.numCells], getattr(b, k)[:b.numCells], rtol=0, atol=1e-15)
+        for k in ("arx", "ary", "arz", "xf", "yf", "zf"):
+            np.testing.assert_allclose(getattr(a, k)[:Fi], getattr(b, k)[:Fi], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(a.facint, b.facint[:Fi], rtol=1e-14)
+        np.testing.assert_allclose(a.Df, b.Df[:Fi], rtol=1e-13)
+        # boundary faces patch by patch (the two generators list the patches in different orders): owner cells, areas and centres
+        def patches(msh):
+            out = {}
+            for ib in range(msh.numBoundaries):
+                if msh.nfaces[ib] == 0:
+                    continue
+                pf = msh.patch_faces(ib)
+                key = ("proc", int(msh.peer_rank[ib])) if msh.bctype[ib] == M.BC_PROCESS else ("phys", msh.bcname[ib])
+                out[key] = (msh.owner[pf], msh.arx[pf], msh.ary[pf], msh.arz[pf], msh.xf[pf], msh.yf[pf], msh.zf[pf])
+            return out
+        pa, pb = patches(a), patches(b)
+        assert set(pa) == set(pb), (sorted(pa), sorted(pb))
+        for key in pa:
+            assert np.array_equal(pa[key][0], pb[key][0]), key
+            for x, y in zip(pa[key][1:], pb[key][1:]):
+                np.testing.assert_allclose(x, y, rtol=0, atol=1e-15)
+    # both sides of a cut list its faces in the same order: face i of rank r's patch towards q and face i of q's patch towards r are the same face
+    for r in range(P - 1):
+        a, b = mine[r], mine[r + 1]
+        fa = a.patch_faces(int(np.nonzero(a.peer_rank == r + 1)[0][0]))
+        fb = b.patch_faces(int(np.nonzero(b.peer_rank == r)[0][0]))
+        assert fa.size == fb.size
+        np.testing.assert_allclose(a.xf[fa], b.xf[fb], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(a.yf[fa], b.yf[fb], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(a.arz[fa], -b.arz[fb], rtol=0, atol=1e-15)

@@ -493,6 +493,7 @@ extern "C" int fcp_comm_mode(const fcp_ctx *ctx) {
   return ctx->comm->p2p ? 1 : 0;
 }
 // raised by a kernel that gave up waiting for a peer (p2p.cuh: p2p_wait)
+const int *comm_error_flag(const FcpComm *c) { return (c && c->p2p) ? &c->h_dev.hdr->error : nullptr; }   // device address
 int comm_check_error(fcp_ctx *ctx) {
   FcpComm *c = ctx->comm;
   if (!c || !c->p2p) return FCP_OK;

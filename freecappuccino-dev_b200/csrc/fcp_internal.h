@@ -49,6 +49,19 @@ static inline int fcp_nchunks(int64_t n) { return (int)((n + FCP_CHUNK - 1) / FC
 // The order of the entries inside a row is the CSR order (columns ascending, diagonal embedded, halo columns
 // >= n last), so row sums round exactly like the reference's sequential CSR loops.
 // ---------------------------------------------------------------------------------------------
+// one triangle of the matrix in level-tile order (see SellPattern::tri)
+struct TriTiles {
+  int32_t ntiles = 0, maxlen = 0;
+  int64_t nent = 0;               // 32 * sum of the tile lengths
+  int64_t *tptr = nullptr;        // [ntiles+1]
+  int32_t *tcol = nullptr;        // [nent] column (0-based) or -1
+  int32_t *tsrc = nullptr;        // [nent] SELL position of the entry in a() or -1
+  int32_t *ttsrc = nullptr;       // [nent] forward only, built with tpos: SELL position of the transposed entry (ILU(0)) or -1
+  const int32_t *prow = nullptr;  // = plev_rows / pblev_rows
+  double *tval = nullptr;         // [nent] values of this solve's matrix
+  double *ttval = nullptr;        // [nent] transposed values (ILU(0) factor), forward only
+  double *dtile = nullptr;        // [32 ntiles] the factor diagonal d in tile order
+};
 struct SellPattern {
   int32_t n = 0;        // rows (numCells)
   int32_t ncols = 0;    // columns (numTotal when halo columns exist)
@@ -80,6 +93,12 @@ struct SellPattern {
   int32_t nplev = 0, npblev = 0;   // padded lengths (multiples of 32)
   int32_t *ready = nullptr;        // [n] epoch of the last sweep that finished the row
   int32_t sweep_epoch = 0;         // host counter: a preconditioner apply uses epoch+1 (forward) and epoch+2 (backward)
+  // flag-in-data sweeps (default): the strictly lower / strictly upper triangle re-stored per TILE of 32 consecutive positions of the padded
+  // level order (tile t, entry k, lane l at ttptr[t] + 32 k + l), so that a warp reads its rows' entries as full lines although the rows of a
+  // level are scattered over the SELL slices; entries keep the CSR order of their row.  Structure once per pattern, values once per solve.
+  TriTiles tri[2];                 // [0] forward (entries before the diagonal), [1] backward (local entries after it)
+  unsigned long long *zll[3] = {nullptr, nullptr, nullptr};   // [2n] LL words each: forward result, backward result, factor diagonal
+  unsigned int ll_epoch = 0;       // sequence number of the last sweep / factor that used the LL arrays
 };
 
 // cell -> faces gather lists, SELL-32 as well (ent, other, slot share the layout)
@@ -106,11 +125,12 @@ struct KrylovWS {
   double *reso = nullptr, *uk = nullptr, *vk = nullptr, *tmp = nullptr;
   KrylovScalars *sc = nullptr;        // device
   KrylovScalars *h_sc = nullptr;      // pinned host mirror
+  int32_t *h_poll = nullptr;          // pinned [4]: the `done` flag ([0,1]) and the peer-memory error word ([2,3]) after each of the two batches in flight
   double *partials = nullptr;         // [4 * maxchunks]
   unsigned int *counter = nullptr;    // last-block ticket
   unsigned int *bar = nullptr;        // [4] grid barrier of the persistent solver kernels: arrivals, generation
   unsigned long long *phase_ns = nullptr;   // [8] per-phase times of the persistent kernels (CTA 0's view), profiler only
-  int persist_grid[4] = {0, 0, 0, 0};       // cooperative grid size per persistent kernel variant on ws_device (0: not queried yet)
+  int persist_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cooperative grid size per persistent / LL-sweep kernel variant on ws_device (0: not queried yet)
   int ws_device = -1;
   int maxchunks = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -335,6 +355,7 @@ int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, 
 void sell_free(SellPattern &p);
 int sell_build_levels(SellPattern &p, cudaStream_t st);
 int sell_build_tpos(SellPattern &p, cudaStream_t st);
+int sell_build_tiles(SellPattern &p, bool with_transposed, cudaStream_t st);
 int sell_values_from_csr(const SellPattern &p, const double *d_a_csr, double *d_a_sell, cudaStream_t st);
 int sell_values_to_csr(const SellPattern &p, const double *d_a_sell, double *d_a_csr, cudaStream_t st);
 template <class T> int dev_upload(T **dptr, const T *h, size_t count);
@@ -358,4 +379,5 @@ const CommDev *comm_dev(const FcpComm *comm);       // device descriptor, nullpt
 const int32_t *comm_chunk_info(const FcpComm *comm); // device copy of CommDev::order, nullptr unless the peer-memory path is active
 unsigned int comm_pk_base(const FcpComm *comm);     // sequence base of the fused direction-vector pushes of the next solve
 void comm_pk_advance(FcpComm *comm, int32_t iters); // after a solve that ran `iters` iterations (identical on all ranks)
-int comm_check_error(fcp_ctx *ctx);
+int comm_check_error(fcp_ctx *ctx);                 // synchronises the stream
+const int *comm_error_flag(const FcpComm *comm);    // device address of the window's error word, nullptr unless the peer-memory path is active

@@ -37,6 +37,7 @@ int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols) {
   FCP_CUDA(cudaStreamSynchronize(0));   // cudaMemset is asynchronous; the solver streams do not order with the legacy stream
   FCP_CUDA(cudaMalloc((void **)&ws.sc, sizeof(KrylovScalars)));
   FCP_CUDA(cudaMallocHost((void **)&ws.h_sc, sizeof(KrylovScalars)));
+  FCP_CUDA(cudaMallocHost((void **)&ws.h_poll, 4 * sizeof(int32_t)));
   FCP_CUDA(cudaEventCreateWithFlags(&ws.ev[0], cudaEventDisableTiming));
   FCP_CUDA(cudaEventCreateWithFlags(&ws.ev[1], cudaEventDisableTiming));
   return FCP_OK;
@@ -54,9 +55,60 @@ void krylov_ws_free(KrylovWS &ws) {
   cudaFree(ws.reso); cudaFree(ws.uk); cudaFree(ws.vk); cudaFree(ws.tmp);
   cudaFree(ws.partials); cudaFree(ws.counter); cudaFree(ws.sc); cudaFree(ws.bar); cudaFree(ws.phase_ns);
   if (ws.h_sc) cudaFreeHost(ws.h_sc);
+  if (ws.h_poll) cudaFreeHost(ws.h_poll);
   if (ws.ev[0]) cudaEventDestroy(ws.ev[0]);
   if (ws.ev[1]) cudaEventDestroy(ws.ev[1]);
   ws = KrylovWS();
+}
+
+// ---------------------------------------------------------------------------------------------
+// L2 residency hints.  On a partition whose Krylov vectors fit the 126 MB L2 (8 ranks at 256^3: 5 x 16.8 MB) the vectors are re-read every
+// iteration while the matrix (176 MB per rank) streams through once per iteration and would evict them: the matrix stream is read evict-first
+// (__ldcs, as before) and, in the HINT variants of the three CG kernels, every vector access carries an L2 cache-policy operand -- evict_last for
+// the vectors the host selected (krylov_l2_masks: by reuse per iteration, while they fit the budget), evict_normal for the others.  A hint never
+// changes a value: bits and iteration counts are those of the plain variants.  FCP_L2=off disables, FCP_L2_MB sets the budget (default 96).
+// ---------------------------------------------------------------------------------------------
+struct L2Pol { unsigned long long last, norm; };
+__device__ __forceinline__ L2Pol l2pol_make() {
+  L2Pol q;
+#ifdef FCP_EMU
+  q.last = q.norm = 0ull;
+#else
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(q.last));
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(q.norm));
+#endif
+  return q;
+}
+__device__ __forceinline__ unsigned long long l2pol_pick(const L2Pol &q, unsigned int mask, int bit) { return (mask >> bit) & 1u ? q.last : q.norm; }
+// vector read through the non-coherent path (the kernel does not write this vector)
+__device__ __forceinline__ double l2_ld_nc(const double *p, unsigned long long pol) {
+#ifdef FCP_EMU
+  (void)pol;
+  return *p;
+#else
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+#endif
+}
+// vector read of an array this kernel also writes (its own rows only)
+__device__ __forceinline__ double l2_ld(const double *p, unsigned long long pol) {
+#ifdef FCP_EMU
+  (void)pol;
+  return *p;
+#else
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void l2_st(double *p, double v, unsigned long long pol) {
+#ifdef FCP_EMU
+  (void)pol;
+  *p = v;
+#else
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -359,6 +411,41 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__re
   cg_pk_chunk<JACOBI>(n, res, adiag, zk, pk, sc->bet, info, cd, seq_base + (unsigned int)sc->iters + 1u);
 }
 
+// the same kernel with L2 cache-policy operands on every vector access (mask bits: 0 pk, 1 res / zk, 2 adiag); the ragged last chunk takes the plain code
+template <bool JACOBI>
+__global__ void __launch_bounds__(FCP_TPB) k_cg_pk_l2(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
+                                                       const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd,
+                                                       const int32_t *__restrict__ chunk_info, unsigned int seq_base, unsigned int mask) {
+  const int32_t info = chunk_info ? __ldg(chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
+  if (sc->done) return;
+  const double bet = sc->bet;
+  const int chunk = info & 0x7fffffff;
+  const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
+  if (base + (FCP_IPT - 1) * FCP_TPB < n) {
+    const L2Pol q = l2pol_make();
+    const unsigned long long p_pk = l2pol_pick(q, mask, 0), p_z = l2pol_pick(q, mask, 1), p_ad = l2pol_pick(q, mask, 2);
+    double z_[FCP_IPT], d_[FCP_IPT], p_[FCP_IPT];
+#pragma unroll
+    for (int j = 0; j < FCP_IPT; ++j) {
+      const int64_t r = base + j * FCP_TPB;
+      if (JACOBI) { z_[j] = l2_ld_nc(res + r, p_z); d_[j] = l2_ld_nc(adiag + r, p_ad); } else { z_[j] = l2_ld_nc(zk + r, p_z); d_[j] = 1.0; }
+      p_[j] = l2_ld(pk + r, p_pk);
+    }
+#pragma unroll
+    for (int j = 0; j < FCP_IPT; ++j) {
+      const double z = JACOBI ? (z_[j] / d_[j]) : z_[j];
+      l2_st(pk + base + j * FCP_TPB, z + bet * p_[j], p_pk);
+    }
+    if (info >= 0) return;
+    const int32_t j0 = cd->chunk_ptr[chunk], j1 = cd->chunk_ptr[chunk + 1];
+    __syncthreads();   // the chunk's pk values are written
+    const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
+    for (int32_t j = j0 + (int32_t)threadIdx.x; j < j1; j += FCP_TPB) p2p_ll_store(cd->push_dst[j], l2_ld(pk + cd->push_cell[j], p_pk), seq);
+    return;
+  }
+  cg_pk_chunk<JACOBI>(n, res, adiag, zk, pk, bet, info, cd, seq_base + (unsigned int)sc->iters + 1u);
+}
+
 // y = A x ; sums: sum v1*y [, sum v2*y | sum y*y]
 template <int NS, bool SQ>
 __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
@@ -396,13 +483,24 @@ __global__ void __launch_bounds__(FCP_TPB) k_spmv_dot(int32_t n, SellView m, con
 // x / v1 loads: NC = true inside an ordinary kernel (the vectors are read-only for the kernel's lifetime: non-coherent path);
 // NC = false inside the persistent solver kernel, where other CTAs rewrite them between grid barriers (plain loads: L1 is invalidated by
 // the barrier's acquire fence, the non-coherent path is not)
-template <bool NC>
-__device__ __forceinline__ double ld_vec(const double *p) { return NC ? __ldg(p) : *p; }
+// VM = 0: non-coherent path (__ldg); 1: coherent L1-cached load (persistent kernel); 2: non-coherent path with an L2 cache-policy operand
+template <int VM>
+__device__ __forceinline__ double ld_vec(const double *p, unsigned long long pol) {
+  if (VM == 0) return __ldg(p);
+  if (VM == 2) return l2_ld_nc(p, pol);
+#ifdef FCP_EMU
+  return *(const volatile double *)p;
+#else
+  double v;      // an L1-cached coherent load the compiler neither turns into the non-coherent path nor orders against the y stores
+  asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#endif
+}
 
 // One chunk of y = A x with the dot-product partial sums of the chunk in s[] (per thread).
-template <int NS, bool SQ, int W, bool NC>
-__device__ __forceinline__ void spmv_dot_chunk(int32_t n, const SellView &m, const double *x, double *y, const double *v1, int32_t info, bool fused,
-                                               const CommDev *cd, unsigned int seq, double (&s)[NS]) {
+template <int NS, bool SQ, int W, int VM>
+__device__ __forceinline__ void spmv_dot_chunk(int32_t n, const SellView &m, const double *x, double *__restrict__ y, const double *v1, int32_t info, bool fused,
+                                               const CommDev *cd, unsigned int seq, double (&s)[NS], unsigned long long px = 0ull, unsigned long long py = 0ull) {
   const int chunk = info & 0x7fffffff;
   const bool halo = fused && info < 0;
   const int64_t base = (int64_t)chunk * FCP_CHUNK + threadIdx.x;
@@ -423,8 +521,8 @@ __device__ __forceinline__ void spmv_dot_chunk(int32_t n, const SellView &m, con
 #pragma unroll
       for (int k = 0; k < W; ++k) av[k] = (k < len) ? __ldcs(m.a + pos + (int64_t)k * 32) : 0.0;
 #pragma unroll
-      for (int k = 0; k < W; ++k) xv[k] = (k < len) ? ld_vec<NC>(x + c[k]) : 0.0;
-      const double vv = v1[r];
+      for (int k = 0; k < W; ++k) xv[k] = (k < len) ? ld_vec<VM>(x + c[k], px) : 0.0;
+      const double vv = ld_vec<VM>(v1 + r, px);
       // next row: meta data and column indices
       int64_t npos = 0;
       int32_t nlen = 0;
@@ -440,7 +538,7 @@ __device__ __forceinline__ void spmv_dot_chunk(int32_t n, const SellView &m, con
 #pragma unroll
       for (int k = 0; k < W; ++k)
         if (k < len) yr = yr + av[k] * xv[k];
-      for (int32_t k = W; k < len; ++k) yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * ld_vec<NC>(x + __ldcs(m.ja + pos + (int64_t)k * 32));
+      for (int32_t k = W; k < len; ++k) yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * ld_vec<VM>(x + __ldcs(m.ja + pos + (int64_t)k * 32), px);
       if (halo) {
         const int32_t full = __ldg(&m.rinfo[r]) & 0xffff;
         for (int32_t k = len; k < full; ++k) {
@@ -448,7 +546,8 @@ __device__ __forceinline__ void spmv_dot_chunk(int32_t n, const SellView &m, con
           yr = yr + __ldcs(m.a + pos + (int64_t)k * 32) * p2p_ll_load(cd->ll + 2 * (size_t)__ldg(cd->ghost_ord + (cg - n)), seq, cd->hdr);
         }
       }
-      y[r] = yr;
+      if (VM == 2) l2_st(y + r, yr, py);
+      else y[r] = yr;
       s[0] = s[0] + vv * yr;
       if (NS > 1 && SQ) s[NS - 1] = s[NS - 1] + yr * yr;
       pos = npos;
@@ -463,7 +562,7 @@ __device__ __forceinline__ void spmv_dot_chunk(int32_t n, const SellView &m, con
       if (r64 >= n) continue;
       const int32_t r = (int32_t)r64;
       double yr;
-      if (NC) yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, cd, seq) : sell_row_sum<false>(m, x, r, 0.0);
+      if (VM != 1) yr = halo ? sell_row_sum_halo<false>(m, x, r, 0.0, cd, seq) : sell_row_sum<false>(m, x, r, 0.0);
       else yr = halo ? sell_row_sum_halo<false, false>(m, x, r, 0.0, cd, seq) : sell_row_sum<false, false>(m, x, r, 0.0);
       y[r] = yr;
       s[0] = s[0] + v1[r] * yr;
@@ -480,7 +579,21 @@ __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
-  spmv_dot_chunk<NS, SQ, W, true>(n, m, x, y, v1, info, fused != 0, ra.cd, seq_base + (unsigned int)sc->iters + 1u, s);
+  spmv_dot_chunk<NS, SQ, W, 0>(n, m, x, y, v1, info, fused != 0, ra.cd, seq_base + (unsigned int)sc->iters + 1u, s);
+  finish_reduce_part<NS>(s, ra, info & 0x7fffffff, (int)gridDim.x);
+}
+// ... with L2 cache-policy operands on the vector accesses (mask bits: 0 x and v1, 1 y)
+template <int NS, bool SQ, int W>
+__global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_dot_pipe_l2(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
+                                                            const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused,
+                                                            unsigned int seq_base, unsigned int mask) {
+  const int32_t info = ra.chunk_info ? __ldg(ra.chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
+  if (sc->done) return;
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  const L2Pol q = l2pol_make();
+  spmv_dot_chunk<NS, SQ, W, 2>(n, m, x, y, v1, info, fused != 0, ra.cd, seq_base + (unsigned int)sc->iters + 1u, s, l2pol_pick(q, mask, 0), l2pol_pick(q, mask, 1));
   finish_reduce_part<NS>(s, ra, info & 0x7fffffff, (int)gridDim.x);
 }
 
@@ -670,6 +783,46 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__rest
   finish_reduce<3>(s, ra);
 }
 
+// ... with L2 cache-policy operands (mask bits: 0 fi, 1 res, 2 pk, 3 zk, 4 adiag); ragged last chunk: the plain code
+template <bool JACOBI>
+__global__ void __launch_bounds__(FCP_TPB) k_cg_update_l2(int32_t n, double *fi, double *res, const double *__restrict__ pk, const double *__restrict__ zk,
+                                                           const double *__restrict__ adiag, const KrylovScalars *sc, RedArgs ra, unsigned int mask) {
+  if (sc->done) return;
+  const double alf = sc->alf;
+  const bool first = sc->iters == 0;
+  double s[3] = {0.0, 0.0, 0.0};
+  const int64_t base = (int64_t)blockIdx.x * FCP_CHUNK + threadIdx.x;
+  if (base + (FCP_IPT - 1) * FCP_TPB < n) {
+    const L2Pol q = l2pol_make();
+    const unsigned long long p_fi = l2pol_pick(q, mask, 0), p_res = l2pol_pick(q, mask, 1), p_pk = l2pol_pick(q, mask, 2), p_zk = l2pol_pick(q, mask, 3),
+                             p_ad = l2pol_pick(q, mask, 4);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      double f_[4], r_[4], p_[4], z_[4], d_[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t r = base + (h * 4 + j) * FCP_TPB;
+        f_[j] = l2_ld(fi + r, p_fi); r_[j] = l2_ld(res + r, p_res); p_[j] = l2_ld_nc(pk + r, p_pk); z_[j] = l2_ld_nc(zk + r, p_zk);
+        d_[j] = (JACOBI || first) ? l2_ld_nc(adiag + r, p_ad) : 1.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t r = base + (h * 4 + j) * FCP_TPB;
+        const double f = f_[j] + alf * p_[j];
+        const double rr = r_[j] - alf * z_[j];
+        l2_st(fi + r, f, p_fi);
+        l2_st(res + r, rr, p_res);
+        s[0] = s[0] + fabs(rr);
+        if (JACOBI) s[1] = s[1] + rr * (rr / d_[j]);
+        if (first) s[2] = s[2] + fabs(d_[j] * f);
+      }
+    }
+  } else {
+    cg_update_chunk<JACOBI>(n, fi, res, pk, zk, adiag, alf, first, (int)blockIdx.x, s);
+  }
+  finish_reduce<3>(s, ra);
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_dpcg_persist: the WHOLE diagonal-PCG solve (linear_solvers.f90:280-358 / src-par/dpcg.f90:79-161) as ONE persistent cooperative kernel.
 // A CTA owns the chunks q = blockIdx.x, blockIdx.x + gridDim.x, ... of the launch order (chunks with process faces first) in all three phases of an
@@ -799,7 +952,7 @@ __global__ void __launch_bounds__(FCP_TPB, MINB) k_dpcg_persist(PersistArgs g) {
     for (int q = blockIdx.x; q < g.nchunks; q += gridDim.x) {
       const int32_t info = order ? __ldg(order + q) : (int32_t)q;
       double s[1] = {0.0};
-      spmv_dot_chunk<1, false, W, false>(g.n, g.m, g.pk, g.zk, g.pk, info, g.fused != 0, g.ra.cd, seq, s);
+      spmv_dot_chunk<1, false, W, 1>(g.n, g.m, g.pk, g.zk, g.pk, info, g.fused != 0, g.ra.cd, seq, s);
       store_chunk_partials<1>(s, g.ra, info & 0x7fffffff);
     }
     {
@@ -1009,6 +1162,154 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_flags(SellView m, Fla
 }
 
 // ---------------------------------------------------------------------------------------------
+// Flag-in-data sweeps (default, FCP_SWEEP=ll): the IC(0)/ILU(0) factor and the two triangular sweeps without ANY grid barrier and without
+// acquire/release traffic.  A result travels as two 8-byte words {32 data bits | 32-bit sequence number} (p2p.cuh: the LL words of the halo
+// protocol, here between the SMs of one GPU): an 8-byte store is atomic, so a word whose tag equals the sweep's sequence number carries valid data --
+// the consumer needs no fence and the producer no release.  Rows are taken in level order, 32 consecutive positions (a tile) per warp, tiles dealt
+// round-robin to the co-resident warps (cooperative launch); every level starts on a warp boundary, so a dependency always lies in an EARLIER tile:
+// the lowest unfinished tile never waits and the sweep cannot deadlock.  Forward tiles are followed directly by the backward tiles (a backward row
+// waits for its own forward value like for any other dependency): one kernel per apply, no barrier in between.  The triangles are read from
+// the level-tile copy (TriTiles: full 256-/128-byte lines per warp although the rows of a level are scattered over the SELL slices).
+// Per-row arithmetic and summation order are those of the sequential reference sweep (linear_solvers.f90:439-445, 458-475, 613-624): same bits.
+// A wait gives up after ~2 s and raises sc->pad (krylov_solve turns it into an error) instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+struct TriView {
+  const int64_t *tptr;
+  const int32_t *tcol;
+  const double *tval, *ttval;
+  const int32_t *prow;
+  double *dtile;
+  int32_t ntiles;
+};
+static TriView tri_view(const TriTiles &t) { return TriView{t.tptr, t.tcol, t.tval, t.ttval, t.prow, t.dtile, t.ntiles}; }
+
+__device__ __forceinline__ double sweep_ll_wait(const unsigned long long *src, unsigned int seq, const KrylovScalars *sc) {
+  unsigned long long w0, w1;
+#ifdef FCP_EMU
+  (void)sc;
+  for (;;) {
+    p2p_ll_load_words(src, w0, w1);
+    if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
+    emu::yield(); emu::os_yield();
+  }
+#else
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    p2p_ll_load_words(src, w0, w1);
+    if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
+    __nanosleep(20);
+    if ((++spins & 4095u) == 0u) {
+      if (*(volatile const int32_t *)&sc->pad) break;
+      const unsigned long long t = p2p_now_ns();
+      if (!t0) t0 = t;
+      else if (t - t0 > 2000000000ull) { *(volatile int32_t *)&const_cast<KrylovScalars *>(sc)->pad = 1; break; }
+    }
+  }
+#endif
+  return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+
+// values of this solve's matrix into the tile order (both triangles; the transposed entries for ILU(0))
+__global__ void __launch_bounds__(FCP_TPB) k_tri_values(int64_t nent, const int32_t *__restrict__ src, const double *__restrict__ a, double *__restrict__ out) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nent; q += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t sp = __ldg(src + q);
+    out[q] = sp >= 0 ? __ldg(a + sp) : 0.0;
+  }
+}
+// d in the order of the backward tiles
+__global__ void __launch_bounds__(FCP_TPB) k_tri_dtile(int32_t np, const int32_t *__restrict__ prow, const double *__restrict__ d, double *__restrict__ dtile) {
+  for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < np; q += gridDim.x * blockDim.x) {
+    const int32_t i = __ldg(prow + q);
+    dtile[q] = i >= 0 ? d[i] : 0.0;
+  }
+}
+
+// d(i) = 1/(a_ii - sum_{k<diag} a_k^2 d(ja_k))               iccg     :439-445
+// d(i) = 1/(a_ii - sum_{k<diag} a_k d(ja_k) a_T(k))          bicgstab :613-624
+template <bool ILU>
+__global__ void __launch_bounds__(FCP_TPB) k_factor_ll(TriView fw, const double *__restrict__ adiag, unsigned long long *dll, unsigned int seq, double *d,
+                                                        const KrylovScalars *sc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp; t < fw.ntiles; t += nwarps) {
+    const int32_t i = __ldg(fw.prow + t * 32 + lane);
+    const int64_t b = __ldg(fw.tptr + t) + lane;
+    const int32_t len = (int32_t)((__ldg(fw.tptr + t + 1) - __ldg(fw.tptr + t)) >> 5);
+    if (i >= 0) {
+      double di = adiag[i];
+      for (int32_t k = 0; k < len; ++k) {
+        const int32_t c = __ldg(fw.tcol + b + (int64_t)k * 32);
+        if (c < 0) break;            // entries of a row are packed from k = 0
+        const double ak = __ldg(fw.tval + b + (int64_t)k * 32);
+        const double dj = sweep_ll_wait(dll + 2 * (size_t)c, seq, sc);
+        if (ILU) di = di - ak * dj * __ldg(fw.ttval + b + (int64_t)k * 32);
+        else di = di - ak * ak * dj;
+      }
+      const double dd = 1.0 / di;
+      d[i] = dd;
+      fw.dtile[t * 32 + lane] = dd;
+      p2p_ll_store(dll + 2 * (size_t)i, dd, seq);
+    }
+  }
+}
+
+// zk = M^-1 rhs : forward sweep, zk/(d+small), backward sweep      (:458-475 ; quirk Q4 kept)
+template <int W>
+__global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriView bw, unsigned long long *zf, unsigned long long *zb, unsigned int seq,
+                                                               const double *__restrict__ rhs, double *__restrict__ zk, const KrylovScalars *sc) {
+  if (sc->done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ntot = (int64_t)fw.ntiles + bw.ntiles;
+  for (int64_t tq = warp; tq < ntot; tq += nwarps) {
+    const bool fwd = tq < fw.ntiles;
+    const TriView &v = fwd ? fw : bw;
+    const int64_t t = fwd ? tq : tq - fw.ntiles;
+    const int32_t i = __ldg(v.prow + t * 32 + lane);
+    const int64_t b = __ldg(v.tptr + t) + lane;
+    const int32_t len = (int32_t)((__ldg(v.tptr + t + 1) - __ldg(v.tptr + t)) >> 5);
+    if (i < 0) continue;
+    const unsigned long long *src = fwd ? zf : zb;
+    // the row's entries and the first look at its dependencies: all loads independent of each other
+    int32_t c[W];
+    double av[W];
+    unsigned long long w0[W], w1[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) c[k] = (k < len) ? __ldg(v.tcol + b + (int64_t)k * 32) : -1;
+#pragma unroll
+    for (int k = 0; k < W; ++k) av[k] = (k < len) ? __ldg(v.tval + b + (int64_t)k * 32) : 0.0;
+    const double di = v.dtile[t * 32 + lane];
+    double z;
+    if (fwd) z = rhs[i];
+    else z = sweep_ll_wait(zf + 2 * (size_t)i, seq, sc) / (di + FCP_SMALL);
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      if (c[k] >= 0) p2p_ll_load_words(src + 2 * (size_t)c[k], w0[k], w1[k]);
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      if (c[k] < 0) continue;
+      double zj;
+      if ((unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq) zj = __longlong_as_double((long long)((w0[k] & 0xffffffffull) | (w1[k] << 32)));
+      else zj = sweep_ll_wait(src + 2 * (size_t)c[k], seq, sc);
+      z = z - av[k] * zj;
+    }
+    for (int32_t k = W; k < len; ++k) {
+      const int32_t cc = __ldg(v.tcol + b + (int64_t)k * 32);
+      if (cc < 0) break;
+      z = z - __ldg(v.tval + b + (int64_t)k * 32) * sweep_ll_wait(src + 2 * (size_t)cc, seq, sc);
+    }
+    z = z * di;
+    if (fwd) {
+      p2p_ll_store(zf + 2 * (size_t)i, z, seq);
+    } else {
+      p2p_ll_store(zb + 2 * (size_t)i, z, seq);
+      zk[i] = z;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gauss-Seidel, linear_solvers.f90:96-201.  One sweep = the sequential loop :139-145
 //     res(i) = rhs(i) - sum_k a(k) fi(ja(k)) ;  fi(i) = fi(i) + res(i)/(a(diag(i)) + small)
 // in which row i sees the NEW values of the rows before it and the OLD values of itself and the rows after it.  Level scheduled over the
@@ -1157,8 +1458,71 @@ static int coop_grid(const void *kernel, int device, int *grid) {
   return FCP_OK;
 }
 
-static int launch_factor(bool ilu, SellPattern &p, const double *a, double *d, cudaStream_t st) {
+// FCP_SWEEP = ll (default: flag-in-data sweeps, no barrier) | barrier (one cooperative grid barrier per level) | flags (per-row ready flags with
+// acquire/release, one barrier between the sweeps).  Read per call: tests and A/B timings switch it inside one process.
+enum { SWEEP_LL = 0, SWEEP_BARRIER, SWEEP_FLAGS };
+static int sweep_mode() {
+  const char *e = getenv("FCP_SWEEP");
+  if (e && !strcmp(e, "barrier")) return SWEEP_BARRIER;
+  if (e && !strcmp(e, "flags")) return SWEEP_FLAGS;
+  return SWEEP_LL;
+}
+// cooperative grid of the LL kernels: all CTAs co-resident; FCP_SWEEP_CTAS caps the CTAs per SM (fewer resident warps = fewer warps polling)
+static int sweep_grid(const void *fn, KrylovWS &ws, int slot, int *grid) {
+  int &cap = ws.persist_grid[slot];
+  if (!cap) FCP_TRY(coop_grid(fn, ws.ws_device, &cap));
+  *grid = cap;
+  if (const char *e = getenv("FCP_SWEEP_CTAS")) {
+    const int v = atoi(e);
+    int nsm = 0;
+    FCP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ws.ws_device));
+    if (v > 0) *grid = std::min(cap, v * std::max(nsm, 1));
+  }
+  return FCP_OK;
+}
+static unsigned int next_ll_epoch(SellPattern &p, cudaStream_t st) {
+  if (p.ll_epoch >= 0xfffffff0u) {          // 32-bit tags: start over (once per ~4e9 sweeps)
+    for (auto *q : p.zll) cudaMemsetAsync(q, 0, sizeof(unsigned long long) * 2 * (size_t)std::max(p.n, 1), st);
+    p.ll_epoch = 0;
+  }
+  return ++p.ll_epoch;
+}
+
+static int launch_factor(bool ilu, SellPattern &p, const double *a, double *d, KrylovWS &ws, cudaStream_t st) {
   if (p.n == 0) return FCP_OK;
+  if (sweep_mode() == SWEEP_LL) {
+    FCP_TRY(sell_build_tiles(p, ilu, st));
+    for (int dir = 0; dir < 2; ++dir) {          // this solve's matrix values in tile order
+      const TriTiles &t = p.tri[dir];
+      if (!t.nent) continue;
+      const int g = (int)std::min<int64_t>((t.nent + FCP_TPB - 1) / FCP_TPB, 148 * 16);
+      k_tri_values<<<g, FCP_TPB, 0, st>>>(t.nent, t.tsrc, a, t.tval);
+      FCP_LAUNCHED();
+      if (dir == 0 && ilu) { k_tri_values<<<g, FCP_TPB, 0, st>>>(t.nent, t.ttsrc, a, t.ttval); FCP_LAUNCHED(); }
+    }
+    TriView fw = tri_view(p.tri[0]);
+    const double *adiag = ws.adiag;
+    unsigned long long *dll = p.zll[2];
+    unsigned int seq = next_ll_epoch(p, st);
+    const KrylovScalars *sc = ws.sc;
+    const void *fn = ilu ? (const void *)k_factor_ll<true> : (const void *)k_factor_ll<false>;
+    int grid = 0;
+    FCP_TRY(sweep_grid(fn, ws, ilu ? 5 : 4, &grid));
+    void *args[] = {&fw, &adiag, &dll, &seq, &d, &sc};
+#ifdef FCP_EMU
+    (void)args;
+    if (ilu) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_factor_ll<true>, fw, adiag, dll, seq, d, sc);
+    else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_factor_ll<false>, fw, adiag, dll, seq, d, sc);
+#else
+    FCP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FCP_TPB), args, 0, st));
+#endif
+    FCP_LAUNCHED();
+    const TriTiles &bt = p.tri[1];
+    k_tri_dtile<<<std::max(1, std::min((bt.ntiles * 32 + FCP_TPB - 1) / FCP_TPB, 148 * 16)), FCP_TPB, 0, st>>>(bt.ntiles * 32, bt.prow, d, bt.dtile);
+    FCP_LAUNCHED();
+    FCP_CHECK_LAUNCH();
+    return FCP_OK;
+  }
   int dev = 0, grid = 0;
   FCP_CUDA(cudaGetDevice(&dev));
   SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
@@ -1177,9 +1541,29 @@ static int launch_factor(bool ilu, SellPattern &p, const double *a, double *d, c
   FCP_LAUNCHED();
   return FCP_OK;
 }
-static int launch_precond(SellPattern &p, const double *a, const double *d, const double *rhs, double *zk, const KrylovScalars *sc,
+static int launch_precond(SellPattern &p, const double *a, const double *d, const double *rhs, double *zk, const KrylovScalars *sc, KrylovWS &ws,
                           cudaStream_t st) {
   if (p.n == 0) return FCP_OK;
+  const int mode = sweep_mode();
+  if (mode == SWEEP_LL) {
+    TriView fw = tri_view(p.tri[0]), bw = tri_view(p.tri[1]);
+    unsigned long long *zf = p.zll[0], *zb = p.zll[1];
+    unsigned int seq = next_ll_epoch(p, st);
+    const bool wide = std::max(p.tri[0].maxlen, p.tri[1].maxlen) > 4;
+    const void *fn = wide ? (const void *)k_precond_apply_ll<8> : (const void *)k_precond_apply_ll<4>;
+    int grid = 0;
+    FCP_TRY(sweep_grid(fn, ws, wide ? 7 : 6, &grid));
+    void *args[] = {&fw, &bw, &zf, &zb, &seq, &rhs, &zk, &sc};
+#ifdef FCP_EMU
+    (void)args;
+    if (wide) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<8>, fw, bw, zf, zb, seq, rhs, zk, sc);
+    else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<4>, fw, bw, zf, zb, seq, rhs, zk, sc);
+#else
+    FCP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FCP_TPB), args, 0, st));
+#endif
+    FCP_LAUNCHED();
+    return FCP_OK;
+  }
   static int grid = 0;
   if (!grid) {
     int dev = 0;
@@ -1189,8 +1573,7 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
   SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
   LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
   const int32_t *llen = p.llen;
-  const char *sweep_env = getenv("FCP_SWEEP");       // read per call: tests and A/B timings switch it inside one process
-  const bool use_flags = sweep_env && !strcmp(sweep_env, "flags");
+  const bool use_flags = mode == SWEEP_FLAGS;
   static bool announced = false;
   if (use_flags && !announced) {
     announced = true;
@@ -1266,7 +1649,7 @@ static int tma_smem_limit(size_t smem) {
 // load/use kernel.  FCP_SPMV=ldg forces the latter (A/B measurements).
 template <int NS, bool SQ>
 static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double *x, double *y, const double *v1, const KrylovScalars *sc,
-                           const RedArgs &ra, cudaStream_t st, int fused = 0, unsigned int seq_base = 0) {
+                           const RedArgs &ra, cudaStream_t st, int fused = 0, unsigned int seq_base = 0, unsigned int l2mask = 0) {
   const int grid = fcp_nchunks(p.n);
   if (!grid) return FCP_OK;
   static int mode = -1;   // 0 ldg, 1 tma
@@ -1295,6 +1678,9 @@ static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double
     const int pgrid = std::min(grid, std::max(1, occ) * nsm);
     k_spmv_dot_tma<NS, SQ><<<pgrid, FCP_TPB, smem, st>>>(p.n, p.nslices, m, x, y, v1, sc, ra, p.tile_cap, nst);
     FCP_CHECK_LAUNCH();
+  } else if (mode != 0 && l2mask) {
+    if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe_l2<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base, l2mask);
+    else k_spmv_dot_pipe_l2<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base, l2mask);
   } else if (mode != 0) {
     if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base);
     else k_spmv_dot_pipe<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base);
@@ -1305,11 +1691,12 @@ static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double
   return FCP_OK;
 }
 
-// FCP_DPCG=kernels: the three-kernel iteration with a host poll per 16 iterations (round 1); default: the persistent cooperative kernel.
-// Read per call so that tests and A/B timings can switch inside one process.
+// FCP_DPCG=persist: the persistent cooperative kernel; default: the three-kernel iteration with pipelined polling.  (Measured on a B200,
+// profiles/r02_dpcg_ab.txt: the persistent kernel gives the same bits and iteration count but its SpMV phase is slower than the stand-alone kernel, so
+// it stays opt-in.)  Read per call so that tests and A/B timings can switch inside one process.
 static bool dpcg_persist_wanted() {
   const char *e = getenv("FCP_DPCG");
-  return !(e && !strcmp(e, "kernels"));
+  return e && !strcmp(e, "persist");
 }
 static int launch_dpcg_persist(const SellPattern &p, const SellView &m, double *fi, KrylovWS &ws, const RedArgs &ra, int fused, unsigned int seq_base,
                                Profiler *prof, cudaStream_t st) {
@@ -1351,7 +1738,54 @@ static int launch_dpcg_persist(const SellPattern &p, const SellView &m, double *
   return FCP_OK;
 }
 
-// poll the device scalars; returns done flag
+// Which Krylov vectors get the evict_last L2 policy: in the order of their reuse per CG iteration (pk: 3 reads + 1 write; res: 2 + 1; zk: 1 + 1;
+// fi: 1 + 1; adiag: 2 reads) while the running total stays inside the budget (FCP_L2_MB, default 96 of the 126 MB).  Nothing fits at 256^3 on one GPU
+// (134 MB per vector): the plain kernels run there.
+struct L2Masks { unsigned int pk = 0, spmv = 0, upd = 0; };
+static L2Masks krylov_l2_masks(int32_t n, int32_t ncols) {
+  L2Masks m;
+  const char *e = getenv("FCP_L2");
+  if (e && !strcmp(e, "off")) return m;
+  double budget = 96e6;
+  if (const char *b = getenv("FCP_L2_MB")) budget = 1e6 * atof(b);
+  if (e && !strcmp(e, "all")) budget = 1e30;
+  double used = 0.0;
+  auto fits = [&](double bytes) { if (used + bytes > budget) return false; used += bytes; return true; };
+  const bool v_pk = fits(8.0 * ncols), v_res = fits(8.0 * n), v_zk = fits(8.0 * ncols), v_fi = fits(8.0 * ncols), v_ad = fits(8.0 * n);
+  m.pk = (v_pk ? 1u : 0u) | ((v_res || v_zk) ? 2u : 0u) | (v_ad ? 4u : 0u);     // bit 1: the z source (res for dpcg, zk for iccg)
+  m.spmv = (v_pk ? 1u : 0u) | (v_zk ? 2u : 0u);
+  m.upd = (v_fi ? 1u : 0u) | (v_res ? 2u : 0u) | (v_pk ? 4u : 0u) | (v_zk ? 8u : 0u) | (v_ad ? 16u : 0u);
+  return m;
+}
+
+// Convergence polling that never drains the stream: after batch b is enqueued its `done` flag is copied to a pinned slot and an event recorded;
+// the host then waits for the event of batch b-1 -- batch b is already queued behind it, so the GPU runs on while the host looks at the flag.
+// (Round 1 synchronised the stream after every batch of 16 iterations: 9 % of an 8-GPU step was idle time.)  When batch b-1 converged, the
+// kernels of batch b return at once on the device-side flag; the final fetch_scalars() waits for them.
+struct BatchPoll {
+  KrylovWS &ws;
+  cudaStream_t st;
+  const int *err_flag;      // peer-memory path: the window's error word (a wait that timed out), polled the same way
+  int posted = 0;
+  int post() {
+    FCP_CUDA(cudaMemcpyAsync(&ws.h_poll[posted & 1], (const char *)ws.sc + offsetof(KrylovScalars, done), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ws.h_poll[2 + (posted & 1)] = 0;
+    if (err_flag) FCP_CUDA(cudaMemcpyAsync(&ws.h_poll[2 + (posted & 1)], err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FCP_CUDA(cudaEventRecord(ws.ev[posted & 1], st));
+    ++posted;
+    return FCP_OK;
+  }
+  int previous_done(bool *done) {
+    *done = false;
+    if (posted < 2) return FCP_OK;
+    FCP_CUDA(cudaEventSynchronize(ws.ev[(posted - 2) & 1]));
+    *done = ws.h_poll[(posted - 2) & 1] != 0;
+    if (ws.h_poll[2 + ((posted - 2) & 1)]) { fcp_set_error("peer-memory protocol timeout: a rank stopped responding"); return FCP_ENCCL; }
+    return FCP_OK;
+  }
+};
+
+// read the device scalars (synchronises the stream)
 static int fetch_scalars(KrylovWS &ws, cudaStream_t st) {
   FCP_CUDA(cudaMemcpyAsync(ws.h_sc, ws.sc, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, st));
   FCP_CUDA(cudaStreamSynchronize(st));
@@ -1385,6 +1819,8 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
   FCP_CUDA(cudaStreamSynchronize(st));   // h_sc is reused as the read-back buffer
   if (n == 0 && !comm) return FCP_OK;
   const int BATCH = 16;
+  BatchPoll poll{ws, st, comm_error_flag(comm)};
+  const L2Masks l2 = krylov_l2_masks(n, p.ncols);
 
   if (solver == FCP_SOLVER_GAUSS_SEIDEL) {
     if (comm) { fcp_set_error("csrsolve: 'gauss-seidel' is a serial-tree solver (src-par has none); not available with a communicator"); return FCP_EINVAL; }
@@ -1412,17 +1848,20 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     } else
     for (int it = 0; it < itr_max;) {
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
-        if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
+        if (grid && l2.pk) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk_l2<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb, l2.pk), FCP_LAUNCHED()));
+        else if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
         FCP_TRY(L.halo_pk());
-        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb))));
+        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb, l2.spmv))));
         FCP_TRY(L.post(EPI_PKAPK, 1));
-        if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
+        if (grid && l2.upd) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update_l2<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE), l2.upd), FCP_LAUNCHED()));
+        else if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
         FCP_TRY(L.post(EPI_CG_UPDATE, 3));
       }
       FCP_CHECK_LAUNCH();
-      FCP_TRY(fetch_scalars(ws, st));
-      if (cd) FCP_TRY(comm_check_error(ctx));   // a peer stopped responding: fail now instead of spinning through every batch
-      if (ws.h_sc->done) break;
+      FCP_TRY(poll.post());
+      bool conv = false;
+      FCP_TRY(poll.previous_done(&conv));      // (also fails when a peer stopped responding, instead of spinning through every batch)
+      if (conv) break;
     }
   } else if (solver == FCP_SOLVER_ICCG) {
     FCP_TRY(sell_build_levels(p, st));
@@ -1432,23 +1871,26 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     FCP_TRY(L.post(EPI_INIT_CG, 2));
     FCP_TRY(fetch_scalars(ws, st));
     if (!ws.h_sc->done) {
-      FCP_TRY(launch_factor(false, p, a, ws.d, st));
+      FCP_TRY(launch_factor(false, p, a, ws.d, ws, st));
       for (int it = 0; it < itr_max;) {
         for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
-          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st)));
+          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, ws, st)));
           if (grid) { k_dot<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.zk, ws.sc, L.red(EPI_SK)); FCP_LAUNCHED(); }
           FCP_TRY(L.post(EPI_SK, 1));
-          if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
+          if (grid && l2.pk) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk_l2<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb, l2.pk), FCP_LAUNCHED()));
+          else if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<false><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
           FCP_TRY(L.halo_pk());
-          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb))));
+          if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb, l2.spmv))));
           FCP_TRY(L.post(EPI_PKAPK, 1));
-          if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
+          if (grid && l2.upd) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update_l2<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE), l2.upd), FCP_LAUNCHED()));
+          else if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<false><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
           FCP_TRY(L.post(EPI_CG_UPDATE, 3));
         }
         FCP_CHECK_LAUNCH();
-        FCP_TRY(fetch_scalars(ws, st));
-        if (cd) FCP_TRY(comm_check_error(ctx));
-        if (ws.h_sc->done) break;
+        FCP_TRY(poll.post());
+        bool conv = false;
+        FCP_TRY(poll.previous_done(&conv));
+        if (conv) break;
       }
     }
   } else {
@@ -1465,16 +1907,16 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     FCP_TRY(L.post(EPI_INIT_BICG, 2));
     FCP_TRY(fetch_scalars(ws, st));
     if (!ws.h_sc->done) {
-      FCP_TRY(launch_factor(true, p, a, ws.d, st));
+      FCP_TRY(launch_factor(true, p, a, ws.d, ws, st));
       for (int it = 0; it < itr_max;) {
         for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
           if (grid) { k_bicg_pk<<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.uk, ws.pk, ws.sc); FCP_LAUNCHED(); }
-          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.pk, ws.zk, ws.sc, st)));
+          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.pk, ws.zk, ws.sc, ws, st)));
           FCP_TRY(L.halo(ws.zk));
           if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.zk, ws.uk, ws.reso, ws.sc, L.red(EPI_UKRESO), st))));
           FCP_TRY(L.post(EPI_UKRESO, 1));
           if (grid) { k_bicg_half<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.zk, ws.uk, ws.sc); FCP_LAUNCHED(); }
-          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, st)));
+          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_precond(p, a, ws.d, ws.res, ws.zk, ws.sc, ws, st)));
           FCP_TRY(L.halo(ws.zk));
           if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<2, true>(p, m, ws.zk, ws.vk, ws.res, ws.sc, L.red(EPI_VK), st))));
           FCP_TRY(L.post(EPI_VK, 2));
@@ -1482,9 +1924,10 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
           FCP_TRY(L.post(EPI_BICG_UPDATE, 3));
         }
         FCP_CHECK_LAUNCH();
-        FCP_TRY(fetch_scalars(ws, st));
-        if (cd) FCP_TRY(comm_check_error(ctx));
-        if (ws.h_sc->done) break;
+        FCP_TRY(poll.post());
+        bool conv = false;
+        FCP_TRY(poll.previous_done(&conv));
+        if (conv) break;
       }
     }
   }

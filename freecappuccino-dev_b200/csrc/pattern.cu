@@ -113,6 +113,8 @@ void sell_free(SellPattern &p) {
   cudaFree(p.slptr); cudaFree(p.rinfo); cudaFree(p.ja); cudaFree(p.ia0); cudaFree(p.llen);
   cudaFree(p.lev_ptr); cudaFree(p.lev_rows); cudaFree(p.blev_ptr); cudaFree(p.blev_rows); cudaFree(p.tpos);
   cudaFree(p.plev_rows); cudaFree(p.pblev_rows); cudaFree(p.ready);
+  for (TriTiles &t : p.tri) { cudaFree(t.tptr); cudaFree(t.tcol); cudaFree(t.tsrc); cudaFree(t.ttsrc); cudaFree(t.tval); cudaFree(t.ttval); cudaFree(t.dtile); }
+  for (auto *q : p.zll) cudaFree(q);
   p = SellPattern();
 }
 
@@ -213,6 +215,87 @@ int sell_build_levels(SellPattern &p, cudaStream_t st) {
     p.sweep_epoch = 0;
   }
   p.levels_built = true;
+  return FCP_OK;
+}
+
+// The two triangles in level-tile order for the flag-in-data sweeps (fcp_internal.h: TriTiles).  with_transposed: also the positions of the
+// transposed entries of the lower triangle (the ILU(0) factor of bicgstab, needs sell_build_tpos).
+int sell_build_tiles(SellPattern &p, bool with_transposed, cudaStream_t st) {
+  FCP_TRY(sell_build_levels(p, st));
+  if (with_transposed) FCP_TRY(sell_build_tpos(p, st));
+  const bool have = p.tri[0].tptr != nullptr;
+  if (have && (!with_transposed || p.tri[0].ttsrc)) return FCP_OK;
+  const int32_t n = p.n;
+  const int32_t *ia = p.h_ia.data(), *ja = p.h_ja.data(), *dg = p.h_diag.data();
+  std::vector<int64_t> slptr(p.nslices + 1);
+  FCP_CUDA(cudaMemcpy(slptr.data(), p.slptr, slptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> tpos;
+  if (with_transposed) {
+    tpos.resize(p.nnzp);
+    FCP_CUDA(cudaMemcpy(tpos.data(), p.tpos, tpos.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  for (int dir = 0; dir < 2; ++dir) {
+    TriTiles &t = p.tri[dir];
+    const int32_t np = dir == 0 ? p.nplev : p.npblev;
+    std::vector<int32_t> prow((size_t)std::max(np, 1), -1);
+    if (np) FCP_CUDA(cudaMemcpy(prow.data(), dir == 0 ? p.plev_rows : p.pblev_rows, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost));
+    const int32_t ntiles = np / 32;
+    std::vector<int64_t> tptr((size_t)ntiles + 1, 0);
+    int32_t maxlen = 0;
+    auto k0 = [&](int32_t i) { return dir == 0 ? ia[i] : dg[i] + 1; };           // 1-based CSR range of the triangle in row i
+    auto k1 = [&](int32_t i) { return dir == 0 ? dg[i] : ia[i + 1]; };           // (exclusive)
+    for (int32_t tt = 0; tt < ntiles; ++tt) {
+      int32_t len = 0;
+      for (int l = 0; l < 32; ++l) {
+        const int32_t i = prow[(size_t)tt * 32 + l];
+        if (i >= 0) len = std::max(len, k1(i) - k0(i));
+      }
+      maxlen = std::max(maxlen, len);
+      tptr[tt + 1] = tptr[tt] + 32 * (int64_t)len;
+    }
+    const int64_t nent = tptr[ntiles];
+    if (!have) {
+      std::vector<int32_t> tcol((size_t)std::max<int64_t>(nent, 1), -1), tsrc((size_t)std::max<int64_t>(nent, 1), -1);
+      for (int32_t tt = 0; tt < ntiles; ++tt)
+        for (int l = 0; l < 32; ++l) {
+          const int32_t i = prow[(size_t)tt * 32 + l];
+          if (i < 0) continue;
+          const int64_t sbase = slptr[i >> 5] + (i & 31);
+          for (int32_t k = k0(i); k < k1(i); ++k) {
+            const int64_t q = tptr[tt] + 32 * (int64_t)(k - k0(i)) + l;
+            tcol[q] = ja[k - 1] - 1;
+            tsrc[q] = (int32_t)(sbase + (int64_t)(k - ia[i]) * 32);
+          }
+        }
+      t.ntiles = ntiles; t.maxlen = maxlen; t.nent = nent;
+      t.prow = dir == 0 ? p.plev_rows : p.pblev_rows;
+      FCP_TRY(dev_upload(&t.tptr, tptr.data(), tptr.size()));
+      FCP_TRY(dev_upload(&t.tcol, tcol.data(), tcol.size()));
+      FCP_TRY(dev_upload(&t.tsrc, tsrc.data(), tsrc.size()));
+      FCP_TRY(dev_alloc(&t.tval, (size_t)std::max<int64_t>(nent, 1)));
+      FCP_TRY(dev_alloc(&t.dtile, (size_t)std::max(np, 1)));
+    }
+    if (dir == 0 && with_transposed && !t.ttsrc) {
+      std::vector<int32_t> ttsrc((size_t)std::max<int64_t>(nent, 1), -1);
+      for (int32_t tt = 0; tt < ntiles; ++tt)
+        for (int l = 0; l < 32; ++l) {
+          const int32_t i = prow[(size_t)tt * 32 + l];
+          if (i < 0) continue;
+          const int64_t sbase = slptr[i >> 5] + (i & 31);
+          for (int32_t k = ia[i]; k < dg[i]; ++k) ttsrc[tptr[tt] + 32 * (int64_t)(k - ia[i]) + l] = tpos[sbase + (int64_t)(k - ia[i]) * 32];
+        }
+      FCP_TRY(dev_upload(&t.ttsrc, ttsrc.data(), ttsrc.size()));
+      FCP_TRY(dev_alloc(&t.ttval, (size_t)std::max<int64_t>(nent, 1)));
+    }
+  }
+  if (!have) {
+    for (auto *&q : p.zll) {
+      FCP_TRY(dev_alloc(&q, (size_t)2 * std::max(n, 1)));
+      FCP_CUDA(cudaMemset(q, 0, sizeof(unsigned long long) * 2 * (size_t)std::max(n, 1)));
+    }
+    FCP_CUDA(cudaStreamSynchronize(0));
+    p.ll_epoch = 0;
+  }
   return FCP_OK;
 }
 

@@ -15,13 +15,17 @@
 // ---------------------------------------------------------------------------------------------
 // grad_gauss   gradients.f90:1607-1693
 // ---------------------------------------------------------------------------------------------
+// WS = faces per cell the shared-memory list stage holds (6: hexahedra and smaller; 10: the ten-faced polyhedra of config 5); longer lists are
+// read from global memory as before
+template <int WS>
 __global__ void __launch_bounds__(FCP_TPB) k_grad_gauss(MeshView m, const double *__restrict__ u, double *__restrict__ g) {
-  FCP_CELL_LOOP(c, m.n) {
+  FCP_STAGE_DYN(WS, stage);
+  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
     double gx = 0.0, gy = 0.0, gz = 0.0;
     const double uc = u[c];
-    constexpr int W = 6;
-    FCP_FACE_BATCHES(m, c, W) {
-      FCP_BATCH_LISTS(m, W, e, o, sl);
+    constexpr int W = WS <= 6 ? 6 : 5;
+    FCP_FACE_BATCHES_STAGED(stage, st, m, c, W) {
+      FCP_BATCH_LISTS_STAGED(stage, st, WS, m, W, e, o, sl);
       double sx[W], sy[W], sz[W], lam[W], uo[W];
 #pragma unroll
       for (int k = 0; k < W; ++k) {
@@ -49,7 +53,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_grad_gauss(MeshView m, const double
     g[3 * (int64_t)c + 0] = gx * volr;
     g[3 * (int64_t)c + 1] = gy * volr;
     g[3 * (int64_t)c + 2] = gz * volr;
-  }
+  FCP_STAGED_LOOP_END
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -95,17 +99,35 @@ __global__ void __launch_bounds__(FCP_TPB) k_lsq_matrix(MeshView m, double *__re
   }
 }
 
-template <bool W>
+template <bool W, int WS>
 __global__ void __launch_bounds__(FCP_TPB) k_grad_lsq(MeshView m, const double *__restrict__ D, const double *__restrict__ phi,
                                                        double *__restrict__ g, int row2_reference) {
-  FCP_CELL_LOOP(c, m.n) {
+  FCP_STAGE_DYN(WS, stage);
+  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
     double b1 = 0.0, b2 = 0.0, b3 = 0.0;
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c], pc = phi[c];
-    FCP_FACE_LOOP(m, c) {
-      FCP_FACE_FETCH(m);
+    constexpr int WB = WS <= 6 ? 6 : 5;
+    FCP_FACE_BATCHES_STAGED(stage, st, m, c, WB) {
+      FCP_BATCH_LISTS_STAGED(stage, st, WS, m, WB, e_, o_, sl_);
+      // every gather of the batch before the first use: cell centres and phi across two-sided faces, face centres and boundary values otherwise
+      double x_[WB], y_[WB], z_[WB], p_[WB];
+#pragma unroll
+      for (int k = 0; k < WB; ++k) {
+        const bool on = e_[k] != 0, two = on && sl_[k] >= 0;
+        const int32_t f = (e_[k] > 0 ? e_[k] : -e_[k]) - 1;
+        x_[k] = !on ? 0.0 : two ? __ldg(m.xc + o_[k]) : __ldg(m.xf + f);
+        y_[k] = !on ? 0.0 : two ? __ldg(m.yc + o_[k]) : __ldg(m.yf + f);
+        z_[k] = !on ? 0.0 : two ? __ldg(m.zc + o_[k]) : __ldg(m.zf + f);
+        p_[k] = on ? __ldg(phi + o_[k]) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < WB; ++k) {
+        if (e_[k] == 0) continue;
+        const int32_t e = e_[k], sl = sl_[k];
+        const int32_t f = (e > 0 ? e : -e) - 1;
       double Dx, Dy, Dz;
       if (sl >= 0) {
-        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o], po = phi[o];
+        const double xo = x_[k], yo = y_[k], zo = z_[k], po = p_[k];
         double dx, dy, dz, dphi;
         if (e > 0) { dx = xo - xc; dy = yo - yc; dz = zo - zc; dphi = po - pc; }
         else       { dx = xc - xo; dy = yc - yo; dz = zc - zo; dphi = pc - po; }
@@ -116,8 +138,8 @@ __global__ void __launch_bounds__(FCP_TPB) k_grad_lsq(MeshView m, const double *
           Dx = dx * dphi; Dy = dy * dphi; Dz = dz * dphi;
         }
       } else {
-        const double dx = m.xf[f] - xc, dy = m.yf[f] - yc, dz = m.zf[f] - zc;
-        const double dphi = phi[o] - pc;
+        const double dx = x_[k] - xc, dy = y_[k] - yc, dz = z_[k] - zc;
+        const double dphi = p_[k] - pc;
         if (W) {
           // quirk Q2 (gradients.f90:1459): the weight's denominator indexes xf with the BOUNDARY COUNTER i, not iface
           const int32_t i = f - m.F;
@@ -129,6 +151,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_grad_lsq(MeshView m, const double *
         }
       }
       b1 = b1 + Dx; b2 = b2 + Dy; b3 = b3 + Dz;
+      }
     }
     const int64_t n = m.n;
     const double D1 = D[0 * n + c], D2 = D[1 * n + c], D3 = D[2 * n + c], D4 = D[3 * n + c], D5 = D[4 * n + c],
@@ -136,7 +159,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_grad_lsq(MeshView m, const double *
     g[3 * (int64_t)c + 0] = b1 * D1 - b2 * D2 + b3 * D3;                   // :886-888 ; row 2 is quirk Q1
     g[3 * (int64_t)c + 1] = row2_reference ? (b1 * D4 - b2 * D5 - b3 * D6) : (b2 * D4 - b1 * D5 - b3 * D6);
     g[3 * (int64_t)c + 2] = b1 * D7 - b2 * D8 + b3 * D9;
-  }
+  FCP_STAGED_LOOP_END
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,19 +338,9 @@ __device__ __forceinline__ void gradp_cell_generic(const MeshView &m, int32_t c,
 // walks; on a structured mesh a quarter of all warps contain a boundary cell, so this is what bounds the kernel.
 // Arithmetic order per cell is unchanged (faces in ascending index).
 template <bool CORRECT, bool WEIGHTED, int W>
-__device__ __forceinline__ void gradp_cell_fast(const MeshView &m, int32_t c, int32_t flen, int scheme, int nstages, double *p,
-                                                const double *__restrict__ apu, double *__restrict__ su, double *__restrict__ sv,
+__device__ __forceinline__ void gradp_cell_fast(const MeshView &m, int32_t c, const int32_t (&e)[W], const int32_t (&o)[W], const int32_t (&sl)[W], int scheme,
+                                                int nstages, double *p, const double *__restrict__ apu, double *__restrict__ su, double *__restrict__ sv,
                                                 double *__restrict__ sw, double *__restrict__ dPdxi, const CorrectArgs &ca) {
-  const int64_t fbase = m.slptr[c >> 5] + (c & 31);
-  int32_t e[W], o[W], sl[W];
-#pragma unroll
-  for (int k = 0; k < W; ++k) {
-    const bool on = k < flen;
-    const int64_t pos = fbase + (int64_t)k * 32;
-    e[k] = on ? __ldcs(m.ent + pos) : 0;
-    o[k] = on ? __ldcs(m.other + pos) : 0;
-    sl[k] = on ? __ldcs(m.slot + pos) : 0;
-  }
   const double pc = p[c];
   const double ac = WEIGHTED ? apu[c] : 0.0;
   const double vol = m.vol[c];
@@ -449,11 +462,16 @@ __global__ void __launch_bounds__(FCP_TPB, 2) k_gradp(MeshView m, int nstages, d
                                                        double *__restrict__ dPdxi, CorrectArgs ca) {
   constexpr int W = 6;
   constexpr int scheme = WEIGHTED ? FCP_PSCHEME_WEIGHTED : FCP_PSCHEME_LINEAR;
-  FCP_CELL_LOOP(c, m.n) {
-    const int32_t flen = m.len[c];
-    if (flen <= W) gradp_cell_fast<CORRECT, WEIGHTED, W>(m, c, flen, scheme, nstages, p, apu, su, sv, sw, dPdxi, ca);
-    else gradp_cell_generic<CORRECT>(m, c, scheme, nstages, p, apu, su, sv, sw, dPdxi, ca);
-  }
+  __shared__ ListStage<W> stage;      // the face list of the NEXT cell travels global -> shared while this cell's gathers are in flight
+  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
+    if (stage.len(st) <= W) {
+      int32_t e[W], o[W], sl[W];
+      stage.read(st, e, o, sl);
+      gradp_cell_fast<CORRECT, WEIGHTED, W>(m, c, e, o, sl, scheme, nstages, p, apu, su, sv, sw, dPdxi, ca);
+    } else {
+      gradp_cell_generic<CORRECT>(m, c, scheme, nstages, p, apu, su, sv, sw, dPdxi, ca);
+    }
+  FCP_STAGED_LOOP_END
 }
 
 // 'central' stage 2 (nablap.f90:129-160): inner-face sum recomputed with face_value_central (interpolation.f90:218-264)
@@ -550,14 +568,16 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp_central2(MeshView m, double *
 // pressure term) and pressure patches do not reset pp (calcp_piso.f90:140-240).
 template <bool PISO, int W>
 __global__ void __launch_bounds__(FCP_TPB, (W >= 3 ? 1 : W == 2 ? 2 : 3)) k_assemble_pcorr(MeshView m, AsmArgs g) {
-  FCP_CELL_LOOP(c, m.n) {
+  constexpr int WS = 6;
+  __shared__ ListStage<WS> stage;     // the face list of the NEXT cell travels global -> shared while this cell's gathers are in flight
+  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
     const double denc = g.den[c], kc = m.vol[c] * g.apu[c];
     const double uc = g.u[c], vc = g.v[c], wc = g.w[c], pc = g.p[c];
     const double gcx = g.dPdxi[3 * (int64_t)c], gcy = g.dPdxi[3 * (int64_t)c + 1], gcz = g.dPdxi[3 * (int64_t)c + 2];
     double dg = 0.0, s = 0.0;
-    FCP_FACE_BATCHES(m, c, W) {
-      FCP_BATCH_LISTS(m, W, e_, o_, sl_);
+    FCP_FACE_BATCHES_STAGED(stage, st, m, c, W) {
+      FCP_BATCH_LISTS_STAGED(stage, st, WS, m, W, e_, o_, sl_);
       double sx_[W], sy_[W], sz_[W], lam_[W], Df_[W], xo_[W], yo_[W], zo_[W], deno_[W], volo_[W], apuo_[W], uo_[W], vo_[W], wo_[W], po_[W],
           gox_[W], goy_[W], goz_[W];
 #pragma unroll
@@ -660,7 +680,7 @@ __global__ void __launch_bounds__(FCP_TPB, (W >= 3 ? 1 : W == 2 ? 2 : 3)) k_asse
     }
     g.a[diag_pos(m, c)] = dg;
     g.su[c] = s;
-  }
+  FCP_STAGED_LOOP_END
 }
 
 // adjustMassFlow faceflux_mass.f90:833-916 (src-par/adjustMassFlow.f90: `call global_sum(flowo)` between the two loops).  Outlet patches are
@@ -770,7 +790,15 @@ __global__ void __launch_bounds__(FCP_TPB) k_nonorth(MeshView m, const double *_
 int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g) {
   if (ctx->B) FCP_CUDA(cudaMemsetAsync(g + 3 * (size_t)ctx->n, 0, sizeof(double) * 3 * (size_t)ctx->B, ctx->stream));
   if (ctx->n == 0) return FCP_OK;
-  FCP_PROF(&ctx->prof, FCP_K_GRAD, ctx->stream, (k_grad_gauss<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), u, g)));
+  size_t smem = 0;
+  const int grid = std::max(fcp_nchunks(ctx->n), 1);
+  if (ctx->max_cell_faces > 6) {
+    FCP_TRY((fcp_stage_smem<10>(k_grad_gauss<10>, &smem)));
+    FCP_PROF(&ctx->prof, FCP_K_GRAD, ctx->stream, (k_grad_gauss<10><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), u, g)));
+  } else {
+    FCP_TRY((fcp_stage_smem<6>(k_grad_gauss<6>, &smem)));
+    FCP_PROF(&ctx->prof, FCP_K_GRAD, ctx->stream, (k_grad_gauss<6><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), u, g)));
+  }
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;
@@ -787,8 +815,13 @@ int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi
   if (ctx->B) FCP_CUDA(cudaMemsetAsync(g + 3 * (size_t)ctx->n, 0, sizeof(double) * 3 * (size_t)ctx->B, ctx->stream));
   if (ctx->n == 0) return FCP_OK;
   size_t tok = ctx->prof.begin(FCP_K_GRAD, ctx->stream);
-  if (weighted) k_grad_lsq<true><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference);
-  else k_grad_lsq<false><<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference);
+  const bool wide = ctx->max_cell_faces > 6;
+  size_t smem = 0;
+  const int grid = std::max(fcp_nchunks(ctx->n), 1);
+  if (weighted && wide) { FCP_TRY((fcp_stage_smem<10>(k_grad_lsq<true, 10>, &smem))); k_grad_lsq<true, 10><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference); }
+  else if (weighted) { FCP_TRY((fcp_stage_smem<6>(k_grad_lsq<true, 6>, &smem))); k_grad_lsq<true, 6><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference); }
+  else if (wide) { FCP_TRY((fcp_stage_smem<10>(k_grad_lsq<false, 10>, &smem))); k_grad_lsq<false, 10><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference); }
+  else { FCP_TRY((fcp_stage_smem<6>(k_grad_lsq<false, 6>, &smem))); k_grad_lsq<false, 6><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference); }
   ctx->prof.end(tok, ctx->stream);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();

@@ -55,6 +55,9 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
 
     def __init__(self, gpu_index=0):
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        if vis and gpu_index < len(vis) and vis[gpu_index].strip().isdigit():
+            gpu_index = int(vis[gpu_index])          # nvidia-smi numbers the physical GPUs
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"

@@ -1210,6 +1210,36 @@ __device__ __forceinline__ double sweep_ll_wait(const unsigned long long *src, u
   return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
 
+// Sentinel wait.  Thousands of warps spinning on their own 32 x (up to 3) LL words saturate the L2 (measured on a B200: 69 % L2 throughput, all of
+// it polls, 6 us per level).  So a warp first parks ONE lane on ONE word -- the last dependency of its last active row, the one most likely to
+// arrive last -- and polls that with a pause in between; only when it has arrived do all lanes look at their own words (and spin for the few
+// stragglers).  One sector per poll per warp instead of ~96.  All 32 lanes of the warp must call this.
+__device__ __forceinline__ void sweep_ll_sentinel(const unsigned long long *src, int32_t col, unsigned int seq, const KrylovScalars *sc) {
+  const unsigned int have = __ballot_sync(0xffffffffu, col >= 0);
+  if (have == 0u) return;
+  const int lead = 31 - __clz((int)have);
+  if ((int)(threadIdx.x & 31) == lead) {
+#ifdef FCP_EMU
+    (void)sweep_ll_wait(src + 2 * (size_t)col, seq, sc);
+#else
+    unsigned long long w0, w1, t0 = 0;
+    unsigned int spins = 0;
+    for (;;) {
+      p2p_ll_load_words(src + 2 * (size_t)col, w0, w1);
+      if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
+      __nanosleep(100);
+      if ((++spins & 1023u) == 0u) {
+        if (*(volatile const int32_t *)&sc->pad) break;
+        const unsigned long long t = p2p_now_ns();
+        if (!t0) t0 = t;
+        else if (t - t0 > 2000000000ull) { *(volatile int32_t *)&const_cast<KrylovScalars *>(sc)->pad = 1; break; }
+      }
+    }
+#endif
+  }
+  __syncwarp();
+}
+
 // values of this solve's matrix into the tile order (both triangles; the transposed entries for ILU(0))
 __global__ void __launch_bounds__(FCP_TPB) k_tri_values(int64_t nent, const int32_t *__restrict__ src, const double *__restrict__ a, double *__restrict__ out) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nent; q += (int64_t)gridDim.x * blockDim.x) {
@@ -1236,6 +1266,12 @@ __global__ void __launch_bounds__(FCP_TPB) k_factor_ll(TriView fw, const double 
     const int32_t i = __ldg(fw.prow + t * 32 + lane);
     const int64_t b = __ldg(fw.tptr + t) + lane;
     const int32_t len = (int32_t)((__ldg(fw.tptr + t + 1) - __ldg(fw.tptr + t)) >> 5);
+    {   // the row's last dependency (entries are packed from k = 0, columns ascending)
+      int32_t clast = -1;
+      if (i >= 0)
+        for (int32_t k = len - 1; k >= 0 && clast < 0; --k) clast = __ldg(fw.tcol + b + (int64_t)k * 32);
+      sweep_ll_sentinel(dll, clast, seq, sc);
+    }
     if (i >= 0) {
       double di = adiag[i];
       for (int32_t k = 0; k < len; ++k) {
@@ -1269,23 +1305,37 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriVie
     const int32_t i = __ldg(v.prow + t * 32 + lane);
     const int64_t b = __ldg(v.tptr + t) + lane;
     const int32_t len = (int32_t)((__ldg(v.tptr + t + 1) - __ldg(v.tptr + t)) >> 5);
-    if (i < 0) continue;
     const unsigned long long *src = fwd ? zf : zb;
     // the row's entries and the first look at its dependencies: all loads independent of each other
     int32_t c[W];
     double av[W];
     unsigned long long w0[W], w1[W];
 #pragma unroll
-    for (int k = 0; k < W; ++k) c[k] = (k < len) ? __ldg(v.tcol + b + (int64_t)k * 32) : -1;
+    for (int k = 0; k < W; ++k) c[k] = (i >= 0 && k < len) ? __ldg(v.tcol + b + (int64_t)k * 32) : -1;
 #pragma unroll
-    for (int k = 0; k < W; ++k) av[k] = (k < len) ? __ldg(v.tval + b + (int64_t)k * 32) : 0.0;
-    const double di = v.dtile[t * 32 + lane];
-    double z;
-    if (fwd) z = rhs[i];
-    else z = sweep_ll_wait(zf + 2 * (size_t)i, seq, sc) / (di + FCP_SMALL);
+    for (int k = 0; k < W; ++k) av[k] = (c[k] >= 0) ? __ldg(v.tval + b + (int64_t)k * 32) : 0.0;
+    const double di = i >= 0 ? v.dtile[t * 32 + lane] : 0.0;
+    const double r0 = (fwd && i >= 0) ? rhs[i] : 0.0;
 #pragma unroll
     for (int k = 0; k < W; ++k)
       if (c[k] >= 0) p2p_ll_load_words(src + 2 * (size_t)c[k], w0[k], w1[k]);
+    bool ready = true;
+    int32_t clast = -1;       // the last dependency inside the register window that has not arrived yet
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      if (c[k] >= 0 && !((unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq)) { ready = false; clast = c[k]; }
+    unsigned long long f0 = 0ull, f1 = 0ull;      // backward sweep: the row's own forward value is its first dependency
+    bool fready = true;
+    if (!fwd && i >= 0) {
+      p2p_ll_load_words(zf + 2 * (size_t)i, f0, f1);
+      fready = (unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq;
+    }
+    if (__any_sync(0xffffffffu, !fready)) sweep_ll_sentinel(zf, fready ? -1 : i, seq, sc);      // (warp-uniform branches)
+    if (__any_sync(0xffffffffu, !ready)) sweep_ll_sentinel(src, clast, seq, sc);
+    if (i < 0) continue;
+    double z;
+    if (fwd) z = r0;
+    else z = (fready ? __longlong_as_double((long long)((f0 & 0xffffffffull) | (f1 << 32))) : sweep_ll_wait(zf + 2 * (size_t)i, seq, sc)) / (di + FCP_SMALL);
 #pragma unroll
     for (int k = 0; k < W; ++k) {
       if (c[k] < 0) continue;
@@ -1745,10 +1795,17 @@ struct L2Masks { unsigned int pk = 0, spmv = 0, upd = 0; };
 static L2Masks krylov_l2_masks(int32_t n, int32_t ncols) {
   L2Masks m;
   const char *e = getenv("FCP_L2");
-  if (e && !strcmp(e, "off")) return m;
+  // Measured on a B200 (profiles/r02_l2_hints.txt): with the default L2 configuration the evict_last operands do NOT keep 84 MB of vectors
+  // resident against the 176 MB matrix stream -- every kernel still runs at HBM speed and the hinted loads cost 5-10 % -- so the hints are opt-in
+  // (FCP_L2=auto | all); FCP_L2=carve additionally sets the persisting-L2 carve-out (cudaLimitPersistingL2CacheSize) to the budget.
+  if (!e || !strcmp(e, "off")) return m;
   double budget = 96e6;
   if (const char *b = getenv("FCP_L2_MB")) budget = 1e6 * atof(b);
   if (e && !strcmp(e, "all")) budget = 1e30;
+  if (e && !strcmp(e, "carve")) {
+    static double carved = 0.0;
+    if (carved != budget) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)budget); carved = budget; }
+  }
   double used = 0.0;
   auto fits = [&](double bytes) { if (used + bytes > budget) return false; used += bytes; return true; };
   const bool v_pk = fits(8.0 * ncols), v_res = fits(8.0 * n), v_zk = fits(8.0 * ncols), v_fi = fits(8.0 * ncols), v_ad = fits(8.0 * n);

@@ -97,6 +97,8 @@ cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags)
 cudaError_t cudaIpcCloseMemHandle(void *p);
 template <class K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }
 template <class K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+enum cudaLimit { cudaLimitPersistingL2CacheSize = 6 };
+inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 
 // ---- launches ---------------------------------------------------------------------------------------------------
 namespace emu {

@@ -14,6 +14,47 @@
 namespace cg = cooperative_groups;
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (FCP_PDL, default on): the three kernels of a CG iteration are launched with the programmatic-stream-
+// serialization attribute and begin with griddepcontrol.wait.  A kernel's CTAs may then be scheduled while the LAST wave of its predecessor is
+// still running (the predecessor's CTAs signal launch_dependents as their first instruction); they sit at the wait until the predecessor has
+// completed and its memory is visible, so launch latency, CTA ramp-up and the predecessor's last-CTA reduction epilogue overlap.  Without the
+// launch attribute both instructions are no-ops.  Nothing about the arithmetic changes.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() {
+#ifndef FCP_EMU
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifndef FCP_EMU
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+static bool pdl_wanted() {
+  const char *e = getenv("FCP_PDL");
+  return !(e && !strcmp(e, "off"));
+}
+#ifdef FCP_EMU
+#define FCP_LAUNCH_PDL(pdl, kernel, grid, st, ...) kernel<<<grid, FCP_TPB, 0, st>>>(__VA_ARGS__)
+#else
+template <class... KA, class... A>
+static void launch_maybe_pdl(bool pdl, void (*k)(KA...), int grid, cudaStream_t st, A &&...a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FCP_TPB);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, k, KA(a)...);
+}
+#define FCP_LAUNCH_PDL(pdl, kernel, grid, st, ...) launch_maybe_pdl(pdl, kernel, grid, st, __VA_ARGS__)
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------------
 int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols) {
@@ -406,7 +447,9 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(FCP_TPB) k_cg_pk(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
                                                     const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd,
                                                     const int32_t *__restrict__ chunk_info, unsigned int seq_base) {
+  pdl_launch_dependents();
   const int32_t info = chunk_info ? __ldg(chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
+  pdl_wait();
   if (sc->done) return;
   cg_pk_chunk<JACOBI>(n, res, adiag, zk, pk, sc->bet, info, cd, seq_base + (unsigned int)sc->iters + 1u);
 }
@@ -416,7 +459,9 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(FCP_TPB) k_cg_pk_l2(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag,
                                                        const double *__restrict__ zk, double *pk, const KrylovScalars *sc, const CommDev *cd,
                                                        const int32_t *__restrict__ chunk_info, unsigned int seq_base, unsigned int mask) {
+  pdl_launch_dependents();
   const int32_t info = chunk_info ? __ldg(chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
+  pdl_wait();
   if (sc->done) return;
   const double bet = sc->bet;
   const int chunk = info & 0x7fffffff;
@@ -574,7 +619,9 @@ template <int NS, bool SQ, int W>
 __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_dot_pipe(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
                                                             const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused,
                                                             unsigned int seq_base) {
+  pdl_launch_dependents();
   const int32_t info = ra.chunk_info ? __ldg(ra.chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
+  pdl_wait();
   if (sc->done) return;
   double s[NS];
 #pragma unroll
@@ -587,7 +634,9 @@ template <int NS, bool SQ, int W>
 __global__ void __launch_bounds__(FCP_TPB, (W <= 8 ? FCP_PIPE_MINB : 2)) k_spmv_dot_pipe_l2(int32_t n, SellView m, const double *__restrict__ x, double *__restrict__ y,
                                                             const double *__restrict__ v1, const KrylovScalars *sc, RedArgs ra, int fused,
                                                             unsigned int seq_base, unsigned int mask) {
+  pdl_launch_dependents();
   const int32_t info = ra.chunk_info ? __ldg(ra.chunk_info + blockIdx.x) : (int32_t)blockIdx.x;
+  pdl_wait();
   if (sc->done) return;
   double s[NS];
 #pragma unroll
@@ -777,6 +826,8 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__restrict__ fi, double *__restrict__ res, const double *__restrict__ pk,
                                                         const double *__restrict__ zk, const double *__restrict__ adiag,
                                                         const KrylovScalars *sc, RedArgs ra) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (sc->done) return;
   double s[3] = {0.0, 0.0, 0.0};
   cg_update_chunk<JACOBI>(n, fi, res, pk, zk, adiag, sc->alf, sc->iters == 0, (int)blockIdx.x, s);
@@ -787,6 +838,8 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_update(int32_t n, double *__rest
 template <bool JACOBI>
 __global__ void __launch_bounds__(FCP_TPB) k_cg_update_l2(int32_t n, double *fi, double *res, const double *__restrict__ pk, const double *__restrict__ zk,
                                                            const double *__restrict__ adiag, const KrylovScalars *sc, RedArgs ra, unsigned int mask) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (sc->done) return;
   const double alf = sc->alf;
   const bool first = sc->iters == 0;
@@ -1214,12 +1267,13 @@ __device__ __forceinline__ double sweep_ll_wait(const unsigned long long *src, u
 // it polls, 6 us per level).  So a warp first parks ONE lane on ONE word -- the last dependency of its last active row, the one most likely to
 // arrive last -- and polls that with a pause in between; only when it has arrived do all lanes look at their own words (and spin for the few
 // stragglers).  One sector per poll per warp instead of ~96.  All 32 lanes of the warp must call this.
-__device__ __forceinline__ void sweep_ll_sentinel(const unsigned long long *src, int32_t col, unsigned int seq, const KrylovScalars *sc) {
+__device__ __forceinline__ void sweep_ll_sentinel(const unsigned long long *src, int32_t col, unsigned int seq, const KrylovScalars *sc, unsigned int pause_ns) {
   const unsigned int have = __ballot_sync(0xffffffffu, col >= 0);
   if (have == 0u) return;
   const int lead = 31 - __clz((int)have);
   if ((int)(threadIdx.x & 31) == lead) {
 #ifdef FCP_EMU
+    (void)pause_ns;
     (void)sweep_ll_wait(src + 2 * (size_t)col, seq, sc);
 #else
     unsigned long long w0, w1, t0 = 0;
@@ -1227,7 +1281,7 @@ __device__ __forceinline__ void sweep_ll_sentinel(const unsigned long long *src,
     for (;;) {
       p2p_ll_load_words(src + 2 * (size_t)col, w0, w1);
       if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
-      __nanosleep(100);
+      if (pause_ns) __nanosleep(pause_ns);
       if ((++spins & 1023u) == 0u) {
         if (*(volatile const int32_t *)&sc->pad) break;
         const unsigned long long t = p2p_now_ns();
@@ -1259,7 +1313,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_tri_dtile(int32_t np, const int32_t
 // d(i) = 1/(a_ii - sum_{k<diag} a_k d(ja_k) a_T(k))          bicgstab :613-624
 template <bool ILU>
 __global__ void __launch_bounds__(FCP_TPB) k_factor_ll(TriView fw, const double *__restrict__ adiag, unsigned long long *dll, unsigned int seq, double *d,
-                                                        const KrylovScalars *sc) {
+                                                        const KrylovScalars *sc, unsigned int pause_ns) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t t = warp; t < fw.ntiles; t += nwarps) {
@@ -1270,7 +1324,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_factor_ll(TriView fw, const double 
       int32_t clast = -1;
       if (i >= 0)
         for (int32_t k = len - 1; k >= 0 && clast < 0; --k) clast = __ldg(fw.tcol + b + (int64_t)k * 32);
-      sweep_ll_sentinel(dll, clast, seq, sc);
+      sweep_ll_sentinel(dll, clast, seq, sc, pause_ns);
     }
     if (i >= 0) {
       double di = adiag[i];
@@ -1293,7 +1347,8 @@ __global__ void __launch_bounds__(FCP_TPB) k_factor_ll(TriView fw, const double 
 // zk = M^-1 rhs : forward sweep, zk/(d+small), backward sweep      (:458-475 ; quirk Q4 kept)
 template <int W>
 __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriView bw, unsigned long long *zf, unsigned long long *zb, unsigned int seq,
-                                                               const double *__restrict__ rhs, double *__restrict__ zk, const KrylovScalars *sc) {
+                                                               const double *__restrict__ rhs, double *__restrict__ zk, const KrylovScalars *sc,
+                                                               unsigned int pause_ns) {
   if (sc->done) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -1330,8 +1385,8 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriVie
       p2p_ll_load_words(zf + 2 * (size_t)i, f0, f1);
       fready = (unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq;
     }
-    if (__any_sync(0xffffffffu, !fready)) sweep_ll_sentinel(zf, fready ? -1 : i, seq, sc);      // (warp-uniform branches)
-    if (__any_sync(0xffffffffu, !ready)) sweep_ll_sentinel(src, clast, seq, sc);
+    if (__any_sync(0xffffffffu, !fready)) sweep_ll_sentinel(zf, fready ? -1 : i, seq, sc, pause_ns);      // (warp-uniform branches)
+    if (__any_sync(0xffffffffu, !ready)) sweep_ll_sentinel(src, clast, seq, sc, pause_ns);
     if (i < 0) continue;
     double z;
     if (fwd) z = r0;
@@ -1530,6 +1585,11 @@ static int sweep_grid(const void *fn, KrylovWS &ws, int slot, int *grid) {
   }
   return FCP_OK;
 }
+// pause of the sentinel lane between two polls (FCP_SWEEP_NS, default 0: it polls back to back -- one sector per poll per warp does not load the L2)
+static unsigned int sweep_pause_ns() {
+  const char *e = getenv("FCP_SWEEP_NS");
+  return e ? (unsigned int)std::max(0, atoi(e)) : 0u;
+}
 static unsigned int next_ll_epoch(SellPattern &p, cudaStream_t st) {
   if (p.ll_epoch >= 0xfffffff0u) {          // 32-bit tags: start over (once per ~4e9 sweeps)
     for (auto *q : p.zll) cudaMemsetAsync(q, 0, sizeof(unsigned long long) * 2 * (size_t)std::max(p.n, 1), st);
@@ -1558,11 +1618,12 @@ static int launch_factor(bool ilu, SellPattern &p, const double *a, double *d, K
     const void *fn = ilu ? (const void *)k_factor_ll<true> : (const void *)k_factor_ll<false>;
     int grid = 0;
     FCP_TRY(sweep_grid(fn, ws, ilu ? 5 : 4, &grid));
-    void *args[] = {&fw, &adiag, &dll, &seq, &d, &sc};
+    unsigned int pause = sweep_pause_ns();
+    void *args[] = {&fw, &adiag, &dll, &seq, &d, &sc, &pause};
 #ifdef FCP_EMU
     (void)args;
-    if (ilu) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_factor_ll<true>, fw, adiag, dll, seq, d, sc);
-    else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_factor_ll<false>, fw, adiag, dll, seq, d, sc);
+    if (ilu) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_factor_ll<true>, fw, adiag, dll, seq, d, sc, pause);
+    else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_factor_ll<false>, fw, adiag, dll, seq, d, sc, pause);
 #else
     FCP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FCP_TPB), args, 0, st));
 #endif
@@ -1603,11 +1664,12 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
     const void *fn = wide ? (const void *)k_precond_apply_ll<8> : (const void *)k_precond_apply_ll<4>;
     int grid = 0;
     FCP_TRY(sweep_grid(fn, ws, wide ? 7 : 6, &grid));
-    void *args[] = {&fw, &bw, &zf, &zb, &seq, &rhs, &zk, &sc};
+    unsigned int pause = sweep_pause_ns();
+    void *args[] = {&fw, &bw, &zf, &zb, &seq, &rhs, &zk, &sc, &pause};
 #ifdef FCP_EMU
     (void)args;
-    if (wide) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<8>, fw, bw, zf, zb, seq, rhs, zk, sc);
-    else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<4>, fw, bw, zf, zb, seq, rhs, zk, sc);
+    if (wide) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<8>, fw, bw, zf, zb, seq, rhs, zk, sc, pause);
+    else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<4>, fw, bw, zf, zb, seq, rhs, zk, sc, pause);
 #else
     FCP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FCP_TPB), args, 0, st));
 #endif
@@ -1699,7 +1761,7 @@ static int tma_smem_limit(size_t smem) {
 // load/use kernel.  FCP_SPMV=ldg forces the latter (A/B measurements).
 template <int NS, bool SQ>
 static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double *x, double *y, const double *v1, const KrylovScalars *sc,
-                           const RedArgs &ra, cudaStream_t st, int fused = 0, unsigned int seq_base = 0, unsigned int l2mask = 0) {
+                           const RedArgs &ra, cudaStream_t st, int fused = 0, unsigned int seq_base = 0, unsigned int l2mask = 0, bool pdl = false) {
   const int grid = fcp_nchunks(p.n);
   if (!grid) return FCP_OK;
   static int mode = -1;   // 0 ldg, 1 tma
@@ -1729,11 +1791,11 @@ static int launch_spmv_dot(const SellPattern &p, const SellView &m, const double
     k_spmv_dot_tma<NS, SQ><<<pgrid, FCP_TPB, smem, st>>>(p.n, p.nslices, m, x, y, v1, sc, ra, p.tile_cap, nst);
     FCP_CHECK_LAUNCH();
   } else if (mode != 0 && l2mask) {
-    if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe_l2<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base, l2mask);
-    else k_spmv_dot_pipe_l2<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base, l2mask);
+    if (p.tile_cap <= 8 * 256) FCP_LAUNCH_PDL(pdl, (k_spmv_dot_pipe_l2<NS, SQ, 8>), grid, st, p.n, m, x, y, v1, sc, ra, fused, seq_base, l2mask);
+    else FCP_LAUNCH_PDL(pdl, (k_spmv_dot_pipe_l2<NS, SQ, 16>), grid, st, p.n, m, x, y, v1, sc, ra, fused, seq_base, l2mask);
   } else if (mode != 0) {
-    if (p.tile_cap <= 8 * 256) k_spmv_dot_pipe<NS, SQ, 8><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base);
-    else k_spmv_dot_pipe<NS, SQ, 16><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base);
+    if (p.tile_cap <= 8 * 256) FCP_LAUNCH_PDL(pdl, (k_spmv_dot_pipe<NS, SQ, 8>), grid, st, p.n, m, x, y, v1, sc, ra, fused, seq_base);
+    else FCP_LAUNCH_PDL(pdl, (k_spmv_dot_pipe<NS, SQ, 16>), grid, st, p.n, m, x, y, v1, sc, ra, fused, seq_base);
   } else {
     k_spmv_dot<NS, SQ><<<grid, FCP_TPB, 0, st>>>(p.n, m, x, y, v1, sc, ra, fused, seq_base);
   }
@@ -1878,6 +1940,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
   const int BATCH = 16;
   BatchPoll poll{ws, st, comm_error_flag(comm)};
   const L2Masks l2 = krylov_l2_masks(n, p.ncols);
+  const bool pdl = pdl_wanted() && (!comm || cd) && !(prof && prof->on);      // (an event between two kernels breaks the programmatic dependency anyway)
 
   if (solver == FCP_SOLVER_GAUSS_SEIDEL) {
     if (comm) { fcp_set_error("csrsolve: 'gauss-seidel' is a serial-tree solver (src-par has none); not available with a communicator"); return FCP_EINVAL; }
@@ -1906,12 +1969,12 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     for (int it = 0; it < itr_max;) {
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
         if (grid && l2.pk) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk_l2<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb, l2.pk), FCP_LAUNCHED()));
-        else if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
+        else if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (FCP_LAUNCH_PDL(pdl, k_cg_pk<true>, grid, st, n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
         FCP_TRY(L.halo_pk());
-        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb, l2.spmv))));
+        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb, l2.spmv, pdl))));
         FCP_TRY(L.post(EPI_PKAPK, 1));
         if (grid && l2.upd) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update_l2<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE), l2.upd), FCP_LAUNCHED()));
-        else if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
+        else if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (FCP_LAUNCH_PDL(pdl, k_cg_update<true>, grid, st, n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
         FCP_TRY(L.post(EPI_CG_UPDATE, 3));
       }
       FCP_CHECK_LAUNCH();

@@ -548,8 +548,8 @@ def main():
     N0, nnz0, F0, B0 = m.numCells, ctx.nnz + ctx.npro, m.numInnerFaces, m.numBoundaryFaces
     kl = {
         "spmv_dot": kernel_line("spmv_dot", 12 * nnz0 + 20 * N0),
-        "cg_pk": kernel_line("cg_pk", 32 * N0),
-        "cg_update": kernel_line("cg_update", 56 * N0),
+        "cg_pk": kernel_line("cg_pk", (32 if args.solver == "dpcg" else 24) * N0),            # dpcg: res, adiag, pk r + pk w; iccg: zk, pk r + pk w
+        "cg_update": kernel_line("cg_update", (56 if args.solver == "dpcg" else 48) * N0),    # fi, res r+w, pk, zk (+ adiag for the Jacobi z)
         "assemble": kernel_line("assemble", 80 * F0 + 124 * N0),
         "gradp": kernel_line("gradp", 40 * F0 + 64 * N0 + 36 * B0),
         "correct_flux": kernel_line("correct_flux", 36 * F0 + 8 * N0),

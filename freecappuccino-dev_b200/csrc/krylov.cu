@@ -1236,12 +1236,31 @@ struct TriView {
 };
 static TriView tri_view(const TriTiles &t) { return TriView{t.tptr, t.tcol, t.tval, t.ttval, t.prow, t.dtile, t.ntiles}; }
 
+// LL words between the SMs of ONE GPU: relaxed accesses at GPU scope.  (p2p.cuh's words travel between GPUs and are volatile = strong at SYSTEM
+// scope; measured on a B200, system-scope polls and stores cost ~3.5 us per dependency hop inside a sweep.)
+__device__ __forceinline__ void gpu_ll_load_words(const unsigned long long *src, unsigned long long &w0, unsigned long long &w1) {
+#ifdef FCP_EMU
+  p2p_ll_load_words(src, w0, w1);
+#else
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void gpu_ll_store(unsigned long long *dst /* 16-byte aligned */, double v, unsigned int seq) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)seq << 32);
+  const unsigned long long w1 = (bits >> 32) | ((unsigned long long)seq << 32);
+#ifdef FCP_EMU
+  p2p_ll_store_words(dst, w0, w1);
+#else
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+#endif
+}
 __device__ __forceinline__ double sweep_ll_wait(const unsigned long long *src, unsigned int seq, const KrylovScalars *sc) {
   unsigned long long w0, w1;
 #ifdef FCP_EMU
   (void)sc;
   for (;;) {
-    p2p_ll_load_words(src, w0, w1);
+    gpu_ll_load_words(src, w0, w1);
     if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
     emu::yield(); emu::os_yield();
   }
@@ -1249,7 +1268,7 @@ __device__ __forceinline__ double sweep_ll_wait(const unsigned long long *src, u
   unsigned int spins = 0;
   unsigned long long t0 = 0;
   for (;;) {
-    p2p_ll_load_words(src, w0, w1);
+    gpu_ll_load_words(src, w0, w1);
     if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
     __nanosleep(20);
     if ((++spins & 4095u) == 0u) {
@@ -1279,7 +1298,7 @@ __device__ __forceinline__ void sweep_ll_sentinel(const unsigned long long *src,
     unsigned long long w0, w1, t0 = 0;
     unsigned int spins = 0;
     for (;;) {
-      p2p_ll_load_words(src + 2 * (size_t)col, w0, w1);
+      gpu_ll_load_words(src + 2 * (size_t)col, w0, w1);
       if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
       if (pause_ns) __nanosleep(pause_ns);
       if ((++spins & 1023u) == 0u) {
@@ -1339,7 +1358,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_factor_ll(TriView fw, const double 
       const double dd = 1.0 / di;
       d[i] = dd;
       fw.dtile[t * 32 + lane] = dd;
-      p2p_ll_store(dll + 2 * (size_t)i, dd, seq);
+      gpu_ll_store(dll + 2 * (size_t)i, dd, seq);
     }
   }
 }
@@ -1373,7 +1392,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriVie
     const double r0 = (fwd && i >= 0) ? rhs[i] : 0.0;
 #pragma unroll
     for (int k = 0; k < W; ++k)
-      if (c[k] >= 0) p2p_ll_load_words(src + 2 * (size_t)c[k], w0[k], w1[k]);
+      if (c[k] >= 0) gpu_ll_load_words(src + 2 * (size_t)c[k], w0[k], w1[k]);
     bool ready = true;
     int32_t clast = -1;       // the last dependency inside the register window that has not arrived yet
 #pragma unroll
@@ -1382,7 +1401,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriVie
     unsigned long long f0 = 0ull, f1 = 0ull;      // backward sweep: the row's own forward value is its first dependency
     bool fready = true;
     if (!fwd && i >= 0) {
-      p2p_ll_load_words(zf + 2 * (size_t)i, f0, f1);
+      gpu_ll_load_words(zf + 2 * (size_t)i, f0, f1);
       fready = (unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq;
     }
     if (__any_sync(0xffffffffu, !fready)) sweep_ll_sentinel(zf, fready ? -1 : i, seq, sc, pause_ns);      // (warp-uniform branches)
@@ -1406,9 +1425,9 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriVie
     }
     z = z * di;
     if (fwd) {
-      p2p_ll_store(zf + 2 * (size_t)i, z, seq);
+      gpu_ll_store(zf + 2 * (size_t)i, z, seq);
     } else {
-      p2p_ll_store(zb + 2 * (size_t)i, z, seq);
+      gpu_ll_store(zb + 2 * (size_t)i, z, seq);
       zk[i] = z;
     }
   }

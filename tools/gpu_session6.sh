@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round 2, sixth GPU call (one B200): LL sweeps with GPU-scope relaxed accesses.
+TAG=${1:-r02}
+OUT=gpurun_out
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+B="python bench.py --no-cpu-baseline"
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_sweep_flags.py tests/test_gpu_host_api.py -m gpu -x -q -k "csrsolve or sweep or wall_distance or calcp_simple" > $OUT/${TAG}_s6_pytest.log 2>&1
+echo "pytest exit $?" >> $OUT/${TAG}_s6_status.txt
+timeout 600 $B --solver iccg --steps 2 --warmup 1 > $OUT/${TAG}_s6_iccg_ll.log 2>&1
+FCP_SWEEP_CTAS=2 timeout 600 $B --solver iccg --steps 2 --warmup 1 > $OUT/${TAG}_s6_iccg_ll_ctas2.log 2>&1
+FCP_SWEEP_CTAS=6 timeout 600 $B --solver iccg --steps 2 --warmup 1 > $OUT/${TAG}_s6_iccg_ll_ctas6.log 2>&1
+timeout 600 $B --cells 128 --solver iccg --steps 2 --warmup 1 > $OUT/${TAG}_s6_iccg_ll_n128.log 2>&1
+echo "iccg done" >> $OUT/${TAG}_s6_status.txt
+NCU="ncu --clock-control none"
+timeout 900 $NCU --set full --import-source on -k "regex:k_precond_apply_ll|k_factor_ll" -c 3 -o $OUT/${TAG}_s6_ncu_iccg_ll -f $B --cells 128 --solver iccg --steps 1 --warmup 0 > $OUT/${TAG}_s6_ncu_iccg_ll.log 2>&1
+timeout 1200 python bench.py --workload poly --steps 3 --warmup 2 > $OUT/${TAG}_s6_poly_n1.log 2>&1
+echo "poly exit $?" >> $OUT/${TAG}_s6_status.txt

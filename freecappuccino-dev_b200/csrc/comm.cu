@@ -427,6 +427,11 @@ static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const HaloPlan &pl) {
   d.ll = (unsigned long long *)((char *)c->win + mine.off_ll);
   d.npro = c->npro; d.n = ctx->n; d.cell = c->d_cell; d.slot = c->d_slot; d.frank = c->d_frank; d.rord = c->d_rord;
   d.ghost_ord = c->d_ghost_ord; d.chunk_ptr = c->d_chunk_ptr; d.push_cell = c->d_push_cell; d.push_dst = c->d_push_dst; d.order = c->d_order;
+  {
+    const char *e = getenv("FCP_P2P_POLL");
+    const unsigned int gpu_scope = (e && !strcmp(e, "gpu")) ? 1u : 0u;
+    FCP_CUDA(cudaMemcpyAsync(&d.hdr->poll_gpu_scope, &gpu_scope, sizeof(gpu_scope), cudaMemcpyHostToDevice, st));
+  }
   FCP_CUDA(cudaMalloc((void **)&c->d_dev, sizeof(CommDev)));
   FCP_CUDA(cudaMemcpyAsync(c->d_dev, &d, sizeof(CommDev), cudaMemcpyHostToDevice, st));
   FCP_CUDA(cudaStreamSynchronize(st));

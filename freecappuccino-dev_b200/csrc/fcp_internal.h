@@ -153,7 +153,8 @@ struct WinHeader {
   // local only
   unsigned long long red_seq;
   unsigned long long timeout_ns;             // how long a spin may last before it raises `error` (20 s; 2 s during the start-up self-check)
-  unsigned int push_ticket, pad0;
+  unsigned int push_ticket;
+  unsigned int poll_gpu_scope;               // 1: polls of this rank's OWN window use relaxed GPU-scope loads (FCP_P2P_POLL=gpu) instead of system-scope volatile ones
   int error, pad1;
 };
 struct CommDev {

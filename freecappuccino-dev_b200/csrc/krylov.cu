@@ -1270,7 +1270,6 @@ __device__ __forceinline__ double sweep_ll_wait(const unsigned long long *src, u
   for (;;) {
     gpu_ll_load_words(src, w0, w1);
     if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
-    __nanosleep(20);
     if ((++spins & 4095u) == 0u) {
       if (*(volatile const int32_t *)&sc->pad) break;
       const unsigned long long t = p2p_now_ns();
@@ -1393,29 +1392,52 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriVie
 #pragma unroll
     for (int k = 0; k < W; ++k)
       if (c[k] >= 0) gpu_ll_load_words(src + 2 * (size_t)c[k], w0[k], w1[k]);
-    bool ready = true;
+    // pending words: bit k = dependency k of the register window, bit W = the row's own forward value (backward sweep)
+    unsigned int pend = 0u;
     int32_t clast = -1;       // the last dependency inside the register window that has not arrived yet
 #pragma unroll
     for (int k = 0; k < W; ++k)
-      if (c[k] >= 0 && !((unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq)) { ready = false; clast = c[k]; }
-    unsigned long long f0 = 0ull, f1 = 0ull;      // backward sweep: the row's own forward value is its first dependency
-    bool fready = true;
+      if (c[k] >= 0 && !((unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq)) { pend |= 1u << k; clast = c[k]; }
+    unsigned long long f0 = 0ull, f1 = 0ull;
     if (!fwd && i >= 0) {
       gpu_ll_load_words(zf + 2 * (size_t)i, f0, f1);
-      fready = (unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq;
+      if (!((unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq)) pend |= 1u << W;
     }
-    if (__any_sync(0xffffffffu, !fready)) sweep_ll_sentinel(zf, fready ? -1 : i, seq, sc, pause_ns);      // (warp-uniform branches)
-    if (__any_sync(0xffffffffu, !ready)) sweep_ll_sentinel(src, clast, seq, sc, pause_ns);
+    if (__any_sync(0xffffffffu, pend != 0u)) {          // (warp-uniform branch)
+      // one lane parks on one word first (see sweep_ll_sentinel), then every lane polls ALL its pending words per round trip -- never one after the other
+      const bool own_only = (pend >> W) != 0u && (pend & ((1u << W) - 1u)) == 0u;
+      sweep_ll_sentinel(own_only ? zf : src, own_only ? i : clast, seq, sc, pause_ns);
+      unsigned int spins = 0;
+      unsigned long long t0 = 0;
+      while (pend) {
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+          if ((pend >> k) & 1u) gpu_ll_load_words(src + 2 * (size_t)c[k], w0[k], w1[k]);
+        if ((pend >> W) & 1u) gpu_ll_load_words(zf + 2 * (size_t)i, f0, f1);
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+          if (((pend >> k) & 1u) && (unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq) pend &= ~(1u << k);
+        if (((pend >> W) & 1u) && (unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq) pend &= ~(1u << W);
+#ifdef FCP_EMU
+        if (pend) { emu::yield(); emu::os_yield(); }
+#else
+        if (pend && (++spins & 4095u) == 0u) {
+          if (*(volatile const int32_t *)&sc->pad) break;
+          const unsigned long long t = p2p_now_ns();
+          if (!t0) t0 = t;
+          else if (t - t0 > 2000000000ull) { *(volatile int32_t *)&const_cast<KrylovScalars *>(sc)->pad = 1; break; }
+        }
+#endif
+      }
+    }
     if (i < 0) continue;
     double z;
     if (fwd) z = r0;
-    else z = (fready ? __longlong_as_double((long long)((f0 & 0xffffffffull) | (f1 << 32))) : sweep_ll_wait(zf + 2 * (size_t)i, seq, sc)) / (di + FCP_SMALL);
+    else z = __longlong_as_double((long long)((f0 & 0xffffffffull) | (f1 << 32))) / (di + FCP_SMALL);
 #pragma unroll
     for (int k = 0; k < W; ++k) {
       if (c[k] < 0) continue;
-      double zj;
-      if ((unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq) zj = __longlong_as_double((long long)((w0[k] & 0xffffffffull) | (w1[k] << 32)));
-      else zj = sweep_ll_wait(src + 2 * (size_t)c[k], seq, sc);
+      const double zj = __longlong_as_double((long long)((w0[k] & 0xffffffffull) | (w1[k] << 32)));
       z = z - av[k] * zj;
     }
     for (int32_t k = W; k < len; ++k) {

@@ -55,8 +55,19 @@ __device__ __forceinline__ void p2p_ll_store(unsigned long long *dst /* 16-byte 
 __device__ __forceinline__ double p2p_ll_load(const unsigned long long *src, unsigned int seq, WinHeader *hdr) {
   unsigned long long w0, w1, t0 = 0;
   unsigned int n = 0;
+  // The word lives in THIS rank's window (the peer wrote it over NVLink into this GPU's memory, whose point of coherence is this GPU's L2): a
+  // relaxed GPU-scope load sees it as soon as the system-scope one does; whether it is cheaper is an A/B switch (FCP_P2P_POLL=gpu), the tag check
+  // makes a stale read harmless (the loop just polls again).
+#ifndef FCP_EMU
+  const bool gpu_scope = hdr->poll_gpu_scope != 0u;
+#endif
   for (;;) {
+#ifdef FCP_EMU
     p2p_ll_load_words(src, w0, w1);
+#else
+    if (gpu_scope) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    else p2p_ll_load_words(src, w0, w1);
+#endif
     if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
     if ((++n & 4095u) == 0u) {
       if (*(volatile int *)&hdr->error) break;     // another wait already gave up: fall through fast, the host reports the error

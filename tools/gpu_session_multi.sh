@@ -21,21 +21,17 @@ wait
 timeout 900 $PT -k "8-" > $OUT/${TAG}_multi_t8.log 2>&1
 tail -n 3 $OUT/${TAG}_multi_t*.log > $OUT/${TAG}_multi_tests_summary.txt 2>&1
 echo "multi tests done" >> $OUT/${TAG}_multi_status.txt
-# ---- (2) contract benchmark, 8 GPUs
+# ---- (2) contract benchmark, 8 GPUs: default, then own-window polls at GPU scope
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 timeout 600 $TR --nproc-per-node 8 --master-port 29611 bench.py --gpus 8 --steps 10 --warmup 3 > $OUT/${TAG}_multi_bench8.log 2>&1
 echo "bench8 exit $?" >> $OUT/${TAG}_multi_status.txt
-FCP_L2=off timeout 600 $TR --nproc-per-node 8 --master-port 29612 bench.py --gpus 8 --steps 10 --warmup 3 > $OUT/${TAG}_multi_bench8_l2off.log 2>&1
-echo "bench8 l2off exit $?" >> $OUT/${TAG}_multi_status.txt
-# ---- (3) polyhedral workload
+FCP_P2P_POLL=gpu timeout 600 $TR --nproc-per-node 8 --master-port 29612 bench.py --gpus 8 --steps 10 --warmup 3 > $OUT/${TAG}_multi_bench8_pollgpu.log 2>&1
+echo "bench8 poll=gpu exit $?" >> $OUT/${TAG}_multi_status.txt
+# ---- (3) polyhedral workload: 8 GPUs, then 4 + 2 GPUs side by side on disjoint GPUs
 timeout 900 $TR --nproc-per-node 8 --master-port 29613 bench.py --gpus 8 --workload poly --steps 3 --warmup 2 > $OUT/${TAG}_multi_poly8.log 2>&1
 echo "poly8 exit $?" >> $OUT/${TAG}_multi_status.txt
 CUDA_VISIBLE_DEVICES=0,1,2,3 timeout 900 $TR --nproc-per-node 4 --master-port 29614 bench.py --gpus 4 --workload poly --steps 3 --warmup 2 > $OUT/${TAG}_multi_poly4.log 2>&1 &
 CUDA_VISIBLE_DEVICES=4,5 timeout 900 $TR --nproc-per-node 2 --master-port 29615 bench.py --gpus 2 --workload poly --steps 3 --warmup 2 > $OUT/${TAG}_multi_poly2.log 2>&1 &
+CUDA_VISIBLE_DEVICES=6,7 timeout 600 $TR --nproc-per-node 2 --master-port 29617 bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/${TAG}_multi_bench2.log 2>&1 &
 wait
-echo "poly4/2 done" >> $OUT/${TAG}_multi_status.txt
-# ---- (4) the cavity on 4 and 2 GPUs side by side (the driver measures these again at round end, one at a time)
-CUDA_VISIBLE_DEVICES=0,1,2,3 timeout 600 $TR --nproc-per-node 4 --master-port 29616 bench.py --gpus 4 --steps 10 --warmup 3 > $OUT/${TAG}_multi_bench4.log 2>&1 &
-CUDA_VISIBLE_DEVICES=4,5 timeout 600 $TR --nproc-per-node 2 --master-port 29617 bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/${TAG}_multi_bench2.log 2>&1 &
-wait
-echo "bench4/2 done" >> $OUT/${TAG}_multi_status.txt
+echo "poly4/2 + bench2 done" >> $OUT/${TAG}_multi_status.txt

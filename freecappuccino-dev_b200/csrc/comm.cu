@@ -84,21 +84,22 @@ struct FcpComm {
   std::vector<void *> peer_win;     // by rank (own = win)
   CommDev h_dev;                    // host copy of the device descriptor
   CommDev *d_dev = nullptr;
-  int32_t *d_frank = nullptr, *d_rord = nullptr, *d_chunk_ptr = nullptr, *d_push_cell = nullptr, *d_ghost_ord = nullptr, *d_order = nullptr;
+  int32_t *d_frank = nullptr, *d_rord = nullptr, *d_chunk_ptr = nullptr, *d_push_cell = nullptr, *d_push_ord = nullptr, *d_ghost_ord = nullptr, *d_order = nullptr;
   unsigned long long **d_push_dst = nullptr;
   unsigned long long xseq = 0;      // sequence number of the generic halo exchanges (identical on all ranks)
   unsigned int pk_base = 0;         // sequence base of the fused direction-vector pushes (advanced after every solve)
 };
 int comm_nranks(const FcpComm *c) { return c ? c->nranks : 1; }
 const CommDev *comm_dev(const FcpComm *c) { return (c && c->p2p) ? c->d_dev : nullptr; }
+const CommDev *comm_dev_host(const FcpComm *c) { return (c && c->p2p) ? &c->h_dev : nullptr; }
 const int32_t *comm_chunk_info(const FcpComm *c) { return (c && c->p2p) ? c->d_order : nullptr; }
 unsigned int comm_pk_base(const FcpComm *c) { return c ? c->pk_base : 0u; }
-void comm_pk_advance(FcpComm *c, int32_t iters) { if (c) c->pk_base += (unsigned int)iters + 1u; }
+void comm_pk_advance(FcpComm *c, int32_t iters) { if (c) c->pk_base += (unsigned int)iters + 2u; }   // the residual-halo scheme tags one push past the last iteration
 void comm_free(FcpComm *c) {
   if (!c) return;
   for (size_t r = 0; r < c->peer_win.size(); ++r)
     if ((int)r != c->rank && c->peer_win[r]) cudaIpcCloseMemHandle(c->peer_win[r]);
-  cudaFree(c->win); cudaFree(c->d_dev); cudaFree(c->d_frank); cudaFree(c->d_rord); cudaFree(c->d_chunk_ptr); cudaFree(c->d_push_cell);
+  cudaFree(c->win); cudaFree(c->d_dev); cudaFree(c->d_frank); cudaFree(c->d_rord); cudaFree(c->d_chunk_ptr); cudaFree(c->d_push_cell); cudaFree(c->d_push_ord);
   cudaFree(c->d_ghost_ord); cudaFree(c->d_order); cudaFree(c->d_push_dst);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_cell); cudaFree(c->d_slot); cudaFree(c->sendbuf); cudaFree(c->recvbuf); cudaFree(c->gather); cudaFree(c->d_scalar);
@@ -406,6 +407,7 @@ static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const HaloPlan &pl) {
   }
   FCP_TRY(dev_upload(&c->d_chunk_ptr, pl.chunk_ptr.data(), pl.chunk_ptr.size()));
   FCP_TRY(dev_upload(&c->d_push_cell, pcell.data(), pcell.size()));
+  FCP_TRY(dev_upload(&c->d_push_ord, pl.chunk_face.data(), pl.chunk_face.size()));
   FCP_TRY(dev_upload(&c->d_push_dst, pdst.data(), pdst.size()));
   FCP_TRY(dev_upload(&c->d_order, pl.order.data(), pl.order.size()));
   FCP_TRY(dev_upload(&c->d_ghost_ord, pl.ghost_ord.data(), pl.ghost_ord.size()));
@@ -426,7 +428,7 @@ static int p2p_setup(fcp_ctx *ctx, FcpComm *c, const HaloPlan &pl) {
   d.hdr = d.peer_hdr[c->rank]; d.stage = d.peer_stage[c->rank]; d.stride = stride;
   d.ll = (unsigned long long *)((char *)c->win + mine.off_ll);
   d.npro = c->npro; d.n = ctx->n; d.cell = c->d_cell; d.slot = c->d_slot; d.frank = c->d_frank; d.rord = c->d_rord;
-  d.ghost_ord = c->d_ghost_ord; d.chunk_ptr = c->d_chunk_ptr; d.push_cell = c->d_push_cell; d.push_dst = c->d_push_dst; d.order = c->d_order;
+  d.ghost_ord = c->d_ghost_ord; d.chunk_ptr = c->d_chunk_ptr; d.push_cell = c->d_push_cell; d.push_ord = c->d_push_ord; d.push_dst = c->d_push_dst; d.order = c->d_order;
   {
     const char *e = getenv("FCP_P2P_POLL");
     const unsigned int gpu_scope = (e && !strcmp(e, "gpu")) ? 1u : 0u;

@@ -174,6 +174,7 @@ struct CommDev {
   // fused push, faces grouped by the 2048-row chunk of their owner cell
   const int32_t *chunk_ptr;                // [nchunks+1]
   const int32_t *push_cell;                // [npro] owner cell, chunk order
+  const int32_t *push_ord;                 // [npro] process-face ordinal (patch order: index into cell / slot / ll), chunk order
   unsigned long long *const *push_dst;     // [npro] address of the face's LL slot in the peer's window, chunk order
   const int32_t *order;                    // [nchunks] launch order: chunk index | bit 31 when the chunk owns process faces (those first)
 };
@@ -377,6 +378,7 @@ int comm_allreduce_minmax(FcpComm *comm, double *d_mm /* {min,max} */, cudaStrea
 void comm_free(FcpComm *comm);
 int comm_nranks(const FcpComm *comm);
 const CommDev *comm_dev(const FcpComm *comm);       // device descriptor, nullptr unless the peer-memory path is active
+const CommDev *comm_dev_host(const FcpComm *comm);  // its host copy (the pointers inside are device pointers)
 const int32_t *comm_chunk_info(const FcpComm *comm); // device copy of CommDev::order, nullptr unless the peer-memory path is active
 unsigned int comm_pk_base(const FcpComm *comm);     // sequence base of the fused direction-vector pushes of the next solve
 void comm_pk_advance(FcpComm *comm, int32_t iters); // after a solve that ran `iters` iterations (identical on all ranks)

@@ -65,7 +65,7 @@ int krylov_ws_alloc(KrylovWS &ws, int32_t n, int32_t ncols) {
   FCP_TRY(dev_alloc(&ws.res, (size_t)n));
   FCP_TRY(dev_alloc(&ws.pk, (size_t)ncols));
   FCP_TRY(dev_alloc(&ws.zk, (size_t)ncols));
-  FCP_TRY(dev_alloc(&ws.adiag, (size_t)n));
+  FCP_TRY(dev_alloc(&ws.adiag, (size_t)ncols));       // ghost slots: the residual-halo scheme keeps the diagonal of the cells across process faces
   ws.maxchunks = fcp_nchunks(n) + 1;
   FCP_TRY(dev_alloc(&ws.partials, (size_t)4 * ws.maxchunks));
   FCP_TRY(dev_alloc(&ws.counter, 1));
@@ -877,6 +877,60 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_update_l2(int32_t n, double *fi,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Residual halo (peer-memory path of DPCG, default; FCP_HALO=pk keeps the scheme above).  `call exchange(pk)` (src-par/dpcg.f90:118) needs the
+// direction vector of the cells across every process face.  Instead of pushing pk from k_cg_pk -- whose completion then waits for its NVLink stores
+// to be acknowledged, and whose values the SpMV has to fetch through flagged loads -- every rank carries the recurrence of its GHOST entries itself:
+//     pk(ghost) = res(ghost) / a_ii(ghost) + bet * pk(ghost)
+// is the very expression its owner evaluates, with the same operands (bet is global, the diagonal is exchanged once per solve, the residual arrives
+// as LL words), hence the same bits.  The residual is pushed by k_cg_update, where the stores travel while the kernel's reduction and the
+// cross-rank sum are under way; k_cg_pk has no remote stores and the SpMV reads ghost columns like any other column.
+// Tags: the residual produced by iteration k (k = 0: k_cg_init) carries seq_base + k + 1 and is consumed by k_cg_pk of iteration k + 1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FCP_TPB) k_push_ll(int32_t npro, const int32_t *__restrict__ push_cell, unsigned long long *const *__restrict__ push_dst,
+                                                      const double *__restrict__ x, unsigned int seq) {
+  for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < npro; j += gridDim.x * blockDim.x) p2p_ll_store(push_dst[j], x[push_cell[j]], seq);
+}
+__global__ void __launch_bounds__(FCP_TPB) k_cg_pk_rh(int32_t n, const double *__restrict__ res, const double *__restrict__ adiag, double *pk,
+                                                       const KrylovScalars *sc, const CommDev *cd, const int32_t *__restrict__ chunk_info,
+                                                       unsigned int seq_base) {
+  pdl_launch_dependents();
+  const int32_t info = __ldg(chunk_info + blockIdx.x);
+  pdl_wait();
+  if (sc->done) return;
+  const double bet = sc->bet;
+  cg_pk_chunk<true>(n, res, adiag, nullptr, pk, bet, info & 0x7fffffff, nullptr, 0u);     // (no halo bit: no push)
+  if (info >= 0) return;
+  // ghost entries behind the process faces of this chunk
+  const int chunk = info & 0x7fffffff;
+  const int32_t j0 = cd->chunk_ptr[chunk], j1 = cd->chunk_ptr[chunk + 1];
+  const unsigned int seq = seq_base + (unsigned int)sc->iters + 1u;
+  for (int32_t j = j0 + (int32_t)threadIdx.x; j < j1; j += FCP_TPB) {
+    const int32_t i = cd->push_ord[j], g = cd->slot[i];
+    const double rg = p2p_ll_load(cd->ll + 2 * (size_t)i, seq, cd->hdr);
+    pk[g] = rg / adiag[g] + bet * pk[g];
+  }
+}
+__global__ void __launch_bounds__(FCP_TPB) k_cg_update_rh(int32_t n, double *__restrict__ fi, double *res, const double *__restrict__ pk,
+                                                           const double *__restrict__ zk, const double *__restrict__ adiag, const KrylovScalars *sc,
+                                                           RedArgs ra, unsigned int seq_base) {
+  pdl_launch_dependents();
+  const int32_t info = __ldg(ra.chunk_info + blockIdx.x);
+  pdl_wait();
+  if (sc->done) return;
+  const int chunk = info & 0x7fffffff;
+  double s[3] = {0.0, 0.0, 0.0};
+  cg_update_chunk<true>(n, fi, res, pk, zk, adiag, sc->alf, sc->iters == 0, chunk, s);
+  if (info < 0) {       // this chunk owns process faces: its fresh residuals go to the neighbours now, the reduction below hides the flight
+    const CommDev *cd = ra.cd;
+    const int32_t j0 = cd->chunk_ptr[chunk], j1 = cd->chunk_ptr[chunk + 1];
+    __syncthreads();
+    const unsigned int seq = seq_base + (unsigned int)sc->iters + 2u;
+    for (int32_t j = j0 + (int32_t)threadIdx.x; j < j1; j += FCP_TPB) p2p_ll_store(cd->push_dst[j], res[cd->push_cell[j]], seq);
+  }
+  finish_reduce_part<3>(s, ra, chunk, (int)gridDim.x);
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_dpcg_persist: the WHOLE diagonal-PCG solve (linear_solvers.f90:280-358 / src-par/dpcg.f90:79-161) as ONE persistent cooperative kernel.
 // A CTA owns the chunks q = blockIdx.x, blockIdx.x + gridDim.x, ... of the launch order (chunks with process faces first) in all three phases of an
 // iteration -- {pk = zk + bet pk [+ halo push]} | {zk = A pk, pk.zk} | {fi, res update, sum|res|, next res.z} -- which run the same per-chunk code
@@ -1363,7 +1417,120 @@ __global__ void __launch_bounds__(FCP_TPB) k_factor_ll(TriView fw, const double 
 }
 
 // zk = M^-1 rhs : forward sweep, zk/(d+small), backward sweep      (:458-475 ; quirk Q4 kept)
+// The static data of a tile comes in two dependent stages -- A: row index, tile pointer, length; B: the entries, d and the right-hand side.
+// PF = true software-pipelines them: while tile j is being processed (which is mostly waiting for dependencies) stage B of the warp's next tile and
+// stage A of the one after are already in flight, so a tile that is due finds everything but its dependencies in registers.
+struct TileA { int32_t i, len; int64_t b; };
+template <int W> struct TileB { int32_t i, len; int64_t b; int32_t c[W]; double av[W], di, r0; };
+__device__ __forceinline__ TileA ll_tile_a(const TriView &fw, const TriView &bw, int64_t tq, int64_t ntot, int lane) {
+  TileA a;
+  a.i = -1; a.len = 0; a.b = 0;
+  if (tq < ntot) {
+    const bool fwd = tq < fw.ntiles;
+    const TriView &v = fwd ? fw : bw;
+    const int64_t t = fwd ? tq : tq - fw.ntiles;
+    a.i = __ldg(v.prow + t * 32 + lane);
+    const int64_t b0 = __ldg(v.tptr + t);
+    a.b = b0 + lane;
+    a.len = (int32_t)((__ldg(v.tptr + t + 1) - b0) >> 5);
+  }
+  return a;
+}
 template <int W>
+__device__ __forceinline__ TileB<W> ll_tile_b(const TriView &fw, const TriView &bw, const TileA &a, int64_t tq, int64_t ntot, int lane,
+                                               const double *__restrict__ rhs) {
+  TileB<W> q;
+  q.i = a.i; q.len = a.len; q.b = a.b; q.di = 0.0; q.r0 = 0.0;
+#pragma unroll
+  for (int k = 0; k < W; ++k) { q.c[k] = -1; q.av[k] = 0.0; }
+  if (tq < ntot) {
+    const bool fwd = tq < fw.ntiles;
+    const TriView &v = fwd ? fw : bw;
+    const int64_t t = fwd ? tq : tq - fw.ntiles;
+#pragma unroll
+    for (int k = 0; k < W; ++k) q.c[k] = (a.i >= 0 && k < a.len) ? __ldg(v.tcol + a.b + (int64_t)k * 32) : -1;
+#pragma unroll
+    for (int k = 0; k < W; ++k) q.av[k] = (q.c[k] >= 0) ? __ldg(v.tval + a.b + (int64_t)k * 32) : 0.0;
+    q.di = a.i >= 0 ? v.dtile[t * 32 + lane] : 0.0;
+    q.r0 = (fwd && a.i >= 0) ? rhs[a.i] : 0.0;
+  }
+  return q;
+}
+template <int W>
+__device__ __forceinline__ void ll_tile_process(const TriView &fw, const TriView &bw, const TileB<W> &q, int64_t tq, unsigned long long *zf,
+                                                unsigned long long *zb, unsigned int seq, double *__restrict__ zk, const KrylovScalars *sc,
+                                                unsigned int pause_ns) {
+  const bool fwd = tq < fw.ntiles;
+  const TriView &v = fwd ? fw : bw;
+  const int32_t i = q.i;
+  const unsigned long long *src = fwd ? zf : zb;
+  // the first look at the dependencies: all loads independent of each other
+  unsigned long long w0[W], w1[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k)
+    if (q.c[k] >= 0) gpu_ll_load_words(src + 2 * (size_t)q.c[k], w0[k], w1[k]);
+  // pending words: bit k = dependency k of the register window, bit W = the row's own forward value (backward sweep)
+  unsigned int pend = 0u;
+  int32_t clast = -1;       // the last dependency inside the register window that has not arrived yet
+#pragma unroll
+  for (int k = 0; k < W; ++k)
+    if (q.c[k] >= 0 && !((unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq)) { pend |= 1u << k; clast = q.c[k]; }
+  unsigned long long f0 = 0ull, f1 = 0ull;
+  if (!fwd && i >= 0) {
+    gpu_ll_load_words(zf + 2 * (size_t)i, f0, f1);
+    if (!((unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq)) pend |= 1u << W;
+  }
+  if (__any_sync(0xffffffffu, pend != 0u)) {          // (warp-uniform branch)
+    // one lane parks on one word first (see sweep_ll_sentinel), then every lane polls ALL its pending words per round trip -- never one after the other
+    const bool own_only = (pend >> W) != 0u && (pend & ((1u << W) - 1u)) == 0u;
+    sweep_ll_sentinel(own_only ? zf : src, own_only ? i : clast, seq, sc, pause_ns);
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    while (pend) {
+#pragma unroll
+      for (int k = 0; k < W; ++k)
+        if ((pend >> k) & 1u) gpu_ll_load_words(src + 2 * (size_t)q.c[k], w0[k], w1[k]);
+      if ((pend >> W) & 1u) gpu_ll_load_words(zf + 2 * (size_t)i, f0, f1);
+#pragma unroll
+      for (int k = 0; k < W; ++k)
+        if (((pend >> k) & 1u) && (unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq) pend &= ~(1u << k);
+      if (((pend >> W) & 1u) && (unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq) pend &= ~(1u << W);
+#ifdef FCP_EMU
+      if (pend) { emu::yield(); emu::os_yield(); }
+#else
+      if (pend && (++spins & 4095u) == 0u) {
+        if (*(volatile const int32_t *)&sc->pad) break;
+        const unsigned long long t = p2p_now_ns();
+        if (!t0) t0 = t;
+        else if (t - t0 > 2000000000ull) { *(volatile int32_t *)&const_cast<KrylovScalars *>(sc)->pad = 1; break; }
+      }
+#endif
+    }
+  }
+  if (i < 0) return;
+  double z;
+  if (fwd) z = q.r0;
+  else z = __longlong_as_double((long long)((f0 & 0xffffffffull) | (f1 << 32))) / (q.di + FCP_SMALL);
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    if (q.c[k] < 0) continue;
+    const double zj = __longlong_as_double((long long)((w0[k] & 0xffffffffull) | (w1[k] << 32)));
+    z = z - q.av[k] * zj;
+  }
+  for (int32_t k = W; k < q.len; ++k) {
+    const int32_t cc = __ldg(v.tcol + q.b + (int64_t)k * 32);
+    if (cc < 0) break;
+    z = z - __ldg(v.tval + q.b + (int64_t)k * 32) * sweep_ll_wait(src + 2 * (size_t)cc, seq, sc);
+  }
+  z = z * q.di;
+  if (fwd) {
+    gpu_ll_store(zf + 2 * (size_t)i, z, seq);
+  } else {
+    gpu_ll_store(zb + 2 * (size_t)i, z, seq);
+    zk[i] = z;
+  }
+}
+template <int W, bool PF>
 __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriView bw, unsigned long long *zf, unsigned long long *zb, unsigned int seq,
                                                                const double *__restrict__ rhs, double *__restrict__ zk, const KrylovScalars *sc,
                                                                unsigned int pause_ns) {
@@ -1371,87 +1538,22 @@ __global__ void __launch_bounds__(FCP_TPB) k_precond_apply_ll(TriView fw, TriVie
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t ntot = (int64_t)fw.ntiles + bw.ntiles;
+  if (!PF) {
+    for (int64_t tq = warp; tq < ntot; tq += nwarps) {
+      const TileA a = ll_tile_a(fw, bw, tq, ntot, lane);
+      const TileB<W> q = ll_tile_b<W>(fw, bw, a, tq, ntot, lane, rhs);
+      ll_tile_process<W>(fw, bw, q, tq, zf, zb, seq, zk, sc, pause_ns);
+    }
+    return;
+  }
+  TileB<W> cur = ll_tile_b<W>(fw, bw, ll_tile_a(fw, bw, warp, ntot, lane), warp, ntot, lane, rhs);
+  TileA na = ll_tile_a(fw, bw, warp + nwarps, ntot, lane);
+#pragma unroll 1
   for (int64_t tq = warp; tq < ntot; tq += nwarps) {
-    const bool fwd = tq < fw.ntiles;
-    const TriView &v = fwd ? fw : bw;
-    const int64_t t = fwd ? tq : tq - fw.ntiles;
-    const int32_t i = __ldg(v.prow + t * 32 + lane);
-    const int64_t b = __ldg(v.tptr + t) + lane;
-    const int32_t len = (int32_t)((__ldg(v.tptr + t + 1) - __ldg(v.tptr + t)) >> 5);
-    const unsigned long long *src = fwd ? zf : zb;
-    // the row's entries and the first look at its dependencies: all loads independent of each other
-    int32_t c[W];
-    double av[W];
-    unsigned long long w0[W], w1[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) c[k] = (i >= 0 && k < len) ? __ldg(v.tcol + b + (int64_t)k * 32) : -1;
-#pragma unroll
-    for (int k = 0; k < W; ++k) av[k] = (c[k] >= 0) ? __ldg(v.tval + b + (int64_t)k * 32) : 0.0;
-    const double di = i >= 0 ? v.dtile[t * 32 + lane] : 0.0;
-    const double r0 = (fwd && i >= 0) ? rhs[i] : 0.0;
-#pragma unroll
-    for (int k = 0; k < W; ++k)
-      if (c[k] >= 0) gpu_ll_load_words(src + 2 * (size_t)c[k], w0[k], w1[k]);
-    // pending words: bit k = dependency k of the register window, bit W = the row's own forward value (backward sweep)
-    unsigned int pend = 0u;
-    int32_t clast = -1;       // the last dependency inside the register window that has not arrived yet
-#pragma unroll
-    for (int k = 0; k < W; ++k)
-      if (c[k] >= 0 && !((unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq)) { pend |= 1u << k; clast = c[k]; }
-    unsigned long long f0 = 0ull, f1 = 0ull;
-    if (!fwd && i >= 0) {
-      gpu_ll_load_words(zf + 2 * (size_t)i, f0, f1);
-      if (!((unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq)) pend |= 1u << W;
-    }
-    if (__any_sync(0xffffffffu, pend != 0u)) {          // (warp-uniform branch)
-      // one lane parks on one word first (see sweep_ll_sentinel), then every lane polls ALL its pending words per round trip -- never one after the other
-      const bool own_only = (pend >> W) != 0u && (pend & ((1u << W) - 1u)) == 0u;
-      sweep_ll_sentinel(own_only ? zf : src, own_only ? i : clast, seq, sc, pause_ns);
-      unsigned int spins = 0;
-      unsigned long long t0 = 0;
-      while (pend) {
-#pragma unroll
-        for (int k = 0; k < W; ++k)
-          if ((pend >> k) & 1u) gpu_ll_load_words(src + 2 * (size_t)c[k], w0[k], w1[k]);
-        if ((pend >> W) & 1u) gpu_ll_load_words(zf + 2 * (size_t)i, f0, f1);
-#pragma unroll
-        for (int k = 0; k < W; ++k)
-          if (((pend >> k) & 1u) && (unsigned int)(w0[k] >> 32) == seq && (unsigned int)(w1[k] >> 32) == seq) pend &= ~(1u << k);
-        if (((pend >> W) & 1u) && (unsigned int)(f0 >> 32) == seq && (unsigned int)(f1 >> 32) == seq) pend &= ~(1u << W);
-#ifdef FCP_EMU
-        if (pend) { emu::yield(); emu::os_yield(); }
-#else
-        if (pend && (++spins & 4095u) == 0u) {
-          if (*(volatile const int32_t *)&sc->pad) break;
-          const unsigned long long t = p2p_now_ns();
-          if (!t0) t0 = t;
-          else if (t - t0 > 2000000000ull) { *(volatile int32_t *)&const_cast<KrylovScalars *>(sc)->pad = 1; break; }
-        }
-#endif
-      }
-    }
-    if (i < 0) continue;
-    double z;
-    if (fwd) z = r0;
-    else z = __longlong_as_double((long long)((f0 & 0xffffffffull) | (f1 << 32))) / (di + FCP_SMALL);
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      if (c[k] < 0) continue;
-      const double zj = __longlong_as_double((long long)((w0[k] & 0xffffffffull) | (w1[k] << 32)));
-      z = z - av[k] * zj;
-    }
-    for (int32_t k = W; k < len; ++k) {
-      const int32_t cc = __ldg(v.tcol + b + (int64_t)k * 32);
-      if (cc < 0) break;
-      z = z - __ldg(v.tval + b + (int64_t)k * 32) * sweep_ll_wait(src + 2 * (size_t)cc, seq, sc);
-    }
-    z = z * di;
-    if (fwd) {
-      gpu_ll_store(zf + 2 * (size_t)i, z, seq);
-    } else {
-      gpu_ll_store(zb + 2 * (size_t)i, z, seq);
-      zk[i] = z;
-    }
+    const TileB<W> nb = ll_tile_b<W>(fw, bw, na, tq + nwarps, ntot, lane, rhs);      // in flight while this tile waits for its dependencies
+    na = ll_tile_a(fw, bw, tq + 2 * nwarps, ntot, lane);
+    ll_tile_process<W>(fw, bw, cur, tq, zf, zb, seq, zk, sc, pause_ns);
+    cur = nb;
   }
 }
 
@@ -1702,15 +1804,21 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
     unsigned long long *zf = p.zll[0], *zb = p.zll[1];
     unsigned int seq = next_ll_epoch(p, st);
     const bool wide = std::max(p.tri[0].maxlen, p.tri[1].maxlen) > 4;
-    const void *fn = wide ? (const void *)k_precond_apply_ll<8> : (const void *)k_precond_apply_ll<4>;
+    const char *pfe = getenv("FCP_SWEEP_PF");
+    const bool pf = !(pfe && !strcmp(pfe, "off"));            // software prefetch of the next tile's static data (default on)
+    const void *fn = wide ? (pf ? (const void *)k_precond_apply_ll<8, true> : (const void *)k_precond_apply_ll<8, false>)
+                          : (pf ? (const void *)k_precond_apply_ll<4, true> : (const void *)k_precond_apply_ll<4, false>);
     int grid = 0;
-    FCP_TRY(sweep_grid(fn, ws, wide ? 7 : 6, &grid));
+    FCP_TRY(sweep_grid(fn, ws, (wide ? 7 : 6), &grid));
+    if (pf) { int g2 = 0; FCP_TRY(coop_grid(fn, ws.ws_device, &g2)); grid = std::min(grid, g2); }
     unsigned int pause = sweep_pause_ns();
     void *args[] = {&fw, &bw, &zf, &zb, &seq, &rhs, &zk, &sc, &pause};
 #ifdef FCP_EMU
     (void)args;
-    if (wide) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<8>, fw, bw, zf, zb, seq, rhs, zk, sc, pause);
-    else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<4>, fw, bw, zf, zb, seq, rhs, zk, sc, pause);
+    if (wide && pf) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<8, true>, fw, bw, zf, zb, seq, rhs, zk, sc, pause);
+    else if (wide) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<8, false>, fw, bw, zf, zb, seq, rhs, zk, sc, pause);
+    else if (pf) emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<4, true>, fw, bw, zf, zb, seq, rhs, zk, sc, pause);
+    else emu::launch_coop(emu::Cfg(grid, FCP_TPB, 0, st), k_precond_apply_ll<4, false>, fw, bw, zf, zb, seq, rhs, zk, sc, pause);
 #else
     FCP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FCP_TPB), args, 0, st));
 #endif
@@ -1980,7 +2088,8 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
   if (n == 0 && !comm) return FCP_OK;
   const int BATCH = 16;
   BatchPoll poll{ws, st, comm_error_flag(comm)};
-  const L2Masks l2 = krylov_l2_masks(n, p.ncols);
+  L2Masks l2 = krylov_l2_masks(n, p.ncols);
+  if (cd) l2 = L2Masks();       // (the hinted kernels exist for the single-GPU / pk-halo forms only)
   const bool pdl = pdl_wanted() && (!comm || cd) && !(prof && prof->on);      // (an event between two kernels breaks the programmatic dependency anyway)
 
   if (solver == FCP_SOLVER_GAUSS_SEIDEL) {
@@ -2003,6 +2112,18 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     FCP_TRY(L.halo(fi));
     if (grid) { k_cg_init<true><<<grid, FCP_TPB, 0, st>>>(n, m, fi, rhs, ws.res, ws.adiag, ws.pk, L.red(EPI_INIT_CG)); FCP_LAUNCHED(); FCP_CHECK_LAUNCH(); }
     FCP_TRY(L.post(EPI_INIT_CG, 2));
+    const char *halo_env = getenv("FCP_HALO");
+    const bool res_halo = cd && !(halo_env && !strcmp(halo_env, "pk")) && !dpcg_persist_wanted();
+    if (res_halo) {
+      // the diagonal of the cells across the process faces, zero ghost directions, and the initial residual as LL words
+      FCP_TRY(comm_exchange(ctx, ws.adiag, 1));
+      if (p.ncols > n) FCP_CUDA(cudaMemsetAsync(ws.pk + n, 0, sizeof(double) * (size_t)(p.ncols - n), st));
+      if (cd && ctx->npro) {
+        const CommDev *hd = comm_dev_host(comm);
+        k_push_ll<<<std::max(1, std::min((ctx->npro + FCP_TPB - 1) / FCP_TPB, 148)), FCP_TPB, 0, st>>>(ctx->npro, hd->push_cell, hd->push_dst, ws.res, sb + 1u);
+        FCP_LAUNCHED();
+      }
+    }
     if (grid && (!comm || cd) && dpcg_persist_wanted()) {
       // the whole iteration loop on the device: one cooperative launch, one read of the scalars (below)
       FCP_TRY(launch_dpcg_persist(p, m, fi, ws, L.red(EPI_NONE), fw, sb, prof, st));
@@ -2010,11 +2131,13 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     for (int it = 0; it < itr_max;) {
       for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
         if (grid && l2.pk) FCP_PROF(prof, FCP_K_CG_PK, st, (k_cg_pk_l2<true><<<grid, FCP_TPB, 0, st>>>(n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb, l2.pk), FCP_LAUNCHED()));
+        else if (grid && res_halo) FCP_PROF(prof, FCP_K_CG_PK, st, (FCP_LAUNCH_PDL(pdl, k_cg_pk_rh, grid, st, n, ws.res, ws.adiag, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
         else if (grid) FCP_PROF(prof, FCP_K_CG_PK, st, (FCP_LAUNCH_PDL(pdl, k_cg_pk<true>, grid, st, n, ws.res, ws.adiag, ws.zk, ws.pk, ws.sc, cd, comm_chunk_info(comm), sb), FCP_LAUNCHED()));
         FCP_TRY(L.halo_pk());
-        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, fw, sb, l2.spmv, pdl))));
+        if (grid) FCP_PROF(prof, FCP_K_SPMV_DOT, st, FCP_TRY((launch_spmv_dot<1, false>(p, m, ws.pk, ws.zk, ws.pk, ws.sc, L.red(EPI_PKAPK), st, res_halo ? 0 : fw, sb, l2.spmv, pdl))));
         FCP_TRY(L.post(EPI_PKAPK, 1));
         if (grid && l2.upd) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (k_cg_update_l2<true><<<grid, FCP_TPB, 0, st>>>(n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE), l2.upd), FCP_LAUNCHED()));
+        else if (grid && res_halo) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (FCP_LAUNCH_PDL(pdl, k_cg_update_rh, grid, st, n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE), sb), FCP_LAUNCHED()));
         else if (grid) FCP_PROF(prof, FCP_K_CG_UPDATE, st, (FCP_LAUNCH_PDL(pdl, k_cg_update<true>, grid, st, n, fi, ws.res, ws.pk, ws.zk, ws.adiag, ws.sc, L.red(EPI_CG_UPDATE)), FCP_LAUNCHED()));
         FCP_TRY(L.post(EPI_CG_UPDATE, 3));
       }

@@ -877,7 +877,9 @@ __global__ void __launch_bounds__(FCP_TPB) k_cg_update_l2(int32_t n, double *fi,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Residual halo (peer-memory path of DPCG, default; FCP_HALO=pk keeps the scheme above).  `call exchange(pk)` (src-par/dpcg.f90:118) needs the
+// Residual halo (peer-memory path of DPCG, opt-in: FCP_HALO=res).  Measured on 8 B200s (profiles/r02_scaling.txt): 100.1 ms per step against 90.0 ms for the
+// direction-vector push above -- the flagged loads of the ghost residuals cost k_cg_pk more (19.7 -> 26.8 us) than its remote stores did, and the SpMV does
+// not get faster without its flagged loads (53.5 -> 53.2 us).  Kept with its parity tests as a measured alternative.  `call exchange(pk)` (src-par/dpcg.f90:118) needs the
 // direction vector of the cells across every process face.  Instead of pushing pk from k_cg_pk -- whose completion then waits for its NVLink stores
 // to be acknowledged, and whose values the SpMV has to fetch through flagged loads -- every rank carries the recurrence of its GHOST entries itself:
 //     pk(ghost) = res(ghost) / a_ii(ghost) + bet * pk(ghost)
@@ -2113,7 +2115,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     if (grid) { k_cg_init<true><<<grid, FCP_TPB, 0, st>>>(n, m, fi, rhs, ws.res, ws.adiag, ws.pk, L.red(EPI_INIT_CG)); FCP_LAUNCHED(); FCP_CHECK_LAUNCH(); }
     FCP_TRY(L.post(EPI_INIT_CG, 2));
     const char *halo_env = getenv("FCP_HALO");
-    const bool res_halo = cd && !(halo_env && !strcmp(halo_env, "pk")) && !dpcg_persist_wanted();
+    const bool res_halo = cd && halo_env && !strcmp(halo_env, "res") && !dpcg_persist_wanted();     // opt-in: measured slower on 8 B200s (see the comment at k_push_ll)
     if (res_halo) {
       // the diagonal of the cells across the process faces, zero ghost directions, and the initial residual as LL words
       FCP_TRY(comm_exchange(ctx, ws.adiag, 1));

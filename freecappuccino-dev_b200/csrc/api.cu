@@ -338,7 +338,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   for (int i = 0; i < FCP_F_COUNT; ++i) cudaFree(c->field[i]);
   for (int i = 0; i < 4; ++i) cudaFree(c->Dmat[i]);
   cudaFree(c->flushbuf); cudaFree(c->d_mmpart); cudaFree(c->d_sum);
-  cudaFree(c->d_oface); cudaFree(c->d_flowo); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
+  cudaFree(c->d_oface); cudaFree(c->d_flowo); cudaFree(c->d_csr_stage); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
   cudaFree(c->per_cell); cudaFree(c->per_face); cudaFree(c->per_slot); cudaFree(c->per_df);
   sell_free(c->pat);
   krylov_ws_free(c->ws);
@@ -396,12 +396,11 @@ extern "C" int fcp_field_upload(fcp_ctx *ctx, int field, const double *host, int
   FCP_TRY(field_count(ctx, field, &cap));
   if (field == FCP_F_A || field == FCP_F_H) {
     if (count != ctx->pat.nnz) { fcp_set_error("upload of a(nnz): count %lld != nnz %lld", (long long)count, (long long)ctx->pat.nnz); return FCP_EINVAL; }
-    double *stage = nullptr;
-    FCP_TRY(dev_alloc(&stage, (size_t)count));
+    if (!ctx->d_csr_stage) FCP_TRY(dev_alloc(&ctx->d_csr_stage, (size_t)count));      // CSR-order staging of a(nnz), kept for the life of the context
+    double *stage = ctx->d_csr_stage;
     FCP_CUDA(cudaMemcpyAsync(stage, host, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
     int rc = sell_values_from_csr(ctx->pat, stage, d, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
     return rc;
   }
   if (count < 0 || count > cap) { fcp_set_error("field %d: count %lld exceeds extent %lld", field, (long long)count, (long long)cap); return FCP_EINVAL; }
@@ -423,15 +422,14 @@ extern "C" int fcp_field_download(fcp_ctx *ctx, int field, double *host, int64_t
   FCP_TRY(field_count(ctx, field, &cap));
   if (field == FCP_F_A || field == FCP_F_H) {
     if (count != ctx->pat.nnz) { fcp_set_error("download of a(nnz): count %lld != nnz %lld", (long long)count, (long long)ctx->pat.nnz); return FCP_EINVAL; }
-    double *stage = nullptr;
-    FCP_TRY(dev_alloc(&stage, (size_t)count));
+    if (!ctx->d_csr_stage) FCP_TRY(dev_alloc(&ctx->d_csr_stage, (size_t)count));
+    double *stage = ctx->d_csr_stage;
     int rc = sell_values_to_csr(ctx->pat, d, stage, ctx->stream);
     if (rc == FCP_OK) {
       cudaError_t e = cudaMemcpyAsync(host, stage, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream);
       if (e != cudaSuccess) rc = FCP_ECUDA;
     }
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
     return rc;
   }
   if (count < 0 || count > cap) { fcp_set_error("field %d: count %lld exceeds extent %lld", field, (long long)count, (long long)cap); return FCP_EINVAL; }

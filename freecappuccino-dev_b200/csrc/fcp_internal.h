@@ -11,7 +11,8 @@
 // error handling
 // ---------------------------------------------------------------------------------------------
 void fcp_set_error(const char *fmt, ...);
-extern int64_t g_fcp_launches;   // number of kernels launched by this library (fcp_launch_count)
+#include <atomic>
+extern std::atomic<int64_t> g_fcp_launches;   // number of kernels launched by this library (fcp_launch_count)
 
 #define FCP_CUDA(call)                                                                         \
   do {                                                                                         \
@@ -130,7 +131,7 @@ struct KrylovWS {
   unsigned int *counter = nullptr;    // last-block ticket
   unsigned int *bar = nullptr;        // [4] grid barrier of the persistent solver kernels: arrivals, generation
   unsigned long long *phase_ns = nullptr;   // [8] per-phase times of the persistent kernels (CTA 0's view), profiler only
-  int persist_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cooperative grid size per persistent / LL-sweep kernel variant on ws_device (0: not queried yet)
+  int persist_grid[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cooperative grid size per cooperative kernel variant on ws_device (0: not queried yet)
   int ws_device = -1;
   int maxchunks = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -247,6 +248,7 @@ struct fcp_ctx {
   int32_t nout = 0;
   int32_t *d_oface = nullptr;                       // outlet faces in patch order (adjustMassFlow)
   double *d_flowo = nullptr;                        // [4] outlet mass flow: local sum, then the sum over all ranks
+  double *d_csr_stage = nullptr;                    // [nnz] CSR-order staging for uploads / downloads of a(nnz) (allocated on first use)
   int32_t *d_aprpos = nullptr;                      // [npro] SELL position of the halo entry of each process face
   int32_t *d_procface = nullptr;                    // [npro] 0-based face index of each process face (patch order)
   std::vector<int32_t> h_procface;

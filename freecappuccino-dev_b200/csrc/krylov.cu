@@ -1827,12 +1827,8 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
     FCP_LAUNCHED();
     return FCP_OK;
   }
-  static int grid = 0;
-  if (!grid) {
-    int dev = 0;
-    FCP_CUDA(cudaGetDevice(&dev));
-    FCP_TRY(coop_grid((const void *)k_precond_apply, dev, &grid));
-  }
+  int &grid = ws.persist_grid[8];         // (per workspace = per device; round 1 cached this per process)
+  if (!grid) FCP_TRY(coop_grid((const void *)k_precond_apply, ws.ws_device, &grid));
   SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
   LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
   const int32_t *llen = p.llen;
@@ -1843,12 +1839,8 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
     fprintf(stderr, "libfcp_b200: FCP_SWEEP=flags: IC(0)/ILU(0) sweeps wait on per-row ready flags instead of a grid barrier per level\n");
   }
   if (use_flags) {
-    static int fgrid = 0;
-    if (!fgrid) {
-      int dev = 0;
-      FCP_CUDA(cudaGetDevice(&dev));
-      FCP_TRY(coop_grid((const void *)k_precond_apply_flags, dev, &fgrid));
-    }
+    int &fgrid = ws.persist_grid[9];
+    if (!fgrid) FCP_TRY(coop_grid((const void *)k_precond_apply_flags, ws.ws_device, &fgrid));
     if (p.sweep_epoch > 2000000000) {          // epochs are int32: start over (once per ~10^9 applies)
       FCP_CUDA(cudaMemsetAsync(p.ready, 0, sizeof(int32_t) * (size_t)std::max(p.n, 1), st));
       p.sweep_epoch = 0;
@@ -1877,14 +1869,10 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
 }
 
 static int launch_gs_sweep(SellPattern &p, const double *a, const double *rhs, const double *fi, double *xn, double *res, double *adiag,
-                           const KrylovScalars *sc, cudaStream_t st) {
+                           const KrylovScalars *sc, KrylovWS &ws, cudaStream_t st) {
   if (p.n == 0) return FCP_OK;
-  static int grid = 0;
-  if (!grid) {
-    int dev = 0;
-    FCP_CUDA(cudaGetDevice(&dev));
-    FCP_TRY(coop_grid((const void *)k_gs_sweep, dev, &grid));
-  }
+  int &grid = ws.persist_grid[10];
+  if (!grid) FCP_TRY(coop_grid((const void *)k_gs_sweep, ws.ws_device, &grid));
   SellView m{p.slptr, p.rinfo, p.ja, a, p.llen};
   LevelView lv{p.lev_ptr, p.lev_rows, p.blev_ptr, p.blev_rows, p.nlevels, p.nblevels};
   void *args[] = {&m, &lv, &rhs, &fi, &xn, &res, &adiag, &sc};
@@ -2102,7 +2090,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     } else {
       for (int it = 0; it < itr_max;) {
         for (int b = 0; b < BATCH && it < itr_max; ++b, ++it) {
-          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_gs_sweep(p, a, rhs, fi, ws.pk, ws.res, ws.adiag, ws.sc, st)));
+          FCP_PROF(prof, FCP_K_PRECOND, st, FCP_TRY(launch_gs_sweep(p, a, rhs, fi, ws.pk, ws.res, ws.adiag, ws.sc, ws, st)));
           if (grid) { k_gs_norms<<<grid, FCP_TPB, 0, st>>>(n, fi, ws.pk, ws.res, ws.adiag, ws.sc, L.red(EPI_GS)); FCP_LAUNCHED(); }
         }
         FCP_CHECK_LAUNCH();

@@ -7,7 +7,7 @@
 #include "fcp_internal.h"
 
 static thread_local char g_err[1024] = "";
-int64_t g_fcp_launches = 0;
+std::atomic<int64_t> g_fcp_launches{0};
 void fcp_set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -16,7 +16,7 @@ void fcp_set_error(const char *fmt, ...) {
 }
 extern "C" const char *fcp_last_error(void) { return g_err; }
 extern "C" int fcp_version(void) { return 100; }
-extern "C" int64_t fcp_launch_count(void) { return g_fcp_launches; }
+extern "C" int64_t fcp_launch_count(void) { return g_fcp_launches.load(); }
 
 template <class T> int dev_alloc(T **dptr, size_t count) {
   *dptr = nullptr;

@@ -557,7 +557,9 @@ def main():
         "cg_pk": kernel_line("cg_pk", (32 if args.solver == "dpcg" else 24) * N0),            # dpcg: res, adiag, pk r + pk w; iccg: zk, pk r + pk w
         "cg_update": kernel_line("cg_update", (56 if args.solver == "dpcg" else 48) * N0),    # fi, res r+w, pk, zk (+ adiag for the Jacobi z)
         "assemble": kernel_line("assemble", 80 * F0 + 124 * N0),
-        "gradp": kernel_line("gradp", 40 * F0 + 64 * N0 + 36 * B0),
+        # two launches per step: gradp_and_sources(p) [40 F + 64 N + 36 B] and the same kernel on pp with the velocity / pressure correction of
+        # calcp_simple.f90:416-429 fused in [+ 120 N: u, v, w r+w, apu, apv, apw, p r+w, pp -- SURVEY 8d row a6]; bytes = their mean
+        "gradp": kernel_line("gradp", 40 * F0 + 64 * N0 + 36 * B0 + 60 * N0),
         "correct_flux": kernel_line("correct_flux", 36 * F0 + 8 * N0),
         "precond": kernel_line("precond", 24 * F0 + 80 * N0),       # IC(0)/ILU(0) apply: both triangles once + ia, diag, d, r, z
     }

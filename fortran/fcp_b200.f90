@@ -240,6 +240,12 @@ module fcp_b200
       integer(c_int), value :: phi_field, grad_field
       integer(c_int) :: rc
     end function
+    function fcp_grad_gauss_iter(ctx, phi_field, grad_field, nigrad) bind(c, name='fcp_grad_gauss_iter') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: phi_field, grad_field, nigrad
+      integer(c_int) :: rc
+    end function
     function fcp_modify_viscosity_sgs(ctx, model, urfVis, viscos) bind(c, name='fcp_modify_viscosity_sgs') result(rc)
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: ctx
@@ -308,6 +314,13 @@ module fcp_b200
       integer(c_int), value :: rank, nranks
       character(kind=c_char), intent(in) :: id128(128)
       integer(c_int32_t), intent(in) :: peer_rank(*)
+      integer(c_int) :: rc
+    end function
+    function fcp_set_process_facint(ctx, fpro, count) bind(c, name='fcp_set_process_facint') result(rc)
+      import :: c_int, c_ptr, c_double, c_int32_t
+      type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: fpro(*)
+      integer(c_int32_t), value :: count
       integer(c_int) :: rc
     end function
     function fcp_exchange(ctx, field) bind(c, name='fcp_exchange') result(rc)

@@ -913,6 +913,20 @@ extern "C" int fcp_grad_gauss_fvx(fcp_ctx *ctx, int phi_field, int grad_field) {
   if (ctx->comm) FCP_TRY(comm_exchange(ctx, phi, 1));
   return fvm_grad_gauss_fvx(ctx, phi, gtmp, g);
 }
+// grad_gauss of the MPI tree, src-par/gradients.f90:1547-1664: nigrad passes of gradco (switchable where the two trees differ)
+extern "C" int fcp_grad_gauss_iter(fcp_ctx *ctx, int phi_field, int grad_field, int nigrad) {
+  if (!ctx) return FCP_EINVAL;
+  if (!fcp_is_gradient_field(grad_field) || phi_field < 0 || phi_field >= FCP_F_COUNT || (phi_field >= FCP_F_DUDXI && phi_field <= FCP_F_H) || fcp_is_gradient_field(phi_field)) {
+    fcp_set_error("fcp_grad_gauss_iter: bad field id");
+    return FCP_EINVAL;
+  }
+  if (nigrad < 1) { fcp_set_error("fcp_grad_gauss_iter: nigrad must be >= 1 (the reference's DO loop would leave the gradient untouched)"); return FCP_EINVAL; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  FIELD(phi, phi_field); FIELD(g, grad_field);
+  FIELD(gtmp, grad_field == FCP_F_G1 ? FCP_F_G0 : FCP_F_G1);
+  if (ctx->comm) FCP_TRY(comm_exchange(ctx, phi, 1));
+  return fvm_grad_gauss_passes(ctx, phi, gtmp, g, nigrad);
+}
 extern "C" int fcp_modify_viscosity_sgs(fcp_ctx *ctx, int model, double urfVis, double viscos) {
   if (!ctx) return FCP_EINVAL;
   if (model != FCP_SGS_WALE && model != FCP_SGS_VREMAN) { fcp_set_error("fcp_modify_viscosity_sgs: unknown model %d", model); return FCP_EINVAL; }

@@ -511,6 +511,26 @@ int comm_check_error(fcp_ctx *ctx) {
   return FCP_OK;
 }
 
+__global__ void k_set_process_facint(int32_t npro, const int32_t *__restrict__ pface, const double *__restrict__ fpro, double *__restrict__ facint) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npro) facint[pface[i]] = fpro[i];
+}
+extern "C" int fcp_set_process_facint(fcp_ctx *ctx, const double *fpro, int32_t count) {
+  if (!ctx || (!fpro && count > 0)) return FCP_EINVAL;
+  if (!ctx->comm) { fcp_set_error("fcp_set_process_facint: call fcp_comm_init first (it fills the process-face geometry this call overrides)"); return FCP_ESTATE; }
+  if (count != ctx->npro) { fcp_set_error("fcp_set_process_facint: %d values for %d process faces", count, ctx->npro); return FCP_EINVAL; }
+  if (count == 0) return FCP_OK;
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  double *d = nullptr;
+  FCP_TRY(dev_upload(&d, fpro, (size_t)count));
+  k_set_process_facint<<<(count + 255) / 256, 256, 0, ctx->stream>>>(count, ctx->d_procface, d, ctx->facint);
+  FCP_LAUNCHED();
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) { fcp_set_error("fcp_set_process_facint: %s", cudaGetErrorString(e)); return FCP_ECUDA; }
+  return FCP_OK;
+}
+
 extern "C" int fcp_comm_unique_id(void *id128) {
   if (!id128) return FCP_EINVAL;
   FCP_TRY(nccl_load());

@@ -350,6 +350,7 @@ int fvm_mu_eff_rlzb(fcp_ctx *ctx, double urf, double viscos, const double *gU, c
 int fvm_minmax(fcp_ctx *ctx, const double *phi, double **mm_out, int32_t count = -1 /* default: numCells */);
 static inline bool fcp_is_gradient_field(int f) { return (f >= FCP_F_DUDXI && f <= FCP_F_G1) || f == FCP_F_DTEDXI || f == FCP_F_DEDDXI; }
 int fvm_grad_gauss_fvx(fcp_ctx *ctx, const double *u, double *gtmp, double *g);
+int fvm_grad_gauss_passes(fcp_ctx *ctx, const double *u, double *gtmp, double *g, int npass);
 int fvm_sgs_viscosity(fcp_ctx *ctx, int model, double urf, double viscos, const double *gU, const double *gV, const double *gW, const double *den,
                       double *vis, double *visw);
 

@@ -513,19 +513,26 @@ __global__ void __launch_bounds__(FCP_TPB) k_sgs_boundary(MeshView m, const int3
   }
 }
 
-int fvm_grad_gauss_fvx(fcp_ctx *ctx, const double *u, double *gtmp, double *g) {
+// npass passes of the gradco gradient: pass 1 interpolates with a zero gradient, pass k with the gradient of pass k-1 (ghost copies exchanged in
+// between on partitions); the last pass writes g, the passes alternate between g and gtmp.  npass = 2: fvxGradient.f90:1549-1662;
+// npass = nigrad: the iterative Gauss gradient of the MPI tree, src-par/gradients.f90:1547-1664.
+int fvm_grad_gauss_passes(fcp_ctx *ctx, const double *u, double *gtmp, double *g, int npass) {
   if (ctx->n == 0) return FCP_OK;
   const MeshView m = fcp_mesh_view(ctx);
   size_t tok = ctx->prof.begin(FCP_K_GRAD, ctx->stream);
-  k_grad_gauss_fvx<<<FCP_GRID(ctx->n)>>>(m, u, nullptr, gtmp);
-  FCP_LAUNCHED();
-  if (ctx->comm) FCP_TRY(comm_exchange(ctx, gtmp, 3));      // the second pass interpolates the first pass's gradient across process faces
-  k_grad_gauss_fvx<<<FCP_GRID(ctx->n)>>>(m, u, gtmp, g);
+  const double *gold = nullptr;
+  for (int lc = 1; lc <= npass; ++lc) {
+    double *out = ((npass - lc) % 2 == 0) ? g : gtmp;
+    k_grad_gauss_fvx<<<FCP_GRID(ctx->n)>>>(m, u, gold, out);
+    FCP_LAUNCHED();
+    if (lc != npass && ctx->comm) FCP_TRY(comm_exchange(ctx, out, 3));      // the next pass interpolates this pass's gradient across process faces
+    gold = out;
+  }
   ctx->prof.end(tok, ctx->stream);
-  FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;
 }
+int fvm_grad_gauss_fvx(fcp_ctx *ctx, const double *u, double *gtmp, double *g) { return fvm_grad_gauss_passes(ctx, u, gtmp, g, 2); }
 int fvm_sgs_viscosity(fcp_ctx *ctx, int model, double urf, double viscos, const double *gU, const double *gV, const double *gW, const double *den,
                       double *vis, double *visw) {
   if (ctx->n == 0) return FCP_OK;

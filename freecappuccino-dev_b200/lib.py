@@ -152,6 +152,7 @@ def lib():
     L.fcp_calc_strain_and_vorticity.argtypes = [vp]
     L.fcp_wall_distance.argtypes = [vp, C.POINTER(Report)]
     L.fcp_grad_gauss_fvx.argtypes = [vp, C.c_int, C.c_int]
+    L.fcp_grad_gauss_iter.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.fcp_modify_viscosity_sgs.argtypes = [vp, C.c_int, C.c_double, C.c_double]
     L.fcp_modify_mu_eff_k_epsilon_rlzb.argtypes = [vp, C.c_double, C.c_double]
     L.fcp_modify_mu_eff_k_omega_sst.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int]
@@ -169,6 +170,7 @@ def lib():
     L.fcp_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p, _pi]
     L.fcp_comm_mode.argtypes = [vp]
     L.fcp_exchange.argtypes = [vp, C.c_int]
+    L.fcp_set_process_facint.argtypes = [vp, _pd, C.c_int32]
     for nm in ("fcp_global_sum", "fcp_global_max", "fcp_global_min"):
         getattr(L, nm).argtypes = [vp, _pd]
     L.fcp_global_isum.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -348,6 +350,10 @@ class Context:
         """Grad of the tensor-field layer: the two-pass Gauss gradient of fvxGradient.f90:1549-1662."""
         check(lib().fcp_grad_gauss_fvx(self.h, field_id(phi), field_id(grad)), "fcp_grad_gauss_fvx")
 
+    def grad_gauss_iter(self, phi, grad, nigrad: int):
+        """grad_gauss of the MPI tree (src-par/gradients.f90:1547-1664): `nigrad` passes of gradco."""
+        check(lib().fcp_grad_gauss_iter(self.h, field_id(phi), field_id(grad), int(nigrad)), "fcp_grad_gauss_iter")
+
     def modify_viscosity_sgs(self, model, urfVis: float, viscos: float):
         """modify_viscosity_wale_sgs / modify_viscosity_vreman_sgs."""
         mid = {"wale": 0, "vreman": 1}[model] if isinstance(model, str) else int(model)
@@ -420,6 +426,12 @@ class Context:
         pr = np.ascontiguousarray(peer_rank, dtype=np.int32)
         buf = C.create_string_buffer(unique_id, 128)
         check(lib().fcp_comm_init(self.h, rank, nranks, buf, _i(pr)), "fcp_comm_init")
+
+    def set_process_facint(self, fpro: np.ndarray):
+        """src-par/geometry.f90:822-868: the interpolation factors of the process faces (patch order), e.g. the line-plane variant of the MPI tree
+        (`mesh.facint_line_plane` on the global mesh, carried into `Mesh.fpro` by `mesh.partition`); overrides what fcp_comm_init computed."""
+        f = np.ascontiguousarray(fpro, dtype=np.float64)
+        check(lib().fcp_set_process_facint(self.h, _d(f), int(f.size)), "fcp_set_process_facint")
 
     def comm_mode(self) -> str:
         """'p2p' (peer-memory stores over NVLink fused into the kernels), 'nccl' (send/recv + all-gather) or 'none'."""

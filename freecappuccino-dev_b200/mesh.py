@@ -166,6 +166,35 @@ def compute_geometry(points: np.ndarray, face_nodes: np.ndarray, face_nnodes: np
                 xc=cc[:, 0].copy(), yc=cc[:, 1].copy(), zc=cc[:, 2].copy(), vol=vol, facint=facint, Df=Df)
 
 
+def facint_line_plane(mesh: "Mesh") -> np.ndarray:
+    """The MPI tree's interpolation factor (quirk Q9, src-par/geometry.f90:780-819 with find_intersection_point :1143-1215): the line P -> N is cut
+    with the plane through the FIRST THREE vertices of the face, facint = |P j'| / |P N| -- where the serial tree (geometry.f90:581-606, what
+    `compute_geometry` returns) takes dist(f,P) / (dist(f,P) + dist(f,N)) with the face centre f.  The two agree where f lies on the line P N
+    (orthogonal meshes) and differ on skewed ones.  Needs the topology (points, face_nodes); inner faces only -- a partition takes its
+    process-face factors `fpro` from the global mesh's values (`partition`) and hands them to the library with `Context.set_process_facint`."""
+    if mesh.points is None or mesh.face_nodes is None:
+        raise ValueError("facint_line_plane needs the mesh topology (points, face_nodes)")
+    F = mesh.numInnerFaces
+    own0 = mesh.owner[:F].astype(np.int64) - 1
+    nb0 = mesh.neighbour.astype(np.int64) - 1
+    fn = mesh.face_nodes[:F].astype(np.int64) - 1
+    (x1, y1, z1), (x2, y2, z2), (x3, y3, z3) = (mesh.points[fn[:, k]].T for k in range(3))
+    x4, y4, z4 = mesh.xc[own0], mesh.yc[own0], mesh.zc[own0]
+    x5, y5, z5 = mesh.xc[nb0], mesh.yc[nb0], mesh.zc[nb0]
+    tiny = float(np.float32(1e-30))             # `real(dp), parameter :: tiny = 1e-30` is a single-precision literal (geometry.f90:38)
+    num = (x2 * (y3 * z4 - y4 * z3) - x1 * (y3 * z4 - y4 * z3) - x3 * (y2 * z4 - y4 * z2) + x1 * (y2 * z4 - y4 * z2) + x3 * (y1 * z4 - y4 * z1)
+           - x2 * (y1 * z4 - y4 * z1) + x4 * (y2 * z3 - y3 * z2) - x1 * (y2 * z3 - y3 * z2) - x4 * (y1 * z3 - y3 * z1) + x2 * (y1 * z3 - y3 * z1)
+           + x4 * (y1 * z2 - y2 * z1) - x3 * (y1 * z2 - y2 * z1))
+    den = (x2 * (y3 * (z5 - z4) - (y5 - y4) * z3) - x1 * (y3 * (z5 - z4) - (y5 - y4) * z3) - x3 * (y2 * (z5 - z4) - (y5 - y4) * z2)
+           + x1 * (y2 * (z5 - z4) - (y5 - y4) * z2) + x3 * (y1 * (z5 - z4) - (y5 - y4) * z1) - x2 * (y1 * (z5 - z4) - (y5 - y4) * z1)
+           + (x5 - x4) * (y2 * z3 - y3 * z2) - (x5 - x4) * (y1 * z3 - y3 * z1) + (x5 - x4) * (y1 * z2 - y2 * z1) + tiny)
+    t = -num / den
+    xj, yj, zj = x4 + (x5 - x4) * t, y4 + (y5 - y4) * t, z4 + (z5 - z4) * t
+    dpn = np.sqrt((x5 - x4) ** 2 + (y5 - y4) ** 2 + (z5 - z4) ** 2)
+    djn = np.sqrt((xj - x4) ** 2 + (yj - y4) ** 2 + (zj - z4) ** 2)
+    return djn / dpn
+
+
 def mesh_from_topology(points, face_nodes, face_nnodes, owner, neighbour, numCells,
                        patches: Sequence[Tuple[str, str, int, int]], geometry: Optional[Dict[str, np.ndarray]] = None) -> Mesh:
     """patches: (name, type, nFaces, startFace) with startFace the 0-based offset of the reference's

@@ -287,6 +287,11 @@ int fcp_modify_mu_eff_k_omega_sst(fcp_ctx *ctx, double urfVis, double viscos, do
  * with the first pass's gradient (skewness correction).  It is what Grad(U) of the tensor-field layer returns with its default flags; note that
  * it is NOT the grad_gauss of gradients.f90 (FCP_GRAD_GAUSS).  Scratch: the G1 gradient field (G0 when grad_field is G1). */
 int fcp_grad_gauss_fvx(fcp_ctx *ctx, int phi_field, int grad_field);
+/* grad_gauss of the MPI tree (src-par/gradients.f90:1547-1664, gradco :1775-1837): `nigrad` passes, pass k interpolates the face value with the
+ * gradient of pass k-1 (zero in the first pass); the serial tree's one-pass grad_gauss is FCP_GRAD_GAUSS, whose face value P + (N - P) lambda
+ * rounds differently from gradco's P fxp + N fxn even for nigrad = 1.  SURVEY 0.1: the two trees are switchable where they differ.  Same scratch
+ * field as fcp_grad_gauss_fvx, which is the nigrad = 2 case. */
+int fcp_grad_gauss_iter(fcp_ctx *ctx, int phi_field, int grad_field, int nigrad);
 /* modify_viscosity_wale_sgs (TurbulenceModels/wale_sgs.f90:33-185) / modify_viscosity_vreman_sgs (vremanSGS.f90:33-179): D = Grad(U) with the
  * gradient above (left in FCP_F_DUDXI/DVDXI/DWDXI), the model's tensor algebra (tensorFields.f90, quirk Q24 of its inner product reproduced),
  * vis = urfVis (mu_sgs + viscos) + (1 - urfVis) vis, then the boundary values: wall faces FCP_F_VISW = vis = max(viscos, 0), periodic pairs the
@@ -319,6 +324,10 @@ int fcp_comm_plan(const fcp_mesh_desc *mesh, const int32_t *peer_rank, int rank,
 /* 1: halo values and reduction partials travel as peer-memory stores over NVLink (CUDA IPC windows, fused into the
  * Krylov kernels); 0: NCCL send/recv + all-gather (FCP_COMM=nccl or peer mapping unavailable); -1: no communicator */
 int fcp_comm_mode(const fcp_ctx *ctx);
+/* Interpolation factors of the `process` faces (src-par/geometry.f90:822-868 `fpro`, patch order, the weight of the GHOST cell seen from this rank).
+ * fcp_comm_init computes them from the ghost cell centres with the serial tree's formula (geometry.f90:581-606); a host that follows the MPI tree's
+ * line-plane variant (quirk Q9) or reads them from a file overrides them here, after fcp_comm_init.  count must equal the number of process faces. */
+int fcp_set_process_facint(fcp_ctx *ctx, const double *fpro, int32_t count);
 int fcp_exchange(fcp_ctx *ctx, int field);                    /* ghost slots of `process` patches <- owner values on the peer */
 int fcp_global_sum(fcp_ctx *ctx, double *value);              /* in place, all ranks */
 int fcp_global_max(fcp_ctx *ctx, double *value);

@@ -1583,10 +1583,11 @@ extern "C" void orc_calcuvw(const orc_mesh *m, const i32 *ia, const i32 *ja, con
 // ------------------------------------------------------------------------------------------
 // LES sub-grid viscosity: fvxGradient's Grad(U) + the tensorFields algebra of wale_sgs.f90 / vremanSGS.f90
 // ------------------------------------------------------------------------------------------
-extern "C" void orc_grad_gauss_fvx(const orc_mesh *m, const double *u, double *dudx, double *dudy, double *dudz) {   // fvxGradient.f90:1549-1662
+// npass = 2: fvxGradient.f90:1549-1662; npass = nigrad: the MPI tree's grad_gauss, src-par/gradients.f90:1547-1664 (same gradco / gradbc)
+extern "C" void orc_grad_gauss_iter(const orc_mesh *m, const double *u, int npass, double *dudx, double *dudy, double *dudz) {
   const i32 n = m->numCells, F = m->numInnerFaces;
   std::vector<double> dfxo(n, 0.0), dfyo(n, 0.0), dfzo(n, 0.0);
-  for (int lc = 1; lc <= 2; ++lc) {
+  for (int lc = 1; lc <= npass; ++lc) {
     for (i32 c = 0; c < n; ++c) dudx[c] = dudy[c] = dudz[c] = 0.0;
     for (i32 i = 0; i < F; ++i) {                                     // gradco :1761-1817
       const i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
@@ -1606,8 +1607,11 @@ extern "C" void orc_grad_gauss_fvx(const orc_mesh *m, const double *u, double *d
       const double volr = 1.0 / m->vol[c];
       dudx[c] = dudx[c] * volr; dudy[c] = dudy[c] * volr; dudz[c] = dudz[c] * volr;
     }
-    if (lc < 2) for (i32 c = 0; c < n; ++c) { dfxo[c] = dudx[c]; dfyo[c] = dudy[c]; dfzo[c] = dudz[c]; }
+    if (lc != npass) for (i32 c = 0; c < n; ++c) { dfxo[c] = dudx[c]; dfyo[c] = dudy[c]; dfzo[c] = dudz[c]; }
   }
+}
+extern "C" void orc_grad_gauss_fvx(const orc_mesh *m, const double *u, double *dudx, double *dudy, double *dudz) {   // fvxGradient.f90:1549-1662
+  orc_grad_gauss_iter(m, u, 2, dudx, dudy, dudz);
 }
 // tensors as t[9] = xx xy xz yx yy yz zx zy zz
 static inline void tf_inner(const double *a, const double *b, double *r) {          // tensorFields.f90:490-513, quirk Q24 in r[6]

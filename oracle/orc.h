@@ -234,6 +234,7 @@ void orc_modify_mu_eff_rlzb(const orc_mesh *m, double urf, double viscos, const 
  * QUIRK Q24: inner_product_rank2_tensors computes its zx component as T1zx*T2xx + T1zx*T2yx + T1zz*T2zx (tensorFields.f90:508: `zx` twice);
  * reproduced.  Boundary: wall faces get visw = vis = max(viscos, 0), a periodic face and its twin the mean of the two cells, every other patch
  * the owner value.  visw is indexed by BOUNDARY FACE ordinal. */
+void orc_grad_gauss_iter(const orc_mesh *m, const double *u, int npass, double *dudx, double *dudy, double *dudz);   /* src-par/gradients.f90:1547-1664 (nigrad passes of gradco) */
 void orc_grad_gauss_fvx(const orc_mesh *m, const double *u, double *dudx, double *dudy, double *dudz);   /* fvxGradient.f90:1549-1662 (two passes, gradco) */
 void orc_modify_viscosity_sgs(const orc_mesh *m, int model, double urf, double viscos, const double *u, const double *v, const double *w,
                               const double *den, double *vis, double *visw);

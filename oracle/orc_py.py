@@ -436,6 +436,14 @@ def grad_gauss_fvx(mesh, u):
     return gx, gy, gz
 
 
+def grad_gauss_iter(mesh, u, nigrad):
+    """src-par/gradients.f90:1547-1664: the MPI tree's grad_gauss, `nigrad` passes of gradco (SoA result, numCells)."""
+    mv = MeshView(mesh)
+    gx, gy, gz = (np.zeros(mesh.numCells) for _ in range(3))
+    lib().orc_grad_gauss_iter(mv.ptr, _d(u), C.c_int(int(nigrad)), _d(gx), _d(gy), _d(gz))
+    return gx, gy, gz
+
+
 SGS_WALE, SGS_VREMAN = 0, 1
 
 

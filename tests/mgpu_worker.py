@@ -203,9 +203,10 @@ def main():
         bz = max(world // 4, 1)
         cr = ((g.xc[:nc] > 0.5).astype(np.int32) + 2 * (g.yc[:nc] > 0.5).astype(np.int32)
               + 4 * np.minimum((g.zc[:nc] * bz).astype(np.int32), bz - 1)) % world
-        parts = M.partition(g, cr.astype(np.int32))
+        cell_rank = cr.astype(np.int32)
     else:
-        parts = M.partition(g, M.slab_partition(g, world))
+        cell_rank = M.slab_partition(g, world)
+    parts = M.partition(g, cell_rank)
     me = parts[rank]
     ctx = L.Context(me, local)
     uid = [L.comm_unique_id() if rank == 0 else None]
@@ -299,6 +300,24 @@ def main():
     ctx.grad(L.GRAD_GAUSS, "S0", "G0")
     gg = O.grad_gauss(g, gf["p"])
     assert rel(ctx.download("G0")[: me.numCells], gg[me.cell_global]) < 1e-12, "gauss gradient"
+    # ---- quirk Q9: the MPI tree's line-plane interpolation factors (src-par/geometry.f90:780-868) on the partitions: inner faces through the mesh
+    # descriptor, process faces through fcp_set_process_facint -- against the unpartitioned oracle on the global mesh with the same factors
+    if g.points is not None and os.environ.get("FCP_TEST_MESH", "hex") == "hex":
+        import copy
+        g9 = copy.copy(g)
+        g9.facint = M.facint_line_plane(g)
+        assert np.abs(g9.facint - g.facint).max() > 1e-6, "the distorted mesh must tell the two variants apart"
+        me9 = M.partition(g9, cell_rank)[rank]
+        ctx9 = L.Context(me9, local)
+        ctx9.comm_init(rank, world, _bcast_uid(dist, rank), me9.peer_rank)
+        ctx9.upload("S0", local_field(gf["p"]))
+        ctx9.grad(L.GRAD_GAUSS, "S0", "G0")
+        wrong = rel(ctx9.download("G0")[: me.numCells], O.grad_gauss(g9, gf["p"])[me.cell_global])
+        ctx9.set_process_facint(me9.fpro)
+        ctx9.grad(L.GRAD_GAUSS, "S0", "G0")
+        right = rel(ctx9.download("G0")[: me.numCells], O.grad_gauss(g9, gf["p"])[me.cell_global])
+        assert right < 1e-12 and (me9.npro == 0 or wrong > 1e-9), ("line-plane facint on partitions", wrong, right)
+        ctx9.close()
     for meth, w in ((L.GRAD_LSQ, False),):
         ctx.create_lsq_grad_matrix(meth)
         ctx.grad(meth, "S0", "G0")
@@ -435,6 +454,10 @@ def main():
     gx, gy, gz = O.grad_gauss_fvx(g, gs["u"])
     gl = ctx2.download("G0")[:nl]
     assert max(rel(gl[:, 0], gx[me.cell_global]), rel(gl[:, 1], gy[me.cell_global]), rel(gl[:, 2], gz[me.cell_global])) < 1e-12, "partitioned fvx gradient"
+    ctx2.grad_gauss_iter("U", "G0", 3)            # the MPI tree's own grad_gauss: nigrad = 3 passes, ghost gradients exchanged between passes
+    gx, gy, gz = O.grad_gauss_iter(g, gs["u"], 3)
+    gl = ctx2.download("G0")[:nl]
+    assert max(rel(gl[:, 0], gx[me.cell_global]), rel(gl[:, 1], gy[me.cell_global]), rel(gl[:, 2], gz[me.cell_global])) < 1e-12, "partitioned iterative Gauss gradient"
     ctx2.upload("VIS", local_field(gs["vis"]))
     ctx2.modify_viscosity_sgs("vreman", 0.7, 0.01)
     vis_o, visw_o = gs["vis"].copy(), gs["visw"].copy()

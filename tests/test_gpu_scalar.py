@@ -225,6 +225,32 @@ def test_grad_gauss_fvx(fcp, orc, allmeshes, name):
 
 
 @pytest.mark.parametrize("name", SC_MESHES)
+@pytest.mark.parametrize("nigrad", [1, 2, 3, 4])
+def test_grad_gauss_iter(fcp, orc, allmeshes, name, nigrad):
+    """The MPI tree's grad_gauss (src-par/gradients.f90:1547-1664): `nigrad` passes of gradco, bit-identical to the oracle for every pass count (odd
+    and even: the passes alternate between the result field and the scratch field); nigrad = 2 is the fvx gradient; nigrad = 1 is the plain Gauss
+    gradient up to the rounding of gradco's P fxp + N fxn against grad_gauss' P + (N - P) lambda."""
+    from fcb200 import lib as L
+    m = allmeshes[name]
+    g = scalar_inputs(m, orc)
+    ctx = make_ctx(m, dict(u=g["u"]))
+    ctx.grad_gauss_iter("U", "DUDXI", nigrad)
+    gx, gy, gz = orc.grad_gauss_iter(m, g["u"], nigrad)
+    got = ctx.download("DUDXI")[: m.numCells]
+    eq(got[:, 0], gx, "dudx"); eq(got[:, 1], gy, "dudy"); eq(got[:, 2], gz, "dudz")
+    if nigrad == 2:
+        fx, fy, fz = orc.grad_gauss_fvx(m, g["u"])
+        assert np.array_equal(fx, gx) and np.array_equal(fy, gy) and np.array_equal(fz, gz)
+    if nigrad == 1:
+        ctx.grad(L.GRAD_GAUSS, "U", "G0")
+        plain = ctx.download("G0")[: m.numCells]
+        assert np.abs(plain - got).max() <= 1e-12 * np.abs(plain).max()
+    with pytest.raises(L.FcpError):
+        ctx.grad_gauss_iter("U", "DUDXI", 0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", SC_MESHES)
 @pytest.mark.parametrize("model", ["wale", "vreman"])
 def test_modify_viscosity_sgs(fcp, orc, allmeshes, name, model):
     """wale_sgs.f90 / vremanSGS.f90 through the tensorFields algebra (pow() involved: 1e-12)."""

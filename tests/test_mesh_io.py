@@ -113,3 +113,26 @@ def test_polyhedral_partition_fast_equals_the_partitioned_global_mesh():
         np.testing.assert_allclose(a.xf[fa], b.xf[fb], rtol=0, atol=1e-15)
         np.testing.assert_allclose(a.yf[fa], b.yf[fb], rtol=0, atol=1e-15)
         np.testing.assert_allclose(a.arz[fa], -b.arz[fb], rtol=0, atol=1e-15)
+
+
+def test_facint_line_plane_variant_of_the_mpi_tree():
+    """Quirk Q9: `mesh.facint_line_plane` (src-par/geometry.f90:780-819, the MATLAB-generated determinant quotient of find_intersection_point) against an
+    independent restatement -- the parameter of the point where the line P -> N meets the plane through the face's first three vertices is
+    n.(p1 - P) / n.(N - P), and |P j'| / |P N| is that parameter -- and against the serial tree's factor: equal on an orthogonal graded mesh (the
+    face centre lies on the line), different on a skewed one."""
+    import numpy as np
+    from fcb200 import mesh as M
+    for m, same in ((M.cavity_mesh(7, bump=0.35), True), (M.cavity_mesh(7, distort=0.25), False)):
+        F = m.numInnerFaces
+        lam = M.facint_line_plane(m)
+        own, nb = m.owner[:F].astype(np.int64) - 1, m.neighbour.astype(np.int64) - 1
+        P = np.stack([m.xc[own], m.yc[own], m.zc[own]], 1)
+        N = np.stack([m.xc[nb], m.yc[nb], m.zc[nb]], 1)
+        fn = m.face_nodes[:F].astype(np.int64) - 1
+        p1, p2, p3 = (m.points[fn[:, k]] for k in range(3))
+        nrm = np.cross(p2 - p1, p3 - p1)
+        t = (nrm * (p1 - P)).sum(1) / (nrm * (N - P)).sum(1)
+        assert ((t > 0) & (t < 1)).all()
+        np.testing.assert_allclose(lam, t, rtol=1e-11, atol=0)
+        d = np.abs(lam - m.facint).max()
+        assert (d < 1e-12) if same else (d > 1e-4), d

@@ -316,6 +316,12 @@ module fcp_b200
       integer(c_int32_t), intent(in) :: peer_rank(*)
       integer(c_int) :: rc
     end function
+    function fcp_set_flux_variant(ctx, variant, grad_method) bind(c, name='fcp_set_flux_variant') result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: variant, grad_method
+      integer(c_int) :: rc
+    end function
     function fcp_set_process_facint(ctx, fpro, count) bind(c, name='fcp_set_process_facint') result(rc)
       import :: c_int, c_ptr, c_double, c_int32_t
       type(c_ptr), value :: ctx

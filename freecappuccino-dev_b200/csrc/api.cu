@@ -656,6 +656,13 @@ extern "C" int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double f
   FIELD(g, FCP_F_DPDXI); FIELD(apu, FCP_F_APU); FIELD(a, FCP_F_A); FIELD(su, FCP_F_SU); FIELD(fl, FCP_F_FLMASS);
   const double *apv = nullptr, *apw = nullptr;
   if (ctx->nper) { FIELD(x1, FCP_F_APV); FIELD(x2, FCP_F_APW); apv = x1; apw = x2; }   // facefluxmass2_periodic weights
+  if (ctx->flux_variant == 1) {
+    // quirk Q10: the MPI tree's facefluxmass on inner faces.  src-par/calcp_simple.f90:40-42: "tentative velocity gradients used for velocity
+    // interpolation: call grad(U,dUdxi) ..." -- with the gradient method the host selected, and BEFORE adjustMassFlow rescales the outlet values (:113)
+    FCP_TRY(fcp_grad(ctx, ctx->flux_grad_method, FCP_F_U, FCP_F_DUDXI, 1));
+    FCP_TRY(fcp_grad(ctx, ctx->flux_grad_method, FCP_F_V, FCP_F_DVDXI, 1));
+    FCP_TRY(fcp_grad(ctx, ctx->flux_grad_method, FCP_F_W, FCP_F_DWDXI, 1));
+  }
   if (!const_mflux && ctx->g_outlet) {                             // adjustMassFlow, calcp_simple.f90:125
     FCP_TRY(ensure_outlet_list(ctx));
     FCP_TRY(fvm_adjust_mass_flow(ctx, ctx->nout, ctx->d_oface, den, u, v, w, fl, flomas));
@@ -666,7 +673,23 @@ extern "C" int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double f
     FCP_TRY(comm_exchange(ctx, g, 3));
   }
   AsmArgs args{den, u, v, w, p, g, apu, apv, apw, pp, u, v, w, a, su, fl};
+  if (ctx->flux_variant == 1) {
+    FIELD(gu, FCP_F_DUDXI); FIELD(gv, FCP_F_DVDXI); FIELD(gw, FCP_F_DWDXI); FIELD(x1, FCP_F_APV); FIELD(x2, FCP_F_APW);
+    args.gU = gu; args.gV = gv; args.gW = gw; args.apv = x1; args.apw = x2;
+  }
   return fvm_assemble_pcorr(ctx, args);
+}
+
+// which mass-flux routine the inner faces of the SIMPLE p' assembly use.  variant 0 (default): facefluxmass2 of the serial
+// tree (calcp_simple.f90:90); variant 1: facefluxmass of the MPI tree (src-par/calcp_simple.f90:52), with the velocity gradients computed by
+// `grad_method` (FCP_GRAD_*) as that routine's `call grad(U,dUdxi)` does.  calcp_piso is not affected (the MPI tree has no PISO).
+extern "C" int fcp_set_flux_variant(fcp_ctx *ctx, int variant, int grad_method) {
+  if (!ctx) return FCP_EINVAL;
+  if (variant != 0 && variant != 1) { fcp_set_error("fcp_set_flux_variant: unknown variant %d", variant); return FCP_EINVAL; }
+  if (variant == 1 && (grad_method < FCP_GRAD_GAUSS || grad_method > FCP_GRAD_LSQ_QR)) { fcp_set_error("fcp_set_flux_variant: unknown gradient method %d", grad_method); return FCP_EINVAL; }
+  ctx->flux_variant = variant;
+  ctx->flux_grad_method = grad_method;
+  return FCP_OK;
 }
 
 // pp(pRefCell) on the rank that owns the reference cell, 0 elsewhere (pRefCell <= 0 = "not on this rank")

@@ -245,6 +245,7 @@ struct fcp_ctx {
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool has_pressure_patch = false, has_outlet = false, has_inout = false;   // from the LOCAL patch table
   bool g_pressure_patch = false, g_outlet = false, g_inout = false;         // the same over ALL ranks (fcp_comm_init); == local without a communicator
+  int flux_variant = 0, flux_grad_method = 0;       // fcp_set_flux_variant: 1 = the MPI tree's facefluxmass on inner faces (quirk Q10), gradients by this method
   int32_t nout = 0;
   int32_t *d_oface = nullptr;                       // outlet faces in patch order (adjustMassFlow)
   double *d_flowo = nullptr;                        // [4] outlet mass flow: local sum, then the sum over all ranks
@@ -284,6 +285,7 @@ struct AsmArgs {
   double *pp;                 // boundary values of pp on pressure patches are zeroed
   double *ub, *vb, *wb;       // same arrays as u,v,w (boundary slots written on pressure patches)
   double *a, *su, *flmass;
+  const double *gU = nullptr, *gV = nullptr, *gW = nullptr;   // non-null: inner faces use the MPI tree's facefluxmass (quirk Q10) with these velocity gradients
 };
 int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g);
 int fvm_lsq_matrix(fcp_ctx *ctx, bool weighted, double *D);

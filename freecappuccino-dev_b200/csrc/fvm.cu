@@ -566,8 +566,11 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp_central2(MeshView m, double *
 // ---------------------------------------------------------------------------------------------
 // PISO = true: facefluxmass_piso (faceflux_mass.f90:389-459): the flux is the plain interpolated HbyA flux (no Rhie-Chow
 // pressure term) and pressure patches do not reset pp (calcp_piso.f90:140-240).
-template <bool PISO, int W>
-__global__ void __launch_bounds__(FCP_TPB, (W >= 3 ? 1 : W == 2 ? 2 : 3)) k_assemble_pcorr(MeshView m, AsmArgs g) {
+// MPIF = true: inner faces take the MPI tree's `facefluxmass` (quirk Q10, src-par/faceflux_mass.f90:28-180; process faces keep facefluxmass2 like
+// src-par/calcp_simple.f90:96-118): gradient-corrected central velocities, per-component (Vol/Ap)_f, the P'/E' pressure correction with its sign
+// quirk Q26.  A switchable variant, not the benchmarked path: its extra operands are plain dependent loads.
+template <bool PISO, int W, bool MPIF = false>
+__global__ void __launch_bounds__(FCP_TPB, ((W >= 3 || MPIF) ? 1 : W == 2 ? 2 : 3)) k_assemble_pcorr(MeshView m, AsmArgs g) {
   constexpr int WS = 6;
   __shared__ ListStage<WS> stage;     // the face list of the NEXT cell travels global -> shared while this cell's gathers are in flight
   FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
@@ -607,6 +610,52 @@ __global__ void __launch_bounds__(FCP_TPB, (W >= 3 ? 1 : W == 2 ? 2 : 3)) k_asse
           const double gox = gox_[k], goy = goy_[k], goz = goz_[k];
           const double lam = lam_[k], fxn = lam, fxp = 1.0 - lam;
           const bool own = e > 0;
+          if (MPIF && o < m.n) {
+            const int32_t cP = own ? c : o, cN = own ? o : c;
+            const double xf = m.xf[f], yf = m.yf[f], zf = m.zf[f];
+            const double xP = m.xc[cP], yP = m.yc[cP], zP = m.zc[cP], xN = m.xc[cN], yN = m.yc[cN], zN = m.zc[cN];
+            const double xpn = xN - xP, ypn = yN - yP, zpn = zN - zP;
+            const double are = sqrt(sx * sx + sy * sy + sz * sz);
+            const double nxx = sx / are, nyy = sy / are, nzz = sz / are;
+            const double volP = m.vol[cP], volN = m.vol[cN];
+            const double Dpu = (fxn * volN * g.apu[cN] + fxp * volP * g.apu[cP]);
+            const double Dpv = (fxn * volN * g.apv[cN] + fxp * volP * g.apv[cP]);
+            const double Dpw = (fxn * volN * g.apw[cN] + fxp * volP * g.apw[cP]);
+            const double dene = g.den[cP] * fxp + g.den[cN] * fxn;
+            const double sfdpnr = 1. / (sx * xpn + sy * ypn + sz * zpn);
+            const double smdpn = (sx * sx + sy * sy + sz * sz) * sfdpnr;
+            const double cap = -dene * Dpu * smdpn;
+            const double *gq[3] = {g.gU, g.gV, g.gW};
+            const double *fq[3] = {g.u, g.v, g.w};
+            double vi[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {            // face_value_central, src-par/interpolation.f90:148-176
+              const double *gg = gq[q];
+              const double gradfidr = gg[3 * (int64_t)cP] * (xf - xP) + gg[3 * (int64_t)cP + 1] * (yf - yP) + gg[3 * (int64_t)cP + 2] * (zf - zP) +
+                                      gg[3 * (int64_t)cN] * (xf - xN) + gg[3 * (int64_t)cN + 1] * (yf - yN) + gg[3 * (int64_t)cN + 2] * (zf - zN);
+              vi[q] = 0.5 * (fq[q][cP] + fq[q][cN] + gradfidr);
+            }
+            const double gPx = g.dPdxi[3 * (int64_t)cP], gPy = g.dPdxi[3 * (int64_t)cP + 1], gPz = g.dPdxi[3 * (int64_t)cP + 2];
+            const double gNx = g.dPdxi[3 * (int64_t)cN], gNy = g.dPdxi[3 * (int64_t)cN + 1], gNz = g.dPdxi[3 * (int64_t)cN + 2];
+            const double dpxi = Dpu * (fxn * gNx + fxp * gPx) * xpn * nxx;
+            const double dpyi = Dpv * (fxn * gNy + fxp * gPy) * ypn * nyy;
+            const double dpzi = Dpw * (fxn * gNz + fxp * gPz) * zpn * nzz;
+            double xpp = xf - (xf - xP) * nxx, ypp = yf - (yf - yP) * nyy, zpp = zf - (zf - zP) * nzz;
+            double xep = xf - (xf - xN) * nxx, yep = yf - (yf - yN) * nyy, zep = zf - (zf - zN) * nzz;
+            xpp = xpp - xP; ypp = ypp - yP; zpp = zpp - zP;
+            xep = xep - xN; yep = yep - yN; zep = zep - zN;
+            double dpe = (g.p[cN] - g.p[cP]);
+            const double dpecorr = (gNx * xep + gNy * yep + gNz * zep - gPx * xpp + gPy * ypp + gPz * zpp);     // quirk Q26 (:158-159)
+            dpe = dpe + dpecorr;
+            const double dpex = Dpu * dpe * sfdpnr * sx, dpey = Dpv * dpe * sfdpnr * sy, dpez = Dpw * dpe * sfdpnr * sz;
+            const double ue = vi[0] - dpex + dpxi, ve = vi[1] - dpey + dpyi, we = vi[2] - dpez + dpzi;
+            const double flm = dene * (ue * sx + ve * sy + we * sz);
+            g.a[sl] = cap;
+            dg = dg - cap;
+            if (own) { s = s - flm; g.flmass[f] = flm; }
+            else     { s = s + flm; }
+            continue;
+          }
           // P = owner side, N = neighbour side of the face, whichever this cell is
           const double xpn = own ? xo - xc : xc - xo, ypn = own ? yo - yc : yc - yo, zpn = own ? zo - zc : zc - zo;
           const double denP = own ? denc : deno, denN = own ? deno : denc;
@@ -866,7 +915,9 @@ int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso) {
   if (w < 0) { const char *e = getenv("FCP_ASM_W"); w = e ? atoi(e) : 2; if (w < 1 || w > 3) w = 2; }
   size_t tok = ctx->prof.begin(FCP_K_ASSEMBLE, ctx->stream);
   MeshView mv = fcp_mesh_view(ctx);
-  if (piso) {
+  if (g.gU) {          // quirk Q10 switch (fcp_set_flux_variant): SIMPLE only, one face per gather round
+    k_assemble_pcorr<false, 1, true><<<FCP_GRID(ctx->n)>>>(mv, g);
+  } else if (piso) {
     if (w == 1) k_assemble_pcorr<true, 1><<<FCP_GRID(ctx->n)>>>(mv, g);
     else if (w == 2) k_assemble_pcorr<true, 2><<<FCP_GRID(ctx->n)>>>(mv, g);
     else k_assemble_pcorr<true, 3><<<FCP_GRID(ctx->n)>>>(mv, g);

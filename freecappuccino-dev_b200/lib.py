@@ -171,6 +171,7 @@ def lib():
     L.fcp_comm_mode.argtypes = [vp]
     L.fcp_exchange.argtypes = [vp, C.c_int]
     L.fcp_set_process_facint.argtypes = [vp, _pd, C.c_int32]
+    L.fcp_set_flux_variant.argtypes = [vp, C.c_int, C.c_int]
     for nm in ("fcp_global_sum", "fcp_global_max", "fcp_global_min"):
         getattr(L, nm).argtypes = [vp, _pd]
     L.fcp_global_isum.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -402,6 +403,10 @@ class Context:
     def gradp_and_sources(self, pscheme, p):
         ps = PSCHEME[pscheme] if isinstance(pscheme, str) else int(pscheme)
         check(lib().fcp_gradp_and_sources(self.h, ps, field_id(p)), "fcp_gradp_and_sources")
+
+    def set_flux_variant(self, variant: int, grad_method: int = 0):
+        """0: facefluxmass2 of the serial tree (default); 1: facefluxmass of the MPI tree on inner faces (quirk Q10), velocity gradients by `grad_method`."""
+        check(lib().fcp_set_flux_variant(self.h, int(variant), int(grad_method)), "fcp_set_flux_variant")
 
     def assemble_pcorr_simple(self, const_mflux: bool = False, flomas: float = 0.0):
         check(lib().fcp_assemble_pcorr_simple(self.h, int(const_mflux), flomas), "fcp_assemble_pcorr_simple")

@@ -167,6 +167,12 @@ int fcp_gradp_and_sources(fcp_ctx *ctx, int pscheme, int p_field);
 /* inner-face + patch assembly of the pressure-correction equation   Pressure/calcp_simple.f90:69-234,
  * fluxes/faceflux_mass.f90:175-249 (facefluxmass2), :765-831, :833-916 */
 int fcp_assemble_pcorr_simple(fcp_ctx *ctx, int const_mflux, double flomas);
+/* Which mass-flux routine the INNER faces of that assembly use (the two trees are switchable where they differ, quirk Q10).
+ * variant 0 (default): facefluxmass2 of the serial tree (calcp_simple.f90:90, faceflux_mass.f90:175-249); variant 1: facefluxmass of the MPI tree
+ * (src-par/calcp_simple.f90:40-79, src-par/faceflux_mass.f90:28-180: face_value_central velocities from grad(U), grad(V), grad(W) computed with
+ * `grad_method` = FCP_GRAD_* into FCP_F_DUDXI/DVDXI/DWDXI, per-component (Vol/Ap)_f from apu, apv, apw, the P'/E' pressure correction).  Process faces
+ * keep facefluxmass2 in both (src-par/calcp_simple.f90:96-118).  Affects fcp_assemble_pcorr_simple and fcp_calcp_simple; calcp_piso has no MPI twin. */
+int fcp_set_flux_variant(fcp_ctx *ctx, int variant, int grad_method);
 /* flux / velocity / pressure correction after the solve   calcp_simple.f90:331-429 */
 int fcp_correct_simple(fcp_ctx *ctx, int pscheme, double urfp, int32_t pRefCell);
 /* non-orthogonal corrector   calcp_simple.f90:433-455 + fluxmc2 faceflux_mass.f90:650-696 */

@@ -502,14 +502,67 @@ extern "C" void orc_gradp_and_sources(const orc_mesh *m, int pscheme, double *p,
 // ------------------------------------------------------------------------------------------
 // pressure-correction assembly  (Pressure/calcp_simple.f90:69-234, fluxes/faceflux_mass.f90)
 // ------------------------------------------------------------------------------------------
-extern "C" void orc_assemble_pcorr(const orc_mesh *m, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell, i32 nnz,
+// facefluxmass of the MPI tree (quirk Q10), src-par/faceflux_mass.f90:28-180: gradient-corrected central velocities (face_value_central,
+// src-par/interpolation.f90:148-176), per-component (Vol/Ap)_f, pressure difference corrected to the points P', E' -- whose correction term is
+// written `N.xep + N.yep + N.zep - P.xpp + P.ypp + P.zpp` (:158-159: only the first P product is subtracted; quirk Q26, reproduced).
+static void facefluxmass_mpi(const orc_mesh *m, i32 ijp, i32 ijn, i32 f, const double *den, const double *u, const double *v, const double *w, const double *p,
+                             const double *dPdxi, const double *apu, const double *apv, const double *apw, const double *gU, const double *gV,
+                             const double *gW, double *cap_out, double *flux_out) {
+  const double xf = m->xf[f], yf = m->yf[f], zf = m->zf[f], arx = m->arx[f], ary = m->ary[f], arz = m->arz[f], lambda = m->facint[f];
+  const double fxn = lambda, fxp = 1.0 - lambda;
+  const double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
+  const double are = std::sqrt(arx * arx + ary * ary + arz * arz);
+  const double nxx = arx / are, nyy = ary / are, nzz = arz / are;
+  const double Dpu = (fxn * m->vol[ijn] * apu[ijn] + fxp * m->vol[ijp] * apu[ijp]);
+  const double Dpv = (fxn * m->vol[ijn] * apv[ijn] + fxp * m->vol[ijp] * apv[ijp]);
+  const double Dpw = (fxn * m->vol[ijn] * apw[ijn] + fxp * m->vol[ijp] * apw[ijp]);
+  const double dene = den[ijp] * fxp + den[ijn] * fxn;
+  const double sfdpnr = 1. / (arx * xpn + ary * ypn + arz * zpn);
+  const double smdpn = (arx * arx + ary * ary + arz * arz) * sfdpnr;
+  const double cap = -dene * Dpu * smdpn;
+  auto central = [&](const double *fi, const double *g) {
+    const double gradfidr = g[3 * ijp] * (xf - m->xc[ijp]) + g[3 * ijp + 1] * (yf - m->yc[ijp]) + g[3 * ijp + 2] * (zf - m->zc[ijp]) +
+                            g[3 * ijn] * (xf - m->xc[ijn]) + g[3 * ijn + 1] * (yf - m->yc[ijn]) + g[3 * ijn + 2] * (zf - m->zc[ijn]);
+    return 0.5 * (fi[ijp] + fi[ijn] + gradfidr);
+  };
+  const double ui = central(u, gU), vi = central(v, gV), wi = central(w, gW);
+  const double dpxi = Dpu * (fxn * dPdxi[3 * ijn + 0] + fxp * dPdxi[3 * ijp + 0]) * xpn * nxx;
+  const double dpyi = Dpv * (fxn * dPdxi[3 * ijn + 1] + fxp * dPdxi[3 * ijp + 1]) * ypn * nyy;
+  const double dpzi = Dpw * (fxn * dPdxi[3 * ijn + 2] + fxp * dPdxi[3 * ijp + 2]) * zpn * nzz;
+  double xpp = xf - (xf - m->xc[ijp]) * nxx, ypp = yf - (yf - m->yc[ijp]) * nyy, zpp = zf - (zf - m->zc[ijp]) * nzz;
+  double xep = xf - (xf - m->xc[ijn]) * nxx, yep = yf - (yf - m->yc[ijn]) * nyy, zep = zf - (zf - m->zc[ijn]) * nzz;
+  xpp = xpp - m->xc[ijp]; ypp = ypp - m->yc[ijp]; zpp = zpp - m->zc[ijp];
+  xep = xep - m->xc[ijn]; yep = yep - m->yc[ijn]; zep = zep - m->zc[ijn];
+  double dpe = (p[ijn] - p[ijp]);
+  const double dpecorr = (dPdxi[3 * ijn + 0] * xep + dPdxi[3 * ijn + 1] * yep + dPdxi[3 * ijn + 2] * zep -
+                          dPdxi[3 * ijp + 0] * xpp + dPdxi[3 * ijp + 1] * ypp + dPdxi[3 * ijp + 2] * zpp);
+  dpe = dpe + dpecorr;
+  const double dpex = Dpu * dpe * sfdpnr * arx, dpey = Dpv * dpe * sfdpnr * ary, dpez = Dpw * dpe * sfdpnr * arz;
+  const double ue = ui - dpex + dpxi, ve = vi - dpey + dpyi, we = wi - dpez + dpzi;
+  *cap_out = cap;
+  *flux_out = dene * (ue * arx + ve * ary + we * arz);
+}
+
+static void assemble_pcorr_impl(const orc_mesh *m, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell, i32 nnz,
                                    const double *den, double *u, double *v, double *w, const double *p, double *pp,
                                    const double *dPdxi, const double *apu, const double *apv, const double *apw, int const_mflux, double flomas,
-                                   double *a, double *su, double *flmass) {
+                                   double *a, double *su, double *flmass, const double *gU, const double *gV, const double *gW) {
   for (i32 k = 0; k < nnz; ++k) a[k] = 0.0;
   for (i32 c = 0; c < m->numCells; ++c) su[c] = 0.0;
   for (i32 i = 0; i < m->numInnerFaces; ++i) {   // :82-118 ; facefluxmass2 faceflux_mass.f90:175-249
     i32 ijp = m->owner[i] - 1, ijn = m->neighbour[i] - 1;
+    if (gU) {                                     // src-par/calcp_simple.f90:47-79 with facefluxmass
+      double cap, flm;
+      facefluxmass_mpi(m, ijp, ijn, i, den, u, v, w, p, dPdxi, apu, apv, apw, gU, gV, gW, &cap, &flm);
+      flmass[i] = flm;
+      a[icell_jcell[i] - 1] = cap;
+      a[jcell_icell[i] - 1] = cap;
+      a[diag[ijp] - 1] = a[diag[ijp] - 1] - cap;
+      a[diag[ijn] - 1] = a[diag[ijn] - 1] - cap;
+      su[ijp] = su[ijp] - flmass[i];
+      su[ijn] = su[ijn] + flmass[i];
+      continue;
+    }
     double arx = m->arx[i], ary = m->ary[i], arz = m->arz[i], lambda = m->facint[i];
     double fxn = lambda, fxp = 1.0 - lambda;
     double xpn = m->xc[ijn] - m->xc[ijp], ypn = m->yc[ijn] - m->yc[ijp], zpn = m->zc[ijn] - m->zc[ijp];
@@ -578,6 +631,19 @@ extern "C" void orc_assemble_pcorr(const orc_mesh *m, const i32 *diag, const i32
       assemble_periodic_patch(m, ib, &lper, diag, icell_jcell, jcell_icell, den, u, v, w, p, dPdxi, apu, apv, apw, a, su, flmass);
     }
   }
+}
+extern "C" void orc_assemble_pcorr(const orc_mesh *m, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell, i32 nnz,
+                                   const double *den, double *u, double *v, double *w, const double *p, double *pp,
+                                   const double *dPdxi, const double *apu, const double *apv, const double *apw, int const_mflux, double flomas,
+                                   double *a, double *su, double *flmass) {
+  assemble_pcorr_impl(m, diag, icell_jcell, jcell_icell, nnz, den, u, v, w, p, pp, dPdxi, apu, apv, apw, const_mflux, flomas, a, su, flmass, nullptr, nullptr, nullptr);
+}
+// the MPI tree's inner-face flux (quirk Q10): gU, gV, gW = grad(U), grad(V), grad(W) as (3,numTotal), src-par/calcp_simple.f90:40-42
+extern "C" void orc_assemble_pcorr_mpi(const orc_mesh *m, const i32 *diag, const i32 *icell_jcell, const i32 *jcell_icell, i32 nnz,
+                                       const double *den, double *u, double *v, double *w, const double *p, double *pp,
+                                       const double *dPdxi, const double *apu, const double *apv, const double *apw, int const_mflux, double flomas,
+                                       double *a, double *su, double *flmass, const double *gU, const double *gV, const double *gW) {
+  assemble_pcorr_impl(m, diag, icell_jcell, jcell_icell, nnz, den, u, v, w, p, pp, dPdxi, apu, apv, apw, const_mflux, flomas, a, su, flmass, gU, gV, gW);
 }
 
 extern "C" void orc_update_velocity_at_boundary(const orc_mesh *m, double *u, double *v, double *w) {  // velocity.f90:1184-1277

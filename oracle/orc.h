@@ -107,6 +107,14 @@ void orc_assemble_pcorr(const orc_mesh *m, const int32_t *diag, const int32_t *i
                         const double *apv, const double *apw /* read on periodic faces only (facefluxmass2_periodic :313-384); may be NULL otherwise */,
                         int const_mflux, double flomas,
                         double *a, double *su, double *flmass);
+/* the same with the MPI tree's inner-face flux `facefluxmass` (quirk Q10; src-par/calcp_simple.f90:40-79, src-par/faceflux_mass.f90:28-180):
+ * gU, gV, gW = the (3,numTotal) gradients of the tentative velocities; apv, apw are read on every inner face */
+void orc_assemble_pcorr_mpi(const orc_mesh *m, const int32_t *diag, const int32_t *icell_jcell,
+                            const int32_t *jcell_icell, int32_t nnz,
+                            const double *den, double *u, double *v, double *w, const double *p,
+                            double *pp, const double *dPdxi, const double *apu, const double *apv, const double *apw,
+                            int const_mflux, double flomas, double *a, double *su, double *flmass,
+                            const double *gU, const double *gV, const double *gW);
 /* calcp_simple.f90:331-429 (one ipcorr pass after the solve) */
 void orc_correct_simple(const orc_mesh *m, const int32_t *icell_jcell, int pscheme,
                         const double *a, const double *den, double *u, double *v, double *w, double *p, double *pp,

@@ -207,6 +207,13 @@ def assemble_pcorr_into(mesh, csr: Csr, den, u, v, w, p, pp, dPdxi, apu, a, su, 
                              C.c_int(int(const_mflux)), C.c_double(flomas), _d(a), _d(su), _d(flmass))
 
 
+def assemble_pcorr_mpi_into(mesh, csr: Csr, den, u, v, w, p, pp, dPdxi, apu, apv, apw, gU, gV, gW, a, su, flmass, const_mflux=False, flomas=0.0):
+    """p' assembly with the MPI tree's inner-face flux (quirk Q10, src-par/faceflux_mass.f90:28-180); gU, gV, gW: (numTotal, 3) velocity gradients."""
+    lib().orc_assemble_pcorr_mpi(csr.mv.ptr, _i(csr.diag), _i(csr.icell_jcell), _i(csr.jcell_icell), C.c_int32(csr.nnz),
+                                 _d(den), _d(u), _d(v), _d(w), _d(p), _d(pp), _d(dPdxi), _d(apu), _d(apv), _d(apw),
+                                 C.c_int(int(const_mflux)), C.c_double(flomas), _d(a), _d(su), _d(flmass), _d(gU), _d(gV), _d(gW))
+
+
 def correct_simple(mesh, csr: Csr, pscheme, a, den, u, v, w, p, pp, apu, apv, apw, urfp, pRefCell, dPdxi, flmass):
     su, sv, sw = (np.zeros(mesh.numCells) for _ in range(3))
     lib().orc_correct_simple(csr.mv.ptr, _i(csr.icell_jcell), C.c_int(pscheme), _d(a), _d(den), _d(u), _d(v), _d(w), _d(p), _d(pp),

@@ -273,3 +273,62 @@ def test_update_boundary(fcp, orc, allmeshes, name):
     orc.update_boundary(m, ref)
     eq(ctx.download("S0"), ref, "updateBoundary")
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["hex10_distorted", "hex12_graded", "channel_inout", "poly_10faces", "channel_pressure"])
+@pytest.mark.parametrize("method", ["gauss", "lsq"])
+def test_assemble_pcorr_with_the_mpi_trees_facefluxmass(fcp, orc, allmeshes, name, method):
+    """Quirk Q10 as a switch (`fcp_set_flux_variant(1, grad_method)`): the inner faces of the SIMPLE p' assembly take `facefluxmass` of the MPI tree
+    (src-par/calcp_simple.f90:40-79, src-par/faceflux_mass.f90:28-180: face_value_central velocities from grad(U,V,W), per-component (Vol/Ap)_f, the
+    P'/E' pressure correction incl. its sign quirk Q26) instead of the serial tree's `facefluxmass2`.  Matrix, sources and fluxes bit-identical to the
+    oracle's restatement; the matrix stays symmetric with zero row sums; on the orthogonal graded mesh the two variants' COEFFICIENTS agree to
+    rounding (the Rhie-Chow fluxes differ by construction)."""
+    import cases
+    from fcb200 import lib as L
+    m = allmeshes[name]
+    f = cases.fields(m)
+    n = m.numCells
+    gm = dict(gauss=L.GRAD_GAUSS, lsq=L.GRAD_LSQ)[method]
+    c = orc.Csr(m)
+    g = {k: v.copy() for k, v in f.items()}
+    dP = np.zeros((m.numTotal, 3))
+    orc.gradp_and_sources(m, 0, g["p"], g["apu"], dP)
+    if method == "gauss":
+        gU, gV, gW = (orc.grad_gauss(m, g[k]) for k in "uvw")
+    else:
+        D = orc.create_matrix_lsq(m, False)
+        gU, gV, gW = (orc.grad_lsq(m, False, D, g[k]) for k in "uvw")
+    a = np.zeros(c.nnz); su = np.zeros(n); flm = np.zeros(m.numFaces)
+    Fi = m.numInnerFaces
+    for ib in range(m.numBoundaries):
+        if m.bctype[ib] == M.BC_INLET:
+            pf = m.patch_faces(ib)
+            ijb = n + pf - Fi
+            flm[pf] = g["den"][ijb] * (g["u"][ijb] * m.arx[pf] + g["v"][ijb] * m.ary[pf] + g["w"][ijb] * m.arz[pf])
+    flm0 = flm.copy()
+    orc.assemble_pcorr_mpi_into(m, c, g["den"], g["u"], g["v"], g["w"], g["p"], g["pp"], dP, g["apu"], g["apv"], g["apw"], gU, gV, gW, a, su, flm, flomas=1.0)
+    ctx = L.Context(m)
+    for k, v in f.items():
+        ctx.upload(k.upper(), v)
+    ctx.upload("FLMASS", flm0)
+    if method == "lsq":
+        ctx.create_lsq_grad_matrix(gm)
+    ctx.gradp_and_sources("linear", "P")
+    ctx.set_flux_variant(1, gm)
+    ctx.assemble_pcorr_simple(False, 1.0)
+    got_a, got_su, got_fl = ctx.download("A"), ctx.download("SU")[:n], ctx.download("FLMASS")
+    assert np.array_equal(got_a, a), np.abs(got_a - a).max()
+    assert np.array_equal(got_su, su) and np.array_equal(got_fl, flm)
+    assert np.array_equal(a[c.icell_jcell[:Fi] - 1], a[c.jcell_icell[:Fi] - 1])
+    ctx.set_flux_variant(0)
+    ctx.upload("FLMASS", flm0)
+    for k in ("u", "v", "w", "pp"):
+        ctx.upload(k.upper(), f[k])
+    ctx.assemble_pcorr_simple(False, 1.0)
+    a2 = ctx.download("A")
+    assert not np.array_equal(ctx.download("FLMASS")[:Fi], flm[:Fi])
+    if name == "hex12_graded":
+        assert np.abs(a2 - a).max() <= 1e-12 * np.abs(a).max()
+    with pytest.raises(L.FcpError):
+        ctx.set_flux_variant(2)
+    ctx.close()

@@ -72,11 +72,15 @@ static inline MeshView fcp_mesh_view(const fcp_ctx *c) {
 // ---------------------------------------------------------------------------------------------
 #ifdef FCP_EMU
 __device__ __forceinline__ void fcp_cp_async4(int32_t *dst_smem, const int32_t *src) { *dst_smem = *src; }
+__device__ __forceinline__ void fcp_cp_async8(double *dst_smem, const double *src) { *dst_smem = *src; }
 __device__ __forceinline__ void fcp_cp_async_commit() {}
 template <int N> __device__ __forceinline__ void fcp_cp_async_wait() {}
 #else
 __device__ __forceinline__ void fcp_cp_async4(int32_t *dst_smem, const int32_t *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void fcp_cp_async8(double *dst_smem, const double *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void fcp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void fcp_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

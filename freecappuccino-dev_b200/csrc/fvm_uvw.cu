@@ -7,6 +7,7 @@
 // One thread owns one cell and walks its faces in ascending index; every face quantity is evaluated in the face's own
 // orientation (P = owner, N = neighbour), so both sides see the same bits and the per-cell sums round like the
 // reference's sequential loops.  Periodic patches: facefluxuvw_periodic on both cells of a pair.  Not built: Crank-Nicolson, buoyancy, MHD.
+#include <algorithm>
 #include "fcp_internal.h"
 #include "fvm_common.cuh"
 #include "interp.cuh"
@@ -54,8 +55,51 @@ __global__ void __launch_bounds__(FCP_TPB) k_update_vel_bnd(MeshView m, const in
   }
 }
 
+// Face stage: everything facefluxuvw reads of ONE two-sided face and of the cell across it (25 doubles), copied global -> shared with cp.async
+// one face ahead of the face being evaluated, so that the ~300 flop of a face overlap the gathers of the next one.  Two stages of [25][256] doubles.
+// Together with the list stage (fvm_common.cuh) a cell costs one exposed memory round trip (its first face) instead of twelve.
+#define FCP_UVW_NV 25
+struct UvwFaceStage {
+  double v[2][FCP_UVW_NV][FCP_TPB];
+  __device__ __forceinline__ void fetch(int s, const MeshView &m, const UvwArgs &g, int32_t e, int32_t o, int32_t sl) {
+    const int t = threadIdx.x;
+    if (e == 0) return;
+    const int32_t f = (e > 0 ? e : -e) - 1;
+    fcp_cp_async8(&v[s][0][t], m.arx + f); fcp_cp_async8(&v[s][1][t], m.ary + f); fcp_cp_async8(&v[s][2][t], m.arz + f);
+    if (sl < 0) return;
+    fcp_cp_async8(&v[s][3][t], m.xf + f); fcp_cp_async8(&v[s][4][t], m.yf + f); fcp_cp_async8(&v[s][5][t], m.zf + f);
+    fcp_cp_async8(&v[s][6][t], g.flmass + f); fcp_cp_async8(&v[s][7][t], m.facint + f); fcp_cp_async8(&v[s][8][t], m.Df + f);
+    fcp_cp_async8(&v[s][9][t], m.xc + o); fcp_cp_async8(&v[s][10][t], m.yc + o); fcp_cp_async8(&v[s][11][t], m.zc + o);
+    fcp_cp_async8(&v[s][12][t], g.u + o); fcp_cp_async8(&v[s][13][t], g.v + o); fcp_cp_async8(&v[s][14][t], g.w + o);
+    fcp_cp_async8(&v[s][15][t], g.vis + o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      fcp_cp_async8(&v[s][16 + k][t], g.dUdxi + 3 * (int64_t)o + k);
+      fcp_cp_async8(&v[s][19 + k][t], g.dVdxi + 3 * (int64_t)o + k);
+      fcp_cp_async8(&v[s][22 + k][t], g.dWdxi + 3 * (int64_t)o + k);
+    }
+  }
+  __device__ __forceinline__ void cell(int s, CellState &c) const {
+    const int t = threadIdx.x;
+    c.x = v[s][9][t]; c.y = v[s][10][t]; c.z = v[s][11][t];
+    c.u = v[s][12][t]; c.v = v[s][13][t]; c.w = v[s][14][t]; c.vis = v[s][15][t];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { c.gu[k] = v[s][16 + k][t]; c.gv[k] = v[s][19 + k][t]; c.gw[k] = v[s][22 + k][t]; }
+  }
+};
+
 __global__ void __launch_bounds__(FCP_TPB) k_uvw_assemble(MeshView m, UvwArgs g) {
-  FCP_CELL_LOOP(c, m.n) {
+  constexpr int WS = 6;
+#ifdef FCP_EMU
+  unsigned char *raw__ = emu::dyn_smem();
+#else
+  extern __shared__ __align__(16) unsigned char raw__[];
+#endif
+  ListStage<WS> &stage = *reinterpret_cast<ListStage<WS> *>(raw__);
+  UvwFaceStage &fs = *reinterpret_cast<UvwFaceStage *>(raw__ + sizeof(ListStage<WS>));
+  int fst = 0;               // face stage of the face about to be evaluated
+  bool have_pref = false;    // its copies were issued while the previous cell was being finished
+  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
     CellState me;
     load_cell(me, m, g, c);
     const double vol = m.vol[c], denc = g.den[c];
@@ -81,17 +125,48 @@ __global__ void __launch_bounds__(FCP_TPB) k_uvw_assemble(MeshView m, UvwArgs g)
       s3 = s3 + apotime * (3 * g.wo[c] - 1.5 * g.woo[c] + third * g.wooo[c]);
       p1 = p1 + c116 * apotime; p2 = p2 + c116 * apotime; p3 = p3 + c116 * apotime;
     }
-    FCP_FACE_LOOP(m, c) {
-      FCP_FACE_FETCH(m);
-      const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
+    const int32_t flen = stage.len(st);
+    const bool staged = flen <= WS;
+    int32_t e_[WS], o_[WS], sl_[WS];
+    if (staged) {
+      stage.read(st, e_, o_, sl_);
+      if (!have_pref) { fs.fetch(fst, m, g, e_[0], o_[0], sl_[0]); fcp_cp_async_commit(); }
+    }
+    const int64_t fbase = staged ? 0 : m.slptr[c >> 5] + (c & 31);
+    for (int32_t q = 0; q < flen; ++q) {
+      int32_t e, o, sl;
+      if (staged) {
+        e = 0; o = 0; sl = -1;
+#pragma unroll
+        for (int k = 0; k < WS; ++k) if (k == q) { e = e_[k]; o = o_[k]; sl = sl_[k]; }
+        // the next face to be evaluated by this thread: face q + 1 of this cell, or the first face of its next cell (whose list is already staged)
+        int32_t ne = 0, no = 0, nsl = -1;
+        if (q + 1 < flen) {
+#pragma unroll
+          for (int k = 0; k < WS; ++k) if (k == q + 1) { ne = e_[k]; no = o_[k]; nsl = sl_[k]; }
+        } else if (j__ + 1 < FCP_IPT && fcp_chunk_cell(j__ + 1) < m.n && stage.len(st ^ 1) <= WS && stage.len(st ^ 1) > 0) {
+          ne = stage.v[st ^ 1][1][threadIdx.x]; no = stage.v[st ^ 1][1 + WS][threadIdx.x]; nsl = stage.v[st ^ 1][1 + 2 * WS][threadIdx.x];
+        }
+        fs.fetch(fst ^ 1, m, g, ne, no, nsl);
+        fcp_cp_async_commit();
+        fcp_cp_async_wait<1>();      // everything but the group just committed has landed: this face's data is in stage fst
+        have_pref = ne != 0 && !(q + 1 < flen);
+      } else {
+        e = __ldcs(m.ent + fbase + (int64_t)q * 32); o = __ldcs(m.other + fbase + (int64_t)q * 32); sl = __ldcs(m.slot + fbase + (int64_t)q * 32);
+        have_pref = false;
+      }
+      const int32_t f = (e > 0 ? e : -e) - 1;
+      const int t__ = threadIdx.x;
+      const double arx = staged ? fs.v[fst][0][t__] : m.arx[f], ary = staged ? fs.v[fst][1][t__] : m.ary[f], arz = staged ? fs.v[fst][2][t__] : m.arz[f];
       if (sl >= 0) {
         // ---- facefluxuvw, velocity.f90:754-878
         CellState ot;
-        load_cell(ot, m, g, o);
+        if (staged) fs.cell(fst, ot);
+        else load_cell(ot, m, g, o);
         const bool own = e > 0;
         const CellState &P = own ? me : ot, &N = own ? ot : me;
-        const double xf = m.xf[f], yf = m.yf[f], zf = m.zf[f];
-        const double flomass = g.flmass[f], lambda = m.facint[f], Df = m.Df[f];
+        const double xf = staged ? fs.v[fst][3][t__] : m.xf[f], yf = staged ? fs.v[fst][4][t__] : m.yf[f], zf = staged ? fs.v[fst][5][t__] : m.zf[f];
+        const double flomass = staged ? fs.v[fst][6][t__] : g.flmass[f], lambda = staged ? fs.v[fst][7][t__] : m.facint[f], Df = staged ? fs.v[fst][8][t__] : m.Df[f];
         const double fxn = lambda, fxp = 1.0 - lambda;
         const double game = P.vis + (N.vis - P.vis) * lambda;
         const double de = game * Df;
@@ -219,11 +294,13 @@ __global__ void __launch_bounds__(FCP_TPB) k_uvw_assemble(MeshView m, UvwArgs g)
           s3 = s3 + vsol * (upb * nxf * nzf + vpb * nyf * nzf + wb * (1. - nzf * nzf));
         }
       }
+      if (staged) fst ^= 1;      // the stage that received the next face's copies becomes the current one
     }
+    if (flen == 0) have_pref = false;
     g.su[c] = s1; g.sv[c] = s2; g.sw[c] = s3;
     g.spu[c] = p1; g.spv[c] = p2; g.sp[c] = p3;
     if (g.rU) { g.rU[c] = s1; g.rV[c] = s2; g.rW[c] = s3; }   // piso: rU = su (:564-568)
-  }
+  FCP_STAGED_LOOP_END
 }
 
 // diagonal + under-relaxation of one momentum equation, velocity.f90:602-620 (U), :651-668 (V), :712-730 (W).
@@ -257,7 +334,9 @@ int fvm_update_vel_bnd(fcp_ctx *ctx, double *u, double *v, double *w) {
 }
 int fvm_uvw_assemble(fcp_ctx *ctx, const UvwArgs &g) {
   if (ctx->n == 0) return FCP_OK;
-  FCP_PROF(&ctx->prof, FCP_K_UVW, ctx->stream, (k_uvw_assemble<<<FCP_GRID(ctx->n)>>>(fcp_mesh_view(ctx), g)));
+  const size_t smem = sizeof(ListStage<6>) + sizeof(UvwFaceStage);       // 38 KB list stage + 100 KB face stage: one CTA per SM (the kernel needs 200+ registers anyway)
+  if (!ctx->uvw_smem_configured) { FCP_CUDA(cudaFuncSetAttribute(k_uvw_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->uvw_smem_configured = true; }
+  FCP_PROF(&ctx->prof, FCP_K_UVW, ctx->stream, (k_uvw_assemble<<<std::max(fcp_nchunks(ctx->n), 1), FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), g)));
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

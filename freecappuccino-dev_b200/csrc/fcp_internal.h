@@ -245,7 +245,7 @@ struct fcp_ctx {
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool has_pressure_patch = false, has_outlet = false, has_inout = false;   // from the LOCAL patch table
   bool g_pressure_patch = false, g_outlet = false, g_inout = false;         // the same over ALL ranks (fcp_comm_init); == local without a communicator
-  bool uvw_smem_configured = false;                 // the dynamic shared-memory limit of k_uvw_assemble has been raised on this context's device
+  int uvw_smem_configured = 0;                      // bit v: the dynamic shared-memory limit of k_uvw_assemble variant v has been raised on this context's device
   int flux_variant = 0, flux_grad_method = 0;       // fcp_set_flux_variant: 1 = the MPI tree's facefluxmass on inner faces (quirk Q10), gradients by this method
   int32_t nout = 0;
   int32_t *d_oface = nullptr;                       // outlet faces in patch order (adjustMassFlow)

@@ -8,6 +8,8 @@
 // orientation (P = owner, N = neighbour), so both sides see the same bits and the per-cell sums round like the
 // reference's sequential loops.  Periodic patches: facefluxuvw_periodic on both cells of a pair.  Not built: Crank-Nicolson, buoyancy, MHD.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include "fcp_internal.h"
 #include "fvm_common.cuh"
 #include "interp.cuh"
@@ -88,7 +90,9 @@ struct UvwFaceStage {
   }
 };
 
-__global__ void __launch_bounds__(FCP_TPB) k_uvw_assemble(MeshView m, UvwArgs g) {
+// FS: face stage on (needs 138 KB of shared memory: one CTA per SM); MINB: resident CTAs per SM the registers are allocated for
+template <bool FS, int MINB>
+__global__ void __launch_bounds__(FCP_TPB, MINB) k_uvw_assemble(MeshView m, UvwArgs g) {
   constexpr int WS = 6;
 #ifdef FCP_EMU
   unsigned char *raw__ = emu::dyn_smem();
@@ -126,13 +130,12 @@ __global__ void __launch_bounds__(FCP_TPB) k_uvw_assemble(MeshView m, UvwArgs g)
       p1 = p1 + c116 * apotime; p2 = p2 + c116 * apotime; p3 = p3 + c116 * apotime;
     }
     const int32_t flen = stage.len(st);
-    const bool staged = flen <= WS;
+    const bool lstaged = flen <= WS;            // the list comes from the list stage
+    const bool staged = FS && lstaged;          // ... and the face operands from the face stage
     int32_t e_[WS], o_[WS], sl_[WS];
-    if (staged) {
-      stage.read(st, e_, o_, sl_);
-      if (!have_pref) { fs.fetch(fst, m, g, e_[0], o_[0], sl_[0]); fcp_cp_async_commit(); }
-    }
-    const int64_t fbase = staged ? 0 : m.slptr[c >> 5] + (c & 31);
+    if (lstaged) stage.read(st, e_, o_, sl_);
+    if (staged && !have_pref) { fs.fetch(fst, m, g, e_[0], o_[0], sl_[0]); fcp_cp_async_commit(); }
+    const int64_t fbase = lstaged ? 0 : m.slptr[c >> 5] + (c & 31);
     for (int32_t q = 0; q < flen; ++q) {
       int32_t e, o, sl;
       if (staged) {
@@ -151,6 +154,10 @@ __global__ void __launch_bounds__(FCP_TPB) k_uvw_assemble(MeshView m, UvwArgs g)
         fcp_cp_async_commit();
         fcp_cp_async_wait<1>();      // everything but the group just committed has landed: this face's data is in stage fst
         have_pref = ne != 0 && !(q + 1 < flen);
+      } else if (lstaged) {
+        e = 0; o = 0; sl = -1;
+#pragma unroll
+        for (int k = 0; k < WS; ++k) if (k == q) { e = e_[k]; o = o_[k]; sl = sl_[k]; }
       } else {
         e = __ldcs(m.ent + fbase + (int64_t)q * 32); o = __ldcs(m.other + fbase + (int64_t)q * 32); sl = __ldcs(m.slot + fbase + (int64_t)q * 32);
         have_pref = false;
@@ -334,9 +341,24 @@ int fvm_update_vel_bnd(fcp_ctx *ctx, double *u, double *v, double *w) {
 }
 int fvm_uvw_assemble(fcp_ctx *ctx, const UvwArgs &g) {
   if (ctx->n == 0) return FCP_OK;
-  const size_t smem = sizeof(ListStage<6>) + sizeof(UvwFaceStage);       // 38 KB list stage + 100 KB face stage: one CTA per SM (the kernel needs 200+ registers anyway)
-  if (!ctx->uvw_smem_configured) { FCP_CUDA(cudaFuncSetAttribute(k_uvw_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->uvw_smem_configured = true; }
-  FCP_PROF(&ctx->prof, FCP_K_UVW, ctx->stream, (k_uvw_assemble<<<std::max(fcp_nchunks(ctx->n), 1), FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), g)));
+  // FCP_UVW = fs (default: list stage + face stage, one CTA per SM) | list (list stage only, registers for one CTA per SM) | list2 (list stage only,
+  // 128 registers = two CTAs per SM): A/B measurements
+  const char *e = getenv("FCP_UVW");
+  const int variant = (e && !strcmp(e, "list")) ? 1 : (e && !strcmp(e, "list2")) ? 2 : 0;
+  const size_t smem = sizeof(ListStage<6>) + (variant == 0 ? sizeof(UvwFaceStage) : 0);
+  const int grid = std::max(fcp_nchunks(ctx->n), 1);
+  if (!(ctx->uvw_smem_configured & (1 << variant))) {
+    cudaError_t ce = variant == 0 ? cudaFuncSetAttribute(k_uvw_assemble<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                   : variant == 1 ? cudaFuncSetAttribute(k_uvw_assemble<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(k_uvw_assemble<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    FCP_CUDA(ce);
+    ctx->uvw_smem_configured |= 1 << variant;
+  }
+  size_t tok = ctx->prof.begin(FCP_K_UVW, ctx->stream);
+  if (variant == 0) k_uvw_assemble<true, 1><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), g);
+  else if (variant == 1) k_uvw_assemble<false, 1><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), g);
+  else k_uvw_assemble<false, 2><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), g);
+  ctx->prof.end(tok, ctx->stream);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;

@@ -1711,19 +1711,29 @@ static int coop_grid(const void *kernel, int device, int *grid) {
 // FCP_SWEEP = ll (default: flag-in-data sweeps, no barrier) | barrier (one cooperative grid barrier per level) | flags (per-row ready flags with
 // acquire/release, one barrier between the sweeps).  Read per call: tests and A/B timings switch it inside one process.
 enum { SWEEP_LL = 0, SWEEP_BARRIER, SWEEP_FLAGS };
-static int sweep_mode() {
+// the sweep switches are read ONCE PER SOLVE (krylov_solve -> sweep_cfg_refresh), not per preconditioner apply
+struct SweepCfg { int mode = SWEEP_LL; bool pf = true; unsigned int pause_ns = 0; int ctas = 0; };
+static thread_local SweepCfg g_sweep;
+static void sweep_cfg_refresh() {
+  SweepCfg c;
   const char *e = getenv("FCP_SWEEP");
-  if (e && !strcmp(e, "barrier")) return SWEEP_BARRIER;
-  if (e && !strcmp(e, "flags")) return SWEEP_FLAGS;
-  return SWEEP_LL;
+  c.mode = (e && !strcmp(e, "barrier")) ? SWEEP_BARRIER : (e && !strcmp(e, "flags")) ? SWEEP_FLAGS : SWEEP_LL;
+  e = getenv("FCP_SWEEP_PF");
+  c.pf = !(e && !strcmp(e, "off"));            // software prefetch of the next tile's static data (default on)
+  e = getenv("FCP_SWEEP_NS");
+  c.pause_ns = e ? (unsigned int)std::max(0, atoi(e)) : 0u;
+  e = getenv("FCP_SWEEP_CTAS");
+  c.ctas = e ? atoi(e) : 0;
+  g_sweep = c;
 }
+static int sweep_mode() { return g_sweep.mode; }
 // cooperative grid of the LL kernels: all CTAs co-resident; FCP_SWEEP_CTAS caps the CTAs per SM (fewer resident warps = fewer warps polling)
 static int sweep_grid(const void *fn, KrylovWS &ws, int slot, int *grid) {
   int &cap = ws.persist_grid[slot];
   if (!cap) FCP_TRY(coop_grid(fn, ws.ws_device, &cap));
   *grid = cap;
-  if (const char *e = getenv("FCP_SWEEP_CTAS")) {
-    const int v = atoi(e);
+  if (g_sweep.ctas > 0) {
+    const int v = g_sweep.ctas;
     int nsm = 0;
     FCP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ws.ws_device));
     if (v > 0) *grid = std::min(cap, v * std::max(nsm, 1));
@@ -1731,10 +1741,7 @@ static int sweep_grid(const void *fn, KrylovWS &ws, int slot, int *grid) {
   return FCP_OK;
 }
 // pause of the sentinel lane between two polls (FCP_SWEEP_NS, default 0: it polls back to back -- one sector per poll per warp does not load the L2)
-static unsigned int sweep_pause_ns() {
-  const char *e = getenv("FCP_SWEEP_NS");
-  return e ? (unsigned int)std::max(0, atoi(e)) : 0u;
-}
+static unsigned int sweep_pause_ns() { return g_sweep.pause_ns; }
 static unsigned int next_ll_epoch(SellPattern &p, cudaStream_t st) {
   if (p.ll_epoch >= 0xfffffff0u) {          // 32-bit tags: start over (once per ~4e9 sweeps)
     for (auto *q : p.zll) cudaMemsetAsync(q, 0, sizeof(unsigned long long) * 2 * (size_t)std::max(p.n, 1), st);
@@ -1806,8 +1813,7 @@ static int launch_precond(SellPattern &p, const double *a, const double *d, cons
     unsigned long long *zf = p.zll[0], *zb = p.zll[1];
     unsigned int seq = next_ll_epoch(p, st);
     const bool wide = std::max(p.tri[0].maxlen, p.tri[1].maxlen) > 4;
-    const char *pfe = getenv("FCP_SWEEP_PF");
-    const bool pf = !(pfe && !strcmp(pfe, "off"));            // software prefetch of the next tile's static data (default on)
+    const bool pf = g_sweep.pf;
     const void *fn = wide ? (pf ? (const void *)k_precond_apply_ll<8, true> : (const void *)k_precond_apply_ll<8, false>)
                           : (pf ? (const void *)k_precond_apply_ll<4, true> : (const void *)k_precond_apply_ll<4, false>);
     int grid = 0;
@@ -2058,6 +2064,7 @@ int krylov_solve(int solver, SellPattern &p, const double *a, double *fi, const 
     return FCP_EINVAL;
   }
   const CommDev *cd = comm_dev(comm);
+  sweep_cfg_refresh();
   FCP_TRY(krylov_ws_alloc(ws, n, p.ncols));
   if (rep) { memset(rep, 0, sizeof(*rep)); rep->solver = solver; }
   const int grid = fcp_nchunks(n);

@@ -275,6 +275,23 @@ static int ctx_build(fcp_ctx *c, const fcp_mesh_desc *md, int device) {
     FCP_TRY(dev_upload(&c->fl.ent, ent.data(), ent.size()));
     FCP_TRY(dev_upload(&c->fl.other, other.data(), other.size()));
     FCP_TRY(dev_upload(&c->fl.slot, slot.data(), slot.size()));
+    std::vector<unsigned long long> kinds(n, 0ull);
+    parallel_for(n, [&](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; ++i) {
+        unsigned long long w = 0;
+        if (cnt[i] > 14) {
+          w = 255ull << 56;
+        } else {
+          for (int32_t k = 0; k < cnt[i]; ++k) {
+            const int32_t sl = slot[fsl[i >> 5] + (int64_t)k * 32 + (i & 31)];
+            if (sl < 0) w |= (unsigned long long)(-sl & 15) << (4 * k);
+          }
+          w |= (unsigned long long)cnt[i] << 56;
+        }
+        kinds[i] = w;
+      }
+    });
+    FCP_TRY(dev_upload(&c->fl.kinds, kinds.data(), kinds.size()));
   }
 
   // ---- mesh arrays --------------------------------------------------------------------------------------------
@@ -334,7 +351,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   cudaFree(c->xf); cudaFree(c->yf); cudaFree(c->zf); cudaFree(c->facint); cudaFree(c->Df);
   cudaFree(c->xc); cudaFree(c->yc); cudaFree(c->zc); cudaFree(c->vol); cudaFree(c->bftype);
   cudaFree(c->kPN); cudaFree(c->kNP);
-  cudaFree(c->fl.slptr); cudaFree(c->fl.len); cudaFree(c->fl.ent); cudaFree(c->fl.other); cudaFree(c->fl.slot);
+  cudaFree(c->fl.slptr); cudaFree(c->fl.len); cudaFree(c->fl.ent); cudaFree(c->fl.other); cudaFree(c->fl.slot); cudaFree(c->fl.kinds);
   for (int i = 0; i < FCP_F_COUNT; ++i) cudaFree(c->field[i]);
   for (int i = 0; i < 4; ++i) cudaFree(c->Dmat[i]);
   cudaFree(c->flushbuf); cudaFree(c->d_mmpart); cudaFree(c->d_sum);

@@ -109,7 +109,8 @@ struct FaceLists {
   int32_t *len = nullptr;     // [n]
   int32_t *ent = nullptr;     // +(f+1): cell is the face's owner (P side), -(f+1): neighbour (N side); 0 padding
   int32_t *other = nullptr;   // field index of the value across the face (cell, ghost slot or boundary slot), 0-based
-  int32_t *slot = nullptr;    // SELL position of a(cell,other) or -1 for physical boundary faces
+  int32_t *slot = nullptr;    // SELL position of a(cell,other) or -1 - bctype for physical boundary faces
+  unsigned long long *kinds = nullptr;   // [n] compact form of len + the sign of slot: nibble k = 0 (two-sided face) or 1 + bctype, top byte = len (255: > 14 faces)
 };
 
 // Krylov workspace (linear_solvers.f90:33  res,reso,pk,zk,d,uk,vk) + device scalars

@@ -17,12 +17,34 @@
 // ---------------------------------------------------------------------------------------------
 // WS = faces per cell the shared-memory list stage holds (6: hexahedra and smaller; 10: the ten-faced polyhedra of config 5); longer lists are
 // read from global memory as before
-template <int WS>
-__global__ void __launch_bounds__(FCP_TPB) k_grad_gauss(MeshView m, const double *__restrict__ u, double *__restrict__ g) {
-  FCP_STAGE_DYN(WS, stage);
-  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
+// MINB = CTAs per SM asked of the compiler; PF = 0: two list stages; PF >= 1: three list stages, and the operands of cell j + 1 are prefetched
+// into the L2 (no registers) while cell j waits for its own gathers -- PF = 1: the cell's own streams and its owner-side faces (first touch; the
+// other faces were read by their owner cells shortly before), PF = 2: every operand
+template <int WS, int NS>
+__device__ __forceinline__ void grad_gauss_prefetch(const MeshView &m, const double *u, const ListStage<WS, NS> &stage, int stn, int64_t cn, int pf) {
+  if (cn >= m.n) return;
+  fcp_prefetch_l2(u + cn); fcp_prefetch_l2(m.vol + cn);
+  const bool cl = m.kinds != nullptr;
+  const int32_t flen = stage.len(stn, cl);
+#pragma unroll
+  for (int k = 0; k < WS; ++k) {
+    if (k >= flen) break;
+    const int32_t e = stage.ent(stn, k);
+    if (pf < 2 && e < 0) continue;
+    const int32_t f = (e > 0 ? e : -e) - 1, o = stage.oth(stn, k);
+    fcp_prefetch_l2(u + o);
+    fcp_prefetch_l2(m.arx + f); fcp_prefetch_l2(m.ary + f); fcp_prefetch_l2(m.arz + f);
+    if (stage.slot(stn, k, cl) >= 0) fcp_prefetch_l2(m.facint + f);
+  }
+}
+template <int WS, int MINB, int PF>
+__global__ void __launch_bounds__(FCP_TPB, MINB) k_grad_gauss(MeshView m, const double *__restrict__ u, double *__restrict__ g) {
+  constexpr int NS = PF ? 3 : 2;
+  FCP_STAGE_DYN_N(WS, NS, stage);
+  FCP_STAGED_LOOP_BEGIN_N(NS, stage, m, m.n, c, st, stn, if (PF) grad_gauss_prefetch<WS, NS>(m, u, stage, stn, fcp_chunk_cell(j__ + 1), PF))
     double gx = 0.0, gy = 0.0, gz = 0.0;
     const double uc = u[c];
+    const double vol = __ldg(m.vol + c);      // with the cell's first loads, not behind the face loop (a second DRAM round trip per cell)
     constexpr int W = WS <= 6 ? 6 : 5;
     FCP_FACE_BATCHES_STAGED(stage, st, m, c, W) {
       FCP_BATCH_LISTS_STAGED(stage, st, WS, m, W, e, o, sl);
@@ -49,7 +71,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_grad_gauss(MeshView m, const double
         }
       }
     }
-    const double volr = 1.0 / m.vol[c];
+    const double volr = 1.0 / vol;
     g[3 * (int64_t)c + 0] = gx * volr;
     g[3 * (int64_t)c + 1] = gy * volr;
     g[3 * (int64_t)c + 2] = gz * volr;
@@ -99,13 +121,38 @@ __global__ void __launch_bounds__(FCP_TPB) k_lsq_matrix(MeshView m, double *__re
   }
 }
 
-template <bool W, int WS>
-__global__ void __launch_bounds__(FCP_TPB) k_grad_lsq(MeshView m, const double *__restrict__ D, const double *__restrict__ phi,
-                                                       double *__restrict__ g, int row2_reference) {
-  FCP_STAGE_DYN(WS, stage);
-  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
+template <int WS, int NS>
+__device__ __forceinline__ void grad_lsq_prefetch(const MeshView &m, const double *D, const double *phi, const ListStage<WS, NS> &stage, int stn, int64_t cn,
+                                                  int pf) {
+  if (cn >= m.n) return;
+  fcp_prefetch_l2(phi + cn); fcp_prefetch_l2(m.xc + cn); fcp_prefetch_l2(m.yc + cn); fcp_prefetch_l2(m.zc + cn);
+#pragma unroll
+  for (int q = 0; q < 9; ++q) fcp_prefetch_l2(D + (int64_t)q * m.n + cn);
+  const bool cl = m.kinds != nullptr;
+  const int32_t flen = stage.len(stn, cl);
+#pragma unroll
+  for (int k = 0; k < WS; ++k) {
+    if (k >= flen) break;
+    const int32_t e = stage.ent(stn, k);
+    if (pf < 2 && e < 0) continue;
+    const int32_t f = (e > 0 ? e : -e) - 1, o = stage.oth(stn, k);
+    fcp_prefetch_l2(phi + o);
+    if (stage.slot(stn, k, cl) >= 0) { fcp_prefetch_l2(m.xc + o); fcp_prefetch_l2(m.yc + o); fcp_prefetch_l2(m.zc + o); }
+    else { fcp_prefetch_l2(m.xf + f); fcp_prefetch_l2(m.yf + f); fcp_prefetch_l2(m.zf + f); }
+  }
+}
+template <bool W, int WS, int MINB, int PF>
+__global__ void __launch_bounds__(FCP_TPB, MINB) k_grad_lsq(MeshView m, const double *__restrict__ D, const double *__restrict__ phi,
+                                                             double *__restrict__ g, int row2_reference) {
+  constexpr int NS = PF ? 3 : 2;
+  FCP_STAGE_DYN_N(WS, NS, stage);
+  FCP_STAGED_LOOP_BEGIN_N(NS, stage, m, m.n, c, st, stn, if (PF) grad_lsq_prefetch<WS, NS>(m, D, phi, stage, stn, fcp_chunk_cell(j__ + 1), PF))
     double b1 = 0.0, b2 = 0.0, b3 = 0.0;
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c], pc = phi[c];
+    const int64_t n = m.n;
+    // the cell's row of the inverse matrix with the cell's first loads, not behind the face loop (a second DRAM round trip per cell)
+    const double D1 = __ldg(D + 0 * n + c), D2 = __ldg(D + 1 * n + c), D3 = __ldg(D + 2 * n + c), D4 = __ldg(D + 3 * n + c), D5 = __ldg(D + 4 * n + c),
+                 D6 = __ldg(D + 5 * n + c), D7 = __ldg(D + 6 * n + c), D8 = __ldg(D + 7 * n + c), D9 = __ldg(D + 8 * n + c);
     constexpr int WB = WS <= 6 ? 6 : 5;
     FCP_FACE_BATCHES_STAGED(stage, st, m, c, WB) {
       FCP_BATCH_LISTS_STAGED(stage, st, WS, m, WB, e_, o_, sl_);
@@ -153,9 +200,6 @@ __global__ void __launch_bounds__(FCP_TPB) k_grad_lsq(MeshView m, const double *
       b1 = b1 + Dx; b2 = b2 + Dy; b3 = b3 + Dz;
       }
     }
-    const int64_t n = m.n;
-    const double D1 = D[0 * n + c], D2 = D[1 * n + c], D3 = D[2 * n + c], D4 = D[3 * n + c], D5 = D[4 * n + c],
-                 D6 = D[5 * n + c], D7 = D[6 * n + c], D8 = D[7 * n + c], D9 = D[8 * n + c];
     g[3 * (int64_t)c + 0] = b1 * D1 - b2 * D2 + b3 * D3;                   // :886-888 ; row 2 is quirk Q1
     g[3 * (int64_t)c + 1] = row2_reference ? (b1 * D4 - b2 * D5 - b3 * D6) : (b2 * D4 - b1 * D5 - b3 * D6);
     g[3 * (int64_t)c + 2] = b1 * D7 - b2 * D8 + b3 * D9;
@@ -456,17 +500,54 @@ __device__ __forceinline__ void gradp_cell_fast(const MeshView &m, int32_t c, co
   }
 }
 
-template <bool CORRECT, bool WEIGHTED>
+// the streams of the fused velocity / pressure correction are only read behind the face loop: asked into the L2 with the cell's first loads, so that
+// the tail costs an L2 hit instead of a second DRAM round trip per cell
+template <bool CORRECT>
+__device__ __forceinline__ void gradp_prefetch_tail(const CorrectArgs &ca, int64_t c) {
+  if (!CORRECT) return;
+  fcp_prefetch_l2(ca.u + c); fcp_prefetch_l2(ca.v + c); fcp_prefetch_l2(ca.w + c);
+  fcp_prefetch_l2(ca.apu + c); fcp_prefetch_l2(ca.apv + c); fcp_prefetch_l2(ca.apw + c);
+  if (ca.pres) fcp_prefetch_l2(ca.pres + c);
+}
+template <bool CORRECT, bool WEIGHTED, int WS, int NS>
+__device__ __forceinline__ void gradp_prefetch(const MeshView &m, const double *p, const double *apu, const CorrectArgs &ca, const ListStage<WS, NS> &stage,
+                                               int stn, int64_t cn, int pf) {
+  if (cn >= m.n) return;
+  fcp_prefetch_l2(p + cn); fcp_prefetch_l2(m.vol + cn);
+  if (WEIGHTED) fcp_prefetch_l2(apu + cn);
+  gradp_prefetch_tail<CORRECT>(ca, cn);
+  const bool cl = m.kinds != nullptr;
+  const int32_t flen = stage.len(stn, cl);
+#pragma unroll
+  for (int k = 0; k < WS; ++k) {
+    if (k >= flen) break;
+    const int32_t e = stage.ent(stn, k);
+    if (pf < 2 && e < 0) continue;
+    const int32_t f = (e > 0 ? e : -e) - 1, o = stage.oth(stn, k), sl = stage.slot(stn, k, cl);
+    fcp_prefetch_l2(m.arx + f); fcp_prefetch_l2(m.ary + f); fcp_prefetch_l2(m.arz + f);
+    if (sl >= 0) {
+      fcp_prefetch_l2(p + o); fcp_prefetch_l2(m.facint + f);
+      if (WEIGHTED) fcp_prefetch_l2(apu + o);
+    } else if (-1 - sl == FCP_BC_PRESSURE) {
+      fcp_prefetch_l2(p + o);
+    }
+  }
+}
+template <bool CORRECT, bool WEIGHTED, int PF>
 __global__ void __launch_bounds__(FCP_TPB, 2) k_gradp(MeshView m, int nstages, double *p, const double *__restrict__ apu,
                                                        double *__restrict__ su, double *__restrict__ sv, double *__restrict__ sw,
                                                        double *__restrict__ dPdxi, CorrectArgs ca) {
   constexpr int W = 6;
+  constexpr int NS = PF ? 3 : 2;
   constexpr int scheme = WEIGHTED ? FCP_PSCHEME_WEIGHTED : FCP_PSCHEME_LINEAR;
-  __shared__ ListStage<W> stage;      // the face list of the NEXT cell travels global -> shared while this cell's gathers are in flight
-  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
-    if (stage.len(st) <= W) {
+  FCP_STAGE_DYN_N(W, NS, stage);      // the face list of the NEXT cell(s) travels global -> shared while this cell's gathers are in flight
+  FCP_STAGED_LOOP_BEGIN_N(NS, stage, m, m.n, c, st, stn,
+                          if (PF) gradp_prefetch<CORRECT, WEIGHTED, W, NS>(m, p, apu, ca, stage, stn, fcp_chunk_cell(j__ + 1), PF))
+    if (!PF && nstages >= 2) gradp_prefetch_tail<CORRECT>(ca, c);
+    const bool cl = m.kinds != nullptr;
+    if (stage.len(st, cl) <= W) {
       int32_t e[W], o[W], sl[W];
-      stage.read(st, e, o, sl);
+      stage.read(st, e, o, sl, cl);
       gradp_cell_fast<CORRECT, WEIGHTED, W>(m, c, e, o, sl, scheme, nstages, p, apu, su, sv, sw, dPdxi, ca);
     } else {
       gradp_cell_generic<CORRECT>(m, c, scheme, nstages, p, apu, su, sv, sw, dPdxi, ca);
@@ -569,11 +650,38 @@ __global__ void __launch_bounds__(FCP_TPB) k_gradp_central2(MeshView m, double *
 // MPIF = true: inner faces take the MPI tree's `facefluxmass` (quirk Q10, src-par/faceflux_mass.f90:28-180; process faces keep facefluxmass2 like
 // src-par/calcp_simple.f90:96-118): gradient-corrected central velocities, per-component (Vol/Ap)_f, the P'/E' pressure correction with its sign
 // quirk Q26.  A switchable variant, not the benchmarked path: its extra operands are plain dependent loads.
-template <bool PISO, int W, bool MPIF = false>
+// PF >= 1: three list stages, and the operands of cell j + 1 are asked into the L2 while cell j is evaluated (see k_grad_gauss), so that the W-face
+// gather rounds of a cell cost L2 hits instead of DRAM round trips
+template <int WS, int NS>
+__device__ __forceinline__ void assemble_pcorr_prefetch(const MeshView &m, const AsmArgs &g, const ListStage<WS, NS> &stage, int stn, int64_t cn, int pf) {
+  if (cn >= m.n) return;
+  fcp_prefetch_l2(m.xc + cn); fcp_prefetch_l2(m.yc + cn); fcp_prefetch_l2(m.zc + cn); fcp_prefetch_l2(g.den + cn); fcp_prefetch_l2(m.vol + cn);
+  fcp_prefetch_l2(g.apu + cn); fcp_prefetch_l2(g.u + cn); fcp_prefetch_l2(g.v + cn); fcp_prefetch_l2(g.w + cn); fcp_prefetch_l2(g.p + cn);
+  fcp_prefetch_l2(g.dPdxi + 3 * cn); fcp_prefetch_l2(g.dPdxi + 3 * cn + 2); fcp_prefetch_l2(m.a_rinfo + cn);
+  const int32_t flen = stage.len(stn);
+#pragma unroll
+  for (int k = 0; k < WS; ++k) {
+    if (k >= flen) break;
+    const int32_t e = stage.ent(stn, k);
+    if (pf < 2 && e < 0) continue;
+    const int32_t f = (e > 0 ? e : -e) - 1;
+    const int64_t o = stage.oth(stn, k);
+    fcp_prefetch_l2(m.arx + f); fcp_prefetch_l2(m.ary + f); fcp_prefetch_l2(m.arz + f);
+    if (stage.slot(stn, k, false) >= 0) {
+      fcp_prefetch_l2(m.facint + f); fcp_prefetch_l2(m.Df + f);
+      fcp_prefetch_l2(m.xc + o); fcp_prefetch_l2(m.yc + o); fcp_prefetch_l2(m.zc + o); fcp_prefetch_l2(g.den + o); fcp_prefetch_l2(m.vol + o);
+      fcp_prefetch_l2(g.apu + o); fcp_prefetch_l2(g.u + o); fcp_prefetch_l2(g.v + o); fcp_prefetch_l2(g.w + o); fcp_prefetch_l2(g.p + o);
+      fcp_prefetch_l2(g.dPdxi + 3 * o); fcp_prefetch_l2(g.dPdxi + 3 * o + 2);
+    }
+  }
+}
+template <bool PISO, int W, bool MPIF = false, int PF = 0>
 __global__ void __launch_bounds__(FCP_TPB, ((W >= 3 || MPIF) ? 1 : W == 2 ? 2 : 3)) k_assemble_pcorr(MeshView m, AsmArgs g) {
   constexpr int WS = 6;
-  __shared__ ListStage<WS> stage;     // the face list of the NEXT cell travels global -> shared while this cell's gathers are in flight
-  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
+  constexpr int NS = PF ? 3 : 2;
+  FCP_STAGE_DYN_N(WS, NS, stage);     // the face list of the NEXT cell(s) travels global -> shared while this cell's gathers are in flight
+  FCP_STAGED_LOOP_BEGIN_N(NS, stage, m, m.n, c, st, stn, if (PF) assemble_pcorr_prefetch<WS, NS>(m, g, stage, stn, fcp_chunk_cell(j__ + 1), PF))
+    const int64_t dpos = diag_pos(m, c);    // with the cell's first loads (a_rinfo is a DRAM stream), not in front of the last store
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c];
     const double denc = g.den[c], kc = m.vol[c] * g.apu[c];
     const double uc = g.u[c], vc = g.v[c], wc = g.w[c], pc = g.p[c];
@@ -727,7 +835,7 @@ __global__ void __launch_bounds__(FCP_TPB, ((W >= 3 || MPIF) ? 1 : W == 2 ? 2 : 
         }
       }
     }
-    g.a[diag_pos(m, c)] = dg;
+    g.a[dpos] = dg;
     g.su[c] = s;
   FCP_STAGED_LOOP_END
 }
@@ -841,13 +949,30 @@ int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g) {
   if (ctx->n == 0) return FCP_OK;
   size_t smem = 0;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
-  if (ctx->max_cell_faces > 6) {
-    FCP_TRY((fcp_stage_smem<10>(k_grad_gauss<10>, &smem)));
-    FCP_PROF(&ctx->prof, FCP_K_GRAD, ctx->stream, (k_grad_gauss<10><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), u, g)));
-  } else {
-    FCP_TRY((fcp_stage_smem<6>(k_grad_gauss<6>, &smem)));
-    FCP_PROF(&ctx->prof, FCP_K_GRAD, ctx->stream, (k_grad_gauss<6><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), u, g)));
-  }
+  MeshView mv = fcp_mesh_view(ctx);
+  const FaceVariant fv = fcp_face_variant();
+  if (fv.cl) mv.kinds = ctx->fl.kinds;
+#define GG_LAUNCH(WS, MINB, PF)                                                                                                      \
+  do {                                                                                                                               \
+    FCP_TRY((fcp_stage_smem<WS, (PF) ? 3 : 2>(k_grad_gauss<WS, MINB, PF>, &smem)));                                                  \
+    FCP_PROF(&ctx->prof, FCP_K_GRAD, ctx->stream, (k_grad_gauss<WS, MINB, PF><<<grid, FCP_TPB, smem, ctx->stream>>>(mv, u, g)));     \
+  } while (0)
+#define GG_LAUNCH_WS(WS)                                            \
+  do {                                                              \
+    if (fv.occ >= 3) {                                              \
+      if (fv.pf == 2) GG_LAUNCH(WS, 3, 2);                          \
+      else if (fv.pf == 1) GG_LAUNCH(WS, 3, 1);                     \
+      else GG_LAUNCH(WS, 3, 0);                                     \
+    } else {                                                        \
+      if (fv.pf == 2) GG_LAUNCH(WS, 2, 2);                          \
+      else if (fv.pf == 1) GG_LAUNCH(WS, 2, 1);                     \
+      else GG_LAUNCH(WS, 2, 0);                                     \
+    }                                                               \
+  } while (0)
+  if (ctx->max_cell_faces > 6) GG_LAUNCH_WS(10);
+  else GG_LAUNCH_WS(6);
+#undef GG_LAUNCH_WS
+#undef GG_LAUNCH
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
   return FCP_OK;
@@ -867,10 +992,32 @@ int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi
   const bool wide = ctx->max_cell_faces > 6;
   size_t smem = 0;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
-  if (weighted && wide) { FCP_TRY((fcp_stage_smem<10>(k_grad_lsq<true, 10>, &smem))); k_grad_lsq<true, 10><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference); }
-  else if (weighted) { FCP_TRY((fcp_stage_smem<6>(k_grad_lsq<true, 6>, &smem))); k_grad_lsq<true, 6><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference); }
-  else if (wide) { FCP_TRY((fcp_stage_smem<10>(k_grad_lsq<false, 10>, &smem))); k_grad_lsq<false, 10><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference); }
-  else { FCP_TRY((fcp_stage_smem<6>(k_grad_lsq<false, 6>, &smem))); k_grad_lsq<false, 6><<<grid, FCP_TPB, smem, ctx->stream>>>(fcp_mesh_view(ctx), D, phi, g, row2_reference); }
+  MeshView mv = fcp_mesh_view(ctx);
+  const FaceVariant fv = fcp_face_variant();
+  if (fv.cl) mv.kinds = ctx->fl.kinds;
+#define LSQ_LAUNCH(WT, WS, MINB, PF)                                                                        \
+  do {                                                                                                      \
+    FCP_TRY((fcp_stage_smem<WS, (PF) ? 3 : 2>(k_grad_lsq<WT, WS, MINB, PF>, &smem)));                       \
+    k_grad_lsq<WT, WS, MINB, PF><<<grid, FCP_TPB, smem, ctx->stream>>>(mv, D, phi, g, row2_reference);      \
+  } while (0)
+#define LSQ_LAUNCH_V(WT, WS)                                         \
+  do {                                                              \
+    if (fv.occ >= 3) {                                              \
+      if (fv.pf == 2) LSQ_LAUNCH(WT, WS, 3, 2);                     \
+      else if (fv.pf == 1) LSQ_LAUNCH(WT, WS, 3, 1);                \
+      else LSQ_LAUNCH(WT, WS, 3, 0);                                \
+    } else {                                                        \
+      if (fv.pf == 2) LSQ_LAUNCH(WT, WS, 2, 2);                     \
+      else if (fv.pf == 1) LSQ_LAUNCH(WT, WS, 2, 1);                \
+      else LSQ_LAUNCH(WT, WS, 2, 0);                                \
+    }                                                               \
+  } while (0)
+  if (weighted && wide) LSQ_LAUNCH_V(true, 10);
+  else if (weighted) LSQ_LAUNCH_V(true, 6);
+  else if (wide) LSQ_LAUNCH_V(false, 10);
+  else LSQ_LAUNCH_V(false, 6);
+#undef LSQ_LAUNCH_V
+#undef LSQ_LAUNCH
   ctx->prof.end(tok, ctx->stream);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();
@@ -890,8 +1037,23 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
   MeshView m = fcp_mesh_view(ctx);
   CorrectArgs ca{};
   if (correct) ca = *correct;
+  size_t smem = 0;
+  const int grid = std::max(fcp_nchunks(ctx->n), 1);
+  const FaceVariant fv = fcp_face_variant();
+  if (fv.cl) m.kinds = ctx->fl.kinds;
+#define GRADP_LAUNCH(C, WG, PF, NST, OUT)                                                                          \
+  do {                                                                                                             \
+    FCP_TRY((fcp_stage_smem<6, (PF) ? 3 : 2>(k_gradp<C, WG, PF>, &smem)));                                         \
+    k_gradp<C, WG, PF><<<grid, FCP_TPB, smem, ctx->stream>>>(m, NST, p, apu, su, sv, sw, OUT, ca);                 \
+  } while (0)
+#define GRADP_LAUNCH_V(C, WG, NST, OUT)                             \
+  do {                                                              \
+    if (fv.pf == 2) GRADP_LAUNCH(C, WG, 2, NST, OUT);               \
+    else if (fv.pf == 1) GRADP_LAUNCH(C, WG, 1, NST, OUT);          \
+    else GRADP_LAUNCH(C, WG, 0, NST, OUT);                          \
+  } while (0)
   if (scheme == FCP_PSCHEME_CENTRAL) {
-    k_gradp<false, false><<<FCP_GRID(ctx->n)>>>(m, 1, p, apu, su, sv, sw, gtmp, ca);
+    GRADP_LAUNCH_V(false, false, 1, gtmp);
     FCP_LAUNCHED();
     if (correct) k_gradp_central2<true><<<FCP_GRID(ctx->n)>>>(m, p, gtmp, su, sv, sw, dPdxi, ca);
     else k_gradp_central2<false><<<FCP_GRID(ctx->n)>>>(m, p, gtmp, su, sv, sw, dPdxi, ca);
@@ -899,33 +1061,51 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
   } else {
     size_t tok = ctx->prof.begin(FCP_K_GRADP, ctx->stream);
     const bool wgt = scheme == FCP_PSCHEME_WEIGHTED;
-    if (correct && wgt) k_gradp<true, true><<<FCP_GRID(ctx->n)>>>(m, 2, p, apu, su, sv, sw, dPdxi, ca);
-    else if (correct) k_gradp<true, false><<<FCP_GRID(ctx->n)>>>(m, 2, p, apu, su, sv, sw, dPdxi, ca);
-    else if (wgt) k_gradp<false, true><<<FCP_GRID(ctx->n)>>>(m, 2, p, apu, su, sv, sw, dPdxi, ca);
-    else k_gradp<false, false><<<FCP_GRID(ctx->n)>>>(m, 2, p, apu, su, sv, sw, dPdxi, ca);
+    if (correct && wgt) GRADP_LAUNCH_V(true, true, 2, dPdxi);
+    else if (correct) GRADP_LAUNCH_V(true, false, 2, dPdxi);
+    else if (wgt) GRADP_LAUNCH_V(false, true, 2, dPdxi);
+    else GRADP_LAUNCH_V(false, false, 2, dPdxi);
     ctx->prof.end(tok, ctx->stream);
     FCP_LAUNCHED();
   }
+#undef GRADP_LAUNCH_V
+#undef GRADP_LAUNCH
   FCP_CHECK_LAUNCH();
   return FCP_OK;
 }
 int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso) {
   if (ctx->n == 0) return FCP_OK;
-  static int w = -1;   // faces per register batch: FCP_ASM_W = 1 | 2 | 3 (A/B measurements)
-  if (w < 0) { const char *e = getenv("FCP_ASM_W"); w = e ? atoi(e) : 2; if (w < 1 || w > 3) w = 2; }
+  int w = 2;           // faces per register batch: FCP_ASM_W = 1 | 2 | 3 (A/B measurements)
+  if (const char *e = getenv("FCP_ASM_W")) { w = atoi(e); if (w < 1 || w > 3) w = 2; }
+  const FaceVariant fv = fcp_face_variant();
+  size_t smem = 0;
+  const int grid = std::max(fcp_nchunks(ctx->n), 1);
   size_t tok = ctx->prof.begin(FCP_K_ASSEMBLE, ctx->stream);
   MeshView mv = fcp_mesh_view(ctx);
+#define ASM_LAUNCH(PISO, W, MPIF, PF)                                                                   \
+  do {                                                                                                  \
+    FCP_TRY((fcp_stage_smem<6, (PF) ? 3 : 2>(k_assemble_pcorr<PISO, W, MPIF, PF>, &smem)));             \
+    k_assemble_pcorr<PISO, W, MPIF, PF><<<grid, FCP_TPB, smem, ctx->stream>>>(mv, g);                   \
+  } while (0)
+#define ASM_LAUNCH_V(PISO, W)                                       \
+  do {                                                              \
+    if (fv.pf == 2) ASM_LAUNCH(PISO, W, false, 2);                  \
+    else if (fv.pf == 1) ASM_LAUNCH(PISO, W, false, 1);             \
+    else ASM_LAUNCH(PISO, W, false, 0);                             \
+  } while (0)
   if (g.gU) {          // quirk Q10 switch (fcp_set_flux_variant): SIMPLE only, one face per gather round
-    k_assemble_pcorr<false, 1, true><<<FCP_GRID(ctx->n)>>>(mv, g);
+    ASM_LAUNCH(false, 1, true, 0);
   } else if (piso) {
-    if (w == 1) k_assemble_pcorr<true, 1><<<FCP_GRID(ctx->n)>>>(mv, g);
-    else if (w == 2) k_assemble_pcorr<true, 2><<<FCP_GRID(ctx->n)>>>(mv, g);
-    else k_assemble_pcorr<true, 3><<<FCP_GRID(ctx->n)>>>(mv, g);
+    if (w == 1) ASM_LAUNCH_V(true, 1);
+    else if (w == 2) ASM_LAUNCH_V(true, 2);
+    else ASM_LAUNCH(true, 3, false, 0);
   } else {
-    if (w == 1) k_assemble_pcorr<false, 1><<<FCP_GRID(ctx->n)>>>(mv, g);
-    else if (w == 2) k_assemble_pcorr<false, 2><<<FCP_GRID(ctx->n)>>>(mv, g);
-    else k_assemble_pcorr<false, 3><<<FCP_GRID(ctx->n)>>>(mv, g);
+    if (w == 1) ASM_LAUNCH_V(false, 1);
+    else if (w == 2) ASM_LAUNCH_V(false, 2);
+    else ASM_LAUNCH(false, 3, false, 0);
   }
+#undef ASM_LAUNCH_V
+#undef ASM_LAUNCH
   ctx->prof.end(tok, ctx->stream);
   FCP_LAUNCHED();
   FCP_CHECK_LAUNCH();

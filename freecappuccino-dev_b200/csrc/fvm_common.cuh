@@ -1,11 +1,16 @@
 // fvm_common.cuh -- mesh view and the cell-centric gather macros shared by fvm.cu and fvm_ext.cu (see fvm.cu header)
 #pragma once
+#include <cstdlib>
 #include "fcp_internal.h"
+#define FCP_FACE_OCC_DEFAULT 2
+#define FCP_FACE_PF_DEFAULT 0
+#define FCP_FACE_CL_DEFAULT 0
 
 struct MeshView {
   int32_t n, F, B;
   const int64_t *slptr;
   const int32_t *len, *ent, *other, *slot;
+  const unsigned long long *kinds;   // compact face kinds per cell (FaceLists::kinds) when the launcher selects the compact lists, else nullptr
   const double *arx, *ary, *arz, *xf, *yf, *zf, *facint, *Df;
   const double *xc, *yc, *zc, *vol;
   const int32_t *owner, *neigh;
@@ -19,7 +24,7 @@ struct MeshView {
 static inline MeshView fcp_mesh_view(const fcp_ctx *c) {
   MeshView m;
   m.n = c->n; m.F = c->F; m.B = c->B;
-  m.slptr = c->fl.slptr; m.len = c->fl.len; m.ent = c->fl.ent; m.other = c->fl.other; m.slot = c->fl.slot;
+  m.slptr = c->fl.slptr; m.len = c->fl.len; m.ent = c->fl.ent; m.other = c->fl.other; m.slot = c->fl.slot; m.kinds = nullptr;
   m.arx = c->arx; m.ary = c->ary; m.arz = c->arz; m.xf = c->xf; m.yf = c->yf; m.zf = c->zf;
   m.facint = c->facint; m.Df = c->Df; m.xc = c->xc; m.yc = c->yc; m.zc = c->zc; m.vol = c->vol;
   m.owner = c->owner; m.neigh = c->neigh;
@@ -85,76 +90,139 @@ __device__ __forceinline__ void fcp_cp_async8(double *dst_smem, const double *sr
 __device__ __forceinline__ void fcp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void fcp_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
-template <int W>
+// The slice pointers of the (up to) FCP_IPT cells a thread walks, fetched ONCE per warp: the cells of iteration j lie in slice
+// blockIdx.x * (FCP_CHUNK / 32) + j * (FCP_TPB / 32) + warp, so lane j holds slptr[that slice] and lane j + FCP_IPT slptr[that slice + 1]; an
+// iteration takes them with two shuffles instead of a dependent load (an L2 round trip per cell in front of every list fetch).
+struct StageSlices {
+  int64_t v;
+  __device__ __forceinline__ void init(const MeshView &m) {
+    static_assert(2 * FCP_IPT <= 32, "one lane per slice bound");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t s = (int64_t)blockIdx.x * (FCP_CHUNK / 32) + (int64_t)(lane % FCP_IPT) * (FCP_TPB / 32) + warp + (lane / FCP_IPT);
+    const int64_t nsl = ((int64_t)m.n + 31) >> 5;
+    v = (lane < 2 * FCP_IPT && s <= nsl) ? __ldg(m.slptr + s) : 0;
+  }
+  // every lane of the warp must call this (shuffles); j = iteration of the cell loop
+  __device__ __forceinline__ void get(int j, int64_t &b0, int64_t &b1) const {
+    b0 = __shfl_sync(0xffffffffu, v, j);
+    b1 = __shfl_sync(0xffffffffu, v, j + FCP_IPT);
+  }
+};
+__device__ __forceinline__ void fcp_prefetch_l2(const void *p) {
+#ifndef FCP_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// Compact lists (m.kinds != nullptr; kernels that need no matrix slot): `slot` only tells a gradient kernel whether a face is two-sided and, if not,
+// the patch type, and `len` is a fourth stream -- both are folded into ONE 8-byte word per cell (FaceLists::kinds: nibble k = 0 for a two-sided face,
+// 1 + bctype otherwise; top byte = the cell's face count, 255 = more than 14 faces: such a cell reads the plain lists).  A hexahedron then reads
+// 56 bytes of list instead of 76.  The word's halves take the place of the `len` row and of the first `slot` row of the stage.
+template <int W, int NS = 2>
 struct ListStage {
-  int32_t v[2][1 + 3 * W][FCP_TPB];
-  // issue the copies of cell c's list into stage st (c >= n: nothing to fetch, the stage reads as an empty list)
-  __device__ __forceinline__ void fetch(const MeshView &m, int64_t c64, int st) {
+  int32_t v[NS][1 + 3 * W][FCP_TPB];
+  // issue the copies of cell c's list into stage st (c >= n: nothing to fetch, the stage reads as an empty list); b0, b1 = slice bounds (StageSlices)
+  __device__ __forceinline__ void fetch(const MeshView &m, int64_t c64, int st, int64_t b0, int64_t b1) {
     const int t = threadIdx.x;
+    const bool cl = m.kinds != nullptr;
     if (c64 < m.n) {
       const int32_t c = (int32_t)c64;
-      const int64_t b0 = __ldg(&m.slptr[c >> 5]);
-      const int32_t width = (int32_t)((__ldg(&m.slptr[(c >> 5) + 1]) - b0) >> 5);
+      const int32_t width = (int32_t)((b1 - b0) >> 5);
       const int64_t fbase = b0 + (c & 31);
-      fcp_cp_async4(&v[st][0][t], m.len + c);
+      if (cl) {
+        const int32_t *kw = reinterpret_cast<const int32_t *>(m.kinds + c);
+        fcp_cp_async4(&v[st][0][t], kw);
+        fcp_cp_async4(&v[st][1 + 2 * W][t], kw + 1);
+      } else {
+        fcp_cp_async4(&v[st][0][t], m.len + c);
+      }
 #pragma unroll
       for (int k = 0; k < W; ++k) {
         if (k < width) {
           const int64_t pos = fbase + (int64_t)k * 32;
           fcp_cp_async4(&v[st][1 + k][t], m.ent + pos);
           fcp_cp_async4(&v[st][1 + W + k][t], m.other + pos);
-          fcp_cp_async4(&v[st][1 + 2 * W + k][t], m.slot + pos);
+          if (!cl) fcp_cp_async4(&v[st][1 + 2 * W + k][t], m.slot + pos);
         } else {
-          v[st][1 + k][t] = 0; v[st][1 + W + k][t] = 0; v[st][1 + 2 * W + k][t] = -1;
+          v[st][1 + k][t] = 0; v[st][1 + W + k][t] = 0;
+          if (!cl) v[st][1 + 2 * W + k][t] = -1;
         }
       }
     } else {
       v[st][0][t] = 0;
+      if (cl) v[st][1 + 2 * W][t] = 0;
     }
     fcp_cp_async_commit();
   }
+  // plain lists
   __device__ __forceinline__ int32_t len(int st) const { return v[st][0][threadIdx.x]; }
-  __device__ __forceinline__ void read(int st, int32_t (&e)[W], int32_t (&o)[W], int32_t (&sl)[W]) const {
-    const int t = threadIdx.x;
-    const int32_t flen = v[st][0][t];
+  __device__ __forceinline__ int32_t ent(int st, int k) const { return v[st][1 + k][threadIdx.x]; }
+  __device__ __forceinline__ int32_t oth(int st, int k) const { return v[st][1 + W + k][threadIdx.x]; }
+  // plain or compact lists (cl = m.kinds != nullptr); len: 255 = "read m.len[c] and the plain lists"
+  __device__ __forceinline__ int32_t len(int st, bool cl) const {
+    return cl ? (int32_t)((uint32_t)v[st][1 + 2 * W][threadIdx.x] >> 24) : v[st][0][threadIdx.x];
+  }
+  __device__ __forceinline__ int32_t slot(int st, int k, bool cl) const {
+    if (!cl) return v[st][1 + 2 * W + k][threadIdx.x];
+    const uint32_t h = (uint32_t)(k < 8 ? v[st][0][threadIdx.x] : v[st][1 + 2 * W][threadIdx.x]);
+    return -(int32_t)((h >> (4 * (k & 7))) & 15u);       // 0 = two-sided (>= 0), -1 - bctype otherwise: what the gradient kernels test
+  }
+  __device__ __forceinline__ void read(int st, int32_t (&e)[W], int32_t (&o)[W], int32_t (&sl)[W], bool cl = false) const {
+    const int32_t flen = len(st, cl);
 #pragma unroll
     for (int k = 0; k < W; ++k) {
       const bool on = k < flen;
-      e[k] = on ? v[st][1 + k][t] : 0;
-      o[k] = on ? v[st][1 + W + k][t] : 0;
-      sl[k] = on ? v[st][1 + 2 * W + k][t] : -1;
+      e[k] = on ? ent(st, k) : 0;
+      o[k] = on ? oth(st, k) : 0;
+      sl[k] = on ? slot(st, k, cl) : -1;
     }
   }
 };
 // a stage in DYNAMIC shared memory (ListStage<10> is 62 KB, over the 48 KB static limit): launch with sizeof(ListStage<WS>) bytes
 #ifdef FCP_EMU
-#define FCP_STAGE_DYN(WS, name) ListStage<WS> &name = *reinterpret_cast<ListStage<WS> *>(emu::dyn_smem())
+#define FCP_STAGE_DYN_N(WS, NS, name) ListStage<WS, NS> &name = *reinterpret_cast<ListStage<WS, NS> *>(emu::dyn_smem())
 #else
-#define FCP_STAGE_DYN(WS, name)                                   \
+#define FCP_STAGE_DYN_N(WS, NS, name)                             \
   extern __shared__ __align__(16) unsigned char stage_raw__[];    \
-  ListStage<WS> &name = *reinterpret_cast<ListStage<WS> *>(stage_raw__)
+  ListStage<WS, NS> &name = *reinterpret_cast<ListStage<WS, NS> *>(stage_raw__)
 #endif
-template <int WS, class K>
+#define FCP_STAGE_DYN(WS, name) FCP_STAGE_DYN_N(WS, 2, name)
+template <int WS, int NS = 2, class K>
 static int fcp_stage_smem(K kernel, size_t *bytes) {
-  *bytes = sizeof(ListStage<WS>);
+  *bytes = sizeof(ListStage<WS, NS>);
   if (*bytes > 48 * 1024) FCP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*bytes));
   return FCP_OK;
 }
 
 // the cell loop of FCP_CELL_LOOP with staged lists: `c` is the cell, `st` the stage that holds its list
 __device__ __forceinline__ int64_t fcp_chunk_cell(int j) { return (int64_t)blockIdx.x * FCP_CHUNK + (int64_t)j * FCP_TPB + threadIdx.x; }
-#define FCP_STAGED_LOOP_BEGIN(stage, m, n, c, st)                                                                    \
-  (stage).fetch((m), fcp_chunk_cell(0), 0);                                                                           \
-  for (int j__ = 0, st = 0; j__ < FCP_IPT; ++j__, st ^= 1) {                                                          \
-    if (j__ + 1 < FCP_IPT) { (stage).fetch((m), fcp_chunk_cell(j__ + 1), st ^ 1); fcp_cp_async_wait<1>(); }          \
-    else fcp_cp_async_wait<0>();                                                                                      \
+// NS stages: the list of cell j + NS - 1 is in flight while cell j is processed; `stn` = the stage of cell j + 1, complete when NS >= 3 (what a
+// prefetch of that cell's gathers needs), the trailing arguments = a statement executed once per iteration after the wait (before the c < n test)
+#define FCP_STAGED_LOOP_BEGIN_N(NS, stage, m, n, c, st, stn, ...)                                                     \
+  StageSlices slices__; slices__.init(m);                                                                             \
+  _Pragma("unroll") for (int s__ = 0; s__ < (NS) - 1; ++s__) {                                                        \
+    int64_t b0__, b1__; slices__.get(s__, b0__, b1__);                                                                \
+    (stage).fetch((m), fcp_chunk_cell(s__), s__, b0__, b1__);                                                         \
+  }                                                                                                                   \
+  for (int j__ = 0, st = 0; j__ < FCP_IPT; ++j__, st = (st + 1 == (NS) ? 0 : st + 1)) {                               \
+    const int stn = st + 1 == (NS) ? 0 : st + 1; (void)stn;                                                           \
+    if (j__ + (NS) - 1 < FCP_IPT) {                                                                                   \
+      int64_t b0__, b1__; slices__.get(j__ + (NS) - 1, b0__, b1__);                                                   \
+      (stage).fetch((m), fcp_chunk_cell(j__ + (NS) - 1), (st + (NS) - 1) % (NS), b0__, b1__);                         \
+      fcp_cp_async_wait<1>();                                                                                         \
+    } else fcp_cp_async_wait<0>();                                                                                    \
+    __VA_ARGS__;                                                                                                      \
     if (fcp_chunk_cell(j__) >= (n)) continue;                                                                         \
     const int32_t c = (int32_t)fcp_chunk_cell(j__);
+#define FCP_STAGED_LOOP_BEGIN(stage, m, n, c, st) FCP_STAGED_LOOP_BEGIN_N(2, stage, m, n, c, st, stn__, (void)0)
 #define FCP_STAGED_LOOP_END }
 
 // FCP_FACE_BATCHES / FCP_BATCH_LISTS with the list taken from the stage when the cell fits it (<= WS faces), else from global memory as before
 #define FCP_FACE_BATCHES_STAGED(stage, st, m, c, W)                                 \
-  const int32_t flen__ = (stage).len(st);                                          \
+  const bool cl__ = (m).kinds != nullptr;                                          \
+  const int32_t slen__ = (stage).len(st, cl__);                                    \
+  const int32_t flen__ = (cl__ && slen__ == 255) ? (m).len[c] : slen__;            \
   const bool staged__ = flen__ <= (int32_t)(sizeof((stage).v[0]) / sizeof((stage).v[0][0]) - 1) / 3;   \
   const int64_t fbase__ = staged__ ? 0 : (m).slptr[(c) >> 5] + ((c) & 31);         \
   for (int32_t q0__ = 0; q0__ < flen__; q0__ += (W))
@@ -164,9 +232,9 @@ __device__ __forceinline__ int64_t fcp_chunk_cell(int j) { return (int64_t)block
     const bool on__ = q0__ + k__ < flen__;                                         \
     if (staged__) {                                                                \
       const int idx__ = on__ ? q0__ + k__ : 0;                                     \
-      e[k__] = on__ ? (stage).v[st][1 + idx__][threadIdx.x] : 0;                   \
-      o[k__] = on__ ? (stage).v[st][1 + (WS) + idx__][threadIdx.x] : 0;            \
-      sl[k__] = on__ ? (stage).v[st][1 + 2 * (WS) + idx__][threadIdx.x] : -1;      \
+      e[k__] = on__ ? (stage).ent(st, idx__) : 0;                                  \
+      o[k__] = on__ ? (stage).oth(st, idx__) : 0;                                  \
+      sl[k__] = on__ ? (stage).slot(st, idx__, cl__) : -1;                         \
     } else {                                                                       \
       const int64_t pos__ = fbase__ + (int64_t)(q0__ + k__) * 32;                  \
       e[k__] = on__ ? __ldcs((m).ent + pos__) : 0;                                 \
@@ -174,6 +242,18 @@ __device__ __forceinline__ int64_t fcp_chunk_cell(int j) { return (int64_t)block
       sl[k__] = on__ ? __ldcs((m).slot + pos__) : -1;                              \
     }                                                                              \
   }
+
+// A/B switches of the face kernels, read at every launch (a handful of launches per step): FCP_FACE_OCC = 2 | 3 CTAs per SM asked of the
+// compiler, FCP_FACE_PF = 0 | 1 | 2 L2 prefetch of the next cell's operands (see k_grad_gauss), FCP_FACE_CL = 0 | 1 compact lists in the gradient
+// kernels (ListStage)
+struct FaceVariant { int occ, pf, cl; };
+static inline FaceVariant fcp_face_variant() {
+  FaceVariant v{FCP_FACE_OCC_DEFAULT, FCP_FACE_PF_DEFAULT, FCP_FACE_CL_DEFAULT};
+  if (const char *e = getenv("FCP_FACE_OCC")) v.occ = atoi(e) >= 3 ? 3 : 2;
+  if (const char *e = getenv("FCP_FACE_PF")) { v.pf = atoi(e); if (v.pf < 0 || v.pf > 2) v.pf = 0; }
+  if (const char *e = getenv("FCP_FACE_CL")) v.cl = atoi(e) != 0;
+  return v;
+}
 
 __device__ __forceinline__ int64_t diag_pos(const MeshView &m, int32_t c) {
   return m.a_slptr[c >> 5] + (c & 31) + (int64_t)((m.a_rinfo[c] >> 16) & 0xffff) * 32;

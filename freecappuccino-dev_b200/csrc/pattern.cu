@@ -42,6 +42,7 @@ template int dev_alloc<unsigned long long>(unsigned long long **, size_t);
 template int dev_upload<double>(double **, const double *, size_t);
 template int dev_upload<int32_t>(int32_t **, const int32_t *, size_t);
 template int dev_upload<int64_t>(int64_t **, const int64_t *, size_t);
+template int dev_upload<unsigned long long>(unsigned long long **, const unsigned long long *, size_t);
 template int dev_upload<unsigned long long *>(unsigned long long ***, unsigned long long *const *, size_t);
 
 int sell_from_csr(SellPattern &p, int32_t n, int32_t ncols, const int32_t *ia1, const int32_t *ja1, const int32_t *diag1,

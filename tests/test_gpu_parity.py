@@ -14,7 +14,7 @@ from fcb200 import mesh as M
 
 pytestmark = pytest.mark.gpu
 
-MESHES = ["ref400", "hex6", "hex12_graded", "hex10_distorted", "slab39_empty", "channel_inout", "channel_pressure", "poly_10faces", "tiny3",
+MESHES = ["ref400", "hex6", "hex12_graded", "hex10_distorted", "slab39_empty", "channel_inout", "channel_pressure", "poly_10faces", "hex_many_faces", "tiny3",
           "channel_periodic", "duct_periodic_x", "duct_periodic_first"]
 
 

@@ -12,7 +12,7 @@ from test_gpu_parity import eq, make_ctx
 from test_gpu_rows2 import uvw_inputs
 
 pytestmark = pytest.mark.gpu
-SC_MESHES = ["hex10_distorted", "channel_inout", "channel_pressure", "poly_10faces", "channel_periodic", "duct_periodic_first", "tiny3"]
+SC_MESHES = ["hex10_distorted", "channel_inout", "channel_pressure", "poly_10faces", "hex_many_faces", "channel_periodic", "duct_periodic_first", "tiny3"]
 
 
 @pytest.fixture(scope="module")

@@ -950,7 +950,7 @@ int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g) {
   size_t smem = 0;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   MeshView mv = fcp_mesh_view(ctx);
-  const FaceVariant fv = fcp_face_variant();
+  const FaceVariant fv = fcp_face_variant(FCP_FK_GRAD_GAUSS);
   if (fv.cl) mv.kinds = ctx->fl.kinds;
 #define GG_LAUNCH(WS, MINB, PF)                                                                                                      \
   do {                                                                                                                               \
@@ -993,7 +993,7 @@ int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi
   size_t smem = 0;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   MeshView mv = fcp_mesh_view(ctx);
-  const FaceVariant fv = fcp_face_variant();
+  const FaceVariant fv = fcp_face_variant(FCP_FK_GRAD_LSQ);
   if (fv.cl) mv.kinds = ctx->fl.kinds;
 #define LSQ_LAUNCH(WT, WS, MINB, PF)                                                                        \
   do {                                                                                                      \
@@ -1039,7 +1039,7 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
   if (correct) ca = *correct;
   size_t smem = 0;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
-  const FaceVariant fv = fcp_face_variant();
+  const FaceVariant fv = fcp_face_variant(FCP_FK_GRADP);
   if (fv.cl) m.kinds = ctx->fl.kinds;
 #define GRADP_LAUNCH(C, WG, PF, NST, OUT)                                                                          \
   do {                                                                                                             \
@@ -1077,7 +1077,7 @@ int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso) {
   if (ctx->n == 0) return FCP_OK;
   int w = 2;           // faces per register batch: FCP_ASM_W = 1 | 2 | 3 (A/B measurements)
   if (const char *e = getenv("FCP_ASM_W")) { w = atoi(e); if (w < 1 || w > 3) w = 2; }
-  const FaceVariant fv = fcp_face_variant();
+  const FaceVariant fv = fcp_face_variant(FCP_FK_ASSEMBLE);
   size_t smem = 0;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   size_t tok = ctx->prof.begin(FCP_K_ASSEMBLE, ctx->stream);

@@ -1,10 +1,8 @@
 // fvm_common.cuh -- mesh view and the cell-centric gather macros shared by fvm.cu and fvm_ext.cu (see fvm.cu header)
 #pragma once
 #include <cstdlib>
+#include <cstring>
 #include "fcp_internal.h"
-#define FCP_FACE_OCC_DEFAULT 2
-#define FCP_FACE_PF_DEFAULT 0
-#define FCP_FACE_CL_DEFAULT 0
 
 struct MeshView {
   int32_t n, F, B;
@@ -243,15 +241,31 @@ __device__ __forceinline__ int64_t fcp_chunk_cell(int j) { return (int64_t)block
     }                                                                              \
   }
 
-// A/B switches of the face kernels, read at every launch (a handful of launches per step): FCP_FACE_OCC = 2 | 3 CTAs per SM asked of the
-// compiler, FCP_FACE_PF = 0 | 1 | 2 L2 prefetch of the next cell's operands (see k_grad_gauss), FCP_FACE_CL = 0 | 1 compact lists in the gradient
-// kernels (ListStage)
+// Switches of the face kernels, read at every launch (a handful of launches per step): FCP_FACE_OCC = 2 | 3 CTAs per SM asked of the compiler,
+// FCP_FACE_PF = 0 | 1 | 2 L2 prefetch of the next cell's operands (see k_grad_gauss), FCP_FACE_CL = 0 | 1 compact lists in the gradient kernels
+// (ListStage).  The environment overrides the defaults, one value for every kernel or a comma-separated value per kernel (tools/face_ab.py); the defaults
+// are per kernel, set from that measurement.
 struct FaceVariant { int occ, pf, cl; };
-static inline FaceVariant fcp_face_variant() {
-  FaceVariant v{FCP_FACE_OCC_DEFAULT, FCP_FACE_PF_DEFAULT, FCP_FACE_CL_DEFAULT};
-  if (const char *e = getenv("FCP_FACE_OCC")) v.occ = atoi(e) >= 3 ? 3 : 2;
-  if (const char *e = getenv("FCP_FACE_PF")) { v.pf = atoi(e); if (v.pf < 0 || v.pf > 2) v.pf = 0; }
-  if (const char *e = getenv("FCP_FACE_CL")) v.cl = atoi(e) != 0;
+enum { FCP_FK_GRAD_GAUSS = 0, FCP_FK_GRAD_LSQ, FCP_FK_GRADP, FCP_FK_ASSEMBLE, FCP_FK_COUNT };
+static inline FaceVariant fcp_face_variant(int kernel) {
+  static const FaceVariant defaults[FCP_FK_COUNT] = {
+      /* k_grad_gauss     */ {2, 0, 0},
+      /* k_grad_lsq       */ {2, 0, 0},
+      /* k_gradp          */ {2, 0, 0},
+      /* k_assemble_pcorr */ {2, 0, 0},
+  };
+  FaceVariant v = defaults[kernel];
+  // "1" = every kernel, "1,0,2,1" = per kernel in the order of the enum
+  auto pick = [kernel](const char *e, int fallback) {
+    if (!e || !*e) return fallback;
+    if (!strchr(e, ',')) return atoi(e);
+    for (int k = 0; k < kernel; ++k) { e = strchr(e, ','); if (!e) return fallback; ++e; }
+    return atoi(e);
+  };
+  v.occ = pick(getenv("FCP_FACE_OCC"), v.occ) >= 3 ? 3 : 2;
+  v.pf = pick(getenv("FCP_FACE_PF"), v.pf);
+  if (v.pf < 0 || v.pf > 2) v.pf = 0;
+  v.cl = pick(getenv("FCP_FACE_CL"), v.cl) != 0;
   return v;
 }
 

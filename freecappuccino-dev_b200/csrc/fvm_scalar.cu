@@ -100,9 +100,161 @@ __global__ void __launch_bounds__(FCP_TPB) k_sst_blend(int32_t n, double viscos,
   }
 }
 
+// operands of one face, gathered for W faces at a time before the first use (k_sc_assemble)
+struct ScCell { double xc, yc, zc, vol, phic, visc, denc, gc[3]; };
+struct ScOps { double arx, ary, arz, xo, yo, zo, phio, viso, go[3], lambda, Df, fm, xf, yf, zf, fso; };
+// e = 0: no face; two = the face is two-sided AND is evaluated in this pass (its 16 neighbour / face operands are needed)
 template <int KIND>
-__global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
-  FCP_CELL_LOOP(c, m.n) {
+__device__ __forceinline__ void sc_gather(const MeshView &m, const ScArgs &g, int32_t c, int32_t e, int32_t o, bool two, ScOps &q) {
+  const int32_t f = (e > 0 ? e : -e) - 1;
+  const bool on = e != 0;
+  q.arx = on ? __ldg(m.arx + f) : 0.0; q.ary = on ? __ldg(m.ary + f) : 0.0; q.arz = on ? __ldg(m.arz + f) : 0.0;
+  q.xo = two ? __ldg(m.xc + o) : 0.0; q.yo = two ? __ldg(m.yc + o) : 0.0; q.zo = two ? __ldg(m.zc + o) : 0.0;
+  q.phio = two ? g.phi[o] : 0.0; q.viso = two ? g.vis[o] : 0.0;
+  q.go[0] = two ? g.g[3 * (int64_t)o] : 0.0; q.go[1] = two ? g.g[3 * (int64_t)o + 1] : 0.0; q.go[2] = two ? g.g[3 * (int64_t)o + 2] : 0.0;
+  q.lambda = two ? __ldg(m.facint + f) : 0.0; q.Df = two ? __ldg(m.Df + f) : 0.0; q.fm = two ? g.flmass[f] : 0.0;
+  q.xf = two ? __ldg(m.xf + f) : 0.0; q.yf = two ? __ldg(m.yf + f) : 0.0; q.zf = two ? __ldg(m.zf + f) : 0.0;
+  q.fso = (two && (KIND == 3 || KIND == 4)) ? g.fsst[e > 0 ? c : o] : 0.0;
+}
+// one face of cell c: e = signed entry, o = index across the face, sl = matrix slot (>= 0) or -1 - bctype; the reference's face body
+template <int KIND>
+__device__ __forceinline__ void sc_face(const MeshView &m, const ScArgs &g, int32_t c, const ScCell &cc, int32_t e, int32_t o, int32_t sl, const ScOps &q,
+                                        double &s, double &p, double &genc, double &phin) {
+  const double xc = cc.xc, yc = cc.yc, zc = cc.zc, vol = cc.vol, phic = cc.phic, visc = cc.visc, denc = cc.denc;
+  const double gc[3] = {cc.gc[0], cc.gc[1], cc.gc[2]};
+  (void)vol; (void)visc; (void)denc; (void)zc; (void)yc; (void)xc; (void)phic;
+  {
+  const int32_t f = (e > 0 ? e : -e) - 1;
+  const double arx = q.arx, ary = q.ary, arz = q.arz;
+  if (sl >= 0) {
+    // ---- facefluxsc, scalar_fluxes.f90:32-141, in the face's orientation (P = owner, N = neighbour)
+    const bool own = e > 0;
+    const double xo = q.xo, yo = q.yo, zo = q.zo, phio_ = q.phio, viso = q.viso;
+    const double go[3] = {q.go[0], q.go[1], q.go[2]};
+    const double lambda = q.lambda, Df = q.Df, fm = q.fm;
+    const double fxn = lambda, fxp = 1.0 - lambda;
+    const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo, xN = own ? xo : xc, yN = own ? yo : yc, zN = own ? zo : zc;
+    const double phiP = own ? phic : phio_, phiN = own ? phio_ : phic;
+    const double visP = own ? visc : viso, visN = own ? viso : visc;
+    const double gP[3] = {own ? gc[0] : go[0], own ? gc[1] : go[1], own ? gc[2] : go[2]};
+    const double gN[3] = {own ? go[0] : gc[0], own ? go[1] : gc[1], own ? go[2] : gc[2]};
+    const double viste = (visP + (visN - visP) * lambda) - g.viscos;
+    const double prf = (KIND == 3 || KIND == 4) ? sst_prtr<KIND>(q.fso) : g.prtr;   // SST: sigma of the face's OWNER cell (gathered as fsst[own ? c : o])
+    const double dcoef = g.viscos + viste * prf;
+    const double xpn = xN - xP, ypn = yN - yP, zpn = zN - zP;
+    const double de = dcoef * Df;
+    const double ce = fmin(fm, 0.0), cp = fmax(fm, 0.0);
+    const double can = -de + ce, cap = -de - cp;
+    double dfixi = gP[0] * fxp + gN[0] * fxn, dfiyi = gP[1] * fxp + gN[1] * fxn, dfizi = gP[2] * fxp + gN[2] * fxn;
+    dfixi = dfixi * (arx - Df * xpn); dfiyi = dfiyi * (ary - Df * ypn); dfizi = dfizi * (arz - Df * zpn);
+    const double fdfie = dcoef * (dfixi + dfiyi + dfizi);
+    const double xf = q.xf, yf = q.yf, zf = q.zf;
+    double fii;
+    if (fm >= 0.0) fii = face_value_dev(g.cscheme, phiP, phiN, gP, gN, xP, yP, zP, xN, yN, zN, xf, yf, zf, fxp);
+    else fii = face_value_dev(g.cscheme, phiN, phiP, gN, gP, xN, yN, zN, xP, yP, zP, xf, yf, zf, fxn);
+    double fcfie = fm * fii;
+    const double fcfii = ce * phiN + cp * phiP;
+    fcfie = g.gds * (fcfie - fcfii);
+    const double suadd = -fcfie + fdfie;
+    if (own) { g.a[sl] = can; s = s + suadd; }          // a(icell,jcell) = can ; su(ijp) += suadd
+    else     { g.a[sl] = cap; s = s - suadd; }          // a(jcell,icell) = cap ; su(ijn) -= suadd
+  } else {
+    const int type = -1 - sl;
+    if (type == FCP_BC_INLET || type == FCP_BC_OUTLET || type == FCP_BC_PRESSURE) {
+      // ---- facefluxsc_boundary :236-300
+      const double prf = (KIND == 3 || KIND == 4) ? sst_prtr<KIND>(g.fsst[c]) : g.prtr;
+      const double viste = g.vis[o] - g.viscos, dcoef = g.viscos + viste * prf;
+      const double xpn = m.xf[f] - xc, ypn = m.yf[f] - yc, zpn = m.zf[f] - zc;
+      const double Dfi = (arx * arx + ary * ary + arz * arz) / (xpn * arx + ypn * ary + zpn * arz);
+      const double de = dcoef * Dfi;
+      const double ce = fmin(g.flmass[f], 0.0);
+      const double can = -de + ce;
+      double dfixi = gc[0], dfiyi = gc[1], dfizi = gc[2];
+      dfixi = dfixi * (arx - Dfi * xpn); dfiyi = dfiyi * (ary - Dfi * ypn); dfizi = dfizi * (arz - Dfi * zpn);
+      const double suadd = dcoef * (dfixi + dfiyi + dfizi);
+      p = p - can;
+      s = s - can * g.phi[o] + suadd;
+    } else if (m.per_cell && (type == FCP_BC_PERIODIC || type == FCP_BC_EMPTY) && m.per_cell[f - m.F] >= 0) {
+      // ---- facefluxsc_periodic :145-232 in the orientation of the PERIODIC face fp (quirk Q21: Df(i), i = ordinal in the patch)
+      const int32_t b = f - m.F, q = m.per_cell[b];
+      const bool own = type == FCP_BC_PERIODIC;
+      const int32_t fp = own ? f : m.per_face[b];
+      const double ax = m.arx[fp], ay = m.ary[fp], az = m.arz[fp];
+      const double xo = m.xc[q], yo = m.yc[q], zo = m.zc[q], phio_ = g.phi[q], viso = g.vis[q];
+      const double go[3] = {g.g[3 * (int64_t)q], g.g[3 * (int64_t)q + 1], g.g[3 * (int64_t)q + 2]};
+      const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo;
+      double phiP = own ? phic : phio_, phiN = own ? phio_ : phic;
+      if (KIND == 2 || KIND == 4) {                      // wall cells already hold their imposed epsilon / omega when a later patch reads them
+        phiP = eps_value_at_face<KIND>(m, g, own ? c : q, fp, phiP);
+        phiN = eps_value_at_face<KIND>(m, g, own ? q : c, fp, phiN);
+      }
+      const double visP = own ? visc : viso, visN = own ? viso : visc;
+      const double gP[3] = {own ? gc[0] : go[0], own ? gc[1] : go[1], own ? gc[2] : go[2]};
+      const double gN[3] = {own ? go[0] : gc[0], own ? go[1] : gc[1], own ? go[2] : gc[2]};
+      const double fxn = 0.5, fxp = fxn;
+      const double prf = (KIND == 3 || KIND == 4) ? 0.5 * (sst_prtr<KIND>(g.fsst[own ? c : q]) + sst_prtr<KIND>(g.fsst[own ? q : c])) : g.prtr;
+      const double viste = 0.5 * (visP + visN) - g.viscos, dcoef = g.viscos + viste * prf;
+      const double xpn = 2 * (m.xf[fp] - xP), ypn = 2 * (m.yf[fp] - yP), zpn = 2 * (m.zf[fp] - zP);
+      const double Dfq = m.per_df[b], fm = g.flmass[fp];
+      const double de = dcoef * Dfq;
+      const double ce = fmin(fm, 0.0), cp = fmax(fm, 0.0);
+      const double can = -de + ce, cap = -de - cp;
+      double dfixi = gP[0] * fxp + gN[0] * fxn, dfiyi = gP[1] * fxp + gN[1] * fxn, dfizi = gP[2] * fxp + gN[2] * fxn;
+      dfixi = dfixi * (ax - Dfq * xpn); dfiyi = dfiyi * (ay - Dfq * ypn); dfizi = dfizi * (az - Dfq * zpn);
+      const double fdfie = dcoef * (dfixi + dfiyi + dfizi);
+      double fii;
+      if (fm >= 0.0) fii = phiP + (phiN - phiP) * fxp; else fii = phiN + (phiP - phiN) * fxn;
+      double fcfie = fm * fii;
+      const double fcfii = ce * phiN + cp * phiP;
+      fcfie = g.gds * (fcfie - fcfii);
+      const double suadd = -fcfie + fdfie;
+      if (own) { g.a[m.per_slot[b]] = can; s = s + suadd; }
+      else     { g.a[m.per_slot[b]] = cap; s = s - suadd; }
+    } else if (type == FCP_BC_WALL && (KIND == 1 || KIND == 3)) {
+      // ---- wall function for k, k_epsilon_rlzb.f90:331-368: production from the wall shear stress replaces the standard one
+      const double viss = fmax(g.viscos, g.visw[o]);
+      const double are = sqrt(arx * arx + ary * ary + arz * arz);
+      const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
+      const double uc = g.u[c], vc = g.v[c], wc = g.w[c];
+      const double Vnp = uc * nxf + vc * nyf + wc * nzf;
+      double xtp = uc - Vnp * nxf, ytp = vc - Vnp * nyf, ztp = wc - Vnp * nzf;
+      const double Vtp = sqrt(xtp * xtp + ytp * ytp + ztp * ztp);
+      xtp = xtp / Vtp; ytp = ytp / Vtp; ztp = ztp / Vtp;
+      const double Ut2 = fabs((g.u[o] - uc) * xtp + (g.v[o] - vc) * ytp + (g.w[o] - wc) * ztp);
+      const double dn = g.dnw[o];
+      const double tau = viss * Ut2 / dn;
+      g.tau[o] = tau;
+      s = s - genc * vol;
+      genc = fabs(tau) * cmu25_dev() * sqrt(phic) / (dn * FCP_CAPPA);
+      s = s + genc * vol;
+    } else if (type == FCP_BC_WALL && KIND == 2) {
+      // ---- wall cells of the epsilon equation :712-728: the row is cleared, sp = 1, su = ed = cmu75 k^1.5/(cappa dnw)
+      const int64_t base = m.a_slptr[c >> 5] + (c & 31);
+      const int32_t len = m.a_rinfo[c] & 0xffff;
+      for (int32_t k = 0; k < len; ++k) g.a[base + (int64_t)k * 32] = 0.0;
+      p = 1.0;
+      phin = wall_imposed_value<2>(g, c, g.dnw[o]);
+      s = phin;
+    } else if (type == FCP_BC_WALL && KIND == 4) {
+      // ---- wall cells of the omega equation, k_omega_SST.f90:668-680
+      const int64_t base = m.a_slptr[c >> 5] + (c & 31);
+      const int32_t len = m.a_rinfo[c] & 0xffff;
+      phin = wall_imposed_value<4>(g, c, g.dnw[o]);
+      s = phin;
+      for (int32_t k = 0; k < len; ++k) g.a[base + (int64_t)k * 32] = 0.0;
+      p = 1.0;
+    }
+  }
+  }
+}
+
+// Staged face lists (fvm_common.cuh) and gather rounds of W = 2 faces: the 19 operands of two faces are in flight together and the list of the
+// next cell travels meanwhile, so a hexahedron costs three memory round trips instead of twelve.  Faces are evaluated one by one in list order
+// (the wall branches overwrite what earlier faces wrote).  Cells with more faces than the stage holds walk the lists in global memory.
+template <int KIND, int WS>
+__global__ void __launch_bounds__(FCP_TPB, 2) k_sc_assemble(MeshView m, ScArgs g) {
+  FCP_STAGE_DYN_N(WS, 2, stage);
+  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c], vol = m.vol[c];
     const double phic = g.phi[c], visc = g.vis[c], denc = g.den[c];
     const double gc[3] = {g.g[3 * (int64_t)c], g.g[3 * (int64_t)c + 1], g.g[3 * (int64_t)c + 2]};
@@ -172,138 +324,45 @@ __global__ void __launch_bounds__(FCP_TPB) k_sc_assemble(MeshView m, ScArgs g) {
     // the reference's order is "inner faces, then the patches", and the wall branches of the epsilon / omega equations overwrite what the inner
     // faces wrote (row, su, sp).  Two passes restore that order: two-sided faces first, boundary faces second.
     const int npass = m.a_llen ? 2 : 1;
-    const int64_t fbase__ = m.slptr[c >> 5] + (c & 31);
-    const int32_t flen__ = m.len[c];
-    for (int pass = 0; pass < npass; ++pass)
-    for (int32_t q__ = 0; q__ < flen__; ++q__) {
-      FCP_FACE_FETCH(m);
-      if (npass == 2 && ((sl >= 0) != (pass == 0))) continue;
-      const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
-      if (sl >= 0) {
-        // ---- facefluxsc, scalar_fluxes.f90:32-141, in the face's orientation (P = owner, N = neighbour)
-        const bool own = e > 0;
-        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o], phio_ = g.phi[o], viso = g.vis[o];
-        const double go[3] = {g.g[3 * (int64_t)o], g.g[3 * (int64_t)o + 1], g.g[3 * (int64_t)o + 2]};
-        const double lambda = m.facint[f], Df = m.Df[f], fm = g.flmass[f];
-        const double fxn = lambda, fxp = 1.0 - lambda;
-        const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo, xN = own ? xo : xc, yN = own ? yo : yc, zN = own ? zo : zc;
-        const double phiP = own ? phic : phio_, phiN = own ? phio_ : phic;
-        const double visP = own ? visc : viso, visN = own ? viso : visc;
-        const double gP[3] = {own ? gc[0] : go[0], own ? gc[1] : go[1], own ? gc[2] : go[2]};
-        const double gN[3] = {own ? go[0] : gc[0], own ? go[1] : gc[1], own ? go[2] : gc[2]};
-        const double viste = (visP + (visN - visP) * lambda) - g.viscos;
-        const double prf = (KIND == 3 || KIND == 4) ? sst_prtr<KIND>(g.fsst[own ? c : o]) : g.prtr;   // SST: sigma of the face's OWNER cell
-        const double dcoef = g.viscos + viste * prf;
-        const double xpn = xN - xP, ypn = yN - yP, zpn = zN - zP;
-        const double de = dcoef * Df;
-        const double ce = fmin(fm, 0.0), cp = fmax(fm, 0.0);
-        const double can = -de + ce, cap = -de - cp;
-        double dfixi = gP[0] * fxp + gN[0] * fxn, dfiyi = gP[1] * fxp + gN[1] * fxn, dfizi = gP[2] * fxp + gN[2] * fxn;
-        dfixi = dfixi * (arx - Df * xpn); dfiyi = dfiyi * (ary - Df * ypn); dfizi = dfizi * (arz - Df * zpn);
-        const double fdfie = dcoef * (dfixi + dfiyi + dfizi);
-        const double xf = m.xf[f], yf = m.yf[f], zf = m.zf[f];
-        double fii;
-        if (fm >= 0.0) fii = face_value_dev(g.cscheme, phiP, phiN, gP, gN, xP, yP, zP, xN, yN, zN, xf, yf, zf, fxp);
-        else fii = face_value_dev(g.cscheme, phiN, phiP, gN, gP, xN, yN, zN, xP, yP, zP, xf, yf, zf, fxn);
-        double fcfie = fm * fii;
-        const double fcfii = ce * phiN + cp * phiP;
-        fcfie = g.gds * (fcfie - fcfii);
-        const double suadd = -fcfie + fdfie;
-        if (own) { g.a[sl] = can; s = s + suadd; }          // a(icell,jcell) = can ; su(ijp) += suadd
-        else     { g.a[sl] = cap; s = s - suadd; }          // a(jcell,icell) = cap ; su(ijn) -= suadd
-      } else {
-        const int type = -1 - sl;
-        if (type == FCP_BC_INLET || type == FCP_BC_OUTLET || type == FCP_BC_PRESSURE) {
-          // ---- facefluxsc_boundary :236-300
-          const double prf = (KIND == 3 || KIND == 4) ? sst_prtr<KIND>(g.fsst[c]) : g.prtr;
-          const double viste = g.vis[o] - g.viscos, dcoef = g.viscos + viste * prf;
-          const double xpn = m.xf[f] - xc, ypn = m.yf[f] - yc, zpn = m.zf[f] - zc;
-          const double Dfi = (arx * arx + ary * ary + arz * arz) / (xpn * arx + ypn * ary + zpn * arz);
-          const double de = dcoef * Dfi;
-          const double ce = fmin(g.flmass[f], 0.0);
-          const double can = -de + ce;
-          double dfixi = gc[0], dfiyi = gc[1], dfizi = gc[2];
-          dfixi = dfixi * (arx - Dfi * xpn); dfiyi = dfiyi * (ary - Dfi * ypn); dfizi = dfizi * (arz - Dfi * zpn);
-          const double suadd = dcoef * (dfixi + dfiyi + dfizi);
-          p = p - can;
-          s = s - can * g.phi[o] + suadd;
-        } else if (m.per_cell && (type == FCP_BC_PERIODIC || type == FCP_BC_EMPTY) && m.per_cell[f - m.F] >= 0) {
-          // ---- facefluxsc_periodic :145-232 in the orientation of the PERIODIC face fp (quirk Q21: Df(i), i = ordinal in the patch)
-          const int32_t b = f - m.F, q = m.per_cell[b];
-          const bool own = type == FCP_BC_PERIODIC;
-          const int32_t fp = own ? f : m.per_face[b];
-          const double ax = m.arx[fp], ay = m.ary[fp], az = m.arz[fp];
-          const double xo = m.xc[q], yo = m.yc[q], zo = m.zc[q], phio_ = g.phi[q], viso = g.vis[q];
-          const double go[3] = {g.g[3 * (int64_t)q], g.g[3 * (int64_t)q + 1], g.g[3 * (int64_t)q + 2]};
-          const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo;
-          double phiP = own ? phic : phio_, phiN = own ? phio_ : phic;
-          if (KIND == 2 || KIND == 4) {                      // wall cells already hold their imposed epsilon / omega when a later patch reads them
-            phiP = eps_value_at_face<KIND>(m, g, own ? c : q, fp, phiP);
-            phiN = eps_value_at_face<KIND>(m, g, own ? q : c, fp, phiN);
+    const ScCell cc{xc, yc, zc, vol, phic, visc, denc, {gc[0], gc[1], gc[2]}};
+    constexpr int W = 2;
+    const int32_t flen = stage.len(st);
+    if (flen <= WS) {
+      for (int pass = 0; pass < npass; ++pass)
+        for (int32_t q0 = 0; q0 < flen; q0 += W) {
+          int32_t e_[W], o_[W], sl_[W];
+          ScOps q_[W];
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            const bool in = q0 + k < flen;
+            const int idx = in ? q0 + k : 0;
+            sl_[k] = in ? stage.slot(st, idx, false) : -1;
+            o_[k] = in ? stage.oth(st, idx) : 0;
+            const bool act = in && !(npass == 2 && ((sl_[k] >= 0) != (pass == 0)));
+            e_[k] = act ? stage.ent(st, idx) : 0;
+            sc_gather<KIND>(m, g, c, e_[k], o_[k], act && sl_[k] >= 0, q_[k]);
           }
-          const double visP = own ? visc : viso, visN = own ? viso : visc;
-          const double gP[3] = {own ? gc[0] : go[0], own ? gc[1] : go[1], own ? gc[2] : go[2]};
-          const double gN[3] = {own ? go[0] : gc[0], own ? go[1] : gc[1], own ? go[2] : gc[2]};
-          const double fxn = 0.5, fxp = fxn;
-          const double prf = (KIND == 3 || KIND == 4) ? 0.5 * (sst_prtr<KIND>(g.fsst[own ? c : q]) + sst_prtr<KIND>(g.fsst[own ? q : c])) : g.prtr;
-          const double viste = 0.5 * (visP + visN) - g.viscos, dcoef = g.viscos + viste * prf;
-          const double xpn = 2 * (m.xf[fp] - xP), ypn = 2 * (m.yf[fp] - yP), zpn = 2 * (m.zf[fp] - zP);
-          const double Dfq = m.per_df[b], fm = g.flmass[fp];
-          const double de = dcoef * Dfq;
-          const double ce = fmin(fm, 0.0), cp = fmax(fm, 0.0);
-          const double can = -de + ce, cap = -de - cp;
-          double dfixi = gP[0] * fxp + gN[0] * fxn, dfiyi = gP[1] * fxp + gN[1] * fxn, dfizi = gP[2] * fxp + gN[2] * fxn;
-          dfixi = dfixi * (ax - Dfq * xpn); dfiyi = dfiyi * (ay - Dfq * ypn); dfizi = dfizi * (az - Dfq * zpn);
-          const double fdfie = dcoef * (dfixi + dfiyi + dfizi);
-          double fii;
-          if (fm >= 0.0) fii = phiP + (phiN - phiP) * fxp; else fii = phiN + (phiP - phiN) * fxn;
-          double fcfie = fm * fii;
-          const double fcfii = ce * phiN + cp * phiP;
-          fcfie = g.gds * (fcfie - fcfii);
-          const double suadd = -fcfie + fdfie;
-          if (own) { g.a[m.per_slot[b]] = can; s = s + suadd; }
-          else     { g.a[m.per_slot[b]] = cap; s = s - suadd; }
-        } else if (type == FCP_BC_WALL && (KIND == 1 || KIND == 3)) {
-          // ---- wall function for k, k_epsilon_rlzb.f90:331-368: production from the wall shear stress replaces the standard one
-          const double viss = fmax(g.viscos, g.visw[o]);
-          const double are = sqrt(arx * arx + ary * ary + arz * arz);
-          const double nxf = arx / are, nyf = ary / are, nzf = arz / are;
-          const double uc = g.u[c], vc = g.v[c], wc = g.w[c];
-          const double Vnp = uc * nxf + vc * nyf + wc * nzf;
-          double xtp = uc - Vnp * nxf, ytp = vc - Vnp * nyf, ztp = wc - Vnp * nzf;
-          const double Vtp = sqrt(xtp * xtp + ytp * ytp + ztp * ztp);
-          xtp = xtp / Vtp; ytp = ytp / Vtp; ztp = ztp / Vtp;
-          const double Ut2 = fabs((g.u[o] - uc) * xtp + (g.v[o] - vc) * ytp + (g.w[o] - wc) * ztp);
-          const double dn = g.dnw[o];
-          const double tau = viss * Ut2 / dn;
-          g.tau[o] = tau;
-          s = s - genc * vol;
-          genc = fabs(tau) * cmu25_dev() * sqrt(phic) / (dn * FCP_CAPPA);
-          s = s + genc * vol;
-        } else if (type == FCP_BC_WALL && KIND == 2) {
-          // ---- wall cells of the epsilon equation :712-728: the row is cleared, sp = 1, su = ed = cmu75 k^1.5/(cappa dnw)
-          const int64_t base = m.a_slptr[c >> 5] + (c & 31);
-          const int32_t len = m.a_rinfo[c] & 0xffff;
-          for (int32_t k = 0; k < len; ++k) g.a[base + (int64_t)k * 32] = 0.0;
-          p = 1.0;
-          phin = wall_imposed_value<2>(g, c, g.dnw[o]);
-          s = phin;
-        } else if (type == FCP_BC_WALL && KIND == 4) {
-          // ---- wall cells of the omega equation, k_omega_SST.f90:668-680
-          const int64_t base = m.a_slptr[c >> 5] + (c & 31);
-          const int32_t len = m.a_rinfo[c] & 0xffff;
-          phin = wall_imposed_value<4>(g, c, g.dnw[o]);
-          s = phin;
-          for (int32_t k = 0; k < len; ++k) g.a[base + (int64_t)k * 32] = 0.0;
-          p = 1.0;
+#pragma unroll
+          for (int k = 0; k < W; ++k)
+            if (e_[k] != 0) sc_face<KIND>(m, g, c, cc, e_[k], o_[k], sl_[k], q_[k], s, p, genc, phin);
         }
-      }
+    } else {
+      const int64_t fbase__ = m.slptr[c >> 5] + (c & 31);
+      const int32_t flen__ = flen;
+      for (int pass = 0; pass < npass; ++pass)
+        for (int32_t q__ = 0; q__ < flen__; ++q__) {
+          FCP_FACE_FETCH(m);
+          if (npass == 2 && ((sl >= 0) != (pass == 0))) continue;
+          ScOps q;
+          sc_gather<KIND>(m, g, c, e, o, sl >= 0, q);
+          sc_face<KIND>(m, g, c, cc, e, o, sl, q, s, p, genc, phin);
+        }
     }
     g.su[c] = s;
     g.sp[c] = p;
     g.phi_new[c] = phin;
     if (KIND == 1 || KIND == 3) g.gen[c] = genc;
-  }
+  FCP_STAGED_LOOP_END
 }
 
 // a(diag) = sp; a(diag) -= a(k) for the off-diagonals in CSR order; under-relaxation; phi <- the value the reference holds at this point
@@ -389,39 +448,63 @@ __global__ void __launch_bounds__(FCP_TPB) k_mu_eff_wall(MeshView m, const int32
 // LES sub-grid viscosity (wale_sgs.f90, vremanSGS.f90): fvxGradient's Grad(U) (the two-pass Gauss gradient with the gradco skewness
 // correction, fvxGradient.f90:1549-1662, 1761-1838) + the tensorFields algebra, one thread per cell.
 // ---------------------------------------------------------------------------------------------
-// one pass: gnew = (sum over faces of fie S)/vol with fie interpolated with the OLD gradient gold (zero in the first pass)
-__global__ void __launch_bounds__(FCP_TPB) k_grad_gauss_fvx(MeshView m, const double *__restrict__ u, const double *__restrict__ gold,
-                                                             double *__restrict__ gnew) {
-  FCP_CELL_LOOP(c, m.n) {
+// one pass: gnew = (sum over faces of fie S)/vol with fie interpolated with the OLD gradient gold (zero in the first pass).  Staged lists and
+// gather rounds of W = 3 faces like k_grad_gauss (fvm.cu): a hexahedron costs two memory round trips instead of twelve; the arithmetic per face
+// and the face order are unchanged.
+template <int WS>
+__global__ void __launch_bounds__(FCP_TPB, 2) k_grad_gauss_fvx(MeshView m, const double *__restrict__ u, const double *__restrict__ gold,
+                                                                double *__restrict__ gnew) {
+  FCP_STAGE_DYN_N(WS, 2, stage);
+  FCP_STAGED_LOOP_BEGIN(stage, m, m.n, c, st)
     const double xc = m.xc[c], yc = m.yc[c], zc = m.zc[c], uc = u[c];
+    const double vol = __ldg(m.vol + c);
     const double ocx = gold ? gold[3 * (int64_t)c] : 0.0, ocy = gold ? gold[3 * (int64_t)c + 1] : 0.0, ocz = gold ? gold[3 * (int64_t)c + 2] : 0.0;
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    FCP_FACE_LOOP(m, c) {
-      FCP_FACE_FETCH(m);
-      const double arx = m.arx[f], ary = m.ary[f], arz = m.arz[f];
-      if (sl >= 0) {                                       // gradco, in the face's orientation (P = owner, N = neighbour)
-        const bool own = e > 0;
-        const double fxn = m.facint[f], fxp = 1.0 - fxn;
-        const double xo = m.xc[o], yo = m.yc[o], zo = m.zc[o], uo = u[o];
-        const double oox = gold ? gold[3 * (int64_t)o] : 0.0, ooy = gold ? gold[3 * (int64_t)o + 1] : 0.0, ooz = gold ? gold[3 * (int64_t)o + 2] : 0.0;
-        const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo, xN = own ? xo : xc, yN = own ? yo : yc, zN = own ? zo : zc;
-        const double uP = own ? uc : uo, uN = own ? uo : uc;
-        const double gPx = own ? ocx : oox, gPy = own ? ocy : ooy, gPz = own ? ocz : ooz;
-        const double gNx = own ? oox : ocx, gNy = own ? ooy : ocy, gNz = own ? ooz : ocz;
-        const double xi = xP * fxp + xN * fxn, yi = yP * fxp + yN * fxn, zi = zP * fxp + zN * fxn;
-        const double dfxi = gPx * fxp + gNx * fxn, dfyi = gPy * fxp + gNy * fxn, dfzi = gPz * fxp + gNz * fxn;
-        const double fie = uP * fxp + uN * fxn + dfxi * (m.xf[f] - xi) + dfyi * (m.yf[f] - yi) + dfzi * (m.zf[f] - zi);
-        const double dfxe = fie * arx, dfye = fie * ary, dfze = fie * arz;
-        if (own) { sx = sx + dfxe; sy = sy + dfye; sz = sz + dfze; }
-        else     { sx = sx - dfxe; sy = sy - dfye; sz = sz - dfze; }
-      } else {                                             // gradbc
-        const double ub = u[o];
-        sx = sx + ub * arx; sy = sy + ub * ary; sz = sz + ub * arz;
+    constexpr int W = 3;
+    FCP_FACE_BATCHES_STAGED(stage, st, m, c, W) {
+      FCP_BATCH_LISTS_STAGED(stage, st, WS, m, W, e_, o_, sl_);
+      double ax_[W], ay_[W], az_[W], lam_[W], fx_[W], fy_[W], fz_[W], xo_[W], yo_[W], zo_[W], uo_[W], gx_[W], gy_[W], gz_[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const int32_t f = (e_[k] > 0 ? e_[k] : -e_[k]) - 1;
+        const bool on = e_[k] != 0, two = on && sl_[k] >= 0;
+        const int64_t o = o_[k];
+        ax_[k] = on ? __ldg(m.arx + f) : 0.0; ay_[k] = on ? __ldg(m.ary + f) : 0.0; az_[k] = on ? __ldg(m.arz + f) : 0.0;
+        uo_[k] = on ? __ldg(u + o) : 0.0;
+        lam_[k] = two ? __ldg(m.facint + f) : 0.0;
+        fx_[k] = two ? __ldg(m.xf + f) : 0.0; fy_[k] = two ? __ldg(m.yf + f) : 0.0; fz_[k] = two ? __ldg(m.zf + f) : 0.0;
+        xo_[k] = two ? __ldg(m.xc + o) : 0.0; yo_[k] = two ? __ldg(m.yc + o) : 0.0; zo_[k] = two ? __ldg(m.zc + o) : 0.0;
+        gx_[k] = (two && gold) ? __ldg(gold + 3 * o) : 0.0; gy_[k] = (two && gold) ? __ldg(gold + 3 * o + 1) : 0.0;
+        gz_[k] = (two && gold) ? __ldg(gold + 3 * o + 2) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        if (e_[k] == 0) continue;
+        const double arx = ax_[k], ary = ay_[k], arz = az_[k];
+        if (sl_[k] >= 0) {                                   // gradco, in the face's orientation (P = owner, N = neighbour)
+          const bool own = e_[k] > 0;
+          const double fxn = lam_[k], fxp = 1.0 - fxn;
+          const double xo = xo_[k], yo = yo_[k], zo = zo_[k], uo = uo_[k];
+          const double oox = gx_[k], ooy = gy_[k], ooz = gz_[k];
+          const double xP = own ? xc : xo, yP = own ? yc : yo, zP = own ? zc : zo, xN = own ? xo : xc, yN = own ? yo : yc, zN = own ? zo : zc;
+          const double uP = own ? uc : uo, uN = own ? uo : uc;
+          const double gPx = own ? ocx : oox, gPy = own ? ocy : ooy, gPz = own ? ocz : ooz;
+          const double gNx = own ? oox : ocx, gNy = own ? ooy : ocy, gNz = own ? ooz : ocz;
+          const double xi = xP * fxp + xN * fxn, yi = yP * fxp + yN * fxn, zi = zP * fxp + zN * fxn;
+          const double dfxi = gPx * fxp + gNx * fxn, dfyi = gPy * fxp + gNy * fxn, dfzi = gPz * fxp + gNz * fxn;
+          const double fie = uP * fxp + uN * fxn + dfxi * (fx_[k] - xi) + dfyi * (fy_[k] - yi) + dfzi * (fz_[k] - zi);
+          const double dfxe = fie * arx, dfye = fie * ary, dfze = fie * arz;
+          if (own) { sx = sx + dfxe; sy = sy + dfye; sz = sz + dfze; }
+          else     { sx = sx - dfxe; sy = sy - dfye; sz = sz - dfze; }
+        } else {                                             // gradbc
+          const double ub = uo_[k];
+          sx = sx + ub * arx; sy = sy + ub * ary; sz = sz + ub * arz;
+        }
       }
     }
-    const double volr = 1.0 / m.vol[c];
+    const double volr = 1.0 / vol;
     gnew[3 * (int64_t)c] = sx * volr; gnew[3 * (int64_t)c + 1] = sy * volr; gnew[3 * (int64_t)c + 2] = sz * volr;
-  }
+  FCP_STAGED_LOOP_END
 }
 
 // tensors as t[9] = xx xy xz yx yy yz zx zy zz (tensorFields.f90)
@@ -518,12 +601,19 @@ __global__ void __launch_bounds__(FCP_TPB) k_sgs_boundary(MeshView m, const int3
 // npass = nigrad: the iterative Gauss gradient of the MPI tree, src-par/gradients.f90:1547-1664.
 int fvm_grad_gauss_passes(fcp_ctx *ctx, const double *u, double *gtmp, double *g, int npass) {
   if (ctx->n == 0) return FCP_OK;
-  const MeshView m = fcp_mesh_view(ctx);
+  MeshView m = fcp_mesh_view(ctx);
+  if (fcp_face_variant(FCP_FK_GRAD_GAUSS).cl) m.kinds = ctx->fl.kinds;
+  const bool wide = ctx->max_cell_faces > 6;
+  const int grid = std::max(fcp_nchunks(ctx->n), 1);
+  size_t smem6 = 0, smem10 = 0;
+  if (wide) FCP_TRY((fcp_stage_smem<10, 2>(k_grad_gauss_fvx<10>, &smem10)));
+  else FCP_TRY((fcp_stage_smem<6, 2>(k_grad_gauss_fvx<6>, &smem6)));
   size_t tok = ctx->prof.begin(FCP_K_GRAD, ctx->stream);
   const double *gold = nullptr;
   for (int lc = 1; lc <= npass; ++lc) {
     double *out = ((npass - lc) % 2 == 0) ? g : gtmp;
-    k_grad_gauss_fvx<<<FCP_GRID(ctx->n)>>>(m, u, gold, out);
+    if (wide) k_grad_gauss_fvx<10><<<grid, FCP_TPB, smem10, ctx->stream>>>(m, u, gold, out);
+    else k_grad_gauss_fvx<6><<<grid, FCP_TPB, smem6, ctx->stream>>>(m, u, gold, out);
     FCP_LAUNCHED();
     if (lc != npass && ctx->comm) FCP_TRY(comm_exchange(ctx, out, 3));      // the next pass interpolates this pass's gradient across process faces
     gold = out;
@@ -632,11 +722,26 @@ int fvm_sc_assemble(fcp_ctx *ctx, const ScParams &q) {
   g.fsst = q.fsst; g.walldist = q.walldist; g.gte = q.gte; g.lowre = q.lowre;
   const MeshView m = fcp_mesh_view(ctx);
   size_t tok = ctx->prof.begin(FCP_K_SCALAR, ctx->stream);
-  if (q.kind == 0) k_sc_assemble<0><<<FCP_GRID(ctx->n)>>>(m, g);
-  else if (q.kind == 1) k_sc_assemble<1><<<FCP_GRID(ctx->n)>>>(m, g);
-  else if (q.kind == 2) k_sc_assemble<2><<<FCP_GRID(ctx->n)>>>(m, g);
-  else if (q.kind == 3) k_sc_assemble<3><<<FCP_GRID(ctx->n)>>>(m, g);
-  else k_sc_assemble<4><<<FCP_GRID(ctx->n)>>>(m, g);
+  {
+    const int grid = std::max(fcp_nchunks(ctx->n), 1);
+    size_t smem = 0;
+#define SC_LAUNCH(KIND)                                                                                   \
+  do {                                                                                                    \
+    if (ctx->max_cell_faces > 6) {                                                                        \
+      FCP_TRY((fcp_stage_smem<10, 2>(k_sc_assemble<KIND, 10>, &smem)));                                   \
+      k_sc_assemble<KIND, 10><<<grid, FCP_TPB, smem, ctx->stream>>>(m, g);                                \
+    } else {                                                                                              \
+      FCP_TRY((fcp_stage_smem<6, 2>(k_sc_assemble<KIND, 6>, &smem)));                                     \
+      k_sc_assemble<KIND, 6><<<grid, FCP_TPB, smem, ctx->stream>>>(m, g);                                 \
+    }                                                                                                     \
+  } while (0)
+    if (q.kind == 0) SC_LAUNCH(0);
+    else if (q.kind == 1) SC_LAUNCH(1);
+    else if (q.kind == 2) SC_LAUNCH(2);
+    else if (q.kind == 3) SC_LAUNCH(3);
+    else SC_LAUNCH(4);
+#undef SC_LAUNCH
+  }
   ctx->prof.end(tok, ctx->stream);
   FCP_LAUNCHED();
   k_sc_diag<<<FCP_GRID(ctx->n)>>>(m, q.a, q.sp, q.su, q.phi_new, q.phi_out, q.urf);

@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--n", "--cells", dest="n", type=int, default=256)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--periodic", action="store_true", help="periodic x and z (channel395-style) instead of the closed cavity")
-    ap.add_argument("--only", default="", help="substring filter on the operation names (A/B runs of one kernel)")
+    ap.add_argument("--only", default="", help="comma-separated substring filter on the operation names (A/B runs of a few kernels)")
     args = ap.parse_args()
     import fcb200  # noqa: F401
     from fcb200 import lib as L
@@ -86,7 +86,7 @@ def main():
     ctx.create_lsq_grad_matrix(L.GRAD_LSQ)
     ctx.calc_strain_and_vorticity()
     for name, fn, klass, nbytes in ops:
-        if args.only and args.only not in name:
+        if args.only and not any(t and t in name for t in args.only.split(",")):
             continue
         fn()                                        # warm-up (allocates lazily created fields, builds level schedules ...)
         ctx.sync()

@@ -12,6 +12,26 @@
 #include "reduce.cuh"
 #include "fvm_common.cuh"
 
+// array-of-structures copy of the face geometry the gather kernels read together (fcp_face_geo)
+__global__ void __launch_bounds__(FCP_TPB) k_build_fgeo(int32_t nF, const double *__restrict__ arx, const double *__restrict__ ary, const double *__restrict__ arz,
+                                                         const double *__restrict__ facint, double *__restrict__ fgeo) {
+  for (int32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+    fgeo[4 * (int64_t)f] = arx[f]; fgeo[4 * (int64_t)f + 1] = ary[f]; fgeo[4 * (int64_t)f + 2] = arz[f]; fgeo[4 * (int64_t)f + 3] = facint[f];
+  }
+}
+int fvm_ensure_fgeo(fcp_ctx *ctx) {
+  if (ctx->fgeo_valid) return FCP_OK;
+  const int32_t nF = ctx->F + ctx->B;
+  if (!ctx->fgeo) FCP_TRY(dev_alloc(&ctx->fgeo, 4 * (size_t)std::max(nF, 1)));
+  if (nF > 0) {
+    k_build_fgeo<<<std::min((nF + FCP_TPB - 1) / FCP_TPB, 148 * 16), FCP_TPB, 0, ctx->stream>>>(nF, ctx->arx, ctx->ary, ctx->arz, ctx->facint, ctx->fgeo);
+    FCP_LAUNCHED();
+    FCP_CHECK_LAUNCH();
+  }
+  ctx->fgeo_valid = true;
+  return FCP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // grad_gauss   gradients.f90:1607-1693
 // ---------------------------------------------------------------------------------------------
@@ -54,8 +74,7 @@ __global__ void __launch_bounds__(FCP_TPB, MINB) k_grad_gauss(MeshView m, const 
         const int32_t f = (e[k] > 0 ? e[k] : -e[k]) - 1;
         const bool on = e[k] != 0;
         uo[k] = on ? __ldg(u + o[k]) : 0.0;
-        lam[k] = (on && sl[k] >= 0) ? __ldg(m.facint + f) : 0.0;
-        sx[k] = on ? __ldg(m.arx + f) : 0.0; sy[k] = on ? __ldg(m.ary + f) : 0.0; sz[k] = on ? __ldg(m.arz + f) : 0.0;
+        fcp_face_geo(m, f, on, on && sl[k] >= 0, sx[k], sy[k], sz[k], lam[k]);
       }
 #pragma unroll
       for (int k = 0; k < W; ++k) {
@@ -399,8 +418,7 @@ __device__ __forceinline__ void gradp_cell_fast(const MeshView &m, int32_t c, co
     // p: inner-face (cell / ghost) values are never written by this kernel -> non-coherent loads; pressure-patch values likewise
     pv[k] = (two || (bnd && (-1 - sl[k]) == FCP_BC_PRESSURE)) ? __ldg(p + o[k]) : 0.0;
     if (WEIGHTED) ao[k] = two ? __ldg(apu + o[k]) : 0.0;
-    lam[k] = two ? __ldg(m.facint + f) : 0.0;
-    sx[k] = on ? __ldg(m.arx + f) : 0.0; sy[k] = on ? __ldg(m.ary + f) : 0.0; sz[k] = on ? __ldg(m.arz + f) : 0.0;
+    fcp_face_geo(m, f, on, two, sx[k], sy[k], sz[k], lam[k]);
   }
   double s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -696,8 +714,8 @@ __global__ void __launch_bounds__(FCP_TPB, ((W >= 3 || MPIF) ? 1 : W == 2 ? 2 : 
         const int32_t f = (e_[k] > 0 ? e_[k] : -e_[k]) - 1;
         const bool on = e_[k] != 0, two = on && sl_[k] >= 0;
         const int32_t o = o_[k];
-        sx_[k] = on ? __ldg(m.arx + f) : 0.0; sy_[k] = on ? __ldg(m.ary + f) : 0.0; sz_[k] = on ? __ldg(m.arz + f) : 0.0;
-        lam_[k] = two ? __ldg(m.facint + f) : 0.0; Df_[k] = two ? __ldg(m.Df + f) : 0.0;
+        fcp_face_geo(m, f, on, two, sx_[k], sy_[k], sz_[k], lam_[k]);
+        Df_[k] = two ? __ldg(m.Df + f) : 0.0;
         xo_[k] = two ? __ldg(m.xc + o) : 0.0; yo_[k] = two ? __ldg(m.yc + o) : 0.0; zo_[k] = two ? __ldg(m.zc + o) : 0.0;
         deno_[k] = two ? __ldg(g.den + o) : 0.0; volo_[k] = two ? __ldg(m.vol + o) : 0.0; apuo_[k] = two ? __ldg(g.apu + o) : 0.0;
         // u, v, w, p cell values are not written by this kernel (only pressure-patch boundary slots are)
@@ -951,7 +969,7 @@ int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g) {
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   MeshView mv = fcp_mesh_view(ctx);
   const FaceVariant fv = fcp_face_variant(FCP_FK_GRAD_GAUSS);
-  if (fv.cl) mv.kinds = ctx->fl.kinds;
+  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, true));
 #define GG_LAUNCH(WS, MINB, PF)                                                                                                      \
   do {                                                                                                                               \
     FCP_TRY((fcp_stage_smem<WS, (PF) ? 3 : 2>(k_grad_gauss<WS, MINB, PF>, &smem)));                                                  \
@@ -994,7 +1012,7 @@ int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   MeshView mv = fcp_mesh_view(ctx);
   const FaceVariant fv = fcp_face_variant(FCP_FK_GRAD_LSQ);
-  if (fv.cl) mv.kinds = ctx->fl.kinds;
+  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, true));
 #define LSQ_LAUNCH(WT, WS, MINB, PF)                                                                        \
   do {                                                                                                      \
     FCP_TRY((fcp_stage_smem<WS, (PF) ? 3 : 2>(k_grad_lsq<WT, WS, MINB, PF>, &smem)));                       \
@@ -1040,7 +1058,7 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
   size_t smem = 0;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   const FaceVariant fv = fcp_face_variant(FCP_FK_GRADP);
-  if (fv.cl) m.kinds = ctx->fl.kinds;
+  FCP_TRY(fcp_apply_face_variant(ctx, fv, m, true));
 #define GRADP_LAUNCH(C, WG, PF, NST, OUT)                                                                          \
   do {                                                                                                             \
     FCP_TRY((fcp_stage_smem<6, (PF) ? 3 : 2>(k_gradp<C, WG, PF>, &smem)));                                         \
@@ -1082,6 +1100,7 @@ int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso) {
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   size_t tok = ctx->prof.begin(FCP_K_ASSEMBLE, ctx->stream);
   MeshView mv = fcp_mesh_view(ctx);
+  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, false));
 #define ASM_LAUNCH(PISO, W, MPIF, PF)                                                                   \
   do {                                                                                                  \
     FCP_TRY((fcp_stage_smem<6, (PF) ? 3 : 2>(k_assemble_pcorr<PISO, W, MPIF, PF>, &smem)));             \

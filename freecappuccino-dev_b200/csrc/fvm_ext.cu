@@ -78,29 +78,17 @@ __global__ void __launch_bounds__(FCP_TPB) k_limiter_cell(MeshView m, const doub
     const int32_t dpos = (ri >> 16) & 0xffff;
     const int32_t len = ri & 0xffff;     // the whole row: on a partition the cells across process faces are neighbours like any other (ghost copies)
     double slopelimit = 1.0;
-    // rounds of LW row entries: every column index of the round, then every centre gather, then the arithmetic in row order -- two memory round
-    // trips per round (a hexahedron's row is one round) instead of two per entry
-    constexpr int LW = 8;
-    for (int32_t k0 = 0; k0 < len; k0 += LW) {
-      int32_t j_[LW];
-#pragma unroll
-      for (int k = 0; k < LW; ++k) j_[k] = (k0 + k < len && k0 + k != dpos) ? __ldg(m.a_ja + base + (int64_t)(k0 + k) * 32) : -1;
-      double x_[LW], y_[LW], z_[LW];
-#pragma unroll
-      for (int k = 0; k < LW; ++k) {
-        const bool on = j_[k] >= 0;
-        x_[k] = on ? __ldg(m.xc + j_[k]) : 0.0; y_[k] = on ? __ldg(m.yc + j_[k]) : 0.0; z_[k] = on ? __ldg(m.zc + j_[k]) : 0.0;
-      }
-#pragma unroll
-      for (int k = 0; k < LW; ++k) {
-        if (j_[k] < 0) continue;
-        const double delta_face = gx * (x_[k] - xc) + gy * (y_[k] - yc) + gz * (z_[k] - zc);
-        double r;
-        if (fabs(delta_face) < eps) r = 1.0;
-        else if (delta_face > 0.0) r = deltamax / delta_face;
-        else r = deltamin / delta_face;
-        slopelimit = fmin(slopelimit, limiter_fn<KIND>(r));
-      }
+    // (a version that gathered a whole row before the arithmetic -- 8 column indices, then 24 centre loads -- was measured SLOWER on a B200, 0.91 ms
+    // against 0.79 ms at 256^3: 102 registers instead of 48 cost more occupancy than the batching bought)
+    for (int32_t k = 0; k < len; ++k) {
+      if (k == dpos) continue;
+      const int32_t j = m.a_ja[base + (int64_t)k * 32];
+      const double delta_face = gx * (m.xc[j] - xc) + gy * (m.yc[j] - yc) + gz * (m.zc[j] - zc);
+      double r;
+      if (fabs(delta_face) < eps) r = 1.0;
+      else if (delta_face > 0.0) r = deltamax / delta_face;
+      else r = deltamin / delta_face;
+      slopelimit = fmin(slopelimit, limiter_fn<KIND>(r));
     }
     g[3 * (int64_t)c] = slopelimit * gx;
     g[3 * (int64_t)c + 1] = slopelimit * gy;

@@ -3,7 +3,7 @@
 
     python tools/face_ab.py [--n 256] [--reps 5] [--out gpurun_out/r02_face_ab.txt]
 
-The library reads FCP_FACE_OCC / FCP_FACE_PF / FCP_FACE_CL / FCP_ASM_W at every launch of a face kernel, so a variant is selected by setting the
+The library reads FCP_FACE_OCC / FCP_FACE_PF / FCP_FACE_CL / FCP_FACE_AOS / FCP_ASM_W at every launch of a face kernel, so a variant is selected by setting the
 environment between calls.  Per variant: the inputs are restored, every operation runs once and a fingerprint of its results (wrap-around sum
 of the 64-bit patterns) is compared with the first variant's -- a variant that changes a bit is flagged, not timed --, then `reps` timed calls
 with the library's per-class profiler (CUDA events around the launches of the class).  Operations: grad_gauss, grad_lsq (class grad),
@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="")
+    ap.add_argument("--round", type=int, default=2, help="which set of variants (see the code)")
     args = ap.parse_args()
     import fcb200  # noqa: F401
     from fcb200 import lib as L
@@ -98,19 +99,25 @@ def main():
         return out
 
     variants = []
-    for cl in (0, 1):
-        for occ, pf in ((2, 0), (2, 1), (2, 2), (3, 0), (3, 1), (3, 2)):
-            variants.append(dict(FCP_FACE_OCC=occ, FCP_FACE_PF=pf, FCP_FACE_CL=cl, FCP_ASM_W=2))
-    for pf in (0, 1, 2):
-        variants.append(dict(FCP_FACE_OCC=2, FCP_FACE_PF=pf, FCP_FACE_CL=0, FCP_ASM_W=1))
+    if args.round == 1:      # occupancy / L2 prefetch / compact lists / faces per assembly round (profiles/r02_face_ab.txt)
+        for cl in (0, 1):
+            for occ, pf in ((2, 0), (2, 1), (2, 2), (3, 0), (3, 1), (3, 2)):
+                variants.append(dict(FCP_FACE_OCC=occ, FCP_FACE_PF=pf, FCP_FACE_CL=cl, FCP_FACE_AOS=0, FCP_ASM_W=2))
+        for pf in (0, 1, 2):
+            variants.append(dict(FCP_FACE_OCC=2, FCP_FACE_PF=pf, FCP_FACE_CL=0, FCP_FACE_AOS=0, FCP_ASM_W=1))
+    else:                    # array-of-structures face geometry x compact lists (profiles/r02_face_ab2.txt)
+        for aos in (0, 1, 2):
+            for cl in (0, 1):
+                variants.append(dict(FCP_FACE_OCC=2, FCP_FACE_PF=0, FCP_FACE_CL=cl, FCP_FACE_AOS=aos, FCP_ASM_W=2))
     ops = ("grad_gauss", "grad_lsq", "gradp_plain", "gradp_fused", "assemble")
     # which switches each operation listens to (the others only repeat a measurement)
-    listens = dict(grad_gauss=("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL"), grad_lsq=("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL"),
-                   gradp_plain=("FCP_FACE_PF", "FCP_FACE_CL"), gradp_fused=("FCP_FACE_PF", "FCP_FACE_CL"), assemble=("FCP_FACE_PF", "FCP_ASM_W"))
+    listens = dict(grad_gauss=("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS"), grad_lsq=("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL"),
+                   gradp_plain=("FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS"), gradp_fused=("FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS"),
+                   assemble=("FCP_FACE_PF", "FCP_FACE_AOS", "FCP_ASM_W"))
     lines, ref_fp, table = [], None, []
     hdr = f"# face-kernel A/B, {n}^3 hex cavity ({N} cells), ms per launch (mean of {args.reps}), (fraction of the {peak:.0f} GB/s HBM peak); setup {setup_s:.1f} s"
     lines.append(hdr)
-    lines.append("# OCC PF CL ASM_W | " + " | ".join(f"{o:>20s}" for o in ops) + " | bits")
+    lines.append("# OCC PF CL AOS ASM_W | " + " | ".join(f"{o:>20s}" for o in ops) + " | bits")
     print(hdr, flush=True)
     for v in variants:
         for k, val in v.items():
@@ -121,7 +128,7 @@ def main():
         same = all(fp[o] == ref_fp[o] for o in ops)
         ms = run_ops("ms") if same else {o: float("nan") for o in ops}
         table.append((v, ms, same))
-        row = (f"  {v['FCP_FACE_OCC']:3d} {v['FCP_FACE_PF']:2d} {v['FCP_FACE_CL']:2d} {v['FCP_ASM_W']:5d} | " +
+        row = (f"  {v['FCP_FACE_OCC']:3d} {v['FCP_FACE_PF']:2d} {v['FCP_FACE_CL']:2d} {v['FCP_FACE_AOS']:3d} {v['FCP_ASM_W']:5d} | " +
                " | ".join(f"{ms[o]:9.3f} ({nbytes[o] / (ms[o] * 1e-3) / 1e9 / peak:5.3f})   " for o in ops) + (" | same" if same else " | DIFFERENT: " +
                                                                                                               ",".join(o for o in ops if fp[o] != ref_fp[o])))
         lines.append(row)
@@ -139,7 +146,7 @@ def main():
         return min(cand, key=lambda t: t[0])[1]
     sel = [best_of(lambda ms: ms["grad_gauss"]), best_of(lambda ms: ms["grad_lsq"]), best_of(lambda ms: ms["gradp_plain"] + ms["gradp_fused"]),
            best_of(lambda ms: ms["assemble"])]
-    export = ("export " + " ".join(f"{k}={','.join(str(v[k]) for v in sel)}" for k in ("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL")) +
+    export = ("export " + " ".join(f"{k}={','.join(str(v[k]) for v in sel)}" for k in ("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS")) +
               f" FCP_ASM_W={sel[3]['FCP_ASM_W']}")
     lines.append("# per kernel (grad_gauss, grad_lsq, gradp, assemble):")
     lines.append(export)

@@ -348,7 +348,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm) comm_free(c->comm);
   cudaFree(c->owner); cudaFree(c->neigh); cudaFree(c->arx); cudaFree(c->ary); cudaFree(c->arz);
-  cudaFree(c->xf); cudaFree(c->yf); cudaFree(c->zf); cudaFree(c->facint); cudaFree(c->Df); cudaFree(c->fgeo);
+  cudaFree(c->xf); cudaFree(c->yf); cudaFree(c->zf); cudaFree(c->facint); cudaFree(c->Df);
   cudaFree(c->xc); cudaFree(c->yc); cudaFree(c->zc); cudaFree(c->vol); cudaFree(c->bftype);
   cudaFree(c->kPN); cudaFree(c->kNP);
   cudaFree(c->fl.slptr); cudaFree(c->fl.len); cudaFree(c->fl.ent); cudaFree(c->fl.other); cudaFree(c->fl.slot); cudaFree(c->fl.kinds);

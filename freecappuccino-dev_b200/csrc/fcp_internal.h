@@ -229,8 +229,6 @@ struct fcp_ctx {
   int32_t *owner = nullptr, *neigh = nullptr;       // 0-based
   double *arx = nullptr, *ary = nullptr, *arz = nullptr, *xf = nullptr, *yf = nullptr, *zf = nullptr;  // [nF]
   double *facint = nullptr, *Df = nullptr;          // [F] (+ process faces in global orientation when partitioned: [nF])
-  double *fgeo = nullptr;                           // [nF][4] = {arx, ary, arz, facint} per face (one 32-byte sector): the face-geometry gathers of the face kernels
-  bool fgeo_valid = false;                          // rebuilt on demand (fvm_ensure_fgeo) after facint changes (fcp_comm_init, fcp_set_process_facint)
   double *xc = nullptr, *yc = nullptr, *zc = nullptr, *vol = nullptr;   // [nT]
   int32_t *bftype = nullptr;                        // [B] patch type of each boundary face
   int32_t *kPN = nullptr, *kNP = nullptr;           // [F] SELL positions of a(P,N), a(N,P)
@@ -291,7 +289,6 @@ struct AsmArgs {
   double *a, *su, *flmass;
   const double *gU = nullptr, *gV = nullptr, *gW = nullptr;   // non-null: inner faces use the MPI tree's facefluxmass (quirk Q10) with these velocity gradients
 };
-int fvm_ensure_fgeo(fcp_ctx *ctx);
 int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g);
 int fvm_lsq_matrix(fcp_ctx *ctx, bool weighted, double *D);
 int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi, double *g, int row2_reference);

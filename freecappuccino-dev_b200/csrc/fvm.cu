@@ -12,26 +12,6 @@
 #include "reduce.cuh"
 #include "fvm_common.cuh"
 
-// array-of-structures copy of the face geometry the gather kernels read together (fcp_face_geo)
-__global__ void __launch_bounds__(FCP_TPB) k_build_fgeo(int32_t nF, const double *__restrict__ arx, const double *__restrict__ ary, const double *__restrict__ arz,
-                                                         const double *__restrict__ facint, double *__restrict__ fgeo) {
-  for (int32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
-    fgeo[4 * (int64_t)f] = arx[f]; fgeo[4 * (int64_t)f + 1] = ary[f]; fgeo[4 * (int64_t)f + 2] = arz[f]; fgeo[4 * (int64_t)f + 3] = facint[f];
-  }
-}
-int fvm_ensure_fgeo(fcp_ctx *ctx) {
-  if (ctx->fgeo_valid) return FCP_OK;
-  const int32_t nF = ctx->F + ctx->B;
-  if (!ctx->fgeo) FCP_TRY(dev_alloc(&ctx->fgeo, 4 * (size_t)std::max(nF, 1)));
-  if (nF > 0) {
-    k_build_fgeo<<<std::min((nF + FCP_TPB - 1) / FCP_TPB, 148 * 16), FCP_TPB, 0, ctx->stream>>>(nF, ctx->arx, ctx->ary, ctx->arz, ctx->facint, ctx->fgeo);
-    FCP_LAUNCHED();
-    FCP_CHECK_LAUNCH();
-  }
-  ctx->fgeo_valid = true;
-  return FCP_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
 // grad_gauss   gradients.f90:1607-1693
 // ---------------------------------------------------------------------------------------------
@@ -74,7 +54,8 @@ __global__ void __launch_bounds__(FCP_TPB, MINB) k_grad_gauss(MeshView m, const 
         const int32_t f = (e[k] > 0 ? e[k] : -e[k]) - 1;
         const bool on = e[k] != 0;
         uo[k] = on ? __ldg(u + o[k]) : 0.0;
-        fcp_face_geo(m, f, on, on && sl[k] >= 0, sx[k], sy[k], sz[k], lam[k]);
+        lam[k] = (on && sl[k] >= 0) ? __ldg(m.facint + f) : 0.0;
+        sx[k] = on ? __ldg(m.arx + f) : 0.0; sy[k] = on ? __ldg(m.ary + f) : 0.0; sz[k] = on ? __ldg(m.arz + f) : 0.0;
       }
 #pragma unroll
       for (int k = 0; k < W; ++k) {
@@ -418,7 +399,8 @@ __device__ __forceinline__ void gradp_cell_fast(const MeshView &m, int32_t c, co
     // p: inner-face (cell / ghost) values are never written by this kernel -> non-coherent loads; pressure-patch values likewise
     pv[k] = (two || (bnd && (-1 - sl[k]) == FCP_BC_PRESSURE)) ? __ldg(p + o[k]) : 0.0;
     if (WEIGHTED) ao[k] = two ? __ldg(apu + o[k]) : 0.0;
-    fcp_face_geo(m, f, on, two, sx[k], sy[k], sz[k], lam[k]);
+    lam[k] = two ? __ldg(m.facint + f) : 0.0;
+    sx[k] = on ? __ldg(m.arx + f) : 0.0; sy[k] = on ? __ldg(m.ary + f) : 0.0; sz[k] = on ? __ldg(m.arz + f) : 0.0;
   }
   double s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -714,8 +696,8 @@ __global__ void __launch_bounds__(FCP_TPB, ((W >= 3 || MPIF) ? 1 : W == 2 ? 2 : 
         const int32_t f = (e_[k] > 0 ? e_[k] : -e_[k]) - 1;
         const bool on = e_[k] != 0, two = on && sl_[k] >= 0;
         const int32_t o = o_[k];
-        fcp_face_geo(m, f, on, two, sx_[k], sy_[k], sz_[k], lam_[k]);
-        Df_[k] = two ? __ldg(m.Df + f) : 0.0;
+        sx_[k] = on ? __ldg(m.arx + f) : 0.0; sy_[k] = on ? __ldg(m.ary + f) : 0.0; sz_[k] = on ? __ldg(m.arz + f) : 0.0;
+        lam_[k] = two ? __ldg(m.facint + f) : 0.0; Df_[k] = two ? __ldg(m.Df + f) : 0.0;
         xo_[k] = two ? __ldg(m.xc + o) : 0.0; yo_[k] = two ? __ldg(m.yc + o) : 0.0; zo_[k] = two ? __ldg(m.zc + o) : 0.0;
         deno_[k] = two ? __ldg(g.den + o) : 0.0; volo_[k] = two ? __ldg(m.vol + o) : 0.0; apuo_[k] = two ? __ldg(g.apu + o) : 0.0;
         // u, v, w, p cell values are not written by this kernel (only pressure-patch boundary slots are)

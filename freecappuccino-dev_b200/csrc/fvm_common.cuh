@@ -8,8 +8,6 @@ struct MeshView {
   int32_t n, F, B;
   const int64_t *slptr;
   const int32_t *len, *ent, *other, *slot;
-  const double *fgeo;                // [nF][4] {arx, ary, arz, facint} per face when the launcher selects the array-of-structures face geometry, else nullptr
-  int fgeo_wide;                     // 1: one 256-bit load per face, 0: two 128-bit loads
   const unsigned long long *kinds;   // compact face kinds per cell (FaceLists::kinds) when the launcher selects the compact lists, else nullptr
   const double *arx, *ary, *arz, *xf, *yf, *zf, *facint, *Df;
   const double *xc, *yc, *zc, *vol;
@@ -24,7 +22,7 @@ struct MeshView {
 static inline MeshView fcp_mesh_view(const fcp_ctx *c) {
   MeshView m;
   m.n = c->n; m.F = c->F; m.B = c->B;
-  m.slptr = c->fl.slptr; m.len = c->fl.len; m.ent = c->fl.ent; m.other = c->fl.other; m.slot = c->fl.slot; m.kinds = nullptr; m.fgeo = nullptr; m.fgeo_wide = 0;
+  m.slptr = c->fl.slptr; m.len = c->fl.len; m.ent = c->fl.ent; m.other = c->fl.other; m.slot = c->fl.slot; m.kinds = nullptr;
   m.arx = c->arx; m.ary = c->ary; m.arz = c->arz; m.xf = c->xf; m.yf = c->yf; m.zf = c->zf;
   m.facint = c->facint; m.Df = c->Df; m.xc = c->xc; m.yc = c->yc; m.zc = c->zc; m.vol = c->vol;
   m.owner = c->owner; m.neigh = c->neigh;
@@ -119,30 +117,6 @@ __device__ __forceinline__ void fcp_prefetch_l2(const void *p) {
 // the patch type, and `len` is a fourth stream -- both are folded into ONE 8-byte word per cell (FaceLists::kinds: nibble k = 0 for a two-sided face,
 // 1 + bctype otherwise; top byte = the cell's face count, 255 = more than 14 faces: such a cell reads the plain lists).  A hexahedron then reads
 // 56 bytes of list instead of 76.  The word's halves take the place of the `len` row and of the first `slot` row of the stage.
-// Face geometry of face f for a gather round: area vector and interpolation factor.  SoA (default): four 8-byte gathers from four arrays; a warp
-// whose lanes walk faces 3 c, 3 c + 3, ... uses a third of every 32-byte sector it pulls.  AoS (m.fgeo): the four values are ONE sector per face.
-__device__ __forceinline__ void fcp_face_geo(const MeshView &m, int32_t f, bool on, bool two, double &sx, double &sy, double &sz, double &lam) {
-  if (m.fgeo) {
-    const double *p = m.fgeo + 4 * (int64_t)f;
-    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-#ifdef FCP_EMU
-    if (on) { a = p[0]; b = p[1]; c = p[2]; d = p[3]; }
-#else
-    if (on) {
-      if (m.fgeo_wide) {
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-      } else {
-        const double2 u = __ldg(reinterpret_cast<const double2 *>(p)), v = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-        a = u.x; b = u.y; c = v.x; d = v.y;
-      }
-    }
-#endif
-    sx = a; sy = b; sz = c; lam = two ? d : 0.0;
-  } else {
-    sx = on ? __ldg(m.arx + f) : 0.0; sy = on ? __ldg(m.ary + f) : 0.0; sz = on ? __ldg(m.arz + f) : 0.0;
-    lam = two ? __ldg(m.facint + f) : 0.0;
-  }
-}
 template <int W, int NS = 2>
 struct ListStage {
   int32_t v[NS][1 + 3 * W][FCP_TPB];
@@ -269,16 +243,16 @@ __device__ __forceinline__ int64_t fcp_chunk_cell(int j) { return (int64_t)block
 
 // Switches of the face kernels, read at every launch (a handful of launches per step): FCP_FACE_OCC = 2 | 3 CTAs per SM asked of the compiler,
 // FCP_FACE_PF = 0 | 1 | 2 L2 prefetch of the next cell's operands (see k_grad_gauss), FCP_FACE_CL = 0 | 1 compact lists in the gradient kernels
-// (ListStage), FCP_FACE_AOS = 0 | 1 | 2 face geometry from the array of structures (fcp_face_geo: two 128-bit loads / one 256-bit load per face).  The environment overrides the defaults, one value for every kernel or a comma-separated value per kernel (tools/face_ab.py); the defaults
+// (ListStage).  The environment overrides the defaults, one value for every kernel or a comma-separated value per kernel (tools/face_ab.py); the defaults
 // are per kernel, set from that measurement.
-struct FaceVariant { int occ, pf, cl, aos; };
+struct FaceVariant { int occ, pf, cl; };
 enum { FCP_FK_GRAD_GAUSS = 0, FCP_FK_GRAD_LSQ, FCP_FK_GRADP, FCP_FK_ASSEMBLE, FCP_FK_COUNT };
 static inline FaceVariant fcp_face_variant(int kernel) {
   static const FaceVariant defaults[FCP_FK_COUNT] = {
-      /* k_grad_gauss     */ {2, 0, 1, 0},
-      /* k_grad_lsq       */ {2, 0, 0, 0},
-      /* k_gradp          */ {2, 0, 1, 0},
-      /* k_assemble_pcorr */ {2, 0, 0, 0},
+      /* k_grad_gauss     */ {2, 0, 1},
+      /* k_grad_lsq       */ {2, 0, 0},
+      /* k_gradp          */ {2, 0, 1},
+      /* k_assemble_pcorr */ {2, 0, 0},
   };
   FaceVariant v = defaults[kernel];
   // "1" = every kernel, "1,0,2,1" = per kernel in the order of the enum
@@ -292,14 +266,11 @@ static inline FaceVariant fcp_face_variant(int kernel) {
   v.pf = pick(getenv("FCP_FACE_PF"), v.pf);
   if (v.pf < 0 || v.pf > 2) v.pf = 0;
   v.cl = pick(getenv("FCP_FACE_CL"), v.cl) != 0;
-  v.aos = pick(getenv("FCP_FACE_AOS"), v.aos);
-  if (v.aos < 0 || v.aos > 2) v.aos = 0;
   return v;
 }
 
 static inline int fcp_apply_face_variant(fcp_ctx *ctx, const FaceVariant &fv, MeshView &m, bool compact_ok) {
   if (fv.cl && compact_ok) m.kinds = ctx->fl.kinds;
-  if (fv.aos) { FCP_TRY(fvm_ensure_fgeo(ctx)); m.fgeo = ctx->fgeo; m.fgeo_wide = fv.aos == 2; }
   return FCP_OK;
 }
 

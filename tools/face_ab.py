@@ -105,7 +105,7 @@ def main():
                 variants.append(dict(FCP_FACE_OCC=occ, FCP_FACE_PF=pf, FCP_FACE_CL=cl, FCP_FACE_AOS=0, FCP_ASM_W=2))
         for pf in (0, 1, 2):
             variants.append(dict(FCP_FACE_OCC=2, FCP_FACE_PF=pf, FCP_FACE_CL=0, FCP_FACE_AOS=0, FCP_ASM_W=1))
-    else:                    # array-of-structures face geometry x compact lists (profiles/r02_face_ab2.txt)
+    elif args.round == 2:    # array-of-structures face geometry x compact lists (profiles/r02_face_ab2.txt; FCP_FACE_AOS was removed from the library afterwards)
         for aos in (0, 1, 2):
             for cl in (0, 1):
                 variants.append(dict(FCP_FACE_OCC=2, FCP_FACE_PF=0, FCP_FACE_CL=cl, FCP_FACE_AOS=aos, FCP_ASM_W=2))

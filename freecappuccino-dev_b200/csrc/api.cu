@@ -254,17 +254,30 @@ static int ctx_build(fcp_ctx *c, const fcp_mesh_desc *md, int device) {
     const int64_t np = fsl[nsl];
     if (np >= (int64_t)2147483647) { fcp_set_error("face lists too large"); return FCP_EINVAL; }
     std::vector<int32_t> ent(np, 0), other(np, 0), slot(np, -1), fill(n, 0);
+    // owner-ordered positions of the faces (fcp_ctx::og): SELL layout of the owner cells, faces of a cell in ascending index
+    std::vector<int32_t> ocnt(n, 0), ofill(n, 0), gpos(std::max(c->nF, 1), 0), gent(np, 0);
+    for (int32_t f = 0; f < c->nF; ++f) ocnt[md->owner[f] - 1]++;
+    std::vector<int64_t> osl(nsl + 1, 0);
+    for (int32_t s = 0; s < nsl; ++s) {
+      int32_t w = 0;
+      for (int32_t r = s * 32; r < std::min(n, s * 32 + 32); ++r) w = std::max(w, ocnt[r]);
+      osl[s + 1] = osl[s] + (int64_t)w * 32;
+    }
+    if (osl[nsl] >= (int64_t)2147483647) { fcp_set_error("face lists too large"); return FCP_EINVAL; }
+    c->og_n = std::max<int64_t>(osl[nsl], 1);
     for (int32_t f = 0; f < c->nF; ++f) {
       int32_t p = md->owner[f] - 1;
       int64_t pos = fsl[p >> 5] + (int64_t)fill[p]++ * 32 + (p & 31);
+      const int32_t gp = (int32_t)(osl[p >> 5] + (int64_t)ofill[p]++ * 32 + (p & 31));
+      gpos[f] = gp;
       if (f < F) {
         int32_t q = md->neighbour[f] - 1;
-        ent[pos] = f + 1; other[pos] = q; slot[pos] = kPN[f];
+        ent[pos] = f + 1; other[pos] = q; slot[pos] = kPN[f]; gent[pos] = gp + 1;
         int64_t pos2 = fsl[q >> 5] + (int64_t)fill[q]++ * 32 + (q & 31);
-        ent[pos2] = -(f + 1); other[pos2] = p; slot[pos2] = kNP[f];
+        ent[pos2] = -(f + 1); other[pos2] = p; slot[pos2] = kNP[f]; gent[pos2] = -(gp + 1);
       } else {
         int32_t i = f - F;
-        ent[pos] = f + 1; other[pos] = n + i;
+        ent[pos] = f + 1; other[pos] = n + i; gent[pos] = gp + 1;
         slot[pos] = bft[i] == FCP_BC_PROCESS ? sellpos(p, halo_k[i]) : -1 - bft[i];
       }
     }
@@ -275,6 +288,8 @@ static int ctx_build(fcp_ctx *c, const fcp_mesh_desc *md, int device) {
     FCP_TRY(dev_upload(&c->fl.ent, ent.data(), ent.size()));
     FCP_TRY(dev_upload(&c->fl.other, other.data(), other.size()));
     FCP_TRY(dev_upload(&c->fl.slot, slot.data(), slot.size()));
+    FCP_TRY(dev_upload(&c->fl.gent, gent.data(), gent.size()));
+    FCP_TRY(dev_upload(&c->d_gpos, gpos.data(), gpos.size()));
     std::vector<unsigned long long> kinds(n, 0ull);
     parallel_for(n, [&](int64_t b, int64_t e) {
       for (int64_t i = b; i < e; ++i) {
@@ -351,7 +366,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   cudaFree(c->xf); cudaFree(c->yf); cudaFree(c->zf); cudaFree(c->facint); cudaFree(c->Df);
   cudaFree(c->xc); cudaFree(c->yc); cudaFree(c->zc); cudaFree(c->vol); cudaFree(c->bftype);
   cudaFree(c->kPN); cudaFree(c->kNP);
-  cudaFree(c->fl.slptr); cudaFree(c->fl.len); cudaFree(c->fl.ent); cudaFree(c->fl.other); cudaFree(c->fl.slot); cudaFree(c->fl.kinds);
+  cudaFree(c->fl.slptr); cudaFree(c->fl.len); cudaFree(c->fl.ent); cudaFree(c->fl.other); cudaFree(c->fl.slot); cudaFree(c->fl.kinds); cudaFree(c->fl.gent); cudaFree(c->d_gpos); cudaFree(c->og);
   for (int i = 0; i < FCP_F_COUNT; ++i) cudaFree(c->field[i]);
   for (int i = 0; i < 4; ++i) cudaFree(c->Dmat[i]);
   cudaFree(c->flushbuf); cudaFree(c->d_mmpart); cudaFree(c->d_sum);

@@ -524,6 +524,7 @@ extern "C" int fcp_set_process_facint(fcp_ctx *ctx, const double *fpro, int32_t 
   double *d = nullptr;
   FCP_TRY(dev_upload(&d, fpro, (size_t)count));
   k_set_process_facint<<<(count + 255) / 256, 256, 0, ctx->stream>>>(count, ctx->d_procface, d, ctx->facint);
+  ctx->og_valid = false;
   FCP_LAUNCHED();
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d);
@@ -582,6 +583,7 @@ extern "C" int fcp_comm_init(fcp_ctx *ctx, int rank, int nranks, const void *id1
   if (ctx->npro) {
     k_process_face_geom<<<(ctx->npro + 255) / 256, 256, 0, ctx->stream>>>(ctx->npro, ctx->d_procface, c->d_cell, c->d_slot, ctx->xc, ctx->yc, ctx->zc,
                                                                           ctx->xf, ctx->yf, ctx->zf, ctx->arx, ctx->ary, ctx->arz, ctx->facint, ctx->Df);
+    ctx->og_valid = false;
     FCP_LAUNCHED();
     FCP_CHECK_LAUNCH();
   }

@@ -110,6 +110,7 @@ struct FaceLists {
   int32_t *ent = nullptr;     // +(f+1): cell is the face's owner (P side), -(f+1): neighbour (N side); 0 padding
   int32_t *other = nullptr;   // field index of the value across the face (cell, ghost slot or boundary slot), 0-based
   int32_t *slot = nullptr;    // SELL position of a(cell,other) or -1 - bctype for physical boundary faces
+  int32_t *gent = nullptr;    // like ent, but +-(g+1) with g = the face's position in the OWNER-ORDERED geometry arrays (fcp_ctx::og): see fvm_ensure_og
   unsigned long long *kinds = nullptr;   // [n] compact form of len + the sign of slot: nibble k = 0 (two-sided face) or 1 + bctype, top byte = len (255: > 14 faces)
 };
 
@@ -234,6 +235,13 @@ struct fcp_ctx {
   int32_t *kPN = nullptr, *kNP = nullptr;           // [F] SELL positions of a(P,N), a(N,P)
   SellPattern pat;
   FaceLists fl;
+  // owner-ordered face geometry: face f sits at gpos[f] = og_slptr[owner >> 5] + 32 * (rank of f among its owner's faces) + (owner & 31), i.e. in the SELL
+  // layout of the OWNER cells.  Lanes that walk consecutive cells then read consecutive addresses for a face's area vector / factor / centre (their own
+  // faces and, on any banded numbering, the faces owned by their neighbours) instead of every third element of a face-ordered array.
+  int32_t *d_gpos = nullptr;      // [nF]
+  int64_t og_n = 0;               // padded length of one owner-ordered array
+  double *og = nullptr;           // [7][og_n]: arx, ary, arz, facint, xf, yf, zf; built on demand (fvm_ensure_og)
+  bool og_valid = false;          // reset when the process-face geometry / factors change (fcp_comm_init, fcp_set_process_facint)
   double *field[FCP_F_COUNT] = {nullptr};
   double *Dmat[4] = {nullptr, nullptr, nullptr, nullptr};   // LSQ matrices per method (index FCP_GRAD_*); QR: [18][n]
   int32_t max_cell_faces = 0;                       // longest cell->face list (the QR gradient holds at most 6)
@@ -289,6 +297,7 @@ struct AsmArgs {
   double *a, *su, *flmass;
   const double *gU = nullptr, *gV = nullptr, *gW = nullptr;   // non-null: inner faces use the MPI tree's facefluxmass (quirk Q10) with these velocity gradients
 };
+int fvm_ensure_og(fcp_ctx *ctx);
 int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g);
 int fvm_lsq_matrix(fcp_ctx *ctx, bool weighted, double *D);
 int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi, double *g, int row2_reference);

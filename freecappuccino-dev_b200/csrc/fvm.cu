@@ -12,6 +12,35 @@
 #include "reduce.cuh"
 #include "fvm_common.cuh"
 
+// owner-ordered copies of the face geometry (fcp_ctx::og); a kernel that uses a face index ONLY to address these seven arrays runs on them by a
+// pointer swap in its MeshView (fcp_apply_face_variant): `ent` then holds +-(position + 1) instead of +-(face + 1)
+__global__ void __launch_bounds__(FCP_TPB) k_build_og(int32_t nF, int64_t og_n, const int32_t *__restrict__ gpos, const double *__restrict__ arx,
+                                                       const double *__restrict__ ary, const double *__restrict__ arz, const double *__restrict__ facint,
+                                                       const double *__restrict__ xf, const double *__restrict__ yf, const double *__restrict__ zf,
+                                                       double *__restrict__ og) {
+  for (int32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+    const int64_t g = gpos[f];
+    og[g] = arx[f]; og[og_n + g] = ary[f]; og[2 * og_n + g] = arz[f]; og[3 * og_n + g] = facint[f];
+    og[4 * og_n + g] = xf[f]; og[5 * og_n + g] = yf[f]; og[6 * og_n + g] = zf[f];
+  }
+}
+int fvm_ensure_og(fcp_ctx *ctx) {
+  if (ctx->og_valid) return FCP_OK;
+  const int32_t nF = ctx->F + ctx->B;
+  if (!ctx->og) {
+    FCP_TRY(dev_alloc(&ctx->og, 7 * (size_t)ctx->og_n));
+    FCP_CUDA(cudaMemsetAsync(ctx->og, 0, sizeof(double) * 7 * (size_t)ctx->og_n, ctx->stream));
+  }
+  if (nF > 0) {
+    k_build_og<<<std::min((nF + FCP_TPB - 1) / FCP_TPB, 148 * 16), FCP_TPB, 0, ctx->stream>>>(nF, ctx->og_n, ctx->d_gpos, ctx->arx, ctx->ary, ctx->arz, ctx->facint,
+                                                                                              ctx->xf, ctx->yf, ctx->zf, ctx->og);
+    FCP_LAUNCHED();
+    FCP_CHECK_LAUNCH();
+  }
+  ctx->og_valid = true;
+  return FCP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // grad_gauss   gradients.f90:1607-1693
 // ---------------------------------------------------------------------------------------------
@@ -951,7 +980,7 @@ int fvm_grad_gauss(fcp_ctx *ctx, const double *u, double *g) {
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   MeshView mv = fcp_mesh_view(ctx);
   const FaceVariant fv = fcp_face_variant(FCP_FK_GRAD_GAUSS);
-  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, true));
+  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, true, true));
 #define GG_LAUNCH(WS, MINB, PF)                                                                                                      \
   do {                                                                                                                               \
     FCP_TRY((fcp_stage_smem<WS, (PF) ? 3 : 2>(k_grad_gauss<WS, MINB, PF>, &smem)));                                                  \
@@ -994,7 +1023,7 @@ int fvm_grad_lsq(fcp_ctx *ctx, bool weighted, const double *D, const double *phi
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   MeshView mv = fcp_mesh_view(ctx);
   const FaceVariant fv = fcp_face_variant(FCP_FK_GRAD_LSQ);
-  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, true));
+  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, true, false));   // (quirk Q2 does arithmetic on the face index: no owner-ordered geometry)
 #define LSQ_LAUNCH(WT, WS, MINB, PF)                                                                        \
   do {                                                                                                      \
     FCP_TRY((fcp_stage_smem<WS, (PF) ? 3 : 2>(k_grad_lsq<WT, WS, MINB, PF>, &smem)));                       \
@@ -1040,11 +1069,12 @@ int fvm_gradp(fcp_ctx *ctx, int scheme, double *p, const double *apu, double *su
   size_t smem = 0;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   const FaceVariant fv = fcp_face_variant(FCP_FK_GRADP);
-  FCP_TRY(fcp_apply_face_variant(ctx, fv, m, true));
+  MeshView mg = m;       // the view of k_gradp (compact lists, owner-ordered geometry); k_gradp_central2 keeps the plain one
+  FCP_TRY(fcp_apply_face_variant(ctx, fv, mg, true, true));
 #define GRADP_LAUNCH(C, WG, PF, NST, OUT)                                                                          \
   do {                                                                                                             \
     FCP_TRY((fcp_stage_smem<6, (PF) ? 3 : 2>(k_gradp<C, WG, PF>, &smem)));                                         \
-    k_gradp<C, WG, PF><<<grid, FCP_TPB, smem, ctx->stream>>>(m, NST, p, apu, su, sv, sw, OUT, ca);                 \
+    k_gradp<C, WG, PF><<<grid, FCP_TPB, smem, ctx->stream>>>(mg, NST, p, apu, su, sv, sw, OUT, ca);                 \
   } while (0)
 #define GRADP_LAUNCH_V(C, WG, NST, OUT)                             \
   do {                                                              \
@@ -1082,7 +1112,7 @@ int fvm_assemble_pcorr(fcp_ctx *ctx, const AsmArgs &g, bool piso) {
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   size_t tok = ctx->prof.begin(FCP_K_ASSEMBLE, ctx->stream);
   MeshView mv = fcp_mesh_view(ctx);
-  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, false));
+  FCP_TRY(fcp_apply_face_variant(ctx, fv, mv, false, false));
 #define ASM_LAUNCH(PISO, W, MPIF, PF)                                                                   \
   do {                                                                                                  \
     FCP_TRY((fcp_stage_smem<6, (PF) ? 3 : 2>(k_assemble_pcorr<PISO, W, MPIF, PF>, &smem)));             \

@@ -243,16 +243,16 @@ __device__ __forceinline__ int64_t fcp_chunk_cell(int j) { return (int64_t)block
 
 // Switches of the face kernels, read at every launch (a handful of launches per step): FCP_FACE_OCC = 2 | 3 CTAs per SM asked of the compiler,
 // FCP_FACE_PF = 0 | 1 | 2 L2 prefetch of the next cell's operands (see k_grad_gauss), FCP_FACE_CL = 0 | 1 compact lists in the gradient kernels
-// (ListStage).  The environment overrides the defaults, one value for every kernel or a comma-separated value per kernel (tools/face_ab.py); the defaults
+// (ListStage), FCP_FACE_OG = 0 | 1 face geometry from the owner-ordered arrays (fcp_ctx::og).  The environment overrides the defaults, one value for every kernel or a comma-separated value per kernel (tools/face_ab.py); the defaults
 // are per kernel, set from that measurement.
-struct FaceVariant { int occ, pf, cl; };
+struct FaceVariant { int occ, pf, cl, og; };
 enum { FCP_FK_GRAD_GAUSS = 0, FCP_FK_GRAD_LSQ, FCP_FK_GRADP, FCP_FK_ASSEMBLE, FCP_FK_COUNT };
 static inline FaceVariant fcp_face_variant(int kernel) {
   static const FaceVariant defaults[FCP_FK_COUNT] = {
-      /* k_grad_gauss     */ {2, 0, 1},
-      /* k_grad_lsq       */ {2, 0, 0},
-      /* k_gradp          */ {2, 0, 1},
-      /* k_assemble_pcorr */ {2, 0, 0},
+      /* k_grad_gauss     */ {2, 0, 1, 0},
+      /* k_grad_lsq       */ {2, 0, 0, 0},
+      /* k_gradp          */ {2, 0, 1, 0},
+      /* k_assemble_pcorr */ {2, 0, 0, 0},
   };
   FaceVariant v = defaults[kernel];
   // "1" = every kernel, "1,0,2,1" = per kernel in the order of the enum
@@ -266,11 +266,20 @@ static inline FaceVariant fcp_face_variant(int kernel) {
   v.pf = pick(getenv("FCP_FACE_PF"), v.pf);
   if (v.pf < 0 || v.pf > 2) v.pf = 0;
   v.cl = pick(getenv("FCP_FACE_CL"), v.cl) != 0;
+  v.og = pick(getenv("FCP_FACE_OG"), v.og) != 0;
   return v;
 }
 
-static inline int fcp_apply_face_variant(fcp_ctx *ctx, const FaceVariant &fv, MeshView &m, bool compact_ok) {
+// compact_ok: the kernel needs no matrix slot; og_ok: the kernel uses a face index only to address arx, ary, arz, facint, xf, yf, zf
+static inline int fcp_apply_face_variant(fcp_ctx *ctx, const FaceVariant &fv, MeshView &m, bool compact_ok, bool og_ok) {
   if (fv.cl && compact_ok) m.kinds = ctx->fl.kinds;
+  if (fv.og && og_ok) {
+    FCP_TRY(fvm_ensure_og(ctx));
+    const int64_t g = ctx->og_n;
+    m.ent = ctx->fl.gent;
+    m.arx = ctx->og; m.ary = ctx->og + g; m.arz = ctx->og + 2 * g; m.facint = ctx->og + 3 * g;
+    m.xf = ctx->og + 4 * g; m.yf = ctx->og + 5 * g; m.zf = ctx->og + 6 * g;
+  }
   return FCP_OK;
 }
 

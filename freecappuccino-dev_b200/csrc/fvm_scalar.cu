@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(FCP_TPB) k_sgs_boundary(MeshView m, const int3
 int fvm_grad_gauss_passes(fcp_ctx *ctx, const double *u, double *gtmp, double *g, int npass) {
   if (ctx->n == 0) return FCP_OK;
   MeshView m = fcp_mesh_view(ctx);
-  if (fcp_face_variant(FCP_FK_GRAD_GAUSS).cl) m.kinds = ctx->fl.kinds;
+  FCP_TRY(fcp_apply_face_variant(ctx, fcp_face_variant(FCP_FK_GRAD_GAUSS), m, true, true));   // k_grad_gauss_fvx: same operands as k_grad_gauss + the face centres
   const bool wide = ctx->max_cell_faces > 6;
   const int grid = std::max(fcp_nchunks(ctx->n), 1);
   size_t smem6 = 0, smem10 = 0;

@@ -3,7 +3,7 @@
 
     python tools/face_ab.py [--n 256] [--reps 5] [--out gpurun_out/r02_face_ab.txt]
 
-The library reads FCP_FACE_OCC / FCP_FACE_PF / FCP_FACE_CL / FCP_FACE_AOS / FCP_ASM_W at every launch of a face kernel, so a variant is selected by setting the
+The library reads FCP_FACE_OCC / FCP_FACE_PF / FCP_FACE_CL / FCP_FACE_OG / FCP_ASM_W at every launch of a face kernel, so a variant is selected by setting the
 environment between calls.  Per variant: the inputs are restored, every operation runs once and a fingerprint of its results (wrap-around sum
 of the 64-bit patterns) is compared with the first variant's -- a variant that changes a bit is flagged, not timed --, then `reps` timed calls
 with the library's per-class profiler (CUDA events around the launches of the class).  Operations: grad_gauss, grad_lsq (class grad),
@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="")
-    ap.add_argument("--round", type=int, default=2, help="which set of variants (see the code)")
+    ap.add_argument("--round", type=int, default=3, help="which set of variants (see the code)")
     args = ap.parse_args()
     import fcb200  # noqa: F401
     from fcb200 import lib as L
@@ -51,7 +51,7 @@ def main():
     ctx.sync()
     setup_s = time.perf_counter() - t0
     peak, _ = bench.hbm_peak()
-    nbytes = dict(grad_gauss=40 * F + 40 * N + 36 * B, grad_lsq=8 * F + 128 * N + 36 * B, gradp_plain=40 * F + 64 * N + 36 * B,
+    nbytes = dict(fvx=2 * (80 * F + 88 * N + 36 * B), grad_gauss=40 * F + 40 * N + 36 * B, grad_lsq=8 * F + 128 * N + 36 * B, gradp_plain=40 * F + 64 * N + 36 * B,
                   gradp_fused=40 * F + 64 * N + 36 * B + 120 * N, assemble=80 * F + 124 * N)
 
     def restore():
@@ -65,7 +65,7 @@ def main():
         """every operation once (record = fingerprints) or args.reps times (record = per-class ms)"""
         out = {}
         reps = 1 if record == "fp" else args.reps
-        for name in ("grad_gauss", "grad_lsq", "gradp_plain", "simple"):
+        for name in ("grad_gauss", "grad_lsq", "fvx", "gradp_plain", "simple"):
             restore()
             ctx.sync()
             if record == "ms":
@@ -75,6 +75,8 @@ def main():
                     ctx.grad(L.GRAD_GAUSS, "P", "G0")
                 elif name == "grad_lsq":
                     ctx.grad(L.GRAD_LSQ, "P", "G0")
+                elif name == "fvx":
+                    ctx.grad_gauss_fvx("P", "G0")
                 elif name == "gradp_plain":
                     ctx.gradp_and_sources("linear", "P")
                 else:
@@ -89,7 +91,7 @@ def main():
                     klass = "gradp" if name == "gradp_plain" else "grad"
                     out[name] = prof[klass][0] / max(prof[klass][1], 1)
             else:
-                if name in ("grad_gauss", "grad_lsq"):
+                if name in ("grad_gauss", "grad_lsq", "fvx"):
                     out[name] = fingerprint(ctx.download("G0"))
                 elif name == "gradp_plain":
                     out[name] = fingerprint(ctx.download("DPDXI")) ^ fingerprint(ctx.download("SU")) ^ fingerprint(ctx.download("P"))
@@ -109,17 +111,22 @@ def main():
         for aos in (0, 1, 2):
             for cl in (0, 1):
                 variants.append(dict(FCP_FACE_OCC=2, FCP_FACE_PF=0, FCP_FACE_CL=cl, FCP_FACE_AOS=aos, FCP_ASM_W=2))
-    ops = ("grad_gauss", "grad_lsq", "gradp_plain", "gradp_fused", "assemble")
+    else:                    # owner-ordered face geometry x compact lists (profiles/r02_face_ab3.txt)
+        for og in (0, 1):
+            for cl in (0, 1):
+                variants.append(dict(FCP_FACE_OCC=2, FCP_FACE_PF=0, FCP_FACE_CL=cl, FCP_FACE_AOS=0, FCP_FACE_OG=og, FCP_ASM_W=2))
+    ops = ("grad_gauss", "grad_lsq", "fvx", "gradp_plain", "gradp_fused", "assemble")
     # which switches each operation listens to (the others only repeat a measurement)
-    listens = dict(grad_gauss=("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS"), grad_lsq=("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL"),
-                   gradp_plain=("FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS"), gradp_fused=("FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS"),
+    listens = dict(grad_gauss=("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS", "FCP_FACE_OG"), grad_lsq=("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL"), fvx=("FCP_FACE_CL", "FCP_FACE_OG"),
+                   gradp_plain=("FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS", "FCP_FACE_OG"), gradp_fused=("FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS", "FCP_FACE_OG"),
                    assemble=("FCP_FACE_PF", "FCP_FACE_AOS", "FCP_ASM_W"))
     lines, ref_fp, table = [], None, []
     hdr = f"# face-kernel A/B, {n}^3 hex cavity ({N} cells), ms per launch (mean of {args.reps}), (fraction of the {peak:.0f} GB/s HBM peak); setup {setup_s:.1f} s"
     lines.append(hdr)
-    lines.append("# OCC PF CL AOS ASM_W | " + " | ".join(f"{o:>20s}" for o in ops) + " | bits")
+    lines.append("# OCC PF CL AOS OG ASM_W | " + " | ".join(f"{o:>20s}" for o in ops) + " | bits")
     print(hdr, flush=True)
     for v in variants:
+        v.setdefault("FCP_FACE_OG", 0)
         for k, val in v.items():
             os.environ[k] = str(val)
         fp = run_ops("fp")
@@ -128,7 +135,7 @@ def main():
         same = all(fp[o] == ref_fp[o] for o in ops)
         ms = run_ops("ms") if same else {o: float("nan") for o in ops}
         table.append((v, ms, same))
-        row = (f"  {v['FCP_FACE_OCC']:3d} {v['FCP_FACE_PF']:2d} {v['FCP_FACE_CL']:2d} {v['FCP_FACE_AOS']:3d} {v['FCP_ASM_W']:5d} | " +
+        row = (f"  {v['FCP_FACE_OCC']:3d} {v['FCP_FACE_PF']:2d} {v['FCP_FACE_CL']:2d} {v['FCP_FACE_AOS']:3d} {v.get('FCP_FACE_OG', 0):2d} {v['FCP_ASM_W']:5d} | " +
                " | ".join(f"{ms[o]:9.3f} ({nbytes[o] / (ms[o] * 1e-3) / 1e9 / peak:5.3f})   " for o in ops) + (" | same" if same else " | DIFFERENT: " +
                                                                                                               ",".join(o for o in ops if fp[o] != ref_fp[o])))
         lines.append(row)
@@ -146,7 +153,7 @@ def main():
         return min(cand, key=lambda t: t[0])[1]
     sel = [best_of(lambda ms: ms["grad_gauss"]), best_of(lambda ms: ms["grad_lsq"]), best_of(lambda ms: ms["gradp_plain"] + ms["gradp_fused"]),
            best_of(lambda ms: ms["assemble"])]
-    export = ("export " + " ".join(f"{k}={','.join(str(v[k]) for v in sel)}" for k in ("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_AOS")) +
+    export = ("export " + " ".join(f"{k}={','.join(str(v[k]) for v in sel)}" for k in ("FCP_FACE_OCC", "FCP_FACE_PF", "FCP_FACE_CL", "FCP_FACE_OG")) +
               f" FCP_ASM_W={sel[3]['FCP_ASM_W']}")
     lines.append("# per kernel (grad_gauss, grad_lsq, gradp, assemble):")
     lines.append(export)

@@ -249,9 +249,9 @@ struct FaceVariant { int occ, pf, cl, og; };
 enum { FCP_FK_GRAD_GAUSS = 0, FCP_FK_GRAD_LSQ, FCP_FK_GRADP, FCP_FK_ASSEMBLE, FCP_FK_COUNT };
 static inline FaceVariant fcp_face_variant(int kernel) {
   static const FaceVariant defaults[FCP_FK_COUNT] = {
-      /* k_grad_gauss     */ {2, 0, 1, 0},
+      /* k_grad_gauss     */ {2, 0, 1, 1},     // (also k_grad_gauss_fvx)
       /* k_grad_lsq       */ {2, 0, 0, 0},
-      /* k_gradp          */ {2, 0, 1, 0},
+      /* k_gradp          */ {2, 0, 1, 1},
       /* k_assemble_pcorr */ {2, 0, 0, 0},
   };
   FaceVariant v = defaults[kernel];

@@ -30,6 +30,17 @@ def test_parity_slice_under_emulation():
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("switches", [dict(FCP_FACE_PF="2", FCP_FACE_CL="0", FCP_FACE_OG="0", FCP_FACE_OCC="3"),
+                                      dict(FCP_FACE_PF="1,0,2,1", FCP_FACE_CL="1", FCP_FACE_OG="1", FCP_ASM_W="1")])
+def test_face_kernel_switches_under_emulation(switches):
+    """the non-default variants of the face kernels (three list stages + L2 prefetch, plain / compact lists, face-ordered / owner-ordered geometry,
+    faces per assembly round), one value for all kernels or one per kernel: same bits as the oracle, on hexahedra and on the mesh whose cells have
+    more faces than the list stages and the compact face-kind word hold"""
+    r = _run(["-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_parity.py", "tests/test_gpu_scalar.py", "-k",
+              "(hex6 or hex_many_faces) and (grad or assemble or calcp or pcorr or fvx)"], **switches)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_rows_f3_f4_slice_under_emulation():
     """periodic pairs, the scalar transport template with both k-epsilon and SST, the SGS models and the chained LES channel steps"""
     r = _run(["-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_scalar.py", "tests/test_gpu_zz_les_channel_loop.py", "-k",

@@ -329,6 +329,13 @@ module fcp_b200
       integer(c_int32_t), value :: count
       integer(c_int) :: rc
     end function
+    function fcp_set_process_orientation(ctx, flipped, count) bind(c, name='fcp_set_process_orientation') result(rc)
+      import :: c_int, c_ptr, c_int32_t
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), intent(in) :: flipped(*)
+      integer(c_int32_t), value :: count
+      integer(c_int) :: rc
+    end function
     function fcp_exchange(ctx, field) bind(c, name='fcp_exchange') result(rc)
       import :: c_int, c_ptr
       type(c_ptr), value :: ctx

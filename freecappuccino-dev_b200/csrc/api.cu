@@ -370,7 +370,7 @@ extern "C" int fcp_ctx_destroy(fcp_ctx *c) {
   for (int i = 0; i < FCP_F_COUNT; ++i) cudaFree(c->field[i]);
   for (int i = 0; i < 4; ++i) cudaFree(c->Dmat[i]);
   cudaFree(c->flushbuf); cudaFree(c->d_mmpart); cudaFree(c->d_sum);
-  cudaFree(c->d_oface); cudaFree(c->d_flowo); cudaFree(c->d_csr_stage); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_ppref);
+  cudaFree(c->d_oface); cudaFree(c->d_flowo); cudaFree(c->d_csr_stage); cudaFree(c->d_aprpos); cudaFree(c->d_procface); cudaFree(c->d_proc_flip); cudaFree(c->d_ppref);
   cudaFree(c->per_cell); cudaFree(c->per_face); cudaFree(c->per_slot); cudaFree(c->per_df);
   sell_free(c->pat);
   krylov_ws_free(c->ws);
@@ -866,8 +866,8 @@ extern "C" int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_fi
     fcp_set_error("calcsc: field %d is not a scalar cell field", phi_field);
     return FCP_EINVAL;
   }
-  if (ctx->comm && is_sst) {   // sigma is taken from the OWNER of a face; a process face sees its local cell as owner on both ranks
-    fcp_set_error("calcsc: the SST pair is not available on partitioned meshes yet");
+  if (ctx->comm && is_sst && ctx->npro && !ctx->d_proc_flip) {   // sigma is taken from the OWNER of a face; a process face sees its local cell as owner on both ranks
+    fcp_set_error("calcsc: the SST pair on a partitioned mesh needs the orientation of the process faces: call fcp_set_process_orientation after fcp_comm_init");
     return FCP_ESTATE;
   }
   FCP_CUDA(cudaSetDevice(ctx->device));
@@ -905,6 +905,7 @@ extern "C" int fcp_calcsc(fcp_ctx *ctx, const fcp_scalar_params *prm, int phi_fi
   }
   FCP_CUDA(cudaMemsetAsync(a, 0, sizeof(double) * (size_t)ctx->pat.nnzp, ctx->stream));      // a = 0
   if (ctx->comm) FCP_TRY(comm_exchange(ctx, vis, 1));       // ghost values of what facefluxsc reads across a process face (phi and its gradient: done by grad)
+  if (ctx->comm && is_sst) { FIELD(fsst, FCP_F_FSST); FCP_TRY(comm_exchange(ctx, fsst, 1)); }   // ... and F1 of the cell across, when that cell owns the face
   FCP_TRY(fvm_sc_assemble(ctx, q));
   FCP_TRY(fcp_csrsolve(ctx, prm->solver, phi_field, FCP_F_SU, prm->maxiter, prm->tol_abs, prm->tol_rel, rep));
   FCP_TRY(fvm_update_boundary(ctx, phi));

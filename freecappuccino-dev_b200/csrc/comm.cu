@@ -532,6 +532,18 @@ extern "C" int fcp_set_process_facint(fcp_ctx *ctx, const double *fpro, int32_t 
   return FCP_OK;
 }
 
+extern "C" int fcp_set_process_orientation(fcp_ctx *ctx, const int32_t *flipped, int32_t count) {
+  if (!ctx || (!flipped && count > 0)) return FCP_EINVAL;
+  if (!ctx->comm) { fcp_set_error("fcp_set_process_orientation: call fcp_comm_init first"); return FCP_ESTATE; }
+  if (count != ctx->npro) { fcp_set_error("fcp_set_process_orientation: %d values for %d process faces", count, ctx->npro); return FCP_EINVAL; }
+  FCP_CUDA(cudaSetDevice(ctx->device));
+  std::vector<int32_t> h((size_t)std::max(ctx->B, 1), 0);
+  for (int32_t i = 0; i < count; ++i) h[ctx->h_procface[i] - ctx->F] = flipped[i] ? 1 : 0;
+  if (ctx->d_proc_flip) { cudaFree(ctx->d_proc_flip); ctx->d_proc_flip = nullptr; }
+  FCP_TRY(dev_upload(&ctx->d_proc_flip, h.data(), h.size()));
+  return FCP_OK;
+}
+
 extern "C" int fcp_comm_unique_id(void *id128) {
   if (!id128) return FCP_EINVAL;
   FCP_TRY(nccl_load());

@@ -262,6 +262,7 @@ struct fcp_ctx {
   double *d_csr_stage = nullptr;                    // [nnz] CSR-order staging for uploads / downloads of a(nnz) (allocated on first use)
   int32_t *d_aprpos = nullptr;                      // [npro] SELL position of the halo entry of each process face
   int32_t *d_procface = nullptr;                    // [npro] 0-based face index of each process face (patch order)
+  int32_t *d_proc_flip = nullptr;                   // [B] per boundary face: 1 = a process face whose owner in the unpartitioned mesh is the PEER's cell (fcp_set_process_orientation)
   std::vector<int32_t> h_procface;
   double *d_ppref = nullptr;                        // [4] broadcast slot for pp(pRefCell)
   // periodic pairs (sparse_matrix.f90:141-171): per BOUNDARY face, for the faces of a periodic patch and of its twin patch

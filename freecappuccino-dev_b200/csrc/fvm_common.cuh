@@ -18,6 +18,7 @@ struct MeshView {
   const int32_t *a_llen;     // local (non-halo) entries per row, nullptr when there are no halo columns
   const int32_t *per_cell, *per_face, *per_slot;   // periodic pairs per boundary face (fcp_internal.h), nullptr without periodic patches
   const double *per_df;
+  const int32_t *proc_flip;  // per boundary face: 1 = process face owned by the peer's cell in the unpartitioned mesh (fcp_set_process_orientation), or nullptr
 };
 static inline MeshView fcp_mesh_view(const fcp_ctx *c) {
   MeshView m;
@@ -26,7 +27,7 @@ static inline MeshView fcp_mesh_view(const fcp_ctx *c) {
   m.arx = c->arx; m.ary = c->ary; m.arz = c->arz; m.xf = c->xf; m.yf = c->yf; m.zf = c->zf;
   m.facint = c->facint; m.Df = c->Df; m.xc = c->xc; m.yc = c->yc; m.zc = c->zc; m.vol = c->vol;
   m.owner = c->owner; m.neigh = c->neigh;
-  m.per_cell = c->per_cell; m.per_face = c->per_face; m.per_slot = c->per_slot; m.per_df = c->per_df;
+  m.per_cell = c->per_cell; m.per_face = c->per_face; m.per_slot = c->per_slot; m.per_df = c->per_df; m.proc_flip = c->d_proc_flip;
   m.a_slptr = c->pat.slptr; m.a_rinfo = c->pat.rinfo; m.a_ja = c->pat.ja; m.a_llen = c->pat.llen;
   return m;
 }

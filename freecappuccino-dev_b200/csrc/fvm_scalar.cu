@@ -114,7 +114,14 @@ __device__ __forceinline__ void sc_gather(const MeshView &m, const ScArgs &g, in
   q.go[0] = two ? g.g[3 * (int64_t)o] : 0.0; q.go[1] = two ? g.g[3 * (int64_t)o + 1] : 0.0; q.go[2] = two ? g.g[3 * (int64_t)o + 2] : 0.0;
   q.lambda = two ? __ldg(m.facint + f) : 0.0; q.Df = two ? __ldg(m.Df + f) : 0.0; q.fm = two ? g.flmass[f] : 0.0;
   q.xf = two ? __ldg(m.xf + f) : 0.0; q.yf = two ? __ldg(m.yf + f) : 0.0; q.zf = two ? __ldg(m.zf + f) : 0.0;
-  q.fso = (two && (KIND == 3 || KIND == 4)) ? g.fsst[e > 0 ? c : o] : 0.0;
+  if (KIND == 3 || KIND == 4) {
+    // 1/sigma comes from the face's OWNER cell; on a process face that is the peer's cell when the face is flipped against the unpartitioned mesh
+    bool own = e > 0;
+    if (two && own && m.proc_flip && f >= m.F) own = __ldg(m.proc_flip + (f - m.F)) == 0;
+    q.fso = two ? g.fsst[own ? c : o] : 0.0;
+  } else {
+    q.fso = 0.0;
+  }
 }
 // one face of cell c: e = signed entry, o = index across the face, sl = matrix slot (>= 0) or -1 - bctype; the reference's face body
 template <int KIND>

@@ -171,6 +171,7 @@ def lib():
     L.fcp_comm_mode.argtypes = [vp]
     L.fcp_exchange.argtypes = [vp, C.c_int]
     L.fcp_set_process_facint.argtypes = [vp, _pd, C.c_int32]
+    L.fcp_set_process_orientation.argtypes = [vp, _pi, C.c_int32]
     L.fcp_set_flux_variant.argtypes = [vp, C.c_int, C.c_int]
     for nm in ("fcp_global_sum", "fcp_global_max", "fcp_global_min"):
         getattr(L, nm).argtypes = [vp, _pd]
@@ -437,6 +438,12 @@ class Context:
         (`mesh.facint_line_plane` on the global mesh, carried into `Mesh.fpro` by `mesh.partition`); overrides what fcp_comm_init computed."""
         f = np.ascontiguousarray(fpro, dtype=np.float64)
         check(lib().fcp_set_process_facint(self.h, _d(f), int(f.size)), "fcp_set_process_facint")
+
+    def set_process_orientation(self, flipped: np.ndarray):
+        """per process face (patch order): non-zero when this rank's cell is the face's NEIGHBOUR in the unpartitioned mesh (`mesh.process_face_flipped`);
+        needed by the k-omega SST pair on a partition, which takes 1/sigma from the face's owner cell (k_omega_SST.f90:440-449)."""
+        f = np.ascontiguousarray(flipped, dtype=np.int32)
+        check(lib().fcp_set_process_orientation(self.h, _i(f), int(f.size)), "fcp_set_process_orientation")
 
     def comm_mode(self) -> str:
         """'p2p' (peer-memory stores over NVLink fused into the kernels), 'nccl' (send/recv + all-gather) or 'none'."""

@@ -750,6 +750,20 @@ def partition(mesh: Mesh, cell_rank: np.ndarray) -> List[Mesh]:
     return parts
 
 
+def process_face_flipped(gmesh: Mesh, part: Mesh) -> np.ndarray:
+    """Per process face of `part` (patch order): 1 when the partition's cell is the face's NEIGHBOUR in the unpartitioned mesh, i.e. the face's owner
+    lives on the peer rank.  Input of `fcp_set_process_orientation` (the k-omega SST pair takes 1/sigma from a face's owner cell)."""
+    out = []
+    for ib in range(part.numBoundaries):
+        if part.bctype[ib] != BC_PROCESS:
+            continue
+        pf = part.patch_faces(ib)
+        local_owner = part.cell_global[part.owner[pf].astype(np.int64) - 1]
+        global_owner = gmesh.owner[part.face_global[pf]].astype(np.int64) - 1
+        out.append((local_owner != global_owner).astype(np.int32))
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.int32)
+
+
 def drop_empty_patches(parts: List[Mesh]) -> List[Mesh]:
     """What a real src-par decomposition hands a rank: the physical patches that have no face on the rank are simply absent from its boundary
     file (``partition`` keeps them with zero faces, which hides every bug that derives a collective from the LOCAL patch table).  The faces do

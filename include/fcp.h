@@ -334,6 +334,12 @@ int fcp_comm_mode(const fcp_ctx *ctx);
  * fcp_comm_init computes them from the ghost cell centres with the serial tree's formula (geometry.f90:581-606); a host that follows the MPI tree's
  * line-plane variant (quirk Q9) or reads them from a file overrides them here, after fcp_comm_init.  count must equal the number of process faces. */
 int fcp_set_process_facint(fcp_ctx *ctx, const double *fpro, int32_t count);
+/* Orientation of the `process` faces in the UNPARTITIONED mesh (patch order): flipped[i] != 0 when the cell of this rank is the face's NEIGHBOUR there
+ * (its owner lives on the peer).  A rank always sees itself as the owner of its process faces (src-par layout), and nearly every face formula of
+ * the path is symmetric in that choice up to rounding -- the exception is the k-omega SST pair, which takes the 1/sigma of a face from the blending
+ * function of the face's OWNER cell (k_omega_SST.f90:440-449): fcp_calcsc(FCP_SC_TKE_SST / FCP_SC_OMEGA_SST) on a partition needs this call (after
+ * fcp_comm_init; the partitioner knows the orientation) and fails with FCP_ESTATE without it.  count must equal the number of process faces. */
+int fcp_set_process_orientation(fcp_ctx *ctx, const int32_t *flipped, int32_t count);
 int fcp_exchange(fcp_ctx *ctx, int field);                    /* ghost slots of `process` patches <- owner values on the peer */
 int fcp_global_sum(fcp_ctx *ctx, double *value);              /* in place, all ranks */
 int fcp_global_max(fcp_ctx *ctx, double *value);

@@ -463,6 +463,47 @@ def main():
     vis_o, visw_o = gs["vis"].copy(), gs["visw"].copy()
     O.modify_viscosity_sgs(g, O.SGS_VREMAN, 0.7, 0.01, gs["u"], gs["v"], gs["w"], gs["den"], vis_o, visw_o)
     assert rel(ctx2.download("VIS")[:nl], vis_o[me.cell_global]) < 1e-11, "partitioned Vreman viscosity"
+    # ---- the k-omega SST pair on the partition: 1/sigma of a face comes from the blending function of the face's OWNER cell (k_omega_SST.f90:440-449), and
+    # both ranks see themselves as the owner of a process face -> fcp_set_process_orientation; F1 starts from a smooth non-trivial field so that the
+    # k equation already depends on the choice
+    gq = TS.scalar_inputs(g, O)
+    gq["ed"] = 40.0 * gq["ed"]
+    ng = g.numCells
+    gq["walldist"] = np.zeros(g.numTotal); gq["walldist"][:ng] = 0.02 + np.minimum(np.abs(g.yc[:ng] - g.yc[:ng].min()), np.abs(g.yc[:ng].max() - g.yc[:ng]))
+    gq["fsst"] = np.zeros(g.numTotal); gq["fsst"][:ng] = 0.5 + 0.45 * np.sin(3.0 * g.xc[:ng] + 2.0 * g.yc[:ng]) * np.cos(2.5 * g.zc[:ng])
+    gq["lowre"] = 0
+    for k in ("u", "v", "w", "den", "vis", "te", "ed"):
+        ctx2.upload(k.upper(), local_field(gq[k]))
+    ctx2.upload("FLMASS", sign * gq["flmass"][me.face_global])
+    ctx2.upload("VISW", local_bslot(gq["visw"])); ctx2.upload("DNW", local_bslot(gq["dnw"]))
+    ctx2.upload("MAGSTRAIN", msl)
+    wdl = np.zeros(me.numTotal); wdl[:nl] = gq["walldist"][me.cell_global]
+    fsl = np.zeros(me.numTotal); fsl[:nl] = gq["fsst"][me.cell_global]
+    ctx2.upload("WALLDIST", wdl); ctx2.upload("FSST", fsl)
+    sst = dict(sc, lowre=False)
+    if me.npro:
+        try:
+            ctx2.calcsc("TE", kind="tke_sst", **sst)
+            raise AssertionError("the SST pair on a partition must ask for the orientation of the process faces")
+        except L.FcpError:
+            pass
+    ctx2.set_process_orientation(M.process_face_flipped(g, me))
+    fq = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in gq.items()}
+    fq["gen"] = np.zeros(ng)
+    qprm = TS.oracle_params(O, O.SC_TKE_SST, "bicgstab", "muscl", "gauss", "Venkatakrishnan", "steady")
+    qprm.maxiter, qprm.tol_rel, qprm.sum_mode = 400, 1e-13, O.SUM_SEQ
+    ctx2.calcsc("TE", kind="tke_sst", **sst)
+    okq = O.calcsc(g, c0, qprm, fq)
+    fq["gen"] = okq["gen"]; fq["dTEdxi"] = okq["grad"]
+    if os.environ.get("FCP_TEST_DEBUG"):
+        ea_, eapr_ = M.localize_matrix(g, c0, okq["a"], me, csrs[rank])
+        print(rank, "DEBUG sst k a", rel(ctx2.download("A"), ea_), "apr", (rel(ctx2.download("APR"), eapr_) if eapr_.size else 0), "te", rel(ctx2.download("TE")[:nl], fq["te"][me.cell_global]), flush=True)
+    assert rel(ctx2.download("TE")[:nl], fq["te"][me.cell_global]) < 1e-8, "partitioned SST k equation"
+    ctx2.calcsc("ED", kind="omega_sst", **sst)
+    qprm.kind = O.SC_OMEGA_SST
+    O.calcsc(g, c0, qprm, fq)
+    assert rel(ctx2.download("FSST")[:nl], fq["fsst"][me.cell_global]) < 1e-9, "partitioned SST blending function"
+    assert rel(ctx2.download("ED")[:nl], fq["ed"][me.cell_global]) < 1e-8, "partitioned SST omega equation"
     ctx2.close()
     ctx.close()
     dist.barrier()
